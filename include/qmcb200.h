@@ -1,0 +1,166 @@
+/*
+ * qmcb200.h -- C ABI of libqmcb200.so: B200-native (sm_100a) evaluation of the PyQMC
+ * walker-batched trial-wave-function hot path.
+ *
+ * The reference (WagnerGroup/pyqmc) has no FFI: its boundary for this path is the
+ * duck-typed Python wave-function protocol (doc/source/wavefunction.rst:1-37) and the
+ * EnergyAccumulator functor (pyqmc/observables/accumulators.py:45-95).  Each entry point
+ * below names the reference method it replaces; the ctypes stub a maintainer would add is in
+ * INTEGRATION.md.  Conventions:
+ *   - every function returns 0 on success, <0 on error; qmcb_last_error() gives the text;
+ *   - the caller owns all host buffers (C-contiguous float64 / int32 / uint8); the library
+ *     owns device memory; calls are synchronous (stream-synchronised before returning)
+ *     unless the name ends in _async;
+ *   - one context per (device, wave function); a context is not thread-safe;
+ *   - `which` selects the factors a call applies to: QMCB_SLATER | QMCB_JASTROW.  With both
+ *     bits the call has MultiplyWF semantics (pyqmc/wf/multiplywf.py:71-132): log-values
+ *     and gradients add, ratios multiply, Laplacian gets the 2 grad_i.grad_j cross term.
+ *   - walkers: configs[N][nelec][3]; electrons 0..nup-1 are spin up (slater.py:236-239).
+ */
+#ifndef QMCB200_H
+#define QMCB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qmcb_ctx qmcb_ctx;
+
+#define QMCB_SLATER 1
+#define QMCB_JASTROW 2
+
+/* Jastrow radial function kinds (pyqmc/wf/func3d.py:52-110 PolyPade, 112-210 CutoffCusp) */
+#define QMCB_FUNC_POLYPADE 0
+#define QMCB_FUNC_CUSP 1
+
+const char *qmcb_last_error(void);
+int qmcb_device_count(void);
+
+int qmcb_create(int device, qmcb_ctx **out);
+void qmcb_destroy(qmcb_ctx *ctx);
+
+/* ---- system description ------------------------------------------------------------ */
+
+/* mol.atom_coords() / mol.atom_charges() (energy.py:38-44, jastrowspin.py:52) */
+int qmcb_set_atoms(qmcb_ctx *ctx, int natom, const double *xyz /*[natom*3]*/,
+                   const double *charges /*[natom]*/);
+
+/* Flattened, NORMALISED shell table: what AtomicOrbitalEvaluator.__init__ builds
+ * (pyqmc/wf/numba/gto.py:435-488).  Shells must be grouped by atom, atoms ascending.
+ * AO order: shells in order, 2l+1 functions per shell, l <= 4. */
+int qmcb_set_basis(qmcb_ctx *ctx, int nshell, const int32_t *shell_atom, const int32_t *shell_l,
+                   const int32_t *prim_off /*[nshell+1]*/, const double *prim_exp,
+                   const double *prim_coef);
+
+/* Slater.__init__ products (slater.py:193-208; determinant_tools.py:39-71):
+ * mo_s [nao][nmo_s] row-major, occ_s [ndet_s][n_s] MO indices of each unique spin
+ * determinant, map_s [ndet] -> unique spin-determinant, det_coeff [ndet]. */
+int qmcb_set_slater(qmcb_ctx *ctx, int nup, int ndn, int nmo_up, const double *mo_up,
+                    int nmo_dn, const double *mo_dn, int ndet_up, const int32_t *occ_up,
+                    int ndet_dn, const int32_t *occ_dn, int ndet, const int32_t *map_up,
+                    const int32_t *map_dn, const double *det_coeff);
+
+/* JastrowSpin.__init__ (jastrowspin.py:34-54): a (electron-ion) and b (electron-electron)
+ * radial bases with one shared cutoff each, acoeff [natom][na][2], bcoeff [nb][3]. */
+int qmcb_set_jastrow(qmcb_ctx *ctx, int nup, int ndn, int na, const int32_t *a_kind,
+                     const double *a_par, double rcut_a, int nb, const int32_t *b_kind,
+                     const double *b_par, double rcut_b, const double *acoeff,
+                     const double *bcoeff);
+
+/* mol._ecp flattened (eval_ecp.py:160-200): for each ECP atom the channel list in COLUMN
+ * order l = 0..lmax then the local channel (l = -1) last; channel c owns terms
+ * term_off[c]..term_off[c+1] of v(r) = sum coef * r^power * exp(-alpha r^2). */
+int qmcb_set_ecp(qmcb_ctx *ctx, int necp, const int32_t *ecp_atom /*[necp]*/,
+                 const int32_t *chan_off /*[necp+1]*/, const int32_t *term_off /*[nchan+1]*/,
+                 const int32_t *term_power, const double *term_alpha, const double *term_coef,
+                 const int32_t *naip /*[necp]*/,
+                 const double *quad /* per ECP atom: naip*3 points then naip weights
+                                       (eval_ecp.py:278-336) */,
+                 double threshold);
+
+/* ---- wave-function protocol ---------------------------------------------------------- */
+
+/* wf.recompute(configs) -> (sign, log|psi|)   slater.py:227-260, jastrowspin.py:56-109 */
+int qmcb_recompute(qmcb_ctx *ctx, int which, int nconf, const double *configs, double *sign,
+                   double *logval);
+/* wf.value()   slater.py:293-299, jastrowspin.py:251-255 */
+int qmcb_value(qmcb_ctx *ctx, int which, double *sign, double *logval);
+/* wf.gradient(e, epos) -> grad[3][N]   slater.py:390-401, jastrowspin.py:258-294 */
+int qmcb_gradient(qmcb_ctx *ctx, int which, int e, const double *epos /*[N][3]*/, double *grad);
+/* wf.gradient_value(e, epos) -> grad[3][N], val[N]; keeps the MO row / position in the
+ * context's saved slot (returned token in *slot) for a following updateinternals
+ * slater.py:403-418, jastrowspin.py:296-340 */
+int qmcb_gradient_value(qmcb_ctx *ctx, int which, int e, const double *epos, double *grad,
+                        double *val, int64_t *slot);
+/* wf.gradient_laplacian(e, epos) -> grad[3][N], lap[N] = lap(psi)/psi
+ * slater.py:420-427, jastrowspin.py:342-385, multiplywf.py:121-129 */
+int qmcb_gradient_laplacian(qmcb_ctx *ctx, int which, int e, const double *epos, double *grad,
+                            double *lap);
+/* wf.testvalue(e, epos, mask) -> ratio[Nm][naip]; epos is [N][naip][3] (rows of unmasked
+ * walkers are ignored); mask NULL = all.  slater.py:429-446, jastrowspin.py:387-419 */
+int qmcb_testvalue(qmcb_ctx *ctx, int which, int e, const double *epos, int naip,
+                   const uint8_t *mask, double *ratio, int64_t *slot);
+/* wf.testvalue_many(e[], epos, mask) -> ratio[Nm][ne_list]  slater.py:448-460 */
+int qmcb_testvalue_many(qmcb_ctx *ctx, int which, int ne_list, const int32_t *elist,
+                        const double *epos /*[N][3]*/, const uint8_t *mask, double *ratio);
+/* wf.updateinternals(e, epos, configs, mask, saved_values): slot = token returned by
+ * gradient_value/testvalue for the same (e, epos), or -1 to re-evaluate the orbitals
+ * slater.py:262-291 (Sherman-Morrison 88-94), jastrowspin.py:111-137, 221-249 */
+int qmcb_updateinternals(qmcb_ctx *ctx, int which, int e, const double *epos,
+                         const uint8_t *mask, int64_t slot);
+/* wf.pgradient(): name in {"det_coeff","mo_coeff_alpha","mo_coeff_beta","acoeff","bcoeff"}
+ * slater.py:462-542, jastrowspin.py:457-464.  out is [N][...param shape]. */
+int qmcb_pgradient(qmcb_ctx *ctx, const char *name, double *out);
+
+/* internal state read-back for tests: "inverse_up","inverse_dn" [N][D_s][n][n];
+ * "dets_up","dets_dn" [2][N][D_s]; "a_partial" [ne][N][I][na]; "b_partial" [ne][N][nb][2];
+ * "avalues" [N][I][na][2]; "bvalues" [N][nb][3]; "configs" [N][ne][3] */
+int qmcb_get_state(qmcb_ctx *ctx, const char *name, double *out);
+
+/* ---- local energy (EnergyAccumulator.__call__, accumulators.py:60-75) ------------------ */
+/* Random variates are drawn by the caller in the reference's order (eval_ecp.py:145, 263):
+ * ecp_u [ne][necp][N] uniform numbers for the stochastic channel mask, ecp_rot
+ * [ne][necp][3][3] rotation matrices.  out [6][N] = ke, ee, ei, ecp, grad2, total. */
+int qmcb_energy(qmcb_ctx *ctx, const double *ecp_u, const double *ecp_rot, double *out);
+
+/* eval_ecp.compute_tmoves (eval_ecp.py:43-80) for electron e:
+ * ratio[N][M], weight[N][M], epos[N][M][3], M = sum of naip over ECP atoms. */
+int qmcb_tmoves(qmcb_ctx *ctx, int e, double tau, const double *ecp_u /*[necp][N]*/,
+                const double *ecp_rot /*[necp][9]*/, double *ratio, double *weight,
+                double *epos);
+
+/* ---- device-resident VMC block (vmc_worker, pyqmc/method/mc.py:102-153) ---------------- */
+/* Runs nsteps sweeps (+ local energy after each sweep when with_energy) on the walkers
+ * currently held by the context (after qmcb_recompute).  Random variates in reference
+ * order: gauss [nsteps][ne][N][3] ~ N(0, tstep), unif [nsteps][ne][N], ecp_u
+ * [nsteps][ne][necp][N], ecp_rot [nsteps][ne][necp][9].
+ * Outputs (any may be NULL): configs [N][ne][3] final positions; accept [nsteps][ne][N]
+ * (uint8); energy [nsteps][6][N]; esum [nsteps][6] walker sums; nacc [nsteps][ne]. */
+int qmcb_vmc_block(qmcb_ctx *ctx, int nsteps, double tstep, int with_energy,
+                   const double *gauss, const double *unif, const double *ecp_u,
+                   const double *ecp_rot, double *configs, uint8_t *accept, double *energy,
+                   double *esum, int64_t *nacc);
+
+/* Same block with all inputs/outputs already in device memory and no host sync: used by
+ * bench.py to time the HBM-resident path.  Pointers are device pointers. */
+int qmcb_vmc_block_device(qmcb_ctx *ctx, int nsteps, double tstep, int with_energy,
+                          const double *d_gauss, const double *d_unif, const double *d_ecp_u,
+                          const double *d_ecp_rot, uint8_t *d_accept, double *d_energy,
+                          double *d_esum, int64_t *d_nacc, void *stream);
+int qmcb_kernel_launches(qmcb_ctx *ctx, int64_t *count); /* launches issued so far */
+
+/* ---- Sherman-Morrison kernel on its own (roofline measurement / unit test) --------------
+ * sherman_morrison_ms (slater.py:88-94) on device arrays: inv [M][n][n], vec [M][n],
+ * mask [M] or NULL, ratio [M].  Launches the same kernel updateinternals uses. */
+int qmcb_sm_update_device(int n, int e, int64_t nmat, double *d_inv, const double *d_vec,
+                          const uint8_t *d_mask, double *d_ratio, void *stream);
+/* host-buffer convenience wrapper (copies in, runs, copies out) */
+int qmcb_sm_update(int n, int e, int64_t nmat, double *inv, const double *vec,
+                   const uint8_t *mask, double *ratio);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

