@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- walker-steps/s of VMC on synthetic H2O ccECP-cc-pVTZ Slater-Jastrow (BASELINE.json
+configs[1]: 4096 walkers per GPU) + HBM roofline of the Sherman-Morrison update kernel.
+
+One "step" = one VMC step of every walker of this rank: a sweep of single-electron
+drift-diffusion moves over all 8 electrons plus the local-energy accumulator (ke, ee, ei, ECP)
+-- one iteration of the loop at pyqmc/method/mc.py:112-152.
+
+  value   device-timed (CUDA events on the launching stream), random variates and walkers
+          already resident in HBM, L2 flushed between timed steps;
+  e2e     the public call pyqmc_b200.vmc(...) with host numpy walkers: host RNG draws in the
+          reference's order, H2D of the variates, the device block, D2H of energies + walkers;
+  cpu_baseline / --impl reference   the numpy oracle (port of the reference path; the reference
+          itself is Python and is not present on the GPU box) on all host cores.
+
+Launch: python bench.py --gpus N --steps K --warmup W   (N>1: under torchrun, one rank per GPU).
+"""
+import argparse
+import ctypes
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("OMP_NUM_THREADS", "1")
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+os.environ.setdefault("MKL_NUM_THREADS", "1")
+
+import numpy as np  # noqa: E402
+
+NWALKERS = 4096
+TSTEP = 0.5
+WORKLOAD = "H2O ccECP-cc-pVTZ-shaped Slater-Jastrow VMC (synthetic basis/MOs), 8 e-, 57 AOs, 4096 walkers/GPU"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on all host cores (the reference's own parallel mechanism is a
+# futures pool over walker partitions, mc.py:156-173)
+# ------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, nwalk, nsteps, warm = args
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    from oracle import vmc_driver
+    from oracle.local_energy import EnergyOracle
+
+    mol, mf, dets = helpers.make_system("h2o")
+    from oracle.jastrow2 import JastrowOracle
+    from oracle.product import ProductOracle
+    from oracle.slater_det import SlaterOracle
+
+    oj = JastrowOracle.default(mol)
+    a0, ac, bc = helpers.jastrow_coefficients(oj.parameters["acoeff"].shape, oj.parameters["bcoeff"].shape, False, 1)
+    oj.parameters["acoeff"][:, a0:, :] = ac[:, a0:, :]
+    oj.parameters["bcoeff"][1:, :] = bc[1:, :]
+    wf = ProductOracle(SlaterOracle(mol, mf), oj)
+    np.random.seed(seed)
+    configs = vmc_driver.initial_guess(mol, nwalk)
+    acc = {"energy": EnergyOracle(mol)}
+    if warm:
+        vmc_driver.vmc_worker(wf, configs, TSTEP, 1, acc)
+    t0 = time.perf_counter()
+    vmc_driver.vmc_worker(wf, configs, TSTEP, nsteps, acc)
+    return time.perf_counter() - t0
+
+
+def cpu_arm(steps, warmup, walkers_per_core=256, cores=None):
+    cores = cores or os.cpu_count() or 1
+    cores = min(cores, 64)
+    with mp.get_context("spawn").Pool(cores) as pool:
+        if warmup:
+            pool.map(_cpu_worker, [(100 + i, 32, 1, False) for i in range(cores)])
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(i, walkers_per_core, steps, False) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    total = walkers_per_core * cores * steps
+    return total / wall, cores, wall, f"{walkers_per_core} walkers/core x {cores} cores x {steps} steps (oracle port, numpy)"
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            out = ""
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def sm_roofline(torch, lib, n, nmat, reps=5):
+    """HBM GB/s of the Sherman-Morrison update kernel alone (same kernel updateinternals launches)."""
+    inv = torch.randn(nmat, n, n, dtype=torch.float64, device="cuda") * 0.1 + torch.eye(n, dtype=torch.float64, device="cuda")
+    vec = torch.randn(nmat, n, dtype=torch.float64, device="cuda") + 2.0 * torch.eye(n, dtype=torch.float64, device="cuda")[n // 2]
+    ratio = torch.empty(nmat, dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    times = []
+    for it in range(reps + 2):
+        flush.fill_(it & 0xFF)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = lib.qmcb_sm_update_device(n, n // 2, nmat, ctypes.c_void_p(inv.data_ptr()), ctypes.c_void_p(vec.data_ptr()),
+                                       None, ctypes.c_void_p(ratio.data_ptr()), ctypes.c_void_p(stream))
+        assert rc == 0, lib.qmcb_last_error()
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            times.append(e0.elapsed_time(e1) * 1e-3)
+    t = float(np.mean(times))
+    bytes_alg = nmat * 8 * (2 * n * n + n + 1)  # read inv + row, write inv + ratio
+    return bytes_alg / t / 1e9, t, bytes_alg
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ["PYQMC_B200_DEVICE"] = str(local)
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as g
+
+    if rank == 0:
+        g.build()
+    if world > 1:
+        dist.barrier()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    import pyqmc_b200 as pq
+    from pyqmc_b200 import _lib, mc
+
+    lib = _lib.load()
+    K, W, N = args.steps, args.warmup, args.walkers
+    mol, mf, wf, _ = helpers.make_pair("h2o", seed=1)
+    acc = pq.EnergyAccumulator(mol)
+    np.random.seed(1000 + rank)
+    configs = pq.initial_guess(mol, N)
+    ne = configs.configs.shape[1]
+    # equilibrate with the public driver (also builds every device buffer)
+    pq.vmc(wf, configs, tstep=TSTEP, nblocks=1, nsteps_per_block=args.equil, accumulators={"energy": acc})
+    ctx = wf._ctx
+
+    # ---------------- device-resident measurement ----------------
+    tot = W + K
+    gauss, unif, ecp_u, ecp_rot = mc.draw_block_variates(N, ne, TSTEP, tot, acc)
+    d_gauss = torch.from_numpy(gauss).cuda()
+    d_unif = torch.from_numpy(unif).cuda()
+    d_u = torch.from_numpy(ecp_u).cuda()
+    d_rot = torch.from_numpy(ecp_rot).cuda()
+    d_energy = torch.empty((6, N), dtype=torch.float64, device="cuda")
+    d_esum = torch.zeros((tot, 8), dtype=torch.float64, device="cuda")
+    d_nacc = torch.zeros((tot, ne), dtype=torch.int64, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    wf.recompute(configs)
+    stream = torch.cuda.current_stream().cuda_stream
+    vp = ctypes.c_void_p
+
+    def run_step(s):
+        rc = lib.qmcb_vmc_block_device(ctx.h, 1, TSTEP, 1, vp(d_gauss[s].data_ptr()), vp(d_unif[s].data_ptr()),
+                                       vp(d_u[s].data_ptr()), vp(d_rot[s].data_ptr()), None, vp(d_energy.data_ptr()),
+                                       vp(d_esum[s].data_ptr()), vp(d_nacc[s].data_ptr()), vp(stream))
+        if rc != 0:
+            raise RuntimeError(lib.qmcb_last_error().decode())
+        if world > 1:  # one allreduce of the block statistics (here: per step) over NVLink
+            dist.all_reduce(d_esum[s])
+
+    for s in range(W):
+        run_step(s)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = ctx.kernel_launches()
+    sampler = ClockSampler(local) if rank == 0 else None
+    evs = []
+    wall0 = time.perf_counter()
+    for s in range(W, tot):
+        flush.fill_(s & 0xFF)  # evict the walker state from L2 between timed steps
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_step(s)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    launches = ctx.kernel_launches() - launches0
+    clocks = sampler.stop() if sampler else None
+    t_dev = sum(a.elapsed_time(b) for a, b in evs) * 1e-3
+    tmax = torch.tensor([t_dev], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    t_dev_max = float(tmax.item())
+    value = N * world * K / t_dev_max
+    e_mean = float(d_esum[W:tot, 5].sum().item()) / (N * world * K)
+    accept = float(d_nacc[W:tot].sum().item()) / (N * ne * K)
+
+    # ---------------- end-to-end through the public API (host buffers) ----------------
+    nb_e2e = max(1, min(3, K // 10))
+    spb = 10
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    df, configs = pq.vmc(wf, configs, tstep=TSTEP, nblocks=nb_e2e, nsteps_per_block=spb, accumulators={"energy": acc})
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    t_e2e = float(te.item())
+    e2e = N * world * nb_e2e * spb / t_e2e
+    necp = acc.necp
+    h2d = spb * ne * N * (3 + 1) * 8 + spb * ne * necp * (N + 9) * 8 + N * ne * 3 * 8
+    d2h = spb * 6 * N * 8 + N * ne * 3 * 8 + spb * ne * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    g32, t32, b32 = sm_roofline(torch, lib, 32, 1 << 17)
+    g4, t4, b4 = sm_roofline(torch, lib, 4, 1 << 22)
+    g4s, t4s, _ = sm_roofline(torch, lib, 4, N)
+    out = {
+        "metric": "walker-steps/sec (VMC, H2O cc-pVTZ SJ); Sherman-Morrison HBM GB/s vs roofline",
+        "value": value, "unit": "walker-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 * t_dev_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "walkers_per_gpu": N, "nelec": ne, "tstep": TSTEP,
+                   "l2": "256 MiB buffer written between timed steps (L2 flush)", "ecp_threshold": 10,
+                   "parallelism": f"walker-sharded x{world}, one NCCL allreduce of the energy sums per step"},
+        "e2e": {"value": e2e, "unit": "walker-steps/s", "h2d_bytes_per_step": h2d / spb, "d2h_bytes_per_step": d2h / spb,
+                "call": f"pyqmc_b200.vmc(nblocks={nb_e2e}, nsteps_per_block={spb}) incl. host legacy-RNG draws"},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "k_sm_warp<32>: Sherman-Morrison row update, n=32 (C4 shape), 131072 matrices",
+                     "bound": "hbm", "achieved": g32, "peak": peak, "unit": "GB/s", "frac": g32 / peak,
+                     "traffic": None, "peak_source": peak_src, "launch_ms": 1e3 * t32, "algorithmic_bytes": b32},
+        "sm_kernel_other_shapes": {
+            "n4_4M_matrices": {"achieved_GBps": g4, "frac": g4 / peak, "launch_ms": 1e3 * t4},
+            "n4_4096_matrices_C2_shape": {"achieved_GBps": g4s, "frac": g4s / peak, "launch_ms": 1e3 * t4s}},
+        "clocks": clocks,
+        "check": {"mean_local_energy": e_mean, "acceptance": accept, "wall_s_timed_region_incl_flush": wall},
+    }
+    if world == 1 and not args.no_cpu:
+        v, cores, cwall, sample = cpu_arm(2, True)
+        out["cpu_baseline"] = {"value": v, "unit": "walker-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                               "wall_s": cwall}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    walkers = 256
+    v, cores, wall, sample = cpu_arm(max(1, min(args.steps, 4)), args.warmup > 0, walkers_per_core=walkers)
+    out = {
+        "impl": "reference",
+        "metric": "walker-steps/sec (VMC, H2O cc-pVTZ SJ); Sherman-Morrison HBM GB/s vs roofline",
+        "value": v, "unit": "walker-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "numpy oracle port of the reference path on host cores; "
+                   "the Python reference is not present on the GPU box"},
+        "cpu_baseline": {"value": v, "unit": "walker-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "walker-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--walkers", type=int, default=NWALKERS)
+    ap.add_argument("--equil", type=int, default=10)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

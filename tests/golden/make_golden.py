@@ -1,0 +1,129 @@
+"""Generates the committed golden vectors by running the UNMODIFIED reference
+(/root/reference, numba GTO evaluator) on the synthetic systems of ``pyqmc_b200.systems``.
+
+    python tests/golden/make_golden.py        # writes tests/golden/<system>.npz
+
+Only this script (and refload.py) touch /root/reference; the fixtures travel to the GPU box.
+Each file holds the inputs (walkers, trial positions, masks, Jastrow coefficients, RNG seeds)
+and the reference's outputs for every wf-protocol call, the energy accumulator and a short
+VMC run.  The reference's numba kernels use fastmath, so outputs are reproducible to rounding
+(~1e-13 relative), not bit-for-bit across LLVM versions -- tests compare at 1e-10.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, HERE)
+
+import helpers  # noqa: E402
+import refload  # noqa: E402
+
+NCONF = 12
+SYSTEMS = ["he", "h2o", "open", "c2", "h2o_md"]
+
+
+def build_reference(name):
+    mol, mf, dets = helpers.make_system(name)
+    wf = refload.build_reference_wf(mol, mf, determinants=dets, seed=0)
+    # same seeded Jastrow coefficients as helpers.make_pair
+    jast = wf.wf_factors[1]
+    has_cusp = len(jast.a_basis) > 4
+    a0, ac, bc = helpers.jastrow_coefficients(jast.parameters["acoeff"].shape, jast.parameters["bcoeff"].shape,
+                                              has_cusp, 1)
+    jast.parameters["acoeff"][:, a0:, :] = ac[:, a0:, :]
+    jast.parameters["bcoeff"][1:, :] = bc[1:, :]
+    return mol, wf
+
+
+def generate(name):
+    import pyqmc.method.mc as mc
+    from pyqmc.observables.accumulators import EnergyAccumulator
+
+    mol, wf = build_reference(name)
+    out = {}
+    np.random.seed(3)
+    configs = mc.initial_guess(mol, NCONF)
+    out["configs0"] = configs.configs.copy()
+    out["acoeff"] = np.array(wf.parameters["wf2acoeff"])
+    out["bcoeff"] = np.array(wf.parameters["wf2bcoeff"])
+    s, l = wf.recompute(configs)
+    out["recompute_sign"], out["recompute_log"] = s, l
+    ne = configs.configs.shape[1]
+    rng = np.random.RandomState(5)
+    elist = sorted({0, ne // 2, ne - 1})
+    out["elist"] = np.array(elist)
+    for i, e in enumerate(elist):
+        newpos = configs.configs[:, e] + 0.3 * rng.randn(NCONF, 3)
+        mask = rng.rand(NCONF) > 0.4
+        aux = configs.configs[:, e][:, None, :] + 0.2 * rng.randn(NCONF, 6, 3)
+        ep = configs.make_irreducible(e, newpos)
+        out[f"q{i}_newpos"], out[f"q{i}_mask"], out[f"q{i}_aux"] = newpos, mask, aux
+        out[f"q{i}_gradient"] = wf.gradient(e, ep)
+        g, v, saved = wf.gradient_value(e, ep)
+        out[f"q{i}_gv_grad"], out[f"q{i}_gv_val"] = g, v
+        g, lap = wf.gradient_laplacian(e, ep)
+        out[f"q{i}_gl_grad"], out[f"q{i}_gl_lap"] = g, lap
+        out[f"q{i}_testvalue"] = wf.testvalue(e, ep)[0]
+        out[f"q{i}_testvalue_mask"] = wf.testvalue(e, ep, mask)[0]
+        out[f"q{i}_testvalue_aux"] = wf.testvalue(e, configs.make_irreducible(e, aux), mask)[0]
+        out[f"q{i}_testvalue_many"] = wf.testvalue_many(np.arange(ne), ep)
+        g, v, saved = wf.gradient_value(e, ep)
+        configs.move(e, ep, mask)
+        wf.updateinternals(e, ep, configs, mask=mask, saved_values=saved)
+        s, l = wf.value()
+        out[f"q{i}_value_sign"], out[f"q{i}_value_log"] = s, l
+    out["configs1"] = configs.configs.copy()
+    sl, ja = wf.wf_factors[0], wf.wf_factors[1]
+    for spin in (0, 1):
+        out[f"inverse{spin}"] = np.array(sl._inverse[spin])
+        out[f"dets{spin}"] = np.array(sl._dets[spin])
+    out["a_partial"], out["b_partial"] = np.array(ja._a_partial), np.array(ja._b_partial)
+    pg = wf.pgradient()
+    for k in pg.keys():
+        out["pgrad_" + k] = np.array(pg[k])
+    np.random.seed(21)
+    en = EnergyAccumulator(mol)(configs, wf)
+    for k, v in en.items():
+        out["energy_" + k] = np.asarray(v)
+    np.random.seed(22)
+    tm = EnergyAccumulator(mol).nonlocal_tmoves(configs, wf, elist[-1], 0.02)
+    out["tmove_ratio"], out["tmove_weight"] = tm["ratio"], tm["weight"]
+    out["tmove_configs"] = tm["configs"].configs
+    # short VMC run (recording the accept masks through a thin wrapper around updateinternals)
+    accepts = []
+    orig = wf.updateinternals
+
+    def spy(e, epos, cfg, mask=None, saved_values=None):
+        accepts.append(np.array(mask))
+        return orig(e, epos, cfg, mask=mask, saved_values=saved_values)
+
+    wf.updateinternals = spy
+    np.random.seed(31)
+    df, configs = mc.vmc(wf, configs, tstep=0.5, nblocks=2, nsteps_per_block=3,
+                         accumulators={"energy": EnergyAccumulator(mol)})
+    wf.updateinternals = orig
+    out["vmc_accept"] = np.array(accepts).reshape(2, 3, ne, NCONF)
+    out["vmc_configs"] = configs.configs.copy()
+    for k in ("energytotal", "energyke", "energyecp", "energyee", "energyei", "energygrad2", "acceptance"):
+        out["vmc_" + k] = df[k]
+    return out
+
+
+def main():
+    warnings.filterwarnings("ignore")
+    refload.load()
+    for name in SYSTEMS:
+        data = generate(name)
+        path = os.path.join(HERE, f"{name}.npz")
+        np.savez_compressed(path, **data)
+        print(f"wrote {path}: {len(data)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,134 @@
+"""CPU tests: the numpy oracle against the committed golden vectors produced by the reference
+(tests/golden/*.npz), and -- when /root/reference is present (this container only) -- directly
+against the live reference."""
+import numpy as np
+import pytest
+
+import golden_replay
+import helpers
+import refload
+
+SYSTEMS = ["he", "h2o", "open", "c2", "h2o_md"]
+
+
+def oracle_vmc(wf, configs, accumulators):
+    from oracle import vmc_driver
+
+    record = []
+    df, configs = vmc_driver.vmc(wf, configs, tstep=0.5, nblocks=2, nsteps_per_block=3, accumulators=accumulators,
+                                 record=record)
+    N, ne = configs.configs.shape[:2]
+    accepts = np.array([r["accept"] for r in record]).reshape(2, 3, ne, N)
+    return df, configs, accepts
+
+
+def check_internal(wf, data):
+    sl, ja = wf.wf_factors
+    for s in (0, 1):
+        assert helpers.relerr(sl._inverse[s], data[f"inverse{s}"]) < 1e-9
+        assert np.array_equal(sl._dets[s][0], data[f"dets{s}"][0])
+        assert np.abs(sl._dets[s][1] - data[f"dets{s}"][1]).max() < 1e-10
+    assert helpers.relerr(ja._a_partial, data["a_partial"]) < 1e-10
+    assert helpers.relerr(ja._b_partial, data["b_partial"]) < 1e-10
+    pg = wf.pgradient()
+    for k in ("wf1det_coeff", "wf1mo_coeff_alpha", "wf1mo_coeff_beta", "wf2acoeff", "wf2bcoeff"):
+        if "pgrad_" + k in data:
+            assert helpers.relerr(pg[k], data["pgrad_" + k]) < 1e-9, k
+
+
+@pytest.mark.parametrize("name", SYSTEMS)
+def test_oracle_reproduces_reference_golden(name):
+    from oracle.local_energy import EnergyOracle
+    from oracle.walkers import Walkers
+
+    data = golden_replay.load(name)
+    mol, mf, _, orc = helpers.make_pair(name, seed=1) if False else _oracle_only(name)
+    assert np.array_equal(orc.wf_factors[1].parameters["acoeff"], data["acoeff"])
+    assert np.array_equal(orc.wf_factors[1].parameters["bcoeff"], data["bcoeff"])
+    configs = Walkers(data["configs0"].copy())
+    golden_replay.replay(data, orc, configs, lambda: EnergyOracle(mol), oracle_vmc, check_internal)
+
+
+def _oracle_only(name):
+    """helpers.make_pair builds the device objects too; here only the oracle side is needed."""
+    from oracle.jastrow2 import JastrowOracle
+    from oracle.product import ProductOracle
+    from oracle.slater_det import SlaterOracle
+
+    mol, mf, dets = helpers.make_system(name)
+    oj = JastrowOracle.default(mol)
+    has_cusp = len(oj.a_basis) > 4
+    a0, ac, bc = helpers.jastrow_coefficients(oj.parameters["acoeff"].shape, oj.parameters["bcoeff"].shape, has_cusp, 1)
+    oj.parameters["acoeff"][:, a0:, :] = ac[:, a0:, :]
+    oj.parameters["bcoeff"][1:, :] = bc[1:, :]
+    return mol, mf, None, ProductOracle(SlaterOracle(mol, mf, determinants=dets), oj)
+
+
+@pytest.mark.parametrize("name", ["h2o", "c2"])
+def test_oracle_tmoves_match_golden(name):
+    from oracle.local_energy import EnergyOracle
+    from oracle.walkers import Walkers
+
+    data = golden_replay.load(name)
+    mol, mf, _, orc = _oracle_only(name)
+    configs = Walkers(data["configs1"].copy())
+    orc.recompute(configs)
+    np.random.seed(22)
+    tm = EnergyOracle(mol).nonlocal_tmoves(configs, orc, int(data["elist"][-1]), 0.02)
+    assert helpers.relerr(tm["ratio"], data["tmove_ratio"]) < 1e-9
+    assert helpers.relerr(tm["weight"], data["tmove_weight"]) < 1e-10
+    assert np.abs(tm["configs"] - data["tmove_configs"]).max() < 1e-12
+
+
+def test_sherman_morrison_oracle_vs_numpy():
+    """tests/unit/test_sherman_morrison.py:20-82 restated for the oracle's rank-1 update."""
+    from oracle.slater_det import rank1_row_update
+
+    rng = np.random.RandomState(0)
+    n, nconf, ndet, e = 10, 4, 8, 2
+    u, _, v = np.linalg.svd(rng.randn(n, n))
+    sv = (rng.rand(nconf, ndet, n) + 1) * rng.choice([-1, 1], (nconf, ndet, n))
+    mat = np.einsum("ij,...hj,jk->...hik", u, sv, v)
+    inv = np.linalg.inv(mat)
+    vec = rng.randn(nconf, ndet, n) + 2 * mat[..., e, :]
+    new = mat.copy()
+    new[..., e, :] = vec
+    ratio, upd = rank1_row_update(e, inv, vec)
+    assert np.abs(ratio - np.linalg.det(new) / np.linalg.det(mat)).max() < 1e-12
+    assert np.abs(upd - np.linalg.inv(new)).max() < 1e-11
+
+
+@pytest.mark.skipif(not refload.available(), reason="/root/reference only exists in the build container")
+def test_solid_harmonics_match_reference_tables():
+    refload.load()
+    import pyqmc.wf.numba.spherical_harmonics as hsh
+    from oracle import solid_harmonics as sh
+
+    rng = np.random.RandomState(0)
+    for _ in range(20):
+        x, y, z = rng.randn(3)
+        s, dx, dy, dz = np.zeros(25), np.zeros(25), np.zeros(25), np.zeros(25)
+        hsh.SPH4_GRAD(x, y, z, x * x, y * y, z * z, s, dx, dy, dz)
+        S, dS = sh.evaluate(4, np.array(x), np.array(y), np.array(z), deriv=True)
+        scale = max(1.0, np.abs(s).max())
+        assert np.abs(S - s).max() < 1e-12 * scale
+        for a, d in enumerate((dx, dy, dz)):
+            assert np.abs(dS[a] - d).max() < 1e-12 * max(1.0, np.abs(d).max())
+
+
+def test_device_sph_tables_equal_oracle_tables():
+    """The CUDA code generator and the oracle must tabulate the same polynomials."""
+    import importlib.util
+    import os
+
+    from oracle import solid_harmonics as sh
+
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pyqmc_b200", "csrc", "gen_sph.py")
+    spec = importlib.util.spec_from_file_location("gen_sph", p)
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    t = gen.tables()
+    for l in range(5):
+        assert len(t[l]) == len(sh.TABLES[l]) == 2 * l + 1
+        for a, b in zip(t[l], sh.TABLES[l]):
+            assert a == b
