@@ -133,19 +133,24 @@ def sm_roofline(torch, lib, n, nmat, reps=5):
     vec = torch.randn(nmat, n, dtype=torch.float64, device="cuda") + 2.0 * torch.eye(n, dtype=torch.float64, device="cuda")[n // 2]
     ratio = torch.empty(nmat, dtype=torch.float64, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
+    # the kernel is launched on this torch stream (a real, non-default stream handle) and the
+    # events are recorded on the same stream
+    ts = torch.cuda.Stream()
+    assert ts.cuda_stream != 0
+    torch.cuda.synchronize()
     times = []
-    for it in range(reps + 2):
-        flush.fill_(it & 0xFF)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        rc = lib.qmcb_sm_update_device(n, n // 2, nmat, ctypes.c_void_p(inv.data_ptr()), ctypes.c_void_p(vec.data_ptr()),
-                                       None, ctypes.c_void_p(ratio.data_ptr()), ctypes.c_void_p(stream))
-        assert rc == 0, lib.qmcb_last_error()
-        e1.record()
-        torch.cuda.synchronize()
-        if it >= 2:
-            times.append(e0.elapsed_time(e1) * 1e-3)
+    with torch.cuda.stream(ts):
+        for it in range(reps + 2):
+            flush.fill_(it & 0xFF)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ts)
+            rc = lib.qmcb_sm_update_device(n, n // 2, nmat, ctypes.c_void_p(inv.data_ptr()), ctypes.c_void_p(vec.data_ptr()),
+                                           None, ctypes.c_void_p(ratio.data_ptr()), ctypes.c_void_p(ts.cuda_stream))
+            assert rc == 0, lib.qmcb_last_error()
+            e1.record(ts)
+            ts.synchronize()
+            if it >= 2:
+                times.append(e0.elapsed_time(e1) * 1e-3)
     t = float(np.mean(times))
     bytes_alg = nmat * 8 * (2 * n * n + n + 1)  # read inv + row, write inv + ratio
     return bytes_alg / t / 1e9, t, bytes_alg
@@ -197,7 +202,12 @@ def gpu_arm(args):
     d_nacc = torch.zeros((tot, ne), dtype=torch.int64, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     wf.recompute(configs)
-    stream = torch.cuda.current_stream().cuda_stream
+    # All kernels of the timed region are launched on this torch stream (passed to the C ABI as a
+    # raw cudaStream_t) and the CUDA events are recorded on the same stream.
+    ts = torch.cuda.Stream()
+    stream = ts.cuda_stream
+    assert stream != 0, "need a real stream handle: 0 would select the library's internal stream"
+    torch.cuda.synchronize()
     vp = ctypes.c_void_p
 
     def run_step(s):
@@ -209,6 +219,7 @@ def gpu_arm(args):
         if world > 1:  # one allreduce of the block statistics (here: per step) over NVLink
             dist.all_reduce(d_esum[s])
 
+    torch.cuda.set_stream(ts)
     for s in range(W):
         run_step(s)
     torch.cuda.synchronize()
@@ -222,18 +233,27 @@ def gpu_arm(args):
     for s in range(W, tot):
         flush.fill_(s & 0xFF)  # evict the walker state from L2 between timed steps
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(ts)
         run_step(s)
-        e1.record()
+        e1.record(ts)
         evs.append((e0, e1))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
+    torch.cuda.set_stream(torch.cuda.default_stream())
     launches = ctx.kernel_launches() - launches0
     clocks = sampler.stop() if sampler else None
     t_dev = sum(a.elapsed_time(b) for a, b in evs) * 1e-3
+    # cross-check of the event timing: run the same K steps back to back, wall-clock, no flush
+    torch.cuda.synchronize()
+    tw0 = time.perf_counter()
+    with torch.cuda.stream(ts):
+        for s in range(W, tot):
+            run_step(s)
+    torch.cuda.synchronize()
+    t_wall_noflush = time.perf_counter() - tw0
     tmax = torch.tensor([t_dev], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -286,7 +306,8 @@ def gpu_arm(args):
             "n4_4M_matrices": {"achieved_GBps": g4, "frac": g4 / peak, "launch_ms": 1e3 * t4},
             "n4_4096_matrices_C2_shape": {"achieved_GBps": g4s, "frac": g4s / peak, "launch_ms": 1e3 * t4s}},
         "clocks": clocks,
-        "check": {"mean_local_energy": e_mean, "acceptance": accept, "wall_s_timed_region_incl_flush": wall},
+        "check": {"mean_local_energy": e_mean, "acceptance": accept, "wall_s_timed_region_incl_flush": wall,
+                  "wall_s_same_steps_back_to_back_no_flush": t_wall_noflush, "device_s_timed_steps": t_dev_max},
     }
     if world == 1 and not args.no_cpu:
         v, cores, cwall, sample = cpu_arm(2, True)

@@ -150,6 +150,9 @@ int qmcb_vmc_block_device(qmcb_ctx *ctx, int nsteps, double tstep, int with_ener
                           const double *d_ecp_rot, uint8_t *d_accept, double *d_energy,
                           double *d_esum, int64_t *d_nacc, void *stream);
 int qmcb_kernel_launches(qmcb_ctx *ctx, int64_t *count); /* launches issued so far */
+/* page-locked host buffers for the per-block variates / results (true async H2D/D2H) */
+int qmcb_pinned_alloc(int64_t bytes, void **out);
+int qmcb_pinned_free(void *p);
 
 /* ---- Sherman-Morrison kernel on its own (roofline measurement / unit test) --------------
  * sherman_morrison_ms (slater.py:88-94) on device arrays: inv [M][n][n], vec [M][n],
@@ -159,6 +162,17 @@ int qmcb_sm_update_device(int n, int e, int64_t nmat, double *d_inv, const doubl
 /* host-buffer convenience wrapper (copies in, runs, copies out) */
 int qmcb_sm_update(int n, int e, int64_t nmat, double *inv, const double *vec,
                    const uint8_t *mask, double *ratio);
+
+/* ---- host-side random variates of one VMC block, bit-identical to the reference's use of the
+ * global legacy numpy RandomState (MT19937): per step and electron normal(scale, (N,3)) then
+ * rand(N) (mc.py:119,132); then per electron and ECP atom random(N) and one scipy
+ * Rotation.random() (eval_ecp.py:145,263).  key[624]/pos/has_gauss/cached_gauss are the fields
+ * of np.random.get_state() and are advanced in place.  ecp_u == NULL skips the ECP draws.
+ * The MT19937 stream is walked sequentially; the log/sqrt of the accepted polar pairs runs on
+ * nthreads host threads. */
+int qmcb_rng_vmc_block(uint32_t *key, int32_t *pos, int32_t *has_gauss, double *cached_gauss,
+                       int nsteps, int ne, int64_t N, int necp, double scale, double *gauss,
+                       double *unif, double *ecp_u, double *ecp_rot, int nthreads);
 
 #ifdef __cplusplus
 }

@@ -53,7 +53,11 @@ SIGNATURES = {
     "qmcb_vmc_block_device": (c_int, [c_void_p, c_int, c_double, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "qmcb_kernel_launches": (c_int, [c_void_p, c_i64_p]),
+    "qmcb_pinned_alloc": (c_int, [c_i64, ctypes.POINTER(c_void_p)]),
+    "qmcb_pinned_free": (c_int, [c_void_p]),
     "qmcb_sm_update_device": (c_int, [c_int, c_int, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "qmcb_rng_vmc_block": (c_int, [ctypes.POINTER(ctypes.c_uint32), c_int_p, c_int_p, c_double_p, c_int, c_int, c_i64,
+                                   c_int, c_double, c_double_p, c_double_p, c_double_p, c_double_p, c_int]),
     "qmcb_sm_update": (c_int, [c_int, c_int, c_i64, c_double_p, c_double_p, c_u8_p, c_double_p]),
 }
 
@@ -105,3 +109,27 @@ def f64(a):
 
 def i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class PinnedArray:
+    """numpy view of a page-locked host buffer (cudaMallocHost) owned by this object."""
+
+    def __init__(self, shape, dtype=np.float64):
+        lib = load()
+        self.shape = tuple(int(x) for x in shape)
+        self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        p = c_void_p()
+        check(lib.qmcb_pinned_alloc(max(nbytes, 1), ctypes.byref(p)))
+        self._ptr = p
+        buf = (ctypes.c_uint8 * max(nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape, dtype=np.int64))).reshape(self.shape)
+
+    def __del__(self):
+        try:
+            if self._ptr:
+                self.array = None
+                load().qmcb_pinned_free(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass

@@ -32,6 +32,8 @@ struct Sys {
   int o_xyz, o_chg, o_prim, o_mo[2], o_apar, o_bpar, o_acoef, o_bcoef, o_talpha, o_tcoef;
   // offsets into the int blob
   int o_atsh, o_shl, o_shprim, o_shao, o_occ[2], o_akind, o_bkind;
+  int o_primatom, o_shatom, o_aoshell, o_sphoff, o_sphtask;  // cooperative (warp-per-walker) tables
+  int nsph, nsphtask;  // sum over atoms of (lmax+1)^2; number of (atom, l) tasks
   int o_ecpatom, o_chanoff, o_termoff, o_tpow, o_naip, o_aipoff;
   int dwords, iwords;  // padded blob lengths (elements)
   const double* dblob;
@@ -43,9 +45,8 @@ struct Sys {
   const int* grp_det[2];  // [ndet]
 };
 
-// Walker state (device pointers).  Slater arrays keep the reference's layout
-// (inverse[s] (N, D_s, n, n) indexed [orbital, electron]; slater.py:254-259); Jastrow caches
-// are walker-minor so thread-per-walker kernels read them coalesced.
+// Walker state (device pointers).  All arrays are walker-major; Slater arrays keep the
+// reference's layout (inverse[s] (N, D_s, n, n) indexed [orbital, electron]; slater.py:254-259).
 struct State {
   int N;
   double* inv[2];    // [N][D_s][n][n]
@@ -54,15 +55,24 @@ struct State {
   double* dv[2];     // [N][D_s]  sign * exp(log - ref[w])          (multi-determinant cache)
   double* W[2];      // [N][D_s]  sum_{D: map_s(D)=d} c_D dv_other  (multi-determinant cache)
   double* ref[2];    // [N]
-  double* conf;      // [ne][3][N]  current walker coordinates (Jastrow._configscurrent)
-  double* a_partial; // [ne][I][na][N]
-  double* b_partial; // [ne][nb][2][N]
-  double* avalues;   // [I][na][2][N]
-  double* bvalues;   // [nb][3][N]
+  double* conf;      // [N][ne][3]  current walker coordinates (Jastrow._configscurrent)
+  double* a_partial; // [N][ne][I][na]
+  double* b_partial; // [N][ne][nb][2]
+  double* avalues;   // [N][I][na][2]
+  double* bvalues;   // [N][nb][3]
+  double* mocache;   // [N][ne][5][ldmax]  MO value/grad/Laplacian rows at the current positions
   double* saved_mo;  // [N][ldc]  MO row at the last gradient_value/testvalue position
   double* saved_pos; // [N][3]
   double* mo_all;    // [N][ne][ldcmax]  recompute scratch
 };
+
+// walker-major accessors: everything one walker owns is contiguous, so a warp that works on one
+// walker touches a handful of cache lines
+#define CONF(st, S, w, e, x) (st).conf[((size_t)(w) * (S).ne + (e)) * 3 + (x)]
+#define APART(st, S, w, e, I, k) (st).a_partial[(((size_t)(w) * (S).ne + (e)) * (S).natom + (I)) * (S).na + (k)]
+#define BPART(st, S, w, e, l, t) (st).b_partial[(((size_t)(w) * (S).ne + (e)) * (S).nb + (l)) * 2 + (t)]
+#define AVAL(st, S, w, I, k, t) (st).avalues[(((size_t)(w) * (S).natom + (I)) * (S).na + (k)) * 2 + (t)]
+#define BVAL(st, S, w, l, t) (st).bvalues[((size_t)(w) * (S).nb + (l)) * 3 + (t)]
 
 // ---------------------------------------------------------------------------------------
 // TMA staging of the table blobs:  [mbarrier | double blob | int blob] in dynamic smem.
@@ -241,6 +251,12 @@ __device__ __forceinline__ void radial_func(int kind, double par, double rcut, d
   }
 }
 
+// out-of-line copy shared by the warp-cooperative kernels (keeps their code footprint small)
+template <int WANT>
+__device__ __noinline__ void radial_ool(int kind, double par, double rcut, double r, double& v, double& g, double& lap) {
+  radial_func<WANT>(kind, par, rcut, r, v, g, lap);
+}
+
 // Jastrow terms for electron e of walker w placed at (px,py,pz).
 //   du  = sum_c coef*(new - cached partial sums)  (log of the ratio; jastrowspin.py:404-415)
 //   g   = grad U,  lap = laplacian U              (jastrowspin.py:296-385)
@@ -261,7 +277,7 @@ __device__ __forceinline__ void jastrow_point(const Sys& S, const double* __rest
     const bool in = r < S.rcut_a;
     for (int k = 0; k < S.na; ++k) {
       const double c = sd[S.o_acoef + (I * S.na + k) * 2 + s];
-      if (WANT != 2) ua_old = fma(c, st.a_partial[((size_t)(e * S.natom + I) * S.na + k) * N + w], ua_old);
+      if (WANT != 2) ua_old = fma(c, APART(st, S, w, e, I, k), ua_old);
       if (in) {
         double v, gg, ll;
         radial_func<WANT>(si[S.o_akind + k], sd[S.o_apar + k], S.rcut_a, r, v, gg, ll);
@@ -279,8 +295,8 @@ __device__ __forceinline__ void jastrow_point(const Sys& S, const double* __rest
   for (int j = 0; j < S.ne; ++j) {
     if (j == e) continue;
     const int sj = j >= S.nup ? 1 : 0;
-    const double dx = px - st.conf[(size_t)(j * 3 + 0) * N + w], dy = py - st.conf[(size_t)(j * 3 + 1) * N + w],
-                 dz = pz - st.conf[(size_t)(j * 3 + 2) * N + w];
+    const double dx = px - CONF(st, S, w, j, 0), dy = py - CONF(st, S, w, j, 1),
+                 dz = pz - CONF(st, S, w, j, 2);
     const double r = sqrt(dx * dx + dy * dy + dz * dz);
     if (r < S.rcut_b) {
       for (int l = 0; l < S.nb; ++l) {
@@ -301,7 +317,7 @@ __device__ __forceinline__ void jastrow_point(const Sys& S, const double* __rest
   if (WANT != 2) {
     for (int l = 0; l < S.nb; ++l)
       for (int t = 0; t < 2; ++t)
-        ub_old = fma(sd[S.o_bcoef + l * 3 + s + t], st.b_partial[((size_t)(e * S.nb + l) * 2 + t) * N + w],
+        ub_old = fma(sd[S.o_bcoef + l * 3 + s + t], BPART(st, S, w, e, l, t),
                      ub_old);
   }
   du = (ub - ub_old) + (ua - ua_old);

@@ -11,6 +11,7 @@
 //                                  eval_ecp.py:83-146, 203-275
 #pragma once
 #include "device_common.cuh"
+#include "coop.cuh"
 
 #define QMCB_SLATER 1
 #define QMCB_JASTROW 2
@@ -221,30 +222,40 @@ __global__ void __launch_bounds__(128) k_point(const Sys S, const State st, cons
 // =========================================================================================
 // Recompute: MO values of every electron, then per (walker, spin determinant) slogdet+inverse.
 // =========================================================================================
-__global__ void __launch_bounds__(128) k_mo_all(const Sys S, const State st) {
+__global__ void __launch_bounds__(128) k_mo_all(const Sys S, const State st, int write_values) {
+  // MO value / gradient / Laplacian rows of every electron at its current position:
+  // values -> mo_all (determinant build, slater.py:239-240), all five -> mocache
   const double* sd;
   const int* si;
   stage_tables(S, sd, si);
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const int N = st.N;
   if (p >= N * S.ne) return;
-  const int e = p / N, w = p - e * N;
+  const int w = p / S.ne, e = p - w * S.ne;
   const int s = e >= S.nup ? 1 : 0;
-  const double px = st.conf[(size_t)(e * 3 + 0) * N + w], py = st.conf[(size_t)(e * 3 + 1) * N + w],
-               pz = st.conf[(size_t)(e * 3 + 2) * N + w];
+  const double px = CONF(st, S, w, e, 0), py = CONF(st, S, w, e, 1), pz = CONF(st, S, w, e, 2);
   const int ldmax = S.ldc[0] > S.ldc[1] ? S.ldc[0] : S.ldc[1];
   double* out = st.mo_all + ((size_t)w * S.ne + e) * ldmax;
+  double* mc = st.mocache + ((size_t)w * S.ne + e) * 5 * ldmax;
   if (S.ldc[s] == 4) {
-    double acc[1][4];
-    eval_mo<0, 4>(S, sd, si, s, px, py, pz, 0, acc);
+    double acc[5][4];
+    eval_mo<2, 4>(S, sd, si, s, px, py, pz, 0, acc);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) out[j] = acc[0][j];
+    for (int j = 0; j < 4; ++j) {
+      if (write_values) out[j] = acc[0][j];
+#pragma unroll
+      for (int c = 0; c < 5; ++c) mc[c * ldmax + j] = acc[c][j];
+    }
   } else {
     for (int mo0 = 0; mo0 < S.ldc[s]; mo0 += 8) {
-      double acc[1][8];
-      eval_mo<0, 8>(S, sd, si, s, px, py, pz, mo0, acc);
+      double acc[5][8];
+      eval_mo<2, 8>(S, sd, si, s, px, py, pz, mo0, acc);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) out[mo0 + j] = acc[0][j];
+      for (int j = 0; j < 8; ++j) {
+        if (write_values) out[mo0 + j] = acc[0][j];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) mc[c * ldmax + mo0 + j] = acc[c][j];
+      }
     }
   }
 }
@@ -394,12 +405,12 @@ __global__ void __launch_bounds__(128) k_value(const Sys S, const State st, int 
   if (which & QMCB_JASTROW) {
     double u = 0.0;
     for (int l = 0; l < S.nb; ++l)
-      for (int t = 0; t < 3; ++t) u = fma(st.bvalues[(size_t)(l * 3 + t) * N + w], sd[S.o_bcoef + l * 3 + t], u);
+      for (int t = 0; t < 3; ++t) u = fma(BVAL(st, S, w, l, t), sd[S.o_bcoef + l * 3 + t], u);
     double ua = 0.0;
     for (int I = 0; I < S.natom; ++I)
       for (int k = 0; k < S.na; ++k)
         for (int t = 0; t < 2; ++t)
-          ua = fma(st.avalues[(size_t)((I * S.na + k) * 2 + t) * N + w], sd[S.o_acoef + (I * S.na + k) * 2 + t], ua);
+          ua = fma(AVAL(st, S, w, I, k, t), sd[S.o_acoef + (I * S.na + k) * 2 + t], ua);
     lg += u + ua;
   }
   o_sign[w] = sign;
@@ -417,13 +428,13 @@ __global__ void __launch_bounds__(128) k_jastrow_recompute(const Sys S, const St
   const int N = st.N;
   if (w >= N) return;
   const int ne = S.ne, na = S.na, nb = S.nb, I_ = S.natom;
-  for (int i = 0; i < I_ * na * 2; ++i) st.avalues[(size_t)i * N + w] = 0.0;
-  for (int i = 0; i < nb * 3; ++i) st.bvalues[(size_t)i * N + w] = 0.0;
-  for (int i = 0; i < ne * nb * 2; ++i) st.b_partial[(size_t)i * N + w] = 0.0;
+  for (int i = 0; i < I_ * na * 2; ++i) st.avalues[(size_t)w * I_ * na * 2 + i] = 0.0;
+  for (int i = 0; i < nb * 3; ++i) st.bvalues[(size_t)w * nb * 3 + i] = 0.0;
+  for (int i = 0; i < ne * nb * 2; ++i) st.b_partial[(size_t)w * ne * nb * 2 + i] = 0.0;
   for (int e = 0; e < ne; ++e) {
     const int s = e >= S.nup ? 1 : 0;
-    const double px = st.conf[(size_t)(e * 3) * N + w], py = st.conf[(size_t)(e * 3 + 1) * N + w],
-                 pz = st.conf[(size_t)(e * 3 + 2) * N + w];
+    const double px = CONF(st, S, w, e, 0), py = CONF(st, S, w, e, 1),
+                 pz = CONF(st, S, w, e, 2);
     for (int I = 0; I < I_; ++I) {
       const double dx = px - sd[S.o_xyz + 3 * I], dy = py - sd[S.o_xyz + 3 * I + 1],
                    dz = pz - sd[S.o_xyz + 3 * I + 2];
@@ -431,22 +442,22 @@ __global__ void __launch_bounds__(128) k_jastrow_recompute(const Sys S, const St
       for (int k = 0; k < na; ++k) {
         double v = 0.0, g, l;
         if (r < S.rcut_a) radial_func<0>(si[S.o_akind + k], sd[S.o_apar + k], S.rcut_a, r, v, g, l);
-        st.a_partial[((size_t)(e * I_ + I) * na + k) * N + w] = v;
-        st.avalues[(size_t)((I * na + k) * 2 + s) * N + w] += v;
+        APART(st, S, w, e, I, k) = v;
+        AVAL(st, S, w, I, k, s) += v;
       }
     }
     for (int j = e + 1; j < ne; ++j) {
       const int sj = j >= S.nup ? 1 : 0;
-      const double dx = px - st.conf[(size_t)(j * 3) * N + w], dy = py - st.conf[(size_t)(j * 3 + 1) * N + w],
-                   dz = pz - st.conf[(size_t)(j * 3 + 2) * N + w];
+      const double dx = px - CONF(st, S, w, j, 0), dy = py - CONF(st, S, w, j, 1),
+                   dz = pz - CONF(st, S, w, j, 2);
       const double r = sqrt(dx * dx + dy * dy + dz * dz);
       if (r < S.rcut_b) {
         for (int l = 0; l < nb; ++l) {
           double v, g, ll;
           radial_func<0>(si[S.o_bkind + l], sd[S.o_bpar + l], S.rcut_b, r, v, g, ll);
-          st.bvalues[(size_t)(l * 3 + s + sj) * N + w] += v;
-          st.b_partial[((size_t)(e * nb + l) * 2 + sj) * N + w] += v;
-          st.b_partial[((size_t)(j * nb + l) * 2 + s) * N + w] += v;
+          BVAL(st, S, w, l, s + sj) += v;
+          BPART(st, S, w, e, l, sj) += v;
+          BPART(st, S, w, j, l, s) += v;
         }
       }
     }
@@ -475,21 +486,20 @@ __global__ void __launch_bounds__(128) k_jastrow_update(const Sys S, const State
       for (int k = 0; k < na; ++k) {
         double v = 0.0, g, l;
         if (r < S.rcut_a) radial_func<0>(si[S.o_akind + k], sd[S.o_apar + k], S.rcut_a, r, v, g, l);
-        const size_t ip = ((size_t)(e * I_ + I) * na + k) * N + w;
-        st.avalues[(size_t)((I * na + k) * 2 + s) * N + w] += v - st.a_partial[ip];
-        st.a_partial[ip] = v;
+        AVAL(st, S, w, I, k, s) += v - APART(st, S, w, e, I, k);
+        APART(st, S, w, e, I, k) = v;
       }
     }
-    const double ox = st.conf[(size_t)(e * 3) * N + w], oy = st.conf[(size_t)(e * 3 + 1) * N + w],
-                 oz = st.conf[(size_t)(e * 3 + 2) * N + w];
+    const double ox = CONF(st, S, w, e, 0), oy = CONF(st, S, w, e, 1),
+                 oz = CONF(st, S, w, e, 2);
     // new partial sums of electron e (accumulated in partner order, as _b_update does)
     for (int l = 0; l < nb; ++l) {
       double bnew[2] = {0.0, 0.0};
       for (int j = 0; j < S.ne; ++j) {
         if (j == e) continue;
         const int sj = j >= S.nup ? 1 : 0;
-        const double jx = st.conf[(size_t)(j * 3) * N + w], jy = st.conf[(size_t)(j * 3 + 1) * N + w],
-                     jz = st.conf[(size_t)(j * 3 + 2) * N + w];
+        const double jx = CONF(st, S, w, j, 0), jy = CONF(st, S, w, j, 1),
+                     jz = CONF(st, S, w, j, 2);
         double dx = nx - jx, dy = ny - jy, dz = nz - jz;
         const double rn = sqrt(dx * dx + dy * dy + dz * dz);
         dx = ox - jx;
@@ -500,18 +510,17 @@ __global__ void __launch_bounds__(128) k_jastrow_update(const Sys S, const State
         if (rn < S.rcut_b) radial_func<0>(si[S.o_bkind + l], sd[S.o_bpar + l], S.rcut_b, rn, vn, g, ll);
         if (ro < S.rcut_b) radial_func<0>(si[S.o_bkind + l], sd[S.o_bpar + l], S.rcut_b, ro, vo, g, ll);
         bnew[sj] += vn;
-        st.b_partial[((size_t)(j * nb + l) * 2 + s) * N + w] += vn - vo;
+        BPART(st, S, w, j, l, s) += vn - vo;
       }
       for (int t = 0; t < 2; ++t) {
-        const size_t ip = ((size_t)(e * nb + l) * 2 + t) * N + w;
-        st.bvalues[(size_t)(l * 3 + s + t) * N + w] += bnew[t] - st.b_partial[ip];
-        st.b_partial[ip] = bnew[t];
+        BVAL(st, S, w, l, s + t) += bnew[t] - BPART(st, S, w, e, l, t);
+        BPART(st, S, w, e, l, t) = bnew[t];
       }
     }
   }
-  st.conf[(size_t)(e * 3) * N + w] = nx;
-  st.conf[(size_t)(e * 3 + 1) * N + w] = ny;
-  st.conf[(size_t)(e * 3 + 2) * N + w] = nz;
+  CONF(st, S, w, e, 0) = nx;
+  CONF(st, S, w, e, 1) = ny;
+  CONF(st, S, w, e, 2) = nz;
 }
 
 // =========================================================================================
@@ -677,8 +686,8 @@ __global__ void __launch_bounds__(128) k_vmc_move(const Sys S, const State st, c
   if (w < N) {
     const int e = ma.e;
     const int s = e >= S.nup ? 1 : 0;
-    const double ox = st.conf[(size_t)(e * 3) * N + w], oy = st.conf[(size_t)(e * 3 + 1) * N + w],
-                 oz = st.conf[(size_t)(e * 3 + 2) * N + w];
+    const double ox = CONF(st, S, w, e, 0), oy = CONF(st, S, w, e, 1),
+                 oz = CONF(st, S, w, e, 2);
     PointEval<1, NMOT> ev;
     ev.run(S, sd, si, st, which, w, e, ox, oy, oz, nullptr, ma.scr + w, ma.scr_stride);
     double grad[3];
@@ -739,6 +748,134 @@ __global__ void __launch_bounds__(128) k_vmc_move(const Sys S, const State st, c
 }
 
 // =========================================================================================
+// Device-resident sweep, warp per walker: ALL electrons of one VMC step in one launch
+// (mc.py:115-137).  Single-determinant wave functions (any occupation, n_s <= 32 staged in
+// shared memory).  Per electron: drift at the old position from the cached MO rows (no orbital
+// evaluation), proposal, cooperative value/gradient/Laplacian evaluation at the new position,
+// Metropolis test, and for accepted moves Sherman-Morrison + Jastrow cache update + refresh of
+// the cached MO rows -- all inside the warp, state in L2-resident global memory.
+// =========================================================================================
+struct SweepArgs {
+  double tstep;
+  const double* gauss;  // [ne][N][3] for this step
+  const double* unif;   // [ne][N]
+  uint8_t* accept;      // [ne][N] or nullptr
+  unsigned long long* nacc;  // [ne]
+};
+
+__device__ __forceinline__ void limdrift3(double (&g)[3]);
+
+template <int G>
+__global__ void __launch_bounds__(128) k_vmc_sweep(const Sys S, const State st, const SweepArgs a) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  extern __shared__ __align__(128) unsigned char qmcb_smem[];
+  const CoopLayout L = coop_layout(S);
+  constexpr int GP = 32 / G;  // walkers per warp
+  const int lane32 = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int lane = lane32 & (G - 1);  // lane within the walker's group
+  const unsigned gm = group_mask<G>(lane32);
+  const int slot = wib * GP + lane32 / G;
+  const int w = blockIdx.x * ((blockDim.x >> 5) * GP) + slot;
+  const int N = st.N;
+  if (w >= N) return;
+  const size_t tab = (16 + (size_t)S.dwords * 8 + (size_t)S.iwords * 4 + 15) & ~(size_t)15;
+  double* ws = reinterpret_cast<double*>(qmcb_smem + tab) + (size_t)slot * L.total;
+  const bool has_s = S.nmo[0] + S.nmo[1] > 0, has_j = (S.na + S.nb) > 0;
+  const int ldmax = S.ldc[0] > S.ldc[1] ? S.ldc[0] : S.ldc[1];
+#pragma unroll 1
+  for (int e = 0; e < S.ne; ++e) {
+    const int s = e >= S.nup ? 1 : 0;
+    const int n = s ? S.ndn : S.nup;
+    const int eeff = e - s * S.nup;
+    const int* __restrict__ occ = si + S.o_occ[s];
+    const double ox = CONF(st, S, w, e, 0), oy = CONF(st, S, w, e, 1), oz = CONF(st, S, w, e, 2);
+    // ---- drift at the current position (cached MO rows . inverse column)
+    double grad[3] = {0.0, 0.0, 0.0};
+    if (has_s) {
+      const double* __restrict__ mc = st.mocache + ((size_t)w * S.ne + e) * 5 * ldmax;
+      const double* __restrict__ inv = st.inv[s] + (size_t)w * n * n + eeff;
+      double r = 0.0;
+      if (lane < 4)
+        for (int k = 0; k < n; ++k) r = fma(mc[lane * ldmax + occ[k]], inv[k * n], r);
+      const double r0 = __shfl_sync(gm, r, 0, G);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        double gs = __shfl_sync(gm, r, 1 + i, G) / r0;
+        if (!isfinite(gs)) gs = 0.0;
+        grad[i] = gs;
+      }
+    }
+    if (has_j) {
+      double du, gj[3], lj;
+      coop_jastrow<1, G>(S, sd, si, st, w, e, ox, oy, oz, lane, gm, du, gj, lj);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) grad[i] = grad[i] + gj[i];
+    }
+    limdrift3(grad);
+    double gauss[3], np_[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) gauss[i] = a.gauss[((size_t)e * N + w) * 3 + i];
+    np_[0] = __dadd_rn(__dadd_rn(ox, gauss[0]), __dmul_rn(grad[0], a.tstep));
+    np_[1] = __dadd_rn(__dadd_rn(oy, gauss[1]), __dmul_rn(grad[1], a.tstep));
+    np_[2] = __dadd_rn(__dadd_rn(oz, gauss[2]), __dmul_rn(grad[2], a.tstep));
+    // ---- value + drift at the proposed position
+    double ngrad[3] = {0.0, 0.0, 0.0}, val = 1.0;
+    if (has_s) {
+      coop_eval_mo<2, G>(S, L, sd, si, s, np_[0], np_[1], np_[2], ws, lane, gm);
+      const double* __restrict__ mo = ws + L.mo;
+      const double* __restrict__ inv = st.inv[s] + (size_t)w * n * n + eeff;
+      double r = 0.0;
+      if (lane < 4)
+        for (int k = 0; k < n; ++k) r = fma(mo[lane * ldmax + occ[k]], inv[k * n], r);
+      const double r0 = __shfl_sync(gm, r, 0, G);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        double gs = __shfl_sync(gm, r, 1 + i, G) / r0;
+        if (!isfinite(gs)) gs = 0.0;
+        ngrad[i] = gs;
+      }
+      val = isfinite(r0) ? r0 : 1.0;
+    }
+    if (has_j) {
+      double du, gj[3], lj;
+      coop_jastrow<1, G>(S, sd, si, st, w, e, np_[0], np_[1], np_[2], lane, gm, du, gj, lj);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) ngrad[i] = ngrad[i] + gj[i];
+      val = val * exp(du);
+    }
+    limdrift3(ngrad);
+    double fwd = 0.0, bwd = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      fwd = __dadd_rn(fwd, __dmul_rn(gauss[i], gauss[i]));
+      const double b = __dadd_rn(gauss[i], __dmul_rn(a.tstep, __dadd_rn(grad[i], ngrad[i])));
+      bwd = __dadd_rn(bwd, __dmul_rn(b, b));
+    }
+    const double tprob = exp(__dmul_rn(1.0 / (2.0 * a.tstep), __dadd_rn(fwd, -bwd)));
+    const double aval = fabs(val);
+    const double ratio = __dmul_rn(__dmul_rn(aval, aval), tprob);
+    // every lane of the group evaluated the same numbers; take lane 0's decision
+    const bool acc = __shfl_sync(gm, (ratio > a.unif[(size_t)e * N + w]) ? 1 : 0, 0, G) != 0;
+    if (lane == 0) {
+      if (a.accept) a.accept[(size_t)e * N + w] = acc ? 1 : 0;
+      if (acc) atomicAdd(a.nacc + e, 1ULL);
+    }
+    if (acc) {
+      if (has_s) {
+        coop_sherman_morrison<G>(S, L, si, st, w, s, eeff, ws, lane, gm);
+        double* __restrict__ mc = st.mocache + ((size_t)w * S.ne + e) * 5 * ldmax;
+        const double* __restrict__ mo = ws + L.mo;
+        for (int i = lane; i < 5 * ldmax; i += G) mc[i] = mo[i];
+      }
+      coop_jastrow_update<G>(S, sd, si, st, w, e, np_[0], np_[1], np_[2], lane, gm, has_j);
+    }
+    __syncwarp(gm);
+  }
+}
+
+// =========================================================================================
 // Local energy.
 // =========================================================================================
 struct EnergyScratch {
@@ -754,42 +891,70 @@ struct EnergyScratch {
   int maxchan;
 };
 
-// kinetic energy pieces: one thread per (electron, walker)  (energy.py:57-65)
-template <int NMOT>
-__global__ void __launch_bounds__(128) k_kinetic(const Sys S, const State st, const EnergyScratch es,
-                                                 double* scr, size_t scr_stride) {
+// kinetic energy pieces: one thread per (walker, electron)  (energy.py:57-65).  The MO value /
+// gradient / Laplacian rows at the current positions come from st.mocache (filled by recompute
+// and refreshed by every accepted move), so no orbital is re-evaluated here.
+__global__ void __launch_bounds__(128) k_kinetic(const Sys S, const State st, const EnergyScratch es) {
   const double* sd;
   const int* si;
   stage_tables(S, sd, si);
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const int N = st.N;
   if (p >= N * S.ne) return;
-  const int e = p / N, w = p - e * N;
+  const int w = p / S.ne, e = p - w * S.ne;
   const int which = (S.nmo[0] + S.nmo[1] > 0 ? QMCB_SLATER : 0) | ((S.na + S.nb) > 0 ? QMCB_JASTROW : 0);
-  const double px = st.conf[(size_t)(e * 3) * N + w], py = st.conf[(size_t)(e * 3 + 1) * N + w],
-               pz = st.conf[(size_t)(e * 3 + 2) * N + w];
-  PointEval<2, NMOT> ev;
-  ev.run(S, sd, si, st, which, w, e, px, py, pz, nullptr, scr + p, scr_stride);
+  const double px = CONF(st, S, w, e, 0), py = CONF(st, S, w, e, 1), pz = CONF(st, S, w, e, 2);
   double gs[3] = {0.0, 0.0, 0.0}, laps = 0.0;
   if (which & QMCB_SLATER) {
+    const int s = e >= S.nup ? 1 : 0;
+    const int n = s ? S.ndn : S.nup;
+    const int eeff = e - s * S.nup;
+    const int ldmax = S.ldc[0] > S.ldc[1] ? S.ldc[0] : S.ldc[1];
+    const double* __restrict__ mc = st.mocache + ((size_t)w * S.ne + e) * 5 * ldmax;
+    const int nds = S.nds[s];
+    const int* __restrict__ occ = si + S.o_occ[s];
+    double num[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, den = 0.0;
+    for (int d = 0; d < nds; ++d) {
+      const double* __restrict__ inv = st.inv[s] + ((size_t)w * nds + d) * n * n + eeff;
+      double r[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+      for (int k = 0; k < n; ++k) {
+        const double a = inv[k * n];
+        const int orb = occ[d * n + k];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) gs[i] = ev.rat[1 + i] / ev.rat[0];
-    laps = ev.rat[4] / ev.rat[0];
+        for (int c = 0; c < 5; ++c) r[c] = fma(mc[c * ldmax + orb], a, r[c]);
+      }
+      if (S.ndet == 1) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) num[c] = r[c];
+        den = 1.0;
+      } else {
+        const double wgt = st.dv[s][(size_t)w * nds + d] * st.W[s][(size_t)w * nds + d];
+        den += wgt;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) num[c] = fma(r[c], wgt, num[c]);
+      }
+    }
+    const double r0 = num[0] / den;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) gs[i] = (num[1 + i] / den) / r0;
+    laps = (num[4] / den) / r0;
   }
-  double lapj = 0.0, cross = 0.0;
+  double lapj = 0.0, cross = 0.0, gj[3] = {0.0, 0.0, 0.0};
   if (which & QMCB_JASTROW) {
-    lapj = ev.lapj + (ev.gj[0] * ev.gj[0] + ev.gj[1] * ev.gj[1] + ev.gj[2] * ev.gj[2]);
-    cross = gs[0] * ev.gj[0] + gs[1] * ev.gj[1] + gs[2] * ev.gj[2];
+    double du, lj;
+    jastrow_point<2>(S, sd, si, st, w, e, px, py, pz, du, gj, lj);
+    lapj = lj + (gj[0] * gj[0] + gj[1] * gj[1] + gj[2] * gj[2]);
+    cross = gs[0] * gj[0] + gs[1] * gj[1] + gs[2] * gj[2];
   }
   const double lap = (laps + lapj) + cross * 2.0;
   double g2 = 0.0;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    const double g = gs[i] + ev.gj[i];
+    const double g = gs[i] + gj[i];
     g2 += g * g;
   }
-  es.ke_e[p] = -0.5 * lap;
-  es.g2_e[p] = g2;
+  es.ke_e[(size_t)e * N + w] = -0.5 * lap;
+  es.g2_e[(size_t)e * N + w] = g2;
 }
 
 // ECP radial channels, stochastic mask and work list: one thread per (electron, ECP atom, walker)
@@ -807,9 +972,9 @@ __global__ void __launch_bounds__(128) k_ecp_prepare(const Sys S, const State st
   const int e = e_only >= 0 ? e_only : ea / S.necp;
   const int a = ea % S.necp;
   const int atom = si[S.o_ecpatom + a];
-  const double dx = st.conf[(size_t)(e * 3) * N + w] - sd[S.o_xyz + 3 * atom],
-               dy = st.conf[(size_t)(e * 3 + 1) * N + w] - sd[S.o_xyz + 3 * atom + 1],
-               dz = st.conf[(size_t)(e * 3 + 2) * N + w] - sd[S.o_xyz + 3 * atom + 2];
+  const double dx = CONF(st, S, w, e, 0) - sd[S.o_xyz + 3 * atom],
+               dy = CONF(st, S, w, e, 1) - sd[S.o_xyz + 3 * atom + 1],
+               dz = CONF(st, S, w, e, 2) - sd[S.o_xyz + 3 * atom + 2];
   const double r = sqrt(dx * dx + dy * dy + dz * dz);
   const int c0 = si[S.o_chanoff + a], c1 = si[S.o_chanoff + a + 1];
   const int nl = c1 - c0;
@@ -894,8 +1059,8 @@ __global__ void __launch_bounds__(128) k_ecp_points(const Sys S, const State st,
     const int naip = si[S.o_naip + a];
     if (q >= naip) continue;
     const int atom = si[S.o_ecpatom + a];
-    const double ex = st.conf[(size_t)(e * 3) * N + w], ey = st.conf[(size_t)(e * 3 + 1) * N + w],
-                 ez = st.conf[(size_t)(e * 3 + 2) * N + w];
+    const double ex = CONF(st, S, w, e, 0), ey = CONF(st, S, w, e, 1),
+                 ez = CONF(st, S, w, e, 2);
     const double rx = ex - sd[S.o_xyz + 3 * atom], ry = ey - sd[S.o_xyz + 3 * atom + 1],
                  rz = ez - sd[S.o_xyz + 3 * atom + 2];
     const double r = sqrt(rx * rx + ry * ry + rz * rz);
@@ -961,20 +1126,20 @@ __global__ void __launch_bounds__(128) k_energy_finalize(const Sys S, const Stat
     ecp += ecp_e;
   }
   for (int i = 0; i < S.ne; ++i) {
-    const double xi = st.conf[(size_t)(i * 3) * N + w], yi = st.conf[(size_t)(i * 3 + 1) * N + w],
-                 zi = st.conf[(size_t)(i * 3 + 2) * N + w];
+    const double xi = CONF(st, S, w, i, 0), yi = CONF(st, S, w, i, 1),
+                 zi = CONF(st, S, w, i, 2);
     for (int j = i + 1; j < S.ne; ++j) {
-      const double dx = xi - st.conf[(size_t)(j * 3) * N + w], dy = yi - st.conf[(size_t)(j * 3 + 1) * N + w],
-                   dz = zi - st.conf[(size_t)(j * 3 + 2) * N + w];
+      const double dx = xi - CONF(st, S, w, j, 0), dy = yi - CONF(st, S, w, j, 1),
+                   dz = zi - CONF(st, S, w, j, 2);
       ee += 1.0 / sqrt(dx * dx + dy * dy + dz * dz);
     }
   }
   for (int I = 0; I < S.natom; ++I) {
     double acc = 0.0;
     for (int i = 0; i < S.ne; ++i) {
-      const double dx = st.conf[(size_t)(i * 3) * N + w] - sd[S.o_xyz + 3 * I],
-                   dy = st.conf[(size_t)(i * 3 + 1) * N + w] - sd[S.o_xyz + 3 * I + 1],
-                   dz = st.conf[(size_t)(i * 3 + 2) * N + w] - sd[S.o_xyz + 3 * I + 2];
+      const double dx = CONF(st, S, w, i, 0) - sd[S.o_xyz + 3 * I],
+                   dy = CONF(st, S, w, i, 1) - sd[S.o_xyz + 3 * I + 1],
+                   dz = CONF(st, S, w, i, 2) - sd[S.o_xyz + 3 * I + 2];
       acc += 1.0 / sqrt(dx * dx + dy * dy + dz * dz);
     }
     ei += -sd[S.o_chg + I] * acc;
@@ -1006,12 +1171,10 @@ __global__ void __launch_bounds__(256) k_colsum(const double* in, int N, double*
 __global__ void k_conf_in(const double* host_layout, double* conf, int N, int ne) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * ne * 3) return;
-  const int w = i / (ne * 3), r = i - w * ne * 3;
-  conf[(size_t)r * N + w] = host_layout[i];
+  conf[i] = host_layout[i];
 }
 __global__ void k_conf_out(const double* conf, double* host_layout, int N, int ne) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * ne * 3) return;
-  const int w = i / (ne * 3), r = i - w * ne * 3;
-  host_layout[i] = conf[(size_t)r * N + w];
+  host_layout[i] = conf[i];
 }

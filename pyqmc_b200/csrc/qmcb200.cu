@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -104,7 +105,7 @@ struct qmcb_ctx {
   State st{};
   int N = 0;
   DBuf<double> b_inv[2], b_dsign[2], b_dlog[2], b_dv[2], b_W[2], b_ref[2];
-  DBuf<double> b_conf, b_ap, b_bp, b_av, b_bv, b_smo, b_spos, b_moall, b_lu;
+  DBuf<double> b_conf, b_ap, b_bp, b_av, b_bv, b_smo, b_spos, b_moall, b_lu, b_mocache;
   // ---- staging / scratch
   DBuf<double> d_in, d_out, d_scr, d_u, d_rot, d_gauss, d_unif, d_energy, d_esum;
   DBuf<uint8_t> d_mask, d_accept;
@@ -120,6 +121,7 @@ struct qmcb_ctx {
   int saved_e = -1, saved_which = 0;
   int64_t nlaunch = 0;
   std::vector<int> shape_sig;
+  bool mocache_valid = false;
 };
 
 namespace {
@@ -241,6 +243,28 @@ int build_tables(qmcb_ctx* c) {
   S.o_shprim = ipush(c->prim_off.data(), c->prim_off.size());
   S.o_shao = ipush(shao.data(), shao.size());
   for (int s = 0; s < 2; ++s) S.o_occ[s] = ipush(c->occ[s].data(), c->have_slater ? c->occ[s].size() : 0);
+  {
+    std::vector<int> primatom(c->pexp.size()), aoshell(S.nao), sphoff(natom + 1, 0), lmax(natom, -1), task;
+    for (int sh = 0; sh < nshell; ++sh) {
+      for (int p = c->prim_off[sh]; p < c->prim_off[sh + 1]; ++p) primatom[p] = c->sh_atom[sh];
+      for (int m = shao[sh]; m < shao[sh + 1]; ++m) aoshell[m] = sh;
+      lmax[c->sh_atom[sh]] = std::max(lmax[c->sh_atom[sh]], c->sh_l[sh]);
+    }
+    for (int a = 0; a < natom; ++a) {
+      sphoff[a + 1] = sphoff[a] + (lmax[a] + 1) * (lmax[a] + 1);
+      for (int l = 0; l <= lmax[a]; ++l) {
+        task.push_back(a);
+        task.push_back(l);
+      }
+    }
+    S.nsph = sphoff[natom];
+    S.nsphtask = (int)task.size() / 2;
+    S.o_primatom = ipush(primatom.data(), primatom.size());
+    S.o_shatom = ipush(c->sh_atom.data(), nshell);
+    S.o_aoshell = ipush(aoshell.data(), aoshell.size());
+    S.o_sphoff = ipush(sphoff.data(), sphoff.size());
+    S.o_sphtask = ipush(task.data(), task.size());
+  }
   S.o_akind = ipush(c->akind.data(), S.na);
   S.o_bkind = ipush(c->bkind.data(), S.nb);
   S.o_ecpatom = ipush(c->ecp_atom.data(), c->ecp_atom.size());
@@ -333,7 +357,8 @@ int ensure_state(qmcb_ctx* c, int N) {
   if (c->b_conf.ensure((size_t)N * S.ne * 3) || c->b_ap.ensure((size_t)N * S.ne * S.natom * std::max(S.na, 1)) ||
       c->b_bp.ensure((size_t)N * S.ne * std::max(S.nb, 1) * 2) || c->b_av.ensure((size_t)N * S.natom * std::max(S.na, 1) * 2) ||
       c->b_bv.ensure((size_t)N * std::max(S.nb, 1) * 3) || c->b_smo.ensure((size_t)N * ldmax) ||
-      c->b_spos.ensure((size_t)N * 3) || c->b_moall.ensure((size_t)N * S.ne * ldmax))
+      c->b_spos.ensure((size_t)N * 3) || c->b_moall.ensure((size_t)N * S.ne * ldmax) ||
+      c->b_mocache.ensure((size_t)N * S.ne * 5 * ldmax))
     return -1;
   st.conf = c->b_conf.p;
   st.a_partial = c->b_ap.p;
@@ -343,6 +368,7 @@ int ensure_state(qmcb_ctx* c, int N) {
   st.saved_mo = c->b_smo.p;
   st.saved_pos = c->b_spos.p;
   st.mo_all = c->b_moall.p;
+  st.mocache = c->b_mocache.p;
   c->N = N;
   c->saved_slot = -1;
   return 0;
@@ -438,7 +464,8 @@ int slater_rebuild(qmcb_ctx* c, cudaStream_t stream) {
     const long long np = (long long)N * S.ne;
     const int block = pick_block(np);
     if (prep_kernel(k_mo_all, c->smem_bytes)) return -1;
-    k_mo_all<<<(unsigned)((np + block - 1) / block), block, c->smem_bytes, stream>>>(S, c->st);
+    k_mo_all<<<(unsigned)((np + block - 1) / block), block, c->smem_bytes, stream>>>(S, c->st, 1);
+    c->mocache_valid = true;
     c->nlaunch++;
     CK(cudaGetLastError());
   }
@@ -545,8 +572,15 @@ int launch_energy_t(qmcb_ctx* c, const double* d_u, const double* d_rot, double*
   {
     const long long np = (long long)N * S.ne;
     const int block = pick_block(np);
-    if (prep_kernel(k_kinetic<NMOT>, sm)) return -1;
-    k_kinetic<NMOT><<<(unsigned)((np + block - 1) / block), block, sm, stream>>>(S, c->st, c->es, c->d_scr.p, (size_t)np);
+    if (!c->mocache_valid && c->have_slater) {  // protocol-path updates do not maintain the cache
+      if (prep_kernel(k_mo_all, sm)) return -1;
+      k_mo_all<<<(unsigned)((np + block - 1) / block), block, sm, stream>>>(S, c->st, 0);
+      c->nlaunch++;
+      CK(cudaGetLastError());
+      c->mocache_valid = true;
+    }
+    if (prep_kernel(k_kinetic, sm)) return -1;
+    k_kinetic<<<(unsigned)((np + block - 1) / block), block, sm, stream>>>(S, c->st, c->es);
     c->nlaunch++;
     CK(cudaGetLastError());
   }
@@ -625,7 +659,7 @@ void qmcb_destroy(qmcb_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   DBuf<double>* dd[] = {&c->d_dblob, &c->d_detc, &c->d_quad, &c->b_conf, &c->b_ap, &c->b_bp, &c->b_av, &c->b_bv,
-                        &c->b_smo, &c->b_spos, &c->b_moall, &c->b_lu, &c->d_in, &c->d_out, &c->d_scr, &c->d_u,
+                        &c->b_smo, &c->b_spos, &c->b_moall, &c->b_lu, &c->b_mocache, &c->d_in, &c->d_out, &c->d_scr, &c->d_u,
                         &c->d_rot, &c->d_gauss, &c->d_unif, &c->d_energy, &c->d_esum, &c->e_ke, &c->e_g2, &c->e_loc,
                         &c->e_vls, &c->e_contrib};
   for (auto* b : dd) b->release();
@@ -958,6 +992,7 @@ int qmcb_updateinternals(qmcb_ctx* c, int which, int e, const double* epos, cons
     CK(cudaMemcpyAsync(c->st.saved_pos, c->d_in.p, N * 3 * 8, cudaMemcpyDeviceToDevice, c->stream));
   }
   if (launch_update(c, which, e, d_mask, c->stream)) return -1;
+  if (which & 1) c->mocache_valid = false;
   CK(cudaStreamSynchronize(c->stream));
   // a shared context may be driven factor by factor (Slater call, then Jastrow call with the
   // same token), so the slot stays valid until the next query overwrites it
@@ -993,26 +1028,19 @@ int qmcb_get_state(qmcb_ctx* c, const char* name, double* out) {
     std::memcpy(out + nd, h.data(), nd * 8);
   } else if (k == "configs") {
     if (fetch(c->st.conf, N * S.ne * 3, h)) return -1;
-    for (size_t w = 0; w < N; ++w)
-      for (int r = 0; r < S.ne * 3; ++r) out[w * S.ne * 3 + r] = h[(size_t)r * N + w];
-  } else if (k == "a_partial") {  // device [e][I][k][w] -> (ne, N, I, na)
-    if (fetch(c->st.a_partial, N * S.ne * S.natom * S.na, h)) return -1;
-    const int M = S.natom * S.na;
+    std::memcpy(out, h.data(), h.size() * 8);
+  } else if (k == "a_partial" || k == "b_partial") {  // device (N, ne, M) -> (ne, N, M)
+    const bool a = k == "a_partial";
+    const int M = a ? S.natom * S.na : S.nb * 2;
+    if (fetch(a ? c->st.a_partial : c->st.b_partial, N * S.ne * M, h)) return -1;
     for (int e = 0; e < S.ne; ++e)
       for (size_t w = 0; w < N; ++w)
-        for (int m = 0; m < M; ++m) out[((size_t)e * N + w) * M + m] = h[((size_t)e * M + m) * N + w];
-  } else if (k == "b_partial") {  // device [e][l][t][w] -> (ne, N, nb, 2)
-    if (fetch(c->st.b_partial, N * S.ne * S.nb * 2, h)) return -1;
-    const int M = S.nb * 2;
-    for (int e = 0; e < S.ne; ++e)
-      for (size_t w = 0; w < N; ++w)
-        for (int m = 0; m < M; ++m) out[((size_t)e * N + w) * M + m] = h[((size_t)e * M + m) * N + w];
-  } else if (k == "avalues" || k == "bvalues") {  // device [m][w] -> (N, m)
+        for (int m = 0; m < M; ++m) out[((size_t)e * N + w) * M + m] = h[(w * S.ne + e) * M + m];
+  } else if (k == "avalues" || k == "bvalues") {
     const bool a = k == "avalues";
     const int M = a ? S.natom * S.na * 2 : S.nb * 3;
     if (fetch(a ? c->st.avalues : c->st.bvalues, N * M, h)) return -1;
-    for (size_t w = 0; w < N; ++w)
-      for (int m = 0; m < M; ++m) out[w * M + m] = h[(size_t)m * N + w];
+    std::memcpy(out, h.data(), h.size() * 8);
   } else
     return fail("unknown state array: " + k);
   return 0;
@@ -1081,8 +1109,49 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
   }
   unsigned long long* nacc = d_nacc ? (unsigned long long*)d_nacc : c->d_nacc.p;
   CK(cudaMemsetAsync(nacc, 0, (size_t)nsteps * S.ne * 8, stream));
+  // warp-per-walker sweep kernel: single determinant, inverse staged in shared memory
+  const CoopLayout CL = coop_layout(S);
+  const size_t tab = (c->smem_bytes + 15) & ~(size_t)15;
+  int G = 8;
+  if (const char* env = std::getenv("QMCB_SWEEP_G")) G = std::atoi(env);
+  if (G != 8 && G != 16 && G != 32) G = 8;
+  const int sweep_warps = 4;
+  const int sweep_walkers = sweep_warps * (32 / G);
+  const size_t sweep_smem = tab + (size_t)sweep_walkers * CL.total * 8;
+  const bool use_sweep = (!c->have_slater || S.ndet == 1) && sweep_smem <= 200 * 1024 && std::getenv("QMCB_NO_SWEEP") == nullptr;
+  if (use_sweep && c->have_slater && !c->mocache_valid) {
+    const long long np = (long long)N * S.ne;
+    const int block = pick_block(np);
+    if (prep_kernel(k_mo_all, c->smem_bytes)) return -1;
+    k_mo_all<<<(unsigned)((np + block - 1) / block), block, c->smem_bytes, stream>>>(S, c->st, 0);
+    c->nlaunch++;
+    CK(cudaGetLastError());
+    c->mocache_valid = true;
+  }
   for (int step = 0; step < nsteps; ++step) {
-    for (int e = 0; e < S.ne; ++e) {
+    if (use_sweep) {
+      const size_t se = (size_t)step * S.ne;
+      SweepArgs sa{};
+      sa.tstep = tstep;
+      sa.gauss = d_gauss + se * N * 3;
+      sa.unif = d_unif + se * N;
+      sa.accept = d_accept ? d_accept + se * N : nullptr;
+      sa.nacc = nacc + se;
+      const unsigned grid = (unsigned)((N + sweep_walkers - 1) / sweep_walkers);
+      if (G == 8) {
+        if (prep_kernel(k_vmc_sweep<8>, sweep_smem)) return -1;
+        k_vmc_sweep<8><<<grid, sweep_warps * 32, sweep_smem, stream>>>(S, c->st, sa);
+      } else if (G == 16) {
+        if (prep_kernel(k_vmc_sweep<16>, sweep_smem)) return -1;
+        k_vmc_sweep<16><<<grid, sweep_warps * 32, sweep_smem, stream>>>(S, c->st, sa);
+      } else {
+        if (prep_kernel(k_vmc_sweep<32>, sweep_smem)) return -1;
+        k_vmc_sweep<32><<<grid, sweep_warps * 32, sweep_smem, stream>>>(S, c->st, sa);
+      }
+      c->nlaunch++;
+      CK(cudaGetLastError());
+    }
+    for (int e = 0; e < S.ne && !use_sweep; ++e) {
       const size_t se = (size_t)step * S.ne + e;
       MoveArgs ma{};
       ma.e = e;
@@ -1096,6 +1165,7 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
       int rc = c->nmot == 4 ? launch_move_t<4>(c, ma, stream) : (c->nmot == 8 ? launch_move_t<8>(c, ma, stream) : launch_move_t<0>(c, ma, stream));
       if (rc) return rc;
       if (launch_update(c, which, e, ma.accept, stream)) return -1;
+      c->mocache_valid = false;
     }
     if (with_energy) {
       double* eo = d_energy ? d_energy + (size_t)step * 6 * N : c->d_energy.p;
@@ -1157,6 +1227,19 @@ int qmcb_vmc_block(qmcb_ctx* c, int nsteps, double tstep, int with_energy, const
   }
   CK(cudaStreamSynchronize(c->stream));
   acc_all.release();
+  return 0;
+}
+
+int qmcb_pinned_alloc(int64_t bytes, void** out) {
+  void* p = nullptr;
+  cudaError_t e = cudaMallocHost(&p, (size_t)std::max<int64_t>(bytes, 1));
+  if (e != cudaSuccess) return fail(std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+  *out = p;
+  return 0;
+}
+
+int qmcb_pinned_free(void* p) {
+  if (p) cudaFreeHost(p);
   return 0;
 }
 

@@ -57,45 +57,123 @@ def _device_path(wf, accumulators):
     return all(isinstance(a, EnergyAccumulator) for a in accumulators.values()) and len(accumulators) <= 1
 
 
-def draw_block_variates(nconf, nelec, tstep, nsteps, accumulator):
-    """All random numbers of one block in the reference's consumption order."""
-    gauss = np.empty((nsteps, nelec, nconf, 3))
-    unif = np.empty((nsteps, nelec, nconf))
+class BlockBuffers:
+    """Page-locked host buffers for the variates and results of one device-resident block."""
+
+    def __init__(self, nconf, nelec, nsteps, necp, with_energy):
+        P = _lib.PinnedArray
+        self.key = (nconf, nelec, nsteps, necp, with_energy)
+        self._own = [P((nsteps, nelec, nconf, 3)), P((nsteps, nelec, nconf))]
+        self.gauss, self.unif = self._own[0].array, self._own[1].array
+        self.ecp_u = self.ecp_rot = self.energy = None
+        if with_energy:
+            self._own += [P((nsteps, nelec, necp, nconf)), P((nsteps, nelec, necp, 3, 3)), P((nsteps, 6, nconf))]
+            self.ecp_u, self.ecp_rot, self.energy = (x.array for x in self._own[2:5])
+        self._own += [P((nconf, nelec, 3)), P((nsteps, nelec), np.int64)]
+        self.newconf, self.nacc = self._own[-2].array, self._own[-1].array
+
+    def variates(self):
+        return self.gauss, self.unif, self.ecp_u, self.ecp_rot
+
+
+def draw_block_variates(nconf, nelec, tstep, nsteps, accumulator, native=True, out=None):
+    """All random numbers of one block in the reference's consumption order.
+
+    native=True runs the draws in ``qmcb_rng_vmc_block`` (csrc/legacy_rng.cpp) on the state of the
+    global legacy ``np.random`` generator and writes the advanced state back: same numbers, same
+    final stream position as the numpy calls below (tests/test_host_cabi.py), several times faster.
+    ``out``: optional (gauss, unif, ecp_u, ecp_rot) arrays to fill (e.g. pinned BlockBuffers)."""
     necp = accumulator.necp if accumulator is not None else 0
-    ecp_u = np.empty((nsteps, nelec, necp, nconf)) if accumulator is not None else None
-    ecp_rot = np.empty((nsteps, nelec, necp, 3, 3)) if accumulator is not None else None
+    if out is None:
+        out = (np.empty((nsteps, nelec, nconf, 3)), np.empty((nsteps, nelec, nconf)),
+               np.empty((nsteps, nelec, necp, nconf)) if accumulator is not None else None,
+               np.empty((nsteps, nelec, necp, 3, 3)) if accumulator is not None else None)
+    gauss, unif, ecp_u, ecp_rot = out
+    if native and _draw_block_variates_native(nconf, nelec, tstep, nsteps, necp, out):
+        return out
     for step in range(nsteps):
         for e in range(nelec):
             gauss[step, e] = np.random.normal(scale=np.sqrt(tstep), size=(nconf, 3))
             unif[step, e] = np.random.rand(nconf)
         if accumulator is not None:
             ecp_u[step], ecp_rot[step] = accumulator.draw_ecp_variates(nconf, nelec)
-    return gauss, unif, ecp_u, ecp_rot
+    return out
 
 
-def vmc_block_device(wf, configs, tstep, nsteps, accumulators, variates=None, return_walker_data=False):
-    """One device-resident block; equivalent of ``vmc_worker`` (mc.py:102-153)."""
+def rng_threads():
+    """Host threads for the log/sqrt phase of the native generator (QMCB_RNG_THREADS overrides)."""
+    import os
+
+    if "QMCB_RNG_THREADS" in os.environ:
+        return max(1, int(os.environ["QMCB_RNG_THREADS"]))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+    return max(1, min(8, (os.cpu_count() or 1) // max(local_world, 1)))
+
+
+def _draw_block_variates_native(nconf, nelec, tstep, nsteps, necp, out):
+    import ctypes
+
+    state = np.random.get_state()
+    if state[0] != "MT19937":
+        return False
+    gauss, unif, ecp_u, ecp_rot = out
+    for a in out:
+        if a is not None and not (a.flags["C_CONTIGUOUS"] and a.dtype == np.float64):
+            return False
+    lib = _lib.load()
+    key = np.ascontiguousarray(state[1], dtype=np.uint32).copy()
+    pos = ctypes.c_int32(int(state[2]))
+    has_gauss = ctypes.c_int32(int(state[3]))
+    cached = ctypes.c_double(float(state[4]))
+    rc = lib.qmcb_rng_vmc_block(key.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), ctypes.byref(pos),
+                                ctypes.byref(has_gauss), ctypes.byref(cached), nsteps, nelec, nconf, necp,
+                                float(np.sqrt(tstep)), _lib.dptr(gauss), _lib.dptr(unif), _lib.dptr(ecp_u),
+                                _lib.dptr(ecp_rot), rng_threads())
+    if rc != 0:
+        return False
+    np.random.set_state(("MT19937", key, pos.value, has_gauss.value, cached.value))
+    return True
+
+
+def _block_buffers(ctx, nconf, nelec, nsteps, accumulator, slot=0):
+    """Two cached sets of pinned buffers per context (double buffering for the RNG prefetch)."""
+    key = (nconf, nelec, nsteps, accumulator.necp if accumulator is not None else 0, accumulator is not None)
+    cache = ctx.__dict__.setdefault("_block_buffers", {})
+    if cache.get(slot) is None or cache[slot].key != key:
+        cache[slot] = BlockBuffers(*key)
+    return cache[slot]
+
+
+def vmc_block_device(wf, configs, tstep, nsteps, accumulators, variates=None, return_walker_data=False,
+                     buffers=None):
+    """One device-resident block; equivalent of ``vmc_worker`` (mc.py:102-153).
+
+    ``variates``: pre-drawn (gauss, unif, ecp_u, ecp_rot) (must have been drawn in stream order);
+    ``buffers``: BlockBuffers whose variates were already filled (RNG prefetch of ``vmc``)."""
     nconf, nelec, _ = configs.configs.shape
     wf.recompute(configs)
     ctx = _device_context(wf)
     acc_name, accumulator = (next(iter(accumulators.items())) if accumulators else (None, None))
     if accumulator is not None:
         accumulator._attach(wf)
+    if buffers is None:
+        buffers = _block_buffers(ctx, nconf, nelec, nsteps, accumulator)
+        if variates is None:
+            draw_block_variates(nconf, nelec, tstep, nsteps, accumulator, out=buffers.variates())
     if variates is None:
-        variates = draw_block_variates(nconf, nelec, tstep, nsteps, accumulator)
+        variates = buffers.variates()
     gauss, unif, ecp_u, ecp_rot = variates
     start = time.perf_counter()
-    newconf = np.empty((nconf, nelec, 3))
     accept = np.empty((nsteps, nelec, nconf), dtype=np.uint8) if return_walker_data else None
-    energy = np.empty((nsteps, 6, nconf)) if accumulator is not None else None
-    nacc = np.zeros((nsteps, nelec), dtype=np.int64)
+    energy = buffers.energy
+    nacc = buffers.nacc
     _lib.check(ctx.lib.qmcb_vmc_block(
         ctx.h, nsteps, float(tstep), 1 if accumulator is not None else 0,
         _lib.dptr(gauss), _lib.dptr(unif), _lib.dptr(ecp_u), _lib.dptr(ecp_rot),
-        _lib.dptr(newconf), _lib.u8ptr(accept), _lib.dptr(energy), None,
+        _lib.dptr(buffers.newconf), _lib.u8ptr(accept), _lib.dptr(energy), None,
         nacc.ctypes.data_as(_lib.c_i64_p)))
     end = time.perf_counter()
-    configs.configs[...] = newconf
+    configs.configs[...] = buffers.newconf
     block_avg = {}
     for step in range(nsteps):
         if accumulator is not None:
@@ -112,7 +190,7 @@ def vmc_block_device(wf, configs, tstep, nsteps, accumulators, variates=None, re
     block_avg["move time"] = end - start
     block_avg["accumulator time"] = 0.0
     if return_walker_data:
-        return block_avg, configs, {"accept": accept.astype(bool), "energy": energy}
+        return block_avg, configs, {"accept": accept.astype(bool), "energy": np.array(energy)}
     return block_avg, configs
 
 
@@ -158,6 +236,51 @@ def vmc_worker(wf, configs, tstep, nsteps, accumulators):
     return block_avg, configs
 
 
+class _VariatePrefetcher:
+    """Draws the variates of block b+1 on a host thread while block b runs on the GPU.
+
+    The draws still happen strictly in stream order (one producer, blocks in sequence) and nothing
+    else in the device-resident driver consumes ``np.random``, so the numbers are those the
+    reference loop would see."""
+
+    def __init__(self, wf, configs, tstep, nsteps, accumulators, nblocks):
+        from concurrent.futures import ThreadPoolExecutor
+
+        nconf, nelec, _ = configs.configs.shape
+        self.args = (nconf, nelec, tstep, nsteps)
+        self.accumulator = next(iter(accumulators.values())) if accumulators else None
+        if _device_context(wf) is None:  # context is created lazily by the first recompute
+            wf.recompute(configs)
+        self.ctx = _device_context(wf)
+        self.remaining = nblocks
+        self.issued = 0
+        self.pool = ThreadPoolExecutor(max_workers=1)
+        self.future = None
+        self._submit()
+
+    def _submit(self):
+        if self.remaining <= 0:
+            self.future = None
+            return
+        nconf, nelec, tstep, nsteps = self.args
+        buf = _block_buffers(self.ctx, nconf, nelec, nsteps, self.accumulator, slot=self.issued % 2)
+        self.issued += 1
+        self.remaining -= 1
+
+        def job():
+            draw_block_variates(nconf, nelec, tstep, nsteps, self.accumulator, out=buf.variates())
+            return buf
+
+        self.future = self.pool.submit(job)
+
+    def next(self):
+        buf = self.future.result()
+        self._submit()
+        if self.future is None:
+            self.pool.shutdown(wait=False)
+        return buf
+
+
 def vmc_parallel(wf, configs, tstep, nsteps_per_block, accumulators, client, npartitions):
     """mc.py:156-173: walker partitions on a futures client, weighted average of the blocks."""
     config = configs.split(npartitions)
@@ -187,10 +310,16 @@ def vmc(wf, configs, tstep=0.5, nblocks=10, nsteps_per_block=10, nsteps=None, bl
     df = []
     if blockoffset >= nblocks:
         logging.warning(f"blockoffset {blockoffset} >= nblocks {nblocks}; no steps will be run.")
+    prefetch = None
+    if client is None and _device_path(wf, accumulators) and nblocks > blockoffset:
+        prefetch = _VariatePrefetcher(wf, configs, tstep, nsteps_per_block, accumulators, nblocks - blockoffset)
     for block in range(blockoffset, nblocks):
         if verbose:
             print("-", end="", flush=True)
-        if client is None:
+        if prefetch is not None:
+            block_avg, configs = vmc_block_device(wf, configs, tstep, nsteps_per_block, accumulators,
+                                                  buffers=prefetch.next())
+        elif client is None:
             block_avg, configs = vmc_worker(wf, configs, tstep, nsteps_per_block, accumulators)
         else:
             block_avg, configs = vmc_parallel(wf, configs, tstep, nsteps_per_block, accumulators, client, npartitions)
