@@ -263,7 +263,7 @@ def gpu_arm(args):
     accept = float(d_nacc[W:tot].sum().item()) / (N * ne * K)
 
     # ---------------- end-to-end through the public API (host buffers) ----------------
-    nb_e2e = max(1, min(3, K // 10))
+    nb_e2e = max(2, min(10, K // 3))
     spb = 10
     torch.cuda.synchronize()
     if world > 1:
