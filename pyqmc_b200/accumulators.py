@@ -116,7 +116,23 @@ class EnergyAccumulator:
         return {k: np.mean(it, axis=0) for k, it in self(configs, wf).items()}
 
     def nonlocal_tmoves(self, configs, wf, e, tau):
-        raise NotImplementedError("T-moves are not implemented on the device yet")
+        """T-move candidates of electron e (``compute_tmoves``, eval_ecp.py:43-80): ratio (N, M),
+        weight (N, M) and the candidate positions (N, M, 3), M = sum of the quadrature sizes of the
+        ECP atoms.  Random variates as in the reference: per ECP atom ``random(N)`` then a rotation."""
+        ctx = self._attach(wf)
+        nconf = configs.configs.shape[0]
+        if self.necp == 0:
+            return {"ratio": np.ones((nconf, 0)), "weight": np.zeros((nconf, 0))}
+        u = np.empty((self.necp, nconf))
+        rot = np.empty((self.necp, 3, 3))
+        for a in range(self.necp):
+            u[a] = np.random.random(size=nconf)
+            rot[a] = scipy.spatial.transform.Rotation.random().as_matrix()
+        M = int(np.sum(self._ecp["naip"]))
+        ratio, weight, epos = np.empty((nconf, M)), np.empty((nconf, M)), np.empty((nconf, M, 3))
+        _lib.check(ctx.lib.qmcb_tmoves(ctx.h, int(e), float(tau), _lib.dptr(u), _lib.dptr(rot), _lib.dptr(ratio),
+                                       _lib.dptr(weight), _lib.dptr(epos)))
+        return {"ratio": ratio, "weight": weight, "configs": configs.make_irreducible(e, epos)}
 
     def has_nonlocal_moves(self):
         return self.mol._ecp != {}

@@ -1099,6 +1099,111 @@ __global__ void __launch_bounds__(128) k_ecp_points(const Sys S, const State st,
   }
 }
 
+// =========================================================================================
+// Parameter gradients of the Slater factor (slater.py:462-542).
+// =========================================================================================
+// AO values of every electron: ao [N][ne][A]   (the reference keeps them as _aovals, slater.py:233)
+__global__ void __launch_bounds__(128) k_ao_all(const Sys S, const State st, double* __restrict__ ao) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= st.N * S.ne) return;
+  const int w = p / S.ne, e = p - w * S.ne;
+  const double px = CONF(st, S, w, e, 0), py = CONF(st, S, w, e, 1), pz = CONF(st, S, w, e, 2);
+  double* out = ao + (size_t)p * S.nao;
+  const double* __restrict__ prim = sd + S.o_prim;
+  for (int a = 0; a < S.natom; ++a) {
+    const double x = px - sd[S.o_xyz + 3 * a], y = py - sd[S.o_xyz + 3 * a + 1], z = pz - sd[S.o_xyz + 3 * a + 2];
+    const double r2 = x * x + y * y + z * z;
+    for (int sh = si[S.o_atsh + a]; sh < si[S.o_atsh + a + 1]; ++sh) {
+      double R = 0.0;
+      for (int q = si[S.o_shprim + sh]; q < si[S.o_shprim + sh + 1]; ++q) R += prim[2 * q + 1] * exp(-prim[2 * q] * r2);
+      double tmp[36];
+      const int l = si[S.o_shl + sh];
+      switch (l) {
+        case 0: sph_store<0, false>(x, y, z, tmp); break;
+        case 1: sph_store<1, false>(x, y, z, tmp); break;
+        case 2: sph_store<2, false>(x, y, z, tmp); break;
+        case 3: sph_store<3, false>(x, y, z, tmp); break;
+        default: sph_store<4, false>(x, y, z, tmp); break;
+      }
+      for (int m = 0; m < 2 * l + 1; ++m) out[si[S.o_shao + sh] + m] = tmp[4 * m] * R;
+    }
+  }
+}
+
+// d ln Psi / d det_coeff [N][ndet] and the per-walker weights G_s[d] = sum_{D: map_s(D)=d} c_D dPsi_D
+__global__ void __launch_bounds__(128) k_pgrad_det(const Sys S, const State st, double* __restrict__ out,
+                                                   double* __restrict__ G, int gstride) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = st.N;
+  if (w >= N) return;
+  double sign, logpsi;
+  if (S.ndet == 1) {
+    const double c = S.detc[0];
+    sign = st.dsign[0][w] * st.dsign[1][w] * (c > 0.0 ? 1.0 : (c < 0.0 ? -1.0 : 0.0));
+    logpsi = st.dlog[0][w] + st.dlog[1][w] + log(fabs(c));
+  } else {
+    double val = 0.0;
+    for (int d = 0; d < S.nds[0]; ++d) val = fma(st.dv[0][(size_t)w * S.nds[0] + d], st.W[0][(size_t)w * S.nds[0] + d], val);
+    sign = val > 0.0 ? 1.0 : (val < 0.0 ? -1.0 : 0.0);
+    logpsi = log(fabs(val)) + st.ref[0][w] + st.ref[1][w];
+  }
+  for (int s = 0; s < 2; ++s)
+    for (int d = 0; d < S.nds[s]; ++d) G[((size_t)s * N + w) * gstride + d] = 0.0;
+  for (int D = 0; D < S.ndet; ++D) {
+    const int d0 = S.map[0][D], d1 = S.map[1][D];
+    double v = 0.0;
+    if (sign != 0.0)
+      v = st.dsign[0][(size_t)w * S.nds[0] + d0] * st.dsign[1][(size_t)w * S.nds[1] + d1] *
+          exp(st.dlog[0][(size_t)w * S.nds[0] + d0] + st.dlog[1][(size_t)w * S.nds[1] + d1] - logpsi) / sign;
+    out[(size_t)w * S.ndet + D] = v;
+    const double cv = S.detc[D] * v;
+    G[((size_t)0 * N + w) * gstride + d0] += cv;
+    G[((size_t)1 * N + w) * gstride + d1] += cv;
+  }
+}
+
+// d ln Psi / d mo_coeff_s [N][A][nmo_s]: sum_d G_s[d] sum_e ao[e][a] inv[d][col_d(i)][e]
+__global__ void __launch_bounds__(128) k_pgrad_mo(const Sys S, const State st, int s, const double* __restrict__ ao,
+                                                  const double* __restrict__ G, int gstride, double* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = st.N, nmo = S.nmo[s], A = S.nao;
+  if (t >= (long long)N * A * nmo) return;
+  const int i = (int)(t % nmo);
+  const int a = (int)((t / nmo) % A);
+  const int w = (int)(t / ((long long)nmo * A));
+  const int n = s ? S.ndn : S.nup, lo = s ? S.nup : 0, nds = S.nds[s];
+  const int* __restrict__ occ = S.iblob + S.o_occ[s];
+  double acc = 0.0;
+  for (int d = 0; d < nds; ++d) {
+    int col = -1;
+    for (int k = 0; k < n; ++k)
+      if (occ[d * n + k] == i) col = k;
+    if (col < 0) continue;
+    const double* __restrict__ inv = st.inv[s] + (((size_t)w * nds + d) * n + col) * n;
+    double v = 0.0;
+    for (int e = 0; e < n; ++e) v = fma(ao[((size_t)w * S.ne + lo + e) * A + a], inv[e], v);
+    acc = fma(G[((size_t)s * N + w) * gstride + d], v, acc);
+  }
+  out[t] = acc;
+}
+
+// T-move tables of walkers whose channel mask rejected: ratio 1, weight 0, position = the
+// electron's current position  (eval_ecp.py:63-72, 104-106)
+__global__ void k_tmove_init(const Sys S, const State st, int e, double* ratio, double* weight, double* pos) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)st.N * S.tot_naip;
+  if (i >= n) return;
+  const int w = (int)(i / S.tot_naip);
+  ratio[i] = 1.0;
+  weight[i] = 0.0;
+  pos[3 * i] = CONF(st, S, w, e, 0);
+  pos[3 * i + 1] = CONF(st, S, w, e, 1);
+  pos[3 * i + 2] = CONF(st, S, w, e, 2);
+}
+
 // Sum everything per walker in the reference's order: out [6][N] = ke, ee, ei, ecp, grad2, total
 __global__ void __launch_bounds__(128) k_energy_finalize(const Sys S, const State st, const EnergyScratch es,
                                                          double* out) {

@@ -1050,7 +1050,47 @@ int qmcb_pgradient(qmcb_ctx* c, const char* name, double* out) {
   const std::string k(name);
   if (k == "acoeff") return qmcb_get_state(c, "avalues", out);
   if (k == "bcoeff") return qmcb_get_state(c, "bvalues", out);
-  return fail("pgradient for '" + k + "' is not implemented on the device yet");
+  Guard g(c);
+  if (c->N == 0) return fail("recompute has not been called");
+  if (build_tables(c)) return -1;
+  if (c->N == 0) return fail("system shapes changed: call recompute again");
+  if (!c->have_slater) return fail("context has no Slater factor");
+  const Sys& S = c->S;
+  const size_t N = c->N;
+  const int gstride = std::max(std::max(S.nds[0], S.nds[1]), 1);
+  DBuf<double> d_det, d_G, d_ao, d_mo;
+  int rc = 0;
+  do {
+    if (d_det.ensure(N * S.ndet) || d_G.ensure(2 * N * gstride)) { rc = -1; break; }
+    k_pgrad_det<<<(unsigned)((N + 127) / 128), 128, 0, c->stream>>>(S, c->st, d_det.p, d_G.p, gstride);
+    c->nlaunch++;
+    if (cudaGetLastError() != cudaSuccess) { rc = fail("k_pgrad_det launch failed"); break; }
+    if (k == "det_coeff") {
+      rc = d2h(c, out, d_det.p, N * S.ndet * 8);
+      break;
+    }
+    int s = -1;
+    if (k == "mo_coeff_alpha") s = 0;
+    if (k == "mo_coeff_beta") s = 1;
+    if (s < 0) { rc = fail("unknown parameter: " + k); break; }
+    const size_t nout = N * S.nao * S.nmo[s];
+    if (nout == 0) break;
+    if (d_ao.ensure(N * S.ne * S.nao) || d_mo.ensure(nout)) { rc = -1; break; }
+    const long long np = (long long)N * S.ne;
+    if (prep_kernel(k_ao_all, c->smem_bytes)) { rc = -1; break; }
+    k_ao_all<<<(unsigned)((np + 127) / 128), 128, c->smem_bytes, c->stream>>>(S, c->st, d_ao.p);
+    c->nlaunch++;
+    k_pgrad_mo<<<(unsigned)((nout + 127) / 128), 128, 0, c->stream>>>(S, c->st, s, d_ao.p, d_G.p, gstride, d_mo.p);
+    c->nlaunch++;
+    if (cudaGetLastError() != cudaSuccess) { rc = fail("k_pgrad_mo launch failed"); break; }
+    rc = d2h(c, out, d_mo.p, nout * 8);
+  } while (0);
+  cudaStreamSynchronize(c->stream);
+  d_det.release();
+  d_G.release();
+  d_ao.release();
+  d_mo.release();
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1072,8 +1112,67 @@ int qmcb_energy(qmcb_ctx* c, const double* ecp_u, const double* ecp_rot, double*
   return d2h(c, out, c->d_energy.p, 6 * N * 8);
 }
 
-int qmcb_tmoves(qmcb_ctx*, int, double, const double*, const double*, double*, double*, double*) {
-  return fail("qmcb_tmoves is not implemented yet");
+int qmcb_tmoves(qmcb_ctx* c, int e, double tau, const double* ecp_u, const double* ecp_rot, double* ratio,
+                double* weight, double* epos) {
+  Guard g(c);
+  if (c->N == 0) return fail("recompute has not been called");
+  if (build_tables(c)) return -1;
+  if (c->N == 0) return fail("system shapes changed: call recompute again");
+  const Sys& S = c->S;
+  if (e < 0 || e >= S.ne) return fail("electron index out of range");
+  if (!(tau > 0.0)) return fail("T-moves need tau > 0");
+  const size_t N = c->N;
+  if (S.necp == 0) return 0;  // ratio/weight have zero columns
+  if (ensure_energy_scratch(c)) return -1;
+  const size_t npts = N * S.necp * S.max_naip;
+  if (ensure_scratch(c, npts, 1)) return -1;
+  const size_t M = (size_t)S.tot_naip;
+  if (c->d_u.ensure((size_t)S.necp * N) || c->d_rot.ensure((size_t)S.necp * 9) || c->d_out.ensure(N * M * 5)) return -1;
+  if (h2d(c, c->d_u.p, ecp_u, (size_t)S.necp * N * 8) || h2d(c, c->d_rot.p, ecp_rot, (size_t)S.necp * 9 * 8)) return -1;
+  double* d_ratio = c->d_out.p;
+  double* d_weight = d_ratio + N * M;
+  double* d_pos = d_weight + N * M;
+  k_tmove_init<<<(unsigned)((N * M + 255) / 256), 256, 0, c->stream>>>(S, c->st, e, d_ratio, d_weight, d_pos);
+  c->nlaunch++;
+  CK(cudaGetLastError());
+  CK(cudaMemsetAsync(c->es.count, 0, sizeof(int), c->stream));
+  const long long nt = (long long)N * S.necp;
+  if (prep_kernel(k_ecp_prepare, c->smem_bytes)) return -1;
+  k_ecp_prepare<<<(unsigned)((nt + 127) / 128), 128, c->smem_bytes, c->stream>>>(S, c->st, c->es, c->d_u.p, e);
+  c->nlaunch++;
+  CK(cudaGetLastError());
+  EcpPointArgs ea{};
+  ea.rot = c->d_rot.p;
+  ea.quad = c->d_quad.p;
+  ea.e_only = e;
+  ea.tmove_tau = tau;
+  ea.tm_ratio = d_ratio;
+  ea.tm_weight = d_weight;
+  ea.tm_pos = d_pos;
+  ea.scr = c->d_scr.p;
+  ea.scr_stride = npts;
+  const long long grid = std::min<long long>(((long long)npts + 127) / 128, 148LL * 16);
+  int rc = 0;
+  const size_t sm = c->smem_bytes;
+  if (c->nmot == 4) {
+    rc = prep_kernel(k_ecp_points<4>, sm);
+    if (!rc) k_ecp_points<4><<<(unsigned)grid, 128, sm, c->stream>>>(S, c->st, c->es, ea);
+  } else if (c->nmot == 8) {
+    rc = prep_kernel(k_ecp_points<8>, sm);
+    if (!rc) k_ecp_points<8><<<(unsigned)grid, 128, sm, c->stream>>>(S, c->st, c->es, ea);
+  } else {
+    rc = prep_kernel(k_ecp_points<0>, sm);
+    if (!rc) k_ecp_points<0><<<(unsigned)grid, 128, sm, c->stream>>>(S, c->st, c->es, ea);
+  }
+  if (rc) return rc;
+  c->nlaunch++;
+  CK(cudaGetLastError());
+  std::vector<double> h(N * M * 5);
+  if (d2h(c, h.data(), c->d_out.p, h.size() * 8)) return -1;
+  std::memcpy(ratio, h.data(), N * M * 8);
+  std::memcpy(weight, h.data() + N * M, N * M * 8);
+  std::memcpy(epos, h.data() + 2 * N * M, N * M * 3 * 8);
+  return 0;
 }
 
 }  // extern "C"

@@ -336,7 +336,22 @@ class Slater(_DeviceFactor):
             len(dc), _lib.iptr(m0), _lib.iptr(m1), _lib.dptr(dc)))
 
     def pgradient(self):
-        raise NotImplementedError("Slater.pgradient is not implemented on the device yet")
+        """d ln Psi / d parameters: det_coeff (N, D), mo_coeff_alpha/beta (N, A, nmo_s)
+        (slater.py:462-542), evaluated on the device from the stored inverses."""
+        ctx = self._ctx
+        N = ctx.nconf
+        p = self.parameters
+        shapes = {"det_coeff": (N, len(p["det_coeff"])),
+                  "mo_coeff_alpha": (N,) + p["mo_coeff_alpha"].shape,
+                  "mo_coeff_beta": (N,) + p["mo_coeff_beta"].shape}
+        out = {}
+        for k, shape in shapes.items():
+            if int(np.prod(shape)) == 0:
+                continue
+            arr = np.empty(shape)
+            _lib.check(ctx.lib.qmcb_pgradient(ctx.h, k.encode(), _lib.dptr(arr)))
+            out[k] = arr
+        return out
 
     # read-back of the reference's internal arrays (tests)
     @property

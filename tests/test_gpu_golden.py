@@ -32,6 +32,10 @@ def check_internal(wf, data):
     pg = ja.pgradient()
     assert helpers.relerr(pg["acoeff"], data["pgrad_wf2acoeff"]) < 1e-10
     assert helpers.relerr(pg["bcoeff"], data["pgrad_wf2bcoeff"]) < 1e-10
+    pgw = wf.pgradient()
+    for k in ("wf1det_coeff", "wf1mo_coeff_alpha", "wf1mo_coeff_beta", "wf2acoeff", "wf2bcoeff"):
+        assert pgw[k].shape == data["pgrad_" + k].shape, k
+        assert helpers.relerr(pgw[k], data["pgrad_" + k]) < 1e-9, k
 
 
 @pytest.mark.parametrize("name", ["he", "h2o", "open", "c2", "h2o_md"])
@@ -43,3 +47,24 @@ def test_cuda_reproduces_reference_golden(lib, name):
     assert np.array_equal(wf.parameters["wf2acoeff"], data["acoeff"])
     configs = pq.OpenConfigs(data["configs0"].copy())
     golden_replay.replay(data, wf, configs, lambda: pq.EnergyAccumulator(mol), device_vmc, check_internal)
+
+
+@pytest.mark.parametrize("name", ["he", "h2o", "c2", "h2o_md"])
+def test_tmoves_match_reference_golden(lib, name):
+    """EnergyAccumulator.nonlocal_tmoves vs compute_tmoves of the reference (eval_ecp.py:43-80)."""
+    import pyqmc_b200 as pq
+
+    data = golden_replay.load(name)
+    mol, mf, wf, _ = helpers.make_pair(name, seed=1)
+    configs = pq.OpenConfigs(data["configs1"].copy())
+    wf.recompute(configs)
+    before = wf.value()[1].copy()
+    acc = pq.EnergyAccumulator(mol)
+    assert acc.has_nonlocal_moves()
+    np.random.seed(22)
+    tm = acc.nonlocal_tmoves(configs, wf, int(data["elist"][-1]), 0.02)
+    assert tm["ratio"].shape == data["tmove_ratio"].shape
+    assert helpers.relerr(tm["ratio"], data["tmove_ratio"]) < 1e-9
+    assert helpers.relerr(tm["weight"], data["tmove_weight"]) < 1e-10
+    assert np.abs(tm["configs"].configs - data["tmove_configs"]).max() < 1e-12
+    assert np.array_equal(wf.value()[1], before), "T-move evaluation must not change the wave function state"
