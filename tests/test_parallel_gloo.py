@@ -1,0 +1,81 @@
+"""world_size-2 gloo test (CPU) of the walker sharding and the one-allreduce-per-block statistics:
+the combined averages must equal the reference's weighted mean of vmc_parallel (mc.py:166-172)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _fake_block(wf, configs, tstep, nsteps, accumulators):
+    """Stands in for the device block: deterministic 'averages' that depend on the walkers."""
+    c = configs.configs
+    avg = {"energytotal": float(np.mean(c[:, 0, 0])), "energyke": float(np.mean(c[:, 0, 1] ** 2)),
+           "acceptance": float(np.mean(c[:, 0, 2] > 0)), "move time": 1.0, "accumulator time": 0.0}
+    configs.configs = c + 1.0
+    return avg, configs
+
+
+def _worker(rank, world, port, nwalk, out_dir):
+    import torch.distributed as dist
+
+    from pyqmc_b200 import parallel
+    from pyqmc_b200.coord import OpenConfigs
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.RandomState(0)
+    configs = OpenConfigs(rng.randn(nwalk, 2, 3))
+    df, local = parallel.vmc_distributed(None, configs, nblocks=3, nsteps_per_block=2, block_fn=_fake_block)
+    allc = parallel.gather_configs(local)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), configs=allc, local=local.configs, **df)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nwalk", [10, 11])
+def test_two_rank_block_statistics(tmp_path, nwalk):
+    import torch.multiprocessing as mp
+
+    from pyqmc_b200.coord import OpenConfigs
+
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), nwalk, str(tmp_path)), nprocs=world, join=True)
+    res = [dict(np.load(tmp_path / f"rank{r}.npz")) for r in range(world)]
+    # serial reference: the vmc_parallel formula on the same partitions
+    rng = np.random.RandomState(0)
+    configs = OpenConfigs(rng.randn(nwalk, 2, 3))
+    parts = configs.split(world)
+    assert [len(p.configs) for p in parts] == [len(a) for a in np.array_split(np.arange(nwalk), world)]
+    expect = {k: [] for k in ("energytotal", "energyke", "acceptance")}
+    for block in range(3):
+        outs = []
+        for i in range(world):
+            avg, parts[i] = _fake_block(None, parts[i], 0.5, 2, {})
+            outs.append(avg)
+        w = np.array([len(p.configs) for p in parts], dtype=float)
+        w /= np.mean(w) * world
+        for k in expect:
+            expect[k].append(np.sum([o[k] * wi for o, wi in zip(outs, w)]))
+    for r in range(world):
+        for k in expect:
+            assert np.allclose(res[r][k], expect[k], rtol=1e-14, atol=1e-14), k
+        assert np.array_equal(res[r]["nconfig"], [2 * nwalk] * 3)
+        assert np.array_equal(res[r]["block"], [0, 1, 2])
+        assert np.allclose(res[r]["configs"], np.concatenate([p.configs for p in parts]))
+    assert len(res[0]["local"]) + len(res[1]["local"]) == nwalk
+
+
+def test_single_process_path_needs_no_process_group():
+    from pyqmc_b200 import parallel
+
+    avg, total = parallel.allreduce_block({"energytotal": 2.0, "acceptance": 0.5, "block": 3}, 7)
+    assert total == 7 and avg == {"acceptance": 0.5, "energytotal": 2.0}
