@@ -34,6 +34,7 @@ import numpy as np  # noqa: E402
 
 NWALKERS = 4096
 TSTEP = 0.5
+SPB = 10  # VMC steps per block (reference default nsteps_per_block)
 WORKLOAD = "H2O ccECP-cc-pVTZ-shaped Slater-Jastrow VMC (synthetic basis/MOs), 8 e-, 57 AOs, 4096 walkers/GPU"
 
 
@@ -96,7 +97,7 @@ class ClockSampler:
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20",
                                        "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
@@ -216,10 +217,12 @@ def gpu_arm(args):
                                        vp(d_esum[s].data_ptr()), vp(d_nacc[s].data_ptr()), vp(stream))
         if rc != 0:
             raise RuntimeError(lib.qmcb_last_error().decode())
-        if world > 1:  # one allreduce of the block statistics (here: per step) over NVLink
-            dist.all_reduce(d_esum[s])
+        if world > 1 and (s + 1) % SPB == 0:
+            # one allreduce per block of SPB steps: the block's energy sums, over NVLink
+            dist.all_reduce(d_esum[s + 1 - SPB : s + 1])
 
     torch.cuda.set_stream(ts)
+    sampler = ClockSampler(local) if rank == 0 else None  # samples the warm-up and the timed steps
     for s in range(W):
         run_step(s)
     torch.cuda.synchronize()
@@ -227,7 +230,6 @@ def gpu_arm(args):
         dist.barrier()
     torch.cuda.synchronize()
     launches0 = ctx.kernel_launches()
-    sampler = ClockSampler(local) if rank == 0 else None
     evs = []
     wall0 = time.perf_counter()
     for s in range(W, tot):
@@ -263,8 +265,8 @@ def gpu_arm(args):
     accept = float(d_nacc[W:tot].sum().item()) / (N * ne * K)
 
     # ---------------- end-to-end through the public API (host buffers) ----------------
-    nb_e2e = max(2, min(10, K // 3))
-    spb = 10
+    nb_e2e = max(2, min(20, K // 10))
+    spb = SPB
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -295,7 +297,7 @@ def gpu_arm(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "walkers_per_gpu": N, "nelec": ne, "tstep": TSTEP,
                    "l2": "256 MiB buffer written between timed steps (L2 flush)", "ecp_threshold": 10,
-                   "parallelism": f"walker-sharded x{world}, one NCCL allreduce of the energy sums per step"},
+                   "parallelism": f"walker-sharded x{world}, one NCCL allreduce of the energy sums per block of {SPB} steps"},
         "e2e": {"value": e2e, "unit": "walker-steps/s", "h2d_bytes_per_step": h2d / spb, "d2h_bytes_per_step": d2h / spb,
                 "call": f"pyqmc_b200.vmc(nblocks={nb_e2e}, nsteps_per_block={spb}) incl. host legacy-RNG draws"},
         "gpu_launches": int(launches),
@@ -310,7 +312,7 @@ def gpu_arm(args):
                   "wall_s_same_steps_back_to_back_no_flush": t_wall_noflush, "device_s_timed_steps": t_dev_max},
     }
     if world == 1 and not args.no_cpu:
-        v, cores, cwall, sample = cpu_arm(2, True)
+        v, cores, cwall, sample = cpu_arm(8, True)
         out["cpu_baseline"] = {"value": v, "unit": "walker-steps/s", "cores": cores, "kind": "port", "sample": sample,
                                "wall_s": cwall}
     print(json.dumps(out), flush=True)
@@ -323,7 +325,7 @@ def reference_arm(args):
     if rank != 0:
         return
     walkers = 256
-    v, cores, wall, sample = cpu_arm(max(1, min(args.steps, 4)), args.warmup > 0, walkers_per_core=walkers)
+    v, cores, wall, sample = cpu_arm(max(1, min(args.steps, 8)), args.warmup > 0, walkers_per_core=walkers)
     out = {
         "impl": "reference",
         "metric": "walker-steps/sec (VMC, H2O cc-pVTZ SJ); Sherman-Morrison HBM GB/s vs roofline",
@@ -342,8 +344,8 @@ def reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--walkers", type=int, default=NWALKERS)
     ap.add_argument("--equil", type=int, default=10)

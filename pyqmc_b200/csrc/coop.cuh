@@ -15,7 +15,7 @@
 #include "device_common.cuh"
 
 struct CoopLayout {  // offsets (doubles) into the per-warp scratch
-  int at, pv, sv, sph, comp, mo, minv, tvec, colv, total;
+  int at, pv, sv, sph, comp, mo, minv, tvec, colv, jtmp, total;
 };
 
 __host__ __device__ inline CoopLayout coop_layout(const Sys& S) {
@@ -41,6 +41,8 @@ __host__ __device__ inline CoopLayout coop_layout(const Sys& S) {
   o += nmax;
   L.colv = o;
   o += nmax;
+  L.jtmp = o;
+  o += (S.ne > 1 ? S.ne - 1 : 0) * S.nb;
   L.total = (o + 1) & ~1;
   return L;
 }
@@ -164,13 +166,35 @@ __device__ __forceinline__ void coop_eval_mo(const Sys& S, const CoopLayout& L, 
   __syncwarp(gm);
   const int ldc = S.ldc[spin];
   const double* __restrict__ C = sd + S.o_mo[spin];
+  if (ldc == 4 && G == 8) {
+    // lanes over components, the four MOs of a row in registers (two 16-byte shared loads per AO)
+    if (lane < NC) {
+      const double* __restrict__ cp = comp + lane * S.nao;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 4
+      for (int mu = 0; mu < S.nao; ++mu) {
+        const double x = cp[mu];
+        const double2 c01 = *reinterpret_cast<const double2*>(C + mu * 4);
+        const double2 c23 = *reinterpret_cast<const double2*>(C + mu * 4 + 2);
+        a0 = fma(x, c01.x, a0);
+        a1 = fma(x, c01.y, a1);
+        a2 = fma(x, c23.x, a2);
+        a3 = fma(x, c23.y, a3);
+      }
+      mo[lane * ldmax] = a0;
+      mo[lane * ldmax + 1] = a1;
+      mo[lane * ldmax + 2] = a2;
+      mo[lane * ldmax + 3] = a3;
+    }
+  } else {
 #pragma unroll 1
-  for (int t = lane; t < NC * ldc; t += G) {
-    const int c = t / ldc, j = t - c * ldc;
-    const double* __restrict__ cp = comp + c * S.nao;
-    double acc = 0.0;
-    for (int mu = 0; mu < S.nao; ++mu) acc = fma(cp[mu], C[mu * ldc + j], acc);
-    mo[c * ldmax + j] = acc;
+    for (int t = lane; t < NC * ldc; t += G) {
+      const int c = t / ldc, j = t - c * ldc;
+      const double* __restrict__ cp = comp + c * S.nao;
+      double acc = 0.0;
+      for (int mu = 0; mu < S.nao; ++mu) acc = fma(cp[mu], C[mu * ldc + j], acc);
+      mo[c * ldmax + j] = acc;
+    }
   }
   __syncwarp(gm);
 }
@@ -183,46 +207,42 @@ __device__ __forceinline__ void coop_jastrow(const Sys& S, const double* __restr
                                           unsigned gm, double& du, double (&g)[3], double& lap) {
   const int s = e >= S.nup ? 1 : 0;
   double unew = 0.0, uold = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0, lp = 0.0;
-  const int ntask = (S.ne - 1) + S.natom;
+  const int ntb = (S.ne - 1) * S.nb, nta = S.natom * S.na;
 #pragma unroll 1
-  for (int t = lane; t < ntask; t += G) {
-    if (t < S.ne - 1) {
-      const int j = t < e ? t : t + 1;
-      const int sj = j >= S.nup ? 1 : 0;
-      const double dx = px - CONF(st, S, w, j, 0), dy = py - CONF(st, S, w, j, 1), dz = pz - CONF(st, S, w, j, 2);
-      const double r = sqrt(dx * dx + dy * dy + dz * dz);
-      if (r < S.rcut_b) {
-#pragma unroll 1
-        for (int l = 0; l < S.nb; ++l) {
-          const double c = sd[S.o_bcoef + l * 3 + s + sj];
-          double v, gg, ll;
-          radial_ool<WANT>(si[S.o_bkind + l], sd[S.o_bpar + l], S.rcut_b, r, v, gg, ll);
-          unew = fma(c, v, unew);
-          const double cg = c * gg;
-          g0 = fma(cg, dx, g0);
-          g1 = fma(cg, dy, g1);
-          g2 = fma(cg, dz, g2);
-          if (WANT == 2) lp = fma(c, ll, lp);
-        }
-      }
+  for (int t = lane; t < ntb + nta; t += G) {
+    double dx, dy, dz, c, rcut, par;
+    int kind;
+    if (t < ntb) {
+      const int jj = t / S.nb, l = t - jj * S.nb;
+      const int j = jj < e ? jj : jj + 1;
+      dx = px - CONF(st, S, w, j, 0);
+      dy = py - CONF(st, S, w, j, 1);
+      dz = pz - CONF(st, S, w, j, 2);
+      c = sd[S.o_bcoef + l * 3 + s + (j >= S.nup ? 1 : 0)];
+      rcut = S.rcut_b;
+      par = sd[S.o_bpar + l];
+      kind = si[S.o_bkind + l];
     } else {
-      const int I = t - (S.ne - 1);
-      const double dx = px - sd[S.o_xyz + 3 * I], dy = py - sd[S.o_xyz + 3 * I + 1], dz = pz - sd[S.o_xyz + 3 * I + 2];
-      const double r = sqrt(dx * dx + dy * dy + dz * dz);
-      if (r < S.rcut_a) {
-#pragma unroll 1
-        for (int k = 0; k < S.na; ++k) {
-          const double c = sd[S.o_acoef + (I * S.na + k) * 2 + s];
-          double v, gg, ll;
-          radial_ool<WANT>(si[S.o_akind + k], sd[S.o_apar + k], S.rcut_a, r, v, gg, ll);
-          unew = fma(c, v, unew);
-          const double cg = c * gg;
-          g0 = fma(cg, dx, g0);
-          g1 = fma(cg, dy, g1);
-          g2 = fma(cg, dz, g2);
-          if (WANT == 2) lp = fma(c, ll, lp);
-        }
-      }
+      const int u = t - ntb;
+      const int I = u / S.na, k = u - I * S.na;
+      dx = px - sd[S.o_xyz + 3 * I];
+      dy = py - sd[S.o_xyz + 3 * I + 1];
+      dz = pz - sd[S.o_xyz + 3 * I + 2];
+      c = sd[S.o_acoef + (I * S.na + k) * 2 + s];
+      rcut = S.rcut_a;
+      par = sd[S.o_apar + k];
+      kind = si[S.o_akind + k];
+    }
+    const double r = sqrt(dx * dx + dy * dy + dz * dz);
+    if (r < rcut) {
+      double v, gg, ll;
+      radial_ool<WANT>(kind, par, rcut, r, v, gg, ll);
+      unew = fma(c, v, unew);
+      const double cg = c * gg;
+      g0 = fma(cg, dx, g0);
+      g1 = fma(cg, dy, g1);
+      g2 = fma(cg, dz, g2);
+      if (WANT == 2) lp = fma(c, ll, lp);
     }
   }
   if (WANT != 2) {
@@ -251,7 +271,7 @@ template <int G>
 __device__ __forceinline__ void coop_jastrow_update(const Sys& S, const double* __restrict__ sd,
                                                  const int* __restrict__ si, const State& st, int w, int e,
                                                  double nx, double ny, double nz, int lane, unsigned gm,
-                                                 bool has_jastrow) {
+                                                 bool has_jastrow, double* __restrict__ jtmp) {
   const int s = e >= S.nup ? 1 : 0;
   if (has_jastrow) {
     for (int t = lane; t < S.natom * S.na; t += G) {
@@ -264,38 +284,37 @@ __device__ __forceinline__ void coop_jastrow_update(const Sys& S, const double* 
       APART(st, S, w, e, I, k) = v;
     }
     const double ox = CONF(st, S, w, e, 0), oy = CONF(st, S, w, e, 1), oz = CONF(st, S, w, e, 2);
-    // lanes over (partner, basis function); new partial sums of electron e are reduced over lanes
+    // lanes over (partner, basis function): patch the partners' partial sums, park the new values
+    const int ntb = (S.ne - 1) * S.nb;
 #pragma unroll 1
-    for (int l = 0; l < S.nb; ++l) {
-      double bn0 = 0.0, bn1 = 0.0;
+    for (int t = lane; t < ntb; t += G) {
+      const int jj = t / S.nb, l = t - jj * S.nb;
+      const int j = jj < e ? jj : jj + 1;
+      const double jx = CONF(st, S, w, j, 0), jy = CONF(st, S, w, j, 1), jz = CONF(st, S, w, j, 2);
+      double dx = nx - jx, dy = ny - jy, dz = nz - jz;
+      const double rn = sqrt(dx * dx + dy * dy + dz * dz);
+      dx = ox - jx;
+      dy = oy - jy;
+      dz = oz - jz;
+      const double ro = sqrt(dx * dx + dy * dy + dz * dz);
+      double vn = 0.0, vo = 0.0, gg, ll;
+      if (rn < S.rcut_b) radial_ool<0>(si[S.o_bkind + l], sd[S.o_bpar + l], S.rcut_b, rn, vn, gg, ll);
+      if (ro < S.rcut_b) radial_ool<0>(si[S.o_bkind + l], sd[S.o_bpar + l], S.rcut_b, ro, vo, gg, ll);
+      BPART(st, S, w, j, l, s) += vn - vo;
+      jtmp[t] = vn;
+    }
+    __syncwarp(gm);
+    // new partial sums of electron e, accumulated in partner order as _b_update does
 #pragma unroll 1
-      for (int t = lane; t < S.ne - 1; t += G) {
-        const int j = t < e ? t : t + 1;
-        const int sj = j >= S.nup ? 1 : 0;
-        const double jx = CONF(st, S, w, j, 0), jy = CONF(st, S, w, j, 1), jz = CONF(st, S, w, j, 2);
-        double dx = nx - jx, dy = ny - jy, dz = nz - jz;
-        const double rn = sqrt(dx * dx + dy * dy + dz * dz);
-        dx = ox - jx;
-        dy = oy - jy;
-        dz = oz - jz;
-        const double ro = sqrt(dx * dx + dy * dy + dz * dz);
-        double vn = 0.0, vo = 0.0, gg, ll;
-        if (rn < S.rcut_b) radial_ool<0>(si[S.o_bkind + l], sd[S.o_bpar + l], S.rcut_b, rn, vn, gg, ll);
-        if (ro < S.rcut_b) radial_ool<0>(si[S.o_bkind + l], sd[S.o_bpar + l], S.rcut_b, ro, vo, gg, ll);
-        if (sj)
-          bn1 += vn;
-        else
-          bn0 += vn;
-        BPART(st, S, w, j, l, s) += vn - vo;
+    for (int t = lane; t < S.nb * 2; t += G) {
+      const int l = t >> 1, tt = t & 1;
+      double bn = 0.0;
+      for (int jj = 0; jj < S.ne - 1; ++jj) {
+        const int j = jj < e ? jj : jj + 1;
+        if ((j >= S.nup ? 1 : 0) == tt) bn += jtmp[jj * S.nb + l];
       }
-      bn0 = group_sum<G>(bn0, gm);
-      bn1 = group_sum<G>(bn1, gm);
-      if (lane == 0) {
-        BVAL(st, S, w, l, s) += bn0 - BPART(st, S, w, e, l, 0);
-        BPART(st, S, w, e, l, 0) = bn0;
-        BVAL(st, S, w, l, s + 1) += bn1 - BPART(st, S, w, e, l, 1);
-        BPART(st, S, w, e, l, 1) = bn1;
-      }
+      BVAL(st, S, w, l, s + tt) += bn - BPART(st, S, w, e, l, tt);
+      BPART(st, S, w, e, l, tt) = bn;
     }
   }
   __syncwarp(gm);

@@ -869,7 +869,7 @@ __global__ void __launch_bounds__(128) k_vmc_sweep(const Sys S, const State st, 
         const double* __restrict__ mo = ws + L.mo;
         for (int i = lane; i < 5 * ldmax; i += G) mc[i] = mo[i];
       }
-      coop_jastrow_update<G>(S, sd, si, st, w, e, np_[0], np_[1], np_[2], lane, gm, has_j);
+      coop_jastrow_update<G>(S, sd, si, st, w, e, np_[0], np_[1], np_[2], lane, gm, has_j, ws + L.jtmp);
     }
     __syncwarp(gm);
   }
@@ -894,11 +894,17 @@ struct EnergyScratch {
 // kinetic energy pieces: one thread per (walker, electron)  (energy.py:57-65).  The MO value /
 // gradient / Laplacian rows at the current positions come from st.mocache (filled by recompute
 // and refreshed by every accepted move), so no orbital is re-evaluated here.
+template <int G>
 __global__ void __launch_bounds__(128) k_kinetic(const Sys S, const State st, const EnergyScratch es) {
+  // G lanes per (walker, electron): lanes 0..4 take the five cached MO components, the Jastrow
+  // sums run over (partner | atom, function) tasks
   const double* sd;
   const int* si;
   stage_tables(S, sd, si);
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane32 = threadIdx.x & 31;
+  const int lane = lane32 & (G - 1);
+  const unsigned gm = group_mask<G>(lane32);
+  const int p = (blockIdx.x * blockDim.x + threadIdx.x) / G;
   const int N = st.N;
   if (p >= N * S.ne) return;
   const int w = p / S.ne, e = p - w * S.ne;
@@ -913,48 +919,46 @@ __global__ void __launch_bounds__(128) k_kinetic(const Sys S, const State st, co
     const double* __restrict__ mc = st.mocache + ((size_t)w * S.ne + e) * 5 * ldmax;
     const int nds = S.nds[s];
     const int* __restrict__ occ = si + S.o_occ[s];
-    double num[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, den = 0.0;
-    for (int d = 0; d < nds; ++d) {
-      const double* __restrict__ inv = st.inv[s] + ((size_t)w * nds + d) * n * n + eeff;
-      double r[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-      for (int k = 0; k < n; ++k) {
-        const double a = inv[k * n];
-        const int orb = occ[d * n + k];
-#pragma unroll
-        for (int c = 0; c < 5; ++c) r[c] = fma(mc[c * ldmax + orb], a, r[c]);
+    double num = 0.0, den = 0.0;
+    if (lane < 5) {
+      for (int d = 0; d < nds; ++d) {
+        const double* __restrict__ inv = st.inv[s] + ((size_t)w * nds + d) * n * n + eeff;
+        double r = 0.0;
+        for (int k = 0; k < n; ++k) r = fma(mc[lane * ldmax + occ[d * n + k]], inv[k * n], r);
+        if (S.ndet == 1) {
+          num = r;
+          den = 1.0;
+        } else {
+          const double wgt = st.dv[s][(size_t)w * nds + d] * st.W[s][(size_t)w * nds + d];
+          den += wgt;
+          num = fma(r, wgt, num);
+        }
       }
-      if (S.ndet == 1) {
-#pragma unroll
-        for (int c = 0; c < 5; ++c) num[c] = r[c];
-        den = 1.0;
-      } else {
-        const double wgt = st.dv[s][(size_t)w * nds + d] * st.W[s][(size_t)w * nds + d];
-        den += wgt;
-#pragma unroll
-        for (int c = 0; c < 5; ++c) num[c] = fma(r[c], wgt, num[c]);
-      }
+      num = num / den;
     }
-    const double r0 = num[0] / den;
+    const double r0 = __shfl_sync(gm, num, 0, G);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) gs[i] = (num[1 + i] / den) / r0;
-    laps = (num[4] / den) / r0;
+    for (int i = 0; i < 3; ++i) gs[i] = __shfl_sync(gm, num, 1 + i, G) / r0;
+    laps = __shfl_sync(gm, num, 4, G) / r0;
   }
   double lapj = 0.0, cross = 0.0, gj[3] = {0.0, 0.0, 0.0};
   if (which & QMCB_JASTROW) {
     double du, lj;
-    jastrow_point<2>(S, sd, si, st, w, e, px, py, pz, du, gj, lj);
+    coop_jastrow<2, G>(S, sd, si, st, w, e, px, py, pz, lane, gm, du, gj, lj);
     lapj = lj + (gj[0] * gj[0] + gj[1] * gj[1] + gj[2] * gj[2]);
     cross = gs[0] * gj[0] + gs[1] * gj[1] + gs[2] * gj[2];
   }
-  const double lap = (laps + lapj) + cross * 2.0;
-  double g2 = 0.0;
+  if (lane == 0) {
+    const double lap = (laps + lapj) + cross * 2.0;
+    double g2 = 0.0;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const double g = gs[i] + gj[i];
-    g2 += g * g;
+    for (int i = 0; i < 3; ++i) {
+      const double g = gs[i] + gj[i];
+      g2 += g * g;
+    }
+    es.ke_e[(size_t)e * N + w] = -0.5 * lap;
+    es.g2_e[(size_t)e * N + w] = g2;
   }
-  es.ke_e[(size_t)e * N + w] = -0.5 * lap;
-  es.g2_e[(size_t)e * N + w] = g2;
 }
 
 // ECP radial channels, stochastic mask and work list: one thread per (electron, ECP atom, walker)
@@ -1205,56 +1209,87 @@ __global__ void k_tmove_init(const Sys S, const State st, int e, double* ratio, 
 }
 
 // Sum everything per walker in the reference's order: out [6][N] = ke, ee, ei, ecp, grad2, total
+template <int G>
 __global__ void __launch_bounds__(128) k_energy_finalize(const Sys S, const State st, const EnergyScratch es,
-                                                         double* out) {
+                                                         double* out, int scratch_doubles) {
+  // G lanes per walker compute the terms in parallel into shared memory; lane 0 then adds them in
+  // the reference's order (energy.py:28-44, eval_ecp.py:21-40), so the result does not depend on G.
   const double* sd;
   const int* si;
   stage_tables(S, sd, si);
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ __align__(128) unsigned char qmcb_smem[];
+  const int lane32 = threadIdx.x & 31;
+  const int lane = lane32 & (G - 1);
+  const unsigned gm = group_mask<G>(lane32);
+  const int slot = threadIdx.x / G;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) / G;
   const int N = st.N;
   if (w >= N) return;
+  const size_t tab = (16 + (size_t)S.dwords * 8 + (size_t)S.iwords * 4 + 15) & ~(size_t)15;
+  double* buf = reinterpret_cast<double*>(qmcb_smem + tab) + (size_t)slot * scratch_doubles;
+  const int ne = S.ne;
+  // ---- ECP: one term per (electron, ECP atom)
+  for (int t = lane; t < ne * S.necp; t += G) {
+    const int e = t / S.necp, a = t - e * S.necp;
+    const size_t gi = ((size_t)e * S.necp + a) * N + w;
+    const int item = es.item_of[gi];
+    double nl = 0.0;
+    if (item >= 0) {
+      const int naip = si[S.o_naip + a];
+      for (int q = 0; q < naip; ++q) nl += es.contrib[(size_t)item * S.max_naip + q];
+    }
+    buf[t] = nl + es.ecp_loc[gi];
+  }
+  __syncwarp(gm);
   double ke = 0.0, g2 = 0.0, ecp = 0.0, ee = 0.0, ei = 0.0;
-  for (int e = 0; e < S.ne; ++e) {
-    ke += es.ke_e[(size_t)e * N + w];
-    g2 += es.g2_e[(size_t)e * N + w];
-    double ecp_e = 0.0;
-    for (int a = 0; a < S.necp; ++a) {
-      const size_t t = ((size_t)e * S.necp + a) * N + w;
-      const int item = es.item_of[t];
-      double nl = 0.0;
-      if (item >= 0) {
-        const int naip = si[S.o_naip + a];
-        for (int q = 0; q < naip; ++q) nl += es.contrib[(size_t)item * S.max_naip + q];
-      }
-      ecp_e += nl + es.ecp_loc[t];
-    }
-    ecp += ecp_e;
-  }
-  for (int i = 0; i < S.ne; ++i) {
-    const double xi = CONF(st, S, w, i, 0), yi = CONF(st, S, w, i, 1),
-                 zi = CONF(st, S, w, i, 2);
-    for (int j = i + 1; j < S.ne; ++j) {
-      const double dx = xi - CONF(st, S, w, j, 0), dy = yi - CONF(st, S, w, j, 1),
-                   dz = zi - CONF(st, S, w, j, 2);
-      ee += 1.0 / sqrt(dx * dx + dy * dy + dz * dz);
+  if (lane == 0) {
+    for (int e = 0; e < ne; ++e) {
+      ke += es.ke_e[(size_t)e * N + w];
+      g2 += es.g2_e[(size_t)e * N + w];
+      double ecp_e = 0.0;
+      for (int a = 0; a < S.necp; ++a) ecp_e += buf[e * S.necp + a];
+      ecp += ecp_e;
     }
   }
-  for (int I = 0; I < S.natom; ++I) {
-    double acc = 0.0;
-    for (int i = 0; i < S.ne; ++i) {
-      const double dx = CONF(st, S, w, i, 0) - sd[S.o_xyz + 3 * I],
-                   dy = CONF(st, S, w, i, 1) - sd[S.o_xyz + 3 * I + 1],
-                   dz = CONF(st, S, w, i, 2) - sd[S.o_xyz + 3 * I + 2];
-      acc += 1.0 / sqrt(dx * dx + dy * dy + dz * dz);
+  __syncwarp(gm);
+  // ---- electron-electron: pairs (i < j) in row-major order
+  const int npair = ne * (ne - 1) / 2;
+  for (int t = lane; t < npair; t += G) {
+    int i = 0, rem = t;
+    while (rem >= ne - 1 - i) {
+      rem -= ne - 1 - i;
+      ++i;
     }
-    ei += -sd[S.o_chg + I] * acc;
+    const int j = i + 1 + rem;
+    const double dx = CONF(st, S, w, i, 0) - CONF(st, S, w, j, 0), dy = CONF(st, S, w, i, 1) - CONF(st, S, w, j, 1),
+                 dz = CONF(st, S, w, i, 2) - CONF(st, S, w, j, 2);
+    buf[t] = 1.0 / sqrt(dx * dx + dy * dy + dz * dz);
   }
-  out[w] = ke;
-  out[(size_t)N + w] = ee;
-  out[(size_t)2 * N + w] = ei;
-  out[(size_t)3 * N + w] = ecp;
-  out[(size_t)4 * N + w] = g2;
-  out[(size_t)5 * N + w] = (((ke + ee) + ei) + ecp) + S.e_ii;
+  __syncwarp(gm);
+  if (lane == 0)
+    for (int t = 0; t < npair; ++t) ee += buf[t];
+  __syncwarp(gm);
+  // ---- electron-ion
+  for (int t = lane; t < S.natom * ne; t += G) {
+    const int I = t / ne, i = t - I * ne;
+    const double dx = CONF(st, S, w, i, 0) - sd[S.o_xyz + 3 * I], dy = CONF(st, S, w, i, 1) - sd[S.o_xyz + 3 * I + 1],
+                 dz = CONF(st, S, w, i, 2) - sd[S.o_xyz + 3 * I + 2];
+    buf[t] = 1.0 / sqrt(dx * dx + dy * dy + dz * dz);
+  }
+  __syncwarp(gm);
+  if (lane == 0) {
+    for (int I = 0; I < S.natom; ++I) {
+      double acc = 0.0;
+      for (int i = 0; i < ne; ++i) acc += buf[I * ne + i];
+      ei += -sd[S.o_chg + I] * acc;
+    }
+    out[w] = ke;
+    out[(size_t)N + w] = ee;
+    out[(size_t)2 * N + w] = ei;
+    out[(size_t)3 * N + w] = ecp;
+    out[(size_t)4 * N + w] = g2;
+    out[(size_t)5 * N + w] = (((ke + ee) + ei) + ecp) + S.e_ii;
+  }
 }
 
 // Deterministic column sums: out[k] = sum_w in[k][w], one block per column (fixed tree order).

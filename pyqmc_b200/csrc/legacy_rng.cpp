@@ -144,28 +144,41 @@ struct GaussPlan {
     const int64_t first = nslots;
     nslots += n;
     const int64_t need_pairs = (nslots - slot_shift + 1) / 2;
-    if ((int64_t)r2.size() < need_pairs) {
-      x1.resize(need_pairs);
-      x2.resize(need_pairs);
-      r2.resize(need_pairs);
+    if ((int64_t)r2.size() < need_pairs + 1) {  // +1: the branch-free loop stores before it tests
+      x1.resize(need_pairs + 1);
+      x2.resize(need_pairs + 1);
+      r2.resize(need_pairs + 1);
     }
     double* X1 = x1.data();
     double* X2 = x2.data();
     double* R2 = r2.data();
     while (npairs < need_pairs) {
-      double a, b, c;
-      if (s.pos <= 620) {  // four outputs available in the tempered block
+      // bulk path: all complete 4-output attempts left in the tempered block, branch-free
+      // compaction (every attempt consumes exactly four outputs, accepted or not)
+      const int avail = (624 - s.pos) / 4;
+      const int64_t want = need_pairs - npairs;
+      if (avail > 0) {
         const uint32_t* t = s.tb + s.pos;
-        s.pos += 4;
-        const double d1 = ((int32_t)(t[0] >> 5) * 67108864.0 + (int32_t)(t[1] >> 6)) / 9007199254740992.0;
-        const double d2 = ((int32_t)(t[2] >> 5) * 67108864.0 + (int32_t)(t[3] >> 6)) / 9007199254740992.0;
-        a = 2.0 * d1 - 1.0;
-        b = 2.0 * d2 - 1.0;
-        c = a * a + b * b;
-        if (c >= 1.0 || c == 0.0) continue;
-      } else {
-        if (!polar_attempt(s, a, b, c)) continue;
+        int used = 0;
+        int64_t np_ = npairs;
+        // stop as soon as enough pairs are accepted: later attempts belong to the next consumer
+        for (; used < avail && np_ < need_pairs; ++used) {
+          const double d1 = ((int32_t)(t[4 * used] >> 5) * 67108864.0 + (int32_t)(t[4 * used + 1] >> 6)) / 9007199254740992.0;
+          const double d2 = ((int32_t)(t[4 * used + 2] >> 5) * 67108864.0 + (int32_t)(t[4 * used + 3] >> 6)) / 9007199254740992.0;
+          const double a = 2.0 * d1 - 1.0, b = 2.0 * d2 - 1.0;
+          const double c = a * a + b * b;
+          X1[np_] = a;
+          X2[np_] = b;
+          R2[np_] = c;
+          np_ += (c < 1.0) & (c != 0.0);
+        }
+        (void)want;
+        npairs = np_;
+        s.pos += 4 * used;
+        continue;
       }
+      double a, b, c;
+      if (!polar_attempt(s, a, b, c)) continue;  // attempt straddling a block boundary
       X1[npairs] = a;
       X2[npairs] = b;
       R2[npairs] = c;
@@ -254,7 +267,7 @@ int qmcb_rng_vmc_block(uint32_t* key, int32_t* pos, int32_t* has_gauss, double* 
     plan.slot_shift = 1;
     plan.carried = *cached_gauss;
   }
-  const int64_t est = (int64_t)nsteps * ne * (N * 3 / 2 + 2 * (ecp_u ? necp : 0)) + 8;
+  const int64_t est = (int64_t)nsteps * ne * (N * 3 / 2 + 1 + 2 * (ecp_u ? necp : 0)) + 16;
   plan.x1.resize(est);
   plan.x2.resize(est);
   plan.r2.resize(est);

@@ -579,8 +579,8 @@ int launch_energy_t(qmcb_ctx* c, const double* d_u, const double* d_rot, double*
       CK(cudaGetLastError());
       c->mocache_valid = true;
     }
-    if (prep_kernel(k_kinetic, sm)) return -1;
-    k_kinetic<<<(unsigned)((np + block - 1) / block), block, sm, stream>>>(S, c->st, c->es);
+    if (prep_kernel(k_kinetic<8>, sm)) return -1;
+    k_kinetic<8><<<(unsigned)((np * 8 + 127) / 128), 128, sm, stream>>>(S, c->st, c->es);
     c->nlaunch++;
     CK(cudaGetLastError());
   }
@@ -607,9 +607,13 @@ int launch_energy_t(qmcb_ctx* c, const double* d_u, const double* d_rot, double*
     CK(cudaGetLastError());
   }
   {
-    const int block = pick_block(N);
-    if (prep_kernel(k_energy_finalize, sm)) return -1;
-    k_energy_finalize<<<(N + block - 1) / block, block, sm, stream>>>(S, c->st, c->es, d_out);
+    const int ne = S.ne;
+    int scr = std::max(std::max(ne * std::max(S.necp, 1), ne * (ne - 1) / 2), S.natom * ne);
+    scr = (scr + 1) & ~1;
+    const size_t tab = (sm + 15) & ~(size_t)15;
+    const size_t fsm = tab + (size_t)(128 / 8) * scr * 8;
+    if (prep_kernel(k_energy_finalize<8>, fsm)) return -1;
+    k_energy_finalize<8><<<(unsigned)(((long long)N * 8 + 127) / 128), 128, fsm, stream>>>(S, c->st, c->es, d_out, scr);
     c->nlaunch++;
     CK(cudaGetLastError());
   }
@@ -1211,9 +1215,9 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
   // warp-per-walker sweep kernel: single determinant, inverse staged in shared memory
   const CoopLayout CL = coop_layout(S);
   const size_t tab = (c->smem_bytes + 15) & ~(size_t)15;
-  int G = 8;
+  int G = 16;
   if (const char* env = std::getenv("QMCB_SWEEP_G")) G = std::atoi(env);
-  if (G != 8 && G != 16 && G != 32) G = 8;
+  if (G != 8 && G != 16 && G != 32) G = 16;
   const int sweep_warps = 4;
   const int sweep_walkers = sweep_warps * (32 / G);
   const size_t sweep_smem = tab + (size_t)sweep_walkers * CL.total * 8;
