@@ -30,6 +30,7 @@ typedef struct qmcb_ctx qmcb_ctx;
 
 #define QMCB_SLATER 1
 #define QMCB_JASTROW 2
+#define QMCB_JASTROW3 4
 
 /* Jastrow radial function kinds (pyqmc/wf/func3d.py:52-110 PolyPade, 112-210 CutoffCusp) */
 #define QMCB_FUNC_POLYPADE 0
@@ -68,6 +69,12 @@ int qmcb_set_jastrow(qmcb_ctx *ctx, int nup, int ndn, int na, const int32_t *a_k
                      const double *a_par, double rcut_a, int nb, const int32_t *b_kind,
                      const double *b_par, double rcut_b, const double *acoeff,
                      const double *bcoeff);
+
+/* ThreeBodyJastrow.__init__ (three_body_jastrow.py:45-64): a / b radial bases and
+ * ccoeff [natom][na][na][nb][3]; the library symmetrises it in (k,l) as recompute does (94-96). */
+int qmcb_set_jastrow3(qmcb_ctx *ctx, int nup, int ndn, int na, const int32_t *a_kind,
+                      const double *a_par, double rcut_a, int nb, const int32_t *b_kind,
+                      const double *b_par, double rcut_b, const double *ccoeff);
 
 /* mol._ecp flattened (eval_ecp.py:160-200): for each ECP atom the channel list in COLUMN
  * order l = 0..lmax then the local channel (l = -1) last; channel c owns terms

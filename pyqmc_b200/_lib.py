@@ -33,6 +33,8 @@ SIGNATURES = {
                                 c_int_p, c_int, c_int_p, c_int, c_int_p, c_int_p, c_double_p]),
     "qmcb_set_jastrow": (c_int, [c_void_p, c_int, c_int, c_int, c_int_p, c_double_p, c_double, c_int,
                                  c_int_p, c_double_p, c_double, c_double_p, c_double_p]),
+    "qmcb_set_jastrow3": (c_int, [c_void_p, c_int, c_int, c_int, c_int_p, c_double_p, c_double, c_int,
+                                  c_int_p, c_double_p, c_double, c_double_p]),
     "qmcb_set_ecp": (c_int, [c_void_p, c_int, c_int_p, c_int_p, c_int_p, c_int_p, c_double_p,
                              c_double_p, c_int_p, c_double_p, c_double]),
     "qmcb_recompute": (c_int, [c_void_p, c_int, c_int, c_double_p, c_double_p, c_double_p]),

@@ -26,8 +26,11 @@ struct Sys {
   int nds[2], ndet;    // unique spin determinants, total determinants
   int fast;            // single determinant with identity occupation and n_s <= 8
   int na, nb;
+  int na3, nb3;  // three-body Jastrow basis sizes (0: factor absent)
   int necp, nchan, nterm, max_naip, tot_naip;
   double rcut_a, rcut_b, ecp_threshold, e_ii;
+  double rcut_a3, rcut_b3;
+  int o_c3, o_a3par, o_b3par, o_a3kind, o_b3kind;  // C[I][k][l][m][3] symmetrised; basis tables
   // offsets into the double blob
   int o_xyz, o_chg, o_prim, o_mo[2], o_apar, o_bpar, o_acoef, o_bcoef, o_talpha, o_tcoef;
   // offsets into the int blob
@@ -61,6 +64,9 @@ struct State {
   double* avalues;   // [N][I][na][2]
   double* bvalues;   // [N][nb][3]
   double* mocache;   // [N][ne][5][ldmax]  MO value/grad/Laplacian rows at the current positions
+  double* a3v;       // [N][ne][I][na3]  three-body a_k(r_eI)      (three_body_jastrow.py:103)
+  double* P3;        // [N][ne]          P_i                       (three_body_jastrow.py:98-101)
+  double* val3;      // [N]              U = 1/2 sum_i P_i
   double* saved_mo;  // [N][ldc]  MO row at the last gradient_value/testvalue position
   double* saved_pos; // [N][3]
   double* mo_all;    // [N][ne][ldcmax]  recompute scratch
@@ -73,6 +79,9 @@ struct State {
 #define BPART(st, S, w, e, l, t) (st).b_partial[(((size_t)(w) * (S).ne + (e)) * (S).nb + (l)) * 2 + (t)]
 #define AVAL(st, S, w, I, k, t) (st).avalues[(((size_t)(w) * (S).natom + (I)) * (S).na + (k)) * 2 + (t)]
 #define BVAL(st, S, w, l, t) (st).bvalues[((size_t)(w) * (S).nb + (l)) * 3 + (t)]
+#define A3V(st, S, w, e, I, k) (st).a3v[(((size_t)(w) * (S).ne + (e)) * (S).natom + (I)) * (S).na3 + (k)]
+#define QMCB_J3_MAXA 128  // natom * na3 held per thread
+#define QMCB_J3_MAXB 8
 
 // ---------------------------------------------------------------------------------------
 // TMA staging of the table blobs:  [mbarrier | double blob | int blob] in dynamic smem.
@@ -321,4 +330,87 @@ __device__ __forceinline__ void jastrow_point(const Sys& S, const double* __rest
                      ub_old);
   }
   du = (ub - ub_old) + (ua - ua_old);
+}
+
+// ---------------------------------------------------------------------------------------
+// Three-body Jastrow (three_body_jastrow.py): pair term of electron e (at pos, with a-values
+// av/ag/al over (I,k)) and partner j:
+//   P_ej = sum_{Iklm} C[I,k,l,m,sp] a_k(r_eI) a_l(r_jI) b_m(r_ej)
+// plus gradient / Laplacian contributions w.r.t. the position of e (454-655).
+// ---------------------------------------------------------------------------------------
+template <int WANT>
+__device__ __forceinline__ void j3_a_values(const Sys& S, const double* __restrict__ sd, const int* __restrict__ si,
+                                            double px, double py, double pz, double* __restrict__ av,
+                                            double* __restrict__ ag, double* __restrict__ al) {
+  for (int I = 0; I < S.natom; ++I) {
+    const double dx = px - sd[S.o_xyz + 3 * I], dy = py - sd[S.o_xyz + 3 * I + 1], dz = pz - sd[S.o_xyz + 3 * I + 2];
+    const double r = sqrt(dx * dx + dy * dy + dz * dz);
+    for (int k = 0; k < S.na3; ++k) {
+      double v = 0.0, g = 0.0, l = 0.0;
+      if (r < S.rcut_a3) radial_ool<WANT>(si[S.o_a3kind + k], sd[S.o_a3par + k], S.rcut_a3, r, v, g, l);
+      av[I * S.na3 + k] = v;
+      if (WANT >= 1) ag[I * S.na3 + k] = g;
+      if (WANT >= 2) al[I * S.na3 + k] = l;
+    }
+  }
+}
+
+template <int WANT>
+__device__ __forceinline__ void j3_pair(const Sys& S, const double* __restrict__ sd, const int* __restrict__ si,
+                                        const State& st, int w, int e, int j, double px, double py, double pz,
+                                        const double* __restrict__ av, const double* __restrict__ ag,
+                                        const double* __restrict__ al, double jx, double jy, double jz, double& P,
+                                        double (&g)[3], double& lap) {
+  const double dx = px - jx, dy = py - jy, dz = pz - jz;
+  const double r = sqrt(dx * dx + dy * dy + dz * dz);
+  if (!(r < S.rcut_b3)) return;
+  double bv[QMCB_J3_MAXB], bg[QMCB_J3_MAXB], bl[QMCB_J3_MAXB];
+  for (int m = 0; m < S.nb3; ++m) {
+    double v, gg = 0.0, ll = 0.0;
+    radial_ool<WANT>(si[S.o_b3kind + m], sd[S.o_b3par + m], S.rcut_b3, r, v, gg, ll);
+    bv[m] = v;
+    bg[m] = gg;
+    bl[m] = ll;
+  }
+  const int sp = (e >= S.nup ? 1 : 0) + (j >= S.nup ? 1 : 0);
+  const int na = S.na3, nb = S.nb3;
+  for (int I = 0; I < S.natom; ++I) {
+    const double ax = px - sd[S.o_xyz + 3 * I], ay = py - sd[S.o_xyz + 3 * I + 1], az = pz - sd[S.o_xyz + 3 * I + 2];
+    const double dot = ax * dx + ay * dy + az * dz;
+    const double* __restrict__ C = sd + S.o_c3 + (size_t)I * na * na * nb * 3 + sp;
+    for (int m = 0; m < nb; ++m) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+      for (int k = 0; k < na; ++k) {
+        double t = 0.0;  // sum_l C[I,k,l,m,sp] a_l(r_jI)
+        for (int l = 0; l < na; ++l) t = fma(C[((k * na + l) * nb + m) * 3], A3V(st, S, w, j, I, l), t);
+        s0 = fma(av[I * na + k], t, s0);
+        if (WANT >= 1) s1 = fma(ag[I * na + k], t, s1);
+        if (WANT >= 2) s2 = fma(al[I * na + k], t, s2);
+      }
+      P = fma(s0, bv[m], P);
+      if (WANT >= 1) {
+        const double ca = s1 * bv[m], cb = s0 * bg[m];
+        g[0] += ca * ax + cb * dx;
+        g[1] += ca * ay + cb * dy;
+        g[2] += ca * az + cb * dz;
+      }
+      if (WANT >= 2) lap += s2 * bv[m] + 2.0 * s1 * bg[m] * dot + s0 * bl[m];
+    }
+  }
+}
+
+// adds the three-body terms of electron e at (px,py,pz) to du, g, lap (raw Laplacian of U)
+template <int WANT>
+__device__ __forceinline__ void jastrow3_point(const Sys& S, const double* __restrict__ sd, const int* __restrict__ si,
+                                               const State& st, int w, int e, double px, double py, double pz,
+                                               double& du, double (&g)[3], double& lap) {
+  double av[QMCB_J3_MAXA], ag[QMCB_J3_MAXA], al[QMCB_J3_MAXA];
+  j3_a_values<WANT>(S, sd, si, px, py, pz, av, ag, al);
+  double P = 0.0;
+  for (int j = 0; j < S.ne; ++j) {
+    if (j == e) continue;
+    j3_pair<WANT>(S, sd, si, st, w, e, j, px, py, pz, av, ag, al, CONF(st, S, w, j, 0), CONF(st, S, w, j, 1),
+                  CONF(st, S, w, j, 2), P, g, lap);
+  }
+  if (WANT != 2) du += P - st.P3[(size_t)w * S.ne + e];
 }

@@ -15,6 +15,7 @@
 
 #define QMCB_SLATER 1
 #define QMCB_JASTROW 2
+#define QMCB_JASTROW3 4
 
 // =========================================================================================
 // Slater part of a single-electron query at one point.
@@ -129,6 +130,9 @@ struct PointEval {
         slater_point_general<DERIV>(S, sd, si, st, w, e, px, py, pz, rat, mo_save, scr, scr_stride);
     }
     if (which & QMCB_JASTROW) jastrow_point<DERIV>(S, sd, si, st, w, e, px, py, pz, du, gj, lapj);
+    // the three-body factor adds to the same log-ratio / grad U / lap U (a sum of Jastrow
+    // exponents combines exactly like the product rule of multiplywf.py:121-129)
+    if (which & QMCB_JASTROW3) jastrow3_point<DERIV>(S, sd, si, st, w, e, px, py, pz, du, gj, lapj);
   }
 };
 
@@ -209,7 +213,7 @@ __global__ void __launch_bounds__(128) k_point(const Sys S, const State st, cons
       laps = ev.rat[4] / ev.rat[0];
     }
     double lapj = 0.0, cross = 0.0;
-    if (pa.which & QMCB_JASTROW) {
+    if (pa.which & (QMCB_JASTROW | QMCB_JASTROW3)) {
       lapj = ev.lapj + (ev.gj[0] * ev.gj[0] + ev.gj[1] * ev.gj[1] + ev.gj[2] * ev.gj[2]);
       cross = gs[0] * ev.gj[0] + gs[1] * ev.gj[1] + gs[2] * ev.gj[2];
     }
@@ -413,6 +417,7 @@ __global__ void __launch_bounds__(128) k_value(const Sys S, const State st, int 
           ua = fma(AVAL(st, S, w, I, k, t), sd[S.o_acoef + (I * S.na + k) * 2 + t], ua);
     lg += u + ua;
   }
+  if (which & QMCB_JASTROW3) lg += st.val3[w];
   o_sign[w] = sign;
   o_log[w] = lg;
 }
@@ -467,7 +472,7 @@ __global__ void __launch_bounds__(128) k_jastrow_recompute(const Sys S, const St
 // updateinternals of the Jastrow caches for accepted walkers (jastrowspin.py:111-137,221-249)
 // and move of the walker coordinates (coord.py:54-62).  New position = st.saved_pos[w].
 __global__ void __launch_bounds__(128) k_jastrow_update(const Sys S, const State st, int e, int do_jastrow,
-                                                        const uint8_t* mask) {
+                                                        int move_conf, const uint8_t* mask) {
   const double* sd;
   const int* si;
   stage_tables(S, sd, si);
@@ -518,9 +523,113 @@ __global__ void __launch_bounds__(128) k_jastrow_update(const Sys S, const State
       }
     }
   }
+  if (!move_conf) return;
   CONF(st, S, w, e, 0) = nx;
   CONF(st, S, w, e, 1) = ny;
   CONF(st, S, w, e, 2) = nz;
+}
+
+// =========================================================================================
+// Three-body Jastrow caches (three_body_jastrow.py:66-104 recompute, 149-189 updateinternals,
+// 657-719 pgradient).  One thread per walker.
+// =========================================================================================
+__global__ void __launch_bounds__(128) k_jastrow3_recompute(const Sys S, const State st) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= st.N) return;
+  double av[QMCB_J3_MAXA], ag[1], al[1];
+  for (int e = 0; e < S.ne; ++e) {
+    j3_a_values<0>(S, sd, si, CONF(st, S, w, e, 0), CONF(st, S, w, e, 1), CONF(st, S, w, e, 2), av, ag, al);
+    for (int i = 0; i < S.natom * S.na3; ++i) st.a3v[((size_t)w * S.ne + e) * S.natom * S.na3 + i] = av[i];
+  }
+  double tot = 0.0;
+  for (int e = 0; e < S.ne; ++e) {
+    const double px = CONF(st, S, w, e, 0), py = CONF(st, S, w, e, 1), pz = CONF(st, S, w, e, 2);
+    for (int i = 0; i < S.natom * S.na3; ++i) av[i] = st.a3v[((size_t)w * S.ne + e) * S.natom * S.na3 + i];
+    double P = 0.0, g[3] = {0.0, 0.0, 0.0}, lap = 0.0;
+    for (int j = 0; j < S.ne; ++j) {
+      if (j == e) continue;
+      j3_pair<0>(S, sd, si, st, w, e, j, px, py, pz, av, ag, al, CONF(st, S, w, j, 0), CONF(st, S, w, j, 1),
+                 CONF(st, S, w, j, 2), P, g, lap);
+    }
+    st.P3[(size_t)w * S.ne + e] = P;
+    tot += P;
+  }
+  st.val3[w] = 0.5 * tot;
+}
+
+__global__ void __launch_bounds__(128) k_jastrow3_update(const Sys S, const State st, int e, int move_conf,
+                                                         const uint8_t* mask) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= st.N) return;
+  if (mask && !mask[w]) return;
+  const double nx = st.saved_pos[(size_t)w * 3], ny = st.saved_pos[(size_t)w * 3 + 1], nz = st.saved_pos[(size_t)w * 3 + 2];
+  const double ox = CONF(st, S, w, e, 0), oy = CONF(st, S, w, e, 1), oz = CONF(st, S, w, e, 2);
+  double av[QMCB_J3_MAXA], ag[1], al[1];
+  const size_t abase = ((size_t)w * S.ne + e) * S.natom * S.na3;
+  // old pair terms (cached a-values, current position) leave the partners' sums ...
+  for (int i = 0; i < S.natom * S.na3; ++i) av[i] = st.a3v[abase + i];
+  for (int j = 0; j < S.ne; ++j) {
+    if (j == e) continue;
+    double Po = 0.0, g[3] = {0.0, 0.0, 0.0}, lap = 0.0;
+    j3_pair<0>(S, sd, si, st, w, e, j, ox, oy, oz, av, ag, al, CONF(st, S, w, j, 0), CONF(st, S, w, j, 1),
+               CONF(st, S, w, j, 2), Po, g, lap);
+    st.P3[(size_t)w * S.ne + j] -= Po;
+  }
+  // ... and the new ones (a-values at the accepted position) enter
+  j3_a_values<0>(S, sd, si, nx, ny, nz, av, ag, al);
+  double newval = 0.0;
+  for (int j = 0; j < S.ne; ++j) {
+    if (j == e) continue;
+    double Pn = 0.0, g[3] = {0.0, 0.0, 0.0}, lap = 0.0;
+    j3_pair<0>(S, sd, si, st, w, e, j, nx, ny, nz, av, ag, al, CONF(st, S, w, j, 0), CONF(st, S, w, j, 1),
+               CONF(st, S, w, j, 2), Pn, g, lap);
+    newval += Pn;
+    st.P3[(size_t)w * S.ne + j] += Pn;
+  }
+  st.val3[w] += newval - st.P3[(size_t)w * S.ne + e];
+  st.P3[(size_t)w * S.ne + e] = newval;
+  for (int i = 0; i < S.natom * S.na3; ++i) st.a3v[abase + i] = av[i];
+  if (!move_conf) return;
+  CONF(st, S, w, e, 0) = nx;
+  CONF(st, S, w, e, 1) = ny;
+  CONF(st, S, w, e, 2) = nz;
+}
+
+// d U / d ccoeff [N][I][na][na][nb][3]: thread per (walker, I, k, l)
+__global__ void __launch_bounds__(128) k_jastrow3_pgrad(const Sys S, const State st, double* __restrict__ out) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  const int na = S.na3, nb = S.nb3;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)st.N * S.natom * na * na) return;
+  const int l = (int)(t % na), k = (int)((t / na) % na), I = (int)((t / (na * na)) % S.natom);
+  const int w = (int)(t / ((long long)na * na * S.natom));
+  double acc[QMCB_J3_MAXB][3];
+  for (int m = 0; m < nb; ++m) acc[m][0] = acc[m][1] = acc[m][2] = 0.0;
+  for (int i = 0; i < S.ne; ++i)
+    for (int j = i + 1; j < S.ne; ++j) {
+      const double dx = CONF(st, S, w, i, 0) - CONF(st, S, w, j, 0), dy = CONF(st, S, w, i, 1) - CONF(st, S, w, j, 1),
+                   dz = CONF(st, S, w, i, 2) - CONF(st, S, w, j, 2);
+      const double r = sqrt(dx * dx + dy * dy + dz * dz);
+      if (!(r < S.rcut_b3)) continue;
+      const int sp = (i >= S.nup ? 1 : 0) + (j >= S.nup ? 1 : 0);
+      // (a_k(i) a_l(j) + a_l(i) a_k(j)) / 2
+      const double aa = 0.5 * (A3V(st, S, w, i, I, k) * A3V(st, S, w, j, I, l) + A3V(st, S, w, i, I, l) * A3V(st, S, w, j, I, k));
+      for (int m = 0; m < nb; ++m) {
+        double v, gg, ll;
+        radial_ool<0>(si[S.o_b3kind + m], sd[S.o_b3par + m], S.rcut_b3, r, v, gg, ll);
+        acc[m][sp] = fma(aa, v, acc[m][sp]);
+      }
+    }
+  for (int m = 0; m < nb; ++m)
+    for (int sp = 0; sp < 3; ++sp) out[(t * nb + m) * 3 + sp] = acc[m][sp];
 }
 
 // =========================================================================================
@@ -681,7 +790,8 @@ __global__ void __launch_bounds__(128) k_vmc_move(const Sys S, const State st, c
   stage_tables(S, sd, si);
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   const int N = st.N;
-  const int which = (S.nmo[0] + S.nmo[1] > 0 ? QMCB_SLATER : 0) | ((S.na + S.nb) > 0 ? QMCB_JASTROW : 0);
+  const int which = (S.nmo[0] + S.nmo[1] > 0 ? QMCB_SLATER : 0) | ((S.na + S.nb) > 0 ? QMCB_JASTROW : 0) |
+                    ((S.na3 + S.nb3) > 0 ? QMCB_JASTROW3 : 0);
   bool acc = false;
   if (w < N) {
     const int e = ma.e;
@@ -908,7 +1018,8 @@ __global__ void __launch_bounds__(128) k_kinetic(const Sys S, const State st, co
   const int N = st.N;
   if (p >= N * S.ne) return;
   const int w = p / S.ne, e = p - w * S.ne;
-  const int which = (S.nmo[0] + S.nmo[1] > 0 ? QMCB_SLATER : 0) | ((S.na + S.nb) > 0 ? QMCB_JASTROW : 0);
+  const int which = (S.nmo[0] + S.nmo[1] > 0 ? QMCB_SLATER : 0) | ((S.na + S.nb) > 0 ? QMCB_JASTROW : 0) |
+                    ((S.na3 + S.nb3) > 0 ? QMCB_JASTROW3 : 0);
   const double px = CONF(st, S, w, e, 0), py = CONF(st, S, w, e, 1), pz = CONF(st, S, w, e, 2);
   double gs[3] = {0.0, 0.0, 0.0}, laps = 0.0;
   if (which & QMCB_SLATER) {
@@ -945,7 +1056,14 @@ __global__ void __launch_bounds__(128) k_kinetic(const Sys S, const State st, co
   if (which & QMCB_JASTROW) {
     double du, lj;
     coop_jastrow<2, G>(S, sd, si, st, w, e, px, py, pz, lane, gm, du, gj, lj);
-    lapj = lj + (gj[0] * gj[0] + gj[1] * gj[1] + gj[2] * gj[2]);
+    lapj = lj;
+  }
+  if (which & QMCB_JASTROW3) {
+    double du3 = 0.0;
+    jastrow3_point<2>(S, sd, si, st, w, e, px, py, pz, du3, gj, lapj);
+  }
+  if (which & (QMCB_JASTROW | QMCB_JASTROW3)) {
+    lapj = lapj + (gj[0] * gj[0] + gj[1] * gj[1] + gj[2] * gj[2]);
     cross = gs[0] * gj[0] + gs[1] * gj[1] + gs[2] * gj[2];
   }
   if (lane == 0) {
@@ -1050,7 +1168,8 @@ __global__ void __launch_bounds__(128) k_ecp_points(const Sys S, const State st,
   const int* si;
   stage_tables(S, sd, si);
   const int N = st.N;
-  const int which = (S.nmo[0] + S.nmo[1] > 0 ? QMCB_SLATER : 0) | ((S.na + S.nb) > 0 ? QMCB_JASTROW : 0);
+  const int which = (S.nmo[0] + S.nmo[1] > 0 ? QMCB_SLATER : 0) | ((S.na + S.nb) > 0 ? QMCB_JASTROW : 0) |
+                    ((S.na3 + S.nb3) > 0 ? QMCB_JASTROW3 : 0);
   const int nitems = *es.count;
   const long long total = (long long)nitems * S.max_naip;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;

@@ -11,6 +11,7 @@
 #include "../../include/qmcb200.h"
 #undef QMCB_SLATER
 #undef QMCB_JASTROW
+#undef QMCB_JASTROW3
 #include "kernels.cuh"
 
 namespace {
@@ -90,6 +91,11 @@ struct qmcb_ctx {
   std::vector<int> akind, bkind;
   std::vector<double> apar, bpar, acoef, bcoef;
   double rcut_a = 1.0, rcut_b = 1.0;
+  bool have_j3 = false;
+  int na3 = 0, nb3 = 0;
+  std::vector<int> a3kind, b3kind;
+  std::vector<double> a3par, b3par, c3;
+  double rcut_a3 = 1.0, rcut_b3 = 1.0;
   int necp = 0;
   std::vector<int> ecp_atom, chan_off, term_off, term_pow, naip;
   std::vector<double> term_alpha, term_coef, quad;
@@ -105,7 +111,7 @@ struct qmcb_ctx {
   State st{};
   int N = 0;
   DBuf<double> b_inv[2], b_dsign[2], b_dlog[2], b_dv[2], b_W[2], b_ref[2];
-  DBuf<double> b_conf, b_ap, b_bp, b_av, b_bv, b_smo, b_spos, b_moall, b_lu, b_mocache;
+  DBuf<double> b_conf, b_ap, b_bp, b_av, b_bv, b_smo, b_spos, b_moall, b_lu, b_mocache, b_a3v, b_P3, b_val3;
   // ---- staging / scratch
   DBuf<double> d_in, d_out, d_scr, d_u, d_rot, d_gauss, d_unif, d_energy, d_esum;
   DBuf<uint8_t> d_mask, d_accept;
@@ -188,6 +194,10 @@ int build_tables(qmcb_ctx* c) {
   S.nb = c->have_jastrow ? c->nb : 0;
   S.rcut_a = c->rcut_a;
   S.rcut_b = c->rcut_b;
+  S.na3 = c->have_j3 ? c->na3 : 0;
+  S.nb3 = c->have_j3 ? c->nb3 : 0;
+  S.rcut_a3 = c->rcut_a3;
+  S.rcut_b3 = c->rcut_b3;
   S.necp = c->necp;
   S.ecp_threshold = c->threshold;
   double eii = 0.0;
@@ -233,6 +243,9 @@ int build_tables(qmcb_ctx* c) {
   S.o_bpar = dpush(c->bpar.data(), S.nb);
   S.o_acoef = dpush(c->acoef.data(), (size_t)natom * S.na * 2);
   S.o_bcoef = dpush(c->bcoef.data(), (size_t)S.nb * 3);
+  S.o_a3par = dpush(c->a3par.data(), S.na3);
+  S.o_b3par = dpush(c->b3par.data(), S.nb3);
+  S.o_c3 = dpush(c->c3.data(), c->have_j3 ? c->c3.size() : 0);
   S.o_talpha = dpush(c->term_alpha.data(), c->term_alpha.size());
   S.o_tcoef = dpush(c->term_coef.data(), c->term_coef.size());
   while (db.size() % 2) db.push_back(0.0);
@@ -267,6 +280,8 @@ int build_tables(qmcb_ctx* c) {
   }
   S.o_akind = ipush(c->akind.data(), S.na);
   S.o_bkind = ipush(c->bkind.data(), S.nb);
+  S.o_a3kind = ipush(c->a3kind.data(), S.na3);
+  S.o_b3kind = ipush(c->b3kind.data(), S.nb3);
   S.o_ecpatom = ipush(c->ecp_atom.data(), c->ecp_atom.size());
   S.o_chanoff = ipush(c->chan_off.data(), c->chan_off.size());
   S.o_termoff = ipush(c->term_off.data(), c->term_off.size());
@@ -325,7 +340,7 @@ int build_tables(qmcb_ctx* c) {
   }
   c->dirty = false;
   // walker state survives a table rebuild unless a shape it depends on changed
-  std::vector<int> sig = {S.natom, S.nup, S.ndn, S.nds[0], S.nds[1], S.ldc[0], S.ldc[1], S.na, S.nb, S.ndet};
+  std::vector<int> sig = {S.natom, S.nup, S.ndn, S.nds[0], S.nds[1], S.ldc[0], S.ldc[1], S.na, S.nb, S.ndet, S.na3, S.nb3};
   if (sig != c->shape_sig) {
     c->shape_sig = sig;
     c->N = 0;
@@ -358,7 +373,9 @@ int ensure_state(qmcb_ctx* c, int N) {
       c->b_bp.ensure((size_t)N * S.ne * std::max(S.nb, 1) * 2) || c->b_av.ensure((size_t)N * S.natom * std::max(S.na, 1) * 2) ||
       c->b_bv.ensure((size_t)N * std::max(S.nb, 1) * 3) || c->b_smo.ensure((size_t)N * ldmax) ||
       c->b_spos.ensure((size_t)N * 3) || c->b_moall.ensure((size_t)N * S.ne * ldmax) ||
-      c->b_mocache.ensure((size_t)N * S.ne * 5 * ldmax))
+      c->b_mocache.ensure((size_t)N * S.ne * 5 * ldmax) ||
+      c->b_a3v.ensure((size_t)N * S.ne * S.natom * std::max(S.na3, 1)) || c->b_P3.ensure((size_t)N * std::max(S.ne, 1)) ||
+      c->b_val3.ensure(N))
     return -1;
   st.conf = c->b_conf.p;
   st.a_partial = c->b_ap.p;
@@ -369,6 +386,9 @@ int ensure_state(qmcb_ctx* c, int N) {
   st.saved_pos = c->b_spos.p;
   st.mo_all = c->b_moall.p;
   st.mocache = c->b_mocache.p;
+  st.a3v = c->b_a3v.p;
+  st.P3 = c->b_P3.p;
+  st.val3 = c->b_val3.p;
   c->N = N;
   c->saved_slot = -1;
   return 0;
@@ -434,6 +454,7 @@ int launch_sm(qmcb_ctx* c, const SmArgs& a, cudaStream_t stream, int64_t* nlaunc
 int which_ok(qmcb_ctx* c, int which) {
   if ((which & 1) && !c->have_slater) return fail("context has no Slater factor");
   if ((which & 2) && !c->have_jastrow) return fail("context has no Jastrow factor");
+  if ((which & 4) && !c->have_j3) return fail("context has no three-body Jastrow factor");
   if (which == 0) return fail("which == 0");
   return 0;
 }
@@ -529,11 +550,24 @@ int launch_update(qmcb_ctx* c, int which, int e, const uint8_t* d_mask, cudaStre
       CK(cudaGetLastError());
     }
   }
+  // The walker coordinates are moved by the LAST factor of the context in the canonical order
+  // (Slater, Jastrow, three-body), so a context driven factor by factor still sees the old
+  // position in every cache update.
+  const int owner = c->have_j3 ? 4 : (c->have_jastrow ? 2 : 1);
   const bool do_j = (which & 2) && c->have_jastrow;
-  if (do_j || !c->have_jastrow) {
+  const bool do_j3 = (which & 4) && c->have_j3;
+  if (do_j || (owner == 1 && (which & 1)) || (owner == 2 && (which & 2))) {
     const int block = pick_block(c->N);
     if (prep_kernel(k_jastrow_update, c->smem_bytes)) return -1;
-    k_jastrow_update<<<(c->N + block - 1) / block, block, c->smem_bytes, stream>>>(S, c->st, e, do_j ? 1 : 0, d_mask);
+    k_jastrow_update<<<(c->N + block - 1) / block, block, c->smem_bytes, stream>>>(S, c->st, e, do_j ? 1 : 0,
+                                                                                (which & owner) && owner != 4 ? 1 : 0, d_mask);
+    c->nlaunch++;
+    CK(cudaGetLastError());
+  }
+  if (do_j3) {
+    const int block = pick_block(c->N);
+    if (prep_kernel(k_jastrow3_update, c->smem_bytes)) return -1;
+    k_jastrow3_update<<<(c->N + block - 1) / block, block, c->smem_bytes, stream>>>(S, c->st, e, 1, d_mask);
     c->nlaunch++;
     CK(cudaGetLastError());
   }
@@ -663,7 +697,7 @@ void qmcb_destroy(qmcb_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   DBuf<double>* dd[] = {&c->d_dblob, &c->d_detc, &c->d_quad, &c->b_conf, &c->b_ap, &c->b_bp, &c->b_av, &c->b_bv,
-                        &c->b_smo, &c->b_spos, &c->b_moall, &c->b_lu, &c->b_mocache, &c->d_in, &c->d_out, &c->d_scr, &c->d_u,
+                        &c->b_smo, &c->b_spos, &c->b_moall, &c->b_lu, &c->b_mocache, &c->b_a3v, &c->b_P3, &c->b_val3, &c->d_in, &c->d_out, &c->d_scr, &c->d_u,
                         &c->d_rot, &c->d_gauss, &c->d_unif, &c->d_energy, &c->d_esum, &c->e_ke, &c->e_g2, &c->e_loc,
                         &c->e_vls, &c->e_contrib};
   for (auto* b : dd) b->release();
@@ -765,6 +799,41 @@ int qmcb_set_jastrow(qmcb_ctx* c, int nup, int ndn, int na, const int32_t* a_kin
   return 0;
 }
 
+int qmcb_set_jastrow3(qmcb_ctx* c, int nup, int ndn, int na, const int32_t* a_kind, const double* a_par,
+                      double rcut_a, int nb, const int32_t* b_kind, const double* b_par, double rcut_b,
+                      const double* ccoeff) {
+  if ((c->have_slater || c->have_jastrow) && (nup != c->nup || ndn != c->ndn))
+    return fail("electron counts differ from the other factors");
+  const int natom = (int)c->chg.size();
+  if (natom == 0) return fail("qmcb_set_atoms must be called before qmcb_set_jastrow3");
+  if (nb > QMCB_J3_MAXB) return fail("three-body Jastrow: more than 8 b functions");
+  if (natom * na > QMCB_J3_MAXA) return fail("three-body Jastrow: natom * na > 128");
+  c->nup = nup;
+  c->ndn = ndn;
+  c->na3 = na;
+  c->nb3 = nb;
+  c->a3kind.assign(a_kind, a_kind + na);
+  c->a3par.assign(a_par, a_par + na);
+  c->b3kind.assign(b_kind, b_kind + nb);
+  c->b3par.assign(b_par, b_par + nb);
+  c->rcut_a3 = rcut_a;
+  c->rcut_b3 = rcut_b;
+  // C = (ccoeff + ccoeff^T(k,l)) / 2   (three_body_jastrow.py:94-96)
+  c->c3.resize((size_t)natom * na * na * nb * 3);
+  for (int I = 0; I < natom; ++I)
+    for (int k = 0; k < na; ++k)
+      for (int l = 0; l < na; ++l)
+        for (int m = 0; m < nb; ++m)
+          for (int t = 0; t < 3; ++t) {
+            const size_t a = ((((size_t)I * na + k) * na + l) * nb + m) * 3 + t;
+            const size_t b = ((((size_t)I * na + l) * na + k) * nb + m) * 3 + t;
+            c->c3[a] = (ccoeff[a] + ccoeff[b]) / 2;
+          }
+  c->have_j3 = true;
+  c->dirty = true;
+  return 0;
+}
+
 int qmcb_set_ecp(qmcb_ctx* c, int necp, const int32_t* ecp_atom, const int32_t* chan_off,
                  const int32_t* term_off, const int32_t* term_power, const double* term_alpha,
                  const double* term_coef, const int32_t* naip, const double* quad, double threshold) {
@@ -808,6 +877,13 @@ int qmcb_recompute(qmcb_ctx* c, int which, int nconf, const double* configs, dou
     const int block = pick_block(nconf);
     if (prep_kernel(k_jastrow_recompute, c->smem_bytes)) return -1;
     k_jastrow_recompute<<<(nconf + block - 1) / block, block, c->smem_bytes, c->stream>>>(S, c->st);
+    c->nlaunch++;
+    CK(cudaGetLastError());
+  }
+  if (which & 4) {
+    const int block = pick_block(nconf);
+    if (prep_kernel(k_jastrow3_recompute, c->smem_bytes)) return -1;
+    k_jastrow3_recompute<<<(nconf + block - 1) / block, block, c->smem_bytes, c->stream>>>(S, c->st);
     c->nlaunch++;
     CK(cudaGetLastError());
   }
@@ -1040,6 +1116,13 @@ int qmcb_get_state(qmcb_ctx* c, const char* name, double* out) {
     for (int e = 0; e < S.ne; ++e)
       for (size_t w = 0; w < N; ++w)
         for (int m = 0; m < M; ++m) out[((size_t)e * N + w) * M + m] = h[(w * S.ne + e) * M + m];
+  } else if (k == "a3_values" || k == "P_i") {  // device (N, ne, M) -> (ne, N, M)
+    const bool a = k == "a3_values";
+    const int M = a ? S.natom * S.na3 : 1;
+    if (fetch(a ? c->st.a3v : c->st.P3, N * S.ne * M, h)) return -1;
+    for (int e = 0; e < S.ne; ++e)
+      for (size_t w = 0; w < N; ++w)
+        for (int m = 0; m < M; ++m) out[((size_t)e * N + w) * M + m] = h[(w * S.ne + e) * M + m];
   } else if (k == "avalues" || k == "bvalues") {
     const bool a = k == "avalues";
     const int M = a ? S.natom * S.na * 2 : S.nb * 3;
@@ -1054,6 +1137,22 @@ int qmcb_pgradient(qmcb_ctx* c, const char* name, double* out) {
   const std::string k(name);
   if (k == "acoeff") return qmcb_get_state(c, "avalues", out);
   if (k == "bcoeff") return qmcb_get_state(c, "bvalues", out);
+  if (k == "ccoeff") {
+    Guard g3(c);
+    if (c->N == 0) return fail("recompute has not been called");
+    if (build_tables(c)) return -1;
+    if (!c->have_j3 || c->N == 0) return fail("context has no three-body Jastrow state");
+    const Sys& S3 = c->S;
+    const size_t nt = (size_t)c->N * S3.natom * S3.na3 * S3.na3;
+    DBuf<double> d;
+    if (d.ensure(nt * S3.nb3 * 3)) return -1;
+    if (prep_kernel(k_jastrow3_pgrad, c->smem_bytes)) return -1;
+    k_jastrow3_pgrad<<<(unsigned)((nt + 127) / 128), 128, c->smem_bytes, c->stream>>>(S3, c->st, d.p);
+    c->nlaunch++;
+    int rc3 = cudaGetLastError() == cudaSuccess ? d2h(c, out, d.p, nt * S3.nb3 * 3 * 8) : fail("k_jastrow3_pgrad launch failed");
+    d.release();
+    return rc3;
+  }
   Guard g(c);
   if (c->N == 0) return fail("recompute has not been called");
   if (build_tables(c)) return -1;
@@ -1203,7 +1302,7 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
   const Sys& S = c->S;
   const size_t N = c->N;
   cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : c->stream;
-  const int which = (c->have_slater ? 1 : 0) | (c->have_jastrow ? 2 : 0);
+  const int which = (c->have_slater ? 1 : 0) | (c->have_jastrow ? 2 : 0) | (c->have_j3 ? 4 : 0);
   if (with_energy && (ensure_energy_scratch(c) || energy_scratch_points(c))) return -1;
   if (ensure_scratch(c, N, 5)) return -1;
   if (c->d_accept.ensure(N) || c->d_nacc.ensure((size_t)nsteps * S.ne)) return -1;
@@ -1221,7 +1320,8 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
   const int sweep_warps = 4;
   const int sweep_walkers = sweep_warps * (32 / G);
   const size_t sweep_smem = tab + (size_t)sweep_walkers * CL.total * 8;
-  const bool use_sweep = (!c->have_slater || S.ndet == 1) && sweep_smem <= 200 * 1024 && std::getenv("QMCB_NO_SWEEP") == nullptr;
+  const bool use_sweep = (!c->have_slater || S.ndet == 1) && !c->have_j3 && sweep_smem <= 200 * 1024 &&
+                         std::getenv("QMCB_NO_SWEEP") == nullptr;
   if (use_sweep && c->have_slater && !c->mocache_valid) {
     const long long np = (long long)N * S.ne;
     const int block = pick_block(np);

@@ -20,6 +20,7 @@ from .func3d import CutoffCuspFunction, PolyPadeFunction  # noqa: F401  (re-expo
 
 SLATER = 1
 JASTROW = 2
+JASTROW3 = 4
 
 
 def default_device():
@@ -428,6 +429,61 @@ class JastrowSpin(_DeviceFactor):
         return self._ctx.get_state("b_partial", (ne, self._ctx.nconf, len(self.b_basis), 2))
 
 
+class ThreeBodyJastrow(_DeviceFactor):
+    """Electron-electron-ion Jastrow factor (reference: ``pyqmc/wf/three_body_jastrow.py``).
+
+    Cache updates use the factor's own copy of the walker coordinates (as ``JastrowSpin`` does),
+    i.e. the behaviour of the reference when ``updateinternals`` is called before ``configs.move``
+    (its test harness, ``testwf.py:116-119``).  The reference's drivers move ``configs`` first
+    (``mc.py:135-136``), after which its ``P_i`` cache no longer matches a fresh ``recompute``;
+    that inconsistency is deliberately not reproduced."""
+
+    _which = JASTROW3
+
+    def __init__(self, mol, a_basis, b_basis, device=None):
+        if hasattr(mol, "a"):
+            raise NotImplementedError("periodic systems are not supported by the B200 backend yet")
+        self._mol = mol
+        self._nelec = tuple(int(x) for x in mol.nelec)
+        self._device = device
+        self._ctx = None
+        self.a_basis = list(a_basis)
+        self.b_basis = list(b_basis)
+        self.parameters = {"ccoeff": np.zeros((mol.natm, len(a_basis), len(a_basis), len(b_basis), 3))}
+
+    def _copy_parameters(self):
+        return {k: np.array(v) for k, v in self.parameters.items()}
+
+    def _push_static(self, ctx):
+        pass
+
+    def _push_parameters(self, ctx):
+        ak = _lib.i32([f.kind for f in self.a_basis])
+        ap = _lib.f64([f.shape_parameter for f in self.a_basis])
+        bk = _lib.i32([f.kind for f in self.b_basis])
+        bp = _lib.f64([f.shape_parameter for f in self.b_basis])
+        ra = float(self.a_basis[0].parameters["rcut"]) if self.a_basis else 1.0
+        rb = float(self.b_basis[0].parameters["rcut"]) if self.b_basis else 1.0
+        cc = _lib.f64(self.parameters["ccoeff"])
+        _lib.check(ctx.lib.qmcb_set_jastrow3(ctx.h, self._nelec[0], self._nelec[1], len(ak), _lib.iptr(ak),
+                                             _lib.dptr(ap), ra, len(bk), _lib.iptr(bk), _lib.dptr(bp), rb,
+                                             _lib.dptr(cc)))
+
+    def pgradient(self):
+        N = self._ctx.nconf
+        out = np.empty((N,) + self.parameters["ccoeff"].shape)
+        _lib.check(self._ctx.lib.qmcb_pgradient(self._ctx.h, b"ccoeff", _lib.dptr(out)))
+        return {"ccoeff": out}
+
+    @property
+    def P_i(self):
+        return self._ctx.get_state("P_i", (sum(self._nelec), self._ctx.nconf))
+
+    @property
+    def a_values(self):
+        return self._ctx.get_state("a3_values", (sum(self._nelec), self._ctx.nconf, self._mol.natm, len(self.a_basis)))
+
+
 class Parameters:
     """``wfN``-prefixed view of the factors' parameter dictionaries (multiplywf.py:18-68)."""
 
@@ -473,8 +529,8 @@ class Parameters:
 class MultiplyWF:
     """Product of wave-function factors (reference: ``pyqmc/wf/multiplywf.py:71-132``).
 
-    One ``Slater`` times one ``JastrowSpin`` of this package is fused into a single device
-    context.  Any other combination falls back to combining the factors' results on the host
+    Any product of at most one ``Slater``, one ``JastrowSpin`` and one ``ThreeBodyJastrow`` of this
+    package is fused into a single device context.  Any other combination falls back to combining the factors' results on the host
     exactly as the reference does (each factor still evaluates on the device).
     """
 
@@ -483,10 +539,14 @@ class MultiplyWF:
         self.parameters = Parameters([wf.parameters for wf in self.wf_factors])
         self.dtype = complex if any(wf.dtype == complex for wf in self.wf_factors) else float
         kinds = [type(wf) for wf in self.wf_factors]
-        self._fused = (len(kinds) == 2 and set(kinds) == {Slater, JastrowSpin}
-                       and self.wf_factors[0]._mol is self.wf_factors[1]._mol)
+        device_kinds = (Slater, JastrowSpin, ThreeBodyJastrow)
+        self._fused = (len(kinds) >= 2 and all(k in device_kinds for k in kinds) and len(set(kinds)) == len(kinds)
+                       and all(wf._mol is self.wf_factors[0]._mol for wf in self.wf_factors))
         self._ctx = None
-        self._which = SLATER | JASTROW
+        self._which = 0
+        if self._fused:
+            for wf in self.wf_factors:
+                self._which |= wf._which
 
     def _ensure_ctx(self):
         if self._ctx is None:

@@ -6,7 +6,7 @@
 import numpy as np
 
 from . import func3d
-from .wf import JastrowSpin, MultiplyWF, Slater
+from .wf import JastrowSpin, MultiplyWF, Slater, ThreeBodyJastrow
 
 
 def generate_slater(mol, mf, optimize_determinants=False, optimize_orbitals=False, optimize_zeros=True,
@@ -73,6 +73,16 @@ def generate_jastrow(mol, ion_cusp=None, na=4, nb=3, rcut=None, cusp_gamma=None,
     to_opt["bcoeff"] = np.ones(jastrow.parameters["bcoeff"].shape).astype(bool)
     to_opt["bcoeff"][0, [0, 1, 2]] = False
     return jastrow, to_opt
+
+
+def generate_jastrow3(mol, na=4, nb=3, rcut=None, jax=False):
+    """wftools.py:155-162: default basis without the electron-ion cusp, zero coefficients."""
+    if jax is True:
+        raise NotImplementedError("JAX 3-body Jastrow not yet implemented")
+    abasis, bbasis = default_jastrow_basis(mol, False, na, nb, rcut)
+    wf = ThreeBodyJastrow(mol, abasis, bbasis)
+    to_opt = {"ccoeff": np.ones(wf.parameters["ccoeff"].shape).astype(bool)}
+    return wf, to_opt
 
 
 def generate_wf(mol, mf, jastrow=generate_jastrow, jastrow_kws=None, slater_kws=None, mc=None, jax=False):

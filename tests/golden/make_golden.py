@@ -25,12 +25,16 @@ import helpers  # noqa: E402
 import refload  # noqa: E402
 
 NCONF = 12
-SYSTEMS = ["he", "h2o", "open", "c2", "h2o_md"]
+SYSTEMS = ["he", "h2o", "open", "c2", "h2o_md", "h2o_3b", "h2o_md_3b"]
 
 
 def build_reference(name):
     mol, mf, dets = helpers.make_system(name)
-    wf = refload.build_reference_wf(mol, mf, determinants=dets, seed=0)
+    three_body = name.endswith("_3b")
+    wf = refload.build_reference_wf(mol, mf, determinants=dets, seed=0, three_body=three_body)
+    if three_body:
+        j3 = wf.wf_factors[2]
+        j3.parameters["ccoeff"][...] = helpers.three_body_coefficients(j3.parameters["ccoeff"].shape)
     # same seeded Jastrow coefficients as helpers.make_pair
     jast = wf.wf_factors[1]
     has_cusp = len(jast.a_basis) > 4
@@ -74,8 +78,10 @@ def generate(name):
         out[f"q{i}_testvalue_aux"] = wf.testvalue(e, configs.make_irreducible(e, aux), mask)[0]
         out[f"q{i}_testvalue_many"] = wf.testvalue_many(np.arange(ne), ep)
         g, v, saved = wf.gradient_value(e, ep)
-        configs.move(e, ep, mask)
+        # update BEFORE moving configs (order of the reference's harness, testwf.py:116-119): the
+        # reference's three-body factor reads the old position of electron e from `configs`
         wf.updateinternals(e, ep, configs, mask=mask, saved_values=saved)
+        configs.move(e, ep, mask)
         s, l = wf.value()
         out[f"q{i}_value_sign"], out[f"q{i}_value_log"] = s, l
     out["configs1"] = configs.configs.copy()
@@ -84,6 +90,8 @@ def generate(name):
         out[f"inverse{spin}"] = np.array(sl._inverse[spin])
         out[f"dets{spin}"] = np.array(sl._dets[spin])
     out["a_partial"], out["b_partial"] = np.array(ja._a_partial), np.array(ja._b_partial)
+    if len(wf.wf_factors) > 2:
+        out["P_i"], out["a3_values"] = np.array(wf.wf_factors[2].P_i), np.array(wf.wf_factors[2].a_values)
     pg = wf.pgradient()
     for k in pg.keys():
         out["pgrad_" + k] = np.array(pg[k])
@@ -95,6 +103,10 @@ def generate(name):
     tm = EnergyAccumulator(mol).nonlocal_tmoves(configs, wf, elist[-1], 0.02)
     out["tmove_ratio"], out["tmove_weight"] = tm["ratio"], tm["weight"]
     out["tmove_configs"] = tm["configs"].configs
+    if len(wf.wf_factors) > 2:
+        # the reference's drivers call updateinternals after configs.move (mc.py:135-136), which
+        # leaves its three-body cache inconsistent; no VMC golden for these systems
+        return out
     # short VMC run (recording the accept masks through a thin wrapper around updateinternals)
     accepts = []
     orig = wf.updateinternals

@@ -44,8 +44,8 @@ def replay(data, wf, configs, make_energy, vmc_fn, check_internal=None):
                "testvalue aux")
         _close(wf.testvalue_many(np.arange(ne), ep), data[f"q{i}_testvalue_many"], "testvalue_many")
         g, v, saved = wf.gradient_value(e, ep)
-        configs.move(e, ep, mask)
         wf.updateinternals(e, ep, configs, mask=mask, saved_values=saved)
+        configs.move(e, ep, mask)
         s, l = wf.value()
         assert np.array_equal(s, data[f"q{i}_value_sign"])
         assert np.abs(l - data[f"q{i}_value_log"]).max() < TOL * max(1.0, np.abs(l).max())
@@ -56,6 +56,8 @@ def replay(data, wf, configs, make_energy, vmc_fn, check_internal=None):
     en = make_energy()(configs, wf)
     for k in ("ke", "ee", "ei", "ecp", "grad2", "total"):
         _close(en[k], data["energy_" + k], "energy " + k)
+    if "vmc_accept" not in data:
+        return
     np.random.seed(31)
     df, configs, accepts = vmc_fn(wf, configs, {"energy": make_energy()})
     if accepts is not None:

@@ -14,6 +14,8 @@ def jastrow_coefficients(shape_a, shape_b, has_cusp, seed, scale=0.1):
 
 
 def make_system(name):
+    if name.endswith("_3b"):
+        return make_system(name[:-3])
     if name == "h2o_md":
         mol, mf = systems.h2o_ccecp_pvtz()
         dets = systems.cas_determinants(4, 6, seed=3)[:40]
@@ -25,8 +27,13 @@ def make_system(name):
     return mol, mf, None
 
 
-def make_pair(name, seed=1, jastrow=True, slater=True):
-    """Returns (mol, mf, b200 wf, oracle wf) with the same parameters."""
+def three_body_coefficients(shape, seed=2, scale=0.02):
+    return scale * np.random.RandomState(seed).randn(*shape)
+
+
+def make_pair(name, seed=1, jastrow=True, slater=True, three_body=None):
+    """Returns (mol, mf, b200 wf, oracle wf) with the same parameters.  Systems named ``*_3b`` get a
+    three-body Jastrow factor as third factor."""
     import pyqmc_b200 as pq
     from oracle.jastrow2 import JastrowOracle
     from oracle.product import ProductOracle
@@ -49,7 +56,19 @@ def make_pair(name, seed=1, jastrow=True, slater=True):
         assert np.array_equal(j.parameters["bcoeff"], oj.parameters["bcoeff"])
         factors.append(j)
         ofactors.append(oj)
-    if len(factors) == 2:
+    if three_body is None:
+        three_body = name.endswith("_3b")
+    if three_body:
+        from oracle.jastrow3 import Jastrow3Oracle
+
+        j3, _ = pq.generate_jastrow3(mol)
+        oj3 = Jastrow3Oracle.default(mol)
+        cc = three_body_coefficients(j3.parameters["ccoeff"].shape)
+        j3.parameters["ccoeff"][...] = cc
+        oj3.parameters["ccoeff"][...] = cc
+        factors.append(j3)
+        ofactors.append(oj3)
+    if len(factors) >= 2:
         return mol, mf, pq.MultiplyWF(*factors), ProductOracle(*ofactors)
     return mol, mf, factors[0], ofactors[0]
 

@@ -22,7 +22,10 @@ def device_vmc(wf, configs, accumulators):
 
 
 def check_internal(wf, data):
-    sl, ja = wf.wf_factors
+    sl, ja = wf.wf_factors[:2]
+    if len(wf.wf_factors) > 2:
+        assert helpers.relerr(wf.wf_factors[2].P_i, data["P_i"]) < 1e-10
+        assert helpers.relerr(wf.wf_factors[2].a_values, data["a3_values"]) < 1e-10
     for s in (0, 1):
         assert helpers.relerr(sl._inverse[s], data[f"inverse{s}"]) < 1e-9
         assert np.array_equal(sl._dets[s][0], data[f"dets{s}"][0])
@@ -33,12 +36,15 @@ def check_internal(wf, data):
     assert helpers.relerr(pg["acoeff"], data["pgrad_wf2acoeff"]) < 1e-10
     assert helpers.relerr(pg["bcoeff"], data["pgrad_wf2bcoeff"]) < 1e-10
     pgw = wf.pgradient()
-    for k in ("wf1det_coeff", "wf1mo_coeff_alpha", "wf1mo_coeff_beta", "wf2acoeff", "wf2bcoeff"):
+    keys = ["wf1det_coeff", "wf1mo_coeff_alpha", "wf1mo_coeff_beta", "wf2acoeff", "wf2bcoeff"]
+    if len(wf.wf_factors) > 2:
+        keys.append("wf3ccoeff")
+    for k in keys:
         assert pgw[k].shape == data["pgrad_" + k].shape, k
         assert helpers.relerr(pgw[k], data["pgrad_" + k]) < 1e-9, k
 
 
-@pytest.mark.parametrize("name", ["he", "h2o", "open", "c2", "h2o_md"])
+@pytest.mark.parametrize("name", ["he", "h2o", "open", "c2", "h2o_md", "h2o_3b", "h2o_md_3b"])
 def test_cuda_reproduces_reference_golden(lib, name):
     import pyqmc_b200 as pq
 

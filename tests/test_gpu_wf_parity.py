@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-10
 N = 37  # deliberately not a multiple of the warp size
 
-SYSTEMS = ["he", "h2o", "open", "c2", "h2o_md"]
+SYSTEMS = ["he", "h2o", "open", "c2", "h2o_md", "h2o_3b"]
 
 
 def setup_pair(name, lib, jastrow=True, slater=True, seed=3):
@@ -30,6 +30,8 @@ def setup_pair(name, lib, jastrow=True, slater=True, seed=3):
 def test_protocol_calls(lib, name, factors):
     if name == "h2o_md" and factors == "j":
         pytest.skip("same Jastrow as h2o")
+    if name.endswith("_3b") and factors != "sj":
+        pytest.skip("three-body factor is tested in the full product and on its own below")
     mol, wf, orc, configs, oconfigs = setup_pair(name, lib, jastrow="j" in factors, slater="s" in factors)
     s1, l1 = wf.recompute(configs)
     s2, l2 = orc.recompute(oconfigs)
@@ -119,7 +121,7 @@ def test_internal_state_matches_reference_layout(lib, name):
     assert relerr(pg["acoeff"], opg["acoeff"]) < TOL and relerr(pg["bcoeff"], opg["bcoeff"]) < TOL
 
 
-@pytest.mark.parametrize("name", ["he", "h2o", "open", "c2", "h2o_md"])
+@pytest.mark.parametrize("name", ["he", "h2o", "open", "c2", "h2o_md", "h2o_3b"])
 def test_energy_accumulator(lib, name):
     import pyqmc_b200 as pq
     from oracle.local_energy import EnergyOracle
@@ -146,7 +148,7 @@ def test_energy_accumulator(lib, name):
         assert abs(avg[k] - oavg[k]) <= TOL * max(1.0, abs(oavg[k]))
 
 
-@pytest.mark.parametrize("name", ["he", "h2o", "open", "c2", "h2o_md"])
+@pytest.mark.parametrize("name", ["he", "h2o", "open", "c2", "h2o_md", "h2o_3b", "h2o_md_3b"])
 def test_vmc_block_matches_oracle(lib, name):
     """Device-resident block vs the oracle's restatement of vmc_worker: accept masks bit-exact,
     positions and energies to rounding."""
@@ -244,3 +246,46 @@ def test_copy_and_pickle(lib):
     wf2.updateinternals(e, ep, configs)
     assert np.array_equal(wf.value()[1], l1)
     assert not np.array_equal(wf2.value()[1], l1)
+
+
+def test_three_body_factor_alone(lib):
+    """ThreeBodyJastrow as a stand-alone wf object (protocol calls, masked updates, pgradient)."""
+    import pyqmc_b200 as pq
+    from oracle.jastrow3 import Jastrow3Oracle
+
+    mol, mf, _ = helpers.make_system("open")
+    j3, _ = pq.generate_jastrow3(mol)
+    oj3 = Jastrow3Oracle.default(mol)
+    cc = helpers.three_body_coefficients(j3.parameters["ccoeff"].shape)
+    j3.parameters["ccoeff"][...] = cc
+    oj3.parameters["ccoeff"][...] = cc
+    np.random.seed(3)
+    configs = pq.initial_guess(mol, N)
+    oconfigs = helpers.to_oracle_walkers(configs)
+    assert relerr(j3.recompute(configs)[1], oj3.recompute(oconfigs)[1]) < TOL
+    rng = np.random.RandomState(1)
+    ne = configs.configs.shape[1]
+    for e in range(ne):
+        newpos = configs.configs[:, e] + 0.3 * rng.randn(N, 3)
+        ep, oep = configs.make_irreducible(e, newpos), oconfigs.make_irreducible(e, newpos.copy())
+        g1, v1, sv = j3.gradient_value(e, ep)
+        g2, v2, _ = oj3.gradient_value(e, oep)
+        assert relerr(g1, g2) < TOL and relerr(v1, v2) < TOL
+        g1, l1 = j3.gradient_laplacian(e, ep)
+        g2, l2 = oj3.gradient_laplacian(e, oep)
+        assert relerr(g1, g2) < TOL and relerr(l1, l2) < TOL
+        mask = rng.rand(N) > 0.5
+        aux = configs.configs[:, e][:, None, :] + 0.2 * rng.randn(N, 6, 3)
+        t1, _ = j3.testvalue(e, configs.make_irreducible(e, aux), mask)
+        t2, _ = oj3.testvalue(e, oconfigs.make_irreducible(e, aux.copy()), mask)
+        assert relerr(t1, t2) < TOL
+        configs.move(e, ep, mask)
+        oconfigs.move(e, oep, mask)
+        j3.updateinternals(e, ep, configs, mask=mask, saved_values=sv)
+        oj3.updateinternals(e, oep, oconfigs, mask=mask)
+        assert relerr(j3.value()[1], oj3.value()[1]) < TOL
+    assert relerr(j3.P_i, oj3.P_i) < TOL
+    assert relerr(j3.pgradient()["ccoeff"], oj3.pgradient()["ccoeff"]) < TOL
+    # cache equals a fresh recompute (the consistency the reference loses when configs moves first)
+    fresh = oj3.recompute(oconfigs)[1]
+    assert relerr(j3.value()[1], fresh) < 1e-9

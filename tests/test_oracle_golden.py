@@ -8,7 +8,7 @@ import golden_replay
 import helpers
 import refload
 
-SYSTEMS = ["he", "h2o", "open", "c2", "h2o_md"]
+SYSTEMS = ["he", "h2o", "open", "c2", "h2o_md", "h2o_3b", "h2o_md_3b"]
 
 
 def oracle_vmc(wf, configs, accumulators):
@@ -23,7 +23,10 @@ def oracle_vmc(wf, configs, accumulators):
 
 
 def check_internal(wf, data):
-    sl, ja = wf.wf_factors
+    sl, ja = wf.wf_factors[:2]
+    if len(wf.wf_factors) > 2:
+        assert helpers.relerr(wf.wf_factors[2].P_i, data["P_i"]) < 1e-10
+        assert helpers.relerr(wf.wf_factors[2].a_values, data["a3_values"]) < 1e-10
     for s in (0, 1):
         assert helpers.relerr(sl._inverse[s], data[f"inverse{s}"]) < 1e-9
         assert np.array_equal(sl._dets[s][0], data[f"dets{s}"][0])
@@ -31,7 +34,7 @@ def check_internal(wf, data):
     assert helpers.relerr(ja._a_partial, data["a_partial"]) < 1e-10
     assert helpers.relerr(ja._b_partial, data["b_partial"]) < 1e-10
     pg = wf.pgradient()
-    for k in ("wf1det_coeff", "wf1mo_coeff_alpha", "wf1mo_coeff_beta", "wf2acoeff", "wf2bcoeff"):
+    for k in ("wf1det_coeff", "wf1mo_coeff_alpha", "wf1mo_coeff_beta", "wf2acoeff", "wf2bcoeff", "wf3ccoeff"):
         if "pgrad_" + k in data:
             assert helpers.relerr(pg[k], data["pgrad_" + k]) < 1e-9, k
 
@@ -61,7 +64,14 @@ def _oracle_only(name):
     a0, ac, bc = helpers.jastrow_coefficients(oj.parameters["acoeff"].shape, oj.parameters["bcoeff"].shape, has_cusp, 1)
     oj.parameters["acoeff"][:, a0:, :] = ac[:, a0:, :]
     oj.parameters["bcoeff"][1:, :] = bc[1:, :]
-    return mol, mf, None, ProductOracle(SlaterOracle(mol, mf, determinants=dets), oj)
+    factors = [SlaterOracle(mol, mf, determinants=dets), oj]
+    if name.endswith("_3b"):
+        from oracle.jastrow3 import Jastrow3Oracle
+
+        oj3 = Jastrow3Oracle.default(mol)
+        oj3.parameters["ccoeff"][...] = helpers.three_body_coefficients(oj3.parameters["ccoeff"].shape)
+        factors.append(oj3)
+    return mol, mf, None, ProductOracle(*factors)
 
 
 @pytest.mark.parametrize("name", ["h2o", "c2"])
