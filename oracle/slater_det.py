@@ -91,9 +91,10 @@ class SlaterOracle:
         pts = epos.configs if mask is None else epos.configs[mask]
         shape = pts.shape[:-1]
         ao = self.basis.eval(deriv, pts.reshape(-1, 3))
+        nao = self.basis.nao  # explicit: reshape(-1) is ambiguous for an empty selection
         if deriv == 0:
-            return ao.reshape(*shape, -1)
-        return ao.reshape(ao.shape[0], *shape, -1)
+            return ao.reshape(*shape, nao)
+        return ao.reshape(ao.shape[0], *shape, nao)
 
     # --- internal state -----------------------------------------------------------
     def recompute(self, configs):

@@ -67,6 +67,18 @@ def build_reference_wf(mol, mf, jastrow=True, determinants=None, seed=0, na=4, n
     slater = pyqmc.wf.slater.Slater(
         mol, mf, determinants=determinants, evaluate_orbitals_with="numba"
     )
+    # The numba evaluator crashes on an empty point set (all-False mask in dmc.py:175 ->
+    # slater.py:279 -> gto.py:494; SURVEY.md 8c caveat 2): harness-side guard, as pyscf tolerates it.
+    _eval = slater.orbitals.eval_gto
+    nao = slater.parameters["mo_coeff_alpha"].shape[0]
+
+    def guarded(eval_str, coords):
+        if len(coords) == 0:
+            nc = {"GTOval_sph": None, "GTOval_sph_deriv1": 4, "GTOval_sph_deriv2": 5}[eval_str]
+            return np.zeros((0, nao)) if nc is None else np.zeros((nc, 0, nao))
+        return _eval(eval_str, coords)
+
+    slater.orbitals.eval_gto = guarded
     if not jastrow:
         return slater
     jast, _ = pyqmc.wftools.generate_jastrow(mol, na=na, nb=nb)

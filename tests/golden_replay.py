@@ -66,3 +66,10 @@ def replay(data, wf, configs, make_energy, vmc_fn, check_internal=None):
     assert np.abs(configs.configs - data["vmc_configs"]).max() < 1e-9
     for k in ("energytotal", "energyke", "energyecp", "energyee", "energyei", "energygrad2"):
         assert np.abs(df[k] - data["vmc_" + k]).max() <= 1e-9 * max(1.0, np.abs(data["vmc_" + k]).max()), k
+
+
+def check_dmc(data, out, configs, weights):
+    assert np.abs(configs.configs - data["dmc_configs"]).max() < 1e-9
+    assert relerr(weights, data["dmc_weights"]) < 1e-9
+    for k in ("energytotal", "energyke", "energyecp", "energygrad2", "weight", "acceptance", "tmove_acceptance"):
+        assert abs(out[k] - data["dmc_" + k]) <= 1e-9 * max(1.0, abs(data["dmc_" + k])), k

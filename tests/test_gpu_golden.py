@@ -74,3 +74,25 @@ def test_tmoves_match_reference_golden(lib, name):
     assert helpers.relerr(tm["weight"], data["tmove_weight"]) < 1e-10
     assert np.abs(tm["configs"].configs - data["tmove_configs"]).max() < 1e-12
     assert np.array_equal(wf.value()[1], before), "T-move evaluation must not change the wave function state"
+
+
+@pytest.mark.parametrize("name", ["h2o", "c2", "open"])
+def test_dmc_propagate_on_device_objects_matches_reference_golden(lib, name):
+    """The DMC loop (dmc.py:123-221: T-moves with masked updates without saved values, fixed-node
+    drift-diffusion, weights) over the pyqmc_b200 protocol objects vs the reference's own run."""
+    import pyqmc_b200 as pq
+    from oracle import dmc_driver
+
+    data = golden_replay.load(name)
+    mol, mf, wf, _ = helpers.make_pair(name, seed=1)
+    configs = pq.OpenConfigs(data["dmc_configs0"].copy())
+    weights = np.ones(len(configs.configs))
+    np.random.seed(41)
+    out, configs, weights = dmc_driver.dmc_propagate(wf, configs, weights, 0.02, 10.0, 1.5, 1.7, nsteps=3,
+                                                     accumulators={"energy": pq.EnergyAccumulator(mol)})
+    golden_replay.check_dmc(data, out, configs, weights)
+    # stochastic-comb branching keeps working on the host container
+    np.random.seed(5)
+    configs, weights, inds = dmc_driver.branch(configs, weights)
+    assert configs.configs.shape == data["dmc_configs"].shape and np.allclose(weights, weights[0])
+    wf.recompute(configs)

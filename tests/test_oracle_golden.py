@@ -142,3 +142,21 @@ def test_device_sph_tables_equal_oracle_tables():
         assert len(t[l]) == len(sh.TABLES[l]) == 2 * l + 1
         for a, b in zip(t[l], sh.TABLES[l]):
             assert a == b
+
+
+@pytest.mark.parametrize("name", ["h2o", "c2", "open"])
+def test_oracle_dmc_propagate_matches_reference_golden(name):
+    """oracle/dmc_driver.py (restating dmc.py:22-235) driving the oracle wave function vs the
+    reference's own dmc_propagate with T-moves: weights, walkers and weighted averages."""
+    from oracle import dmc_driver
+    from oracle.local_energy import EnergyOracle
+    from oracle.walkers import Walkers
+
+    data = golden_replay.load(name)
+    mol, mf, _, orc = _oracle_only(name)
+    configs = Walkers(data["dmc_configs0"].copy())
+    weights = np.ones(len(configs.configs))
+    np.random.seed(41)
+    out, configs, weights = dmc_driver.dmc_propagate(orc, configs, weights, 0.02, 10.0, 1.5, 1.7, nsteps=3,
+                                                     accumulators={"energy": EnergyOracle(mol)})
+    golden_replay.check_dmc(data, out, configs, weights)
