@@ -250,7 +250,22 @@ def open_shell_probe(seed=9):
     return mol, MF(mo_coeff, occ)
 
 
+def h_atom_like(seed=13):
+    """One spin-up electron, no ECP, all-electron cusp term: exercises n_dn = 0 (empty determinant),
+    an empty ECP list and Jastrow sums without partners."""
+    basis = {"H": [_contracted(0, _even_tempered(0.12, 3.0, 4), seed), _single(0, 0.3), _single(1, 0.8)]}
+    mol = Mol([("H", (0.1, -0.2, 0.3))], basis, {}, (1, 0), [1.0])
+    nao = mol.nao
+    c = _random_orthonormal_mos(nao, nao, seed)
+    c[:, 0] = 0.0
+    c[0, 0], c[1, 0] = 0.9, 0.2
+    occ = np.zeros((2, nao))
+    occ[0, 0] = 1
+    return mol, MF(np.array([c, c]), occ)
+
+
 SYSTEMS = {
+    "hatom": h_atom_like,
     "he": he_ccecp_pvdz,
     "h2o": h2o_ccecp_pvtz,
     "c2": c2_probe,
