@@ -312,7 +312,7 @@ def gpu_arm(args):
                   "wall_s_same_steps_back_to_back_no_flush": t_wall_noflush, "device_s_timed_steps": t_dev_max},
     }
     if world == 1 and not args.no_cpu:
-        v, cores, cwall, sample = cpu_arm(8, True)
+        v, cores, cwall, sample = cpu_arm(16, True)
         out["cpu_baseline"] = {"value": v, "unit": "walker-steps/s", "cores": cores, "kind": "port", "sample": sample,
                                "wall_s": cwall}
     print(json.dumps(out), flush=True)

@@ -156,6 +156,15 @@ int qmcb_vmc_block_device(qmcb_ctx *ctx, int nsteps, double tstep, int with_ener
                           const double *d_gauss, const double *d_unif, const double *d_ecp_u,
                           const double *d_ecp_rot, uint8_t *d_accept, double *d_energy,
                           double *d_esum, int64_t *d_nacc, void *stream);
+/* Pipelined variant: qmcb_vmc_upload copies one block's variates (pinned host buffers) into device
+ * slot 0..2 asynchronously on a copy stream -- callable from the host thread that draws them while
+ * another thread runs qmcb_vmc_block_slot on the other slot; _slot waits for the upload event. */
+int qmcb_vmc_upload(qmcb_ctx *ctx, int slot, int nsteps, int ne, int64_t N, int necp,
+                    const double *gauss, const double *unif, const double *ecp_u,
+                    const double *ecp_rot);
+int qmcb_vmc_block_slot(qmcb_ctx *ctx, int slot, int nsteps, double tstep, int with_energy,
+                        double *configs, uint8_t *accept, double *energy, double *esum,
+                        int64_t *nacc);
 int qmcb_kernel_launches(qmcb_ctx *ctx, int64_t *count); /* launches issued so far */
 /* page-locked host buffers for the per-block variates / results (true async H2D/D2H) */
 int qmcb_pinned_alloc(int64_t bytes, void **out);
@@ -180,6 +189,17 @@ int qmcb_sm_update(int n, int e, int64_t nmat, double *inv, const double *vec,
 int qmcb_rng_vmc_block(uint32_t *key, int32_t *pos, int32_t *has_gauss, double *cached_gauss,
                        int nsteps, int ne, int64_t N, int necp, double scale, double *gauss,
                        double *unif, double *ecp_u, double *ecp_rot, int nthreads);
+
+/* two-stage form of the same generator: phase A (sequential walk of the MT19937 stream; fills the
+ * uniform outputs, records the accepted polar pairs, advances the state) and phase B (log/sqrt of
+ * the pairs and the Gaussian outputs, nthreads host threads) on a plan handle, so phase A of the
+ * next block can overlap phase B of the current one. */
+void *qmcb_rng_plan_create(void);
+void qmcb_rng_plan_destroy(void *plan);
+int qmcb_rng_phase_a(void *plan, uint32_t *key, int32_t *pos, int32_t *has_gauss,
+                     double *cached_gauss, int nsteps, int ne, int64_t N, int necp, double scale,
+                     double *gauss, double *unif, double *ecp_u, double *ecp_rot, int nthreads);
+int qmcb_rng_phase_b(void *plan, int nthreads);
 
 #ifdef __cplusplus
 }

@@ -54,12 +54,21 @@ SIGNATURES = {
                                c_double_p, c_double_p, c_u8_p, c_double_p, c_double_p, c_i64_p]),
     "qmcb_vmc_block_device": (c_int, [c_void_p, c_int, c_double, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "qmcb_vmc_upload": (c_int, [c_void_p, c_int, c_int, c_int, c_i64, c_int, c_double_p, c_double_p, c_double_p,
+                                c_double_p]),
+    "qmcb_vmc_block_slot": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_double_p, c_u8_p, c_double_p,
+                                    c_double_p, c_i64_p]),
     "qmcb_kernel_launches": (c_int, [c_void_p, c_i64_p]),
     "qmcb_pinned_alloc": (c_int, [c_i64, ctypes.POINTER(c_void_p)]),
     "qmcb_pinned_free": (c_int, [c_void_p]),
     "qmcb_sm_update_device": (c_int, [c_int, c_int, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "qmcb_rng_vmc_block": (c_int, [ctypes.POINTER(ctypes.c_uint32), c_int_p, c_int_p, c_double_p, c_int, c_int, c_i64,
                                    c_int, c_double, c_double_p, c_double_p, c_double_p, c_double_p, c_int]),
+    "qmcb_rng_plan_create": (c_void_p, []),
+    "qmcb_rng_plan_destroy": (None, [c_void_p]),
+    "qmcb_rng_phase_a": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_uint32), c_int_p, c_int_p, c_double_p, c_int, c_int,
+                                 c_i64, c_int, c_double, c_double_p, c_double_p, c_double_p, c_double_p, c_int]),
+    "qmcb_rng_phase_b": (c_int, [c_void_p, c_int]),
     "qmcb_sm_update": (c_int, [c_int, c_int, c_i64, c_double_p, c_double_p, c_u8_p, c_double_p]),
 }
 

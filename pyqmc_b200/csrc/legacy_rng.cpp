@@ -13,64 +13,215 @@
 // construction (a>>5, b>>6); numpy's legacy Gaussian = Marsaglia polar method with one cached
 // value; scipy's random rotation = normalised 4-vector of standard normals read as a quaternion
 // (x, y, z, w) converted to a matrix.
+// numpy rounds every operation separately: no FMA contraction anywhere in this file
+#pragma GCC optimize("fp-contract=off")
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <atomic>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <chrono>
 #include <cstdio>
+#include <cstring>
+#include <memory>
 #include <thread>
 #include <vector>
 
 namespace {
 
-// MT19937 state block + its tempered image; outputs are consumed from the tempered block.
-struct MT {
-  uint32_t* key;
-  int pos;
-  uint32_t tb[624];
+// The MT19937 recurrence is inherently sequential, so it runs on its own producer thread that
+// stays a few blocks ahead: each ring slot holds one 624-word state block (raw, for handing the
+// state back to numpy) and its tempered image (the outputs).  The consumer (phase A below) walks
+// the tempered blocks in order.  With one thread the blocks are generated inline.
+struct Ring {
+  static constexpr int K = 64;
+  uint32_t raw[K][624];
+  uint32_t tb[K][624];
+  std::atomic<long> produced{0};  // blocks 0..produced-1 are ready
+  std::atomic<long> consumed{0};  // the consumer is working on block `consumed`
+  std::atomic<bool> stop{false};
+  bool threaded = false;
+  uint32_t key[624];  // producer-private running state
 };
 
-__attribute__((target_clones("avx2", "default"))) void mt_reload(uint32_t* mt) {
-  const int N = 624, M = 397;
-  const uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, MATRIX_A = 0x9908b0dfu;
-  int kk;
-  uint32_t y;
-  for (kk = 0; kk < N - M; kk++) {
-    y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
-    mt[kk] = mt[kk + M] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MATRIX_A);
-  }
-  for (; kk < N - 1; kk++) {
-    y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
-    mt[kk] = mt[kk + (M - N)] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MATRIX_A);
-  }
-  y = (mt[N - 1] & UPPER) | (mt[0] & LOWER);
-  mt[N - 1] = mt[M - 1] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MATRIX_A);
+struct MT {
+  const uint32_t* tb;
+  int pos;
+  long blk;
+  Ring* ring;
+};
+
+void mt_reload(uint32_t* __restrict__ mt);
+void temper_raw(const uint32_t* key, uint32_t* out);
+
+inline void produce_block(Ring& r, long index) {
+  mt_reload(r.key);
+  const int slot = (int)(index % Ring::K);
+  std::memcpy(r.raw[slot], r.key, sizeof(r.key));
+  temper_raw(r.key, r.tb[slot]);
 }
 
-__attribute__((target_clones("avx2", "default"))) void temper_block(MT& s) {
+void producer_loop(Ring* r) {
+  long next = 1;  // block 0 is the state handed in by the caller
+  while (!r->stop.load(std::memory_order_acquire)) {
+    if (next - r->consumed.load(std::memory_order_acquire) < Ring::K - 1) {
+      produce_block(*r, next);
+      ++next;
+      r->produced.store(next, std::memory_order_release);
+    } else {
+      std::this_thread::yield();
+    }
+  }
+}
+
+inline void refill(MT& s) {
+  Ring& r = *s.ring;
+  const long want = s.blk + 1;
+  if (r.threaded) {
+    while (r.produced.load(std::memory_order_acquire) <= want) {
+    }
+  } else {
+    produce_block(r, want);
+    r.produced.store(want + 1, std::memory_order_relaxed);
+  }
+  s.blk = want;
+  s.tb = r.tb[want % Ring::K];
+  s.pos = 0;
+  r.consumed.store(want, std::memory_order_release);
+}
+
+// One MT19937 state transition (624 new words).  The recurrence reads mt[kk+1] (not yet rewritten)
+// and mt[kk+397 mod 624] (rewritten >= 227 iterations earlier), so blocks of up to 227 iterations are
+// independent: the loops are marked ivdep and split so the compiler vectorises them.
+__attribute__((target_clones("avx512f", "avx2", "default"))) void mt_reload(uint32_t* __restrict__ mt) {
+  constexpr int N = 624, M = 397;
+  constexpr uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, MATRIX_A = 0x9908b0dfu;
+  uint32_t nxt[N + 1];
+  std::memcpy(nxt, mt + 1, (N - 1) * sizeof(uint32_t));  // old mt[kk+1] for kk < N-1
+#pragma GCC ivdep
+  for (int kk = 0; kk < N - M; kk++) {
+    const uint32_t y = (mt[kk] & UPPER) | (nxt[kk] & LOWER);
+    mt[kk] = mt[kk + M] ^ (y >> 1) ^ ((0u - (y & 1u)) & MATRIX_A);
+  }
+  // kk in [227, 454): reads mt[kk-227] (new values written by the loop above)
+#pragma GCC ivdep
+  for (int kk = N - M; kk < 2 * (N - M); kk++) {
+    const uint32_t y = (mt[kk] & UPPER) | (nxt[kk] & LOWER);
+    mt[kk] = mt[kk - (N - M)] ^ (y >> 1) ^ ((0u - (y & 1u)) & MATRIX_A);
+  }
+  // kk in [454, 623): reads mt[kk-227] written by the second loop
+#pragma GCC ivdep
+  for (int kk = 2 * (N - M); kk < N - 1; kk++) {
+    const uint32_t y = (mt[kk] & UPPER) | (nxt[kk] & LOWER);
+    mt[kk] = mt[kk - (N - M)] ^ (y >> 1) ^ ((0u - (y & 1u)) & MATRIX_A);
+  }
+  const uint32_t y = (mt[N - 1] & UPPER) | (mt[0] & LOWER);
+  mt[N - 1] = mt[M - 1] ^ (y >> 1) ^ ((0u - (y & 1u)) & MATRIX_A);
+}
+
+__attribute__((target_clones("avx512f", "avx2", "default"))) void temper_raw(const uint32_t* key, uint32_t* out) {
   for (int i = 0; i < 624; ++i) {
-    uint32_t y = s.key[i];
+    uint32_t y = key[i];
     y ^= (y >> 11);
     y ^= (y << 7) & 0x9d2c5680u;
     y ^= (y << 15) & 0xefc60000u;
     y ^= (y >> 18);
-    s.tb[i] = y;
+    out[i] = y;
   }
 }
 
 inline uint32_t next32(MT& s) {
-  if (s.pos == 624) {
-    mt_reload(s.key);
-    temper_block(s);
-    s.pos = 0;
-  }
+  if (s.pos == 624) refill(s);
   return s.tb[s.pos++];
 }
 
 inline double next_double(MT& s) {
   const int32_t a = next32(s) >> 5, b = next32(s) >> 6;
   return (a * 67108864.0 + b) / 9007199254740992.0;
+}
+
+// 53-bit double from two consecutive outputs: ((a>>5) * 2^26 + (b>>6)) / 2^53.  The integer
+// (a>>5)<<26 | (b>>6) is below 2^53, so converting it and scaling by 2^-53 gives the same bits.
+void convert_pairs_scalar(const uint32_t* t, double* out, int64_t m) {
+  for (int64_t k = 0; k < m; ++k) {
+    const int32_t a = t[2 * k] >> 5, b = t[2 * k + 1] >> 6;
+    out[k] = (a * 67108864.0 + b) / 9007199254740992.0;
+  }
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx512f,avx512dq"))) void convert_pairs_avx512(const uint32_t* t, double* out, int64_t m) {
+  int64_t k = 0;
+  const __m512d scale = _mm512_set1_pd(1.0 / 9007199254740992.0);
+  for (; k + 8 <= m; k += 8) {
+    const __m512i v = _mm512_loadu_si512(t + 2 * k);                                  // 8 x (lo = a, hi = b)
+    const __m512i a = _mm512_srli_epi64(_mm512_and_si512(v, _mm512_set1_epi64(0xffffffffLL)), 5);
+    const __m512i b = _mm512_srli_epi64(v, 32 + 6);
+    const __m512i x = _mm512_or_si512(_mm512_slli_epi64(a, 26), b);
+    _mm512_storeu_pd(out + k, _mm512_mul_pd(_mm512_cvtepi64_pd(x), scale));
+  }
+  convert_pairs_scalar(t + 2 * k, out + k, m - k);
+}
+
+// Polar attempts on 4-output groups: x1 = 2 d1 - 1, x2 = 2 d2 - 1, r2 = x1^2 + x2^2; accepted
+// (r2 < 1 and r2 != 0) triples are compress-stored.  Returns the number of attempts consumed; never
+// consumes past the attempt that completes `need` accepted pairs.
+__attribute__((target("avx512f,avx512dq"))) int polar_block_avx512(const uint32_t* t, int avail, int64_t need,
+                                                                    double* X1, double* X2, double* R2,
+                                                                    int64_t* naccepted) {
+  const __m512d scale = _mm512_set1_pd(1.0 / 9007199254740992.0);
+  const __m512d two = _mm512_set1_pd(2.0), one = _mm512_set1_pd(1.0), zero = _mm512_setzero_pd();
+  const __m512i lomask = _mm512_set1_epi64(0xffffffffLL);
+  // gather indices: attempt j uses outputs 4j..4j+3 -> as 64-bit lanes: d1 = lane 2j, d2 = lane 2j+1
+  const __m512i idx1 = _mm512_setr_epi64(0, 2, 4, 6, 8, 10, 12, 14);
+  const __m512i idx2 = _mm512_setr_epi64(1, 3, 5, 7, 9, 11, 13, 15);
+  int used = 0;
+  int64_t np_ = 0;
+  while (used + 8 <= avail && np_ + 8 <= need) {
+    const __m512i v0 = _mm512_loadu_si512(t + 4 * used);       // attempts 0..3
+    const __m512i v1 = _mm512_loadu_si512(t + 4 * used + 16);  // attempts 4..7
+    const __m512i p1 = _mm512_permutex2var_epi64(v0, idx1, v1);  // the 8 (a,b) pairs of d1
+    const __m512i p2 = _mm512_permutex2var_epi64(v0, idx2, v1);  // the 8 (a,b) pairs of d2
+    const __m512i xa = _mm512_or_si512(_mm512_slli_epi64(_mm512_srli_epi64(_mm512_and_si512(p1, lomask), 5), 26),
+                                       _mm512_srli_epi64(p1, 38));
+    const __m512i xb = _mm512_or_si512(_mm512_slli_epi64(_mm512_srli_epi64(_mm512_and_si512(p2, lomask), 5), 26),
+                                       _mm512_srli_epi64(p2, 38));
+    const __m512d d1 = _mm512_mul_pd(_mm512_cvtepi64_pd(xa), scale);
+    const __m512d d2 = _mm512_mul_pd(_mm512_cvtepi64_pd(xb), scale);
+    // 2.0*d - 1.0 and x1*x1 + x2*x2 with separate roundings (no FMA), as the scalar code
+    const __m512d x1 = _mm512_sub_pd(_mm512_mul_pd(two, d1), one);
+    const __m512d x2 = _mm512_sub_pd(_mm512_mul_pd(two, d2), one);
+    const __m512d r2 = _mm512_add_pd(_mm512_mul_pd(x1, x1), _mm512_mul_pd(x2, x2));
+    const __mmask8 ok = _mm512_cmp_pd_mask(r2, one, _CMP_LT_OQ) & _mm512_cmp_pd_mask(r2, zero, _CMP_NEQ_OQ);
+    _mm512_mask_compressstoreu_pd(X1 + np_, ok, x1);
+    _mm512_mask_compressstoreu_pd(X2 + np_, ok, x2);
+    _mm512_mask_compressstoreu_pd(R2 + np_, ok, r2);
+    np_ += __builtin_popcount((unsigned)ok);
+    used += 8;
+  }
+  *naccepted = np_;
+  return used;
+}
+#endif
+
+static bool have_avx512() {
+#if defined(__x86_64__)
+  static const bool ok = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq") &&
+                         std::getenv("QMCB_RNG_NOAVX512") == nullptr;
+  return ok;
+#else
+  return false;
+#endif
+}
+
+inline void convert_pairs(const uint32_t* t, double* out, int64_t m) {
+#if defined(__x86_64__)
+  if (have_avx512()) return convert_pairs_avx512(t, out, m);
+#endif
+  convert_pairs_scalar(t, out, m);
 }
 
 inline void fill_uniform(MT& s, double* out, int64_t n) {
@@ -81,11 +232,7 @@ inline void fill_uniform(MT& s, double* out, int64_t n) {
       continue;
     }
     const int64_t m = std::min<int64_t>(n - i, (624 - s.pos) / 2);
-    const uint32_t* t = s.tb + s.pos;
-    for (int64_t k = 0; k < m; ++k) {
-      const int32_t a = t[2 * k] >> 5, b = t[2 * k + 1] >> 6;
-      out[i + k] = (a * 67108864.0 + b) / 9007199254740992.0;
-    }
+    convert_pairs(s.tb + s.pos, out + i, m);
     s.pos += (int)(2 * m);
     i += m;
   }
@@ -131,8 +278,33 @@ struct Segment {
   int is_rotation;
 };
 
+// uninitialised growable buffer (std::vector::resize would zero-fill ~16 MB per block)
+struct RawBuf {
+  double* p = nullptr;
+  size_t cap = 0;
+  double* data() { return p; }
+  size_t size() const { return cap; }
+  void resize(size_t n) {
+    if (n <= cap) return;
+    double* q = static_cast<double*>(std::malloc(n * sizeof(double)));
+    if (p) {
+      std::memcpy(q, p, cap * sizeof(double));
+      std::free(p);
+    }
+    p = q;
+    cap = n;
+  }
+  double& operator[](size_t i) { return p[i]; }
+  const double& operator[](size_t i) const { return p[i]; }
+};
+
+struct PairBuffers {
+  RawBuf x1, x2, r2, f;
+};
+
 struct GaussPlan {
-  std::vector<double> x1, x2, r2, f;
+  RawBuf &x1, &x2, &r2, &f;
+  explicit GaussPlan(PairBuffers& b) : x1(b.x1), x2(b.x2), r2(b.r2), f(b.f) {}
   std::vector<Segment> segs;
   int64_t npairs = 0;      // accepted pairs generated so far
   int64_t nslots = 0;      // slots handed out so far
@@ -144,10 +316,10 @@ struct GaussPlan {
     const int64_t first = nslots;
     nslots += n;
     const int64_t need_pairs = (nslots - slot_shift + 1) / 2;
-    if ((int64_t)r2.size() < need_pairs + 1) {  // +1: the branch-free loop stores before it tests
-      x1.resize(need_pairs + 1);
-      x2.resize(need_pairs + 1);
-      r2.resize(need_pairs + 1);
+    if ((int64_t)r2.size() < need_pairs + 16) {  // slack: the branch-free loops store before they test
+      x1.resize(need_pairs + 16);
+      x2.resize(need_pairs + 16);
+      r2.resize(need_pairs + 16);
     }
     double* X1 = x1.data();
     double* X2 = x2.data();
@@ -159,6 +331,17 @@ struct GaussPlan {
       const int64_t want = need_pairs - npairs;
       if (avail > 0) {
         const uint32_t* t = s.tb + s.pos;
+#if defined(__x86_64__)
+        if (have_avx512() && avail >= 8 && want >= 8) {
+          int64_t got = 0;
+          const int u8 = polar_block_avx512(t, avail, want, X1 + npairs, X2 + npairs, R2 + npairs, &got);
+          if (u8 > 0) {
+            npairs += got;
+            s.pos += 4 * u8;
+            continue;
+          }
+        }
+#endif
         int used = 0;
         int64_t np_ = npairs;
         // stop as soon as enough pairs are accepted: later attempts belong to the next consumer
@@ -249,25 +432,41 @@ void write_rotation(const double* q, double* m) {
 
 }  // namespace
 
-extern "C" {
-
-// Fills gauss [nsteps][ne][N][3], unif [nsteps][ne][N], and (if necp >= 0 and ecp_u != NULL)
-// ecp_u [nsteps][ne][necp][N], ecp_rot [nsteps][ne][necp][9]; advances the MT19937 state in place.
-int qmcb_rng_vmc_block(uint32_t* key, int32_t* pos, int32_t* has_gauss, double* cached_gauss, int nsteps,
-                       int ne, int64_t N, int necp, double scale, double* gauss, double* unif, double* ecp_u,
-                       double* ecp_rot, int nthreads) {
-  if (*pos < 0 || *pos > 624) return -1;
-  auto t0 = std::chrono::steady_clock::now();
-  static thread_local MT s;
-  s.key = key;
-  s.pos = *pos;
-  temper_block(s);
+struct RngPlan {
+  PairBuffers buffers;
   GaussPlan plan;
+  RngPlan() : plan(buffers) {}
+  void reset() {
+    plan.segs.clear();
+    plan.npairs = 0;
+    plan.nslots = 0;
+    plan.slot_shift = 0;
+    plan.carried = 0.0;
+  }
+};
+
+// Phase A: walks the MT19937 stream for one block (sequential), fills the uniform outputs, records
+// the accepted polar pairs and the destination segments of every Gaussian; advances the state.
+int rng_phase_a(RngPlan& rp, uint32_t* key, int32_t* pos, int32_t* has_gauss, double* cached_gauss, int nsteps, int ne,
+                int64_t N, int necp, double scale, double* gauss, double* unif, double* ecp_u, double* ecp_rot,
+                int nthreads) {
+  if (*pos < 0 || *pos > 624) return -1;
+  std::unique_ptr<Ring> ring(new Ring());
+  std::memcpy(ring->key, key, sizeof(ring->key));
+  std::memcpy(ring->raw[0], key, sizeof(ring->key));
+  temper_raw(key, ring->tb[0]);
+  ring->produced.store(1);
+  ring->threaded = nthreads > 1;
+  std::thread producer;
+  if (ring->threaded) producer = std::thread(producer_loop, ring.get());
+  MT s{ring->tb[0], *pos, 0, ring.get()};
+  rp.reset();
+  GaussPlan& plan = rp.plan;
   if (*has_gauss) {
     plan.slot_shift = 1;
     plan.carried = *cached_gauss;
   }
-  const int64_t est = (int64_t)nsteps * ne * (N * 3 / 2 + 1 + 2 * (ecp_u ? necp : 0)) + 16;
+  const int64_t est = (int64_t)nsteps * ne * (N * 3 / 2 + 1 + 2 * (ecp_u ? necp : 0)) + 64;
   plan.x1.resize(est);
   plan.x2.resize(est);
   plan.r2.resize(est);
@@ -286,31 +485,68 @@ int qmcb_rng_vmc_block(uint32_t* key, int32_t* pos, int32_t* has_gauss, double* 
         }
     }
   }
-  const bool dbg = std::getenv("QMCB_RNG_DEBUG") != nullptr;
-  auto tA = std::chrono::steady_clock::now();
-  run_phase_b(plan, nthreads);
-  if (dbg) {
-    auto tB = std::chrono::steady_clock::now();
-    std::fprintf(stderr, "[rng] phase A %.3f ms, phase B %.3f ms (%d threads, %lld pairs)\n",
-                 std::chrono::duration<double, std::milli>(tA - t0).count(),
-                 std::chrono::duration<double, std::milli>(tB - tA).count(), nthreads, (long long)plan.npairs);
+  if (ring->threaded) {
+    ring->stop.store(true, std::memory_order_release);
+    producer.join();
   }
-  // state of the legacy Gaussian cache after the last slot handed out
-  const int64_t used = plan.nslots - plan.slot_shift;  // slots taken from generated pairs
+  // state of the legacy Gaussian cache after the last slot handed out: the second value of the
+  // last pair stays cached when an odd number of values was taken from the generated pairs
+  const int64_t used = plan.nslots - plan.slot_shift;
   if (plan.nslots == 0) {
     // nothing consumed: cache unchanged
   } else if (used <= 0) {
-    *has_gauss = 0;  // only the carried value was consumed
+    *has_gauss = 0;
     *cached_gauss = 0.0;
   } else if (used & 1) {
     const int64_t p = used >> 1;
+    const double f = std::sqrt(-2.0 * std::log(plan.r2[p]) / plan.r2[p]);
     *has_gauss = 1;
-    *cached_gauss = plan.f[p] * plan.x1[p];
+    *cached_gauss = f * plan.x1[p];
   } else {
     *has_gauss = 0;
     *cached_gauss = 0.0;
   }
+  std::memcpy(key, ring->raw[s.blk % Ring::K], sizeof(ring->key));
   *pos = s.pos;
+  return 0;
+}
+
+extern "C" {
+
+// handles for the two-stage host pipeline: phase A of block b+1 may run while phase B of block b
+// (the log/sqrt of its accepted pairs) is still in flight on other threads
+void* qmcb_rng_plan_create(void) { return new RngPlan(); }
+void qmcb_rng_plan_destroy(void* p) { delete static_cast<RngPlan*>(p); }
+
+int qmcb_rng_phase_a(void* plan, uint32_t* key, int32_t* pos, int32_t* has_gauss, double* cached_gauss, int nsteps,
+                     int ne, int64_t N, int necp, double scale, double* gauss, double* unif, double* ecp_u,
+                     double* ecp_rot, int nthreads) {
+  return rng_phase_a(*static_cast<RngPlan*>(plan), key, pos, has_gauss, cached_gauss, nsteps, ne, N, necp, scale, gauss,
+                     unif, ecp_u, ecp_rot, nthreads);
+}
+
+int qmcb_rng_phase_b(void* plan, int nthreads) {
+  run_phase_b(static_cast<RngPlan*>(plan)->plan, nthreads);
+  return 0;
+}
+
+int qmcb_rng_vmc_block(uint32_t* key, int32_t* pos, int32_t* has_gauss, double* cached_gauss, int nsteps,
+                       int ne, int64_t N, int necp, double scale, double* gauss, double* unif, double* ecp_u,
+                       double* ecp_rot, int nthreads) {
+  static thread_local RngPlan rp;  // reused across blocks by the drawing thread
+  const bool dbg = std::getenv("QMCB_RNG_DEBUG") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  const int rc = rng_phase_a(rp, key, pos, has_gauss, cached_gauss, nsteps, ne, N, necp, scale, gauss, unif, ecp_u,
+                             ecp_rot, nthreads);
+  if (rc) return rc;
+  auto tA = std::chrono::steady_clock::now();
+  run_phase_b(rp.plan, nthreads);
+  if (dbg) {
+    auto tB = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[rng] phase A %.3f ms, phase B %.3f ms (%d threads, %lld pairs)\n",
+                 std::chrono::duration<double, std::milli>(tA - t0).count(),
+                 std::chrono::duration<double, std::milli>(tB - tA).count(), nthreads, (long long)rp.plan.npairs);
+  }
   return 0;
 }
 

@@ -128,6 +128,12 @@ struct qmcb_ctx {
   int64_t nlaunch = 0;
   std::vector<int> shape_sig;
   bool mocache_valid = false;
+  // double-buffered device copies of a block's variates, filled on a copy stream by the host
+  // thread that draws them (qmcb_vmc_upload) while the previous block computes
+  static constexpr int NSLOT = 3;
+  DBuf<double> s_gauss[NSLOT], s_unif[NSLOT], s_u[NSLOT], s_rot[NSLOT];
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t slot_ready[NSLOT] = {nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -688,6 +694,8 @@ int qmcb_create(int device, qmcb_ctx** out) {
   qmcb_ctx* c = new qmcb_ctx();
   c->device = device;
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < qmcb_ctx::NSLOT; ++i) CK(cudaEventCreateWithFlags(&c->slot_ready[i], cudaEventDisableTiming));
   *out = c;
   return 0;
 }
@@ -722,6 +730,14 @@ void qmcb_destroy(qmcb_ctx* c) {
   c->d_nacc.release();
   c->h_in.release();
   c->h_out.release();
+  for (int i = 0; i < qmcb_ctx::NSLOT; ++i) {
+    c->s_gauss[i].release();
+    c->s_unif[i].release();
+    c->s_u[i].release();
+    c->s_rot[i].release();
+    if (c->slot_ready[i]) cudaEventDestroy(c->slot_ready[i]);
+  }
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1410,6 +1426,67 @@ int qmcb_vmc_block(qmcb_ctx* c, int nsteps, double tstep, int with_energy, const
   if (with_energy && (c->d_energy.ensure((size_t)nsteps * 6 * N) || c->d_esum.ensure((size_t)nsteps * 6))) return -1;
   int rc = qmcb_vmc_block_device(c, nsteps, tstep, with_energy, c->d_gauss.p, c->d_unif.p, c->d_u.p, c->d_rot.p,
                                  accept ? acc_all.p : nullptr, with_energy ? c->d_energy.p : nullptr,
+                                 with_energy ? c->d_esum.p : nullptr, nullptr, c->stream);
+  if (rc) {
+    acc_all.release();
+    return rc;
+  }
+  if (accept) CK(cudaMemcpyAsync(accept, acc_all.p, nse * N, cudaMemcpyDeviceToHost, c->stream));
+  if (energy && with_energy)
+    CK(cudaMemcpyAsync(energy, c->d_energy.p, (size_t)nsteps * 6 * N * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (esum && with_energy) CK(cudaMemcpyAsync(esum, c->d_esum.p, (size_t)nsteps * 6 * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (nacc) CK(cudaMemcpyAsync(nacc, c->d_nacc.p, nse * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (configs) {
+    const size_t nel = N * S.ne * 3;
+    if (c->d_in.ensure(nel)) return -1;
+    k_conf_out<<<(unsigned)((nel + 255) / 256), 256, 0, c->stream>>>(c->st.conf, c->d_in.p, (int)N, S.ne);
+    c->nlaunch++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(configs, c->d_in.p, nel * 8, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  acc_all.release();
+  return 0;
+}
+
+// Asynchronous upload of one block's variates (pinned host buffers) into device slot 0/1 on the
+// context's copy stream.  May be called from the host thread that draws the variates while another
+// thread runs qmcb_vmc_block_slot on the other slot.
+int qmcb_vmc_upload(qmcb_ctx* c, int slot, int nsteps, int ne, int64_t N, int necp, const double* gauss,
+                    const double* unif, const double* ecp_u, const double* ecp_rot) {
+  if (slot < 0 || slot >= qmcb_ctx::NSLOT) return fail("slot out of range");
+  cudaSetDevice(c->device);
+  const size_t nse = (size_t)nsteps * ne;
+  if (c->s_gauss[slot].ensure(nse * N * 3) || c->s_unif[slot].ensure(nse * N)) return -1;
+  CK(cudaMemcpyAsync(c->s_gauss[slot].p, gauss, nse * N * 3 * 8, cudaMemcpyHostToDevice, c->copy_stream));
+  CK(cudaMemcpyAsync(c->s_unif[slot].p, unif, nse * N * 8, cudaMemcpyHostToDevice, c->copy_stream));
+  if (ecp_u && necp > 0) {
+    if (c->s_u[slot].ensure(nse * necp * N) || c->s_rot[slot].ensure(nse * necp * 9)) return -1;
+    CK(cudaMemcpyAsync(c->s_u[slot].p, ecp_u, nse * necp * N * 8, cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaMemcpyAsync(c->s_rot[slot].p, ecp_rot, nse * necp * 9 * 8, cudaMemcpyHostToDevice, c->copy_stream));
+  }
+  CK(cudaEventRecord(c->slot_ready[slot], c->copy_stream));
+  return 0;
+}
+
+// qmcb_vmc_block on variates previously uploaded into `slot`.
+int qmcb_vmc_block_slot(qmcb_ctx* c, int slot, int nsteps, double tstep, int with_energy, double* configs,
+                        uint8_t* accept, double* energy, double* esum, int64_t* nacc) {
+  Guard g(c);
+  if (slot < 0 || slot >= qmcb_ctx::NSLOT) return fail("slot out of range");
+  if (c->N == 0) return fail("recompute has not been called");
+  if (build_tables(c)) return -1;
+  if (c->N == 0) return fail("system shapes changed: call recompute again");
+  const Sys& S = c->S;
+  const size_t N = c->N;
+  const size_t nse = (size_t)nsteps * S.ne;
+  if (c->s_gauss[slot].n < nse * N * 3) return fail("slot was not uploaded for this block shape");
+  CK(cudaStreamWaitEvent(c->stream, c->slot_ready[slot], 0));
+  DBuf<uint8_t> acc_all;
+  if (accept && acc_all.ensure(nse * N)) return -1;
+  if (with_energy && (c->d_energy.ensure((size_t)nsteps * 6 * N) || c->d_esum.ensure((size_t)nsteps * 6))) return -1;
+  int rc = qmcb_vmc_block_device(c, nsteps, tstep, with_energy, c->s_gauss[slot].p, c->s_unif[slot].p, c->s_u[slot].p,
+                                 c->s_rot[slot].p, accept ? acc_all.p : nullptr, with_energy ? c->d_energy.p : nullptr,
                                  with_energy ? c->d_esum.p : nullptr, nullptr, c->stream);
   if (rc) {
     acc_all.release();

@@ -167,11 +167,19 @@ def vmc_block_device(wf, configs, tstep, nsteps, accumulators, variates=None, re
     accept = np.empty((nsteps, nelec, nconf), dtype=np.uint8) if return_walker_data else None
     energy = buffers.energy
     nacc = buffers.nacc
-    _lib.check(ctx.lib.qmcb_vmc_block(
-        ctx.h, nsteps, float(tstep), 1 if accumulator is not None else 0,
-        _lib.dptr(gauss), _lib.dptr(unif), _lib.dptr(ecp_u), _lib.dptr(ecp_rot),
-        _lib.dptr(buffers.newconf), _lib.u8ptr(accept), _lib.dptr(energy), None,
-        nacc.ctypes.data_as(_lib.c_i64_p)))
+    slot = getattr(buffers, "uploaded_slot", None)
+    if slot is not None:  # variates already on their way to the device (RNG prefetch thread)
+        buffers.uploaded_slot = None
+        _lib.check(ctx.lib.qmcb_vmc_block_slot(
+            ctx.h, slot, nsteps, float(tstep), 1 if accumulator is not None else 0,
+            _lib.dptr(buffers.newconf), _lib.u8ptr(accept), _lib.dptr(energy), None,
+            nacc.ctypes.data_as(_lib.c_i64_p)))
+    else:
+        _lib.check(ctx.lib.qmcb_vmc_block(
+            ctx.h, nsteps, float(tstep), 1 if accumulator is not None else 0,
+            _lib.dptr(gauss), _lib.dptr(unif), _lib.dptr(ecp_u), _lib.dptr(ecp_rot),
+            _lib.dptr(buffers.newconf), _lib.u8ptr(accept), _lib.dptr(energy), None,
+            nacc.ctypes.data_as(_lib.c_i64_p)))
     end = time.perf_counter()
     configs.configs[...] = buffers.newconf
     block_avg = {}
@@ -237,11 +245,16 @@ def vmc_worker(wf, configs, tstep, nsteps, accumulators):
 
 
 class _VariatePrefetcher:
-    """Draws the variates of block b+1 on a host thread while block b runs on the GPU.
+    """Three-stage host/device pipeline for the device-resident driver.
 
-    The draws still happen strictly in stream order (one producer, blocks in sequence) and nothing
-    else in the device-resident driver consumes ``np.random``, so the numbers are those the
-    reference loop would see."""
+    Stage 1 (one thread, blocks strictly in order): phase A of the native generator -- the
+    sequential walk of the global legacy MT19937 stream for block b (np.random state read before,
+    written back after).  Stage 2 (one thread): phase B (log/sqrt of the accepted pairs) and the
+    asynchronous host->device copy into one of three device slots.  The caller's thread runs the
+    GPU block.  Nothing else in this driver consumes ``np.random``, so the numbers are exactly
+    those the reference loop would draw."""
+
+    NSLOT = 3
 
     def __init__(self, wf, configs, tstep, nsteps, accumulators, nblocks):
         from concurrent.futures import ThreadPoolExecutor
@@ -252,33 +265,82 @@ class _VariatePrefetcher:
         if _device_context(wf) is None:  # context is created lazily by the first recompute
             wf.recompute(configs)
         self.ctx = _device_context(wf)
+        self.lib = self.ctx.lib
         self.remaining = nblocks
         self.issued = 0
-        self.pool = ThreadPoolExecutor(max_workers=1)
-        self.future = None
-        self._submit()
+        self.stage1 = ThreadPoolExecutor(max_workers=1)
+        self.stage2 = ThreadPoolExecutor(max_workers=1)
+        self.plans = [self.lib.qmcb_rng_plan_create() for _ in range(self.NSLOT)]
+        self.queue = []
+        for _ in range(self.NSLOT - 1):
+            self._submit()
 
     def _submit(self):
         if self.remaining <= 0:
-            self.future = None
             return
+        import ctypes
+
         nconf, nelec, tstep, nsteps = self.args
-        buf = _block_buffers(self.ctx, nconf, nelec, nsteps, self.accumulator, slot=self.issued % 2)
+        slot = self.issued % self.NSLOT
+        buf = _block_buffers(self.ctx, nconf, nelec, nsteps, self.accumulator, slot=slot)
+        plan = ctypes.c_void_p(self.plans[slot])
         self.issued += 1
         self.remaining -= 1
+        ctx, lib = self.ctx, self.lib
+        necp = self.accumulator.necp if self.accumulator is not None else 0
+        g, u, eu, er = buf.variates()
+        nthreads = rng_threads()
 
-        def job():
-            draw_block_variates(nconf, nelec, tstep, nsteps, self.accumulator, out=buf.variates())
+        def phase_a():
+            state = np.random.get_state()
+            if state[0] != "MT19937":
+                return False
+            key = np.ascontiguousarray(state[1], dtype=np.uint32).copy()
+            pos, has_gauss = ctypes.c_int32(int(state[2])), ctypes.c_int32(int(state[3]))
+            cached = ctypes.c_double(float(state[4]))
+            rc = lib.qmcb_rng_phase_a(plan, key.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), ctypes.byref(pos),
+                                      ctypes.byref(has_gauss), ctypes.byref(cached), nsteps, nelec, nconf, necp,
+                                      float(np.sqrt(tstep)), _lib.dptr(g), _lib.dptr(u), _lib.dptr(eu), _lib.dptr(er),
+                                      nthreads)
+            if rc != 0:
+                raise RuntimeError("native RNG failed")
+            np.random.set_state(("MT19937", key, pos.value, has_gauss.value, cached.value))
+            return True
+
+        fa = self.stage1.submit(phase_a)
+
+        def phase_b():
+            if fa.result():
+                lib.qmcb_rng_phase_b(plan, nthreads)
+            else:  # non-MT19937 global generator: plain numpy draws (still in order: stage 1 is idle)
+                draw_block_variates(nconf, nelec, tstep, nsteps, self.accumulator, native=False, out=buf.variates())
+            _lib.check(lib.qmcb_vmc_upload(ctx.h, slot, nsteps, nelec, nconf, necp, _lib.dptr(g), _lib.dptr(u),
+                                           _lib.dptr(eu), _lib.dptr(er)))
+            buf.uploaded_slot = slot
             return buf
 
-        self.future = self.pool.submit(job)
+        self.queue.append(self.stage2.submit(phase_b))
 
     def next(self):
-        buf = self.future.result()
+        buf = self.queue.pop(0).result()
         self._submit()
-        if self.future is None:
-            self.pool.shutdown(wait=False)
+        if not self.queue and self.remaining <= 0:
+            self.close()
         return buf
+
+    def close(self):
+        if self.plans:
+            self.stage1.shutdown(wait=True)
+            self.stage2.shutdown(wait=True)
+            for p in self.plans:
+                self.lib.qmcb_rng_plan_destroy(ctypes_void(p))
+            self.plans = []
+
+
+def ctypes_void(p):
+    import ctypes
+
+    return ctypes.c_void_p(p)
 
 
 def vmc_parallel(wf, configs, tstep, nsteps_per_block, accumulators, client, npartitions):
