@@ -42,7 +42,7 @@ __host__ __device__ inline CoopLayout coop_layout(const Sys& S) {
   L.colv = o;
   o += nmax;
   L.jtmp = o;
-  o += (S.ne > 1 ? S.ne - 1 : 0) * S.nb;
+  o += 2 * (S.ne > 1 ? S.ne - 1 : 0) * S.nb + S.natom * S.na;
   L.total = (o + 1) & ~1;
   return L;
 }
@@ -357,6 +357,188 @@ __device__ __forceinline__ void coop_sherman_morrison(const Sys& S, const CoopLa
   if (lane == 0) {
     st.dsign[s][w] *= (ratio > 0.0 ? 1.0 : (ratio < 0.0 ? -1.0 : 0.0));
     st.dlog[s][w] += log(fabs(ratio));
+  }
+  __syncwarp(gm);
+}
+
+// ---------------------------------------------------------------------------------------
+// Pair-cached Jastrow for the sweep kernel.  Per walker the context keeps, for every electron
+// pair (i<j), the basis values b_l(r_ij) and the gradient term  sum_l c_l g_l(r_ij) (r_i - r_j),
+// and for every electron the electron-ion gradient term.  The drift at the CURRENT position is
+// then a sum of cached terms, and an accepted move needs no radial-function evaluation beyond
+// the ones already done for the proposed position (same arithmetic as jastrowspin.py:296-340,
+// 111-137, 221-249; only the order of the partner sum differs).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int pair_index(int ne, int i, int j) {  // i < j
+  return i * ne - (i * (i + 1)) / 2 + (j - i - 1);
+}
+#define BPAIR(st, S, w, p, l) (st).bpair[((size_t)(w) * (S).npair + (p)) * (S).nb + (l)]
+#define GPAIR(st, S, w, p, x) (st).gpair[((size_t)(w) * (S).npair + (p)) * 3 + (x)]
+#define AGRAD(st, S, w, e, x) (st).agrad[((size_t)(w) * (S).ne + (e)) * 3 + (x)]
+
+template <int G>
+__device__ __forceinline__ void coop_jastrow_cached_grad(const Sys& S, const State& st, int w, int e, int lane,
+                                                         unsigned gm, double (&g)[3]) {
+  double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+#pragma unroll 1
+  for (int t = lane; t < S.ne - 1; t += G) {
+    const int j = t < e ? t : t + 1;
+    const int p = e < j ? pair_index(S.ne, e, j) : pair_index(S.ne, j, e);
+    const double sg = e < j ? 1.0 : -1.0;
+    g0 += sg * GPAIR(st, S, w, p, 0);
+    g1 += sg * GPAIR(st, S, w, p, 1);
+    g2 += sg * GPAIR(st, S, w, p, 2);
+  }
+  if (lane == 0) {
+    g0 += AGRAD(st, S, w, e, 0);
+    g1 += AGRAD(st, S, w, e, 1);
+    g2 += AGRAD(st, S, w, e, 2);
+  }
+  g[0] = group_sum<G>(g0, gm);
+  g[1] = group_sum<G>(g1, gm);
+  g[2] = group_sum<G>(g2, gm);
+}
+
+// value + gradient at the proposed position; parks per-task values for a possible commit:
+//   jt[t]            = b_l(r)                 t = jj * nb + l
+//   jt[ntb + t]      = c * g_l(r)             (gradient factor of that task)
+//   jt[2 ntb + u]    = a_k(r_eI)              u = I * na + k
+// ga = electron-ion part of the gradient (all lanes).
+template <int G>
+__device__ __forceinline__ void coop_jastrow_propose(const Sys& S, const double* __restrict__ sd,
+                                                     const int* __restrict__ si, const State& st, int w, int e,
+                                                     double px, double py, double pz, int lane, unsigned gm,
+                                                     double* __restrict__ jt, double& du, double (&g)[3],
+                                                     double (&ga)[3]) {
+  const int s = e >= S.nup ? 1 : 0;
+  const int ntb = (S.ne - 1) * S.nb, nta = S.natom * S.na;
+  double unew = 0.0, uold = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll 1
+  for (int t = lane; t < ntb + nta; t += G) {
+    double dx, dy, dz, c, rcut, par;
+    int kind;
+    const bool isb = t < ntb;
+    if (isb) {
+      const int jj = t / S.nb, l = t - jj * S.nb;
+      const int j = jj < e ? jj : jj + 1;
+      dx = px - CONF(st, S, w, j, 0);
+      dy = py - CONF(st, S, w, j, 1);
+      dz = pz - CONF(st, S, w, j, 2);
+      c = sd[S.o_bcoef + l * 3 + s + (j >= S.nup ? 1 : 0)];
+      rcut = S.rcut_b;
+      par = sd[S.o_bpar + l];
+      kind = si[S.o_bkind + l];
+    } else {
+      const int u = t - ntb;
+      const int I = u / S.na, k = u - I * S.na;
+      dx = px - sd[S.o_xyz + 3 * I];
+      dy = py - sd[S.o_xyz + 3 * I + 1];
+      dz = pz - sd[S.o_xyz + 3 * I + 2];
+      c = sd[S.o_acoef + (I * S.na + k) * 2 + s];
+      rcut = S.rcut_a;
+      par = sd[S.o_apar + k];
+      kind = si[S.o_akind + k];
+    }
+    const double r = sqrt(dx * dx + dy * dy + dz * dz);
+    double v = 0.0, gg = 0.0, ll;
+    if (r < rcut) radial_ool<1>(kind, par, rcut, r, v, gg, ll);
+    unew = fma(c, v, unew);
+    const double cg = c * gg;
+    if (isb) {
+      jt[t] = v;
+      jt[ntb + t] = cg;
+      b0 = fma(cg, dx, b0);
+      b1 = fma(cg, dy, b1);
+      b2 = fma(cg, dz, b2);
+    } else {
+      jt[2 * ntb + (t - ntb)] = v;
+      a0 = fma(cg, dx, a0);
+      a1 = fma(cg, dy, a1);
+      a2 = fma(cg, dz, a2);
+    }
+  }
+  const int na_items = nta, nb_items = S.nb * 2;
+#pragma unroll 1
+  for (int t = lane; t < na_items + nb_items; t += G) {
+    if (t < na_items) {
+      const int I = t / S.na, k = t - I * S.na;
+      uold = fma(sd[S.o_acoef + (I * S.na + k) * 2 + s], APART(st, S, w, e, I, k), uold);
+    } else {
+      const int u = t - na_items;
+      const int l = u >> 1, tt = u & 1;
+      uold = fma(sd[S.o_bcoef + l * 3 + s + tt], BPART(st, S, w, e, l, tt), uold);
+    }
+  }
+  du = group_sum<G>(unew, gm) - group_sum<G>(uold, gm);
+  ga[0] = group_sum<G>(a0, gm);
+  ga[1] = group_sum<G>(a1, gm);
+  ga[2] = group_sum<G>(a2, gm);
+  g[0] = group_sum<G>(b0, gm) + ga[0];
+  g[1] = group_sum<G>(b1, gm) + ga[1];
+  g[2] = group_sum<G>(b2, gm) + ga[2];
+  __syncwarp(gm);
+}
+
+// accepted move: every cache is refreshed from the parked values (no radial evaluations)
+template <int G>
+__device__ __forceinline__ void coop_jastrow_commit(const Sys& S, const double* __restrict__ sd,
+                                                    const int* __restrict__ si, const State& st, int w, int e,
+                                                    double nx, double ny, double nz, int lane, unsigned gm,
+                                                    bool has_jastrow, const double* __restrict__ jt,
+                                                    const double (&ga)[3]) {
+  const int s = e >= S.nup ? 1 : 0;
+  if (has_jastrow) {
+    const int ntb = (S.ne - 1) * S.nb;
+#pragma unroll 1
+    for (int u = lane; u < S.natom * S.na; u += G) {
+      const int I = u / S.na, k = u - I * S.na;
+      const double v = jt[2 * ntb + u];
+      AVAL(st, S, w, I, k, s) += v - APART(st, S, w, e, I, k);
+      APART(st, S, w, e, I, k) = v;
+    }
+#pragma unroll 1
+    for (int t = lane; t < ntb; t += G) {
+      const int jj = t / S.nb, l = t - jj * S.nb;
+      const int j = jj < e ? jj : jj + 1;
+      const int p = e < j ? pair_index(S.ne, e, j) : pair_index(S.ne, j, e);
+      const double vn = jt[t];
+      BPART(st, S, w, j, l, s) += vn - BPAIR(st, S, w, p, l);
+      BPAIR(st, S, w, p, l) = vn;
+    }
+#pragma unroll 1
+    for (int t = lane; t < S.nb * 2; t += G) {
+      const int l = t >> 1, tt = t & 1;
+      double bn = 0.0;
+      for (int jj = 0; jj < S.ne - 1; ++jj) {
+        const int j = jj < e ? jj : jj + 1;
+        if ((j >= S.nup ? 1 : 0) == tt) bn += jt[jj * S.nb + l];
+      }
+      BVAL(st, S, w, l, s + tt) += bn - BPART(st, S, w, e, l, tt);
+      BPART(st, S, w, e, l, tt) = bn;
+    }
+#pragma unroll 1
+    for (int jj = lane; jj < S.ne - 1; jj += G) {
+      const int j = jj < e ? jj : jj + 1;
+      const int p = e < j ? pair_index(S.ne, e, j) : pair_index(S.ne, j, e);
+      double gs = 0.0;
+      for (int l = 0; l < S.nb; ++l) gs += jt[ntb + jj * S.nb + l];
+      const double sg = e < j ? 1.0 : -1.0;
+      // NOTE: sum_l (c g_l) * d differs from sum_l (c g_l d) only by rounding
+      GPAIR(st, S, w, p, 0) = sg * gs * (nx - CONF(st, S, w, j, 0));
+      GPAIR(st, S, w, p, 1) = sg * gs * (ny - CONF(st, S, w, j, 1));
+      GPAIR(st, S, w, p, 2) = sg * gs * (nz - CONF(st, S, w, j, 2));
+    }
+    if (lane == 0) {
+      AGRAD(st, S, w, e, 0) = ga[0];
+      AGRAD(st, S, w, e, 1) = ga[1];
+      AGRAD(st, S, w, e, 2) = ga[2];
+    }
+  }
+  __syncwarp(gm);
+  if (lane == 0) {
+    CONF(st, S, w, e, 0) = nx;
+    CONF(st, S, w, e, 1) = ny;
+    CONF(st, S, w, e, 2) = nz;
   }
   __syncwarp(gm);
 }

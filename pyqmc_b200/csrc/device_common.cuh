@@ -27,6 +27,7 @@ struct Sys {
   int fast;            // single determinant with identity occupation and n_s <= 8
   int na, nb;
   int na3, nb3;  // three-body Jastrow basis sizes (0: factor absent)
+  int npair;     // ne (ne - 1) / 2
   int necp, nchan, nterm, max_naip, tot_naip;
   double rcut_a, rcut_b, ecp_threshold, e_ii;
   double rcut_a3, rcut_b3;
@@ -64,6 +65,9 @@ struct State {
   double* avalues;   // [N][I][na][2]
   double* bvalues;   // [N][nb][3]
   double* mocache;   // [N][ne][5][ldmax]  MO value/grad/Laplacian rows at the current positions
+  double* bpair;     // [N][npair][nb]  b_l(r_ij) of every electron pair        (sweep kernel cache)
+  double* gpair;     // [N][npair][3]   sum_l c_l g_l(r_ij) (r_i - r_j)          (sweep kernel cache)
+  double* agrad;     // [N][ne][3]      electron-ion part of grad_e U            (sweep kernel cache)
   double* a3v;       // [N][ne][I][na3]  three-body a_k(r_eI)      (three_body_jastrow.py:103)
   double* P3;        // [N][ne]          P_i                       (three_body_jastrow.py:98-101)
   double* val3;      // [N]              U = 1/2 sum_i P_i

@@ -865,6 +865,61 @@ __global__ void __launch_bounds__(128) k_vmc_move(const Sys S, const State st, c
 // Metropolis test, and for accepted moves Sherman-Morrison + Jastrow cache update + refresh of
 // the cached MO rows -- all inside the warp, state in L2-resident global memory.
 // =========================================================================================
+// builds the pair caches of the sweep kernel from the current walker positions: one thread per
+// (walker, pair) and per (walker, electron)
+__global__ void __launch_bounds__(128) k_pair_cache_build(const Sys S, const State st) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = S.npair + S.ne;
+  if (t >= (long long)st.N * per) return;
+  const int w = (int)(t / per), r0 = (int)(t - (long long)w * per);
+  if (r0 < S.npair) {
+    int i = 0, rem = r0;
+    while (rem >= S.ne - 1 - i) {
+      rem -= S.ne - 1 - i;
+      ++i;
+    }
+    const int j = i + 1 + rem;
+    const double dx = CONF(st, S, w, i, 0) - CONF(st, S, w, j, 0), dy = CONF(st, S, w, i, 1) - CONF(st, S, w, j, 1),
+                 dz = CONF(st, S, w, i, 2) - CONF(st, S, w, j, 2);
+    const double r = sqrt(dx * dx + dy * dy + dz * dz);
+    const int sp = (i >= S.nup ? 1 : 0) + (j >= S.nup ? 1 : 0);
+    double gs = 0.0;
+    for (int l = 0; l < S.nb; ++l) {
+      double v = 0.0, gg = 0.0, ll;
+      if (r < S.rcut_b) radial_ool<1>(si[S.o_bkind + l], sd[S.o_bpar + l], S.rcut_b, r, v, gg, ll);
+      BPAIR(st, S, w, r0, l) = v;
+      gs += sd[S.o_bcoef + l * 3 + sp] * gg;
+    }
+    GPAIR(st, S, w, r0, 0) = gs * dx;
+    GPAIR(st, S, w, r0, 1) = gs * dy;
+    GPAIR(st, S, w, r0, 2) = gs * dz;
+  } else {
+    const int e = r0 - S.npair;
+    const int s = e >= S.nup ? 1 : 0;
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+    for (int I = 0; I < S.natom; ++I) {
+      const double dx = CONF(st, S, w, e, 0) - sd[S.o_xyz + 3 * I], dy = CONF(st, S, w, e, 1) - sd[S.o_xyz + 3 * I + 1],
+                   dz = CONF(st, S, w, e, 2) - sd[S.o_xyz + 3 * I + 2];
+      const double r = sqrt(dx * dx + dy * dy + dz * dz);
+      if (!(r < S.rcut_a)) continue;
+      for (int k2 = 0; k2 < S.na; ++k2) {
+        double v, gg, ll;
+        radial_ool<1>(si[S.o_akind + k2], sd[S.o_apar + k2], S.rcut_a, r, v, gg, ll);
+        const double cg = sd[S.o_acoef + (I * S.na + k2) * 2 + s] * gg;
+        g0 = fma(cg, dx, g0);
+        g1 = fma(cg, dy, g1);
+        g2 = fma(cg, dz, g2);
+      }
+    }
+    AGRAD(st, S, w, e, 0) = g0;
+    AGRAD(st, S, w, e, 1) = g1;
+    AGRAD(st, S, w, e, 2) = g2;
+  }
+}
+
 struct SweepArgs {
   double tstep;
   const double* gauss;  // [ne][N][3] for this step
@@ -918,8 +973,8 @@ __global__ void __launch_bounds__(128) k_vmc_sweep(const Sys S, const State st, 
       }
     }
     if (has_j) {
-      double du, gj[3], lj;
-      coop_jastrow<1, G>(S, sd, si, st, w, e, ox, oy, oz, lane, gm, du, gj, lj);
+      double gj[3];
+      coop_jastrow_cached_grad<G>(S, st, w, e, lane, gm, gj);
 #pragma unroll
       for (int i = 0; i < 3; ++i) grad[i] = grad[i] + gj[i];
     }
@@ -948,9 +1003,10 @@ __global__ void __launch_bounds__(128) k_vmc_sweep(const Sys S, const State st, 
       }
       val = isfinite(r0) ? r0 : 1.0;
     }
+    double ga[3] = {0.0, 0.0, 0.0};
     if (has_j) {
-      double du, gj[3], lj;
-      coop_jastrow<1, G>(S, sd, si, st, w, e, np_[0], np_[1], np_[2], lane, gm, du, gj, lj);
+      double du, gj[3];
+      coop_jastrow_propose<G>(S, sd, si, st, w, e, np_[0], np_[1], np_[2], lane, gm, ws + L.jtmp, du, gj, ga);
 #pragma unroll
       for (int i = 0; i < 3; ++i) ngrad[i] = ngrad[i] + gj[i];
       val = val * exp(du);
@@ -979,7 +1035,7 @@ __global__ void __launch_bounds__(128) k_vmc_sweep(const Sys S, const State st, 
         const double* __restrict__ mo = ws + L.mo;
         for (int i = lane; i < 5 * ldmax; i += G) mc[i] = mo[i];
       }
-      coop_jastrow_update<G>(S, sd, si, st, w, e, np_[0], np_[1], np_[2], lane, gm, has_j, ws + L.jtmp);
+      coop_jastrow_commit<G>(S, sd, si, st, w, e, np_[0], np_[1], np_[2], lane, gm, has_j, ws + L.jtmp, ga);
     }
     __syncwarp(gm);
   }

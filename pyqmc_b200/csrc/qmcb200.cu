@@ -111,7 +111,7 @@ struct qmcb_ctx {
   State st{};
   int N = 0;
   DBuf<double> b_inv[2], b_dsign[2], b_dlog[2], b_dv[2], b_W[2], b_ref[2];
-  DBuf<double> b_conf, b_ap, b_bp, b_av, b_bv, b_smo, b_spos, b_moall, b_lu, b_mocache, b_a3v, b_P3, b_val3;
+  DBuf<double> b_conf, b_ap, b_bp, b_av, b_bv, b_smo, b_spos, b_moall, b_lu, b_mocache, b_a3v, b_P3, b_val3, b_bpair, b_gpair, b_agrad;
   // ---- staging / scratch
   DBuf<double> d_in, d_out, d_scr, d_u, d_rot, d_gauss, d_unif, d_energy, d_esum;
   DBuf<uint8_t> d_mask, d_accept;
@@ -128,6 +128,7 @@ struct qmcb_ctx {
   int64_t nlaunch = 0;
   std::vector<int> shape_sig;
   bool mocache_valid = false;
+  bool paircache_valid = false;  // Jastrow pair caches of the sweep kernel match the walkers
   // double-buffered device copies of a block's variates, filled on a copy stream by the host
   // thread that draws them (qmcb_vmc_upload) while the previous block computes
   static constexpr int NSLOT = 3;
@@ -175,6 +176,7 @@ int build_tables(qmcb_ctx* c) {
   S.nup = c->nup;
   S.ndn = c->ndn;
   S.ne = c->nup + c->ndn;
+  S.npair = S.ne * (S.ne - 1) / 2;
   S.ndet = c->have_slater ? c->ndet : 0;
   bool ident = c->have_slater && c->ndet == 1;
   for (int s = 0; s < 2; ++s) {
@@ -381,7 +383,8 @@ int ensure_state(qmcb_ctx* c, int N) {
       c->b_spos.ensure((size_t)N * 3) || c->b_moall.ensure((size_t)N * S.ne * ldmax) ||
       c->b_mocache.ensure((size_t)N * S.ne * 5 * ldmax) ||
       c->b_a3v.ensure((size_t)N * S.ne * S.natom * std::max(S.na3, 1)) || c->b_P3.ensure((size_t)N * std::max(S.ne, 1)) ||
-      c->b_val3.ensure(N))
+      c->b_val3.ensure(N) || c->b_bpair.ensure((size_t)N * std::max(S.npair, 1) * std::max(S.nb, 1)) ||
+      c->b_gpair.ensure((size_t)N * std::max(S.npair, 1) * 3) || c->b_agrad.ensure((size_t)N * std::max(S.ne, 1) * 3))
     return -1;
   st.conf = c->b_conf.p;
   st.a_partial = c->b_ap.p;
@@ -395,6 +398,9 @@ int ensure_state(qmcb_ctx* c, int N) {
   st.a3v = c->b_a3v.p;
   st.P3 = c->b_P3.p;
   st.val3 = c->b_val3.p;
+  st.bpair = c->b_bpair.p;
+  st.gpair = c->b_gpair.p;
+  st.agrad = c->b_agrad.p;
   c->N = N;
   c->saved_slot = -1;
   return 0;
@@ -705,7 +711,7 @@ void qmcb_destroy(qmcb_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   DBuf<double>* dd[] = {&c->d_dblob, &c->d_detc, &c->d_quad, &c->b_conf, &c->b_ap, &c->b_bp, &c->b_av, &c->b_bv,
-                        &c->b_smo, &c->b_spos, &c->b_moall, &c->b_lu, &c->b_mocache, &c->b_a3v, &c->b_P3, &c->b_val3, &c->d_in, &c->d_out, &c->d_scr, &c->d_u,
+                        &c->b_smo, &c->b_spos, &c->b_moall, &c->b_lu, &c->b_mocache, &c->b_a3v, &c->b_P3, &c->b_val3, &c->b_bpair, &c->b_gpair, &c->b_agrad, &c->d_in, &c->d_out, &c->d_scr, &c->d_u,
                         &c->d_rot, &c->d_gauss, &c->d_unif, &c->d_energy, &c->d_esum, &c->e_ke, &c->e_g2, &c->e_loc,
                         &c->e_vls, &c->e_contrib};
   for (auto* b : dd) b->release();
@@ -904,6 +910,7 @@ int qmcb_recompute(qmcb_ctx* c, int which, int nconf, const double* configs, dou
     CK(cudaGetLastError());
   }
   c->saved_slot = -1;
+  c->paircache_valid = false;
   if (sign || logval) return qmcb_value(c, which, sign, logval);
   CK(cudaStreamSynchronize(c->stream));
   return 0;
@@ -1089,6 +1096,7 @@ int qmcb_updateinternals(qmcb_ctx* c, int which, int e, const double* epos, cons
   }
   if (launch_update(c, which, e, d_mask, c->stream)) return -1;
   if (which & 1) c->mocache_valid = false;
+  c->paircache_valid = false;
   CK(cudaStreamSynchronize(c->stream));
   // a shared context may be driven factor by factor (Slater call, then Jastrow call with the
   // same token), so the slot stays valid until the next query overwrites it
@@ -1347,6 +1355,14 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
     CK(cudaGetLastError());
     c->mocache_valid = true;
   }
+  if (use_sweep && c->have_jastrow && !c->paircache_valid) {  // pair caches, from the current positions
+    const long long nt = (long long)N * (S.npair + S.ne);
+    if (prep_kernel(k_pair_cache_build, c->smem_bytes)) return -1;
+    k_pair_cache_build<<<(unsigned)((nt + 127) / 128), 128, c->smem_bytes, stream>>>(S, c->st);
+    c->nlaunch++;
+    CK(cudaGetLastError());
+    c->paircache_valid = true;
+  }
   for (int step = 0; step < nsteps; ++step) {
     if (use_sweep) {
       const size_t se = (size_t)step * S.ne;
@@ -1385,6 +1401,7 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
       if (rc) return rc;
       if (launch_update(c, which, e, ma.accept, stream)) return -1;
       c->mocache_valid = false;
+      c->paircache_valid = false;
     }
     if (with_energy) {
       double* eo = d_energy ? d_energy + (size_t)step * 6 * N : c->d_energy.p;
