@@ -265,8 +265,10 @@ def gpu_arm(args):
     accept = float(d_nacc[W:tot].sum().item()) / (N * ne * K)
 
     # ---------------- end-to-end through the public API (host buffers) ----------------
-    nb_e2e = max(2, min(20, K // 10))
+    nb_e2e = max(2, min(50, K // 4))
     spb = SPB
+    # warm-up of the same call shape (pinned block buffers, generator plans, worker threads)
+    df, configs = pq.vmc(wf, configs, tstep=TSTEP, nblocks=3, nsteps_per_block=spb, accumulators={"energy": acc})
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

@@ -186,6 +186,22 @@ __device__ __forceinline__ void coop_eval_mo(const Sys& S, const CoopLayout& L, 
       mo[lane * ldmax + 2] = a2;
       mo[lane * ldmax + 3] = a3;
     }
+  } else if (ldc == 4 && 2 * NC <= G) {
+    // lanes over (component, MO pair): two MOs of a row in registers, one 16-byte load per AO
+    if (lane < 2 * NC) {
+      const int c = lane >> 1, jh = (lane & 1) * 2;
+      const double* __restrict__ cp = comp + c * S.nao;
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll 4
+      for (int mu = 0; mu < S.nao; ++mu) {
+        const double x = cp[mu];
+        const double2 cc = *reinterpret_cast<const double2*>(C + mu * 4 + jh);
+        a0 = fma(x, cc.x, a0);
+        a1 = fma(x, cc.y, a1);
+      }
+      mo[c * ldmax + jh] = a0;
+      mo[c * ldmax + jh + 1] = a1;
+    }
   } else {
 #pragma unroll 1
     for (int t = lane; t < NC * ldc; t += G) {

@@ -278,7 +278,6 @@ __device__ __forceinline__ void jastrow_point(const Sys& S, const double* __rest
                                               const int* __restrict__ si, const State& st, int w,
                                               int e, double px, double py, double pz, double& du,
                                               double (&g)[3], double& lap) {
-  const int N = st.N;
   const int s = e >= S.nup ? 1 : 0;
   double ua = 0.0, ub = 0.0, ua_old = 0.0, ub_old = 0.0;
   g[0] = g[1] = g[2] = 0.0;
