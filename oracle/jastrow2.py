@@ -115,10 +115,24 @@ class JastrowOracle:
             "acoeff": np.zeros((len(self.atoms), len(a_funcs), 2)),
         }
         self.dtype = float
+        # periodic systems: every displacement goes through the minimal-image convention of the
+        # walkers' ``dist`` object (jastrowspin.py uses ``configs.dist`` throughout)
+        self._minimal = None
+        if hasattr(mol, "a"):
+            from .pbc import MinimalImage
+
+            self._minimal = MinimalImage(mol.lattice_vectors())
+
+    def _mi(self, d):
+        return d if self._minimal is None else self._minimal(d)
 
     @classmethod
-    def default(cls, mol, na=4, nb=3, rcut=7.5):
+    def default(cls, mol, na=4, nb=3, rcut=None):
         """Same parameter defaults as wftools.generate_jastrow (wftools.py:99-152)."""
+        if rcut is None:  # wftools.py:81-85
+            rcut = 7.5
+            if hasattr(mol, "a"):
+                rcut = np.amin(np.pi / np.linalg.norm(mol.reciprocal_vectors(), axis=1))
         a_funcs, b_funcs, cusp_atoms = default_basis(mol, na, nb, rcut)
         j = cls(mol, a_funcs, b_funcs, rcut)
         if len(cusp_atoms) > 0:
@@ -139,7 +153,7 @@ class JastrowOracle:
 
     def _a_terms(self, pos, want):
         """pos (..., 3) -> displacement to atoms (..., I, 3) and basis values."""
-        d = pos[..., None, :] - self.atoms
+        d = self._mi(pos[..., None, :] - self.atoms)
         r = np.linalg.norm(d, axis=-1)
         return (d,) + self.a_basis.eval(r, want)
 
@@ -150,6 +164,7 @@ class JastrowOracle:
             d = pos[:, :, None, :] - oth[:, None, :, :]
         else:
             d = pos[:, None, :] - oth
+        d = self._mi(d)
         r = np.linalg.norm(d, axis=-1)
         return (d,) + self.b_basis.eval(r, want)
 
@@ -177,7 +192,7 @@ class JastrowOracle:
         self._bvalues = np.zeros((N, nb, 3))
         for i in range(ne):
             for j in range(i + 1, ne):
-                r = np.linalg.norm(c[:, i] - c[:, j], axis=-1)
+                r = np.linalg.norm(self._mi(c[:, i] - c[:, j]), axis=-1)
                 v, _, _ = self.b_basis.eval(r, 0)
                 self._bvalues[:, :, int(i >= nup) + int(j >= nup)] += v
         return self.value()
@@ -208,7 +223,7 @@ class JastrowOracle:
         self._a_partial[e][mask] = av
         # patch the partial sums of every other electron: b(new) - b(old)
         oth = self._others(e)
-        old = self._cur[mask][:, e][:, None, :] - self._cur[mask][:, oth]
+        old = self._mi(self._cur[mask][:, e][:, None, :] - self._cur[mask][:, oth])
         ov, _, _ = self.b_basis.eval(np.linalg.norm(old, axis=-1), 0)
         diff = np.moveaxis(bv - ov, 1, 0)  # (ne-1, Nm, nb)
         idx = np.nonzero(oth)[0]
@@ -276,7 +291,7 @@ class JastrowOracle:
         cur = self._cur[mask]
         out = np.zeros((pos.shape[0], len(e)))
         _, av, _, _ = self._a_terms(pos, 0)  # (M, I, na)
-        d = pos[:, None, :] - cur
+        d = self._mi(pos[:, None, :] - cur)
         bv, _, _ = self.b_basis.eval(np.linalg.norm(d, axis=-1), 0)  # (M, ne, nb)
         nup = self._nup
         tot = np.stack([bv[:, :nup].sum(axis=1), bv[:, nup:].sum(axis=1)], axis=-1)  # (M, nb, 2)

@@ -99,6 +99,8 @@ def ecp_electron_atom(channels, apos, configs, wf, e, threshold, naip=None):
     """eval_ecp.py:83-132 for one (electron, atom) pair."""
     N = configs.configs.shape[0]
     rvec = configs.configs[:, e, :] - apos
+    if getattr(configs, "dist", None) is not None:  # periodic: minimal image (eval_ecp.py:94)
+        rvec = configs.dist(rvec)
     r = np.linalg.norm(rvec, axis=-1)
     v = channels.v_l(r)
     # stochastic channel mask (eval_ecp.py:135-146)
@@ -140,7 +142,7 @@ def ecp_electron_atom(channels, apos, configs, wf, e, threshold, naip=None):
 class EnergyOracle:
     """Restatement of EnergyAccumulator (open boundary conditions, old ECP path)."""
 
-    def __init__(self, mol, threshold=10, naip=None):
+    def __init__(self, mol, threshold=10, naip=None, **ewald_kwargs):
         self.mol = mol
         self.threshold = threshold
         self.naip = naip
@@ -155,6 +157,11 @@ class EnergyOracle:
             for j in range(i + 1, len(self.atoms)):
                 ii += self.charges[i] * self.charges[j] / np.linalg.norm(self.atoms[i] - self.atoms[j])
         self.ii = ii
+        self.ewald = None
+        if hasattr(mol, "a"):  # accumulators.py:52-55
+            from .pbc import EwaldOracle
+
+            self.ewald = EwaldOracle(mol, **ewald_kwargs)
 
     def ee(self, configs):
         c = configs.configs
@@ -193,11 +200,14 @@ class EnergyOracle:
         return ke, grad2
 
     def __call__(self, configs, wf):
-        ee, ei = self.ee(configs), self.ei(configs)
+        if self.ewald is not None:
+            ee, ei, ii = self.ewald.energy(configs)
+        else:
+            ee, ei, ii = self.ee(configs), self.ei(configs), self.ii
         ecp = self.ecp(configs, wf)
         ke, grad2 = self.kinetic(configs, wf)
         return {"ke": ke, "ee": ee, "ei": ei, "ecp": ecp, "grad2": grad2,
-                "total": ke + ee + ei + ecp + self.ii}
+                "total": ke + ee + ei + ecp + ii}
 
     def avg(self, configs, wf):
         return {k: np.mean(v, axis=0) for k, v in self(configs, wf).items()}

@@ -83,6 +83,9 @@ class SlaterOracle:
     def _mo_coeff(self, s):
         return self.parameters["mo_coeff_alpha" if s == 0 else "mo_coeff_beta"]
 
+    def _mos(self, ao, s):
+        return ao @ self._mo_coeff(s)
+
     def _spin(self, e):
         s = int(e >= self._nelec[0])
         return s, e - s * self._nelec[0]
@@ -104,7 +107,7 @@ class SlaterOracle:
         for s in (0, 1):
             lo = self._nelec[0] * s
             hi = self._nelec[0] + self._nelec[1] * s
-            mo = self._aovals[:, lo:hi, :] @ self._mo_coeff(s)  # (N, n_s, nmo)
+            mo = self._mos(self._aovals[:, lo:hi], s)  # (N, n_s, nmo)
             mats = np.swapaxes(mo[:, :, self._det_occup[s]], 1, 2)  # (N, D_s, n_s, n_s)
             assert mats.shape[-1] == mats.shape[-2]
             sign, logdet = np.linalg.slogdet(mats)
@@ -129,7 +132,7 @@ class SlaterOracle:
             return
         if saved_values is None:
             ao = self._ao(0, epos, mask)
-            mo = ao @ self._mo_coeff(s)
+            mo = self._mos(ao, s)
         else:
             ao_all, mo_all = saved_values
             ao, mo = ao_all[mask], mo_all[mask]
@@ -177,14 +180,14 @@ class SlaterOracle:
     # --- single-electron queries ----------------------------------------------------
     def gradient(self, e, epos):
         s, _ = self._spin(e)
-        mo = self._ao(1, epos) @ self._mo_coeff(s)  # (4, N, nmo)
+        mo = self._mos(self._ao(1, epos), s)  # (4, N, nmo)
         r = self._ratios(e, mo[:, :, None, :])[:, :, 0]
         return r[1:] / r[0]
 
     def gradient_value(self, e, epos):
         s, _ = self._spin(e)
         ao = self._ao(1, epos)
-        mo = ao @ self._mo_coeff(s)
+        mo = self._mos(ao, s)
         r = self._ratios(e, mo[:, :, None, :])[:, :, 0]
         with np.errstate(divide="ignore", invalid="ignore"):
             g = r[1:] / r[0]
@@ -195,7 +198,7 @@ class SlaterOracle:
 
     def gradient_laplacian(self, e, epos):
         s, _ = self._spin(e)
-        mo = self._ao(2, epos) @ self._mo_coeff(s)  # (5, N, nmo)
+        mo = self._mos(self._ao(2, epos), s)  # (5, N, nmo)
         r = self._ratios(e, mo[:, :, None, :])[:, :, 0]
         r = r / r[:1]
         return r[1:4], r[4]
@@ -205,7 +208,7 @@ class SlaterOracle:
         if mask is not None:
             mask = np.asarray(mask, dtype=bool)
         ao = self._ao(0, epos, mask)  # (Nm, [aip,] A)
-        mo = ao @ self._mo_coeff(s)
+        mo = self._mos(ao, s)
         aux = mo.ndim == 3
         mo4 = mo[None] if aux else mo[None, :, None, :]
         r = self._ratios(e, mo4, mask)[0]
@@ -215,12 +218,12 @@ class SlaterOracle:
         e = np.asarray(e)
         spins = (e >= self._nelec[0]).astype(int)
         ao = self._ao(0, epos, mask)  # (Nm, A)
-        out = np.zeros((ao.shape[0], len(e)))
+        out = np.zeros((ao.shape[0], len(e)))  # ao.shape[0] = Nm in both layouts
         for s in (0, 1):
             idx = np.nonzero(spins == s)[0]
             if len(idx) == 0:
                 continue
-            mo = ao @ self._mo_coeff(s)
+            mo = self._mos(ao, s)
             rows = mo[:, self._det_occup[s]]  # (Nm, D_s, n_s)
             sel = slice(None) if mask is None else mask
             inv = self._inverse[s][sel]  # (Nm, D_s, n_s, n_s)

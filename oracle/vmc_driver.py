@@ -29,6 +29,10 @@ def initial_guess(mol, nconfig, r=1.0):
             inds = np.argpartition(np.random.random((nconfig, len(wts))), left, axis=1)[:, :left]
             epos[:, lo + nassigned : lo + mol.nelec[s], :] = coords[inds]
     epos += r * np.random.randn(*epos.shape)
+    if hasattr(mol, "a"):  # mc.py:69-70
+        from .pbc import PeriodicWalkers
+
+        return PeriodicWalkers(epos, mol.lattice_vectors())
     return Walkers(epos)
 
 

@@ -1,0 +1,352 @@
+"""Periodic boundary conditions: duck-typed pyscf ``Cell`` stand-ins and the host-side tables the
+device needs (lattice images and cutoffs of the orbital evaluator, minimal-image shifts, Ewald
+reciprocal points).
+
+Reference statements (relative to /root/reference):
+  * ``enforce_pbc``                       pyqmc/pbc/pbc.py:17-49
+  * supercell construction / k-points    pyqmc/pbc/supercell.py:18-75
+  * twist -> primitive k-point indices    pyqmc/pbc/twists.py:34-65
+  * image list, per-shell cutoffs, phases pyqmc/wf/numba/pbcgto.py:518-621 (``max_Ls``,
+    ``PeriodicAtomicOrbitalEvaluator.__init__``), ``_estimate_rcut`` 672-695
+  * minimal-image shift table             pyqmc/configurations/distance.py:83-121
+  * Ewald set-up                          pyqmc/observables/ewald.py:93-200, 356-379
+
+pyscf is a third-party dependency of the reference (``pyscf>=2.8.0,<3.0.0``, pyproject.toml:12) that
+is neither vendored under /root/reference nor installable here.  Two of its functions feed TABLES
+into this path -- ``Cell.get_lattice_Ls`` (the candidate list of lattice images) and
+``pyscf.pbc.gto.cell.estimate_rcut`` (the starting radius of the cutoff estimate).  They are
+restated below from their published algorithm (``Cell.get_lattice_Ls`` / ``_estimate_rcut`` of
+pyscf/pbc/gto/cell.py, 2.8 series); PARITY UNPINNED at that boundary.  Everything the reference
+itself computes from those tables (sorting, ``max_Ls`` cutoffs, phases) is pinned against the
+reference run in-container with the same stand-ins (tests/golden/make_golden.py).
+"""
+import numpy as np
+
+from . import basis as _basis
+from .systems import Mol
+
+
+def enforce_pbc(lattvecs, epos):
+    """pbc.py:17-49: positions wrapped into the cell and the integer wrap vectors."""
+    recpvecs = np.linalg.inv(lattvecs)
+    frac = np.einsum("...ij,jk->...ik", epos, recpvecs)
+    wrap, rem = np.divmod(frac, 1)
+    return np.dot(rem, lattvecs), wrap
+
+
+class Cell(Mol):
+    """Minimal pyscf-``Cell`` look-alike (Bohr units): a ``Mol`` with lattice vectors ``a``."""
+
+    dimension = 3
+
+    def __init__(self, atoms, basis, ecp, nelec, charges, a):
+        super().__init__(atoms, basis, ecp, nelec, charges)
+        self.a = np.asarray(a, dtype=float).tolist()
+        self._shells = None
+
+    def lattice_vectors(self):
+        return np.asarray(self.a, dtype=float)
+
+    def reciprocal_vectors(self):
+        return 2 * np.pi * np.linalg.inv(self.lattice_vectors()).T
+
+    @property
+    def vol(self):
+        return abs(float(np.linalg.det(self.lattice_vectors())))
+
+    # --- shell accessors used by the rcut estimate (orbitals.py:262-278) ---
+    def _shell_list(self):
+        if self._shells is None:
+            out = []
+            for i in range(len(self._atom)):
+                for shell in self._basis[self.atom_pure_symbol(i)]:
+                    prim = np.asarray(shell[1:], dtype=float)
+                    out.append((int(shell[0]), prim[:, 0], prim[:, 1]))
+            self._shells = out
+        return self._shells
+
+    @property
+    def nbas(self):
+        return len(self._shell_list())
+
+    def bas_angular(self, ib):
+        return self._shell_list()[ib][0]
+
+    def bas_exp(self, ib):
+        return self._shell_list()[ib][1]
+
+    def _libcint_ctr_coeff(self, ib):
+        l, exps, coefs = self._shell_list()[ib]
+        return _basis.normalized_coefficients(l, exps, coefs)[:, None]
+
+    def get_lattice_Ls(self, rcut, dimension=3):
+        """Candidate lattice images: every lattice vector with ``|L| < rcut + d_max`` (d_max = the
+        largest inter-atomic distance in the cell).  Restates the published pyscf behaviour
+        (``discard=True``); the consumers sort by norm and trim by their own cutoffs
+        (pbcgto.py:603-614), so any superset of the images inside those cutoffs gives the same
+        orbital values."""
+        a = self.lattice_vectors()
+        r = self.atom_coords()
+        dmax = float(np.linalg.norm(r[:, None] - r[None], axis=2).max()) if len(r) > 1 else 0.0
+        heights = 1.0 / np.linalg.norm(np.linalg.inv(a).T, axis=1)  # plane spacings
+        bounds = np.ceil((rcut + dmax) / heights).astype(int) + 1
+        grids = [np.arange(-b, b + 1) for b in bounds]
+        Ts = np.stack(np.meshgrid(*grids, indexing="ij"), axis=-1).reshape(-1, 3)
+        Ls = Ts @ a
+        keep = np.linalg.norm(Ls, axis=1) < rcut + dmax
+        return np.ascontiguousarray(Ls[keep])
+
+
+def estimate_rcut(cell, precision):
+    """Stand-in for ``pyscf.pbc.gto.cell.estimate_rcut`` (most diffuse primitive of each shell,
+    two fixed-point iterations of  c^2 (2l+1) alpha r^(2l+2) exp(-alpha r^2 / 2) < precision)."""
+    rmax = 0.01
+    for ib in range(cell.nbas):
+        l = cell.bas_angular(ib)
+        es = cell.bas_exp(ib)
+        i = int(np.argmin(es))
+        alpha = float(es[i])
+        c = float(abs(cell._libcint_ctr_coeff(ib)[i]).max())
+        C = c * c * (2 * l + 1) * alpha / precision
+        r0 = 20.0
+        for _ in range(2):
+            r0 = np.sqrt(2.0 * np.log(C * (r0 * r0 * alpha) ** (l + 1) + 1.0) / alpha)
+        rmax = max(rmax, float(r0))
+    return rmax
+
+
+def shell_rcut(cell, eval_gto_precision):
+    """``_estimate_rcut`` of the reference (orbitals.py:258-278 == pbcgto.py:672-695)."""
+    vol = cell.vol
+    init_rcut = estimate_rcut(cell, eval_gto_precision)
+    precision = eval_gto_precision / max(vol, 1)
+    rcut = []
+    for ib in range(cell.nbas):
+        l = cell.bas_angular(ib)
+        es = cell.bas_exp(ib)
+        cs = abs(cell._libcint_ctr_coeff(ib)).max(axis=1)
+        norm_ang = ((2 * l + 1) / (4 * np.pi)) ** 0.5
+        fac = 2 * np.pi / vol * cs * norm_ang / es / precision
+        r = init_rcut
+        for _ in range(2):
+            r = (np.log(fac * r ** (l + 1) + 1.0) / es) ** 0.5
+        rcut.append(r.max())
+    return np.array(rcut)
+
+
+def get_supercell_copies(latvec, S):
+    """supercell.py:33-43."""
+    Sinv = np.linalg.inv(S).T
+    u = [0, 1]
+    unit_box = np.stack([x.ravel() for x in np.meshgrid(*[u] * 3, indexing="ij")]).T
+    unit_box_ = np.dot(unit_box, S)
+    xyz_range = np.stack([f(unit_box_, axis=0) for f in (np.amin, np.amax)]).T
+    mesh = np.meshgrid(*[np.arange(*r) for r in xyz_range], indexing="ij")
+    possible_pts = np.dot(np.stack([x.ravel() for x in mesh]).T, Sinv.T)
+    in_unit_box = (possible_pts >= 0) * (possible_pts < 1 - 1e-12)
+    select = np.where(np.all(in_unit_box, axis=1))[0]
+    return np.linalg.multi_dot((possible_pts[select], S, latvec))
+
+
+def get_supercell_kpts(supercell):
+    """supercell.py:18-30: primitive-cell k-points that fold onto the supercell Gamma point."""
+    Sinv = np.linalg.inv(supercell.S).T
+    u = [0, 1]
+    unit_box = np.stack([x.ravel() for x in np.meshgrid(*[u] * 3, indexing="ij")]).T
+    unit_box_ = np.dot(unit_box, np.asarray(supercell.S).T)
+    xyz_range = np.stack([f(unit_box_, axis=0) for f in (np.amin, np.amax)]).T
+    kptmesh = np.meshgrid(*[np.arange(*r) for r in xyz_range], indexing="ij")
+    possible_kpts = np.dot(np.stack([x.ravel() for x in kptmesh]).T, Sinv)
+    in_unit_box = (possible_kpts >= 0) * (possible_kpts < 1 - 1e-12)
+    select = np.where(np.all(in_unit_box, axis=1))[0]
+    reclatvec = np.linalg.inv(supercell.original_cell.lattice_vectors()).T * 2 * np.pi
+    return np.dot(possible_kpts[select], reclatvec)
+
+
+def get_supercell(cell, S):
+    """supercell.py:46-75 without pyscf: the simulation cell ``S . a`` with the atoms of every
+    primitive copy (copies of one primitive atom are consecutive)."""
+    S = np.asarray(S)
+    scale = abs(int(np.round(np.linalg.det(S))))
+    superlattice = np.dot(S, cell.lattice_vectors())
+    Rpts = get_supercell_copies(cell.lattice_vectors(), S)
+    atoms, charges = [], []
+    for (name, xyz), z in zip(cell._atom, cell.atom_charges()):
+        for R in Rpts:
+            atoms.append((name, np.asarray(xyz) + R))
+            charges.append(z)
+    sc = Cell(atoms, cell._basis, cell._ecp, (cell.nelec[0] * scale, cell.nelec[1] * scale), charges, superlattice)
+    sc.original_cell = cell
+    sc.S = S.tolist()
+    sc.scale = scale
+    return sc
+
+
+def create_supercell_twists(supercell, mf, tol=12):
+    """twists.py:34-65."""
+    kpts = np.asarray(mf.kpts)
+    srv = supercell.reciprocal_vectors()
+    frac = kpts @ np.linalg.inv(srv)
+    frac = np.around(frac, tol) % 1
+    super_kpts = frac @ srv
+    twists, indices, counts = np.unique(np.round(super_kpts, tol), axis=0, return_counts=True, return_inverse=True)
+    indices = np.asarray(indices).reshape(-1)
+    kinds = [np.argwhere(indices == i)[:, 0] for i in range(twists.shape[0])]
+    return {"twists": twists, "counts": counts, "primitive_ks": kinds}
+
+
+class KMF:
+    """k-point mean-field look-alike in KUHF layout: ``kpts (nk,3)``, ``mo_coeff[s][k] (A, nmo)``,
+    ``mo_occ[s][k] (nmo,)`` (read at pyqmc/pyscftools.py:140-186, 206-219)."""
+
+    def __init__(self, kpts, mo_coeff, mo_occ):
+        self.kpts = np.asarray(kpts, dtype=float)
+        self.mo_coeff = np.asarray(mo_coeff)
+        self.mo_occ = np.asarray(mo_occ)
+
+    def to_uhf(self, *args):
+        return self
+
+
+# ---- orbital-evaluator tables (pbcgto.py:518-621) ---------------------------------------------
+def max_distance_in_cell(lvecs):
+    combos = np.array([[1.0, 1.0, 1.0], [-1.0, 1.0, 1.0], [1.0, -1.0, 1.0], [1.0, 1.0, -1.0]])
+    vecs = combos @ lvecs
+    d = np.sum(vecs**2, axis=-1)
+    return vecs[np.argmax(d)] / 2
+
+
+def image_tables(cell, kpts, eval_gto_precision=None):
+    """Sorted image list ``Ls``, ``num_Ls`` per atom, r^2 cutoffs per atom / per shell and the
+    phase table ``exp(i Ls . k)`` -- what ``PeriodicAtomicOrbitalEvaluator.__init__`` builds
+    (pbcgto.py:594-621) with ``max_Ls`` (551-591)."""
+    prec = 1e-2 if eval_gto_precision is None else eval_gto_precision
+    t = _basis.shell_tables(cell)
+    rcut = shell_rcut(cell, prec)
+    Ls = cell.get_lattice_Ls(rcut=rcut.max(), dimension=3)
+    Ls = Ls[np.argsort(np.linalg.norm(Ls, axis=1))]
+    expcutoff = -3.5 * np.log(prec)
+    natom = len(cell._atom)
+    v = max_distance_in_cell(cell.lattice_vectors())
+    r2 = np.sum((v - Ls) ** 2, axis=-1)
+    nshell = len(t["shell_l"])
+    l_cutoff = np.zeros(nshell)
+    atom_cutoff = np.zeros(natom)
+    Lmax_a = np.zeros(natom, dtype=np.int32)
+    for sh in range(nshell):
+        a, l = int(t["shell_atom"][sh]), int(t["shell_l"][sh])
+        al = t["exps"][t["prim_off"][sh]:t["prim_off"][sh + 1]]
+        cf = t["coefs"][t["prim_off"][sh]:t["prim_off"][sh + 1]]
+        log_c = np.log(np.abs(cf))
+        if l == 0:
+            l_cutoff[sh] = np.amax((expcutoff + log_c) / al)
+        else:
+            r2sup = 0.5 * l / np.amin(al)
+            lconst = 0.5 * np.log(r2sup) * l
+            l_cutoff[sh] = np.amax((expcutoff + log_c + lconst) / al)
+        atom_cutoff[a] = max(atom_cutoff[a], l_cutoff[sh])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            min_exp = np.amin(al[None, :] * r2[:, None] - log_c[None, :] - 0.5 * np.log(r2)[:, None] * l, axis=1)
+        where = np.where(min_exp < expcutoff)[0]
+        lm = where.max() + 1 if len(where) > 0 else 1
+        Lmax_a[a] = max(Lmax_a[a], lm)
+    Lmax = int(Lmax_a.max())
+    phases = np.real_if_close(np.exp(1j * Ls[:Lmax] @ np.asarray(kpts).T))
+    return dict(Ls=np.ascontiguousarray(Ls[:Lmax]), num_Ls=Lmax_a, atom_cutoff=atom_cutoff, l_cutoff=l_cutoff,
+                phases=phases)
+
+
+# ---- minimal image (distance.py:83-121) --------------------------------------------------------
+def minimal_image_tables(latvec):
+    """(mode, shifts (27,3)): mode 1 diagonal, 2 orthogonal, 3 general (27-shift argmin)."""
+    latvec = np.asarray(latvec, dtype=float)
+    tol = 1e-10
+
+    def is_diag(M):
+        return np.all(np.abs(M - np.diag(np.diagonal(M))) < tol)
+
+    if is_diag(latvec):
+        mode = 1
+    elif is_diag(np.dot(latvec, latvec.T)):
+        mode = 2
+    else:
+        mode = 3
+    mesh_grid = np.meshgrid(*[np.array(range(3)) for _ in range(3)])
+    point_list = np.stack([m.ravel() for m in mesh_grid], axis=0).T - 1
+    return mode, np.dot(point_list, latvec)
+
+
+# ---- Ewald tables (ewald.py:93-200, 356-379) ----------------------------------------------------
+def ewald_tables(cell, ewald_gmax=200, nlatvec=1):
+    """alpha, real-space displacements, selected reciprocal points / weights, ion structure factor
+    and the position-independent constants of ``Ewald.__init__``."""
+    latvec = cell.lattice_vectors()
+    charges = np.asarray(cell.atom_charges(), dtype=float)
+    coords = cell.atom_coords()
+    XYZ = np.meshgrid(*[np.arange(-nlatvec, nlatvec + 1)] * 3, indexing="ij")
+    xyz = np.stack(XYZ, axis=-1).reshape((-1, 3))
+    disp = np.dot(xyz, latvec)
+    cellvolume = np.linalg.det(latvec)
+    recvec = np.linalg.inv(latvec).T
+    smallestheight = np.amin(1 / np.linalg.norm(recvec, axis=1))
+    alpha = 5.0 / smallestheight
+    # generate_positive_gpoints(gmax) enumerates (2 gmax + 1)^3 / 2 integer triples and select_big
+    # keeps gweight > 1e-10; the same points in the same order follow from a box that encloses the
+    # sphere |G| < Gcut where the weight first drops below that threshold.
+    gcut2 = 4 * alpha**2 * 40.0  # exp(-40) / (V G^2) << 1e-10 for any physical cell
+    while 4 * np.pi * np.exp(-gcut2 / (4 * alpha**2)) / (abs(cellvolume) * gcut2) > 1e-11:
+        gcut2 *= 1.5
+    nmax = np.minimum(np.ceil(np.sqrt(gcut2) * np.linalg.norm(latvec, axis=1) / (2 * np.pi)).astype(int) + 1, ewald_gmax)
+    nx, ny, nz = (int(v) for v in nmax)
+    gXpos = np.mgrid[1:nx + 1, -ny:ny + 1, -nz:nz + 1].reshape(3, -1)
+    gX0Ypos = np.mgrid[0:1, 1:ny + 1, -nz:nz + 1].reshape(3, -1)
+    gX0Y0Zpos = np.mgrid[0:1, 0:1, 1:nz + 1].reshape(3, -1)
+    gpts = np.concatenate([gXpos, gX0Ypos, gX0Y0Zpos], axis=1)
+    gpoints = np.einsum("ji,jk->ik", gpts, recvec * 2 * np.pi)
+    gsquared = np.einsum("jk,jk->j", gpoints, gpoints)
+    gweight = 4 * np.pi * np.exp(-gsquared / (4 * alpha**2))
+    gweight /= cellvolume * gsquared
+    big = gweight > 1e-10
+    gpoints, gweight = gpoints[big], gweight[big]
+    i_sum = np.sum(charges)
+    ii_sum2 = np.sum(charges**2)
+    ii_sum = (i_sum**2 - ii_sum2) / 2
+    ijconst = -np.pi / (cellvolume * alpha**2)
+    squareconst = -alpha / np.sqrt(np.pi) + ijconst / 2
+    ii_const = ii_sum * ijconst + ii_sum2 * squareconst
+    # ion-ion (ewald.py:202-240)
+    from scipy.special import erfc
+
+    if len(charges) == 1:
+        ion_ion_real = 0.0
+    else:
+        mode, shifts = minimal_image_tables(latvec)
+        ion_ion_real = 0.0
+        for i in range(len(charges)):
+            for j in range(i + 1, len(charges)):
+                d = minimal_image(coords[i] - coords[j], latvec, mode, shifts)
+                r = np.linalg.norm(d[None, :] + disp, axis=-1)
+                ion_ion_real += charges[i] * charges[j] * np.sum(erfc(alpha * r) / r)
+    GdotR = np.dot(gpoints, coords.T)
+    ion_exp = np.dot(np.exp(1j * GdotR), charges)
+    ion_ion_rec = np.dot(gweight, np.abs(ion_exp) ** 2)
+    return dict(alpha=float(alpha), disp=disp, gpoints=np.ascontiguousarray(gpoints), gweight=np.ascontiguousarray(gweight),
+                ion_exp=ion_exp, ijconst=float(ijconst), squareconst=float(squareconst), i_sum=float(i_sum),
+                ii=float(ion_ion_real + ion_ion_rec + ii_const))
+
+
+def minimal_image(d, latvec, mode, shifts):
+    """distance.py:133-159 for one displacement vector (host-side set-up only)."""
+    d = np.asarray(d, dtype=float)
+    if mode == 1:
+        out = d.copy()
+        for i in range(3):
+            L = latvec[i, i]
+            out[i] = (out[i] + L / 2) % L - L / 2
+        return out
+    if mode == 2:
+        frac = d @ np.linalg.inv(latvec)
+        frac = (frac + 0.5) % 1 - 0.5
+        return frac @ latvec
+    allv = d[None, :] + shifts
+    return allv[np.argmin(np.sum(allv**2, axis=-1))]

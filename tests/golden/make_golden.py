@@ -26,6 +26,8 @@ import refload  # noqa: E402
 
 NCONF = 12
 SYSTEMS = ["he", "h2o", "open", "c2", "h2o_md", "h2o_3b", "h2o_md_3b"]
+PBC_SYSTEMS = ["diamond211", "ortho", "rotcubic"]
+EWALD_GMAX = 10  # the reference enumerates (2 gmax + 1)^3 / 2 reciprocal points: keep the fixture run small
 
 
 def build_reference(name):
@@ -49,11 +51,15 @@ def generate(name):
     import pyqmc.method.mc as mc
     from pyqmc.observables.accumulators import EnergyAccumulator
 
+    periodic = name in PBC_SYSTEMS
     mol, wf = build_reference(name)
+    ekw = {"ewald_gmax": EWALD_GMAX} if periodic else {}
     out = {}
     np.random.seed(3)
     configs = mc.initial_guess(mol, NCONF)
     out["configs0"] = configs.configs.copy()
+    if periodic:
+        out["wrap0"] = configs.wrap.copy()
     out["acoeff"] = np.array(wf.parameters["wf2acoeff"])
     out["bcoeff"] = np.array(wf.parameters["wf2bcoeff"])
     s, l = wf.recompute(configs)
@@ -92,15 +98,18 @@ def generate(name):
     out["a_partial"], out["b_partial"] = np.array(ja._a_partial), np.array(ja._b_partial)
     if len(wf.wf_factors) > 2:
         out["P_i"], out["a3_values"] = np.array(wf.wf_factors[2].P_i), np.array(wf.wf_factors[2].a_values)
-    pg = wf.pgradient()
-    for k in pg.keys():
-        out["pgrad_" + k] = np.array(pg[k])
+    if not periodic:
+        pg = wf.pgradient()
+        for k in pg.keys():
+            out["pgrad_" + k] = np.array(pg[k])
+    else:
+        out["wrap1"] = configs.wrap.copy()
     np.random.seed(21)
-    en = EnergyAccumulator(mol)(configs, wf)
+    en = EnergyAccumulator(mol, **ekw)(configs, wf)
     for k, v in en.items():
         out["energy_" + k] = np.asarray(v)
     np.random.seed(22)
-    tm = EnergyAccumulator(mol).nonlocal_tmoves(configs, wf, elist[-1], 0.02)
+    tm = EnergyAccumulator(mol, **ekw).nonlocal_tmoves(configs, wf, elist[-1], 0.02)
     out["tmove_ratio"], out["tmove_weight"] = tm["ratio"], tm["weight"]
     out["tmove_configs"] = tm["configs"].configs
     if len(wf.wf_factors) > 2:
@@ -118,10 +127,12 @@ def generate(name):
     wf.updateinternals = spy
     np.random.seed(31)
     df, configs = mc.vmc(wf, configs, tstep=0.5, nblocks=2, nsteps_per_block=3,
-                         accumulators={"energy": EnergyAccumulator(mol)})
+                         accumulators={"energy": EnergyAccumulator(mol, **ekw)})
     wf.updateinternals = orig
     out["vmc_accept"] = np.array(accepts).reshape(2, 3, ne, NCONF)
     out["vmc_configs"] = configs.configs.copy()
+    if periodic:
+        out["vmc_wrap"] = configs.wrap.copy()
     for k in ("energytotal", "energyke", "energyecp", "energyee", "energyei", "energygrad2", "acceptance"):
         out["vmc_" + k] = df[k]
     if name in ("h2o", "c2", "open"):
@@ -132,7 +143,7 @@ def generate(name):
         weights = np.ones(NCONF)
         np.random.seed(41)
         dret, configs, weights = dmc.dmc_propagate(wf, configs, weights, 0.02, 10.0, 1.5, 1.7, nsteps=3,
-                                                  accumulators={"energy": EnergyAccumulator(mol)})
+                                                  accumulators={"energy": EnergyAccumulator(mol, **ekw)})
         out["dmc_configs"] = configs.configs.copy()
         out["dmc_weights"] = weights.copy()
         for k, v in dret.items():
@@ -143,7 +154,8 @@ def generate(name):
 def main():
     warnings.filterwarnings("ignore")
     refload.load()
-    for name in SYSTEMS:
+    names = sys.argv[1:] if len(sys.argv) > 1 else SYSTEMS + PBC_SYSTEMS
+    for name in names:
         data = generate(name)
         path = os.path.join(HERE, f"{name}.npz")
         np.savez_compressed(path, **data)

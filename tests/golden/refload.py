@@ -30,6 +30,15 @@ _STUBS = [
 ]
 
 
+def _estimate_rcut(cell, precision=None):
+    root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from pyqmc_b200 import pbc
+
+    return pbc.estimate_rcut(cell, precision)
+
+
 def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "pyqmc"))
 
@@ -47,6 +56,11 @@ def load():
                 parent, child = name.rsplit(".", 1)
                 setattr(sys.modules[parent], child, m)
     sys.modules["h5py"].File = object
+    # periodic path: the two pyscf functions that feed TABLES into the reference's numba evaluator
+    # (pyqmc/wf/orbitals.py:164-166,268) are replaced by the stand-ins of pyqmc_b200.pbc; the
+    # mean-field objects used here are already in k-point UHF layout
+    sys.modules["pyscf.pbc.scf.addons"].convert_to_khf = lambda mf: mf
+    sys.modules["pyscf.pbc.gto.cell"].estimate_rcut = _estimate_rcut
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     import pyqmc.api as pyq  # noqa: E402
@@ -72,10 +86,12 @@ def build_reference_wf(mol, mf, jastrow=True, determinants=None, seed=0, na=4, n
     _eval = slater.orbitals.eval_gto
     nao = slater.parameters["mo_coeff_alpha"].shape[0]
 
+    nk = (len(slater.orbitals._kpts),) if hasattr(mol, "a") else ()
+
     def guarded(eval_str, coords):
         if len(coords) == 0:
-            nc = {"GTOval_sph": None, "GTOval_sph_deriv1": 4, "GTOval_sph_deriv2": 5}[eval_str]
-            return np.zeros((0, nao)) if nc is None else np.zeros((nc, 0, nao))
+            nc = {"GTOval_sph": None, "GTOval_sph_deriv1": 4, "GTOval_sph_deriv2": 5}[eval_str.replace("PBC", "")]
+            return np.zeros(nk + (0, nao)) if nc is None else np.zeros(nk + (nc, 0, nao))
         return _eval(eval_str, coords)
 
     slater.orbitals.eval_gto = guarded

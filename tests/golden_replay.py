@@ -50,6 +50,8 @@ def replay(data, wf, configs, make_energy, vmc_fn, check_internal=None):
         assert np.array_equal(s, data[f"q{i}_value_sign"])
         assert np.abs(l - data[f"q{i}_value_log"]).max() < TOL * max(1.0, np.abs(l).max())
     assert np.abs(configs.configs - data["configs1"]).max() == 0.0
+    if "wrap1" in data:
+        assert np.array_equal(configs.wrap, data["wrap1"])
     if check_internal is not None:
         check_internal(wf, data)
     np.random.seed(21)
@@ -64,6 +66,8 @@ def replay(data, wf, configs, make_energy, vmc_fn, check_internal=None):
         assert np.array_equal(accepts, data["vmc_accept"]), "accept masks differ from the reference"
     assert np.array_equal(df["acceptance"], data["vmc_acceptance"])
     assert np.abs(configs.configs - data["vmc_configs"]).max() < 1e-9
+    if "vmc_wrap" in data:
+        assert np.array_equal(configs.wrap, data["vmc_wrap"])
     for k in ("energytotal", "energyke", "energyecp", "energyee", "energyei", "energygrad2"):
         assert np.abs(df[k] - data["vmc_" + k]).max() <= 1e-9 * max(1.0, np.abs(data["vmc_" + k]).max()), k
 

@@ -2,7 +2,7 @@
 identical seeded parameters."""
 import numpy as np
 
-from pyqmc_b200 import systems
+from pyqmc_b200 import pbc_systems, systems
 
 
 def jastrow_coefficients(shape_a, shape_b, has_cusp, seed, scale=0.1):
@@ -23,6 +23,9 @@ def make_system(name):
     if name == "h2o_cas":
         mol, mf = systems.h2o_ccecp_pvtz()
         return mol, mf, systems.cas_determinants(4, 8, seed=3)
+    if name in pbc_systems.PBC_SYSTEMS:
+        mol, mf = pbc_systems.PBC_SYSTEMS[name]()
+        return mol, mf, None
     mol, mf = systems.SYSTEMS[name]()
     return mol, mf, None
 
@@ -43,7 +46,12 @@ def make_pair(name, seed=1, jastrow=True, slater=True, three_body=None):
     factors, ofactors = [], []
     if slater:
         factors.append(pq.Slater(mol, mf, determinants=dets))
-        ofactors.append(SlaterOracle(mol, mf, determinants=dets))
+        if hasattr(mol, "a"):
+            from oracle.pbc import SlaterPbcOracle
+
+            ofactors.append(SlaterPbcOracle(mol, mf, determinants=dets))
+        else:
+            ofactors.append(SlaterOracle(mol, mf, determinants=dets))
     if jastrow:
         j, _ = pq.generate_jastrow(mol)
         oj = JastrowOracle.default(mol)
@@ -76,6 +84,12 @@ def make_pair(name, seed=1, jastrow=True, slater=True, three_body=None):
 def to_oracle_walkers(configs):
     from oracle.walkers import Walkers
 
+    if hasattr(configs, "wrap"):
+        from oracle.pbc import PeriodicWalkers
+
+        w = PeriodicWalkers(configs.configs.copy(), configs.lvecs)
+        w.wrap = configs.wrap.copy()
+        return w
     return Walkers(configs.configs.copy())
 
 
