@@ -87,6 +87,42 @@ int qmcb_set_ecp(qmcb_ctx *ctx, int necp, const int32_t *ecp_atom /*[necp]*/,
                                        (eval_ecp.py:278-336) */,
                  double threshold);
 
+/* ---- periodic systems ------------------------------------------------------------------ */
+
+/* Simulation-cell lattice vectors (rows, Bohr) and the minimal-image convention of
+ * MinimalImageDistance (pyqmc/configurations/distance.py:83-121): mode 1 diagonal, 2 orthogonal,
+ * 3 general; shifts [27][3] = the reference's point_list . latvec (same order: np.argmin ties). */
+int qmcb_set_lattice(qmcb_ctx *ctx, const double *lat /*[9]*/, int mode, const double *shifts /*[81]*/);
+
+/* Tables of PBCOrbitalEvaluatorKpoints / PeriodicAtomicOrbitalEvaluator (pyqmc/wf/orbitals.py:118-186,
+ * pyqmc/wf/numba/pbcgto.py:594-621): the shell table of qmcb_set_basis then refers to the nbatom
+ * PRIMITIVE-cell atoms bxyz; lprim = primitive lattice, smat = supercell matrix S, kpts [nk][3],
+ * Ls [nL][3] images sorted by norm, num_Ls [nbatom], r^2 cutoffs per atom / per shell (max_Ls,
+ * pbcgto.py:551-591), phases [nL][nk] = Re exp(i Ls.k), mo_k_* = k-point index of every MO column
+ * of the concatenated coefficient matrices (orbitals.py:155-160).  Real phases only. */
+int qmcb_set_pbc_orbitals(qmcb_ctx *ctx, int nbatom, const double *bxyz, const double *lprim,
+                          const double *smat, int nk, const double *kpts, int nL, const double *Ls,
+                          const int32_t *num_Ls, const double *atom_cutoff, int nshell,
+                          const double *l_cutoff, const double *phases, int nmo_up,
+                          const int32_t *mo_k_up, int nmo_dn, const int32_t *mo_k_dn, int isgamma);
+
+/* Ewald.__init__ products (pyqmc/observables/ewald.py:93-200): alpha, real-space displacements
+ * [ndisp][3], selected reciprocal points / weights, ion structure factor, the pair / square
+ * constants, sum of charges and the ion-ion energy (ion_ion + ii_const). */
+int qmcb_set_ewald(qmcb_ctx *ctx, double alpha, int ndisp, const double *disp, int nG,
+                   const double *gpoints, const double *gweight, const double *ion_re,
+                   const double *ion_im, double ijconst, double squareconst, double i_sum,
+                   double e_ii);
+
+/* Wrap vectors (PeriodicElectron.wrap, pyqmc/configurations/coord.py:115-134) of the positions
+ * passed to the NEXT point call (gradient*, testvalue*, updateinternals): [count][3], count = N
+ * or N * naip.  Consumed by that call. */
+int qmcb_set_point_wrap(qmcb_ctx *ctx, const double *wrap, int64_t count);
+
+/* wf.recompute(configs) for PeriodicConfigs: wrap [N][nelec][3] (NULL = zero). */
+int qmcb_recompute_pbc(qmcb_ctx *ctx, int which, int nconf, const double *configs,
+                       const double *wrap, double *sign, double *logval);
+
 /* ---- wave-function protocol ---------------------------------------------------------- */
 
 /* wf.recompute(configs) -> (sign, log|psi|)   slater.py:227-260, jastrowspin.py:56-109 */
@@ -123,7 +159,7 @@ int qmcb_pgradient(qmcb_ctx *ctx, const char *name, double *out);
 
 /* internal state read-back for tests: "inverse_up","inverse_dn" [N][D_s][n][n];
  * "dets_up","dets_dn" [2][N][D_s]; "a_partial" [ne][N][I][na]; "b_partial" [ne][N][nb][2];
- * "avalues" [N][I][na][2]; "bvalues" [N][nb][3]; "configs" [N][ne][3] */
+ * "avalues" [N][I][na][2]; "bvalues" [N][nb][3]; "configs" [N][ne][3]; "wrap" [N][ne][3] */
 int qmcb_get_state(qmcb_ctx *ctx, const char *name, double *out);
 
 /* ---- local energy (EnergyAccumulator.__call__, accumulators.py:60-75) ------------------ */

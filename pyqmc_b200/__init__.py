@@ -5,7 +5,7 @@ the local-energy accumulator, behind the reference's ``pyqmc.wf`` object protoco
 Importing the package does not touch the GPU; creating a wave function's device context does,
 and fails loudly without the CUDA library or a CUDA device (there is no CPU fallback).
 """
-from .coord import OpenConfigs, OpenElectron  # noqa: F401
+from .coord import OpenConfigs, OpenElectron, PeriodicConfigs, PeriodicElectron  # noqa: F401
 from .func3d import CutoffCuspFunction, PolyPadeFunction  # noqa: F401
 from .wf import JastrowSpin, MultiplyWF, Slater, ThreeBodyJastrow  # noqa: F401
 from .wftools import generate_jastrow, generate_jastrow3, generate_slater, generate_wf  # noqa: F401
@@ -13,7 +13,7 @@ from .accumulators import EnergyAccumulator  # noqa: F401
 from .mc import initial_guess, limdrift, vmc  # noqa: F401
 
 __all__ = [
-    "OpenConfigs", "OpenElectron", "CutoffCuspFunction", "PolyPadeFunction", "JastrowSpin", "MultiplyWF",
+    "OpenConfigs", "OpenElectron", "PeriodicConfigs", "PeriodicElectron", "CutoffCuspFunction", "PolyPadeFunction", "JastrowSpin", "MultiplyWF",
     "Slater", "ThreeBodyJastrow", "generate_jastrow", "generate_jastrow3", "generate_slater", "generate_wf", "EnergyAccumulator", "initial_guess",
     "limdrift", "vmc",
 ]

@@ -37,6 +37,14 @@ SIGNATURES = {
                                   c_int_p, c_double_p, c_double, c_double_p]),
     "qmcb_set_ecp": (c_int, [c_void_p, c_int, c_int_p, c_int_p, c_int_p, c_int_p, c_double_p,
                              c_double_p, c_int_p, c_double_p, c_double]),
+    "qmcb_set_lattice": (c_int, [c_void_p, c_double_p, c_int, c_double_p]),
+    "qmcb_set_pbc_orbitals": (c_int, [c_void_p, c_int, c_double_p, c_double_p, c_double_p, c_int, c_double_p, c_int,
+                                      c_double_p, c_int_p, c_double_p, c_int, c_double_p, c_double_p, c_int, c_int_p,
+                                      c_int, c_int_p, c_int]),
+    "qmcb_set_ewald": (c_int, [c_void_p, c_double, c_int, c_double_p, c_int, c_double_p, c_double_p, c_double_p,
+                               c_double_p, c_double, c_double, c_double, c_double]),
+    "qmcb_set_point_wrap": (c_int, [c_void_p, c_double_p, c_i64]),
+    "qmcb_recompute_pbc": (c_int, [c_void_p, c_int, c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     "qmcb_recompute": (c_int, [c_void_p, c_int, c_int, c_double_p, c_double_p, c_double_p]),
     "qmcb_value": (c_int, [c_void_p, c_int, c_double_p, c_double_p]),
     "qmcb_gradient": (c_int, [c_void_p, c_int, c_int, c_double_p, c_double_p]),

@@ -68,8 +68,6 @@ class EnergyAccumulator:
     """Returns local energy of each configuration in a dictionary."""
 
     def __init__(self, mol, threshold=10, naip=None, use_old_ecp=True, **kwargs):
-        if hasattr(mol, "a"):
-            raise NotImplementedError("periodic systems (Ewald) are not supported by the B200 backend yet")
         if not use_old_ecp:
             raise NotImplementedError("only the default ECP path (use_old_ecp=True) is implemented")
         self.mol = mol
@@ -77,6 +75,11 @@ class EnergyAccumulator:
         self.naip = naip
         self._ecp = flatten_ecp(mol, naip)
         self.necp = len(self._ecp["ecp_atom"])
+        self._ewald = None
+        if hasattr(mol, "a"):  # accumulators.py:52-55: Ewald replaces the open-boundary Coulomb sums
+            from . import pbc
+
+            self._ewald = pbc.ewald_tables(mol, **kwargs)
 
     def _attach(self, wf):
         ctx = _device_context(wf)
@@ -89,6 +92,13 @@ class EnergyAccumulator:
                                             _lib.iptr(t["term_off"]), _lib.iptr(t["power"]), _lib.dptr(t["alpha"]),
                                             _lib.dptr(t["coef"]), _lib.iptr(t["naip"]), _lib.dptr(t["quad"]),
                                             float(self.threshold)))
+            if self._ewald is not None:
+                t = self._ewald
+                disp, gp, gw = _lib.f64(t["disp"]), _lib.f64(t["gpoints"]), _lib.f64(t["gweight"])
+                ire, iim = _lib.f64(np.real(t["ion_exp"])), _lib.f64(np.imag(t["ion_exp"]))
+                _lib.check(ctx.lib.qmcb_set_ewald(ctx.h, t["alpha"], len(disp), _lib.dptr(disp), len(gw), _lib.dptr(gp),
+                                                  _lib.dptr(gw), _lib.dptr(ire), _lib.dptr(iim), t["ijconst"],
+                                                  t["squareconst"], t["i_sum"], t["ii"]))
             ctx.ecp_key = key
         return ctx
 

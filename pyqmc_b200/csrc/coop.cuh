@@ -24,7 +24,7 @@ __host__ __device__ inline CoopLayout coop_layout(const Sys& S) {
   const int nmax = S.nup > S.ndn ? S.nup : S.ndn;
   int o = 0;
   L.at = o;
-  o += 4 * S.natom;
+  o += 4 * (S.nbatom > S.natom ? S.nbatom : S.natom);
   L.pv = o;
   o += 3 * S.nprim;
   L.sv = o;
@@ -95,8 +95,8 @@ __device__ __forceinline__ void coop_eval_mo(const Sys& S, const CoopLayout& L, 
   double* __restrict__ comp = ws + L.comp;
   double* __restrict__ mo = ws + L.mo;
 #pragma unroll 1
-  for (int a = lane; a < S.natom; a += G) {
-    const double x = px - sd[S.o_xyz + 3 * a], y = py - sd[S.o_xyz + 3 * a + 1], z = pz - sd[S.o_xyz + 3 * a + 2];
+  for (int a = lane; a < S.nbatom; a += G) {
+    const double x = px - sd[S.o_bxyz + 3 * a], y = py - sd[S.o_bxyz + 3 * a + 1], z = pz - sd[S.o_bxyz + 3 * a + 2];
     at[4 * a] = x;
     at[4 * a + 1] = y;
     at[4 * a + 2] = z;

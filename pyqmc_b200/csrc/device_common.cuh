@@ -47,6 +47,21 @@ struct Sys {
   const double* detc;     // [ndet]
   const int* grp_off[2];  // [nds+1] CSR: total determinants that use unique spin det d
   const int* grp_det[2];  // [ndet]
+  // ---- periodic boundary conditions (pbc == 0: open).  pbc is the minimal-image mode of
+  // MinimalImageDistance (distance.py:97-110): 1 diagonal, 2 orthogonal, 3 general (27 shifts).
+  int pbc;
+  int nbatom, o_bxyz;  // atoms that carry basis shells: the PRIMITIVE cell when periodic, else == natom / o_xyz
+  int nk, nL, isgamma, ncand, maxao_atom;
+  int o_lat, o_latinv, o_shifts;                 // simulation cell rows, inverse, 27 image shifts
+  int o_lprim, o_lpriminv, o_smat, o_kl;         // primitive cell, supercell matrix S, k . a_i  [nk][3]
+  int o_Ls, o_atomcut, o_lcut, o_phase;          // sorted images, r^2 cutoffs (pbcgto.py:551-591), exp(i L.k) [nL][nk]
+  int o_numLs, o_candoff, o_mok[2];              // int blob: images per atom, prefix sum, MO -> k-point index
+  // Ewald tables stay in global memory (ewald.py:93-200)
+  int ew_ndisp, ew_nG;
+  double ew_alpha, ew_ijconst, ew_sqconst, ew_isum;
+  const double* ew_disp;  // [ndisp][3]
+  const double* ew_g;     // [nG][4]  G vector, weight
+  const double* ew_ion;   // [nG][2]  Re, Im of sum_I Z_I exp(i G.R_I)
 };
 
 // Walker state (device pointers).  All arrays are walker-major; Slater arrays keep the
@@ -74,6 +89,10 @@ struct State {
   double* saved_mo;  // [N][ldc]  MO row at the last gradient_value/testvalue position
   double* saved_pos; // [N][3]
   double* mo_all;    // [N][ne][ldcmax]  recompute scratch
+  double* wrap;      // [N][ne][3]  periodic: integer wrap vectors of the walkers (coord.py:137-152)
+  double* saved_wrap;// [N][3]      wrap of the position in saved_pos
+  double* monew;     // [N][5][ldmax]  periodic VMC: MO rows at the proposed position
+  double* gold;      // [N][3]      periodic VMC: limited drift at the old position
 };
 
 // walker-major accessors: everything one walker owns is contiguous, so a warp that works on one
@@ -182,6 +201,94 @@ __device__ __forceinline__ void shell_accumulate(double x, double y, double z, d
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Periodic boundary conditions: numpy's float divmod (npy_divmod) and Python's %, enforce_pbc
+// (pbc/pbc.py:17-49) and the minimal-image conventions of distance.py:133-159.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double py_mod(double a, double b) {
+  double m = fmod(a, b);
+  if (m != 0.0) {
+    if ((b < 0.0) != (m < 0.0)) m += b;
+  } else {
+    m = copysign(0.0, b);
+  }
+  return m;
+}
+
+__device__ __forceinline__ void np_divmod1(double a, double& q, double& r) {  // np.divmod(a, 1)
+  double mod = fmod(a, 1.0);
+  double div = a - mod;
+  if (mod != 0.0) {
+    if (mod < 0.0) {
+      mod += 1.0;
+      div -= 1.0;
+    }
+  } else {
+    mod = 0.0;
+  }
+  double fl;
+  if (div != 0.0) {
+    fl = floor(div);
+    if (div - fl > 0.5) fl += 1.0;
+  } else {
+    fl = copysign(0.0, a);
+  }
+  q = fl;
+  r = mod;
+}
+
+// position -> (position inside the cell, integer wrap): lat / inv are row-major 3x3 (rows = lattice vectors)
+__device__ __forceinline__ void wrap_cell(const double* __restrict__ lat, const double* __restrict__ inv, double x,
+                                          double y, double z, double (&o)[3], double (&w)[3]) {
+  double rem[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double f = __dadd_rn(__dadd_rn(__dmul_rn(x, inv[k]), __dmul_rn(y, inv[3 + k])), __dmul_rn(z, inv[6 + k]));
+    np_divmod1(f, w[k], rem[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    o[k] = __dadd_rn(__dadd_rn(__dmul_rn(rem[0], lat[k]), __dmul_rn(rem[1], lat[3 + k])), __dmul_rn(rem[2], lat[6 + k]));
+}
+
+__device__ __forceinline__ void min_image(const Sys& S, const double* __restrict__ sd, double& x, double& y, double& z) {
+  if (S.pbc == 3) {
+    const double* __restrict__ sh = sd + S.o_shifts;
+    double best = INFINITY, bx = x, by = y, bz = z;
+#pragma unroll 9
+    for (int i = 0; i < 27; ++i) {
+      const double ax = x + sh[3 * i], ay = y + sh[3 * i + 1], az = z + sh[3 * i + 2];
+      const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
+      if (d2 < best) {  // first minimum in shift order, as np.argmin
+        best = d2;
+        bx = ax;
+        by = ay;
+        bz = az;
+      }
+    }
+    x = bx;
+    y = by;
+    z = bz;
+  } else if (S.pbc == 1) {
+    const double* __restrict__ lat = sd + S.o_lat;
+    x = py_mod(x + lat[0] / 2, lat[0]) - lat[0] / 2;
+    y = py_mod(y + lat[4] / 2, lat[4]) - lat[4] / 2;
+    z = py_mod(z + lat[8] / 2, lat[8]) - lat[8] / 2;
+  } else if (S.pbc == 2) {
+    const double* __restrict__ lat = sd + S.o_lat;
+    const double* __restrict__ inv = sd + S.o_latinv;
+    double f[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double v = __dadd_rn(__dadd_rn(__dmul_rn(x, inv[k]), __dmul_rn(y, inv[3 + k])), __dmul_rn(z, inv[6 + k]));
+      f[k] = py_mod(v + 0.5, 1.0) - 0.5;
+    }
+    x = __dadd_rn(__dadd_rn(__dmul_rn(f[0], lat[0]), __dmul_rn(f[1], lat[3])), __dmul_rn(f[2], lat[6]));
+    y = __dadd_rn(__dadd_rn(__dmul_rn(f[0], lat[1]), __dmul_rn(f[1], lat[4])), __dmul_rn(f[2], lat[7]));
+    z = __dadd_rn(__dadd_rn(__dmul_rn(f[0], lat[2]), __dmul_rn(f[1], lat[5])), __dmul_rn(f[2], lat[8]));
+  }
+}
+
 template <int DERIV, int NMOT>
 __device__ __forceinline__ void eval_mo(const Sys& S, const double* __restrict__ sd,
                                         const int* __restrict__ si, int spin, double px, double py,
@@ -194,9 +301,9 @@ __device__ __forceinline__ void eval_mo(const Sys& S, const double* __restrict__
   const double* __restrict__ prim = sd + S.o_prim;  // (alpha, coef) pairs
   const double* __restrict__ C = sd + S.o_mo[spin] + mo0;
   const int ldc = S.ldc[spin];
-  for (int a = 0; a < S.natom; ++a) {
-    const double x = px - sd[S.o_xyz + 3 * a], y = py - sd[S.o_xyz + 3 * a + 1],
-                 z = pz - sd[S.o_xyz + 3 * a + 2];
+  for (int a = 0; a < S.nbatom; ++a) {
+    const double x = px - sd[S.o_bxyz + 3 * a], y = py - sd[S.o_bxyz + 3 * a + 1],
+                 z = pz - sd[S.o_bxyz + 3 * a + 2];
     const double r2 = x * x + y * y + z * z;
     const int sh1 = si[S.o_atsh + a + 1];
     for (int sh = si[S.o_atsh + a]; sh < sh1; ++sh) {
@@ -283,8 +390,8 @@ __device__ __forceinline__ void jastrow_point(const Sys& S, const double* __rest
   g[0] = g[1] = g[2] = 0.0;
   lap = 0.0;
   for (int I = 0; I < S.natom; ++I) {
-    const double dx = px - sd[S.o_xyz + 3 * I], dy = py - sd[S.o_xyz + 3 * I + 1],
-                 dz = pz - sd[S.o_xyz + 3 * I + 2];
+    double dx = px - sd[S.o_xyz + 3 * I], dy = py - sd[S.o_xyz + 3 * I + 1], dz = pz - sd[S.o_xyz + 3 * I + 2];
+    if (S.pbc) min_image(S, sd, dx, dy, dz);
     const double r = sqrt(dx * dx + dy * dy + dz * dz);
     const bool in = r < S.rcut_a;
     for (int k = 0; k < S.na; ++k) {
@@ -307,8 +414,8 @@ __device__ __forceinline__ void jastrow_point(const Sys& S, const double* __rest
   for (int j = 0; j < S.ne; ++j) {
     if (j == e) continue;
     const int sj = j >= S.nup ? 1 : 0;
-    const double dx = px - CONF(st, S, w, j, 0), dy = py - CONF(st, S, w, j, 1),
-                 dz = pz - CONF(st, S, w, j, 2);
+    double dx = px - CONF(st, S, w, j, 0), dy = py - CONF(st, S, w, j, 1), dz = pz - CONF(st, S, w, j, 2);
+    if (S.pbc) min_image(S, sd, dx, dy, dz);
     const double r = sqrt(dx * dx + dy * dy + dz * dz);
     if (r < S.rcut_b) {
       for (int l = 0; l < S.nb; ++l) {

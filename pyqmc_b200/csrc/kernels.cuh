@@ -12,6 +12,7 @@
 #pragma once
 #include "device_common.cuh"
 #include "coop.cuh"
+#include "pbc.cuh"
 
 #define QMCB_SLATER 1
 #define QMCB_JASTROW 2
@@ -65,7 +66,8 @@ __device__ __forceinline__ void slater_point_general(const Sys& S, const double*
   const int n = s ? S.ndn : S.nup;
   const int eeff = e - s * S.nup;
   const int ldc = S.ldc[s];
-  for (int mo0 = 0; mo0 < ldc; mo0 += 8) {
+  // periodic systems: the lattice-summed MO rows of this point were written by k_pbc_mo
+  for (int mo0 = 0; mo0 < ldc && !S.pbc; mo0 += 8) {
     double acc[NC][8];
     eval_mo<DERIV, 8>(S, sd, si, s, px, py, pz, mo0, acc);
 #pragma unroll
@@ -441,8 +443,8 @@ __global__ void __launch_bounds__(128) k_jastrow_recompute(const Sys S, const St
     const double px = CONF(st, S, w, e, 0), py = CONF(st, S, w, e, 1),
                  pz = CONF(st, S, w, e, 2);
     for (int I = 0; I < I_; ++I) {
-      const double dx = px - sd[S.o_xyz + 3 * I], dy = py - sd[S.o_xyz + 3 * I + 1],
-                   dz = pz - sd[S.o_xyz + 3 * I + 2];
+      double dx = px - sd[S.o_xyz + 3 * I], dy = py - sd[S.o_xyz + 3 * I + 1], dz = pz - sd[S.o_xyz + 3 * I + 2];
+      if (S.pbc) min_image(S, sd, dx, dy, dz);
       const double r = sqrt(dx * dx + dy * dy + dz * dz);
       for (int k = 0; k < na; ++k) {
         double v = 0.0, g, l;
@@ -453,8 +455,8 @@ __global__ void __launch_bounds__(128) k_jastrow_recompute(const Sys S, const St
     }
     for (int j = e + 1; j < ne; ++j) {
       const int sj = j >= S.nup ? 1 : 0;
-      const double dx = px - CONF(st, S, w, j, 0), dy = py - CONF(st, S, w, j, 1),
-                   dz = pz - CONF(st, S, w, j, 2);
+      double dx = px - CONF(st, S, w, j, 0), dy = py - CONF(st, S, w, j, 1), dz = pz - CONF(st, S, w, j, 2);
+      if (S.pbc) min_image(S, sd, dx, dy, dz);
       const double r = sqrt(dx * dx + dy * dy + dz * dz);
       if (r < S.rcut_b) {
         for (int l = 0; l < nb; ++l) {
@@ -485,8 +487,8 @@ __global__ void __launch_bounds__(128) k_jastrow_update(const Sys S, const State
   if (do_jastrow) {
     const int na = S.na, nb = S.nb, I_ = S.natom;
     for (int I = 0; I < I_; ++I) {
-      const double dx = nx - sd[S.o_xyz + 3 * I], dy = ny - sd[S.o_xyz + 3 * I + 1],
-                   dz = nz - sd[S.o_xyz + 3 * I + 2];
+      double dx = nx - sd[S.o_xyz + 3 * I], dy = ny - sd[S.o_xyz + 3 * I + 1], dz = nz - sd[S.o_xyz + 3 * I + 2];
+      if (S.pbc) min_image(S, sd, dx, dy, dz);
       const double r = sqrt(dx * dx + dy * dy + dz * dz);
       for (int k = 0; k < na; ++k) {
         double v = 0.0, g, l;
@@ -506,10 +508,12 @@ __global__ void __launch_bounds__(128) k_jastrow_update(const Sys S, const State
         const double jx = CONF(st, S, w, j, 0), jy = CONF(st, S, w, j, 1),
                      jz = CONF(st, S, w, j, 2);
         double dx = nx - jx, dy = ny - jy, dz = nz - jz;
+        if (S.pbc) min_image(S, sd, dx, dy, dz);
         const double rn = sqrt(dx * dx + dy * dy + dz * dz);
         dx = ox - jx;
         dy = oy - jy;
         dz = oz - jz;
+        if (S.pbc) min_image(S, sd, dx, dy, dz);
         const double ro = sqrt(dx * dx + dy * dy + dz * dz);
         double vn = 0.0, vo = 0.0, g, ll;
         if (rn < S.rcut_b) radial_func<0>(si[S.o_bkind + l], sd[S.o_bpar + l], S.rcut_b, rn, vn, g, ll);
@@ -527,6 +531,8 @@ __global__ void __launch_bounds__(128) k_jastrow_update(const Sys S, const State
   CONF(st, S, w, e, 0) = nx;
   CONF(st, S, w, e, 1) = ny;
   CONF(st, S, w, e, 2) = nz;
+  if (S.pbc)
+    for (int i = 0; i < 3; ++i) st.wrap[((size_t)w * S.ne + e) * 3 + i] = st.saved_wrap[(size_t)w * 3 + i];
 }
 
 // =========================================================================================
@@ -1055,6 +1061,9 @@ struct EnergyScratch {
   double* ratio;     // [items][max_naip]  (T-moves)
   int* count;        // [1]
   int maxchan;
+  double* ewald;     // [2][N]  periodic: Ewald ee, ei per walker (k_ewald)
+  double* ecp_pos;   // [ne*necp*N*max_naip][3]  periodic: wrapped quadrature points
+  double* ecp_wrap;  // same shape: their wrap vectors
 };
 
 // kinetic energy pieces: one thread per (walker, electron)  (energy.py:57-65).  The MO value /
@@ -1111,7 +1120,10 @@ __global__ void __launch_bounds__(128) k_kinetic(const Sys S, const State st, co
   double lapj = 0.0, cross = 0.0, gj[3] = {0.0, 0.0, 0.0};
   if (which & QMCB_JASTROW) {
     double du, lj;
-    coop_jastrow<2, G>(S, sd, si, st, w, e, px, py, pz, lane, gm, du, gj, lj);
+    if (S.pbc)
+      coop_jastrow_pbc<2, G>(S, sd, si, st, w, e, px, py, pz, lane, gm, du, gj, lj);
+    else
+      coop_jastrow<2, G>(S, sd, si, st, w, e, px, py, pz, lane, gm, du, gj, lj);
     lapj = lj;
   }
   if (which & QMCB_JASTROW3) {
@@ -1150,9 +1162,9 @@ __global__ void __launch_bounds__(128) k_ecp_prepare(const Sys S, const State st
   const int e = e_only >= 0 ? e_only : ea / S.necp;
   const int a = ea % S.necp;
   const int atom = si[S.o_ecpatom + a];
-  const double dx = CONF(st, S, w, e, 0) - sd[S.o_xyz + 3 * atom],
-               dy = CONF(st, S, w, e, 1) - sd[S.o_xyz + 3 * atom + 1],
-               dz = CONF(st, S, w, e, 2) - sd[S.o_xyz + 3 * atom + 2];
+  double dx = CONF(st, S, w, e, 0) - sd[S.o_xyz + 3 * atom], dy = CONF(st, S, w, e, 1) - sd[S.o_xyz + 3 * atom + 1],
+         dz = CONF(st, S, w, e, 2) - sd[S.o_xyz + 3 * atom + 2];
+  if (S.pbc) min_image(S, sd, dx, dy, dz);  // configs.dist.dist_i (eval_ecp.py:94)
   const double r = sqrt(dx * dx + dy * dy + dz * dz);
   const int c0 = si[S.o_chanoff + a], c1 = si[S.o_chanoff + a + 1];
   const int nl = c1 - c0;
@@ -1215,6 +1227,12 @@ struct EcpPointArgs {
   double* tm_pos;     // [N][tot_naip][3]
   double* scr;
   size_t scr_stride;
+  // periodic systems run the kernel twice around k_pbc_mo: pass 0 (pos_out != nullptr) only writes
+  // the quadrature points wrapped into the simulation cell (make_irreducible, eval_ecp.py:114) and
+  // their wrap vectors; pass 1 (pos_in != nullptr) evaluates with the MO rows found in scr
+  double* pos_out;
+  double* wrap_out;
+  const double* pos_in;
 };
 
 template <int NMOT>
@@ -1236,12 +1254,15 @@ __global__ void __launch_bounds__(128) k_ecp_points(const Sys S, const State st,
     const int e = ea.e_only >= 0 ? ea.e_only : eai / S.necp;
     const int a = eai % S.necp;
     const int naip = si[S.o_naip + a];
-    if (q >= naip) continue;
+    if (q >= naip) {
+      if (ea.pos_out) ea.pos_out[3 * p] = NAN;  // k_pbc_mo skips this slot
+      continue;
+    }
     const int atom = si[S.o_ecpatom + a];
     const double ex = CONF(st, S, w, e, 0), ey = CONF(st, S, w, e, 1),
                  ez = CONF(st, S, w, e, 2);
-    const double rx = ex - sd[S.o_xyz + 3 * atom], ry = ey - sd[S.o_xyz + 3 * atom + 1],
-                 rz = ez - sd[S.o_xyz + 3 * atom + 2];
+    double rx = ex - sd[S.o_xyz + 3 * atom], ry = ey - sd[S.o_xyz + 3 * atom + 1], rz = ez - sd[S.o_xyz + 3 * atom + 2];
+    if (S.pbc) min_image(S, sd, rx, ry, rz);
     const double r = sqrt(rx * rx + ry * ry + rz * rz);
     const double* R = ea.rot + (size_t)eai * 9;
     const double* qt = ea.quad + (size_t)si[S.o_aipoff + a] * 4;
@@ -1252,7 +1273,22 @@ __global__ void __launch_bounds__(128) k_ecp_points(const Sys S, const State st,
                  uz = R[6] * qx + R[7] * qy + R[8] * qz;
     const double dx = r * ux, dy = r * uy, dz = r * uz;
     const double cosang = (rx * dx + ry * dy + rz * dz) / (r * sqrt(dx * dx + dy * dy + dz * dz));
-    const double px = (ex - rx) + dx, py = (ey - ry) + dy, pz = (ez - rz) + dz;
+    double px = (ex - rx) + dx, py = (ey - ry) + dy, pz = (ez - rz) + dz;
+    const double upx = px, upy = py, upz = pz;  // before the wrap: what the T-move table reports
+    if (S.pbc) {
+      if (ea.pos_out) {
+        double o[3], ww[3];
+        wrap_cell(sd + S.o_lat, sd + S.o_latinv, px, py, pz, o, ww);
+        for (int i = 0; i < 3; ++i) {
+          ea.pos_out[3 * p + i] = o[i];
+          ea.wrap_out[3 * p + i] = st.wrap[((size_t)w * S.ne + e) * 3 + i] + ww[i];
+        }
+        continue;
+      }
+      px = ea.pos_in[3 * p];
+      py = ea.pos_in[3 * p + 1];
+      pz = ea.pos_in[3 * p + 2];
+    }
     PointEval<0, NMOT> ev;
     ev.run(S, sd, si, st, which, w, e, px, py, pz, nullptr, ea.scr + p, ea.scr_stride);
     const double ratio = ev.rat[0] * exp(ev.du);
@@ -1271,9 +1307,9 @@ __global__ void __launch_bounds__(128) k_ecp_points(const Sys S, const State st,
       const size_t o = (size_t)w * S.tot_naip + (size_t)(si[S.o_aipoff + a] - 0) + q;
       ea.tm_ratio[o] = ratio;
       ea.tm_weight[o] = wt;
-      ea.tm_pos[o * 3] = px;
-      ea.tm_pos[o * 3 + 1] = py;
-      ea.tm_pos[o * 3 + 2] = pz;
+      ea.tm_pos[o * 3] = upx;  // periodic: the caller's make_irreducible wraps it (coord.py:168-184)
+      ea.tm_pos[o * 3 + 1] = upy;
+      ea.tm_pos[o * 3 + 2] = upz;
     }
   }
 }
@@ -1292,8 +1328,8 @@ __global__ void __launch_bounds__(128) k_ao_all(const Sys S, const State st, dou
   const double px = CONF(st, S, w, e, 0), py = CONF(st, S, w, e, 1), pz = CONF(st, S, w, e, 2);
   double* out = ao + (size_t)p * S.nao;
   const double* __restrict__ prim = sd + S.o_prim;
-  for (int a = 0; a < S.natom; ++a) {
-    const double x = px - sd[S.o_xyz + 3 * a], y = py - sd[S.o_xyz + 3 * a + 1], z = pz - sd[S.o_xyz + 3 * a + 2];
+  for (int a = 0; a < S.nbatom; ++a) {
+    const double x = px - sd[S.o_bxyz + 3 * a], y = py - sd[S.o_bxyz + 3 * a + 1], z = pz - sd[S.o_bxyz + 3 * a + 2];
     const double r2 = x * x + y * y + z * z;
     for (int sh = si[S.o_atsh + a]; sh < si[S.o_atsh + a + 1]; ++sh) {
       double R = 0.0;
@@ -1427,6 +1463,19 @@ __global__ void __launch_bounds__(128) k_energy_finalize(const Sys S, const Stat
     }
   }
   __syncwarp(gm);
+  if (S.pbc) {  // Coulomb terms come from the Ewald kernel (accumulators.py:52-55, ewald.py:330-354)
+    if (lane == 0) {
+      ee = es.ewald[w];
+      ei = es.ewald[(size_t)N + w];
+      out[w] = ke;
+      out[(size_t)N + w] = ee;
+      out[(size_t)2 * N + w] = ei;
+      out[(size_t)3 * N + w] = ecp;
+      out[(size_t)4 * N + w] = g2;
+      out[(size_t)5 * N + w] = (((ke + ee) + ei) + ecp) + S.e_ii;
+    }
+    return;
+  }
   // ---- electron-electron: pairs (i < j) in row-major order
   const int npair = ne * (ne - 1) / 2;
   for (int t = lane; t < npair; t += G) {

@@ -1,0 +1,603 @@
+// pbc.cuh -- periodic-boundary kernels of libqmcb200.
+//
+// Reference statements (relative to /root/reference):
+//   lattice-summed GTOs            pyqmc/wf/numba/pbcgto.py:98-515 (_pbc_eval_gto{,_grad,_lap})
+//   primitive-cell wrap, wrap phase, per-k MO contraction   pyqmc/wf/orbitals.py:192-239
+//   minimal-image Jastrow          pyqmc/wf/jastrowspin.py:56-419 with configs.dist (distance.py:83-159)
+//   VMC move with make_irreducible pyqmc/method/mc.py:115-137, configurations/coord.py:168-194
+//   Ewald sums                     pyqmc/observables/ewald.py:242-354
+#pragma once
+#include "coop.cuh"
+
+__device__ __forceinline__ void limdrift3(double (&g)[3]);
+
+// =========================================================================================
+// k_pbc_mo: MO rows (value [, gradient [, Laplacian]]) of lattice-summed Bloch orbitals at a list
+// of points.  G lanes per point.  Per point:
+//   0  wrap into the PRIMITIVE cell (orbitals.py:201), zero the AO accumulators ao[k][mu][c]
+//   1  lanes over candidate (basis atom, image) pairs: r^2 test against the atom cutoff, survivors
+//      are compacted into a list (ballot + prefix count)
+//   A  lanes over surviving pairs: solid harmonics, radial sums with the per-shell cutoff, chi,
+//      grad chi, lap chi of that atom's AOs -> staging slot in shared memory
+//   B  lanes over (k, mu, c): ao[k][mu][c] += phase[L][k] * staged                 (pbcgto.py:216-227)
+//   C  lanes over (c, MO j): mo = wrapphase[k(j)] * sum_mu ao[k(j)][mu][c] C[mu][j] (orbitals.py:204-229)
+// =========================================================================================
+struct PbcMoArgs {
+  long long npoints;
+  const int* count;  // optional device counter: npoints = *count * per_item
+  int per_item;
+  const double* pos;   // [..][3] indexed by posidx
+  const double* wrap;  // [..][3] simulation-cell wrap vectors of the points (nullptr: zero)
+  const int* idx;      // optional compacted walker list: posidx = idx[p / naip] * naip + p % naip
+  int naip;
+  int spin_mode;       // 0: `spin`; 1: electron = posidx % ne; 2: electron of ECP work item p / per_item
+  int spin;
+  const int* work;     // spin_mode 2: es.work
+  int workN, necp, e_only;
+  const uint8_t* mask; // optional per-point-walker mask (posidx / naip)
+  double* out;         // out[p * stride_p + c * stride_c + j * stride_j]
+  long long stride_p, stride_c, stride_j;
+  double* out_val;     // optional second copy of the value row: out_val[p * stride_vp + j]
+  long long stride_vp;
+};
+
+__host__ __device__ inline int pbc_mo_scratch_doubles(const Sys& S, int nc, int G) {
+  return S.nk * S.nao * nc + G * S.maxao_atom * nc + G + 2;  // accumulators, staging, candidate list (2G ints)
+}
+
+template <int DERIV, int G>
+__global__ void __launch_bounds__(128) k_pbc_mo(const Sys S, const State st, const PbcMoArgs a) {
+  constexpr int NC = NComp<DERIV>::value;
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  extern __shared__ __align__(128) unsigned char qmcb_smem[];
+  const int lane32 = threadIdx.x & 31;
+  const int lane = lane32 & (G - 1);
+  const unsigned gm = group_mask<G>(lane32);
+  const int gshift = lane32 & ~(G - 1);
+  const int gslot = threadIdx.x / G, gper = blockDim.x / G;
+  const size_t tab = (16 + (size_t)S.dwords * 8 + (size_t)S.iwords * 4 + 15) & ~(size_t)15;
+  const int per = pbc_mo_scratch_doubles(S, NC, G);
+  double* ws = reinterpret_cast<double*>(qmcb_smem + tab) + (size_t)gslot * per;
+  double* __restrict__ ao = ws;
+  double* __restrict__ stg = ws + S.nk * S.nao * NC;
+  int* __restrict__ lst = reinterpret_cast<int*>(stg + G * S.maxao_atom * NC);
+  const int stg_stride = S.maxao_atom * NC;
+  const long long np = a.count ? (long long)(*a.count) * a.per_item : a.npoints;
+  const double* __restrict__ Ls = sd + S.o_Ls;
+  const double* __restrict__ prim = sd + S.o_prim;
+  const double* __restrict__ phase = sd + S.o_phase;
+  for (long long p = (long long)blockIdx.x * gper + gslot; p < np; p += (long long)gridDim.x * gper) {
+    long long posidx = p;
+    if (a.idx) posidx = (long long)a.idx[p / a.naip] * a.naip + p % a.naip;
+    if (a.mask && !a.mask[posidx / a.naip]) continue;
+    const double px = a.pos[3 * posidx], py = a.pos[3 * posidx + 1], pz = a.pos[3 * posidx + 2];
+    if (isnan(px)) continue;
+    int spin = a.spin;
+    if (a.spin_mode == 1) spin = (int)(posidx % S.ne) >= S.nup ? 1 : 0;
+    if (a.spin_mode == 2) {
+      const int t = a.work[p / a.per_item];
+      const int e = a.e_only >= 0 ? a.e_only : (t / a.workN) / a.necp;
+      spin = e >= S.nup ? 1 : 0;
+    }
+    double q[3], pw[3];
+    wrap_cell(sd + S.o_lprim, sd + S.o_lpriminv, px, py, pz, q, pw);
+    for (int i = lane; i < S.nk * S.nao * NC; i += G) ao[i] = 0.0;
+    __syncwarp(gm);
+
+    // ---- phases A and B on `cnt` compacted (atom, image) pairs lst[0..cnt)
+    auto process = [&](int cnt) {
+      if (lane < cnt) {
+        const int c = lst[lane];
+        int at = 0;
+        while (c >= si[S.o_candoff + at + 1]) ++at;
+        const int j = c - si[S.o_candoff + at];
+        const double x = (q[0] - sd[S.o_bxyz + 3 * at]) - Ls[3 * j], y = (q[1] - sd[S.o_bxyz + 3 * at + 1]) - Ls[3 * j + 1],
+                     z = (q[2] - sd[S.o_bxyz + 3 * at + 2]) - Ls[3 * j + 2];
+        const double r2 = x * x + y * y + z * z;
+        double* __restrict__ o = stg + lane * stg_stride;
+        const int ao0 = si[S.o_shao + si[S.o_atsh + at]];
+        double sph[36];
+        int lastl = -1;
+        for (int sh = si[S.o_atsh + at]; sh < si[S.o_atsh + at + 1]; ++sh) {
+          const int l = si[S.o_shl + sh];
+          const int m0 = si[S.o_shao + sh] - ao0;
+          const double lcut = sd[S.o_lcut + sh];
+          // value kernel keeps r2 < cutoff (pbcgto.py:215); the derivative kernels skip r2 > cutoff (348, 490)
+          const bool in = DERIV == 0 ? (r2 < lcut) : !(r2 > lcut);
+          if (!in) {
+            for (int m = 0; m < (2 * l + 1) * NC; ++m) o[m0 * NC + m] = 0.0;
+            continue;
+          }
+          if (l != lastl) {
+            switch (l) {
+              case 0: sph_store<0, (DERIV > 0)>(x, y, z, sph); break;
+              case 1: sph_store<1, (DERIV > 0)>(x, y, z, sph); break;
+              case 2: sph_store<2, (DERIV > 0)>(x, y, z, sph); break;
+              case 3: sph_store<3, (DERIV > 0)>(x, y, z, sph); break;
+              default: sph_store<4, (DERIV > 0)>(x, y, z, sph); break;
+            }
+            lastl = l;
+          }
+          double R = 0.0, Rp = 0.0, Rl = 0.0;
+          for (int pp = si[S.o_shprim + sh]; pp < si[S.o_shprim + sh + 1]; ++pp) {
+            const double al = prim[2 * pp], cf = prim[2 * pp + 1];
+            const double g = cf * exp(-al * r2);
+            R += g;
+            if (DERIV > 0) {
+              const double t = 2.0 * al * g;
+              Rp -= t;
+              if (DERIV > 1) Rl = fma(t, 2.0 * al * r2 - 3.0, Rl);
+            }
+          }
+          const double dRx = Rp * x, dRy = Rp * y, dRz = Rp * z;
+          for (int m = 0; m < 2 * l + 1; ++m) {
+            const double s = sph[4 * m];
+            double* __restrict__ om = o + (m0 + m) * NC;
+            om[0] = s * R;
+            if (DERIV > 0) {
+              const double gx = sph[4 * m + 1], gy = sph[4 * m + 2], gz = sph[4 * m + 3];
+              om[1] = gx * R + s * dRx;
+              om[2] = gy * R + s * dRy;
+              om[3] = gz * R + s * dRz;
+              if (DERIV > 1) om[4] = s * Rl + 2.0 * (gx * dRx + gy * dRy + gz * dRz);
+            }
+          }
+        }
+      }
+      __syncwarp(gm);
+      for (int s = 0; s < cnt; ++s) {
+        const int c = lst[s];
+        int at = 0;
+        while (c >= si[S.o_candoff + at + 1]) ++at;
+        const int j = c - si[S.o_candoff + at];
+        const int ao0 = si[S.o_shao + si[S.o_atsh + at]];
+        const int nloc = (si[S.o_shao + si[S.o_atsh + at + 1]] - ao0) * NC;
+        const double* __restrict__ src = stg + s * stg_stride;
+        for (int i = lane; i < S.nk * nloc; i += G) {
+          const int k = i / nloc, rem = i - k * nloc;
+          ao[(k * S.nao + ao0) * NC + rem] = fma(phase[j * S.nk + k], src[rem], ao[(k * S.nao + ao0) * NC + rem]);
+        }
+      }
+      __syncwarp(gm);
+    };
+
+    int pending = 0;
+    for (int base = 0; base < S.ncand; base += G) {
+      const int c = base + lane;
+      bool ok = false;
+      if (c < S.ncand) {
+        int at = 0;
+        while (c >= si[S.o_candoff + at + 1]) ++at;
+        const int j = c - si[S.o_candoff + at];
+        const double x = (q[0] - sd[S.o_bxyz + 3 * at]) - Ls[3 * j], y = (q[1] - sd[S.o_bxyz + 3 * at + 1]) - Ls[3 * j + 1],
+                     z = (q[2] - sd[S.o_bxyz + 3 * at + 2]) - Ls[3 * j + 2];
+        ok = !(x * x + y * y + z * z > sd[S.o_atomcut + at]);  // pbcgto.py:207
+      }
+      unsigned b = __ballot_sync(gm, ok);
+      b = G == 32 ? b : ((b >> gshift) & ((1u << G) - 1u));
+      if (ok) lst[pending + __popc(b & ((1u << lane) - 1u))] = c;
+      pending += __popc(b);
+      __syncwarp(gm);
+      if (pending >= G) {
+        process(G);
+        const int rest = pending - G;
+        int tmp = 0;
+        if (lane < rest) tmp = lst[G + lane];
+        __syncwarp(gm);
+        if (lane < rest) lst[lane] = tmp;
+        __syncwarp(gm);
+        pending = rest;
+      }
+    }
+    if (pending > 0) process(pending);
+
+    // ---- phase C: wrap phase and per-k MO contraction
+    const int ldc = S.ldc[spin], nmo = S.nmo[spin];
+    const double* __restrict__ C = sd + S.o_mo[spin];
+    const int* __restrict__ mok = si + S.o_mok[spin];
+    double wt[3] = {pw[0], pw[1], pw[2]};
+    if (!S.isgamma && a.wrap) {
+      const double* __restrict__ Sm = sd + S.o_smat;
+      const double w0 = a.wrap[3 * posidx], w1 = a.wrap[3 * posidx + 1], w2 = a.wrap[3 * posidx + 2];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) wt[k] = (w0 * Sm[k] + w1 * Sm[3 + k] + w2 * Sm[6 + k]) + pw[k];
+    }
+    for (int t = lane; t < NC * ldc; t += G) {
+      const int c = t / ldc, j = t - c * ldc;
+      double acc = 0.0;
+      if (j < nmo) {
+        const int k = mok[j];
+        const double* __restrict__ ak = ao + (size_t)k * S.nao * NC + c;
+        for (int mu = 0; mu < S.nao; ++mu) acc = fma(ak[mu * NC], C[mu * ldc + j], acc);
+        if (!S.isgamma) {  // (-1) ** round(k.R / pi)  (orbitals.py:34-35, 204-213)
+          const double* __restrict__ kl = sd + S.o_kl + 3 * k;
+          const double kd = kl[0] * wt[0] + kl[1] * wt[1] + kl[2] * wt[2];
+          const double n = rint(kd / 3.141592653589793);
+          if (fmod(fabs(n), 2.0) == 1.0) acc = -acc;
+        }
+      }
+      a.out[p * a.stride_p + c * a.stride_c + j * a.stride_j] = acc;
+      if (c == 0 && a.out_val) a.out_val[p * a.stride_vp + j] = acc;
+    }
+    __syncwarp(gm);
+  }
+}
+
+// =========================================================================================
+// Minimal-image Jastrow with lanes over PARTNERS (other electrons, then atoms): one 27-shift search
+// per partner, all radial functions of that partner on the same lane.
+// WANT 1: du (log ratio vs cached partial sums) and grad U;  WANT 2: grad U and laplacian U.
+// =========================================================================================
+template <int WANT, int G>
+__device__ __forceinline__ void coop_jastrow_pbc(const Sys& S, const double* __restrict__ sd,
+                                                 const int* __restrict__ si, const State& st, int w, int e, double px,
+                                                 double py, double pz, int lane, unsigned gm, double& du,
+                                                 double (&g)[3], double& lap) {
+  const int s = e >= S.nup ? 1 : 0;
+  double unew = 0.0, uold = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0, lp = 0.0;
+  const int npart = (S.nb > 0 ? S.ne - 1 : 0), nat = (S.na > 0 ? S.natom : 0);
+#pragma unroll 1
+  for (int t = lane; t < npart + nat; t += G) {
+    double dx, dy, dz, rcut;
+    int nfun;
+    const bool isb = t < npart;
+    int j = 0, I = 0;
+    if (isb) {
+      j = t < e ? t : t + 1;
+      dx = px - CONF(st, S, w, j, 0);
+      dy = py - CONF(st, S, w, j, 1);
+      dz = pz - CONF(st, S, w, j, 2);
+      rcut = S.rcut_b;
+      nfun = S.nb;
+    } else {
+      I = t - npart;
+      dx = px - sd[S.o_xyz + 3 * I];
+      dy = py - sd[S.o_xyz + 3 * I + 1];
+      dz = pz - sd[S.o_xyz + 3 * I + 2];
+      rcut = S.rcut_a;
+      nfun = S.na;
+    }
+    if (S.pbc) min_image(S, sd, dx, dy, dz);
+    const double r = sqrt(dx * dx + dy * dy + dz * dz);
+    if (r < rcut) {
+      const int sj = j >= S.nup ? 1 : 0;
+      for (int l = 0; l < nfun; ++l) {
+        double v, gg, ll;
+        double c;
+        if (isb) {
+          c = sd[S.o_bcoef + l * 3 + s + sj];
+          radial_ool<WANT>(si[S.o_bkind + l], sd[S.o_bpar + l], rcut, r, v, gg, ll);
+        } else {
+          c = sd[S.o_acoef + (I * S.na + l) * 2 + s];
+          radial_ool<WANT>(si[S.o_akind + l], sd[S.o_apar + l], rcut, r, v, gg, ll);
+        }
+        unew = fma(c, v, unew);
+        const double cg = c * gg;
+        g0 = fma(cg, dx, g0);
+        g1 = fma(cg, dy, g1);
+        g2 = fma(cg, dz, g2);
+        if (WANT == 2) lp = fma(c, ll, lp);
+      }
+    }
+  }
+  if (WANT != 2) {
+    const int na_items = S.natom * S.na, nb_items = S.nb * 2;
+    for (int t = lane; t < na_items + nb_items; t += G) {
+      if (t < na_items) {
+        const int I = t / S.na, k = t - I * S.na;
+        uold = fma(sd[S.o_acoef + (I * S.na + k) * 2 + s], APART(st, S, w, e, I, k), uold);
+      } else {
+        const int u = t - na_items;
+        const int l = u >> 1, tt = u & 1;
+        uold = fma(sd[S.o_bcoef + l * 3 + s + tt], BPART(st, S, w, e, l, tt), uold);
+      }
+    }
+  }
+  du = group_sum<G>(unew, gm) - group_sum<G>(uold, gm);
+  g[0] = group_sum<G>(g0, gm);
+  g[1] = group_sum<G>(g1, gm);
+  g[2] = group_sum<G>(g2, gm);
+  lap = WANT == 2 ? group_sum<G>(lp, gm) : 0.0;
+}
+
+// Jastrow caches of walker w after electron e moved from its current position to (nx,ny,nz)
+// (jastrowspin.py:111-137, 221-249), lanes over partners; jtmp: (ne - 1) * nb doubles per walker.
+template <int G>
+__device__ __forceinline__ void coop_jastrow_update_pbc(const Sys& S, const double* __restrict__ sd,
+                                                        const int* __restrict__ si, const State& st, int w, int e,
+                                                        double nx, double ny, double nz, int lane, unsigned gm,
+                                                        double* __restrict__ jtmp) {
+  const int s = e >= S.nup ? 1 : 0;
+  if (S.na > 0) {
+    for (int I = lane; I < S.natom; I += G) {
+      double dx = nx - sd[S.o_xyz + 3 * I], dy = ny - sd[S.o_xyz + 3 * I + 1], dz = nz - sd[S.o_xyz + 3 * I + 2];
+      if (S.pbc) min_image(S, sd, dx, dy, dz);
+      const double r = sqrt(dx * dx + dy * dy + dz * dz);
+      for (int k = 0; k < S.na; ++k) {
+        double v = 0.0, gg, ll;
+        if (r < S.rcut_a) radial_ool<0>(si[S.o_akind + k], sd[S.o_apar + k], S.rcut_a, r, v, gg, ll);
+        AVAL(st, S, w, I, k, s) += v - APART(st, S, w, e, I, k);
+        APART(st, S, w, e, I, k) = v;
+      }
+    }
+  }
+  if (S.nb > 0) {
+    const double ox = CONF(st, S, w, e, 0), oy = CONF(st, S, w, e, 1), oz = CONF(st, S, w, e, 2);
+#pragma unroll 1
+    for (int jj = lane; jj < S.ne - 1; jj += G) {
+      const int j = jj < e ? jj : jj + 1;
+      const double jx = CONF(st, S, w, j, 0), jy = CONF(st, S, w, j, 1), jz = CONF(st, S, w, j, 2);
+      double dx = nx - jx, dy = ny - jy, dz = nz - jz;
+      if (S.pbc) min_image(S, sd, dx, dy, dz);
+      const double rn = sqrt(dx * dx + dy * dy + dz * dz);
+      dx = ox - jx;
+      dy = oy - jy;
+      dz = oz - jz;
+      if (S.pbc) min_image(S, sd, dx, dy, dz);
+      const double ro = sqrt(dx * dx + dy * dy + dz * dz);
+      for (int l = 0; l < S.nb; ++l) {
+        double vn = 0.0, vo = 0.0, gg, ll;
+        if (rn < S.rcut_b) radial_ool<0>(si[S.o_bkind + l], sd[S.o_bpar + l], S.rcut_b, rn, vn, gg, ll);
+        if (ro < S.rcut_b) radial_ool<0>(si[S.o_bkind + l], sd[S.o_bpar + l], S.rcut_b, ro, vo, gg, ll);
+        BPART(st, S, w, j, l, s) += vn - vo;
+        jtmp[jj * S.nb + l] = vn;
+      }
+    }
+    __syncwarp(gm);
+#pragma unroll 1
+    for (int t = lane; t < S.nb * 2; t += G) {
+      const int l = t >> 1, tt = t & 1;
+      double bn = 0.0;
+      for (int jj = 0; jj < S.ne - 1; ++jj) {
+        const int j = jj < e ? jj : jj + 1;
+        if ((j >= S.nup ? 1 : 0) == tt) bn += jtmp[jj * S.nb + l];
+      }
+      BVAL(st, S, w, l, s + tt) += bn - BPART(st, S, w, e, l, tt);
+      BPART(st, S, w, e, l, tt) = bn;
+    }
+  }
+  __syncwarp(gm);
+}
+
+// =========================================================================================
+// Device-resident VMC move for periodic single-determinant wave functions, one warp per walker,
+// around k_pbc_mo and the Sherman-Morrison kernel (mc.py:115-137):
+//   k_pbc_propose : drift at the current position (cached MO rows . inverse column + Jastrow),
+//                   proposal, wrap into the simulation cell (make_irreducible)
+//   k_pbc_mo<2>   : MO rows at the proposed positions -> st.monew
+//   k_pbc_accept  : ratio + drift at the proposed position, Metropolis test; accepted walkers update
+//                   the Jastrow caches, the cached MO rows, the coordinates and wrap vectors
+//   k_sm_warp     : masked Sherman-Morrison update of the inverse from the value row in st.monew
+// =========================================================================================
+struct PbcMoveArgs {
+  int e;
+  double tstep;
+  const double* gauss;  // [N][3]
+  const double* unif;   // [N]
+  uint8_t* accept;      // [N]
+  unsigned long long* nacc;
+};
+
+template <int G>
+__device__ __forceinline__ void slater_row_ratio4(const Sys& S, const int* __restrict__ si, const State& st, int w,
+                                                  int s, int eeff, const double* __restrict__ rows, int ldmax, int lane,
+                                                  unsigned gm, double (&r)[4]) {
+  const int n = s ? S.ndn : S.nup;
+  const int* __restrict__ occ = si + S.o_occ[s];
+  const double* __restrict__ inv = st.inv[s] + (size_t)w * n * n + eeff;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  for (int k = lane; k < n; k += G) {
+    const double c = inv[k * n];
+    const int o = occ[k];
+    a0 = fma(rows[o], c, a0);
+    a1 = fma(rows[ldmax + o], c, a1);
+    a2 = fma(rows[2 * ldmax + o], c, a2);
+    a3 = fma(rows[3 * ldmax + o], c, a3);
+  }
+  r[0] = group_sum<G>(a0, gm);
+  r[1] = group_sum<G>(a1, gm);
+  r[2] = group_sum<G>(a2, gm);
+  r[3] = group_sum<G>(a3, gm);
+}
+
+__global__ void __launch_bounds__(128) k_pbc_propose(const Sys S, const State st, const PbcMoveArgs a) {
+  constexpr int G = 32;
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  const int lane = threadIdx.x & 31;
+  const unsigned gm = 0xffffffffu;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int N = st.N;
+  if (w >= N) return;
+  const int e = a.e;
+  const int s = e >= S.nup ? 1 : 0;
+  const int eeff = e - s * S.nup;
+  const int ldmax = S.ldc[0] > S.ldc[1] ? S.ldc[0] : S.ldc[1];
+  const double ox = CONF(st, S, w, e, 0), oy = CONF(st, S, w, e, 1), oz = CONF(st, S, w, e, 2);
+  double grad[3] = {0.0, 0.0, 0.0};
+  if (S.nmo[0] + S.nmo[1] > 0) {
+    double r[4];
+    slater_row_ratio4<G>(S, si, st, w, s, eeff, st.mocache + ((size_t)w * S.ne + e) * 5 * ldmax, ldmax, lane, gm, r);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double gs = r[1 + i] / r[0];
+      if (!isfinite(gs)) gs = 0.0;
+      grad[i] = gs;
+    }
+  }
+  if (S.na + S.nb > 0) {
+    double du, gj[3], lj;
+    coop_jastrow_pbc<1, G>(S, sd, si, st, w, e, ox, oy, oz, lane, gm, du, gj, lj);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) grad[i] = grad[i] + gj[i];
+  }
+  limdrift3(grad);
+  if (lane == 0) {
+    const double* __restrict__ gauss = a.gauss + (size_t)w * 3;
+    const double nx = __dadd_rn(__dadd_rn(ox, gauss[0]), __dmul_rn(grad[0], a.tstep));
+    const double ny = __dadd_rn(__dadd_rn(oy, gauss[1]), __dmul_rn(grad[1], a.tstep));
+    const double nz = __dadd_rn(__dadd_rn(oz, gauss[2]), __dmul_rn(grad[2], a.tstep));
+    double o[3] = {nx, ny, nz}, ww[3] = {0.0, 0.0, 0.0};
+    if (S.pbc) wrap_cell(sd + S.o_lat, sd + S.o_latinv, nx, ny, nz, o, ww);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      st.saved_pos[(size_t)w * 3 + i] = o[i];
+      st.saved_wrap[(size_t)w * 3 + i] = st.wrap[((size_t)w * S.ne + e) * 3 + i] + ww[i];
+      st.gold[(size_t)w * 3 + i] = grad[i];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_pbc_accept(const Sys S, const State st, const PbcMoveArgs a) {
+  constexpr int G = 32;
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  extern __shared__ __align__(128) unsigned char qmcb_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const unsigned gm = 0xffffffffu;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int N = st.N;
+  if (w >= N) return;
+  const size_t tab = (16 + (size_t)S.dwords * 8 + (size_t)S.iwords * 4 + 15) & ~(size_t)15;
+  const int jper = ((S.ne > 1 ? S.ne - 1 : 0) * S.nb + 1) & ~1;
+  double* jtmp = reinterpret_cast<double*>(qmcb_smem + tab) + (size_t)wib * jper;
+  const int e = a.e;
+  const int s = e >= S.nup ? 1 : 0;
+  const int eeff = e - s * S.nup;
+  const int ldmax = S.ldc[0] > S.ldc[1] ? S.ldc[0] : S.ldc[1];
+  const double nx = st.saved_pos[(size_t)w * 3], ny = st.saved_pos[(size_t)w * 3 + 1], nz = st.saved_pos[(size_t)w * 3 + 2];
+  const double* __restrict__ rows = st.monew + (size_t)w * 5 * ldmax;
+  const bool has_s = S.nmo[0] + S.nmo[1] > 0, has_j = S.na + S.nb > 0;
+  double ngrad[3] = {0.0, 0.0, 0.0}, val = 1.0;
+  if (has_s) {
+    double r[4];
+    slater_row_ratio4<G>(S, si, st, w, s, eeff, rows, ldmax, lane, gm, r);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double gs = r[1 + i] / r[0];
+      if (!isfinite(gs)) gs = 0.0;
+      ngrad[i] = gs;
+    }
+    val = isfinite(r[0]) ? r[0] : 1.0;
+  }
+  if (has_j) {
+    double du, gj[3], lj;
+    coop_jastrow_pbc<1, G>(S, sd, si, st, w, e, nx, ny, nz, lane, gm, du, gj, lj);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) ngrad[i] = ngrad[i] + gj[i];
+    val = val * exp(du);
+  }
+  limdrift3(ngrad);
+  const double* __restrict__ gauss = a.gauss + (size_t)w * 3;
+  double fwd = 0.0, bwd = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    fwd = __dadd_rn(fwd, __dmul_rn(gauss[i], gauss[i]));
+    const double b = __dadd_rn(gauss[i], __dmul_rn(a.tstep, __dadd_rn(st.gold[(size_t)w * 3 + i], ngrad[i])));
+    bwd = __dadd_rn(bwd, __dmul_rn(b, b));
+  }
+  const double tprob = exp(__dmul_rn(1.0 / (2.0 * a.tstep), __dadd_rn(fwd, -bwd)));
+  const double aval = fabs(val);
+  const double ratio = __dmul_rn(__dmul_rn(aval, aval), tprob);
+  const bool acc = __shfl_sync(gm, (ratio > a.unif[w]) ? 1 : 0, 0) != 0;
+  if (lane == 0) {
+    a.accept[w] = acc ? 1 : 0;
+    if (acc) atomicAdd(a.nacc, 1ULL);
+  }
+  if (!acc) return;
+  if (has_j) coop_jastrow_update_pbc<G>(S, sd, si, st, w, e, nx, ny, nz, lane, gm, jtmp);
+  if (has_s) {
+    double* __restrict__ mc = st.mocache + ((size_t)w * S.ne + e) * 5 * ldmax;
+    for (int i = lane; i < 5 * ldmax; i += G) mc[i] = rows[i];
+  }
+  __syncwarp(gm);
+  if (lane < 3) {
+    CONF(st, S, w, e, lane) = st.saved_pos[(size_t)w * 3 + lane];
+    st.wrap[((size_t)w * S.ne + e) * 3 + lane] = st.saved_wrap[(size_t)w * 3 + lane];
+  }
+}
+
+// =========================================================================================
+// Ewald energy, one CTA per walker (ewald.py:242-354): real-space electron-ion and electron-
+// electron sums over the minimal image plus the (2 nlatvec + 1)^3 displacements, reciprocal sums
+// over the selected G points, and the self / charged-system constants.  out: [2][N] = ee, ei.
+// Terms with alpha r > 6.5 (erfc < 4e-20) are skipped.
+// =========================================================================================
+__global__ void __launch_bounds__(128) k_ewald(const Sys S, const State st, double* __restrict__ out) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  extern __shared__ __align__(128) unsigned char qmcb_smem[];
+  const size_t tab = (16 + (size_t)S.dwords * 8 + (size_t)S.iwords * 4 + 15) & ~(size_t)15;
+  double* conf = reinterpret_cast<double*>(qmcb_smem + tab);  // [ne][3]
+  double* red = conf + 3 * S.ne;                               // [4 warps][4]
+  const int w = blockIdx.x;
+  const int N = st.N;
+  const int ne = S.ne;
+  for (int i = threadIdx.x; i < 3 * ne; i += blockDim.x) conf[i] = st.conf[(size_t)w * ne * 3 + i];
+  __syncthreads();
+  const double alpha = S.ew_alpha;
+  double ei_real = 0.0, ee_real = 0.0, ee_rec = 0.0, ei_rec = 0.0;
+  auto cij = [&](double dx, double dy, double dz) {
+    min_image(S, sd, dx, dy, dz);
+    double acc = 0.0;
+    for (int d = 0; d < S.ew_ndisp; ++d) {
+      const double x = dx + S.ew_disp[3 * d], y = dy + S.ew_disp[3 * d + 1], z = dz + S.ew_disp[3 * d + 2];
+      const double r = sqrt(x * x + y * y + z * z);
+      const double ar = alpha * r;
+      if (ar < 6.5) acc += erfc(ar) / r;
+    }
+    return acc;
+  };
+  for (int t = threadIdx.x; t < S.natom * ne; t += blockDim.x) {
+    const int I = t / ne, i = t - I * ne;
+    ei_real -= sd[S.o_chg + I] * cij(conf[3 * i] - sd[S.o_xyz + 3 * I], conf[3 * i + 1] - sd[S.o_xyz + 3 * I + 1],
+                                     conf[3 * i + 2] - sd[S.o_xyz + 3 * I + 2]);
+  }
+  const int npair = ne * (ne - 1) / 2;
+  for (int t = threadIdx.x; t < npair; t += blockDim.x) {
+    int i = 0, rem = t;
+    while (rem >= ne - 1 - i) {
+      rem -= ne - 1 - i;
+      ++i;
+    }
+    const int j = i + 1 + rem;
+    ee_real += cij(conf[3 * i] - conf[3 * j], conf[3 * i + 1] - conf[3 * j + 1], conf[3 * i + 2] - conf[3 * j + 2]);
+  }
+  for (int gI = threadIdx.x; gI < S.ew_nG; gI += blockDim.x) {
+    const double gx = S.ew_g[4 * gI], gy = S.ew_g[4 * gI + 1], gz = S.ew_g[4 * gI + 2], wgt = S.ew_g[4 * gI + 3];
+    double ssin = 0.0, scos = 0.0;
+    for (int i = 0; i < ne; ++i) {
+      double sn, cs;
+      sincos(conf[3 * i] * gx + conf[3 * i + 1] * gy + conf[3 * i + 2] * gz, &sn, &cs);
+      ssin += sn;
+      scos += cs;
+    }
+    ee_rec = fma(ssin * ssin + scos * scos, wgt, ee_rec);
+    ei_rec = fma(-S.ew_ion[2 * gI] * scos - S.ew_ion[2 * gI + 1] * ssin, wgt, ei_rec);
+  }
+  double v[4] = {ei_real, ee_real, ee_rec, ei_rec};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0)
+    for (int k = 0; k < 4; ++k) red[wid * 4 + k] = v[k];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q)
+      for (int k = 0; k < 4; ++k) tot[k] += red[q * 4 + k];
+    const double dne = (double)ne;
+    const double ee = (tot[1] + tot[2]) + (dne * (dne - 1.0) / 2.0 * S.ew_ijconst + dne * S.ew_sqconst);  // ee_const
+    const double ei = (tot[0] + 2.0 * tot[3]) + (-dne * S.ew_isum * S.ew_ijconst);                        // ei_const
+    out[w] = ee;
+    out[(size_t)N + w] = ei;
+  }
+}

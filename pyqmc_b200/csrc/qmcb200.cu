@@ -100,6 +100,19 @@ struct qmcb_ctx {
   std::vector<int> ecp_atom, chan_off, term_off, term_pow, naip;
   std::vector<double> term_alpha, term_coef, quad;
   double threshold = 10.0;
+  // periodic systems
+  int pbc_mode = 0;
+  std::vector<double> lat, shifts;
+  bool have_pbc_orb = false;
+  int nk = 0, nL = 0, isgamma = 1;
+  std::vector<double> bxyz, lprim, smat, kpts, Ls, atomcut, lcut, phases;
+  std::vector<int> numLs, mok[2];
+  bool have_ewald = false;
+  double ew_alpha = 0, ew_ij = 0, ew_sq = 0, ew_isum = 0, ew_eii = 0;
+  int ew_ndisp = 0, ew_nG = 0;
+  DBuf<double> d_ewdisp, d_ewg, d_ewion;
+  DBuf<double> b_wrap, b_swrap, b_monew, b_gold, d_pwrap, e_ewald, e_ecppos, e_ecpwrap;
+  bool pending_wrap = false;  // d_pwrap holds the wrap vectors of the next point call
   bool dirty = true;
   // ---- device tables
   Sys S{};
@@ -165,13 +178,16 @@ int build_tables(qmcb_ctx* c) {
   S.nshell = nshell;
   S.nprim = (int)c->pexp.size();
   std::vector<int> atsh(natom + 1, 0), shao(nshell + 1, 0);
+  const int nbatom_host = (c->pbc_mode && c->have_pbc_orb) ? (int)c->bxyz.size() / 3 : natom;
+  atsh.assign(nbatom_host + 1, 0);
   for (int s = 0; s < nshell; ++s) {
+    if (c->sh_atom[s] >= nbatom_host) return fail("shell table refers to an atom outside the basis-atom list");
     if (c->sh_l[s] > QMCB_MAX_ATOM_L || c->sh_l[s] < 0) return fail("angular momentum l > 4 is not supported");
     if (s > 0 && c->sh_atom[s] < c->sh_atom[s - 1]) return fail("shells must be grouped by atom");
     atsh[c->sh_atom[s] + 1]++;
     shao[s + 1] = shao[s] + 2 * c->sh_l[s] + 1;
   }
-  for (int a = 0; a < natom; ++a) atsh[a + 1] += atsh[a];
+  for (int a = 0; a < nbatom_host; ++a) atsh[a + 1] += atsh[a];
   S.nao = shao[nshell];
   S.nup = c->nup;
   S.ndn = c->ndn;
@@ -190,6 +206,7 @@ int build_tables(qmcb_ctx* c) {
     }
   }
   const int nmax = std::max(S.nmo[0], S.nmo[1]);
+  if (c->pbc_mode) ident = false;  // periodic orbitals always go through k_pbc_mo + the general path
   if (ident && nmax <= 4)
     c->nmot = 4;
   else if (ident && nmax <= 8)
@@ -231,6 +248,52 @@ int build_tables(qmcb_ctx* c) {
   };
   S.o_xyz = dpush(c->xyz.data(), c->xyz.size());
   S.o_chg = dpush(c->chg.data(), c->chg.size());
+  S.pbc = c->pbc_mode;
+  S.nbatom = natom;
+  S.o_bxyz = S.o_xyz;
+  S.isgamma = 1;
+  if (c->pbc_mode) {
+    auto inv3 = [](const std::vector<double>& m) {
+      std::vector<double> r(9);
+      const double det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+      r[0] = (m[4] * m[8] - m[5] * m[7]) / det;
+      r[1] = (m[2] * m[7] - m[1] * m[8]) / det;
+      r[2] = (m[1] * m[5] - m[2] * m[4]) / det;
+      r[3] = (m[5] * m[6] - m[3] * m[8]) / det;
+      r[4] = (m[0] * m[8] - m[2] * m[6]) / det;
+      r[5] = (m[2] * m[3] - m[0] * m[5]) / det;
+      r[6] = (m[3] * m[7] - m[4] * m[6]) / det;
+      r[7] = (m[1] * m[6] - m[0] * m[7]) / det;
+      r[8] = (m[0] * m[4] - m[1] * m[3]) / det;
+      return r;
+    };
+    S.o_lat = dpush(c->lat.data(), 9);
+    std::vector<double> li = inv3(c->lat);
+    S.o_latinv = dpush(li.data(), 9);
+    S.o_shifts = dpush(c->shifts.data(), 81);
+    if (c->have_slater && !c->have_pbc_orb) return fail("periodic Slater factor: qmcb_set_pbc_orbitals has not been called");
+    if (c->have_pbc_orb) {
+      S.nbatom = (int)c->bxyz.size() / 3;
+      S.o_bxyz = dpush(c->bxyz.data(), c->bxyz.size());
+      S.nk = c->nk;
+      S.nL = c->nL;
+      S.isgamma = c->isgamma;
+      S.o_lprim = dpush(c->lprim.data(), 9);
+      std::vector<double> lpi = inv3(c->lprim);
+      S.o_lpriminv = dpush(lpi.data(), 9);
+      S.o_smat = dpush(c->smat.data(), 9);
+      std::vector<double> kl((size_t)c->nk * 3);
+      for (int k = 0; k < c->nk; ++k)
+        for (int i = 0; i < 3; ++i)
+          kl[3 * k + i] = c->kpts[3 * k] * c->lprim[3 * i] + c->kpts[3 * k + 1] * c->lprim[3 * i + 1] + c->kpts[3 * k + 2] * c->lprim[3 * i + 2];
+      S.o_kl = dpush(kl.data(), kl.size());
+      S.o_Ls = dpush(c->Ls.data(), c->Ls.size());
+      S.o_atomcut = dpush(c->atomcut.data(), c->atomcut.size());
+      if ((int)c->lcut.size() != nshell) return fail("qmcb_set_pbc_orbitals: l_cutoff must have one entry per shell");
+      S.o_lcut = dpush(c->lcut.data(), c->lcut.size());
+      S.o_phase = dpush(c->phases.data(), c->phases.size());
+    }
+  }
   if (db.size() % 2) db.push_back(0.0);
   {
     std::vector<double> prim(2 * c->pexp.size());
@@ -265,26 +328,47 @@ int build_tables(qmcb_ctx* c) {
   S.o_shao = ipush(shao.data(), shao.size());
   for (int s = 0; s < 2; ++s) S.o_occ[s] = ipush(c->occ[s].data(), c->have_slater ? c->occ[s].size() : 0);
   {
-    std::vector<int> primatom(c->pexp.size()), aoshell(S.nao), sphoff(natom + 1, 0), lmax(natom, -1), task;
+    const int nba = nbatom_host;
+    std::vector<int> primatom(c->pexp.size()), aoshell(S.nao), sphoff(nba + 1, 0), lmax(nba, -1), task;
     for (int sh = 0; sh < nshell; ++sh) {
       for (int p = c->prim_off[sh]; p < c->prim_off[sh + 1]; ++p) primatom[p] = c->sh_atom[sh];
       for (int m = shao[sh]; m < shao[sh + 1]; ++m) aoshell[m] = sh;
       lmax[c->sh_atom[sh]] = std::max(lmax[c->sh_atom[sh]], c->sh_l[sh]);
     }
-    for (int a = 0; a < natom; ++a) {
+    for (int a = 0; a < nba; ++a) {
       sphoff[a + 1] = sphoff[a] + (lmax[a] + 1) * (lmax[a] + 1);
       for (int l = 0; l <= lmax[a]; ++l) {
         task.push_back(a);
         task.push_back(l);
       }
     }
-    S.nsph = sphoff[natom];
+    S.nsph = sphoff[nba];
     S.nsphtask = (int)task.size() / 2;
     S.o_primatom = ipush(primatom.data(), primatom.size());
     S.o_shatom = ipush(c->sh_atom.data(), nshell);
     S.o_aoshell = ipush(aoshell.data(), aoshell.size());
     S.o_sphoff = ipush(sphoff.data(), sphoff.size());
     S.o_sphtask = ipush(task.data(), task.size());
+  }
+  if (c->pbc_mode && c->have_pbc_orb) {
+    S.o_numLs = ipush(c->numLs.data(), c->numLs.size());
+    std::vector<int> candoff(S.nbatom + 1, 0);
+    int mx = 0;
+    for (int a = 0; a < S.nbatom; ++a) {
+      candoff[a + 1] = candoff[a] + c->numLs[a];
+      mx = std::max(mx, shao[atsh[a + 1]] - shao[atsh[a]]);
+    }
+    S.ncand = candoff[S.nbatom];
+    S.maxao_atom = mx;
+    S.o_candoff = ipush(candoff.data(), candoff.size());
+    for (int s = 0; s < 2; ++s) {
+      std::vector<int> mk(S.ldc[s], 0);
+      if (c->have_slater) {
+        if ((int)c->mok[s].size() != S.nmo[s]) return fail("qmcb_set_pbc_orbitals: MO -> k-point map does not match the MO count");
+        for (int j = 0; j < S.nmo[s]; ++j) mk[j] = c->mok[s][j];
+      }
+      S.o_mok[s] = ipush(mk.data(), mk.size());
+    }
   }
   S.o_akind = ipush(c->akind.data(), S.na);
   S.o_bkind = ipush(c->bkind.data(), S.nb);
@@ -346,9 +430,21 @@ int build_tables(qmcb_ctx* c) {
     if (c->d_quad.ensure(c->quad.size())) return -1;
     CK(cudaMemcpy(c->d_quad.p, c->quad.data(), c->quad.size() * 8, cudaMemcpyHostToDevice));
   }
+  if (c->pbc_mode && c->have_ewald) {
+    S.ew_ndisp = c->ew_ndisp;
+    S.ew_nG = c->ew_nG;
+    S.ew_alpha = c->ew_alpha;
+    S.ew_ijconst = c->ew_ij;
+    S.ew_sqconst = c->ew_sq;
+    S.ew_isum = c->ew_isum;
+    S.ew_disp = c->d_ewdisp.p;
+    S.ew_g = c->d_ewg.p;
+    S.ew_ion = c->d_ewion.p;
+    S.e_ii = c->ew_eii;
+  }
   c->dirty = false;
   // walker state survives a table rebuild unless a shape it depends on changed
-  std::vector<int> sig = {S.natom, S.nup, S.ndn, S.nds[0], S.nds[1], S.ldc[0], S.ldc[1], S.na, S.nb, S.ndet, S.na3, S.nb3};
+  std::vector<int> sig = {S.natom, S.nup, S.ndn, S.nds[0], S.nds[1], S.ldc[0], S.ldc[1], S.na, S.nb, S.ndet, S.na3, S.nb3, S.pbc};
   if (sig != c->shape_sig) {
     c->shape_sig = sig;
     c->N = 0;
@@ -401,6 +497,17 @@ int ensure_state(qmcb_ctx* c, int N) {
   st.bpair = c->b_bpair.p;
   st.gpair = c->b_gpair.p;
   st.agrad = c->b_agrad.p;
+  if (S.pbc) {
+    if (c->b_wrap.ensure((size_t)N * S.ne * 3) || c->b_swrap.ensure((size_t)N * 3) || c->b_monew.ensure((size_t)N * 5 * ldmax) ||
+        c->b_gold.ensure((size_t)N * 3))
+      return -1;
+    cudaMemset(c->b_wrap.p, 0, (size_t)N * S.ne * 3 * 8);
+    cudaMemset(c->b_swrap.p, 0, (size_t)N * 3 * 8);
+  }
+  st.wrap = c->b_wrap.p;
+  st.saved_wrap = c->b_swrap.p;
+  st.monew = c->b_monew.p;
+  st.gold = c->b_gold.p;
   c->N = N;
   c->saved_slot = -1;
   return 0;
@@ -490,18 +597,67 @@ int d2h(qmcb_ctx* c, void* dst, const void* src, size_t bytes) {
   return 0;
 }
 
-int slater_rebuild(qmcb_ctx* c, cudaStream_t stream) {
+// lattice-summed MO rows at a point list (periodic systems): 16 lanes per point, 4 points per CTA
+int launch_pbc_mo(qmcb_ctx* c, int deriv, const PbcMoArgs& a, long long max_points, cudaStream_t stream) {
+  if (max_points <= 0) return 0;
+  constexpr int G = 16, BLOCK = 64;
+  const int nc = deriv == 0 ? 1 : (deriv == 1 ? 4 : 5);
+  const size_t tab = (c->smem_bytes + 15) & ~(size_t)15;
+  const size_t sm = tab + (size_t)(BLOCK / G) * pbc_mo_scratch_doubles(c->S, nc, G) * 8;
+  if (sm > 200 * 1024) return fail("periodic orbital evaluation: shared-memory scratch exceeds 200 KB (nk * nao too large)");
+  const long long grid = std::min<long long>((max_points + (BLOCK / G) - 1) / (BLOCK / G), 148LL * 16);
+  if (deriv == 0) {
+    if (prep_kernel(k_pbc_mo<0, G>, sm)) return -1;
+    k_pbc_mo<0, G><<<(unsigned)grid, BLOCK, sm, stream>>>(c->S, c->st, a);
+  } else if (deriv == 1) {
+    if (prep_kernel(k_pbc_mo<1, G>, sm)) return -1;
+    k_pbc_mo<1, G><<<(unsigned)grid, BLOCK, sm, stream>>>(c->S, c->st, a);
+  } else {
+    if (prep_kernel(k_pbc_mo<2, G>, sm)) return -1;
+    k_pbc_mo<2, G><<<(unsigned)grid, BLOCK, sm, stream>>>(c->S, c->st, a);
+  }
+  c->nlaunch++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// MO value / gradient / Laplacian rows of every electron at its current position -> mocache
+// (and the value rows -> mo_all when write_values)
+int launch_mo_all(qmcb_ctx* c, int write_values, cudaStream_t stream) {
   const Sys& S = c->S;
-  const int N = c->N;
-  {
-    const long long np = (long long)N * S.ne;
+  const long long np = (long long)c->N * S.ne;
+  if (S.pbc) {
+    const int ldmax = std::max(S.ldc[0], S.ldc[1]);
+    PbcMoArgs a{};
+    a.npoints = np;
+    a.pos = c->st.conf;
+    a.wrap = c->st.wrap;
+    a.naip = 1;
+    a.spin_mode = 1;
+    a.out = c->st.mocache;
+    a.stride_p = 5 * ldmax;
+    a.stride_c = ldmax;
+    a.stride_j = 1;
+    if (write_values) {
+      a.out_val = c->st.mo_all;
+      a.stride_vp = ldmax;
+    }
+    if (launch_pbc_mo(c, 2, a, np, stream)) return -1;
+  } else {
     const int block = pick_block(np);
     if (prep_kernel(k_mo_all, c->smem_bytes)) return -1;
-    k_mo_all<<<(unsigned)((np + block - 1) / block), block, c->smem_bytes, stream>>>(S, c->st, 1);
-    c->mocache_valid = true;
+    k_mo_all<<<(unsigned)((np + block - 1) / block), block, c->smem_bytes, stream>>>(S, c->st, write_values);
     c->nlaunch++;
     CK(cudaGetLastError());
   }
+  c->mocache_valid = true;
+  return 0;
+}
+
+int slater_rebuild(qmcb_ctx* c, cudaStream_t stream) {
+  const Sys& S = c->S;
+  const int N = c->N;
+  if (launch_mo_all(c, 1, stream)) return -1;
   for (int s = 0; s < 2; ++s) {
     const int n = s ? S.ndn : S.nup;
     const long long nt = (long long)N * S.nds[s];
@@ -607,6 +763,48 @@ int ensure_energy_scratch(qmcb_ctx* c) {
   es.ratio = nullptr;
   es.count = c->e_count.p;
   es.maxchan = maxchan;
+  if (S.pbc) {
+    const size_t npts = nea * std::max(S.max_naip, 1);
+    if (c->e_ewald.ensure(2 * N) || c->e_ecppos.ensure(npts * 3) || c->e_ecpwrap.ensure(npts * 3)) return -1;
+  }
+  es.ewald = c->e_ewald.p;
+  es.ecp_pos = c->e_ecppos.p;
+  es.ecp_wrap = c->e_ecpwrap.p;
+  return 0;
+}
+
+// periodic systems: pass 0 of k_ecp_points writes the wrapped quadrature points, k_pbc_mo evaluates
+// the orbitals there into the scratch that pass 1 reads (ea is completed for pass 1)
+template <int NMOT>
+int ecp_points_pbc_prepass(qmcb_ctx* c, EcpPointArgs& ea, long long maxpts, long long grid, cudaStream_t stream) {
+  const Sys& S = c->S;
+  ea.pos_out = c->es.ecp_pos;
+  ea.wrap_out = c->es.ecp_wrap;
+  ea.pos_in = nullptr;
+  k_ecp_points<NMOT><<<(unsigned)grid, 128, c->smem_bytes, stream>>>(S, c->st, c->es, ea);
+  c->nlaunch++;
+  CK(cudaGetLastError());
+  if (c->have_slater) {
+    PbcMoArgs a{};
+    a.count = c->es.count;
+    a.per_item = S.max_naip;
+    a.pos = c->es.ecp_pos;
+    a.wrap = c->es.ecp_wrap;
+    a.naip = 1;
+    a.spin_mode = 2;
+    a.work = c->es.work;
+    a.workN = c->N;
+    a.necp = S.necp;
+    a.e_only = ea.e_only;
+    a.out = ea.scr;
+    a.stride_p = 1;
+    a.stride_c = 0;  // value rows only
+    a.stride_j = (long long)ea.scr_stride;
+    if (launch_pbc_mo(c, 0, a, maxpts, stream)) return -1;
+  }
+  ea.pos_out = nullptr;
+  ea.wrap_out = nullptr;
+  ea.pos_in = c->es.ecp_pos;
   return 0;
 }
 
@@ -618,12 +816,9 @@ int launch_energy_t(qmcb_ctx* c, const double* d_u, const double* d_rot, double*
   {
     const long long np = (long long)N * S.ne;
     const int block = pick_block(np);
+    (void)block;
     if (!c->mocache_valid && c->have_slater) {  // protocol-path updates do not maintain the cache
-      if (prep_kernel(k_mo_all, sm)) return -1;
-      k_mo_all<<<(unsigned)((np + block - 1) / block), block, sm, stream>>>(S, c->st, 0);
-      c->nlaunch++;
-      CK(cudaGetLastError());
-      c->mocache_valid = true;
+      if (launch_mo_all(c, 0, stream)) return -1;
     }
     if (prep_kernel(k_kinetic<8>, sm)) return -1;
     k_kinetic<8><<<(unsigned)((np * 8 + 127) / 128), 128, sm, stream>>>(S, c->st, c->es);
@@ -648,13 +843,26 @@ int launch_energy_t(qmcb_ctx* c, const double* d_u, const double* d_rot, double*
     const long long maxpts = nt * S.max_naip;
     const long long grid = std::min<long long>((maxpts + 127) / 128, 148LL * 16);
     if (prep_kernel(k_ecp_points<NMOT>, sm)) return -1;
+    if (S.pbc) {
+      if (ecp_points_pbc_prepass<NMOT>(c, ea, maxpts, grid, stream)) return -1;
+    }
     k_ecp_points<NMOT><<<(unsigned)grid, 128, sm, stream>>>(S, c->st, c->es, ea);
+    c->nlaunch++;
+    CK(cudaGetLastError());
+  }
+  if (S.pbc) {
+    if (!c->have_ewald) return fail("periodic energy: qmcb_set_ewald has not been called");
+    const size_t tab = (sm + 15) & ~(size_t)15;
+    const size_t esm = tab + (size_t)(3 * S.ne + 16) * 8;
+    if (prep_kernel(k_ewald, esm)) return -1;
+    k_ewald<<<(unsigned)N, 128, esm, stream>>>(S, c->st, c->es.ewald);
     c->nlaunch++;
     CK(cudaGetLastError());
   }
   {
     const int ne = S.ne;
     int scr = std::max(std::max(ne * std::max(S.necp, 1), ne * (ne - 1) / 2), S.natom * ne);
+    if (S.pbc) scr = ne * std::max(S.necp, 1);  // the Coulomb terms come from k_ewald
     scr = (scr + 1) & ~1;
     const size_t tab = (sm + 15) & ~(size_t)15;
     const size_t fsm = tab + (size_t)(128 / 8) * scr * 8;
@@ -715,6 +923,9 @@ void qmcb_destroy(qmcb_ctx* c) {
                         &c->d_rot, &c->d_gauss, &c->d_unif, &c->d_energy, &c->d_esum, &c->e_ke, &c->e_g2, &c->e_loc,
                         &c->e_vls, &c->e_contrib};
   for (auto* b : dd) b->release();
+  DBuf<double>* pb[] = {&c->d_ewdisp, &c->d_ewg, &c->d_ewion, &c->b_wrap, &c->b_swrap, &c->b_monew, &c->b_gold, &c->d_pwrap,
+                        &c->e_ewald, &c->e_ecppos, &c->e_ecpwrap};
+  for (auto* b : pb) b->release();
   for (int s = 0; s < 2; ++s) {
     c->b_inv[s].release();
     c->b_dsign[s].release();
@@ -881,14 +1092,106 @@ int qmcb_set_ecp(qmcb_ctx* c, int necp, const int32_t* ecp_atom, const int32_t* 
   return 0;
 }
 
+int qmcb_set_lattice(qmcb_ctx* c, const double* lat, int mode, const double* shifts) {
+  if (mode < 1 || mode > 3) return fail("minimal-image mode must be 1 (diagonal), 2 (orthogonal) or 3 (general)");
+  c->lat.assign(lat, lat + 9);
+  c->shifts.assign(shifts, shifts + 81);
+  c->pbc_mode = mode;
+  c->dirty = true;
+  return 0;
+}
+
+int qmcb_set_pbc_orbitals(qmcb_ctx* c, int nbatom, const double* bxyz, const double* lprim, const double* smat, int nk,
+                          const double* kpts, int nL, const double* Ls, const int32_t* num_Ls,
+                          const double* atom_cutoff, int nshell, const double* l_cutoff, const double* phases,
+                          int nmo_up, const int32_t* mo_k_up, int nmo_dn, const int32_t* mo_k_dn, int isgamma) {
+  if (!c->pbc_mode) return fail("qmcb_set_lattice must be called before qmcb_set_pbc_orbitals");
+  if (nk < 1 || nL < 1 || nbatom < 1) return fail("qmcb_set_pbc_orbitals: empty k-point / image / atom list");
+  c->bxyz.assign(bxyz, bxyz + 3 * nbatom);
+  c->lprim.assign(lprim, lprim + 9);
+  c->smat.assign(smat, smat + 9);
+  c->nk = nk;
+  c->kpts.assign(kpts, kpts + 3 * nk);
+  c->nL = nL;
+  c->Ls.assign(Ls, Ls + 3 * nL);
+  c->numLs.assign(num_Ls, num_Ls + nbatom);
+  for (int v : c->numLs)
+    if (v < 1 || v > nL) return fail("qmcb_set_pbc_orbitals: num_Ls out of range");
+  c->atomcut.assign(atom_cutoff, atom_cutoff + nbatom);
+  c->lcut.assign(l_cutoff, l_cutoff + nshell);
+  c->phases.assign(phases, phases + (size_t)nL * nk);
+  c->mok[0].assign(mo_k_up, mo_k_up + nmo_up);
+  c->mok[1].assign(mo_k_dn, mo_k_dn + nmo_dn);
+  for (int s = 0; s < 2; ++s)
+    for (int v : c->mok[s])
+      if (v < 0 || v >= nk) return fail("qmcb_set_pbc_orbitals: k-point index out of range");
+  c->isgamma = isgamma ? 1 : 0;
+  c->have_pbc_orb = true;
+  c->dirty = true;
+  return 0;
+}
+
+int qmcb_set_ewald(qmcb_ctx* c, double alpha, int ndisp, const double* disp, int nG, const double* gpoints,
+                   const double* gweight, const double* ion_re, const double* ion_im, double ijconst,
+                   double squareconst, double i_sum, double e_ii) {
+  Guard g(c);
+  if (!c->pbc_mode) return fail("qmcb_set_lattice must be called before qmcb_set_ewald");
+  std::vector<double> gt((size_t)std::max(nG, 1) * 4, 0.0), ion((size_t)std::max(nG, 1) * 2, 0.0);
+  for (int i = 0; i < nG; ++i) {
+    gt[4 * i] = gpoints[3 * i];
+    gt[4 * i + 1] = gpoints[3 * i + 1];
+    gt[4 * i + 2] = gpoints[3 * i + 2];
+    gt[4 * i + 3] = gweight[i];
+    ion[2 * i] = ion_re[i];
+    ion[2 * i + 1] = ion_im[i];
+  }
+  if (c->d_ewdisp.ensure((size_t)std::max(ndisp, 1) * 3) || c->d_ewg.ensure(gt.size()) || c->d_ewion.ensure(ion.size())) return -1;
+  CK(cudaMemcpy(c->d_ewdisp.p, disp, (size_t)ndisp * 3 * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_ewg.p, gt.data(), gt.size() * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_ewion.p, ion.data(), ion.size() * 8, cudaMemcpyHostToDevice));
+  c->ew_alpha = alpha;
+  c->ew_ndisp = ndisp;
+  c->ew_nG = nG;
+  c->ew_ij = ijconst;
+  c->ew_sq = squareconst;
+  c->ew_isum = i_sum;
+  c->ew_eii = e_ii;
+  c->have_ewald = true;
+  c->dirty = true;
+  return 0;
+}
+
+int qmcb_set_point_wrap(qmcb_ctx* c, const double* wrap, int64_t count) {
+  Guard g(c);
+  if (count <= 0 || !wrap) {
+    c->pending_wrap = false;
+    return 0;
+  }
+  if (c->d_pwrap.ensure((size_t)count * 3)) return -1;
+  if (h2d(c, c->d_pwrap.p, wrap, (size_t)count * 3 * 8)) return -1;
+  c->pending_wrap = true;
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------
 int qmcb_recompute(qmcb_ctx* c, int which, int nconf, const double* configs, double* sign, double* logval) {
+  return qmcb_recompute_pbc(c, which, nconf, configs, nullptr, sign, logval);
+}
+
+int qmcb_recompute_pbc(qmcb_ctx* c, int which, int nconf, const double* configs, const double* wrap, double* sign,
+                       double* logval) {
   Guard g(c);
   if (which_ok(c, which)) return -1;
   if (ensure_state(c, nconf)) return -1;
   const Sys& S = c->S;
   const size_t nel = (size_t)nconf * S.ne * 3;
   if (c->d_in.ensure(nel) || c->d_out.ensure((size_t)nconf * 8)) return -1;
+  if (S.pbc) {
+    if (wrap) {
+      if (h2d(c, c->st.wrap, wrap, nel * 8)) return -1;
+    } else
+      CK(cudaMemsetAsync(c->st.wrap, 0, nel * 8, c->stream));
+  }
   if (h2d(c, c->d_in.p, configs, nel * 8)) return -1;
   k_conf_in<<<(unsigned)((nel + 255) / 256), 256, 0, c->stream>>>(c->d_in.p, c->st.conf, nconf, S.ne);
   c->nlaunch++;
@@ -933,6 +1236,27 @@ int qmcb_value(qmcb_ctx* c, int which, double* sign, double* logval) {
   return 0;
 }
 
+// periodic systems: lattice-summed MO rows of electron e's spin at the points of a protocol call,
+// in the scratch layout slater_point_general reads (scr[(c * ldc + j) * stride + p])
+static int pbc_point_rows(qmcb_ctx* c, int deriv, int e, const double* d_pos, const double* d_wrap, const int* d_idx,
+                          int naip, long long npoints, size_t stride, cudaStream_t stream) {
+  const Sys& S = c->S;
+  const int s = e >= S.nup ? 1 : 0;
+  PbcMoArgs a{};
+  a.npoints = npoints;
+  a.pos = d_pos;
+  a.wrap = d_wrap;
+  a.idx = d_idx;
+  a.naip = naip;
+  a.spin_mode = 0;
+  a.spin = s;
+  a.out = c->d_scr.p;
+  a.stride_p = 1;
+  a.stride_c = (long long)S.ldc[s] * (long long)stride;
+  a.stride_j = (long long)stride;
+  return launch_pbc_mo(c, deriv, a, npoints, stream);
+}
+
 static int point_call(qmcb_ctx* c, int mode, int which, int e, const double* epos, int naip, const uint8_t* mask,
                       double* o1, double* o2, int64_t* slot) {
   Guard g(c);
@@ -972,6 +1296,12 @@ static int point_call(qmcb_ctx* c, int mode, int which, int e, const double* epo
   if (ensure_scratch(c, pa.npoints, 5)) return -1;
   pa.scr = c->d_scr.p;
   pa.scr_stride = std::max(pa.npoints, 1);
+  const double* d_pwrap = c->pending_wrap ? c->d_pwrap.p : nullptr;
+  c->pending_wrap = false;
+  if (S.pbc && (which & 1)) {
+    const int deriv = mode == PV_VALUE ? 0 : (mode == PV_GRADLAP ? 2 : 1);
+    if (pbc_point_rows(c, deriv, e, c->d_in.p, d_pwrap, pa.idx, naip, pa.npoints, pa.scr_stride, c->stream)) return -1;
+  }
   int rc = 0;
   switch (mode) {
     case PV_VALUE: rc = launch_point<PV_VALUE>(c, pa, c->stream); break;
@@ -980,6 +1310,12 @@ static int point_call(qmcb_ctx* c, int mode, int which, int e, const double* epo
     default: rc = launch_point<PV_GRADLAP>(c, pa, c->stream); break;
   }
   if (rc) return rc;
+  if (save && S.pbc) {
+    if (d_pwrap)
+      CK(cudaMemcpyAsync(c->st.saved_wrap, d_pwrap, N * 3 * 8, cudaMemcpyDeviceToDevice, c->stream));
+    else
+      CK(cudaMemsetAsync(c->st.saved_wrap, 0, N * 3 * 8, c->stream));
+  }
   if (save) {
     c->saved_slot = ++c->slot_counter;
     c->saved_e = e;
@@ -1038,8 +1374,13 @@ int qmcb_testvalue_many(qmcb_ctx* c, int which, int ne_list, const int32_t* elis
     pa.idx = c->d_idx.p;
   }
   if (ensure_scratch(c, nm, 5)) return -1;
+  const double* d_pwrap = c->pending_wrap ? c->d_pwrap.p : nullptr;
+  c->pending_wrap = false;
   for (int i = 0; i < ne_list; ++i) {
     if (elist[i] < 0 || elist[i] >= S.ne) return fail("electron index out of range");
+    if (S.pbc && (which & 1) &&
+        pbc_point_rows(c, 0, elist[i], c->d_in.p, d_pwrap, pa.idx, 1, (long long)nm, std::max<size_t>(nm, 1), c->stream))
+      return -1;
     pa.which = which;
     pa.e = elist[i];
     pa.naip = 1;
@@ -1090,10 +1431,19 @@ int qmcb_updateinternals(qmcb_ctx* c, int which, int e, const double* epos, cons
       if (ensure_scratch(c, N, 5)) return -1;
       pa.scr = c->d_scr.p;
       pa.scr_stride = N;
+      if (S.pbc && pbc_point_rows(c, 0, e, c->d_in.p, c->pending_wrap ? c->d_pwrap.p : nullptr, nullptr, 1, (long long)N, N, c->stream))
+        return -1;
       if (launch_point<PV_MOSAVE>(c, pa, c->stream)) return -1;
     }
     CK(cudaMemcpyAsync(c->st.saved_pos, c->d_in.p, N * 3 * 8, cudaMemcpyDeviceToDevice, c->stream));
+    if (S.pbc) {
+      if (c->pending_wrap)
+        CK(cudaMemcpyAsync(c->st.saved_wrap, c->d_pwrap.p, N * 3 * 8, cudaMemcpyDeviceToDevice, c->stream));
+      else
+        CK(cudaMemsetAsync(c->st.saved_wrap, 0, N * 3 * 8, c->stream));
+    }
   }
+  c->pending_wrap = false;
   if (launch_update(c, which, e, d_mask, c->stream)) return -1;
   if (which & 1) c->mocache_valid = false;
   c->paircache_valid = false;
@@ -1130,6 +1480,10 @@ int qmcb_get_state(qmcb_ctx* c, const char* name, double* out) {
     std::memcpy(out, h.data(), nd * 8);
     if (fetch(c->st.dlog[s], nd, h)) return -1;
     std::memcpy(out + nd, h.data(), nd * 8);
+  } else if (k == "wrap") {
+    if (!S.pbc) return fail("wrap vectors exist only for periodic systems");
+    if (fetch(c->st.wrap, N * S.ne * 3, h)) return -1;
+    std::memcpy(out, h.data(), h.size() * 8);
   } else if (k == "configs") {
     if (fetch(c->st.conf, N * S.ne * 3, h)) return -1;
     std::memcpy(out, h.data(), h.size() * 8);
@@ -1289,6 +1643,7 @@ int qmcb_tmoves(qmcb_ctx* c, int e, double tau, const double* ecp_u, const doubl
     if (!rc) k_ecp_points<8><<<(unsigned)grid, 128, sm, c->stream>>>(S, c->st, c->es, ea);
   } else {
     rc = prep_kernel(k_ecp_points<0>, sm);
+    if (!rc && S.pbc) rc = ecp_points_pbc_prepass<0>(c, ea, (long long)npts, grid, c->stream);
     if (!rc) k_ecp_points<0><<<(unsigned)grid, 128, sm, c->stream>>>(S, c->st, c->es, ea);
   }
   if (rc) return rc;
@@ -1344,8 +1699,14 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
   const int sweep_warps = 4;
   const int sweep_walkers = sweep_warps * (32 / G);
   const size_t sweep_smem = tab + (size_t)sweep_walkers * CL.total * 8;
-  const bool use_sweep = (!c->have_slater || S.ndet == 1) && !c->have_j3 && sweep_smem <= 200 * 1024 &&
+  const bool use_sweep = (!c->have_slater || S.ndet == 1) && !c->have_j3 && sweep_smem <= 200 * 1024 && !S.pbc &&
                          std::getenv("QMCB_NO_SWEEP") == nullptr;
+  const bool use_pbc = S.pbc != 0;
+  if (use_pbc && ((c->have_slater && S.ndet != 1) || c->have_j3))
+    return fail("device-resident periodic VMC supports single-determinant Slater-Jastrow wave functions; "
+                "drive other periodic wave functions through the per-call protocol");
+  if (use_pbc && c->have_slater && !c->mocache_valid)
+    if (launch_mo_all(c, 0, stream)) return -1;
   if (use_sweep && c->have_slater && !c->mocache_valid) {
     const long long np = (long long)N * S.ne;
     const int block = pick_block(np);
@@ -1386,7 +1747,60 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
       c->nlaunch++;
       CK(cudaGetLastError());
     }
-    for (int e = 0; e < S.ne && !use_sweep; ++e) {
+    for (int e = 0; e < S.ne && use_pbc; ++e) {
+      const size_t se = (size_t)step * S.ne + e;
+      const int s = e >= S.nup ? 1 : 0;
+      const int ldmax = std::max(S.ldc[0], S.ldc[1]);
+      PbcMoveArgs ma{};
+      ma.e = e;
+      ma.tstep = tstep;
+      ma.gauss = d_gauss + se * N * 3;
+      ma.unif = d_unif + se * N;
+      ma.accept = d_accept ? d_accept + se * N : c->d_accept.p;
+      ma.nacc = nacc + se;
+      const unsigned wgrid = (unsigned)((N * 32 + 127) / 128);
+      if (prep_kernel(k_pbc_propose, c->smem_bytes)) return -1;
+      k_pbc_propose<<<wgrid, 128, c->smem_bytes, stream>>>(S, c->st, ma);
+      c->nlaunch++;
+      CK(cudaGetLastError());
+      if (c->have_slater) {
+        PbcMoArgs a{};
+        a.npoints = (long long)N;
+        a.pos = c->st.saved_pos;
+        a.wrap = c->st.saved_wrap;
+        a.naip = 1;
+        a.spin_mode = 0;
+        a.spin = s;
+        a.out = c->st.monew;
+        a.stride_p = 5 * ldmax;
+        a.stride_c = ldmax;
+        a.stride_j = 1;
+        if (launch_pbc_mo(c, 2, a, (long long)N, stream)) return -1;
+      }
+      const int jper = ((S.ne > 1 ? S.ne - 1 : 0) * S.nb + 1) & ~1;
+      const size_t asm_ = ((c->smem_bytes + 15) & ~(size_t)15) + (size_t)4 * jper * 8;
+      if (prep_kernel(k_pbc_accept, asm_)) return -1;
+      k_pbc_accept<<<wgrid, 128, asm_, stream>>>(S, c->st, ma);
+      c->nlaunch++;
+      CK(cudaGetLastError());
+      if (c->have_slater) {
+        SmArgs sa{};
+        sa.n = s ? S.ndn : S.nup;
+        sa.e = e - s * S.nup;
+        sa.nds = 1;
+        sa.vec_stride = 5 * ldmax;
+        sa.nmat = (long long)N;
+        sa.inv = c->st.inv[s];
+        sa.vec = c->st.monew;
+        sa.occ = S.iblob + S.o_occ[s];
+        sa.mask = ma.accept;
+        sa.dsign = c->st.dsign[s];
+        sa.dlog = c->st.dlog[s];
+        if (launch_sm(c, sa, stream, &c->nlaunch)) return -1;
+      }
+      c->paircache_valid = false;
+    }
+    for (int e = 0; e < S.ne && !use_sweep && !use_pbc; ++e) {
       const size_t se = (size_t)step * S.ne + e;
       MoveArgs ma{};
       ma.e = e;

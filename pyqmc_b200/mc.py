@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _lib
 from .accumulators import KEYS, EnergyAccumulator, _device_context
-from .coord import OpenConfigs
+from .coord import OpenConfigs, PeriodicConfigs
 
 
 def initial_guess(mol, nconfig, r=1.0):
@@ -38,7 +38,7 @@ def initial_guess(mol, nconfig, r=1.0):
             epos[:, ind0 + nassigned : ind0 + mol.nelec[s], :] = coords[inds]
     epos += r * np.random.randn(*epos.shape)
     if hasattr(mol, "a"):
-        raise NotImplementedError("periodic systems are not supported by the B200 backend yet")
+        return PeriodicConfigs(epos, mol.lattice_vectors())
     return OpenConfigs(epos)
 
 
@@ -182,6 +182,8 @@ def vmc_block_device(wf, configs, tstep, nsteps, accumulators, variates=None, re
             nacc.ctypes.data_as(_lib.c_i64_p)))
     end = time.perf_counter()
     configs.configs[...] = buffers.newconf
+    if ctx.periodic:
+        configs.wrap[...] = ctx.get_state("wrap", configs.wrap.shape)
     block_avg = {}
     for step in range(nsteps):
         if accumulator is not None:

@@ -69,6 +69,13 @@ class DeviceContext:
         self.nelec = tuple(int(x) for x in mol.nelec)
         self.ecp_key = None
         self.has_basis = False
+        self.periodic = hasattr(mol, "a")
+        if self.periodic:
+            from . import pbc
+
+            lat = _lib.f64(mol.lattice_vectors())
+            mode, shifts = pbc.minimal_image_tables(lat)
+            _lib.check(self.lib.qmcb_set_lattice(h, _lib.dptr(lat), mode, _lib.dptr(_lib.f64(shifts))))
 
     def __del__(self):
         try:
@@ -81,7 +88,8 @@ class DeviceContext:
     def set_basis(self):
         if self.has_basis:
             return
-        t = _basis.shell_tables(self.mol)
+        # periodic systems: the orbitals live on the primitive cell (orbitals.py:141, 201)
+        t = _basis.shell_tables(self.mol.original_cell if self.periodic else self.mol)
         self.nao = t["nao"]
         _lib.check(self.lib.qmcb_set_basis(self.h, len(t["shell_l"]), _lib.iptr(t["shell_atom"]),
                                            _lib.iptr(t["shell_l"]), _lib.iptr(t["prim_off"]),
@@ -89,11 +97,16 @@ class DeviceContext:
         self.has_basis = True
 
     # ---- protocol calls -----------------------------------------------------------------
-    def recompute(self, which, configs):
+    def recompute(self, which, configs, wrap=None):
         c = _lib.f64(configs)
         n = c.shape[0]
         sign, logv = np.empty(n), np.empty(n)
-        _lib.check(self.lib.qmcb_recompute(self.h, which, n, _lib.dptr(c), _lib.dptr(sign), _lib.dptr(logv)))
+        if self.periodic:
+            wr = None if wrap is None else _lib.f64(wrap)
+            _lib.check(self.lib.qmcb_recompute_pbc(self.h, which, n, _lib.dptr(c), _lib.dptr(wr), _lib.dptr(sign),
+                                                   _lib.dptr(logv)))
+        else:
+            _lib.check(self.lib.qmcb_recompute(self.h, which, n, _lib.dptr(c), _lib.dptr(sign), _lib.dptr(logv)))
         self.nconf = n
         return sign, logv
 
@@ -107,6 +120,15 @@ class DeviceContext:
         want = (self.nconf, 3) if naip == 1 and p.ndim == 2 else (self.nconf, naip, 3)
         if p.shape != want:
             raise ValueError(f"electron positions have shape {p.shape}, expected {want}")
+        if self.periodic:  # PeriodicElectron.wrap travels with the positions (coord.py:115-134)
+            wrap = getattr(epos, "wrap", None)
+            if wrap is not None:
+                wr = _lib.f64(wrap)
+                if wr.shape != p.shape:
+                    raise ValueError(f"wrap vectors have shape {wr.shape}, expected {p.shape}")
+                _lib.check(self.lib.qmcb_set_point_wrap(self.h, _lib.dptr(wr), wr.size // 3))
+            else:
+                _lib.check(self.lib.qmcb_set_point_wrap(self.h, None, 0))
         return p
 
     def gradient(self, which, e, epos):
@@ -245,7 +267,7 @@ class _DeviceFactor:
 
     # ---- the wf protocol ------------------------------------------------------------------
     def recompute(self, configs):
-        return self._sync().recompute(self._which, configs.configs)
+        return self._sync().recompute(self._which, configs.configs, getattr(configs, "wrap", None))
 
     def value(self):
         return self._ctx.value(self._which)
@@ -280,8 +302,6 @@ class Slater(_DeviceFactor):
 
     def __init__(self, mol, mf, mc=None, tol=None, twist=0, determinants=None,
                  eval_gto_precision=None, evaluate_orbitals_with="b200", device=None):
-        if hasattr(mol, "a"):
-            raise NotImplementedError("periodic systems are not supported by the B200 backend yet")
         if mc is not None and determinants is None:
             raise NotImplementedError("pass determinants=[(weight, [occ_up, occ_dn]), ...]; "
                                       "reading pyscf CI objects needs pyscf")
@@ -290,6 +310,10 @@ class Slater(_DeviceFactor):
         self._nelec = tuple(int(x) for x in mol.nelec)
         self._device = device
         self._ctx = None
+        self._pbc = None
+        if hasattr(mol, "a"):
+            self._init_periodic(mol, mf, determinants, twist, eval_gto_precision)
+            return
         if determinants is None:
             determinants = _single_determinant(mf)
         try:
@@ -317,11 +341,76 @@ class Slater(_DeviceFactor):
             "mo_coeff_beta": np.array(mo[1][:, : top[1]], dtype=float),
         }
 
+    def _init_periodic(self, mol, mf, determinants, twist, eval_gto_precision):
+        """Bloch orbitals on a supercell: k-points of the twist, per-k MO blocks concatenated,
+        determinant lists flattened over k (pyscftools.py:140-186, determinant_tools.py:92-106) and the
+        image / cutoff / phase tables of the reference's in-tree evaluator (pbcgto.py:594-621)."""
+        from . import pbc
+
+        if not hasattr(mol, "original_cell"):
+            mol = pbc.get_supercell(mol, np.eye(3, dtype=int))
+            self._mol = mol
+        try:
+            mfu = mf.to_uhf()
+        except TypeError:
+            mfu = mf.to_uhf(mf)
+        kinds = pbc.create_supercell_twists(mol, mfu)["primitive_ks"][twist]
+        if len(kinds) != mol.scale:
+            raise ValueError(f"Found {len(kinds)} k-points but should have found {mol.scale}.")
+        if determinants is None:
+            determinants = [(1.0, [[list(np.nonzero(np.asarray(k) > 0.5)[0]) for k in s] for s in mfu.mo_occ])]
+
+        def f_max_orb(a):
+            return int(np.max(a, initial=0)) + 1 if len(a) > 0 else 0
+
+        max_orb = np.amax([[[f_max_orb(k) for k in s] for s in det] for _, det in determinants], axis=0)
+        blocks = [[np.asarray(mfu.mo_coeff[s][k])[:, 0:max_orb[s][k]] for k in kinds] for s in (0, 1)]
+        offs = np.cumsum(max_orb[:, kinds], axis=1)
+        offs = np.pad(offs[:, :-1], ((0, 0), (1, 0)))
+        flat = []
+        for wt, det in determinants:
+            fd = [list(np.concatenate([np.asarray(det_s[k], dtype=int) + off_s[ki] for ki, k in enumerate(kinds)]).astype(int))
+                  for det_s, off_s in zip(det, offs)]
+            flat.append((wt, fd))
+        coeff, self._det_occup, self._det_map = _pack_determinants(flat, self.tol)
+        for s in (0, 1):
+            for o in self._det_occup[s]:
+                if len(o) != self._nelec[s]:
+                    raise AssertionError(
+                        f"disagreement between number of electrons and number of orbitals: "
+                        f"{self._nelec[s]} electrons and {len(o)} orbitals")
+        mo = [np.concatenate(blocks[s], axis=1) for s in (0, 1)]
+        if np.iscomplexobj(mo[0]) or np.iscomplexobj(mo[1]):
+            raise NotImplementedError("complex orbitals are not supported by the B200 backend yet")
+        kpts = np.asarray(mfu.kpts)[kinds].reshape(-1, 3)
+        tables = pbc.image_tables(mol.original_cell, kpts, eval_gto_precision)
+        if np.iscomplexobj(tables["phases"]):
+            raise NotImplementedError("k-points with complex Bloch phases (general twists) are not supported "
+                                      "by the B200 backend yet")
+        self._pbc = dict(
+            kpts=kpts, tables=tables, isgamma=bool(np.abs(kpts).sum() < 1e-9),
+            mo_k=[np.concatenate([np.full(b.shape[1], ki, dtype=np.int32) for ki, b in enumerate(blocks[s])]
+                                 or [np.zeros(0, dtype=np.int32)]) for s in (0, 1)])
+        self.parameters = {"det_coeff": coeff, "mo_coeff_alpha": np.array(mo[0], dtype=float),
+                           "mo_coeff_beta": np.array(mo[1], dtype=float)}
+
     def _copy_parameters(self):
         return {k: np.array(v) for k, v in self.parameters.items()}
 
     def _push_static(self, ctx):
         ctx.set_basis()
+        if self._pbc is not None:
+            cell = self._mol.original_cell
+            t = self._pbc["tables"]
+            bxyz, lprim = _lib.f64(cell.atom_coords()), _lib.f64(cell.lattice_vectors())
+            smat, kpts = _lib.f64(self._mol.S), _lib.f64(self._pbc["kpts"])
+            Ls, ncut, acut = _lib.f64(t["Ls"]), _lib.i32(t["num_Ls"]), _lib.f64(t["atom_cutoff"])
+            lcut, ph = _lib.f64(t["l_cutoff"]), _lib.f64(np.real(t["phases"]))
+            mk = [_lib.i32(m) for m in self._pbc["mo_k"]]
+            _lib.check(ctx.lib.qmcb_set_pbc_orbitals(
+                ctx.h, len(bxyz), _lib.dptr(bxyz), _lib.dptr(lprim), _lib.dptr(smat), len(kpts), _lib.dptr(kpts),
+                len(Ls), _lib.dptr(Ls), _lib.iptr(ncut), _lib.dptr(acut), len(lcut), _lib.dptr(lcut), _lib.dptr(ph),
+                len(mk[0]), _lib.iptr(mk[0]), len(mk[1]), _lib.iptr(mk[1]), 1 if self._pbc["isgamma"] else 0))
 
     def _push_parameters(self, ctx):
         p = self.parameters
@@ -342,6 +431,8 @@ class Slater(_DeviceFactor):
         ctx = self._ctx
         N = ctx.nconf
         p = self.parameters
+        if self._pbc is not None:
+            raise NotImplementedError("parameter gradients of periodic Slater wave functions")
         shapes = {"det_coeff": (N, len(p["det_coeff"])),
                   "mo_coeff_alpha": (N,) + p["mo_coeff_alpha"].shape,
                   "mo_coeff_beta": (N,) + p["mo_coeff_beta"].shape}
@@ -377,8 +468,6 @@ class JastrowSpin(_DeviceFactor):
     _which = JASTROW
 
     def __init__(self, mol, a_basis, b_basis, device=None):
-        if hasattr(mol, "a"):
-            raise NotImplementedError("periodic systems are not supported by the B200 backend yet")
         self._mol = mol
         self._nelec = tuple(int(x) for x in mol.nelec)
         self._device = device
@@ -578,7 +667,7 @@ class MultiplyWF:
             ctx = self._ensure_ctx()
             for f in self.wf_factors:
                 f._push_parameters(ctx)
-            return ctx.recompute(self._which, configs.configs)
+            return ctx.recompute(self._which, configs.configs, getattr(configs, "wrap", None))
         signs, vals = np.ones(len(configs.configs)), np.zeros(len(configs.configs))
         for wf in self.wf_factors:
             s, v = wf.recompute(configs)

@@ -40,7 +40,10 @@ def default_jastrow_basis(mol, ion_cusp=False, na=4, nb=3, rcut=None, cusp_gamma
     if cusp_gamma is None:
         cusp_gamma = 24
     if rcut is None:
-        rcut = 7.5
+        if hasattr(mol, "a"):  # inscribed radius of the simulation cell (wftools.py:82-83)
+            rcut = np.amin(np.pi / np.linalg.norm(mol.reciprocal_vectors(), axis=1))
+        else:
+            rcut = 7.5
     abasis = [func3d.CutoffCuspFunction(gamma=cusp_gamma, rcut=rcut)] if ion_cusp else []
     abasis += [func3d.PolyPadeFunction(beta=b, rcut=rcut) for b in expand_beta_qwalk(beta_a, na)]
     bbasis = [func3d.CutoffCuspFunction(gamma=cusp_gamma, rcut=rcut)]

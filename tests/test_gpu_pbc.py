@@ -1,0 +1,126 @@
+"""GPU parity for periodic systems: the CUDA path against the reference's golden vectors
+(tests/golden/{ortho,rotcubic,diamond211}.npz: the three minimal-image modes, two k-points with
+the wrap phase, Ewald energy, stochastic ECP, VMC accept masks) and against the numpy oracle."""
+import numpy as np
+import pytest
+
+import golden_replay
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+PBC_SYSTEMS = ["ortho", "rotcubic", "diamond211"]
+EWALD_GMAX = 10  # as in tests/golden/make_golden.py
+
+
+def periodic_configs(data, mol, key="configs0", wkey="wrap0"):
+    import pyqmc_b200 as pq
+
+    c = pq.PeriodicConfigs(data[key].copy(), mol.lattice_vectors())
+    c.configs = data[key].copy()
+    c.wrap = data[wkey].copy()
+    return c
+
+
+def device_vmc(wf, configs, accumulators):
+    from pyqmc_b200 import mc
+
+    rows, accepts = [], []
+    for block in range(2):
+        avg, configs, data = mc.vmc_block_device(wf, configs, 0.5, 3, accumulators, return_walker_data=True)
+        rows.append(avg)
+        accepts.append(data["accept"])
+    df = {k: np.asarray([r[k] for r in rows]) for k in rows[0]}
+    return df, configs, np.array(accepts)
+
+
+def check_internal(wf, data):
+    sl, ja = wf.wf_factors[:2]
+    for s in (0, 1):
+        assert helpers.relerr(sl._inverse[s], data[f"inverse{s}"]) < 1e-9
+        assert np.array_equal(sl._dets[s][0], data[f"dets{s}"][0])
+        assert np.abs(sl._dets[s][1] - data[f"dets{s}"][1]).max() < 1e-10
+    assert helpers.relerr(ja._a_partial, data["a_partial"]) < 1e-10
+    assert helpers.relerr(ja._b_partial, data["b_partial"]) < 1e-10
+
+
+@pytest.mark.parametrize("name", PBC_SYSTEMS)
+def test_cuda_reproduces_reference_golden_periodic(lib, name):
+    import pyqmc_b200 as pq
+
+    data = golden_replay.load(name)
+    mol, mf, wf, _ = helpers.make_pair(name, seed=1)
+    assert np.array_equal(wf.parameters["wf2acoeff"], data["acoeff"])
+    configs = periodic_configs(data, mol)
+    golden_replay.replay(data, wf, configs, lambda: pq.EnergyAccumulator(mol, ewald_gmax=EWALD_GMAX), device_vmc,
+                         check_internal)
+
+
+@pytest.mark.parametrize("name", PBC_SYSTEMS)
+def test_periodic_per_call_vmc_equals_device_resident_block(lib, name):
+    """The reference driver loop over the protocol calls and the device-resident periodic block
+    consume the same variates and must accept the same moves."""
+    import pyqmc_b200 as pq
+    from pyqmc_b200 import mc
+
+    mol, mf, wf, _ = helpers.make_pair(name, seed=1)
+    np.random.seed(11)
+    c1 = pq.initial_guess(mol, 40)
+    c2 = c1.copy()
+    acc = {"energy": pq.EnergyAccumulator(mol, ewald_gmax=EWALD_GMAX)}
+    np.random.seed(12)
+    avg1, c1 = mc.vmc_block_device(wf, c1, 0.4, 2, acc)
+    mol2, mf2, wf2, _ = helpers.make_pair(name, seed=1)
+
+    class Plain:  # hides the device accumulator type so vmc_worker takes the per-call loop
+        def __init__(self, a):
+            self.a = a
+
+        def avg(self, configs, wf):
+            return self.a.avg(configs, wf)
+
+    np.random.seed(12)
+    avg2, c2 = mc.vmc_worker(wf2, c2, 0.4, 2, {"energy": Plain(pq.EnergyAccumulator(mol2, ewald_gmax=EWALD_GMAX))})
+    assert avg1["acceptance"] == avg2["acceptance"]
+    assert np.abs(c1.configs - c2.configs).max() < 1e-9
+    assert np.array_equal(c1.wrap, c2.wrap)
+    for k in ("energytotal", "energyke", "energyee", "energyei", "energyecp"):
+        assert abs(avg1[k] - avg2[k]) <= 1e-9 * max(1.0, abs(avg2[k])), k
+
+
+def test_diamond_supercell_against_oracle(lib):
+    """Config C4 shape (2x2x2 diamond, 64 electrons, 8 k-points, n = 32 Sherman-Morrison) at a few
+    walkers: protocol calls and the energy against the numpy oracle."""
+    import pyqmc_b200 as pq
+    from oracle.local_energy import EnergyOracle
+
+    mol, mf, wf, orc = helpers.make_pair("diamond222", seed=1)
+    np.random.seed(3)
+    configs = pq.initial_guess(mol, 6)
+    oc = helpers.to_oracle_walkers(configs)
+    s, l = wf.recompute(configs)
+    so, lo = orc.recompute(oc)
+    assert np.array_equal(s, so)
+    assert np.abs(l - lo).max() < 1e-9 * max(1.0, np.abs(lo).max())
+    rng = np.random.RandomState(4)
+    for e in (0, 31, 40, 63):
+        new = configs.configs[:, e] + 0.3 * rng.randn(6, 3)
+        ep, eo = configs.make_irreducible(e, new.copy()), oc.make_irreducible(e, new.copy())
+        g, v, saved = wf.gradient_value(e, ep)
+        go, vo, savedo = orc.gradient_value(e, eo)
+        assert helpers.relerr(g, go) < 1e-8 and helpers.relerr(v, vo) < 1e-8
+        gl, lap = wf.gradient_laplacian(e, ep)
+        glo, lapo = orc.gradient_laplacian(e, eo)
+        assert helpers.relerr(lap, lapo) < 1e-8
+        mask = rng.rand(6) > 0.4
+        wf.updateinternals(e, ep, configs, mask=mask, saved_values=saved)
+        orc.updateinternals(e, eo, oc, mask=mask, saved_values=savedo)
+        configs.move(e, ep, mask)
+        oc.move(e, eo, mask)
+        assert np.abs(wf.value()[1] - orc.value()[1]).max() < 1e-8 * max(1.0, np.abs(lo).max())
+    np.random.seed(9)
+    en = pq.EnergyAccumulator(mol, ewald_gmax=EWALD_GMAX)(configs, wf)
+    np.random.seed(9)
+    eno = EnergyOracle(mol, ewald_gmax=EWALD_GMAX)(oc, orc)
+    for k in ("ke", "ee", "ei", "ecp", "total"):
+        assert helpers.relerr(en[k], eno[k]) < 1e-8, k
