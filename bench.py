@@ -36,6 +36,17 @@ NWALKERS = 4096
 TSTEP = 0.5
 SPB = 10  # VMC steps per block (reference default nsteps_per_block)
 WORKLOAD = "H2O ccECP-cc-pVTZ-shaped Slater-Jastrow VMC (synthetic basis/MOs), 8 e-, 57 AOs, 4096 walkers/GPU"
+# --workload c4 (not the headline line): BASELINE.json configs[3], diamond 2x2x2 supercell, 64 e-, 8 k-points
+WORKLOADS = {
+    "c2": dict(system="h2o", walkers=4096, text=WORKLOAD, cpu_walkers=256, cpu_steps=200),
+    "c4": dict(system="diamond222", walkers=1024, cpu_walkers=8, cpu_steps=2,
+               metric="walker-steps/sec (VMC, diamond 2x2x2 PBC SJ); Sherman-Morrison HBM GB/s vs roofline",
+               text="diamond-C 2x2x2 supercell PBC Slater-Jastrow VMC (synthetic basis/MOs, 8 k-points), 64 e-, "
+                    "16 atoms, Ewald + ECP, 1024 walkers/GPU"),
+}
+# DRAM bytes per launch of k_sm_warp<32> on 131072 matrices from the committed ncu --set full capture
+# (profiles/r1_ncu_k_sm_warp32.txt: dram__bytes_read.sum + dram__bytes_write.sum)
+SM32_TRAFFIC_BYTES = 2.12e9
 
 
 def peaks():
@@ -52,13 +63,13 @@ def peaks():
 # futures pool over walker partitions, mc.py:156-173)
 # ------------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    seed, nwalk, nsteps, warm = args
+    seed, nwalk, nsteps, warm, system = args
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import helpers
     from oracle import vmc_driver
     from oracle.local_energy import EnergyOracle
 
-    mol, mf, dets = helpers.make_system("h2o")
+    mol, mf, dets = helpers.make_system(system)
     from oracle.jastrow2 import JastrowOracle
     from oracle.product import ProductOracle
     from oracle.slater_det import SlaterOracle
@@ -67,7 +78,12 @@ def _cpu_worker(args):
     a0, ac, bc = helpers.jastrow_coefficients(oj.parameters["acoeff"].shape, oj.parameters["bcoeff"].shape, False, 1)
     oj.parameters["acoeff"][:, a0:, :] = ac[:, a0:, :]
     oj.parameters["bcoeff"][1:, :] = bc[1:, :]
-    wf = ProductOracle(SlaterOracle(mol, mf), oj)
+    if hasattr(mol, "a"):
+        from oracle.pbc import SlaterPbcOracle
+
+        wf = ProductOracle(SlaterPbcOracle(mol, mf), oj)
+    else:
+        wf = ProductOracle(SlaterOracle(mol, mf), oj)
     np.random.seed(seed)
     configs = vmc_driver.initial_guess(mol, nwalk)
     acc = {"energy": EnergyOracle(mol)}
@@ -78,14 +94,14 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
-def cpu_arm(steps, warmup, walkers_per_core=256, cores=None):
+def cpu_arm(steps, warmup, walkers_per_core=256, cores=None, system="h2o"):
     cores = cores or os.cpu_count() or 1
     cores = min(cores, 64)
     with mp.get_context("spawn").Pool(cores) as pool:
         if warmup:
-            pool.map(_cpu_worker, [(100 + i, 32, 1, False) for i in range(cores)])
+            pool.map(_cpu_worker, [(100 + i, min(32, walkers_per_core), 1, False, system) for i in range(cores)])
         t0 = time.perf_counter()
-        pool.map(_cpu_worker, [(i, walkers_per_core, steps, False) for i in range(cores)])
+        pool.map(_cpu_worker, [(i, walkers_per_core, steps, False, system) for i in range(cores)])
         wall = time.perf_counter() - t0
     total = walkers_per_core * cores * steps
     return total / wall, cores, wall, f"{walkers_per_core} walkers/core x {cores} cores x {steps} steps (oracle port, numpy)"
@@ -181,8 +197,9 @@ def gpu_arm(args):
     from pyqmc_b200 import _lib, mc
 
     lib = _lib.load()
-    K, W, N = args.steps, args.warmup, args.walkers
-    mol, mf, wf, _ = helpers.make_pair("h2o", seed=1)
+    wl = WORKLOADS[args.workload]
+    K, W, N = args.steps, args.warmup, (args.walkers or wl["walkers"])
+    mol, mf, wf, _ = helpers.make_pair(wl["system"], seed=1)
     acc = pq.EnergyAccumulator(mol)
     np.random.seed(1000 + rank)
     configs = pq.initial_guess(mol, N)
@@ -293,11 +310,12 @@ def gpu_arm(args):
     g4, t4, b4 = sm_roofline(torch, lib, 4, 1 << 22)
     g4s, t4s, _ = sm_roofline(torch, lib, 4, N)
     out = {
-        "metric": "walker-steps/sec (VMC, H2O cc-pVTZ SJ); Sherman-Morrison HBM GB/s vs roofline",
+        "metric": wl.get("metric", "walker-steps/sec (VMC, H2O cc-pVTZ SJ); Sherman-Morrison HBM GB/s vs roofline"),
         "value": value, "unit": "walker-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * t_dev_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "walkers_per_gpu": N, "nelec": ne, "tstep": TSTEP,
+        "config": {"workload": wl["text"].replace(f"{wl['walkers']} walkers/GPU", f"{N} walkers/GPU"),
+                   "walkers_per_gpu": N, "nelec": ne, "tstep": TSTEP,
                    "l2": "256 MiB buffer written between timed steps (L2 flush)", "ecp_threshold": 10,
                    "parallelism": f"walker-sharded x{world}, one NCCL allreduce of the energy sums per block of {SPB} steps"},
         "e2e": {"value": e2e, "unit": "walker-steps/s", "h2d_bytes_per_step": h2d / spb, "d2h_bytes_per_step": d2h / spb,
@@ -305,7 +323,8 @@ def gpu_arm(args):
         "gpu_launches": int(launches),
         "roofline": {"kernel": "k_sm_warp<32>: Sherman-Morrison row update, n=32 (C4 shape), 131072 matrices",
                      "bound": "hbm", "achieved": g32, "peak": peak, "unit": "GB/s", "frac": g32 / peak,
-                     "traffic": None, "peak_source": peak_src, "launch_ms": 1e3 * t32, "algorithmic_bytes": b32},
+                     "traffic": SM32_TRAFFIC_BYTES, "traffic_source": "profiles/r1_ncu_k_sm_warp32.txt (ncu --set full, same launch shape)",
+                     "peak_source": peak_src, "launch_ms": 1e3 * t32, "algorithmic_bytes": b32},
         "sm_kernel_other_shapes": {
             "n4_4M_matrices": {"achieved_GBps": g4, "frac": g4 / peak, "launch_ms": 1e3 * t4},
             "n4_4096_matrices_C2_shape": {"achieved_GBps": g4s, "frac": g4s / peak, "launch_ms": 1e3 * t4s}},
@@ -314,7 +333,7 @@ def gpu_arm(args):
                   "wall_s_same_steps_back_to_back_no_flush": t_wall_noflush, "device_s_timed_steps": t_dev_max},
     }
     if world == 1 and not args.no_cpu:
-        v, cores, cwall, sample = cpu_arm(16, True)
+        v, cores, cwall, sample = cpu_arm(wl["cpu_steps"], True, walkers_per_core=wl["cpu_walkers"], system=wl["system"])
         out["cpu_baseline"] = {"value": v, "unit": "walker-steps/s", "cores": cores, "kind": "port", "sample": sample,
                                "wall_s": cwall}
     print(json.dumps(out), flush=True)
@@ -326,15 +345,18 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    walkers = 256
-    v, cores, wall, sample = cpu_arm(max(1, min(args.steps, 8)), args.warmup > 0, walkers_per_core=walkers)
+    wl = WORKLOADS[args.workload]
+    # each of the K "steps" of this arm is one VMC step of a bounded sample (cpu_walkers per core on
+    # every host core); K is capped so the whole run stays within a few minutes
+    v, cores, wall, sample = cpu_arm(max(1, min(args.steps, wl["cpu_steps"])), args.warmup > 0,
+                                     walkers_per_core=wl["cpu_walkers"], system=wl["system"])
     out = {
         "impl": "reference",
         "metric": "walker-steps/sec (VMC, H2O cc-pVTZ SJ); Sherman-Morrison HBM GB/s vs roofline",
         "value": v, "unit": "walker-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "numpy oracle port of the reference path on host cores; "
+        "config": {"workload": wl["text"], "note": "numpy oracle port of the reference path on host cores; "
                    "the Python reference is not present on the GPU box"},
         "cpu_baseline": {"value": v, "unit": "walker-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "walker-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -349,7 +371,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--walkers", type=int, default=NWALKERS)
+    ap.add_argument("--walkers", type=int, default=0)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--equil", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
