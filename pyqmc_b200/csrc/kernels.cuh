@@ -349,6 +349,103 @@ __global__ void __launch_bounds__(64) k_invert(const Sys S, const State st, int 
   st.dlog[s][t] = logdet;
 }
 
+// Same Gauss-Jordan (same pivoting, same operation order per element) with ONE WARP PER MATRIX for
+// 8 < n <= 32: the matrix lives in shared memory with row stride n + 1, lane k owns column k, the
+// pivot search runs with lanes over rows.  Used by recompute for large determinants (n = 32 for the
+// 2x2x2 diamond supercell), where a thread per matrix is two orders of magnitude slower.
+__global__ void __launch_bounds__(128) k_invert_warp(const Sys S, const State st, int s) {
+  extern __shared__ __align__(128) unsigned char qmcb_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nds = S.nds[s];
+  const int N = st.N;
+  if (t >= (long long)N * nds) return;
+  const int w = (int)(t / nds), d = (int)(t - (long long)w * nds);
+  const int n = s ? S.ndn : S.nup;
+  const int lo = s ? S.nup : 0;
+  const int ldmax = S.ldc[0] > S.ldc[1] ? S.ldc[0] : S.ldc[1];
+  const int ld = n + 1;
+  double* __restrict__ a = reinterpret_cast<double*>(qmcb_smem) + (size_t)wib * (32 * 33 + 32);
+  int* __restrict__ piv = reinterpret_cast<int*>(a + 32 * 33);
+  const int* __restrict__ occ = S.iblob + S.o_occ[s] + d * n;
+  const bool act = lane < n;
+  // M[i][k] = mo(electron lo + i, orbital occ[k])   (slater.py:239-240)
+  const int myorb = act ? occ[lane] : 0;
+  for (int i = 0; i < n; ++i)
+    if (act) a[i * ld + lane] = st.mo_all[((size_t)w * S.ne + lo + i) * ldmax + myorb];
+  __syncwarp();
+  double sign = 1.0, logdet = 0.0;
+  bool singular = false;
+  for (int c = 0; c < n; ++c) {
+    // pivot: first row r >= c with the largest |a[r][c]|
+    double v = (lane >= c && act) ? fabs(a[lane * ld + c]) : -1.0;
+    int p = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int op = __shfl_xor_sync(0xffffffffu, p, o);
+      if (ov > v || (ov == v && op < p)) {
+        v = ov;
+        p = op;
+      }
+    }
+    if (lane == 0) piv[c] = p;
+    if (p != c) {
+      sign = -sign;
+      if (act) {
+        const double tmp = a[c * ld + lane];
+        a[c * ld + lane] = a[p * ld + lane];
+        a[p * ld + lane] = tmp;
+      }
+    }
+    __syncwarp();
+    const double pv = a[c * ld + c];
+    if (pv == 0.0 || !isfinite(pv)) {
+      singular = true;
+      break;
+    }
+    if (pv < 0.0) sign = -sign;
+    logdet += log(fabs(pv));
+    const double ipv = 1.0 / pv;
+    const double f = act ? a[lane * ld + c] : 0.0;  // lane r holds a[r][c] (before the row scaling)
+    __syncwarp();
+    if (act) a[c * ld + lane] = (lane == c ? 1.0 : a[c * ld + lane]) * ipv;
+    __syncwarp();
+    const double rc = act ? a[c * ld + lane] : 0.0;
+    for (int r = 0; r < n; ++r) {
+      const double fr = __shfl_sync(0xffffffffu, f, r);
+      if (r == c || !act) continue;
+      const double x = lane == c ? 0.0 : a[r * ld + lane];
+      a[r * ld + lane] = fma(-fr, rc, x);
+    }
+    __syncwarp();
+  }
+  double* out = st.inv[s] + (size_t)t * n * n;
+  if (singular) {
+    for (int i = lane; i < n * n; i += 32) out[i] = 0.0;
+    if (lane == 0) {
+      st.dsign[s][t] = 0.0;
+      st.dlog[s][t] = -INFINITY;
+    }
+    return;
+  }
+  for (int c = n - 1; c >= 0; --c) {
+    const int p = piv[c];
+    if (p != c && act) {  // lane = row: swap columns c and p
+      const double tmp = a[lane * ld + c];
+      a[lane * ld + c] = a[lane * ld + p];
+      a[lane * ld + p] = tmp;
+    }
+    __syncwarp();
+  }
+  for (int i = 0; i < n; ++i)
+    if (act) out[i * n + lane] = a[i * ld + lane];
+  if (lane == 0) {
+    st.dsign[s][t] = sign;
+    st.dlog[s][t] = logdet;
+  }
+}
+
 // Multi-determinant caches for walker w:  ref_s = max_d log_s[d], dv_s[d] = sign*exp(log-ref),
 // W_s[d] = sum_{D: map_s(D)=d} c_D dv_other[map_other(D)]   (determinant_tools.py:74-88 with a
 // per-walker instead of a global reference exponent; the reference cancels in every ratio).
@@ -468,6 +565,76 @@ __global__ void __launch_bounds__(128) k_jastrow_recompute(const Sys S, const St
         }
       }
     }
+  }
+}
+
+// Cooperative form of the same recompute for many-electron systems: one CTA per walker, threads over
+// electrons.  Every electron accumulates its own partial sums over its partners in ascending partner
+// order (the order the pair loop above produces), the pair sums follow from the partial sums:
+//   bvalues[l][uu] = 1/2 sum_{e up} b_partial[e][l][up],  [ud] = sum_{e up} b_partial[e][l][dn],
+//   bvalues[l][dd] = 1/2 sum_{e dn} b_partial[e][l][dn]
+__global__ void __launch_bounds__(128) k_jastrow_recompute_coop(const Sys S, const State st) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  const int w = blockIdx.x;
+  const int ne = S.ne, na = S.na, nb = S.nb, I_ = S.natom;
+  for (int e = threadIdx.x; e < ne; e += blockDim.x) {
+    const double px = CONF(st, S, w, e, 0), py = CONF(st, S, w, e, 1), pz = CONF(st, S, w, e, 2);
+    for (int I = 0; I < I_; ++I) {
+      double dx = px - sd[S.o_xyz + 3 * I], dy = py - sd[S.o_xyz + 3 * I + 1], dz = pz - sd[S.o_xyz + 3 * I + 2];
+      if (S.pbc) min_image(S, sd, dx, dy, dz);
+      const double r = sqrt(dx * dx + dy * dy + dz * dz);
+      for (int k = 0; k < na; ++k) {
+        double v = 0.0, g, l;
+        if (r < S.rcut_a) radial_ool<0>(si[S.o_akind + k], sd[S.o_apar + k], S.rcut_a, r, v, g, l);
+        APART(st, S, w, e, I, k) = v;
+      }
+    }
+    double bs[8][2];
+    for (int l = 0; l < 8; ++l) bs[l][0] = bs[l][1] = 0.0;
+    for (int j = 0; j < ne; ++j) {
+      if (j == e) continue;
+      const int sj = j >= S.nup ? 1 : 0;
+      double dx = px - CONF(st, S, w, j, 0), dy = py - CONF(st, S, w, j, 1), dz = pz - CONF(st, S, w, j, 2);
+      if (S.pbc) min_image(S, sd, dx, dy, dz);
+      const double r = sqrt(dx * dx + dy * dy + dz * dz);
+      if (r < S.rcut_b) {
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+          if (l < nb) {
+            double v, g, ll;
+            radial_ool<0>(si[S.o_bkind + l], sd[S.o_bpar + l], S.rcut_b, r, v, g, ll);
+            bs[l][sj] += v;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < 8; ++l)
+      if (l < nb) {
+        BPART(st, S, w, e, l, 0) = bs[l][0];
+        BPART(st, S, w, e, l, 1) = bs[l][1];
+      }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < I_ * na * 2; t += blockDim.x) {
+    const int s2 = t & 1, k = (t >> 1) % na, I = (t >> 1) / na;
+    double acc = 0.0;
+    const int e0 = s2 ? S.nup : 0, e1 = s2 ? ne : S.nup;
+    for (int e = e0; e < e1; ++e) acc += APART(st, S, w, e, I, k);
+    AVAL(st, S, w, I, k, s2) = acc;
+  }
+  for (int t = threadIdx.x; t < nb * 3; t += blockDim.x) {
+    const int l = t / 3, sp = t - l * 3;
+    double acc = 0.0;
+    if (sp == 0)
+      for (int e = 0; e < S.nup; ++e) acc += BPART(st, S, w, e, l, 0);
+    else if (sp == 1)
+      for (int e = 0; e < S.nup; ++e) acc += BPART(st, S, w, e, l, 1);
+    else
+      for (int e = S.nup; e < ne; ++e) acc += BPART(st, S, w, e, l, 1);
+    BVAL(st, S, w, l, sp) = sp == 1 ? acc : 0.5 * acc;
   }
 }
 

@@ -225,6 +225,215 @@ __global__ void __launch_bounds__(128) k_pbc_mo(const Sys S, const State st, con
   }
 }
 
+// chi, grad chi, lap chi of one shell at displacement (x,y,z) -> om[m * NC + c]
+template <int L, int DERIV>
+__device__ __forceinline__ void pbc_stage_shell(double x, double y, double z, double R, double Rp, double Rl,
+                                                double* __restrict__ om) {
+  constexpr int NC = NComp<DERIV>::value;
+  constexpr int NF = 2 * L + 1;
+  double s[NF], gx[NF], gy[NF], gz[NF];
+  if constexpr (L == 0) sph_l0<(DERIV > 0)>(x, y, z, s, gx, gy, gz);
+  if constexpr (L == 1) sph_l1<(DERIV > 0)>(x, y, z, s, gx, gy, gz);
+  if constexpr (L == 2) sph_l2<(DERIV > 0)>(x, y, z, s, gx, gy, gz);
+  if constexpr (L == 3) sph_l3<(DERIV > 0)>(x, y, z, s, gx, gy, gz);
+  if constexpr (L == 4) sph_l4<(DERIV > 0)>(x, y, z, s, gx, gy, gz);
+  const double dRx = Rp * x, dRy = Rp * y, dRz = Rp * z;
+#pragma unroll
+  for (int m = 0; m < NF; ++m) {
+    om[m * NC] = s[m] * R;
+    if (DERIV > 0) {
+      om[m * NC + 1] = gx[m] * R + s[m] * dRx;
+      om[m * NC + 2] = gy[m] * R + s[m] * dRy;
+      om[m * NC + 3] = gz[m] * R + s[m] * dRz;
+      if (DERIV > 1) om[m * NC + 4] = s[m] * Rl + 2.0 * (gx[m] * dRx + gy[m] * dRy + gz[m] * dRz);
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// k_pbc_mo_cta: the same evaluation with ONE CTA PER POINT (T = blockDim.x threads), for launches
+// whose point count alone cannot fill the machine (the per-electron proposals of the periodic VMC
+// block: N points) -- and measured faster per point than the lane-group form in general.
+//   A  threads over (candidate pair, shell of its atom) tasks: r^2 cutoffs, radial sums, solid
+//      harmonics of that shell, chi / grad chi / lap chi -> staging slot of the pair (no compaction)
+//   B  thread r owns the (mu, c) column r of the accumulators for ALL k in registers:
+//      acc[k] += phase[L][k] * staged[r]                                    (pbcgto.py:216-227)
+//   C  threads over (c, MO)                                                 (orbitals.py:204-229)
+// Limits (else the lane-group kernel runs): nk <= 8, nao * NC <= 2 T, ncand * stride fits smem.
+// -----------------------------------------------------------------------------------------
+#define QMCB_PBC_NKMAX 8
+#define QMCB_PBC_RU 2
+
+__host__ __device__ inline int pbc_mo_cta_chunk(const Sys& S) { return S.ncand < 64 ? S.ncand : 64; }
+__host__ __device__ inline size_t pbc_mo_cta_scratch_bytes(const Sys& S, int nc) {
+  const int chunk = pbc_mo_cta_chunk(S);
+  return ((size_t)S.nk * S.nao * nc + (size_t)chunk * S.maxao_atom * nc) * 8 + (size_t)chunk * 2 * 4 + 16;
+}
+
+template <int DERIV>
+__global__ void __launch_bounds__(256, 2) k_pbc_mo_cta(const Sys S, const State st, const PbcMoArgs a) {
+  constexpr int NC = NComp<DERIV>::value;
+  const int T = blockDim.x;
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  extern __shared__ __align__(128) unsigned char qmcb_smem[];
+  const size_t tab = (16 + (size_t)S.dwords * 8 + (size_t)S.iwords * 4 + 15) & ~(size_t)15;
+  const int chunk = pbc_mo_cta_chunk(S);
+  const int ncol = S.nao * NC;
+  const int stg_stride = S.maxao_atom * NC;
+  double* __restrict__ ao = reinterpret_cast<double*>(qmcb_smem + tab);  // [nk][nao][NC]
+  double* __restrict__ stg = ao + (size_t)S.nk * ncol;
+  int* __restrict__ meta = reinterpret_cast<int*>(stg + (size_t)chunk * stg_stride);  // [chunk][2]: atom (-1 invalid), image
+  const int tid = threadIdx.x;
+  const double* __restrict__ Ls = sd + S.o_Ls;
+  const double* __restrict__ prim = sd + S.o_prim;
+  const double* __restrict__ phase = sd + S.o_phase;
+  // this thread's accumulator columns r = tid + T u: atom of mu and offset inside the atom's block
+  int cat[QMCB_PBC_RU], coff[QMCB_PBC_RU];
+#pragma unroll
+  for (int u = 0; u < QMCB_PBC_RU; ++u) {
+    const int r = tid + T * u;
+    cat[u] = -2;
+    coff[u] = 0;
+    if (r < ncol) {
+      const int sh = si[S.o_aoshell + r / NC];
+      const int at = si[S.o_shatom + sh];
+      cat[u] = at;
+      coff[u] = r - si[S.o_shao + si[S.o_atsh + at]] * NC;
+    }
+  }
+  int maxsh = 1;
+  for (int at = 0; at < S.nbatom; ++at) maxsh = max(maxsh, si[S.o_atsh + at + 1] - si[S.o_atsh + at]);
+  const long long np = a.count ? (long long)(*a.count) * a.per_item : a.npoints;
+  for (long long p = blockIdx.x; p < np; p += gridDim.x) {
+    long long posidx = p;
+    if (a.idx) posidx = (long long)a.idx[p / a.naip] * a.naip + p % a.naip;
+    if (a.mask && !a.mask[posidx / a.naip]) continue;
+    const double px = a.pos[3 * posidx], py = a.pos[3 * posidx + 1], pz = a.pos[3 * posidx + 2];
+    if (isnan(px)) continue;
+    int spin = a.spin;
+    if (a.spin_mode == 1) spin = (int)(posidx % S.ne) >= S.nup ? 1 : 0;
+    if (a.spin_mode == 2) {
+      const int tt = a.work[p / a.per_item];
+      const int e = a.e_only >= 0 ? a.e_only : (tt / a.workN) / a.necp;
+      spin = e >= S.nup ? 1 : 0;
+    }
+    double q[3], pw[3];
+    wrap_cell(sd + S.o_lprim, sd + S.o_lpriminv, px, py, pz, q, pw);
+    double acc[QMCB_PBC_RU][QMCB_PBC_NKMAX];
+#pragma unroll
+    for (int u = 0; u < QMCB_PBC_RU; ++u)
+#pragma unroll
+      for (int k = 0; k < QMCB_PBC_NKMAX; ++k) acc[u][k] = 0.0;
+    for (int base = 0; base < S.ncand; base += chunk) {
+      const int cnt = (S.ncand - base) < chunk ? (S.ncand - base) : chunk;
+      // ---- phase A: (pair, shell) tasks
+      for (int task = tid; task < cnt * maxsh; task += T) {
+        const int slot = task / maxsh, ish = task - slot * maxsh;
+        const int c = base + slot;
+        int at = 0;
+        while (c >= si[S.o_candoff + at + 1]) ++at;
+        const int j = c - si[S.o_candoff + at];
+        const double x = (q[0] - sd[S.o_bxyz + 3 * at]) - Ls[3 * j], y = (q[1] - sd[S.o_bxyz + 3 * at + 1]) - Ls[3 * j + 1],
+                     z = (q[2] - sd[S.o_bxyz + 3 * at + 2]) - Ls[3 * j + 2];
+        const double r2 = x * x + y * y + z * z;
+        const bool near = !(r2 > sd[S.o_atomcut + at]);  // pbcgto.py:207
+        if (ish == 0) {
+          meta[2 * slot] = near ? at : -1;
+          meta[2 * slot + 1] = j;
+        }
+        const int sh = si[S.o_atsh + at] + ish;
+        if (!near || sh >= si[S.o_atsh + at + 1]) continue;
+        const int l = si[S.o_shl + sh];
+        double* __restrict__ om = stg + (size_t)slot * stg_stride + (si[S.o_shao + sh] - si[S.o_shao + si[S.o_atsh + at]]) * NC;
+        const double lcut = sd[S.o_lcut + sh];
+        // value kernel keeps r2 < cutoff (pbcgto.py:215); the derivative kernels skip r2 > cutoff (348, 490)
+        const bool in = DERIV == 0 ? (r2 < lcut) : !(r2 > lcut);
+        if (!in) {
+          for (int m = 0; m < (2 * l + 1) * NC; ++m) om[m] = 0.0;
+          continue;
+        }
+        double R = 0.0, Rp = 0.0, Rl = 0.0;
+        for (int pp = si[S.o_shprim + sh]; pp < si[S.o_shprim + sh + 1]; ++pp) {
+          const double al = prim[2 * pp], cf = prim[2 * pp + 1];
+          const double g = cf * exp(-al * r2);
+          R += g;
+          if (DERIV > 0) {
+            const double t2 = 2.0 * al * g;
+            Rp -= t2;
+            if (DERIV > 1) Rl = fma(t2, 2.0 * al * r2 - 3.0, Rl);
+          }
+        }
+        switch (l) {
+          case 0: pbc_stage_shell<0, DERIV>(x, y, z, R, Rp, Rl, om); break;
+          case 1: pbc_stage_shell<1, DERIV>(x, y, z, R, Rp, Rl, om); break;
+          case 2: pbc_stage_shell<2, DERIV>(x, y, z, R, Rp, Rl, om); break;
+          case 3: pbc_stage_shell<3, DERIV>(x, y, z, R, Rp, Rl, om); break;
+          default: pbc_stage_shell<4, DERIV>(x, y, z, R, Rp, Rl, om); break;
+        }
+      }
+      __syncthreads();
+      // ---- phase B
+      for (int s2 = 0; s2 < cnt; ++s2) {
+        const int at = meta[2 * s2];
+        if (at < 0) continue;
+        const double* __restrict__ ph = phase + meta[2 * s2 + 1] * S.nk;
+        const double* __restrict__ src = stg + (size_t)s2 * stg_stride;
+#pragma unroll
+        for (int u = 0; u < QMCB_PBC_RU; ++u) {
+          if (cat[u] == at) {
+            const double f = src[coff[u]];
+#pragma unroll
+            for (int k = 0; k < QMCB_PBC_NKMAX; ++k)
+              if (k < S.nk) acc[u][k] = fma(ph[k], f, acc[u][k]);
+          }
+        }
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < QMCB_PBC_RU; ++u) {
+      const int r = tid + T * u;
+      if (r < ncol) {
+#pragma unroll
+        for (int k = 0; k < QMCB_PBC_NKMAX; ++k)
+          if (k < S.nk) ao[k * ncol + r] = acc[u][k];
+      }
+    }
+    __syncthreads();
+    // ---- phase C: wrap phase and per-k MO contraction
+    const int ldc = S.ldc[spin], nmo = S.nmo[spin];
+    const double* __restrict__ C = sd + S.o_mo[spin];
+    const int* __restrict__ mok = si + S.o_mok[spin];
+    double wt[3] = {pw[0], pw[1], pw[2]};
+    if (!S.isgamma && a.wrap) {
+      const double* __restrict__ Sm = sd + S.o_smat;
+      const double w0 = a.wrap[3 * posidx], w1 = a.wrap[3 * posidx + 1], w2 = a.wrap[3 * posidx + 2];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) wt[k] = (w0 * Sm[k] + w1 * Sm[3 + k] + w2 * Sm[6 + k]) + pw[k];
+    }
+    for (int t = tid; t < NC * ldc; t += T) {
+      const int c = t / ldc, j = t - c * ldc;
+      double v = 0.0;
+      if (j < nmo) {
+        const int k = mok[j];
+        const double* __restrict__ ak = ao + (size_t)k * ncol + c;
+        for (int mu = 0; mu < S.nao; ++mu) v = fma(ak[mu * NC], C[mu * ldc + j], v);
+        if (!S.isgamma) {
+          const double* __restrict__ kl = sd + S.o_kl + 3 * k;
+          const double kd = kl[0] * wt[0] + kl[1] * wt[1] + kl[2] * wt[2];
+          const double n = rint(kd / 3.141592653589793);
+          if (fmod(fabs(n), 2.0) == 1.0) v = -v;
+        }
+      }
+      a.out[p * a.stride_p + c * a.stride_c + j * a.stride_j] = v;
+      if (c == 0 && a.out_val) a.out_val[p * a.stride_vp + j] = v;
+    }
+    __syncthreads();
+  }
+}
+
 // =========================================================================================
 // Minimal-image Jastrow with lanes over PARTNERS (other electrons, then atoms): one 27-shift search
 // per partner, all radial functions of that partner on the same lane.

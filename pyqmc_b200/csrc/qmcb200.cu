@@ -603,6 +603,29 @@ int launch_pbc_mo(qmcb_ctx* c, int deriv, const PbcMoArgs& a, long long max_poin
   constexpr int G = 16, BLOCK = 64;
   const int nc = deriv == 0 ? 1 : (deriv == 1 ? 4 : 5);
   const size_t tab = (c->smem_bytes + 15) & ~(size_t)15;
+  // one CTA per point (k_pbc_mo_cta) whenever the accumulator columns fit its registers
+  const size_t csm = tab + pbc_mo_cta_scratch_bytes(c->S, nc);
+  const int ncol = c->S.nao * nc;
+  if (c->S.nk <= QMCB_PBC_NKMAX && ncol <= QMCB_PBC_RU * 256 && csm <= 100 * 1024 &&
+      std::getenv("QMCB_PBC_NO_CTA") == nullptr) {
+    int T = std::max(std::max(ncol, nc * std::max(c->S.ldc[0], c->S.ldc[1])), 64);
+    T = std::min((T + 31) / 32 * 32, 256);
+    if (ncol > T) T = std::min(((ncol + 1) / 2 + 31) / 32 * 32, 256);
+    const unsigned grid = (unsigned)std::min<long long>(max_points, 148LL * 64);
+    if (deriv == 0) {
+      if (prep_kernel(k_pbc_mo_cta<0>, csm)) return -1;
+      k_pbc_mo_cta<0><<<grid, T, csm, stream>>>(c->S, c->st, a);
+    } else if (deriv == 1) {
+      if (prep_kernel(k_pbc_mo_cta<1>, csm)) return -1;
+      k_pbc_mo_cta<1><<<grid, T, csm, stream>>>(c->S, c->st, a);
+    } else {
+      if (prep_kernel(k_pbc_mo_cta<2>, csm)) return -1;
+      k_pbc_mo_cta<2><<<grid, T, csm, stream>>>(c->S, c->st, a);
+    }
+    c->nlaunch++;
+    CK(cudaGetLastError());
+    return 0;
+  }
   const size_t sm = tab + (size_t)(BLOCK / G) * pbc_mo_scratch_doubles(c->S, nc, G) * 8;
   if (sm > 200 * 1024) return fail("periodic orbital evaluation: shared-memory scratch exceeds 200 KB (nk * nao too large)");
   const long long grid = std::min<long long>((max_points + (BLOCK / G) - 1) / (BLOCK / G), 148LL * 16);
@@ -665,7 +688,10 @@ int slater_rebuild(qmcb_ctx* c, cudaStream_t stream) {
     const unsigned grid = (unsigned)((nt + block - 1) / block);
     if (n <= 8)
       k_invert<8><<<grid, block, 0, stream>>>(S, c->st, s, nullptr);
-    else if (n <= 16)
+    else if (n <= 32 && std::getenv("QMCB_NO_WARP_INVERT") == nullptr) {
+      const size_t ism = (size_t)4 * (32 * 33 + 32) * 8;
+      k_invert_warp<<<(unsigned)((nt * 32 + 127) / 128), 128, ism, stream>>>(S, c->st, s);
+    } else if (n <= 16)
       k_invert<16><<<grid, block, 0, stream>>>(S, c->st, s, nullptr);
     else if (n <= 64) {
       if (c->b_lu.ensure((size_t)nt * n * n)) return -1;
@@ -1199,9 +1225,16 @@ int qmcb_recompute_pbc(qmcb_ctx* c, int which, int nconf, const double* configs,
   if (which & 1)
     if (slater_rebuild(c, c->stream)) return -1;
   if (which & 2) {
-    const int block = pick_block(nconf);
-    if (prep_kernel(k_jastrow_recompute, c->smem_bytes)) return -1;
-    k_jastrow_recompute<<<(nconf + block - 1) / block, block, c->smem_bytes, c->stream>>>(S, c->st);
+    if (S.ne >= 16 && S.nb <= 8 && std::getenv("QMCB_NO_COOP_JRECOMPUTE") == nullptr) {
+      // many electrons: CTA per walker, threads over electrons
+      const int block = S.ne <= 32 ? 32 : (S.ne <= 64 ? 64 : 128);
+      if (prep_kernel(k_jastrow_recompute_coop, c->smem_bytes)) return -1;
+      k_jastrow_recompute_coop<<<nconf, block, c->smem_bytes, c->stream>>>(S, c->st);
+    } else {
+      const int block = pick_block(nconf);
+      if (prep_kernel(k_jastrow_recompute, c->smem_bytes)) return -1;
+      k_jastrow_recompute<<<(nconf + block - 1) / block, block, c->smem_bytes, c->stream>>>(S, c->st);
+    }
     c->nlaunch++;
     CK(cudaGetLastError());
   }
