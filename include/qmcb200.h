@@ -202,6 +202,24 @@ int qmcb_vmc_block_slot(qmcb_ctx *ctx, int slot, int nsteps, double tstep, int w
                         double *configs, uint8_t *accept, double *energy, double *esum,
                         int64_t *nacc);
 int qmcb_kernel_launches(qmcb_ctx *ctx, int64_t *count); /* launches issued so far */
+
+/* ---- device-resident DMC propagation (dmc_propagate, pyqmc/method/dmc.py:123-221) ------------
+ * nsteps steps without branching on the walkers held by the context (after qmcb_recompute):
+ * initial local energy, then per step T-moves of every electron (propose_tmoves 73-120), the
+ * drift-diffusion sweep with Umrigar drift limit and fixed-node rejection (49-70), the local
+ * energy and the weight update (compute_S 224-235).  Open-boundary single-determinant
+ * Slater-Jastrow only.  Random variates in the reference's consumption order:
+ *   ecp_u [nsteps+1][ne][necp][N], ecp_rot [nsteps+1][ne][necp][9]  energy evaluations (first = before step 0)
+ *   tm_u [nsteps][ne][necp][N], tm_rot [nsteps][ne][necp][9]         nonlocal_tmoves masks / rotations
+ *   tm_sel [nsteps][ne][N]  select_walker's rand();  tm_acc [nsteps][ne][N]  T-move acceptance
+ *   gauss [nsteps][ne][N][3] ~ N(0, tstep), unif [nsteps][ne][N]     drift-diffusion
+ * weights [N] in/out; configs [N][ne][3] out; wsums [nsteps][8] = sum_w w*(ke,ee,ei,ecp,grad2,total),
+ * sum_w w, 0; nacc / ntacc [nsteps][ne] accepted diffusion / T-moves. */
+int qmcb_dmc_block(qmcb_ctx *ctx, int nsteps, double tstep, double branchcut, double e_trial,
+                   double e_est, const double *gauss, const double *unif, const double *ecp_u,
+                   const double *ecp_rot, const double *tm_u, const double *tm_rot,
+                   const double *tm_sel, const double *tm_acc, double *weights, double *configs,
+                   double *wsums, int64_t *nacc, int64_t *ntacc);
 /* page-locked host buffers for the per-block variates / results (true async H2D/D2H) */
 int qmcb_pinned_alloc(int64_t bytes, void **out);
 int qmcb_pinned_free(void *p);

@@ -11,9 +11,10 @@ from .wf import JastrowSpin, MultiplyWF, Slater, ThreeBodyJastrow  # noqa: F401
 from .wftools import generate_jastrow, generate_jastrow3, generate_slater, generate_wf  # noqa: F401
 from .accumulators import EnergyAccumulator  # noqa: F401
 from .mc import initial_guess, limdrift, vmc  # noqa: F401
+from .dmc import rundmc  # noqa: F401
 
 __all__ = [
     "OpenConfigs", "OpenElectron", "PeriodicConfigs", "PeriodicElectron", "CutoffCuspFunction", "PolyPadeFunction", "JastrowSpin", "MultiplyWF",
     "Slater", "ThreeBodyJastrow", "generate_jastrow", "generate_jastrow3", "generate_slater", "generate_wf", "EnergyAccumulator", "initial_guess",
-    "limdrift", "vmc",
+    "limdrift", "vmc", "rundmc",
 ]

@@ -67,6 +67,9 @@ SIGNATURES = {
     "qmcb_vmc_block_slot": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_double_p, c_u8_p, c_double_p,
                                     c_double_p, c_i64_p]),
     "qmcb_kernel_launches": (c_int, [c_void_p, c_i64_p]),
+    "qmcb_dmc_block": (c_int, [c_void_p, c_int, c_double, c_double, c_double, c_double, c_double_p, c_double_p,
+                               c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                               c_double_p, c_double_p, c_i64_p, c_i64_p]),
     "qmcb_pinned_alloc": (c_int, [c_i64, ctypes.POINTER(c_void_p)]),
     "qmcb_pinned_free": (c_int, [c_void_p]),
     "qmcb_sm_update_device": (c_int, [c_int, c_int, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -1099,11 +1099,26 @@ struct SweepArgs {
   const double* unif;   // [ne][N]
   uint8_t* accept;      // [ne][N] or nullptr
   unsigned long long* nacc;  // [ne]
+  double* r2prop;       // DMC: [N] sum over electrons of |gauss + drift|^2          (dmc.py:68, 190-191)
+  double* r2acc;        // DMC: [N] the same for accepted moves
 };
 
 __device__ __forceinline__ void limdrift3(double (&g)[3]);
 
-template <int G>
+// Umrigar's drift limiter, result already multiplied by the (effective) time step (dmc.py:22-35)
+__device__ __forceinline__ void limdrift_dmc(double (&g)[3], double tau) {
+  const double acyrus = 0.5;
+  const double v2 = __dadd_rn(__dadd_rn(__dmul_rn(g[0], g[0]), __dmul_rn(g[1], g[1])), __dmul_rn(g[2], g[2]));
+  double taueff = tau;
+  if (v2 > 1e-8) taueff = (sqrt(__dadd_rn(1.0, __dmul_rn(__dmul_rn(__dmul_rn(2.0, tau), acyrus), v2))) - 1.0) / __dmul_rn(acyrus, v2);
+  g[0] = __dmul_rn(g[0], taueff);
+  g[1] = __dmul_rn(g[1], taueff);
+  g[2] = __dmul_rn(g[2], taueff);
+}
+
+// DMC = false: VMC move (mc.py:115-137).  DMC = true: drift-diffusion move of dmc.py:49-70 (Umrigar
+// drift limit, fixed-node rejection of sign changes, |gauss + drift|^2 bookkeeping for tdamp).
+template <int G, bool DMC>
 __global__ void __launch_bounds__(128) k_vmc_sweep(const Sys S, const State st, const SweepArgs a) {
   const double* sd;
   const int* si;
@@ -1151,13 +1166,20 @@ __global__ void __launch_bounds__(128) k_vmc_sweep(const Sys S, const State st, 
 #pragma unroll
       for (int i = 0; i < 3; ++i) grad[i] = grad[i] + gj[i];
     }
-    limdrift3(grad);
     double gauss[3], np_[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) gauss[i] = a.gauss[((size_t)e * N + w) * 3 + i];
-    np_[0] = __dadd_rn(__dadd_rn(ox, gauss[0]), __dmul_rn(grad[0], a.tstep));
-    np_[1] = __dadd_rn(__dadd_rn(oy, gauss[1]), __dmul_rn(grad[1], a.tstep));
-    np_[2] = __dadd_rn(__dadd_rn(oz, gauss[2]), __dmul_rn(grad[2], a.tstep));
+    if (DMC) {
+      limdrift_dmc(grad, a.tstep);
+      np_[0] = __dadd_rn(__dadd_rn(ox, gauss[0]), grad[0]);
+      np_[1] = __dadd_rn(__dadd_rn(oy, gauss[1]), grad[1]);
+      np_[2] = __dadd_rn(__dadd_rn(oz, gauss[2]), grad[2]);
+    } else {
+      limdrift3(grad);
+      np_[0] = __dadd_rn(__dadd_rn(ox, gauss[0]), __dmul_rn(grad[0], a.tstep));
+      np_[1] = __dadd_rn(__dadd_rn(oy, gauss[1]), __dmul_rn(grad[1], a.tstep));
+      np_[2] = __dadd_rn(__dadd_rn(oz, gauss[2]), __dmul_rn(grad[2], a.tstep));
+    }
     // ---- value + drift at the proposed position
     double ngrad[3] = {0.0, 0.0, 0.0}, val = 1.0;
     if (has_s) {
@@ -1184,22 +1206,37 @@ __global__ void __launch_bounds__(128) k_vmc_sweep(const Sys S, const State st, 
       for (int i = 0; i < 3; ++i) ngrad[i] = ngrad[i] + gj[i];
       val = val * exp(du);
     }
-    limdrift3(ngrad);
-    double fwd = 0.0, bwd = 0.0;
+    if (DMC)
+      limdrift_dmc(ngrad, a.tstep);
+    else
+      limdrift3(ngrad);
+    double fwd = 0.0, bwd = 0.0, r2 = 0.0;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       fwd = __dadd_rn(fwd, __dmul_rn(gauss[i], gauss[i]));
-      const double b = __dadd_rn(gauss[i], __dmul_rn(a.tstep, __dadd_rn(grad[i], ngrad[i])));
+      double b;
+      if (DMC) {
+        const double gd = __dadd_rn(gauss[i], grad[i]);
+        r2 = __dadd_rn(r2, __dmul_rn(gd, gd));
+        b = __dadd_rn(gd, ngrad[i]);
+      } else {
+        b = __dadd_rn(gauss[i], __dmul_rn(a.tstep, __dadd_rn(grad[i], ngrad[i])));
+      }
       bwd = __dadd_rn(bwd, __dmul_rn(b, b));
     }
     const double tprob = exp(__dmul_rn(1.0 / (2.0 * a.tstep), __dadd_rn(fwd, -bwd)));
     const double aval = fabs(val);
-    const double ratio = __dmul_rn(__dmul_rn(aval, aval), tprob);
+    double ratio = __dmul_rn(__dmul_rn(aval, aval), tprob);
+    if (DMC) ratio = __dmul_rn(ratio, val > 0.0 ? 1.0 : (val < 0.0 ? -1.0 : 0.0));  // fixed node (dmc.py:65-66)
     // every lane of the group evaluated the same numbers; take lane 0's decision
     const bool acc = __shfl_sync(gm, (ratio > a.unif[(size_t)e * N + w]) ? 1 : 0, 0, G) != 0;
     if (lane == 0) {
       if (a.accept) a.accept[(size_t)e * N + w] = acc ? 1 : 0;
       if (acc) atomicAdd(a.nacc + e, 1ULL);
+      if (DMC) {
+        a.r2prop[w] = __dadd_rn(a.r2prop[w], r2);
+        if (acc) a.r2acc[w] = __dadd_rn(a.r2acc[w], r2);
+      }
     }
     if (acc) {
       if (has_s) {
@@ -1708,4 +1745,110 @@ __global__ void k_conf_out(const double* conf, double* host_layout, int N, int n
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * ne * 3) return;
   host_layout[i] = conf[i];
+}
+
+// =========================================================================================
+// DMC block pieces (pyqmc/method/dmc.py).
+// =========================================================================================
+// T-move selection for electron e (propose_tmoves, dmc.py:73-120, and the acceptance test of
+// dmc_propagate 170-177): one thread per walker over its M = tot_naip candidate moves.
+struct TmoveSelectArgs {
+  int e, M;
+  const double* ratio;   // [N][M]
+  const double* weight;  // [N][M]
+  const double* pos;     // [N][M][3]
+  const double* sel_u;   // [N]  select_walker's rand()
+  const double* acc_u;   // [N]
+  uint8_t* accept;       // [N]
+  unsigned long long* ntacc;
+};
+
+__global__ void __launch_bounds__(128) k_tmove_select(const Sys S, const State st, const TmoveSelectArgs a) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  bool acc = false;
+  if (w < st.N) {
+    const int M = a.M;
+    const double* __restrict__ ra = a.ratio + (size_t)w * M;
+    const double* __restrict__ wt = a.weight + (size_t)w * M;
+    double norm = 1.0;
+    {
+      double sum = 0.0;
+      for (int m = 0; m < M; ++m) {
+        const double amp = __dmul_rn(ra[m], wt[m]);
+        if (amp > 0.0) sum = __dadd_rn(sum, amp);
+      }
+      norm = __dadd_rn(1.0, sum);  // EQN 34
+    }
+    // selected = searchsorted(cumsum(forward / norm), r): number of entries with cdf < r
+    const double r = a.sel_u[w];
+    int sel = 0;
+    double cdf = 0.0;
+    for (int m = 0; m < M; ++m) {
+      const double amp = __dmul_rn(ra[m], wt[m]);
+      const double f = amp > 0.0 ? amp : 0.0;
+      cdf = __dadd_rn(cdf, f / norm);
+      if (cdf < r) ++sel;
+    }
+    const bool chosen = sel < M;
+    double px = CONF(st, S, w, a.e, 0), py = CONF(st, S, w, a.e, 1), pz = CONF(st, S, w, a.e, 2);
+    double acceptance = 0.0;
+    if (chosen) {
+      px = a.pos[((size_t)w * M + sel) * 3];
+      py = a.pos[((size_t)w * M + sel) * 3 + 1];
+      pz = a.pos[((size_t)w * M + sel) * 3 + 2];
+      const double rev = 1.0 / ra[sel];
+      double bsum = 0.0;
+      for (int m = 0; m < M; ++m) {
+        double b = m == sel ? __dmul_rn(rev, wt[m]) : __dmul_rn(__dmul_rn(ra[m], wt[m]), rev);
+        if (b < 0.0) b = 0.0;
+        bsum = __dadd_rn(bsum, b);
+      }
+      acceptance = norm / __dadd_rn(1.0, bsum);
+    }
+    acc = chosen && (acceptance > a.acc_u[w]);
+    a.accept[w] = acc ? 1 : 0;
+    st.saved_pos[(size_t)w * 3] = px;
+    st.saved_pos[(size_t)w * 3 + 1] = py;
+    st.saved_pos[(size_t)w * 3 + 2] = pz;
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, acc);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(a.ntacc, (unsigned long long)__popc(b));
+}
+
+// Weight update of one DMC step (dmc.py:183-198, compute_S 224-235) and the weighted observables:
+// prod [7][N] = w * (ke, ee, ei, ecp, grad2, total), w.  eold / v2old carry E_L and v^2 to the next step.
+struct DmcWeightArgs {
+  double tstep, branchcut, e_trial, e_est;
+  const double* energy;  // [6][N] of this step
+  const double* r2prop;
+  const double* r2acc;
+  double* eold;     // [N]
+  double* v2old;    // [N]
+  double* weights;  // [N]
+  double* prod;     // [7][N]
+  int init;         // 1: only record eold / v2old (the evaluation before the first step)
+};
+
+__device__ __forceinline__ double dmc_compute_s(const DmcWeightArgs& a, double v2, double eloc, int nelec) {
+  double e_cut = a.e_est - eloc;
+  if (fabs(e_cut) > a.branchcut) e_cut = a.branchcut * (e_cut > 0.0 ? 1.0 : (e_cut < 0.0 ? -1.0 : 0.0));
+  const double q = v2 * a.tstep / (double)nelec;
+  return (a.e_trial - a.e_est) + e_cut / sqrt(1.0 + q * q);
+}
+
+__global__ void __launch_bounds__(128) k_dmc_weights(const Sys S, const State st, const DmcWeightArgs a) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = st.N;
+  if (w >= N) return;
+  const double eloc = a.energy[(size_t)5 * N + w], v2 = a.energy[(size_t)4 * N + w];
+  if (!a.init) {
+    const double tdamp = a.r2acc[w] / a.r2prop[w];
+    const double snew = dmc_compute_s(a, v2, eloc, S.ne), sold = dmc_compute_s(a, a.v2old[w], a.eold[w], S.ne);
+    const double wt = a.weights[w] * exp(a.tstep * tdamp * (0.5 * snew + 0.5 * sold));
+    a.weights[w] = wt;
+    for (int k = 0; k < 6; ++k) a.prod[(size_t)k * N + w] = wt * a.energy[(size_t)k * N + w];
+    a.prod[(size_t)6 * N + w] = wt;
+  }
+  a.eold[w] = eloc;
+  a.v2old[w] = v2;
 }

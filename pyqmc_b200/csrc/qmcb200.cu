@@ -1768,14 +1768,14 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
       sa.nacc = nacc + se;
       const unsigned grid = (unsigned)((N + sweep_walkers - 1) / sweep_walkers);
       if (G == 8) {
-        if (prep_kernel(k_vmc_sweep<8>, sweep_smem)) return -1;
-        k_vmc_sweep<8><<<grid, sweep_warps * 32, sweep_smem, stream>>>(S, c->st, sa);
+        if (prep_kernel(k_vmc_sweep<8, false>, sweep_smem)) return -1;
+        k_vmc_sweep<8, false><<<grid, sweep_warps * 32, sweep_smem, stream>>>(S, c->st, sa);
       } else if (G == 16) {
-        if (prep_kernel(k_vmc_sweep<16>, sweep_smem)) return -1;
-        k_vmc_sweep<16><<<grid, sweep_warps * 32, sweep_smem, stream>>>(S, c->st, sa);
+        if (prep_kernel(k_vmc_sweep<16, false>, sweep_smem)) return -1;
+        k_vmc_sweep<16, false><<<grid, sweep_warps * 32, sweep_smem, stream>>>(S, c->st, sa);
       } else {
-        if (prep_kernel(k_vmc_sweep<32>, sweep_smem)) return -1;
-        k_vmc_sweep<32><<<grid, sweep_warps * 32, sweep_smem, stream>>>(S, c->st, sa);
+        if (prep_kernel(k_vmc_sweep<32, false>, sweep_smem)) return -1;
+        k_vmc_sweep<32, false><<<grid, sweep_warps * 32, sweep_smem, stream>>>(S, c->st, sa);
       }
       c->nlaunch++;
       CK(cudaGetLastError());
@@ -1972,6 +1972,227 @@ int qmcb_vmc_block_slot(qmcb_ctx* c, int slot, int nsteps, double tstep, int wit
   CK(cudaStreamSynchronize(c->stream));
   acc_all.release();
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Device-resident DMC propagation (dmc_propagate, pyqmc/method/dmc.py:123-221) for single-determinant
+// open-boundary Slater-Jastrow wave functions: initial local energy, then per step the T-moves of every
+// electron, the drift-diffusion sweep (k_vmc_sweep<G, true>), the local energy and the weight update.
+static int dmc_tmove_electron(qmcb_ctx* c, int e, double tau, const double* d_u, const double* d_rot,
+                              const double* d_sel, const double* d_acc, unsigned long long* ntacc, int which,
+                              cudaStream_t stream) {
+  const Sys& S = c->S;
+  const size_t N = c->N, M = (size_t)S.tot_naip;
+  double* d_ratio = c->d_out.p;
+  double* d_weight = d_ratio + N * M;
+  double* d_pos = d_weight + N * M;
+  k_tmove_init<<<(unsigned)((N * M + 255) / 256), 256, 0, stream>>>(S, c->st, e, d_ratio, d_weight, d_pos);
+  c->nlaunch++;
+  CK(cudaGetLastError());
+  CK(cudaMemsetAsync(c->es.count, 0, sizeof(int), stream));
+  const long long nt = (long long)N * S.necp;
+  if (prep_kernel(k_ecp_prepare, c->smem_bytes)) return -1;
+  k_ecp_prepare<<<(unsigned)((nt + 127) / 128), 128, c->smem_bytes, stream>>>(S, c->st, c->es, d_u, e);
+  c->nlaunch++;
+  CK(cudaGetLastError());
+  const size_t npts = N * S.necp * S.max_naip;
+  EcpPointArgs ea{};
+  ea.rot = d_rot;
+  ea.quad = c->d_quad.p;
+  ea.e_only = e;
+  ea.tmove_tau = tau;
+  ea.tm_ratio = d_ratio;
+  ea.tm_weight = d_weight;
+  ea.tm_pos = d_pos;
+  ea.scr = c->d_scr.p;
+  ea.scr_stride = npts;
+  const long long grid = std::min<long long>(((long long)npts + 127) / 128, 148LL * 16);
+  const size_t sm = c->smem_bytes;
+  if (c->nmot == 4) {
+    if (prep_kernel(k_ecp_points<4>, sm)) return -1;
+    k_ecp_points<4><<<(unsigned)grid, 128, sm, stream>>>(S, c->st, c->es, ea);
+  } else if (c->nmot == 8) {
+    if (prep_kernel(k_ecp_points<8>, sm)) return -1;
+    k_ecp_points<8><<<(unsigned)grid, 128, sm, stream>>>(S, c->st, c->es, ea);
+  } else {
+    if (prep_kernel(k_ecp_points<0>, sm)) return -1;
+    k_ecp_points<0><<<(unsigned)grid, 128, sm, stream>>>(S, c->st, c->es, ea);
+  }
+  c->nlaunch++;
+  CK(cudaGetLastError());
+  TmoveSelectArgs ts{};
+  ts.e = e;
+  ts.M = (int)M;
+  ts.ratio = d_ratio;
+  ts.weight = d_weight;
+  ts.pos = d_pos;
+  ts.sel_u = d_sel;
+  ts.acc_u = d_acc;
+  ts.accept = c->d_accept.p;
+  ts.ntacc = ntacc;
+  k_tmove_select<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(S, c->st, ts);
+  c->nlaunch++;
+  CK(cudaGetLastError());
+  if (c->have_slater) {  // MO row at the selected position of the accepted walkers (no saved values, dmc.py:176)
+    PointArgs pa{};
+    pa.which = 1;
+    pa.e = e;
+    pa.naip = 1;
+    pa.pos = c->st.saved_pos;
+    pa.npoints = (int)N;
+    pa.mask = c->d_accept.p;
+    pa.save = 1;
+    pa.scr = c->d_scr.p;
+    pa.scr_stride = N;
+    if (launch_point<PV_MOSAVE>(c, pa, stream)) return -1;
+  }
+  if (launch_update(c, which, e, c->d_accept.p, stream)) return -1;
+  c->mocache_valid = false;
+  c->paircache_valid = false;
+  return 0;
+}
+
+int qmcb_dmc_block(qmcb_ctx* c, int nsteps, double tstep, double branchcut, double e_trial, double e_est,
+                   const double* gauss, const double* unif, const double* ecp_u, const double* ecp_rot,
+                   const double* tm_u, const double* tm_rot, const double* tm_sel, const double* tm_acc,
+                   double* weights, double* configs, double* wsums, int64_t* nacc, int64_t* ntacc) {
+  Guard g(c);
+  if (c->N == 0) return fail("recompute has not been called");
+  if (build_tables(c)) return -1;
+  if (c->N == 0) return fail("system shapes changed: call recompute again");
+  const Sys& S = c->S;
+  const size_t N = c->N;
+  cudaStream_t stream = c->stream;
+  const int which = (c->have_slater ? 1 : 0) | (c->have_jastrow ? 2 : 0);
+  if (S.pbc || c->have_j3 || (c->have_slater && S.ndet != 1))
+    return fail("device-resident DMC supports open-boundary single-determinant Slater-Jastrow wave functions; "
+                "other wave functions run through the per-call protocol");
+  const CoopLayout CL = coop_layout(S);
+  const size_t tab = (c->smem_bytes + 15) & ~(size_t)15;
+  const int G = 16, sweep_warps = 4, sweep_walkers = sweep_warps * (32 / G);
+  const size_t sweep_smem = tab + (size_t)sweep_walkers * CL.total * 8;
+  if (sweep_smem > 200 * 1024) return fail("device-resident DMC: sweep scratch exceeds shared memory");
+  const bool tmoves = S.necp > 0;
+  if (ensure_energy_scratch(c) || energy_scratch_points(c)) return -1;
+  const size_t M = (size_t)S.tot_naip;
+  const size_t nse = (size_t)nsteps * S.ne;
+  const size_t nu1 = (size_t)S.ne * S.necp * N, nr1 = (size_t)S.ne * S.necp * 9;
+  DBuf<double> d_tmu, d_tmrot, d_tmsel, d_tmacc, d_w, d_eold, d_v2old, d_r2p, d_r2a, d_prod, d_ws;
+  DBuf<unsigned long long> d_ntacc;
+  int rc = 0;
+  do {
+    if (c->d_gauss.ensure(nse * N * 3) || c->d_unif.ensure(nse * N) || c->d_u.ensure((size_t)(nsteps + 1) * nu1) ||
+        c->d_rot.ensure((size_t)(nsteps + 1) * nr1) || c->d_energy.ensure(6 * N) || c->d_accept.ensure(N) ||
+        c->d_nacc.ensure(nse) || d_ntacc.ensure(nse) || d_w.ensure(N) || d_eold.ensure(N) || d_v2old.ensure(N) ||
+        d_r2p.ensure(N) || d_r2a.ensure(N) || d_prod.ensure(7 * N) || d_ws.ensure((size_t)nsteps * 8) ||
+        c->d_out.ensure(std::max<size_t>(N * M * 5, N * 8)) || ensure_scratch(c, std::max<size_t>(N * S.necp * S.max_naip, N), 5)) {
+      rc = -1;
+      break;
+    }
+    auto up = [&](double* dst, const double* src, size_t n) {
+      return n == 0 ? cudaSuccess : cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyHostToDevice, stream);
+    };
+    if (up(c->d_gauss.p, gauss, nse * N * 3) != cudaSuccess || up(c->d_unif.p, unif, nse * N) != cudaSuccess ||
+        up(d_w.p, weights, N) != cudaSuccess) {
+      rc = fail("H2D copy failed");
+      break;
+    }
+    if (tmoves) {
+      if (!ecp_u || !ecp_rot || !tm_u || !tm_rot || !tm_sel || !tm_acc) {
+        rc = fail("DMC with ECPs needs the energy and T-move variates");
+        break;
+      }
+      if (d_tmu.ensure(nse * S.necp * N) || d_tmrot.ensure(nse * S.necp * 9) || d_tmsel.ensure(nse * N) || d_tmacc.ensure(nse * N)) {
+        rc = -1;
+        break;
+      }
+      if (up(c->d_u.p, ecp_u, (size_t)(nsteps + 1) * nu1) != cudaSuccess || up(c->d_rot.p, ecp_rot, (size_t)(nsteps + 1) * nr1) != cudaSuccess ||
+          up(d_tmu.p, tm_u, nse * S.necp * N) != cudaSuccess || up(d_tmrot.p, tm_rot, nse * S.necp * 9) != cudaSuccess ||
+          up(d_tmsel.p, tm_sel, nse * N) != cudaSuccess || up(d_tmacc.p, tm_acc, nse * N) != cudaSuccess) {
+        rc = fail("H2D copy failed");
+        break;
+      }
+    }
+    cudaMemsetAsync(c->d_nacc.p, 0, nse * 8, stream);
+    cudaMemsetAsync(d_ntacc.p, 0, nse * 8, stream);
+    // E_L and v^2 before the first step (dmc.py:150-152)
+    if ((rc = launch_energy(c, c->d_u.p, c->d_rot.p, c->d_energy.p, stream))) break;
+    DmcWeightArgs wa{};
+    wa.tstep = tstep;
+    wa.branchcut = branchcut;
+    wa.e_trial = e_trial;
+    wa.e_est = e_est;
+    wa.energy = c->d_energy.p;
+    wa.r2prop = d_r2p.p;
+    wa.r2acc = d_r2a.p;
+    wa.eold = d_eold.p;
+    wa.v2old = d_v2old.p;
+    wa.weights = d_w.p;
+    wa.prod = d_prod.p;
+    wa.init = 1;
+    k_dmc_weights<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(S, c->st, wa);
+    c->nlaunch++;
+    wa.init = 0;
+    for (int step = 0; step < nsteps && rc == 0; ++step) {
+      if (tmoves) {
+        for (int e = 0; e < S.ne && rc == 0; ++e) {
+          const size_t se = (size_t)step * S.ne + e;
+          rc = dmc_tmove_electron(c, e, tstep, d_tmu.p + se * S.necp * N, d_tmrot.p + se * S.necp * 9, d_tmsel.p + se * N,
+                                  d_tmacc.p + se * N, d_ntacc.p + se, which, stream);
+        }
+        if (rc) break;
+      }
+      if (c->have_slater && !c->mocache_valid) {
+        if ((rc = launch_mo_all(c, 0, stream))) break;
+      }
+      if (c->have_jastrow && !c->paircache_valid) {
+        const long long nt = (long long)N * (S.npair + S.ne);
+        if ((rc = prep_kernel(k_pair_cache_build, c->smem_bytes))) break;
+        k_pair_cache_build<<<(unsigned)((nt + 127) / 128), 128, c->smem_bytes, stream>>>(S, c->st);
+        c->nlaunch++;
+        c->paircache_valid = true;
+      }
+      cudaMemsetAsync(d_r2p.p, 0, N * 8, stream);
+      cudaMemsetAsync(d_r2a.p, 0, N * 8, stream);
+      SweepArgs sa{};
+      sa.tstep = tstep;
+      sa.gauss = c->d_gauss.p + (size_t)step * S.ne * N * 3;
+      sa.unif = c->d_unif.p + (size_t)step * S.ne * N;
+      sa.accept = nullptr;
+      sa.nacc = c->d_nacc.p + (size_t)step * S.ne;
+      sa.r2prop = d_r2p.p;
+      sa.r2acc = d_r2a.p;
+      if ((rc = prep_kernel(k_vmc_sweep<16, true>, sweep_smem))) break;
+      k_vmc_sweep<16, true><<<(unsigned)((N + sweep_walkers - 1) / sweep_walkers), sweep_warps * 32, sweep_smem, stream>>>(S, c->st, sa);
+      c->nlaunch++;
+      if (cudaGetLastError() != cudaSuccess) {
+        rc = fail("k_vmc_sweep<16, true> launch failed");
+        break;
+      }
+      if ((rc = launch_energy(c, c->d_u.p + (size_t)(step + 1) * nu1, c->d_rot.p + (size_t)(step + 1) * nr1, c->d_energy.p, stream))) break;
+      k_dmc_weights<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(S, c->st, wa);
+      c->nlaunch++;
+      k_colsum<<<7, 256, 0, stream>>>(d_prod.p, (int)N, d_ws.p + (size_t)step * 8);
+      c->nlaunch++;
+    }
+    if (rc) break;
+    if (cudaGetLastError() != cudaSuccess) {
+      rc = fail("DMC kernel launch failed");
+      break;
+    }
+    cudaMemcpyAsync(weights, d_w.p, N * 8, cudaMemcpyDeviceToHost, stream);
+    if (wsums) cudaMemcpyAsync(wsums, d_ws.p, (size_t)nsteps * 8 * 8, cudaMemcpyDeviceToHost, stream);
+    if (nacc) cudaMemcpyAsync(nacc, c->d_nacc.p, nse * 8, cudaMemcpyDeviceToHost, stream);
+    if (ntacc) cudaMemcpyAsync(ntacc, d_ntacc.p, nse * 8, cudaMemcpyDeviceToHost, stream);
+    if (configs) cudaMemcpyAsync(configs, c->st.conf, N * S.ne * 3 * 8, cudaMemcpyDeviceToHost, stream);
+    if (cudaStreamSynchronize(stream) != cudaSuccess) rc = fail(std::string("DMC block failed: ") + cudaGetErrorString(cudaGetLastError()));
+  } while (0);
+  cudaStreamSynchronize(stream);
+  DBuf<double>* tmp[] = {&d_tmu, &d_tmrot, &d_tmsel, &d_tmacc, &d_w, &d_eold, &d_v2old, &d_r2p, &d_r2a, &d_prod, &d_ws};
+  for (auto* b : tmp) b->release();
+  d_ntacc.release();
+  c->saved_slot = -1;
+  return rc;
 }
 
 int qmcb_pinned_alloc(int64_t bytes, void** out) {

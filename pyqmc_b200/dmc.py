@@ -1,0 +1,314 @@
+"""DMC driver with the reference's signatures (``pyqmc/method/dmc.py``).
+
+``limdrift`` (22-35), ``get_V2`` (38-46), ``propose_drift_diffusion`` (49-70), ``propose_tmoves``
+(73-120), ``dmc_propagate`` (123-221), ``compute_S`` (224-235), ``branch`` (342-376) and ``rundmc``
+(412-586, without the HDF5 restart file) keep the reference's arguments, RNG consumption order and
+output dictionaries.
+
+When the wave function is a fused single-determinant Slater-Jastrow on an open-boundary system and
+the only accumulator is a ``pyqmc_b200.EnergyAccumulator``, ``dmc_propagate`` runs DEVICE-RESIDENT:
+every random variate of the block is drawn up front from the global legacy ``np.random`` stream in
+exactly the order the reference loop consumes it, shipped once, and ``qmcb_dmc_block`` executes the
+T-moves, drift-diffusion sweeps, local energies and weight updates without host round trips.  Any
+other combination goes through the generic loop over the wave-function protocol calls.
+"""
+import logging
+
+import numpy as np
+import scipy.spatial.transform
+
+from . import _lib, mc
+from .accumulators import KEYS, EnergyAccumulator, _device_context
+from .wf import JASTROW, SLATER
+
+
+def limdrift(g, tau, acyrus=0.5):
+    v2 = np.sum(g**2, axis=1)
+    mask = v2 > 1e-8
+    taueff = np.ones(v2.shape) * tau
+    taueff[mask] = (np.sqrt(1 + 2 * tau * acyrus * v2[mask]) - 1) / (acyrus * v2[mask])
+    return g * taueff[:, np.newaxis]
+
+
+def get_V2(configs, wf, acc_out):
+    if "grad2" in acc_out.keys():
+        return acc_out["grad2"]
+    nconfig, nelec = configs.configs.shape[0:2]
+    v2 = np.zeros(nconfig)
+    for e in range(nelec):
+        v2 += np.sum(np.abs(wf.gradient(e, configs.electron(e))).T ** 2, axis=1)
+    return v2
+
+
+def propose_drift_diffusion(wf, configs, tstep, e):
+    nconfig = configs.configs.shape[0]
+    grad = limdrift(np.real(wf.gradient(e, configs.electron(e)).T), tstep)
+    gauss = np.random.normal(scale=np.sqrt(tstep), size=(nconfig, 3))
+    eposnew = configs.configs[:, e, :] + gauss + grad
+    newepos = configs.make_irreducible(e, eposnew)
+    g, wfratio, saved = wf.gradient_value(e, newepos)
+    new_grad = limdrift(np.real(g.T), tstep)
+    forward = np.sum(gauss**2, axis=1)
+    backward = np.sum((gauss + grad + new_grad) ** 2, axis=1)
+    t_prob = np.exp(1 / (2 * tstep) * (forward - backward))
+    ratio = np.abs(wfratio) ** 2 * t_prob
+    if wf.dtype == float:
+        ratio *= np.sign(wfratio)
+    accept = ratio > np.random.rand(nconfig)
+    r2 = np.sum((gauss + grad) ** 2, axis=1)
+    return newepos, accept, r2, saved
+
+
+def propose_tmoves(wf, configs, energy_accumulator, tstep, e):
+    moves = energy_accumulator.nonlocal_tmoves(configs, wf, e, tstep)
+    t_amplitudes = moves["ratio"] * moves["weight"]
+    forward_probability = np.zeros_like(t_amplitudes)
+    forward_probability[t_amplitudes > 0] = t_amplitudes[t_amplitudes > 0]
+    norm = 1.0 + np.sum(forward_probability, axis=1)
+    cdf = np.cumsum(forward_probability / norm[:, np.newaxis], axis=1)
+    selected_moves = np.array([np.searchsorted(row, np.random.rand()) for row in cdf], dtype=int).reshape(len(cdf))
+    move_selected = selected_moves < t_amplitudes.shape[1]
+    newpos = np.zeros((norm.shape[0], 3))
+    reverse_ratio = np.zeros((norm.shape[0]))
+    backward_amplitudes = t_amplitudes.copy()
+    for walker, move in enumerate(selected_moves):
+        if move_selected[walker]:
+            newpos[walker, :] = moves["configs"].configs[walker, move, :]
+            reverse_ratio[walker] = 1.0 / moves["ratio"][walker, move]
+            backward_amplitudes[walker, :] *= reverse_ratio[walker]
+            backward_amplitudes[walker, move] = reverse_ratio[walker] * moves["weight"][walker, move]
+        else:
+            newpos[walker, :] = configs.configs[walker, e, :]
+            reverse_ratio[walker] = 0.0
+    newpos = configs.make_irreducible(e, newpos)
+    backward_amplitudes[backward_amplitudes < 0] = 0.0
+    back_norm = 1.0 + np.sum(backward_amplitudes, axis=1)
+    acceptance = norm / back_norm
+    acceptance[move_selected == False] = 0.0  # noqa: E712
+    return newpos, move_selected, acceptance, np.sum(t_amplitudes)
+
+
+def compute_S(e_trial, e_est, branchcut, v2, tau, eloc, nelec):
+    e_cut = e_est - eloc
+    mask = np.abs(e_cut) > branchcut
+    e_cut[mask] = branchcut * np.sign(e_cut[mask])
+    denominator = np.sqrt(1 + (v2 * tau / nelec) ** 2)
+    return e_trial - e_est + e_cut / denominator
+
+
+def _device_dmc_path(wf, accumulators, ekey):
+    """Device-resident propagation: fused single-determinant Slater x JastrowSpin, open boundary
+    conditions, one EnergyAccumulator under ``ekey[0]``."""
+    try:
+        ctx = _device_context(wf)
+    except TypeError:
+        return False
+    if len(accumulators) != 1 or not isinstance(accumulators.get(ekey[0]), EnergyAccumulator) or ekey[1] != "total":
+        return False
+    which = getattr(wf, "_which", 0)
+    if which & ~(SLATER | JASTROW) or not (which & SLATER):
+        return False
+    factors = getattr(wf, "wf_factors", [wf])
+    if len(factors[0].parameters["det_coeff"]) != 1:
+        return False
+    mol = factors[0]._mol
+    del ctx
+    return not hasattr(mol, "a")
+
+
+def draw_dmc_block_variates(nconf, nelec, tstep, nsteps, accumulator):
+    """Every random number of one ``dmc_propagate`` call in the reference's order: the energy
+    evaluation before the first step; then per step, for every electron the T-move draws
+    (``nonlocal_tmoves``: per ECP atom ``random(N)`` + a rotation; ``select_walker``: one ``rand()``
+    per walker; acceptance ``rand(N)``), for every electron ``normal(N, 3)`` + ``rand(N)``, and the
+    energy evaluation."""
+    necp = accumulator.necp
+    ecp_u = np.empty((nsteps + 1, nelec, necp, nconf))
+    ecp_rot = np.empty((nsteps + 1, nelec, necp, 3, 3))
+    tm_u = np.empty((nsteps, nelec, necp, nconf))
+    tm_rot = np.empty((nsteps, nelec, necp, 3, 3))
+    tm_sel = np.empty((nsteps, nelec, nconf))
+    tm_acc = np.empty((nsteps, nelec, nconf))
+    gauss = np.empty((nsteps, nelec, nconf, 3))
+    unif = np.empty((nsteps, nelec, nconf))
+    ecp_u[0], ecp_rot[0] = accumulator.draw_ecp_variates(nconf, nelec)
+    tmoves = accumulator.has_nonlocal_moves()
+    for step in range(nsteps):
+        if tmoves:
+            for e in range(nelec):
+                for a in range(necp):
+                    tm_u[step, e, a] = np.random.random(size=nconf)
+                    tm_rot[step, e, a] = scipy.spatial.transform.Rotation.random().as_matrix()
+                tm_sel[step, e] = np.random.rand(nconf)  # == nconf successive scalar rand() calls
+                tm_acc[step, e] = np.random.rand(nconf)
+        for e in range(nelec):
+            gauss[step, e] = np.random.normal(scale=np.sqrt(tstep), size=(nconf, 3))
+            unif[step, e] = np.random.rand(nconf)
+        ecp_u[step + 1], ecp_rot[step + 1] = accumulator.draw_ecp_variates(nconf, nelec)
+    return dict(ecp_u=ecp_u, ecp_rot=ecp_rot, tm_u=tm_u, tm_rot=tm_rot, tm_sel=tm_sel, tm_acc=tm_acc, gauss=gauss,
+                unif=unif)
+
+
+def dmc_propagate_device(wf, configs, weights, tstep, branchcut_start, e_trial, e_est, nsteps, accumulators, ekey):
+    nconf, nelec, _ = configs.configs.shape
+    wf.recompute(configs)
+    ctx = _device_context(wf)
+    accumulator = accumulators[ekey[0]]
+    accumulator._attach(wf)
+    v = draw_dmc_block_variates(nconf, nelec, tstep, nsteps, accumulator)
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    newconf = np.empty((nconf, nelec, 3))
+    wsums = np.zeros((nsteps, 8))
+    nacc = np.zeros((nsteps, nelec), dtype=np.int64)
+    ntacc = np.zeros((nsteps, nelec), dtype=np.int64)
+    d = _lib.dptr
+    _lib.check(ctx.lib.qmcb_dmc_block(
+        ctx.h, nsteps, float(tstep), float(branchcut_start), float(e_trial), float(e_est), d(v["gauss"]), d(v["unif"]),
+        d(v["ecp_u"]), d(v["ecp_rot"]), d(v["tm_u"]), d(v["tm_rot"]), d(v["tm_sel"]), d(v["tm_acc"]), d(w), d(newconf),
+        d(wsums), nacc.ctypes.data_as(_lib.c_i64_p), ntacc.ctypes.data_as(_lib.c_i64_p)))
+    configs.configs[...] = newconf
+    if w is not weights:
+        weights[...] = w
+    rows = []
+    for step in range(nsteps):
+        wavg = wsums[step, 6] / nconf
+        avg = {ekey[0] + k: wsums[step, i] / (nconf * wavg) for i, k in enumerate(KEYS)}
+        avg["weight"] = wavg
+        avg["acceptance"] = np.mean(nacc[step] / nconf)
+        avg["tmove_acceptance"] = np.mean(ntacc[step] / nconf)
+        rows.append(avg)
+    return _collect(rows), configs, weights
+
+
+def _collect(df):
+    weight = np.asarray([d["weight"] for d in df])
+    avg_weight = weight / np.mean(weight)
+    df_ret = {k: np.mean([d[k] * w for d, w in zip(df, avg_weight)], axis=0) for k in df[0].keys()}
+    df_ret["weight"] = np.mean(weight)
+    return df_ret
+
+
+def dmc_propagate(wf, configs, weights, tstep, branchcut_start, e_trial, e_est, nsteps=5, accumulators=None,
+                  ekey=("energy", "total")):
+    """Propagate DMC without branching (dmc.py:123-221)."""
+    assert accumulators is not None, "Need an energy accumulator for DMC"
+    if _device_dmc_path(wf, accumulators, ekey):
+        return dmc_propagate_device(wf, configs, weights, tstep, branchcut_start, e_trial, e_est, nsteps, accumulators,
+                                    ekey)
+    nconfig, nelec = configs.configs.shape[0:2]
+    wf.recompute(configs)
+    energy_acc = accumulators[ekey[0]](configs, wf)
+    eloc = energy_acc[ekey[1]].real
+    v2 = get_V2(configs, wf, energy_acc)
+    df = []
+    for _ in range(nsteps):
+        r2_accepted = np.zeros(nconfig)
+        r2_proposed = np.zeros(nconfig)
+        prob_acceptance = np.zeros(nconfig)
+        tmove_acceptance = np.zeros(nconfig)
+        if accumulators[ekey[0]].has_nonlocal_moves():
+            for e in range(nelec):
+                newepos, mask, probability, _ = propose_tmoves(wf, configs, accumulators[ekey[0]], tstep, e)
+                accept = mask & (probability > np.random.rand(nconfig))
+                configs.move(e, newepos, accept)
+                wf.updateinternals(e, newepos, configs, mask=accept)
+                tmove_acceptance += accept / nelec
+        for e in range(nelec):
+            newepos, accept, r2, saved = propose_drift_diffusion(wf, configs, tstep, e)
+            configs.move(e, newepos, accept)
+            wf.updateinternals(e, newepos, configs, mask=accept, saved_values=saved)
+            r2_proposed += r2
+            r2_accepted[accept] += r2[accept]
+            prob_acceptance += accept / nelec
+        elocold = eloc.copy()
+        v2old = v2.copy()
+        energydat = accumulators[ekey[0]](configs, wf)
+        eloc = energydat[ekey[1]].real
+        tdamp = r2_accepted / r2_proposed
+        v2 = get_V2(configs, wf, energydat)
+        Snew = compute_S(e_trial, e_est, branchcut_start, v2, tstep, eloc, nelec)
+        Sold = compute_S(e_trial, e_est, branchcut_start, v2old, tstep, elocold, nelec)
+        wmult = np.exp(tstep * tdamp * (0.5 * Snew + 0.5 * Sold))
+        weights *= wmult
+        wavg = np.mean(weights)
+        avg = {}
+        for k, accumulator in accumulators.items():
+            dat = accumulator(configs, wf) if k != ekey[0] else energydat
+            for m, res in dat.items():
+                avg[k + m] = np.einsum("...i,i...->...", weights, res) / (nconfig * wavg)
+        avg["weight"] = wavg
+        avg["acceptance"] = np.mean(prob_acceptance)
+        avg["tmove_acceptance"] = np.mean(tmove_acceptance)
+        df.append(avg)
+    return _collect(df), configs, weights
+
+
+def branch(configs, weights):
+    """Stochastic-comb branching (dmc.py:342-376)."""
+    nconfig = configs.configs.shape[0]
+    if np.any(weights > 2.0):
+        logging.warning("Some weights are larger than 2")
+    probability = np.cumsum(weights)
+    wtot = probability[-1]
+    base = np.random.rand() * wtot
+    newinds = np.searchsorted(probability, (base + np.linspace(0, wtot, nconfig, endpoint=False)) % wtot)
+    unique, counts = np.unique(newinds, return_counts=True)
+    configs.resample(newinds)
+    weights.fill(wtot / nconfig)
+    return configs, weights, {"max branches": np.max(counts), "Number of walkers killed": nconfig - unique.shape[0]}
+
+
+def estimate_energy(df, ekey):
+    en = np.asarray([d[ekey[0] + ekey[1]] for d in df])
+    wt = np.asarray([d["weight"] for d in df])
+    warmup = int(len(en) / 4)
+    return np.average(en[warmup:], weights=wt[warmup:]).real
+
+
+def rundmc(wf, configs, weights=None, tstep=0.01, nblocks=200, nsteps_per_block=None, blockoffset=0, accumulators=None,
+           verbose=False, hdf_file=None, continue_from=None, client=None, npartitions=None, ekey=("energy", "total"),
+           vmc_warmup=10, branchcut_start=10, feedback=1.0):
+    """Same arguments and return value as ``pyqmc.method.dmc.rundmc`` (dmc.py:412-586); the HDF5
+    restart file and the futures client are outside the accelerated path."""
+    if hdf_file is not None or continue_from is not None:
+        raise NotImplementedError("HDF5 checkpointing is outside the accelerated path; pass hdf_file=None "
+                                  "or drive these wave functions with pyqmc.method.dmc.rundmc")
+    if client is not None:
+        raise NotImplementedError("walker partitions are sharded one process per GPU (pyqmc_b200.parallel)")
+    if nsteps_per_block is None:
+        nsteps_per_block = max(1, int(0.1 / tstep))
+    df, configs = mc.vmc(wf, configs, verbose=verbose, nblocks=vmc_warmup)
+    wf.recompute(configs)
+    en = accumulators[ekey[0]](configs, wf)[ekey[1]]
+    eref = np.mean(en).real
+    e_trial = eref
+    e_est = eref
+    esigma = np.std(en)
+    if verbose:
+        print("eref start", eref, "esigma", esigma)
+    nconfig = configs.configs.shape[0]
+    if weights is None:
+        weights = np.ones(nconfig)
+    df = []
+    if blockoffset >= nblocks:
+        logging.warning(f"blockoffset {blockoffset} >= nblocks {nblocks}; no steps will be run.")
+    for block in range(blockoffset, nblocks):
+        df_, configs, weights = dmc_propagate(wf, configs, weights, tstep, branchcut_start * esigma, e_trial=e_trial,
+                                              e_est=e_est, nsteps=nsteps_per_block, accumulators=accumulators,
+                                              ekey=ekey)
+        df_["e_trial"] = e_trial
+        df_["e_est"] = e_est
+        df_["block"] = block
+        df_["esigma"] = esigma
+        df_["tstep"] = tstep
+        df_["weight_std"] = np.std(weights)
+        df_["nsteps_per_block"] = nsteps_per_block
+        configs, weights, branch_info = branch(configs, weights)
+        df_.update(branch_info)
+        df.append(df_)
+        e_est = estimate_energy(df, ekey)
+        e_trial = e_est - feedback * np.log(np.mean(weights)).real
+        if verbose:
+            print("energy", df_[ekey[0] + ekey[1]], "e_trial", e_trial, "e_est", e_est, "sigma(w)", df_["weight_std"])
+    df_ret = {k: np.asarray([d[k] for d in df]) for k in df[0].keys()} if len(df) > 0 else {}
+    return df_ret, configs, weights
