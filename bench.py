@@ -44,6 +44,11 @@ WORKLOADS = {
                text="diamond-C 2x2x2 supercell PBC Slater-Jastrow VMC (synthetic basis/MOs, 8 k-points), 64 e-, "
                     "16 atoms, Ewald + ECP, 1024 walkers/GPU"),
 }
+WORKLOADS["c5"] = dict(
+    system="h2o", walkers=2048, cpu_walkers=128, cpu_steps=20, tstep=0.02, spb=5,
+    metric="walker-steps/sec (DMC with T-moves, H2O cc-pVTZ SJ, tstep 0.02); Sherman-Morrison HBM GB/s vs roofline",
+    text="H2O ccECP-cc-pVTZ-shaped Slater-Jastrow DMC (synthetic basis/MOs), tstep 0.02, 5 steps per block, T-moves, "
+         "branching every block, 2048 walkers/GPU")
 # DRAM bytes per launch of k_sm_warp<32> on 131072 matrices from the committed ncu --set full capture
 # (profiles/r1_ncu_k_sm_warp32.txt: dram__bytes_read.sum + dram__bytes_write.sum)
 SM32_TRAFFIC_BYTES = 2.12e9
@@ -92,6 +97,41 @@ def _cpu_worker(args):
     t0 = time.perf_counter()
     vmc_driver.vmc_worker(wf, configs, TSTEP, nsteps, acc)
     return time.perf_counter() - t0
+
+
+def _cpu_worker_dmc(args):
+    seed, nwalk, nsteps, system = args
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    from oracle import dmc_driver, vmc_driver
+    from oracle.jastrow2 import JastrowOracle
+    from oracle.local_energy import EnergyOracle
+    from oracle.product import ProductOracle
+    from oracle.slater_det import SlaterOracle
+
+    mol, mf, dets = helpers.make_system(system)
+    oj = JastrowOracle.default(mol)
+    a0, ac, bc = helpers.jastrow_coefficients(oj.parameters["acoeff"].shape, oj.parameters["bcoeff"].shape, False, 1)
+    oj.parameters["acoeff"][:, a0:, :] = ac[:, a0:, :]
+    oj.parameters["bcoeff"][1:, :] = bc[1:, :]
+    wf = ProductOracle(SlaterOracle(mol, mf), oj)
+    np.random.seed(seed)
+    configs = vmc_driver.initial_guess(mol, nwalk)
+    t0 = time.perf_counter()
+    dmc_driver.dmc_propagate(wf, configs, np.ones(nwalk), WORKLOADS["c5"]["tstep"], 10.0, 20.0, 20.0, nsteps=nsteps,
+                             accumulators={"energy": EnergyOracle(mol)})
+    return time.perf_counter() - t0
+
+
+def cpu_arm_dmc(steps, walkers_per_core, cores=None, system="h2o"):
+    cores = min(cores or os.cpu_count() or 1, 64)
+    with mp.get_context("spawn").Pool(cores) as pool:
+        pool.map(_cpu_worker_dmc, [(100 + i, 16, 1, system) for i in range(cores)])
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker_dmc, [(i, walkers_per_core, steps, system) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    return (walkers_per_core * cores * steps / wall, cores, wall,
+            f"{walkers_per_core} walkers/core x {cores} cores x {steps} DMC steps with T-moves (oracle port, numpy)")
 
 
 def cpu_arm(steps, warmup, walkers_per_core=256, cores=None, system="h2o"):
@@ -341,6 +381,117 @@ def gpu_arm(args):
         dist.destroy_process_group()
 
 
+def gpu_arm_dmc(args):
+    """--workload c5: DMC blocks (dmc_propagate + branch) through pyqmc_b200.dmc; one step = T-moves of
+    every electron + drift-diffusion sweep + local energy + weight update for every walker."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ["PYQMC_B200_DEVICE"] = str(local)
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as g
+
+    if rank == 0:
+        g.build()
+    if world > 1:
+        dist.barrier()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    import pyqmc_b200 as pq
+    from pyqmc_b200 import dmc
+
+    wl = WORKLOADS["c5"]
+    N, tstep, spb = (args.walkers or wl["walkers"]), wl["tstep"], wl["spb"]
+    K, W = max(1, args.steps // spb), max(1, args.warmup // spb)  # blocks
+    mol, mf, wf, _ = helpers.make_pair(wl["system"], seed=1)
+    acc = {"energy": pq.EnergyAccumulator(mol)}
+    np.random.seed(1000 + rank)
+    configs = pq.initial_guess(mol, N)
+    df0, configs = pq.vmc(wf, configs, tstep=0.5, nblocks=2, nsteps_per_block=args.equil, accumulators=acc)
+    weights = np.ones(N)
+    ctx = wf._ctx
+    e0 = float(df0["energytotal"][-1])  # trial / estimated energy from the VMC warm-up (rundmc, dmc.py:497-506)
+
+    def block():
+        nonlocal configs, weights
+        out, configs, weights = dmc.dmc_propagate(wf, configs, weights, tstep, 10.0, e0, e0, nsteps=spb, accumulators=acc)
+        from pyqmc_b200 import parallel
+
+        glob, _ = parallel.allreduce_dmc_block(out, N)  # one allreduce of the block's weighted sums (dmc.py:288-303)
+        configs, weights, _ = parallel.branch_global(configs, weights)  # comb over the global population
+        return out
+
+    for _ in range(W):
+        block()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ctx.kernel_launches()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        out = block()
+    torch.cuda.synchronize()
+    t = time.perf_counter() - t0
+    launches = ctx.kernel_launches() - l0
+    clocks = sampler.stop() if sampler else None
+    tt = torch.tensor([t], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t = float(tt.item())
+    e2e = N * world * K * spb / t
+    # device share: the same blocks with the variates drawn beforehand (qmcb_dmc_block incl. its H2D/D2H)
+    import pyqmc_b200.dmc as D
+
+    pre = [D.draw_dmc_block_variates(N, configs.configs.shape[1], tstep, spb, acc["energy"]) for _ in range(K)]
+    orig = D.draw_dmc_block_variates
+    it = iter(pre)
+    D.draw_dmc_block_variates = lambda *a, **k: next(it)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    for _ in range(K):
+        out, configs, weights = dmc.dmc_propagate(wf, configs, weights, tstep, 10.0, e0, e0, nsteps=spb, accumulators=acc)
+    torch.cuda.synchronize()
+    tdev = time.perf_counter() - t1
+    D.draw_dmc_block_variates = orig
+    td = torch.tensor([tdev], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(td, op=dist.ReduceOp.MAX)
+    value = N * world * K * spb / float(td.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ne, necp = configs.configs.shape[1], acc["energy"].necp
+    per_step = ne * N * (3 + 1) * 8 + ne * necp * (N + 9) * 8 * 2 + ne * N * 2 * 8
+    res = {
+        "metric": wl["metric"], "value": value, "unit": "walker-steps/s", "n_gpus": world, "steps": K * spb, "warmup": W * spb,
+        "ms_per_step": 1e3 * float(td.item()) / (K * spb), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["text"].replace("2048 walkers/GPU", f"{N} walkers/GPU"), "walkers_per_gpu": N, "tstep": tstep,
+                   "l2": "walker state (2 KB/walker) is L2-resident by design; no flush between blocks",
+                   "value_definition": "dmc_propagate with pre-drawn variates (recompute + qmcb_dmc_block incl. H2D/D2H), wall clock"},
+        "e2e": {"value": e2e, "unit": "walker-steps/s", "h2d_bytes_per_step": per_step + N * ne * 3 * 8 / spb,
+                "d2h_bytes_per_step": (N * ne * 3 * 8 + N * 8) / spb,
+                "call": "pyqmc_b200.dmc.dmc_propagate + branch per block incl. host legacy-RNG draws"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "check": {"block_energy": float(out["energytotal"]), "acceptance": float(out["acceptance"]),
+                  "tmove_acceptance": float(out["tmove_acceptance"]), "weight": float(out["weight"])},
+    }
+    if world == 1 and not args.no_cpu:
+        v, cores, cwall, sample = cpu_arm_dmc(wl["cpu_steps"], wl["cpu_walkers"], system=wl["system"])
+        res["cpu_baseline"] = {"value": v, "unit": "walker-steps/s", "cores": cores, "kind": "port", "sample": sample, "wall_s": cwall}
+    print(json.dumps(res), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -378,6 +529,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
+    elif args.workload == "c5":
+        gpu_arm_dmc(args)
     else:
         gpu_arm(args)
 

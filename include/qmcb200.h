@@ -244,6 +244,13 @@ int qmcb_rng_vmc_block(uint32_t *key, int32_t *pos, int32_t *has_gauss, double *
                        int nsteps, int ne, int64_t N, int necp, double scale, double *gauss,
                        double *unif, double *ecp_u, double *ecp_rot, int nthreads);
 
+/* generic draw program on the same bit-identical generator: op i draws count[i] values into the
+ * host buffer at address dst[i]; kind[i] = 0 uniform [0,1) doubles, 1 normals times scale[i], 2 one
+ * scipy Rotation.random() matrix (dst[i][9]).  Used for the DMC block (pyqmc/method/dmc.py:150-198). */
+int qmcb_rng_program(uint32_t *key, int32_t *pos, int32_t *has_gauss, double *cached_gauss,
+                     int64_t nops, const int32_t *kind, const int64_t *count, const uint64_t *dst,
+                     const double *scale, int nthreads);
+
 /* two-stage form of the same generator: phase A (sequential walk of the MT19937 stream; fills the
  * uniform outputs, records the accepted polar pairs, advances the state) and phase B (log/sqrt of
  * the pairs and the Gaussian outputs, nthreads host threads) on a plan handle, so phase A of the

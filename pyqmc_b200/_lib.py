@@ -75,6 +75,8 @@ SIGNATURES = {
     "qmcb_sm_update_device": (c_int, [c_int, c_int, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "qmcb_rng_vmc_block": (c_int, [ctypes.POINTER(ctypes.c_uint32), c_int_p, c_int_p, c_double_p, c_int, c_int, c_i64,
                                    c_int, c_double, c_double_p, c_double_p, c_double_p, c_double_p, c_int]),
+    "qmcb_rng_program": (c_int, [ctypes.POINTER(ctypes.c_uint32), c_int_p, c_int_p, c_double_p, c_i64, c_int_p, c_i64_p,
+                                 ctypes.POINTER(ctypes.c_uint64), c_double_p, c_int]),
     "qmcb_rng_plan_create": (c_void_p, []),
     "qmcb_rng_plan_destroy": (None, [c_void_p]),
     "qmcb_rng_phase_a": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_uint32), c_int_p, c_int_p, c_double_p, c_int, c_int,

@@ -445,11 +445,12 @@ struct RngPlan {
   }
 };
 
-// Phase A: walks the MT19937 stream for one block (sequential), fills the uniform outputs, records
-// the accepted polar pairs and the destination segments of every Gaussian; advances the state.
-int rng_phase_a(RngPlan& rp, uint32_t* key, int32_t* pos, int32_t* has_gauss, double* cached_gauss, int nsteps, int ne,
-                int64_t N, int necp, double scale, double* gauss, double* unif, double* ecp_u, double* ecp_rot,
-                int nthreads) {
+// Phase A: walks the MT19937 stream (sequential), fills the uniform outputs, records the accepted
+// polar pairs and the destination segments of every Gaussian; advances the state.  `body(s, plan)`
+// issues the draws in the caller's order through fill_uniform / plan.take.
+template <class Body>
+int rng_run_phase_a(RngPlan& rp, uint32_t* key, int32_t* pos, int32_t* has_gauss, double* cached_gauss, int64_t est_pairs,
+                    int nthreads, Body body) {
   if (*pos < 0 || *pos > 624) return -1;
   std::unique_ptr<Ring> ring(new Ring());
   std::memcpy(ring->key, key, sizeof(ring->key));
@@ -466,25 +467,10 @@ int rng_phase_a(RngPlan& rp, uint32_t* key, int32_t* pos, int32_t* has_gauss, do
     plan.slot_shift = 1;
     plan.carried = *cached_gauss;
   }
-  const int64_t est = (int64_t)nsteps * ne * (N * 3 / 2 + 1 + 2 * (ecp_u ? necp : 0)) + 64;
-  plan.x1.resize(est);
-  plan.x2.resize(est);
-  plan.r2.resize(est);
-  for (int step = 0; step < nsteps; ++step) {
-    for (int e = 0; e < ne; ++e) {
-      double* go = gauss + ((int64_t)step * ne + e) * N * 3;
-      plan.segs.push_back(Segment{go, N * 3, plan.take(s, N * 3), scale, 0});
-      fill_uniform(s, unif + ((int64_t)step * ne + e) * N, N);
-    }
-    if (ecp_u) {
-      for (int e = 0; e < ne; ++e)
-        for (int a = 0; a < necp; ++a) {
-          const int64_t ea = ((int64_t)step * ne + e) * necp + a;
-          fill_uniform(s, ecp_u + ea * N, N);
-          plan.segs.push_back(Segment{ecp_rot + ea * 9, 4, plan.take(s, 4), 1.0, 1});
-        }
-    }
-  }
+  plan.x1.resize(est_pairs);
+  plan.x2.resize(est_pairs);
+  plan.r2.resize(est_pairs);
+  body(s, plan);
   if (ring->threaded) {
     ring->stop.store(true, std::memory_order_release);
     producer.join();
@@ -509,6 +495,31 @@ int rng_phase_a(RngPlan& rp, uint32_t* key, int32_t* pos, int32_t* has_gauss, do
   std::memcpy(key, ring->raw[s.blk % Ring::K], sizeof(ring->key));
   *pos = s.pos;
   return 0;
+}
+
+// one VMC block: per step and electron normal(N,3), rand(N); then per electron and ECP atom
+// random(N) and a rotation (mc.py:119,132; eval_ecp.py:145,263)
+int rng_phase_a(RngPlan& rp, uint32_t* key, int32_t* pos, int32_t* has_gauss, double* cached_gauss, int nsteps, int ne,
+                int64_t N, int necp, double scale, double* gauss, double* unif, double* ecp_u, double* ecp_rot,
+                int nthreads) {
+  const int64_t est = (int64_t)nsteps * ne * (N * 3 / 2 + 1 + 2 * (ecp_u ? necp : 0)) + 64;
+  return rng_run_phase_a(rp, key, pos, has_gauss, cached_gauss, est, nthreads, [&](MT& s, GaussPlan& plan) {
+    for (int step = 0; step < nsteps; ++step) {
+      for (int e = 0; e < ne; ++e) {
+        double* go = gauss + ((int64_t)step * ne + e) * N * 3;
+        plan.segs.push_back(Segment{go, N * 3, plan.take(s, N * 3), scale, 0});
+        fill_uniform(s, unif + ((int64_t)step * ne + e) * N, N);
+      }
+      if (ecp_u) {
+        for (int e = 0; e < ne; ++e)
+          for (int a = 0; a < necp; ++a) {
+            const int64_t ea = ((int64_t)step * ne + e) * necp + a;
+            fill_uniform(s, ecp_u + ea * N, N);
+            plan.segs.push_back(Segment{ecp_rot + ea * 9, 4, plan.take(s, 4), 1.0, 1});
+          }
+      }
+    }
+  });
 }
 
 extern "C" {
@@ -547,6 +558,31 @@ int qmcb_rng_vmc_block(uint32_t* key, int32_t* pos, int32_t* has_gauss, double* 
                  std::chrono::duration<double, std::milli>(tA - t0).count(),
                  std::chrono::duration<double, std::milli>(tB - tA).count(), nthreads, (long long)rp.plan.npairs);
   }
+  return 0;
+}
+
+// Generic draw program on the same generator: op i is kind[i] = 0 uniform doubles (np.random.random /
+// rand), 1 normals scaled by scale[i] (np.random.normal / randn), 2 one scipy Rotation.random()
+// matrix (4 normals -> dst[9]); count[i] values go to dst[i].  Used for the DMC block, whose draw
+// order (dmc.py:150-198) interleaves T-move, diffusion and energy variates.
+int qmcb_rng_program(uint32_t* key, int32_t* pos, int32_t* has_gauss, double* cached_gauss, int64_t nops,
+                     const int32_t* kind, const int64_t* count, const uint64_t* dst, const double* scale, int nthreads) {
+  static thread_local RngPlan rp;
+  int64_t est = 64;
+  for (int64_t i = 0; i < nops; ++i) est += kind[i] == 1 ? count[i] / 2 + 1 : (kind[i] == 2 ? 3 : 0);
+  const int rc = rng_run_phase_a(rp, key, pos, has_gauss, cached_gauss, est, nthreads, [&](MT& s, GaussPlan& plan) {
+    for (int64_t i = 0; i < nops; ++i) {
+      double* d = reinterpret_cast<double*>(static_cast<uintptr_t>(dst[i]));
+      if (kind[i] == 0)
+        fill_uniform(s, d, count[i]);
+      else if (kind[i] == 1)
+        plan.segs.push_back(Segment{d, count[i], plan.take(s, count[i]), scale[i], 0});
+      else
+        plan.segs.push_back(Segment{d, 4, plan.take(s, 4), 1.0, 1});
+    }
+  });
+  if (rc) return rc;
+  run_phase_b(rp.plan, nthreads);
   return 0;
 }
 

@@ -116,7 +116,7 @@ def _device_dmc_path(wf, accumulators, ekey):
     return not hasattr(mol, "a")
 
 
-def draw_dmc_block_variates(nconf, nelec, tstep, nsteps, accumulator):
+def draw_dmc_block_variates(nconf, nelec, tstep, nsteps, accumulator, native=True):
     """Every random number of one ``dmc_propagate`` call in the reference's order: the energy
     evaluation before the first step; then per step, for every electron the T-move draws
     (``nonlocal_tmoves``: per ECP atom ``random(N)`` + a rotation; ``select_walker``: one ``rand()``
@@ -131,22 +131,69 @@ def draw_dmc_block_variates(nconf, nelec, tstep, nsteps, accumulator):
     tm_acc = np.empty((nsteps, nelec, nconf))
     gauss = np.empty((nsteps, nelec, nconf, 3))
     unif = np.empty((nsteps, nelec, nconf))
-    ecp_u[0], ecp_rot[0] = accumulator.draw_ecp_variates(nconf, nelec)
     tmoves = accumulator.has_nonlocal_moves()
+    # the draw program, in consumption order: (kind, destination array view, scale)
+    ops = []
+
+    def energy_draws(k):
+        for e in range(nelec):
+            for a in range(necp):
+                ops.append((0, ecp_u[k, e, a], 1.0))
+                ops.append((2, ecp_rot[k, e, a], 1.0))
+
+    energy_draws(0)
     for step in range(nsteps):
         if tmoves:
             for e in range(nelec):
                 for a in range(necp):
-                    tm_u[step, e, a] = np.random.random(size=nconf)
-                    tm_rot[step, e, a] = scipy.spatial.transform.Rotation.random().as_matrix()
-                tm_sel[step, e] = np.random.rand(nconf)  # == nconf successive scalar rand() calls
-                tm_acc[step, e] = np.random.rand(nconf)
+                    ops.append((0, tm_u[step, e, a], 1.0))
+                    ops.append((2, tm_rot[step, e, a], 1.0))
+                ops.append((0, tm_sel[step, e], 1.0))  # == nconf successive scalar rand() calls
+                ops.append((0, tm_acc[step, e], 1.0))
         for e in range(nelec):
-            gauss[step, e] = np.random.normal(scale=np.sqrt(tstep), size=(nconf, 3))
-            unif[step, e] = np.random.rand(nconf)
-        ecp_u[step + 1], ecp_rot[step + 1] = accumulator.draw_ecp_variates(nconf, nelec)
+            ops.append((1, gauss[step, e], float(np.sqrt(tstep))))
+            ops.append((0, unif[step, e], 1.0))
+        energy_draws(step + 1)
+    if not (native and _run_draw_program_native(ops)):
+        for kind, dst, scale in ops:
+            if kind == 0:
+                dst[...] = np.random.random(size=dst.shape)
+            elif kind == 1:
+                dst[...] = np.random.normal(scale=scale, size=dst.shape)
+            else:
+                dst[...] = scipy.spatial.transform.Rotation.random().as_matrix()
     return dict(ecp_u=ecp_u, ecp_rot=ecp_rot, tm_u=tm_u, tm_rot=tm_rot, tm_sel=tm_sel, tm_acc=tm_acc, gauss=gauss,
                 unif=unif)
+
+
+def _run_draw_program_native(ops):
+    """Runs the draw program in csrc/legacy_rng.cpp on the state of the global legacy generator
+    (bit-identical to the numpy / scipy calls, several times faster); False if not applicable."""
+    import ctypes
+
+    state = np.random.get_state()
+    if state[0] != "MT19937":
+        return False
+    for _, dst, _ in ops:
+        if not (dst.flags["C_CONTIGUOUS"] and dst.dtype == np.float64):
+            return False
+    lib = _lib.load()
+    kind = np.array([o[0] for o in ops], dtype=np.int32)
+    count = np.array([o[1].size for o in ops], dtype=np.int64)
+    dst = np.array([o[1].ctypes.data for o in ops], dtype=np.uint64)
+    scale = np.array([o[2] for o in ops], dtype=np.float64)
+    key = np.ascontiguousarray(state[1], dtype=np.uint32).copy()
+    pos = ctypes.c_int32(int(state[2]))
+    has_gauss = ctypes.c_int32(int(state[3]))
+    cached = ctypes.c_double(float(state[4]))
+    rc = lib.qmcb_rng_program(key.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), ctypes.byref(pos),
+                              ctypes.byref(has_gauss), ctypes.byref(cached), len(ops), _lib.iptr(kind),
+                              count.ctypes.data_as(_lib.c_i64_p), dst.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)),
+                              _lib.dptr(scale), mc.rng_threads())
+    if rc != 0:
+        return False
+    np.random.set_state(("MT19937", key, pos.value, has_gauss.value, cached.value))
+    return True
 
 
 def dmc_propagate_device(wf, configs, weights, tstep, branchcut_start, e_trial, e_est, nsteps, accumulators, ekey):

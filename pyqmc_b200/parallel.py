@@ -86,3 +86,59 @@ def gather_configs(local, group=None):
     parts = [None] * dist.get_world_size(group)
     dist.all_gather_object(parts, local.configs, group=group)
     return np.concatenate(parts, axis=0)
+
+
+# ---- DMC: weighted block statistics and global branching ------------------------------------------
+def allreduce_dmc_block(block_avg, nconf, group=None, device=None):
+    """Combination rule of ``dmc_propagate_parallel`` (dmc.py:238-303) with one allreduce: every rank
+    contributes ``[n_p, w_p n_p, <O>_p w_p n_p ...]``; the global weight is ``sum w_p n_p / sum n_p``
+    and the observables are averaged with the weights ``w_p n_p``."""
+    import torch
+    import torch.distributed as dist
+
+    keys = sorted(k for k in block_avg if k not in SKIP_KEYS and k != "weight")
+    wn = float(block_avg["weight"]) * nconf
+    vec = np.array([nconf, wn] + [float(block_avg[k]) * wn for k in keys])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        if device is None:
+            device = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        t = torch.from_numpy(vec).to(device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        vec = t.cpu().numpy()
+    out = {k: vec[2 + i] / vec[1] for i, k in enumerate(keys)}
+    out["weight"] = vec[1] / vec[0]
+    return out, int(round(vec[0]))
+
+
+def branch_global(local, weights, group=None):
+    """Stochastic-comb branching over the GLOBAL population (``branch``, dmc.py:342-376, applied after
+    ``configs.join`` as the reference's parallel driver does): the shards' walkers and weights are
+    gathered (a few hundred KB), rank 0's ``np.random.rand()`` fixes the comb offset for everybody,
+    every rank computes the same resampling indices and keeps its ``np.array_split`` slice of the
+    resampled population.  Returns (local configs, local weights, info)."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        from .dmc import branch
+
+        return branch(local, weights)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    parts = [None] * world
+    payload = (local.configs, getattr(local, "wrap", None), np.asarray(weights))
+    dist.all_gather_object(parts, payload, group=group)
+    allc = np.concatenate([p[0] for p in parts], axis=0)
+    allw = np.concatenate([p[2] for p in parts])
+    box = [np.random.rand() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    nconfig = len(allw)
+    probability = np.cumsum(allw)
+    wtot = probability[-1]
+    base = box[0] * wtot
+    newinds = np.searchsorted(probability, (base + np.linspace(0, wtot, nconfig, endpoint=False)) % wtot)
+    unique, counts = np.unique(newinds, return_counts=True)
+    mine = np.array_split(newinds, world)[rank]
+    local.configs = allc[mine]
+    if parts[0][1] is not None:
+        local.wrap = np.concatenate([p[1] for p in parts], axis=0)[mine]
+    new_w = np.full(len(mine), wtot / nconfig)
+    return local, new_w, {"max branches": np.max(counts), "Number of walkers killed": nconfig - unique.shape[0]}

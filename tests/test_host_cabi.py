@@ -175,3 +175,28 @@ def test_native_rng_is_bit_identical_to_numpy_legacy_stream(lib, seed):
     for x, y in zip(a, b):
         assert (x is None and y is None) or np.array_equal(x, y)
     assert np.array_equal(sa[1], sb[1]) and sa[2:] == sb[2:]
+
+
+def test_native_draw_program_is_bit_identical_to_numpy_for_the_dmc_block():
+    """qmcb_rng_program (csrc/legacy_rng.cpp) on the DMC draw order (dmc.py:150-198): same numbers as
+    the numpy / scipy calls, same final state of the global legacy generator, with a cached Gaussian
+    carried in."""
+    import numpy as np
+
+    from pyqmc_b200 import dmc, systems
+    from pyqmc_b200.accumulators import EnergyAccumulator
+
+    mol, mf = systems.h2o_ccecp_pvtz()
+    acc = EnergyAccumulator(mol)
+    for nconf in (5, 48):
+        np.random.seed(3)
+        np.random.normal(size=1)
+        a = dmc.draw_dmc_block_variates(nconf, 8, 0.02, 2, acc, native=True)
+        ta = (np.random.rand(), np.random.normal())
+        np.random.seed(3)
+        np.random.normal(size=1)
+        b = dmc.draw_dmc_block_variates(nconf, 8, 0.02, 2, acc, native=False)
+        tb = (np.random.rand(), np.random.normal())
+        assert ta == tb
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k

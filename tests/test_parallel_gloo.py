@@ -79,3 +79,52 @@ def test_single_process_path_needs_no_process_group():
 
     avg, total = parallel.allreduce_block({"energytotal": 2.0, "acceptance": 0.5, "block": 3}, 7)
     assert total == 7 and avg == {"acceptance": 0.5, "energytotal": 2.0}
+
+
+def _dmc_worker(rank, world, port, nwalk, out_dir):
+    import torch.distributed as dist
+
+    from pyqmc_b200 import parallel
+    from pyqmc_b200.coord import OpenConfigs
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.RandomState(1)
+    allc, allw = rng.randn(nwalk, 2, 3), 0.5 + rng.rand(nwalk)
+    idx = np.array_split(np.arange(nwalk), world)[rank]
+    local, w = OpenConfigs(allc[idx].copy()), allw[idx].copy()
+    block = {"energytotal": float(np.average(allc[idx, 0, 0], weights=w)), "weight": float(np.mean(w)), "acceptance": 0.9}
+    glob, total = parallel.allreduce_dmc_block(block, len(idx))
+    np.random.seed(7)  # only rank 0's draw is used
+    local, w, info = parallel.branch_global(local, w)
+    np.savez(os.path.join(out_dir, f"dmc{rank}.npz"), configs=local.configs, weights=w, energy=glob["energytotal"],
+             weight=glob["weight"], total=total, killed=info["Number of walkers killed"])
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nwalk", [12, 13])
+def test_two_rank_dmc_statistics_and_global_branching(tmp_path, nwalk):
+    """allreduce_dmc_block == the weighting of dmc_propagate_parallel (dmc.py:238-303); branch_global ==
+    join -> branch (dmc.py:342-376) -> split with the same comb offset."""
+    import torch.multiprocessing as mp
+
+    from pyqmc_b200 import dmc
+    from pyqmc_b200.coord import OpenConfigs
+
+    world = 2
+    mp.spawn(_dmc_worker, args=(world, _free_port(), nwalk, str(tmp_path)), nprocs=world, join=True)
+    res = [dict(np.load(tmp_path / f"dmc{r}.npz")) for r in range(world)]
+    rng = np.random.RandomState(1)
+    allc, allw = rng.randn(nwalk, 2, 3), 0.5 + rng.rand(nwalk)
+    for r in range(world):
+        assert np.isclose(res[r]["energy"], np.average(allc[:, 0, 0], weights=allw), rtol=1e-13)
+        assert np.isclose(res[r]["weight"], np.mean(allw), rtol=1e-13)
+        assert res[r]["total"] == nwalk
+    serial = OpenConfigs(allc.copy())
+    np.random.seed(7)
+    serial, w, info = dmc.branch(serial, allw.copy())
+    got = np.concatenate([res[r]["configs"] for r in range(world)], axis=0)
+    assert np.array_equal(got, serial.configs)
+    assert np.allclose(np.concatenate([res[r]["weights"] for r in range(world)]), w)
+    assert res[0]["killed"] == info["Number of walkers killed"]
