@@ -203,6 +203,16 @@ int qmcb_vmc_block_slot(qmcb_ctx *ctx, int slot, int nsteps, double tstep, int w
                         int64_t *nacc);
 int qmcb_kernel_launches(qmcb_ctx *ctx, int64_t *count); /* launches issued so far */
 
+/* ---- StochasticReconfiguration.avg (pyqmc/observables/stochastic_reconfiguration.py:85-118) ----
+ * Parameter j of the serialised gradient (LinearTransform.serialize_gradients, accumulators.py:161-172)
+ * is element off[j] of one walker's block of source array src[j]: 0 det_coeff [ndet], 1 / 2
+ * mo_coeff_alpha / beta [nao][nmo_s], 3 acoeff [natom][na][2], 4 bcoeff [nb][3], 5 ccoeff.
+ * weights [N] normalised to sum 1; ECP variates as qmcb_energy.  Outputs: energy_avg [6] weighted means
+ * of ke, ee, ei, ecp, grad2, total; dpH [P], dppsi [P], dpidpj [P][P]. */
+int qmcb_sr_avg(qmcb_ctx *ctx, int nparam, const int32_t *src, const int64_t *off,
+                const double *weights, const double *ecp_u, const double *ecp_rot,
+                double nodal_cutoff, double *energy_avg, double *dpH, double *dppsi, double *dpidpj);
+
 /* ---- device-resident DMC propagation (dmc_propagate, pyqmc/method/dmc.py:123-221) ------------
  * nsteps steps without branching on the walkers held by the context (after qmcb_recompute):
  * initial local energy, then per step T-moves of every electron (propose_tmoves 73-120), the

@@ -12,9 +12,10 @@ from .wftools import generate_jastrow, generate_jastrow3, generate_slater, gener
 from .accumulators import EnergyAccumulator  # noqa: F401
 from .mc import initial_guess, limdrift, vmc  # noqa: F401
 from .dmc import rundmc  # noqa: F401
+from .sr import LinearTransform, PGradTransform, StochasticReconfiguration, gradient_generator  # noqa: F401
 
 __all__ = [
     "OpenConfigs", "OpenElectron", "PeriodicConfigs", "PeriodicElectron", "CutoffCuspFunction", "PolyPadeFunction", "JastrowSpin", "MultiplyWF",
     "Slater", "ThreeBodyJastrow", "generate_jastrow", "generate_jastrow3", "generate_slater", "generate_wf", "EnergyAccumulator", "initial_guess",
-    "limdrift", "vmc", "rundmc",
+    "limdrift", "vmc", "rundmc", "LinearTransform", "PGradTransform", "StochasticReconfiguration", "gradient_generator",
 ]

@@ -1852,3 +1852,115 @@ __global__ void __launch_bounds__(128) k_dmc_weights(const Sys S, const State st
   a.eold[w] = eloc;
   a.v2old[w] = v2;
 }
+
+// =========================================================================================
+// Stochastic-reconfiguration accumulator (pyqmc/observables/stochastic_reconfiguration.py:74-118):
+//   dp[i][j]  = d ln Psi_i / d p_j gathered from the parameter-gradient arrays (LinearTransform.
+//               serialize_gradients, accumulators.py:161-172)
+//   f_i       = nodal regularisation polynomial of 1/|grad Psi|^2 (20-46)
+//   dppsi     = sum_i w_i f_i dp_ij,  dpH = sum_i E_i w_i f_i dp_ij,  dpidpj = sum_i dp_ij w_i f_i dp_ik
+// =========================================================================================
+struct SrArgs {
+  int P;
+  const int* src;          // [P] source array of parameter j
+  const long long* off;    // [P] flat offset inside one walker's block of that array
+  const double* base[6];   // det_coeff, mo_alpha, mo_beta, acoeff (avalues), bcoeff (bvalues), ccoeff
+  long long stride[6];     // doubles per walker
+  const double* weights;   // [N] normalised
+  const double* energy;    // [6][N]
+  double cutoff;
+  double* dp;              // [N][P]
+  double* wdpr;            // [N][P]  w_i f_i dp_ij
+};
+
+__global__ void __launch_bounds__(128) k_sr_gather(const State st, const SrArgs a) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = st.N;
+  if (t >= (long long)N * a.P) return;
+  const int i = (int)(t / a.P), j = (int)(t - (long long)i * a.P);
+  const int s = a.src[j];
+  const double v = a.base[s][(long long)i * a.stride[s] + a.off[j]];
+  const double r = 1.0 / a.energy[(size_t)4 * N + i];
+  double f = 1.0;
+  if (r < a.cutoff * a.cutoff) {
+    const double c2 = a.cutoff * a.cutoff, c4 = c2 * c2, c6 = c4 * c2;
+    f = 9.0 / c2 * r + -15.0 / c4 * (r * r) + 7.0 / c6 * (r * r * r);
+  }
+  a.dp[t] = v;
+  a.wdpr[t] = a.weights[i] * (v * f);
+}
+
+// column reductions: out[0][j] = sum_i wdpr_ij (dppsi), out[1][j] = sum_i E_i wdpr_ij (dpH); the first
+// six extra columns (j = P..P+5) are the weighted energy averages
+__global__ void __launch_bounds__(256) k_sr_colsum(const State st, const SrArgs a, double* __restrict__ out) {
+  __shared__ double sh[2][256];
+  const int j = blockIdx.x, N = st.N, P = a.P;
+  double s0 = 0.0, s1 = 0.0;
+  for (int i = threadIdx.x; i < N; i += 256) {
+    if (j < P) {
+      const double v = a.wdpr[(size_t)i * P + j];
+      s0 += v;
+      s1 = fma(a.energy[(size_t)5 * N + i], v, s1);
+    } else {
+      s0 = fma(a.weights[i], a.energy[(size_t)(j - P) * N + i], s0);
+    }
+  }
+  sh[0][threadIdx.x] = s0;
+  sh[1][threadIdx.x] = s1;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + s];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[j] = sh[0][0];
+    if (j < P) out[(size_t)(P + 6) + j] = sh[1][0];
+  }
+}
+
+// C[j][k] = sum_i A[i][j] B[i][k]  (A, B: [N][P] row-major, C: [P][P]): 64 x 64 output tile per CTA, 16
+// rows of A and B staged per iteration, 4 x 4 accumulators per thread -- the one genuinely dense
+// product of this path (FP64: no tensor-core path on tcgen05).
+__global__ void __launch_bounds__(256) k_gemm_tn(const double* __restrict__ A, const double* __restrict__ B, int N,
+                                                 int P, double* __restrict__ C) {
+  __shared__ double sa[16][64 + 1], sb[16][64 + 1];
+  const int tj = blockIdx.y * 64, tk = blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+  for (int i0 = 0; i0 < N; i0 += 16) {
+    for (int t = threadIdx.x; t < 16 * 64; t += 256) {
+      const int r = t >> 6, c = t & 63;
+      const int i = i0 + r;
+      sa[r][c] = (i < N && tj + c < P) ? A[(size_t)i * P + tj + c] : 0.0;
+      sb[r][c] = (i < N && tk + c < P) ? B[(size_t)i * P + tk + c] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) av[u] = sa[r][ty * 4 + u];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) bv[v] = sb[r][tx * 4 + v];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int j = tj + ty * 4 + u, k = tk + tx * 4 + v;
+      if (j < P && k < P) C[(size_t)j * P + k] = acc[u][v];
+    }
+}

@@ -2195,6 +2195,127 @@ int qmcb_dmc_block(qmcb_ctx* c, int nsteps, double tstep, double branchcut, doub
   return rc;
 }
 
+// ---------------------------------------------------------------------------------------
+// StochasticReconfiguration.avg on the device (stochastic_reconfiguration.py:85-118): local energy,
+// parameter gradients, nodal regularisation, the weighted sums and the P x P overlap product.
+int qmcb_sr_avg(qmcb_ctx* c, int nparam, const int32_t* src, const int64_t* off, const double* weights,
+                const double* ecp_u, const double* ecp_rot, double nodal_cutoff, double* energy_avg, double* dpH,
+                double* dppsi, double* dpidpj) {
+  Guard g(c);
+  if (c->N == 0) return fail("recompute has not been called");
+  if (build_tables(c)) return -1;
+  if (c->N == 0) return fail("system shapes changed: call recompute again");
+  const Sys& S = c->S;
+  const size_t N = c->N, P = (size_t)nparam;
+  cudaStream_t stream = c->stream;
+  if (S.pbc) return fail("parameter gradients of periodic wave functions are not supported");
+  bool need[6] = {false, false, false, false, false, false};
+  for (size_t j = 0; j < P; ++j) {
+    if (src[j] < 0 || src[j] > 5) return fail("qmcb_sr_avg: unknown parameter source");
+    need[src[j]] = true;
+  }
+  if ((need[0] || need[1] || need[2]) && !c->have_slater) return fail("context has no Slater factor");
+  if ((need[3] || need[4]) && !c->have_jastrow) return fail("context has no Jastrow factor");
+  if (need[5] && !c->have_j3) return fail("context has no three-body Jastrow factor");
+  if (ensure_energy_scratch(c) || energy_scratch_points(c)) return -1;
+  const size_t nu = (size_t)S.ne * S.necp * N, nr = (size_t)S.ne * S.necp * 9;
+  if (c->d_u.ensure(nu) || c->d_rot.ensure(nr) || c->d_energy.ensure(6 * N)) return -1;
+  if (S.necp > 0) {
+    if (!ecp_u || !ecp_rot) return fail("ECP random variates missing");
+    if (h2d(c, c->d_u.p, ecp_u, nu * 8) || h2d(c, c->d_rot.p, ecp_rot, nr * 8)) return -1;
+  }
+  if (launch_energy(c, c->d_u.p, c->d_rot.p, c->d_energy.p, stream)) return -1;
+  const int gstride = std::max(std::max(S.nds[0], S.nds[1]), 1);
+  DBuf<double> d_det, d_G, d_ao, d_mo[2], d_c3, d_w, d_dp, d_wdpr, d_red, d_C;
+  DBuf<int> d_src;
+  DBuf<long long> d_off;
+  int rc = 0;
+  do {
+    SrArgs a{};
+    a.P = (int)P;
+    a.cutoff = nodal_cutoff;
+    if (need[0] || need[1] || need[2]) {
+      if (d_det.ensure(N * std::max(S.ndet, 1)) || d_G.ensure(2 * N * gstride)) { rc = -1; break; }
+      k_pgrad_det<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(S, c->st, d_det.p, d_G.p, gstride);
+      c->nlaunch++;
+      a.base[0] = d_det.p;
+      a.stride[0] = S.ndet;
+    }
+    if (need[1] || need[2]) {
+      if (d_ao.ensure(N * S.ne * S.nao)) { rc = -1; break; }
+      const long long np = (long long)N * S.ne;
+      if ((rc = prep_kernel(k_ao_all, c->smem_bytes))) break;
+      k_ao_all<<<(unsigned)((np + 127) / 128), 128, c->smem_bytes, stream>>>(S, c->st, d_ao.p);
+      c->nlaunch++;
+      for (int s = 0; s < 2; ++s) {
+        if (!need[1 + s]) continue;
+        const size_t nout = N * S.nao * S.nmo[s];
+        if (d_mo[s].ensure(nout)) { rc = -1; break; }
+        k_pgrad_mo<<<(unsigned)((nout + 127) / 128), 128, 0, stream>>>(S, c->st, s, d_ao.p, d_G.p, gstride, d_mo[s].p);
+        c->nlaunch++;
+        a.base[1 + s] = d_mo[s].p;
+        a.stride[1 + s] = (long long)S.nao * S.nmo[s];
+      }
+      if (rc) break;
+    }
+    a.base[3] = c->st.avalues;
+    a.stride[3] = (long long)S.natom * S.na * 2;
+    a.base[4] = c->st.bvalues;
+    a.stride[4] = (long long)S.nb * 3;
+    if (need[5]) {
+      const size_t nt = N * S.natom * S.na3 * S.na3;
+      if (d_c3.ensure(nt * S.nb3 * 3)) { rc = -1; break; }
+      if ((rc = prep_kernel(k_jastrow3_pgrad, c->smem_bytes))) break;
+      k_jastrow3_pgrad<<<(unsigned)((nt + 127) / 128), 128, c->smem_bytes, stream>>>(S, c->st, d_c3.p);
+      c->nlaunch++;
+      a.base[5] = d_c3.p;
+      a.stride[5] = (long long)S.natom * S.na3 * S.na3 * S.nb3 * 3;
+    }
+    for (size_t j = 0; j < P; ++j)
+      if (off[j] < 0 || off[j] >= a.stride[src[j]]) { rc = fail("qmcb_sr_avg: parameter offset out of range"); break; }
+    if (rc) break;
+    std::vector<long long> off64(off, off + P);
+    if (d_src.ensure(P) || d_off.ensure(P) || d_w.ensure(N) || d_dp.ensure(N * std::max<size_t>(P, 1)) ||
+        d_wdpr.ensure(N * std::max<size_t>(P, 1)) || d_red.ensure(2 * (P + 6)) || d_C.ensure(std::max<size_t>(P * P, 1))) { rc = -1; break; }
+    cudaMemcpyAsync(d_src.p, src, P * 4, cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(d_off.p, off64.data(), P * 8, cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(d_w.p, weights, N * 8, cudaMemcpyHostToDevice, stream);
+    cudaStreamSynchronize(stream);  // off64 / caller buffers are read by the copies above
+    a.src = d_src.p;
+    a.off = d_off.p;
+    a.weights = d_w.p;
+    a.energy = c->d_energy.p;
+    a.dp = d_dp.p;
+    a.wdpr = d_wdpr.p;
+    if (P > 0) {
+      k_sr_gather<<<(unsigned)((N * P + 127) / 128), 128, 0, stream>>>(c->st, a);
+      c->nlaunch++;
+    }
+    k_sr_colsum<<<(unsigned)(P + 6), 256, 0, stream>>>(c->st, a, d_red.p);
+    c->nlaunch++;
+    if (P > 0) {
+      dim3 grid((unsigned)((P + 63) / 64), (unsigned)((P + 63) / 64));
+      k_gemm_tn<<<grid, 256, 0, stream>>>(d_dp.p, d_wdpr.p, (int)N, (int)P, d_C.p);
+      c->nlaunch++;
+    }
+    if (cudaGetLastError() != cudaSuccess) { rc = fail("stochastic-reconfiguration kernel launch failed"); break; }
+    std::vector<double> red(2 * (P + 6));
+    if ((rc = d2h(c, red.data(), d_red.p, red.size() * 8))) break;
+    for (size_t j = 0; j < P; ++j) {
+      dppsi[j] = red[j];
+      dpH[j] = red[P + 6 + j];
+    }
+    for (int k = 0; k < 6; ++k) energy_avg[k] = red[P + k];
+    if (P > 0) rc = d2h(c, dpidpj, d_C.p, P * P * 8);
+  } while (0);
+  cudaStreamSynchronize(stream);
+  DBuf<double>* tmp[] = {&d_det, &d_G, &d_ao, &d_mo[0], &d_mo[1], &d_c3, &d_w, &d_dp, &d_wdpr, &d_red, &d_C};
+  for (auto* b : tmp) b->release();
+  d_src.release();
+  d_off.release();
+  return rc;
+}
+
 int qmcb_pinned_alloc(int64_t bytes, void** out) {
   void* p = nullptr;
   cudaError_t e = cudaMallocHost(&p, (size_t)std::max<int64_t>(bytes, 1));

@@ -151,9 +151,50 @@ def generate(name):
     return out
 
 
+SR_SYSTEMS = ["h2o", "h2o_md"]
+
+
+def sr_inputs(parameters, nconf):
+    """Deterministic optimisation mask (everything but the cusp row of bcoeff) and walker weights."""
+    to_opt = {}
+    for k in parameters.keys():
+        m = np.ones(np.shape(parameters[k]), dtype=bool)
+        if k.endswith("bcoeff"):
+            m[0, :] = False
+        if "mo_coeff" in k:  # a slice of the orbital coefficients keeps the P x P fixture small
+            m[:] = False
+            m[3:9, :] = True
+        to_opt[k] = m
+    return to_opt, 0.5 + np.random.RandomState(4).rand(nconf)
+
+
+def generate_sr(name):
+    """StochasticReconfiguration.avg of the reference (stochastic_reconfiguration.py:85-118) on the walkers
+    `configs1` of the main golden file -> tests/golden/sr_<name>.npz."""
+    import pyqmc.configurations.coord as coord
+    from pyqmc.observables.accumulators import EnergyAccumulator, LinearTransform
+    from pyqmc.observables.stochastic_reconfiguration import StochasticReconfiguration
+
+    mol, wf = build_reference(name)
+    data = dict(np.load(os.path.join(HERE, f"{name}.npz")))
+    configs = coord.OpenConfigs(data["configs1"].copy())
+    wf.recompute(configs)
+    to_opt, weights = sr_inputs(wf.parameters, len(configs.configs))
+    acc = StochasticReconfiguration(EnergyAccumulator(mol), LinearTransform(wf.parameters, to_opt))
+    np.random.seed(77)
+    d = acc.avg(configs, wf, weights=weights)
+    return {"sr_" + k: np.asarray(v) for k, v in d.items()}
+
+
 def main():
     warnings.filterwarnings("ignore")
     refload.load()
+    if len(sys.argv) > 1 and sys.argv[1] == "sr":
+        for name in SR_SYSTEMS:
+            path = os.path.join(HERE, f"sr_{name}.npz")
+            np.savez_compressed(path, **generate_sr(name))
+            print("wrote", path)
+        return
     names = sys.argv[1:] if len(sys.argv) > 1 else SYSTEMS + PBC_SYSTEMS
     for name in names:
         data = generate(name)

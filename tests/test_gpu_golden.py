@@ -96,3 +96,65 @@ def test_dmc_propagate_on_device_objects_matches_reference_golden(lib, name):
     configs, weights, inds = dmc_driver.branch(configs, weights)
     assert configs.configs.shape == data["dmc_configs"].shape and np.allclose(weights, weights[0])
     wf.recompute(configs)
+
+
+@pytest.mark.parametrize("name", ["h2o", "open", "h2o_md", "h2o_3b"])
+def test_stochastic_reconfiguration_avg_on_device(lib, name):
+    """StochasticReconfiguration.avg (stochastic_reconfiguration.py:85-118) on the device vs the reference
+    formula evaluated with numpy on the per-walker arrays of the same objects (same ECP variates), for
+    Jastrow, determinant and orbital parameters, with weights and a regularised walker."""
+    import pyqmc_b200 as pq
+    from pyqmc_b200 import sr
+
+    data = golden_replay.load(name)
+    mol, mf, wf, _ = helpers.make_pair(name, seed=1)
+    configs = pq.OpenConfigs(data["configs1"].copy())
+    wf.recompute(configs)
+    rng = np.random.RandomState(4)
+    to_opt = {}
+    for k in wf.parameters.keys():
+        shape = np.shape(wf.parameters[k])
+        m = rng.rand(*shape) > 0.35
+        if k.endswith("bcoeff"):
+            m[0, :] = False
+        if np.any(m):
+            to_opt[k] = m
+    acc = sr.StochasticReconfiguration(pq.EnergyAccumulator(mol), sr.LinearTransform(wf.parameters, to_opt))
+    weights = 0.5 + rng.rand(len(configs.configs))
+    np.random.seed(77)
+    dev = acc.avg(configs, wf, weights=weights)
+    # numpy evaluation of the reference formula on the same per-walker quantities
+    np.random.seed(77)
+    den = acc.enacc(configs, wf)
+    dp = acc.transform.serialize_gradients(wf.pgradient())
+    assert dp.shape == (len(weights), acc.transform.nparams) and acc.transform.nparams > 20
+    w = weights / weights.sum()
+    _, f = sr.nodal_regularization(den["grad2"])
+    dpr = dp * f[:, None]
+    assert helpers.relerr(dev["dppsi"], np.average(dpr, weights=w, axis=0)) < 1e-10
+    assert helpers.relerr(dev["dpH"], np.einsum("i,ij->j", den["total"], w[:, None] * dpr)) < 1e-10
+    assert helpers.relerr(dev["dpidpj"], np.einsum("ij,ik->jk", dp, w[:, None] * dpr)) < 1e-10
+    for k in ("ke", "ee", "ei", "ecp", "grad2", "total"):
+        assert abs(dev[k] - np.average(den[k], weights=w)) <= 1e-10 * max(1.0, abs(np.average(den[k], weights=w))), k
+    steps, report = acc.delta_p([0.1, 0.2], dev)
+    assert len(steps) == 2 and np.all(np.isfinite(steps[0])) and np.isfinite(report["SRdot"])
+
+
+@pytest.mark.parametrize("name", ["h2o", "h2o_md"])
+def test_stochastic_reconfiguration_matches_reference_golden(lib, name):
+    """qmcb_sr_avg vs the reference's own StochasticReconfiguration.avg (tests/golden/sr_<name>.npz)."""
+    import make_golden
+    import pyqmc_b200 as pq
+    from pyqmc_b200 import sr
+
+    data = golden_replay.load(name)
+    gold = golden_replay.load("sr_" + name)
+    mol, mf, wf, _ = helpers.make_pair(name, seed=1)
+    configs = pq.OpenConfigs(data["configs1"].copy())
+    wf.recompute(configs)
+    to_opt, weights = make_golden.sr_inputs(wf.parameters, len(configs.configs))
+    acc = sr.StochasticReconfiguration(pq.EnergyAccumulator(mol), sr.LinearTransform(wf.parameters, to_opt))
+    np.random.seed(77)
+    d = acc.avg(configs, wf, weights=weights)
+    for k in ("dpH", "dppsi", "dpidpj", "total", "ke", "ecp", "grad2"):
+        assert helpers.relerr(np.asarray(d[k]), gold["sr_" + k]) < 1e-9, k

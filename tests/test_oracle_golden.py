@@ -194,3 +194,31 @@ def test_oracle_dmc_propagate_matches_reference_golden(name):
     out, configs, weights = dmc_driver.dmc_propagate(orc, configs, weights, 0.02, 10.0, 1.5, 1.7, nsteps=3,
                                                      accumulators={"energy": EnergyOracle(mol)})
     golden_replay.check_dmc(data, out, configs, weights)
+
+
+@pytest.mark.parametrize("name", ["h2o", "h2o_md"])
+def test_oracle_stochastic_reconfiguration_matches_reference_golden(name):
+    """The SR averages (stochastic_reconfiguration.py:85-118) formed with numpy from the oracle's
+    pgradient and energy vs the reference's own accumulator output."""
+    import make_golden
+    from oracle.local_energy import EnergyOracle
+    from oracle.walkers import Walkers
+
+    data = golden_replay.load(name)
+    gold = golden_replay.load("sr_" + name)
+    mol, mf, _, orc = _oracle_only(name)
+    configs = Walkers(data["configs1"].copy())
+    orc.recompute(configs)
+    to_opt, weights = make_golden.sr_inputs(orc.parameters, len(configs.configs))
+    pg = orc.pgradient()
+    dp = np.concatenate([pg[k].reshape(len(weights), -1)[:, m.ravel()] for k, m in to_opt.items()], axis=1)
+    np.random.seed(77)
+    en = EnergyOracle(mol)(configs, orc)
+    w = weights / weights.sum()
+    r = 1.0 / en["grad2"]
+    cut = 1e-3
+    f = np.where(r < cut**2, 9 / cut**2 * r - 15 / cut**4 * r**2 + 7 / cut**6 * r**3, 1.0)
+    dpr = dp * f[:, None]
+    assert helpers.relerr(np.average(dpr, weights=w, axis=0), gold["sr_dppsi"]) < 1e-9
+    assert helpers.relerr(np.einsum("i,ij->j", en["total"], w[:, None] * dpr), gold["sr_dpH"]) < 1e-9
+    assert helpers.relerr(np.einsum("ij,ik->jk", dp, w[:, None] * dpr), gold["sr_dpidpj"]) < 1e-9
