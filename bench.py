@@ -44,6 +44,11 @@ WORKLOADS = {
                text="diamond-C 2x2x2 supercell PBC Slater-Jastrow VMC (synthetic basis/MOs, 8 k-points), 64 e-, "
                     "16 atoms, Ewald + ECP, 1024 walkers/GPU"),
 }
+WORKLOADS["c3"] = dict(
+    system="h2o_cas_3b", walkers=4096, cpu_walkers=16, cpu_steps=1,
+    metric="walker-steps/sec (VMC, H2O CAS(8e,8o) 4900 determinants + 3-body Jastrow); Sherman-Morrison HBM GB/s vs roofline",
+    text="H2O ccECP-cc-pVTZ-shaped multi-determinant (full CAS(8e,8o): 70 x 70 = 4900 determinants) x 2-body x 3-body "
+         "Jastrow VMC (synthetic basis/MOs/CI coefficients), 4096 walkers/GPU")
 WORKLOADS["c5"] = dict(
     system="h2o", walkers=2048, cpu_walkers=128, cpu_steps=20, tstep=0.02, spb=5,
     metric="walker-steps/sec (DMC with T-moves, H2O cc-pVTZ SJ, tstep 0.02); Sherman-Morrison HBM GB/s vs roofline",
@@ -87,8 +92,14 @@ def _cpu_worker(args):
         from oracle.pbc import SlaterPbcOracle
 
         wf = ProductOracle(SlaterPbcOracle(mol, mf), oj)
+    elif system.endswith("_3b"):
+        from oracle.jastrow3 import Jastrow3Oracle
+
+        oj3 = Jastrow3Oracle.default(mol)
+        oj3.parameters["ccoeff"][...] = helpers.three_body_coefficients(oj3.parameters["ccoeff"].shape)
+        wf = ProductOracle(SlaterOracle(mol, mf, determinants=dets), oj, oj3)
     else:
-        wf = ProductOracle(SlaterOracle(mol, mf), oj)
+        wf = ProductOracle(SlaterOracle(mol, mf, determinants=dets), oj)
     np.random.seed(seed)
     configs = vmc_driver.initial_guess(mol, nwalk)
     acc = {"energy": EnergyOracle(mol)}

@@ -47,6 +47,8 @@ struct Sys {
   const double* detc;     // [ndet]
   const int* grp_off[2];  // [nds+1] CSR: total determinants that use unique spin det d
   const int* grp_det[2];  // [ndet]
+  const double* grp_coef[2];  // [ndet] c_D in group order
+  const int* grp_other[2];    // [ndet] map_other(D) in group order
   // ---- periodic boundary conditions (pbc == 0: open).  pbc is the minimal-image mode of
   // MinimalImageDistance (distance.py:97-110): 1 diagonal, 2 orthogonal, 3 general (27 shifts).
   int pbc;

@@ -449,28 +449,34 @@ __global__ void __launch_bounds__(128) k_invert_warp(const Sys S, const State st
 // Multi-determinant caches for walker w:  ref_s = max_d log_s[d], dv_s[d] = sign*exp(log-ref),
 // W_s[d] = sum_{D: map_s(D)=d} c_D dv_other[map_other(D)]   (determinant_tools.py:74-88 with a
 // per-walker instead of a global reference exponent; the reference cancels in every ratio).
-__global__ void __launch_bounds__(128) k_det_cache(const Sys S, const State st, const uint8_t* mask) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) k_det_cache(const Sys S, const State st, const uint8_t* mask, int spin) {
+  // one warp per walker, lanes over unique spin determinants.  spin >= 0: only the determinants of
+  // that spin changed (single-electron move): refresh ref / dv of that spin and W of the other one.
+  const int lane = threadIdx.x & 31;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= st.N) return;
   if (mask && !mask[w]) return;
   for (int s = 0; s < 2; ++s) {
+    if (spin >= 0 && s != spin) continue;
     const int nds = S.nds[s];
     double ref = -INFINITY;
-    for (int d = 0; d < nds; ++d) ref = fmax(ref, st.dlog[s][(size_t)w * nds + d]);
+    for (int d = lane; d < nds; d += 32) ref = fmax(ref, st.dlog[s][(size_t)w * nds + d]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ref = fmax(ref, __shfl_xor_sync(0xffffffffu, ref, o));
     if (!isfinite(ref)) ref = 0.0;
-    st.ref[s][w] = ref;
-    for (int d = 0; d < nds; ++d)
-      st.dv[s][(size_t)w * nds + d] =
-          st.dsign[s][(size_t)w * nds + d] * exp(st.dlog[s][(size_t)w * nds + d] - ref);
+    if (lane == 0) st.ref[s][w] = ref;
+    for (int d = lane; d < nds; d += 32)
+      st.dv[s][(size_t)w * nds + d] = st.dsign[s][(size_t)w * nds + d] * exp(st.dlog[s][(size_t)w * nds + d] - ref);
   }
+  __syncwarp();
   for (int s = 0; s < 2; ++s) {
+    if (spin >= 0 && s == spin) continue;  // W_s depends on dv of the OTHER spin only
     const int nds = S.nds[s], o = 1 - s, ndo = S.nds[o];
-    for (int d = 0; d < nds; ++d) {
+    const double* __restrict__ dvo = st.dv[o] + (size_t)w * ndo;
+    for (int d = lane; d < nds; d += 32) {
       double acc = 0.0;
-      for (int k = S.grp_off[s][d]; k < S.grp_off[s][d + 1]; ++k) {
-        const int D = S.grp_det[s][k];
-        acc = fma(S.detc[D], st.dv[o][(size_t)w * ndo + S.map[o][D]], acc);
-      }
+      const int k1 = S.grp_off[s][d + 1];
+      for (int k = S.grp_off[s][d]; k < k1; ++k) acc = fma(S.grp_coef[s][k], dvo[S.grp_other[s][k]], acc);
       st.W[s][(size_t)w * nds + d] = acc;
     }
   }
@@ -1031,6 +1037,244 @@ __global__ void __launch_bounds__(128) k_vmc_move(const Sys S, const State st, c
 }
 
 // =========================================================================================
+// Cooperative forms for multi-determinant and three-body wave functions (G lanes per walker).
+// =========================================================================================
+// three-body terms of electron e at (px,py,pz): a-values by lanes over (atom, function) into shared
+// memory, pair terms by lanes over partners (three_body_jastrow.py:454-655); adds to du / g / lap.
+template <int WANT, int G>
+__device__ __forceinline__ void coop_jastrow3(const Sys& S, const double* __restrict__ sd, const int* __restrict__ si,
+                                              const State& st, int w, int e, double px, double py, double pz, int lane,
+                                              unsigned gm, double* __restrict__ abuf, double& du, double (&g)[3],
+                                              double& lap) {
+  const int na_tot = S.natom * S.na3;
+  double* __restrict__ av = abuf;
+  double* __restrict__ ag = abuf + na_tot;
+  double* __restrict__ al = abuf + 2 * na_tot;
+  for (int t = lane; t < na_tot; t += G) {
+    const int I = t / S.na3, k = t - I * S.na3;
+    const double dx = px - sd[S.o_xyz + 3 * I], dy = py - sd[S.o_xyz + 3 * I + 1], dz = pz - sd[S.o_xyz + 3 * I + 2];
+    const double r = sqrt(dx * dx + dy * dy + dz * dz);
+    double v = 0.0, gg = 0.0, ll = 0.0;
+    if (r < S.rcut_a3) radial_ool<WANT>(si[S.o_a3kind + k], sd[S.o_a3par + k], S.rcut_a3, r, v, gg, ll);
+    av[t] = v;
+    ag[t] = gg;
+    al[t] = ll;
+  }
+  __syncwarp(gm);
+  double P = 0.0, gl[3] = {0.0, 0.0, 0.0}, lp = 0.0;
+  for (int jj = lane; jj < S.ne - 1; jj += G) {
+    const int j = jj < e ? jj : jj + 1;
+    j3_pair<WANT>(S, sd, si, st, w, e, j, px, py, pz, av, ag, al, CONF(st, S, w, j, 0), CONF(st, S, w, j, 1),
+                  CONF(st, S, w, j, 2), P, gl, lp);
+  }
+  P = group_sum<G>(P, gm);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) g[i] += group_sum<G>(gl[i], gm);
+  lap += group_sum<G>(lp, gm);
+  if (WANT != 2) du += P - st.P3[(size_t)w * S.ne + e];
+  __syncwarp(gm);
+}
+
+// Slater ratios (value, d/dx, d/dy, d/dz) of electron e from MO rows rows[c * ld + orbital], lanes over
+// the unique spin determinants (slater.py:301-380, determinant_tools.py:74-88)
+template <int G>
+__device__ __forceinline__ void coop_det_ratio4(const Sys& S, const int* __restrict__ si, const State& st, int w, int s,
+                                                int eeff, const double* __restrict__ rows, int ld, int lane,
+                                                unsigned gm, double (&rat)[4]) {
+  const int n = s ? S.ndn : S.nup;
+  const int nds = S.nds[s];
+  const int* __restrict__ occ = si + S.o_occ[s];
+  double num[4] = {0.0, 0.0, 0.0, 0.0}, den = 0.0;
+  for (int d = lane; d < nds; d += G) {
+    const double* __restrict__ inv = st.inv[s] + ((size_t)w * nds + d) * n * n + eeff;
+    double r[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = 0; k < n; ++k) {
+      const double a = inv[k * n];
+      const int orb = occ[d * n + k];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) r[c] = fma(rows[c * ld + orb], a, r[c]);
+    }
+    const double wgt = S.ndet == 1 ? 1.0 : st.dv[s][(size_t)w * nds + d] * st.W[s][(size_t)w * nds + d];
+    den += wgt;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) num[c] = fma(r[c], wgt, num[c]);
+  }
+  den = group_sum<G>(den, gm);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) rat[c] = group_sum<G>(num[c], gm) / den;
+}
+
+// mc.py:115-137 for electron e with G lanes per walker (general wave functions: any number of
+// determinants, optional two- and three-body Jastrow factors).  The drift at the current position comes
+// from the cached MO rows; accepted walkers refresh their cached rows (value, gradient, Laplacian) from
+// the evaluation at the proposed position.  Saves the value row / position for the update kernels.
+template <int G>
+__global__ void __launch_bounds__(128) k_vmc_move_coop(const Sys S, const State st, const MoveArgs ma) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  extern __shared__ __align__(128) unsigned char qmcb_smem[];
+  const CoopLayout L = coop_layout(S);
+  const int lane32 = threadIdx.x & 31;
+  const int lane = lane32 & (G - 1);
+  const unsigned gm = group_mask<G>(lane32);
+  const int slot = threadIdx.x / G;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int N = st.N;
+  if (w >= N) return;
+  const size_t tab = (16 + (size_t)S.dwords * 8 + (size_t)S.iwords * 4 + 15) & ~(size_t)15;
+  const int j3n = 3 * S.natom * S.na3;
+  double* ws = reinterpret_cast<double*>(qmcb_smem + tab) + (size_t)slot * (L.total + j3n);
+  double* abuf = ws + L.total;
+  const bool has_s = S.nmo[0] + S.nmo[1] > 0, has_j = (S.na + S.nb) > 0, has_j3 = (S.na3 + S.nb3) > 0;
+  const int ldmax = S.ldc[0] > S.ldc[1] ? S.ldc[0] : S.ldc[1];
+  const int e = ma.e;
+  const int s = e >= S.nup ? 1 : 0;
+  const int eeff = e - s * S.nup;
+  const double ox = CONF(st, S, w, e, 0), oy = CONF(st, S, w, e, 1), oz = CONF(st, S, w, e, 2);
+  double grad[3] = {0.0, 0.0, 0.0};
+  if (has_s) {
+    double r[4];
+    coop_det_ratio4<G>(S, si, st, w, s, eeff, st.mocache + ((size_t)w * S.ne + e) * 5 * ldmax, ldmax, lane, gm, r);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double gs = r[1 + i] / r[0];
+      if (!isfinite(gs)) gs = 0.0;
+      grad[i] = gs;
+    }
+  }
+  {
+    double du = 0.0, gj[3] = {0.0, 0.0, 0.0}, lj = 0.0;
+    if (has_j) coop_jastrow<1, G>(S, sd, si, st, w, e, ox, oy, oz, lane, gm, du, gj, lj);
+    if (has_j3) coop_jastrow3<1, G>(S, sd, si, st, w, e, ox, oy, oz, lane, gm, abuf, du, gj, lj);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) grad[i] = grad[i] + gj[i];
+  }
+  limdrift3(grad);
+  double gauss[3], np_[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) gauss[i] = ma.gauss[(size_t)w * 3 + i];
+  np_[0] = __dadd_rn(__dadd_rn(ox, gauss[0]), __dmul_rn(grad[0], ma.tstep));
+  np_[1] = __dadd_rn(__dadd_rn(oy, gauss[1]), __dmul_rn(grad[1], ma.tstep));
+  np_[2] = __dadd_rn(__dadd_rn(oz, gauss[2]), __dmul_rn(grad[2], ma.tstep));
+  double ngrad[3] = {0.0, 0.0, 0.0}, val = 1.0;
+  if (has_s) {
+    coop_eval_mo<2, G>(S, L, sd, si, s, np_[0], np_[1], np_[2], ws, lane, gm);
+    double r[4];
+    coop_det_ratio4<G>(S, si, st, w, s, eeff, ws + L.mo, ldmax, lane, gm, r);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double gs = r[1 + i] / r[0];
+      if (!isfinite(gs)) gs = 0.0;
+      ngrad[i] = gs;
+    }
+    val = isfinite(r[0]) ? r[0] : 1.0;
+  }
+  {
+    double du = 0.0, gj[3] = {0.0, 0.0, 0.0}, lj = 0.0;
+    if (has_j) coop_jastrow<1, G>(S, sd, si, st, w, e, np_[0], np_[1], np_[2], lane, gm, du, gj, lj);
+    if (has_j3) coop_jastrow3<1, G>(S, sd, si, st, w, e, np_[0], np_[1], np_[2], lane, gm, abuf, du, gj, lj);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) ngrad[i] = ngrad[i] + gj[i];
+    val = val * exp(du);
+  }
+  limdrift3(ngrad);
+  double fwd = 0.0, bwd = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    fwd = __dadd_rn(fwd, __dmul_rn(gauss[i], gauss[i]));
+    const double b = __dadd_rn(gauss[i], __dmul_rn(ma.tstep, __dadd_rn(grad[i], ngrad[i])));
+    bwd = __dadd_rn(bwd, __dmul_rn(b, b));
+  }
+  const double tprob = exp(__dmul_rn(1.0 / (2.0 * ma.tstep), __dadd_rn(fwd, -bwd)));
+  const double aval = fabs(val);
+  const double ratio = __dmul_rn(__dmul_rn(aval, aval), tprob);
+  const bool acc = __shfl_sync(gm, (ratio > ma.unif[w]) ? 1 : 0, 0, G) != 0;
+  if (lane == 0) {
+    ma.accept[w] = acc ? 1 : 0;
+    if (acc) atomicAdd(ma.nacc, 1ULL);
+    st.saved_pos[(size_t)w * 3] = np_[0];
+    st.saved_pos[(size_t)w * 3 + 1] = np_[1];
+    st.saved_pos[(size_t)w * 3 + 2] = np_[2];
+  }
+  if (has_s) {
+    const double* __restrict__ mo = ws + L.mo;
+    double* __restrict__ sv = st.saved_mo + (size_t)w * S.ldc[s];
+    for (int j = lane; j < S.ldc[s]; j += G) sv[j] = mo[j];
+    if (acc) {
+      double* __restrict__ mc = st.mocache + ((size_t)w * S.ne + e) * 5 * ldmax;
+      for (int i = lane; i < 5 * ldmax; i += G) mc[i] = mo[i];
+    }
+  }
+}
+
+// three-body cache update with G lanes per walker, lanes over partners (three_body_jastrow.py:149-189)
+template <int G>
+__global__ void __launch_bounds__(128) k_jastrow3_update_coop(const Sys S, const State st, int e, int move_conf,
+                                                              const uint8_t* mask) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  extern __shared__ __align__(128) unsigned char qmcb_smem[];
+  const int lane32 = threadIdx.x & 31;
+  const int lane = lane32 & (G - 1);
+  const unsigned gm = group_mask<G>(lane32);
+  const int slot = threadIdx.x / G;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  if (w >= st.N) return;
+  if (mask && !mask[w]) return;
+  const size_t tab = (16 + (size_t)S.dwords * 8 + (size_t)S.iwords * 4 + 15) & ~(size_t)15;
+  const int na_tot = S.natom * S.na3;
+  double* av = reinterpret_cast<double*>(qmcb_smem + tab) + (size_t)slot * na_tot;
+  double ag[1], al[1];
+  const double nx = st.saved_pos[(size_t)w * 3], ny = st.saved_pos[(size_t)w * 3 + 1], nz = st.saved_pos[(size_t)w * 3 + 2];
+  const double ox = CONF(st, S, w, e, 0), oy = CONF(st, S, w, e, 1), oz = CONF(st, S, w, e, 2);
+  const size_t abase = ((size_t)w * S.ne + e) * na_tot;
+  for (int i = lane; i < na_tot; i += G) av[i] = st.a3v[abase + i];
+  __syncwarp(gm);
+  // old pair terms (cached a-values, current position) leave the partners' sums ...
+  for (int jj = lane; jj < S.ne - 1; jj += G) {
+    const int j = jj < e ? jj : jj + 1;
+    double Po = 0.0, g[3] = {0.0, 0.0, 0.0}, lap = 0.0;
+    j3_pair<0>(S, sd, si, st, w, e, j, ox, oy, oz, av, ag, al, CONF(st, S, w, j, 0), CONF(st, S, w, j, 1),
+               CONF(st, S, w, j, 2), Po, g, lap);
+    st.P3[(size_t)w * S.ne + j] -= Po;
+  }
+  __syncwarp(gm);
+  // ... and the new ones (a-values at the accepted position) enter
+  for (int t = lane; t < na_tot; t += G) {
+    const int I = t / S.na3, k = t - I * S.na3;
+    const double dx = nx - sd[S.o_xyz + 3 * I], dy = ny - sd[S.o_xyz + 3 * I + 1], dz = nz - sd[S.o_xyz + 3 * I + 2];
+    const double r = sqrt(dx * dx + dy * dy + dz * dz);
+    double v = 0.0, gg, ll;
+    if (r < S.rcut_a3) radial_ool<0>(si[S.o_a3kind + k], sd[S.o_a3par + k], S.rcut_a3, r, v, gg, ll);
+    av[t] = v;
+  }
+  __syncwarp(gm);
+  double newval = 0.0;
+  for (int jj = lane; jj < S.ne - 1; jj += G) {
+    const int j = jj < e ? jj : jj + 1;
+    double Pn = 0.0, g[3] = {0.0, 0.0, 0.0}, lap = 0.0;
+    j3_pair<0>(S, sd, si, st, w, e, j, nx, ny, nz, av, ag, al, CONF(st, S, w, j, 0), CONF(st, S, w, j, 1),
+               CONF(st, S, w, j, 2), Pn, g, lap);
+    newval += Pn;
+    st.P3[(size_t)w * S.ne + j] += Pn;
+  }
+  newval = group_sum<G>(newval, gm);
+  if (lane == 0) {
+    st.val3[w] += newval - st.P3[(size_t)w * S.ne + e];
+    st.P3[(size_t)w * S.ne + e] = newval;
+  }
+  for (int i = lane; i < na_tot; i += G) st.a3v[abase + i] = av[i];
+  __syncwarp(gm);
+  if (move_conf && lane == 0) {
+    CONF(st, S, w, e, 0) = nx;
+    CONF(st, S, w, e, 1) = ny;
+    CONF(st, S, w, e, 2) = nz;
+  }
+}
+
+// =========================================================================================
 // Device-resident sweep, warp per walker: ALL electrons of one VMC step in one launch
 // (mc.py:115-137).  Single-determinant wave functions (any occupation, n_s <= 32 staged in
 // shared memory).  Per electron: drift at the old position from the cached MO rows (no orbital
@@ -1331,8 +1575,11 @@ __global__ void __launch_bounds__(128) k_kinetic(const Sys S, const State st, co
     lapj = lj;
   }
   if (which & QMCB_JASTROW3) {
+    extern __shared__ __align__(128) unsigned char qmcb_smem[];
+    const size_t tab3 = (16 + (size_t)S.dwords * 8 + (size_t)S.iwords * 4 + 15) & ~(size_t)15;
+    double* abuf = reinterpret_cast<double*>(qmcb_smem + tab3) + (size_t)(threadIdx.x / G) * (3 * S.natom * S.na3);
     double du3 = 0.0;
-    jastrow3_point<2>(S, sd, si, st, w, e, px, py, pz, du3, gj, lapj);
+    coop_jastrow3<2, G>(S, sd, si, st, w, e, px, py, pz, lane, gm, abuf, du3, gj, lapj);
   }
   if (which & (QMCB_JASTROW | QMCB_JASTROW3)) {
     lapj = lapj + (gj[0] * gj[0] + gj[1] * gj[1] + gj[2] * gj[2]);

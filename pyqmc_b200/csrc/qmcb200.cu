@@ -117,7 +117,8 @@ struct qmcb_ctx {
   // ---- device tables
   Sys S{};
   DBuf<double> d_dblob, d_detc, d_quad;
-  DBuf<int> d_iblob, d_map[2], d_grp_off[2], d_grp_det[2];
+  DBuf<int> d_iblob, d_map[2], d_grp_off[2], d_grp_det[2], d_grp_other[2];
+  DBuf<double> d_grp_coef[2];
   size_t smem_bytes = 0;
   int nmot = 0;  // 4 / 8: register fast path, 0: general path
   // ---- walker state
@@ -424,6 +425,17 @@ int build_tables(qmcb_ctx* c) {
       CK(cudaMemcpy(c->d_grp_det[s].p, lst.data(), lst.size() * 4, cudaMemcpyHostToDevice));
       S.grp_off[s] = c->d_grp_off[s].p;
       S.grp_det[s] = c->d_grp_det[s].p;
+      std::vector<double> gcoef(lst.size());
+      std::vector<int> gother(lst.size());
+      for (size_t k = 0; k < lst.size(); ++k) {
+        gcoef[k] = c->detc[lst[k]];
+        gother[k] = c->dmap[1 - s][lst[k]];
+      }
+      if (c->d_grp_coef[s].ensure(lst.size()) || c->d_grp_other[s].ensure(lst.size())) return -1;
+      CK(cudaMemcpy(c->d_grp_coef[s].p, gcoef.data(), gcoef.size() * 8, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(c->d_grp_other[s].p, gother.data(), gother.size() * 4, cudaMemcpyHostToDevice));
+      S.grp_coef[s] = c->d_grp_coef[s].p;
+      S.grp_other[s] = c->d_grp_other[s].p;
     }
   }
   if (c->necp > 0) {
@@ -702,7 +714,7 @@ int slater_rebuild(qmcb_ctx* c, cudaStream_t stream) {
     CK(cudaGetLastError());
   }
   if (S.ndet > 1) {
-    k_det_cache<<<(N + 127) / 128, 128, 0, stream>>>(S, c->st, nullptr);
+    k_det_cache<<<(unsigned)(((long long)N * 32 + 127) / 128), 128, 0, stream>>>(S, c->st, nullptr, -1);
     c->nlaunch++;
     CK(cudaGetLastError());
   }
@@ -739,7 +751,7 @@ int launch_update(qmcb_ctx* c, int which, int e, const uint8_t* d_mask, cudaStre
     a.dlog = c->st.dlog[s];
     if (launch_sm(c, a, stream, &c->nlaunch)) return -1;
     if (S.ndet > 1) {
-      k_det_cache<<<(c->N + 127) / 128, 128, 0, stream>>>(S, c->st, d_mask);
+      k_det_cache<<<(unsigned)(((long long)c->N * 32 + 127) / 128), 128, 0, stream>>>(S, c->st, d_mask, s);
       c->nlaunch++;
       CK(cudaGetLastError());
     }
@@ -759,9 +771,10 @@ int launch_update(qmcb_ctx* c, int which, int e, const uint8_t* d_mask, cudaStre
     CK(cudaGetLastError());
   }
   if (do_j3) {
-    const int block = pick_block(c->N);
-    if (prep_kernel(k_jastrow3_update, c->smem_bytes)) return -1;
-    k_jastrow3_update<<<(c->N + block - 1) / block, block, c->smem_bytes, stream>>>(S, c->st, e, 1, d_mask);
+    constexpr int G3 = 8;
+    const size_t sm3 = ((c->smem_bytes + 15) & ~(size_t)15) + (size_t)(128 / G3) * S.natom * S.na3 * 8;
+    if (prep_kernel(k_jastrow3_update_coop<G3>, sm3)) return -1;
+    k_jastrow3_update_coop<G3><<<(unsigned)(((long long)c->N * G3 + 127) / 128), 128, sm3, stream>>>(S, c->st, e, 1, d_mask);
     c->nlaunch++;
     CK(cudaGetLastError());
   }
@@ -846,8 +859,10 @@ int launch_energy_t(qmcb_ctx* c, const double* d_u, const double* d_rot, double*
     if (!c->mocache_valid && c->have_slater) {  // protocol-path updates do not maintain the cache
       if (launch_mo_all(c, 0, stream)) return -1;
     }
-    if (prep_kernel(k_kinetic<8>, sm)) return -1;
-    k_kinetic<8><<<(unsigned)((np * 8 + 127) / 128), 128, sm, stream>>>(S, c->st, c->es);
+    // three-body factor: per-group a-value scratch behind the tables
+    const size_t ksm = c->have_j3 ? ((sm + 15) & ~(size_t)15) + (size_t)(128 / 8) * 3 * S.natom * S.na3 * 8 : sm;
+    if (prep_kernel(k_kinetic<8>, ksm)) return -1;
+    k_kinetic<8><<<(unsigned)((np * 8 + 127) / 128), 128, ksm, stream>>>(S, c->st, c->es);
     c->nlaunch++;
     CK(cudaGetLastError());
   }
@@ -962,6 +977,8 @@ void qmcb_destroy(qmcb_ctx* c) {
     c->d_map[s].release();
     c->d_grp_off[s].release();
     c->d_grp_det[s].release();
+    c->d_grp_coef[s].release();
+    c->d_grp_other[s].release();
   }
   c->d_iblob.release();
   c->d_idx.release();
@@ -1844,6 +1861,20 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
       ma.nacc = nacc + se;
       ma.scr = c->d_scr.p;
       ma.scr_stride = N;
+      // general wave functions (multi-determinant and / or three-body): G lanes per walker, cached MO rows
+      constexpr int GM = 16;
+      const size_t msm = tab + (size_t)(128 / GM) * (CL.total + 3 * S.natom * S.na3) * 8;
+      if (msm <= 200 * 1024 && std::getenv("QMCB_NO_COOP_MOVE") == nullptr) {
+        if (c->have_slater && !c->mocache_valid)
+          if (launch_mo_all(c, 0, stream)) return -1;
+        if (prep_kernel(k_vmc_move_coop<GM>, msm)) return -1;
+        k_vmc_move_coop<GM><<<(unsigned)(((long long)N * GM + 127) / 128), 128, msm, stream>>>(S, c->st, ma);
+        c->nlaunch++;
+        CK(cudaGetLastError());
+        if (launch_update(c, which, e, ma.accept, stream)) return -1;
+        c->paircache_valid = false;  // the cached MO rows stay valid: accepted walkers refreshed theirs
+        continue;
+      }
       int rc = c->nmot == 4 ? launch_move_t<4>(c, ma, stream) : (c->nmot == 8 ? launch_move_t<8>(c, ma, stream) : launch_move_t<0>(c, ma, stream));
       if (rc) return rc;
       if (launch_update(c, which, e, ma.accept, stream)) return -1;
