@@ -149,6 +149,7 @@ struct qmcb_ctx {
   DBuf<double> s_gauss[NSLOT], s_unif[NSLOT], s_u[NSLOT], s_rot[NSLOT];
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t slot_ready[NSLOT] = {nullptr, nullptr, nullptr};
+  cudaEvent_t done_event = nullptr;  // blocking-sync event: the host thread sleeps while a block runs
 };
 
 namespace {
@@ -689,6 +690,13 @@ int launch_mo_all(qmcb_ctx* c, int write_values, cudaStream_t stream) {
   return 0;
 }
 
+// wait for the context's stream without spinning: the block drivers run next to the host RNG threads
+int sync_blocking(qmcb_ctx* c) {
+  CK(cudaEventRecord(c->done_event, c->stream));
+  CK(cudaEventSynchronize(c->done_event));
+  return 0;
+}
+
 int slater_rebuild(qmcb_ctx* c, cudaStream_t stream) {
   const Sys& S = c->S;
   const int N = c->N;
@@ -951,6 +959,7 @@ int qmcb_create(int device, qmcb_ctx** out) {
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < qmcb_ctx::NSLOT; ++i) CK(cudaEventCreateWithFlags(&c->slot_ready[i], cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->done_event, cudaEventDisableTiming | cudaEventBlockingSync));
   *out = c;
   return 0;
 }
@@ -997,6 +1006,7 @@ void qmcb_destroy(qmcb_ctx* c) {
     c->s_rot[i].release();
     if (c->slot_ready[i]) cudaEventDestroy(c->slot_ready[i]);
   }
+  if (c->done_event) cudaEventDestroy(c->done_event);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -1939,7 +1949,7 @@ int qmcb_vmc_block(qmcb_ctx* c, int nsteps, double tstep, int with_energy, const
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(configs, c->d_in.p, nel * 8, cudaMemcpyDeviceToHost, c->stream));
   }
-  CK(cudaStreamSynchronize(c->stream));
+  if (sync_blocking(c)) return -1;
   acc_all.release();
   return 0;
 }
@@ -2000,7 +2010,7 @@ int qmcb_vmc_block_slot(qmcb_ctx* c, int slot, int nsteps, double tstep, int wit
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(configs, c->d_in.p, nel * 8, cudaMemcpyDeviceToHost, c->stream));
   }
-  CK(cudaStreamSynchronize(c->stream));
+  if (sync_blocking(c)) return -1;
   acc_all.release();
   return 0;
 }
@@ -2216,7 +2226,7 @@ int qmcb_dmc_block(qmcb_ctx* c, int nsteps, double tstep, double branchcut, doub
     if (nacc) cudaMemcpyAsync(nacc, c->d_nacc.p, nse * 8, cudaMemcpyDeviceToHost, stream);
     if (ntacc) cudaMemcpyAsync(ntacc, d_ntacc.p, nse * 8, cudaMemcpyDeviceToHost, stream);
     if (configs) cudaMemcpyAsync(configs, c->st.conf, N * S.ne * 3 * 8, cudaMemcpyDeviceToHost, stream);
-    if (cudaStreamSynchronize(stream) != cudaSuccess) rc = fail(std::string("DMC block failed: ") + cudaGetErrorString(cudaGetLastError()));
+    if (sync_blocking(c)) rc = -1;
   } while (0);
   cudaStreamSynchronize(stream);
   DBuf<double>* tmp[] = {&d_tmu, &d_tmrot, &d_tmsel, &d_tmacc, &d_w, &d_eold, &d_v2old, &d_r2p, &d_r2a, &d_prod, &d_ws};

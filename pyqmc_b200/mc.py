@@ -107,7 +107,9 @@ def rng_threads():
     if "QMCB_RNG_THREADS" in os.environ:
         return max(1, int(os.environ["QMCB_RNG_THREADS"]))
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
-    return max(1, min(8, (os.cpu_count() or 1) // max(local_world, 1)))
+    cores = (os.cpu_count() or 1) // max(local_world, 1)
+    # leave a core each for the sequential stream walk and its producer thread when cores are scarce
+    return max(1, min(8, cores - 2 if cores <= 6 else cores))
 
 
 def _draw_block_variates_native(nconf, nelec, tstep, nsteps, necp, out):
