@@ -61,11 +61,15 @@ SM32_TRAFFIC_BYTES = 2.12e9
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
+    try:
         with open(p) as f:
             d = json.load(f)
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        v = d["hbm_gbs"]
+        if isinstance(v, dict):  # tolerate {"value": ...} style entries
+            v = v.get("value", v.get("burst"))
+        return float(v), "measured (MEASURED_PEAKS.json)"
+    except (OSError, KeyError, TypeError, ValueError):
+        return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 # ------------------------------------------------------------------------------------------

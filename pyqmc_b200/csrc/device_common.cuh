@@ -255,22 +255,26 @@ __device__ __forceinline__ void wrap_cell(const double* __restrict__ lat, const 
 
 __device__ __forceinline__ void min_image(const Sys& S, const double* __restrict__ sd, double& x, double& y, double& z) {
   if (S.pbc == 3) {
+    // argmin_i |d + s_i|^2 = argmin_i (2 d.s_i + |s_i|^2): three FMAs per shift; |s_i|^2 is tabulated
+    // behind the shifts.  First minimum in shift order, as np.argmin (distance.py:133-142); a different
+    // pick than the reference's direct evaluation is only possible at an exact tie of two images, i.e. on
+    // the Wigner-Seitz boundary, beyond every cutoff of this path.
     const double* __restrict__ sh = sd + S.o_shifts;
-    double best = INFINITY, bx = x, by = y, bz = z;
-#pragma unroll 9
+    const double* __restrict__ sh2 = sh + 81;
+    const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+    double best = INFINITY;
+    int bi = 0;
+#pragma unroll
     for (int i = 0; i < 27; ++i) {
-      const double ax = x + sh[3 * i], ay = y + sh[3 * i + 1], az = z + sh[3 * i + 2];
-      const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
-      if (d2 < best) {  // first minimum in shift order, as np.argmin
-        best = d2;
-        bx = ax;
-        by = ay;
-        bz = az;
+      const double sc = fma(tx, sh[3 * i], fma(ty, sh[3 * i + 1], fma(tz, sh[3 * i + 2], sh2[i])));
+      if (sc < best) {
+        best = sc;
+        bi = i;
       }
     }
-    x = bx;
-    y = by;
-    z = bz;
+    x = x + sh[3 * bi];
+    y = y + sh[3 * bi + 1];
+    z = z + sh[3 * bi + 2];
   } else if (S.pbc == 1) {
     const double* __restrict__ lat = sd + S.o_lat;
     x = py_mod(x + lat[0] / 2, lat[0]) - lat[0] / 2;

@@ -272,7 +272,11 @@ int build_tables(qmcb_ctx* c) {
     S.o_lat = dpush(c->lat.data(), 9);
     std::vector<double> li = inv3(c->lat);
     S.o_latinv = dpush(li.data(), 9);
-    S.o_shifts = dpush(c->shifts.data(), 81);
+    {
+      std::vector<double> sh(c->shifts);  // 27 shifts followed by their squared norms
+      for (int i = 0; i < 27; ++i) sh.push_back(c->shifts[3 * i] * c->shifts[3 * i] + c->shifts[3 * i + 1] * c->shifts[3 * i + 1] + c->shifts[3 * i + 2] * c->shifts[3 * i + 2]);
+      S.o_shifts = dpush(sh.data(), sh.size());
+    }
     if (c->have_slater && !c->have_pbc_orb) return fail("periodic Slater factor: qmcb_set_pbc_orbitals has not been called");
     if (c->have_pbc_orb) {
       S.nbatom = (int)c->bxyz.size() / 3;
