@@ -42,7 +42,7 @@ __host__ __device__ inline CoopLayout coop_layout(const Sys& S) {
   L.colv = o;
   o += nmax;
   L.jtmp = o;
-  o += 2 * (S.ne > 1 ? S.ne - 1 : 0) * S.nb + S.natom * S.na;
+  o += 3 * (S.ne > 1 ? S.ne - 1 : 0) * S.nb + S.natom * S.na;
   L.total = (o + 1) & ~1;
   return L;
 }
@@ -391,6 +391,8 @@ __device__ __forceinline__ int pair_index(int ne, int i, int j) {  // i < j
 #define BPAIR(st, S, w, p, l) (st).bpair[((size_t)(w) * (S).npair + (p)) * (S).nb + (l)]
 #define GPAIR(st, S, w, p, x) (st).gpair[((size_t)(w) * (S).npair + (p)) * 3 + (x)]
 #define AGRAD(st, S, w, e, x) (st).agrad[((size_t)(w) * (S).ne + (e)) * 3 + (x)]
+#define LPAIR(st, S, w, p) (st).lpair[(size_t)(w) * (S).npair + (p)]
+#define ALAP(st, S, w, e) (st).alap[(size_t)(w) * (S).ne + (e)]
 
 template <int G>
 __device__ __forceinline__ void coop_jastrow_cached_grad(const Sys& S, const State& st, int w, int e, int lane,
@@ -415,20 +417,35 @@ __device__ __forceinline__ void coop_jastrow_cached_grad(const Sys& S, const Sta
   g[2] = group_sum<G>(g2, gm);
 }
 
+// Laplacian of U with respect to electron e from the cached pair / electron-ion terms
+template <int G>
+__device__ __forceinline__ double coop_jastrow_cached_lap(const Sys& S, const State& st, int w, int e, int lane,
+                                                          unsigned gm) {
+  double l = 0.0;
+#pragma unroll 1
+  for (int t = lane; t < S.ne - 1; t += G) {
+    const int j = t < e ? t : t + 1;
+    l += LPAIR(st, S, w, e < j ? pair_index(S.ne, e, j) : pair_index(S.ne, j, e));
+  }
+  if (lane == 0) l += ALAP(st, S, w, e);
+  return group_sum<G>(l, gm);
+}
+
 // value + gradient at the proposed position; parks per-task values for a possible commit:
 //   jt[t]            = b_l(r)                 t = jj * nb + l
 //   jt[ntb + t]      = c * g_l(r)             (gradient factor of that task)
 //   jt[2 ntb + u]    = a_k(r_eI)              u = I * na + k
-// ga = electron-ion part of the gradient (all lanes).
+//   jt[2 ntb + nta + t] = c * lap_l(r)        (Laplacian term of that task)
+// ga = electron-ion part of the gradient, la = electron-ion part of the Laplacian (all lanes).
 template <int G>
 __device__ __forceinline__ void coop_jastrow_propose(const Sys& S, const double* __restrict__ sd,
                                                      const int* __restrict__ si, const State& st, int w, int e,
                                                      double px, double py, double pz, int lane, unsigned gm,
                                                      double* __restrict__ jt, double& du, double (&g)[3],
-                                                     double (&ga)[3]) {
+                                                     double (&ga)[3], double& la) {
   const int s = e >= S.nup ? 1 : 0;
   const int ntb = (S.ne - 1) * S.nb, nta = S.natom * S.na;
-  double unew = 0.0, uold = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  double unew = 0.0, uold = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, a0 = 0.0, a1 = 0.0, a2 = 0.0, al = 0.0;
 #pragma unroll 1
   for (int t = lane; t < ntb + nta; t += G) {
     double dx, dy, dz, c, rcut, par;
@@ -456,13 +473,14 @@ __device__ __forceinline__ void coop_jastrow_propose(const Sys& S, const double*
       kind = si[S.o_akind + k];
     }
     const double r = sqrt(dx * dx + dy * dy + dz * dz);
-    double v = 0.0, gg = 0.0, ll;
-    if (r < rcut) radial_ool<1>(kind, par, rcut, r, v, gg, ll);
+    double v = 0.0, gg = 0.0, ll = 0.0;
+    if (r < rcut) radial_ool<2>(kind, par, rcut, r, v, gg, ll);
     unew = fma(c, v, unew);
     const double cg = c * gg;
     if (isb) {
       jt[t] = v;
       jt[ntb + t] = cg;
+      jt[2 * ntb + nta + t] = c * ll;
       b0 = fma(cg, dx, b0);
       b1 = fma(cg, dy, b1);
       b2 = fma(cg, dz, b2);
@@ -471,6 +489,7 @@ __device__ __forceinline__ void coop_jastrow_propose(const Sys& S, const double*
       a0 = fma(cg, dx, a0);
       a1 = fma(cg, dy, a1);
       a2 = fma(cg, dz, a2);
+      al = fma(c, ll, al);
     }
   }
   const int na_items = nta, nb_items = S.nb * 2;
@@ -489,6 +508,7 @@ __device__ __forceinline__ void coop_jastrow_propose(const Sys& S, const double*
   ga[0] = group_sum<G>(a0, gm);
   ga[1] = group_sum<G>(a1, gm);
   ga[2] = group_sum<G>(a2, gm);
+  la = group_sum<G>(al, gm);
   g[0] = group_sum<G>(b0, gm) + ga[0];
   g[1] = group_sum<G>(b1, gm) + ga[1];
   g[2] = group_sum<G>(b2, gm) + ga[2];
@@ -501,7 +521,7 @@ __device__ __forceinline__ void coop_jastrow_commit(const Sys& S, const double* 
                                                     const int* __restrict__ si, const State& st, int w, int e,
                                                     double nx, double ny, double nz, int lane, unsigned gm,
                                                     bool has_jastrow, const double* __restrict__ jt,
-                                                    const double (&ga)[3]) {
+                                                    const double (&ga)[3], double la) {
   const int s = e >= S.nup ? 1 : 0;
   if (has_jastrow) {
     const int ntb = (S.ne - 1) * S.nb;
@@ -536,8 +556,13 @@ __device__ __forceinline__ void coop_jastrow_commit(const Sys& S, const double* 
     for (int jj = lane; jj < S.ne - 1; jj += G) {
       const int j = jj < e ? jj : jj + 1;
       const int p = e < j ? pair_index(S.ne, e, j) : pair_index(S.ne, j, e);
-      double gs = 0.0;
-      for (int l = 0; l < S.nb; ++l) gs += jt[ntb + jj * S.nb + l];
+      double gs = 0.0, ls = 0.0;
+      const int nta = S.natom * S.na;
+      for (int l = 0; l < S.nb; ++l) {
+        gs += jt[ntb + jj * S.nb + l];
+        ls += jt[2 * ntb + nta + jj * S.nb + l];
+      }
+      LPAIR(st, S, w, p) = ls;
       const double sg = e < j ? 1.0 : -1.0;
       // NOTE: sum_l (c g_l) * d differs from sum_l (c g_l d) only by rounding
       GPAIR(st, S, w, p, 0) = sg * gs * (nx - CONF(st, S, w, j, 0));
@@ -548,6 +573,7 @@ __device__ __forceinline__ void coop_jastrow_commit(const Sys& S, const double* 
       AGRAD(st, S, w, e, 0) = ga[0];
       AGRAD(st, S, w, e, 1) = ga[1];
       AGRAD(st, S, w, e, 2) = ga[2];
+      ALAP(st, S, w, e) = la;
     }
   }
   __syncwarp(gm);

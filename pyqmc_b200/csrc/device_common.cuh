@@ -85,6 +85,8 @@ struct State {
   double* bpair;     // [N][npair][nb]  b_l(r_ij) of every electron pair        (sweep kernel cache)
   double* gpair;     // [N][npair][3]   sum_l c_l g_l(r_ij) (r_i - r_j)          (sweep kernel cache)
   double* agrad;     // [N][ne][3]      electron-ion part of grad_e U            (sweep kernel cache)
+  double* lpair;     // [N][npair]      sum_l c_l lap_l(r_ij)                    (sweep kernel cache)
+  double* alap;      // [N][ne]         electron-ion part of lap_e U             (sweep kernel cache)
   double* a3v;       // [N][ne][I][na3]  three-body a_k(r_eI)      (three_body_jastrow.py:103)
   double* P3;        // [N][ne]          P_i                       (three_body_jastrow.py:98-101)
   double* val3;      // [N]              U = 1/2 sum_i P_i

@@ -1303,20 +1303,22 @@ __global__ void __launch_bounds__(128) k_pair_cache_build(const Sys S, const Sta
                  dz = CONF(st, S, w, i, 2) - CONF(st, S, w, j, 2);
     const double r = sqrt(dx * dx + dy * dy + dz * dz);
     const int sp = (i >= S.nup ? 1 : 0) + (j >= S.nup ? 1 : 0);
-    double gs = 0.0;
+    double gs = 0.0, ls = 0.0;
     for (int l = 0; l < S.nb; ++l) {
-      double v = 0.0, gg = 0.0, ll;
-      if (r < S.rcut_b) radial_ool<1>(si[S.o_bkind + l], sd[S.o_bpar + l], S.rcut_b, r, v, gg, ll);
+      double v = 0.0, gg = 0.0, ll = 0.0;
+      if (r < S.rcut_b) radial_ool<2>(si[S.o_bkind + l], sd[S.o_bpar + l], S.rcut_b, r, v, gg, ll);
       BPAIR(st, S, w, r0, l) = v;
       gs += sd[S.o_bcoef + l * 3 + sp] * gg;
+      ls += sd[S.o_bcoef + l * 3 + sp] * ll;
     }
+    LPAIR(st, S, w, r0) = ls;
     GPAIR(st, S, w, r0, 0) = gs * dx;
     GPAIR(st, S, w, r0, 1) = gs * dy;
     GPAIR(st, S, w, r0, 2) = gs * dz;
   } else {
     const int e = r0 - S.npair;
     const int s = e >= S.nup ? 1 : 0;
-    double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0, la = 0.0;
     for (int I = 0; I < S.natom; ++I) {
       const double dx = CONF(st, S, w, e, 0) - sd[S.o_xyz + 3 * I], dy = CONF(st, S, w, e, 1) - sd[S.o_xyz + 3 * I + 1],
                    dz = CONF(st, S, w, e, 2) - sd[S.o_xyz + 3 * I + 2];
@@ -1324,13 +1326,15 @@ __global__ void __launch_bounds__(128) k_pair_cache_build(const Sys S, const Sta
       if (!(r < S.rcut_a)) continue;
       for (int k2 = 0; k2 < S.na; ++k2) {
         double v, gg, ll;
-        radial_ool<1>(si[S.o_akind + k2], sd[S.o_apar + k2], S.rcut_a, r, v, gg, ll);
+        radial_ool<2>(si[S.o_akind + k2], sd[S.o_apar + k2], S.rcut_a, r, v, gg, ll);
         const double cg = sd[S.o_acoef + (I * S.na + k2) * 2 + s] * gg;
         g0 = fma(cg, dx, g0);
         g1 = fma(cg, dy, g1);
         g2 = fma(cg, dz, g2);
+        la = fma(sd[S.o_acoef + (I * S.na + k2) * 2 + s], ll, la);
       }
     }
+    ALAP(st, S, w, e) = la;
     AGRAD(st, S, w, e, 0) = g0;
     AGRAD(st, S, w, e, 1) = g1;
     AGRAD(st, S, w, e, 2) = g2;
@@ -1343,6 +1347,8 @@ struct SweepArgs {
   const double* unif;   // [ne][N]
   uint8_t* accept;      // [ne][N] or nullptr
   unsigned long long* nacc;  // [ne]
+  double* ke_e;         // optional [ne][N]: kinetic-energy pieces of the final positions (energy.py:57-65) ...
+  double* g2_e;         // ... and |grad ln Psi|^2, from the caches, so the energy pipeline skips k_kinetic
   double* r2prop;       // DMC: [N] sum over electrons of |gauss + drift|^2          (dmc.py:68, 190-191)
   double* r2acc;        // DMC: [N] the same for accepted moves
 };
@@ -1363,7 +1369,7 @@ __device__ __forceinline__ void limdrift_dmc(double (&g)[3], double tau) {
 // DMC = false: VMC move (mc.py:115-137).  DMC = true: drift-diffusion move of dmc.py:49-70 (Umrigar
 // drift limit, fixed-node rejection of sign changes, |gauss + drift|^2 bookkeeping for tdamp).
 template <int G, bool DMC>
-__global__ void __launch_bounds__(128) k_vmc_sweep(const Sys S, const State st, const SweepArgs a) {
+__global__ void __launch_bounds__(128, 4) k_vmc_sweep(const Sys S, const State st, const SweepArgs a) {
   const double* sd;
   const int* si;
   stage_tables(S, sd, si);
@@ -1442,10 +1448,10 @@ __global__ void __launch_bounds__(128) k_vmc_sweep(const Sys S, const State st, 
       }
       val = isfinite(r0) ? r0 : 1.0;
     }
-    double ga[3] = {0.0, 0.0, 0.0};
+    double ga[3] = {0.0, 0.0, 0.0}, la = 0.0;
     if (has_j) {
       double du, gj[3];
-      coop_jastrow_propose<G>(S, sd, si, st, w, e, np_[0], np_[1], np_[2], lane, gm, ws + L.jtmp, du, gj, ga);
+      coop_jastrow_propose<G>(S, sd, si, st, w, e, np_[0], np_[1], np_[2], lane, gm, ws + L.jtmp, du, gj, ga, la);
 #pragma unroll
       for (int i = 0; i < 3; ++i) ngrad[i] = ngrad[i] + gj[i];
       val = val * exp(du);
@@ -1489,9 +1495,81 @@ __global__ void __launch_bounds__(128) k_vmc_sweep(const Sys S, const State st, 
         const double* __restrict__ mo = ws + L.mo;
         for (int i = lane; i < 5 * ldmax; i += G) mc[i] = mo[i];
       }
-      coop_jastrow_commit<G>(S, sd, si, st, w, e, np_[0], np_[1], np_[2], lane, gm, has_j, ws + L.jtmp, ga);
+      coop_jastrow_commit<G>(S, sd, si, st, w, e, np_[0], np_[1], np_[2], lane, gm, has_j, ws + L.jtmp, ga, la);
     }
     __syncwarp(gm);
+  }
+  if (a.ke_e == nullptr) return;
+  // ---- kinetic-energy pieces of the final walkers from the caches (energy.py:57-65, multiplywf.py:121-129),
+  // lanes over (electron, component) for the Slater ratios (cached MO rows . inverse column), then lanes
+  // over electrons for the Jastrow gradient / Laplacian sums over the pair caches
+  double* __restrict__ rat = ws + L.comp;  // [ne][5]; the AO scratch (5 nao doubles) is free after the sweep
+  const bool rat_fits = S.ne * 5 <= 5 * S.nao;
+  if (has_s && rat_fits) {
+#pragma unroll 1
+    for (int t = lane; t < S.ne * 5; t += G) {
+      const int e = t / 5, c = t - e * 5;
+      const int s = e >= S.nup ? 1 : 0;
+      const int n = s ? S.ndn : S.nup;
+      const int* __restrict__ occ = si + S.o_occ[s];
+      const double* __restrict__ mc = st.mocache + ((size_t)w * S.ne + e) * 5 * ldmax + c * ldmax;
+      const double* __restrict__ inv = st.inv[s] + (size_t)w * n * n + (e - s * S.nup);
+      double r = 0.0;
+      for (int k = 0; k < n; ++k) r = fma(mc[occ[k]], inv[k * n], r);
+      rat[t] = r;
+    }
+  }
+  __syncwarp(gm);
+#pragma unroll 1
+  for (int e = lane; e < S.ne; e += G) {
+    double gs[3] = {0.0, 0.0, 0.0}, laps = 0.0;
+    if (has_s) {
+      double r[5];
+      if (rat_fits) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) r[c] = rat[e * 5 + c];
+      } else {
+        const int s = e >= S.nup ? 1 : 0;
+        const int n = s ? S.ndn : S.nup;
+        const int* __restrict__ occ = si + S.o_occ[s];
+        const double* __restrict__ mc = st.mocache + ((size_t)w * S.ne + e) * 5 * ldmax;
+        const double* __restrict__ inv = st.inv[s] + (size_t)w * n * n + (e - s * S.nup);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          r[c] = 0.0;
+          for (int k = 0; k < n; ++k) r[c] = fma(mc[c * ldmax + occ[k]], inv[k * n], r[c]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) gs[i] = r[1 + i] / r[0];
+      laps = r[4] / r[0];
+    }
+    double gj[3] = {0.0, 0.0, 0.0}, lapj = 0.0, cross = 0.0;
+    if (has_j) {
+      double lj = ALAP(st, S, w, e);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) gj[i] = AGRAD(st, S, w, e, i);
+      for (int j = 0; j < S.ne; ++j) {
+        if (j == e) continue;
+        const int p = e < j ? pair_index(S.ne, e, j) : pair_index(S.ne, j, e);
+        const double sg = e < j ? 1.0 : -1.0;
+        gj[0] += sg * GPAIR(st, S, w, p, 0);
+        gj[1] += sg * GPAIR(st, S, w, p, 1);
+        gj[2] += sg * GPAIR(st, S, w, p, 2);
+        lj += LPAIR(st, S, w, p);
+      }
+      lapj = lj + (gj[0] * gj[0] + gj[1] * gj[1] + gj[2] * gj[2]);
+      cross = gs[0] * gj[0] + gs[1] * gj[1] + gs[2] * gj[2];
+    }
+    const double lap = (laps + lapj) + cross * 2.0;
+    double g2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double g = gs[i] + gj[i];
+      g2 += g * g;
+    }
+    a.ke_e[(size_t)e * N + w] = -0.5 * lap;
+    a.g2_e[(size_t)e * N + w] = g2;
   }
 }
 

@@ -125,7 +125,7 @@ struct qmcb_ctx {
   State st{};
   int N = 0;
   DBuf<double> b_inv[2], b_dsign[2], b_dlog[2], b_dv[2], b_W[2], b_ref[2];
-  DBuf<double> b_conf, b_ap, b_bp, b_av, b_bv, b_smo, b_spos, b_moall, b_lu, b_mocache, b_a3v, b_P3, b_val3, b_bpair, b_gpair, b_agrad;
+  DBuf<double> b_conf, b_ap, b_bp, b_av, b_bv, b_smo, b_spos, b_moall, b_lu, b_mocache, b_a3v, b_P3, b_val3, b_bpair, b_gpair, b_agrad, b_lpair, b_alap;
   // ---- staging / scratch
   DBuf<double> d_in, d_out, d_scr, d_u, d_rot, d_gauss, d_unif, d_energy, d_esum;
   DBuf<uint8_t> d_mask, d_accept;
@@ -143,6 +143,7 @@ struct qmcb_ctx {
   std::vector<int> shape_sig;
   bool mocache_valid = false;
   bool paircache_valid = false;  // Jastrow pair caches of the sweep kernel match the walkers
+  bool kinetic_valid = false;    // es.ke_e / es.g2_e were written by the sweep kernel for the current walkers
   // double-buffered device copies of a block's variates, filled on a copy stream by the host
   // thread that draws them (qmcb_vmc_upload) while the previous block computes
   static constexpr int NSLOT = 3;
@@ -497,7 +498,8 @@ int ensure_state(qmcb_ctx* c, int N) {
       c->b_mocache.ensure((size_t)N * S.ne * 5 * ldmax) ||
       c->b_a3v.ensure((size_t)N * S.ne * S.natom * std::max(S.na3, 1)) || c->b_P3.ensure((size_t)N * std::max(S.ne, 1)) ||
       c->b_val3.ensure(N) || c->b_bpair.ensure((size_t)N * std::max(S.npair, 1) * std::max(S.nb, 1)) ||
-      c->b_gpair.ensure((size_t)N * std::max(S.npair, 1) * 3) || c->b_agrad.ensure((size_t)N * std::max(S.ne, 1) * 3))
+      c->b_gpair.ensure((size_t)N * std::max(S.npair, 1) * 3) || c->b_agrad.ensure((size_t)N * std::max(S.ne, 1) * 3) ||
+      c->b_lpair.ensure((size_t)N * std::max(S.npair, 1)) || c->b_alap.ensure((size_t)N * std::max(S.ne, 1)))
     return -1;
   st.conf = c->b_conf.p;
   st.a_partial = c->b_ap.p;
@@ -514,6 +516,8 @@ int ensure_state(qmcb_ctx* c, int N) {
   st.bpair = c->b_bpair.p;
   st.gpair = c->b_gpair.p;
   st.agrad = c->b_agrad.p;
+  st.lpair = c->b_lpair.p;
+  st.alap = c->b_alap.p;
   if (S.pbc) {
     if (c->b_wrap.ensure((size_t)N * S.ne * 3) || c->b_swrap.ensure((size_t)N * 3) || c->b_monew.ensure((size_t)N * 5 * ldmax) ||
         c->b_gold.ensure((size_t)N * 3))
@@ -868,6 +872,7 @@ int launch_energy_t(qmcb_ctx* c, const double* d_u, const double* d_rot, double*
     const long long np = (long long)N * S.ne;
     const int block = pick_block(np);
     (void)block;
+    if (!c->kinetic_valid) {
     if (!c->mocache_valid && c->have_slater) {  // protocol-path updates do not maintain the cache
       if (launch_mo_all(c, 0, stream)) return -1;
     }
@@ -877,6 +882,8 @@ int launch_energy_t(qmcb_ctx* c, const double* d_u, const double* d_rot, double*
     k_kinetic<8><<<(unsigned)((np * 8 + 127) / 128), 128, ksm, stream>>>(S, c->st, c->es);
     c->nlaunch++;
     CK(cudaGetLastError());
+    }
+    c->kinetic_valid = false;
   }
   if (S.necp > 0) {
     CK(cudaMemsetAsync(c->es.count, 0, sizeof(int), stream));
@@ -973,7 +980,7 @@ void qmcb_destroy(qmcb_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   DBuf<double>* dd[] = {&c->d_dblob, &c->d_detc, &c->d_quad, &c->b_conf, &c->b_ap, &c->b_bp, &c->b_av, &c->b_bv,
-                        &c->b_smo, &c->b_spos, &c->b_moall, &c->b_lu, &c->b_mocache, &c->b_a3v, &c->b_P3, &c->b_val3, &c->b_bpair, &c->b_gpair, &c->b_agrad, &c->d_in, &c->d_out, &c->d_scr, &c->d_u,
+                        &c->b_smo, &c->b_spos, &c->b_moall, &c->b_lu, &c->b_mocache, &c->b_a3v, &c->b_P3, &c->b_val3, &c->b_bpair, &c->b_gpair, &c->b_agrad, &c->b_lpair, &c->b_alap, &c->d_in, &c->d_out, &c->d_scr, &c->d_u,
                         &c->d_rot, &c->d_gauss, &c->d_unif, &c->d_energy, &c->d_esum, &c->e_ke, &c->e_g2, &c->e_loc,
                         &c->e_vls, &c->e_contrib};
   for (auto* b : dd) b->release();
@@ -1278,6 +1285,7 @@ int qmcb_recompute_pbc(qmcb_ctx* c, int which, int nconf, const double* configs,
   }
   c->saved_slot = -1;
   c->paircache_valid = false;
+  c->kinetic_valid = false;
   if (sign || logval) return qmcb_value(c, which, sign, logval);
   CK(cudaStreamSynchronize(c->stream));
   return 0;
@@ -1511,6 +1519,7 @@ int qmcb_updateinternals(qmcb_ctx* c, int which, int e, const double* epos, cons
   if (launch_update(c, which, e, d_mask, c->stream)) return -1;
   if (which & 1) c->mocache_valid = false;
   c->paircache_valid = false;
+  c->kinetic_valid = false;
   CK(cudaStreamSynchronize(c->stream));
   // a shared context may be driven factor by factor (Slater call, then Jastrow call with the
   // same token), so the slot stays valid until the next query overwrites it
@@ -1797,6 +1806,11 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
       sa.unif = d_unif + se * N;
       sa.accept = d_accept ? d_accept + se * N : nullptr;
       sa.nacc = nacc + se;
+      if (with_energy) {  // kinetic pieces of the final positions straight from the sweep's caches
+        sa.ke_e = c->es.ke_e;
+        sa.g2_e = c->es.g2_e;
+        c->kinetic_valid = true;
+      }
       const unsigned grid = (unsigned)((N + sweep_walkers - 1) / sweep_walkers);
       if (G == 8) {
         if (prep_kernel(k_vmc_sweep<8, false>, sweep_smem)) return -1;
@@ -2207,6 +2221,9 @@ int qmcb_dmc_block(qmcb_ctx* c, int nsteps, double tstep, double branchcut, doub
       sa.nacc = c->d_nacc.p + (size_t)step * S.ne;
       sa.r2prop = d_r2p.p;
       sa.r2acc = d_r2a.p;
+      sa.ke_e = c->es.ke_e;
+      sa.g2_e = c->es.g2_e;
+      c->kinetic_valid = true;
       if ((rc = prep_kernel(k_vmc_sweep<16, true>, sweep_smem))) break;
       k_vmc_sweep<16, true><<<(unsigned)((N + sweep_walkers - 1) / sweep_walkers), sweep_warps * 32, sweep_smem, stream>>>(S, c->st, sa);
       c->nlaunch++;
