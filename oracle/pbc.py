@@ -286,8 +286,11 @@ class SlaterPbcOracle(SlaterOracle):
     def _mos(self, ao, s):
         return self.orbitals.mos(ao, s)
 
-    def pgradient(self):
-        raise NotImplementedError("orbital-coefficient gradients of periodic wave functions")
+    def _ao_for_mo(self, ao, s, i):
+        """slater.py:509-522 with PBCOrbitalEvaluatorKpoints.pgradient (orbitals.py:241-255): MO i is a
+        combination of the AOs of its own k-point only."""
+        k = int(np.searchsorted(self.orbitals.param_split[s], i, side="right"))
+        return ao[:, :, k, :]
 
 
 class EwaldOracle:

@@ -86,6 +86,9 @@ class SlaterOracle:
     def _mos(self, ao, s):
         return ao @ self._mo_coeff(s)
 
+    def _ao_for_mo(self, ao, s, i):
+        return ao
+
     def _spin(self, e):
         s = int(e >= self._nelec[0])
         return s, e - s * self._nelec[0]
@@ -250,13 +253,14 @@ class SlaterOracle:
         out = {"det_coeff": dcoef}
         for s, name in ((0, "mo_coeff_alpha"), (1, "mo_coeff_beta")):
             lo = s * self._nelec[0]
-            ao = self._aovals[:, lo : lo + self._nelec[s], :]  # (N, n_s, A)
+            ao_all = self._aovals[:, lo : lo + self._nelec[s]]  # (N, n_s, [nk,] A)
             nmo = self._mo_coeff(s).shape[1]
-            A = ao.shape[-1]
+            A = ao_all.shape[-1]
             # d ln D_d / d C[a, i] = sum_e ao[e, a] inv[d, col(i), e] if orbital i is occupied in d
             per_det = np.zeros((len(self._det_occup[s]), N, A, nmo))
             for d, occ in enumerate(self._det_occup[s]):
                 for col, i in enumerate(occ):
+                    ao = self._ao_for_mo(ao_all, s, i)  # (N, n_s, A): the AO set MO i is expanded in
                     per_det[d, :, :, i] = np.einsum("nea,ne->na", ao, self._inverse[s][:, d, col, :])
             g = np.zeros((N, A, nmo))
             for D, c in enumerate(coeff):

@@ -1910,6 +1910,7 @@ __global__ void __launch_bounds__(128) k_pgrad_det(const Sys S, const State st, 
 }
 
 // d ln Psi / d mo_coeff_s [N][A][nmo_s]: sum_d G_s[d] sum_e ao[e][a] inv[d][col_d(i)][e]
+// periodic: ao is [N][ne][nk][A] and MO i uses the AO set of its own k-point (orbitals.py:241-255)
 __global__ void __launch_bounds__(128) k_pgrad_mo(const Sys S, const State st, int s, const double* __restrict__ ao,
                                                   const double* __restrict__ G, int gstride, double* __restrict__ out) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1928,7 +1929,12 @@ __global__ void __launch_bounds__(128) k_pgrad_mo(const Sys S, const State st, i
     if (col < 0) continue;
     const double* __restrict__ inv = st.inv[s] + (((size_t)w * nds + d) * n + col) * n;
     double v = 0.0;
-    for (int e = 0; e < n; ++e) v = fma(ao[((size_t)w * S.ne + lo + e) * A + a], inv[e], v);
+    if (S.pbc) {
+      const int k = S.iblob[S.o_mok[s] + i];
+      for (int e = 0; e < n; ++e) v = fma(ao[(((size_t)w * S.ne + lo + e) * S.nk + k) * A + a], inv[e], v);
+    } else {
+      for (int e = 0; e < n; ++e) v = fma(ao[((size_t)w * S.ne + lo + e) * A + a], inv[e], v);
+    }
     acc = fma(G[((size_t)s * N + w) * gstride + d], v, acc);
   }
   out[t] = acc;

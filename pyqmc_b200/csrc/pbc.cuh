@@ -39,6 +39,8 @@ struct PbcMoArgs {
   long long stride_p, stride_c, stride_j;
   double* out_val;     // optional second copy of the value row: out_val[p * stride_vp + j]
   long long stride_vp;
+  double* ao_out;      // DERIV 0, CTA kernel only: AO values with the wrap phase, ao_out[(p * nk + k) * nao + mu]
+                       // (Slater._aovals of the reference, slater.py:233) instead of the MO contraction
 };
 
 __host__ __device__ inline int pbc_mo_scratch_doubles(const Sys& S, int nc, int G) {
@@ -412,6 +414,21 @@ __global__ void __launch_bounds__(256, 2) k_pbc_mo_cta(const Sys S, const State 
       const double w0 = a.wrap[3 * posidx], w1 = a.wrap[3 * posidx + 1], w2 = a.wrap[3 * posidx + 2];
 #pragma unroll
       for (int k = 0; k < 3; ++k) wt[k] = (w0 * Sm[k] + w1 * Sm[3 + k] + w2 * Sm[6 + k]) + pw[k];
+    }
+    if (DERIV == 0 && a.ao_out) {
+      for (int t = tid; t < S.nk * S.nao; t += T) {
+        const int k = t / S.nao;
+        double v = ao[t];
+        if (!S.isgamma) {
+          const double* __restrict__ kl = sd + S.o_kl + 3 * k;
+          const double kd = kl[0] * wt[0] + kl[1] * wt[1] + kl[2] * wt[2];
+          const double n = rint(kd / 3.141592653589793);
+          if (fmod(fabs(n), 2.0) == 1.0) v = -v;
+        }
+        a.ao_out[(size_t)p * S.nk * S.nao + t] = v;
+      }
+      __syncthreads();
+      continue;
     }
     for (int t = tid; t < NC * ldc; t += T) {
       const int c = t / ldc, j = t - c * ldc;

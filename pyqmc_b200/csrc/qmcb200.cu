@@ -705,6 +705,37 @@ int sync_blocking(qmcb_ctx* c) {
   return 0;
 }
 
+// AO values of every electron at its current position: [N][ne][A], periodic [N][ne][nk][A] with the
+// wrap phase (the reference's _aovals, slater.py:233)
+int launch_ao_all(qmcb_ctx* c, double* d_ao, cudaStream_t stream) {
+  const Sys& S = c->S;
+  const long long np = (long long)c->N * S.ne;
+  if (S.pbc) {
+    const size_t tab = (c->smem_bytes + 15) & ~(size_t)15;
+    const size_t csm = tab + pbc_mo_cta_scratch_bytes(S, 1);
+    if (S.nk > QMCB_PBC_NKMAX || S.nao > QMCB_PBC_RU * 256 || csm > 100 * 1024)
+      return fail("periodic parameter gradients: k-point / AO count beyond the CTA orbital kernel's limits");
+    PbcMoArgs a{};
+    a.npoints = np;
+    a.pos = c->st.conf;
+    a.wrap = c->st.wrap;
+    a.naip = 1;
+    a.spin_mode = 1;
+    a.ao_out = d_ao;
+    a.out = d_ao;  // unused in AO mode
+    int T = std::min((std::max(S.nao, 64) + 31) / 32 * 32, 256);
+    if (S.nao > T) T = std::min(((S.nao + 1) / 2 + 31) / 32 * 32, 256);
+    if (prep_kernel(k_pbc_mo_cta<0>, csm)) return -1;
+    k_pbc_mo_cta<0><<<(unsigned)std::min<long long>(np, 148LL * 64), T, csm, stream>>>(S, c->st, a);
+  } else {
+    if (prep_kernel(k_ao_all, c->smem_bytes)) return -1;
+    k_ao_all<<<(unsigned)((np + 127) / 128), 128, c->smem_bytes, stream>>>(S, c->st, d_ao);
+  }
+  c->nlaunch++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int slater_rebuild(qmcb_ctx* c, cudaStream_t stream) {
   const Sys& S = c->S;
   const int N = c->N;
@@ -1629,11 +1660,8 @@ int qmcb_pgradient(qmcb_ctx* c, const char* name, double* out) {
     if (s < 0) { rc = fail("unknown parameter: " + k); break; }
     const size_t nout = N * S.nao * S.nmo[s];
     if (nout == 0) break;
-    if (d_ao.ensure(N * S.ne * S.nao) || d_mo.ensure(nout)) { rc = -1; break; }
-    const long long np = (long long)N * S.ne;
-    if (prep_kernel(k_ao_all, c->smem_bytes)) { rc = -1; break; }
-    k_ao_all<<<(unsigned)((np + 127) / 128), 128, c->smem_bytes, c->stream>>>(S, c->st, d_ao.p);
-    c->nlaunch++;
+    if (d_ao.ensure(N * S.ne * S.nao * (S.pbc ? S.nk : 1)) || d_mo.ensure(nout)) { rc = -1; break; }
+    if (launch_ao_all(c, d_ao.p, c->stream)) { rc = -1; break; }
     k_pgrad_mo<<<(unsigned)((nout + 127) / 128), 128, 0, c->stream>>>(S, c->st, s, d_ao.p, d_G.p, gstride, d_mo.p);
     c->nlaunch++;
     if (cudaGetLastError() != cudaSuccess) { rc = fail("k_pgrad_mo launch failed"); break; }
@@ -2270,7 +2298,6 @@ int qmcb_sr_avg(qmcb_ctx* c, int nparam, const int32_t* src, const int64_t* off,
   const Sys& S = c->S;
   const size_t N = c->N, P = (size_t)nparam;
   cudaStream_t stream = c->stream;
-  if (S.pbc) return fail("parameter gradients of periodic wave functions are not supported");
   bool need[6] = {false, false, false, false, false, false};
   for (size_t j = 0; j < P; ++j) {
     if (src[j] < 0 || src[j] > 5) return fail("qmcb_sr_avg: unknown parameter source");
@@ -2304,11 +2331,8 @@ int qmcb_sr_avg(qmcb_ctx* c, int nparam, const int32_t* src, const int64_t* off,
       a.stride[0] = S.ndet;
     }
     if (need[1] || need[2]) {
-      if (d_ao.ensure(N * S.ne * S.nao)) { rc = -1; break; }
-      const long long np = (long long)N * S.ne;
-      if ((rc = prep_kernel(k_ao_all, c->smem_bytes))) break;
-      k_ao_all<<<(unsigned)((np + 127) / 128), 128, c->smem_bytes, stream>>>(S, c->st, d_ao.p);
-      c->nlaunch++;
+      if (d_ao.ensure(N * S.ne * S.nao * (S.pbc ? S.nk : 1))) { rc = -1; break; }
+      if ((rc = launch_ao_all(c, d_ao.p, stream))) break;
       for (int s = 0; s < 2; ++s) {
         if (!need[1 + s]) continue;
         const size_t nout = N * S.nao * S.nmo[s];

@@ -107,7 +107,7 @@ class StochasticReconfiguration:
             ctx = _device_context(wf)
         except TypeError:
             return None
-        if ctx is None or ctx.periodic:
+        if ctx is None:
             return None
         return ctx
 

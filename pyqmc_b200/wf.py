@@ -431,8 +431,6 @@ class Slater(_DeviceFactor):
         ctx = self._ctx
         N = ctx.nconf
         p = self.parameters
-        if self._pbc is not None:
-            raise NotImplementedError("parameter gradients of periodic Slater wave functions")
         shapes = {"det_coeff": (N, len(p["det_coeff"])),
                   "mo_coeff_alpha": (N,) + p["mo_coeff_alpha"].shape,
                   "mo_coeff_beta": (N,) + p["mo_coeff_beta"].shape}

@@ -98,11 +98,10 @@ def generate(name):
     out["a_partial"], out["b_partial"] = np.array(ja._a_partial), np.array(ja._b_partial)
     if len(wf.wf_factors) > 2:
         out["P_i"], out["a3_values"] = np.array(wf.wf_factors[2].P_i), np.array(wf.wf_factors[2].a_values)
-    if not periodic:
-        pg = wf.pgradient()
-        for k in pg.keys():
-            out["pgrad_" + k] = np.array(pg[k])
-    else:
+    pg = wf.pgradient()
+    for k in pg.keys():
+        out["pgrad_" + k] = np.array(pg[k])
+    if periodic:
         out["wrap1"] = configs.wrap.copy()
     np.random.seed(21)
     en = EnergyAccumulator(mol, **ekw)(configs, wf)

@@ -42,6 +42,10 @@ def check_internal(wf, data):
         assert np.abs(sl._dets[s][1] - data[f"dets{s}"][1]).max() < 1e-10
     assert helpers.relerr(ja._a_partial, data["a_partial"]) < 1e-10
     assert helpers.relerr(ja._b_partial, data["b_partial"]) < 1e-10
+    pg = wf.pgradient()  # periodic orbitals: every MO column uses the AO set of its own k-point
+    for k in ("wf1det_coeff", "wf1mo_coeff_alpha", "wf1mo_coeff_beta", "wf2acoeff", "wf2bcoeff"):
+        assert pg[k].shape == data["pgrad_" + k].shape, k
+        assert helpers.relerr(pg[k], data["pgrad_" + k]) < 1e-9, k
 
 
 @pytest.mark.parametrize("name", PBC_SYSTEMS)
@@ -124,3 +128,29 @@ def test_diamond_supercell_against_oracle(lib):
     eno = EnergyOracle(mol, ewald_gmax=EWALD_GMAX)(oc, orc)
     for k in ("ke", "ee", "ei", "ecp", "total"):
         assert helpers.relerr(en[k], eno[k]) < 1e-8, k
+
+
+def test_periodic_stochastic_reconfiguration_avg(lib):
+    """qmcb_sr_avg on a periodic wave function (Jastrow and orbital parameters) vs numpy on the same
+    per-walker arrays."""
+    import pyqmc_b200 as pq
+    from pyqmc_b200 import sr
+
+    data = golden_replay.load("diamond211")
+    mol, mf, wf, _ = helpers.make_pair("diamond211", seed=1)
+    configs = periodic_configs(data, mol)
+    wf.recompute(configs)
+    to_opt = {k: np.ones(np.shape(wf.parameters[k]), dtype=bool) for k in wf.parameters.keys()}
+    to_opt["wf2bcoeff"][0, :] = False
+    acc = sr.StochasticReconfiguration(pq.EnergyAccumulator(mol, ewald_gmax=EWALD_GMAX), sr.LinearTransform(wf.parameters, to_opt))
+    np.random.seed(77)
+    dev = acc.avg(configs, wf)
+    np.random.seed(77)
+    den = acc.enacc(configs, wf)
+    dp = acc.transform.serialize_gradients(wf.pgradient())
+    w = np.full(len(dp), 1.0 / len(dp))
+    _, f = sr.nodal_regularization(den["grad2"])
+    dpr = dp * f[:, None]
+    assert helpers.relerr(dev["dppsi"], np.average(dpr, weights=w, axis=0)) < 1e-10
+    assert helpers.relerr(dev["dpH"], np.einsum("i,ij->j", den["total"], w[:, None] * dpr)) < 1e-10
+    assert helpers.relerr(dev["dpidpj"], np.einsum("ij,ik->jk", dp, w[:, None] * dpr)) < 1e-10
