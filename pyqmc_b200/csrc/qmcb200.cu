@@ -113,6 +113,9 @@ struct qmcb_ctx {
   DBuf<double> d_ewdisp, d_ewg, d_ewion;
   DBuf<double> b_wrap, b_swrap, b_monew, b_gold, d_pwrap, e_ewald, e_ecppos, e_ecpwrap;
   bool pending_wrap = false;  // d_pwrap holds the wrap vectors of the next point call
+  // DMC block scratch (kept across blocks: a cudaMalloc / cudaFree pair costs more than a DMC step)
+  DBuf<double> m_tmu, m_tmrot, m_tmsel, m_tmacc, m_w, m_eold, m_v2old, m_r2p, m_r2a, m_prod, m_ws;
+  DBuf<unsigned long long> m_ntacc;
   bool dirty = true;
   // ---- device tables
   Sys S{};
@@ -1015,6 +1018,9 @@ void qmcb_destroy(qmcb_ctx* c) {
                         &c->d_rot, &c->d_gauss, &c->d_unif, &c->d_energy, &c->d_esum, &c->e_ke, &c->e_g2, &c->e_loc,
                         &c->e_vls, &c->e_contrib};
   for (auto* b : dd) b->release();
+  DBuf<double>* mb[] = {&c->m_tmu, &c->m_tmrot, &c->m_tmsel, &c->m_tmacc, &c->m_w, &c->m_eold, &c->m_v2old, &c->m_r2p, &c->m_r2a, &c->m_prod, &c->m_ws};
+  for (auto* b : mb) b->release();
+  c->m_ntacc.release();
   DBuf<double>* pb[] = {&c->d_ewdisp, &c->d_ewg, &c->d_ewion, &c->b_wrap, &c->b_swrap, &c->b_monew, &c->b_gold, &c->d_pwrap,
                         &c->e_ewald, &c->e_ecppos, &c->e_ecpwrap};
   for (auto* b : pb) b->release();
@@ -2164,8 +2170,10 @@ int qmcb_dmc_block(qmcb_ctx* c, int nsteps, double tstep, double branchcut, doub
   const size_t M = (size_t)S.tot_naip;
   const size_t nse = (size_t)nsteps * S.ne;
   const size_t nu1 = (size_t)S.ne * S.necp * N, nr1 = (size_t)S.ne * S.necp * 9;
-  DBuf<double> d_tmu, d_tmrot, d_tmsel, d_tmacc, d_w, d_eold, d_v2old, d_r2p, d_r2a, d_prod, d_ws;
-  DBuf<unsigned long long> d_ntacc;
+  DBuf<double>&d_tmu = c->m_tmu, &d_tmrot = c->m_tmrot, &d_tmsel = c->m_tmsel, &d_tmacc = c->m_tmacc, &d_w = c->m_w,
+              &d_eold = c->m_eold, &d_v2old = c->m_v2old, &d_r2p = c->m_r2p, &d_r2a = c->m_r2a, &d_prod = c->m_prod,
+              &d_ws = c->m_ws;
+  DBuf<unsigned long long>& d_ntacc = c->m_ntacc;
   int rc = 0;
   do {
     if (c->d_gauss.ensure(nse * N * 3) || c->d_unif.ensure(nse * N) || c->d_u.ensure((size_t)(nsteps + 1) * nu1) ||
@@ -2278,9 +2286,6 @@ int qmcb_dmc_block(qmcb_ctx* c, int nsteps, double tstep, double branchcut, doub
     if (sync_blocking(c)) rc = -1;
   } while (0);
   cudaStreamSynchronize(stream);
-  DBuf<double>* tmp[] = {&d_tmu, &d_tmrot, &d_tmsel, &d_tmacc, &d_w, &d_eold, &d_v2old, &d_r2p, &d_r2a, &d_prod, &d_ws};
-  for (auto* b : tmp) b->release();
-  d_ntacc.release();
   c->saved_slot = -1;
   return rc;
 }

@@ -116,21 +116,32 @@ def _device_dmc_path(wf, accumulators, ekey):
     return not hasattr(mol, "a")
 
 
-def draw_dmc_block_variates(nconf, nelec, tstep, nsteps, accumulator, native=True):
+def _dmc_buffers(shapes, pinned_owner):
+    """Arrays for one block's variates; page-locked (true async H2D) and cached on the device context
+    when an owner is given."""
+    if pinned_owner is None:
+        return {k: np.empty(s) for k, s in shapes.items()}
+    key = tuple(sorted((k, tuple(s)) for k, s in shapes.items()))
+    cache = pinned_owner.__dict__.setdefault("_dmc_buffers", {})
+    if cache.get("key") != key:
+        cache["key"] = key
+        cache["own"] = {k: _lib.PinnedArray(s) for k, s in shapes.items()}
+    return {k: v.array for k, v in cache["own"].items()}
+
+
+def draw_dmc_block_variates(nconf, nelec, tstep, nsteps, accumulator, native=True, pinned_owner=None):
     """Every random number of one ``dmc_propagate`` call in the reference's order: the energy
     evaluation before the first step; then per step, for every electron the T-move draws
     (``nonlocal_tmoves``: per ECP atom ``random(N)`` + a rotation; ``select_walker``: one ``rand()``
     per walker; acceptance ``rand(N)``), for every electron ``normal(N, 3)`` + ``rand(N)``, and the
     energy evaluation."""
     necp = accumulator.necp
-    ecp_u = np.empty((nsteps + 1, nelec, necp, nconf))
-    ecp_rot = np.empty((nsteps + 1, nelec, necp, 3, 3))
-    tm_u = np.empty((nsteps, nelec, necp, nconf))
-    tm_rot = np.empty((nsteps, nelec, necp, 3, 3))
-    tm_sel = np.empty((nsteps, nelec, nconf))
-    tm_acc = np.empty((nsteps, nelec, nconf))
-    gauss = np.empty((nsteps, nelec, nconf, 3))
-    unif = np.empty((nsteps, nelec, nconf))
+    b = _dmc_buffers(dict(ecp_u=(nsteps + 1, nelec, necp, nconf), ecp_rot=(nsteps + 1, nelec, necp, 3, 3),
+                          tm_u=(nsteps, nelec, necp, nconf), tm_rot=(nsteps, nelec, necp, 3, 3),
+                          tm_sel=(nsteps, nelec, nconf), tm_acc=(nsteps, nelec, nconf),
+                          gauss=(nsteps, nelec, nconf, 3), unif=(nsteps, nelec, nconf)), pinned_owner)
+    ecp_u, ecp_rot, tm_u, tm_rot = b["ecp_u"], b["ecp_rot"], b["tm_u"], b["tm_rot"]
+    tm_sel, tm_acc, gauss, unif = b["tm_sel"], b["tm_acc"], b["gauss"], b["unif"]
     tmoves = accumulator.has_nonlocal_moves()
     # the draw program, in consumption order: (kind, destination array view, scale)
     ops = []
@@ -202,7 +213,7 @@ def dmc_propagate_device(wf, configs, weights, tstep, branchcut_start, e_trial, 
     ctx = _device_context(wf)
     accumulator = accumulators[ekey[0]]
     accumulator._attach(wf)
-    v = draw_dmc_block_variates(nconf, nelec, tstep, nsteps, accumulator)
+    v = draw_dmc_block_variates(nconf, nelec, tstep, nsteps, accumulator, pinned_owner=ctx)
     w = np.ascontiguousarray(weights, dtype=np.float64)
     newconf = np.empty((nconf, nelec, 3))
     wsums = np.zeros((nsteps, 8))
