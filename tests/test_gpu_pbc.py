@@ -154,3 +154,21 @@ def test_periodic_stochastic_reconfiguration_avg(lib):
     assert helpers.relerr(dev["dppsi"], np.average(dpr, weights=w, axis=0)) < 1e-10
     assert helpers.relerr(dev["dpH"], np.einsum("i,ij->j", den["total"], w[:, None] * dpr)) < 1e-10
     assert helpers.relerr(dev["dpidpj"], np.einsum("ij,ik->jk", dp, w[:, None] * dpr)) < 1e-10
+
+
+@pytest.mark.parametrize("name", PBC_SYSTEMS)
+def test_periodic_tmoves_match_reference_golden(lib, name):
+    """EnergyAccumulator.nonlocal_tmoves on a periodic system vs compute_tmoves of the reference
+    (eval_ecp.py:43-80 with make_irreducible, coord.py:168-184): ratios, weights, wrapped positions."""
+    import pyqmc_b200 as pq
+
+    data = golden_replay.load(name)
+    mol, mf, wf, _ = helpers.make_pair(name, seed=1)
+    configs = periodic_configs(data, mol, "configs1", "wrap1")
+    wf.recompute(configs)
+    acc = pq.EnergyAccumulator(mol, ewald_gmax=EWALD_GMAX)
+    np.random.seed(22)
+    tm = acc.nonlocal_tmoves(configs, wf, int(data["elist"][-1]), 0.02)
+    assert helpers.relerr(tm["ratio"], data["tmove_ratio"]) < 1e-9
+    assert helpers.relerr(tm["weight"], data["tmove_weight"]) < 1e-10
+    assert np.abs(tm["configs"].configs - data["tmove_configs"]).max() < 1e-9

@@ -222,3 +222,19 @@ def test_oracle_stochastic_reconfiguration_matches_reference_golden(name):
     assert helpers.relerr(np.average(dpr, weights=w, axis=0), gold["sr_dppsi"]) < 1e-9
     assert helpers.relerr(np.einsum("i,ij->j", en["total"], w[:, None] * dpr), gold["sr_dpH"]) < 1e-9
     assert helpers.relerr(np.einsum("ij,ik->jk", dp, w[:, None] * dpr), gold["sr_dpidpj"]) < 1e-9
+
+
+@pytest.mark.parametrize("name", PBC_SYSTEMS)
+def test_oracle_periodic_tmoves_match_golden(name):
+    from oracle.local_energy import EnergyOracle
+    from oracle.pbc import PeriodicWalkers
+
+    data = golden_replay.load(name)
+    mol, mf, _, orc = _oracle_only(name)
+    configs = periodic_walkers(PeriodicWalkers, data, mol, "configs1", "wrap1")
+    orc.recompute(configs)
+    np.random.seed(22)
+    tm = EnergyOracle(mol, ewald_gmax=EWALD_GMAX).nonlocal_tmoves(configs, orc, int(data["elist"][-1]), 0.02)
+    assert helpers.relerr(tm["ratio"], data["tmove_ratio"]) < 1e-9
+    assert helpers.relerr(tm["weight"], data["tmove_weight"]) < 1e-10
+    assert np.abs(tm["configs"] - data["tmove_configs"]).max() < 1e-12
