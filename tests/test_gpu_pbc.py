@@ -172,3 +172,29 @@ def test_periodic_tmoves_match_reference_golden(lib, name):
     assert helpers.relerr(tm["ratio"], data["tmove_ratio"]) < 1e-9
     assert helpers.relerr(tm["weight"], data["tmove_weight"]) < 1e-10
     assert np.abs(tm["configs"].configs - data["tmove_configs"]).max() < 1e-9
+
+
+@pytest.mark.parametrize("name", ["ortho", "diamond211"])
+def test_periodic_dmc_through_the_protocol(lib, name):
+    """dmc_propagate (dmc.py:123-221: T-moves, fixed-node drift-diffusion, weights) driving the periodic
+    device objects through the protocol calls vs the same loop over the oracle objects."""
+    import pyqmc_b200 as pq
+    from oracle import dmc_driver
+    from oracle.local_energy import EnergyOracle
+
+    mol, mf, wf, orc = helpers.make_pair(name, seed=1)
+    np.random.seed(3)
+    configs = pq.initial_guess(mol, 10)
+    oc = helpers.to_oracle_walkers(configs)
+    w1, w2 = np.ones(10), np.ones(10)
+    np.random.seed(4)
+    out1, configs, w1 = dmc_driver.dmc_propagate(wf, configs, w1, 0.02, 10.0, -5.0, -5.1, nsteps=2,
+                                                 accumulators={"energy": pq.EnergyAccumulator(mol, ewald_gmax=EWALD_GMAX)})
+    np.random.seed(4)
+    out2, oc, w2 = dmc_driver.dmc_propagate(orc, oc, w2, 0.02, 10.0, -5.0, -5.1, nsteps=2,
+                                            accumulators={"energy": EnergyOracle(mol, ewald_gmax=EWALD_GMAX)})
+    assert np.abs(configs.configs - oc.configs).max() < 1e-9
+    assert np.array_equal(configs.wrap, oc.wrap)
+    assert helpers.relerr(w1, w2) < 1e-8
+    for k in ("energytotal", "acceptance", "tmove_acceptance", "weight"):
+        assert abs(out1[k] - out2[k]) <= 1e-8 * max(1.0, abs(out2[k])), k
