@@ -433,13 +433,16 @@ def gpu_arm_dmc(args):
     ctx = wf._ctx
     e0 = float(df0["energytotal"][-1])  # trial / estimated energy from the VMC warm-up (rundmc, dmc.py:497-506)
 
+    prefetch = dmc.DmcPrefetcher(wf, configs, tstep, spb, acc["energy"], W + K)  # host draws overlap the device block
+
     def block():
         nonlocal configs, weights
-        out, configs, weights = dmc.dmc_propagate(wf, configs, weights, tstep, 10.0, e0, e0, nsteps=spb, accumulators=acc)
+        out, configs, weights = dmc.dmc_propagate(wf, configs, weights, tstep, 10.0, e0, e0, nsteps=spb, accumulators=acc,
+                                                  variates=prefetch.next())
         from pyqmc_b200 import parallel
 
         glob, _ = parallel.allreduce_dmc_block(out, N)  # one allreduce of the block's weighted sums (dmc.py:288-303)
-        configs, weights, _ = parallel.branch_global(configs, weights)  # comb over the global population
+        configs, weights, _ = parallel.branch_global(configs, weights, base_draw=prefetch.branch_draw())  # global comb
         return out
 
     for _ in range(W):

@@ -739,47 +739,6 @@ __global__ void __launch_bounds__(128) k_jastrow3_recompute(const Sys S, const S
   st.val3[w] = 0.5 * tot;
 }
 
-__global__ void __launch_bounds__(128) k_jastrow3_update(const Sys S, const State st, int e, int move_conf,
-                                                         const uint8_t* mask) {
-  const double* sd;
-  const int* si;
-  stage_tables(S, sd, si);
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= st.N) return;
-  if (mask && !mask[w]) return;
-  const double nx = st.saved_pos[(size_t)w * 3], ny = st.saved_pos[(size_t)w * 3 + 1], nz = st.saved_pos[(size_t)w * 3 + 2];
-  const double ox = CONF(st, S, w, e, 0), oy = CONF(st, S, w, e, 1), oz = CONF(st, S, w, e, 2);
-  double av[QMCB_J3_MAXA], ag[1], al[1];
-  const size_t abase = ((size_t)w * S.ne + e) * S.natom * S.na3;
-  // old pair terms (cached a-values, current position) leave the partners' sums ...
-  for (int i = 0; i < S.natom * S.na3; ++i) av[i] = st.a3v[abase + i];
-  for (int j = 0; j < S.ne; ++j) {
-    if (j == e) continue;
-    double Po = 0.0, g[3] = {0.0, 0.0, 0.0}, lap = 0.0;
-    j3_pair<0>(S, sd, si, st, w, e, j, ox, oy, oz, av, ag, al, CONF(st, S, w, j, 0), CONF(st, S, w, j, 1),
-               CONF(st, S, w, j, 2), Po, g, lap);
-    st.P3[(size_t)w * S.ne + j] -= Po;
-  }
-  // ... and the new ones (a-values at the accepted position) enter
-  j3_a_values<0>(S, sd, si, nx, ny, nz, av, ag, al);
-  double newval = 0.0;
-  for (int j = 0; j < S.ne; ++j) {
-    if (j == e) continue;
-    double Pn = 0.0, g[3] = {0.0, 0.0, 0.0}, lap = 0.0;
-    j3_pair<0>(S, sd, si, st, w, e, j, nx, ny, nz, av, ag, al, CONF(st, S, w, j, 0), CONF(st, S, w, j, 1),
-               CONF(st, S, w, j, 2), Pn, g, lap);
-    newval += Pn;
-    st.P3[(size_t)w * S.ne + j] += Pn;
-  }
-  st.val3[w] += newval - st.P3[(size_t)w * S.ne + e];
-  st.P3[(size_t)w * S.ne + e] = newval;
-  for (int i = 0; i < S.natom * S.na3; ++i) st.a3v[abase + i] = av[i];
-  if (!move_conf) return;
-  CONF(st, S, w, e, 0) = nx;
-  CONF(st, S, w, e, 1) = ny;
-  CONF(st, S, w, e, 2) = nz;
-}
-
 // d U / d ccoeff [N][I][na][na][nb][3]: thread per (walker, I, k, l)
 __global__ void __launch_bounds__(128) k_jastrow3_pgrad(const Sys S, const State st, double* __restrict__ out) {
   const double* sd;

@@ -116,20 +116,21 @@ def _device_dmc_path(wf, accumulators, ekey):
     return not hasattr(mol, "a")
 
 
-def _dmc_buffers(shapes, pinned_owner):
+def _dmc_buffers(shapes, pinned_owner, slot=0):
     """Arrays for one block's variates; page-locked (true async H2D) and cached on the device context
-    when an owner is given."""
+    (one set per ``slot``: the prefetcher fills one set while the device reads the other) when an owner
+    is given."""
     if pinned_owner is None:
         return {k: np.empty(s) for k, s in shapes.items()}
     key = tuple(sorted((k, tuple(s)) for k, s in shapes.items()))
-    cache = pinned_owner.__dict__.setdefault("_dmc_buffers", {})
+    cache = pinned_owner.__dict__.setdefault("_dmc_buffers", {}).setdefault(slot, {})
     if cache.get("key") != key:
         cache["key"] = key
         cache["own"] = {k: _lib.PinnedArray(s) for k, s in shapes.items()}
     return {k: v.array for k, v in cache["own"].items()}
 
 
-def draw_dmc_block_variates(nconf, nelec, tstep, nsteps, accumulator, native=True, pinned_owner=None):
+def draw_dmc_block_variates(nconf, nelec, tstep, nsteps, accumulator, native=True, pinned_owner=None, slot=0):
     """Every random number of one ``dmc_propagate`` call in the reference's order: the energy
     evaluation before the first step; then per step, for every electron the T-move draws
     (``nonlocal_tmoves``: per ECP atom ``random(N)`` + a rotation; ``select_walker``: one ``rand()``
@@ -139,7 +140,7 @@ def draw_dmc_block_variates(nconf, nelec, tstep, nsteps, accumulator, native=Tru
     b = _dmc_buffers(dict(ecp_u=(nsteps + 1, nelec, necp, nconf), ecp_rot=(nsteps + 1, nelec, necp, 3, 3),
                           tm_u=(nsteps, nelec, necp, nconf), tm_rot=(nsteps, nelec, necp, 3, 3),
                           tm_sel=(nsteps, nelec, nconf), tm_acc=(nsteps, nelec, nconf),
-                          gauss=(nsteps, nelec, nconf, 3), unif=(nsteps, nelec, nconf)), pinned_owner)
+                          gauss=(nsteps, nelec, nconf, 3), unif=(nsteps, nelec, nconf)), pinned_owner, slot)
     ecp_u, ecp_rot, tm_u, tm_rot = b["ecp_u"], b["ecp_rot"], b["tm_u"], b["tm_rot"]
     tm_sel, tm_acc, gauss, unif = b["tm_sel"], b["tm_acc"], b["gauss"], b["unif"]
     tmoves = accumulator.has_nonlocal_moves()
@@ -207,13 +208,74 @@ def _run_draw_program_native(ops):
     return True
 
 
-def dmc_propagate_device(wf, configs, weights, tstep, branchcut_start, e_trial, e_est, nsteps, accumulators, ekey):
+class DmcPrefetcher:
+    """Draws the variates of block b+1 on a host thread while block b runs on the device.  The global
+    legacy stream is consumed in the reference's order -- block variates, then the one ``rand()`` of
+    ``branch`` (dmc.py:361), then the next block's variates -- so the branching draw of block b is
+    taken by the same thread just before it draws block b+1; nothing else touches ``np.random`` while
+    the thread runs."""
+
+    def __init__(self, wf, configs, tstep, nsteps, accumulator, nblocks, with_branch=True):
+        from concurrent.futures import ThreadPoolExecutor
+
+        self.shape = configs.configs.shape[:2]
+        self.args = (tstep, nsteps, accumulator)
+        if _device_context(wf) is None:
+            wf.recompute(configs)
+        self.ctx = _device_context(wf)
+        self.remaining = nblocks
+        self.with_branch = with_branch
+        self.issued = 0
+        self.pool = ThreadPoolExecutor(max_workers=1)
+        self.future = self.pool.submit(self._draw, False)
+        self.remaining -= 1
+
+    def _draw(self, branch_first):
+        base = np.random.rand() if branch_first else None
+        tstep, nsteps, accumulator = self.args
+        slot = self.issued % 2
+        self.issued += 1
+        v = draw_dmc_block_variates(self.shape[0], self.shape[1], tstep, nsteps, accumulator, pinned_owner=self.ctx, slot=slot)
+        return base, v
+
+    def next(self):
+        """Variates of the next block; also starts drawing the one after (preceded by this block's
+        branching draw, returned by ``branch_draw``)."""
+        self._prev_base, v = self.future.result()
+        if self.remaining > 0:
+            self.future = self.pool.submit(self._draw, self.with_branch)
+            self.remaining -= 1
+        else:
+            self.future = None
+        return v
+
+    def branch_draw(self):
+        """The ``np.random.rand()`` of this block's ``branch`` call."""
+        if self.future is None:
+            self.pool.shutdown(wait=True)
+            return np.random.rand() if self.with_branch else None
+        base, v = self.future.result()  # waits for the thread: it drew the branching number first
+        self.future = _Done((None, v))
+        return base
+
+
+class _Done:
+    def __init__(self, value):
+        self.value = value
+
+    def result(self):
+        return self.value
+
+
+def dmc_propagate_device(wf, configs, weights, tstep, branchcut_start, e_trial, e_est, nsteps, accumulators, ekey,
+                         variates=None):
     nconf, nelec, _ = configs.configs.shape
     wf.recompute(configs)
     ctx = _device_context(wf)
     accumulator = accumulators[ekey[0]]
     accumulator._attach(wf)
-    v = draw_dmc_block_variates(nconf, nelec, tstep, nsteps, accumulator, pinned_owner=ctx)
+    v = variates if variates is not None else draw_dmc_block_variates(nconf, nelec, tstep, nsteps, accumulator,
+                                                                        pinned_owner=ctx)
     w = np.ascontiguousarray(weights, dtype=np.float64)
     newconf = np.empty((nconf, nelec, 3))
     wsums = np.zeros((nsteps, 8))
@@ -247,12 +309,13 @@ def _collect(df):
 
 
 def dmc_propagate(wf, configs, weights, tstep, branchcut_start, e_trial, e_est, nsteps=5, accumulators=None,
-                  ekey=("energy", "total")):
-    """Propagate DMC without branching (dmc.py:123-221)."""
+                  ekey=("energy", "total"), variates=None):
+    """Propagate DMC without branching (dmc.py:123-221).  ``variates``: pre-drawn random numbers of the
+    block (device-resident path only; see ``DmcPrefetcher``)."""
     assert accumulators is not None, "Need an energy accumulator for DMC"
     if _device_dmc_path(wf, accumulators, ekey):
         return dmc_propagate_device(wf, configs, weights, tstep, branchcut_start, e_trial, e_est, nsteps, accumulators,
-                                    ekey)
+                                    ekey, variates=variates)
     nconfig, nelec = configs.configs.shape[0:2]
     wf.recompute(configs)
     energy_acc = accumulators[ekey[0]](configs, wf)
@@ -301,14 +364,15 @@ def dmc_propagate(wf, configs, weights, tstep, branchcut_start, e_trial, e_est, 
     return _collect(df), configs, weights
 
 
-def branch(configs, weights):
-    """Stochastic-comb branching (dmc.py:342-376)."""
+def branch(configs, weights, base_draw=None):
+    """Stochastic-comb branching (dmc.py:342-376).  ``base_draw``: the ``np.random.rand()`` of line 361
+    when it was drawn ahead of time (``DmcPrefetcher``)."""
     nconfig = configs.configs.shape[0]
     if np.any(weights > 2.0):
         logging.warning("Some weights are larger than 2")
     probability = np.cumsum(weights)
     wtot = probability[-1]
-    base = np.random.rand() * wtot
+    base = (np.random.rand() if base_draw is None else base_draw) * wtot
     newinds = np.searchsorted(probability, (base + np.linspace(0, wtot, nconfig, endpoint=False)) % wtot)
     unique, counts = np.unique(newinds, return_counts=True)
     configs.resample(newinds)
@@ -350,10 +414,13 @@ def rundmc(wf, configs, weights=None, tstep=0.01, nblocks=200, nsteps_per_block=
     df = []
     if blockoffset >= nblocks:
         logging.warning(f"blockoffset {blockoffset} >= nblocks {nblocks}; no steps will be run.")
+    prefetch = None
+    if nblocks > blockoffset and _device_dmc_path(wf, accumulators, ekey):
+        prefetch = DmcPrefetcher(wf, configs, tstep, nsteps_per_block, accumulators[ekey[0]], nblocks - blockoffset)
     for block in range(blockoffset, nblocks):
         df_, configs, weights = dmc_propagate(wf, configs, weights, tstep, branchcut_start * esigma, e_trial=e_trial,
                                               e_est=e_est, nsteps=nsteps_per_block, accumulators=accumulators,
-                                              ekey=ekey)
+                                              ekey=ekey, variates=prefetch.next() if prefetch else None)
         df_["e_trial"] = e_trial
         df_["e_est"] = e_est
         df_["block"] = block
@@ -361,7 +428,7 @@ def rundmc(wf, configs, weights=None, tstep=0.01, nblocks=200, nsteps_per_block=
         df_["tstep"] = tstep
         df_["weight_std"] = np.std(weights)
         df_["nsteps_per_block"] = nsteps_per_block
-        configs, weights, branch_info = branch(configs, weights)
+        configs, weights, branch_info = branch(configs, weights, prefetch.branch_draw() if prefetch else None)
         df_.update(branch_info)
         df.append(df_)
         e_est = estimate_energy(df, ekey)

@@ -110,7 +110,7 @@ def allreduce_dmc_block(block_avg, nconf, group=None, device=None):
     return out, int(round(vec[0]))
 
 
-def branch_global(local, weights, group=None):
+def branch_global(local, weights, group=None, base_draw=None):
     """Stochastic-comb branching over the GLOBAL population (``branch``, dmc.py:342-376, applied after
     ``configs.join`` as the reference's parallel driver does): the shards' walkers and weights are
     gathered (a few hundred KB), rank 0's ``np.random.rand()`` fixes the comb offset for everybody,
@@ -121,14 +121,14 @@ def branch_global(local, weights, group=None):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         from .dmc import branch
 
-        return branch(local, weights)
+        return branch(local, weights, base_draw)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     parts = [None] * world
     payload = (local.configs, getattr(local, "wrap", None), np.asarray(weights))
     dist.all_gather_object(parts, payload, group=group)
     allc = np.concatenate([p[0] for p in parts], axis=0)
     allw = np.concatenate([p[2] for p in parts])
-    box = [np.random.rand() if rank == 0 else None]
+    box = [(np.random.rand() if base_draw is None else base_draw) if rank == 0 else None]
     dist.broadcast_object_list(box, src=0, group=group)
     nconfig = len(allw)
     probability = np.cumsum(allw)

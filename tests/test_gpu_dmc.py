@@ -71,3 +71,27 @@ def test_rundmc_runs_blocks_with_branching(lib):
     assert np.all(df["nsteps_per_block"] == 5)
     assert np.allclose(weights, weights[0]) and configs.configs.shape == (256, 8, 3)
     assert 0.5 < df["acceptance"].min() <= 1.0
+
+
+def test_rundmc_prefetch_reproduces_the_sequential_stream(lib):
+    """rundmc with the variate prefetcher (block draws and branching draws taken ahead of time on a
+    host thread) vs the plain sequence dmc_propagate -> branch -> ... with the same seed: identical
+    walkers, weights and stream position."""
+    import pyqmc_b200 as pq
+    from pyqmc_b200 import dmc
+
+    def run(prefetch):
+        mol, mf, wf, _ = helpers.make_pair("h2o", seed=1)
+        acc = {"energy": pq.EnergyAccumulator(mol)}
+        np.random.seed(9)
+        configs = pq.initial_guess(mol, 64)
+        weights = np.ones(64)
+        pf = dmc.DmcPrefetcher(wf, configs, 0.02, 3, acc["energy"], 3) if prefetch else None
+        for b in range(3):
+            out, configs, weights = dmc.dmc_propagate(wf, configs, weights, 0.02, 10.0, 20.0, 20.1, nsteps=3, accumulators=acc,
+                                                      variates=pf.next() if pf else None)
+            configs, weights, info = dmc.branch(configs, weights, pf.branch_draw() if pf else None)
+        return configs.configs.copy(), weights.copy(), out["energytotal"], np.random.rand()
+
+    a, b = run(False), run(True)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2] and a[3] == b[3]
