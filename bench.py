@@ -380,6 +380,12 @@ def gpu_arm(args):
                      "bound": "hbm", "achieved": g32, "peak": peak, "unit": "GB/s", "frac": g32 / peak,
                      "traffic": SM32_TRAFFIC_BYTES, "traffic_source": "profiles/r1_ncu_k_sm_warp32.txt (ncu --set full, same launch shape)",
                      "peak_source": peak_src, "launch_ms": 1e3 * t32, "algorithmic_bytes": b32},
+        # the whole VMC step against the same HBM roof (~27.5 KB of algorithmic traffic per
+        # walker-step -- 15 KB sweep + ~10 KB energy accumulator); the step is FP64-latency bound, not HBM bound
+        "roofline_step": {"kernel": "k_vmc_sweep<16> + energy kernels (one VMC step)", "bound": "hbm",
+                          "achieved": 27.5e3 * N * K / t_dev / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": 27.5e3 * N * K / t_dev / 1e9 / peak, "algorithmic_bytes_per_walker_step": 27.5e3,
+                          "binding_limit": "FP64 dependent-instruction latency at 14 warps/SM (4096 walkers x 16 lanes)"},
         "sm_kernel_other_shapes": {
             "n4_4M_matrices": {"achieved_GBps": g4, "frac": g4 / peak, "launch_ms": 1e3 * t4},
             "n4_4096_matrices_C2_shape": {"achieved_GBps": g4s, "frac": g4s / peak, "launch_ms": 1e3 * t4s}},
@@ -387,6 +393,8 @@ def gpu_arm(args):
         "check": {"mean_local_energy": e_mean, "acceptance": accept, "wall_s_timed_region_incl_flush": wall,
                   "wall_s_same_steps_back_to_back_no_flush": t_wall_noflush, "device_s_timed_steps": t_dev_max},
     }
+    if args.workload != "c2":
+        out.pop("roofline_step")  # the per-walker-step byte count above is the C2 figure
     if world == 1 and not args.no_cpu:
         v, cores, cwall, sample = cpu_arm(wl["cpu_steps"], True, walkers_per_core=wl["cpu_walkers"], system=wl["system"])
         out["cpu_baseline"] = {"value": v, "unit": "walker-steps/s", "cores": cores, "kind": "port", "sample": sample,
