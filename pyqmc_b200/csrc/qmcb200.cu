@@ -976,8 +976,9 @@ int launch_energy(qmcb_ctx* c, const double* d_u, const double* d_rot, double* d
 
 int energy_scratch_points(qmcb_ctx* c) {
   const Sys& S = c->S;
+  // value rows only (one component) at the quadrature points of the general / periodic path
   const size_t pts = std::max<size_t>((size_t)c->N * S.ne * std::max(S.necp, 1) * std::max(S.max_naip, 1), (size_t)c->N * S.ne);
-  return ensure_scratch(c, pts, 5);
+  return ensure_scratch(c, pts, 1);
 }
 
 }  // namespace
