@@ -587,6 +587,34 @@ __device__ __forceinline__ void coop_jastrow_update_pbc(const Sys& S, const doub
   __syncwarp(gm);
 }
 
+// updateinternals of the Jastrow caches with G lanes per walker (lanes over partners), open or periodic;
+// same contract as the thread-per-walker k_jastrow_update: new position = st.saved_pos[w]
+template <int G>
+__global__ void __launch_bounds__(128) k_jastrow_update_coop(const Sys S, const State st, int e, int do_jastrow,
+                                                             int move_conf, const uint8_t* mask) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  extern __shared__ __align__(128) unsigned char qmcb_smem[];
+  const int lane32 = threadIdx.x & 31;
+  const int lane = lane32 & (G - 1);
+  const unsigned gm = group_mask<G>(lane32);
+  const int slot = threadIdx.x / G;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  if (w >= st.N) return;
+  if (mask && !mask[w]) return;
+  const size_t tab = (16 + (size_t)S.dwords * 8 + (size_t)S.iwords * 4 + 15) & ~(size_t)15;
+  const int jper = ((S.ne > 1 ? S.ne - 1 : 0) * S.nb + 1) & ~1;
+  double* jtmp = reinterpret_cast<double*>(qmcb_smem + tab) + (size_t)slot * jper;
+  const double nx = st.saved_pos[(size_t)w * 3], ny = st.saved_pos[(size_t)w * 3 + 1], nz = st.saved_pos[(size_t)w * 3 + 2];
+  if (do_jastrow) coop_jastrow_update_pbc<G>(S, sd, si, st, w, e, nx, ny, nz, lane, gm, jtmp);
+  __syncwarp(gm);
+  if (move_conf && lane < 3) {
+    CONF(st, S, w, e, lane) = st.saved_pos[(size_t)w * 3 + lane];
+    if (S.pbc) st.wrap[((size_t)w * S.ne + e) * 3 + lane] = st.saved_wrap[(size_t)w * 3 + lane];
+  }
+}
+
 // =========================================================================================
 // Device-resident VMC move for periodic single-determinant wave functions, one warp per walker,
 // around k_pbc_mo and the Sherman-Morrison kernel (mc.py:115-137):

@@ -813,10 +813,18 @@ int launch_update(qmcb_ctx* c, int which, int e, const uint8_t* d_mask, cudaStre
   const bool do_j = (which & 2) && c->have_jastrow;
   const bool do_j3 = (which & 4) && c->have_j3;
   if (do_j || (owner == 1 && (which & 1)) || (owner == 2 && (which & 2))) {
-    const int block = pick_block(c->N);
-    if (prep_kernel(k_jastrow_update, c->smem_bytes)) return -1;
-    k_jastrow_update<<<(c->N + block - 1) / block, block, c->smem_bytes, stream>>>(S, c->st, e, do_j ? 1 : 0,
-                                                                                (which & owner) && owner != 4 ? 1 : 0, d_mask);
+    const int mv = (which & owner) && owner != 4 ? 1 : 0;
+    constexpr int GJ = 8;
+    const int jper = ((S.ne > 1 ? S.ne - 1 : 0) * S.nb + 1) & ~1;
+    const size_t jsm = ((c->smem_bytes + 15) & ~(size_t)15) + (size_t)(128 / GJ) * jper * 8;
+    if (do_j && jsm <= 100 * 1024 && std::getenv("QMCB_NO_COOP_JUPDATE") == nullptr) {
+      if (prep_kernel(k_jastrow_update_coop<GJ>, jsm)) return -1;
+      k_jastrow_update_coop<GJ><<<(unsigned)(((long long)c->N * GJ + 127) / 128), 128, jsm, stream>>>(S, c->st, e, 1, mv, d_mask);
+    } else {
+      const int block = pick_block(c->N);
+      if (prep_kernel(k_jastrow_update, c->smem_bytes)) return -1;
+      k_jastrow_update<<<(c->N + block - 1) / block, block, c->smem_bytes, stream>>>(S, c->st, e, do_j ? 1 : 0, mv, d_mask);
+    }
     c->nlaunch++;
     CK(cudaGetLastError());
   }
