@@ -251,13 +251,15 @@ __device__ __forceinline__ void coop_jastrow(const Sys& S, const double* __restr
     }
     const double r = sqrt(dx * dx + dy * dy + dz * dz);
     if (r < rcut) {
-      double v, gg, ll;
+      double v, gg = 0.0, ll = 0.0;
       radial_ool<WANT>(kind, par, rcut, r, v, gg, ll);
       unew = fma(c, v, unew);
-      const double cg = c * gg;
-      g0 = fma(cg, dx, g0);
-      g1 = fma(cg, dy, g1);
-      g2 = fma(cg, dz, g2);
+      if (WANT >= 1) {
+        const double cg = c * gg;
+        g0 = fma(cg, dx, g0);
+        g1 = fma(cg, dy, g1);
+        g2 = fma(cg, dz, g2);
+      }
       if (WANT == 2) lp = fma(c, ll, lp);
     }
   }

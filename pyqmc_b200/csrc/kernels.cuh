@@ -1802,6 +1802,98 @@ __global__ void __launch_bounds__(128) k_ecp_points(const Sys S, const State st,
   }
 }
 
+// Cooperative form of k_ecp_points for the T-move tables of open-boundary systems (few points per
+// launch: one electron, the walkers that passed the stochastic channel mask): G lanes per quadrature
+// point -- orbital evaluation through coop_eval_mo, determinant ratios with lanes over determinants,
+// Jastrow sums with lanes over tasks / partners.  With ~10^3 points a thread per point leaves the launch
+// bound by the latency of one thread's ~60 exponentials and its AO -> MO contraction.
+template <int G>
+__global__ void __launch_bounds__(64) k_ecp_points_coop(const Sys S, const State st, const EnergyScratch es,
+                                                        const EcpPointArgs ea) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  extern __shared__ __align__(128) unsigned char qmcb_smem[];
+  const CoopLayout L = coop_layout(S);
+  const int lane32 = threadIdx.x & 31;
+  const int lane = lane32 & (G - 1);
+  const unsigned gm = group_mask<G>(lane32);
+  const int slot = threadIdx.x / G, gper = blockDim.x / G;
+  const size_t tab = (16 + (size_t)S.dwords * 8 + (size_t)S.iwords * 4 + 15) & ~(size_t)15;
+  const int j3n = 3 * S.natom * S.na3;
+  double* ws = reinterpret_cast<double*>(qmcb_smem + tab) + (size_t)slot * (L.total + j3n);
+  double* abuf = ws + L.total;
+  const int N = st.N;
+  const bool has_s = S.nmo[0] + S.nmo[1] > 0, has_j = (S.na + S.nb) > 0, has_j3 = (S.na3 + S.nb3) > 0;
+  const int nitems = *es.count;
+  const long long total = (long long)nitems * S.max_naip;
+  for (long long p = (long long)blockIdx.x * gper + slot; p < total; p += (long long)gridDim.x * gper) {
+    const int item = (int)(p / S.max_naip), q = (int)(p - (long long)item * S.max_naip);
+    const int t = es.work[item];
+    const int eai = t / N, w = t - eai * N;
+    const int e = ea.e_only >= 0 ? ea.e_only : eai / S.necp;
+    const int a = eai % S.necp;
+    const int naip = si[S.o_naip + a];
+    if (q >= naip) continue;
+    const int atom = si[S.o_ecpatom + a];
+    const double ex = CONF(st, S, w, e, 0), ey = CONF(st, S, w, e, 1), ez = CONF(st, S, w, e, 2);
+    const double rx = ex - sd[S.o_xyz + 3 * atom], ry = ey - sd[S.o_xyz + 3 * atom + 1], rz = ez - sd[S.o_xyz + 3 * atom + 2];
+    const double r = sqrt(rx * rx + ry * ry + rz * rz);
+    const double* R = ea.rot + (size_t)eai * 9;
+    const double* qt = ea.quad + (size_t)si[S.o_aipoff + a] * 4;
+    const double qx = qt[q * 3], qy = qt[q * 3 + 1], qz = qt[q * 3 + 2];
+    const double wq = qt[naip * 3 + q];
+    const double ux = R[0] * qx + R[1] * qy + R[2] * qz, uy = R[3] * qx + R[4] * qy + R[5] * qz,
+                 uz = R[6] * qx + R[7] * qy + R[8] * qz;
+    const double dx = r * ux, dy = r * uy, dz = r * uz;
+    const double cosang = (rx * dx + ry * dy + rz * dz) / (r * sqrt(dx * dx + dy * dy + dz * dz));
+    const double px = (ex - rx) + dx, py = (ey - ry) + dy, pz = (ez - rz) + dz;
+    const int s = e >= S.nup ? 1 : 0;
+    double rat = 1.0;
+    if (has_s) {
+      coop_eval_mo<0, G>(S, L, sd, si, s, px, py, pz, ws, lane, gm);
+      const double* __restrict__ mo = ws + L.mo;
+      const int n = s ? S.ndn : S.nup, nds = S.nds[s], eeff = e - s * S.nup;
+      const int* __restrict__ occ = si + S.o_occ[s];
+      double num = 0.0, den = 0.0;
+      for (int d = lane; d < nds; d += G) {
+        const double* __restrict__ inv = st.inv[s] + ((size_t)w * nds + d) * n * n + eeff;
+        double rr = 0.0;
+        for (int k = 0; k < n; ++k) rr = fma(mo[occ[d * n + k]], inv[k * n], rr);
+        const double wgt = S.ndet == 1 ? 1.0 : st.dv[s][(size_t)w * nds + d] * st.W[s][(size_t)w * nds + d];
+        den += wgt;
+        num = fma(rr, wgt, num);
+      }
+      rat = group_sum<G>(num, gm) / group_sum<G>(den, gm);
+    }
+    double du = 0.0, gj[3] = {0.0, 0.0, 0.0}, lj = 0.0;
+    if (has_j) coop_jastrow<0, G>(S, sd, si, st, w, e, px, py, pz, lane, gm, du, gj, lj);
+    if (has_j3) coop_jastrow3<0, G>(S, sd, si, st, w, e, px, py, pz, lane, gm, abuf, du, gj, lj);
+    if (lane == 0) {
+      const double ratio = rat * exp(du);
+      const int nlm1 = si[S.o_chanoff + a + 1] - si[S.o_chanoff + a] - 1;
+      if (ea.tmove_tau <= 0.0) {
+        double acc = 0.0;
+        for (int l = 0; l < nlm1; ++l)
+          acc += es.vls[(size_t)item * es.maxchan + l] * ((double)(2 * l + 1) * legendre_p(l, cosang) * wq);
+        es.contrib[(size_t)item * S.max_naip + q] = ratio * acc;
+      } else {
+        double wt = 0.0;
+        for (int l = 0; l < nlm1; ++l)
+          wt += (exp(-ea.tmove_tau * es.vls[(size_t)item * es.maxchan + l]) - 1.0) *
+                ((double)(2 * l + 1) * legendre_p(l, cosang) * wq);
+        const size_t o = (size_t)w * S.tot_naip + (size_t)si[S.o_aipoff + a] + q;
+        ea.tm_ratio[o] = ratio;
+        ea.tm_weight[o] = wt;
+        ea.tm_pos[o * 3] = px;
+        ea.tm_pos[o * 3 + 1] = py;
+        ea.tm_pos[o * 3 + 2] = pz;
+      }
+    }
+    __syncwarp(gm);
+  }
+}
+
 // =========================================================================================
 // Parameter gradients of the Slater factor (slater.py:462-542).
 // =========================================================================================

@@ -2110,7 +2110,15 @@ static int dmc_tmove_electron(qmcb_ctx* c, int e, double tau, const double* d_u,
   ea.scr_stride = npts;
   const long long grid = std::min<long long>(((long long)npts + 127) / 128, 148LL * 16);
   const size_t sm = c->smem_bytes;
-  if (c->nmot == 4) {
+  constexpr int GE = 8, BE = 64;
+  const CoopLayout CLe = coop_layout(S);
+  const size_t esm = ((sm + 15) & ~(size_t)15) + (size_t)(BE / GE) * (CLe.total + 3 * S.natom * S.na3) * 8;
+  if (esm <= 100 * 1024 && std::getenv("QMCB_NO_COOP_ECP") == nullptr) {
+    // few points per launch (one electron, masked walkers): lanes cooperate on a point
+    const long long cgrid = std::max<long long>(1, std::min<long long>(((long long)npts + (BE / GE) - 1) / (BE / GE), 148LL * 8));
+    if (prep_kernel(k_ecp_points_coop<GE>, esm)) return -1;
+    k_ecp_points_coop<GE><<<(unsigned)cgrid, BE, esm, stream>>>(S, c->st, c->es, ea);
+  } else if (c->nmot == 4) {
     if (prep_kernel(k_ecp_points<4>, sm)) return -1;
     k_ecp_points<4><<<(unsigned)grid, 128, sm, stream>>>(S, c->st, c->es, ea);
   } else if (c->nmot == 8) {
