@@ -865,29 +865,11 @@ __global__ void __launch_bounds__(256) k_sm_warp(const SmArgs a) {
   const int d = (int)(m - w * a.nds);
   if (a.mask && !a.mask[w]) return;
   const int n = a.n;
-  double* __restrict__ inv = a.inv + m * (long long)n * n;
+  double* inv = a.inv + m * (long long)n * n;
   const double* __restrict__ vb = a.vec + w * a.vec_stride;
-  const bool act = lane < n;
   double vk = 0.0;
-  if (act) vk = a.occ ? vb[a.occ[d * n + lane]] : vb[(long long)d * n + lane];
-  double A[NPAD];
-#pragma unroll
-  for (int k = 0; k < NPAD; ++k) A[k] = (k < n && act) ? inv[k * n + lane] : 0.0;
-  double t = 0.0;
-#pragma unroll
-  for (int k = 0; k < NPAD; ++k) {
-    const double v = __shfl_sync(0xffffffffu, vk, k);
-    t = fma(v, A[k], t);
-  }
-  const double ratio = __shfl_sync(0xffffffffu, t, a.e);
-  // lane k fetches inv[k][e] (just read by lane e -> L1/L2 hit) and does one division
-  double col = 0.0;
-  if (act) col = inv[lane * n + a.e] / ratio;
-#pragma unroll
-  for (int k = 0; k < NPAD; ++k) {
-    const double ck = __shfl_sync(0xffffffffu, col, k);
-    if (k < n && act) inv[k * n + lane] = (lane == a.e) ? ck : fma(-ck, t, A[k]);
-  }
+  if (lane < n) vk = a.occ ? vb[a.occ[d * n + lane]] : vb[(long long)d * n + lane];
+  const double ratio = sm_warp_apply<NPAD>(inv, n, a.e, lane, vk);
   if (lane == 0) {
     if (a.ratio) a.ratio[m] = ratio;
     if (a.dsign) a.dsign[m] *= sgn(ratio);

@@ -10,6 +10,7 @@
 #include "coop.cuh"
 
 __device__ __forceinline__ void limdrift3(double (&g)[3]);
+__device__ __forceinline__ double sgn(double x);
 
 // =========================================================================================
 // k_pbc_mo: MO rows (value [, gradient [, Laplacian]]) of lattice-summed Bloch orbitals at a list
@@ -625,6 +626,33 @@ __global__ void __launch_bounds__(128) k_jastrow_update_coop(const Sys S, const 
 //                   the Jastrow caches, the cached MO rows, the coordinates and wrap vectors
 //   k_sm_warp     : masked Sherman-Morrison update of the inverse from the value row in st.monew
 // =========================================================================================
+// Sherman-Morrison row replacement by one warp, lane j owns column j (n <= NPAD <= 32): the arithmetic of
+// k_sm_thread / k_sm_warp (kernels.cuh), shared by the stand-alone kernel and the fused periodic move kernel.
+// v = this lane's entry of the new row (0 for lanes >= n).  Returns the determinant ratio on every lane.
+template <int NPAD>
+__device__ __forceinline__ double sm_warp_apply(double* inv, int n, int e, int lane, double vk) {
+  const bool act = lane < n;
+  double A[NPAD];
+#pragma unroll
+  for (int k = 0; k < NPAD; ++k) A[k] = (k < n && act) ? inv[k * n + lane] : 0.0;
+  double t = 0.0;
+#pragma unroll
+  for (int k = 0; k < NPAD; ++k) {
+    const double v = __shfl_sync(0xffffffffu, vk, k);
+    t = fma(v, A[k], t);
+  }
+  const double ratio = __shfl_sync(0xffffffffu, t, e);
+  // lane k fetches inv[k][e] (just read by lane e -> L1/L2 hit) and does one division
+  double col = 0.0;
+  if (act) col = inv[lane * n + e] / ratio;
+#pragma unroll
+  for (int k = 0; k < NPAD; ++k) {
+    const double ck = __shfl_sync(0xffffffffu, col, k);
+    if (k < n && act) inv[k * n + lane] = (lane == e) ? ck : fma(-ck, t, A[k]);
+  }
+  return ratio;
+}
+
 struct PbcMoveArgs {
   int e;
   double tstep;
@@ -632,6 +660,7 @@ struct PbcMoveArgs {
   const double* unif;   // [N]
   uint8_t* accept;      // [N]
   unsigned long long* nacc;
+  const double* gauss_next;  // fused kernel: variates of electron e + 1 (nullptr after the last electron)
 };
 
 template <int G>
@@ -656,17 +685,11 @@ __device__ __forceinline__ void slater_row_ratio4(const Sys& S, const int* __res
   r[3] = group_sum<G>(a3, gm);
 }
 
-__global__ void __launch_bounds__(128) k_pbc_propose(const Sys S, const State st, const PbcMoveArgs a) {
+// drift at the current position of electron e, proposal, wrap: one warp per walker
+__device__ __forceinline__ void pbc_propose_warp(const Sys& S, const double* sd, const int* si, const State& st, int w,
+                                                 int e, double tstep, const double* __restrict__ gauss_e, int lane) {
   constexpr int G = 32;
-  const double* sd;
-  const int* si;
-  stage_tables(S, sd, si);
-  const int lane = threadIdx.x & 31;
   const unsigned gm = 0xffffffffu;
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int N = st.N;
-  if (w >= N) return;
-  const int e = a.e;
   const int s = e >= S.nup ? 1 : 0;
   const int eeff = e - s * S.nup;
   const int ldmax = S.ldc[0] > S.ldc[1] ? S.ldc[0] : S.ldc[1];
@@ -690,10 +713,10 @@ __global__ void __launch_bounds__(128) k_pbc_propose(const Sys S, const State st
   }
   limdrift3(grad);
   if (lane == 0) {
-    const double* __restrict__ gauss = a.gauss + (size_t)w * 3;
-    const double nx = __dadd_rn(__dadd_rn(ox, gauss[0]), __dmul_rn(grad[0], a.tstep));
-    const double ny = __dadd_rn(__dadd_rn(oy, gauss[1]), __dmul_rn(grad[1], a.tstep));
-    const double nz = __dadd_rn(__dadd_rn(oz, gauss[2]), __dmul_rn(grad[2], a.tstep));
+    const double* __restrict__ gauss = gauss_e + (size_t)w * 3;
+    const double nx = __dadd_rn(__dadd_rn(ox, gauss[0]), __dmul_rn(grad[0], tstep));
+    const double ny = __dadd_rn(__dadd_rn(oy, gauss[1]), __dmul_rn(grad[1], tstep));
+    const double nz = __dadd_rn(__dadd_rn(oz, gauss[2]), __dmul_rn(grad[2], tstep));
     double o[3] = {nx, ny, nz}, ww[3] = {0.0, 0.0, 0.0};
     if (S.pbc) wrap_cell(sd + S.o_lat, sd + S.o_latinv, nx, ny, nz, o, ww);
 #pragma unroll
@@ -705,6 +728,20 @@ __global__ void __launch_bounds__(128) k_pbc_propose(const Sys S, const State st
   }
 }
 
+__global__ void __launch_bounds__(128) k_pbc_propose(const Sys S, const State st, const PbcMoveArgs a) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  const int lane = threadIdx.x & 31;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= st.N) return;
+  pbc_propose_warp(S, sd, si, st, w, a.e, a.tstep, a.gauss, lane);
+}
+
+// FUSED: the accepted walkers' inverse is updated by the same warp (sm_warp_apply, n <= 32, one determinant)
+// and the proposal of electron e + 1 follows in the same launch -- two launches per electron move
+// (orbitals at the proposed points, this kernel) instead of four.
+template <bool FUSED>
 __global__ void __launch_bounds__(128) k_pbc_accept(const Sys S, const State st, const PbcMoveArgs a) {
   constexpr int G = 32;
   const double* sd;
@@ -762,16 +799,38 @@ __global__ void __launch_bounds__(128) k_pbc_accept(const Sys S, const State st,
     a.accept[w] = acc ? 1 : 0;
     if (acc) atomicAdd(a.nacc, 1ULL);
   }
-  if (!acc) return;
-  if (has_j) coop_jastrow_update_pbc<G>(S, sd, si, st, w, e, nx, ny, nz, lane, gm, jtmp);
-  if (has_s) {
-    double* __restrict__ mc = st.mocache + ((size_t)w * S.ne + e) * 5 * ldmax;
-    for (int i = lane; i < 5 * ldmax; i += G) mc[i] = rows[i];
+  if (!acc && !FUSED) return;
+  if (acc) {
+    if (has_j) coop_jastrow_update_pbc<G>(S, sd, si, st, w, e, nx, ny, nz, lane, gm, jtmp);
+    if (has_s) {
+      double* __restrict__ mc = st.mocache + ((size_t)w * S.ne + e) * 5 * ldmax;
+      for (int i = lane; i < 5 * ldmax; i += G) mc[i] = rows[i];
+      if (FUSED) {
+        const int n = s ? S.ndn : S.nup;
+        double* inv = st.inv[s] + (size_t)w * n * n;
+        const double vk = lane < n ? rows[si[S.o_occ[s] + lane]] : 0.0;
+        double dr;
+        if (n <= 8)
+          dr = sm_warp_apply<8>(inv, n, eeff, lane, vk);
+        else if (n <= 16)
+          dr = sm_warp_apply<16>(inv, n, eeff, lane, vk);
+        else
+          dr = sm_warp_apply<32>(inv, n, eeff, lane, vk);
+        if (lane == 0) {
+          st.dsign[s][w] *= sgn(dr);
+          st.dlog[s][w] += log(fabs(dr));
+        }
+      }
+    }
+    __syncwarp(gm);
+    if (lane < 3) {
+      CONF(st, S, w, e, lane) = st.saved_pos[(size_t)w * 3 + lane];
+      st.wrap[((size_t)w * S.ne + e) * 3 + lane] = st.saved_wrap[(size_t)w * 3 + lane];
+    }
   }
-  __syncwarp(gm);
-  if (lane < 3) {
-    CONF(st, S, w, e, lane) = st.saved_pos[(size_t)w * 3 + lane];
-    st.wrap[((size_t)w * S.ne + e) * 3 + lane] = st.saved_wrap[(size_t)w * 3 + lane];
+  if (FUSED && a.gauss_next != nullptr) {
+    __syncwarp(gm);  // the walker's caches, inverse and position written above are read by all lanes below
+    pbc_propose_warp(S, sd, si, st, w, e + 1, a.tstep, a.gauss_next, lane);
   }
 }
 

@@ -1868,6 +1868,11 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
       c->nlaunch++;
       CK(cudaGetLastError());
     }
+    // Periodic move chain.  Fused flavour (n <= 32 per spin): [propose(0)] then per electron the orbitals at the
+    // proposed points and ONE warp-per-walker kernel doing Metropolis test, cache updates, the Sherman-Morrison
+    // update and the proposal of electron e + 1.  QMCB_PBC_UNFUSED=1 keeps the four-launch chain (A/B checks).
+    const bool fuse_pbc = use_pbc && (!c->have_slater || (S.nup <= 32 && S.ndn <= 32)) &&
+                          std::getenv("QMCB_PBC_UNFUSED") == nullptr;
     for (int e = 0; e < S.ne && use_pbc; ++e) {
       const size_t se = (size_t)step * S.ne + e;
       const int s = e >= S.nup ? 1 : 0;
@@ -1879,11 +1884,14 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
       ma.unif = d_unif + se * N;
       ma.accept = d_accept ? d_accept + se * N : c->d_accept.p;
       ma.nacc = nacc + se;
+      ma.gauss_next = (fuse_pbc && e + 1 < S.ne) ? d_gauss + (se + 1) * N * 3 : nullptr;
       const unsigned wgrid = (unsigned)((N * 32 + 127) / 128);
-      if (prep_kernel(k_pbc_propose, c->smem_bytes)) return -1;
-      k_pbc_propose<<<wgrid, 128, c->smem_bytes, stream>>>(S, c->st, ma);
-      c->nlaunch++;
-      CK(cudaGetLastError());
+      if (!fuse_pbc || e == 0) {
+        if (prep_kernel(k_pbc_propose, c->smem_bytes)) return -1;
+        k_pbc_propose<<<wgrid, 128, c->smem_bytes, stream>>>(S, c->st, ma);
+        c->nlaunch++;
+        CK(cudaGetLastError());
+      }
       if (c->have_slater) {
         PbcMoArgs a{};
         a.npoints = (long long)N;
@@ -1900,11 +1908,16 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
       }
       const int jper = ((S.ne > 1 ? S.ne - 1 : 0) * S.nb + 1) & ~1;
       const size_t asm_ = ((c->smem_bytes + 15) & ~(size_t)15) + (size_t)4 * jper * 8;
-      if (prep_kernel(k_pbc_accept, asm_)) return -1;
-      k_pbc_accept<<<wgrid, 128, asm_, stream>>>(S, c->st, ma);
+      if (fuse_pbc) {
+        if (prep_kernel(k_pbc_accept<true>, asm_)) return -1;
+        k_pbc_accept<true><<<wgrid, 128, asm_, stream>>>(S, c->st, ma);
+      } else {
+        if (prep_kernel(k_pbc_accept<false>, asm_)) return -1;
+        k_pbc_accept<false><<<wgrid, 128, asm_, stream>>>(S, c->st, ma);
+      }
       c->nlaunch++;
       CK(cudaGetLastError());
-      if (c->have_slater) {
+      if (c->have_slater && !fuse_pbc) {
         SmArgs sa{};
         sa.n = s ? S.ndn : S.nup;
         sa.e = e - s * S.nup;
