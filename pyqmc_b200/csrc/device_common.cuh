@@ -97,6 +97,7 @@ struct State {
   double* saved_wrap;// [N][3]      wrap of the position in saved_pos
   double* monew;     // [N][5][ldmax]  periodic VMC: MO rows at the proposed position
   double* gold;      // [N][3]      periodic VMC: limited drift at the old position
+  double* jold;      // [N][ne-1][nb] periodic block driver: b_l(r_ej) at the old position of the proposed electron (or null)
 };
 
 // walker-major accessors: everything one walker owns is contiguous, so a warp that works on one

@@ -461,7 +461,10 @@ template <int WANT, int G>
 __device__ __forceinline__ void coop_jastrow_pbc(const Sys& S, const double* __restrict__ sd,
                                                  const int* __restrict__ si, const State& st, int w, int e, double px,
                                                  double py, double pz, int lane, unsigned gm, double& du,
-                                                 double (&g)[3], double& lap) {
+                                                 double (&g)[3], double& lap, double* vb_store = nullptr,
+                                                 double* va_store = nullptr) {
+  // vb_store [(ne-1)][nb] / va_store [natom][na]: the radial values at this point (0 beyond the cutoff), kept
+  // by the fused periodic move kernel for the cache update of an accepted move
   const int s = e >= S.nup ? 1 : 0;
   double unew = 0.0, uold = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0, lp = 0.0;
   const int npart = (S.nb > 0 ? S.ne - 1 : 0), nat = (S.na > 0 ? S.natom : 0);
@@ -488,6 +491,9 @@ __device__ __forceinline__ void coop_jastrow_pbc(const Sys& S, const double* __r
     }
     if (S.pbc) min_image(S, sd, dx, dy, dz);
     const double r = sqrt(dx * dx + dy * dy + dz * dz);
+    double* vst = isb ? (vb_store ? vb_store + t * S.nb : nullptr) : (va_store ? va_store + I * S.na : nullptr);
+    if (vst != nullptr && !(r < rcut))
+      for (int l = 0; l < nfun; ++l) vst[l] = 0.0;
     if (r < rcut) {
       const int sj = j >= S.nup ? 1 : 0;
       for (int l = 0; l < nfun; ++l) {
@@ -500,6 +506,7 @@ __device__ __forceinline__ void coop_jastrow_pbc(const Sys& S, const double* __r
           c = sd[S.o_acoef + (I * S.na + l) * 2 + s];
           radial_ool<WANT>(si[S.o_akind + l], sd[S.o_apar + l], rcut, r, v, gg, ll);
         }
+        if (vst != nullptr) vst[l] = v;
         unew = fma(c, v, unew);
         const double cg = c * gg;
         g0 = fma(cg, dx, g0);
@@ -626,6 +633,43 @@ __global__ void __launch_bounds__(128) k_jastrow_update_coop(const Sys S, const 
 //                   the Jastrow caches, the cached MO rows, the coordinates and wrap vectors
 //   k_sm_warp     : masked Sherman-Morrison update of the inverse from the value row in st.monew
 // =========================================================================================
+// Cache update of an accepted move from stored radial values: jnew_b / jnew_a hold b_l / a_k at the new
+// position (coop_jastrow_pbc's vb_store / va_store), jold_b the b_l at the old one (stored by the proposal).
+// Same bookkeeping as coop_jastrow_update_pbc (jastrowspin.py:221-249) without any distance or radial work.
+template <int G>
+__device__ __forceinline__ void coop_jastrow_commit_pbc(const Sys& S, const State& st, int w, int e, int lane,
+                                                        unsigned gm, const double* jnew_b, const double* jnew_a,
+                                                        const double* jold_b) {
+  const int s = e >= S.nup ? 1 : 0;
+  if (S.na > 0) {
+    for (int t = lane; t < S.natom * S.na; t += G) {
+      const int I = t / S.na, k = t - I * S.na;
+      const double v = jnew_a[t];
+      AVAL(st, S, w, I, k, s) += v - APART(st, S, w, e, I, k);
+      APART(st, S, w, e, I, k) = v;
+    }
+  }
+  if (S.nb > 0) {
+    for (int t = lane; t < (S.ne - 1) * S.nb; t += G) {
+      const int jj = t / S.nb, l = t - jj * S.nb;
+      const int j = jj < e ? jj : jj + 1;
+      BPART(st, S, w, j, l, s) += jnew_b[t] - jold_b[t];
+    }
+#pragma unroll 1
+    for (int t = lane; t < S.nb * 2; t += G) {
+      const int l = t >> 1, tt = t & 1;
+      double bn = 0.0;
+      for (int jj = 0; jj < S.ne - 1; ++jj) {
+        const int j = jj < e ? jj : jj + 1;
+        if ((j >= S.nup ? 1 : 0) == tt) bn += jnew_b[jj * S.nb + l];
+      }
+      BVAL(st, S, w, l, s + tt) += bn - BPART(st, S, w, e, l, tt);
+      BPART(st, S, w, e, l, tt) = bn;
+    }
+  }
+  __syncwarp(gm);
+}
+
 // Sherman-Morrison row replacement by one warp, lane j owns column j (n <= NPAD <= 32): the arithmetic of
 // k_sm_thread / k_sm_warp (kernels.cuh), shared by the stand-alone kernel and the fused periodic move kernel.
 // v = this lane's entry of the new row (0 for lanes >= n).  Returns the determinant ratio on every lane.
@@ -707,7 +751,8 @@ __device__ __forceinline__ void pbc_propose_warp(const Sys& S, const double* sd,
   }
   if (S.na + S.nb > 0) {
     double du, gj[3], lj;
-    coop_jastrow_pbc<1, G>(S, sd, si, st, w, e, ox, oy, oz, lane, gm, du, gj, lj);
+    double* jold = (st.jold != nullptr && S.nb > 0) ? st.jold + (size_t)w * (S.ne - 1) * S.nb : nullptr;
+    coop_jastrow_pbc<1, G>(S, sd, si, st, w, e, ox, oy, oz, lane, gm, du, gj, lj, jold);
 #pragma unroll
     for (int i = 0; i < 3; ++i) grad[i] = grad[i] + gj[i];
   }
@@ -754,8 +799,10 @@ __global__ void __launch_bounds__(128) k_pbc_accept(const Sys S, const State st,
   const int N = st.N;
   if (w >= N) return;
   const size_t tab = (16 + (size_t)S.dwords * 8 + (size_t)S.iwords * 4 + 15) & ~(size_t)15;
-  const int jper = ((S.ne > 1 ? S.ne - 1 : 0) * S.nb + 1) & ~1;
+  const int npb = (S.ne > 1 ? S.ne - 1 : 0) * S.nb;
+  const int jper = (npb + S.natom * S.na + 1) & ~1;
   double* jtmp = reinterpret_cast<double*>(qmcb_smem + tab) + (size_t)wib * jper;
+  const bool cached = FUSED && st.jold != nullptr;  // radial values kept from the two point evaluations
   const int e = a.e;
   const int s = e >= S.nup ? 1 : 0;
   const int eeff = e - s * S.nup;
@@ -777,7 +824,8 @@ __global__ void __launch_bounds__(128) k_pbc_accept(const Sys S, const State st,
   }
   if (has_j) {
     double du, gj[3], lj;
-    coop_jastrow_pbc<1, G>(S, sd, si, st, w, e, nx, ny, nz, lane, gm, du, gj, lj);
+    coop_jastrow_pbc<1, G>(S, sd, si, st, w, e, nx, ny, nz, lane, gm, du, gj, lj, cached ? jtmp : nullptr,
+                           cached ? jtmp + npb : nullptr);
 #pragma unroll
     for (int i = 0; i < 3; ++i) ngrad[i] = ngrad[i] + gj[i];
     val = val * exp(du);
@@ -801,7 +849,12 @@ __global__ void __launch_bounds__(128) k_pbc_accept(const Sys S, const State st,
   }
   if (!acc && !FUSED) return;
   if (acc) {
-    if (has_j) coop_jastrow_update_pbc<G>(S, sd, si, st, w, e, nx, ny, nz, lane, gm, jtmp);
+    if (has_j && cached) {
+      __syncwarp(gm);
+      coop_jastrow_commit_pbc<G>(S, st, w, e, lane, gm, jtmp, jtmp + npb, st.jold + (size_t)w * npb);
+    } else if (has_j) {
+      coop_jastrow_update_pbc<G>(S, sd, si, st, w, e, nx, ny, nz, lane, gm, jtmp);
+    }
     if (has_s) {
       double* __restrict__ mc = st.mocache + ((size_t)w * S.ne + e) * 5 * ldmax;
       for (int i = lane; i < 5 * ldmax; i += G) mc[i] = rows[i];

@@ -111,7 +111,7 @@ struct qmcb_ctx {
   double ew_alpha = 0, ew_ij = 0, ew_sq = 0, ew_isum = 0, ew_eii = 0;
   int ew_ndisp = 0, ew_nG = 0;
   DBuf<double> d_ewdisp, d_ewg, d_ewion;
-  DBuf<double> b_wrap, b_swrap, b_monew, b_gold, d_pwrap, e_ewald, e_ecppos, e_ecpwrap;
+  DBuf<double> b_wrap, b_swrap, b_monew, b_gold, b_jold, d_pwrap, e_ewald, e_ecppos, e_ecpwrap;
   bool pending_wrap = false;  // d_pwrap holds the wrap vectors of the next point call
   // DMC block scratch (kept across blocks: a cudaMalloc / cudaFree pair costs more than a DMC step)
   DBuf<double> m_tmu, m_tmrot, m_tmsel, m_tmacc, m_w, m_eold, m_v2old, m_r2p, m_r2a, m_prod, m_ws;
@@ -523,7 +523,7 @@ int ensure_state(qmcb_ctx* c, int N) {
   st.alap = c->b_alap.p;
   if (S.pbc) {
     if (c->b_wrap.ensure((size_t)N * S.ne * 3) || c->b_swrap.ensure((size_t)N * 3) || c->b_monew.ensure((size_t)N * 5 * ldmax) ||
-        c->b_gold.ensure((size_t)N * 3))
+        c->b_gold.ensure((size_t)N * 3) || c->b_jold.ensure((size_t)N * std::max(1, (S.ne - 1) * S.nb)))
       return -1;
     cudaMemset(c->b_wrap.p, 0, (size_t)N * S.ne * 3 * 8);
     cudaMemset(c->b_swrap.p, 0, (size_t)N * 3 * 8);
@@ -532,6 +532,7 @@ int ensure_state(qmcb_ctx* c, int N) {
   st.saved_wrap = c->b_swrap.p;
   st.monew = c->b_monew.p;
   st.gold = c->b_gold.p;
+  st.jold = nullptr;  // set by the fused periodic block driver only
   c->N = N;
   c->saved_slot = -1;
   return 0;
@@ -1030,7 +1031,7 @@ void qmcb_destroy(qmcb_ctx* c) {
   DBuf<double>* mb[] = {&c->m_tmu, &c->m_tmrot, &c->m_tmsel, &c->m_tmacc, &c->m_w, &c->m_eold, &c->m_v2old, &c->m_r2p, &c->m_r2a, &c->m_prod, &c->m_ws};
   for (auto* b : mb) b->release();
   c->m_ntacc.release();
-  DBuf<double>* pb[] = {&c->d_ewdisp, &c->d_ewg, &c->d_ewion, &c->b_wrap, &c->b_swrap, &c->b_monew, &c->b_gold, &c->d_pwrap,
+  DBuf<double>* pb[] = {&c->d_ewdisp, &c->d_ewg, &c->d_ewion, &c->b_wrap, &c->b_swrap, &c->b_monew, &c->b_gold, &c->b_jold, &c->d_pwrap,
                         &c->e_ewald, &c->e_ecppos, &c->e_ecpwrap};
   for (auto* b : pb) b->release();
   for (int s = 0; s < 2; ++s) {
@@ -1873,6 +1874,8 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
     // update and the proposal of electron e + 1.  QMCB_PBC_UNFUSED=1 keeps the four-launch chain (A/B checks).
     const bool fuse_pbc = use_pbc && (!c->have_slater || (S.nup <= 32 && S.ndn <= 32)) &&
                           std::getenv("QMCB_PBC_UNFUSED") == nullptr;
+    State stf = c->st;  // fused chain: the proposal keeps the pair values at the old position for the cache update
+    if (fuse_pbc && c->have_jastrow && S.nb > 0) stf.jold = c->b_jold.p;
     for (int e = 0; e < S.ne && use_pbc; ++e) {
       const size_t se = (size_t)step * S.ne + e;
       const int s = e >= S.nup ? 1 : 0;
@@ -1888,7 +1891,7 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
       const unsigned wgrid = (unsigned)((N * 32 + 127) / 128);
       if (!fuse_pbc || e == 0) {
         if (prep_kernel(k_pbc_propose, c->smem_bytes)) return -1;
-        k_pbc_propose<<<wgrid, 128, c->smem_bytes, stream>>>(S, c->st, ma);
+        k_pbc_propose<<<wgrid, 128, c->smem_bytes, stream>>>(S, stf, ma);
         c->nlaunch++;
         CK(cudaGetLastError());
       }
@@ -1906,11 +1909,11 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
         a.stride_j = 1;
         if (launch_pbc_mo(c, 2, a, (long long)N, stream)) return -1;
       }
-      const int jper = ((S.ne > 1 ? S.ne - 1 : 0) * S.nb + 1) & ~1;
+      const int jper = ((S.ne > 1 ? S.ne - 1 : 0) * S.nb + S.natom * S.na + 1) & ~1;
       const size_t asm_ = ((c->smem_bytes + 15) & ~(size_t)15) + (size_t)4 * jper * 8;
       if (fuse_pbc) {
         if (prep_kernel(k_pbc_accept<true>, asm_)) return -1;
-        k_pbc_accept<true><<<wgrid, 128, asm_, stream>>>(S, c->st, ma);
+        k_pbc_accept<true><<<wgrid, 128, asm_, stream>>>(S, stf, ma);
       } else {
         if (prep_kernel(k_pbc_accept<false>, asm_)) return -1;
         k_pbc_accept<false><<<wgrid, 128, asm_, stream>>>(S, c->st, ma);
