@@ -2125,6 +2125,8 @@ struct TmoveSelectArgs {
   const double* acc_u;   // [N]
   uint8_t* accept;       // [N]
   unsigned long long* ntacc;
+  const int* item_of;    // k_tmove_apply: [necp][N] work item of (ECP atom, walker) or -1 (not sampled)
+  int* count;            // k_tmove_apply: work-item counter, reset for the next electron
 };
 
 __global__ void __launch_bounds__(128) k_tmove_select(const Sys S, const State st, const TmoveSelectArgs a) {
@@ -2177,6 +2179,111 @@ __global__ void __launch_bounds__(128) k_tmove_select(const Sys S, const State s
   }
   const unsigned b = __ballot_sync(0xffffffffu, acc);
   if ((threadIdx.x & 31) == 0 && b) atomicAdd(a.ntacc, (unsigned long long)__popc(b));
+}
+
+// T-move selection AND application for electron e in one launch, G lanes per walker: the group leader
+// runs the selection arithmetic of k_tmove_select over the walker's candidate table (entries of ECP atoms
+// that were not sampled count as ratio 1 / weight 0 / current position, which is what compute_tmoves
+// returns for them, eval_ecp.py:62-70); an accepted walker then evaluates the orbitals at the selected
+// position (no saved values, dmc.py:176), applies the Sherman-Morrison update, patches the Jastrow caches
+// and moves its coordinate.  Replaces k_tmove_init + k_tmove_select + k_point<MOSAVE> + k_sm_* +
+// k_jastrow_update_coop of the launch-per-stage chain (single-determinant open-boundary wave functions).
+template <int G>
+__global__ void __launch_bounds__(128) k_tmove_apply(const Sys S, const State st, const TmoveSelectArgs a) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  extern __shared__ __align__(128) unsigned char qmcb_smem[];
+  const CoopLayout L = coop_layout(S);
+  const int lane32 = threadIdx.x & 31;
+  const int lane = lane32 & (G - 1);
+  const unsigned gm = group_mask<G>(lane32);
+  const int slot = threadIdx.x / G, gper = blockDim.x / G;
+  const size_t tab = (16 + (size_t)S.dwords * 8 + (size_t)S.iwords * 4 + 15) & ~(size_t)15;
+  double* ws = reinterpret_cast<double*>(qmcb_smem + tab) + (size_t)slot * L.total;
+  const int N = st.N, e = a.e, M = a.M;
+  const int w = blockIdx.x * gper + slot;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.count) *a.count = 0;  // every reader of the counter ran before this launch
+  bool acc = false;
+  double px = 0.0, py = 0.0, pz = 0.0;
+  if (w < N) {
+    if (lane == 0) {
+      const double cx = CONF(st, S, w, e, 0), cy = CONF(st, S, w, e, 1), cz = CONF(st, S, w, e, 2);
+      const double* __restrict__ ra = a.ratio + (size_t)w * M;
+      const double* __restrict__ wt = a.weight + (size_t)w * M;
+      // amplitudes in table order; m -> ECP atom through the per-atom offsets
+      double sum = 0.0;
+      for (int ia = 0; ia < S.necp; ++ia) {
+        if (a.item_of[(size_t)ia * N + w] < 0) continue;
+        for (int m = si[S.o_aipoff + ia]; m < si[S.o_aipoff + ia] + si[S.o_naip + ia]; ++m) {
+          const double amp = __dmul_rn(ra[m], wt[m]);
+          if (amp > 0.0) sum = __dadd_rn(sum, amp);
+        }
+      }
+      const double norm = __dadd_rn(1.0, sum);  // EQN 34
+      const double r = a.sel_u[w];
+      int sel = 0, sel_atom = -1;
+      double cdf = 0.0;
+      for (int ia = 0; ia < S.necp; ++ia) {
+        const bool on = a.item_of[(size_t)ia * N + w] >= 0;
+        for (int m = si[S.o_aipoff + ia]; m < si[S.o_aipoff + ia] + si[S.o_naip + ia]; ++m) {
+          double f = 0.0;
+          if (on) {
+            const double amp = __dmul_rn(ra[m], wt[m]);
+            f = amp > 0.0 ? amp : 0.0;
+          }
+          cdf = __dadd_rn(cdf, f / norm);
+          if (cdf < r) {
+            ++sel;
+          } else if (sel_atom < 0 && sel == m) {
+            sel_atom = on ? ia : -2;
+          }
+        }
+      }
+      const bool chosen = sel < M;
+      double acceptance = 0.0;
+      px = cx;
+      py = cy;
+      pz = cz;
+      if (chosen) {
+        const bool sel_on = sel_atom >= 0;
+        if (sel_on) {
+          px = a.pos[((size_t)w * M + sel) * 3];
+          py = a.pos[((size_t)w * M + sel) * 3 + 1];
+          pz = a.pos[((size_t)w * M + sel) * 3 + 2];
+        }
+        const double rev = 1.0 / (sel_on ? ra[sel] : 1.0);
+        double bsum = 0.0;
+        for (int ia = 0; ia < S.necp; ++ia) {
+          const bool on = a.item_of[(size_t)ia * N + w] >= 0;
+          for (int m = si[S.o_aipoff + ia]; m < si[S.o_aipoff + ia] + si[S.o_naip + ia]; ++m) {
+            const double rm = on ? ra[m] : 1.0, wm = on ? wt[m] : 0.0;
+            double b = m == sel ? __dmul_rn(rev, wm) : __dmul_rn(__dmul_rn(rm, wm), rev);
+            if (b < 0.0) b = 0.0;
+            bsum = __dadd_rn(bsum, b);
+          }
+        }
+        acceptance = norm / __dadd_rn(1.0, bsum);
+      }
+      acc = chosen && (acceptance > a.acc_u[w]);
+      a.accept[w] = acc ? 1 : 0;
+    }
+    const int leader = lane32 & ~(G - 1);
+    acc = __shfl_sync(gm, acc ? 1 : 0, leader) != 0;
+    px = __shfl_sync(gm, px, leader);
+    py = __shfl_sync(gm, py, leader);
+    pz = __shfl_sync(gm, pz, leader);
+    if (acc) {
+      const int s = e >= S.nup ? 1 : 0;
+      if (S.nmo[0] + S.nmo[1] > 0) {
+        coop_eval_mo<0, G>(S, L, sd, si, s, px, py, pz, ws, lane, gm);
+        coop_sherman_morrison<G>(S, L, si, st, w, s, e - s * S.nup, ws, lane, gm);
+      }
+      coop_jastrow_update<G>(S, sd, si, st, w, e, px, py, pz, lane, gm, (S.na + S.nb) > 0, ws + L.jtmp);
+    }
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, acc && lane == 0 && w < N);
+  if (lane32 == 0 && b) atomicAdd(a.ntacc, (unsigned long long)__popc(b));
 }
 
 // Weight update of one DMC step (dmc.py:183-198, compute_S 224-235) and the weighted observables:

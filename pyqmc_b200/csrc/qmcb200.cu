@@ -2104,10 +2104,18 @@ static int dmc_tmove_electron(qmcb_ctx* c, int e, double tau, const double* d_u,
   double* d_ratio = c->d_out.p;
   double* d_weight = d_ratio + N * M;
   double* d_pos = d_weight + N * M;
-  k_tmove_init<<<(unsigned)((N * M + 255) / 256), 256, 0, stream>>>(S, c->st, e, d_ratio, d_weight, d_pos);
-  c->nlaunch++;
-  CK(cudaGetLastError());
-  CK(cudaMemsetAsync(c->es.count, 0, sizeof(int), stream));
+  // fused selection + application (k_tmove_apply): 3 launches per electron instead of 8
+  constexpr int GA = 16;
+  const CoopLayout CLa = coop_layout(S);
+  const size_t apply_sm = ((c->smem_bytes + 15) & ~(size_t)15) + (size_t)(128 / GA) * CLa.total * 8;
+  const bool fused = S.ndet == 1 && !c->have_j3 && !S.pbc && apply_sm <= 200 * 1024 &&
+                     std::getenv("QMCB_TMOVE_UNFUSED") == nullptr;
+  if (!fused) {
+    k_tmove_init<<<(unsigned)((N * M + 255) / 256), 256, 0, stream>>>(S, c->st, e, d_ratio, d_weight, d_pos);
+    c->nlaunch++;
+    CK(cudaGetLastError());
+  }
+  if (!fused || e == 0) CK(cudaMemsetAsync(c->es.count, 0, sizeof(int), stream));
   const long long nt = (long long)N * S.necp;
   if (prep_kernel(k_ecp_prepare, c->smem_bytes)) return -1;
   k_ecp_prepare<<<(unsigned)((nt + 127) / 128), 128, c->smem_bytes, stream>>>(S, c->st, c->es, d_u, e);
@@ -2156,23 +2164,33 @@ static int dmc_tmove_electron(qmcb_ctx* c, int e, double tau, const double* d_u,
   ts.acc_u = d_acc;
   ts.accept = c->d_accept.p;
   ts.ntacc = ntacc;
-  k_tmove_select<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(S, c->st, ts);
-  c->nlaunch++;
-  CK(cudaGetLastError());
-  if (c->have_slater) {  // MO row at the selected position of the accepted walkers (no saved values, dmc.py:176)
-    PointArgs pa{};
-    pa.which = 1;
-    pa.e = e;
-    pa.naip = 1;
-    pa.pos = c->st.saved_pos;
-    pa.npoints = (int)N;
-    pa.mask = c->d_accept.p;
-    pa.save = 1;
-    pa.scr = c->d_scr.p;
-    pa.scr_stride = N;
-    if (launch_point<PV_MOSAVE>(c, pa, stream)) return -1;
+  if (fused) {
+    ts.item_of = c->es.item_of;
+    ts.count = c->es.count;
+    if (prep_kernel(k_tmove_apply<GA>, apply_sm)) return -1;
+    k_tmove_apply<GA><<<(unsigned)((N + (128 / GA) - 1) / (128 / GA)), 128, apply_sm, stream>>>(S, c->st, ts);
+    c->nlaunch++;
+    CK(cudaGetLastError());
+    c->saved_slot = -1;
+  } else {
+    k_tmove_select<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(S, c->st, ts);
+    c->nlaunch++;
+    CK(cudaGetLastError());
+    if (c->have_slater) {  // MO row at the selected position of the accepted walkers (no saved values, dmc.py:176)
+      PointArgs pa{};
+      pa.which = 1;
+      pa.e = e;
+      pa.naip = 1;
+      pa.pos = c->st.saved_pos;
+      pa.npoints = (int)N;
+      pa.mask = c->d_accept.p;
+      pa.save = 1;
+      pa.scr = c->d_scr.p;
+      pa.scr_stride = N;
+      if (launch_point<PV_MOSAVE>(c, pa, stream)) return -1;
+    }
+    if (launch_update(c, which, e, c->d_accept.p, stream)) return -1;
   }
-  if (launch_update(c, which, e, c->d_accept.p, stream)) return -1;
   c->mocache_valid = false;
   c->paircache_valid = false;
   return 0;
