@@ -644,6 +644,79 @@ __global__ void __launch_bounds__(128) k_jastrow_recompute_coop(const Sys S, con
   }
 }
 
+// Few-electron form of the same recompute: G lanes per walker.  Lanes over electrons evaluate the radial
+// functions once per pair into shared memory; lanes over cache entries then add them in exactly the order
+// of the one-thread loop above (pairs in (i, j) order, partners ascending), so the caches are the same sums.
+template <int G>
+__global__ void __launch_bounds__(128) k_jastrow_recompute_group(const Sys S, const State st) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  extern __shared__ __align__(128) unsigned char qmcb_smem[];
+  const int lane32 = threadIdx.x & 31;
+  const int lane = lane32 & (G - 1);
+  const unsigned gm = group_mask<G>(lane32);
+  const int slot = threadIdx.x / G;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  if (w >= st.N) return;
+  const int ne = S.ne, na = S.na, nb = S.nb, I_ = S.natom;
+  const size_t tab = (16 + (size_t)S.dwords * 8 + (size_t)S.iwords * 4 + 15) & ~(size_t)15;
+  const int per = (S.npair * nb + 1) & ~1;
+  double* pv = reinterpret_cast<double*>(qmcb_smem + tab) + (size_t)slot * per;
+  for (int e = lane; e < ne; e += G) {
+    const double px = CONF(st, S, w, e, 0), py = CONF(st, S, w, e, 1), pz = CONF(st, S, w, e, 2);
+    for (int I = 0; I < I_; ++I) {
+      double dx = px - sd[S.o_xyz + 3 * I], dy = py - sd[S.o_xyz + 3 * I + 1], dz = pz - sd[S.o_xyz + 3 * I + 2];
+      if (S.pbc) min_image(S, sd, dx, dy, dz);
+      const double r = sqrt(dx * dx + dy * dy + dz * dz);
+      for (int k = 0; k < na; ++k) {
+        double v = 0.0, g, l;
+        if (r < S.rcut_a) radial_ool<0>(si[S.o_akind + k], sd[S.o_apar + k], S.rcut_a, r, v, g, l);
+        APART(st, S, w, e, I, k) = v;
+      }
+    }
+    for (int j = e + 1; j < ne; ++j) {
+      double dx = px - CONF(st, S, w, j, 0), dy = py - CONF(st, S, w, j, 1), dz = pz - CONF(st, S, w, j, 2);
+      if (S.pbc) min_image(S, sd, dx, dy, dz);
+      const double r = sqrt(dx * dx + dy * dy + dz * dz);
+      double* out = pv + pair_index(ne, e, j) * nb;
+      for (int l = 0; l < nb; ++l) {
+        double v = 0.0, g, ll;
+        if (r < S.rcut_b) radial_ool<0>(si[S.o_bkind + l], sd[S.o_bpar + l], S.rcut_b, r, v, g, ll);
+        out[l] = v;
+      }
+    }
+  }
+  __syncwarp(gm);
+  for (int t = lane; t < I_ * na * 2; t += G) {
+    const int s2 = t & 1, k = (t >> 1) % na, I = (t >> 1) / na;
+    double acc = 0.0;
+    const int e0 = s2 ? S.nup : 0, e1 = s2 ? ne : S.nup;
+    for (int e = e0; e < e1; ++e) acc += APART(st, S, w, e, I, k);
+    AVAL(st, S, w, I, k, s2) = acc;
+  }
+  for (int t = lane; t < ne * nb * 2; t += G) {
+    const int tt = t & 1, l = (t >> 1) % nb, x = (t >> 1) / nb;
+    double acc = 0.0;
+    const int p0 = tt ? S.nup : 0, p1 = tt ? ne : S.nup;
+    for (int p = p0; p < p1; ++p) {
+      if (p == x) continue;
+      acc += pv[pair_index(ne, p < x ? p : x, p < x ? x : p) * nb + l];
+    }
+    BPART(st, S, w, x, l, tt) = acc;
+  }
+  for (int t = lane; t < nb * 3; t += G) {
+    const int l = t / 3, cls = t - l * 3;
+    double acc = 0.0;
+    for (int e = 0; e < ne; ++e) {
+      const int s = e >= S.nup ? 1 : 0;
+      for (int j = e + 1; j < ne; ++j)
+        if (s + (j >= S.nup ? 1 : 0) == cls) acc += pv[pair_index(ne, e, j) * nb + l];
+    }
+    BVAL(st, S, w, l, cls) = acc;
+  }
+}
+
 // updateinternals of the Jastrow caches for accepted walkers (jastrowspin.py:111-137,221-249)
 // and move of the walker coordinates (coord.py:54-62).  New position = st.saved_pos[w].
 __global__ void __launch_bounds__(128) k_jastrow_update(const Sys S, const State st, int e, int do_jastrow,

@@ -1315,6 +1315,13 @@ int qmcb_recompute_pbc(qmcb_ctx* c, int which, int nconf, const double* configs,
       const int block = S.ne <= 32 ? 32 : (S.ne <= 64 ? 64 : 128);
       if (prep_kernel(k_jastrow_recompute_coop, c->smem_bytes)) return -1;
       k_jastrow_recompute_coop<<<nconf, block, c->smem_bytes, c->stream>>>(S, c->st);
+    } else if (S.ne >= 2 && S.ne < 16 && S.npair * S.nb <= 512 && std::getenv("QMCB_NO_COOP_JRECOMPUTE") == nullptr) {
+      // few electrons: 8 lanes per walker, pair values through shared memory, sums in the one-thread order
+      constexpr int GR = 8;
+      const int per = (S.npair * S.nb + 1) & ~1;
+      const size_t rsm = ((c->smem_bytes + 15) & ~(size_t)15) + (size_t)(128 / GR) * per * 8;
+      if (prep_kernel(k_jastrow_recompute_group<GR>, rsm)) return -1;
+      k_jastrow_recompute_group<GR><<<(unsigned)(((long long)nconf * GR + 127) / 128), 128, rsm, c->stream>>>(S, c->st);
     } else {
       const int block = pick_block(nconf);
       if (prep_kernel(k_jastrow_recompute, c->smem_bytes)) return -1;
