@@ -273,8 +273,8 @@ __host__ __device__ inline size_t pbc_mo_cta_scratch_bytes(const Sys& S, int nc)
   return ((size_t)S.nk * S.nao * nc + (size_t)chunk * S.maxao_atom * nc) * 8 + (size_t)chunk * 2 * 4 + 16;
 }
 
-template <int DERIV>
-__global__ void __launch_bounds__(256, 2) k_pbc_mo_cta(const Sys S, const State st, const PbcMoArgs a) {
+template <int DERIV, int MAXT = 256, int MINB = 2>
+__global__ void __launch_bounds__(MAXT, MINB) k_pbc_mo_cta(const Sys S, const State st, const PbcMoArgs a) {
   constexpr int NC = NComp<DERIV>::value;
   const int T = blockDim.x;
   const double* sd;

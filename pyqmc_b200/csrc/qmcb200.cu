@@ -643,6 +643,11 @@ int launch_pbc_mo(qmcb_ctx* c, int deriv, const PbcMoArgs& a, long long max_poin
     } else if (deriv == 1) {
       if (prep_kernel(k_pbc_mo_cta<1>, csm)) return -1;
       k_pbc_mo_cta<1><<<grid, T, csm, stream>>>(c->S, c->st, a);
+    } else if (T <= 160 && 4 * csm <= 220 * 1024 && std::getenv("QMCB_PBC_MO_OCC2") == nullptr) {
+      // 96 registers: four CTAs per SM, so the 1024 points of a C4 move are two waves instead of three
+      const unsigned g4 = std::min(grid, 148u * 4u);  // one resident wave, CTAs stride over the points
+      if (prep_kernel(k_pbc_mo_cta<2, 160, 4>, csm)) return -1;
+      k_pbc_mo_cta<2, 160, 4><<<g4, T, csm, stream>>>(c->S, c->st, a);
     } else {
       if (prep_kernel(k_pbc_mo_cta<2>, csm)) return -1;
       k_pbc_mo_cta<2><<<grid, T, csm, stream>>>(c->S, c->st, a);
