@@ -123,6 +123,12 @@ int qmcb_set_point_wrap(qmcb_ctx *ctx, const double *wrap, int64_t count);
 int qmcb_recompute_pbc(qmcb_ctx *ctx, int which, int nconf, const double *configs,
                        const double *wrap, double *sign, double *logval);
 
+/* wf.recompute(configs) for the walkers the device ALREADY holds (the configurations a
+ * device-resident block just returned; mc.py:110 calls wf.recompute at the start of every block):
+ * same kernels as qmcb_recompute without the upload and the value read-back; asynchronous on the
+ * context's stream.  Valid only while nothing else changed the walker state. */
+int qmcb_recompute_resident(qmcb_ctx *ctx, int which);
+
 /* ---- wave-function protocol ---------------------------------------------------------- */
 
 /* wf.recompute(configs) -> (sign, log|psi|)   slater.py:227-260, jastrowspin.py:56-109 */

@@ -46,6 +46,7 @@ SIGNATURES = {
     "qmcb_set_point_wrap": (c_int, [c_void_p, c_double_p, c_i64]),
     "qmcb_recompute_pbc": (c_int, [c_void_p, c_int, c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     "qmcb_recompute": (c_int, [c_void_p, c_int, c_int, c_double_p, c_double_p, c_double_p]),
+    "qmcb_recompute_resident": (c_int, [c_void_p, c_int]),
     "qmcb_value": (c_int, [c_void_p, c_int, c_double_p, c_double_p]),
     "qmcb_gradient": (c_int, [c_void_p, c_int, c_int, c_double_p, c_double_p]),
     "qmcb_gradient_value": (c_int, [c_void_p, c_int, c_int, c_double_p, c_double_p, c_double_p, c_i64_p]),

@@ -33,12 +33,13 @@
 namespace {
 
 // The MT19937 recurrence is inherently sequential, so it runs on its own producer thread that
-// stays a few blocks ahead: each ring slot holds one 624-word state block (raw, for handing the
-// state back to numpy) and its tempered image (the outputs).  The consumer (phase A below) walks
-// the tempered blocks in order.  With one thread the blocks are generated inline.
+// stays a few blocks ahead: each ring slot holds the tempered image (the outputs) of one 624-word
+// state block.  The consumer (phase A below) walks the tempered blocks in order; the raw state handed
+// back to numpy at the end is recovered by inverting the tempering of the block the consumer stopped in
+// (copying the raw block into the ring as well cost more than the recurrence and the tempering together).
+// With one thread the blocks are generated inline.
 struct Ring {
   static constexpr int K = 64;
-  uint32_t raw[K][624];
   uint32_t tb[K][624];
   std::atomic<long> produced{0};  // blocks 0..produced-1 are ready
   std::atomic<long> consumed{0};  // the consumer is working on block `consumed`
@@ -60,7 +61,6 @@ void temper_raw(const uint32_t* key, uint32_t* out);
 inline void produce_block(Ring& r, long index) {
   mt_reload(r.key);
   const int slot = (int)(index % Ring::K);
-  std::memcpy(r.raw[slot], r.key, sizeof(r.key));
   temper_raw(r.key, r.tb[slot]);
 }
 
@@ -130,6 +130,21 @@ __attribute__((target_clones("avx512f", "avx2", "default"))) void temper_raw(con
     y ^= (y << 15) & 0xefc60000u;
     y ^= (y >> 18);
     out[i] = y;
+  }
+}
+
+// inverse of temper_raw (each of the four xor-shift steps is a bijection on 32-bit words)
+inline void untemper_block(const uint32_t* t, uint32_t* key) {
+  for (int i = 0; i < 624; ++i) {
+    uint32_t y = t[i];
+    y ^= y >> 18;
+    y ^= (y << 15) & 0xefc60000u;
+    uint32_t x = y;
+    for (int k = 0; k < 4; ++k) x = y ^ ((x << 7) & 0x9d2c5680u);
+    y = x;
+    x = y ^ (y >> 11);
+    x = y ^ (x >> 11);
+    key[i] = x;
   }
 }
 
@@ -454,10 +469,13 @@ int rng_run_phase_a(RngPlan& rp, uint32_t* key, int32_t* pos, int32_t* has_gauss
   if (*pos < 0 || *pos > 624) return -1;
   std::unique_ptr<Ring> ring(new Ring());
   std::memcpy(ring->key, key, sizeof(ring->key));
-  std::memcpy(ring->raw[0], key, sizeof(ring->key));
   temper_raw(key, ring->tb[0]);
   ring->produced.store(1);
-  ring->threaded = nthreads > 1;
+  // A separate producer thread for the recurrence pays off only where handing 2.5 KB blocks from core to
+  // core is cheap; on the B200 hosts (measured, profiles/rng_host_timing.py) generating the blocks inline
+  // is 1.5x faster (0.22 vs 0.33 ms per C2 step), so the thread is opt-in.
+  const bool use_producer = std::getenv("QMCB_RNG_PRODUCER") != nullptr;
+  ring->threaded = nthreads > 1 && use_producer;
   std::thread producer;
   if (ring->threaded) producer = std::thread(producer_loop, ring.get());
   MT s{ring->tb[0], *pos, 0, ring.get()};
@@ -492,7 +510,7 @@ int rng_run_phase_a(RngPlan& rp, uint32_t* key, int32_t* pos, int32_t* has_gauss
     *has_gauss = 0;
     *cached_gauss = 0.0;
   }
-  std::memcpy(key, ring->raw[s.blk % Ring::K], sizeof(ring->key));
+  untemper_block(ring->tb[s.blk % Ring::K], key);
   *pos = s.pos;
   return 0;
 }

@@ -1290,28 +1290,9 @@ int qmcb_set_point_wrap(qmcb_ctx* c, const double* wrap, int64_t count) {
 }
 
 // ---------------------------------------------------------------------------------------
-int qmcb_recompute(qmcb_ctx* c, int which, int nconf, const double* configs, double* sign, double* logval) {
-  return qmcb_recompute_pbc(c, which, nconf, configs, nullptr, sign, logval);
-}
-
-int qmcb_recompute_pbc(qmcb_ctx* c, int which, int nconf, const double* configs, const double* wrap, double* sign,
-                       double* logval) {
-  Guard g(c);
-  if (which_ok(c, which)) return -1;
-  if (ensure_state(c, nconf)) return -1;
+// recompute kernels of the selected factors from the device-resident coordinates (no copies, no sync)
+static int recompute_from_resident(qmcb_ctx* c, int which, int nconf) {
   const Sys& S = c->S;
-  const size_t nel = (size_t)nconf * S.ne * 3;
-  if (c->d_in.ensure(nel) || c->d_out.ensure((size_t)nconf * 8)) return -1;
-  if (S.pbc) {
-    if (wrap) {
-      if (h2d(c, c->st.wrap, wrap, nel * 8)) return -1;
-    } else
-      CK(cudaMemsetAsync(c->st.wrap, 0, nel * 8, c->stream));
-  }
-  if (h2d(c, c->d_in.p, configs, nel * 8)) return -1;
-  k_conf_in<<<(unsigned)((nel + 255) / 256), 256, 0, c->stream>>>(c->d_in.p, c->st.conf, nconf, S.ne);
-  c->nlaunch++;
-  CK(cudaGetLastError());
   if (which & 1)
     if (slater_rebuild(c, c->stream)) return -1;
   if (which & 2) {
@@ -1345,9 +1326,47 @@ int qmcb_recompute_pbc(qmcb_ctx* c, int which, int nconf, const double* configs,
   c->saved_slot = -1;
   c->paircache_valid = false;
   c->kinetic_valid = false;
+  return 0;
+}
+
+int qmcb_recompute(qmcb_ctx* c, int which, int nconf, const double* configs, double* sign, double* logval) {
+  return qmcb_recompute_pbc(c, which, nconf, configs, nullptr, sign, logval);
+}
+
+int qmcb_recompute_pbc(qmcb_ctx* c, int which, int nconf, const double* configs, const double* wrap, double* sign,
+                       double* logval) {
+  Guard g(c);
+  if (which_ok(c, which)) return -1;
+  if (ensure_state(c, nconf)) return -1;
+  const Sys& S = c->S;
+  const size_t nel = (size_t)nconf * S.ne * 3;
+  if (c->d_in.ensure(nel) || c->d_out.ensure((size_t)nconf * 8)) return -1;
+  if (S.pbc) {
+    if (wrap) {
+      if (h2d(c, c->st.wrap, wrap, nel * 8)) return -1;
+    } else
+      CK(cudaMemsetAsync(c->st.wrap, 0, nel * 8, c->stream));
+  }
+  if (h2d(c, c->d_in.p, configs, nel * 8)) return -1;
+  k_conf_in<<<(unsigned)((nel + 255) / 256), 256, 0, c->stream>>>(c->d_in.p, c->st.conf, nconf, S.ne);
+  c->nlaunch++;
+  CK(cudaGetLastError());
+  if (recompute_from_resident(c, which, nconf)) return -1;
   if (sign || logval) return qmcb_value(c, which, sign, logval);
   CK(cudaStreamSynchronize(c->stream));
   return 0;
+}
+
+// wf.recompute for coordinates that are ALREADY on the device (the walkers a device-resident block just
+// returned): same kernels as qmcb_recompute, no upload, no value read-back, asynchronous on the context's
+// stream.  The host driver uses it at the start of block b+1 when nothing touched the state since block b.
+int qmcb_recompute_resident(qmcb_ctx* c, int which) {
+  Guard g(c);
+  if (which_ok(c, which)) return -1;
+  if (c->N == 0) return fail("recompute has not been called");
+  if (build_tables(c)) return -1;
+  if (c->N == 0) return fail("system shapes changed: call recompute again");
+  return recompute_from_resident(c, which, (int)c->N);
 }
 
 int qmcb_value(qmcb_ctx* c, int which, double* sign, double* logval) {

@@ -286,6 +286,7 @@ def dmc_propagate_device(wf, configs, weights, tstep, branchcut_start, e_trial, 
         ctx.h, nsteps, float(tstep), float(branchcut_start), float(e_trial), float(e_est), d(v["gauss"]), d(v["unif"]),
         d(v["ecp_u"]), d(v["ecp_rot"]), d(v["tm_u"]), d(v["tm_rot"]), d(v["tm_sel"]), d(v["tm_acc"]), d(w), d(newconf),
         d(wsums), nacc.ctypes.data_as(_lib.c_i64_p), ntacc.ctypes.data_as(_lib.c_i64_p)))
+    ctx.epoch += 1  # the block moved the walkers on the device
     configs.configs[...] = newconf
     if w is not weights:
         weights[...] = w

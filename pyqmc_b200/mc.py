@@ -146,6 +146,37 @@ def _block_buffers(ctx, nconf, nelec, nsteps, accumulator, slot=0):
     return cache[slot]
 
 
+def _recompute_resident(wf, configs):
+    """``wf.recompute(configs)`` without the host round trip when ``configs`` are the walkers the device
+    already holds: the coordinates the previous device-resident block returned, untouched since (no
+    protocol call changed the device state, the host array still equals the returned one).  The recompute
+    kernels then run from the resident coordinates (qmcb_recompute_resident); parameters are pushed as
+    ``recompute`` would.  False = not applicable, the caller does the ordinary recompute."""
+    import os
+
+    if os.environ.get("QMCB_NO_RESIDENT_RECOMPUTE"):
+        return False
+    try:
+        ctx = _device_context(wf)
+    except TypeError:
+        return False
+    res = getattr(ctx, "_resident", None) if ctx is not None else None
+    if res is None or ctx.periodic or res[1] != ctx.epoch or res[0].shape != configs.configs.shape:
+        return False
+    if not np.array_equal(res[0], configs.configs):
+        return False
+    factors = getattr(wf, "wf_factors", None)
+    if factors is not None:
+        if not getattr(wf, "_fused", False):
+            return False
+        for f in factors:
+            f._push_parameters(ctx)
+    else:
+        wf._push_parameters(ctx)
+    ctx.recompute_resident(wf._which)
+    return True
+
+
 def vmc_block_device(wf, configs, tstep, nsteps, accumulators, variates=None, return_walker_data=False,
                      buffers=None):
     """One device-resident block; equivalent of ``vmc_worker`` (mc.py:102-153).
@@ -153,7 +184,8 @@ def vmc_block_device(wf, configs, tstep, nsteps, accumulators, variates=None, re
     ``variates``: pre-drawn (gauss, unif, ecp_u, ecp_rot) (must have been drawn in stream order);
     ``buffers``: BlockBuffers whose variates were already filled (RNG prefetch of ``vmc``)."""
     nconf, nelec, _ = configs.configs.shape
-    wf.recompute(configs)
+    if not _recompute_resident(wf, configs):
+        wf.recompute(configs)
     ctx = _device_context(wf)
     acc_name, accumulator = (next(iter(accumulators.items())) if accumulators else (None, None))
     if accumulator is not None:
@@ -186,19 +218,22 @@ def vmc_block_device(wf, configs, tstep, nsteps, accumulators, variates=None, re
     configs.configs[...] = buffers.newconf
     if ctx.periodic:
         configs.wrap[...] = ctx.get_state("wrap", configs.wrap.shape)
+    else:  # the device holds exactly these walkers: the next block may recompute from them in place
+        ctx._resident = (buffers.newconf, ctx.epoch)
     block_avg = {}
-    for step in range(nsteps):
-        if accumulator is not None:
-            for i, m in enumerate(KEYS):
-                res = np.mean(energy[step, i], axis=0)
-                if acc_name + m not in block_avg:
-                    block_avg[acc_name + m] = res / nsteps
-                else:
-                    block_avg[acc_name + m] += res / nsteps
-        acc = 0.0
-        for e in range(nelec):
-            acc += (nacc[step, e] / nconf) / nelec
-        block_avg["acceptance"] = acc
+    if accumulator is not None:
+        # per-step walker means (one pairwise-summed reduction per (step, key) row, as np.mean of the row),
+        # accumulated over the steps in order as the reference loop does (mc.py:139-147)
+        means = np.mean(energy[:nsteps], axis=2)
+        for i, m in enumerate(KEYS):
+            tot = means[0, i] / nsteps
+            for step in range(1, nsteps):
+                tot += means[step, i] / nsteps
+            block_avg[acc_name + m] = tot
+    acc = 0.0
+    for e in range(nelec):
+        acc += (nacc[nsteps - 1, e] / nconf) / nelec
+    block_avg["acceptance"] = acc
     block_avg["move time"] = end - start
     block_avg["accumulator time"] = 0.0
     if return_walker_data:

@@ -66,6 +66,8 @@ class DeviceContext:
         _lib.check(self.lib.qmcb_set_atoms(h, len(chg), _lib.dptr(xyz), _lib.dptr(chg)))
         self.natom = len(chg)
         self.nconf = 0
+        self.epoch = 0  # bumped by every call that changes the walker state (recompute, updateinternals)
+        self._resident = None  # (host copy of the walkers a device block returned, epoch) -- mc.vmc_block_device
         self.nelec = tuple(int(x) for x in mol.nelec)
         self.ecp_key = None
         self.has_basis = False
@@ -98,6 +100,7 @@ class DeviceContext:
 
     # ---- protocol calls -----------------------------------------------------------------
     def recompute(self, which, configs, wrap=None):
+        self.epoch += 1
         c = _lib.f64(configs)
         n = c.shape[0]
         sign, logv = np.empty(n), np.empty(n)
@@ -181,7 +184,12 @@ class DeviceContext:
                                                 _lib.u8ptr(m), _lib.dptr(out)))
         return out
 
+    def recompute_resident(self, which):
+        """recompute from the coordinates the device already holds (block driver, see mc.vmc_block_device)"""
+        _lib.check(self.lib.qmcb_recompute_resident(self.h, which))
+
     def updateinternals(self, which, e, epos, mask=None, saved_values=None):
+        self.epoch += 1
         p = self._epos(epos)
         m, _ = self._mask(mask, self.nconf)
         _lib.check(self.lib.qmcb_updateinternals(self.h, which, int(e), _lib.dptr(p), _lib.u8ptr(m),

@@ -159,3 +159,34 @@ def test_finite_difference_gradient_and_laplacian(lib, name):
             num_lap += (rp + rm - 2.0) / delta**2
         assert np.abs(num_grad - grad).max() < 1e-5 * max(1.0, np.abs(grad).max())
         assert np.abs(num_lap - lap).max() < 2e-4 * max(1.0, np.abs(lap).max())
+
+
+def test_resident_recompute_between_blocks_is_bit_identical(lib, monkeypatch):
+    """vmc() recomputes the wave function at the start of every block (mc.py:110).  When the walkers are the
+    ones the previous device block returned, the driver recomputes from the device-resident coordinates
+    (qmcb_recompute_resident) instead of uploading them again: same numbers, bit for bit, as the ordinary
+    recompute, also after a parameter change and after the host array was modified between blocks."""
+    import pyqmc_b200 as pq
+
+    def run(modify):
+        mol, mf, wf, _ = helpers.make_pair("h2o", seed=1)
+        acc = pq.EnergyAccumulator(mol)
+        np.random.seed(11)
+        configs = pq.initial_guess(mol, 96)
+        df1, configs = pq.vmc(wf, configs, tstep=0.5, nblocks=3, nsteps_per_block=4, accumulators={"energy": acc})
+        wf.parameters["wf2bcoeff"][1, :] *= 1.01  # parameters change between runs; state must follow
+        if modify:
+            configs.configs[3, 2, :] += 0.125  # host array no longer equals the resident walkers
+        df2, configs = pq.vmc(wf, configs, tstep=0.5, nblocks=2, nsteps_per_block=4, accumulators={"energy": acc})
+        return df1, df2, configs.configs.copy(), wf.recompute(configs)
+
+    for modify in (False, True):
+        monkeypatch.delenv("QMCB_NO_RESIDENT_RECOMPUTE", raising=False)
+        a = run(modify)
+        monkeypatch.setenv("QMCB_NO_RESIDENT_RECOMPUTE", "1")
+        b = run(modify)
+        for k in a[0]:
+            if "time" not in k:
+                assert np.array_equal(a[0][k], b[0][k]) and np.array_equal(a[1][k], b[1][k]), k
+        assert np.array_equal(a[2], b[2])
+        assert np.array_equal(a[3][0], b[3][0]) and np.array_equal(a[3][1], b[3][1])

@@ -152,14 +152,20 @@ def test_initial_guess_matches_oracle_stream():
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("producer", [False, True])
 @pytest.mark.parametrize("seed", range(12))
-def test_native_rng_is_bit_identical_to_numpy_legacy_stream(lib, seed):
+def test_native_rng_is_bit_identical_to_numpy_legacy_stream(lib, seed, producer, monkeypatch):
     """qmcb_rng_vmc_block (csrc/legacy_rng.cpp) vs the numpy/scipy calls of the reference loop:
     same variates, same final MT19937 position and Gaussian cache, incl. odd sizes and a cached
-    Gaussian carried in."""
+    Gaussian carried in; with the recurrence inline (default) and on its producer thread."""
     from pyqmc_b200 import mc
     from pyqmc_b200.accumulators import EnergyAccumulator
 
+    if producer:
+        monkeypatch.setenv("QMCB_RNG_PRODUCER", "1")
+        monkeypatch.setenv("QMCB_RNG_THREADS", "3")
+    else:
+        monkeypatch.delenv("QMCB_RNG_PRODUCER", raising=False)
     mol, mf, _ = helpers.make_system("c2" if seed % 2 else "h2o")
     acc = EnergyAccumulator(mol) if seed % 3 else None
     N = 1 + 37 * seed % 23
