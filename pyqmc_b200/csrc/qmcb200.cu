@@ -117,6 +117,7 @@ struct qmcb_ctx {
   DBuf<double> m_tmu, m_tmrot, m_tmsel, m_tmacc, m_w, m_eold, m_v2old, m_r2p, m_r2a, m_prod, m_ws;
   DBuf<unsigned long long> m_ntacc;
   bool dirty = true;
+  std::vector<unsigned char> key_slater, key_jastrow, key_j3;  // last parameter sets (ParamKey)
   // ---- device tables
   Sys S{};
   DBuf<double> d_dblob, d_detc, d_quad;
@@ -1094,6 +1095,24 @@ int qmcb_set_basis(qmcb_ctx* c, int nshell, const int32_t* shell_atom, const int
   return 0;
 }
 
+// Parameter setters are called before every recompute (the host objects push their current parameters);
+// an unchanged parameter set must not invalidate the packed device tables, or every block would re-pack and
+// re-upload them.  Each setter keeps the raw bytes of its last inputs and returns early on an exact match.
+extern "C++" {
+struct ParamKey {
+  std::vector<unsigned char> b;
+  template <class T>
+  void add(const T* p, size_t n) {
+    const unsigned char* q = reinterpret_cast<const unsigned char*>(p);
+    b.insert(b.end(), q, q + n * sizeof(T));
+  }
+  template <class T>
+  void val(T v) {
+    add(&v, 1);
+  }
+};
+}  // extern "C++"
+
 int qmcb_set_slater(qmcb_ctx* c, int nup, int ndn, int nmo_up, const double* mo_up, int nmo_dn,
                     const double* mo_dn, int ndet_up, const int32_t* occ_up, int ndet_dn,
                     const int32_t* occ_dn, int ndet, const int32_t* map_up, const int32_t* map_dn,
@@ -1102,6 +1121,16 @@ int qmcb_set_slater(qmcb_ctx* c, int nup, int ndn, int nmo_up, const double* mo_
   for (size_t s = 0; s < c->sh_l.size(); ++s) nao += 2 * c->sh_l[s] + 1;
   if (nao == 0) return fail("qmcb_set_basis must be called before qmcb_set_slater");
   if (c->have_jastrow && (nup != c->nup || ndn != c->ndn)) return fail("electron counts differ from the Jastrow factor");
+  ParamKey key;
+  for (int v : {nao, nup, ndn, nmo_up, nmo_dn, ndet_up, ndet_dn, ndet}) key.val(v);
+  key.add(mo_up, (size_t)nao * nmo_up);
+  key.add(mo_dn, (size_t)nao * nmo_dn);
+  key.add(occ_up, (size_t)ndet_up * nup);
+  key.add(occ_dn, (size_t)ndet_dn * ndn);
+  key.add(map_up, (size_t)ndet);
+  key.add(map_dn, (size_t)ndet);
+  key.add(det_coeff, (size_t)ndet);
+  if (c->have_slater && key.b == c->key_slater) return 0;
   c->nup = nup;
   c->ndn = ndn;
   c->nmo[0] = nmo_up;
@@ -1122,6 +1151,7 @@ int qmcb_set_slater(qmcb_ctx* c, int nup, int ndn, int nmo_up, const double* mo_
   c->detc.assign(det_coeff, det_coeff + ndet);
   c->have_slater = true;
   c->dirty = true;
+  c->key_slater.swap(key.b);
   return 0;
 }
 
@@ -1131,6 +1161,17 @@ int qmcb_set_jastrow(qmcb_ctx* c, int nup, int ndn, int na, const int32_t* a_kin
   if (c->have_slater && (nup != c->nup || ndn != c->ndn)) return fail("electron counts differ from the Slater factor");
   const int natom = (int)c->chg.size();
   if (natom == 0) return fail("qmcb_set_atoms must be called before qmcb_set_jastrow");
+  ParamKey key;
+  for (int v : {natom, nup, ndn, na, nb}) key.val(v);
+  key.val(rcut_a);
+  key.val(rcut_b);
+  key.add(a_kind, (size_t)na);
+  key.add(a_par, (size_t)na);
+  key.add(b_kind, (size_t)nb);
+  key.add(b_par, (size_t)nb);
+  key.add(acoeff, (size_t)natom * na * 2);
+  key.add(bcoeff, (size_t)nb * 3);
+  if (c->have_jastrow && key.b == c->key_jastrow) return 0;
   c->nup = nup;
   c->ndn = ndn;
   c->na = na;
@@ -1145,6 +1186,7 @@ int qmcb_set_jastrow(qmcb_ctx* c, int nup, int ndn, int na, const int32_t* a_kin
   c->bcoef.assign(bcoeff, bcoeff + (size_t)nb * 3);
   c->have_jastrow = true;
   c->dirty = true;
+  c->key_jastrow.swap(key.b);
   return 0;
 }
 
@@ -1157,6 +1199,16 @@ int qmcb_set_jastrow3(qmcb_ctx* c, int nup, int ndn, int na, const int32_t* a_ki
   if (natom == 0) return fail("qmcb_set_atoms must be called before qmcb_set_jastrow3");
   if (nb > QMCB_J3_MAXB) return fail("three-body Jastrow: more than 8 b functions");
   if (natom * na > QMCB_J3_MAXA) return fail("three-body Jastrow: natom * na > 128");
+  ParamKey key;
+  for (int v : {natom, nup, ndn, na, nb}) key.val(v);
+  key.val(rcut_a);
+  key.val(rcut_b);
+  key.add(a_kind, (size_t)na);
+  key.add(a_par, (size_t)na);
+  key.add(b_kind, (size_t)nb);
+  key.add(b_par, (size_t)nb);
+  key.add(ccoeff, (size_t)natom * na * na * nb * 3);
+  if (c->have_j3 && key.b == c->key_j3) return 0;
   c->nup = nup;
   c->ndn = ndn;
   c->na3 = na;
@@ -1180,6 +1232,7 @@ int qmcb_set_jastrow3(qmcb_ctx* c, int nup, int ndn, int na, const int32_t* a_ki
           }
   c->have_j3 = true;
   c->dirty = true;
+  c->key_j3.swap(key.b);
   return 0;
 }
 
