@@ -108,8 +108,8 @@ def rng_threads():
         return max(1, int(os.environ["QMCB_RNG_THREADS"]))
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
     cores = (os.cpu_count() or 1) // max(local_world, 1)
-    # leave a core each for the sequential stream walk and its producer thread when cores are scarce
-    return max(1, min(8, cores - 2 if cores <= 6 else cores))
+    # leave a core for the sequential stream walk (phase A of the next block) when cores are scarce
+    return max(1, min(8, cores - 1 if cores <= 6 else cores))
 
 
 def _draw_block_variates_native(nconf, nelec, tstep, nsteps, necp, out):
