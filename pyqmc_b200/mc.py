@@ -161,9 +161,9 @@ def _recompute_resident(wf, configs):
     except TypeError:
         return False
     res = getattr(ctx, "_resident", None) if ctx is not None else None
-    if res is None or ctx.periodic or res[1] != ctx.epoch or res[0].shape != configs.configs.shape:
+    if res is None or ctx.periodic or res[1] != ctx.epoch or res[0].newconf.shape != configs.configs.shape:
         return False
-    if not np.array_equal(res[0], configs.configs):
+    if not np.array_equal(res[0].newconf, configs.configs):
         return False
     factors = getattr(wf, "wf_factors", None)
     if factors is not None:
@@ -219,7 +219,7 @@ def vmc_block_device(wf, configs, tstep, nsteps, accumulators, variates=None, re
     if ctx.periodic:
         configs.wrap[...] = ctx.get_state("wrap", configs.wrap.shape)
     else:  # the device holds exactly these walkers: the next block may recompute from them in place
-        ctx._resident = (buffers.newconf, ctx.epoch)
+        ctx._resident = (buffers, ctx.epoch)  # the BlockBuffers object keeps the pinned memory alive
     block_avg = {}
     if accumulator is not None:
         # per-step walker means (one pairwise-summed reduction per (step, key) row, as np.mean of the row),

@@ -67,7 +67,7 @@ class DeviceContext:
         self.natom = len(chg)
         self.nconf = 0
         self.epoch = 0  # bumped by every call that changes the walker state (recompute, updateinternals)
-        self._resident = None  # (host copy of the walkers a device block returned, epoch) -- mc.vmc_block_device
+        self._resident = None  # (BlockBuffers whose newconf a device block returned, epoch) -- mc.vmc_block_device
         self.nelec = tuple(int(x) for x in mol.nelec)
         self.ecp_key = None
         self.has_basis = False
