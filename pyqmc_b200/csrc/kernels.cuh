@@ -2280,67 +2280,68 @@ __global__ void __launch_bounds__(128) k_tmove_apply(const Sys S, const State st
   bool acc = false;
   double px = 0.0, py = 0.0, pz = 0.0;
   if (w < N) {
-    if (lane == 0) {
-      const double cx = CONF(st, S, w, e, 0), cy = CONF(st, S, w, e, 1), cz = CONF(st, S, w, e, 2);
+    // the walker's candidate table into shared memory, all lanes loading (entries of unsampled atoms take
+    // the values compute_tmoves gives them: ratio 1, weight 0); the leader then runs k_tmove_select's
+    // sequential arithmetic on it
+    double* tra = ws;
+    double* twt = ws + M;
+    {
       const double* __restrict__ ra = a.ratio + (size_t)w * M;
       const double* __restrict__ wt = a.weight + (size_t)w * M;
-      // amplitudes in table order; m -> ECP atom through the per-atom offsets
-      double sum = 0.0;
       for (int ia = 0; ia < S.necp; ++ia) {
-        if (a.item_of[(size_t)ia * N + w] < 0) continue;
-        for (int m = si[S.o_aipoff + ia]; m < si[S.o_aipoff + ia] + si[S.o_naip + ia]; ++m) {
-          const double amp = __dmul_rn(ra[m], wt[m]);
-          if (amp > 0.0) sum = __dadd_rn(sum, amp);
+        const bool on = a.item_of[(size_t)ia * N + w] >= 0;
+        const int m0 = si[S.o_aipoff + ia], m1 = m0 + si[S.o_naip + ia];
+        for (int m = m0 + lane; m < m1; m += G) {
+          tra[m] = on ? ra[m] : 1.0;
+          twt[m] = on ? wt[m] : 0.0;
         }
+      }
+    }
+    __syncwarp(gm);
+    if (lane == 0) {
+      double sum = 0.0;
+      for (int m = 0; m < M; ++m) {
+        const double amp = __dmul_rn(tra[m], twt[m]);
+        if (amp > 0.0) sum = __dadd_rn(sum, amp);
       }
       const double norm = __dadd_rn(1.0, sum);  // EQN 34
       const double r = a.sel_u[w];
-      int sel = 0, sel_atom = -1;
+      int sel = 0;
       double cdf = 0.0;
-      for (int ia = 0; ia < S.necp; ++ia) {
-        const bool on = a.item_of[(size_t)ia * N + w] >= 0;
-        for (int m = si[S.o_aipoff + ia]; m < si[S.o_aipoff + ia] + si[S.o_naip + ia]; ++m) {
-          double f = 0.0;
-          if (on) {
-            const double amp = __dmul_rn(ra[m], wt[m]);
-            f = amp > 0.0 ? amp : 0.0;
-          }
-          cdf = __dadd_rn(cdf, f / norm);
-          if (cdf < r) {
-            ++sel;
-          } else if (sel_atom < 0 && sel == m) {
-            sel_atom = on ? ia : -2;
-          }
-        }
+      for (int m = 0; m < M; ++m) {
+        const double amp = __dmul_rn(tra[m], twt[m]);
+        const double f = amp > 0.0 ? amp : 0.0;
+        cdf = __dadd_rn(cdf, f / norm);
+        if (cdf < r) ++sel;
       }
       const bool chosen = sel < M;
       double acceptance = 0.0;
-      px = cx;
-      py = cy;
-      pz = cz;
+      px = CONF(st, S, w, e, 0);
+      py = CONF(st, S, w, e, 1);
+      pz = CONF(st, S, w, e, 2);
       if (chosen) {
-        const bool sel_on = sel_atom >= 0;
+        bool sel_on = false;
+        for (int ia = 0; ia < S.necp; ++ia)
+          if (sel >= si[S.o_aipoff + ia] && sel < si[S.o_aipoff + ia] + si[S.o_naip + ia])
+            sel_on = a.item_of[(size_t)ia * N + w] >= 0;
         if (sel_on) {
           px = a.pos[((size_t)w * M + sel) * 3];
           py = a.pos[((size_t)w * M + sel) * 3 + 1];
           pz = a.pos[((size_t)w * M + sel) * 3 + 2];
         }
-        const double rev = 1.0 / (sel_on ? ra[sel] : 1.0);
+        const double rev = 1.0 / tra[sel];
         double bsum = 0.0;
-        for (int ia = 0; ia < S.necp; ++ia) {
-          const bool on = a.item_of[(size_t)ia * N + w] >= 0;
-          for (int m = si[S.o_aipoff + ia]; m < si[S.o_aipoff + ia] + si[S.o_naip + ia]; ++m) {
-            const double rm = on ? ra[m] : 1.0, wm = on ? wt[m] : 0.0;
-            double b = m == sel ? __dmul_rn(rev, wm) : __dmul_rn(__dmul_rn(rm, wm), rev);
-            if (b < 0.0) b = 0.0;
-            bsum = __dadd_rn(bsum, b);
-          }
+        for (int m = 0; m < M; ++m) {
+          double b = m == sel ? __dmul_rn(rev, twt[m]) : __dmul_rn(__dmul_rn(tra[m], twt[m]), rev);
+          if (b < 0.0) b = 0.0;
+          bsum = __dadd_rn(bsum, b);
         }
         acceptance = norm / __dadd_rn(1.0, bsum);
       }
       acc = chosen && (acceptance > a.acc_u[w]);
       a.accept[w] = acc ? 1 : 0;
     }
+    __syncwarp(gm);  // the table in ws is dead from here on: coop_eval_mo reuses the scratch
     const int leader = lane32 & ~(G - 1);
     acc = __shfl_sync(gm, acc ? 1 : 0, leader) != 0;
     px = __shfl_sync(gm, px, leader);

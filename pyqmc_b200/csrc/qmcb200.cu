@@ -2192,7 +2192,7 @@ static int dmc_tmove_electron(qmcb_ctx* c, int e, double tau, const double* d_u,
   constexpr int GA = 16;
   const CoopLayout CLa = coop_layout(S);
   const size_t apply_sm = ((c->smem_bytes + 15) & ~(size_t)15) + (size_t)(128 / GA) * CLa.total * 8;
-  const bool fused = S.ndet == 1 && !c->have_j3 && !S.pbc && apply_sm <= 200 * 1024 &&
+  const bool fused = S.ndet == 1 && !c->have_j3 && !S.pbc && apply_sm <= 200 * 1024 && 2 * (int)M <= CLa.total &&
                      std::getenv("QMCB_TMOVE_UNFUSED") == nullptr;
   if (!fused) {
     k_tmove_init<<<(unsigned)((N * M + 255) / 256), 256, 0, stream>>>(S, c->st, e, d_ratio, d_weight, d_pos);
