@@ -190,3 +190,34 @@ def test_resident_recompute_between_blocks_is_bit_identical(lib, monkeypatch):
                 assert np.array_equal(a[0][k], b[0][k]) and np.array_equal(a[1][k], b[1][k]), k
         assert np.array_equal(a[2], b[2])
         assert np.array_equal(a[3][0], b[3][0]) and np.array_equal(a[3][1], b[3][1])
+
+
+def test_resident_recompute_is_dropped_after_protocol_calls(lib, monkeypatch):
+    """A protocol call that changes the device state between two blocks (here a masked updateinternals that
+    moves some walkers' first electron, with the host array left as the block returned it) must make the next
+    block fall back to the ordinary recompute from the HOST walkers, as the reference's vmc_worker would."""
+    import pyqmc_b200 as pq
+    from pyqmc_b200 import mc
+
+    def run(disable):
+        if disable:
+            monkeypatch.setenv("QMCB_NO_RESIDENT_RECOMPUTE", "1")
+        else:
+            monkeypatch.delenv("QMCB_NO_RESIDENT_RECOMPUTE", raising=False)
+        mol, mf, wf, _ = helpers.make_pair("h2o", seed=1)
+        acc = pq.EnergyAccumulator(mol)
+        np.random.seed(5)
+        configs = pq.initial_guess(mol, 40)
+        _, configs = mc.vmc_block_device(wf, configs, 0.5, 3, {"energy": acc})
+        epos = configs.electron(0)
+        moved = pq.OpenElectron(epos.configs + 0.05, epos.dist)
+        mask = np.arange(40) % 3 == 0
+        wf.updateinternals(0, moved, configs, mask=mask)  # device walkers now differ from the host array
+        avg, configs = mc.vmc_block_device(wf, configs, 0.5, 3, {"energy": acc})
+        return avg, configs.configs.copy()
+
+    a, b = run(False), run(True)
+    for k in a[0]:
+        if "time" not in k:
+            assert np.array_equal(a[0][k], b[0][k]), k
+    assert np.array_equal(a[1], b[1])
