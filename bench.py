@@ -525,11 +525,14 @@ def reference_arm(args):
     wl = WORKLOADS[args.workload]
     # each of the K "steps" of this arm is one VMC step of a bounded sample (cpu_walkers per core on
     # every host core); K is capped so the whole run stays within a few minutes
-    v, cores, wall, sample = cpu_arm(max(1, min(args.steps, wl["cpu_steps"])), args.warmup > 0,
-                                     walkers_per_core=wl["cpu_walkers"], system=wl["system"])
+    if args.workload == "c5":
+        v, cores, wall, sample = cpu_arm_dmc(max(1, min(args.steps, wl["cpu_steps"])), wl["cpu_walkers"], system=wl["system"])
+    else:
+        v, cores, wall, sample = cpu_arm(max(1, min(args.steps, wl["cpu_steps"])), args.warmup > 0,
+                                         walkers_per_core=wl["cpu_walkers"], system=wl["system"])
     out = {
         "impl": "reference",
-        "metric": "walker-steps/sec (VMC, H2O cc-pVTZ SJ); Sherman-Morrison HBM GB/s vs roofline",
+        "metric": wl.get("metric", "walker-steps/sec (VMC, H2O cc-pVTZ SJ); Sherman-Morrison HBM GB/s vs roofline"),
         "value": v, "unit": "walker-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
