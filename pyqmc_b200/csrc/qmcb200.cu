@@ -1103,8 +1103,9 @@ struct ParamKey {
   std::vector<unsigned char> b;
   template <class T>
   void add(const T* p, size_t n) {
-    const unsigned char* q = reinterpret_cast<const unsigned char*>(p);
-    b.insert(b.end(), q, q + n * sizeof(T));
+    const size_t old = b.size(), bytes = n * sizeof(T);
+    b.resize(old + bytes);
+    if (bytes) std::memcpy(b.data() + old, p, bytes);
   }
   template <class T>
   void val(T v) {
