@@ -183,6 +183,35 @@ def test_native_rng_is_bit_identical_to_numpy_legacy_stream(lib, seed, producer,
     assert np.array_equal(sa[1], sb[1]) and sa[2:] == sb[2:]
 
 
+@pytest.mark.parametrize("producer", [False, True])
+def test_native_rng_at_bench_size_matches_numpy(lib, producer, monkeypatch):
+    """The C2 block shape of bench.py (4096 walkers, 8 electrons, 3 ECP atoms; ~1600 MT19937 state blocks for
+    two steps): every variate and the final generator state equal numpy's, with 1 and 5 host threads, with the
+    recurrence inline and on the producer thread, starting mid-block with a cached Gaussian."""
+    from pyqmc_b200 import mc
+    from pyqmc_b200.accumulators import EnergyAccumulator
+
+    mol, mf, _ = helpers.make_system("h2o")
+    acc = EnergyAccumulator(mol)
+    if producer:
+        monkeypatch.setenv("QMCB_RNG_PRODUCER", "1")
+    else:
+        monkeypatch.delenv("QMCB_RNG_PRODUCER", raising=False)
+    np.random.seed(77)
+    np.random.normal(size=301)  # odd count: mid-block position and a cached second Gaussian
+    st0 = np.random.get_state()
+    a = mc.draw_block_variates(4096, 8, 0.5, 2, acc, native=False)
+    sa = np.random.get_state()
+    for threads in ("1", "5"):
+        monkeypatch.setenv("QMCB_RNG_THREADS", threads)
+        np.random.set_state(st0)
+        b = mc.draw_block_variates(4096, 8, 0.5, 2, acc, native=True)
+        sb = np.random.get_state()
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+        assert np.array_equal(sa[1], sb[1]) and sa[2:] == sb[2:]
+
+
 def test_native_draw_program_is_bit_identical_to_numpy_for_the_dmc_block():
     """qmcb_rng_program (csrc/legacy_rng.cpp) on the DMC draw order (dmc.py:150-198): same numbers as
     the numpy / scipy calls, same final state of the global legacy generator, with a cached Gaussian
