@@ -353,7 +353,9 @@ def gpu_arm(args):
     t_e2e = float(te.item())
     e2e = N * world * nb_e2e * spb / t_e2e
     necp = acc.necp
-    h2d = spb * ne * N * (3 + 1) * 8 + spb * ne * necp * (N + 9) * 8 + N * ne * 3 * 8
+    # per block: the variates (gauss, unif, ECP uniforms + rotations); the walkers themselves are uploaded by the
+    # first block only (later blocks recompute from the device-resident walkers, qmcb_recompute_resident)
+    h2d = spb * ne * N * (3 + 1) * 8 + spb * ne * necp * (N + 9) * 8 + N * ne * 3 * 8 / nb_e2e
     d2h = spb * 6 * N * 8 + N * ne * 3 * 8 + spb * ne * 8
 
     if rank != 0:
