@@ -185,9 +185,38 @@ def generate_sr(name):
     return {"sr_" + k: np.asarray(v) for k, v in d.items()}
 
 
+RUNDMC_SYSTEMS = ["h2o", "c2"]
+
+
+def generate_rundmc(name, nconf=16):
+    """The reference's whole DMC driver (dmc.py:413-591: VMC warm-up without accumulators, energy
+    reference, propagation with T-moves, branching, e_trial feedback) -> tests/golden/rundmc_<name>.npz."""
+    import pyqmc.method.dmc as dmc
+    import pyqmc.method.mc as mc
+    from pyqmc.observables.accumulators import EnergyAccumulator
+
+    mol, wf = build_reference(name)
+    np.random.seed(51)
+    configs = mc.initial_guess(mol, nconf)
+    out = {"configs0": configs.configs.copy()}
+    np.random.seed(52)
+    df, configs, weights = dmc.rundmc(wf, configs, tstep=0.02, nblocks=3, nsteps_per_block=2, vmc_warmup=2,
+                                      accumulators={"energy": EnergyAccumulator(mol)})
+    out["configs"], out["weights"] = configs.configs.copy(), np.asarray(weights)
+    for k, v in df.items():
+        out["df_" + k] = np.asarray(v)
+    return out
+
+
 def main():
     warnings.filterwarnings("ignore")
     refload.load()
+    if len(sys.argv) > 1 and sys.argv[1] == "rundmc":
+        for name in RUNDMC_SYSTEMS:
+            path = os.path.join(HERE, f"rundmc_{name}.npz")
+            np.savez_compressed(path, **generate_rundmc(name))
+            print("wrote", path)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "sr":
         for name in SR_SYSTEMS:
             path = os.path.join(HERE, f"sr_{name}.npz")
