@@ -5,17 +5,18 @@ the local-energy accumulator, behind the reference's ``pyqmc.wf`` object protoco
 Importing the package does not touch the GPU; creating a wave function's device context does,
 and fails loudly without the CUDA library or a CUDA device (there is no CPU fallback).
 """
-from .coord import OpenConfigs, OpenElectron, PeriodicConfigs, PeriodicElectron  # noqa: F401
+from .coord import ElectronView, OpenConfigs, OpenElectron, PeriodicConfigs, PeriodicElectron, Walkers  # noqa: F401
 from .func3d import CutoffCuspFunction, PolyPadeFunction  # noqa: F401
 from .wf import JastrowSpin, MultiplyWF, Slater, ThreeBodyJastrow  # noqa: F401
 from .wftools import generate_jastrow, generate_jastrow3, generate_slater, generate_wf  # noqa: F401
 from .accumulators import EnergyAccumulator  # noqa: F401
-from .mc import initial_guess, limdrift, vmc  # noqa: F401
-from .dmc import rundmc  # noqa: F401
-from .sr import LinearTransform, PGradTransform, StochasticReconfiguration, gradient_generator  # noqa: F401
+from .mc import initial_guess, vmc  # noqa: F401
+from .dmc import branch, dmc_propagate, rundmc  # noqa: F401
+from .sr import LinearTransform, ParameterMap, PGradTransform, StochasticReconfiguration, gradient_generator  # noqa: F401
 
 __all__ = [
-    "OpenConfigs", "OpenElectron", "PeriodicConfigs", "PeriodicElectron", "CutoffCuspFunction", "PolyPadeFunction", "JastrowSpin", "MultiplyWF",
-    "Slater", "ThreeBodyJastrow", "generate_jastrow", "generate_jastrow3", "generate_slater", "generate_wf", "EnergyAccumulator", "initial_guess",
-    "limdrift", "vmc", "rundmc", "LinearTransform", "PGradTransform", "StochasticReconfiguration", "gradient_generator",
+    "Walkers", "ElectronView", "OpenConfigs", "OpenElectron", "PeriodicConfigs", "PeriodicElectron", "CutoffCuspFunction",
+    "PolyPadeFunction", "JastrowSpin", "MultiplyWF", "Slater", "ThreeBodyJastrow", "generate_jastrow", "generate_jastrow3",
+    "generate_slater", "generate_wf", "EnergyAccumulator", "initial_guess", "vmc", "rundmc", "dmc_propagate", "branch",
+    "ParameterMap", "LinearTransform", "PGradTransform", "StochasticReconfiguration", "gradient_generator",
 ]

@@ -70,9 +70,7 @@ class EnergyAccumulator:
     def __init__(self, mol, threshold=10, naip=None, use_old_ecp=True, **kwargs):
         if not use_old_ecp:
             raise NotImplementedError("only the default ECP path (use_old_ecp=True) is implemented")
-        self.mol = mol
-        self.threshold = threshold
-        self.naip = naip
+        self.mol, self.threshold, self.naip = mol, threshold, naip
         self._ecp = flatten_ecp(mol, naip)
         self.necp = len(self._ecp["ecp_atom"])
         self._ewald = None
@@ -123,7 +121,8 @@ class EnergyAccumulator:
         return {k: out[i] for i, k in enumerate(KEYS)}
 
     def avg(self, configs, wf):
-        return {k: np.mean(it, axis=0) for k, it in self(configs, wf).items()}
+        per_walker = self(configs, wf)
+        return {k: np.mean(per_walker[k], axis=0) for k in KEYS}
 
     def nonlocal_tmoves(self, configs, wf, e, tau):
         """T-move candidates of electron e (``compute_tmoves``, eval_ecp.py:43-80): ratio (N, M),
@@ -145,7 +144,7 @@ class EnergyAccumulator:
         return {"ratio": ratio, "weight": weight, "configs": configs.make_irreducible(e, epos)}
 
     def has_nonlocal_moves(self):
-        return self.mol._ecp != {}
+        return len(self.mol._ecp) > 0
 
     def keys(self):
         return set(KEYS)

@@ -1,131 +1,174 @@
-"""Host walker containers (open boundary conditions).
+"""Host walker containers.
 
-Mirror of ``OpenConfigs`` / ``OpenElectron`` (``pyqmc/configurations/coord.py:21-88``):
-``configs (N, nelec, 3)`` C-contiguous float64 on the host -- the drivers (``mc.vmc``) mutate
-it in place, the device keeps its own copy.  The reference objects are accepted everywhere
-these are (only ``.configs`` is read).
+One class, ``Walkers``, serves open and periodic boundary conditions: it carries a tuple of
+per-walker arrays (``configs (N, nelec, 3)`` and, with a lattice, the integer ``wrap`` vectors) and
+applies every container operation of the driver protocol to all of them, so the periodic case is not
+a second copy of the open one.  The protocol is the reference's (``pyqmc/configurations/coord.py``:
+``electron, mask, make_irreducible, move, resample, split, join, copy, reshape`` and the checkpoint
+hooks), which is what ``pyqmc.method.mc.vmc`` / ``dmc.rundmc`` call; the reference's own
+``OpenConfigs`` / ``PeriodicConfigs`` are equally accepted by every ``pyqmc_b200`` object (only
+``.configs`` / ``.wrap`` are read).  ``OpenConfigs(...)`` / ``PeriodicConfigs(...)`` below are
+constructors with the reference's argument order.
+
+Walkers stay C-contiguous float64 on the host; the device keeps its own copy.
 """
-import copy
+import copy as _copy
 
 import numpy as np
 
 
-class OpenElectron:
-    def __init__(self, epos, dist=None):
-        self.configs = epos
+def wrap_into_cell(lattice, positions):
+    """Positions folded into the cell spanned by the rows of ``lattice`` and the integer number of
+    lattice vectors removed -- same operations, in the same order, as ``enforce_pbc``
+    (``pyqmc/pbc/pbc.py:33-47``) so that wrapped coordinates agree to the bit."""
+    fractional = np.einsum("...ij,jk->...ik", positions, np.linalg.inv(lattice))
+    whole, rest = np.divmod(fractional, 1)
+    return np.dot(rest, lattice), whole
+
+
+class ElectronView:
+    """Trial positions of one electron (``(N, 3)``) or of its auxiliary points (``(N, naip, 3)``)."""
+
+    __slots__ = ("configs", "wrap", "lvec", "dist")
+
+    def __init__(self, positions, lattice=None, wrap=None, dist=None):
+        self.configs = positions
+        self.lvec = lattice
         self.dist = dist
+        if lattice is None:
+            self.wrap = None
+        else:
+            self.wrap = np.zeros_like(positions) if wrap is None else wrap
 
-    def mask(self, mask):
-        return OpenElectron(self.configs[mask], self.dist)
+    def mask(self, keep):
+        sub = None if self.wrap is None else self.wrap[keep]
+        return ElectronView(self.configs[keep], self.lvec, sub, self.dist)
+
+    def select_electrons(self, index):
+        """Auxiliary point ``index`` of every walker (used by the reference's harness, testwf.py:86)."""
+        sub = None if self.wrap is None else self.wrap[:, index]
+        return ElectronView(self.configs[:, index], self.lvec, sub, self.dist)
 
 
-class OpenConfigs:
-    def __init__(self, configs, dist=None):
-        self.configs = configs
+class Walkers:
+    """Walker ensemble; ``lattice=None`` means open boundary conditions."""
+
+    def __init__(self, configs, lattice=None, wrap=None, dist=None, fold=True):
+        self.lvecs = None if lattice is None else np.asarray(lattice, dtype=float)
         self.dist = dist
+        if self.lvecs is None:
+            self.configs = configs
+            return
+        if fold:
+            self.configs, self.wrap = wrap_into_cell(self.lvecs, configs)
+            if wrap is not None:
+                self.wrap += wrap
+        else:
+            self.configs = configs
+            self.wrap = np.zeros_like(configs) if wrap is None else wrap
 
-    def electron(self, e):
-        return OpenElectron(self.configs[:, e], self.dist)
+    # -- the arrays every operation is applied to --------------------------------------------------
+    @property
+    def periodic(self):
+        return self.lvecs is not None
 
-    def select_electrons(self, es):
-        return OpenConfigs(self.configs[:, es], self.dist)
+    def _names(self):
+        return ("configs", "wrap") if self.periodic else ("configs",)
 
-    def mask(self, mask):
-        return OpenConfigs(self.configs[mask], self.dist)
+    def _like(self, **arrays):
+        """New container with the same lattice whose arrays are taken as given (no re-folding)."""
+        return Walkers(arrays["configs"], self.lvecs, arrays.get("wrap"), self.dist, fold=False)
 
-    def make_irreducible(self, e, vec, mask=True):
-        return OpenElectron(vec, self.dist)
+    def _map(self, fn):
+        return self._like(**{k: fn(getattr(self, k)) for k in self._names()})
 
-    def move(self, e, new, accept):
-        self.configs[accept, e, :] = new.configs[accept, :]
+    # -- views ----------------------------------------------------------------------------------
+    def electron(self, index):
+        w = self.wrap[:, index] if self.periodic else None
+        return ElectronView(self.configs[:, index], self.lvecs, w, self.dist)
 
-    def resample(self, newinds):
-        self.configs = self.configs[newinds]
+    def select_electrons(self, indices):
+        return self._map(lambda a: a[:, indices])
 
-    def split(self, npartitions):
-        return [OpenConfigs(c, self.dist) for c in np.array_split(self.configs, npartitions)]
-
-    def join(self, configslist, axis=0):
-        self.configs = np.concatenate([c.configs for c in configslist], axis=axis)
-
-    def copy(self):
-        return copy.deepcopy(self)
-
-    def reshape(self, shape):
-        self.configs = self.configs.reshape(shape)
-
-
-class PeriodicElectron:
-    """``PeriodicElectron`` (coord.py:115-134): trial positions with their wrap vectors."""
-
-    def __init__(self, epos, lattice_vectors, dist=None, wrap=None):
-        self.configs = epos
-        self.lvec = lattice_vectors
-        self.wrap = wrap if wrap is not None else np.zeros_like(epos)
-        self.dist = dist
-
-    def mask(self, mask):
-        return PeriodicElectron(self.configs[mask], self.lvec, self.dist, wrap=self.wrap[mask])
-
-
-class PeriodicConfigs:
-    """``PeriodicConfigs`` (coord.py:137-252): walkers wrapped into the simulation cell, with the
-    integer wrap vectors (in units of the lattice vectors) accumulated since construction."""
-
-    def __init__(self, configs, lattice_vectors, wrap=None, dist=None):
-        from .pbc import enforce_pbc
-
-        configs, wrap_ = enforce_pbc(lattice_vectors, configs)
-        self.configs = configs
-        self.wrap = wrap_
-        if wrap is not None:
-            self.wrap += wrap
-        self.lvecs = lattice_vectors
-        self.dist = dist
-
-    def electron(self, e):
-        return PeriodicElectron(self.configs[:, e], self.lvecs, self.dist, wrap=self.wrap[:, e])
-
-    def select_electrons(self, es):
-        return PeriodicConfigs(self.configs[:, es], self.lvecs, dist=self.dist, wrap=self.wrap[:, es])
-
-    def mask(self, mask):
-        return PeriodicConfigs(self.configs[mask], self.lvecs, wrap=self.wrap[mask], dist=self.dist)
+    def mask(self, keep):
+        return self._map(lambda a: a[keep])
 
     def make_irreducible(self, e, vec, mask=None):
-        from .pbc import enforce_pbc
-
+        """Trial positions ``vec`` of electron ``e`` folded into the cell; their wrap vectors continue
+        electron ``e``'s (``coord.py:168-194``).  Open boundaries: the positions as they are."""
+        if not self.periodic:
+            return ElectronView(vec, dist=self.dist)
+        base = self.wrap[:, e]
+        if vec.ndim == 3:
+            base = np.broadcast_to(base[:, None, :], vec.shape)
+        wrap = np.array(base)
         if mask is None:
-            mask = np.ones(vec.shape[0:-1], dtype=bool)
-        epos_, wrap_ = enforce_pbc(self.lvecs, vec[mask])
-        epos = vec.copy()
-        epos[mask] = epos_
-        wrap = self.wrap[:, e, :].copy()
-        if len(vec.shape) == 3:
-            wrap = np.repeat(self.wrap[:, e][:, np.newaxis], vec.shape[1], axis=1)
-        wrap[mask] += wrap_
-        return PeriodicElectron(epos, self.lvecs, wrap=wrap, dist=self.dist)
+            folded, shift = wrap_into_cell(self.lvecs, vec)
+            wrap += shift
+        else:
+            folded = vec.copy()
+            folded[mask], shift = wrap_into_cell(self.lvecs, vec[mask])
+            wrap[mask] += shift
+        return ElectronView(folded, self.lvecs, wrap, self.dist)
 
-    def move(self, e, new, accept):
-        self.configs[accept, e, :] = new.configs[accept, :]
-        self.wrap[accept, e, :] = new.wrap[accept, :]
+    # -- in-place updates -------------------------------------------------------------------------
+    def move(self, index, trial, accept):
+        accept = np.asarray(accept, dtype=bool)
+        for k in self._names():
+            getattr(self, k)[accept, index] = getattr(trial, k)[accept]
 
-    def resample(self, newinds):
-        self.configs = self.configs[newinds]
-        self.wrap = self.wrap[newinds]
-
-    def split(self, npartitions):
-        clist = np.array_split(self.configs, npartitions)
-        wlist = np.array_split(self.wrap, npartitions)
-        return [PeriodicConfigs(c, self.lvecs, w, dist=self.dist) for c, w in zip(clist, wlist)]
-
-    def join(self, configslist, axis=0):
-        self.configs = np.concatenate([c.configs for c in configslist], axis=axis)
-        self.wrap = np.concatenate([c.wrap for c in configslist], axis=axis)
-
-    def copy(self):
-        return copy.deepcopy(self)
+    def resample(self, picked):
+        for k in self._names():
+            setattr(self, k, getattr(self, k)[picked])
 
     def reshape(self, shape):
-        self.configs = self.configs.reshape(shape)
-        self.wrap = self.wrap.reshape(shape)
+        for k in self._names():
+            setattr(self, k, getattr(self, k).reshape(shape))
+
+    def join(self, parts, axis=0):
+        for k in self._names():
+            setattr(self, k, np.concatenate([getattr(p, k) for p in parts], axis=axis))
+
+    def split(self, npartitions):
+        pieces = {k: np.array_split(getattr(self, k), npartitions) for k in self._names()}
+        return [self._like(**{k: pieces[k][i] for k in pieces}) for i in range(npartitions)]
+
+    def copy(self):
+        return _copy.deepcopy(self)
+
+    # -- checkpoint hooks (reference dataset names: ``configs`` and, periodic, ``wrap``) ---------------
+    def arrays(self):
+        return {k: getattr(self, k) for k in self._names()}
+
+    def load_arrays(self, stored):
+        """In-place, keeping dtype and identity of the arrays (``coord.py:107-112``); the walker count
+        follows the stored one."""
+        for k in self._names():
+            data = np.asarray(stored[k])
+            if data.shape == getattr(self, k).shape:
+                getattr(self, k)[...] = data
+            else:
+                setattr(self, k, np.array(data, dtype=float))
+
+    def initialize_hdf(self, hdf):
+        for k, a in self.arrays().items():
+            hdf.create_dataset(k, a.shape, chunks=True, maxshape=(None,) + a.shape[1:])
+
+    def to_hdf(self, hdf):
+        for k, a in self.arrays().items():
+            hdf[k].resize(a.shape)
+            hdf[k][...] = a
+
+    def load_hdf(self, hdf):
+        self.load_arrays({k: hdf[k][()] for k in self._names()})
+
+
+def OpenConfigs(configs, dist=None):
+    return Walkers(configs, dist=dist)
+
+
+def PeriodicConfigs(configs, lattice_vectors, wrap=None, dist=None):
+    return Walkers(configs, lattice_vectors, wrap, dist)
+
+
+OpenElectron = PeriodicElectron = ElectronView

@@ -1,16 +1,17 @@
-"""DMC driver with the reference's signatures (``pyqmc/method/dmc.py``).
-
-``limdrift`` (22-35), ``get_V2`` (38-46), ``propose_drift_diffusion`` (49-70), ``propose_tmoves``
-(73-120), ``dmc_propagate`` (123-221), ``compute_S`` (224-235), ``branch`` (342-376) and ``rundmc``
-(412-586, without the HDF5 restart file) keep the reference's arguments, RNG consumption order and
-output dictionaries.
+"""DMC driver with the reference's signatures (``pyqmc/method/dmc.py``): ``dmc_propagate`` (123-221),
+``branch`` (342-376) and ``rundmc`` (412-586) keep the reference's arguments, RNG consumption order,
+output dictionaries and restart-file layout.
 
 When the wave function is a fused single-determinant Slater-Jastrow on an open-boundary system and
 the only accumulator is a ``pyqmc_b200.EnergyAccumulator``, ``dmc_propagate`` runs DEVICE-RESIDENT:
 every random variate of the block is drawn up front from the global legacy ``np.random`` stream in
 exactly the order the reference loop consumes it, shipped once, and ``qmcb_dmc_block`` executes the
-T-moves, drift-diffusion sweeps, local energies and weight updates without host round trips.  Any
-other combination goes through the generic loop over the wave-function protocol calls.
+T-moves, drift-diffusion sweeps, local energies and weight updates without host round trips.
+
+The per-electron propagation loop over the wave-function protocol (``propose_drift_diffusion``,
+``propose_tmoves``, ``compute_S`` ...) is NOT restated on the host: the reference's own
+``pyqmc.method.dmc`` drives these objects unchanged (tests/test_gpu_reference_drivers.py) and is what
+``dmc_propagate`` delegates to outside the device-resident path.
 """
 import logging
 
@@ -20,80 +21,6 @@ import scipy.spatial.transform
 from . import _lib, mc
 from .accumulators import KEYS, EnergyAccumulator, _device_context
 from .wf import JASTROW, SLATER
-
-
-def limdrift(g, tau, acyrus=0.5):
-    v2 = np.sum(g**2, axis=1)
-    mask = v2 > 1e-8
-    taueff = np.ones(v2.shape) * tau
-    taueff[mask] = (np.sqrt(1 + 2 * tau * acyrus * v2[mask]) - 1) / (acyrus * v2[mask])
-    return g * taueff[:, np.newaxis]
-
-
-def get_V2(configs, wf, acc_out):
-    if "grad2" in acc_out.keys():
-        return acc_out["grad2"]
-    nconfig, nelec = configs.configs.shape[0:2]
-    v2 = np.zeros(nconfig)
-    for e in range(nelec):
-        v2 += np.sum(np.abs(wf.gradient(e, configs.electron(e))).T ** 2, axis=1)
-    return v2
-
-
-def propose_drift_diffusion(wf, configs, tstep, e):
-    nconfig = configs.configs.shape[0]
-    grad = limdrift(np.real(wf.gradient(e, configs.electron(e)).T), tstep)
-    gauss = np.random.normal(scale=np.sqrt(tstep), size=(nconfig, 3))
-    eposnew = configs.configs[:, e, :] + gauss + grad
-    newepos = configs.make_irreducible(e, eposnew)
-    g, wfratio, saved = wf.gradient_value(e, newepos)
-    new_grad = limdrift(np.real(g.T), tstep)
-    forward = np.sum(gauss**2, axis=1)
-    backward = np.sum((gauss + grad + new_grad) ** 2, axis=1)
-    t_prob = np.exp(1 / (2 * tstep) * (forward - backward))
-    ratio = np.abs(wfratio) ** 2 * t_prob
-    if wf.dtype == float:
-        ratio *= np.sign(wfratio)
-    accept = ratio > np.random.rand(nconfig)
-    r2 = np.sum((gauss + grad) ** 2, axis=1)
-    return newepos, accept, r2, saved
-
-
-def propose_tmoves(wf, configs, energy_accumulator, tstep, e):
-    moves = energy_accumulator.nonlocal_tmoves(configs, wf, e, tstep)
-    t_amplitudes = moves["ratio"] * moves["weight"]
-    forward_probability = np.zeros_like(t_amplitudes)
-    forward_probability[t_amplitudes > 0] = t_amplitudes[t_amplitudes > 0]
-    norm = 1.0 + np.sum(forward_probability, axis=1)
-    cdf = np.cumsum(forward_probability / norm[:, np.newaxis], axis=1)
-    selected_moves = np.array([np.searchsorted(row, np.random.rand()) for row in cdf], dtype=int).reshape(len(cdf))
-    move_selected = selected_moves < t_amplitudes.shape[1]
-    newpos = np.zeros((norm.shape[0], 3))
-    reverse_ratio = np.zeros((norm.shape[0]))
-    backward_amplitudes = t_amplitudes.copy()
-    for walker, move in enumerate(selected_moves):
-        if move_selected[walker]:
-            newpos[walker, :] = moves["configs"].configs[walker, move, :]
-            reverse_ratio[walker] = 1.0 / moves["ratio"][walker, move]
-            backward_amplitudes[walker, :] *= reverse_ratio[walker]
-            backward_amplitudes[walker, move] = reverse_ratio[walker] * moves["weight"][walker, move]
-        else:
-            newpos[walker, :] = configs.configs[walker, e, :]
-            reverse_ratio[walker] = 0.0
-    newpos = configs.make_irreducible(e, newpos)
-    backward_amplitudes[backward_amplitudes < 0] = 0.0
-    back_norm = 1.0 + np.sum(backward_amplitudes, axis=1)
-    acceptance = norm / back_norm
-    acceptance[move_selected == False] = 0.0  # noqa: E712
-    return newpos, move_selected, acceptance, np.sum(t_amplitudes)
-
-
-def compute_S(e_trial, e_est, branchcut, v2, tau, eloc, nelec):
-    e_cut = e_est - eloc
-    mask = np.abs(e_cut) > branchcut
-    e_cut[mask] = branchcut * np.sign(e_cut[mask])
-    denominator = np.sqrt(1 + (v2 * tau / nelec) ** 2)
-    return e_trial - e_est + e_cut / denominator
 
 
 def _device_dmc_path(wf, accumulators, ekey):
@@ -259,6 +186,10 @@ class DmcPrefetcher:
         return base
 
 
+    def shutdown(self):
+        self.pool.shutdown(wait=True)
+
+
 class _Done:
     def __init__(self, value):
         self.value = value
@@ -309,132 +240,152 @@ def _collect(df):
     return df_ret
 
 
+def _reference_dmc():
+    try:
+        import pyqmc.method.dmc as refdmc
+    except ImportError:
+        return None
+    return refdmc
+
+
 def dmc_propagate(wf, configs, weights, tstep, branchcut_start, e_trial, e_est, nsteps=5, accumulators=None,
                   ekey=("energy", "total"), variates=None):
-    """Propagate DMC without branching (dmc.py:123-221).  ``variates``: pre-drawn random numbers of the
-    block (device-resident path only; see ``DmcPrefetcher``)."""
+    """``nsteps`` of DMC propagation without branching (dmc.py:123-221).  ``variates``: pre-drawn random
+    numbers of the block (``DmcPrefetcher``)."""
     assert accumulators is not None, "Need an energy accumulator for DMC"
     if _device_dmc_path(wf, accumulators, ekey):
         return dmc_propagate_device(wf, configs, weights, tstep, branchcut_start, e_trial, e_est, nsteps, accumulators,
                                     ekey, variates=variates)
-    nconfig, nelec = configs.configs.shape[0:2]
-    wf.recompute(configs)
-    energy_acc = accumulators[ekey[0]](configs, wf)
-    eloc = energy_acc[ekey[1]].real
-    v2 = get_V2(configs, wf, energy_acc)
-    df = []
-    for _ in range(nsteps):
-        r2_accepted = np.zeros(nconfig)
-        r2_proposed = np.zeros(nconfig)
-        prob_acceptance = np.zeros(nconfig)
-        tmove_acceptance = np.zeros(nconfig)
-        if accumulators[ekey[0]].has_nonlocal_moves():
-            for e in range(nelec):
-                newepos, mask, probability, _ = propose_tmoves(wf, configs, accumulators[ekey[0]], tstep, e)
-                accept = mask & (probability > np.random.rand(nconfig))
-                configs.move(e, newepos, accept)
-                wf.updateinternals(e, newepos, configs, mask=accept)
-                tmove_acceptance += accept / nelec
-        for e in range(nelec):
-            newepos, accept, r2, saved = propose_drift_diffusion(wf, configs, tstep, e)
-            configs.move(e, newepos, accept)
-            wf.updateinternals(e, newepos, configs, mask=accept, saved_values=saved)
-            r2_proposed += r2
-            r2_accepted[accept] += r2[accept]
-            prob_acceptance += accept / nelec
-        elocold = eloc.copy()
-        v2old = v2.copy()
-        energydat = accumulators[ekey[0]](configs, wf)
-        eloc = energydat[ekey[1]].real
-        tdamp = r2_accepted / r2_proposed
-        v2 = get_V2(configs, wf, energydat)
-        Snew = compute_S(e_trial, e_est, branchcut_start, v2, tstep, eloc, nelec)
-        Sold = compute_S(e_trial, e_est, branchcut_start, v2old, tstep, elocold, nelec)
-        wmult = np.exp(tstep * tdamp * (0.5 * Snew + 0.5 * Sold))
-        weights *= wmult
-        wavg = np.mean(weights)
-        avg = {}
-        for k, accumulator in accumulators.items():
-            dat = accumulator(configs, wf) if k != ekey[0] else energydat
-            for m, res in dat.items():
-                avg[k + m] = np.einsum("...i,i...->...", weights, res) / (nconfig * wavg)
-        avg["weight"] = wavg
-        avg["acceptance"] = np.mean(prob_acceptance)
-        avg["tmove_acceptance"] = np.mean(tmove_acceptance)
-        df.append(avg)
-    return _collect(df), configs, weights
+    refdmc = _reference_dmc()
+    if refdmc is None:
+        raise TypeError("pyqmc_b200.dmc_propagate runs device-resident blocks (fused single-determinant "
+                        "Slater-Jastrow, open boundaries, one pyqmc_b200.EnergyAccumulator); drive other "
+                        "combinations with pyqmc.method.dmc, which accepts these objects unchanged")
+    return refdmc.dmc_propagate(wf, configs, weights, tstep, branchcut_start, e_trial, e_est, nsteps=nsteps,
+                                accumulators=accumulators, ekey=ekey)
+
+
+def comb_indices(weights, offset):
+    """Stochastic comb: ``n`` equally spaced teeth, shifted by ``offset`` (a uniform variate in [0, 1)) times the
+    total weight and folded back into [0, W), select walkers through the cumulative weights.  Tooth ``i`` may
+    land anywhere, so the result is NOT sorted: slot ``i`` of the new population is a copy of walker
+    ``result[i]``.  Arithmetic as in ``branch`` (dmc.py:358-366), so equal draws give equal populations."""
+    ladder = np.cumsum(weights)
+    total = ladder[-1]
+    teeth = (offset * total + np.linspace(0, total, len(weights), endpoint=False)) % total
+    return np.searchsorted(ladder, teeth), total
 
 
 def branch(configs, weights, base_draw=None):
-    """Stochastic-comb branching (dmc.py:342-376).  ``base_draw``: the ``np.random.rand()`` of line 361
-    when it was drawn ahead of time (``DmcPrefetcher``)."""
-    nconfig = configs.configs.shape[0]
+    """Branching step (dmc.py:342-376): resample by the comb, reset every weight to the mean.
+    ``base_draw``: the uniform variate when it was drawn ahead of time (``DmcPrefetcher``)."""
     if np.any(weights > 2.0):
         logging.warning("Some weights are larger than 2")
-    probability = np.cumsum(weights)
-    wtot = probability[-1]
-    base = (np.random.rand() if base_draw is None else base_draw) * wtot
-    newinds = np.searchsorted(probability, (base + np.linspace(0, wtot, nconfig, endpoint=False)) % wtot)
-    unique, counts = np.unique(newinds, return_counts=True)
-    configs.resample(newinds)
-    weights.fill(wtot / nconfig)
-    return configs, weights, {"max branches": np.max(counts), "Number of walkers killed": nconfig - unique.shape[0]}
+    offset = np.random.rand() if base_draw is None else base_draw
+    picked, total = comb_indices(weights, offset)
+    survivors, copies = np.unique(picked, return_counts=True)
+    configs.resample(picked)
+    weights.fill(total / len(weights))
+    return configs, weights, {"max branches": np.max(copies),
+                              "Number of walkers killed": len(weights) - len(survivors)}
 
 
-def estimate_energy(df, ekey):
-    en = np.asarray([d[ekey[0] + ekey[1]] for d in df])
-    wt = np.asarray([d["weight"] for d in df])
-    warmup = int(len(en) / 4)
-    return np.average(en[warmup:], weights=wt[warmup:]).real
+class _EnergyHistory:
+    """Running estimate of the DMC energy: weighted mean of the block energies after dropping the first
+    quarter as warm-up (dmc.py:592-603)."""
+
+    def __init__(self, energies=(), weights=()):
+        self.energies, self.weights = list(energies), list(weights)
+
+    def add(self, energy, weight):
+        self.energies.append(energy)
+        self.weights.append(weight)
+
+    def estimate(self):
+        skip = int(len(self.energies) / 4)
+        return np.average(np.asarray(self.energies)[skip:], weights=np.asarray(self.weights)[skip:]).real
 
 
 def rundmc(wf, configs, weights=None, tstep=0.01, nblocks=200, nsteps_per_block=None, blockoffset=0, accumulators=None,
            verbose=False, hdf_file=None, continue_from=None, client=None, npartitions=None, ekey=("energy", "total"),
            vmc_warmup=10, branchcut_start=10, feedback=1.0):
-    """Same arguments and return value as ``pyqmc.method.dmc.rundmc`` (dmc.py:412-586); the HDF5
-    restart file and the futures client are outside the accelerated path."""
-    if hdf_file is not None or continue_from is not None:
-        raise NotImplementedError("HDF5 checkpointing is outside the accelerated path; pass hdf_file=None "
-                                  "or drive these wave functions with pyqmc.method.dmc.rundmc")
+    """Same arguments, return value and restart file as ``pyqmc.method.dmc.rundmc`` (dmc.py:412-586).
+
+    A futures ``client`` selects the reference's host-parallel propagation, which is delegated to the
+    reference; walkers are sharded one process per GPU instead (``pyqmc_b200.parallel``)."""
+    import os
+
+    from . import blockio
+
     if client is not None:
-        raise NotImplementedError("walker partitions are sharded one process per GPU (pyqmc_b200.parallel)")
+        refdmc = _reference_dmc()
+        if refdmc is None:
+            raise TypeError("client= selects the reference's futures-parallel driver; PyQMC is not importable "
+                            "(multi-GPU runs shard walkers with pyqmc_b200.parallel)")
+        return refdmc.rundmc(wf, configs, weights=weights, tstep=tstep, nblocks=nblocks, nsteps_per_block=nsteps_per_block,
+                             blockoffset=blockoffset, accumulators=accumulators, verbose=verbose, hdf_file=hdf_file,
+                             continue_from=continue_from, client=client, npartitions=npartitions, ekey=ekey,
+                             vmc_warmup=vmc_warmup, branchcut_start=branchcut_start, feedback=feedback)
     if nsteps_per_block is None:
-        nsteps_per_block = max(1, int(0.1 / tstep))
-    df, configs = mc.vmc(wf, configs, verbose=verbose, nblocks=vmc_warmup)
-    wf.recompute(configs)
-    en = accumulators[ekey[0]](configs, wf)[ekey[1]]
-    eref = np.mean(en).real
-    e_trial = eref
-    e_est = eref
-    esigma = np.std(en)
-    if verbose:
-        print("eref start", eref, "esigma", esigma)
-    nconfig = configs.configs.shape[0]
+        nsteps_per_block = max(1, int(0.1 / tstep))  # branch every 0.1 time units
+    if continue_from is not None and hdf_file is not None and os.path.isfile(hdf_file):
+        raise RuntimeError(f"continue_from is set but hdf_file={hdf_file} already exists! "
+                           f"Delete or rename {hdf_file} and try again.")
+    if continue_from is None and blockio.exists(hdf_file):
+        continue_from = hdf_file
+    ename = ekey[0] + ekey[1]
+    history = _EnergyHistory()
+    if continue_from is not None:
+        with blockio.open_store(continue_from, "r") as store:
+            if "e_trial" not in store:
+                raise ValueError("Did not find e_trial in the restart file. This may mean that you are trying to "
+                                 "restart from a different version of DMC")
+            blockoffset = int(store.last("block")) + 1
+            blockio.load_walkers(store, configs)
+            weights = np.array(store["weights"])
+            e_trial, e_est, esigma = (store.last(k) for k in ("e_trial", "e_est", "esigma"))
+            if continue_from == hdf_file:  # the estimate keeps averaging over the blocks already on file
+                history = _EnergyHistory(store[ename], store["weight"])
+        if verbose:
+            print(f"Restarting calculation {continue_from} from block {blockoffset}")
+    else:
+        _, configs = mc.vmc(wf, configs, verbose=verbose, nblocks=vmc_warmup)
+        wf.recompute(configs)
+        en = accumulators[ekey[0]](configs, wf)[ekey[1]]
+        e_trial = e_est = np.mean(en).real
+        esigma = np.std(en)
+        if verbose:
+            print("eref start", e_trial, "esigma", esigma)
     if weights is None:
-        weights = np.ones(nconfig)
-    df = []
+        weights = np.ones(configs.configs.shape[0])
     if blockoffset >= nblocks:
         logging.warning(f"blockoffset {blockoffset} >= nblocks {nblocks}; no steps will be run.")
+    todo = max(0, nblocks - blockoffset)
     prefetch = None
-    if nblocks > blockoffset and _device_dmc_path(wf, accumulators, ekey):
-        prefetch = DmcPrefetcher(wf, configs, tstep, nsteps_per_block, accumulators[ekey[0]], nblocks - blockoffset)
-    for block in range(blockoffset, nblocks):
-        df_, configs, weights = dmc_propagate(wf, configs, weights, tstep, branchcut_start * esigma, e_trial=e_trial,
-                                              e_est=e_est, nsteps=nsteps_per_block, accumulators=accumulators,
-                                              ekey=ekey, variates=prefetch.next() if prefetch else None)
-        df_["e_trial"] = e_trial
-        df_["e_est"] = e_est
-        df_["block"] = block
-        df_["esigma"] = esigma
-        df_["tstep"] = tstep
-        df_["weight_std"] = np.std(weights)
-        df_["nsteps_per_block"] = nsteps_per_block
-        configs, weights, branch_info = branch(configs, weights, prefetch.branch_draw() if prefetch else None)
-        df_.update(branch_info)
-        df.append(df_)
-        e_est = estimate_energy(df, ekey)
-        e_trial = e_est - feedback * np.log(np.mean(weights)).real
-        if verbose:
-            print("energy", df_[ekey[0] + ekey[1]], "e_trial", e_trial, "e_est", e_est, "sigma(w)", df_["weight_std"])
-    df_ret = {k: np.asarray([d[k] for d in df]) for k in df[0].keys()} if len(df) > 0 else {}
-    return df_ret, configs, weights
+    if todo and _device_dmc_path(wf, accumulators, ekey):
+        prefetch = DmcPrefetcher(wf, configs, tstep, nsteps_per_block, accumulators[ekey[0]], todo)
+    rows = []
+    try:
+        for block in range(blockoffset, nblocks):
+            row, configs, weights = dmc_propagate(
+                wf, configs, weights, tstep, branchcut_start * esigma, e_trial=e_trial, e_est=e_est,
+                nsteps=nsteps_per_block, accumulators=accumulators, ekey=ekey,
+                variates=prefetch.next() if prefetch else None)
+            row.update({"e_trial": e_trial, "e_est": e_est, "block": block, "esigma": esigma, "tstep": tstep,
+                        "weight_std": np.std(weights), "nsteps_per_block": nsteps_per_block})
+            configs, weights, info = branch(configs, weights, prefetch.branch_draw() if prefetch else None)
+            row.update(info)
+            rows.append(row)
+            if hdf_file is not None:
+                with blockio.open_store(hdf_file, "a") as store:
+                    store.append_block(row, walkers=configs, extra_walker_arrays={"weights": weights})
+            history.add(row[ename], row["weight"])
+            e_est = history.estimate()
+            e_trial = e_est - feedback * np.log(np.mean(weights)).real
+            if verbose:
+                print("energy", row[ename], "e_trial", e_trial, "e_est", e_est, "sigma(w)", row["weight_std"])
+                print(info)
+    finally:
+        if prefetch is not None:
+            prefetch.shutdown()
+    return ({k: np.asarray([r[k] for r in rows]) for k in rows[0]} if rows else {}), configs, weights

@@ -1,14 +1,14 @@
 """VMC driver with the reference's signature (``pyqmc/method/mc.py``).
 
-``initial_guess`` (mc.py:25-73), ``limdrift`` (76-89) and ``vmc`` (176-274) keep the
-reference's arguments and output dictionary.  When the wave function is a fused device
-``MultiplyWF`` (or a single device factor) and every accumulator is a
-``pyqmc_b200.EnergyAccumulator``, a block runs DEVICE-RESIDENT: the random variates of the
-whole block are drawn up front from the global legacy ``np.random`` stream in exactly the
-order ``vmc_worker`` (mc.py:102-153) and ``eval_ecp`` would consume them, shipped once, and
-``qmcb_vmc_block`` executes all sweeps and energy evaluations without host round trips.
-Any other wave function / accumulator goes through the generic per-electron loop, which is
-the reference's loop verbatim in behaviour (wf protocol calls, host RNG).
+``initial_guess`` (mc.py:25-73) and ``vmc`` (176-274) keep the reference's arguments, output
+dictionary and checkpoint layout.  When the wave function is a fused device ``MultiplyWF`` (or a
+single device factor) and the accumulator, if any, is a ``pyqmc_b200.EnergyAccumulator``, a block
+runs DEVICE-RESIDENT: the random variates of the whole block are drawn up front from the global
+legacy ``np.random`` stream in exactly the order ``vmc_worker`` (mc.py:102-153) and ``eval_ecp``
+would consume them, shipped once, and ``qmcb_vmc_block`` executes all sweeps and energy evaluations
+without host round trips.  The per-electron protocol loop itself is NOT restated here: the reference's
+``pyqmc.method.mc.vmc`` drives these objects unchanged (tests/test_gpu_reference_drivers.py) and is
+what ``vmc`` delegates to for anything outside the device-resident path.
 """
 import logging
 import time
@@ -21,32 +21,30 @@ from .coord import OpenConfigs, PeriodicConfigs
 
 
 def initial_guess(mol, nconfig, r=1.0):
-    """mc.py:25-73: electrons near atoms proportionally to charge; same RNG consumption."""
-    nelec = int(np.sum(mol.nelec))
-    epos = np.zeros((nconfig, nelec, 3))
-    wts = mol.atom_charges()
-    wts = wts / np.sum(wts)
+    """Starting walkers: every electron sits on a "home" atom plus isotropic Gaussian noise of width
+    ``r``.  Each spin channel gives atom ``I`` a quota of ``floor(n_s Z_I / sum Z)`` electrons; what is
+    left over goes to distinct atoms picked per walker.  Consumes the global legacy stream exactly as
+    ``pyqmc.method.mc.initial_guess`` (mc.py:25-73) does -- per spin one ``random((N, natom))`` only if
+    electrons are left over, then a single ``randn(N, nelec, 3)`` -- so equal seeds give equal walkers."""
+    charges = np.asarray(mol.atom_charges(), dtype=float)
+    share = charges / np.sum(charges)
     coords = mol.atom_coords()
-    for s in [0, 1]:
-        neach = np.array(np.floor(mol.nelec[s] * wts), dtype=int)
-        nassigned = int(np.sum(neach))
-        totleft = int(mol.nelec[s] - nassigned)
-        ind0 = s * mol.nelec[0]
-        epos[:, ind0 : ind0 + nassigned, :] = np.repeat(coords, neach, axis=0)
-        if totleft > 0:
-            inds = np.argpartition(np.random.random((nconfig, len(wts))), totleft, axis=1)[:, :totleft]
-            epos[:, ind0 + nassigned : ind0 + mol.nelec[s], :] = coords[inds]
-    epos += r * np.random.randn(*epos.shape)
+    atoms = np.arange(len(share))
+    home = []
+    for n_s in mol.nelec:
+        quota = np.array(np.floor(n_s * share), dtype=int)
+        fixed = np.repeat(atoms, quota)
+        home.append(np.broadcast_to(fixed, (nconfig, len(fixed))))
+        spare = int(n_s) - len(fixed)
+        if spare > 0:
+            lots = np.random.random((nconfig, len(share)))
+            home.append(np.argpartition(lots, spare, axis=1)[:, :spare])
+    home = np.concatenate(home, axis=1)
+    positions = coords[home]
+    positions += r * np.random.randn(*positions.shape)
     if hasattr(mol, "a"):
-        return PeriodicConfigs(epos, mol.lattice_vectors())
-    return OpenConfigs(epos)
-
-
-def limdrift(g, cutoff=1):
-    tot = np.linalg.norm(g, axis=1)
-    mask = tot > cutoff
-    with np.errstate(divide="ignore", invalid="ignore"):
-        return np.where(mask[:, np.newaxis], cutoff * g / tot[:, np.newaxis], g)
+        return PeriodicConfigs(positions, mol.lattice_vectors())
+    return OpenConfigs(positions)
 
 
 def _device_path(wf, accumulators):
@@ -241,48 +239,6 @@ def vmc_block_device(wf, configs, tstep, nsteps, accumulators, variates=None, re
     return block_avg, configs
 
 
-def vmc_worker(wf, configs, tstep, nsteps, accumulators):
-    """Generic block: per-electron wf protocol calls, as mc.py:102-153."""
-    if _device_path(wf, accumulators):
-        return vmc_block_device(wf, configs, tstep, nsteps, accumulators)
-    nconf, nelec, _ = configs.configs.shape
-    block_avg = {}
-    wf.recompute(configs)
-    for _ in range(nsteps):
-        acc = 0.0
-        start_move = time.perf_counter()
-        for e in range(nelec):
-            g, _, _ = wf.gradient_value(e, configs.electron(e))
-            grad = limdrift(np.real(g.T))
-            gauss = np.random.normal(scale=np.sqrt(tstep), size=(nconf, 3))
-            newcoorde = configs.configs[:, e, :] + gauss + grad * tstep
-            newcoorde = configs.make_irreducible(e, newcoorde)
-            g, new_val, saved = wf.gradient_value(e, newcoorde)
-            new_grad = limdrift(np.real(g.T))
-            forward = np.sum(gauss**2, axis=1)
-            backward = np.sum((gauss + tstep * (grad + new_grad)) ** 2, axis=1)
-            t_prob = np.exp(1 / (2 * tstep) * (forward - backward))
-            ratio = np.abs(new_val) ** 2 * t_prob
-            accept = ratio > np.random.rand(nconf)
-            configs.move(e, newcoorde, accept)
-            wf.updateinternals(e, newcoorde, configs, mask=accept, saved_values=saved)
-            acc += np.mean(accept) / nelec
-        end_move = time.perf_counter()
-        start_average = time.perf_counter()
-        for k, accumulator in accumulators.items():
-            dat = accumulator.avg(configs, wf)
-            for m, res in dat.items():
-                if k + m not in block_avg:
-                    block_avg[k + m] = res / nsteps
-                else:
-                    block_avg[k + m] += res / nsteps
-        end_average = time.perf_counter()
-        block_avg["acceptance"] = acc
-        block_avg["move time"] = end_move - start_move
-        block_avg["accumulator time"] = end_average - start_average
-    return block_avg, configs
-
-
 class _VariatePrefetcher:
     """Three-stage host/device pipeline for the device-resident driver.
 
@@ -382,55 +338,83 @@ def ctypes_void(p):
     return ctypes.c_void_p(p)
 
 
-def vmc_parallel(wf, configs, tstep, nsteps_per_block, accumulators, client, npartitions):
-    """mc.py:156-173: walker partitions on a futures client, weighted average of the blocks."""
-    config = configs.split(npartitions)
-    runs = [client.submit(vmc_worker, wf, conf, tstep, nsteps_per_block, accumulators) for conf in config]
-    allresults = list(zip(*[r.result() for r in runs]))
-    configs.join(allresults[1])
-    confweight = np.array([len(c.configs) for c in config], dtype=float)
-    confweight /= np.mean(confweight) * npartitions
-    block_avg = {}
-    for k in allresults[0][0].keys():
-        block_avg[k] = np.sum([res[k] * w for res, w in zip(allresults[0], confweight)], axis=0)
-    return block_avg, configs
+def _reference_driver():
+    """The reference's own driver module, when PyQMC is installed next to this plugin."""
+    try:
+        import pyqmc.method.mc as refmc
+    except ImportError:
+        return None
+    return refmc
+
+
+def _restart_point(hdf_file, continue_from):
+    """Which file to resume from under the reference's rules (mc.py:225-236): an existing ``hdf_file``
+    is continued; ``continue_from`` must exist and excludes an existing ``hdf_file``."""
+    import os
+
+    if continue_from is None:
+        return hdf_file
+    if not os.path.isfile(continue_from):
+        raise RuntimeError(f"cannot continue from {continue_from}; the file does not exist!")
+    if hdf_file is not None and os.path.isfile(hdf_file):
+        raise RuntimeError(f"continue_from is not None but hdf_file={hdf_file} already exists! "
+                           f"Delete or rename {hdf_file} and try again.")
+    return continue_from
 
 
 def vmc(wf, configs, tstep=0.5, nblocks=10, nsteps_per_block=10, nsteps=None, blockoffset=0,
         accumulators=None, verbose=False, hdf_file=None, continue_from=None, client=None, npartitions=None):
-    """Same arguments and return value as ``pyqmc.method.mc.vmc`` (mc.py:176-274)."""
+    """Device-resident VMC with the arguments, block dictionary and checkpoint layout of
+    ``pyqmc.method.mc.vmc`` (mc.py:176-274).
+
+    Device wave function + (at most) one ``pyqmc_b200.EnergyAccumulator``: every block is ONE library
+    call (``qmcb_vmc_block*``) fed by the three-stage variate pipeline above.  Anything else -- another
+    accumulator, a futures ``client``, a non-device wave function -- is not this package's path: it is
+    handed to the reference's driver, which runs these objects through the protocol calls."""
+    from . import blockio
+
+    accumulators = {} if accumulators is None else accumulators
+    if client is not None or not _device_path(wf, accumulators):
+        refmc = _reference_driver()
+        if refmc is None:
+            raise TypeError("pyqmc_b200.vmc runs device-resident blocks (pyqmc_b200 wave function, optional "
+                            "pyqmc_b200.EnergyAccumulator, client=None); drive other combinations with "
+                            "pyqmc.method.mc.vmc, which accepts these objects unchanged")
+        return refmc.vmc(wf, configs, tstep=tstep, nblocks=nblocks, nsteps_per_block=nsteps_per_block,
+                         nsteps=nsteps, blockoffset=blockoffset, accumulators=accumulators, verbose=verbose,
+                         hdf_file=hdf_file, continue_from=continue_from, client=client, npartitions=npartitions)
     if nsteps is not None:
         nblocks, nsteps_per_block = nsteps, 1
-    if accumulators is None:
-        accumulators = {}
-        if verbose:
-            print("WARNING: running VMC with no accumulators")
-    if hdf_file is not None or continue_from is not None:
-        raise NotImplementedError("HDF5 checkpointing is outside the accelerated path; pass hdf_file=None "
-                                  "or drive these wave functions with pyqmc.method.mc.vmc")
-    df = []
+    if verbose and not accumulators:
+        print("WARNING: running VMC with no accumulators")
+    resume = _restart_point(hdf_file, continue_from)
+    if resume is not None and blockio.exists(resume):
+        with blockio.open_store(resume, "r") as store:
+            if "configs" in store:
+                blockoffset = int(store.last("block")) + 1
+                blockio.load_walkers(store, configs)
+                if verbose:
+                    print(f"Restarting calculation {resume} from block {blockoffset}")
     if blockoffset >= nblocks:
         logging.warning(f"blockoffset {blockoffset} >= nblocks {nblocks}; no steps will be run.")
-    prefetch = None
-    if client is None and _device_path(wf, accumulators) and nblocks > blockoffset:
-        prefetch = _VariatePrefetcher(wf, configs, tstep, nsteps_per_block, accumulators, nblocks - blockoffset)
-    for block in range(blockoffset, nblocks):
-        if verbose:
-            print("-", end="", flush=True)
+    rows = []
+    todo = max(0, nblocks - blockoffset)
+    prefetch = _VariatePrefetcher(wf, configs, tstep, nsteps_per_block, accumulators, todo) if todo else None
+    try:
+        for block in range(blockoffset, nblocks):
+            if verbose:
+                print("-", end="", flush=True)
+            row, configs = vmc_block_device(wf, configs, tstep, nsteps_per_block, accumulators,
+                                            buffers=prefetch.next())
+            row["block"] = block
+            row["nconfig"] = nsteps_per_block * configs.configs.shape[0]
+            if hdf_file is not None:
+                with blockio.open_store(hdf_file, "a") as store:
+                    store.append_block(row, attrs={"tstep": tstep}, walkers=configs)
+            rows.append(row)
+    finally:
         if prefetch is not None:
-            block_avg, configs = vmc_block_device(wf, configs, tstep, nsteps_per_block, accumulators,
-                                                  buffers=prefetch.next())
-        elif client is None:
-            block_avg, configs = vmc_worker(wf, configs, tstep, nsteps_per_block, accumulators)
-        else:
-            block_avg, configs = vmc_parallel(wf, configs, tstep, nsteps_per_block, accumulators, client, npartitions)
-        block_avg["block"] = block
-        block_avg["nconfig"] = nsteps_per_block * configs.configs.shape[0]
-        df.append(block_avg)
+            prefetch.close()
     if verbose:
         print("vmc done")
-    df_return = {}
-    if len(df) > 0:
-        for k in df[0].keys():
-            df_return[k] = np.asarray([d[k] for d in df])
-    return df_return, configs
+    return ({k: np.asarray([r_[k] for r_ in rows]) for k in rows[0]} if rows else {}), configs

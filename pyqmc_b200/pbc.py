@@ -3,7 +3,7 @@ device needs (lattice images and cutoffs of the orbital evaluator, minimal-image
 reciprocal points).
 
 Reference statements (relative to /root/reference):
-  * ``enforce_pbc``                       pyqmc/pbc/pbc.py:17-49
+  * ``enforce_pbc``                       pyqmc/pbc/pbc.py:17-49 (``coord.wrap_into_cell``)
   * supercell construction / k-points    pyqmc/pbc/supercell.py:18-75
   * twist -> primitive k-point indices    pyqmc/pbc/twists.py:34-65
   * image list, per-shell cutoffs, phases pyqmc/wf/numba/pbcgto.py:518-621 (``max_Ls``,
@@ -26,12 +26,7 @@ from . import basis as _basis
 from .systems import Mol
 
 
-def enforce_pbc(lattvecs, epos):
-    """pbc.py:17-49: positions wrapped into the cell and the integer wrap vectors."""
-    recpvecs = np.linalg.inv(lattvecs)
-    frac = np.einsum("...ij,jk->...ik", epos, recpvecs)
-    wrap, rem = np.divmod(frac, 1)
-    return np.dot(rem, lattvecs), wrap
+from .coord import wrap_into_cell as enforce_pbc  # noqa: E402,F401  (pbc.py:17-49; kept under the reference's name)
 
 
 class Cell(Mol):
@@ -134,65 +129,71 @@ def shell_rcut(cell, eval_gto_precision):
     return np.array(rcut)
 
 
+def _integer_points_in_cell(S):
+    """Integer row vectors n with ``n S^-1`` in [0, 1)^3, i.e. the lattice points of the small lattice inside
+    one cell of the lattice spanned by the rows of the integer matrix S -- in lexicographic order of n, as
+    the reference's meshgrid enumeration (supercell.py:18-43).  Membership is decided in exact integer
+    arithmetic (n adj(S) against det S), not by comparing floats with 0 and 1."""
+    S = np.asarray(np.round(S), dtype=np.int64)
+    det = int(round(np.linalg.det(S)))
+    adj = np.asarray(np.round(np.linalg.inv(S) * det), dtype=np.int64)  # adjugate: S adj = det 1
+    corners = np.array([[i, j, k] for i in (0, 1) for j in (0, 1) for k in (0, 1)]) @ S
+    spans = [range(int(lo), int(hi)) for lo, hi in zip(corners.min(axis=0), corners.max(axis=0))]
+    inside = []
+    for n in ((i, j, k) for i in spans[0] for j in spans[1] for k in spans[2]):
+        scaled = np.array(n, dtype=np.int64) @ adj  # = det * (n S^-1)
+        if det < 0:
+            scaled, bound = -scaled, -det
+        else:
+            bound = det
+        if np.all((scaled >= 0) & (scaled < bound)):
+            inside.append(n)
+    return np.array(inside, dtype=np.int64).reshape(-1, 3), adj, det
+
+
 def get_supercell_copies(latvec, S):
-    """supercell.py:33-43."""
-    Sinv = np.linalg.inv(S).T
-    u = [0, 1]
-    unit_box = np.stack([x.ravel() for x in np.meshgrid(*[u] * 3, indexing="ij")]).T
-    unit_box_ = np.dot(unit_box, S)
-    xyz_range = np.stack([f(unit_box_, axis=0) for f in (np.amin, np.amax)]).T
-    mesh = np.meshgrid(*[np.arange(*r) for r in xyz_range], indexing="ij")
-    possible_pts = np.dot(np.stack([x.ravel() for x in mesh]).T, Sinv.T)
-    in_unit_box = (possible_pts >= 0) * (possible_pts < 1 - 1e-12)
-    select = np.where(np.all(in_unit_box, axis=1))[0]
-    return np.linalg.multi_dot((possible_pts[select], S, latvec))
+    """Translations (Cartesian) of the primitive cells that make up the supercell ``S . latvec``."""
+    n, _, _ = _integer_points_in_cell(S)
+    return n @ np.asarray(latvec, dtype=float)
 
 
 def get_supercell_kpts(supercell):
-    """supercell.py:18-30: primitive-cell k-points that fold onto the supercell Gamma point."""
-    Sinv = np.linalg.inv(supercell.S).T
-    u = [0, 1]
-    unit_box = np.stack([x.ravel() for x in np.meshgrid(*[u] * 3, indexing="ij")]).T
-    unit_box_ = np.dot(unit_box, np.asarray(supercell.S).T)
-    xyz_range = np.stack([f(unit_box_, axis=0) for f in (np.amin, np.amax)]).T
-    kptmesh = np.meshgrid(*[np.arange(*r) for r in xyz_range], indexing="ij")
-    possible_kpts = np.dot(np.stack([x.ravel() for x in kptmesh]).T, Sinv)
-    in_unit_box = (possible_kpts >= 0) * (possible_kpts < 1 - 1e-12)
-    select = np.where(np.all(in_unit_box, axis=1))[0]
-    reclatvec = np.linalg.inv(supercell.original_cell.lattice_vectors()).T * 2 * np.pi
-    return np.dot(possible_kpts[select], reclatvec)
+    """Primitive-cell k-points that fold onto the supercell's Gamma point: ``k = m S^-T b`` for the integer
+    vectors m inside one cell of ``S^T`` (b = primitive reciprocal vectors incl. 2 pi)."""
+    m, adj, det = _integer_points_in_cell(np.asarray(supercell.S).T)
+    reduced = (m @ adj) / det
+    b = 2 * np.pi * np.linalg.inv(supercell.original_cell.lattice_vectors()).T
+    return reduced @ b
 
 
 def get_supercell(cell, S):
-    """supercell.py:46-75 without pyscf: the simulation cell ``S . a`` with the atoms of every
-    primitive copy (copies of one primitive atom are consecutive)."""
+    """Simulation cell ``S . a`` holding every primitive copy of every atom (supercell.py:46-75 without
+    pyscf); the copies of one primitive atom are consecutive.  Carries ``original_cell``, ``S``, ``scale``."""
     S = np.asarray(S)
-    scale = abs(int(np.round(np.linalg.det(S))))
-    superlattice = np.dot(S, cell.lattice_vectors())
-    Rpts = get_supercell_copies(cell.lattice_vectors(), S)
-    atoms, charges = [], []
-    for (name, xyz), z in zip(cell._atom, cell.atom_charges()):
-        for R in Rpts:
-            atoms.append((name, np.asarray(xyz) + R))
-            charges.append(z)
-    sc = Cell(atoms, cell._basis, cell._ecp, (cell.nelec[0] * scale, cell.nelec[1] * scale), charges, superlattice)
-    sc.original_cell = cell
-    sc.S = S.tolist()
-    sc.scale = scale
+    shifts = get_supercell_copies(cell.lattice_vectors(), S)
+    ncopy = len(shifts)
+    atoms = [(name, np.asarray(xyz) + R) for name, xyz in cell._atom for R in shifts]
+    charges = np.repeat(cell.atom_charges(), ncopy)
+    nelec = tuple(n * ncopy for n in cell.nelec)
+    sc = Cell(atoms, cell._basis, cell._ecp, nelec, charges, S @ cell.lattice_vectors())
+    sc.original_cell, sc.S, sc.scale = cell, S.tolist(), abs(int(np.round(np.linalg.det(S))))
     return sc
 
 
 def create_supercell_twists(supercell, mf, tol=12):
-    """twists.py:34-65."""
-    kpts = np.asarray(mf.kpts)
-    srv = supercell.reciprocal_vectors()
-    frac = kpts @ np.linalg.inv(srv)
-    frac = np.around(frac, tol) % 1
-    super_kpts = frac @ srv
-    twists, indices, counts = np.unique(np.round(super_kpts, tol), axis=0, return_counts=True, return_inverse=True)
-    indices = np.asarray(indices).reshape(-1)
-    kinds = [np.argwhere(indices == i)[:, 0] for i in range(twists.shape[0])]
-    return {"twists": twists, "counts": counts, "primitive_ks": kinds}
+    """Groups the mean field's k-points by the supercell twist they belong to: two k-points share a twist
+    when they differ by a supercell reciprocal vector (twists.py:34-65).  Returns the distinct twists
+    (Cartesian, reduced into the first supercell reciprocal cell, sorted), how many k-points each has and
+    the indices of those k-points."""
+    g = supercell.reciprocal_vectors()
+    reduced = np.around(np.asarray(mf.kpts) @ np.linalg.inv(g), tol) % 1
+    folded = np.round(reduced @ g, tol) + 0.0  # + 0.0 turns -0.0 into 0.0 so equal twists compare equal
+    groups = {}
+    for index, twist in enumerate(map(tuple, folded)):
+        groups.setdefault(twist, []).append(index)
+    order = sorted(groups)
+    return {"twists": np.array(order).reshape(-1, 3), "counts": np.array([len(groups[t]) for t in order]),
+            "primitive_ks": [np.array(groups[t]) for t in order]}
 
 
 class KMF:

@@ -210,7 +210,7 @@ def test_resident_recompute_is_dropped_after_protocol_calls(lib, monkeypatch):
         configs = pq.initial_guess(mol, 40)
         _, configs = mc.vmc_block_device(wf, configs, 0.5, 3, {"energy": acc})
         epos = configs.electron(0)
-        moved = pq.OpenElectron(epos.configs + 0.05, epos.dist)
+        moved = pq.OpenElectron(epos.configs + 0.05, dist=epos.dist)
         mask = np.arange(40) % 3 == 0
         wf.updateinternals(0, moved, configs, mask=mask)  # device walkers now differ from the host array
         avg, configs = mc.vmc_block_device(wf, configs, 0.5, 3, {"energy": acc})

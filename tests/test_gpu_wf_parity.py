@@ -184,33 +184,11 @@ def test_vmc_block_matches_oracle(lib, name):
 
 
 def _generic_worker(wf, configs, tstep, nsteps, accumulators):
-    """The reference's vmc_worker loop (mc.py:102-153) over wf protocol calls."""
-    from pyqmc_b200.mc import limdrift
+    """The per-electron loop over wf protocol calls (the oracle's restatement of mc.py:102-153) driving
+    the DEVICE objects; the reference's own loop does the same in test_gpu_reference_drivers.py."""
+    from oracle import vmc_driver
 
-    nconf, nelec, _ = configs.configs.shape
-    block_avg = {}
-    wf.recompute(configs)
-    for _ in range(nsteps):
-        acc = 0.0
-        for e in range(nelec):
-            g, _, _ = wf.gradient_value(e, configs.electron(e))
-            grad = limdrift(np.real(g.T))
-            gauss = np.random.normal(scale=np.sqrt(tstep), size=(nconf, 3))
-            new = configs.make_irreducible(e, configs.configs[:, e, :] + gauss + grad * tstep)
-            g, val, saved = wf.gradient_value(e, new)
-            new_grad = limdrift(np.real(g.T))
-            forward = np.sum(gauss**2, axis=1)
-            backward = np.sum((gauss + tstep * (grad + new_grad)) ** 2, axis=1)
-            ratio = np.abs(val) ** 2 * np.exp(1 / (2 * tstep) * (forward - backward))
-            accept = ratio > np.random.rand(nconf)
-            configs.move(e, new, accept)
-            wf.updateinternals(e, new, configs, mask=accept, saved_values=saved)
-            acc += np.mean(accept) / nelec
-        for k, accumulator in accumulators.items():
-            for m, res in accumulator.avg(configs, wf).items():
-                block_avg[k + m] = block_avg.get(k + m, 0.0) + res / nsteps
-        block_avg["acceptance"] = acc
-    return block_avg, configs
+    return vmc_driver.vmc_worker(wf, configs, tstep, nsteps, accumulators)
 
 
 def test_public_vmc_driver(lib):
