@@ -10,8 +10,11 @@ drift-diffusion moves over all 8 electrons plus the local-energy accumulator (ke
           already resident in HBM, L2 flushed between timed steps;
   e2e     the public call pyqmc_b200.vmc(...) with host numpy walkers: host RNG draws in the
           reference's order, H2D of the variates, the device block, D2H of energies + walkers;
-  cpu_baseline / --impl reference   the numpy oracle (port of the reference path; the reference
-          itself is Python and is not present on the GPU box) on all host cores.
+  cpu_baseline / --impl reference   the UNMODIFIED reference (oracle/_ref: pyqmc's numpy + numba path,
+          staged by oracle/stage_reference.py) driven by its own mc.vmc / dmc.rundmc on all host cores through
+          its own parallel mechanism (a ProcessPoolExecutor client, npartitions = cores; precedent
+          tests/integration/test_vmc_parallel.py:40-49).  Falls back to the numpy oracle port (kind "port")
+          only when the staged copy is absent.
 
 Launch: python bench.py --gpus N --steps K --warmup W   (N>1: under torchrun, one rank per GPU).
 """
@@ -38,25 +41,54 @@ SPB = 10  # VMC steps per block (reference default nsteps_per_block)
 WORKLOAD = "H2O ccECP-cc-pVTZ-shaped Slater-Jastrow VMC (synthetic basis/MOs), 8 e-, 57 AOs, 4096 walkers/GPU"
 # --workload c4 (not the headline line): BASELINE.json configs[3], diamond 2x2x2 supercell, 64 e-, 8 k-points
 WORKLOADS = {
-    "c2": dict(system="h2o", walkers=4096, text=WORKLOAD, cpu_walkers=256, cpu_steps=200),
-    "c4": dict(system="diamond222", walkers=1024, cpu_walkers=8, cpu_steps=2,
+    # cpu_*: the bounded sample of the CPU arm (walkers per host core, steps per block, blocks)
+    "c2": dict(system="h2o", walkers=4096, text=WORKLOAD, cpu_walkers=512, cpu_steps=200, cpu_blocks=2),
+    "c4": dict(system="diamond222", walkers=1024, cpu_walkers=8, cpu_steps=2, cpu_spb=1, cpu_blocks=2,
                metric="walker-steps/sec (VMC, diamond 2x2x2 PBC SJ); Sherman-Morrison HBM GB/s vs roofline",
                text="diamond-C 2x2x2 supercell PBC Slater-Jastrow VMC (synthetic basis/MOs, 8 k-points), 64 e-, "
                     "16 atoms, Ewald + ECP, 1024 walkers/GPU"),
 }
 WORKLOADS["c3"] = dict(
-    system="h2o_cas_3b", walkers=4096, cpu_walkers=16, cpu_steps=1,
+    system="h2o_cas_3b", walkers=4096, cpu_walkers=32, cpu_steps=1, cpu_spb=2, cpu_blocks=1,
     metric="walker-steps/sec (VMC, H2O CAS(8e,8o) 4900 determinants + 3-body Jastrow); Sherman-Morrison HBM GB/s vs roofline",
     text="H2O ccECP-cc-pVTZ-shaped multi-determinant (full CAS(8e,8o): 70 x 70 = 4900 determinants) x 2-body x 3-body "
          "Jastrow VMC (synthetic basis/MOs/CI coefficients), 4096 walkers/GPU")
 WORKLOADS["c5"] = dict(
-    system="h2o", walkers=2048, cpu_walkers=128, cpu_steps=20, tstep=0.02, spb=5,
+    system="h2o", walkers=2048, cpu_walkers=128, cpu_steps=20, tstep=0.02, spb=5, cpu_blocks=2,
     metric="walker-steps/sec (DMC with T-moves, H2O cc-pVTZ SJ, tstep 0.02); Sherman-Morrison HBM GB/s vs roofline",
     text="H2O ccECP-cc-pVTZ-shaped Slater-Jastrow DMC (synthetic basis/MOs), tstep 0.02, 5 steps per block, T-moves, "
          "branching every block, 2048 walkers/GPU")
 # DRAM bytes per launch of k_sm_warp<32> on 131072 matrices from the committed ncu --set full capture
 # (profiles/r1_ncu_k_sm_warp32.txt: dram__bytes_read.sum + dram__bytes_write.sum)
 SM32_TRAFFIC_BYTES = 2.12e9
+
+
+E2E_MIN_S = 2.0
+NELEC = {"h2o": 8, "h2o_cas_3b": 8, "diamond222": 64}
+
+
+def workload_config(workload, walkers_per_gpu, world):
+    """The `config` object of the JSON line -- identical for the device arm and the reference arm."""
+    wl = WORKLOADS[workload]
+    cfg = {"workload": wl["text"].replace(f"{wl['walkers']} walkers/GPU", f"{walkers_per_gpu} walkers/GPU"),
+           "walkers_per_gpu": walkers_per_gpu, "nelec": NELEC[wl["system"]], "tstep": wl.get("tstep", TSTEP),
+           "ecp_threshold": 10}
+    if workload == "c5":
+        cfg["l2"] = "walker state (2 KB/walker) is L2-resident by design; no flush between blocks"
+        cfg["parallelism"] = f"walker-sharded x{world}, one NCCL allreduce of the weighted sums + global branching per block"
+    else:
+        cfg["l2"] = "256 MiB buffer written between timed steps (L2 flush)"
+        cfg["parallelism"] = f"walker-sharded x{world}, one NCCL allreduce of the energy sums per block of {SPB} steps"
+    return cfg
+
+
+def e2e_bytes_per_block(N, ne, necp, spb, nblocks):
+    """Host<->device bytes of one block of pyqmc_b200.vmc: the variates in (gauss, unif, ECP uniforms + rotations; the
+    walkers themselves are uploaded by the first block only, later blocks recompute from the resident walkers) and the
+    per-walker energies, the walkers and the acceptance counts out."""
+    h2d = spb * ne * N * (3 + 1) * 8 + spb * ne * necp * (N + 9) * 8 + N * ne * 3 * 8 / nblocks
+    d2h = spb * 6 * N * 8 + N * ne * 3 * 8 + spb * ne * 8
+    return h2d, d2h
 
 
 def peaks():
@@ -162,41 +194,158 @@ def cpu_arm(steps, warmup, walkers_per_core=256, cores=None, system="h2o"):
     return total / wall, cores, wall, f"{walkers_per_core} walkers/core x {cores} cores x {steps} steps (oracle port, numpy)"
 
 
+def reference_available():
+    from oracle import refload
+
+    return refload.available()
+
+
+def reference_objects(system):
+    """The reference's own wave function + energy accumulator for a workload, with the parameters the
+    device arm uses (tests/helpers.py seeds)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    import helpers
+    import make_golden
+    from oracle import refload
+
+    refload.load()
+    from pyqmc.observables.accumulators import EnergyAccumulator
+
+    mol, wf = make_golden.build_reference(system)
+    ekw = {"ewald_gmax": 200} if hasattr(mol, "a") else {}
+    del helpers
+    return mol, wf, EnergyAccumulator(mol, **ekw)
+
+
+def reference_cpu_arm(workload, nblocks, cores=None):
+    """walker-steps/s of the reference itself: pyqmc.method.mc.vmc (or dmc.rundmc) with
+    evaluate_orbitals_with="numba", client = ProcessPoolExecutor(cores), npartitions = cores."""
+    import concurrent.futures
+
+    wl = WORKLOADS[workload]
+    cores = min(cores or os.cpu_count() or 1, 64)
+    mol, wf, enacc = reference_objects(wl["system"])
+    import pyqmc.method.dmc as refdmc
+    import pyqmc.method.mc as refmc
+
+    n = wl["cpu_walkers"] * cores
+    spb = wl.get("cpu_spb", wl.get("spb", SPB))
+    tstep = wl.get("tstep", TSTEP)
+    np.random.seed(17)
+    configs = refmc.initial_guess(mol, n)
+    acc = {"energy": enacc}
+    # numba JIT in the parent (one walker partition, protocol calls + accumulator), so that the forked
+    # workers inherit the compiled kernels; then one untimed pass through the pool
+    small = configs.split(cores)[0]
+    refmc.vmc(wf, small, tstep=tstep, nblocks=1, nsteps_per_block=1, accumulators=acc)
+    if workload == "c5":
+        refdmc.dmc_propagate(wf, small, np.ones(len(small.configs)), tstep, 10.0, 0.0, 0.0, nsteps=1, accumulators=acc)
+    with concurrent.futures.ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("fork")) as client:
+        refmc.vmc(wf, configs, tstep=0.5, nblocks=1, nsteps_per_block=1, accumulators=acc, client=client, npartitions=cores)
+        t0 = time.perf_counter()
+        if workload == "c5":
+            refdmc.rundmc(wf, configs, tstep=tstep, nblocks=nblocks, nsteps_per_block=spb, accumulators=acc, vmc_warmup=0,
+                          client=client, npartitions=cores)
+            what = f"pyqmc.method.dmc.rundmc(tstep={tstep}, nblocks={nblocks}, nsteps_per_block={spb}, T-moves, branching)"
+        else:
+            refmc.vmc(wf, configs, tstep=tstep, nblocks=nblocks, nsteps_per_block=spb, accumulators=acc, client=client,
+                      npartitions=cores)
+            what = f"pyqmc.method.mc.vmc(tstep={tstep}, nblocks={nblocks}, nsteps_per_block={spb})"
+        wall = time.perf_counter() - t0
+    sample = (f"{what} of the unmodified reference (numba orbitals, EnergyAccumulator), {wl['cpu_walkers']} walkers/core x "
+              f"{cores} cores via ProcessPoolExecutor(client), npartitions={cores}")
+    return n * nblocks * spb / wall, cores, wall, sample
+
+
+def cpu_reference_or_port(workload, steps, warmup):
+    """(value, cores, wall, sample, kind): the staged reference when present, else the oracle port."""
+    wl = WORKLOADS[workload]
+    if reference_available():
+        spb = wl.get("cpu_spb", wl.get("spb", SPB))
+        nblocks = max(1, min(steps // spb, wl.get("cpu_blocks", 2)))
+        return reference_cpu_arm(workload, nblocks) + ("reference",)
+    if workload == "c5":
+        return cpu_arm_dmc(max(1, min(steps, wl["cpu_steps"])), wl["cpu_walkers"], system=wl["system"]) + ("port",)
+    return cpu_arm(max(1, min(steps, wl["cpu_steps"])), warmup > 0, walkers_per_core=wl["cpu_walkers"],
+                   system=wl["system"]) + ("port",)
+
+
+def cpu_baseline_subprocess(workload, steps):
+    """cpu_baseline of the device arm: the reference arm in a fresh interpreter (no CUDA context to fork)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload, "--steps", str(steps),
+           "--warmup", "1"]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1500)
+    for line in reversed(out.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)["cpu_baseline"]
+    raise RuntimeError("reference arm printed no JSON line: " + out.stderr[-2000:])
+
+
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
-    def __init__(self, index):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """Polls NVML in-process (SM clock, max SM clock, throttle reasons) every few milliseconds from a
+    thread, from construction until stop(): the window covers the warm-up, the timed steps and the
+    cross-check run, so it holds samples even when the timed region is a few milliseconds long."""
+
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+
+    def __init__(self, index, period_s=0.004):
+        import threading
+
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.marks = []
+        self._stop = threading.Event()
+        self.thread = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20",
-                                       "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.p = None
+            self.nv = None
+            return
+        self.period = period_s
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))))
+                bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for name, bit in self.REASONS.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def mark(self):
+        """Timestamp (start / end of the timed region) to report how many samples fell inside it."""
+        self.marks.append(time.perf_counter())
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        self.p.terminate()
-        try:
-            out, _ = self.p.communicate(timeout=5)
-        except Exception:
-            out = ""
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
-            except ValueError:
-                continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self._stop.set()
+        self.thread.join(timeout=2)
+        mhz = [m for _, m in self.samples]
+        inside = [m for t, m in self.samples if len(self.marks) >= 2 and self.marks[0] <= t <= self.marks[1]]
+        return {"sm_mhz": float(np.median(inside if inside else mhz)) if mhz else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(mhz), "samples_in_timed_region": len(inside),
+                "sm_mhz_median_whole_window": float(np.median(mhz)) if mhz else None,
+                "window": "NVML polled every 4 ms from the first warm-up step to the end of the e2e runs"}
 
 
 def sm_roofline(torch, lib, n, nmat, reps=5):
@@ -303,6 +452,8 @@ def gpu_arm(args):
     torch.cuda.synchronize()
     launches0 = ctx.kernel_launches()
     evs = []
+    if sampler:
+        sampler.mark()
     wall0 = time.perf_counter()
     for s in range(W, tot):
         flush.fill_(s & 0xFF)  # evict the walker state from L2 between timed steps
@@ -316,9 +467,10 @@ def gpu_arm(args):
         dist.barrier()
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
+    if sampler:
+        sampler.mark()
     torch.cuda.set_stream(torch.cuda.default_stream())
     launches = ctx.kernel_launches() - launches0
-    clocks = sampler.stop() if sampler else None
     t_dev = sum(a.elapsed_time(b) for a, b in evs) * 1e-3
     # cross-check of the event timing: run the same K steps back to back, wall-clock, no flush
     torch.cuda.synchronize()
@@ -337,26 +489,41 @@ def gpu_arm(args):
     accept = float(d_nacc[W:tot].sum().item()) / (N * ne * K)
 
     # ---------------- end-to-end through the public API (host buffers) ----------------
-    nb_e2e = max(2, min(50, K // 4))
+    # The sample is independent of --steps: the long call runs >= 50 blocks and >= E2E_MIN_S seconds.  Two calls
+    # of different length separate the pipeline fill (first blocks of a call: generator plans, first variates)
+    # from the steady state: steady = extra blocks / extra time.
     spb = SPB
-    # warm-up of the same call shape (pinned block buffers, generator plans, worker threads)
-    df, configs = pq.vmc(wf, configs, tstep=TSTEP, nblocks=3, nsteps_per_block=spb, accumulators={"energy": acc})
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     t0 = time.perf_counter()
-    df, configs = pq.vmc(wf, configs, tstep=TSTEP, nblocks=nb_e2e, nsteps_per_block=spb, accumulators={"energy": acc})
-    t_e2e = time.perf_counter() - t0
-    te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+    df, configs = pq.vmc(wf, configs, tstep=TSTEP, nblocks=6, nsteps_per_block=spb, accumulators={"energy": acc})
+    t_block = (time.perf_counter() - t0) / 6  # warm-up of the call shape doubles as the block-time estimate
+    nb_long = int(max(50, np.ceil(E2E_MIN_S / max(t_block, 1e-4))))
+    nb_short = max(4, nb_long // 4)
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    t_e2e = float(te.item())
-    e2e = N * world * nb_e2e * spb / t_e2e
+        nbt = torch.tensor([nb_long], dtype=torch.int64, device="cuda")
+        dist.all_reduce(nbt, op=dist.ReduceOp.MAX)
+        nb_long = int(nbt.item())
+        nb_short = max(4, nb_long // 4)
+
+    def timed_vmc(nb):
+        nonlocal configs
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        _, configs = pq.vmc(wf, configs, tstep=TSTEP, nblocks=nb, nsteps_per_block=spb, accumulators={"energy": acc})
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    t_short = timed_vmc(nb_short)
+    t_long = timed_vmc(nb_long)
+    nb_e2e, t_e2e = nb_long, t_long
+    e2e = N * world * nb_long * spb / t_long
+    e2e_steady = N * world * (nb_long - nb_short) * spb / max(t_long - t_short, 1e-9)
     necp = acc.necp
-    # per block: the variates (gauss, unif, ECP uniforms + rotations); the walkers themselves are uploaded by the
-    # first block only (later blocks recompute from the device-resident walkers, qmcb_recompute_resident)
-    h2d = spb * ne * N * (3 + 1) * 8 + spb * ne * necp * (N + 9) * 8 + N * ne * 3 * 8 / nb_e2e
-    d2h = spb * 6 * N * 8 + N * ne * 3 * 8 + spb * ne * 8
+    h2d, d2h = e2e_bytes_per_block(N, ne, necp, spb, nb_e2e)
+    clocks = sampler.stop() if sampler else None
 
     if rank != 0:
         if world > 1:
@@ -371,12 +538,12 @@ def gpu_arm(args):
         "value": value, "unit": "walker-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * t_dev_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["text"].replace(f"{wl['walkers']} walkers/GPU", f"{N} walkers/GPU"),
-                   "walkers_per_gpu": N, "nelec": ne, "tstep": TSTEP,
-                   "l2": "256 MiB buffer written between timed steps (L2 flush)", "ecp_threshold": 10,
-                   "parallelism": f"walker-sharded x{world}, one NCCL allreduce of the energy sums per block of {SPB} steps"},
+        "config": workload_config(args.workload, N, world),
         "e2e": {"value": e2e, "unit": "walker-steps/s", "h2d_bytes_per_step": h2d / spb, "d2h_bytes_per_step": d2h / spb,
-                "call": f"pyqmc_b200.vmc(nblocks={nb_e2e}, nsteps_per_block={spb}) incl. host legacy-RNG draws"},
+                "call": f"pyqmc_b200.vmc(nblocks={nb_e2e}, nsteps_per_block={spb}), host walkers in / host walkers + block "
+                        f"averages out, bit-exact legacy RNG stream; {t_e2e:.2f} s",
+                "e2e_fill_included": e2e, "e2e_steady": e2e_steady,
+                "steady_definition": f"({nb_long} - {nb_short}) blocks / (t[{nb_long} blocks] - t[{nb_short} blocks])"},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "k_sm_warp<32>: Sherman-Morrison row update, n=32 (C4 shape), 131072 matrices",
                      "bound": "hbm", "achieved": g32, "peak": peak, "unit": "GB/s", "frac": g32 / peak,
@@ -398,9 +565,7 @@ def gpu_arm(args):
     if args.workload != "c2":
         out.pop("roofline_step")  # the per-walker-step byte count above is the C2 figure
     if world == 1 and not args.no_cpu:
-        v, cores, cwall, sample = cpu_arm(wl["cpu_steps"], True, walkers_per_core=wl["cpu_walkers"], system=wl["system"])
-        out["cpu_baseline"] = {"value": v, "unit": "walker-steps/s", "cores": cores, "kind": "port", "sample": sample,
-                               "wall_s": cwall}
+        out["cpu_baseline"] = cpu_baseline_subprocess(args.workload, K)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -502,9 +667,7 @@ def gpu_arm_dmc(args):
         "metric": wl["metric"], "value": value, "unit": "walker-steps/s", "n_gpus": world, "steps": K * spb, "warmup": W * spb,
         "ms_per_step": 1e3 * float(td.item()) / (K * spb), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["text"].replace("2048 walkers/GPU", f"{N} walkers/GPU"), "walkers_per_gpu": N, "tstep": tstep,
-                   "l2": "walker state (2 KB/walker) is L2-resident by design; no flush between blocks",
-                   "value_definition": "dmc_propagate with pre-drawn variates (recompute + qmcb_dmc_block incl. H2D/D2H), wall clock"},
+        "config": workload_config("c5", N, world),
         "e2e": {"value": e2e, "unit": "walker-steps/s", "h2d_bytes_per_step": per_step + N * ne * 3 * 8 / spb,
                 "d2h_bytes_per_step": (N * ne * 3 * 8 + N * 8) / spb,
                 "call": "pyqmc_b200.dmc.dmc_propagate + branch per block incl. host legacy-RNG draws"},
@@ -513,34 +676,28 @@ def gpu_arm_dmc(args):
                   "tmove_acceptance": float(out["tmove_acceptance"]), "weight": float(out["weight"])},
     }
     if world == 1 and not args.no_cpu:
-        v, cores, cwall, sample = cpu_arm_dmc(wl["cpu_steps"], wl["cpu_walkers"], system=wl["system"])
-        res["cpu_baseline"] = {"value": v, "unit": "walker-steps/s", "cores": cores, "kind": "port", "sample": sample, "wall_s": cwall}
+        res["cpu_baseline"] = cpu_baseline_subprocess("c5", K * spb)
     print(json.dumps(res), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 def reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path on all host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    # each of the K "steps" of this arm is one VMC step of a bounded sample (cpu_walkers per core on
-    # every host core); K is capped so the whole run stays within a few minutes
-    if args.workload == "c5":
-        v, cores, wall, sample = cpu_arm_dmc(max(1, min(args.steps, wl["cpu_steps"])), wl["cpu_walkers"], system=wl["system"])
-    else:
-        v, cores, wall, sample = cpu_arm(max(1, min(args.steps, wl["cpu_steps"])), args.warmup > 0,
-                                         walkers_per_core=wl["cpu_walkers"], system=wl["system"])
+    v, cores, wall, sample, kind = cpu_reference_or_port(args.workload, args.steps, args.warmup)
     out = {
         "impl": "reference",
         "metric": wl.get("metric", "walker-steps/sec (VMC, H2O cc-pVTZ SJ); Sherman-Morrison HBM GB/s vs roofline"),
         "value": v, "unit": "walker-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": wl["text"], "note": "numpy oracle port of the reference path on host cores; "
-                   "the Python reference is not present on the GPU box"},
-        "cpu_baseline": {"value": v, "unit": "walker-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args.workload, args.walkers or wl["walkers"], args.gpus),
+        "cpu_baseline": {"value": v, "unit": "walker-steps/s", "cores": cores, "kind": kind, "sample": sample,
+                         "wall_s": wall},
         "e2e": {"value": v, "unit": "walker-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

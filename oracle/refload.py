@@ -72,6 +72,24 @@ def load():
     return pyq
 
 
+class GuardedEvalGto:
+    """Empty-input guard around the reference's numba ``eval_gto`` (picklable: the reference's
+    parallel drivers ship the wave function to worker processes)."""
+
+    NCOMP = {"GTOval_sph": None, "GTOval_sph_deriv1": 4, "GTOval_sph_deriv2": 5}
+
+    def __init__(self, inner, nk, nao):
+        self.inner, self.nk, self.nao = inner, tuple(nk), nao
+
+    def __call__(self, eval_str, coords):
+        import numpy as np
+
+        if len(coords) == 0:
+            nc = self.NCOMP[eval_str.replace("PBC", "")]
+            return np.zeros(self.nk + (0, self.nao)) if nc is None else np.zeros(self.nk + (nc, 0, self.nao))
+        return self.inner(eval_str, coords)
+
+
 def build_reference_wf(mol, mf, jastrow=True, determinants=None, seed=0, na=4, nb=3,
                        three_body=False, coeff_scale=0.1):
     """Reference Slater(numba) x JastrowSpin [x ThreeBodyJastrow] with seeded coefficients."""
@@ -87,18 +105,9 @@ def build_reference_wf(mol, mf, jastrow=True, determinants=None, seed=0, na=4, n
     )
     # The numba evaluator crashes on an empty point set (all-False mask in dmc.py:175 ->
     # slater.py:279 -> gto.py:494; SURVEY.md 8c caveat 2): harness-side guard, as pyscf tolerates it.
-    _eval = slater.orbitals.eval_gto
     nao = slater.parameters["mo_coeff_alpha"].shape[0]
-
     nk = (len(slater.orbitals._kpts),) if hasattr(mol, "a") else ()
-
-    def guarded(eval_str, coords):
-        if len(coords) == 0:
-            nc = {"GTOval_sph": None, "GTOval_sph_deriv1": 4, "GTOval_sph_deriv2": 5}[eval_str.replace("PBC", "")]
-            return np.zeros(nk + (0, nao)) if nc is None else np.zeros(nk + (nc, 0, nao))
-        return _eval(eval_str, coords)
-
-    slater.orbitals.eval_gto = guarded
+    slater.orbitals.eval_gto = GuardedEvalGto(slater.orbitals.eval_gto, nk, nao)
     if not jastrow:
         return slater
     jast, _ = pyqmc.wftools.generate_jastrow(mol, na=na, nb=nb)

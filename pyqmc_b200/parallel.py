@@ -61,7 +61,7 @@ def vmc_distributed(wf, configs, tstep=0.5, nblocks=10, nsteps_per_block=10, acc
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if block_fn is None:
-        from .mc import vmc_worker as block_fn
+        from .mc import vmc_block_device as block_fn
     if seed is not None:
         np.random.seed(seed + rank)
     local = shard(configs, rank, world)

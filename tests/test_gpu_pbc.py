@@ -76,15 +76,10 @@ def test_periodic_per_call_vmc_equals_device_resident_block(lib, name):
     avg1, c1 = mc.vmc_block_device(wf, c1, 0.4, 2, acc)
     mol2, mf2, wf2, _ = helpers.make_pair(name, seed=1)
 
-    class Plain:  # hides the device accumulator type so vmc_worker takes the per-call loop
-        def __init__(self, a):
-            self.a = a
-
-        def avg(self, configs, wf):
-            return self.a.avg(configs, wf)
-
     np.random.seed(12)
-    avg2, c2 = mc.vmc_worker(wf2, c2, 0.4, 2, {"energy": Plain(pq.EnergyAccumulator(mol2, ewald_gmax=EWALD_GMAX))})
+    from oracle import vmc_driver  # the oracle's restatement of the reference loop (mc.py:102-153), over device objects
+
+    avg2, c2 = vmc_driver.vmc_worker(wf2, c2, 0.4, 2, {"energy": pq.EnergyAccumulator(mol2, ewald_gmax=EWALD_GMAX)})
     assert avg1["acceptance"] == avg2["acceptance"]
     assert np.abs(c1.configs - c2.configs).max() < 1e-9
     assert np.array_equal(c1.wrap, c2.wrap)
