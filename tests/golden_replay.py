@@ -65,11 +65,11 @@ def replay(data, wf, configs, make_energy, vmc_fn, check_internal=None):
     if accepts is not None:
         assert np.array_equal(accepts, data["vmc_accept"]), "accept masks differ from the reference"
     assert np.array_equal(df["acceptance"], data["vmc_acceptance"])
-    assert np.abs(configs.configs - data["vmc_configs"]).max() < 1e-9
+    assert np.abs(configs.configs - data["vmc_configs"]).max() < TOL
     if "vmc_wrap" in data:
         assert np.array_equal(configs.wrap, data["vmc_wrap"])
     for k in ("energytotal", "energyke", "energyecp", "energyee", "energyei", "energygrad2"):
-        assert np.abs(df[k] - data["vmc_" + k]).max() <= 1e-9 * max(1.0, np.abs(data["vmc_" + k]).max()), k
+        assert np.abs(df[k] - data["vmc_" + k]).max() <= TOL * max(1.0, np.abs(data["vmc_" + k]).max()), k
 
 
 def check_dmc(data, out, configs, weights):

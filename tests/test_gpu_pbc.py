@@ -100,29 +100,29 @@ def test_diamond_supercell_against_oracle(lib):
     s, l = wf.recompute(configs)
     so, lo = orc.recompute(oc)
     assert np.array_equal(s, so)
-    assert np.abs(l - lo).max() < 1e-9 * max(1.0, np.abs(lo).max())
+    assert np.abs(l - lo).max() < 1e-10 * max(1.0, np.abs(lo).max())
     rng = np.random.RandomState(4)
     for e in (0, 31, 40, 63):
         new = configs.configs[:, e] + 0.3 * rng.randn(6, 3)
         ep, eo = configs.make_irreducible(e, new.copy()), oc.make_irreducible(e, new.copy())
         g, v, saved = wf.gradient_value(e, ep)
         go, vo, savedo = orc.gradient_value(e, eo)
-        assert helpers.relerr(g, go) < 1e-8 and helpers.relerr(v, vo) < 1e-8
+        assert helpers.relerr(g, go) < 1e-10 and helpers.relerr(v, vo) < 1e-10
         gl, lap = wf.gradient_laplacian(e, ep)
         glo, lapo = orc.gradient_laplacian(e, eo)
-        assert helpers.relerr(lap, lapo) < 1e-8
+        assert helpers.relerr(lap, lapo) < 1e-10
         mask = rng.rand(6) > 0.4
         wf.updateinternals(e, ep, configs, mask=mask, saved_values=saved)
         orc.updateinternals(e, eo, oc, mask=mask, saved_values=savedo)
         configs.move(e, ep, mask)
         oc.move(e, eo, mask)
-        assert np.abs(wf.value()[1] - orc.value()[1]).max() < 1e-8 * max(1.0, np.abs(lo).max())
+        assert np.abs(wf.value()[1] - orc.value()[1]).max() < 1e-10 * max(1.0, np.abs(lo).max())
     np.random.seed(9)
     en = pq.EnergyAccumulator(mol, ewald_gmax=EWALD_GMAX)(configs, wf)
     np.random.seed(9)
     eno = EnergyOracle(mol, ewald_gmax=EWALD_GMAX)(oc, orc)
     for k in ("ke", "ee", "ei", "ecp", "total"):
-        assert helpers.relerr(en[k], eno[k]) < 1e-8, k
+        assert helpers.relerr(en[k], eno[k]) < 1e-10, k
 
 
 def test_periodic_stochastic_reconfiguration_avg(lib):

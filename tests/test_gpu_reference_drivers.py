@@ -124,7 +124,7 @@ def run_testwf_harness(name, wf, mol, pgradient=True):
 
 @pytest.mark.gpu
 @needs_reference
-@pytest.mark.parametrize("name", ["he", "h2o", "open", "c2", "h2o_md", "ortho", "rotcubic", "diamond211"])
+@pytest.mark.parametrize("name", ["he", "h2o", "open", "c2", "h2o_md", "h2o_cas", "ortho", "rotcubic", "diamond211"])
 def test_reference_vmc_drives_device_objects(lib, name):
     """mc.vmc of the reference over device wf + device accumulator == the reference-only golden run."""
     import pyqmc_b200 as pq

@@ -171,7 +171,7 @@ def test_vmc_block_matches_oracle(lib, name):
     assert np.abs(configs.configs - oconfigs.configs).max() < 1e-9
     assert blk["acceptance"] == oblk["acceptance"]
     for k in ("energytotal", "energyke", "energyecp", "energyee", "energyei", "energygrad2"):
-        assert abs(blk[k] - oblk[k]) <= 1e-9 * max(1.0, abs(oblk[k])), k
+        assert abs(blk[k] - oblk[k]) <= 1e-10 * max(1.0, abs(oblk[k])), k
     # the generic per-electron path (unchanged reference driver loop over protocol calls)
     mol, wf2, orc2, configs2, oconfigs2 = setup_pair(name, lib)
     np.random.seed(41)
@@ -180,7 +180,7 @@ def test_vmc_block_matches_oracle(lib, name):
     oblk2, oconfigs2 = vmc_driver.vmc_worker(orc2, oconfigs2, tstep, 2, {"energy": EnergyOracle(mol)})
     assert np.abs(configs2.configs - oconfigs2.configs).max() < 1e-9
     assert blk2["acceptance"] == oblk2["acceptance"]
-    assert abs(blk2["energytotal"] - oblk2["energytotal"]) <= 1e-9 * max(1.0, abs(oblk2["energytotal"]))
+    assert abs(blk2["energytotal"] - oblk2["energytotal"]) <= 1e-10 * max(1.0, abs(oblk2["energytotal"]))
 
 
 def _generic_worker(wf, configs, tstep, nsteps, accumulators):
@@ -203,7 +203,7 @@ def test_public_vmc_driver(lib):
     odf, oconfigs = vmc_driver.vmc(orc, oconfigs, nblocks=2, nsteps_per_block=2, accumulators={"energy": EnergyOracle(mol)})
     assert set(["energyke", "energyee", "energyei", "energyecp", "energygrad2", "energytotal", "acceptance", "block", "nconfig"]) <= set(df)
     assert np.array_equal(df["acceptance"], odf["acceptance"])
-    assert np.abs(df["energytotal"] - odf["energytotal"]).max() < 1e-9 * np.abs(odf["energytotal"]).max()
+    assert np.abs(df["energytotal"] - odf["energytotal"]).max() < 1e-10 * np.abs(odf["energytotal"]).max()
     assert np.abs(configs.configs - oconfigs.configs).max() < 1e-9
 
 

@@ -8,7 +8,7 @@ import golden_replay
 import helpers
 import refload
 
-SYSTEMS = ["he", "h2o", "open", "c2", "h2o_md", "h2o_3b", "h2o_md_3b"]
+SYSTEMS = ["he", "h2o", "open", "c2", "h2o_md", "h2o_3b", "h2o_md_3b", "h2o_cas", "h2o_cas_3b"]
 
 
 def oracle_vmc(wf, configs, accumulators):
