@@ -245,6 +245,22 @@ def _pack_determinants(determinants, tol):
     return np.array(coeff), occ, np.array(dmap, dtype=np.int32)
 
 
+class _Seed:
+    """Walkers read back from a device context (what a copied wave function starts from)."""
+
+    def __init__(self, configs, wrap):
+        self.configs = configs
+        if wrap is not None:
+            self.wrap = wrap
+
+
+def _resident_walkers(ctx):
+    if ctx is None or ctx.nconf == 0:
+        return None
+    shape = (ctx.nconf, sum(ctx.nelec), 3)
+    return _Seed(ctx.get_state("configs", shape), ctx.get_state("wrap", shape) if ctx.periodic else None)
+
+
 class _DeviceFactor:
     """Shared plumbing of the two device-resident factors."""
 
@@ -284,35 +300,49 @@ class _DeviceFactor:
         new = self.__class__.__new__(self.__class__)
         new.__dict__.update(self.__getstate__())
         new.parameters = self._copy_parameters()
+        new._seed = _resident_walkers(self._ctx)
         return new
 
     def __deepcopy__(self, memo):
         return self.__copy__()
 
+    def _live(self):
+        """The device context holding this object's walker state.  A copy owns its own context, created on
+        first use from the walkers the original held when it was copied: the reference's harness queries
+        ``copy.copy(wf)`` without a recompute of its own (testwf.py:44-54), as a shallow copy of numpy-backed
+        objects allows."""
+        if (self._ctx is None or self._ctx.nconf == 0) and getattr(self, "_seed", None) is not None:
+            seed, self._seed = self._seed, None
+            self.recompute(seed)
+        if self._ctx is None:
+            raise RuntimeError("wf.recompute(configs) must be called first")
+        return self._ctx
+
     # ---- the wf protocol ------------------------------------------------------------------
     def recompute(self, configs):
+        self._seed = None
         return self._sync().recompute(self._which, configs.configs, getattr(configs, "wrap", None))
 
     def value(self):
-        return self._ctx.value(self._which)
+        return self._live().value(self._which)
 
     def gradient(self, e, epos):
-        return self._ctx.gradient(self._which, e, epos)
+        return self._live().gradient(self._which, e, epos)
 
     def gradient_value(self, e, epos):
-        return self._ctx.gradient_value(self._which, e, epos)
+        return self._live().gradient_value(self._which, e, epos)
 
     def gradient_laplacian(self, e, epos):
-        return self._ctx.gradient_laplacian(self._which, e, epos)
+        return self._live().gradient_laplacian(self._which, e, epos)
 
     def testvalue(self, e, epos, mask=None):
-        return self._ctx.testvalue(self._which, e, epos, mask)
+        return self._live().testvalue(self._which, e, epos, mask)
 
     def testvalue_many(self, e, epos, mask=None):
-        return self._ctx.testvalue_many(self._which, e, epos, mask)
+        return self._live().testvalue_many(self._which, e, epos, mask)
 
     def updateinternals(self, e, epos, configs, mask=None, saved_values=None):
-        self._ctx.updateinternals(self._which, e, epos, mask, saved_values)
+        self._live().updateinternals(self._which, e, epos, mask, saved_values)
 
 
 class Slater(_DeviceFactor):
@@ -679,12 +709,27 @@ class MultiplyWF:
     def __copy__(self):
         import copy as _copy
 
-        return MultiplyWF(*[_copy.copy(f) for f in self.wf_factors])
+        new = MultiplyWF(*[_copy.copy(f) for f in self.wf_factors])
+        if self._fused:
+            for f in new.wf_factors:
+                f._seed = None
+            new._seed = _resident_walkers(self._ctx)
+        return new
 
     def __deepcopy__(self, memo):
         return self.__copy__()
 
+    def _live(self):
+        """See ``_DeviceFactor._live``: a copy starts from the walkers its original held."""
+        if (self._ctx is None or self._ctx.nconf == 0) and getattr(self, "_seed", None) is not None:
+            seed, self._seed = self._seed, None
+            self.recompute(seed)
+        if self._ctx is None:
+            raise RuntimeError("wf.recompute(configs) must be called first")
+        return self._ctx
+
     def recompute(self, configs):
+        self._seed = None
         if self._fused:
             ctx = self._ensure_ctx()
             for f in self.wf_factors:
@@ -698,13 +743,13 @@ class MultiplyWF:
 
     def value(self):
         if self._fused:
-            return self._ctx.value(self._which)
+            return self._live().value(self._which)
         res = np.array([wf.value() for wf in self.wf_factors])
         return np.prod(res[:, 0, :], axis=0), np.sum(res[:, 1, :], axis=0)
 
     def updateinternals(self, e, epos, configs, mask=None, saved_values=None):
         if self._fused:
-            return self._ctx.updateinternals(self._which, e, epos, mask, saved_values)
+            return self._live().updateinternals(self._which, e, epos, mask, saved_values)
         if saved_values is None or isinstance(saved_values, SavedSlot):
             saved_values = [saved_values] * len(self.wf_factors)
         for wf, sv in zip(self.wf_factors, saved_values):
@@ -712,18 +757,18 @@ class MultiplyWF:
 
     def gradient(self, e, epos):
         if self._fused:
-            return self._ctx.gradient(self._which, e, epos)
+            return self._live().gradient(self._which, e, epos)
         return np.sum([wf.gradient(e, epos) for wf in self.wf_factors], axis=0)
 
     def gradient_value(self, e, epos):
         if self._fused:
-            return self._ctx.gradient_value(self._which, e, epos)
+            return self._live().gradient_value(self._which, e, epos)
         grads, vals, saved = zip(*[wf.gradient_value(e, epos) for wf in self.wf_factors])
         return np.sum(grads, axis=0), np.prod(vals, axis=0), saved
 
     def gradient_laplacian(self, e, epos):
         if self._fused:
-            return self._ctx.gradient_laplacian(self._which, e, epos)
+            return self._live().gradient_laplacian(self._which, e, epos)
         grads, laps = zip(*[wf.gradient_laplacian(e, epos) for wf in self.wf_factors])
         cross = np.zeros(laps[0].shape, dtype=self.dtype)
         for i in range(len(grads)):
@@ -733,13 +778,13 @@ class MultiplyWF:
 
     def testvalue(self, e, epos, mask=None):
         if self._fused:
-            return self._ctx.testvalue(self._which, e, epos, mask)
+            return self._live().testvalue(self._which, e, epos, mask)
         vals, saved = zip(*[wf.testvalue(e, epos, mask=mask) for wf in self.wf_factors])
         return np.prod(vals, axis=0), saved
 
     def testvalue_many(self, e, epos, mask=None):
         if self._fused:
-            return self._ctx.testvalue_many(self._which, e, epos, mask)
+            return self._live().testvalue_many(self._which, e, epos, mask)
         return np.prod([wf.testvalue_many(e, epos, mask=mask) for wf in self.wf_factors], axis=0)
 
     def pgradient(self):
