@@ -100,7 +100,8 @@ def run_testwf_harness(name, wf, mol, pgradient=True):
     from pyqmc.wf import testwf
 
     np.random.seed(5)
-    configs = refmc.initial_guess(mol, 11)
+    # test_wf_gradient_value indexes a per-walker array by electron (testwf.py:264,276): needs nconf >= nelec
+    configs = refmc.initial_guess(mol, max(11, int(sum(mol.nelec)) + 1))
     if not name.endswith("_3b"):  # the reference's vmc leaves a three-body cache stale: harness only
         _, configs = refmc.vmc(wf, configs, nblocks=1, nsteps=2, tstep=1)
     for k, item in testwf.test_updateinternals(wf, configs).items():
@@ -109,7 +110,7 @@ def run_testwf_harness(name, wf, mol, pgradient=True):
     np.random.seed(6)
     testwf.test_mask(wf, 0, configs.electron(0))
     testwf.test_testvalue_many(wf, configs)
-    aux = configs.make_irreducible(0, configs.configs[:, 0][:, None, :] + 0.2 * np.random.randn(len(configs.configs), 6, 3))
+    aux = configs.make_irreducible(0, configs.configs[:, 0][:, None, :] + 0.2 * np.random.randn(len(configs.configs), 6, 3))  # noqa: E501
     aux_configs = _ref_configs(mol, aux.configs, getattr(aux, "wrap", None))
     testwf.test_testvalue_aux(wf, configs, aux_configs)
     err = [testwf.test_wf_gradient(wf, configs, delta) for delta in (1e-4, 1e-5, 1e-6)]
