@@ -278,6 +278,24 @@ int qmcb_rng_phase_a(void *plan, uint32_t *key, int32_t *pos, int32_t *has_gauss
                      double *gauss, double *unif, double *ecp_u, double *ecp_rot, int nthreads);
 int qmcb_rng_phase_b(void *plan, int nthreads);
 
+/* ---- the same bit-identical legacy generator, DEVICE-RESIDENT (csrc/device_rng.cuh): the MT19937 stream of
+ * np.random (mc.py:119,132; eval_ecp.py:145,263) is continued on the GPU from the state handed over once, so the
+ * variates of a block are produced where they are consumed.  set_state / get_state exchange the fields of
+ * np.random.get_state(); programs run asynchronously on the context's copy stream and chain through the state kept
+ * on the device.  qmcb_devrng_program: ops as qmcb_rng_program, dst[i] = DEVICE addresses.
+ * qmcb_devrng_vmc_block: the draw program of one VMC block into variate slot `slot` (consumed by
+ * qmcb_vmc_block_slot).  qmcb_glibc_log_mismatches: how many of nsamples arguments the restated glibc log
+ * (csrc/glibc_log.h) rounds differently from this host's libm log(); callers use the device generator only if 0. */
+int qmcb_devrng_set_state(qmcb_ctx *ctx, const uint32_t *key, int32_t pos, int32_t has_gauss,
+                          double cached_gauss);
+int qmcb_devrng_get_state(qmcb_ctx *ctx, uint32_t *key, int32_t *pos, int32_t *has_gauss,
+                          double *cached_gauss);
+int qmcb_devrng_program(qmcb_ctx *ctx, int64_t nops, const int32_t *kind, const int64_t *count,
+                        const uint64_t *dst, const double *scale);
+int qmcb_devrng_vmc_block(qmcb_ctx *ctx, int slot, int nsteps, int ne, int64_t N, int necp,
+                          double sigma);
+int64_t qmcb_glibc_log_mismatches(int64_t nsamples, uint64_t seed);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,7 @@
 #undef QMCB_JASTROW
 #undef QMCB_JASTROW3
 #include "kernels.cuh"
+#include "device_rng.cuh"
 
 namespace {
 
@@ -155,7 +156,12 @@ struct qmcb_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t slot_ready[NSLOT] = {nullptr, nullptr, nullptr};
   cudaEvent_t done_event = nullptr;  // blocking-sync event: the host thread sleeps while a block runs
+  void* devrng = nullptr;            // DevRng (devrng_api.cuh): device-resident legacy generator
 };
+
+extern "C" {
+static void devrng_free(qmcb_ctx* c);
+}
 
 namespace {
 
@@ -1071,6 +1077,7 @@ void qmcb_destroy(qmcb_ctx* c) {
     if (c->slot_ready[i]) cudaEventDestroy(c->slot_ready[i]);
   }
   if (c->done_event) cudaEventDestroy(c->done_event);
+  devrng_free(c);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -2616,5 +2623,7 @@ int qmcb_sm_update(int n, int e, int64_t nmat, double* inv, const double* vec, c
   dm.release();
   return rc;
 }
+
+#include "devrng_api.cuh"
 
 }  // extern "C"

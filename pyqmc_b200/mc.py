@@ -338,6 +338,94 @@ def ctypes_void(p):
     return ctypes.c_void_p(p)
 
 
+_DEVICE_RNG_OK = None
+
+
+def device_rng_usable():
+    """The device generator reproduces numpy's Gaussians only if its restated ``log`` (csrc/glibc_log.h) rounds
+    like THIS host's libm -- checked once per process on 2^16 arguments -- and the global generator is the
+    legacy MT19937.  ``QMCB_HOST_RNG=1`` forces the host generator (csrc/legacy_rng.cpp)."""
+    import os
+
+    global _DEVICE_RNG_OK
+    if os.environ.get("QMCB_HOST_RNG"):
+        return False
+    if _DEVICE_RNG_OK is None:
+        _DEVICE_RNG_OK = _lib.load().qmcb_glibc_log_mismatches(1 << 16, 12345) == 0
+    return _DEVICE_RNG_OK and np.random.get_state()[0] == "MT19937"
+
+
+class _DeviceVariates:
+    """Variate source of the device-resident driver when the generator itself runs on the GPU
+    (csrc/device_rng.cuh): the global legacy ``np.random`` state is handed to the device once, every block's
+    draw program is enqueued one block ahead on the copy stream (it overlaps the previous block's kernels), and
+    the advanced state is written back to ``np.random`` by ``close()`` -- the stream ends where the reference's
+    loop would have left it.  Same interface as ``_VariatePrefetcher``."""
+
+    NSLOT = 3
+
+    def __init__(self, wf, configs, tstep, nsteps, accumulators, nblocks):
+        import ctypes
+
+        nconf, nelec, _ = configs.configs.shape
+        self.accumulator = next(iter(accumulators.values())) if accumulators else None
+        if _device_context(wf) is None:
+            wf.recompute(configs)
+        self.ctx = _device_context(wf)
+        self.lib = self.ctx.lib
+        self.shape = (nsteps, nelec, nconf, self.accumulator.necp if self.accumulator is not None else 0)
+        self.sigma = float(np.sqrt(tstep))
+        self.remaining, self.issued, self.queue, self.open = nblocks, 0, [], True
+        state = np.random.get_state()
+        key = np.ascontiguousarray(state[1], dtype=np.uint32)
+        _lib.check(self.lib.qmcb_devrng_set_state(self.ctx.h, key.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
+                                                  int(state[2]), int(state[3]), float(state[4])))
+        for _ in range(2):
+            self._submit()
+
+    def _submit(self):
+        if self.remaining <= 0:
+            return
+        nsteps, nelec, nconf, necp = self.shape
+        slot = self.issued % self.NSLOT
+        self.issued += 1
+        self.remaining -= 1
+        _lib.check(self.lib.qmcb_devrng_vmc_block(self.ctx.h, slot, nsteps, nelec, nconf, necp, self.sigma))
+        buf = _block_buffers(self.ctx, nconf, nelec, nsteps, self.accumulator, slot=slot)
+        buf.uploaded_slot = slot
+        self.queue.append(buf)
+
+    def next(self):
+        buf = self.queue.pop(0)
+        self._submit()
+        return buf
+
+    def close(self):
+        """Fetches the generator state back into ``np.random`` (also surfaces a generator error)."""
+        import ctypes
+
+        if not self.open:
+            return
+        self.open = False
+        key = np.empty(624, dtype=np.uint32)
+        pos, has_gauss, cached = ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_double(0.0)
+        _lib.check(self.lib.qmcb_devrng_get_state(self.ctx.h, key.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
+                                                  ctypes.byref(pos), ctypes.byref(has_gauss), ctypes.byref(cached)))
+        np.random.set_state(("MT19937", key, pos.value, has_gauss.value, cached.value))
+
+
+def _variate_source(wf, configs, tstep, nsteps, accumulators, nblocks):
+    ctx = None
+    try:
+        ctx = _device_context(wf)
+    except TypeError:
+        pass
+    if device_rng_usable():
+        return _DeviceVariates(wf, configs, tstep, nsteps, accumulators, nblocks)
+    del ctx
+    return _VariatePrefetcher(wf, configs, tstep, nsteps, accumulators, nblocks)
+
+
 def _reference_driver():
     """The reference's own driver module, when PyQMC is installed next to this plugin."""
     try:
@@ -399,7 +487,7 @@ def vmc(wf, configs, tstep=0.5, nblocks=10, nsteps_per_block=10, nsteps=None, bl
         logging.warning(f"blockoffset {blockoffset} >= nblocks {nblocks}; no steps will be run.")
     rows = []
     todo = max(0, nblocks - blockoffset)
-    prefetch = _VariatePrefetcher(wf, configs, tstep, nsteps_per_block, accumulators, todo) if todo else None
+    prefetch = _variate_source(wf, configs, tstep, nsteps_per_block, accumulators, todo) if todo else None
     try:
         for block in range(blockoffset, nblocks):
             if verbose:
