@@ -278,6 +278,14 @@ int qmcb_rng_phase_a(void *plan, uint32_t *key, int32_t *pos, int32_t *has_gauss
                      double *gauss, double *unif, double *ecp_u, double *ecp_rot, int nthreads);
 int qmcb_rng_phase_b(void *plan, int nthreads);
 
+/* asynchronous form of qmcb_vmc_block_slot for the pipelined driver (pyqmc_b200.mc.vmc): _begin optionally
+ * recomputes the factors `recompute_which` from the resident walkers (wf.recompute at the start of vmc_worker,
+ * mc.py:110), enqueues the block on the variates of `slot` and the device->host copies of its results (buffers must
+ * stay valid, page-locked for true overlap) and returns; _end blocks until they have arrived. */
+int qmcb_vmc_block_slot_begin(qmcb_ctx *ctx, int slot, int nsteps, double tstep, int with_energy,
+                              int recompute_which, double *configs, double *energy, int64_t *nacc);
+int qmcb_vmc_block_slot_end(qmcb_ctx *ctx, int slot);
+
 /* ---- the same bit-identical legacy generator, DEVICE-RESIDENT (csrc/device_rng.cuh): the MT19937 stream of
  * np.random (mc.py:119,132; eval_ecp.py:145,263) is continued on the GPU from the state handed over once, so the
  * variates of a block are produced where they are consumed.  set_state / get_state exchange the fields of

@@ -67,6 +67,8 @@ SIGNATURES = {
                                 c_double_p]),
     "qmcb_vmc_block_slot": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_double_p, c_u8_p, c_double_p,
                                     c_double_p, c_i64_p]),
+    "qmcb_vmc_block_slot_begin": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_int, c_double_p, c_double_p, c_i64_p]),
+    "qmcb_vmc_block_slot_end": (c_int, [c_void_p, c_int]),
     "qmcb_kernel_launches": (c_int, [c_void_p, c_i64_p]),
     "qmcb_sr_avg": (c_int, [c_void_p, c_int, c_int_p, c_i64_p, c_double_p, c_double_p, c_double_p, c_double, c_double_p,
                             c_double_p, c_double_p, c_double_p]),

@@ -6,20 +6,24 @@
 // host (legacy_rng.cpp) and shipped ~1.8 MB of variates per step over PCIe; the sequential host walk of the
 // stream (0.22-0.35 ms per C2 step) then bounded the end-to-end rate above the 0.26 ms device step.  Here the
 // device continues the SAME stream from the state np.random.get_state() hands over (2.5 KB), so a block's
-// variates never exist on the host:
+// variates never exist on the host.  The work is split by what is inherently sequential:
 //
-//   k_mt_generate  one CTA: the MT19937 recurrence, 624-word state blocks ping-ponged in shared memory
-//                  (3 dependent phases of <= 227 independent words per block), tempered words to HBM;
-//   k_rng_plan     one CTA walks the "draw program" (the ordered list of uniform / normal / rotation draws of
-//                  the block): uniform draws consume 2 words each; a normal draw of n values consumes 4 words
-//                  per polar attempt until ceil((n - cached) / 2) attempts were accepted -- found with block
-//                  scans over the accept flags (x1^2 + x2^2 < 1, exact IEEE arithmetic) -- which fixes the stream
-//                  offset of every draw, the per-chunk accepted-pair prefix and the cached value carried out;
-//   k_rng_fill     many CTAs, one per (draw, chunk): converts words to doubles; for accepted attempts evaluates
-//                  f = sqrt(-2 log(r2) / r2) with glibc's log (glibc_log.h) and scatters f x2, f x1 to their slots
-//                  (scale applied as numpy does: 0.0 + scale * g); rotations: 4 normals -> unit quaternion -> matrix;
-//   k_rng_finalize recovers the raw state block the stream stopped in (inverse tempering), position and cached
-//                  Gaussian -> the state of the NEXT block's k_mt_generate and what set_state() gets at the end.
+//   k_mt_generate  (one CTA, own stream, runs ahead of everything else) the MT19937 recurrence: 624-word state
+//                  blocks ping-ponged in shared memory, ONE barrier per block (the three dependent phases of the
+//                  textbook reload are substituted into each other), RAW state words to HBM -- tempering is
+//                  left to the parallel consumers;
+//   k_rng_flags    (grid) accept flag of every possible polar attempt -- 4 consecutive words, x1^2 + x2^2 < 1 in
+//                  numpy's exact arithmetic -- as bitmaps.  Attempts start at the running stream offset, which only
+//                  ever moves by multiples of 2 words, so two alignment classes (offset mod 4) cover every case;
+//   k_rng_plan     (one CTA) walks the draw program: a uniform draw of n values moves the offset by 2n words, a
+//                  normal draw of n values by 4 words per attempt until ceil((n - cached)/2) attempts were accepted
+//                  = position of the m-th set bit of the class bitmap after the offset (popcount scan).  Produces the
+//                  stream offset of every draw and the cached Gaussian carried from draw to draw;
+//   k_rng_fill     (grid, one CTA per (draw, chunk)) tempers and converts words to doubles; for accepted attempts
+//                  evaluates f = sqrt(-2 log(r2) / r2) with glibc's log (glibc_log.h) and scatters f x2, f x1 to their
+//                  slots (0.0 + scale * g, as numpy); rotations: 4 normals -> unit quaternion -> matrix;
+//   k_rng_rebase / k_rng_finalize   bookkeeping: restart the word buffer at the block the stream is in; export
+//                  numpy's (key, pos, has_gauss, cached) for np.random.set_state().
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -28,18 +32,16 @@
 namespace devrng {
 
 constexpr int KIND_UNIFORM = 0, KIND_NORMAL = 1, KIND_ROTATION = 2;
-constexpr int PLAN_THREADS = 1024;
-constexpr int CHUNK_ATTEMPTS = 4096;  // polar attempts per (draw, chunk) work item: 4 per thread
-constexpr int CHUNK_UNIFORM = 4096;   // doubles per uniform work item
+constexpr int THREADS = 256;
+constexpr int CHUNK_GROUPS = 32 * THREADS;  // polar attempts per (draw, chunk) work item: one bitmap word per thread
+constexpr int CHUNK_UNIFORM = 8 * THREADS;  // doubles per uniform work item
 
 struct Op {            // host-built, one per draw, in consumption order
   double* dst;         // device destination (rotation: 9 doubles)
   long long count;     // values (rotation: 4 normals)
   double scale;
   int kind;
-  int chunk0;          // first slot of this draw in the chunk-prefix array
-  int maxchunks;       // slots reserved (upper bound of chunks the draw may need)
-  int small;           // 1: few values (rotation) -- chunks of 32 attempts handled by one warp
+  int maxchunks;       // work items reserved for this draw
 };
 
 struct OpPlan {        // written by k_rng_plan
@@ -47,17 +49,21 @@ struct OpPlan {        // written by k_rng_plan
   long long pairs;     // accepted pairs this draw consumes
   double cached_in;
   int has_in;
-  int nchunks;
+  int pad;
 };
 
 struct State {
-  uint32_t key[624];
-  int pos;             // numpy convention: index of the next word in key, 624 = regenerate first
-  int has_gauss;
+  long long cur;       // stream offset (word index into the buffer) of the next draw
   double cached;
-  long long cur_end;   // scratch: word offset (relative to the generated buffer) where the program stopped
-  int error;           // 1: generated buffer exhausted (host sized it too small)
+  int has_gauss;
+  int error;           // 1: the program needed words / flags that were not generated (host bound too small)
+  uint32_t key[624];   // filled by k_rng_finalize: numpy's view of the state
+  int pos;
   int pad;
+};
+
+struct GenState {
+  uint32_t key[624];   // raw state block generated last
 };
 
 struct Work {          // one CTA of k_rng_fill
@@ -73,33 +79,74 @@ __device__ __forceinline__ uint32_t temper(uint32_t y) {
   return y;
 }
 
-__device__ __forceinline__ uint32_t untemper(uint32_t y) {
-  y ^= y >> 18;
-  y ^= (y << 15) & 0xefc60000u;
-  uint32_t x = y;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) x = y ^ ((x << 7) & 0x9d2c5680u);
-  y = x;
-  x = y ^ (y >> 11);
-  x = y ^ (x >> 11);
-  return x;
+// the "magic" part of the recurrence: twist of the word pair (a, b) without the far term
+__device__ __forceinline__ uint32_t mt_f(uint32_t a, uint32_t b) {
+  const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+  return (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu);
 }
 
-__device__ __forceinline__ uint32_t mt_twist(uint32_t cur, uint32_t nxt, uint32_t far) {
-  const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
-  return far ^ (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu);
+// Word k of the NEXT state block written directly in terms of the CURRENT block o[0..623].  The textbook
+// reload has three dependent phases (words 227.. need the new words 0..226, words 454.. need the new words
+// 227..); substituting the recurrence into itself removes the dependency -- every new word is an XOR of one
+// old word and at most three twists of old pairs -- so a whole block costs ONE barrier instead of three.
+__device__ __forceinline__ uint32_t mt_next_word(const uint32_t* o, int k) {
+  if (k < 227) return o[k + 397] ^ mt_f(o[k], o[k + 1]);
+  if (k < 454) return o[k + 170] ^ mt_f(o[k - 227], o[k - 226]) ^ mt_f(o[k], o[k + 1]);
+  const uint32_t nxt = k < 623 ? o[k + 1] : (o[397] ^ mt_f(o[0], o[1]));  // word 623 pairs with the NEW word 0
+  return o[k - 57] ^ mt_f(o[k - 454], o[k - 453]) ^ mt_f(o[k - 227], o[k - 226]) ^ mt_f(o[k], nxt);
+}
+
+// Generates raw state blocks [first, first + nblocks) of the buffer from the block generated last (g->key).
+// STORE = 0: every thread stores its words (LSU); 1: the finished block leaves shared memory as ONE bulk
+// async copy (cp.async.bulk shared -> global, 2496 B) issued by thread 0, four blocks in flight; 2: no stores
+// except the state (timing experiments only).
+template <int STORE>
+__global__ void __launch_bounds__(320) k_mt_generate(GenState* g, uint32_t* __restrict__ W, long long first, int nblocks) {
+  constexpr int NBUF = 4;
+  __shared__ __align__(128) uint32_t buf[NBUF][624];
+  const int t = threadIdx.x;
+  for (int i = t; i < 624; i += 320) buf[0][i] = g->key[i];
+  __syncthreads();
+  // 312 threads own two words each (k and k + 312)
+  for (int b = 0; b < nblocks; ++b) {
+    const uint32_t* o = buf[b % NBUF];
+    uint32_t* n = buf[(b + 1) % NBUF];
+    uint32_t* out = W + (size_t)(first + b) * 624;
+    if (t < 312) {
+      const uint32_t v0 = mt_next_word(o, t), v1 = mt_next_word(o, t + 312);
+      n[t] = v0;
+      n[t + 312] = v1;
+      if (STORE == 0) {
+        out[t] = v0;
+        out[t + 312] = v1;
+      }
+      if (STORE == 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (STORE == 1 && t == 0) {
+      const uint32_t src = (uint32_t)__cvta_generic_to_shared(n);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out), "r"(src), "r"(2496) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      // buffer (b + 2) % NBUF is written next iteration: the copy that last read it (two commits ago) must be done
+      asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+    }
+  }
+  if (STORE == 1 && t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  __syncthreads();
+  for (int i = t; i < 624; i += 320) g->key[i] = buf[nblocks % NBUF][i];
 }
 
 // numpy's random_double: (a >> 5, b >> 6) -> (a * 2^26 + b) / 2^53; the integer is below 2^53, so this is exact
 __device__ __forceinline__ double to_double(uint32_t a, uint32_t b) {
   const unsigned long long v = ((unsigned long long)(a >> 5) << 26) | (unsigned long long)(b >> 6);
-  return __dmul_rn((double)v, 1.0 / 9007199254740992.0);
+  return __dmul_rn((double)(long long)v, 1.0 / 9007199254740992.0);
 }
 
-// one polar attempt from 4 consecutive words; numpy: x = 2.0 * double - 1.0; r2 = x1*x1 + x2*x2 (each rounded)
-__device__ __forceinline__ bool polar(const uint32_t* w, double& x1, double& x2, double& r2) {
-  x1 = __dsub_rn(__dmul_rn(2.0, to_double(w[0], w[1])), 1.0);
-  x2 = __dsub_rn(__dmul_rn(2.0, to_double(w[2], w[3])), 1.0);
+// one polar attempt from 4 consecutive RAW words; numpy: x = 2.0 * double - 1.0; r2 = x1*x1 + x2*x2 (each rounded)
+__device__ __forceinline__ bool polar(const uint32_t* __restrict__ w, double& x1, double& x2, double& r2) {
+  const uint32_t a = temper(__ldg(w)), b = temper(__ldg(w + 1)), c = temper(__ldg(w + 2)), d = temper(__ldg(w + 3));
+  x1 = __dsub_rn(__dmul_rn(2.0, to_double(a, b)), 1.0);
+  x2 = __dsub_rn(__dmul_rn(2.0, to_double(c, d)), 1.0);
   r2 = __dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2));
   return !(r2 >= 1.0 || r2 == 0.0);
 }
@@ -108,47 +155,25 @@ __device__ __forceinline__ double polar_factor(double r2) {
   return __dsqrt_rn(__ddiv_rn(__dmul_rn(-2.0, qmcb_glibc_log(r2)), r2));
 }
 
-// W holds `nblocks` consecutive tempered state blocks; block 0 is the state handed in.
-__global__ void __launch_bounds__(256) k_mt_generate(const State* st, uint32_t* __restrict__ W, int nblocks) {
-  __shared__ uint32_t buf[2][624];
-  const int t = threadIdx.x;
-  for (int i = t; i < 624; i += 256) {
-    const uint32_t v = st->key[i];
-    buf[0][i] = v;
-    W[i] = temper(v);
-  }
-  __syncthreads();
-  int cur = 0;
-  for (int b = 1; b < nblocks; ++b) {
-    const uint32_t* o = buf[cur];
-    uint32_t* n = buf[cur ^ 1];
-    uint32_t* out = W + (size_t)b * 624;
-    if (t < 227) {
-      const uint32_t v = mt_twist(o[t], o[t + 1], o[t + 397]);
-      n[t] = v;
-      out[t] = temper(v);
-    }
-    __syncthreads();
-    if (t < 227) {
-      const int kk = 227 + t;
-      const uint32_t v = mt_twist(o[kk], o[kk + 1], n[t]);
-      n[kk] = v;
-      out[kk] = temper(v);
-    }
-    __syncthreads();
-    if (t < 170) {
-      const int kk = 454 + t;
-      const uint32_t nxt = kk < 623 ? o[kk + 1] : n[0];
-      const uint32_t v = mt_twist(o[kk], nxt, n[kk - 227]);
-      n[kk] = v;
-      out[kk] = temper(v);
-    }
-    __syncthreads();
-    cur ^= 1;
+// word offset of attempt group `grp` of alignment class c (classes: offsets congruent to r0 and r0 + 2 mod 4)
+__device__ __forceinline__ long long group_word(int r0, int c, long long grp) { return ((r0 + 2 * c) & 3) + 4 * grp; }
+
+// Accept flags of the attempt groups [g_lo, g_hi) (multiples of 32) of both classes; every word they read exists.
+__global__ void __launch_bounds__(THREADS) k_rng_flags(const uint32_t* __restrict__ W, uint32_t* __restrict__ F0,
+                                                        uint32_t* __restrict__ F1, int r0, long long g_lo, long long g_hi) {
+  const long long grp = g_lo + (long long)blockIdx.x * THREADS + threadIdx.x;
+  const bool live = grp < g_hi;  // (g_hi - g_lo is a multiple of 32: whole warps are live or not)
+  double x1, x2, r2;
+  const bool ok0 = live && polar(W + group_word(r0, 0, grp), x1, x2, r2);
+  const bool ok1 = live && polar(W + group_word(r0, 1, grp), x1, x2, r2);
+  const unsigned m0 = __ballot_sync(0xffffffffu, ok0), m1 = __ballot_sync(0xffffffffu, ok1);
+  if (live && (threadIdx.x & 31) == 0) {
+    F0[grp >> 5] = m0;
+    F1[grp >> 5] = m1;
   }
 }
 
-// exclusive scan of one int per thread over the CTA (blockDim = PLAN_THREADS); returns the prefix, total in *total
+// exclusive scan of one int per thread over the CTA (blockDim = THREADS); total broadcast through *total
 __device__ __forceinline__ int block_scan(int v, int* warp_sums, int* total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int inc = v;
@@ -160,14 +185,14 @@ __device__ __forceinline__ int block_scan(int v, int* warp_sums, int* total) {
   if (lane == 31) warp_sums[warp] = inc;
   __syncthreads();
   if (warp == 0) {
-    int s = warp_sums[lane];
+    const int s = lane < THREADS / 32 ? warp_sums[lane] : 0;
     int sinc = s;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const int o = __shfl_up_sync(0xffffffffu, sinc, d);
       if (lane >= d) sinc += o;
     }
-    warp_sums[lane] = sinc - s;  // exclusive
+    if (lane < THREADS / 32) warp_sums[lane] = sinc - s;  // exclusive
     if (lane == 31) *total = sinc;
   }
   __syncthreads();
@@ -176,138 +201,112 @@ __device__ __forceinline__ int block_scan(int v, int* warp_sums, int* total) {
   return pre;
 }
 
-// accept flags of the attempts thread t owns in (draw, chunk): attempts [first, first + A)
-__device__ __forceinline__ int attempt_flags(const uint32_t* __restrict__ W, long long a0, long long first, int A,
-                                             long long nwords, int* overflow) {
-  int flags = 0;
-  for (int q = 0; q < A; ++q) {
-    const long long w0 = a0 + 4 * (first + q);
-    if (w0 + 4 > nwords) {  // beyond the generated words: not an attempt; an error only if the draw needs it
-      *overflow = 1;
-      break;
-    }
-    uint32_t w[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) w[i] = __ldg(W + w0 + i);
-    double x1, x2, r2;
-    if (polar(w, x1, x2, r2)) flags |= 1 << q;
-  }
-  return flags;
+// bitmap word `wi` of a draw that starts at group g0: bits before g0 and at / after `valid` are not attempts of it
+__device__ __forceinline__ uint32_t draw_word(const uint32_t* __restrict__ F, long long wi, long long g0, long long valid) {
+  if (wi * 32 >= valid) return 0u;
+  uint32_t w = __ldg(F + wi);
+  if (wi == (g0 >> 5)) w &= ~((1u << (g0 & 31)) - 1u);
+  if ((wi + 1) * 32 > valid) w &= (1u << (valid & 31)) - 1u;
+  return w;
 }
 
-__global__ void __launch_bounds__(PLAN_THREADS) k_rng_plan(const Op* __restrict__ ops, int nops, State* st,
-                                                            const uint32_t* __restrict__ W, long long nwords,
-                                                            OpPlan* __restrict__ plan, long long* __restrict__ chunk_prefix) {
+// One CTA walks the draw program.  `valid` = attempt groups whose flags exist; `nwords` = words generated.
+__global__ void __launch_bounds__(THREADS) k_rng_plan(const Op* __restrict__ ops, int nops, State* st,
+                                                       const uint32_t* __restrict__ W, const uint32_t* __restrict__ F0,
+                                                       const uint32_t* __restrict__ F1, int r0, long long valid,
+                                                       long long nwords, OpPlan* __restrict__ plan) {
+  constexpr int TILE = 256;
+  __shared__ Op s_ops[TILE];
   __shared__ int warp_sums[32];
-  __shared__ int s_total, s_overflow, s_soft, s_end_attempt_lo, s_end_attempt_hi;
+  __shared__ int s_total;
+  __shared__ long long s_end_group;
   __shared__ double s_cached_out;
   const int t = threadIdx.x;
-  long long cur = st->pos;  // all threads track the same scalars (uniform control flow)
+  // every thread carries the same running scalars (uniform control flow)
+  long long cur = st->cur;
   int has = st->has_gauss;
   double cached = st->cached;
-  if (t == 0) {
-    s_overflow = 0;
-    s_soft = 0;
-  }
-  __syncthreads();
-  for (int op = 0; op < nops; ++op) {
-    const Op o = ops[op];
-    const long long n = o.kind == KIND_ROTATION ? 4 : o.count;
-    if (t == 0) {
-      plan[op].start_word = cur;
-      plan[op].has_in = has;
-      plan[op].cached_in = cached;
-    }
-    if (o.kind == KIND_UNIFORM) {
+  int error = st->error;
+  for (int base = 0; base < nops && !error; base += TILE) {
+    __syncthreads();
+    if (base + t < nops) s_ops[t] = ops[base + t];
+    __syncthreads();
+    const int tile_n = min(TILE, nops - base);
+    for (int i = 0; i < tile_n && !error; ++i) {
+      const Op o = s_ops[i];
+      const long long n = o.kind == KIND_ROTATION ? 4 : o.count;
       if (t == 0) {
-        plan[op].pairs = 0;
-        plan[op].nchunks = (int)((n + CHUNK_UNIFORM - 1) / CHUNK_UNIFORM);
+        OpPlan p;
+        p.start_word = cur;
+        p.has_in = has;
+        p.cached_in = cached;
+        p.pairs = 0;
+        p.pad = 0;
+        if (o.kind != KIND_UNIFORM) {
+          const long long need0 = n - ((has && n > 0) ? 1 : 0);
+          p.pairs = (need0 + 1) / 2;
+        }
+        plan[base + i] = p;
       }
-      cur += 2 * n;
-      if (cur > nwords) {
-        if (t == 0) s_overflow = 1;
+      if (o.kind == KIND_UNIFORM) {
+        cur += 2 * n;
+        if (cur > nwords) error = 1;
+        continue;
+      }
+      long long need = n;
+      if (has && n > 0) {  // the cached value is handed out first
+        need -= 1;
+        has = 0;
+        cached = 0.0;
+      }
+      const long long m = (need + 1) / 2;
+      if (m == 0) continue;
+      const bool odd = (2 * m - need) == 1;  // the second value of the last pair stays cached
+      const int c = ((cur - r0) & 3) ? 1 : 0;
+      const uint32_t* F = c ? F1 : F0;
+      const long long g0 = (cur - ((r0 + 2 * c) & 3)) >> 2;
+      long long accepted = 0;
+      long long wi0 = g0 >> 5;
+      while (true) {
+        const long long wi = wi0 + t;
+        const uint32_t w = draw_word(F, wi, g0, valid);
+        const int cnt = __popc(w);
+        const int pre = block_scan(cnt, warp_sums, &s_total);
+        const int total = s_total;
+        const long long rem = m - accepted;
+        if (total >= rem && cnt > 0 && pre < rem && rem <= pre + cnt) {
+          const int bit = __fns(w, 0, (int)(rem - pre));  // position of the (rem - pre)-th set bit
+          const long long ge = wi * 32 + bit;
+          s_end_group = ge;
+          if (odd) {
+            double x1, x2, r2;
+            polar(W + group_word(r0, c, ge), x1, x2, r2);
+            s_cached_out = __dmul_rn(polar_factor(r2), x1);
+          }
+        }
         __syncthreads();
-        break;
-      }
-      continue;
-    }
-    long long need = n;
-    if (has && n > 0) {  // the cached value is handed out first
-      need -= 1;
-      has = 0;
-      cached = 0.0;
-    }
-    const long long m = (need + 1) / 2;
-    long long accepted = 0;
-    int chunk = 0;
-    const int A = o.small ? 1 : CHUNK_ATTEMPTS / PLAN_THREADS;
-    const int nact = o.small ? 32 : PLAN_THREADS;
-    long long end_attempt = 0;
-    while (accepted < m) {
-      if (chunk >= o.maxchunks) {  // reserved prefix slots exhausted: treat as overflow (host bound too tight)
-        if (t == 0) s_overflow = 1;
-        break;
-      }
-      const long long first = (long long)chunk * nact * A + (long long)t * A;
-      int ovf = 0;
-      const int flags = t < nact ? attempt_flags(W, cur, first, A, nwords, &ovf) : 0;
-      if (ovf) s_soft = 1;
-      const int cnt = __popc(flags);
-      int total;
-      const int pre = block_scan(cnt, warp_sums, &s_total);
-      total = s_total;
-      if (t == 0) chunk_prefix[o.chunk0 + chunk] = accepted;
-      const long long remaining = m - accepted;
-      if (total >= remaining && cnt > 0 && pre < remaining && remaining <= pre + cnt) {
-        // this thread owns the attempt that completes the draw: the (remaining - pre)-th set flag
-        int k = (int)(remaining - pre), q = 0;
-        for (; q < A; ++q)
-          if ((flags >> q) & 1)
-            if (--k == 0) break;
-        const long long e = first + q + 1;
-        s_end_attempt_lo = (int)(e & 0xffffffffll);
-        s_end_attempt_hi = (int)(e >> 32);
-        if ((2 * m - need) == 1) {  // odd request: the second value of the last pair stays cached
-          uint32_t w[4];
-          for (int i = 0; i < 4; ++i) w[i] = __ldg(W + cur + 4 * (first + q) + i);
-          double x1, x2, r2;
-          polar(w, x1, x2, r2);
-          s_cached_out = __dmul_rn(polar_factor(r2), x1);
+        if (total >= rem) break;
+        accepted += total;
+        wi0 += THREADS;
+        if (wi0 * 32 >= valid) {  // ran out of generated flags before the draw completed
+          error = 1;
+          break;
         }
       }
-      __syncthreads();
-      accepted += total;
-      ++chunk;
-      if (accepted >= m) end_attempt = ((long long)s_end_attempt_hi << 32) | (unsigned int)s_end_attempt_lo;
-      const bool starved = s_soft && accepted < m;  // ran past the generated words before the draw completed
-      __syncthreads();
-      if (starved) {
-        if (t == 0) s_overflow = 1;
-        break;
-      }
-    }
-    __syncthreads();
-    if (s_overflow) break;
-    if (m > 0) {
-      cur += 4 * end_attempt;
-      if ((2 * m - need) == 1) {
+      if (error) break;
+      cur = group_word(r0, c, s_end_group + 1);
+      if (odd) {
         has = 1;
         cached = s_cached_out;
       }
+      __syncthreads();  // s_end_group / s_cached_out are rewritten by the next normal draw
     }
-    if (t == 0) {
-      plan[op].pairs = m;
-      plan[op].nchunks = (chunk == 0 && n > 0) ? 1 : chunk;  // a draw served by the cached value alone still writes it
-      s_soft = 0;
-    }
-    __syncthreads();
   }
-  __syncthreads();
   if (t == 0) {
-    st->cur_end = cur;
+    st->cur = cur;
     st->has_gauss = has;
     st->cached = cached;
-    st->error = s_overflow;
+    st->error = error;
   }
 }
 
@@ -330,10 +329,10 @@ __device__ __forceinline__ void write_rotation(const double* q, double* m) {
   m[8] = __dadd_rn(__dadd_rn(__dsub_rn(-x2, y2), z2), w2);
 }
 
-__global__ void __launch_bounds__(PLAN_THREADS) k_rng_fill(const Op* __restrict__ ops, const OpPlan* __restrict__ plan,
-                                                            const long long* __restrict__ chunk_prefix,
-                                                            const Work* __restrict__ work, const State* st,
-                                                            const uint32_t* __restrict__ W, long long nwords) {
+__global__ void __launch_bounds__(THREADS) k_rng_fill(const Op* __restrict__ ops, const OpPlan* __restrict__ plan,
+                                                       const Work* __restrict__ work, const State* st,
+                                                       const uint32_t* __restrict__ W, const uint32_t* __restrict__ F0,
+                                                       const uint32_t* __restrict__ F1, int r0, long long valid) {
   __shared__ int warp_sums[32];
   __shared__ int s_total;
   __shared__ double s_q[4];
@@ -341,16 +340,16 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_rng_fill(const Op* __restrict_
   const Work wk = work[blockIdx.x];
   const Op o = ops[wk.op];
   const OpPlan p = plan[wk.op];
-  if (wk.chunk >= p.nchunks) return;
   const int t = threadIdx.x;
   if (o.kind == KIND_UNIFORM) {
     const long long i0 = (long long)wk.chunk * CHUNK_UNIFORM;
+    if (i0 >= o.count) return;
 #pragma unroll
-    for (int q = 0; q < CHUNK_UNIFORM / PLAN_THREADS; ++q) {
-      const long long i = i0 + (long long)q * PLAN_THREADS + t;
+    for (int q = 0; q < CHUNK_UNIFORM / THREADS; ++q) {
+      const long long i = i0 + (long long)q * THREADS + t;
       if (i < o.count) {
         const long long w0 = p.start_word + 2 * i;
-        o.dst[i] = to_double(__ldg(W + w0), __ldg(W + w0 + 1));
+        o.dst[i] = to_double(temper(__ldg(W + w0)), temper(__ldg(W + w0 + 1)));
       }
     }
     return;
@@ -358,42 +357,36 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_rng_fill(const Op* __restrict_
   const long long n = o.kind == KIND_ROTATION ? 4 : o.count;
   double* dst = o.kind == KIND_ROTATION ? s_q : o.dst;
   const double scale = o.kind == KIND_ROTATION ? 1.0 : o.scale;
-  if (wk.chunk == 0 && t == 0 && p.has_in && n > 0) dst[0] = __dadd_rn(0.0, __dmul_rn(scale, p.cached_in));
-  if (p.pairs == 0) return;  // (a rotation always needs pairs: n = 4)
-  const int A = o.small ? 1 : CHUNK_ATTEMPTS / PLAN_THREADS;
-  const int nact = o.small ? 32 : PLAN_THREADS;
-  const long long first = (long long)wk.chunk * nact * A + (long long)t * A;
-  int flags = 0;
-  double X1[CHUNK_ATTEMPTS / PLAN_THREADS], X2[CHUNK_ATTEMPTS / PLAN_THREADS], R2[CHUNK_ATTEMPTS / PLAN_THREADS];
-  if (t < nact) {
-#pragma unroll
-    for (int q = 0; q < CHUNK_ATTEMPTS / PLAN_THREADS; ++q) {
-      if (q < A) {
-        const long long w0 = p.start_word + 4 * (first + q);
-        if (w0 + 4 <= nwords) {  // (attempts past the generated words lie after the end of the draw)
-          uint32_t w[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) w[i] = __ldg(W + w0 + i);
-          if (polar(w, X1[q], X2[q], R2[q])) flags |= 1 << q;
-        }
-      }
-    }
-  }
-  const int cnt = __popc(flags);
-  const int pre = block_scan(cnt, warp_sums, &s_total);
-  long long pair = chunk_prefix[o.chunk0 + wk.chunk] + pre;
   const int shift = p.has_in && n > 0 ? 1 : 0;
-#pragma unroll
-  for (int q = 0; q < CHUNK_ATTEMPTS / PLAN_THREADS; ++q) {
-    if (q < A && ((flags >> q) & 1)) {
-      if (pair < p.pairs) {
-        const double f = polar_factor(R2[q]);
-        const long long slot = shift + 2 * pair;
-        dst[slot] = __dadd_rn(0.0, __dmul_rn(scale, __dmul_rn(f, X2[q])));
-        if (slot + 1 < n) dst[slot + 1] = __dadd_rn(0.0, __dmul_rn(scale, __dmul_rn(f, X1[q])));
-      }
-      ++pair;
-    }
+  if (wk.chunk == 0 && t == 0 && shift) dst[0] = __dadd_rn(0.0, __dmul_rn(scale, p.cached_in));
+  if (p.pairs == 0) return;  // (a rotation always needs pairs: n = 4)
+  const long long cur = p.start_word;
+  const int c = ((cur - r0) & 3) ? 1 : 0;
+  const uint32_t* F = c ? F1 : F0;
+  const long long g0 = (cur - ((r0 + 2 * c) & 3)) >> 2;
+  // accepted pairs of this draw before this chunk
+  long long before = 0;
+  for (int cc = 0; cc < wk.chunk; ++cc) {
+    const int cnt = __popc(draw_word(F, (g0 >> 5) + (long long)cc * THREADS + t, g0, valid));
+    block_scan(cnt, warp_sums, &s_total);
+    before += s_total;
+    __syncthreads();
+  }
+  if (before >= p.pairs) return;  // the draw ended in an earlier chunk (uniform across the CTA)
+  const long long wi = (g0 >> 5) + (long long)wk.chunk * THREADS + t;
+  uint32_t w = draw_word(F, wi, g0, valid);
+  const int pre = block_scan(__popc(w), warp_sums, &s_total);
+  long long pair = before + pre;
+  while (w && pair < p.pairs) {
+    const int bit = __ffs(w) - 1;
+    w &= w - 1;
+    double x1, x2, r2;
+    polar(W + group_word(r0, c, wi * 32 + bit), x1, x2, r2);
+    const double f = polar_factor(r2);
+    const long long slot = shift + 2 * pair;
+    dst[slot] = __dadd_rn(0.0, __dmul_rn(scale, __dmul_rn(f, x2)));
+    if (slot + 1 < n) dst[slot + 1] = __dadd_rn(0.0, __dmul_rn(scale, __dmul_rn(f, x1)));
+    ++pair;
   }
   if (o.kind == KIND_ROTATION) {
     __syncthreads();
@@ -401,32 +394,44 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_rng_fill(const Op* __restrict_
   }
 }
 
-// New generator state after the program: the raw state block the stream stopped in, numpy's position
-// convention (1..624 after any draw), cached Gaussian already stored by the plan kernel.
-__global__ void __launch_bounds__(256) k_rng_finalize(State* st, const uint32_t* __restrict__ W) {
+// Restart the buffer at the state block the stream is in: block bi moves to the front, the offset follows
+// (624 is a multiple of 4, so the alignment classes keep their meaning).
+__global__ void __launch_bounds__(320) k_rng_rebase(State* st, GenState* g, uint32_t* __restrict__ W) {
+  __shared__ long long s_bi;
+  // (cur - 1) / 624: an offset exactly on a block boundary stays "position 624 of the previous block", which is
+  // what numpy reports after consuming a whole block
+  if (threadIdx.x == 0) s_bi = st->cur > 0 ? (st->cur - 1) / 624 : 0;
+  __syncthreads();
+  const long long bi = s_bi;
+  uint32_t v[2];
+  int k = 0;
+  for (int i = threadIdx.x; i < 624; i += 320) v[k++] = W[bi * 624 + i];
+  __syncthreads();
+  k = 0;
+  for (int i = threadIdx.x; i < 624; i += 320) {
+    W[i] = v[k];
+    g->key[i] = v[k++];
+  }
+  if (threadIdx.x == 0) st->cur -= bi * 624;
+}
+
+// numpy's view of the generator after the programs run so far: the raw state block the stream stopped in and
+// the position in it (1..624 after any draw: numpy regenerates lazily, on the next draw).
+__global__ void __launch_bounds__(320) k_rng_finalize(State* st, const uint32_t* __restrict__ W) {
   __shared__ long long s_block;
-  __shared__ int s_pos;
-  if (st->error) return;
   if (threadIdx.x == 0) {
-    const long long cur = st->cur_end;
+    const long long cur = st->cur;
     long long b = cur / 624;
     int pos = (int)(cur % 624);
-    if (pos == 0 && b > 0) {  // numpy leaves pos = 624 at a block boundary and regenerates on the next draw
+    if (pos == 0 && b > 0) {
       b -= 1;
       pos = 624;
     }
     s_block = b;
-    s_pos = pos;
+    st->pos = pos;
   }
   __syncthreads();
-  const uint32_t* blk = W + (size_t)s_block * 624;
-  uint32_t v[3];
-  int k = 0;
-  for (int i = threadIdx.x; i < 624; i += 256) v[k++] = untemper(blk[i]);
-  __syncthreads();
-  k = 0;
-  for (int i = threadIdx.x; i < 624; i += 256) st->key[i] = v[k++];
-  if (threadIdx.x == 0) st->pos = s_pos;
+  for (int i = threadIdx.x; i < 624; i += 320) st->key[i] = W[s_block * 624 + i];
 }
 
 }  // namespace devrng

@@ -6,7 +6,6 @@ struct DevRngProgram {
   std::vector<long long> key;  // (kind, count, dst, scale bits) of every op: rebuilt only when it changes
   DBuf<devrng::Op> d_ops;
   DBuf<devrng::OpPlan> d_plan;
-  DBuf<long long> d_prefix;
   DBuf<devrng::Work> d_work;
   int nops = 0, nwork = 0;
   long long words_bound = 0;
@@ -14,32 +13,53 @@ struct DevRngProgram {
 
 struct DevRng {
   DBuf<devrng::State> st;
-  DBuf<uint32_t> W;
+  DBuf<devrng::GenState> gen;
+  DBuf<uint32_t> W, F0, F1;
+  long long cap_blocks = 0;   // capacity of W in 624-word state blocks
+  long long gen_blocks = 0;   // blocks generated (block 0 = the state handed in / rebased onto)
+  long long flagged = 0;      // attempt groups whose accept flags exist (multiple of 32)
+  long long upper = 0;        // upper bound of the stream offset after the programs enqueued so far
+  int r0 = 0;                 // alignment class of the stream offset (mod 4)
+  cudaStream_t gen_stream = nullptr;
+  cudaEvent_t ev_gen = nullptr, ev_plan = nullptr;
   DevRngProgram slot_prog[qmcb_ctx::NSLOT];
   DevRngProgram generic;
   bool have_state = false;
-  long long programs_run = 0;
+  long long programs_run = 0, rebases = 0;
 };
 
 static DevRng* devrng_of(qmcb_ctx* c) {
-  if (!c->devrng) c->devrng = new DevRng();
+  if (!c->devrng) {
+    DevRng* r = new DevRng();
+    cudaStreamCreateWithFlags(&r->gen_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&r->ev_gen, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&r->ev_plan, cudaEventDisableTiming);
+    c->devrng = r;
+  }
   return static_cast<DevRng*>(c->devrng);
 }
 
 static void devrng_free(qmcb_ctx* c) {
   if (!c->devrng) return;
   DevRng* r = static_cast<DevRng*>(c->devrng);
+  if (r->gen_stream) cudaStreamSynchronize(r->gen_stream);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   r->st.release();
+  r->gen.release();
   r->W.release();
+  r->F0.release();
+  r->F1.release();
   DevRngProgram* ps[qmcb_ctx::NSLOT + 1];
   for (int i = 0; i < qmcb_ctx::NSLOT; ++i) ps[i] = &r->slot_prog[i];
   ps[qmcb_ctx::NSLOT] = &r->generic;
   for (auto* p : ps) {
     p->d_ops.release();
     p->d_plan.release();
-    p->d_prefix.release();
     p->d_work.release();
   }
+  if (r->ev_gen) cudaEventDestroy(r->ev_gen);
+  if (r->ev_plan) cudaEventDestroy(r->ev_plan);
+  if (r->gen_stream) cudaStreamDestroy(r->gen_stream);
   delete r;
   c->devrng = nullptr;
 }
@@ -66,58 +86,123 @@ static int devrng_build(qmcb_ctx* c, DevRngProgram& P, int nops, const int* kind
   std::vector<devrng::Op> ops(nops);
   std::vector<devrng::Work> work;
   long long words = 0;
-  int chunk0 = 0;
   for (int i = 0; i < nops; ++i) {
     devrng::Op& o = ops[i];
     o.dst = dst[i];
     o.kind = kind[i];
     o.count = kind[i] == devrng::KIND_ROTATION ? 4 : count[i];
     o.scale = scale[i];
-    o.chunk0 = chunk0;
-    o.small = kind[i] == devrng::KIND_ROTATION ? 1 : 0;
     if (kind[i] == devrng::KIND_UNIFORM) {
       o.maxchunks = (int)((o.count + devrng::CHUNK_UNIFORM - 1) / devrng::CHUNK_UNIFORM);
       words += 2 * o.count;
     } else if (kind[i] == devrng::KIND_NORMAL || kind[i] == devrng::KIND_ROTATION) {
       const long long m = (o.count + 1) / 2;
       const long long att = attempts_bound(m);
-      const long long per = o.small ? 32 : devrng::CHUNK_ATTEMPTS;
-      o.maxchunks = (int)((att + per - 1) / per) + 1;
+      // a chunk is THREADS bitmap words starting at the word that holds the draw's first attempt
+      o.maxchunks = (int)((att + 31 + devrng::CHUNK_GROUPS - 1) / devrng::CHUNK_GROUPS);
       words += 4 * att;
     } else {
       return fail("devrng: unknown op kind");
     }
-    chunk0 += o.maxchunks;
     for (int k = 0; k < std::max(o.maxchunks, o.count > 0 ? 1 : 0); ++k) work.push_back(devrng::Work{i, k});
   }
-  if (P.d_ops.ensure(nops) || P.d_plan.ensure(nops) || P.d_prefix.ensure((size_t)chunk0 + 1) || P.d_work.ensure(work.size() + 1))
-    return -1;
-  // (a program is rebuilt only when its shape changes; the copies are ordered after earlier work of the stream)
-  CK(cudaMemcpyAsync(P.d_ops.p, ops.data(), nops * sizeof(devrng::Op), cudaMemcpyHostToDevice, c->copy_stream));
-  CK(cudaMemcpyAsync(P.d_work.p, work.data(), work.size() * sizeof(devrng::Work), cudaMemcpyHostToDevice, c->copy_stream));
-  CK(cudaStreamSynchronize(c->copy_stream));  // the host vectors die with this call
+  // the previous version of this program may still be in flight
+  CK(cudaStreamSynchronize(c->copy_stream));
+  if (P.d_ops.ensure(nops) || P.d_plan.ensure(nops) || P.d_work.ensure(work.size() + 1)) return -1;
+  CK(cudaMemcpy(P.d_ops.p, ops.data(), nops * sizeof(devrng::Op), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(P.d_work.p, work.data(), work.size() * sizeof(devrng::Work), cudaMemcpyHostToDevice));
   P.nops = nops;
   P.nwork = (int)work.size();
-  P.words_bound = words + 8LL * devrng::CHUNK_ATTEMPTS;
+  P.words_bound = words + 1024;
   P.key.swap(key);
+  return 0;
+}
+
+// (re)allocation of the word buffer and the flag bitmaps; keeps state block 0
+static int devrng_reserve(qmcb_ctx* c, DevRng* r, long long blocks) {
+  if (blocks <= r->cap_blocks) return 0;
+  CK(cudaStreamSynchronize(r->gen_stream));
+  CK(cudaStreamSynchronize(c->copy_stream));
+  DBuf<uint32_t> W;
+  if (W.ensure((size_t)blocks * 624)) return -1;
+  if (r->W.p) CK(cudaMemcpy(W.p, r->W.p, 624 * 4, cudaMemcpyDeviceToDevice));
+  r->W.release();
+  r->W = W;
+  const size_t fwords = (size_t)blocks * 156 / 32 + 64;  // 156 attempt groups per state block and class
+  r->F0.release();
+  r->F1.release();
+  if (r->F0.ensure(fwords) || r->F1.ensure(fwords)) return -1;
+  r->cap_blocks = blocks;
+  r->gen_blocks = std::min<long long>(r->gen_blocks, 1);  // only block 0 was carried over
+  r->flagged = 0;
+  return 0;
+}
+
+// generate + flag so that `blocks` state blocks exist; records ev_gen on the generator stream
+static int devrng_generate(qmcb_ctx* c, DevRng* r, long long blocks) {
+  if (blocks <= r->gen_blocks) return 0;
+  static const int store_mode = std::getenv("QMCB_MT_STORE") ? std::atoi(std::getenv("QMCB_MT_STORE")) : 0;
+  const int nb = (int)(blocks - r->gen_blocks);
+  if (store_mode == 0)
+    devrng::k_mt_generate<0><<<1, 320, 0, r->gen_stream>>>(r->gen.p, r->W.p, r->gen_blocks, nb);
+  else if (store_mode == 2)
+    devrng::k_mt_generate<2><<<1, 320, 0, r->gen_stream>>>(r->gen.p, r->W.p, r->gen_blocks, nb);
+  else
+    devrng::k_mt_generate<1><<<1, 320, 0, r->gen_stream>>>(r->gen.p, r->W.p, r->gen_blocks, nb);
+  r->gen_blocks = blocks;
+  const long long avail = blocks * 624;
+  const long long g_hi = ((avail - 3) / 4) / 32 * 32;
+  if (g_hi > r->flagged) {
+    const long long ng = g_hi - r->flagged;
+    devrng::k_rng_flags<<<(unsigned)((ng + devrng::THREADS - 1) / devrng::THREADS), devrng::THREADS, 0, r->gen_stream>>>(
+        r->W.p, r->F0.p, r->F1.p, r->r0, r->flagged, g_hi);
+    r->flagged = g_hi;
+  }
+  c->nlaunch += 2;
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(r->ev_gen, r->gen_stream));
   return 0;
 }
 
 static int devrng_run(qmcb_ctx* c, DevRngProgram& P) {
   DevRng* r = devrng_of(c);
   if (!r->have_state) return fail("qmcb_devrng_set_state has not been called");
-  const int nblocks = (int)((624 + P.words_bound + 623) / 624) + 2;
-  const long long nwords = (long long)nblocks * 624;
-  if (r->W.ensure((size_t)nwords)) return -1;
+  const long long prog_blocks = (P.words_bound + 623) / 624 + 2;
+  long long need_blocks = (r->upper + P.words_bound + 623) / 624 + 2;
+  if (need_blocks > r->cap_blocks) {
+    if (r->upper > 624) {
+      // rebase: move the state block the stream is in to the front of the buffer.  Ordered after every plan so far
+      // (copy stream) and after the generator (it may be writing ahead); the generator restarts behind it.
+      CK(cudaStreamWaitEvent(c->copy_stream, r->ev_gen, 0));
+      devrng::k_rng_rebase<<<1, 320, 0, c->copy_stream>>>(r->st.p, r->gen.p, r->W.p);
+      CK(cudaEventRecord(r->ev_plan, c->copy_stream));
+      CK(cudaStreamWaitEvent(r->gen_stream, r->ev_plan, 0));
+      c->nlaunch++;
+      r->gen_blocks = 1;
+      r->flagged = 0;
+      r->upper = 624;
+      r->rebases++;
+      need_blocks = (r->upper + P.words_bound + 623) / 624 + 2;
+    }
+    const long long want = std::max<long long>(need_blocks + prog_blocks, 32 * prog_blocks);
+    if (need_blocks > r->cap_blocks && devrng_reserve(c, r, std::min<long long>(want, std::max<long long>(need_blocks + 2, (3LL << 30) / 2496))))
+      return -1;
+  }
+  if (devrng_generate(c, r, need_blocks)) return -1;
   cudaStream_t s = c->copy_stream;
-  devrng::k_mt_generate<<<1, 256, 0, s>>>(r->st.p, r->W.p, nblocks);
-  devrng::k_rng_plan<<<1, devrng::PLAN_THREADS, 0, s>>>(P.d_ops.p, P.nops, r->st.p, r->W.p, nwords, P.d_plan.p, P.d_prefix.p);
+  CK(cudaStreamWaitEvent(s, r->ev_gen, 0));
+  const long long nwords = r->gen_blocks * 624, valid = r->flagged;
+  devrng::k_rng_plan<<<1, devrng::THREADS, 0, s>>>(P.d_ops.p, P.nops, r->st.p, r->W.p, r->F0.p, r->F1.p, r->r0, valid, nwords,
+                                                    P.d_plan.p);
   if (P.nwork > 0)
-    devrng::k_rng_fill<<<P.nwork, devrng::PLAN_THREADS, 0, s>>>(P.d_ops.p, P.d_plan.p, P.d_prefix.p, P.d_work.p, r->st.p, r->W.p,
-                                                               nwords);
-  devrng::k_rng_finalize<<<1, 256, 0, s>>>(r->st.p, r->W.p);
-  c->nlaunch += 4;
+    devrng::k_rng_fill<<<P.nwork, devrng::THREADS, 0, s>>>(P.d_ops.p, P.d_plan.p, P.d_work.p, r->st.p, r->W.p, r->F0.p, r->F1.p,
+                                                           r->r0, valid);
+  c->nlaunch += 2;
   CK(cudaGetLastError());
+  r->upper += P.words_bound;
+  // run the generator ahead by one more program of this size: the next plan then finds its words ready
+  const long long ahead = std::min<long long>(r->cap_blocks, (r->upper + P.words_bound + 623) / 624 + 2);
+  if (devrng_generate(c, r, ahead)) return -1;
   r->programs_run++;
   return 0;
 }
@@ -126,15 +211,22 @@ int qmcb_devrng_set_state(qmcb_ctx* c, const uint32_t* key, int32_t pos, int32_t
   Guard g(c);
   if (pos < 0 || pos > 624) return fail("MT19937 position out of range");
   DevRng* r = devrng_of(c);
-  if (r->st.ensure(1)) return -1;
+  CK(cudaStreamSynchronize(r->gen_stream));
+  CK(cudaStreamSynchronize(c->copy_stream));
+  if (r->st.ensure(1) || r->gen.ensure(1)) return -1;
+  if (r->cap_blocks == 0 && devrng_reserve(c, r, 64)) return -1;
   devrng::State h;
   std::memset(&h, 0, sizeof(h));
-  std::memcpy(h.key, key, sizeof(h.key));
-  h.pos = pos;
+  h.cur = pos;
   h.has_gauss = has_gauss;
   h.cached = cached_gauss;
-  CK(cudaStreamSynchronize(c->copy_stream));
   CK(cudaMemcpy(r->st.p, &h, sizeof(h), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(r->gen.p, key, 624 * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(r->W.p, key, 624 * 4, cudaMemcpyHostToDevice));
+  r->r0 = pos & 3;
+  r->gen_blocks = 1;
+  r->flagged = 0;
+  r->upper = pos;
   r->have_state = true;
   return 0;
 }
@@ -143,6 +235,8 @@ int qmcb_devrng_get_state(qmcb_ctx* c, uint32_t* key, int32_t* pos, int32_t* has
   Guard g(c);
   DevRng* r = devrng_of(c);
   if (!r->have_state) return fail("qmcb_devrng_set_state has not been called");
+  devrng::k_rng_finalize<<<1, 320, 0, c->copy_stream>>>(r->st.p, r->W.p);
+  c->nlaunch++;
   CK(cudaStreamSynchronize(c->copy_stream));
   devrng::State h;
   CK(cudaMemcpy(&h, r->st.p, sizeof(h), cudaMemcpyDeviceToHost));
@@ -200,6 +294,8 @@ int qmcb_devrng_vmc_block(qmcb_ctx* c, int slot, int nsteps, int ne, int64_t N, 
       }
   }
   if (devrng_build(c, r->slot_prog[slot], (int)kind.size(), kind.data(), count.data(), dst.data(), scale.data())) return -1;
+  // the slot's previous variates may still be read by a block begun with qmcb_vmc_block_slot_begin
+  if (c->block_pending[slot]) CK(cudaStreamWaitEvent(c->copy_stream, c->block_done[slot], 0));
   if (devrng_run(c, r->slot_prog[slot])) return -1;
   CK(cudaEventRecord(c->slot_ready[slot], c->copy_stream));
   return 0;

@@ -156,6 +156,8 @@ struct qmcb_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t slot_ready[NSLOT] = {nullptr, nullptr, nullptr};
   cudaEvent_t done_event = nullptr;  // blocking-sync event: the host thread sleeps while a block runs
+  cudaEvent_t block_done[NSLOT] = {nullptr, nullptr, nullptr};  // qmcb_vmc_block_slot_begin / _end
+  bool block_pending[NSLOT] = {false, false, false};
   void* devrng = nullptr;            // DevRng (devrng_api.cuh): device-resident legacy generator
 };
 
@@ -1027,6 +1029,8 @@ int qmcb_create(int device, qmcb_ctx** out) {
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < qmcb_ctx::NSLOT; ++i) CK(cudaEventCreateWithFlags(&c->slot_ready[i], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->done_event, cudaEventDisableTiming | cudaEventBlockingSync));
+  for (int i = 0; i < qmcb_ctx::NSLOT; ++i)
+    CK(cudaEventCreateWithFlags(&c->block_done[i], cudaEventDisableTiming | cudaEventBlockingSync));
   *out = c;
   return 0;
 }
@@ -1075,6 +1079,7 @@ void qmcb_destroy(qmcb_ctx* c) {
     c->s_u[i].release();
     c->s_rot[i].release();
     if (c->slot_ready[i]) cudaEventDestroy(c->slot_ready[i]);
+    if (c->block_done[i]) cudaEventDestroy(c->block_done[i]);
   }
   if (c->done_event) cudaEventDestroy(c->done_event);
   devrng_free(c);
@@ -2181,6 +2186,50 @@ int qmcb_vmc_block_slot(qmcb_ctx* c, int slot, int nsteps, double tstep, int wit
   }
   if (sync_blocking(c)) return -1;
   acc_all.release();
+  return 0;
+}
+
+// Asynchronous pair of qmcb_vmc_block_slot: _begin enqueues (optionally the recompute of the selected factors from
+// the resident walkers, then) the block on the variates of `slot` and the copies of its results into the caller's
+// (page-locked) buffers, and returns; _end sleeps until that block's results have landed.  The host driver begins
+// block b+1 before it ends block b, so result read-back and host bookkeeping leave the critical path.
+int qmcb_vmc_block_slot_begin(qmcb_ctx* c, int slot, int nsteps, double tstep, int with_energy, int recompute_which,
+                              double* configs, double* energy, int64_t* nacc) {
+  Guard g(c);
+  if (slot < 0 || slot >= qmcb_ctx::NSLOT) return fail("slot out of range");
+  if (c->N == 0) return fail("recompute has not been called");
+  if (build_tables(c)) return -1;
+  if (c->N == 0) return fail("system shapes changed: call recompute again");
+  const Sys& S = c->S;
+  const size_t N = c->N;
+  const size_t nse = (size_t)nsteps * S.ne;
+  if (c->s_gauss[slot].n < nse * N * 3) return fail("slot was not uploaded for this block shape");
+  if (recompute_which) {
+    if (which_ok(c, recompute_which)) return -1;
+    if (recompute_from_resident(c, recompute_which, (int)N)) return -1;
+  }
+  CK(cudaStreamWaitEvent(c->stream, c->slot_ready[slot], 0));
+  if (with_energy && (c->d_energy.ensure((size_t)nsteps * 6 * N) || c->d_esum.ensure((size_t)nsteps * 6))) return -1;
+  int rc = qmcb_vmc_block_device(c, nsteps, tstep, with_energy, c->s_gauss[slot].p, c->s_unif[slot].p, c->s_u[slot].p,
+                                 c->s_rot[slot].p, nullptr, with_energy ? c->d_energy.p : nullptr,
+                                 with_energy ? c->d_esum.p : nullptr, nullptr, c->stream);
+  if (rc) return rc;
+  if (energy && with_energy)
+    CK(cudaMemcpyAsync(energy, c->d_energy.p, (size_t)nsteps * 6 * N * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (nacc) CK(cudaMemcpyAsync(nacc, c->d_nacc.p, nse * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (configs) CK(cudaMemcpyAsync(configs, c->st.conf, N * S.ne * 3 * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaEventRecord(c->block_done[slot], c->stream));
+  c->block_pending[slot] = true;
+  return 0;
+}
+
+int qmcb_vmc_block_slot_end(qmcb_ctx* c, int slot) {
+  Guard g(c);
+  if (slot < 0 || slot >= qmcb_ctx::NSLOT) return fail("slot out of range");
+  if (!c->block_pending[slot]) return fail("no block was begun on this slot");
+  CK(cudaEventSynchronize(c->block_done[slot]));
+  c->block_pending[slot] = false;
+  CK(cudaGetLastError());
   return 0;
 }
 

@@ -175,6 +175,25 @@ def _recompute_resident(wf, configs):
     return True
 
 
+def _block_averages(buffers, nsteps, nconf, nelec, acc_name, accumulator):
+    """Block dictionary entries from the per-walker results a device block left in ``buffers``."""
+    block_avg = {}
+    if accumulator is not None:
+        # per-step walker means (one pairwise-summed reduction per (step, key) row, as np.mean of the row),
+        # accumulated over the steps in order as the reference loop does (mc.py:139-147)
+        means = np.mean(buffers.energy[:nsteps], axis=2)
+        for i, m in enumerate(KEYS):
+            tot = means[0, i] / nsteps
+            for step in range(1, nsteps):
+                tot += means[step, i] / nsteps
+            block_avg[acc_name + m] = tot
+    acc = 0.0
+    for e in range(nelec):
+        acc += (buffers.nacc[nsteps - 1, e] / nconf) / nelec
+    block_avg["acceptance"] = acc
+    return block_avg
+
+
 def vmc_block_device(wf, configs, tstep, nsteps, accumulators, variates=None, return_walker_data=False,
                      buffers=None):
     """One device-resident block; equivalent of ``vmc_worker`` (mc.py:102-153).
@@ -218,20 +237,7 @@ def vmc_block_device(wf, configs, tstep, nsteps, accumulators, variates=None, re
         configs.wrap[...] = ctx.get_state("wrap", configs.wrap.shape)
     else:  # the device holds exactly these walkers: the next block may recompute from them in place
         ctx._resident = (buffers, ctx.epoch)  # the BlockBuffers object keeps the pinned memory alive
-    block_avg = {}
-    if accumulator is not None:
-        # per-step walker means (one pairwise-summed reduction per (step, key) row, as np.mean of the row),
-        # accumulated over the steps in order as the reference loop does (mc.py:139-147)
-        means = np.mean(energy[:nsteps], axis=2)
-        for i, m in enumerate(KEYS):
-            tot = means[0, i] / nsteps
-            for step in range(1, nsteps):
-                tot += means[step, i] / nsteps
-            block_avg[acc_name + m] = tot
-    acc = 0.0
-    for e in range(nelec):
-        acc += (nacc[nsteps - 1, e] / nconf) / nelec
-    block_avg["acceptance"] = acc
+    block_avg = _block_averages(buffers, nsteps, nconf, nelec, acc_name, accumulator)
     block_avg["move time"] = end - start
     block_avg["accumulator time"] = 0.0
     if return_walker_data:
@@ -426,6 +432,51 @@ def _variate_source(wf, configs, tstep, nsteps, accumulators, nblocks):
     return _VariatePrefetcher(wf, configs, tstep, nsteps, accumulators, nblocks)
 
 
+def _pipelined_blocks(wf, configs, tstep, nsteps, accumulators, source, blocks, on_block):
+    """The block loop with block b+1 enqueued before block b's results are read (qmcb_vmc_block_slot_begin / _end):
+    the device never waits for the host's read-back and bookkeeping.  Needs the device generator (no host thread has
+    to produce block b+1's variates) and open boundaries.  ``on_block(block_index, row, configs)`` is called in order."""
+    nconf, nelec, _ = configs.configs.shape
+    ctx = _device_context(wf)
+    acc_name, accumulator = (next(iter(accumulators.items())) if accumulators else (None, None))
+    with_energy = 1 if accumulator is not None else 0
+    if not _recompute_resident(wf, configs):
+        wf.recompute(configs)
+    if accumulator is not None:
+        accumulator._attach(wf)
+    which = wf._which
+    i64p = _lib.c_i64_p
+
+    def begin(buf, recompute):
+        slot = buf.uploaded_slot
+        buf.uploaded_slot = None
+        _lib.check(ctx.lib.qmcb_vmc_block_slot_begin(ctx.h, slot, nsteps, float(tstep), with_energy, which if recompute else 0,
+                                                     _lib.dptr(buf.newconf), _lib.dptr(buf.energy), buf.nacc.ctypes.data_as(i64p)))
+        return slot, buf, time.perf_counter()
+
+    inflight = begin(source.next(), False)
+    for k, block in enumerate(blocks):
+        following = begin(source.next(), True) if k + 1 < len(blocks) else None
+        slot, buf, started = inflight
+        _lib.check(ctx.lib.qmcb_vmc_block_slot_end(ctx.h, slot))
+        row = _block_averages(buf, nsteps, nconf, nelec, acc_name, accumulator)
+        row["move time"] = time.perf_counter() - started
+        row["accumulator time"] = 0.0
+        configs.configs[...] = buf.newconf
+        ctx._resident = (buf, ctx.epoch)
+        on_block(block, row, configs)
+        inflight = following
+    return configs
+
+
+def _can_pipeline(wf, source):
+    import os
+
+    ctx = _device_context(wf)
+    return (isinstance(source, _DeviceVariates) and ctx is not None and not ctx.periodic
+            and not os.environ.get("QMCB_NO_PIPELINE"))
+
+
 def _reference_driver():
     """The reference's own driver module, when PyQMC is installed next to this plugin."""
     try:
@@ -488,18 +539,26 @@ def vmc(wf, configs, tstep=0.5, nblocks=10, nsteps_per_block=10, nsteps=None, bl
     rows = []
     todo = max(0, nblocks - blockoffset)
     prefetch = _variate_source(wf, configs, tstep, nsteps_per_block, accumulators, todo) if todo else None
+
+    def finish_block(block, row, walkers):
+        row["block"] = block
+        row["nconfig"] = nsteps_per_block * walkers.configs.shape[0]
+        if hdf_file is not None:
+            with blockio.open_store(hdf_file, "a") as store:
+                store.append_block(row, attrs={"tstep": tstep}, walkers=walkers)
+        rows.append(row)
+
     try:
-        for block in range(blockoffset, nblocks):
-            if verbose:
-                print("-", end="", flush=True)
-            row, configs = vmc_block_device(wf, configs, tstep, nsteps_per_block, accumulators,
-                                            buffers=prefetch.next())
-            row["block"] = block
-            row["nconfig"] = nsteps_per_block * configs.configs.shape[0]
-            if hdf_file is not None:
-                with blockio.open_store(hdf_file, "a") as store:
-                    store.append_block(row, attrs={"tstep": tstep}, walkers=configs)
-            rows.append(row)
+        if todo and _can_pipeline(wf, prefetch):
+            configs = _pipelined_blocks(wf, configs, tstep, nsteps_per_block, accumulators, prefetch,
+                                        list(range(blockoffset, nblocks)), finish_block)
+        else:
+            for block in range(blockoffset, nblocks):
+                if verbose:
+                    print("-", end="", flush=True)
+                row, configs = vmc_block_device(wf, configs, tstep, nsteps_per_block, accumulators,
+                                                buffers=prefetch.next())
+                finish_block(block, row, configs)
     finally:
         if prefetch is not None:
             prefetch.close()
