@@ -82,12 +82,18 @@ def workload_config(workload, walkers_per_gpu, world):
     return cfg
 
 
-def e2e_bytes_per_block(N, ne, necp, spb, nblocks):
-    """Host<->device bytes of one block of pyqmc_b200.vmc: the variates in (gauss, unif, ECP uniforms + rotations; the
-    walkers themselves are uploaded by the first block only, later blocks recompute from the resident walkers) and the
-    per-walker energies, the walkers and the acceptance counts out."""
-    h2d = spb * ne * N * (3 + 1) * 8 + spb * ne * necp * (N + 9) * 8 + N * ne * 3 * 8 / nblocks
+def e2e_bytes_per_block(N, ne, necp, spb, nblocks, device_rng):
+    """Host<->device bytes of one block of pyqmc_b200.vmc.  In: the walkers (uploaded by the first block only, later
+    blocks recompute from the resident walkers) and either the generator state once per call (device generator: the
+    variates are produced on the GPU) or the block's variates (host generator: gauss, unif, ECP uniforms + rotations).
+    Out: the per-walker energies, the walkers and the acceptance counts of every block, the generator state once."""
+    h2d = N * ne * 3 * 8 / nblocks
     d2h = spb * 6 * N * 8 + N * ne * 3 * 8 + spb * ne * 8
+    if device_rng:
+        h2d += (624 * 4 + 24) / nblocks
+        d2h += (624 * 4 + 24) / nblocks
+    else:
+        h2d += spb * ne * N * (3 + 1) * 8 + spb * ne * necp * (N + 9) * 8
     return h2d, d2h
 
 
@@ -522,7 +528,8 @@ def gpu_arm(args):
     e2e = N * world * nb_long * spb / t_long
     e2e_steady = N * world * (nb_long - nb_short) * spb / max(t_long - t_short, 1e-9)
     necp = acc.necp
-    h2d, d2h = e2e_bytes_per_block(N, ne, necp, spb, nb_e2e)
+    device_rng = mc.device_rng_usable()
+    h2d, d2h = e2e_bytes_per_block(N, ne, necp, spb, nb_e2e, device_rng)
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:
@@ -541,7 +548,10 @@ def gpu_arm(args):
         "config": workload_config(args.workload, N, world),
         "e2e": {"value": e2e, "unit": "walker-steps/s", "h2d_bytes_per_step": h2d / spb, "d2h_bytes_per_step": d2h / spb,
                 "call": f"pyqmc_b200.vmc(nblocks={nb_e2e}, nsteps_per_block={spb}), host walkers in / host walkers + block "
-                        f"averages out, bit-exact legacy RNG stream; {t_e2e:.2f} s",
+                        f"averages out, bit-exact legacy np.random stream "
+                        f"({'continued on the device from np.random.get_state()' if device_rng else 'host generator'}); "
+                        f"{t_e2e:.2f} s",
+                "rng": "device" if device_rng else "host",
                 "e2e_fill_included": e2e, "e2e_steady": e2e_steady,
                 "steady_definition": f"({nb_long} - {nb_short}) blocks / (t[{nb_long} blocks] - t[{nb_short} blocks])"},
         "gpu_launches": int(launches),
