@@ -7,7 +7,7 @@ drift-diffusion moves over all 8 electrons plus the local-energy accumulator (ke
 -- one iteration of the loop at pyqmc/method/mc.py:112-152.
 
   value   device-timed (CUDA events on the launching stream), random variates and walkers
-          already resident in HBM, L2 flushed between timed steps;
+          already resident in HBM, one library call per block of 10 steps, L2 flushed between timed blocks;
   e2e     the public call pyqmc_b200.vmc(...) with host numpy walkers: host RNG draws in the
           reference's order, H2D of the variates, the device block, D2H of energies + walkers;
   cpu_baseline / --impl reference   the UNMODIFIED reference (oracle/_ref: pyqmc's numpy + numba path,
@@ -77,7 +77,7 @@ def workload_config(workload, walkers_per_gpu, world):
         cfg["l2"] = "walker state (2 KB/walker) is L2-resident by design; no flush between blocks"
         cfg["parallelism"] = f"walker-sharded x{world}, one NCCL allreduce of the weighted sums + global branching per block"
     else:
-        cfg["l2"] = "256 MiB buffer written between timed steps (L2 flush)"
+        cfg["l2"] = f"256 MiB buffer written between timed blocks of {SPB} steps (L2 flush); one library call per block"
         cfg["parallelism"] = f"walker-sharded x{world}, one NCCL allreduce of the energy sums per block of {SPB} steps"
     return cfg
 
@@ -425,8 +425,8 @@ def gpu_arm(args):
     d_unif = torch.from_numpy(unif).cuda()
     d_u = torch.from_numpy(ecp_u).cuda()
     d_rot = torch.from_numpy(ecp_rot).cuda()
-    d_energy = torch.empty((6, N), dtype=torch.float64, device="cuda")
-    d_esum = torch.zeros((tot, 8), dtype=torch.float64, device="cuda")
+    d_energy = torch.empty((SPB, 6, N), dtype=torch.float64, device="cuda")
+    d_esum = torch.zeros((tot, 6), dtype=torch.float64, device="cuda")
     d_nacc = torch.zeros((tot, ne), dtype=torch.int64, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     wf.recompute(configs)
@@ -438,20 +438,25 @@ def gpu_arm(args):
     torch.cuda.synchronize()
     vp = ctypes.c_void_p
 
-    def run_step(s):
-        rc = lib.qmcb_vmc_block_device(ctx.h, 1, TSTEP, 1, vp(d_gauss[s].data_ptr()), vp(d_unif[s].data_ptr()),
+    def chunks(lo, hi):
+        """[lo, hi) cut into blocks of SPB steps (the reference's nsteps_per_block; the last one may be shorter)."""
+        return [(s, min(SPB, hi - s)) for s in range(lo, hi, SPB)]
+
+    def run_block(s, n):
+        """n consecutive VMC steps in ONE library call, as the public driver issues them (a block)."""
+        rc = lib.qmcb_vmc_block_device(ctx.h, n, TSTEP, 1, vp(d_gauss[s].data_ptr()), vp(d_unif[s].data_ptr()),
                                        vp(d_u[s].data_ptr()), vp(d_rot[s].data_ptr()), None, vp(d_energy.data_ptr()),
                                        vp(d_esum[s].data_ptr()), vp(d_nacc[s].data_ptr()), vp(stream))
         if rc != 0:
             raise RuntimeError(lib.qmcb_last_error().decode())
-        if world > 1 and (s + 1) % SPB == 0:
-            # one allreduce per block of SPB steps: the block's energy sums, over NVLink
-            dist.all_reduce(d_esum[s + 1 - SPB : s + 1])
+        if world > 1:
+            # one allreduce per block: the block's energy sums, over NVLink
+            dist.all_reduce(d_esum[s : s + n])
 
     torch.cuda.set_stream(ts)
     sampler = ClockSampler(local) if rank == 0 else None  # samples the warm-up and the timed steps
-    for s in range(W):
-        run_step(s)
+    for s, n in chunks(0, W):
+        run_block(s, n)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -461,11 +466,11 @@ def gpu_arm(args):
     if sampler:
         sampler.mark()
     wall0 = time.perf_counter()
-    for s in range(W, tot):
-        flush.fill_(s & 0xFF)  # evict the walker state from L2 between timed steps
+    for s, n in chunks(W, tot):
+        flush.fill_(s & 0xFF)  # evict the walker state from L2 between timed blocks
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(ts)
-        run_step(s)
+        run_block(s, n)
         e1.record(ts)
         evs.append((e0, e1))
     torch.cuda.synchronize()
@@ -482,10 +487,22 @@ def gpu_arm(args):
     torch.cuda.synchronize()
     tw0 = time.perf_counter()
     with torch.cuda.stream(ts):
-        for s in range(W, tot):
-            run_step(s)
+        for s, n in chunks(W, tot):
+            run_block(s, n)
     torch.cuda.synchronize()
     t_wall_noflush = time.perf_counter() - tw0
+    # the same steps as K single-step calls (no step of one call can overlap the next): what round 1 reported
+    single = []
+    with torch.cuda.stream(ts):
+        for s in range(W, tot):
+            flush.fill_(s & 0xFF)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ts)
+            run_block(s, 1)
+            e1.record(ts)
+            single.append((e0, e1))
+    torch.cuda.synchronize()
+    t_single = sum(a.elapsed_time(b) for a, b in single) * 1e-3
     tmax = torch.tensor([t_dev], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -570,6 +587,7 @@ def gpu_arm(args):
             "n4_4096_matrices_C2_shape": {"achieved_GBps": g4s, "frac": g4s / peak, "launch_ms": 1e3 * t4s}},
         "clocks": clocks,
         "check": {"mean_local_energy": e_mean, "acceptance": accept, "wall_s_timed_region_incl_flush": wall,
+                  "ms_per_step_as_single_step_calls": 1e3 * t_single / K,
                   "wall_s_same_steps_back_to_back_no_flush": t_wall_noflush, "device_s_timed_steps": t_dev_max},
     }
     if args.workload != "c2":

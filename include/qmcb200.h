@@ -303,6 +303,8 @@ int qmcb_devrng_program(qmcb_ctx *ctx, int64_t nops, const int32_t *kind, const 
 int qmcb_devrng_vmc_block(qmcb_ctx *ctx, int slot, int nsteps, int ne, int64_t N, int necp,
                           double sigma);
 int64_t qmcb_glibc_log_mismatches(int64_t nsamples, uint64_t seed);
+/* diagnostics: SM cycles, nanoseconds and state blocks of the last k_mt_generate launch (out3[3]) */
+int qmcb_devrng_generator_timing(qmcb_ctx *ctx, int64_t *out3);
 
 #ifdef __cplusplus
 }

@@ -64,6 +64,7 @@ struct State {
 
 struct GenState {
   uint32_t key[624];   // raw state block generated last
+  long long cycles, nanos, blocks;  // of the last k_mt_generate launch (clock64 / globaltimer): profiles/devrng_microbench.py
 };
 
 struct Work {          // one CTA of k_rng_fill
@@ -97,43 +98,55 @@ __device__ __forceinline__ uint32_t mt_next_word(const uint32_t* o, int k) {
 }
 
 // Generates raw state blocks [first, first + nblocks) of the buffer from the block generated last (g->key).
-// STORE = 0: every thread stores its words (LSU); 1: the finished block leaves shared memory as ONE bulk
-// async copy (cp.async.bulk shared -> global, 2496 B) issued by thread 0, four blocks in flight; 2: no stores
-// except the state (timing experiments only).
-template <int STORE>
-__global__ void __launch_bounds__(320) k_mt_generate(GenState* g, uint32_t* __restrict__ W, long long first, int nblocks) {
-  constexpr int NBUF = 4;
-  __shared__ __align__(128) uint32_t buf[NBUF][624];
+// MODE 0: every new word straight from the old block (mt_next_word: up to three twists per word, ONE barrier per
+// block).  MODE 1: the 624 twists h[j] = f(o[j], o[j+1]) are computed once into shared memory, then every new word
+// is an XOR of one old word and up to three h's (two barriers, ~40 % fewer instructions: the single CTA is
+// issue-bound, profiles/devrng_microbench.py).
+template <int MODE>
+__global__ void __launch_bounds__(640) k_mt_generate(GenState* g, uint32_t* __restrict__ W, long long first, int nblocks) {
+  __shared__ uint32_t buf[2][624];
+  __shared__ uint32_t h[624];
   const int t = threadIdx.x;
-  for (int i = t; i < 624; i += 320) buf[0][i] = g->key[i];
+  if (t < 624) buf[0][t] = g->key[t];
   __syncthreads();
-  // 312 threads own two words each (k and k + 312)
+  long long c0 = 0, n0 = 0;
+  if (t == 0) {
+    c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(n0));
+  }
+  int cur = 0;
+  // one word per thread: 20 warps hide the dependent shared-memory / ALU latencies of the short per-word chain
   for (int b = 0; b < nblocks; ++b) {
-    const uint32_t* o = buf[b % NBUF];
-    uint32_t* n = buf[(b + 1) % NBUF];
+    const uint32_t* o = buf[cur];
+    uint32_t* n = buf[cur ^ 1];
     uint32_t* out = W + (size_t)(first + b) * 624;
-    if (t < 312) {
-      const uint32_t v0 = mt_next_word(o, t), v1 = mt_next_word(o, t + 312);
-      n[t] = v0;
-      n[t + 312] = v1;
-      if (STORE == 0) {
-        out[t] = v0;
-        out[t + 312] = v1;
+    if (MODE == 0) {
+      if (t < 624) {
+        const uint32_t v = mt_next_word(o, t);
+        n[t] = v;
+        out[t] = v;
       }
-      if (STORE == 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    } else {
+      if (t < 624) h[t] = mt_f(o[t], t < 623 ? o[t + 1] : (o[397] ^ mt_f(o[0], o[1])));  // word 623 pairs with the NEW word 0
+      __syncthreads();
+      if (t < 624) {
+        const uint32_t v = t < 227 ? (o[t + 397] ^ h[t])
+                                   : (t < 454 ? (o[t + 170] ^ h[t - 227] ^ h[t]) : (o[t - 57] ^ h[t - 454] ^ h[t - 227] ^ h[t]));
+        n[t] = v;
+        out[t] = v;
+      }
     }
     __syncthreads();
-    if (STORE == 1 && t == 0) {
-      const uint32_t src = (uint32_t)__cvta_generic_to_shared(n);
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out), "r"(src), "r"(2496) : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      // buffer (b + 2) % NBUF is written next iteration: the copy that last read it (two commits ago) must be done
-      asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
-    }
+    cur ^= 1;
   }
-  if (STORE == 1 && t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  __syncthreads();
-  for (int i = t; i < 624; i += 320) g->key[i] = buf[nblocks % NBUF][i];
+  if (t < 624) g->key[t] = buf[cur][t];
+  if (t == 0) {
+    long long n1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(n1));
+    g->cycles = clock64() - c0;
+    g->nanos = n1 - n0;
+    g->blocks = nblocks;
+  }
 }
 
 // numpy's random_double: (a >> 5, b >> 6) -> (a * 2^26 + b) / 2^53; the integer is below 2^53, so this is exact

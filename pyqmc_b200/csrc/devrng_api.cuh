@@ -31,7 +31,11 @@ struct DevRng {
 static DevRng* devrng_of(qmcb_ctx* c) {
   if (!c->devrng) {
     DevRng* r = new DevRng();
-    cudaStreamCreateWithFlags(&r->gen_stream, cudaStreamNonBlocking);
+    // highest priority: the generator is one long-lived CTA that everything downstream waits for; it must not queue
+    // behind the hundreds of CTAs of the compute kernels
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    cudaStreamCreateWithPriority(&r->gen_stream, cudaStreamNonBlocking, hi);
     cudaEventCreateWithFlags(&r->ev_gen, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&r->ev_plan, cudaEventDisableTiming);
     c->devrng = r;
@@ -141,14 +145,12 @@ static int devrng_reserve(qmcb_ctx* c, DevRng* r, long long blocks) {
 // generate + flag so that `blocks` state blocks exist; records ev_gen on the generator stream
 static int devrng_generate(qmcb_ctx* c, DevRng* r, long long blocks) {
   if (blocks <= r->gen_blocks) return 0;
-  static const int store_mode = std::getenv("QMCB_MT_STORE") ? std::atoi(std::getenv("QMCB_MT_STORE")) : 0;
+  static const int mode = std::getenv("QMCB_MT_MODE") ? std::atoi(std::getenv("QMCB_MT_MODE")) : 1;
   const int nb = (int)(blocks - r->gen_blocks);
-  if (store_mode == 0)
-    devrng::k_mt_generate<0><<<1, 320, 0, r->gen_stream>>>(r->gen.p, r->W.p, r->gen_blocks, nb);
-  else if (store_mode == 2)
-    devrng::k_mt_generate<2><<<1, 320, 0, r->gen_stream>>>(r->gen.p, r->W.p, r->gen_blocks, nb);
+  if (mode == 0)
+    devrng::k_mt_generate<0><<<1, 640, 0, r->gen_stream>>>(r->gen.p, r->W.p, r->gen_blocks, nb);
   else
-    devrng::k_mt_generate<1><<<1, 320, 0, r->gen_stream>>>(r->gen.p, r->W.p, r->gen_blocks, nb);
+    devrng::k_mt_generate<1><<<1, 640, 0, r->gen_stream>>>(r->gen.p, r->W.p, r->gen_blocks, nb);
   r->gen_blocks = blocks;
   const long long avail = blocks * 624;
   const long long g_hi = ((avail - 3) / 4) / 32 * 32;
@@ -245,6 +247,20 @@ int qmcb_devrng_get_state(qmcb_ctx* c, uint32_t* key, int32_t* pos, int32_t* has
   *pos = h.pos;
   *has_gauss = h.has_gauss;
   *cached_gauss = h.cached;
+  return 0;
+}
+
+// timing of the last generator launch: SM cycles, nanoseconds, state blocks (diagnostics)
+int qmcb_devrng_generator_timing(qmcb_ctx* c, int64_t* out3) {
+  Guard g(c);
+  DevRng* r = devrng_of(c);
+  if (!r->gen.p) return fail("no generator state");
+  CK(cudaStreamSynchronize(r->gen_stream));
+  devrng::GenState h;
+  CK(cudaMemcpy(&h, r->gen.p, sizeof(h), cudaMemcpyDeviceToHost));
+  out3[0] = h.cycles;
+  out3[1] = h.nanos;
+  out3[2] = h.blocks;
   return 0;
 }
 

@@ -159,6 +159,17 @@ struct qmcb_ctx {
   cudaEvent_t block_done[NSLOT] = {nullptr, nullptr, nullptr};  // qmcb_vmc_block_slot_begin / _end
   bool block_pending[NSLOT] = {false, false, false};
   void* devrng = nullptr;            // DevRng (devrng_api.cuh): device-resident legacy generator
+  // overlapped step loop of qmcb_vmc_block_device: the energy accumulator of step s runs on its own stream from a
+  // snapshot of the arrays it reads while the sweep of step s+1 already moves the walkers
+  cudaStream_t energy_stream = nullptr;
+  cudaEvent_t ev_snap = nullptr, ev_edone = nullptr;
+  DBuf<double> sn_inv[2], sn_conf, sn_ap, sn_bp, e_ke2, e_g22;
+  // per-slot result staging of qmcb_vmc_block_slot_begin: the device->host copies of block b run on their own
+  // stream (copy engine) while block b+1 computes
+  cudaStream_t d2h_stream = nullptr;
+  cudaEvent_t ev_block = nullptr;
+  DBuf<double> r_energy[NSLOT], r_conf[NSLOT], r_esum[NSLOT];
+  DBuf<unsigned long long> r_nacc[NSLOT];
 };
 
 extern "C" {
@@ -920,8 +931,11 @@ int ecp_points_pbc_prepass(qmcb_ctx* c, EcpPointArgs& ea, long long maxpts, long
   return 0;
 }
 
+// `st` / `es`: the walker state and energy scratch the kernels read -- the live ones, or the snapshot the
+// overlapped step loop hands over (qmcb_vmc_block_device)
 template <int NMOT>
-int launch_energy_t(qmcb_ctx* c, const double* d_u, const double* d_rot, double* d_out, cudaStream_t stream) {
+int launch_energy_t(qmcb_ctx* c, const State& st, const EnergyScratch& es, const double* d_u, const double* d_rot,
+                    double* d_out, cudaStream_t stream) {
   const Sys& S = c->S;
   const int N = c->N;
   const size_t sm = c->smem_bytes;
@@ -936,18 +950,18 @@ int launch_energy_t(qmcb_ctx* c, const double* d_u, const double* d_rot, double*
     // three-body factor: per-group a-value scratch behind the tables
     const size_t ksm = c->have_j3 ? ((sm + 15) & ~(size_t)15) + (size_t)(128 / 8) * 3 * S.natom * S.na3 * 8 : sm;
     if (prep_kernel(k_kinetic<8>, ksm)) return -1;
-    k_kinetic<8><<<(unsigned)((np * 8 + 127) / 128), 128, ksm, stream>>>(S, c->st, c->es);
+    k_kinetic<8><<<(unsigned)((np * 8 + 127) / 128), 128, ksm, stream>>>(S, st, es);
     c->nlaunch++;
     CK(cudaGetLastError());
     }
     c->kinetic_valid = false;
   }
   if (S.necp > 0) {
-    CK(cudaMemsetAsync(c->es.count, 0, sizeof(int), stream));
+    CK(cudaMemsetAsync(es.count, 0, sizeof(int), stream));
     const long long nt = (long long)N * S.ne * S.necp;
     const int block = 128;
     if (prep_kernel(k_ecp_prepare, sm)) return -1;
-    k_ecp_prepare<<<(unsigned)((nt + block - 1) / block), block, sm, stream>>>(S, c->st, c->es, d_u, -1);
+    k_ecp_prepare<<<(unsigned)((nt + block - 1) / block), block, sm, stream>>>(S, st, es, d_u, -1);
     c->nlaunch++;
     CK(cudaGetLastError());
     EcpPointArgs ea{};
@@ -963,7 +977,7 @@ int launch_energy_t(qmcb_ctx* c, const double* d_u, const double* d_rot, double*
     if (S.pbc) {
       if (ecp_points_pbc_prepass<NMOT>(c, ea, maxpts, grid, stream)) return -1;
     }
-    k_ecp_points<NMOT><<<(unsigned)grid, 128, sm, stream>>>(S, c->st, c->es, ea);
+    k_ecp_points<NMOT><<<(unsigned)grid, 128, sm, stream>>>(S, st, es, ea);
     c->nlaunch++;
     CK(cudaGetLastError());
   }
@@ -972,7 +986,7 @@ int launch_energy_t(qmcb_ctx* c, const double* d_u, const double* d_rot, double*
     const size_t tab = (sm + 15) & ~(size_t)15;
     const size_t esm = tab + (size_t)(3 * S.ne + 16) * 8;
     if (prep_kernel(k_ewald, esm)) return -1;
-    k_ewald<<<(unsigned)N, 128, esm, stream>>>(S, c->st, c->es.ewald);
+    k_ewald<<<(unsigned)N, 128, esm, stream>>>(S, st, es.ewald);
     c->nlaunch++;
     CK(cudaGetLastError());
   }
@@ -984,17 +998,22 @@ int launch_energy_t(qmcb_ctx* c, const double* d_u, const double* d_rot, double*
     const size_t tab = (sm + 15) & ~(size_t)15;
     const size_t fsm = tab + (size_t)(128 / 8) * scr * 8;
     if (prep_kernel(k_energy_finalize<8>, fsm)) return -1;
-    k_energy_finalize<8><<<(unsigned)(((long long)N * 8 + 127) / 128), 128, fsm, stream>>>(S, c->st, c->es, d_out, scr);
+    k_energy_finalize<8><<<(unsigned)(((long long)N * 8 + 127) / 128), 128, fsm, stream>>>(S, st, es, d_out, scr);
     c->nlaunch++;
     CK(cudaGetLastError());
   }
   return 0;
 }
 
+int launch_energy_on(qmcb_ctx* c, const State& st, const EnergyScratch& es, const double* d_u, const double* d_rot,
+                     double* d_out, cudaStream_t stream) {
+  if (c->nmot == 4) return launch_energy_t<4>(c, st, es, d_u, d_rot, d_out, stream);
+  if (c->nmot == 8) return launch_energy_t<8>(c, st, es, d_u, d_rot, d_out, stream);
+  return launch_energy_t<0>(c, st, es, d_u, d_rot, d_out, stream);
+}
+
 int launch_energy(qmcb_ctx* c, const double* d_u, const double* d_rot, double* d_out, cudaStream_t stream) {
-  if (c->nmot == 4) return launch_energy_t<4>(c, d_u, d_rot, d_out, stream);
-  if (c->nmot == 8) return launch_energy_t<8>(c, d_u, d_rot, d_out, stream);
-  return launch_energy_t<0>(c, d_u, d_rot, d_out, stream);
+  return launch_energy_on(c, c->st, c->es, d_u, d_rot, d_out, stream);
 }
 
 int energy_scratch_points(qmcb_ctx* c) {
@@ -1026,11 +1045,20 @@ int qmcb_create(int device, qmcb_ctx** out) {
   qmcb_ctx* c = new qmcb_ctx();
   c->device = device;
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;  // the copy stream also runs the draw-program kernels of the device generator: ahead of compute
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, hi));
+  }
   for (int i = 0; i < qmcb_ctx::NSLOT; ++i) CK(cudaEventCreateWithFlags(&c->slot_ready[i], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->done_event, cudaEventDisableTiming | cudaEventBlockingSync));
   for (int i = 0; i < qmcb_ctx::NSLOT; ++i)
     CK(cudaEventCreateWithFlags(&c->block_done[i], cudaEventDisableTiming | cudaEventBlockingSync));
+  CK(cudaStreamCreateWithFlags(&c->energy_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->ev_block, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_edone, cudaEventDisableTiming));
   *out = c;
   return 0;
 }
@@ -1082,6 +1110,22 @@ void qmcb_destroy(qmcb_ctx* c) {
     if (c->block_done[i]) cudaEventDestroy(c->block_done[i]);
   }
   if (c->done_event) cudaEventDestroy(c->done_event);
+  if (c->energy_stream) cudaStreamSynchronize(c->energy_stream);
+  for (auto* b : {&c->sn_inv[0], &c->sn_inv[1], &c->sn_conf, &c->sn_ap, &c->sn_bp, &c->e_ke2, &c->e_g22}) b->release();
+  if (c->ev_snap) cudaEventDestroy(c->ev_snap);
+  if (c->ev_edone) cudaEventDestroy(c->ev_edone);
+  if (c->energy_stream) cudaStreamDestroy(c->energy_stream);
+  if (c->d2h_stream) {
+    cudaStreamSynchronize(c->d2h_stream);
+    cudaStreamDestroy(c->d2h_stream);
+  }
+  if (c->ev_block) cudaEventDestroy(c->ev_block);
+  for (int i = 0; i < qmcb_ctx::NSLOT; ++i) {
+    c->r_energy[i].release();
+    c->r_conf[i].release();
+    c->r_esum[i].release();
+    c->r_nacc[i].release();
+  }
   devrng_free(c);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
@@ -1910,7 +1954,8 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
   int G = 16;
   if (const char* env = std::getenv("QMCB_SWEEP_G")) G = std::atoi(env);
   if (G != 8 && G != 16 && G != 32) G = 16;
-  const int sweep_warps = 4;
+  int sweep_warps = 4;
+  if (const char* env = std::getenv("QMCB_SWEEP_WARPS")) sweep_warps = std::max(1, std::min(4, std::atoi(env)));
   const int sweep_walkers = sweep_warps * (32 / G);
   const size_t sweep_smem = tab + (size_t)sweep_walkers * CL.total * 8;
   const bool use_sweep = (!c->have_slater || S.ndet == 1) && !c->have_j3 && sweep_smem <= 200 * 1024 && !S.pbc &&
@@ -1938,6 +1983,28 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
     CK(cudaGetLastError());
     c->paircache_valid = true;
   }
+  // Overlap (single-determinant fast path): the energy kernels read the inverse, the coordinates and the Jastrow
+  // partial sums only (slater_point_fast / jastrow_point), ~1.7 KB per walker.  After the sweep of step s those
+  // arrays are copied aside (device-to-device, a few microseconds) and the accumulator of step s runs from the
+  // copy on the energy stream while the sweep of step s+1 proceeds; the kinetic pieces alternate between two buffers.
+  const bool overlap = use_sweep && with_energy && c->have_slater && c->have_jastrow && (c->nmot == 4 || c->nmot == 8) &&
+                       nsteps > 1 && std::getenv("QMCB_NO_ENERGY_OVERLAP") == nullptr;
+  State snap = c->st;
+  EnergyScratch es_alt[2] = {c->es, c->es};
+  if (overlap) {
+    const size_t ninv0 = N * (size_t)S.nup * S.nup, ninv1 = N * (size_t)S.ndn * S.ndn;
+    const size_t nap = N * (size_t)S.ne * S.natom * S.na, nbp = N * (size_t)S.ne * S.nb * 2;
+    if (c->sn_inv[0].ensure(ninv0) || c->sn_inv[1].ensure(ninv1) || c->sn_conf.ensure(N * S.ne * 3) || c->sn_ap.ensure(nap) ||
+        c->sn_bp.ensure(nbp) || c->e_ke2.ensure(S.ne * N) || c->e_g22.ensure(S.ne * N))
+      return -1;
+    snap.inv[0] = c->sn_inv[0].p;
+    snap.inv[1] = c->sn_inv[1].p;
+    snap.conf = c->sn_conf.p;
+    snap.a_partial = c->sn_ap.p;
+    snap.b_partial = c->sn_bp.p;
+    es_alt[1].ke_e = c->e_ke2.p;
+    es_alt[1].g2_e = c->e_g22.p;
+  }
   for (int step = 0; step < nsteps; ++step) {
     if (use_sweep) {
       const size_t se = (size_t)step * S.ne;
@@ -1948,8 +2015,9 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
       sa.accept = d_accept ? d_accept + se * N : nullptr;
       sa.nacc = nacc + se;
       if (with_energy) {  // kinetic pieces of the final positions straight from the sweep's caches
-        sa.ke_e = c->es.ke_e;
-        sa.g2_e = c->es.g2_e;
+        const EnergyScratch& esw = overlap ? es_alt[step & 1] : c->es;
+        sa.ke_e = esw.ke_e;
+        sa.g2_e = esw.g2_e;
         c->kinetic_valid = true;
       }
       const unsigned grid = (unsigned)((N + sweep_walkers - 1) / sweep_walkers);
@@ -2068,14 +2136,37 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
     if (with_energy) {
       double* eo = d_energy ? d_energy + (size_t)step * 6 * N : c->d_energy.p;
       const size_t ue = (size_t)step * S.ne * S.necp;
-      if (launch_energy(c, d_ecp_u ? d_ecp_u + ue * N : nullptr, d_ecp_rot ? d_ecp_rot + ue * 9 : nullptr, eo, stream)) return -1;
-      if (d_esum) {
-        k_colsum<<<6, 256, 0, stream>>>(eo, (int)N, d_esum + (size_t)step * 6);
-        c->nlaunch++;
-        CK(cudaGetLastError());
+      const double* su = d_ecp_u ? d_ecp_u + ue * N : nullptr;
+      const double* sr = d_ecp_rot ? d_ecp_rot + ue * 9 : nullptr;
+      if (overlap) {
+        cudaStream_t es_ = c->energy_stream;
+        if (step > 0) CK(cudaStreamWaitEvent(stream, c->ev_edone, 0));  // the previous accumulator still reads the copy
+        CK(cudaMemcpyAsync(snap.inv[0], c->st.inv[0], N * (size_t)S.nup * S.nup * 8, cudaMemcpyDeviceToDevice, stream));
+        CK(cudaMemcpyAsync(snap.inv[1], c->st.inv[1], N * (size_t)S.ndn * S.ndn * 8, cudaMemcpyDeviceToDevice, stream));
+        CK(cudaMemcpyAsync(snap.conf, c->st.conf, N * S.ne * 3 * 8, cudaMemcpyDeviceToDevice, stream));
+        CK(cudaMemcpyAsync(snap.a_partial, c->st.a_partial, N * (size_t)S.ne * S.natom * S.na * 8, cudaMemcpyDeviceToDevice, stream));
+        CK(cudaMemcpyAsync(snap.b_partial, c->st.b_partial, N * (size_t)S.ne * S.nb * 2 * 8, cudaMemcpyDeviceToDevice, stream));
+        CK(cudaEventRecord(c->ev_snap, stream));
+        CK(cudaStreamWaitEvent(es_, c->ev_snap, 0));
+        if (launch_energy_on(c, snap, es_alt[step & 1], su, sr, eo, es_)) return -1;
+        if (d_esum) {
+          k_colsum<<<6, 256, 0, es_>>>(eo, (int)N, d_esum + (size_t)step * 6);
+          c->nlaunch++;
+          CK(cudaGetLastError());
+        }
+        CK(cudaEventRecord(c->ev_edone, es_));
+        c->kinetic_valid = false;
+      } else {
+        if (launch_energy(c, su, sr, eo, stream)) return -1;
+        if (d_esum) {
+          k_colsum<<<6, 256, 0, stream>>>(eo, (int)N, d_esum + (size_t)step * 6);
+          c->nlaunch++;
+          CK(cudaGetLastError());
+        }
       }
     }
   }
+  if (overlap) CK(cudaStreamWaitEvent(stream, c->ev_edone, 0));  // the caller's stream sees every step's energies
   c->saved_slot = -1;
   return 0;
 }
@@ -2209,16 +2300,21 @@ int qmcb_vmc_block_slot_begin(qmcb_ctx* c, int slot, int nsteps, double tstep, i
     if (recompute_from_resident(c, recompute_which, (int)N)) return -1;
   }
   CK(cudaStreamWaitEvent(c->stream, c->slot_ready[slot], 0));
-  if (with_energy && (c->d_energy.ensure((size_t)nsteps * 6 * N) || c->d_esum.ensure((size_t)nsteps * 6))) return -1;
+  if (with_energy && (c->r_energy[slot].ensure((size_t)nsteps * 6 * N) || c->r_esum[slot].ensure((size_t)nsteps * 6))) return -1;
+  if (c->r_nacc[slot].ensure(nse) || c->r_conf[slot].ensure(N * S.ne * 3)) return -1;
   int rc = qmcb_vmc_block_device(c, nsteps, tstep, with_energy, c->s_gauss[slot].p, c->s_unif[slot].p, c->s_u[slot].p,
-                                 c->s_rot[slot].p, nullptr, with_energy ? c->d_energy.p : nullptr,
-                                 with_energy ? c->d_esum.p : nullptr, nullptr, c->stream);
+                                 c->s_rot[slot].p, nullptr, with_energy ? c->r_energy[slot].p : nullptr,
+                                 with_energy ? c->r_esum[slot].p : nullptr, (int64_t*)c->r_nacc[slot].p, c->stream);
   if (rc) return rc;
+  // results are staged per slot, so their way to the host (own stream) overlaps the next block
+  if (configs) CK(cudaMemcpyAsync(c->r_conf[slot].p, c->st.conf, N * S.ne * 3 * 8, cudaMemcpyDeviceToDevice, c->stream));
+  CK(cudaEventRecord(c->ev_block, c->stream));
+  CK(cudaStreamWaitEvent(c->d2h_stream, c->ev_block, 0));
   if (energy && with_energy)
-    CK(cudaMemcpyAsync(energy, c->d_energy.p, (size_t)nsteps * 6 * N * 8, cudaMemcpyDeviceToHost, c->stream));
-  if (nacc) CK(cudaMemcpyAsync(nacc, c->d_nacc.p, nse * 8, cudaMemcpyDeviceToHost, c->stream));
-  if (configs) CK(cudaMemcpyAsync(configs, c->st.conf, N * S.ne * 3 * 8, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaEventRecord(c->block_done[slot], c->stream));
+    CK(cudaMemcpyAsync(energy, c->r_energy[slot].p, (size_t)nsteps * 6 * N * 8, cudaMemcpyDeviceToHost, c->d2h_stream));
+  if (nacc) CK(cudaMemcpyAsync(nacc, c->r_nacc[slot].p, nse * 8, cudaMemcpyDeviceToHost, c->d2h_stream));
+  if (configs) CK(cudaMemcpyAsync(configs, c->r_conf[slot].p, N * S.ne * 3 * 8, cudaMemcpyDeviceToHost, c->d2h_stream));
+  CK(cudaEventRecord(c->block_done[slot], c->d2h_stream));
   c->block_pending[slot] = true;
   return 0;
 }
