@@ -112,33 +112,81 @@ def allreduce_dmc_block(block_avg, nconf, group=None, device=None):
 
 def branch_global(local, weights, group=None, base_draw=None):
     """Stochastic-comb branching over the GLOBAL population (``branch``, dmc.py:342-376, applied after
-    ``configs.join`` as the reference's parallel driver does): the shards' walkers and weights are
-    gathered (a few hundred KB), rank 0's ``np.random.rand()`` fixes the comb offset for everybody,
-    every rank computes the same resampling indices and keeps its ``np.array_split`` slice of the
-    resampled population.  Returns (local configs, local weights, info)."""
+    ``configs.join`` as the reference's parallel driver does) without ever assembling that population:
+
+    1. one all-gather of the WEIGHTS (8 bytes per walker; rank 0's slot also carries its ``np.random.rand()``,
+       the comb offset for everybody);
+    2. every rank computes the same resampling indices (``dmc.comb_indices``) and, from the ``np.array_split``
+       layout, which rank holds which walker before and after;
+    3. one ``all_to_all_single`` moves only the walkers that change owner (``nelec * 24`` bytes each, 48 with the
+       periodic wrap vectors); copies that stay on their rank never leave it.
+
+    Equal to join -> branch -> split of the reference with the same offset (tests/test_parallel_gloo.py).
+    Returns (local configs, local weights, info)."""
+    import torch
     import torch.distributed as dist
 
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        from .dmc import branch
+    from .dmc import branch, comb_indices
 
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return branch(local, weights, base_draw)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    parts = [None] * world
-    payload = (local.configs, getattr(local, "wrap", None), np.asarray(weights))
-    dist.all_gather_object(parts, payload, group=group)
-    allc = np.concatenate([p[0] for p in parts], axis=0)
-    allw = np.concatenate([p[2] for p in parts])
-    box = [(np.random.rand() if base_draw is None else base_draw) if rank == 0 else None]
-    dist.broadcast_object_list(box, src=0, group=group)
-    nconfig = len(allw)
-    probability = np.cumsum(allw)
-    wtot = probability[-1]
-    base = box[0] * wtot
-    newinds = np.searchsorted(probability, (base + np.linspace(0, wtot, nconfig, endpoint=False)) % wtot)
-    unique, counts = np.unique(newinds, return_counts=True)
-    mine = np.array_split(newinds, world)[rank]
-    local.configs = allc[mine]
-    if parts[0][1] is not None:
-        local.wrap = np.concatenate([p[1] for p in parts], axis=0)[mine]
-    new_w = np.full(len(mine), wtot / nconfig)
-    return local, new_w, {"max branches": np.max(counts), "Number of walkers killed": nconfig - unique.shape[0]}
+    device = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    weights = np.asarray(weights, dtype=np.float64)
+    n_local = len(weights)
+    counts_t = torch.zeros(world, dtype=torch.int64, device=device)
+    counts_t[rank] = n_local
+    dist.all_reduce(counts_t, group=group)
+    counts = counts_t.cpu().numpy()
+    width = int(counts.max()) + 1  # last column: the comb offset (rank 0's draw)
+    row = np.zeros(width)
+    row[:n_local] = weights
+    if rank == 0:
+        row[-1] = np.random.rand() if base_draw is None else base_draw
+    pieces = [torch.empty(width, dtype=torch.float64, device=device) for _ in range(world)]
+    dist.all_gather(pieces, torch.from_numpy(row).to(device), group=group)
+    gathered = torch.stack(pieces).cpu().numpy()
+    allw = np.concatenate([gathered[r, : counts[r]] for r in range(world)])
+    picked, total = comb_indices(allw, gathered[0, -1])
+    if np.any(allw > 2.0) and rank == 0:
+        import logging
+
+        logging.warning("Some weights are larger than 2")
+    # ownership before (contiguous ranges of global ids) and after (array_split of the resampled population)
+    first = np.concatenate([[0], np.cumsum(counts)])
+    owner = np.searchsorted(first, picked, side="right") - 1
+    after = np.array_split(np.arange(len(picked)), world)
+    fields = [local.configs.reshape(n_local, -1)]
+    if getattr(local, "wrap", None) is not None:
+        fields.append(local.wrap.reshape(n_local, -1))
+    rows = np.concatenate(fields, axis=1)
+    send_rows, send_counts, recv_counts = [], [], []
+    for dst in range(world):
+        ids = picked[after[dst]]
+        mine = ids[owner[after[dst]] == rank] - first[rank]  # in the order rank `dst` will place them
+        send_counts.append(0 if dst == rank else len(mine))
+        if dst != rank:
+            send_rows.append(rows[mine])
+        recv_counts.append(0 if dst == rank else int(np.sum(owner[after[rank]] == dst)))
+    width_r = rows.shape[1]
+    out = np.empty((len(after[rank]), width_r))
+    my_ids, my_owner = picked[after[rank]], owner[after[rank]]
+    out[my_owner == rank] = rows[my_ids[my_owner == rank] - first[rank]]  # copies that never leave this rank
+    send = np.concatenate(send_rows, axis=0) if send_rows and sum(send_counts) else np.empty((0, width_r))
+    send_t = torch.from_numpy(np.ascontiguousarray(send)).to(device)
+    recv_t = torch.empty((sum(recv_counts), width_r), dtype=torch.float64, device=device)
+    dist.all_to_all_single(recv_t, send_t, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=group)
+    recv = recv_t.cpu().numpy()
+    at = 0
+    for src in range(world):
+        if src == rank:
+            continue
+        out[my_owner == src] = recv[at : at + recv_counts[src]]
+        at += recv_counts[src]
+    ncfg = fields[0].shape[1]
+    local.configs = np.ascontiguousarray(out[:, :ncfg]).reshape((len(out),) + local.configs.shape[1:])
+    if len(fields) > 1:
+        local.wrap = np.ascontiguousarray(out[:, ncfg:]).reshape(local.configs.shape)
+    survivors, copies = np.unique(picked, return_counts=True)
+    new_w = np.full(len(out), total / len(picked))
+    return local, new_w, {"max branches": np.max(copies), "Number of walkers killed": len(picked) - len(survivors)}
