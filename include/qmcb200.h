@@ -278,6 +278,11 @@ int qmcb_rng_phase_a(void *plan, uint32_t *key, int32_t *pos, int32_t *has_gauss
                      double *gauss, double *unif, double *ecp_u, double *ecp_rot, int nthreads);
 int qmcb_rng_phase_b(void *plan, int nthreads);
 
+/* Orbitals at arbitrary points (open boundaries): out[p][j] = sum_mu chi_mu(pos[p]) coeff[mu][j], the
+ * evaluation OBDMAccumulator needs (pyqmc/observables/obdm.py:150-153,231-233 -> orbitals.py:85-96). */
+int qmcb_orbitals_at_points(qmcb_ctx *ctx, int64_t npoints, const double *pos, int norb,
+                            const double *coeff, double *out);
+
 /* asynchronous form of qmcb_vmc_block_slot for the pipelined driver (pyqmc_b200.mc.vmc): _begin optionally
  * recomputes the factors `recompute_which` from the resident walkers (wf.recompute at the start of vmc_worker,
  * mc.py:110), enqueues the block on the variates of `slot` and the device->host copies of its results (buffers must

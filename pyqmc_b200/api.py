@@ -11,6 +11,7 @@ Recipes, line minimisation, HDF5 I/O and the density-matrix accumulators are out
 path: use the reference's own drivers on these objects for those.
 """
 from .accumulators import EnergyAccumulator  # noqa: F401
+from .obdm import OBDMAccumulator  # noqa: F401
 from .coord import OpenConfigs, PeriodicConfigs  # noqa: F401
 from .dmc import rundmc  # noqa: F401
 from .mc import initial_guess, vmc  # noqa: F401

@@ -1983,6 +1983,54 @@ __global__ void __launch_bounds__(128) k_ao_all(const Sys S, const State st, dou
   }
 }
 
+// Orbitals sum_mu chi_mu(r_p) C[mu][j] at arbitrary points (open boundary conditions): the orbital evaluation the
+// density-matrix accumulators need (obdm.py:150-153, 231-233 with MoleculeOrbitalEvaluator.aos/mos,
+// orbitals.py:85-96).  Thread per point; the AO values of a shell are contracted into NT orbital accumulators at
+// a time, so the (P, nao) AO matrix is never stored.
+template <int NT>
+__global__ void __launch_bounds__(128) k_orbitals_points(const Sys S, const double* __restrict__ pos, long long P,
+                                                         const double* __restrict__ C, int norb, double* __restrict__ out) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const double px = pos[3 * p], py = pos[3 * p + 1], pz = pos[3 * p + 2];
+  const double* __restrict__ prim = sd + S.o_prim;
+  for (int j0 = 0; j0 < norb; j0 += NT) {
+    double acc[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[j] = 0.0;
+    for (int a = 0; a < S.nbatom; ++a) {
+      const double x = px - sd[S.o_bxyz + 3 * a], y = py - sd[S.o_bxyz + 3 * a + 1], z = pz - sd[S.o_bxyz + 3 * a + 2];
+      const double r2 = x * x + y * y + z * z;
+      for (int sh = si[S.o_atsh + a]; sh < si[S.o_atsh + a + 1]; ++sh) {
+        double R = 0.0;
+        for (int q = si[S.o_shprim + sh]; q < si[S.o_shprim + sh + 1]; ++q) R += prim[2 * q + 1] * exp(-prim[2 * q] * r2);
+        double tmp[36];
+        const int l = si[S.o_shl + sh];
+        switch (l) {
+          case 0: sph_store<0, false>(x, y, z, tmp); break;
+          case 1: sph_store<1, false>(x, y, z, tmp); break;
+          case 2: sph_store<2, false>(x, y, z, tmp); break;
+          case 3: sph_store<3, false>(x, y, z, tmp); break;
+          default: sph_store<4, false>(x, y, z, tmp); break;
+        }
+        for (int m = 0; m < 2 * l + 1; ++m) {
+          const double chi = tmp[4 * m] * R;
+          const double* __restrict__ row = C + (size_t)(si[S.o_shao + sh] + m) * norb + j0;
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+            if (j0 + j < norb) acc[j] = fma(chi, row[j], acc[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+      if (j0 + j < norb) out[(size_t)p * norb + j0 + j] = acc[j];
+  }
+}
+
 // d ln Psi / d det_coeff [N][ndet] and the per-walker weights G_s[d] = sum_{D: map_s(D)=d} c_D dPsi_D
 __global__ void __launch_bounds__(128) k_pgrad_det(const Sys S, const State st, double* __restrict__ out,
                                                    double* __restrict__ G, int gstride) {

@@ -2769,6 +2769,45 @@ int qmcb_sm_update(int n, int e, int64_t nmat, double* inv, const double* vec, c
   return rc;
 }
 
+// Orbitals at arbitrary points for the density-matrix accumulators: out[p][j] = sum_mu chi_mu(pos[p]) coeff[mu][j]
+// (MoleculeOrbitalEvaluator.aos + mos, orbitals.py:85-96).  Host buffers; needs the basis of the context.
+int qmcb_orbitals_at_points(qmcb_ctx* c, int64_t npoints, const double* pos, int norb, const double* coeff, double* out) {
+  Guard g(c);
+  if (build_tables(c)) return -1;
+  const Sys& S = c->S;
+  if (S.pbc) return fail("qmcb_orbitals_at_points: periodic orbitals are evaluated through the Slater factor");
+  if (S.nao == 0) return fail("qmcb_orbitals_at_points: no basis (qmcb_set_basis)");
+  if (npoints == 0 || norb == 0) return 0;
+  DBuf<double> d_pos, d_c, d_out;
+  int rc = 0;
+  do {
+    if (d_pos.ensure(npoints * 3) || d_c.ensure((size_t)S.nao * norb) || d_out.ensure((size_t)npoints * norb)) {
+      rc = -1;
+      break;
+    }
+    cudaMemcpyAsync(d_pos.p, pos, npoints * 3 * 8, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(d_c.p, coeff, (size_t)S.nao * norb * 8, cudaMemcpyHostToDevice, c->stream);
+    if (prep_kernel(k_orbitals_points<8>, c->smem_bytes)) {
+      rc = -1;
+      break;
+    }
+    const int block = pick_block(npoints);
+    k_orbitals_points<8><<<(unsigned)((npoints + block - 1) / block), block, c->smem_bytes, c->stream>>>(S, d_pos.p, npoints, d_c.p, norb,
+                                                                                                     d_out.p);
+    c->nlaunch++;
+    if (cudaGetLastError() != cudaSuccess) {
+      rc = fail("k_orbitals_points launch failed");
+      break;
+    }
+    cudaMemcpyAsync(out, d_out.p, (size_t)npoints * norb * 8, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(std::string("qmcb_orbitals_at_points: ") + cudaGetErrorString(cudaGetLastError()));
+  } while (0);
+  d_pos.release();
+  d_c.release();
+  d_out.release();
+  return rc;
+}
+
 #include "devrng_api.cuh"
 
 }  // extern "C"

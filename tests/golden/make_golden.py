@@ -208,9 +208,44 @@ def generate_rundmc(name, nconf=16):
     return out
 
 
+def obdm_inputs(mol, mf):
+    """Orbitals of the density matrix: the first 6 spin-up MOs of the synthetic mean field."""
+    return np.ascontiguousarray(np.asarray(mf.mo_coeff[0])[:, :6])
+
+
+def generate_obdm(name="h2o"):
+    """OBDMAccumulator of the reference (obdm.py:25-214; in-tree numba orbital evaluator) on the walkers
+    `configs1` of the main golden file -> tests/golden/obdm_<name>.npz."""
+    import pyqmc.configurations.coord as coord
+    import pyqmc.wf.orbitals
+    from pyqmc.observables.obdm import OBDMAccumulator
+
+    mol, wf = build_reference(name)
+    _, mf, _ = helpers.make_system(name)
+    data = dict(np.load(os.path.join(HERE, f"{name}.npz")))
+    configs = coord.OpenConfigs(data["configs1"].copy())
+    wf.recompute(configs)
+    c = obdm_inputs(mol, mf)
+    out = {}
+    for tag, kw in (("all", {}), ("up", {"spin": 0})):
+        acc = OBDMAccumulator(mol, c, nsweeps=3, tstep=0.5, warmup=25, **kw)
+        acc.orbitals = pyqmc.wf.orbitals.MoleculeOrbitalEvaluator(mol, [c, c], evaluate_orbitals_with="numba")
+        np.random.seed(61)
+        first = acc(configs, wf)
+        second = acc.avg(configs, wf)  # continues the auxiliary walk
+        out[f"{tag}_value"], out[f"{tag}_norm"] = first["value"], first["norm"]
+        out[f"{tag}_avg_value"], out[f"{tag}_avg_norm"] = second["value"], second["norm"]
+    return out
+
+
 def main():
     warnings.filterwarnings("ignore")
     refload.load()
+    if len(sys.argv) > 1 and sys.argv[1] == "obdm":
+        path = os.path.join(HERE, "obdm_h2o.npz")
+        np.savez_compressed(path, **generate_obdm("h2o"))
+        print("wrote", path)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "rundmc":
         for name in RUNDMC_SYSTEMS:
             path = os.path.join(HERE, f"rundmc_{name}.npz")
