@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE (oracle) -- real solid harmonics S_lm(x,y,z) as explicit polynomials.
 
 Restates the functions tabulated in the reference at
-``pyqmc/wf/numba/spherical_harmonics.py:40-300`` (COMPUTE_SPH_L0..L4 and their
+``pyqmc/wf/numba/spherical_harmonics.py:40-300`` (COMPUTE_SPH_L0..L5 and their
 derivative macros): orthonormal real spherical harmonics multiplied by r^l, flattened
 index ``l*l + b``.  Ordering inside a shell follows the reference: l = 1 is (x, y, z)
 (``spherical_harmonics.py:57-67``), every other l runs m = -l..l
@@ -13,11 +13,11 @@ differentiating the polynomial.  The same tables generate the CUDA device code
 (``pyqmc_b200/csrc/gen_sph.py``), so kernel and oracle share one definition that is
 itself pinned against the reference functions in ``tests/test_oracle_vs_reference.py``.
 """
-from math import pi, sqrt
+from math import comb, factorial, pi, sqrt
 
 import numpy as np
 
-LMAX = 4
+LMAX = 5
 
 
 def _poly(*terms):
@@ -86,7 +86,41 @@ def _build_tables():
         _poly((b4, 3, 0, 1), (-3 * b4, 1, 2, 1)),  # xz(x2-3y2)
         _poly((g4, 4, 0, 0), (-6 * g4, 2, 2, 0), (g4, 0, 4, 0)),  # x4-6x2y2+y4
     ]
+    # l = 5 (COMPUTE_SPH_L5, spherical_harmonics.py:270-300): from the closed form; the same closed form
+    # reproduces the tabulated l = 2..4 above (tests/test_oracle_golden.py) and the reference's SPH5
+    t[5] = [closed_form(5, m) for m in range(-5, 6)]
     return t
+
+
+def _mul(p, q):
+    out = {}
+    for (a, b, c), u in p.items():
+        for (d, e, f), v in q.items():
+            k = (a + d, b + e, c + f)
+            out[k] = out.get(k, 0.0) + u * v
+    return out
+
+
+def closed_form(l, m):
+    """S_lm = N_lm Pi_l^|m|(z, r^2) {Re, Im}(x + iy)^|m| as a polynomial (real solid harmonic, orthonormal on
+    the sphere, m >= 0 takes the real part, m < 0 the imaginary part)."""
+    am = abs(m)
+    xy = {}
+    for q in range(am + 1):
+        if (q % 2 == 0) == (m >= 0):
+            xy[(am - q, q, 0)] = xy.get((am - q, q, 0), 0.0) + (-1) ** (q // 2) * comb(am, q)
+    r2 = {(2, 0, 0): 1.0, (0, 2, 0): 1.0, (0, 0, 2): 1.0}
+    radial = {}
+    for k in range((l - am) // 2 + 1):
+        c = (-1) ** k * 2.0 ** (-l) * comb(l, k) * comb(2 * l - 2 * k, l) * factorial(l - 2 * k) / factorial(l - 2 * k - am)
+        term = {(0, 0, l - 2 * k - am): c}
+        for _ in range(k):
+            term = _mul(term, r2)
+        for key, v in term.items():
+            radial[key] = radial.get(key, 0.0) + v
+    norm = sqrt((2 * l + 1) / (4 * pi)) if m == 0 else sqrt((2 * l + 1) / (2 * pi))
+    norm *= sqrt(factorial(l - am) / factorial(l + am))
+    return {k: norm * v for k, v in _mul(radial, xy).items() if abs(v) > 1e-300}
 
 
 TABLES = _build_tables()

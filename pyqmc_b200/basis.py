@@ -30,8 +30,8 @@ def shell_tables(mol):
             if prim.ndim != 2 or prim.shape[1] != 2:
                 raise NotImplementedError("general contractions: one contraction column per shell is required "
                                           "(as in the reference numba evaluator, gto.py:441-456)")
-            if l > 4:
-                raise NotImplementedError("angular momentum l > 4")
+            if l > 5:  # the reference's evaluator dispatches l <= 5 (gto.py:107-118)
+                raise NotImplementedError("angular momentum l > 5")
             shell_atom.append(a)
             shell_l.append(l)
             exps.extend(prim[:, 0])

@@ -70,6 +70,7 @@ __device__ __forceinline__ void sph_store(double x, double y, double z, double* 
   if constexpr (L == 2) sph_l2<D>(x, y, z, s, gx, gy, gz);
   if constexpr (L == 3) sph_l3<D>(x, y, z, s, gx, gy, gz);
   if constexpr (L == 4) sph_l4<D>(x, y, z, s, gx, gy, gz);
+  if constexpr (L == 5) sph_l5<D>(x, y, z, s, gx, gy, gz);
 #pragma unroll
   for (int m = 0; m < NF; ++m) {
     out[4 * m] = s[m];
@@ -126,7 +127,8 @@ __device__ __forceinline__ void coop_eval_mo(const Sys& S, const CoopLayout& L, 
       case 1: sph_store<1, (DERIV > 0)>(x, y, z, out); break;
       case 2: sph_store<2, (DERIV > 0)>(x, y, z, out); break;
       case 3: sph_store<3, (DERIV > 0)>(x, y, z, out); break;
-      default: sph_store<4, (DERIV > 0)>(x, y, z, out); break;
+      case 4: sph_store<4, (DERIV > 0)>(x, y, z, out); break;
+      default: sph_store<5, (DERIV > 0)>(x, y, z, out); break;
     }
   }
   __syncwarp(gm);

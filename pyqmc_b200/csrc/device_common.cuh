@@ -12,7 +12,7 @@
 
 #include "sph_gen.cuh"
 
-#define QMCB_MAX_ATOM_L 4
+#define QMCB_MAX_ATOM_L 5
 
 // ---------------------------------------------------------------------------------------
 // System description: small POD passed by value to every kernel.  The tables themselves live
@@ -334,7 +334,8 @@ __device__ __forceinline__ void eval_mo(const Sys& S, const double* __restrict__
         case 1: shell_accumulate<1, DERIV, NMOT>(x, y, z, R, Rp, Rl, Crow, ldc, acc); break;
         case 2: shell_accumulate<2, DERIV, NMOT>(x, y, z, R, Rp, Rl, Crow, ldc, acc); break;
         case 3: shell_accumulate<3, DERIV, NMOT>(x, y, z, R, Rp, Rl, Crow, ldc, acc); break;
-        default: shell_accumulate<4, DERIV, NMOT>(x, y, z, R, Rp, Rl, Crow, ldc, acc); break;
+        case 4: shell_accumulate<4, DERIV, NMOT>(x, y, z, R, Rp, Rl, Crow, ldc, acc); break;
+        default: shell_accumulate<5, DERIV, NMOT>(x, y, z, R, Rp, Rl, Crow, ldc, acc); break;
       }
     }
   }

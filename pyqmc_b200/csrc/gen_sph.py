@@ -1,4 +1,4 @@
-"""Generates ``sph_gen.cuh``: real solid harmonics S_lm (l <= 4) and their gradients as
+"""Generates ``sph_gen.cuh``: real solid harmonics S_lm (l <= 5) and their gradients as
 straight-line FP64 device code, one function per l so a shell only pays for its own l.
 
 The functions are the ones the reference tabulates in
@@ -7,8 +7,10 @@ r^l; l = 1 ordered x, y, z; other l ordered m = -l..l).  They are written here a
 polynomials in x, y, z with closed-form normalisation constants; gradients are the
 polynomial derivatives.  Run ``python gen_sph.py`` to regenerate the header.
 """
-from math import pi, sqrt
+from math import comb, factorial, pi, sqrt
 import os
+
+LMAX = 5
 
 
 def _poly(*terms):
@@ -66,7 +68,54 @@ def tables():
         _poly((b4, 3, 0, 1), (-3 * b4, 1, 2, 1)),
         _poly((g4, 4, 0, 0), (-6 * g4, 2, 2, 0), (g4, 0, 4, 0)),
     ]
+    for l in range(5, LMAX + 1):  # closed form (checked against the tabulated l = 2..4 in self_check)
+        t[l] = [solid_harmonic(l, m) for m in range(-l, l + 1)]
     return t
+
+
+def _mul(p, q):
+    out = {}
+    for (a, b, c), u in p.items():
+        for (d, e, f), v in q.items():
+            k = (a + d, b + e, c + f)
+            out[k] = out.get(k, 0.0) + u * v
+    return out
+
+
+def solid_harmonic(l, m):
+    """Orthonormal real spherical harmonic times r^l as a polynomial {(i, j, k): c} in x^i y^j z^k:
+    S_lm = N_lm Pi_l^|m|(z, r^2) A_|m|(x, y)  (m >= 0)  or  ... B_|m|(x, y)  (m < 0), with
+    A_m + i B_m = (x + i y)^m and Pi_l^m = sqrt((l-m)!/(l+m)!) sum_k (-1)^k 2^-l C(l,k) C(2l-2k,l) (l-2k)!/(l-2k-m)!
+    r^2k z^(l-2k-m); N = sqrt((2l+1)/4pi) (m = 0), sqrt((2l+1)/2pi) otherwise."""
+    am = abs(m)
+    xy = {}
+    for q in range(am + 1):
+        if (q % 2 == 0) == (m >= 0):
+            sign = (-1) ** (q // 2)
+            xy[(am - q, q, 0)] = xy.get((am - q, q, 0), 0.0) + sign * comb(am, q)
+    r2 = {(2, 0, 0): 1.0, (0, 2, 0): 1.0, (0, 0, 2): 1.0}
+    radial = {}
+    for k in range((l - am) // 2 + 1):
+        c = (-1) ** k * 2.0 ** (-l) * comb(l, k) * comb(2 * l - 2 * k, l) * factorial(l - 2 * k) / factorial(l - 2 * k - am)
+        term = {(0, 0, l - 2 * k - am): c}
+        for _ in range(k):
+            term = _mul(term, r2)
+        for key, v in term.items():
+            radial[key] = radial.get(key, 0.0) + v
+    norm = sqrt((2 * l + 1) / (4 * pi)) if m == 0 else sqrt((2 * l + 1) / (2 * pi))
+    norm *= sqrt(factorial(l - am) / factorial(l + am))
+    p = _mul(radial, xy)
+    return {k: norm * v for k, v in p.items() if abs(v) > 1e-300}
+
+
+def self_check():
+    """The closed form reproduces the tabulated polynomials for l = 2..4 (same ordering m = -l..l and signs)."""
+    t = tables()
+    for l in (2, 3, 4):
+        for i, m in enumerate(range(-l, l + 1)):
+            a, b = t[l][i], solid_harmonic(l, m)
+            keys = set(a) | set(b)
+            assert all(abs(a.get(k, 0.0) - b.get(k, 0.0)) < 1e-13 for k in keys), (l, m)
 
 
 def deriv(p, axis):
@@ -102,9 +151,10 @@ def expr(p):
 
 def generate():
     t = tables()
-    out = ["// GENERATED by gen_sph.py -- do not edit.  Real solid harmonics, l <= 4.",
+    self_check()
+    out = [f"// GENERATED by gen_sph.py -- do not edit.  Real solid harmonics, l <= {LMAX}.",
            "#pragma once", ""]
-    for l in range(5):
+    for l in range(LMAX + 1):
         n = 2 * l + 1
         out.append(f"template <bool D> __device__ __forceinline__ void sph_l{l}(double x, double y, double z,")
         out.append(f"    double (&s)[{n}], double (&gx)[{n}], double (&gy)[{n}], double (&gz)[{n}]) {{")

@@ -1969,14 +1969,15 @@ __global__ void __launch_bounds__(128) k_ao_all(const Sys S, const State st, dou
     for (int sh = si[S.o_atsh + a]; sh < si[S.o_atsh + a + 1]; ++sh) {
       double R = 0.0;
       for (int q = si[S.o_shprim + sh]; q < si[S.o_shprim + sh + 1]; ++q) R += prim[2 * q + 1] * exp(-prim[2 * q] * r2);
-      double tmp[36];
+      double tmp[44];
       const int l = si[S.o_shl + sh];
       switch (l) {
         case 0: sph_store<0, false>(x, y, z, tmp); break;
         case 1: sph_store<1, false>(x, y, z, tmp); break;
         case 2: sph_store<2, false>(x, y, z, tmp); break;
         case 3: sph_store<3, false>(x, y, z, tmp); break;
-        default: sph_store<4, false>(x, y, z, tmp); break;
+        case 4: sph_store<4, false>(x, y, z, tmp); break;
+        default: sph_store<5, false>(x, y, z, tmp); break;
       }
       for (int m = 0; m < 2 * l + 1; ++m) out[si[S.o_shao + sh] + m] = tmp[4 * m] * R;
     }
@@ -2007,14 +2008,15 @@ __global__ void __launch_bounds__(128) k_orbitals_points(const Sys S, const doub
       for (int sh = si[S.o_atsh + a]; sh < si[S.o_atsh + a + 1]; ++sh) {
         double R = 0.0;
         for (int q = si[S.o_shprim + sh]; q < si[S.o_shprim + sh + 1]; ++q) R += prim[2 * q + 1] * exp(-prim[2 * q] * r2);
-        double tmp[36];
+        double tmp[44];
         const int l = si[S.o_shl + sh];
         switch (l) {
           case 0: sph_store<0, false>(x, y, z, tmp); break;
           case 1: sph_store<1, false>(x, y, z, tmp); break;
           case 2: sph_store<2, false>(x, y, z, tmp); break;
           case 3: sph_store<3, false>(x, y, z, tmp); break;
-          default: sph_store<4, false>(x, y, z, tmp); break;
+          case 4: sph_store<4, false>(x, y, z, tmp); break;
+          default: sph_store<5, false>(x, y, z, tmp); break;
         }
         for (int m = 0; m < 2 * l + 1; ++m) {
           const double chi = tmp[4 * m] * R;

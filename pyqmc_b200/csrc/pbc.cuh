@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(128) k_pbc_mo(const Sys S, const State st, con
         const double r2 = x * x + y * y + z * z;
         double* __restrict__ o = stg + lane * stg_stride;
         const int ao0 = si[S.o_shao + si[S.o_atsh + at]];
-        double sph[36];
+        double sph[44];
         int lastl = -1;
         for (int sh = si[S.o_atsh + at]; sh < si[S.o_atsh + at + 1]; ++sh) {
           const int l = si[S.o_shl + sh];
@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(128) k_pbc_mo(const Sys S, const State st, con
               case 1: sph_store<1, (DERIV > 0)>(x, y, z, sph); break;
               case 2: sph_store<2, (DERIV > 0)>(x, y, z, sph); break;
               case 3: sph_store<3, (DERIV > 0)>(x, y, z, sph); break;
-              default: sph_store<4, (DERIV > 0)>(x, y, z, sph); break;
+              case 4: sph_store<4, (DERIV > 0)>(x, y, z, sph); break;
+              default: sph_store<5, (DERIV > 0)>(x, y, z, sph); break;
             }
             lastl = l;
           }
@@ -373,7 +374,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_pbc_mo_cta(const Sys S, const St
           case 1: pbc_stage_shell<1, DERIV>(x, y, z, R, Rp, Rl, om); break;
           case 2: pbc_stage_shell<2, DERIV>(x, y, z, R, Rp, Rl, om); break;
           case 3: pbc_stage_shell<3, DERIV>(x, y, z, R, Rp, Rl, om); break;
-          default: pbc_stage_shell<4, DERIV>(x, y, z, R, Rp, Rl, om); break;
+          case 4: pbc_stage_shell<4, DERIV>(x, y, z, R, Rp, Rl, om); break;
+          default: pbc_stage_shell<5, DERIV>(x, y, z, R, Rp, Rl, om); break;
         }
       }
       __syncthreads();

@@ -208,7 +208,7 @@ int build_tables(qmcb_ctx* c) {
   atsh.assign(nbatom_host + 1, 0);
   for (int s = 0; s < nshell; ++s) {
     if (c->sh_atom[s] >= nbatom_host) return fail("shell table refers to an atom outside the basis-atom list");
-    if (c->sh_l[s] > QMCB_MAX_ATOM_L || c->sh_l[s] < 0) return fail("angular momentum l > 4 is not supported");
+    if (c->sh_l[s] > QMCB_MAX_ATOM_L || c->sh_l[s] < 0) return fail("angular momentum l > 5 is not supported (the reference dispatches l <= 5, gto.py:107-118)");
     if (s > 0 && c->sh_atom[s] < c->sh_atom[s - 1]) return fail("shells must be grouped by atom");
     atsh[c->sh_atom[s] + 1]++;
     shao[s + 1] = shao[s] + 2 * c->sh_l[s] + 1;

@@ -264,8 +264,35 @@ def h_atom_like(seed=13):
     return mol, MF(np.array([c, c]), occ)
 
 
+def high_l_probe(seed=17):
+    """He-like two-electron probe whose basis reaches l = 5 (s, p, d, f, g, h shells): exercises every branch of the
+    solid-harmonic dispatch the reference has (COMPUTE_SPH_L0..L5, gto.py:107-118)."""
+    basis = {
+        "He": [
+            _contracted(0, _even_tempered(0.35, 2.9, 4), seed),
+            _single(0, 0.30),
+            _single(1, 1.10),
+            _single(2, 0.90),
+            _single(3, 0.80),
+            _single(4, 0.75),
+            _single(5, 0.70),
+        ]
+    }
+    ecp = {"He": _ecp_entry(0, 2.0, (32.0, 32.0, 33.7, -27.7), [(1.0, 0.0)])}
+    mol = Mol([("He", (0.05, -0.1, 0.15))], basis, ecp, (1, 1), [2.0])
+    nao = mol.nao
+    assert nao == 2 + 3 + 5 + 7 + 9 + 11, nao
+    rng = np.random.RandomState(seed)
+    c = 0.25 * rng.randn(nao, nao)  # an occupied orbital with weight on every shell
+    c[0, 0] += 1.0
+    occ = np.zeros((2, nao))
+    occ[:, :1] = 1
+    return mol, MF(np.array([c, c]), occ)
+
+
 SYSTEMS = {
     "hatom": h_atom_like,
+    "high_l": high_l_probe,
     "he": he_ccecp_pvdz,
     "h2o": h2o_ccecp_pvtz,
     "c2": c2_probe,

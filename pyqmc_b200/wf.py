@@ -231,6 +231,29 @@ def _single_determinant(mf):
     return [(1.0, [list(np.nonzero(np.asarray(o) > 0.5)[0]) for o in mfu.mo_occ])]
 
 
+def _realify_orbitals(mo, what="orbital"):
+    """Real orbital coefficients from complex ones when every orbital is real up to a constant phase.
+
+    Mean-field codes hand out complex128 coefficients even where the orbitals can be chosen real (pyscf k-point
+    objects at Gamma or at time-reversal-invariant k-points).  Each column is rotated by the
+    phase of its largest coefficient; if what remains has a negligible imaginary part the real part is returned
+    (the wave function changes by a constant global phase, which no observable of this path depends on), otherwise
+    the orbitals are genuinely complex and the caller raises."""
+    mo = np.asarray(mo)
+    if not np.iscomplexobj(mo):
+        return np.array(mo, dtype=float)
+    out = np.empty(mo.shape, dtype=float)
+    for j in range(mo.shape[1]):
+        col = mo[:, j]
+        big = col[np.argmax(np.abs(col))] if len(col) else 1.0
+        rot = col * (np.conj(big) / abs(big)) if abs(big) > 0 else col
+        if np.abs(rot.imag).max(initial=0.0) > 1e-9 * max(np.abs(rot).max(initial=0.0), 1e-300):
+            raise NotImplementedError(f"{what} {j} is genuinely complex (general twist): complex wave functions are "
+                                      "not supported by the B200 backend yet")
+        out[:, j] = rot.real
+    return out
+
+
 def _pack_determinants(determinants, tol):
     coeff, occ, dmap = [], [[], []], [[], []]
     for w, spin_occ in determinants:
@@ -387,12 +410,10 @@ class Slater(_DeviceFactor):
                         f"disagreement between number of electrons and number of orbitals: "
                         f"{self._nelec[s]} electrons and {len(o)} orbitals")
         mo = mfu.mo_coeff
-        if np.iscomplexobj(mo[0]) or np.iscomplexobj(mo[1]):
-            raise NotImplementedError("complex orbitals are not supported by the B200 backend yet")
         self.parameters = {
             "det_coeff": coeff,
-            "mo_coeff_alpha": np.array(mo[0][:, : top[0]], dtype=float),
-            "mo_coeff_beta": np.array(mo[1][:, : top[1]], dtype=float),
+            "mo_coeff_alpha": _realify_orbitals(np.asarray(mo[0])[:, : top[0]], "spin-up orbital"),
+            "mo_coeff_beta": _realify_orbitals(np.asarray(mo[1])[:, : top[1]], "spin-down orbital"),
         }
 
     def _init_periodic(self, mol, mf, determinants, twist, eval_gto_precision):
@@ -433,9 +454,8 @@ class Slater(_DeviceFactor):
                     raise AssertionError(
                         f"disagreement between number of electrons and number of orbitals: "
                         f"{self._nelec[s]} electrons and {len(o)} orbitals")
+        blocks = [[_realify_orbitals(b, f"k-point {k} orbital") for k, b in zip(kinds, blocks[s])] for s in (0, 1)]
         mo = [np.concatenate(blocks[s], axis=1) for s in (0, 1)]
-        if np.iscomplexobj(mo[0]) or np.iscomplexobj(mo[1]):
-            raise NotImplementedError("complex orbitals are not supported by the B200 backend yet")
         kpts = np.asarray(mfu.kpts)[kinds].reshape(-1, 3)
         tables = pbc.image_tables(mol.original_cell, kpts, eval_gto_precision)
         if np.iscomplexobj(tables["phases"]):

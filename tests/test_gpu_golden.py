@@ -44,7 +44,7 @@ def check_internal(wf, data):
         assert helpers.relerr(pgw[k], data["pgrad_" + k]) < 1e-9, k
 
 
-@pytest.mark.parametrize("name", ["he", "h2o", "open", "c2", "h2o_md", "h2o_3b", "h2o_md_3b", "h2o_cas", "h2o_cas_3b"])
+@pytest.mark.parametrize("name", ["he", "h2o", "open", "c2", "h2o_md", "h2o_3b", "h2o_md_3b", "h2o_cas", "h2o_cas_3b", "high_l"])
 def test_cuda_reproduces_reference_golden(lib, name):
     import pyqmc_b200 as pq
 

@@ -8,7 +8,7 @@ import golden_replay
 import helpers
 import refload
 
-SYSTEMS = ["he", "h2o", "open", "c2", "h2o_md", "h2o_3b", "h2o_md_3b", "h2o_cas", "h2o_cas_3b"]
+SYSTEMS = ["he", "h2o", "open", "c2", "h2o_md", "h2o_3b", "h2o_md_3b", "h2o_cas", "h2o_cas_3b", "high_l"]
 
 
 def oracle_vmc(wf, configs, accumulators):
@@ -149,11 +149,15 @@ def test_solid_harmonics_match_reference_tables():
     from oracle import solid_harmonics as sh
 
     rng = np.random.RandomState(0)
+    for l in (2, 3, 4):  # the closed form used for l = 5 reproduces the hand-tabulated polynomials
+        for i, m in enumerate(range(-l, l + 1)):
+            a, b = sh.TABLES[l][i], sh.closed_form(l, m)
+            assert all(abs(a.get(k, 0.0) - b.get(k, 0.0)) < 1e-13 for k in set(a) | set(b)), (l, m)
     for _ in range(20):
         x, y, z = rng.randn(3)
-        s, dx, dy, dz = np.zeros(25), np.zeros(25), np.zeros(25), np.zeros(25)
-        hsh.SPH4_GRAD(x, y, z, x * x, y * y, z * z, s, dx, dy, dz)
-        S, dS = sh.evaluate(4, np.array(x), np.array(y), np.array(z), deriv=True)
+        s, dx, dy, dz = np.zeros(36), np.zeros(36), np.zeros(36), np.zeros(36)
+        hsh.SPH5_GRAD(x, y, z, x * x, y * y, z * z, s, dx, dy, dz)
+        S, dS = sh.evaluate(5, np.array(x), np.array(y), np.array(z), deriv=True)
         scale = max(1.0, np.abs(s).max())
         assert np.abs(S - s).max() < 1e-12 * scale
         for a, d in enumerate((dx, dy, dz)):
@@ -172,7 +176,7 @@ def test_device_sph_tables_equal_oracle_tables():
     gen = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(gen)
     t = gen.tables()
-    for l in range(5):
+    for l in range(6):
         assert len(t[l]) == len(sh.TABLES[l]) == 2 * l + 1
         for a, b in zip(t[l], sh.TABLES[l]):
             assert a == b
