@@ -182,6 +182,7 @@ __device__ __forceinline__ void shell_accumulate(double x, double y, double z, d
   if constexpr (L == 2) sph_l2<(DERIV > 0)>(x, y, z, s, gx, gy, gz);
   if constexpr (L == 3) sph_l3<(DERIV > 0)>(x, y, z, s, gx, gy, gz);
   if constexpr (L == 4) sph_l4<(DERIV > 0)>(x, y, z, s, gx, gy, gz);
+  if constexpr (L == 5) sph_l5<(DERIV > 0)>(x, y, z, s, gx, gy, gz);
   const double dRx = Rp * x, dRy = Rp * y, dRz = Rp * z;  // dR/dx_i (gto.py:290-296)
 #pragma unroll
   for (int m = 0; m < NF; ++m) {

@@ -241,6 +241,7 @@ __device__ __forceinline__ void pbc_stage_shell(double x, double y, double z, do
   if constexpr (L == 2) sph_l2<(DERIV > 0)>(x, y, z, s, gx, gy, gz);
   if constexpr (L == 3) sph_l3<(DERIV > 0)>(x, y, z, s, gx, gy, gz);
   if constexpr (L == 4) sph_l4<(DERIV > 0)>(x, y, z, s, gx, gy, gz);
+  if constexpr (L == 5) sph_l5<(DERIV > 0)>(x, y, z, s, gx, gy, gz);
   const double dRx = Rp * x, dRy = Rp * y, dRz = Rp * z;
 #pragma unroll
   for (int m = 0; m < NF; ++m) {
