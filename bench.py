@@ -61,6 +61,9 @@ WORKLOADS["c5"] = dict(
 # DRAM bytes per launch of k_sm_warp<32> on 131072 matrices from the committed ncu --set full capture
 # (profiles/r1_ncu_k_sm_warp32.txt: dram__bytes_read.sum + dram__bytes_write.sum)
 SM32_TRAFFIC_BYTES = 2.12e9
+# FP64 flop of one C2 step at 4096 walkers from the committed ncu capture (profiles/r2_ncu_c2_step_raw.csv):
+# (2 DFMA + DADD + DMUL) thread instructions per cycle x elapsed cycles, summed over the four step kernels
+SWEEP_STEP_FLOP = 6.49e8
 
 
 E2E_MIN_S = 2.0
@@ -554,6 +557,8 @@ def gpu_arm(args):
             dist.destroy_process_group()
         return
     peak, peak_src = peaks()
+    fp64_peak = ctypes.c_double(0.0)
+    lib.qmcb_fp64_peak(local, ctypes.byref(fp64_peak))
     g32, t32, b32 = sm_roofline(torch, lib, 32, 1 << 17)
     g4, t4, b4 = sm_roofline(torch, lib, 4, 1 << 22)
     g4s, t4s, _ = sm_roofline(torch, lib, 4, N)
@@ -578,10 +583,20 @@ def gpu_arm(args):
                      "peak_source": peak_src, "launch_ms": 1e3 * t32, "algorithmic_bytes": b32},
         # the whole VMC step against the same HBM roof (~27.5 KB of algorithmic traffic per
         # walker-step -- 15 KB sweep + ~10 KB energy accumulator); the step is FP64-latency bound, not HBM bound
-        "roofline_step": {"kernel": "k_vmc_sweep<16> + energy kernels (one VMC step)", "bound": "hbm",
-                          "achieved": 27.5e3 * N * K / t_dev / 1e9, "peak": peak, "unit": "GB/s",
-                          "frac": 27.5e3 * N * K / t_dev / 1e9 / peak, "algorithmic_bytes_per_walker_step": 27.5e3,
-                          "binding_limit": "FP64 dependent-instruction latency at 14 warps/SM (4096 walkers x 16 lanes)"},
+        # the whole VMC step: against the HBM roof (~27.5 KB of algorithmic traffic per walker-step) it sits at
+        # a few per cent because it is not memory bound; against the FP64 roof (measured here: qmcb_fp64_peak) with the
+        # FP64 operation count of the committed ncu capture (profiles/r2_ncu_c2_step_raw.csv: DFMA x2 + DADD + DMUL thread
+        # instructions of k_vmc_sweep<16,0> + k_ecp_points<4> + k_energy_finalize<8> + k_ecp_prepare per step, 4096 walkers)
+        "roofline_step": {"kernel": "k_vmc_sweep<16> + energy kernels (one VMC step)", "bound": "fp64",
+                          "achieved": SWEEP_STEP_FLOP * (N / 4096.0) * K / t_dev / 1e12, "peak": fp64_peak.value,
+                          "unit": "TFLOP/s", "frac": SWEEP_STEP_FLOP * (N / 4096.0) * K / t_dev / 1e12 / max(fp64_peak.value, 1e-9),
+                          "peak_source": "measured in this run (qmcb_fp64_peak: 8 independent DFMA chains per thread)",
+                          "flop_per_step_source": "profiles/r2_ncu_c2_step_raw.csv",
+                          "hbm_view": {"achieved_GBps": 27.5e3 * N * K / t_dev / 1e9, "frac": 27.5e3 * N * K / t_dev / 1e9 / peak,
+                                       "algorithmic_bytes_per_walker_step": 27.5e3},
+                          "binding_limit": "dependent FP64 / shared-memory latency of one walker's chain of 8 electron moves: "
+                                           "0.20 ms at 1024 walkers, 0.23 ms at 4096, throughput-bound only above ~16 k walkers "
+                                           "(profiles/r2_walker_scaling.txt)"},
         "sm_kernel_other_shapes": {
             "n4_4M_matrices": {"achieved_GBps": g4, "frac": g4 / peak, "launch_ms": 1e3 * t4},
             "n4_4096_matrices_C2_shape": {"achieved_GBps": g4s, "frac": g4s / peak, "launch_ms": 1e3 * t4s}},

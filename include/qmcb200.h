@@ -278,6 +278,10 @@ int qmcb_rng_phase_a(void *plan, uint32_t *key, int32_t *pos, int32_t *has_gauss
                      double *gauss, double *unif, double *ecp_u, double *ecp_rot, int nthreads);
 int qmcb_rng_phase_b(void *plan, int nthreads);
 
+/* measured FP64 FMA throughput of the device in TFLOP/s (8 independent DFMA chains per thread): the roof the
+ * FP64-bound kernels of this path are reported against in bench.py */
+int qmcb_fp64_peak(int device, double *tflops);
+
 /* Orbitals at arbitrary points (open boundaries): out[p][j] = sum_mu chi_mu(pos[p]) coeff[mu][j], the
  * evaluation OBDMAccumulator needs (pyqmc/observables/obdm.py:150-153,231-233 -> orbitals.py:85-96). */
 int qmcb_orbitals_at_points(qmcb_ctx *ctx, int64_t npoints, const double *pos, int norb,

@@ -25,9 +25,21 @@ class Jastrow3Oracle:
         na, nb = len(a_funcs), len(b_funcs)
         self.parameters = {"ccoeff": np.zeros((len(self.atoms), na, na, nb, 3))}
         self.dtype = float
+        self._minimal = None
+        if hasattr(mol, "a"):
+            from .pbc import MinimalImage
+
+            self._minimal = MinimalImage(mol.lattice_vectors())
+
+    def _mi(self, d):
+        return d if self._minimal is None else self._minimal(d)
 
     @classmethod
-    def default(cls, mol, na=4, nb=3, rcut=7.5, gamma=24.0, beta_a=0.2, beta_b=0.5):
+    def default(cls, mol, na=4, nb=3, rcut=None, gamma=24.0, beta_a=0.2, beta_b=0.5):
+        if rcut is None:  # wftools.py:81-85
+            rcut = 7.5
+            if hasattr(mol, "a"):
+                rcut = np.amin(np.pi / np.linalg.norm(mol.reciprocal_vectors(), axis=1))
         a_funcs = [("pade", b) for b in expand_beta(beta_a, na)]
         b_funcs = [("cusp", gamma)] + [("pade", b) for b in expand_beta(beta_b, nb)]
         return cls(mol, a_funcs, b_funcs, rcut)
@@ -41,7 +53,7 @@ class Jastrow3Oracle:
         return int(e >= self._nup) + int(j >= self._nup)
 
     def _a_at(self, pos, want):
-        d = pos[..., None, :] - self.atoms  # (..., I, 3)
+        d = self._mi(pos[..., None, :] - self.atoms)  # (..., I, 3)
         r = np.linalg.norm(d, axis=-1)
         return (d,) + self.a_basis.eval(r, want)
 
@@ -54,7 +66,7 @@ class Jastrow3Oracle:
             if j == e:
                 continue
             oth = cur[:, j]
-            dv = pos - (oth[:, None, :] if pos.ndim == 3 else oth)
+            dv = self._mi(pos - (oth[:, None, :] if pos.ndim == 3 else oth))
             r = np.linalg.norm(dv, axis=-1)
             bv, bg, bl = self.b_basis.eval(r, want)
             aj = avals[j]  # (M, I, na)
@@ -155,7 +167,7 @@ class Jastrow3Oracle:
         ders = np.zeros((N, len(self.atoms), na, na, nb, 3))
         for i in range(ne):
             for j in range(i + 1, ne):
-                r = np.linalg.norm(c[:, i] - c[:, j], axis=-1)
+                r = np.linalg.norm(self._mi(c[:, i] - c[:, j]), axis=-1)
                 bv, _, _ = self.b_basis.eval(r, 0)
                 ders[..., self._pair_index(i, j)] += np.einsum(
                     "nIk,nIl,nm->nIklm", self.a_values[i], self.a_values[j], bv)

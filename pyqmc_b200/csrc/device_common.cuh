@@ -464,7 +464,8 @@ __device__ __forceinline__ void j3_a_values(const Sys& S, const double* __restri
                                             double px, double py, double pz, double* __restrict__ av,
                                             double* __restrict__ ag, double* __restrict__ al) {
   for (int I = 0; I < S.natom; ++I) {
-    const double dx = px - sd[S.o_xyz + 3 * I], dy = py - sd[S.o_xyz + 3 * I + 1], dz = pz - sd[S.o_xyz + 3 * I + 2];
+    double dx = px - sd[S.o_xyz + 3 * I], dy = py - sd[S.o_xyz + 3 * I + 1], dz = pz - sd[S.o_xyz + 3 * I + 2];
+    if (S.pbc) min_image(S, sd, dx, dy, dz);  // MinimalImageDistance (distance.py:133-159)
     const double r = sqrt(dx * dx + dy * dy + dz * dz);
     for (int k = 0; k < S.na3; ++k) {
       double v = 0.0, g = 0.0, l = 0.0;
@@ -482,7 +483,8 @@ __device__ __forceinline__ void j3_pair(const Sys& S, const double* __restrict__
                                         const double* __restrict__ av, const double* __restrict__ ag,
                                         const double* __restrict__ al, double jx, double jy, double jz, double& P,
                                         double (&g)[3], double& lap) {
-  const double dx = px - jx, dy = py - jy, dz = pz - jz;
+  double dx = px - jx, dy = py - jy, dz = pz - jz;
+  if (S.pbc) min_image(S, sd, dx, dy, dz);
   const double r = sqrt(dx * dx + dy * dy + dz * dz);
   if (!(r < S.rcut_b3)) return;
   double bv[QMCB_J3_MAXB], bg[QMCB_J3_MAXB], bl[QMCB_J3_MAXB];
@@ -496,7 +498,8 @@ __device__ __forceinline__ void j3_pair(const Sys& S, const double* __restrict__
   const int sp = (e >= S.nup ? 1 : 0) + (j >= S.nup ? 1 : 0);
   const int na = S.na3, nb = S.nb3;
   for (int I = 0; I < S.natom; ++I) {
-    const double ax = px - sd[S.o_xyz + 3 * I], ay = py - sd[S.o_xyz + 3 * I + 1], az = pz - sd[S.o_xyz + 3 * I + 2];
+    double ax = px - sd[S.o_xyz + 3 * I], ay = py - sd[S.o_xyz + 3 * I + 1], az = pz - sd[S.o_xyz + 3 * I + 2];
+    if (WANT >= 1 && S.pbc) min_image(S, sd, ax, ay, az);
     const double dot = ax * dx + ay * dy + az * dz;
     const double* __restrict__ C = sd + S.o_c3 + (size_t)I * na * na * nb * 3 + sp;
     for (int m = 0; m < nb; ++m) {

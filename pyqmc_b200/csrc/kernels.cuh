@@ -826,8 +826,9 @@ __global__ void __launch_bounds__(128) k_jastrow3_pgrad(const Sys S, const State
   for (int m = 0; m < nb; ++m) acc[m][0] = acc[m][1] = acc[m][2] = 0.0;
   for (int i = 0; i < S.ne; ++i)
     for (int j = i + 1; j < S.ne; ++j) {
-      const double dx = CONF(st, S, w, i, 0) - CONF(st, S, w, j, 0), dy = CONF(st, S, w, i, 1) - CONF(st, S, w, j, 1),
-                   dz = CONF(st, S, w, i, 2) - CONF(st, S, w, j, 2);
+      double dx = CONF(st, S, w, i, 0) - CONF(st, S, w, j, 0), dy = CONF(st, S, w, i, 1) - CONF(st, S, w, j, 1),
+             dz = CONF(st, S, w, i, 2) - CONF(st, S, w, j, 2);
+      if (S.pbc) min_image(S, sd, dx, dy, dz);
       const double r = sqrt(dx * dx + dy * dy + dz * dz);
       if (!(r < S.rcut_b3)) continue;
       const int sp = (i >= S.nup ? 1 : 0) + (j >= S.nup ? 1 : 0);

@@ -275,7 +275,9 @@ __host__ __device__ inline size_t pbc_mo_cta_scratch_bytes(const Sys& S, int nc)
   return ((size_t)S.nk * S.nao * nc + (size_t)chunk * S.maxao_atom * nc) * 8 + (size_t)chunk * 2 * 4 + 16;
 }
 
-template <int DERIV, int MAXT = 256, int MINB = 2>
+// LMAX: highest angular momentum the instantiation dispatches.  The l <= 4 form is the tuned one (register budget
+// of the 4-CTAs-per-SM variant); bases that reach l = 5 use the LMAX = 5 instantiations.
+template <int DERIV, int MAXT = 256, int MINB = 2, int LMAX = 4>
 __global__ void __launch_bounds__(MAXT, MINB) k_pbc_mo_cta(const Sys S, const State st, const PbcMoArgs a) {
   constexpr int NC = NComp<DERIV>::value;
   const int T = blockDim.x;
@@ -375,8 +377,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_pbc_mo_cta(const Sys S, const St
           case 1: pbc_stage_shell<1, DERIV>(x, y, z, R, Rp, Rl, om); break;
           case 2: pbc_stage_shell<2, DERIV>(x, y, z, R, Rp, Rl, om); break;
           case 3: pbc_stage_shell<3, DERIV>(x, y, z, R, Rp, Rl, om); break;
-          case 4: pbc_stage_shell<4, DERIV>(x, y, z, R, Rp, Rl, om); break;
-          default: pbc_stage_shell<5, DERIV>(x, y, z, R, Rp, Rl, om); break;
+          default:
+            if (LMAX >= 5 && l == 5)
+              pbc_stage_shell<LMAX >= 5 ? 5 : 4, DERIV>(x, y, z, R, Rp, Rl, om);
+            else
+              pbc_stage_shell<4, DERIV>(x, y, z, R, Rp, Rl, om);
+            break;
         }
       }
       __syncthreads();

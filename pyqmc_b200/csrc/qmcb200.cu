@@ -657,20 +657,25 @@ int launch_pbc_mo(qmcb_ctx* c, int deriv, const PbcMoArgs& a, long long max_poin
     T = std::min((T + 31) / 32 * 32, 256);
     if (ncol > T) T = std::min(((ncol + 1) / 2 + 31) / 32 * 32, 256);
     const unsigned grid = (unsigned)std::min<long long>(max_points, 148LL * 64);
-    if (deriv == 0) {
-      if (prep_kernel(k_pbc_mo_cta<0>, csm)) return -1;
-      k_pbc_mo_cta<0><<<grid, T, csm, stream>>>(c->S, c->st, a);
-    } else if (deriv == 1) {
-      if (prep_kernel(k_pbc_mo_cta<1>, csm)) return -1;
-      k_pbc_mo_cta<1><<<grid, T, csm, stream>>>(c->S, c->st, a);
-    } else if (T <= 160 && 4 * csm <= 220 * 1024 && std::getenv("QMCB_PBC_MO_OCC2") == nullptr) {
-      // 96 registers: four CTAs per SM, so the 1024 points of a C4 move are two waves instead of three
-      const unsigned g4 = std::min(grid, 148u * 4u);  // one resident wave, CTAs stride over the points
-      if (prep_kernel(k_pbc_mo_cta<2, 160, 4>, csm)) return -1;
-      k_pbc_mo_cta<2, 160, 4><<<g4, T, csm, stream>>>(c->S, c->st, a);
+    int maxl = 0;
+    for (int l : c->sh_l) maxl = std::max(maxl, l);
+    const bool tuned4 = T <= 160 && 4 * csm <= 220 * 1024 && std::getenv("QMCB_PBC_MO_OCC2") == nullptr;
+    // 96 registers: four CTAs per SM, so the 1024 points of a C4 move are two waves instead of three
+    const unsigned g4 = std::min(grid, 148u * 4u);  // one resident wave, CTAs stride over the points
+#define QMCB_PBC_CTA(D, MAXT_, MINB_, LM, GRID)                                  \
+  do {                                                                           \
+    if (prep_kernel(k_pbc_mo_cta<D, MAXT_, MINB_, LM>, csm)) return -1;          \
+    k_pbc_mo_cta<D, MAXT_, MINB_, LM><<<GRID, T, csm, stream>>>(c->S, c->st, a); \
+  } while (0)
+    if (maxl <= 4) {
+      if (deriv == 0) QMCB_PBC_CTA(0, 256, 2, 4, grid);
+      else if (deriv == 1) QMCB_PBC_CTA(1, 256, 2, 4, grid);
+      else if (tuned4) QMCB_PBC_CTA(2, 160, 4, 4, g4);
+      else QMCB_PBC_CTA(2, 256, 2, 4, grid);
     } else {
-      if (prep_kernel(k_pbc_mo_cta<2>, csm)) return -1;
-      k_pbc_mo_cta<2><<<grid, T, csm, stream>>>(c->S, c->st, a);
+      if (deriv == 0) QMCB_PBC_CTA(0, 256, 2, 5, grid);
+      else if (deriv == 1) QMCB_PBC_CTA(1, 256, 2, 5, grid);
+      else QMCB_PBC_CTA(2, 256, 2, 5, grid);
     }
     c->nlaunch++;
     CK(cudaGetLastError());
@@ -754,8 +759,15 @@ int launch_ao_all(qmcb_ctx* c, double* d_ao, cudaStream_t stream) {
     a.out = d_ao;  // unused in AO mode
     int T = std::min((std::max(S.nao, 64) + 31) / 32 * 32, 256);
     if (S.nao > T) T = std::min(((S.nao + 1) / 2 + 31) / 32 * 32, 256);
-    if (prep_kernel(k_pbc_mo_cta<0>, csm)) return -1;
-    k_pbc_mo_cta<0><<<(unsigned)std::min<long long>(np, 148LL * 64), T, csm, stream>>>(S, c->st, a);
+    int maxl = 0;
+    for (int l : c->sh_l) maxl = std::max(maxl, l);
+    if (maxl <= 4) {
+      if (prep_kernel(k_pbc_mo_cta<0>, csm)) return -1;
+      k_pbc_mo_cta<0><<<(unsigned)std::min<long long>(np, 148LL * 64), T, csm, stream>>>(S, c->st, a);
+    } else {
+      if (prep_kernel(k_pbc_mo_cta<0, 256, 2, 5>, csm)) return -1;
+      k_pbc_mo_cta<0, 256, 2, 5><<<(unsigned)std::min<long long>(np, 148LL * 64), T, csm, stream>>>(S, c->st, a);
+    }
   } else {
     if (prep_kernel(k_ao_all, c->smem_bytes)) return -1;
     k_ao_all<<<(unsigned)((np + 127) / 128), 128, c->smem_bytes, stream>>>(S, c->st, d_ao);
@@ -2767,6 +2779,53 @@ int qmcb_sm_update(int n, int e, int64_t nmat, double* inv, const double* vec, c
   dr.release();
   dm.release();
   return rc;
+}
+
+// FP64 FMA roof of this device, measured: 8 independent DFMA chains per thread, enough resident warps to saturate
+// the FP64 pipe.  bench.py reports the sweep kernel's FP64 rate against it (the step is FP64-latency bound, HBM is
+// the wrong roof for it).
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0,
+         x7 = x0 + 7.0;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b);
+    x1 = fma(x1, a, b);
+    x2 = fma(x2, a, b);
+    x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b);
+    x5 = fma(x5, a, b);
+    x6 = fma(x6, a, b);
+    x7 = fma(x7, a, b);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+int qmcb_fp64_peak(int device, double* tflops) {
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  const int grid = prop.multiProcessorCount * 8, block = 256, iters = 1 << 14;
+  double* d = nullptr;
+  CK(cudaMalloc(&d, (size_t)grid * block * 8));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CK(cudaEventRecord(e0, 0));
+    k_fp64_peak<<<grid, block>>>(d, iters, 0.999999, 1e-6);
+    CK(cudaEventRecord(e1, 0));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = 2.0 * 8.0 * iters * (double)grid * block / (ms * 1e-3) / 1e12;
+    if (rep > 0) best = std::max(best, tf);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return 0;
 }
 
 // Orbitals at arbitrary points for the density-matrix accumulators: out[p][j] = sum_mu chi_mu(pos[p]) coeff[mu][j]

@@ -52,6 +52,16 @@ def _device_path(wf, accumulators):
         _device_context(wf)
     except TypeError:
         return False
+    factors = getattr(wf, "wf_factors", [wf])
+    if hasattr(factors[0]._mol, "a"):
+        # the device-resident periodic block covers single-determinant Slater x JastrowSpin; periodic multi-determinant
+        # and three-body wave functions run through the protocol calls (the reference's driver)
+        from .wf import ThreeBodyJastrow
+
+        if any(isinstance(f, ThreeBodyJastrow) for f in factors):
+            return False
+        if any(len(f.parameters.get("det_coeff", [0])) > 1 for f in factors if hasattr(f, "_det_map")):
+            return False
     return all(isinstance(a, EnergyAccumulator) for a in accumulators.values()) and len(accumulators) <= 1
 
 

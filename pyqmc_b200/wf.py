@@ -602,8 +602,8 @@ class ThreeBodyJastrow(_DeviceFactor):
     _which = JASTROW3
 
     def __init__(self, mol, a_basis, b_basis, device=None):
-        if hasattr(mol, "a"):
-            raise NotImplementedError("periodic systems are not supported by the B200 backend yet")
+        # periodic systems: every displacement goes through the minimal image (distance.py:83-159), evaluated through
+        # the per-call protocol kernels (the device-resident periodic block covers Slater x JastrowSpin)
         self._mol = mol
         self._nelec = tuple(int(x) for x in mol.nelec)
         self._device = device

@@ -43,12 +43,16 @@ def check_internal(wf, data):
     assert helpers.relerr(ja._a_partial, data["a_partial"]) < 1e-10
     assert helpers.relerr(ja._b_partial, data["b_partial"]) < 1e-10
     pg = wf.pgradient()  # periodic orbitals: every MO column uses the AO set of its own k-point
-    for k in ("wf1det_coeff", "wf1mo_coeff_alpha", "wf1mo_coeff_beta", "wf2acoeff", "wf2bcoeff"):
+    keys = ["wf1det_coeff", "wf1mo_coeff_alpha", "wf1mo_coeff_beta", "wf2acoeff", "wf2bcoeff"]
+    if len(wf.wf_factors) > 2:  # periodic three-body factor (minimal-image displacements)
+        keys.append("wf3ccoeff")
+        assert helpers.relerr(wf.wf_factors[2].P_i, data["P_i"]) < 1e-10
+    for k in keys:
         assert pg[k].shape == data["pgrad_" + k].shape, k
         assert helpers.relerr(pg[k], data["pgrad_" + k]) < 1e-9, k
 
 
-@pytest.mark.parametrize("name", PBC_SYSTEMS)
+@pytest.mark.parametrize("name", PBC_SYSTEMS + ["ortho_3b", "diamond211_3b"])
 def test_cuda_reproduces_reference_golden_periodic(lib, name):
     import pyqmc_b200 as pq
 

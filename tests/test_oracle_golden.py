@@ -66,7 +66,7 @@ def periodic_walkers(cls, data, mol, key="configs0", wkey="wrap0"):
     return w
 
 
-@pytest.mark.parametrize("name", PBC_SYSTEMS)
+@pytest.mark.parametrize("name", PBC_SYSTEMS + ["ortho_3b", "diamond211_3b"])
 def test_oracle_reproduces_reference_golden_periodic(name):
     """Periodic systems (minimal-image modes diagonal / orthogonal / general, two k-points with the
     wrap phase, Ewald): the oracle replays the reference's recorded calls."""
