@@ -1067,7 +1067,8 @@ __device__ __forceinline__ void coop_jastrow3(const Sys& S, const double* __rest
   double* __restrict__ al = abuf + 2 * na_tot;
   for (int t = lane; t < na_tot; t += G) {
     const int I = t / S.na3, k = t - I * S.na3;
-    const double dx = px - sd[S.o_xyz + 3 * I], dy = py - sd[S.o_xyz + 3 * I + 1], dz = pz - sd[S.o_xyz + 3 * I + 2];
+    double dx = px - sd[S.o_xyz + 3 * I], dy = py - sd[S.o_xyz + 3 * I + 1], dz = pz - sd[S.o_xyz + 3 * I + 2];
+    if (S.pbc) min_image(S, sd, dx, dy, dz);
     const double r = sqrt(dx * dx + dy * dy + dz * dz);
     double v = 0.0, gg = 0.0, ll = 0.0;
     if (r < S.rcut_a3) radial_ool<WANT>(si[S.o_a3kind + k], sd[S.o_a3par + k], S.rcut_a3, r, v, gg, ll);
@@ -1259,7 +1260,8 @@ __global__ void __launch_bounds__(128) k_jastrow3_update_coop(const Sys S, const
   // ... and the new ones (a-values at the accepted position) enter
   for (int t = lane; t < na_tot; t += G) {
     const int I = t / S.na3, k = t - I * S.na3;
-    const double dx = nx - sd[S.o_xyz + 3 * I], dy = ny - sd[S.o_xyz + 3 * I + 1], dz = nz - sd[S.o_xyz + 3 * I + 2];
+    double dx = nx - sd[S.o_xyz + 3 * I], dy = ny - sd[S.o_xyz + 3 * I + 1], dz = nz - sd[S.o_xyz + 3 * I + 2];
+    if (S.pbc) min_image(S, sd, dx, dy, dz);
     const double r = sqrt(dx * dx + dy * dy + dz * dz);
     double v = 0.0, gg, ll;
     if (r < S.rcut_a3) radial_ool<0>(si[S.o_a3kind + k], sd[S.o_a3par + k], S.rcut_a3, r, v, gg, ll);
@@ -1286,6 +1288,8 @@ __global__ void __launch_bounds__(128) k_jastrow3_update_coop(const Sys S, const
     CONF(st, S, w, e, 0) = nx;
     CONF(st, S, w, e, 1) = ny;
     CONF(st, S, w, e, 2) = nz;
+    if (S.pbc)
+      for (int i = 0; i < 3; ++i) st.wrap[((size_t)w * S.ne + e) * 3 + i] = st.saved_wrap[(size_t)w * 3 + i];
   }
 }
 

@@ -178,6 +178,36 @@ def test_reference_accumulator_contract(lib):
             assert shapes[ka] == np.shape(avg[ka]), (ka, np.shape(avg[ka]))
 
 
+@pytest.mark.gpu
+@needs_reference
+@pytest.mark.parametrize("name", ["ortho_3b", "diamond211_3b"])
+def test_periodic_three_body_under_the_reference_driver(lib, name):
+    """Periodic Slater x Jastrow x three-body: the reference's mc.vmc over the device objects (pyqmc_b200.vmc hands this
+    combination to it) against the oracle loop over the oracle objects -- the reference's own three-body factor goes
+    stale in driver order, so the oracle is the checker here."""
+    import pyqmc_b200 as pq
+    from oracle import vmc_driver
+    from oracle.local_energy import EnergyOracle
+
+    refload.load()  # makes `pyqmc` importable: pyqmc_b200.vmc delegates to pyqmc.method.mc.vmc
+    mol, mf, wf, orc = helpers.make_pair(name, seed=1)
+    np.random.seed(4)
+    configs = pq.initial_guess(mol, 9)
+    oconfigs = helpers.to_oracle_walkers(configs)
+    accepts = _spy_accepts(wf)
+    np.random.seed(8)
+    df, configs = pq.vmc(wf, configs, nblocks=1, nsteps_per_block=2, accumulators={"energy": pq.EnergyAccumulator(mol, **EWALD)})
+    record = []
+    np.random.seed(8)
+    odf, oconfigs = vmc_driver.vmc(orc, oconfigs, nblocks=1, nsteps_per_block=2, accumulators={"energy": EnergyOracle(mol, **EWALD)},
+                                   record=record)
+    assert len(accepts) == len(record) > 0, "the protocol loop of the reference driver must have run"
+    assert all(np.array_equal(a, r["accept"]) for a, r in zip(accepts, record))
+    assert np.abs(configs.configs - oconfigs.configs).max() < 1e-10 and np.array_equal(configs.wrap, oconfigs.wrap)
+    for k in ("energytotal", "energyke", "energyecp", "energyee"):
+        assert helpers.relerr(df[k], odf[k]) < TOL, k
+
+
 # ---- CPU self-check of the harness above: the same functions over the REFERENCE's own wave functions must
 # reproduce the golden files (run in the build container; proves the test plumbing, not the product) ----------
 @needs_reference
