@@ -651,7 +651,8 @@ def gpu_arm_dmc(args):
     ctx = wf._ctx
     e0 = float(df0["energytotal"][-1])  # trial / estimated energy from the VMC warm-up (rundmc, dmc.py:497-506)
 
-    prefetch = dmc.DmcPrefetcher(wf, configs, tstep, spb, acc["energy"], W + K)  # host draws overlap the device block
+    # the block's variates + the branching draw: generated on the device one block ahead (host thread if unavailable)
+    prefetch = dmc.dmc_variate_source(wf, configs, tstep, spb, acc["energy"], W + K)
 
     def block():
         nonlocal configs, weights
@@ -677,6 +678,7 @@ def gpu_arm_dmc(args):
     t = time.perf_counter() - t0
     launches = ctx.kernel_launches() - l0
     clocks = sampler.stop() if sampler else None
+    prefetch.shutdown()
     tt = torch.tensor([t], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -705,15 +707,18 @@ def gpu_arm_dmc(args):
             dist.destroy_process_group()
         return
     ne, necp = configs.configs.shape[1], acc["energy"].necp
-    per_step = ne * N * (3 + 1) * 8 + ne * necp * (N + 9) * 8 * 2 + ne * N * 2 * 8
+    # H2D per step: the variates when the host generator is used; with the device generator only the walkers and
+    # weights go up (per block: dmc_propagate recomputes from host walkers, as the reference does)
+    per_step = 0 if isinstance(prefetch, dmc.DeviceDmcVariates) else ne * N * (3 + 1) * 8 + ne * necp * (N + 9) * 8 * 2 + ne * N * 2 * 8
     res = {
         "metric": wl["metric"], "value": value, "unit": "walker-steps/s", "n_gpus": world, "steps": K * spb, "warmup": W * spb,
         "ms_per_step": 1e3 * float(td.item()) / (K * spb), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": workload_config("c5", N, world),
-        "e2e": {"value": e2e, "unit": "walker-steps/s", "h2d_bytes_per_step": per_step + N * ne * 3 * 8 / spb,
+        "e2e": {"value": e2e, "unit": "walker-steps/s", "h2d_bytes_per_step": per_step + (N * ne * 3 * 8 + N * 8) / spb,
                 "d2h_bytes_per_step": (N * ne * 3 * 8 + N * 8) / spb,
-                "call": "pyqmc_b200.dmc.dmc_propagate + branch per block incl. host legacy-RNG draws"},
+                "call": "pyqmc_b200.dmc.dmc_propagate + global branching per block; bit-exact legacy np.random stream ("
+                        + ("continued on the device" if isinstance(prefetch, dmc.DeviceDmcVariates) else "host generator") + ")"},
         "gpu_launches": int(launches), "clocks": clocks,
         "check": {"block_energy": float(out["energytotal"]), "acceptance": float(out["acceptance"]),
                   "tmove_acceptance": float(out["tmove_acceptance"]), "weight": float(out["weight"])},

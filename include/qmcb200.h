@@ -311,6 +311,13 @@ int qmcb_devrng_program(qmcb_ctx *ctx, int64_t nops, const int32_t *kind, const 
                         const uint64_t *dst, const double *scale);
 int qmcb_devrng_vmc_block(qmcb_ctx *ctx, int slot, int nsteps, int ne, int64_t N, int necp,
                           double sigma);
+/* DMC: the draw program of one dmc_propagate call (+ the branching draw) into DMC variate slot 0/1, and
+ * qmcb_dmc_block on such a slot (no variate upload); *branch_draw = the rand() of branch (dmc.py:361) */
+int qmcb_devrng_dmc_block(qmcb_ctx *ctx, int slot, int nsteps, int ne, int64_t N, int necp,
+                          double sigma, int tmoves, int with_branch);
+int qmcb_dmc_block_slot(qmcb_ctx *ctx, int slot, int nsteps, double tstep, double branchcut,
+                        double e_trial, double e_est, double *weights, double *configs,
+                        double *wsums, int64_t *nacc, int64_t *ntacc, double *branch_draw);
 int64_t qmcb_glibc_log_mismatches(int64_t nsamples, uint64_t seed);
 /* diagnostics: SM cycles, nanoseconds and state blocks of the last k_mt_generate launch (out3[3]) */
 int qmcb_devrng_generator_timing(qmcb_ctx *ctx, int64_t *out3);

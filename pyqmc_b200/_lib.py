@@ -94,6 +94,9 @@ SIGNATURES = {
     "qmcb_devrng_get_state": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_uint32), c_int_p, c_int_p, c_double_p]),
     "qmcb_devrng_program": (c_int, [c_void_p, c_i64, c_int_p, c_i64_p, ctypes.POINTER(ctypes.c_uint64), c_double_p]),
     "qmcb_devrng_vmc_block": (c_int, [c_void_p, c_int, c_int, c_int, c_i64, c_int, c_double]),
+    "qmcb_devrng_dmc_block": (c_int, [c_void_p, c_int, c_int, c_int, c_i64, c_int, c_double, c_int, c_int]),
+    "qmcb_dmc_block_slot": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_double, c_double, c_double_p, c_double_p,
+                                    c_double_p, c_i64_p, c_i64_p, c_double_p]),
     "qmcb_glibc_log_mismatches": (c_i64, [c_i64, ctypes.c_uint64]),
     "qmcb_devrng_generator_timing": (c_int, [c_void_p, c_i64_p]),
 }

@@ -23,6 +23,7 @@ struct DevRng {
   cudaStream_t gen_stream = nullptr;
   cudaEvent_t ev_gen = nullptr, ev_plan = nullptr;
   DevRngProgram slot_prog[qmcb_ctx::NSLOT];
+  DevRngProgram dmc_prog[2];
   DevRngProgram generic;
   bool have_state = false;
   long long programs_run = 0, rebases = 0;
@@ -53,9 +54,11 @@ static void devrng_free(qmcb_ctx* c) {
   r->W.release();
   r->F0.release();
   r->F1.release();
-  DevRngProgram* ps[qmcb_ctx::NSLOT + 1];
+  DevRngProgram* ps[qmcb_ctx::NSLOT + 3];
   for (int i = 0; i < qmcb_ctx::NSLOT; ++i) ps[i] = &r->slot_prog[i];
   ps[qmcb_ctx::NSLOT] = &r->generic;
+  ps[qmcb_ctx::NSLOT + 1] = &r->dmc_prog[0];
+  ps[qmcb_ctx::NSLOT + 2] = &r->dmc_prog[1];
   for (auto* p : ps) {
     p->d_ops.release();
     p->d_plan.release();
@@ -314,6 +317,67 @@ int qmcb_devrng_vmc_block(qmcb_ctx* c, int slot, int nsteps, int ne, int64_t N, 
   if (c->block_pending[slot]) CK(cudaStreamWaitEvent(c->copy_stream, c->block_done[slot], 0));
   if (devrng_run(c, r->slot_prog[slot])) return -1;
   CK(cudaEventRecord(c->slot_ready[slot], c->copy_stream));
+  return 0;
+}
+
+// Variates of one DMC block (dmc_propagate, dmc.py:123-221) generated into DMC slot `slot` in the reference's
+// consumption order: the energy evaluation before the first step; per step, for every electron the T-move draws
+// (per ECP atom random(N) + a rotation; select_walker: N scalar rand(); acceptance rand(N)), for every electron
+// normal(N, 3) + rand(N), the energy evaluation; finally (with_branch) the rand() of branch (dmc.py:361).
+int qmcb_devrng_dmc_block(qmcb_ctx* c, int slot, int nsteps, int ne, int64_t N, int necp, double sigma, int tmoves,
+                          int with_branch) {
+  Guard g(c);
+  if (slot < 0 || slot > 1) return fail("slot out of range");
+  DevRng* r = devrng_of(c);
+  qmcb_ctx::DmcSlot& sl = c->dmc_slot[slot];
+  const size_t nse = (size_t)nsteps * ne, nu1 = (size_t)ne * necp * N, nr1 = (size_t)ne * necp * 9;
+  if (sl.gauss.ensure(nse * N * 3) || sl.unif.ensure(nse * N) || sl.u.ensure((size_t)(nsteps + 1) * nu1) ||
+      sl.rot.ensure((size_t)(nsteps + 1) * nr1) || sl.tmu.ensure(nse * necp * N) || sl.tmrot.ensure(nse * necp * 9) ||
+      sl.tmsel.ensure(nse * N) || sl.tmacc.ensure(nse * N) || sl.branch.ensure(1))
+    return -1;
+  if (!sl.ready) CK(cudaEventCreateWithFlags(&sl.ready, cudaEventDisableTiming));
+  std::vector<int> kind;
+  std::vector<long long> count;
+  std::vector<double*> dst;
+  std::vector<double> scale;
+  auto push = [&](int k, long long n, double* d, double s) {
+    kind.push_back(k);
+    count.push_back(n);
+    dst.push_back(d);
+    scale.push_back(s);
+  };
+  auto energy_draws = [&](int k) {
+    for (int e = 0; e < ne; ++e)
+      for (int a = 0; a < necp; ++a) {
+        const size_t ea = (size_t)e * necp + a;
+        push(devrng::KIND_UNIFORM, N, sl.u.p + (size_t)k * nu1 + ea * N, 1.0);
+        push(devrng::KIND_ROTATION, 4, sl.rot.p + (size_t)k * nr1 + ea * 9, 1.0);
+      }
+  };
+  energy_draws(0);
+  for (int step = 0; step < nsteps; ++step) {
+    if (tmoves)
+      for (int e = 0; e < ne; ++e) {
+        const size_t se = (size_t)step * ne + e;
+        for (int a = 0; a < necp; ++a) {
+          push(devrng::KIND_UNIFORM, N, sl.tmu.p + (se * necp + a) * N, 1.0);
+          push(devrng::KIND_ROTATION, 4, sl.tmrot.p + (se * necp + a) * 9, 1.0);
+        }
+        push(devrng::KIND_UNIFORM, N, sl.tmsel.p + se * N, 1.0);
+        push(devrng::KIND_UNIFORM, N, sl.tmacc.p + se * N, 1.0);
+      }
+    for (int e = 0; e < ne; ++e) {
+      const size_t se = (size_t)step * ne + e;
+      push(devrng::KIND_NORMAL, 3 * N, sl.gauss.p + se * N * 3, sigma);
+      push(devrng::KIND_UNIFORM, N, sl.unif.p + se * N, 1.0);
+    }
+    energy_draws(step + 1);
+  }
+  if (with_branch) push(devrng::KIND_UNIFORM, 1, sl.branch.p, 1.0);
+  if (devrng_build(c, r->dmc_prog[slot], (int)kind.size(), kind.data(), count.data(), dst.data(), scale.data())) return -1;
+  if (devrng_run(c, r->dmc_prog[slot])) return -1;
+  CK(cudaEventRecord(sl.ready, c->copy_stream));
+  sl.filled = true;
   return 0;
 }
 

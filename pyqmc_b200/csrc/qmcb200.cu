@@ -164,6 +164,14 @@ struct qmcb_ctx {
   cudaStream_t energy_stream = nullptr;
   cudaEvent_t ev_snap = nullptr, ev_edone = nullptr;
   DBuf<double> sn_inv[2], sn_conf, sn_ap, sn_bp, e_ke2, e_g22;
+  // variates of a DMC block generated on the device (qmcb_devrng_dmc_block), two sets: the generator fills one
+  // while qmcb_dmc_block_slot consumes the other
+  struct DmcSlot {
+    DBuf<double> gauss, unif, u, rot, tmu, tmrot, tmsel, tmacc, branch;
+    cudaEvent_t ready = nullptr;
+    bool filled = false;
+  } dmc_slot[2];
+  int dmc_use_slot = -1;
   // per-slot result staging of qmcb_vmc_block_slot_begin: the device->host copies of block b run on their own
   // stream (copy engine) while block b+1 computes
   cudaStream_t d2h_stream = nullptr;
@@ -1132,6 +1140,10 @@ void qmcb_destroy(qmcb_ctx* c) {
     cudaStreamDestroy(c->d2h_stream);
   }
   if (c->ev_block) cudaEventDestroy(c->ev_block);
+  for (auto& sl : c->dmc_slot) {
+    for (auto* b : {&sl.gauss, &sl.unif, &sl.u, &sl.rot, &sl.tmu, &sl.tmrot, &sl.tmsel, &sl.tmacc, &sl.branch}) b->release();
+    if (sl.ready) cudaEventDestroy(sl.ready);
+  }
   for (int i = 0; i < qmcb_ctx::NSLOT; ++i) {
     c->r_energy[i].release();
     c->r_conf[i].release();
@@ -2487,12 +2499,30 @@ int qmcb_dmc_block(qmcb_ctx* c, int nsteps, double tstep, double branchcut, doub
     auto up = [&](double* dst, const double* src, size_t n) {
       return n == 0 ? cudaSuccess : cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyHostToDevice, stream);
     };
-    if (up(c->d_gauss.p, gauss, nse * N * 3) != cudaSuccess || up(c->d_unif.p, unif, nse * N) != cudaSuccess ||
-        up(d_w.p, weights, N) != cudaSuccess) {
+    // the block's variates: uploaded from the host, or already on the device (qmcb_devrng_dmc_block -> slot)
+    const int from_slot = c->dmc_use_slot;
+    c->dmc_use_slot = -1;
+    double *pg = c->d_gauss.p, *pu = c->d_unif.p, *peu = c->d_u.p, *per = c->d_rot.p;
+    double *ptu = nullptr, *ptr_ = nullptr, *pts = nullptr, *pta = nullptr;
+    if (from_slot >= 0) {
+      qmcb_ctx::DmcSlot& sl = c->dmc_slot[from_slot];
+      if (!sl.filled || sl.gauss.n < nse * N * 3) {
+        rc = fail("qmcb_dmc_block_slot: the slot holds no variates of this block shape");
+        break;
+      }
+      cudaStreamWaitEvent(stream, sl.ready, 0);
+      pg = sl.gauss.p; pu = sl.unif.p; peu = sl.u.p; per = sl.rot.p;
+      ptu = sl.tmu.p; ptr_ = sl.tmrot.p; pts = sl.tmsel.p; pta = sl.tmacc.p;
+      if (up(d_w.p, weights, N) != cudaSuccess) {
+        rc = fail("H2D copy failed");
+        break;
+      }
+    } else if (up(c->d_gauss.p, gauss, nse * N * 3) != cudaSuccess || up(c->d_unif.p, unif, nse * N) != cudaSuccess ||
+               up(d_w.p, weights, N) != cudaSuccess) {
       rc = fail("H2D copy failed");
       break;
     }
-    if (tmoves) {
+    if (tmoves && from_slot < 0) {
       if (!ecp_u || !ecp_rot || !tm_u || !tm_rot || !tm_sel || !tm_acc) {
         rc = fail("DMC with ECPs needs the energy and T-move variates");
         break;
@@ -2507,11 +2537,12 @@ int qmcb_dmc_block(qmcb_ctx* c, int nsteps, double tstep, double branchcut, doub
         rc = fail("H2D copy failed");
         break;
       }
+      ptu = d_tmu.p; ptr_ = d_tmrot.p; pts = d_tmsel.p; pta = d_tmacc.p;
     }
     cudaMemsetAsync(c->d_nacc.p, 0, nse * 8, stream);
     cudaMemsetAsync(d_ntacc.p, 0, nse * 8, stream);
     // E_L and v^2 before the first step (dmc.py:150-152)
-    if ((rc = launch_energy(c, c->d_u.p, c->d_rot.p, c->d_energy.p, stream))) break;
+    if ((rc = launch_energy(c, peu, per, c->d_energy.p, stream))) break;
     DmcWeightArgs wa{};
     wa.tstep = tstep;
     wa.branchcut = branchcut;
@@ -2532,8 +2563,8 @@ int qmcb_dmc_block(qmcb_ctx* c, int nsteps, double tstep, double branchcut, doub
       if (tmoves) {
         for (int e = 0; e < S.ne && rc == 0; ++e) {
           const size_t se = (size_t)step * S.ne + e;
-          rc = dmc_tmove_electron(c, e, tstep, d_tmu.p + se * S.necp * N, d_tmrot.p + se * S.necp * 9, d_tmsel.p + se * N,
-                                  d_tmacc.p + se * N, d_ntacc.p + se, which, stream);
+          rc = dmc_tmove_electron(c, e, tstep, ptu + se * S.necp * N, ptr_ + se * S.necp * 9, pts + se * N, pta + se * N,
+                                  d_ntacc.p + se, which, stream);
         }
         if (rc) break;
       }
@@ -2551,8 +2582,8 @@ int qmcb_dmc_block(qmcb_ctx* c, int nsteps, double tstep, double branchcut, doub
       cudaMemsetAsync(d_r2a.p, 0, N * 8, stream);
       SweepArgs sa{};
       sa.tstep = tstep;
-      sa.gauss = c->d_gauss.p + (size_t)step * S.ne * N * 3;
-      sa.unif = c->d_unif.p + (size_t)step * S.ne * N;
+      sa.gauss = pg + (size_t)step * S.ne * N * 3;
+      sa.unif = pu + (size_t)step * S.ne * N;
       sa.accept = nullptr;
       sa.nacc = c->d_nacc.p + (size_t)step * S.ne;
       sa.r2prop = d_r2p.p;
@@ -2567,7 +2598,7 @@ int qmcb_dmc_block(qmcb_ctx* c, int nsteps, double tstep, double branchcut, doub
         rc = fail("k_vmc_sweep<16, true> launch failed");
         break;
       }
-      if ((rc = launch_energy(c, c->d_u.p + (size_t)(step + 1) * nu1, c->d_rot.p + (size_t)(step + 1) * nr1, c->d_energy.p, stream))) break;
+      if ((rc = launch_energy(c, peu + (size_t)(step + 1) * nu1, per + (size_t)(step + 1) * nr1, c->d_energy.p, stream))) break;
       k_dmc_weights<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(S, c->st, wa);
       c->nlaunch++;
       k_colsum<<<7, 256, 0, stream>>>(d_prod.p, (int)N, d_ws.p + (size_t)step * 8);
@@ -2588,6 +2619,20 @@ int qmcb_dmc_block(qmcb_ctx* c, int nsteps, double tstep, double branchcut, doub
   cudaStreamSynchronize(stream);
   c->saved_slot = -1;
   return rc;
+}
+
+// qmcb_dmc_block on the variates qmcb_devrng_dmc_block generated into `slot`; *branch_draw receives the uniform
+// variate of this block's branching step (dmc.py:361), drawn right after the block's variates.
+int qmcb_dmc_block_slot(qmcb_ctx* c, int slot, int nsteps, double tstep, double branchcut, double e_trial, double e_est,
+                        double* weights, double* configs, double* wsums, int64_t* nacc, int64_t* ntacc, double* branch_draw) {
+  if (slot < 0 || slot > 1) return fail("slot out of range");
+  c->dmc_use_slot = slot;
+  int rc = qmcb_dmc_block(c, nsteps, tstep, branchcut, e_trial, e_est, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                          nullptr, nullptr, weights, configs, wsums, nacc, ntacc);
+  c->dmc_use_slot = -1;
+  if (rc) return rc;
+  if (branch_draw) CK(cudaMemcpy(branch_draw, c->dmc_slot[slot].branch.p, 8, cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -198,6 +198,67 @@ class _Done:
         return self.value
 
 
+class DeviceDmcVariates:
+    """``DmcPrefetcher`` with the generator on the GPU (csrc/device_rng.cuh): the global legacy ``np.random`` state is
+    handed to the device once, each block's draw program -- block variates, then the one ``rand()`` of ``branch``
+    (dmc.py:361) -- is enqueued one block ahead into one of two device slots, and ``shutdown()`` writes the advanced
+    state back to ``np.random``.  Same interface as ``DmcPrefetcher``."""
+
+    def __init__(self, wf, configs, tstep, nsteps, accumulator, nblocks, with_branch=True):
+        import ctypes
+
+        self.shape = configs.configs.shape[:2]
+        self.args = (float(np.sqrt(tstep)), nsteps, accumulator)
+        if _device_context(wf) is None:
+            wf.recompute(configs)
+        self.ctx = _device_context(wf)
+        self.remaining, self.issued, self.with_branch = nblocks, 0, with_branch
+        self.queue, self.current, self.open = [], None, True
+        st = np.random.get_state()
+        key = np.ascontiguousarray(st[1], dtype=np.uint32)
+        _lib.check(self.ctx.lib.qmcb_devrng_set_state(self.ctx.h, key.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
+                                                      int(st[2]), int(st[3]), float(st[4])))
+        self._submit()
+
+    def _submit(self):
+        if self.remaining <= 0:
+            return
+        sigma, nsteps, accumulator = self.args
+        slot = self.issued % 2
+        self.issued += 1
+        self.remaining -= 1
+        _lib.check(self.ctx.lib.qmcb_devrng_dmc_block(self.ctx.h, slot, nsteps, self.shape[1], self.shape[0], accumulator.necp,
+                                                      sigma, 1 if accumulator.has_nonlocal_moves() else 0,
+                                                      1 if self.with_branch else 0))
+        self.queue.append({"device_slot": slot})
+
+    def next(self):
+        self.current = self.queue.pop(0)
+        self._submit()  # the following block's program: generated while this block runs
+        return self.current
+
+    def branch_draw(self):
+        return self.current.get("branch") if self.with_branch else None
+
+    def shutdown(self):
+        import ctypes
+
+        if not self.open:
+            return
+        self.open = False
+        key = np.empty(624, dtype=np.uint32)
+        pos, has_gauss, cached = ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_double(0.0)
+        _lib.check(self.ctx.lib.qmcb_devrng_get_state(self.ctx.h, key.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
+                                                      ctypes.byref(pos), ctypes.byref(has_gauss), ctypes.byref(cached)))
+        np.random.set_state(("MT19937", key, pos.value, has_gauss.value, cached.value))
+
+
+def dmc_variate_source(wf, configs, tstep, nsteps, accumulator, nblocks, with_branch=True):
+    """Device generator when it reproduces this host's libm (``mc.device_rng_usable``), else the host thread."""
+    cls = DeviceDmcVariates if mc.device_rng_usable() else DmcPrefetcher
+    return cls(wf, configs, tstep, nsteps, accumulator, nblocks, with_branch)
+
+
 def dmc_propagate_device(wf, configs, weights, tstep, branchcut_start, e_trial, e_est, nsteps, accumulators, ekey,
                          variates=None):
     nconf, nelec, _ = configs.configs.shape
@@ -213,10 +274,19 @@ def dmc_propagate_device(wf, configs, weights, tstep, branchcut_start, e_trial, 
     nacc = np.zeros((nsteps, nelec), dtype=np.int64)
     ntacc = np.zeros((nsteps, nelec), dtype=np.int64)
     d = _lib.dptr
-    _lib.check(ctx.lib.qmcb_dmc_block(
-        ctx.h, nsteps, float(tstep), float(branchcut_start), float(e_trial), float(e_est), d(v["gauss"]), d(v["unif"]),
-        d(v["ecp_u"]), d(v["ecp_rot"]), d(v["tm_u"]), d(v["tm_rot"]), d(v["tm_sel"]), d(v["tm_acc"]), d(w), d(newconf),
-        d(wsums), nacc.ctypes.data_as(_lib.c_i64_p), ntacc.ctypes.data_as(_lib.c_i64_p)))
+    if "device_slot" in v:  # variates generated on the device (DeviceDmcVariates)
+        import ctypes
+
+        branch = ctypes.c_double(0.0)
+        _lib.check(ctx.lib.qmcb_dmc_block_slot(
+            ctx.h, v["device_slot"], nsteps, float(tstep), float(branchcut_start), float(e_trial), float(e_est), d(w),
+            d(newconf), d(wsums), nacc.ctypes.data_as(_lib.c_i64_p), ntacc.ctypes.data_as(_lib.c_i64_p), ctypes.byref(branch)))
+        v["branch"] = branch.value
+    else:
+        _lib.check(ctx.lib.qmcb_dmc_block(
+            ctx.h, nsteps, float(tstep), float(branchcut_start), float(e_trial), float(e_est), d(v["gauss"]), d(v["unif"]),
+            d(v["ecp_u"]), d(v["ecp_rot"]), d(v["tm_u"]), d(v["tm_rot"]), d(v["tm_sel"]), d(v["tm_acc"]), d(w), d(newconf),
+            d(wsums), nacc.ctypes.data_as(_lib.c_i64_p), ntacc.ctypes.data_as(_lib.c_i64_p)))
     ctx.epoch += 1  # the block moved the walkers on the device
     configs.configs[...] = newconf
     if w is not weights:
@@ -363,7 +433,7 @@ def rundmc(wf, configs, weights=None, tstep=0.01, nblocks=200, nsteps_per_block=
     todo = max(0, nblocks - blockoffset)
     prefetch = None
     if todo and _device_dmc_path(wf, accumulators, ekey):
-        prefetch = DmcPrefetcher(wf, configs, tstep, nsteps_per_block, accumulators[ekey[0]], todo)
+        prefetch = dmc_variate_source(wf, configs, tstep, nsteps_per_block, accumulators[ekey[0]], todo)
     rows = []
     try:
         for block in range(blockoffset, nblocks):

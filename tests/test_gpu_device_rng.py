@@ -149,3 +149,26 @@ def test_public_vmc_device_generator_equals_host_generator(lib, monkeypatch):
     for k in ("energytotal", "energyecp", "energyke", "acceptance"):
         assert np.array_equal(d1[k], d2[k]), k
     assert np.array_equal(s1[1], s2[1]) and s1[2:] == s2[2:]
+
+
+def test_rundmc_device_generator_equals_host_generator(lib, monkeypatch):
+    """pyqmc_b200.rundmc (T-moves, weights, branching draw between blocks): identical results and final np.random
+    state whether the legacy stream is continued on the device or drawn by the host generator."""
+    import pyqmc_b200 as pq
+
+    results = []
+    for host in (False, True):
+        if host:
+            monkeypatch.setenv("QMCB_HOST_RNG", "1")
+        mol, mf, wf, _ = helpers.make_pair("h2o", seed=1)
+        np.random.seed(19)
+        configs = pq.initial_guess(mol, 63)
+        np.random.seed(20)
+        df, configs, weights = pq.rundmc(wf, configs, tstep=0.02, nblocks=3, nsteps_per_block=2, vmc_warmup=2,
+                                         accumulators={"energy": pq.EnergyAccumulator(mol)})
+        results.append((df, configs.configs.copy(), weights.copy(), np.random.get_state()))
+    (d1, c1, w1, s1), (d2, c2, w2, s2) = results
+    assert np.array_equal(c1, c2) and np.array_equal(w1, w2)
+    for k in ("energytotal", "weight", "acceptance", "tmove_acceptance", "e_trial", "max branches"):
+        assert np.array_equal(d1[k], d2[k]), k
+    assert np.array_equal(s1[1], s2[1]) and s1[2:] == s2[2:]
