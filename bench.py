@@ -684,20 +684,19 @@ def gpu_arm_dmc(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t = float(tt.item())
     e2e = N * world * K * spb / t
-    # device share: the same blocks with the variates drawn beforehand (qmcb_dmc_block incl. its H2D/D2H)
-    import pyqmc_b200.dmc as D
-
-    pre = [D.draw_dmc_block_variates(N, configs.configs.shape[1], tstep, spb, acc["energy"]) for _ in range(K)]
-    orig = D.draw_dmc_block_variates
-    it = iter(pre)
-    D.draw_dmc_block_variates = lambda *a, **k: next(it)
+    # device share: the same blocks without branching / allreduce, variates ready before each block (generated on the
+    # device one block ahead, or drawn by the host thread): recompute + qmcb_dmc_block incl. its H2D/D2H
+    src = dmc.dmc_variate_source(wf, configs, tstep, spb, acc["energy"], K + 1, with_branch=False)
+    out, configs, weights = dmc.dmc_propagate(wf, configs, weights, tstep, 10.0, e0, e0, nsteps=spb, accumulators=acc,
+                                              variates=src.next())
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     for _ in range(K):
-        out, configs, weights = dmc.dmc_propagate(wf, configs, weights, tstep, 10.0, e0, e0, nsteps=spb, accumulators=acc)
+        out, configs, weights = dmc.dmc_propagate(wf, configs, weights, tstep, 10.0, e0, e0, nsteps=spb, accumulators=acc,
+                                                  variates=src.next())
     torch.cuda.synchronize()
     tdev = time.perf_counter() - t1
-    D.draw_dmc_block_variates = orig
+    src.shutdown()
     td = torch.tensor([tdev], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(td, op=dist.ReduceOp.MAX)
