@@ -63,6 +63,25 @@ int qmcb_set_slater(qmcb_ctx *ctx, int nup, int ndn, int nmo_up, const double *m
                     int ndet_dn, const int32_t *occ_dn, int ndet, const int32_t *map_up,
                     const int32_t *map_dn, const double *det_coeff);
 
+/* COMPLEX wave functions: complex MO and / or determinant coefficients (Slater.__init__ sets
+ * dtype = complex when orbitals.mo_dtype == complex or any parameter is complex, slater.py:212-216;
+ * MoleculeOrbitalEvaluator / PBCOrbitalEvaluatorKpoints take mo_dtype from the coefficients,
+ * orbitals.py:61-65, 160-165).  Same arguments as qmcb_set_slater with the real and imaginary parts
+ * separate.  A context set up this way is COMPLEX (qmcb_is_complex): for every call whose `which`
+ * includes QMCB_SLATER the wave-function-valued outputs -- sign (the unit phase, get_complex_phase
+ * slater.py:32-33), gradient, value / ratio, laplacian, testvalue(_many) ratios, T-move ratios,
+ * pgradient of det_coeff / mo_coeff_*, the "inverse_*" / "dets_*" state arrays -- are complex128
+ * (interleaved re, im) of the same shape; log values stay real.  qmcb_energy returns 8 rows (see
+ * there).  The device-resident block drivers (qmcb_vmc_block*, qmcb_dmc_block*, qmcb_sr_avg) are
+ * real-only and fail on a complex context: the reference's drivers run it through the protocol. */
+int qmcb_set_slater_cx(qmcb_ctx *ctx, int nup, int ndn, int nmo_up, const double *mo_up_re,
+                       const double *mo_up_im, int nmo_dn, const double *mo_dn_re,
+                       const double *mo_dn_im, int ndet_up, const int32_t *occ_up, int ndet_dn,
+                       const int32_t *occ_dn, int ndet, const int32_t *map_up,
+                       const int32_t *map_dn, const double *det_re, const double *det_im);
+/* 1 when the context holds a complex Slater factor */
+int qmcb_is_complex(qmcb_ctx *ctx);
+
 /* JastrowSpin.__init__ (jastrowspin.py:34-54): a (electron-ion) and b (electron-electron)
  * radial bases with one shared cutoff each, acoeff [natom][na][2], bcoeff [nb][3]. */
 int qmcb_set_jastrow(qmcb_ctx *ctx, int nup, int ndn, int na, const int32_t *a_kind,
@@ -98,13 +117,19 @@ int qmcb_set_lattice(qmcb_ctx *ctx, const double *lat /*[9]*/, int mode, const d
  * pyqmc/wf/numba/pbcgto.py:594-621): the shell table of qmcb_set_basis then refers to the nbatom
  * PRIMITIVE-cell atoms bxyz; lprim = primitive lattice, smat = supercell matrix S, kpts [nk][3],
  * Ls [nL][3] images sorted by norm, num_Ls [nbatom], r^2 cutoffs per atom / per shell (max_Ls,
- * pbcgto.py:551-591), phases [nL][nk] = Re exp(i Ls.k), mo_k_* = k-point index of every MO column
- * of the concatenated coefficient matrices (orbitals.py:155-160).  Real phases only. */
+ * pbcgto.py:551-591), phases [nL][nk] = Re exp(i Ls.k) (imaginary parts: qmcb_set_pbc_phases_imag),
+ * mo_k_* = k-point index of every MO column of the concatenated coefficient matrices
+ * (orbitals.py:155-160). */
 int qmcb_set_pbc_orbitals(qmcb_ctx *ctx, int nbatom, const double *bxyz, const double *lprim,
                           const double *smat, int nk, const double *kpts, int nL, const double *Ls,
                           const int32_t *num_Ls, const double *atom_cutoff, int nshell,
                           const double *l_cutoff, const double *phases, int nmo_up,
                           const int32_t *mo_k_up, int nmo_dn, const int32_t *mo_k_dn, int isgamma);
+
+/* General twists: Im exp(i Ls.k) [nL][nk] (PeriodicAtomicOrbitalEvaluator.phases, pbcgto.py:620-621, complex
+ * unless every k-point is real) after qmcb_set_pbc_orbitals passed the real parts.  Used by complex
+ * contexts (qmcb_set_slater_cx), whose wrap phase is exp(i k.R) (get_wrapphase_complex, orbitals.py:38-39). */
+int qmcb_set_pbc_phases_imag(qmcb_ctx *ctx, int nL, int nk, const double *phases_im);
 
 /* Ewald.__init__ products (pyqmc/observables/ewald.py:93-200): alpha, real-space displacements
  * [ndisp][3], selected reciprocal points / weights, ion structure factor, the pair / square
@@ -171,7 +196,9 @@ int qmcb_get_state(qmcb_ctx *ctx, const char *name, double *out);
 /* ---- local energy (EnergyAccumulator.__call__, accumulators.py:60-75) ------------------ */
 /* Random variates are drawn by the caller in the reference's order (eval_ecp.py:145, 263):
  * ecp_u [ne][necp][N] uniform numbers for the stochastic channel mask, ecp_rot
- * [ne][necp][3][3] rotation matrices.  out [6][N] = ke, ee, ei, ecp, grad2, total. */
+ * [ne][necp][3][3] rotation matrices.  out [6][N] = ke, ee, ei, ecp, grad2, total.
+ * Complex contexts: out [8][N], rows 6 and 7 = Im ecp, Im total (ke = -Re(lap)/2 and grad2 =
+ * sum |grad|^2 are real, energy.py:63-64; the ECP values carry wf.dtype, eval_ecp.py:26). */
 int qmcb_energy(qmcb_ctx *ctx, const double *ecp_u, const double *ecp_rot, double *out);
 
 /* eval_ecp.compute_tmoves (eval_ecp.py:43-80) for electron e:

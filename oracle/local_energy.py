@@ -132,7 +132,7 @@ def ecp_electron_atom(channels, apos, configs, wf, e, threshold, naip=None):
         ratio = wf.testvalue(e, epos, mask)[0]
     else:
         ratio = np.zeros((0, naip))
-    total = np.zeros(N)
+    total = np.zeros(N, dtype=wf.dtype)  # eval_ecp.py:90
     total[mask] = np.einsum("ij,ik,ijk->i", ratio, mv, P)
     total += v[:, -1]
     return {"total": total, "v_l": mv, "local": v[:, -1], "P_l": P, "ratio": ratio,
@@ -181,9 +181,9 @@ class EnergyOracle:
 
     def ecp(self, configs, wf):
         N, ne = configs.configs.shape[:2]
-        tot = np.zeros(N)
+        tot = np.zeros(N, dtype=wf.dtype)  # eval_ecp.py:26
         for e in range(ne):
-            per_e = np.zeros(N)
+            per_e = np.zeros(N, dtype=wf.dtype)
             for i, ch in self.ecp_atoms:
                 per_e += ecp_electron_atom(ch, self.atoms[i], configs, wf, e, self.threshold,
                                            self.naip)["total"]
@@ -222,7 +222,7 @@ class EnergyOracle:
             d = ecp_electron_atom(ch, self.atoms[i], configs, wf, e, self.threshold, self.naip)
             npts = d["ratio"].shape[1]
             w = np.zeros((N, npts))
-            r = np.ones((N, npts))
+            r = np.ones((N, npts), dtype=d["ratio"].dtype)
             w[d["mask"]] = np.einsum("ik,ijk->ij", np.exp(-tau * d["v_l"]) - 1, d["P_l"])
             r[d["mask"]] = d["ratio"]
             ratios.append(r)

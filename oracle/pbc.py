@@ -136,16 +136,14 @@ class PbcBasis:
         self.num_Ls = np.asarray(tables["num_Ls"])
         self.atom_cutoff = np.asarray(tables["atom_cutoff"], dtype=float)
         self.l_cutoff = np.asarray(tables["l_cutoff"], dtype=float)
-        self.phases = np.asarray(tables["phases"])
-        if np.iscomplexobj(self.phases):
-            raise NotImplementedError("complex phases")
+        self.phases = np.asarray(tables["phases"])  # complex for general twists (pbcgto.py:620-621)
 
     def eval(self, deriv, points):
         """points (P,3) inside the primitive cell -> (nk, P, A) or (nk, nc, P, A)."""
         points = np.asarray(points, dtype=float).reshape(-1, 3)
         P, nk = len(points), len(self.kpts)
         nc = (1, 4, 5)[deriv]
-        out = np.zeros((nk, nc, P, self.nao))
+        out = np.zeros((nk, nc, P, self.nao), dtype=self.phases.dtype)
         for a, center in enumerate(self.atom_coords):
             rv0 = points - center
             for j in range(int(self.num_Ls[a])):
@@ -189,7 +187,8 @@ class PbcBasis:
 
 
 class PbcOrbitals:
-    """orbitals.py:118-239 (numba evaluator selected, real phases)."""
+    """orbitals.py:118-239 (numba evaluator selected); complex coefficients select the complex wrap phase
+    exp(i k.R) (orbitals.py:38-39, 160-165)."""
 
     def __init__(self, supercell, mo_coeff, kpts, tables):
         self.cell = supercell.original_cell
@@ -204,6 +203,7 @@ class PbcOrbitals:
             "mo_coeff_alpha": np.concatenate(mo_coeff[0], axis=1),
             "mo_coeff_beta": np.concatenate(mo_coeff[1], axis=1),
         }
+        self.iscomplex = any(np.iscomplexobj(v) for v in self.parameters.values())
 
     def aos(self, deriv, epos, mask=None):
         """-> ([nc,] shape..., nk, A): k axis next to the AO axis."""
@@ -220,7 +220,7 @@ class PbcOrbitals:
             wrap = epos.wrap if mask is None else epos.wrap[mask]
             wrap = np.dot(wrap, self.S).reshape(-1, 3) + primwrap
             kdotR = np.linalg.multi_dot((self.kpts, self.Lprim.T, wrap.T))  # (nk, P)
-            phase = (-1.0) ** np.round(kdotR / np.pi)
+            phase = np.exp(1j * kdotR) if self.iscomplex else (-1.0) ** np.round(kdotR / np.pi)
             ao = np.einsum("k...,k...a->k...a", phase, ao) if deriv == 0 else np.einsum("kp,kcpa->kcpa", phase, ao)
         if deriv == 0:
             return np.moveaxis(ao, 0, -2).reshape(*shape, len(self.kpts), self.basis.nao)
@@ -230,7 +230,7 @@ class PbcOrbitals:
     def mos(self, ao, s):
         C = self.parameters["mo_coeff_alpha" if s == 0 else "mo_coeff_beta"]
         ps = [0] + list(self.param_split[s])
-        out = np.zeros(ao.shape[:-2] + (C.shape[1],))
+        out = np.zeros(ao.shape[:-2] + (C.shape[1],), dtype=complex if self.iscomplex else float)
         for k in range(len(ps) - 1):
             out[..., ps[k]:ps[k + 1]] = ao[..., k, :] @ C[:, ps[k]:ps[k + 1]]
         return out
@@ -278,7 +278,7 @@ class SlaterPbcOracle(SlaterOracle):
         coeff, self._det_occup, self._det_map = pack_determinants(flat, tol)
         self.parameters = {"det_coeff": coeff}
         self.parameters.update(self.orbitals.parameters)
-        self.dtype = float
+        self.dtype = complex if any(np.iscomplexobj(v) for v in self.parameters.values()) else float
 
     def _ao(self, deriv, epos, mask=None):
         return self.orbitals.aos(deriv, epos, mask)

@@ -10,7 +10,7 @@ import numpy as np
 class ProductOracle:
     def __init__(self, *factors):
         self.wf_factors = list(factors)
-        self.dtype = float
+        self.dtype = complex if any(f.dtype == complex for f in factors) else float  # multiplywf.py:79-80
 
     @property
     def parameters(self):

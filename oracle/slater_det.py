@@ -48,7 +48,8 @@ def pack_determinants(determinants, tol):
             else:
                 dmap[s].append(len(occ[s]))
                 occ[s].append(o)
-    return np.array(weights, dtype=float), occ, np.array(dmap, dtype=int)
+    weights = np.array(weights)
+    return (weights if np.iscomplexobj(weights) else weights.astype(float)), occ, np.array(dmap, dtype=int)
 
 
 def determinants_from_mf(mf):
@@ -73,11 +74,12 @@ class SlaterOracle:
         coeff, self._det_occup, self._det_map = pack_determinants(determinants, tol)
         self.parameters = {
             "det_coeff": coeff,
-            "mo_coeff_alpha": np.array(mfu.mo_coeff[0][:, : top[0]], dtype=float),
-            "mo_coeff_beta": np.array(mfu.mo_coeff[1][:, : top[1]], dtype=float),
+            "mo_coeff_alpha": np.array(mfu.mo_coeff[0][:, : top[0]]),
+            "mo_coeff_beta": np.array(mfu.mo_coeff[1][:, : top[1]]),
         }
         self.basis = BasisTable(mol)
-        self.dtype = float
+        # slater.py:212-216: complex when any parameter is complex; the phase of a determinant then replaces its sign
+        self.dtype = complex if any(np.iscomplexobj(v) for v in self.parameters.values()) else float
 
     # --- orbital evaluation -------------------------------------------------------
     def _mo_coeff(self, s):
@@ -142,14 +144,14 @@ class SlaterOracle:
         self._aovals[mask, e, :] = ao
         rows = mo[:, self._det_occup[s]]  # (Nm, D_s, n_s)
         ratio, self._inverse[s][mask] = rank1_row_update(eeff, self._inverse[s][mask], rows)
-        self._dets[s][0, mask] *= np.sign(ratio)
+        self._dets[s][0, mask] *= (ratio / np.abs(ratio)) if self.dtype == complex else np.sign(ratio)
         self._dets[s][1, mask] += np.log(np.abs(ratio))
 
     def _det_weights(self, mask=None):
         """(N[m], D) array of c_D * sign * exp(log - global refs) and its row sums' factors."""
         sel = slice(None) if mask is None else mask
-        upref = np.amax(self._dets[0][1])
-        dnref = np.amax(self._dets[1][1])
+        upref = np.amax(self._dets[0][1]).real
+        dnref = np.amax(self._dets[1][1]).real
         m0, m1 = self._det_map
         up, dn = self._dets[0][:, sel], self._dets[1][:, sel]
         amp = up[0][:, m0] * dn[0][:, m1] * np.exp(up[1][:, m0] + dn[1][:, m1] - upref - dnref)
@@ -221,7 +223,7 @@ class SlaterOracle:
         e = np.asarray(e)
         spins = (e >= self._nelec[0]).astype(int)
         ao = self._ao(0, epos, mask)  # (Nm, A)
-        out = np.zeros((ao.shape[0], len(e)))  # ao.shape[0] = Nm in both layouts
+        out = np.zeros((ao.shape[0], len(e)), dtype=self.dtype)  # ao.shape[0] = Nm in both layouts
         for s in (0, 1):
             idx = np.nonzero(spins == s)[0]
             if len(idx) == 0:
@@ -242,7 +244,7 @@ class SlaterOracle:
         m0, m1 = self._det_map
         nz = sign != 0.0
         N = len(sign)
-        dcoef = np.zeros((N, len(coeff)))
+        dcoef = np.zeros((N, len(coeff)), dtype=self.dtype)
         up, dn = self._dets
         dcoef[nz] = (
             up[0][nz][:, m0]
@@ -257,12 +259,12 @@ class SlaterOracle:
             nmo = self._mo_coeff(s).shape[1]
             A = ao_all.shape[-1]
             # d ln D_d / d C[a, i] = sum_e ao[e, a] inv[d, col(i), e] if orbital i is occupied in d
-            per_det = np.zeros((len(self._det_occup[s]), N, A, nmo))
+            per_det = np.zeros((len(self._det_occup[s]), N, A, nmo), dtype=self.dtype)
             for d, occ in enumerate(self._det_occup[s]):
                 for col, i in enumerate(occ):
                     ao = self._ao_for_mo(ao_all, s, i)  # (N, n_s, A): the AO set MO i is expanded in
                     per_det[d, :, :, i] = np.einsum("nea,ne->na", ao, self._inverse[s][:, d, col, :])
-            g = np.zeros((N, A, nmo))
+            g = np.zeros((N, A, nmo), dtype=self.dtype)
             for D, c in enumerate(coeff):
                 g += per_det[self._det_map[s][D]] * c * dcoef[:, D, None, None]
             out[name] = g

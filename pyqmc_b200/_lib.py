@@ -31,6 +31,10 @@ SIGNATURES = {
     "qmcb_set_basis": (c_int, [c_void_p, c_int, c_int_p, c_int_p, c_int_p, c_double_p, c_double_p]),
     "qmcb_set_slater": (c_int, [c_void_p, c_int, c_int, c_int, c_double_p, c_int, c_double_p, c_int,
                                 c_int_p, c_int, c_int_p, c_int, c_int_p, c_int_p, c_double_p]),
+    "qmcb_set_slater_cx": (c_int, [c_void_p, c_int, c_int, c_int, c_double_p, c_double_p, c_int, c_double_p, c_double_p,
+                                   c_int, c_int_p, c_int, c_int_p, c_int, c_int_p, c_int_p, c_double_p, c_double_p]),
+    "qmcb_is_complex": (c_int, [c_void_p]),
+    "qmcb_set_pbc_phases_imag": (c_int, [c_void_p, c_int, c_int, c_double_p]),
     "qmcb_set_jastrow": (c_int, [c_void_p, c_int, c_int, c_int, c_int_p, c_double_p, c_double, c_int,
                                  c_int_p, c_double_p, c_double, c_double_p, c_double_p]),
     "qmcb_set_jastrow3": (c_int, [c_void_p, c_int, c_int, c_int, c_int_p, c_double_p, c_double, c_int,

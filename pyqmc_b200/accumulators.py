@@ -116,9 +116,13 @@ class EnergyAccumulator:
         if nconf != ctx.nconf:
             raise ValueError("configs and the wave function's internal state disagree on the walker count")
         u, rot = self.draw_ecp_variates(nconf, nelec)
-        out = np.empty((6, nconf))
+        out = np.empty((8 if ctx.cplx else 6, nconf))
         _lib.check(ctx.lib.qmcb_energy(ctx.h, _lib.dptr(u), _lib.dptr(rot), _lib.dptr(out)))
-        return {k: out[i] for i, k in enumerate(KEYS)}
+        res = {k: out[i] for i, k in enumerate(KEYS)}
+        if ctx.cplx:  # the ECP values (and with them the total) carry wf.dtype (eval_ecp.py:26)
+            res["ecp"] = out[3] + 1j * out[6]
+            res["total"] = out[5] + 1j * out[7]
+        return res
 
     def avg(self, configs, wf):
         per_walker = self(configs, wf)
@@ -138,7 +142,8 @@ class EnergyAccumulator:
             u[a] = np.random.random(size=nconf)
             rot[a] = scipy.spatial.transform.Rotation.random().as_matrix()
         M = int(np.sum(self._ecp["naip"]))
-        ratio, weight, epos = np.empty((nconf, M)), np.empty((nconf, M)), np.empty((nconf, M, 3))
+        ratio = np.empty((nconf, M), dtype=complex if ctx.cplx else float)
+        weight, epos = np.empty((nconf, M)), np.empty((nconf, M, 3))
         _lib.check(ctx.lib.qmcb_tmoves(ctx.h, int(e), float(tau), _lib.dptr(u), _lib.dptr(rot), _lib.dptr(ratio),
                                        _lib.dptr(weight), _lib.dptr(epos)))
         return {"ratio": ratio, "weight": weight, "configs": configs.make_irreducible(e, epos)}

@@ -64,6 +64,16 @@ struct Sys {
   const double* ew_disp;  // [ndisp][3]
   const double* ew_g;     // [nG][4]  G vector, weight
   const double* ew_ion;   // [nG][2]  Re, Im of sum_I Z_I exp(i G.R_I)
+  // ---- complex wave functions (slater.py:212-216, orbitals.py:34-39,61-65,160-165): complex MO coefficients and /
+  // or complex Bloch phases.  An MO row then holds nmo_t real parts followed (at column cxoff) by nmo_t imaginary
+  // parts, so nmo[s] = 2 nmo_t[s] and every row buffer keeps its real layout; for open boundaries the coefficient
+  // table is [Re C | Im C] and the orbital evaluation itself is unchanged.  Inverses, determinant phases and the
+  // multi-determinant caches carry a separate imaginary array (State::*_im).
+  int cplx;
+  int nkp;                 // phase-table columns / AO accumulator planes: nk (real), 2 nk (cos | sin) when complex
+  int nmo_t[2], cxoff[2];  // true orbital count per spin; column offset of the imaginary parts in an MO row
+  const double* detc_im;       // [ndet]
+  const double* grp_coef_im[2];  // [ndet] Im c_D in group order
 };
 
 // Walker state (device pointers).  All arrays are walker-major; Slater arrays keep the
@@ -98,6 +108,11 @@ struct State {
   double* monew;     // [N][5][ldmax]  periodic VMC: MO rows at the proposed position
   double* gold;      // [N][3]      periodic VMC: limited drift at the old position
   double* jold;      // [N][ne-1][nb] periodic block driver: b_l(r_ej) at the old position of the proposed electron (or null)
+  // complex wave functions: imaginary parts (dsign / dphs_im = Re / Im of the unit phase of each determinant)
+  double* inv_im[2];
+  double* dphs_im[2];
+  double* dv_im[2];
+  double* W_im[2];
 };
 
 // walker-major accessors: everything one walker owns is contiguous, so a warp that works on one

@@ -2564,3 +2564,5 @@ __global__ void __launch_bounds__(256) k_gemm_tn(const double* __restrict__ A, c
       if (j < P && k < P) C[(size_t)j * P + k] = acc[u][v];
     }
 }
+
+#include "cplx.cuh"

@@ -45,7 +45,34 @@ struct PbcMoArgs {
 };
 
 __host__ __device__ inline int pbc_mo_scratch_doubles(const Sys& S, int nc, int G) {
-  return S.nk * S.nao * nc + G * S.maxao_atom * nc + G + 2;  // accumulators, staging, candidate list (2G ints)
+  return S.nkp * S.nao * nc + G * S.maxao_atom * nc + G + 2;  // accumulators, staging, candidate list (2G ints)
+}
+
+// Complex Bloch orbital j (component c) from the cos / sin accumulator planes of its k-point, complex MO
+// coefficients [Re C | Im C] and the wrap phase exp(i k.R) (orbitals.py:38-39, 204-229).
+__device__ __forceinline__ void pbc_mo_cx(const Sys& S, const double* __restrict__ sd, const double* __restrict__ ak_re,
+                                          const double* __restrict__ ak_im, int nc, const double* __restrict__ C, int ldc,
+                                          int j, int off, int k, const double (&wt)[3], double& re, double& im) {
+  double rr = 0.0, ii = 0.0, ri = 0.0, ir = 0.0;
+  for (int mu = 0; mu < S.nao; ++mu) {
+    const double a = ak_re[mu * nc], b = ak_im[mu * nc];
+    const double cr = C[mu * ldc + j], ci = C[mu * ldc + off + j];
+    rr = fma(a, cr, rr);
+    ii = fma(b, ci, ii);
+    ri = fma(a, ci, ri);
+    ir = fma(b, cr, ir);
+  }
+  re = rr - ii;
+  im = ri + ir;
+  if (!S.isgamma) {
+    const double* __restrict__ kl = sd + S.o_kl + 3 * k;
+    const double kd = kl[0] * wt[0] + kl[1] * wt[1] + kl[2] * wt[2];
+    double sn, cs;
+    sincos(kd, &sn, &cs);
+    const double t = re * cs - im * sn;
+    im = re * sn + im * cs;
+    re = t;
+  }
 }
 
 template <int DERIV, int G>
@@ -64,7 +91,7 @@ __global__ void __launch_bounds__(128) k_pbc_mo(const Sys S, const State st, con
   const int per = pbc_mo_scratch_doubles(S, NC, G);
   double* ws = reinterpret_cast<double*>(qmcb_smem + tab) + (size_t)gslot * per;
   double* __restrict__ ao = ws;
-  double* __restrict__ stg = ws + S.nk * S.nao * NC;
+  double* __restrict__ stg = ws + S.nkp * S.nao * NC;
   int* __restrict__ lst = reinterpret_cast<int*>(stg + G * S.maxao_atom * NC);
   const int stg_stride = S.maxao_atom * NC;
   const long long np = a.count ? (long long)(*a.count) * a.per_item : a.npoints;
@@ -86,7 +113,7 @@ __global__ void __launch_bounds__(128) k_pbc_mo(const Sys S, const State st, con
     }
     double q[3], pw[3];
     wrap_cell(sd + S.o_lprim, sd + S.o_lpriminv, px, py, pz, q, pw);
-    for (int i = lane; i < S.nk * S.nao * NC; i += G) ao[i] = 0.0;
+    for (int i = lane; i < S.nkp * S.nao * NC; i += G) ao[i] = 0.0;
     __syncwarp(gm);
 
     // ---- phases A and B on `cnt` compacted (atom, image) pairs lst[0..cnt)
@@ -159,9 +186,9 @@ __global__ void __launch_bounds__(128) k_pbc_mo(const Sys S, const State st, con
         const int ao0 = si[S.o_shao + si[S.o_atsh + at]];
         const int nloc = (si[S.o_shao + si[S.o_atsh + at + 1]] - ao0) * NC;
         const double* __restrict__ src = stg + s * stg_stride;
-        for (int i = lane; i < S.nk * nloc; i += G) {
+        for (int i = lane; i < S.nkp * nloc; i += G) {
           const int k = i / nloc, rem = i - k * nloc;
-          ao[(k * S.nao + ao0) * NC + rem] = fma(phase[j * S.nk + k], src[rem], ao[(k * S.nao + ao0) * NC + rem]);
+          ao[(k * S.nao + ao0) * NC + rem] = fma(phase[j * S.nkp + k], src[rem], ao[(k * S.nao + ao0) * NC + rem]);
         }
       }
       __syncwarp(gm);
@@ -207,6 +234,25 @@ __global__ void __launch_bounds__(128) k_pbc_mo(const Sys S, const State st, con
       const double w0 = a.wrap[3 * posidx], w1 = a.wrap[3 * posidx + 1], w2 = a.wrap[3 * posidx + 2];
 #pragma unroll
       for (int k = 0; k < 3; ++k) wt[k] = (w0 * Sm[k] + w1 * Sm[3 + k] + w2 * Sm[6 + k]) + pw[k];
+    }
+    if (S.cplx) {
+      const int nmt = S.nmo_t[spin], off = S.cxoff[spin];
+      for (int t = lane; t < NC * ldc; t += G) {
+        const int c = t / ldc, j = t - c * ldc;
+        if (j >= nmt && j < off + nmt) continue;  // imaginary columns: written with their real partner
+        double re = 0.0, im = 0.0;
+        if (j < nmt) {
+          const int k = mok[j];
+          pbc_mo_cx(S, sd, ao + (size_t)k * S.nao * NC + c, ao + (size_t)(S.nk + k) * S.nao * NC + c, NC, C, ldc, j, off, k,
+                    wt, re, im);
+          a.out[p * a.stride_p + c * a.stride_c + (off + j) * a.stride_j] = im;
+          if (c == 0 && a.out_val) a.out_val[p * a.stride_vp + off + j] = im;
+        }
+        a.out[p * a.stride_p + c * a.stride_c + j * a.stride_j] = re;
+        if (c == 0 && a.out_val) a.out_val[p * a.stride_vp + j] = re;
+      }
+      __syncwarp(gm);
+      continue;
     }
     for (int t = lane; t < NC * ldc; t += G) {
       const int c = t / ldc, j = t - c * ldc;
@@ -272,7 +318,7 @@ __device__ __forceinline__ void pbc_stage_shell(double x, double y, double z, do
 __host__ __device__ inline int pbc_mo_cta_chunk(const Sys& S) { return S.ncand < 64 ? S.ncand : 64; }
 __host__ __device__ inline size_t pbc_mo_cta_scratch_bytes(const Sys& S, int nc) {
   const int chunk = pbc_mo_cta_chunk(S);
-  return ((size_t)S.nk * S.nao * nc + (size_t)chunk * S.maxao_atom * nc) * 8 + (size_t)chunk * 2 * 4 + 16;
+  return ((size_t)S.nkp * S.nao * nc + (size_t)chunk * S.maxao_atom * nc) * 8 + (size_t)chunk * 2 * 4 + 16;
 }
 
 // LMAX: highest angular momentum the instantiation dispatches.  The l <= 4 form is the tuned one (register budget
@@ -290,7 +336,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_pbc_mo_cta(const Sys S, const St
   const int ncol = S.nao * NC;
   const int stg_stride = S.maxao_atom * NC;
   double* __restrict__ ao = reinterpret_cast<double*>(qmcb_smem + tab);  // [nk][nao][NC]
-  double* __restrict__ stg = ao + (size_t)S.nk * ncol;
+  double* __restrict__ stg = ao + (size_t)S.nkp * ncol;
   int* __restrict__ meta = reinterpret_cast<int*>(stg + (size_t)chunk * stg_stride);  // [chunk][2]: atom (-1 invalid), image
   const int tid = threadIdx.x;
   const double* __restrict__ Ls = sd + S.o_Ls;
@@ -390,7 +436,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_pbc_mo_cta(const Sys S, const St
       for (int s2 = 0; s2 < cnt; ++s2) {
         const int at = meta[2 * s2];
         if (at < 0) continue;
-        const double* __restrict__ ph = phase + meta[2 * s2 + 1] * S.nk;
+        const double* __restrict__ ph = phase + meta[2 * s2 + 1] * S.nkp;
         const double* __restrict__ src = stg + (size_t)s2 * stg_stride;
 #pragma unroll
         for (int u = 0; u < QMCB_PBC_RU; ++u) {
@@ -398,7 +444,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_pbc_mo_cta(const Sys S, const St
             const double f = src[coff[u]];
 #pragma unroll
             for (int k = 0; k < QMCB_PBC_NKMAX; ++k)
-              if (k < S.nk) acc[u][k] = fma(ph[k], f, acc[u][k]);
+              if (k < S.nkp) acc[u][k] = fma(ph[k], f, acc[u][k]);
           }
         }
       }
@@ -410,7 +456,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_pbc_mo_cta(const Sys S, const St
       if (r < ncol) {
 #pragma unroll
         for (int k = 0; k < QMCB_PBC_NKMAX; ++k)
-          if (k < S.nk) ao[k * ncol + r] = acc[u][k];
+          if (k < S.nkp) ao[k * ncol + r] = acc[u][k];
       }
     }
     __syncthreads();
@@ -424,6 +470,44 @@ __global__ void __launch_bounds__(MAXT, MINB) k_pbc_mo_cta(const Sys S, const St
       const double w0 = a.wrap[3 * posidx], w1 = a.wrap[3 * posidx + 1], w2 = a.wrap[3 * posidx + 2];
 #pragma unroll
       for (int k = 0; k < 3; ++k) wt[k] = (w0 * Sm[k] + w1 * Sm[3 + k] + w2 * Sm[6 + k]) + pw[k];
+    }
+    if (DERIV == 0 && a.ao_out && S.cplx) {
+      // complex AO values with the wrap phase: ao_out[((p * 2 + re/im) * nk + k) * nao + mu]
+      for (int t = tid; t < S.nk * S.nao; t += T) {
+        const int k = t / S.nao;
+        double re = ao[t], im = ao[(size_t)S.nk * S.nao + t];
+        if (!S.isgamma) {
+          const double* __restrict__ kl = sd + S.o_kl + 3 * k;
+          const double kd = kl[0] * wt[0] + kl[1] * wt[1] + kl[2] * wt[2];
+          double sn, cs;
+          sincos(kd, &sn, &cs);
+          const double tr = re * cs - im * sn;
+          im = re * sn + im * cs;
+          re = tr;
+        }
+        a.ao_out[(size_t)p * 2 * S.nk * S.nao + t] = re;
+        a.ao_out[((size_t)p * 2 + 1) * S.nk * S.nao + t] = im;
+      }
+      __syncthreads();
+      continue;
+    }
+    if (S.cplx) {
+      const int nmt = S.nmo_t[spin], off = S.cxoff[spin];
+      for (int t = tid; t < NC * ldc; t += T) {
+        const int c = t / ldc, j = t - c * ldc;
+        if (j >= nmt && j < off + nmt) continue;  // imaginary columns: written with their real partner
+        double re = 0.0, im = 0.0;
+        if (j < nmt) {
+          const int k = mok[j];
+          pbc_mo_cx(S, sd, ao + (size_t)k * ncol + c, ao + (size_t)(S.nk + k) * ncol + c, NC, C, ldc, j, off, k, wt, re, im);
+          a.out[p * a.stride_p + c * a.stride_c + (off + j) * a.stride_j] = im;
+          if (c == 0 && a.out_val) a.out_val[p * a.stride_vp + off + j] = im;
+        }
+        a.out[p * a.stride_p + c * a.stride_c + j * a.stride_j] = re;
+        if (c == 0 && a.out_val) a.out_val[p * a.stride_vp + j] = re;
+      }
+      __syncthreads();
+      continue;
     }
     if (DERIV == 0 && a.ao_out) {
       for (int t = tid; t < S.nk * S.nao; t += T) {

@@ -88,6 +88,11 @@ struct qmcb_ctx {
   int nmo[2] = {0, 0}, nds[2] = {0, 0}, ndet = 0;
   std::vector<double> mo[2], detc;
   std::vector<int> occ[2], dmap[2];
+  // complex wave functions (qmcb_set_slater_cx / qmcb_set_pbc_phases_imag): imaginary parts of the MO and determinant
+  // coefficients and of the Bloch phase table; nmo[] stays the true orbital count
+  bool cplx = false;
+  std::vector<double> mo_im[2], detc_im, phases_im;
+  DBuf<double> b_inv_im[2], b_dphs_im[2], b_dv_im[2], b_W_im[2], d_detc_im, d_grp_coef_im[2], b_cxwork, e_contrib_im;
   int na = 0, nb = 0;
   std::vector<int> akind, bkind;
   std::vector<double> apar, bpar, acoef, bcoef;
@@ -229,8 +234,12 @@ int build_tables(qmcb_ctx* c) {
   S.npair = S.ne * (S.ne - 1) / 2;
   S.ndet = c->have_slater ? c->ndet : 0;
   bool ident = c->have_slater && c->ndet == 1;
+  const bool cx = c->have_slater && c->cplx;
+  S.cplx = cx ? 1 : 0;
   for (int s = 0; s < 2; ++s) {
-    S.nmo[s] = c->have_slater ? c->nmo[s] : 0;
+    S.nmo_t[s] = c->have_slater ? c->nmo[s] : 0;
+    S.cxoff[s] = cx ? S.nmo_t[s] : 0;
+    S.nmo[s] = (cx ? 2 : 1) * S.nmo_t[s];
     S.nds[s] = c->have_slater ? c->nds[s] : 0;
     const int n = s ? c->ndn : c->nup;
     if (c->have_slater) {
@@ -241,6 +250,7 @@ int build_tables(qmcb_ctx* c) {
   }
   const int nmax = std::max(S.nmo[0], S.nmo[1]);
   if (c->pbc_mode) ident = false;  // periodic orbitals always go through k_pbc_mo + the general path
+  if (cx) ident = false;           // complex wave functions: general path + the kernels of cplx.cuh
   if (ident && nmax <= 4)
     c->nmot = 4;
   else if (ident && nmax <= 8)
@@ -314,6 +324,7 @@ int build_tables(qmcb_ctx* c) {
       S.nbatom = (int)c->bxyz.size() / 3;
       S.o_bxyz = dpush(c->bxyz.data(), c->bxyz.size());
       S.nk = c->nk;
+      S.nkp = cx ? 2 * c->nk : c->nk;
       S.nL = c->nL;
       S.isgamma = c->isgamma;
       S.o_lprim = dpush(c->lprim.data(), 9);
@@ -329,7 +340,17 @@ int build_tables(qmcb_ctx* c) {
       S.o_atomcut = dpush(c->atomcut.data(), c->atomcut.size());
       if ((int)c->lcut.size() != nshell) return fail("qmcb_set_pbc_orbitals: l_cutoff must have one entry per shell");
       S.o_lcut = dpush(c->lcut.data(), c->lcut.size());
-      S.o_phase = dpush(c->phases.data(), c->phases.size());
+      if (cx) {  // [nL][2 nk]: cos | sin planes of exp(i L.k)  (pbcgto.py:620)
+        std::vector<double> ph((size_t)c->nL * 2 * c->nk, 0.0);
+        const bool have_im = c->phases_im.size() == c->phases.size();
+        for (int L = 0; L < c->nL; ++L)
+          for (int k = 0; k < c->nk; ++k) {
+            ph[((size_t)L * 2) * c->nk + k] = c->phases[(size_t)L * c->nk + k];
+            ph[((size_t)L * 2 + 1) * c->nk + k] = have_im ? c->phases_im[(size_t)L * c->nk + k] : 0.0;
+          }
+        S.o_phase = dpush(ph.data(), ph.size());
+      } else
+        S.o_phase = dpush(c->phases.data(), c->phases.size());
     }
   }
   if (db.size() % 2) db.push_back(0.0);
@@ -345,7 +366,10 @@ int build_tables(qmcb_ctx* c) {
     std::vector<double> cm((size_t)std::max(S.nao, 1) * S.ldc[s], 0.0);
     if (c->have_slater)
       for (int a = 0; a < S.nao; ++a)
-        for (int j = 0; j < S.nmo[s]; ++j) cm[(size_t)a * S.ldc[s] + j] = c->mo[s][(size_t)a * S.nmo[s] + j];
+        for (int j = 0; j < S.nmo_t[s]; ++j) {
+          cm[(size_t)a * S.ldc[s] + j] = c->mo[s][(size_t)a * S.nmo_t[s] + j];
+          if (cx) cm[(size_t)a * S.ldc[s] + S.cxoff[s] + j] = c->mo_im[s][(size_t)a * S.nmo_t[s] + j];
+        }
     S.o_mo[s] = dpush(cm.data(), cm.size());
   }
   S.o_apar = dpush(c->apar.data(), S.na);
@@ -402,8 +426,8 @@ int build_tables(qmcb_ctx* c) {
     for (int s = 0; s < 2; ++s) {
       std::vector<int> mk(S.ldc[s], 0);
       if (c->have_slater) {
-        if ((int)c->mok[s].size() != S.nmo[s]) return fail("qmcb_set_pbc_orbitals: MO -> k-point map does not match the MO count");
-        for (int j = 0; j < S.nmo[s]; ++j) mk[j] = c->mok[s][j];
+        if ((int)c->mok[s].size() != S.nmo_t[s]) return fail("qmcb_set_pbc_orbitals: MO -> k-point map does not match the MO count");
+        for (int j = 0; j < S.nmo_t[s]; ++j) mk[j] = c->mok[s][j];
       }
       S.o_mok[s] = ipush(mk.data(), mk.size());
     }
@@ -473,6 +497,18 @@ int build_tables(qmcb_ctx* c) {
       CK(cudaMemcpy(c->d_grp_other[s].p, gother.data(), gother.size() * 4, cudaMemcpyHostToDevice));
       S.grp_coef[s] = c->d_grp_coef[s].p;
       S.grp_other[s] = c->d_grp_other[s].p;
+      if (cx) {
+        std::vector<double> gim(lst.size());
+        for (size_t k = 0; k < lst.size(); ++k) gim[k] = c->detc_im[lst[k]];
+        if (c->d_grp_coef_im[s].ensure(lst.size())) return -1;
+        CK(cudaMemcpy(c->d_grp_coef_im[s].p, gim.data(), gim.size() * 8, cudaMemcpyHostToDevice));
+        S.grp_coef_im[s] = c->d_grp_coef_im[s].p;
+      }
+    }
+    if (cx) {
+      if (c->d_detc_im.ensure(c->ndet)) return -1;
+      CK(cudaMemcpy(c->d_detc_im.p, c->detc_im.data(), (size_t)c->ndet * 8, cudaMemcpyHostToDevice));
+      S.detc_im = c->d_detc_im.p;
     }
   }
   if (c->necp > 0) {
@@ -493,7 +529,7 @@ int build_tables(qmcb_ctx* c) {
   }
   c->dirty = false;
   // walker state survives a table rebuild unless a shape it depends on changed
-  std::vector<int> sig = {S.natom, S.nup, S.ndn, S.nds[0], S.nds[1], S.ldc[0], S.ldc[1], S.na, S.nb, S.ndet, S.na3, S.nb3, S.pbc};
+  std::vector<int> sig = {S.natom, S.nup, S.ndn, S.nds[0], S.nds[1], S.ldc[0], S.ldc[1], S.na, S.nb, S.ndet, S.na3, S.nb3, S.pbc, S.cplx};
   if (sig != c->shape_sig) {
     c->shape_sig = sig;
     c->N = 0;
@@ -520,6 +556,15 @@ int ensure_state(qmcb_ctx* c, int N) {
     st.dv[s] = c->b_dv[s].p;
     st.W[s] = c->b_W[s].p;
     st.ref[s] = c->b_ref[s].p;
+    if (S.cplx) {
+      if (c->b_inv_im[s].ensure(nd * std::max(n * n, 1)) || c->b_dphs_im[s].ensure(nd) || c->b_dv_im[s].ensure(nd) ||
+          c->b_W_im[s].ensure(nd))
+        return -1;
+    }
+    st.inv_im[s] = c->b_inv_im[s].p;
+    st.dphs_im[s] = c->b_dphs_im[s].p;
+    st.dv_im[s] = c->b_dv_im[s].p;
+    st.W_im[s] = c->b_W_im[s].p;
   }
   const int ldmax = std::max(S.ldc[0], S.ldc[1]);
   if (c->b_conf.ensure((size_t)N * S.ne * 3) || c->b_ap.ensure((size_t)N * S.ne * S.natom * std::max(S.na, 1)) ||
@@ -578,7 +623,10 @@ int launch_point(qmcb_ctx* c, const PointArgs& pa, cudaStream_t stream) {
   const int grid = (pa.npoints + block - 1) / block;
   if (grid == 0) return 0;
   const size_t sm = c->smem_bytes;
-  if (c->nmot == 4) {
+  if (c->S.cplx && ((pa.which & 1) || MODE == PV_MOSAVE)) {
+    if (prep_kernel(k_cx_point<MODE>, sm)) return -1;
+    k_cx_point<MODE><<<grid, block, sm, stream>>>(c->S, c->st, pa);
+  } else if (c->nmot == 4) {
     if (prep_kernel(k_point<MODE, 4>, sm)) return -1;
     k_point<MODE, 4><<<grid, block, sm, stream>>>(c->S, c->st, pa);
   } else if (c->nmot == 8) {
@@ -659,7 +707,7 @@ int launch_pbc_mo(qmcb_ctx* c, int deriv, const PbcMoArgs& a, long long max_poin
   // one CTA per point (k_pbc_mo_cta) whenever the accumulator columns fit its registers
   const size_t csm = tab + pbc_mo_cta_scratch_bytes(c->S, nc);
   const int ncol = c->S.nao * nc;
-  if (c->S.nk <= QMCB_PBC_NKMAX && ncol <= QMCB_PBC_RU * 256 && csm <= 100 * 1024 &&
+  if (c->S.nkp <= QMCB_PBC_NKMAX && ncol <= QMCB_PBC_RU * 256 && csm <= 100 * 1024 &&
       std::getenv("QMCB_PBC_NO_CTA") == nullptr) {
     int T = std::max(std::max(ncol, nc * std::max(c->S.ldc[0], c->S.ldc[1])), 64);
     T = std::min((T + 31) / 32 * 32, 256);
@@ -755,7 +803,7 @@ int launch_ao_all(qmcb_ctx* c, double* d_ao, cudaStream_t stream) {
   if (S.pbc) {
     const size_t tab = (c->smem_bytes + 15) & ~(size_t)15;
     const size_t csm = tab + pbc_mo_cta_scratch_bytes(S, 1);
-    if (S.nk > QMCB_PBC_NKMAX || S.nao > QMCB_PBC_RU * 256 || csm > 100 * 1024)
+    if (S.nkp > QMCB_PBC_NKMAX || S.nao > QMCB_PBC_RU * 256 || csm > 100 * 1024)
       return fail("periodic parameter gradients: k-point / AO count beyond the CTA orbital kernel's limits");
     PbcMoArgs a{};
     a.npoints = np;
@@ -789,6 +837,23 @@ int slater_rebuild(qmcb_ctx* c, cudaStream_t stream) {
   const Sys& S = c->S;
   const int N = c->N;
   if (launch_mo_all(c, 1, stream)) return -1;
+  if (S.cplx) {
+    for (int s = 0; s < 2; ++s) {
+      const int n = s ? S.ndn : S.nup;
+      const long long nt = (long long)N * S.nds[s];
+      if (n > QMCB_CX_NMAX) return fail("complex wave functions: more than 64 electrons per spin is not supported");
+      if (c->b_cxwork.ensure((size_t)nt * std::max(n * n, 1) * 2)) return -1;
+      k_cx_invert<<<(unsigned)((nt * 32 + 127) / 128), 128, 0, stream>>>(S, c->st, s, reinterpret_cast<cd*>(c->b_cxwork.p));
+      c->nlaunch++;
+      CK(cudaGetLastError());
+    }
+    if (S.ndet > 1) {
+      k_cx_det_cache<<<(unsigned)(((long long)N * 32 + 127) / 128), 128, 0, stream>>>(S, c->st, nullptr, -1);
+      c->nlaunch++;
+      CK(cudaGetLastError());
+    }
+    return 0;
+  }
   for (int s = 0; s < 2; ++s) {
     const int n = s ? S.ndn : S.nup;
     const long long nt = (long long)N * S.nds[s];
@@ -819,6 +884,13 @@ int slater_rebuild(qmcb_ctx* c, cudaStream_t stream) {
 
 int launch_value(qmcb_ctx* c, int which, double* d_sign, double* d_log, cudaStream_t stream) {
   const int block = pick_block(c->N);
+  if (c->S.cplx && (which & 1)) {  // d_sign: [N] complex phases (interleaved), d_log: [N]
+    if (prep_kernel(k_cx_value, c->smem_bytes)) return -1;
+    k_cx_value<<<(c->N + block - 1) / block, block, c->smem_bytes, stream>>>(c->S, c->st, which, d_sign, d_log);
+    c->nlaunch++;
+    CK(cudaGetLastError());
+    return 0;
+  }
   if (prep_kernel(k_value, c->smem_bytes)) return -1;
   k_value<<<(c->N + block - 1) / block, block, c->smem_bytes, stream>>>(c->S, c->st, which, d_sign, d_log);
   c->nlaunch++;
@@ -830,7 +902,20 @@ int launch_value(qmcb_ctx* c, int which, double* d_sign, double* d_log, cudaStre
 // and the new position are in st.saved_mo / st.saved_pos.
 int launch_update(qmcb_ctx* c, int which, int e, const uint8_t* d_mask, cudaStream_t stream) {
   const Sys& S = c->S;
-  if ((which & 1) && c->have_slater) {
+  if ((which & 1) && c->have_slater && S.cplx) {
+    const int s = e >= S.nup ? 1 : 0;
+    const long long nt = (long long)c->N * S.nds[s];
+    if ((s ? S.ndn : S.nup) > 0) {
+      k_cx_sm<<<(unsigned)((nt * 32 + 127) / 128), 128, 0, stream>>>(S, c->st, s, e - s * S.nup, d_mask);
+      c->nlaunch++;
+      CK(cudaGetLastError());
+    }
+    if (S.ndet > 1) {
+      k_cx_det_cache<<<(unsigned)(((long long)c->N * 32 + 127) / 128), 128, 0, stream>>>(S, c->st, d_mask, s);
+      c->nlaunch++;
+      CK(cudaGetLastError());
+    }
+  } else if ((which & 1) && c->have_slater) {
     const int s = e >= S.nup ? 1 : 0;
     SmArgs a{};
     a.n = s ? S.ndn : S.nup;
@@ -969,8 +1054,13 @@ int launch_energy_t(qmcb_ctx* c, const State& st, const EnergyScratch& es, const
     }
     // three-body factor: per-group a-value scratch behind the tables
     const size_t ksm = c->have_j3 ? ((sm + 15) & ~(size_t)15) + (size_t)(128 / 8) * 3 * S.natom * S.na3 * 8 : sm;
+    if (S.cplx) {
+      if (prep_kernel(k_cx_kinetic, sm)) return -1;
+      k_cx_kinetic<<<(unsigned)((np + 63) / 64), 64, sm, stream>>>(S, st, es);
+    } else {
     if (prep_kernel(k_kinetic<8>, ksm)) return -1;
     k_kinetic<8><<<(unsigned)((np * 8 + 127) / 128), 128, ksm, stream>>>(S, st, es);
+    }
     c->nlaunch++;
     CK(cudaGetLastError());
     }
@@ -997,6 +1087,12 @@ int launch_energy_t(qmcb_ctx* c, const State& st, const EnergyScratch& es, const
     if (S.pbc) {
       if (ecp_points_pbc_prepass<NMOT>(c, ea, maxpts, grid, stream)) return -1;
     }
+    if (S.cplx) {
+      if (c->e_contrib_im.ensure((size_t)nt * std::max(S.max_naip, 1))) return -1;
+      EcpCxArgs cxa{c->e_contrib_im.p, nullptr};
+      if (prep_kernel(k_cx_ecp_points, sm)) return -1;
+      k_cx_ecp_points<<<(unsigned)grid, 128, sm, stream>>>(S, st, es, ea, cxa);
+    } else
     k_ecp_points<NMOT><<<(unsigned)grid, 128, sm, stream>>>(S, st, es, ea);
     c->nlaunch++;
     CK(cudaGetLastError());
@@ -1021,6 +1117,14 @@ int launch_energy_t(qmcb_ctx* c, const State& st, const EnergyScratch& es, const
     k_energy_finalize<8><<<(unsigned)(((long long)N * 8 + 127) / 128), 128, fsm, stream>>>(S, st, es, d_out, scr);
     c->nlaunch++;
     CK(cudaGetLastError());
+  }
+  if (S.cplx) {  // rows 6, 7 of the output: Im ecp, Im total
+    if (S.necp > 0) {
+      k_cx_ecp_imag<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(S, st, es, c->e_contrib_im.p, d_out + (size_t)6 * N);
+      c->nlaunch++;
+      CK(cudaGetLastError());
+    } else
+      CK(cudaMemsetAsync(d_out + (size_t)6 * N, 0, (size_t)2 * N * 8, stream));
   }
   return 0;
 }
@@ -1194,10 +1298,17 @@ struct ParamKey {
 };
 }  // extern "C++"
 
+static thread_local bool g_setting_cx = false;
+
 int qmcb_set_slater(qmcb_ctx* c, int nup, int ndn, int nmo_up, const double* mo_up, int nmo_dn,
                     const double* mo_dn, int ndet_up, const int32_t* occ_up, int ndet_dn,
                     const int32_t* occ_dn, int ndet, const int32_t* map_up, const int32_t* map_dn,
                     const double* det_coeff) {
+  if (!g_setting_cx && c->cplx) {  // a real parameter set replaces a complex one
+    c->cplx = false;
+    c->dirty = true;
+    c->key_slater.clear();
+  }
   int nao = 0;
   for (size_t s = 0; s < c->sh_l.size(); ++s) nao += 2 * c->sh_l[s] + 1;
   if (nao == 0) return fail("qmcb_set_basis must be called before qmcb_set_slater");
@@ -1235,6 +1346,41 @@ int qmcb_set_slater(qmcb_ctx* c, int nup, int ndn, int nmo_up, const double* mo_
   c->key_slater.swap(key.b);
   return 0;
 }
+
+int qmcb_set_slater_cx(qmcb_ctx* c, int nup, int ndn, int nmo_up, const double* mo_up_re, const double* mo_up_im,
+                       int nmo_dn, const double* mo_dn_re, const double* mo_dn_im, int ndet_up, const int32_t* occ_up,
+                       int ndet_dn, const int32_t* occ_dn, int ndet, const int32_t* map_up, const int32_t* map_dn,
+                       const double* det_re, const double* det_im) {
+  int nao = 0;
+  for (size_t s = 0; s < c->sh_l.size(); ++s) nao += 2 * c->sh_l[s] + 1;
+  if (nao == 0) return fail("qmcb_set_basis must be called before qmcb_set_slater_cx");
+  // the imaginary parts are part of the parameter key: keep them before the real setter compares / swaps its key
+  std::vector<double> im_up(mo_up_im, mo_up_im + (size_t)nao * nmo_up), im_dn(mo_dn_im, mo_dn_im + (size_t)nao * nmo_dn),
+      im_det(det_im, det_im + ndet);
+  const bool same_im = c->cplx && im_up == c->mo_im[0] && im_dn == c->mo_im[1] && im_det == c->detc_im;
+  g_setting_cx = true;
+  const int rc = qmcb_set_slater(c, nup, ndn, nmo_up, mo_up_re, nmo_dn, mo_dn_re, ndet_up, occ_up, ndet_dn, occ_dn, ndet,
+                                 map_up, map_dn, det_re);
+  g_setting_cx = false;
+  if (rc) return -1;
+  if (!same_im) {
+    c->mo_im[0].swap(im_up);
+    c->mo_im[1].swap(im_dn);
+    c->detc_im.swap(im_det);
+    c->cplx = true;
+    c->dirty = true;
+  }
+  return 0;
+}
+
+int qmcb_set_pbc_phases_imag(qmcb_ctx* c, int nL, int nk, const double* phases_im) {
+  if (!c->have_pbc_orb || nL != c->nL || nk != c->nk) return fail("qmcb_set_pbc_phases_imag: call qmcb_set_pbc_orbitals first (same nL, nk)");
+  c->phases_im.assign(phases_im, phases_im + (size_t)nL * nk);
+  c->dirty = true;
+  return 0;
+}
+
+int qmcb_is_complex(qmcb_ctx* c) { return c->cplx && c->have_slater ? 1 : 0; }
 
 int qmcb_set_jastrow(qmcb_ctx* c, int nup, int ndn, int na, const int32_t* a_kind, const double* a_par,
                      double rcut_a, int nb, const int32_t* b_kind, const double* b_par, double rcut_b,
@@ -1510,13 +1656,14 @@ int qmcb_value(qmcb_ctx* c, int which, double* sign, double* logval) {
   if (build_tables(c)) return -1;
   if (c->N == 0) return fail("system shapes changed: call recompute again");
   const size_t N = c->N;
+  const size_t cw = (c->S.cplx && (which & 1)) ? 2 : 1;  // complex context: `sign` is the complex unit phase
   if (c->d_out.ensure(N * 8)) return -1;
-  if (launch_value(c, which, c->d_out.p, c->d_out.p + N, c->stream)) return -1;
-  if (c->h_out.ensure(2 * N * 8)) return -1;
-  CK(cudaMemcpyAsync(c->h_out.p, c->d_out.p, 2 * N * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (launch_value(c, which, c->d_out.p, c->d_out.p + cw * N, c->stream)) return -1;
+  if (c->h_out.ensure((cw + 1) * N * 8)) return -1;
+  CK(cudaMemcpyAsync(c->h_out.p, c->d_out.p, (cw + 1) * N * 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  if (sign) std::memcpy(sign, c->h_out.p, N * 8);
-  if (logval) std::memcpy(logval, (double*)c->h_out.p + N, N * 8);
+  if (sign) std::memcpy(sign, c->h_out.p, cw * N * 8);
+  if (logval) std::memcpy(logval, (double*)c->h_out.p + cw * N, N * 8);
   return 0;
 }
 
@@ -1551,7 +1698,8 @@ static int point_call(qmcb_ctx* c, int mode, int which, int e, const double* epo
   const Sys& S = c->S;
   if (e < 0 || e >= S.ne) return fail("electron index out of range");
   const size_t N = c->N;
-  if (c->d_in.ensure(N * naip * 3) || c->d_out.ensure(std::max<size_t>(N * 8, N * naip))) return -1;
+  const size_t cw = (S.cplx && (which & 1)) ? 2 : 1;  // complex context: wave-function-valued outputs are complex128
+  if (c->d_in.ensure(N * naip * 3) || c->d_out.ensure(cw * std::max<size_t>(N * 8, N * naip))) return -1;
   if (h2d(c, c->d_in.p, epos, N * naip * 3 * 8)) return -1;
   PointArgs pa{};
   pa.which = which;
@@ -1571,9 +1719,9 @@ static int point_call(qmcb_ctx* c, int mode, int which, int e, const double* epo
     pa.idx = c->d_idx.p;
   }
   pa.npoints = (int)(nm * naip);
-  pa.o_val = c->d_out.p + 3 * N;
+  pa.o_val = c->d_out.p + cw * 3 * N;
   pa.o_grad = c->d_out.p;
-  pa.o_lap = c->d_out.p + 3 * N;
+  pa.o_lap = c->d_out.p + cw * 3 * N;
   if (mode == PV_VALUE) pa.o_val = c->d_out.p;
   const bool save = (mode == PV_GRADVAL) || (mode == PV_VALUE && naip == 1 && !mask);
   pa.save = save ? 1 : 0;
@@ -1608,14 +1756,14 @@ static int point_call(qmcb_ctx* c, int mode, int which, int e, const double* epo
   } else if (slot)
     *slot = -1;
   if (mode == PV_VALUE) {
-    if (d2h(c, o1, c->d_out.p, nm * naip * 8)) return -1;
+    if (d2h(c, o1, c->d_out.p, cw * nm * naip * 8)) return -1;
   } else {
-    const size_t nout = (mode == PV_GRAD) ? 3 * N : 4 * N;
+    const size_t nout = cw * ((mode == PV_GRAD) ? 3 * N : 4 * N);
     if (c->h_out.ensure(nout * 8)) return -1;
     CK(cudaMemcpyAsync(c->h_out.p, c->d_out.p, nout * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    std::memcpy(o1, c->h_out.p, 3 * N * 8);
-    if (o2) std::memcpy(o2, (double*)c->h_out.p + 3 * N, N * 8);
+    std::memcpy(o1, c->h_out.p, cw * 3 * N * 8);
+    if (o2) std::memcpy(o2, (double*)c->h_out.p + cw * 3 * N, cw * N * 8);
   }
   return 0;
 }
@@ -1643,7 +1791,8 @@ int qmcb_testvalue_many(qmcb_ctx* c, int which, int ne_list, const int32_t* elis
   if (c->N == 0) return fail("system shapes changed: call recompute again");
   const Sys& S = c->S;
   const size_t N = c->N;
-  if (c->d_in.ensure(N * 3) || c->d_out.ensure(std::max<size_t>(N * ne_list, 8 * N))) return -1;
+  const size_t cw = (S.cplx && (which & 1)) ? 2 : 1;
+  if (c->d_in.ensure(N * 3) || c->d_out.ensure(cw * std::max<size_t>(N * ne_list, 8 * N))) return -1;
   if (h2d(c, c->d_in.p, epos, N * 3 * 8)) return -1;
   size_t nm = N;
   PointArgs pa{};
@@ -1670,16 +1819,17 @@ int qmcb_testvalue_many(qmcb_ctx* c, int which, int ne_list, const int32_t* elis
     pa.naip = 1;
     pa.pos = c->d_in.p;
     pa.npoints = (int)nm;
-    pa.o_val = c->d_out.p + (size_t)i * nm;
+    pa.o_val = c->d_out.p + cw * (size_t)i * nm;
     pa.save = 0;
     pa.scr = c->d_scr.p;
     pa.scr_stride = std::max<size_t>(nm, 1);
     if (launch_point<PV_VALUE>(c, pa, c->stream)) return -1;
   }
-  std::vector<double> tmp(nm * ne_list);
+  std::vector<double> tmp(cw * nm * ne_list);
   if (d2h(c, tmp.data(), c->d_out.p, tmp.size() * 8)) return -1;
   for (size_t m = 0; m < nm; ++m)
-    for (int i = 0; i < ne_list; ++i) ratio[m * ne_list + i] = tmp[(size_t)i * nm + m];
+    for (int i = 0; i < ne_list; ++i)
+      for (size_t r = 0; r < cw; ++r) ratio[(m * ne_list + i) * cw + r] = tmp[((size_t)i * nm + m) * cw + r];
   c->saved_slot = -1;
   return 0;
 }
@@ -1757,11 +1907,30 @@ int qmcb_get_state(qmcb_ctx* c, const char* name, double* out) {
     const int s = k == "inverse_dn";
     const int n = s ? S.ndn : S.nup;
     if (fetch(c->st.inv[s], N * S.nds[s] * n * n, h)) return -1;
-    std::memcpy(out, h.data(), h.size() * 8);
+    if (S.cplx) {  // complex128 (interleaved)
+      std::vector<double> hi;
+      if (fetch(c->st.inv_im[s], h.size(), hi)) return -1;
+      for (size_t i = 0; i < h.size(); ++i) {
+        out[2 * i] = h[i];
+        out[2 * i + 1] = hi[i];
+      }
+    } else
+      std::memcpy(out, h.data(), h.size() * 8);
   } else if (k == "dets_up" || k == "dets_dn") {
     const int s = k == "dets_dn";
     const size_t nd = N * S.nds[s];
     if (fetch(c->st.dsign[s], nd, h)) return -1;
+    if (S.cplx) {  // [2][N][D_s] complex128: phase, then log (imaginary part 0), like the reference's _dets
+      std::vector<double> hi, hl;
+      if (fetch(c->st.dphs_im[s], nd, hi) || fetch(c->st.dlog[s], nd, hl)) return -1;
+      for (size_t i = 0; i < nd; ++i) {
+        out[2 * i] = h[i];
+        out[2 * i + 1] = hi[i];
+        out[2 * (nd + i)] = hl[i];
+        out[2 * (nd + i) + 1] = 0.0;
+      }
+      return 0;
+    }
     std::memcpy(out, h.data(), nd * 8);
     if (fetch(c->st.dlog[s], nd, h)) return -1;
     std::memcpy(out + nd, h.data(), nd * 8);
@@ -1826,6 +1995,38 @@ int qmcb_pgradient(qmcb_ctx* c, const char* name, double* out) {
   const int gstride = std::max(std::max(S.nds[0], S.nds[1]), 1);
   DBuf<double> d_det, d_G, d_ao, d_mo;
   int rc = 0;
+  if (S.cplx) {  // complex128 outputs (slater.py:462-542 with complex determinants / orbitals)
+    do {
+      if (d_det.ensure(2 * N * S.ndet) || d_G.ensure(4 * N * gstride)) { rc = -1; break; }
+      k_cx_pgrad_det<<<(unsigned)((N + 127) / 128), 128, 0, c->stream>>>(S, c->st, reinterpret_cast<cd*>(d_det.p),
+                                                                          reinterpret_cast<cd*>(d_G.p), gstride);
+      c->nlaunch++;
+      if (cudaGetLastError() != cudaSuccess) { rc = fail("k_cx_pgrad_det launch failed"); break; }
+      if (k == "det_coeff") {
+        rc = d2h(c, out, d_det.p, 2 * N * S.ndet * 8);
+        break;
+      }
+      int s = -1;
+      if (k == "mo_coeff_alpha") s = 0;
+      if (k == "mo_coeff_beta") s = 1;
+      if (s < 0) { rc = fail("unknown parameter: " + k); break; }
+      const size_t nout = N * S.nao * S.nmo_t[s];
+      if (nout == 0) break;
+      if (d_ao.ensure(N * S.ne * S.nao * (S.pbc ? 2 * S.nk : 1)) || d_mo.ensure(2 * nout)) { rc = -1; break; }
+      if (launch_ao_all(c, d_ao.p, c->stream)) { rc = -1; break; }
+      k_cx_pgrad_mo<<<(unsigned)((nout + 127) / 128), 128, 0, c->stream>>>(S, c->st, s, d_ao.p, reinterpret_cast<cd*>(d_G.p),
+                                                                           gstride, reinterpret_cast<cd*>(d_mo.p));
+      c->nlaunch++;
+      if (cudaGetLastError() != cudaSuccess) { rc = fail("k_cx_pgrad_mo launch failed"); break; }
+      rc = d2h(c, out, d_mo.p, 2 * nout * 8);
+    } while (0);
+    cudaStreamSynchronize(c->stream);
+    d_det.release();
+    d_G.release();
+    d_ao.release();
+    d_mo.release();
+    return rc;
+  }
   do {
     if (d_det.ensure(N * S.ndet) || d_G.ensure(2 * N * gstride)) { rc = -1; break; }
     k_pgrad_det<<<(unsigned)((N + 127) / 128), 128, 0, c->stream>>>(S, c->st, d_det.p, d_G.p, gstride);
@@ -1866,13 +2067,14 @@ int qmcb_energy(qmcb_ctx* c, const double* ecp_u, const double* ecp_rot, double*
   const size_t N = c->N;
   if (ensure_energy_scratch(c) || energy_scratch_points(c)) return -1;
   const size_t nu = (size_t)S.ne * S.necp * N, nr = (size_t)S.ne * S.necp * 9;
-  if (c->d_u.ensure(nu) || c->d_rot.ensure(nr) || c->d_energy.ensure(6 * N)) return -1;
+  const size_t rows = S.cplx ? 8 : 6;  // complex wave functions: + Im ecp, Im total
+  if (c->d_u.ensure(nu) || c->d_rot.ensure(nr) || c->d_energy.ensure(rows * N)) return -1;
   if (S.necp > 0) {
     if (!ecp_u || !ecp_rot) return fail("ECP random variates missing");
     if (h2d(c, c->d_u.p, ecp_u, nu * 8) || h2d(c, c->d_rot.p, ecp_rot, nr * 8)) return -1;
   }
   if (launch_energy(c, c->d_u.p, c->d_rot.p, c->d_energy.p, c->stream)) return -1;
-  return d2h(c, out, c->d_energy.p, 6 * N * 8);
+  return d2h(c, out, c->d_energy.p, rows * N * 8);
 }
 
 int qmcb_tmoves(qmcb_ctx* c, int e, double tau, const double* ecp_u, const double* ecp_rot, double* ratio,
@@ -1890,7 +2092,7 @@ int qmcb_tmoves(qmcb_ctx* c, int e, double tau, const double* ecp_u, const doubl
   const size_t npts = N * S.necp * S.max_naip;
   if (ensure_scratch(c, npts, 1)) return -1;
   const size_t M = (size_t)S.tot_naip;
-  if (c->d_u.ensure((size_t)S.necp * N) || c->d_rot.ensure((size_t)S.necp * 9) || c->d_out.ensure(N * M * 5)) return -1;
+  if (c->d_u.ensure((size_t)S.necp * N) || c->d_rot.ensure((size_t)S.necp * 9) || c->d_out.ensure(N * M * 6)) return -1;
   if (h2d(c, c->d_u.p, ecp_u, (size_t)S.necp * N * 8) || h2d(c, c->d_rot.p, ecp_rot, (size_t)S.necp * 9 * 8)) return -1;
   double* d_ratio = c->d_out.p;
   double* d_weight = d_ratio + N * M;
@@ -1898,6 +2100,8 @@ int qmcb_tmoves(qmcb_ctx* c, int e, double tau, const double* ecp_u, const doubl
   k_tmove_init<<<(unsigned)((N * M + 255) / 256), 256, 0, c->stream>>>(S, c->st, e, d_ratio, d_weight, d_pos);
   c->nlaunch++;
   CK(cudaGetLastError());
+  double* d_ratio_im = d_pos + N * M * 3;  // complex wave functions: Im ratio (0 for the masked-out walkers)
+  if (S.cplx) CK(cudaMemsetAsync(d_ratio_im, 0, N * M * 8, c->stream));
   CK(cudaMemsetAsync(c->es.count, 0, sizeof(int), c->stream));
   const long long nt = (long long)N * S.necp;
   if (prep_kernel(k_ecp_prepare, c->smem_bytes)) return -1;
@@ -1917,7 +2121,12 @@ int qmcb_tmoves(qmcb_ctx* c, int e, double tau, const double* ecp_u, const doubl
   const long long grid = std::min<long long>(((long long)npts + 127) / 128, 148LL * 16);
   int rc = 0;
   const size_t sm = c->smem_bytes;
-  if (c->nmot == 4) {
+  if (S.cplx) {
+    EcpCxArgs cxa{nullptr, d_ratio_im};
+    rc = prep_kernel(k_cx_ecp_points, sm);
+    if (!rc && S.pbc) rc = ecp_points_pbc_prepass<0>(c, ea, (long long)npts, grid, c->stream);
+    if (!rc) k_cx_ecp_points<<<(unsigned)grid, 128, sm, c->stream>>>(S, c->st, c->es, ea, cxa);
+  } else if (c->nmot == 4) {
     rc = prep_kernel(k_ecp_points<4>, sm);
     if (!rc) k_ecp_points<4><<<(unsigned)grid, 128, sm, c->stream>>>(S, c->st, c->es, ea);
   } else if (c->nmot == 8) {
@@ -1931,9 +2140,15 @@ int qmcb_tmoves(qmcb_ctx* c, int e, double tau, const double* ecp_u, const doubl
   if (rc) return rc;
   c->nlaunch++;
   CK(cudaGetLastError());
-  std::vector<double> h(N * M * 5);
+  std::vector<double> h(N * M * 6);
   if (d2h(c, h.data(), c->d_out.p, h.size() * 8)) return -1;
-  std::memcpy(ratio, h.data(), N * M * 8);
+  if (S.cplx) {  // `ratio` is complex128
+    for (size_t i = 0; i < N * M; ++i) {
+      ratio[2 * i] = h[i];
+      ratio[2 * i + 1] = h[N * M * 5 + i];
+    }
+  } else
+    std::memcpy(ratio, h.data(), N * M * 8);
   std::memcpy(weight, h.data() + N * M, N * M * 8);
   std::memcpy(epos, h.data() + 2 * N * M, N * M * 3 * 8);
   return 0;
@@ -1963,6 +2178,7 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
   const Sys& S = c->S;
   const size_t N = c->N;
   cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : c->stream;
+  if (S.cplx) return fail("complex wave functions are served by the protocol calls and the energy accumulator; the device-resident block / SR drivers are real-only");
   const int which = (c->have_slater ? 1 : 0) | (c->have_jastrow ? 2 : 0) | (c->have_j3 ? 4 : 0);
   if (with_energy && (ensure_energy_scratch(c) || energy_scratch_points(c))) return -1;
   if (ensure_scratch(c, N, 5)) return -1;
@@ -2469,6 +2685,7 @@ int qmcb_dmc_block(qmcb_ctx* c, int nsteps, double tstep, double branchcut, doub
   const size_t N = c->N;
   cudaStream_t stream = c->stream;
   const int which = (c->have_slater ? 1 : 0) | (c->have_jastrow ? 2 : 0);
+  if (S.cplx) return fail("complex wave functions are served by the protocol calls and the energy accumulator; the device-resident block / SR drivers are real-only");
   if (S.pbc || c->have_j3 || (c->have_slater && S.ndet != 1))
     return fail("device-resident DMC supports open-boundary single-determinant Slater-Jastrow wave functions; "
                 "other wave functions run through the per-call protocol");
@@ -2648,6 +2865,7 @@ int qmcb_sr_avg(qmcb_ctx* c, int nparam, const int32_t* src, const int64_t* off,
   const Sys& S = c->S;
   const size_t N = c->N, P = (size_t)nparam;
   cudaStream_t stream = c->stream;
+  if (S.cplx) return fail("complex wave functions are served by the protocol calls and the energy accumulator; the device-resident block / SR drivers are real-only");
   bool need[6] = {false, false, false, false, false, false};
   for (size_t j = 0; j < P; ++j) {
     if (src[j] < 0 || src[j] > 5) return fail("qmcb_sr_avg: unknown parameter source");

@@ -33,7 +33,7 @@ def _device_dmc_path(wf, accumulators, ekey):
     if len(accumulators) != 1 or not isinstance(accumulators.get(ekey[0]), EnergyAccumulator) or ekey[1] != "total":
         return False
     which = getattr(wf, "_which", 0)
-    if which & ~(SLATER | JASTROW) or not (which & SLATER):
+    if which & ~(SLATER | JASTROW) or not (which & SLATER) or wf.dtype == complex:
         return False
     factors = getattr(wf, "wf_factors", [wf])
     if len(factors[0].parameters["det_coeff"]) != 1:

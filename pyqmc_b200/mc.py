@@ -53,6 +53,8 @@ def _device_path(wf, accumulators):
     except TypeError:
         return False
     factors = getattr(wf, "wf_factors", [wf])
+    if wf.dtype == complex:  # complex wave functions run through the protocol calls (csrc/cplx.cuh), not the block kernels
+        return False
     if hasattr(factors[0]._mol, "a"):
         # the device-resident periodic block covers single-determinant Slater x JastrowSpin; periodic multi-determinant
         # and three-body wave functions run through the protocol calls (the reference's driver)

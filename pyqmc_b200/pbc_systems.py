@@ -9,7 +9,7 @@ supercell Gamma point (``pyqmc/pbc/supercell.py:18-30``), so all phases are real
 import numpy as np
 
 from . import pbc
-from .systems import _contracted, _ecp_entry, _even_tempered, _random_orthonormal_mos, _single
+from .systems import _contracted, _ecp_entry, _even_tempered, _random_orthonormal_mos, _random_unitary_mos, _single
 
 ANG = 1.0 / 0.52917721092
 A_DIAMOND = 3.5668 * ANG
@@ -37,29 +37,35 @@ def diamond_primitive(seed=17):
     return pbc.Cell(atoms, basis, ecp, (4, 4), [4.0, 4.0], lat)
 
 
-def _kmf(cell, supercell, nocc, seed):
+def _kmf(cell, supercell, nocc, seed, twist=None):
+    """``twist``: fractional shift (supercell reciprocal vectors) of the whole k-mesh -- a general twist, for which
+    the Bloch phases exp(i k.L) and the orbitals are genuinely complex (pyqmc/pbc/twists.py:19-25)."""
     kpts = pbc.get_supercell_kpts(supercell)
+    make_mos = _random_orthonormal_mos
+    if twist is not None:
+        kpts = kpts + np.asarray(twist, dtype=float) @ supercell.reciprocal_vectors()
+        make_mos = _random_unitary_mos
     nao = cell.nao
     mo, occ = [[], []], [[], []]
     for s in (0, 1):
         for k in range(len(kpts)):
-            mo[s].append(_random_orthonormal_mos(nao, nao, seed + 31 * k))  # same orbitals for both spins
+            mo[s].append(make_mos(nao, nao, seed + 31 * k))  # same orbitals for both spins
             o = np.zeros(nao)
             o[:nocc[s]] = 1
             occ[s].append(o)
     return pbc.KMF(kpts, np.array(mo), np.array(occ))
 
 
-def diamond(S=None, seed=17):
+def diamond(S=None, seed=17, twist=None):
     """(supercell, mf): diamond ``S`` supercell (default 2x2x2 = config C4: 16 atoms, 32+32
     electrons, 8 k-points with 4 occupied orbitals each per spin)."""
     S = 2 * np.eye(3, dtype=int) if S is None else np.asarray(S, dtype=int)
     cell = diamond_primitive(seed)
     sc = pbc.get_supercell(cell, S)
-    return sc, _kmf(cell, sc, cell.nelec, seed)
+    return sc, _kmf(cell, sc, cell.nelec, seed, twist)
 
 
-def _probe_cell(lat, seed, nelec=(2, 2)):
+def _probe_cell(lat, seed, nelec=(2, 2), twist=None):
     """Two pseudo-carbon atoms in an arbitrary cell, 2+2 electrons (minimal-image mode probes)."""
     basis, ecp = _carbon_basis_ecp(seed)
     lat = np.asarray(lat, dtype=float)
@@ -67,12 +73,15 @@ def _probe_cell(lat, seed, nelec=(2, 2)):
     atoms = [("C", tuple(f @ lat)) for f in frac]
     cell = pbc.Cell(atoms, basis, ecp, nelec, [2.0, 2.0], lat)
     sc = pbc.get_supercell(cell, np.eye(3, dtype=int))
-    return sc, _kmf(cell, sc, nelec, seed)
+    return sc, _kmf(cell, sc, nelec, seed, twist)
 
 
-def orthorhombic_probe(seed=23):
+TWIST = (0.21, -0.13, 0.37)  # a general (non time-reversal-invariant) twist
+
+
+def orthorhombic_probe(seed=23, twist=None):
     """Diagonal lattice: the per-axis minimal image of distance.py:152-159."""
-    return _probe_cell(np.diag([7.1, 7.9, 8.6]), seed)
+    return _probe_cell(np.diag([7.1, 7.9, 8.6]), seed, twist=twist)
 
 
 def rotated_cubic_probe(seed=29):
@@ -87,5 +96,8 @@ PBC_SYSTEMS = {
     "diamond211": lambda: diamond(np.diag([2, 1, 1])),
     "diamond222": diamond,
     "ortho": orthorhombic_probe,
+    # complex wave functions: the same cells at a general twist (complex Bloch phases, wrap phase exp(i k.R))
+    "ortho_twist": lambda: orthorhombic_probe(twist=TWIST),
+    "diamond211_twist": lambda: diamond(np.diag([2, 1, 1]), twist=TWIST),
     "rotcubic": rotated_cubic_probe,
 }

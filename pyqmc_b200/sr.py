@@ -38,29 +38,42 @@ class ParameterMap:
             if not flags.any():
                 continue
             value = np.asarray(parameters[name])
-            if np.iscomplexobj(value):
-                raise NotImplementedError("complex parameters are not supported by the B200 backend")
             self.to_opt[name] = flags
             self.shapes[name], self.dtypes[name] = value.shape, value.dtype
             self.slices[name] = value.size
             self._picked[name] = np.flatnonzero(flags)
         self.nparams = sum(len(i) for i in self._picked.values())
+        # complex parameters contribute their imaginary parts as extra real variables appended after all the real
+        # parts (the reference's layout, accumulators.py:121-133, 142, 155)
+        self.complex = {k: np.issubdtype(d, np.complexfloating) for k, d in self.dtypes.items()}
+        flags = [np.full(len(i), self.complex[k]) for k, i in self._picked.items()]
+        self._imag = np.concatenate(flags) if any(self.complex.values()) else np.zeros(0, dtype=bool)
 
     def serialize_parameters(self, parameters):
         parts = [np.ravel(np.asarray(parameters[k]))[i] for k, i in self._picked.items()]
-        return np.real(np.concatenate(parts)) if parts else np.zeros(0)
+        if not parts:
+            return np.zeros(0)
+        flat = np.concatenate(parts)
+        return np.concatenate((flat.real, flat[self._imag].imag)) if len(self._imag) else np.real(flat)
 
     def serialize_gradients(self, pgrad):
-        """(N, P) matrix of d ln Psi / d p from a ``pgradient()`` dictionary of (N, *shape) arrays."""
+        """(N, P) matrix of d ln Psi / d p from a ``pgradient()`` dictionary of (N, *shape) arrays; the derivative
+        with respect to an imaginary part is i times the one with respect to the real part."""
         parts = [np.asarray(pgrad[k]).reshape(len(pgrad[k]), -1)[:, i] for k, i in self._picked.items()]
-        return np.concatenate(parts, axis=1) if parts else np.zeros(0)
+        if not parts:
+            return np.zeros(0)
+        dp = np.concatenate(parts, axis=1)
+        return np.concatenate((dp, dp[:, self._imag] * 1j), axis=1) if len(self._imag) else dp
 
     def deserialize(self, wf, vector):
         """Parameter dictionary with the optimisable entries replaced by ``vector`` (others as in ``wf``)."""
-        out, start = {}, 0
+        out, start, istart = {}, 0, self.nparams
         for name, picked in self._picked.items():
             full = np.array(wf.parameters[name], dtype=self.dtypes[name]).ravel()
             full[picked] = np.real(vector[start:start + len(picked)])
+            if self.complex[name]:
+                full[picked] += 1j * np.asarray(vector[istart:istart + len(picked)])
+                istart += len(picked)
             out[name] = full.reshape(self.shapes[name])
             start += len(picked)
         return out
@@ -132,6 +145,8 @@ class StochasticReconfiguration:
 
     def _device(self, wf):
         if not isinstance(self.enacc, EnergyAccumulator):
+            return None
+        if wf.dtype == complex:  # qmcb_sr_avg reduces real gradients: complex ones are reduced below from pgradient()
             return None
         try:
             return _device_context(wf)

@@ -109,6 +109,13 @@ def _random_orthonormal_mos(nao, nmo, seed):
     return q[:, :nmo].copy()
 
 
+def _random_unitary_mos(nao, nmo, seed):
+    """Genuinely complex orthonormal orbitals (complex wave functions: slater.py:212-216)."""
+    rng = np.random.RandomState(seed)
+    q, _ = np.linalg.qr(rng.randn(nao, nao) + 1j * rng.randn(nao, nao))
+    return q[:, :nmo].copy()
+
+
 def he_ccecp_pvdz(seed=7):
     """Config C1: He atom, Z_eff = 2, [2s1p] basis (A = 5), 1 up + 1 down electron."""
     basis = {
@@ -290,7 +297,16 @@ def high_l_probe(seed=17):
     return mol, MF(np.array([c, c]), occ)
 
 
+def h2o_complex(seed=11):
+    """The H2O system with complex orbital coefficients (what tests/integration/test_complex_linemin.py of the
+    reference builds from a real mean field): every protocol output becomes complex."""
+    mol, mf = h2o_ccecp_pvtz(seed)
+    c = _random_unitary_mos(mol.nao, mol.nao, seed + 100)
+    return mol, MF(np.array([c, c]), mf.mo_occ)
+
+
 SYSTEMS = {
+    "h2o_cx": h2o_complex,
     "hatom": h_atom_like,
     "high_l": high_l_probe,
     "he": he_ccecp_pvdz,

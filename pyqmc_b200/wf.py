@@ -87,6 +87,7 @@ class DeviceContext:
         self.nelec = tuple(int(x) for x in mol.nelec)
         self.ecp_key = None
         self.has_basis = False
+        self.cplx = False  # set by a complex Slater factor (qmcb_set_slater_cx): Slater-valued outputs are complex128
         self.periodic = hasattr(mol, "a")
         if self.periodic:
             from . import pbc
@@ -114,12 +115,17 @@ class DeviceContext:
                                            _lib.dptr(t["exps"]), _lib.dptr(t["coefs"])))
         self.has_basis = True
 
+    def _dt(self, which):
+        """dtype of the wave-function-valued outputs of a call on the factors ``which`` (include/qmcb200.h,
+        qmcb_set_slater_cx): complex when the context's Slater factor is complex and takes part."""
+        return complex if (self.cplx and (which & SLATER)) else float
+
     # ---- protocol calls -----------------------------------------------------------------
     def recompute(self, which, configs, wrap=None):
         self.epoch += 1
         c = _lib.f64(configs)
         n = c.shape[0]
-        sign, logv = np.empty(n), np.empty(n)
+        sign, logv = np.empty(n, dtype=self._dt(which)), np.empty(n)
         if self.periodic:
             wr = None if wrap is None else _lib.f64(wrap)
             _lib.check(self.lib.qmcb_recompute_pbc(self.h, which, n, _lib.dptr(c), _lib.dptr(wr), _lib.dptr(sign),
@@ -130,7 +136,7 @@ class DeviceContext:
         return sign, logv
 
     def value(self, which):
-        sign, logv = np.empty(self.nconf), np.empty(self.nconf)
+        sign, logv = np.empty(self.nconf, dtype=self._dt(which)), np.empty(self.nconf)
         _lib.check(self.lib.qmcb_value(self.h, which, _lib.dptr(sign), _lib.dptr(logv)))
         return sign, logv
 
@@ -152,13 +158,13 @@ class DeviceContext:
 
     def gradient(self, which, e, epos):
         p = self._epos(epos)
-        g = np.empty((3, self.nconf))
+        g = np.empty((3, self.nconf), dtype=self._dt(which))
         _lib.check(self.lib.qmcb_gradient(self.h, which, int(e), _lib.dptr(p), _lib.dptr(g)))
         return g
 
     def gradient_value(self, which, e, epos):
         p = self._epos(epos)
-        g, v = np.empty((3, self.nconf)), np.empty(self.nconf)
+        g, v = np.empty((3, self.nconf), dtype=self._dt(which)), np.empty(self.nconf, dtype=self._dt(which))
         slot = ctypes.c_int64(-1)
         _lib.check(self.lib.qmcb_gradient_value(self.h, which, int(e), _lib.dptr(p), _lib.dptr(g),
                                                 _lib.dptr(v), ctypes.byref(slot)))
@@ -166,7 +172,7 @@ class DeviceContext:
 
     def gradient_laplacian(self, which, e, epos):
         p = self._epos(epos)
-        g, lap = np.empty((3, self.nconf)), np.empty(self.nconf)
+        g, lap = np.empty((3, self.nconf), dtype=self._dt(which)), np.empty(self.nconf, dtype=self._dt(which))
         _lib.check(self.lib.qmcb_gradient_laplacian(self.h, which, int(e), _lib.dptr(p), _lib.dptr(g),
                                                     _lib.dptr(lap)))
         return g, lap
@@ -185,7 +191,7 @@ class DeviceContext:
         naip = epos.configs.shape[1] if aux else 1
         p = self._epos(epos, naip)
         m, nm = self._mask(mask, self.nconf)
-        out = np.empty((nm, naip))
+        out = np.empty((nm, naip), dtype=self._dt(which))
         slot = ctypes.c_int64(-1)
         _lib.check(self.lib.qmcb_testvalue(self.h, which, int(e), _lib.dptr(p), naip, _lib.u8ptr(m),
                                            _lib.dptr(out), ctypes.byref(slot)))
@@ -195,7 +201,7 @@ class DeviceContext:
         el = _lib.i32(np.asarray(e))
         p = self._epos(epos)
         m, nm = self._mask(mask, self.nconf)
-        out = np.empty((nm, len(el)))
+        out = np.empty((nm, len(el)), dtype=self._dt(which))
         _lib.check(self.lib.qmcb_testvalue_many(self.h, which, len(el), _lib.iptr(el), _lib.dptr(p),
                                                 _lib.u8ptr(m), _lib.dptr(out)))
         return out
@@ -211,8 +217,8 @@ class DeviceContext:
         _lib.check(self.lib.qmcb_updateinternals(self.h, which, int(e), _lib.dptr(p), _lib.u8ptr(m),
                                                  _token(saved_values)))
 
-    def get_state(self, name, shape):
-        out = np.empty(shape)
+    def get_state(self, name, shape, dtype=float):
+        out = np.empty(shape, dtype=dtype)
         _lib.check(self.lib.qmcb_get_state(self.h, name.encode(), _lib.dptr(out)))
         return out
 
@@ -232,13 +238,14 @@ def _single_determinant(mf):
 
 
 def _realify_orbitals(mo, what="orbital"):
-    """Real orbital coefficients from complex ones when every orbital is real up to a constant phase.
+    """Real orbital coefficients from complex ones when every orbital is real up to a constant phase, else ``None``.
 
     Mean-field codes hand out complex128 coefficients even where the orbitals can be chosen real (pyscf k-point
     objects at Gamma or at time-reversal-invariant k-points).  Each column is rotated by the
     phase of its largest coefficient; if what remains has a negligible imaginary part the real part is returned
-    (the wave function changes by a constant global phase, which no observable of this path depends on), otherwise
-    the orbitals are genuinely complex and the caller raises."""
+    (the wave function changes by a constant global phase, which no observable of this path depends on) and the
+    wave function stays on the real kernels.  Genuinely complex orbitals return ``None``: the caller keeps the
+    complex coefficients (``dtype = complex``, the kernels of ``csrc/cplx.cuh``)."""
     mo = np.asarray(mo)
     if not np.iscomplexobj(mo):
         return np.array(mo, dtype=float)
@@ -248,10 +255,18 @@ def _realify_orbitals(mo, what="orbital"):
         big = col[np.argmax(np.abs(col))] if len(col) else 1.0
         rot = col * (np.conj(big) / abs(big)) if abs(big) > 0 else col
         if np.abs(rot.imag).max(initial=0.0) > 1e-9 * max(np.abs(rot).max(initial=0.0), 1e-300):
-            raise NotImplementedError(f"{what} {j} is genuinely complex (general twist): complex wave functions are "
-                                      "not supported by the B200 backend yet")
+            return None
         out[:, j] = rot.real
     return out
+
+
+def _orbital_coefficients(blocks):
+    """Real coefficient blocks when EVERY block can be realified, else all of them as complex128 (one dtype per
+    wave function, slater.py:212-216)."""
+    real = [_realify_orbitals(b) for b in blocks]
+    if all(r is not None for r in real):
+        return real
+    return [np.array(b, dtype=complex) for b in blocks]
 
 
 def _pack_determinants(determinants, tol):
@@ -259,7 +274,7 @@ def _pack_determinants(determinants, tol):
     for w, spin_occ in determinants:
         if abs(w) <= tol:
             continue
-        coeff.append(float(w))
+        coeff.append(w if np.iscomplexobj(w) and np.imag(w) != 0 else float(np.real(w)))
         for s in (0, 1):
             o = [int(i) for i in spin_occ[s]]
             if o not in occ[s]:
@@ -409,12 +424,8 @@ class Slater(_DeviceFactor):
                     raise AssertionError(
                         f"disagreement between number of electrons and number of orbitals: "
                         f"{self._nelec[s]} electrons and {len(o)} orbitals")
-        mo = mfu.mo_coeff
-        self.parameters = {
-            "det_coeff": coeff,
-            "mo_coeff_alpha": _realify_orbitals(np.asarray(mo[0])[:, : top[0]], "spin-up orbital"),
-            "mo_coeff_beta": _realify_orbitals(np.asarray(mo[1])[:, : top[1]], "spin-down orbital"),
-        }
+        mo = _orbital_coefficients([np.asarray(mfu.mo_coeff[0])[:, : top[0]], np.asarray(mfu.mo_coeff[1])[:, : top[1]]])
+        self.parameters = {"det_coeff": coeff, "mo_coeff_alpha": mo[0], "mo_coeff_beta": mo[1]}
 
     def _init_periodic(self, mol, mf, determinants, twist, eval_gto_precision):
         """Bloch orbitals on a supercell: k-points of the twist, per-k MO blocks concatenated,
@@ -454,19 +465,20 @@ class Slater(_DeviceFactor):
                     raise AssertionError(
                         f"disagreement between number of electrons and number of orbitals: "
                         f"{self._nelec[s]} electrons and {len(o)} orbitals")
-        blocks = [[_realify_orbitals(b, f"k-point {k} orbital") for k, b in zip(kinds, blocks[s])] for s in (0, 1)]
-        mo = [np.concatenate(blocks[s], axis=1) for s in (0, 1)]
         kpts = np.asarray(mfu.kpts)[kinds].reshape(-1, 3)
         tables = pbc.image_tables(mol.original_cell, kpts, eval_gto_precision)
-        if np.iscomplexobj(tables["phases"]):
-            raise NotImplementedError("k-points with complex Bloch phases (general twists) are not supported "
-                                      "by the B200 backend yet")
+        flatb = blocks[0] + blocks[1]
+        if np.iscomplexobj(tables["phases"]):  # general twist: complex Bloch phases -> a complex wave function
+            flatb = [np.array(b, dtype=complex) for b in flatb]
+        else:
+            flatb = _orbital_coefficients(flatb)
+        blocks = [flatb[:len(kinds)], flatb[len(kinds):]]
+        mo = [np.concatenate(blocks[s], axis=1) for s in (0, 1)]
         self._pbc = dict(
             kpts=kpts, tables=tables, isgamma=bool(np.abs(kpts).sum() < 1e-9),
             mo_k=[np.concatenate([np.full(b.shape[1], ki, dtype=np.int32) for ki, b in enumerate(blocks[s])]
                                  or [np.zeros(0, dtype=np.int32)]) for s in (0, 1)])
-        self.parameters = {"det_coeff": coeff, "mo_coeff_alpha": np.array(mo[0], dtype=float),
-                           "mo_coeff_beta": np.array(mo[1], dtype=float)}
+        self.parameters = {"det_coeff": coeff, "mo_coeff_alpha": np.array(mo[0]), "mo_coeff_beta": np.array(mo[1])}
 
     def _copy_parameters(self):
         return {k: np.array(v) for k, v in self.parameters.items()}
@@ -485,19 +497,39 @@ class Slater(_DeviceFactor):
                 ctx.h, len(bxyz), _lib.dptr(bxyz), _lib.dptr(lprim), _lib.dptr(smat), len(kpts), _lib.dptr(kpts),
                 len(Ls), _lib.dptr(Ls), _lib.iptr(ncut), _lib.dptr(acut), len(lcut), _lib.dptr(lcut), _lib.dptr(ph),
                 len(mk[0]), _lib.iptr(mk[0]), len(mk[1]), _lib.iptr(mk[1]), 1 if self._pbc["isgamma"] else 0))
+            if np.iscomplexobj(t["phases"]):
+                phi = _lib.f64(np.imag(t["phases"]))
+                _lib.check(ctx.lib.qmcb_set_pbc_phases_imag(ctx.h, phi.shape[0], phi.shape[1], _lib.dptr(phi)))
+
+    @property
+    def dtype(self):
+        """complex when any parameter or the Bloch phase table is complex (slater.py:212-216)."""
+        cx = any(np.iscomplexobj(v) for v in self.parameters.values())
+        if self._pbc is not None and np.iscomplexobj(self._pbc["tables"]["phases"]):
+            cx = True
+        return complex if cx else float
 
     def _push_parameters(self, ctx):
         p = self.parameters
-        cu, cd = _lib.f64(p["mo_coeff_alpha"]), _lib.f64(p["mo_coeff_beta"])
         occ = [_lib.i32(np.asarray(self._det_occup[s]).reshape(len(self._det_occup[s]), -1)) for s in (0, 1)]
         m0, m1 = _lib.i32(self._det_map[0]), _lib.i32(self._det_map[1])
+        if self.dtype == complex:
+            arr = [np.asarray(p[k], dtype=complex) for k in ("mo_coeff_alpha", "mo_coeff_beta", "det_coeff")]
+            re, im = [_lib.f64(a.real) for a in arr], [_lib.f64(a.imag) for a in arr]
+            _lib.check(ctx.lib.qmcb_set_slater_cx(
+                ctx.h, self._nelec[0], self._nelec[1], re[0].shape[1], _lib.dptr(re[0]), _lib.dptr(im[0]),
+                re[1].shape[1], _lib.dptr(re[1]), _lib.dptr(im[1]),
+                len(self._det_occup[0]), _lib.iptr(occ[0]), len(self._det_occup[1]), _lib.iptr(occ[1]),
+                len(re[2]), _lib.iptr(m0), _lib.iptr(m1), _lib.dptr(re[2]), _lib.dptr(im[2])))
+            ctx.cplx = True
+            return
+        cu, cd = _lib.f64(p["mo_coeff_alpha"]), _lib.f64(p["mo_coeff_beta"])
         dc = _lib.f64(p["det_coeff"])
-        if np.iscomplexobj(p["det_coeff"]):
-            raise NotImplementedError("complex determinant coefficients")
         _lib.check(ctx.lib.qmcb_set_slater(
             ctx.h, self._nelec[0], self._nelec[1], cu.shape[1], _lib.dptr(cu), cd.shape[1], _lib.dptr(cd),
             len(self._det_occup[0]), _lib.iptr(occ[0]), len(self._det_occup[1]), _lib.iptr(occ[1]),
             len(dc), _lib.iptr(m0), _lib.iptr(m1), _lib.dptr(dc)))
+        ctx.cplx = False
 
     def pgradient(self):
         """d ln Psi / d parameters: det_coeff (N, D), mo_coeff_alpha/beta (N, A, nmo_s)
@@ -512,7 +544,7 @@ class Slater(_DeviceFactor):
         for k, shape in shapes.items():
             if int(np.prod(shape)) == 0:
                 continue
-            arr = np.empty(shape)
+            arr = np.empty(shape, dtype=self.dtype)
             _lib.check(ctx.lib.qmcb_pgradient(ctx.h, k.encode(), _lib.dptr(arr)))
             out[k] = arr
         return out
@@ -524,13 +556,13 @@ class Slater(_DeviceFactor):
         out = []
         for s, name in ((0, "inverse_up"), (1, "inverse_dn")):
             n = self._nelec[s]
-            out.append(self._ctx.get_state(name, (N, len(self._det_occup[s]), n, n)))
+            out.append(self._ctx.get_state(name, (N, len(self._det_occup[s]), n, n), self.dtype))
         return out
 
     @property
     def _dets(self):
         N = self._ctx.nconf
-        return [self._ctx.get_state(name, (2, N, len(self._det_occup[s])))
+        return [self._ctx.get_state(name, (2, N, len(self._det_occup[s])), self.dtype)
                 for s, name in ((0, "dets_up"), (1, "dets_dn"))]
 
 
@@ -698,7 +730,6 @@ class MultiplyWF:
     def __init__(self, *wf_factors):
         self.wf_factors = list(wf_factors)
         self.parameters = Parameters([wf.parameters for wf in self.wf_factors])
-        self.dtype = complex if any(wf.dtype == complex for wf in self.wf_factors) else float
         kinds = [type(wf) for wf in self.wf_factors]
         device_kinds = (Slater, JastrowSpin, ThreeBodyJastrow)
         self._fused = (len(kinds) >= 2 and all(k in device_kinds for k in kinds) and len(set(kinds)) == len(kinds)
@@ -708,6 +739,10 @@ class MultiplyWF:
         if self._fused:
             for wf in self.wf_factors:
                 self._which |= wf._which
+
+    @property
+    def dtype(self):
+        return complex if any(wf.dtype == complex for wf in self.wf_factors) else float
 
     def _ensure_ctx(self):
         if self._ctx is None:

@@ -25,8 +25,10 @@ import helpers  # noqa: E402
 import refload  # noqa: E402
 
 NCONF = 12
-SYSTEMS = ["he", "h2o", "open", "c2", "h2o_md", "h2o_3b", "h2o_md_3b", "h2o_cas", "h2o_cas_3b", "high_l"]
-PBC_SYSTEMS = ["diamond211", "ortho", "rotcubic", "diamond211_3b", "ortho_3b"]
+SYSTEMS = ["he", "h2o", "open", "c2", "h2o_md", "h2o_3b", "h2o_md_3b", "h2o_cas", "h2o_cas_3b", "high_l",
+           "h2o_cx", "h2o_md_cx"]  # *_cx: complex orbital (and determinant) coefficients
+PBC_SYSTEMS = ["diamond211", "ortho", "rotcubic", "diamond211_3b", "ortho_3b",
+               "ortho_twist", "diamond211_twist"]  # *_twist: general twist = complex Bloch phases
 EWALD_GMAX = 10  # the reference enumerates (2 gmax + 1)^3 / 2 reciprocal points: keep the fixture run small
 
 

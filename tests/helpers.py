@@ -20,6 +20,11 @@ def make_system(name):
         mol, mf = systems.h2o_ccecp_pvtz()
         dets = systems.cas_determinants(4, 6, seed=3)[:40]
         return mol, mf, dets
+    if name == "h2o_md_cx":  # complex orbitals AND complex determinant coefficients
+        mol, mf = systems.h2o_complex()
+        dets = systems.cas_determinants(4, 6, seed=3)[:12]
+        ph = np.exp(2j * np.pi * np.random.RandomState(4).rand(len(dets)))
+        return mol, mf, [(w * p, occ) for (w, occ), p in zip(dets, ph)]
     if name == "h2o_cas":
         mol, mf = systems.h2o_ccecp_pvtz()
         return mol, mf, systems.cas_determinants(4, 8, seed=3)
@@ -94,7 +99,9 @@ def to_oracle_walkers(configs):
 
 
 def relerr(a, b):
-    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    a, b = np.asarray(a), np.asarray(b)
+    if not (np.iscomplexobj(a) or np.iscomplexobj(b)):
+        a, b = a.astype(float), b.astype(float)
     assert a.shape == b.shape, (a.shape, b.shape)
     if a.size == 0:
         return 0.0
