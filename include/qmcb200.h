@@ -305,6 +305,14 @@ int qmcb_rng_phase_a(void *plan, uint32_t *key, int32_t *pos, int32_t *has_gauss
                      double *gauss, double *unif, double *ecp_u, double *ecp_rot, int nthreads);
 int qmcb_rng_phase_b(void *plan, int nthreads);
 
+/* The dense product of StochasticReconfiguration.avg on its own (stochastic_reconfiguration.py:110-113,
+ * einsum "ij,ik->jk" of dp with weights * dp_regularized): C [P][P] = A^T B for host arrays A, B [N][P].
+ * variant 0 = FP64-FMA tiles, 1 = DMMA (mma.sync m8n8k4 f64) with a split walker range, -1 = the default
+ * qmcb_sr_avg uses.  Runs `reps` timed launches after one warm-up and returns the mean time in *ms
+ * (tests / profiles: the tensor-pipe evidence of the path's one GEMM). */
+int qmcb_gemm_tn(int device, int64_t N, int P, const double *A, const double *B, double *C,
+                 int variant, int reps, double *ms);
+
 /* measured FP64 FMA throughput of the device in TFLOP/s (8 independent DFMA chains per thread): the roof the
  * FP64-bound kernels of this path are reported against in bench.py */
 int qmcb_fp64_peak(int device, double *tflops);

@@ -12,6 +12,8 @@ wave function already holds.  Random variates are drawn on the host from the glo
 (eval_ecp.py:145) then one ``scipy Rotation.random()`` (eval_ecp.py:263) -- so seeded runs
 reproduce the reference's stochastic ECP masks and rotations.
 """
+import itertools
+
 import numpy as np
 import scipy.spatial.transform
 
@@ -19,6 +21,7 @@ from . import _lib, quadrature
 from .wf import MultiplyWF, _DeviceFactor
 
 KEYS = ("ke", "ee", "ei", "ecp", "grad2", "total")
+_SERIAL = itertools.count(1)  # identity of an accumulator's device tables (id() is recycled after garbage collection)
 
 
 def flatten_ecp(mol, naip=None):
@@ -71,6 +74,7 @@ class EnergyAccumulator:
         if not use_old_ecp:
             raise NotImplementedError("only the default ECP path (use_old_ecp=True) is implemented")
         self.mol, self.threshold, self.naip = mol, threshold, naip
+        self._serial = next(_SERIAL)
         self._ecp = flatten_ecp(mol, naip)
         self.necp = len(self._ecp["ecp_atom"])
         self._ewald = None
@@ -83,7 +87,7 @@ class EnergyAccumulator:
         ctx = _device_context(wf)
         if ctx is None or ctx.nconf == 0:
             raise RuntimeError("wf.recompute(configs) must be called before the energy accumulator")
-        key = (id(self), self.threshold, self.naip)
+        key = (self._serial, self.threshold, self.naip)
         if ctx.ecp_key != key:
             t = self._ecp
             _lib.check(ctx.lib.qmcb_set_ecp(ctx.h, self.necp, _lib.iptr(t["ecp_atom"]), _lib.iptr(t["chan_off"]),

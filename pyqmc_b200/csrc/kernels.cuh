@@ -2227,15 +2227,15 @@ __global__ void __launch_bounds__(256) k_colsum(const double* in, int N, double*
   if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
 }
 
-// layout conversions between the host's (N, ne, 3) and the device's [ne][3][N]
+// walker coordinates between the staging buffer and the state (both walker-major (N, ne, 3), the host layout)
 __global__ void k_conf_in(const double* host_layout, double* conf, int N, int ne) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * ne * 3) return;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)N * ne * 3) return;
   conf[i] = host_layout[i];
 }
 __global__ void k_conf_out(const double* conf, double* host_layout, int N, int ne) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * ne * 3) return;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)N * ne * 3) return;
   host_layout[i] = conf[i];
 }
 
@@ -2563,6 +2563,72 @@ __global__ void __launch_bounds__(256) k_gemm_tn(const double* __restrict__ A, c
       const int j = tj + ty * 4 + u, k = tk + tx * 4 + v;
       if (j < P && k < P) C[(size_t)j * P + k] = acc[u][v];
     }
+}
+
+// The same product on the FP64 tensor pipe: mma.sync.aligned.m8n8k4 (DMMA; tcgen05 has no FP64 path, so this is the
+// only tensor-core route for the path's one dense product).  64 x 64 output tile per CTA, four warps of 32 x 32
+// (4 x 4 DMMA tiles, 32 accumulator registers per thread), 16 walkers staged per iteration; gridDim.z splits the
+// walker range so that P / 64 squared tiles still fill the machine -- partial tiles go to Cpart[z][P][P] and are
+// added in a fixed order by k_gemm_reduce (deterministic, unlike atomics).
+// Fragment layout (PTX ISA, m8n8k4 .f64): A[row = lane / 4][k = lane % 4], B[k = lane % 4][col = lane / 4],
+// C[row = lane / 4][col = 2 (lane % 4) + {0, 1}].  Here "A" = dp^T, so both operands read tile[i0 + lane % 4][x0 + lane / 4].
+#define QMCB_GEMM_LD 72  // 64 + 8: the fragment loads hit every shared-memory bank pair exactly twice
+__global__ void __launch_bounds__(128) k_gemm_tn_dmma(const double* __restrict__ A, const double* __restrict__ B, int N,
+                                                      int P, int rows_per_split, double* __restrict__ Cpart) {
+  __shared__ double sa[16][QMCB_GEMM_LD], sb[16][QMCB_GEMM_LD];
+  const int tj = blockIdx.y * 64, tk = blockIdx.x * 64;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wj = (warp >> 1) * 32, wk = (warp & 1) * 32;
+  const int fr = lane & 3, fc = lane >> 2;
+  double acc[4][4][2];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
+  const int ibeg = blockIdx.z * rows_per_split, iend = min(N, ibeg + rows_per_split);
+  for (int i0 = ibeg; i0 < iend; i0 += 16) {
+    for (int t = threadIdx.x; t < 16 * 64; t += 128) {
+      const int r = t >> 6, c = t & 63;
+      const int i = i0 + r;
+      sa[r][c] = (i < iend && tj + c < P) ? A[(size_t)i * P + tj + c] : 0.0;
+      sb[r][c] = (i < iend && tk + c < P) ? B[(size_t)i * P + tk + c] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; kk += 4) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) af[u] = sa[kk + fr][wj + 8 * u + fc];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) bf[v] = sb[kk + fr][wk + 8 * v + fc];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                       : "+d"(acc[u][v][0]), "+d"(acc[u][v][1])
+                       : "d"(af[u]), "d"(bf[v]));
+    }
+    __syncthreads();
+  }
+  double* __restrict__ C = Cpart + (size_t)blockIdx.z * P * P;
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int j = tj + wj + 8 * u + fc, k = tk + wk + 8 * v + 2 * fr;
+      if (j < P && k < P) C[(size_t)j * P + k] = acc[u][v][0];
+      if (j < P && k + 1 < P) C[(size_t)j * P + k + 1] = acc[u][v][1];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gemm_reduce(const double* __restrict__ Cpart, int nsplit, size_t n,
+                                                     double* __restrict__ C) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double acc = 0.0;
+  for (int z = 0; z < nsplit; ++z) acc += Cpart[(size_t)z * n + i];
+  C[i] = acc;
 }
 
 #include "cplx.cuh"

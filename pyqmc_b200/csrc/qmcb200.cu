@@ -92,6 +92,7 @@ struct qmcb_ctx {
   // coefficients and of the Bloch phase table; nmo[] stays the true orbital count
   bool cplx = false;
   std::vector<double> mo_im[2], detc_im, phases_im;
+  DBuf<double> b_gemm;  // split partial tiles of the SR product
   DBuf<double> b_inv_im[2], b_dphs_im[2], b_dv_im[2], b_W_im[2], d_detc_im, d_grp_coef_im[2], b_cxwork, e_contrib_im;
   int na = 0, nb = 0;
   std::vector<int> akind, bkind;
@@ -667,6 +668,31 @@ int launch_sm(qmcb_ctx* c, const SmArgs& a, cudaStream_t stream, int64_t* nlaunc
 #undef SM_T
   if (nlaunch) (*nlaunch)++;
   (void)c;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// C[P][P] = A^T B for A, B [N][P] (dp^T (w f dp), stochastic_reconfiguration.py:110-113).  variant 0: the FP64-FMA
+// tile kernel; 1: DMMA (mma.sync m8n8k4) with the walker range split over gridDim.z; -1: default (QMCB_GEMM_FMA=1
+// selects 0, else 1).
+int launch_gemm_tn(const double* A, const double* B, int N, int P, double* C, DBuf<double>& work, int variant,
+                   cudaStream_t stream) {
+  if (variant < 0) variant = std::getenv("QMCB_GEMM_FMA") ? 0 : 1;
+  const unsigned tiles = (unsigned)((P + 63) / 64);
+  if (variant == 0) {
+    k_gemm_tn<<<dim3(tiles, tiles), 256, 0, stream>>>(A, B, N, P, C);
+    CK(cudaGetLastError());
+    return 0;
+  }
+  // enough splits for ~4 CTAs per SM, at least 64 walkers per split
+  int nsplit = (int)std::max<long long>(1, std::min<long long>((148LL * 4 + tiles * tiles - 1) / ((long long)tiles * tiles), (N + 63) / 64));
+  int rows = ((N + nsplit - 1) / nsplit + 15) / 16 * 16;
+  nsplit = (N + rows - 1) / rows;
+  if (work.ensure((size_t)nsplit * P * P)) return -1;
+  k_gemm_tn_dmma<<<dim3(tiles, tiles, (unsigned)nsplit), 128, 0, stream>>>(A, B, N, P, rows, work.p);
+  CK(cudaGetLastError());
+  const size_t n = (size_t)P * P;
+  k_gemm_reduce<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(work.p, nsplit, n, C);
   CK(cudaGetLastError());
   return 0;
 }
@@ -2948,9 +2974,8 @@ int qmcb_sr_avg(qmcb_ctx* c, int nparam, const int32_t* src, const int64_t* off,
     k_sr_colsum<<<(unsigned)(P + 6), 256, 0, stream>>>(c->st, a, d_red.p);
     c->nlaunch++;
     if (P > 0) {
-      dim3 grid((unsigned)((P + 63) / 64), (unsigned)((P + 63) / 64));
-      k_gemm_tn<<<grid, 256, 0, stream>>>(d_dp.p, d_wdpr.p, (int)N, (int)P, d_C.p);
-      c->nlaunch++;
+      if (launch_gemm_tn(d_dp.p, d_wdpr.p, (int)N, (int)P, d_C.p, c->b_gemm, -1, stream)) { rc = -1; break; }
+      c->nlaunch += 2;
     }
     if (cudaGetLastError() != cudaSuccess) { rc = fail("stochastic-reconfiguration kernel launch failed"); break; }
     std::vector<double> red(2 * (P + 6));
@@ -3061,6 +3086,35 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, doubl
     x7 = fma(x7, a, b);
   }
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+int qmcb_gemm_tn(int device, int64_t N, int P, const double* A, const double* B, double* C, int variant, int reps,
+                 double* ms) {
+  cudaSetDevice(device);
+  DBuf<double> dA, dB, dC, work;
+  const size_t nA = (size_t)N * P;
+  if (dA.ensure(nA) || dB.ensure(nA) || dC.ensure((size_t)P * P)) return -1;
+  CK(cudaMemcpy(dA.p, A, nA * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB.p, B, nA * 8, cudaMemcpyHostToDevice));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  int rc = launch_gemm_tn(dA.p, dB.p, (int)N, P, dC.p, work, variant, nullptr);  // warm-up
+  CK(cudaEventRecord(e0, nullptr));
+  for (int r = 0; r < reps && !rc; ++r) rc = launch_gemm_tn(dA.p, dB.p, (int)N, P, dC.p, work, variant, nullptr);
+  CK(cudaEventRecord(e1, nullptr));
+  CK(cudaEventSynchronize(e1));
+  float t = 0.f;
+  CK(cudaEventElapsedTime(&t, e0, e1));
+  if (ms) *ms = reps > 0 ? t / reps : 0.0;
+  if (!rc) CK(cudaMemcpy(C, dC.p, (size_t)P * P * 8, cudaMemcpyDeviceToHost));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  dA.release();
+  dB.release();
+  dC.release();
+  work.release();
+  return rc;
 }
 
 int qmcb_fp64_peak(int device, double* tflops) {
