@@ -365,7 +365,7 @@ def sm_roofline(torch, lib, n, nmat, reps=5):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     # the kernel is launched on this torch stream (a real, non-default stream handle) and the
     # events are recorded on the same stream
-    ts = torch.cuda.Stream()
+    ts = torch.cuda.Stream(priority=-1)  # above the library's energy stream (lowest priority), as its own stream is
     assert ts.cuda_stream != 0
     torch.cuda.synchronize()
     times = []
@@ -435,7 +435,7 @@ def gpu_arm(args):
     wf.recompute(configs)
     # All kernels of the timed region are launched on this torch stream (passed to the C ABI as a
     # raw cudaStream_t) and the CUDA events are recorded on the same stream.
-    ts = torch.cuda.Stream()
+    ts = torch.cuda.Stream(priority=-1)
     stream = ts.cuda_stream
     assert stream != 0, "need a real stream handle: 0 would select the library's internal stream"
     torch.cuda.synchronize()
@@ -654,14 +654,18 @@ def gpu_arm_dmc(args):
     # the block's variates + the branching draw: generated on the device one block ahead (host thread if unavailable)
     prefetch = dmc.dmc_variate_source(wf, configs, tstep, spb, acc["energy"], W + K)
 
+    e_trial = e0
+
     def block():
-        nonlocal configs, weights
-        out, configs, weights = dmc.dmc_propagate(wf, configs, weights, tstep, 10.0, e0, e0, nsteps=spb, accumulators=acc,
-                                                  variates=prefetch.next())
+        nonlocal configs, weights, e_trial
+        out, configs, weights = dmc.dmc_propagate(wf, configs, weights, tstep, 10.0, e_trial, e0, nsteps=spb,
+                                                  accumulators=acc, variates=prefetch.next())
         from pyqmc_b200 import parallel
 
-        glob, _ = parallel.allreduce_dmc_block(out, N)  # one allreduce of the block's weighted sums (dmc.py:288-303)
-        configs, weights, _ = parallel.branch_global(configs, weights, base_draw=prefetch.branch_draw())  # global comb
+        # global comb; the block's weighted sums (dmc.py:288-303) ride on its weights all-gather
+        configs, weights, info = parallel.branch_global(configs, weights, base_draw=prefetch.branch_draw(), block_avg=out)
+        # population control as in rundmc (dmc.py:572): e_trial = e_est - feedback * log(mean weight), feedback = 1
+        e_trial = e0 - np.log(info["block_avg"]["weight"])
         return out
 
     for _ in range(W):

@@ -169,7 +169,11 @@ struct qmcb_ctx {
   // snapshot of the arrays it reads while the sweep of step s+1 already moves the walkers
   cudaStream_t energy_stream = nullptr;
   cudaEvent_t ev_snap = nullptr, ev_edone = nullptr;
-  DBuf<double> sn_inv[2], sn_conf, sn_ap, sn_bp, e_ke2, e_g22;
+  DBuf<double> sn_inv[2], sn_conf, sn_ap, sn_bp, sn_wrap, e_ke2, e_g22;
+  // grid cap of the persistent periodic orbital kernel while it runs as overlapped background work: its CTAs stride
+  // over the points and hold their SM's shared memory until the launch ends, so a full-machine grid would stall the
+  // short kernels of the walker moves it is supposed to hide behind (0 = no cap)
+  unsigned pbc_mo_grid_cap = 0;
   // variates of a DMC block generated on the device (qmcb_devrng_dmc_block), two sets: the generator fills one
   // while qmcb_dmc_block_slot consumes the other
   struct DmcSlot {
@@ -738,7 +742,8 @@ int launch_pbc_mo(qmcb_ctx* c, int deriv, const PbcMoArgs& a, long long max_poin
     int T = std::max(std::max(ncol, nc * std::max(c->S.ldc[0], c->S.ldc[1])), 64);
     T = std::min((T + 31) / 32 * 32, 256);
     if (ncol > T) T = std::min(((ncol + 1) / 2 + 31) / 32 * 32, 256);
-    const unsigned grid = (unsigned)std::min<long long>(max_points, 148LL * 64);
+    unsigned grid = (unsigned)std::min<long long>(max_points, 148LL * 64);
+    if (c->pbc_mo_grid_cap) grid = std::min(grid, c->pbc_mo_grid_cap);
     int maxl = 0;
     for (int l : c->sh_l) maxl = std::max(maxl, l);
     const bool tuned4 = T <= 160 && 4 * csm <= 220 * 1024 && std::getenv("QMCB_PBC_MO_OCC2") == nullptr;
@@ -1064,34 +1069,37 @@ int ecp_points_pbc_prepass(qmcb_ctx* c, EcpPointArgs& ea, long long maxpts, long
 
 // `st` / `es`: the walker state and energy scratch the kernels read -- the live ones, or the snapshot the
 // overlapped step loop hands over (qmcb_vmc_block_device)
+// kinetic-energy pieces (es.ke_e / es.g2_e) from the cached MO rows, unless the sweep kernel already wrote them
+int launch_kinetic(qmcb_ctx* c, const State& st, const EnergyScratch& es, cudaStream_t stream) {
+  const Sys& S = c->S;
+  const size_t sm = c->smem_bytes;
+  const long long np = (long long)c->N * S.ne;
+  if (c->kinetic_valid) return 0;
+  if (!c->mocache_valid && c->have_slater) {  // protocol-path updates do not maintain the cache
+    if (launch_mo_all(c, 0, stream)) return -1;
+  }
+  // three-body factor: per-group a-value scratch behind the tables
+  const size_t ksm = c->have_j3 ? ((sm + 15) & ~(size_t)15) + (size_t)(128 / 8) * 3 * S.natom * S.na3 * 8 : sm;
+  if (S.cplx) {
+    if (prep_kernel(k_cx_kinetic, sm)) return -1;
+    k_cx_kinetic<<<(unsigned)((np + 63) / 64), 64, sm, stream>>>(S, st, es);
+  } else {
+    if (prep_kernel(k_kinetic<8>, ksm)) return -1;
+    k_kinetic<8><<<(unsigned)((np * 8 + 127) / 128), 128, ksm, stream>>>(S, st, es);
+  }
+  c->nlaunch++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 template <int NMOT>
 int launch_energy_t(qmcb_ctx* c, const State& st, const EnergyScratch& es, const double* d_u, const double* d_rot,
                     double* d_out, cudaStream_t stream) {
   const Sys& S = c->S;
   const int N = c->N;
   const size_t sm = c->smem_bytes;
-  {
-    const long long np = (long long)N * S.ne;
-    const int block = pick_block(np);
-    (void)block;
-    if (!c->kinetic_valid) {
-    if (!c->mocache_valid && c->have_slater) {  // protocol-path updates do not maintain the cache
-      if (launch_mo_all(c, 0, stream)) return -1;
-    }
-    // three-body factor: per-group a-value scratch behind the tables
-    const size_t ksm = c->have_j3 ? ((sm + 15) & ~(size_t)15) + (size_t)(128 / 8) * 3 * S.natom * S.na3 * 8 : sm;
-    if (S.cplx) {
-      if (prep_kernel(k_cx_kinetic, sm)) return -1;
-      k_cx_kinetic<<<(unsigned)((np + 63) / 64), 64, sm, stream>>>(S, st, es);
-    } else {
-    if (prep_kernel(k_kinetic<8>, ksm)) return -1;
-    k_kinetic<8><<<(unsigned)((np * 8 + 127) / 128), 128, ksm, stream>>>(S, st, es);
-    }
-    c->nlaunch++;
-    CK(cudaGetLastError());
-    }
-    c->kinetic_valid = false;
-  }
+  if (launch_kinetic(c, st, es, stream)) return -1;
+  c->kinetic_valid = false;
   if (S.necp > 0) {
     CK(cudaMemsetAsync(es.count, 0, sizeof(int), stream));
     const long long nt = (long long)N * S.ne * S.necp;
@@ -1194,11 +1202,13 @@ int qmcb_create(int device, qmcb_ctx** out) {
   CK(cudaSetDevice(device));
   qmcb_ctx* c = new qmcb_ctx();
   c->device = device;
-  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   {
     int lo = 0, hi = 0;  // the copy stream also runs the draw-program kernels of the device generator: ahead of compute
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CK(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, hi));
+    // the walker moves are a dependent chain of short kernels: their CTAs go ahead of the overlapped energy
+    // accumulator's (energy_stream, lowest priority), which only needs to finish before the next snapshot
+    CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, lo > hi ? lo - 1 : lo));
   }
   for (int i = 0; i < qmcb_ctx::NSLOT; ++i) CK(cudaEventCreateWithFlags(&c->slot_ready[i], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->done_event, cudaEventDisableTiming | cudaEventBlockingSync));
@@ -1261,7 +1271,7 @@ void qmcb_destroy(qmcb_ctx* c) {
   }
   if (c->done_event) cudaEventDestroy(c->done_event);
   if (c->energy_stream) cudaStreamSynchronize(c->energy_stream);
-  for (auto* b : {&c->sn_inv[0], &c->sn_inv[1], &c->sn_conf, &c->sn_ap, &c->sn_bp, &c->e_ke2, &c->e_g22}) b->release();
+  for (auto* b : {&c->sn_inv[0], &c->sn_inv[1], &c->sn_conf, &c->sn_ap, &c->sn_bp, &c->sn_wrap, &c->e_ke2, &c->e_g22}) b->release();
   if (c->ev_snap) cudaEventDestroy(c->ev_snap);
   if (c->ev_edone) cudaEventDestroy(c->ev_edone);
   if (c->energy_stream) cudaStreamDestroy(c->energy_stream);
@@ -2255,9 +2265,19 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
   // copy on the energy stream while the sweep of step s+1 proceeds; the kinetic pieces alternate between two buffers.
   const bool overlap = use_sweep && with_energy && c->have_slater && c->have_jastrow && (c->nmot == 4 || c->nmot == 8) &&
                        nsteps > 1 && std::getenv("QMCB_NO_ENERGY_OVERLAP") == nullptr;
+  // Periodic chain: the same overlap with the kinetic pieces computed on the main stream first (they read the cached
+  // MO rows, 80 KB per walker at C4 -- not worth copying); the ECP, Ewald and finalize kernels (3 of the 8 ms of a C4
+  // step) then run from the copy of inverse / coordinates / wrap / Jastrow partial sums while the next step's moves,
+  // which leave most of the machine idle at 1024 walkers, proceed.
+  const bool overlap_pbc = use_pbc && with_energy && c->have_slater && c->have_jastrow && nsteps > 1 &&
+                           std::getenv("QMCB_NO_ENERGY_OVERLAP") == nullptr;
   State snap = c->st;
   EnergyScratch es_alt[2] = {c->es, c->es};
-  if (overlap) {
+  if (overlap_pbc) {
+    if (c->sn_wrap.ensure(N * S.ne * 3)) return -1;
+    snap.wrap = c->sn_wrap.p;
+  }
+  if (overlap || overlap_pbc) {
     const size_t ninv0 = N * (size_t)S.nup * S.nup, ninv1 = N * (size_t)S.ndn * S.ndn;
     const size_t nap = N * (size_t)S.ne * S.natom * S.na, nbp = N * (size_t)S.ne * S.nb * 2;
     if (c->sn_inv[0].ensure(ninv0) || c->sn_inv[1].ensure(ninv1) || c->sn_conf.ensure(N * S.ne * 3) || c->sn_ap.ensure(nap) ||
@@ -2404,9 +2424,14 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
       const size_t ue = (size_t)step * S.ne * S.necp;
       const double* su = d_ecp_u ? d_ecp_u + ue * N : nullptr;
       const double* sr = d_ecp_rot ? d_ecp_rot + ue * 9 : nullptr;
-      if (overlap) {
+      if (overlap || overlap_pbc) {
         cudaStream_t es_ = c->energy_stream;
+        if (overlap_pbc) {
+          if (launch_kinetic(c, c->st, es_alt[step & 1], stream)) return -1;
+          c->kinetic_valid = true;
+        }
         if (step > 0) CK(cudaStreamWaitEvent(stream, c->ev_edone, 0));  // the previous accumulator still reads the copy
+        if (overlap_pbc) CK(cudaMemcpyAsync(snap.wrap, c->st.wrap, N * S.ne * 3 * 8, cudaMemcpyDeviceToDevice, stream));
         CK(cudaMemcpyAsync(snap.inv[0], c->st.inv[0], N * (size_t)S.nup * S.nup * 8, cudaMemcpyDeviceToDevice, stream));
         CK(cudaMemcpyAsync(snap.inv[1], c->st.inv[1], N * (size_t)S.ndn * S.ndn * 8, cudaMemcpyDeviceToDevice, stream));
         CK(cudaMemcpyAsync(snap.conf, c->st.conf, N * S.ne * 3 * 8, cudaMemcpyDeviceToDevice, stream));
@@ -2414,7 +2439,13 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
         CK(cudaMemcpyAsync(snap.b_partial, c->st.b_partial, N * (size_t)S.ne * S.nb * 2 * 8, cudaMemcpyDeviceToDevice, stream));
         CK(cudaEventRecord(c->ev_snap, stream));
         CK(cudaStreamWaitEvent(es_, c->ev_snap, 0));
-        if (launch_energy_on(c, snap, es_alt[step & 1], su, sr, eo, es_)) return -1;
+        if (overlap_pbc) {
+          static const unsigned cap = std::getenv("QMCB_PBC_BG_GRID") ? (unsigned)std::atoi(std::getenv("QMCB_PBC_BG_GRID")) : 592u;
+          c->pbc_mo_grid_cap = cap;
+        }
+        const int erc = launch_energy_on(c, snap, es_alt[step & 1], su, sr, eo, es_);
+        c->pbc_mo_grid_cap = 0;
+        if (erc) return -1;
         if (d_esum) {
           k_colsum<<<6, 256, 0, es_>>>(eo, (int)N, d_esum + (size_t)step * 6);
           c->nlaunch++;
@@ -2432,7 +2463,7 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
       }
     }
   }
-  if (overlap) CK(cudaStreamWaitEvent(stream, c->ev_edone, 0));  // the caller's stream sees every step's energies
+  if (overlap || overlap_pbc) CK(cudaStreamWaitEvent(stream, c->ev_edone, 0));  // the caller's stream sees every step's energies
   c->saved_slot = -1;
   return 0;
 }

@@ -110,83 +110,121 @@ def allreduce_dmc_block(block_avg, nconf, group=None, device=None):
     return out, int(round(vec[0]))
 
 
-def branch_global(local, weights, group=None, base_draw=None):
+def _walker_counts(local, n_local, group, device):
+    """Walkers held by every rank.  ``branch_global`` leaves the layout it produced (``np.array_split`` shares of a
+    population whose size never changes) on the walker container it returns; a container without that note -- the
+    first block, or walkers re-sharded by the caller -- costs one all-reduce.  Every rank runs the same program, so
+    all of them take the same branch here."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    note = getattr(local, "_rank_layout", None)
+    if note is not None and len(note) == world and note[rank] == n_local:
+        return note
+    counts_t = torch.zeros(world, dtype=torch.int64, device=device)
+    counts_t[rank] = n_local
+    dist.all_reduce(counts_t, group=group)
+    return counts_t.cpu().numpy()
+
+
+def branch_global(local, weights, group=None, base_draw=None, block_avg=None):
     """Stochastic-comb branching over the GLOBAL population (``branch``, dmc.py:342-376, applied after
     ``configs.join`` as the reference's parallel driver does) without ever assembling that population:
 
     1. one all-gather of the WEIGHTS (8 bytes per walker; rank 0's slot also carries its ``np.random.rand()``,
-       the comb offset for everybody);
+       the comb offset for everybody, and -- with ``block_avg`` -- every rank's block statistics, so the
+       combination of ``allreduce_dmc_block`` needs no collective of its own);
     2. every rank computes the same resampling indices (``dmc.comb_indices``) and, from the ``np.array_split``
        layout, which rank holds which walker before and after;
     3. one ``all_to_all_single`` moves only the walkers that change owner (``nelec * 24`` bytes each, 48 with the
        periodic wrap vectors); copies that stay on their rank never leave it.
 
     Equal to join -> branch -> split of the reference with the same offset (tests/test_parallel_gloo.py).
-    Returns (local configs, local weights, info)."""
+    Returns (local configs, local weights, info); with ``block_avg`` the info dictionary also holds
+    ``"block_avg"``: the globally combined block dictionary (``allreduce_dmc_block``'s first result)."""
     import torch
     import torch.distributed as dist
 
     from .dmc import branch, comb_indices
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return branch(local, weights, base_draw)
+        res = branch(local, weights, base_draw)
+        if block_avg is not None:
+            res[2]["block_avg"] = allreduce_dmc_block(block_avg, len(weights), group)[0]
+        return res
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     device = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
     weights = np.asarray(weights, dtype=np.float64)
     n_local = len(weights)
-    counts_t = torch.zeros(world, dtype=torch.int64, device=device)
-    counts_t[rank] = n_local
-    dist.all_reduce(counts_t, group=group)
-    counts = counts_t.cpu().numpy()
-    width = int(counts.max()) + 1  # last column: the comb offset (rank 0's draw)
+    counts = _walker_counts(local, n_local, group, device)
+    stat_keys = sorted(k for k in block_avg if k not in SKIP_KEYS and k != "weight") if block_avg is not None else []
+    nstat = 2 + len(stat_keys) if block_avg is not None else 0
+    width = int(counts.max()) + 1 + nstat  # after the weights: the comb offset (rank 0's draw), then the statistics
     row = np.zeros(width)
     row[:n_local] = weights
     if rank == 0:
-        row[-1] = np.random.rand() if base_draw is None else base_draw
-    pieces = [torch.empty(width, dtype=torch.float64, device=device) for _ in range(world)]
-    dist.all_gather(pieces, torch.from_numpy(row).to(device), group=group)
-    gathered = torch.stack(pieces).cpu().numpy()
+        row[int(counts.max())] = np.random.rand() if base_draw is None else base_draw
+    if block_avg is not None:
+        wn = float(block_avg["weight"]) * n_local
+        row[width - nstat:] = [n_local, wn] + [float(block_avg[k]) * wn for k in stat_keys]
+    if device == "cuda":  # NCCL: one output tensor, no per-rank pieces to allocate and stack
+        gathered_t = torch.empty((world, width), dtype=torch.float64, device=device)
+        dist.all_gather_into_tensor(gathered_t, torch.from_numpy(row).to(device), group=group)
+        gathered = gathered_t.cpu().numpy()
+    else:
+        pieces = [torch.empty(width, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(pieces, torch.from_numpy(row), group=group)
+        gathered = torch.stack(pieces).numpy()
     allw = np.concatenate([gathered[r, : counts[r]] for r in range(world)])
-    picked, total = comb_indices(allw, gathered[0, -1])
+    picked, total = comb_indices(allw, gathered[0, int(counts.max())])
+    combined = None
+    if block_avg is not None:  # the rule of allreduce_dmc_block on the gathered per-rank vectors
+        vec = gathered[:, width - nstat:].sum(axis=0)
+        combined = {k: vec[2 + i] / vec[1] for i, k in enumerate(stat_keys)}
+        combined["weight"] = vec[1] / vec[0]
     if np.any(allw > 2.0) and rank == 0:
         import logging
 
         logging.warning("Some weights are larger than 2")
-    # ownership before (contiguous ranges of global ids) and after (array_split of the resampled population)
+    # ownership before (contiguous ranges of global ids) and after (array_split of the resampled population: slot i
+    # of the new population belongs to the rank whose contiguous slot range holds i)
     first = np.concatenate([[0], np.cumsum(counts)])
     owner = np.searchsorted(first, picked, side="right") - 1
-    after = np.array_split(np.arange(len(picked)), world)
+    total_n = len(picked)
+    share = np.array([total_n // world + (1 if r < total_n % world else 0) for r in range(world)])  # np.array_split sizes
+    bounds = np.concatenate([[0], np.cumsum(share)])
+    dest = np.repeat(np.arange(world), share)
     fields = [local.configs.reshape(n_local, -1)]
     if getattr(local, "wrap", None) is not None:
         fields.append(local.wrap.reshape(n_local, -1))
-    rows = np.concatenate(fields, axis=1)
-    send_rows, send_counts, recv_counts = [], [], []
-    for dst in range(world):
-        ids = picked[after[dst]]
-        mine = ids[owner[after[dst]] == rank] - first[rank]  # in the order rank `dst` will place them
-        send_counts.append(0 if dst == rank else len(mine))
-        if dst != rank:
-            send_rows.append(rows[mine])
-        recv_counts.append(0 if dst == rank else int(np.sum(owner[after[rank]] == dst)))
+    rows = fields[0] if len(fields) == 1 else np.concatenate(fields, axis=1)
     width_r = rows.shape[1]
-    out = np.empty((len(after[rank]), width_r))
-    my_ids, my_owner = picked[after[rank]], owner[after[rank]]
-    out[my_owner == rank] = rows[my_ids[my_owner == rank] - first[rank]]  # copies that never leave this rank
-    send = np.concatenate(send_rows, axis=0) if send_rows and sum(send_counts) else np.empty((0, width_r))
+    # what this rank sends: its walkers picked for slots of other ranks, in slot order (= grouped by destination)
+    leaving = np.flatnonzero((owner == rank) & (dest != rank))
+    send_counts = np.bincount(dest[leaving], minlength=world).tolist()
+    send = rows[picked[leaving] - first[rank]]
+    # what it keeps / receives: its own slot range
+    lo, hi = bounds[rank], bounds[rank + 1]
+    my_ids, my_owner = picked[lo:hi], owner[lo:hi]
+    stay = my_owner == rank
+    out = np.empty((hi - lo, width_r))
+    out[stay] = rows[my_ids[stay] - first[rank]]  # copies that never leave this rank
+    arriving = np.flatnonzero(~stay)
+    recv_counts = np.bincount(my_owner[arriving], minlength=world).tolist()
     send_t = torch.from_numpy(np.ascontiguousarray(send)).to(device)
-    recv_t = torch.empty((sum(recv_counts), width_r), dtype=torch.float64, device=device)
+    recv_t = torch.empty((len(arriving), width_r), dtype=torch.float64, device=device)
     dist.all_to_all_single(recv_t, send_t, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=group)
-    recv = recv_t.cpu().numpy()
-    at = 0
-    for src in range(world):
-        if src == rank:
-            continue
-        out[my_owner == src] = recv[at : at + recv_counts[src]]
-        at += recv_counts[src]
+    # the pieces arrive grouped by source rank, each in the sender's slot order
+    out[arriving[np.argsort(my_owner[arriving], kind="stable")]] = recv_t.cpu().numpy()
     ncfg = fields[0].shape[1]
     local.configs = np.ascontiguousarray(out[:, :ncfg]).reshape((len(out),) + local.configs.shape[1:])
     if len(fields) > 1:
         local.wrap = np.ascontiguousarray(out[:, ncfg:]).reshape(local.configs.shape)
     survivors, copies = np.unique(picked, return_counts=True)
     new_w = np.full(len(out), total / len(picked))
-    return local, new_w, {"max branches": np.max(copies), "Number of walkers killed": len(picked) - len(survivors)}
+    local._rank_layout = share
+    info = {"max branches": np.max(copies), "Number of walkers killed": len(picked) - len(survivors)}
+    if combined is not None:
+        info["block_avg"] = combined
+    return local, new_w, info

@@ -97,9 +97,17 @@ def _dmc_worker(rank, world, port, nwalk, out_dir):
     block = {"energytotal": float(np.average(allc[idx, 0, 0], weights=w)), "weight": float(np.mean(w)), "acceptance": 0.9}
     glob, total = parallel.allreduce_dmc_block(block, len(idx))
     np.random.seed(7)  # only rank 0's draw is used
-    local, w, info = parallel.branch_global(local, w)
-    np.savez(os.path.join(out_dir, f"dmc{rank}.npz"), configs=local.configs, weights=w, energy=glob["energytotal"],
-             weight=glob["weight"], total=total, killed=info["Number of walkers killed"])
+    local, w, info = parallel.branch_global(local, w, block_avg=block)  # statistics ride on the weights all-gather
+    fused = info["block_avg"]
+    assert np.isclose(fused["energytotal"], glob["energytotal"], rtol=1e-14) and np.isclose(fused["weight"], glob["weight"], rtol=1e-14)
+    first = dict(configs=local.configs.copy(), weights=w.copy())
+    # second round on the returned container: the rank layout it carries replaces the counts all-reduce
+    assert getattr(local, "_rank_layout", None) is not None
+    w2 = w * (0.5 + np.random.RandomState(100 + rank).rand(len(w)))
+    local, w2b, _ = parallel.branch_global(local, w2, base_draw=0.37)
+    np.savez(os.path.join(out_dir, f"dmc{rank}.npz"), configs=first["configs"], weights=first["weights"],
+             energy=glob["energytotal"], weight=glob["weight"], total=total, killed=info["Number of walkers killed"],
+             w2=w2, configs2=local.configs, weights2=w2b)
     dist.destroy_process_group()
 
 
@@ -128,3 +136,8 @@ def test_two_rank_dmc_statistics_and_global_branching(tmp_path, nwalk):
     assert np.array_equal(got, serial.configs)
     assert np.allclose(np.concatenate([res[r]["weights"] for r in range(world)]), w)
     assert res[0]["killed"] == info["Number of walkers killed"]
+    # second round (cached rank layout, explicit comb offset)
+    w2 = np.concatenate([res[r]["w2"] for r in range(world)])
+    serial2, w2s, _ = dmc.branch(serial, w2.copy(), base_draw=0.37)
+    assert np.array_equal(np.concatenate([res[r]["configs2"] for r in range(world)], axis=0), serial2.configs)
+    assert np.allclose(np.concatenate([res[r]["weights2"] for r in range(world)]), w2s)
