@@ -149,6 +149,45 @@ __global__ void __launch_bounds__(640) k_mt_generate(GenState* g, uint32_t* __re
   }
 }
 
+// Jump-ahead: the state block that starts QMCB_MT_SEG_BLOCKS blocks after the block at `src` (raw words src[0..623],
+// followed in the buffer by the 32 blocks generated from it).  With g(x) = x^J mod phi(x), J = 624 SEG - 1 and phi the
+// characteristic polynomial of the generator (tools/mt_jump_poly.py -> mt_jump_poly.h), every raw word J positions
+// ahead is the XOR of the words of a 19937-word window selected by g:   w[t + J] = XOR_{g_i = 1} w[t + i],  t >= 1,
+// so dst[k] = w[1 + k + J], k = 0..623, needs src[1 .. 20560] only.  That lets several single-CTA generators produce
+// disjoint segments of the SAME stream concurrently: the sequential recurrence bounded the end-to-end rate.
+// One CTA per 16 output words, threads over the polynomial's coefficients, XOR tree through shared memory.
+constexpr int JUMP_OUT = 16, JUMP_THREADS = 256, JUMP_DEGREE = 19937;
+__global__ void __launch_bounds__(JUMP_THREADS) k_mt_jump(const uint32_t* __restrict__ src, const uint32_t* __restrict__ poly,
+                                                          uint32_t* __restrict__ dst, GenState* gnext) {
+  __shared__ uint32_t red[JUMP_THREADS][JUMP_OUT + 1];
+  const int k0 = blockIdx.x * JUMP_OUT;
+  uint32_t acc[JUMP_OUT];
+#pragma unroll
+  for (int o = 0; o < JUMP_OUT; ++o) acc[o] = 0u;
+  for (int i = threadIdx.x; i < JUMP_DEGREE; i += JUMP_THREADS) {
+    if ((__ldg(poly + (i >> 5)) >> (i & 31)) & 1u) {
+      const uint32_t* __restrict__ p = src + 1 + k0 + i;
+#pragma unroll
+      for (int o = 0; o < JUMP_OUT; ++o) acc[o] ^= __ldg(p + o);
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < JUMP_OUT; ++o) red[threadIdx.x][o] = acc[o];
+  __syncthreads();
+  for (int stride = JUMP_THREADS / 2; stride > 0; stride >>= 1) {
+    if ((int)threadIdx.x < stride) {
+#pragma unroll
+      for (int o = 0; o < JUMP_OUT; ++o) red[threadIdx.x][o] ^= red[threadIdx.x + stride][o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < JUMP_OUT && k0 + (int)threadIdx.x < 624) {
+    const uint32_t v = red[0][threadIdx.x];
+    dst[k0 + threadIdx.x] = v;
+    gnext->key[k0 + threadIdx.x] = v;
+  }
+}
+
 // numpy's random_double: (a >> 5, b >> 6) -> (a * 2^26 + b) / 2^53; the integer is below 2^53, so this is exact
 __device__ __forceinline__ double to_double(uint32_t a, uint32_t b) {
   const unsigned long long v = ((unsigned long long)(a >> 5) << 26) | (unsigned long long)(b >> 6);

@@ -14,6 +14,13 @@ struct DevRngProgram {
 struct DevRng {
   DBuf<devrng::State> st;
   DBuf<devrng::GenState> gen;
+  // segmented generation (k_mt_jump): per-segment generator states, their streams and events
+  static constexpr int NSEG_STREAMS = 8;
+  DBuf<devrng::GenState> gen_seg;
+  DBuf<uint32_t> d_poly;
+  cudaStream_t seg_stream[NSEG_STREAMS] = {};
+  std::vector<cudaEvent_t> ev_head, ev_done;
+  long long segmented_launches = 0;
   DBuf<uint32_t> W, F0, F1;
   long long cap_blocks = 0;   // capacity of W in 624-word state blocks
   long long gen_blocks = 0;   // blocks generated (block 0 = the state handed in / rebased onto)
@@ -39,6 +46,7 @@ static DevRng* devrng_of(qmcb_ctx* c) {
     cudaStreamCreateWithPriority(&r->gen_stream, cudaStreamNonBlocking, hi);
     cudaEventCreateWithFlags(&r->ev_gen, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&r->ev_plan, cudaEventDisableTiming);
+    for (int i = 0; i < DevRng::NSEG_STREAMS; ++i) cudaStreamCreateWithPriority(&r->seg_stream[i], cudaStreamNonBlocking, hi);
     c->devrng = r;
   }
   return static_cast<DevRng*>(c->devrng);
@@ -49,6 +57,15 @@ static void devrng_free(qmcb_ctx* c) {
   DevRng* r = static_cast<DevRng*>(c->devrng);
   if (r->gen_stream) cudaStreamSynchronize(r->gen_stream);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  for (int i = 0; i < DevRng::NSEG_STREAMS; ++i)
+    if (r->seg_stream[i]) {
+      cudaStreamSynchronize(r->seg_stream[i]);
+      cudaStreamDestroy(r->seg_stream[i]);
+    }
+  for (auto e : r->ev_head) cudaEventDestroy(e);
+  for (auto e : r->ev_done) cudaEventDestroy(e);
+  r->gen_seg.release();
+  r->d_poly.release();
   r->st.release();
   r->gen.release();
   r->W.release();
@@ -146,14 +163,64 @@ static int devrng_reserve(qmcb_ctx* c, DevRng* r, long long blocks) {
 }
 
 // generate + flag so that `blocks` state blocks exist; records ev_gen on the generator stream
+static void devrng_launch_generator(DevRng* r, devrng::GenState* g, long long first, int nb, cudaStream_t s) {
+  static const int mode = std::getenv("QMCB_MT_MODE") ? std::atoi(std::getenv("QMCB_MT_MODE")) : 1;
+  if (nb <= 0) return;
+  if (mode == 0)
+    devrng::k_mt_generate<0><<<1, 640, 0, s>>>(g, r->W.p, first, nb);
+  else
+    devrng::k_mt_generate<1><<<1, 640, 0, s>>>(g, r->W.p, first, nb);
+}
+
 static int devrng_generate(qmcb_ctx* c, DevRng* r, long long blocks) {
   if (blocks <= r->gen_blocks) return 0;
-  static const int mode = std::getenv("QMCB_MT_MODE") ? std::atoi(std::getenv("QMCB_MT_MODE")) : 1;
-  const int nb = (int)(blocks - r->gen_blocks);
-  if (mode == 0)
-    devrng::k_mt_generate<0><<<1, 640, 0, r->gen_stream>>>(r->gen.p, r->W.p, r->gen_blocks, nb);
-  else
-    devrng::k_mt_generate<1><<<1, 640, 0, r->gen_stream>>>(r->gen.p, r->W.p, r->gen_blocks, nb);
+  const long long nb = blocks - r->gen_blocks, g0 = r->gen_blocks;
+  constexpr long long SEG = QMCB_MT_SEG_BLOCKS, HEAD = 32;  // 33 blocks (the start block + 32) feed one jump
+  static const bool segmented = std::getenv("QMCB_MT_SEGMENTS") == nullptr || std::atoi(std::getenv("QMCB_MT_SEGMENTS")) != 0;
+  if (!segmented || nb < 2 * SEG) {
+    devrng_launch_generator(r, r->gen.p, g0, (int)nb, r->gen_stream);
+  } else {
+    // Segments of SEG blocks generated concurrently, one single-CTA generator each.  The start block of segment k
+    // is the jump (k_mt_jump) of the start block of segment k - 1, which needs that segment's first 32 blocks: every
+    // segment runs as head (32 blocks) + tail on its own stream, and the jump for the next one sits between them.
+    const int S = (int)((nb + SEG - 1) / SEG);
+    if (r->gen_seg.ensure((size_t)S)) return -1;
+    if (!r->d_poly.p) {
+      if (r->d_poly.ensure(QMCB_MT_POLY_WORDS)) return -1;
+      CK(cudaMemcpy(r->d_poly.p, qmcb_mt_jump_poly, sizeof(qmcb_mt_jump_poly), cudaMemcpyHostToDevice));
+    }
+    while ((int)r->ev_head.size() < S) {
+      cudaEvent_t a, b;
+      CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+      r->ev_head.push_back(a);
+      r->ev_done.push_back(b);
+    }
+    // the segment streams start behind everything the generator stream has been given so far (rebase, earlier blocks)
+    CK(cudaEventRecord(r->ev_done[0], r->gen_stream));
+    devrng_launch_generator(r, r->gen.p, g0, (int)HEAD, r->gen_stream);
+    CK(cudaEventRecord(r->ev_head[0], r->gen_stream));
+    devrng_launch_generator(r, r->gen.p, g0 + HEAD, (int)(SEG - HEAD), r->gen_stream);
+    for (int k = 1; k < S; ++k) {
+      cudaStream_t s = r->seg_stream[(k - 1) % DevRng::NSEG_STREAMS];
+      const long long len = std::min<long long>(SEG, nb - (long long)k * SEG), head = std::min<long long>(HEAD, len);
+      if (k == 1) CK(cudaStreamWaitEvent(s, r->ev_done[0], 0));
+      CK(cudaStreamWaitEvent(s, r->ev_head[k - 1], 0));
+      uint32_t* src = r->W.p + (size_t)(g0 - 1 + (long long)(k - 1) * SEG) * 624;
+      devrng::k_mt_jump<<<(624 + devrng::JUMP_OUT - 1) / devrng::JUMP_OUT, devrng::JUMP_THREADS, 0, s>>>(
+          src, r->d_poly.p, src + (size_t)SEG * 624, r->gen_seg.p + k);
+      devrng_launch_generator(r, r->gen_seg.p + k, g0 + (long long)k * SEG, (int)head, s);
+      if (k + 1 < S) CK(cudaEventRecord(r->ev_head[k], s));
+      devrng_launch_generator(r, r->gen_seg.p + k, g0 + (long long)k * SEG + head, (int)(len - head), s);
+      CK(cudaEventRecord(r->ev_done[k], s));
+      c->nlaunch += 3;
+    }
+    for (int k = 1; k < S; ++k) CK(cudaStreamWaitEvent(r->gen_stream, r->ev_done[k], 0));
+    // the generator state continues from the last block of the last segment
+    CK(cudaMemcpyAsync(r->gen.p, r->W.p + (size_t)(blocks - 1) * 624, 624 * 4, cudaMemcpyDeviceToDevice, r->gen_stream));
+    r->segmented_launches++;
+    c->nlaunch += 1;
+  }
   r->gen_blocks = blocks;
   const long long avail = blocks * 624;
   const long long g_hi = ((avail - 3) / 4) / 32 * 32;

@@ -14,6 +14,7 @@
 #undef QMCB_JASTROW3
 #include "kernels.cuh"
 #include "device_rng.cuh"
+#include "mt_jump_poly.h"
 
 namespace {
 

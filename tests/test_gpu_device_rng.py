@@ -128,6 +128,39 @@ def test_vmc_block_program_matches_host_generator(lib):
     _check(lib, ops, seed=7, predraw=17)
 
 
+def test_segmented_generation_with_jump_ahead(lib):
+    """Programs long enough for the generator to split the stream into concurrent segments (k_mt_jump: start blocks
+    from the jump-ahead polynomial x^J mod phi, tools/mt_jump_poly.py): a full C2 block (10 steps, ~8400 state blocks =
+    nine segments), twice in a row through the device-resident state, from a position inside a state block with a
+    cached Gaussian -- every value and the final np.random state equal numpy's."""
+    nsteps, ne, N, necp, sigma = 10, 8, 4096, 3, float(np.sqrt(0.5))
+    ops = []
+    for _ in range(nsteps):
+        for _ in range(ne):
+            ops += [(1, 3 * N, sigma), (0, N, 1.0)]
+        for _ in range(ne * necp):
+            ops += [(0, N, 1.0), (2, 4, 1.0)]
+    h = _ctx(lib)
+    try:
+        np.random.seed(11)
+        np.random.random(size=77)
+        np.random.normal(size=5)
+        _set_state_from_numpy(lib, h)
+        for _ in range(2):
+            dev, state = _run_program(lib, h, ops)
+            for i, (a, b) in enumerate(zip(dev, _numpy_program(ops))):
+                assert np.array_equal(a, b), f"op {i}: {np.sum(a != b)} of {a.size} values differ"
+            st = np.random.get_state()
+            assert np.array_equal(state[0], st[1]) and state[1:] == (st[2], st[3], st[4])
+    finally:
+        lib.qmcb_destroy(h)
+
+
+def test_one_huge_uniform_draw_across_many_segments(lib):
+    """A single draw of 3 million doubles (9600 state blocks): every word of every segment is consumed."""
+    _check(lib, [(0, 3_000_000, 1.0), (1, 9, 1.0)], seed=12, predraw=5)
+
+
 def test_public_vmc_device_generator_equals_host_generator(lib, monkeypatch):
     """pyqmc_b200.vmc: same accept counts, energies, walkers and final np.random state with either generator."""
     import pyqmc_b200 as pq
