@@ -49,6 +49,10 @@ struct Sys {
   const int* grp_det[2];  // [ndet]
   const double* grp_coef[2];  // [ndet] c_D in group order
   const int* grp_other[2];    // [ndet] map_other(D) in group order
+  // dense determinant-coefficient matrix (CAS-like expansions, nds[0] * nds[1] <= 65536, else null):
+  // dense[s][j * nds[s] + d] = sum of c_D over the determinants D with map_s(D) = d and map_other(D) = j, so that
+  // lanes over d read consecutive addresses in the W update (k_det_cache)
+  const double* dense[2];
   // ---- periodic boundary conditions (pbc == 0: open).  pbc is the minimal-image mode of
   // MinimalImageDistance (distance.py:97-110): 1 diagonal, 2 orthogonal, 3 general (27 shifts).
   int pbc;

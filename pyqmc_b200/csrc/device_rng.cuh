@@ -155,8 +155,8 @@ __global__ void __launch_bounds__(640) k_mt_generate(GenState* g, uint32_t* __re
 // ahead is the XOR of the words of a 19937-word window selected by g:   w[t + J] = XOR_{g_i = 1} w[t + i],  t >= 1,
 // so dst[k] = w[1 + k + J], k = 0..623, needs src[1 .. 20560] only.  That lets several single-CTA generators produce
 // disjoint segments of the SAME stream concurrently: the sequential recurrence bounded the end-to-end rate.
-// One CTA per 16 output words, threads over the polynomial's coefficients, XOR tree through shared memory.
-constexpr int JUMP_OUT = 16, JUMP_THREADS = 256, JUMP_DEGREE = 19937;
+// One CTA per 4 output words, threads over the polynomial's coefficients, XOR tree through shared memory.
+constexpr int JUMP_OUT = 4, JUMP_THREADS = 256, JUMP_DEGREE = 19937;
 __global__ void __launch_bounds__(JUMP_THREADS) k_mt_jump(const uint32_t* __restrict__ src, const uint32_t* __restrict__ poly,
                                                           uint32_t* __restrict__ dst, GenState* gnext) {
   __shared__ uint32_t red[JUMP_THREADS][JUMP_OUT + 1];

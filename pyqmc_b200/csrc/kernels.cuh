@@ -449,13 +449,9 @@ __global__ void __launch_bounds__(128) k_invert_warp(const Sys S, const State st
 // Multi-determinant caches for walker w:  ref_s = max_d log_s[d], dv_s[d] = sign*exp(log-ref),
 // W_s[d] = sum_{D: map_s(D)=d} c_D dv_other[map_other(D)]   (determinant_tools.py:74-88 with a
 // per-walker instead of a global reference exponent; the reference cancels in every ratio).
-__global__ void __launch_bounds__(128) k_det_cache(const Sys S, const State st, const uint8_t* mask, int spin) {
+__device__ __forceinline__ void det_cache_warp(const Sys& S, const State& st, int w, int lane, int spin) {
   // one warp per walker, lanes over unique spin determinants.  spin >= 0: only the determinants of
   // that spin changed (single-electron move): refresh ref / dv of that spin and W of the other one.
-  const int lane = threadIdx.x & 31;
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= st.N) return;
-  if (mask && !mask[w]) return;
   for (int s = 0; s < 2; ++s) {
     if (spin >= 0 && s != spin) continue;
     const int nds = S.nds[s];
@@ -473,6 +469,15 @@ __global__ void __launch_bounds__(128) k_det_cache(const Sys S, const State st, 
     if (spin >= 0 && s == spin) continue;  // W_s depends on dv of the OTHER spin only
     const int nds = S.nds[s], o = 1 - s, ndo = S.nds[o];
     const double* __restrict__ dvo = st.dv[o] + (size_t)w * ndo;
+    if (S.dense[s] != nullptr) {  // dense matrix-vector product, coalesced over d
+      const double* __restrict__ Cm = S.dense[s];
+      for (int d = lane; d < nds; d += 32) {
+        double acc = 0.0;
+        for (int j = 0; j < ndo; ++j) acc = fma(Cm[(size_t)j * nds + d], dvo[j], acc);
+        st.W[s][(size_t)w * nds + d] = acc;
+      }
+      continue;
+    }
     for (int d = lane; d < nds; d += 32) {
       double acc = 0.0;
       const int k1 = S.grp_off[s][d + 1];
@@ -480,6 +485,14 @@ __global__ void __launch_bounds__(128) k_det_cache(const Sys S, const State st, 
       st.W[s][(size_t)w * nds + d] = acc;
     }
   }
+}
+
+__global__ void __launch_bounds__(128) k_det_cache(const Sys S, const State st, const uint8_t* mask, int spin) {
+  const int lane = threadIdx.x & 31;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= st.N) return;
+  if (mask && !mask[w]) return;
+  det_cache_warp(S, st, w, lane, spin);
 }
 
 // wf.value(): sign and log of  [sum_D c_D D_up D_dn] * exp(U)
@@ -867,19 +880,11 @@ struct SmArgs {
 
 __device__ __forceinline__ double sgn(double x) { return x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : 0.0); }
 
-// one thread per matrix, matrix in registers (n <= 8)
+// Sherman-Morrison row replacement of one NN x NN matrix held in registers (n <= 8): v = the new row (orbital
+// values through the occupation list), e = the replaced row's index.  Returns the determinant ratio.
 template <int NN>
-__global__ void __launch_bounds__(128) k_sm_thread(const SmArgs a) {
-  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= a.nmat) return;
-  const long long w = m / a.nds;
-  const int d = (int)(m - w * a.nds);
-  if (a.mask && !a.mask[w]) return;
-  double* __restrict__ inv = a.inv + m * (NN * NN);
-  double A[NN][NN], v[NN], t[NN];
-  const double* __restrict__ vb = a.vec + w * a.vec_stride;
-#pragma unroll
-  for (int k = 0; k < NN; ++k) v[k] = a.occ ? vb[a.occ[d * NN + k]] : vb[d * NN + k];
+__device__ __forceinline__ double sm_thread_apply(double* __restrict__ inv, const double (&v)[NN], int e) {
+  double A[NN][NN], t[NN];
   if (NN % 2 == 0) {
     const double2* __restrict__ p = reinterpret_cast<const double2*>(inv);
 #pragma unroll
@@ -902,16 +907,16 @@ __global__ void __launch_bounds__(128) k_sm_thread(const SmArgs a) {
   double ratio = 0.0;
 #pragma unroll
   for (int j = 0; j < NN; ++j)
-    if (j == a.e) ratio = t[j];
+    if (j == e) ratio = t[j];
 #pragma unroll
   for (int k = 0; k < NN; ++k) {
     double ake = 0.0;
 #pragma unroll
     for (int j = 0; j < NN; ++j)
-      if (j == a.e) ake = A[k][j];
+      if (j == e) ake = A[k][j];
     const double col = ake / ratio;
 #pragma unroll
-    for (int j = 0; j < NN; ++j) A[k][j] = (j == a.e) ? col : fma(-col, t[j], A[k][j]);
+    for (int j = 0; j < NN; ++j) A[k][j] = (j == e) ? col : fma(-col, t[j], A[k][j]);
   }
   if (NN % 2 == 0) {
     double2* __restrict__ p = reinterpret_cast<double2*>(inv);
@@ -922,9 +927,51 @@ __global__ void __launch_bounds__(128) k_sm_thread(const SmArgs a) {
 #pragma unroll
     for (int i = 0; i < NN * NN; ++i) inv[i] = A[i / NN][i % NN];
   }
+  return ratio;
+}
+
+// one thread per matrix, matrix in registers (n <= 8)
+template <int NN>
+__global__ void __launch_bounds__(128) k_sm_thread(const SmArgs a) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= a.nmat) return;
+  const long long w = m / a.nds;
+  const int d = (int)(m - w * a.nds);
+  if (a.mask && !a.mask[w]) return;
+  double v[NN];
+  const double* __restrict__ vb = a.vec + w * a.vec_stride;
+#pragma unroll
+  for (int k = 0; k < NN; ++k) v[k] = a.occ ? vb[a.occ[d * NN + k]] : vb[d * NN + k];
+  const double ratio = sm_thread_apply<NN>(a.inv + m * (NN * NN), v, a.e);
   if (a.ratio) a.ratio[m] = ratio;
   if (a.dsign) a.dsign[m] *= sgn(ratio);
   if (a.dlog) a.dlog[m] += log(fabs(ratio));
+}
+
+// Multi-determinant update of one accepted move in ONE launch (slater.py:262-291 + the caches of
+// determinant_tools.py:74-88): one warp per walker, lanes over the unique determinants of the moved spin -- each
+// lane applies the register Sherman-Morrison update to its determinants -- then the same warp refreshes dv of that
+// spin and W of the other one (det_cache_warp).  Replaces k_sm_thread + k_det_cache for n <= 8.
+template <int NN>
+__global__ void __launch_bounds__(128) k_det_update(const Sys S, const State st, int s, int e, const uint8_t* mask) {
+  const int lane = threadIdx.x & 31;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= st.N) return;
+  if (mask && !mask[w]) return;
+  const int nds = S.nds[s];
+  const int* __restrict__ occ = S.iblob + S.o_occ[s];
+  const double* __restrict__ vb = st.saved_mo + (size_t)w * S.ldc[s];
+  for (int d = lane; d < nds; d += 32) {
+    const size_t m = (size_t)w * nds + d;
+    double v[NN];
+#pragma unroll
+    for (int k = 0; k < NN; ++k) v[k] = vb[occ[d * NN + k]];
+    const double ratio = sm_thread_apply<NN>(st.inv[s] + m * (NN * NN), v, e);
+    st.dsign[s][m] *= sgn(ratio);
+    st.dlog[s][m] += log(fabs(ratio));
+  }
+  __syncwarp();
+  det_cache_warp(S, st, w, lane, s);
 }
 
 // one warp per matrix, lane j owns column j (8 < n <= 32); rows are read/written coalesced and
@@ -1640,6 +1687,31 @@ __global__ void __launch_bounds__(128) k_kinetic(const Sys S, const State st, co
     const double* __restrict__ mc = st.mocache + ((size_t)w * S.ne + e) * 5 * ldmax;
     const int nds = S.nds[s];
     const int* __restrict__ occ = si + S.o_occ[s];
+    if (nds >= G) {
+      // multi-determinant expansions: lanes over the unique spin determinants, all five components per lane
+      // (the C3 expansion has 70 per spin; five busy lanes walking all of them made this the slowest energy kernel)
+      double num5[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, den = 0.0;
+      for (int d = lane; d < nds; d += G) {
+        const double* __restrict__ inv = st.inv[s] + ((size_t)w * nds + d) * n * n + eeff;
+        double r[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int k = 0; k < n; ++k) {
+          const double a = inv[k * n];
+          const int orb = occ[d * n + k];
+#pragma unroll
+          for (int c = 0; c < 5; ++c) r[c] = fma(mc[c * ldmax + orb], a, r[c]);
+        }
+        const double wgt = st.dv[s][(size_t)w * nds + d] * st.W[s][(size_t)w * nds + d];
+        den += wgt;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) num5[c] = fma(r[c], wgt, num5[c]);
+      }
+      den = group_sum<G>(den, gm);
+#pragma unroll
+      for (int c = 0; c < 5; ++c) num5[c] = group_sum<G>(num5[c], gm) / den;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) gs[i] = num5[1 + i] / num5[0];
+      laps = num5[4] / num5[0];
+    } else {
     double num = 0.0, den = 0.0;
     if (lane < 5) {
       for (int d = 0; d < nds; ++d) {
@@ -1661,6 +1733,7 @@ __global__ void __launch_bounds__(128) k_kinetic(const Sys S, const State st, co
 #pragma unroll
     for (int i = 0; i < 3; ++i) gs[i] = __shfl_sync(gm, num, 1 + i, G) / r0;
     laps = __shfl_sync(gm, num, 4, G) / r0;
+    }
   }
   double lapj = 0.0, cross = 0.0, gj[3] = {0.0, 0.0, 0.0};
   if (which & QMCB_JASTROW) {

@@ -130,7 +130,7 @@ struct qmcb_ctx {
   Sys S{};
   DBuf<double> d_dblob, d_detc, d_quad;
   DBuf<int> d_iblob, d_map[2], d_grp_off[2], d_grp_det[2], d_grp_other[2];
-  DBuf<double> d_grp_coef[2];
+  DBuf<double> d_grp_coef[2], d_dense[2];
   size_t smem_bytes = 0;
   int nmot = 0;  // 4 / 8: register fast path, 0: general path
   // ---- walker state
@@ -503,6 +503,15 @@ int build_tables(qmcb_ctx* c) {
       CK(cudaMemcpy(c->d_grp_other[s].p, gother.data(), gother.size() * 4, cudaMemcpyHostToDevice));
       S.grp_coef[s] = c->d_grp_coef[s].p;
       S.grp_other[s] = c->d_grp_other[s].p;
+      S.dense[s] = nullptr;
+      if (!cx && c->ndet > 1 && (long long)c->nds[0] * c->nds[1] <= 65536 && std::getenv("QMCB_NO_DENSE_DET") == nullptr) {
+        const int nd = c->nds[s], no = c->nds[1 - s];
+        std::vector<double> dm((size_t)nd * no, 0.0);
+        for (int D = 0; D < c->ndet; ++D) dm[(size_t)c->dmap[1 - s][D] * nd + c->dmap[s][D]] += c->detc[D];
+        if (c->d_dense[s].ensure(dm.size())) return -1;
+        CK(cudaMemcpy(c->d_dense[s].p, dm.data(), dm.size() * 8, cudaMemcpyHostToDevice));
+        S.dense[s] = c->d_dense[s].p;
+      }
       if (cx) {
         std::vector<double> gim(lst.size());
         for (size_t k = 0; k < lst.size(); ++k) gim[k] = c->detc_im[lst[k]];
@@ -947,6 +956,18 @@ int launch_update(qmcb_ctx* c, int which, int e, const uint8_t* d_mask, cudaStre
       c->nlaunch++;
       CK(cudaGetLastError());
     }
+  } else if ((which & 1) && c->have_slater && S.ndet > 1 && (e >= S.nup ? S.ndn : S.nup) >= 1 &&
+             (e >= S.nup ? S.ndn : S.nup) <= 8 && std::getenv("QMCB_NO_DET_UPDATE_FUSION") == nullptr) {
+    // multi-determinant, n <= 8: Sherman-Morrison of every spin determinant + the dv / W caches in one launch
+    const int s = e >= S.nup ? 1 : 0, n = s ? S.ndn : S.nup, ee = e - s * S.nup;
+    const unsigned grid = (unsigned)(((long long)c->N * 32 + 127) / 128);
+    switch (n) {
+#define DU_T(NN) case NN: k_det_update<NN><<<grid, 128, 0, stream>>>(S, c->st, s, ee, d_mask); break;
+      DU_T(1) DU_T(2) DU_T(3) DU_T(4) DU_T(5) DU_T(6) DU_T(7) DU_T(8)
+#undef DU_T
+    }
+    c->nlaunch++;
+    CK(cudaGetLastError());
   } else if ((which & 1) && c->have_slater) {
     const int s = e >= S.nup ? 1 : 0;
     SmArgs a{};
@@ -1250,6 +1271,7 @@ void qmcb_destroy(qmcb_ctx* c) {
     c->d_grp_off[s].release();
     c->d_grp_det[s].release();
     c->d_grp_coef[s].release();
+    c->d_dense[s].release();
     c->d_grp_other[s].release();
   }
   c->d_iblob.release();
