@@ -305,6 +305,11 @@ int qmcb_rng_phase_a(void *plan, uint32_t *key, int32_t *pos, int32_t *has_gauss
                      double *gauss, double *unif, double *ecp_u, double *ecp_rot, int nthreads);
 int qmcb_rng_phase_b(void *plan, int nthreads);
 
+/* Host helper (no device): the stochastic comb of the DMC branching step, `branch` (pyqmc/method/dmc.py:358-366) --
+ * picked = searchsorted(cumsum(weights), (offset * W + linspace(0, W, n, endpoint=False)) % W), W = sum of the
+ * weights -- in the reference's floating-point arithmetic, as one linear pass.  picked [n], *total = W. */
+int qmcb_comb_indices(int64_t n, const double *weights, double offset, int64_t *picked, double *total);
+
 /* The dense product of StochasticReconfiguration.avg on its own (stochastic_reconfiguration.py:110-113,
  * einsum "ij,ik->jk" of dp with weights * dp_regularized): C [P][P] = A^T B for host arrays A, B [N][P].
  * variant 0 = FP64-FMA tiles, 1 = DMMA (mma.sync m8n8k4 f64) with a split walker range, -1 = the default

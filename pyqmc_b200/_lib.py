@@ -73,6 +73,7 @@ SIGNATURES = {
                                     c_double_p, c_i64_p]),
     "qmcb_vmc_block_slot_begin": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_int, c_double_p, c_double_p, c_i64_p]),
     "qmcb_vmc_block_slot_end": (c_int, [c_void_p, c_int]),
+    "qmcb_comb_indices": (c_int, [c_i64, c_double_p, c_double, c_i64_p, c_double_p]),
     "qmcb_fp64_peak": (c_int, [c_int, c_double_p]),
     "qmcb_gemm_tn": (c_int, [c_int, c_i64, c_int, c_double_p, c_double_p, c_double_p, c_int, c_int, c_double_p]),
     "qmcb_orbitals_at_points": (c_int, [c_void_p, c_i64, c_double_p, c_int, c_double_p, c_double_p]),

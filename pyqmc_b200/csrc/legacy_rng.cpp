@@ -604,4 +604,40 @@ int qmcb_rng_program(uint32_t* key, int32_t* pos, int32_t* has_gauss, double* ca
   return 0;
 }
 
+// Stochastic comb of the DMC branching step (dmc.py:358-366) in the reference's arithmetic: ladder = cumsum(weights)
+// (sequential adds, as numpy), total = ladder[-1], teeth = (offset * total + linspace(0, total, n, endpoint=False)) %
+// total with linspace = i * (total / n) + 0.0, and picked = searchsorted(ladder, teeth) (side = left).  The teeth wrap
+// at most once (0 <= offset < 1), so x % total is x - total for x >= total (exact, like fmod) and both runs are ascending:
+// one two-pointer pass per run instead of n binary searches -- on 16384 walkers every rank of an 8-GPU run spent ~1 ms
+// per block in the numpy version.  picked[i] = the walker slot i of the new population copies.
+int qmcb_comb_indices(int64_t n, const double* weights, double offset, int64_t* picked, double* total_out) {
+  if (n <= 0) return -1;
+  std::vector<double> ladder((size_t)n);
+  double acc = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    acc += weights[i];
+    ladder[(size_t)i] = acc;
+  }
+  const double total = ladder[(size_t)n - 1];
+  const double step = total / (double)n;
+  const double shift = offset * total;
+  int64_t j = 0;
+  bool wrapped = false;
+  for (int64_t i = 0; i < n; ++i) {
+    const double x = shift + ((double)i * step + 0.0);
+    double tooth = x;
+    if (x >= total) {
+      tooth = std::fmod(x, total);
+      if (!wrapped) {  // second ascending run starts: restart the ladder pointer
+        wrapped = true;
+        j = 0;
+      }
+    }
+    while (j < n && ladder[(size_t)j] < tooth) ++j;
+    picked[i] = j;
+  }
+  if (total_out) *total_out = total;
+  return 0;
+}
+
 }  // extern "C"

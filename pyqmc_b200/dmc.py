@@ -340,6 +340,20 @@ def comb_indices(weights, offset):
     total weight and folded back into [0, W), select walkers through the cumulative weights.  Tooth ``i`` may
     land anywhere, so the result is NOT sorted: slot ``i`` of the new population is a copy of walker
     ``result[i]``.  Arithmetic as in ``branch`` (dmc.py:358-366), so equal draws give equal populations."""
+    import ctypes
+
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    if len(w) == 0 or not np.all(np.isfinite(w)) or np.any(w < 0):
+        return comb_indices_numpy(w, offset)
+    picked, total = np.empty(len(w), dtype=np.int64), ctypes.c_double(0.0)
+    _lib.check(_lib.load().qmcb_comb_indices(len(w), _lib.dptr(w), float(offset), picked.ctypes.data_as(_lib.c_i64_p),
+                                             ctypes.byref(total)))
+    return picked, total.value
+
+
+def comb_indices_numpy(weights, offset):
+    """The same comb in numpy, written as the reference writes it: the definition ``qmcb_comb_indices`` (one linear pass
+    in native code, csrc/legacy_rng.cpp) is checked against (tests/test_parallel_gloo.py)."""
     ladder = np.cumsum(weights)
     total = ladder[-1]
     teeth = (offset * total + np.linspace(0, total, len(weights), endpoint=False)) % total

@@ -221,10 +221,10 @@ def branch_global(local, weights, group=None, base_draw=None, block_avg=None):
     local.configs = np.ascontiguousarray(out[:, :ncfg]).reshape((len(out),) + local.configs.shape[1:])
     if len(fields) > 1:
         local.wrap = np.ascontiguousarray(out[:, ncfg:]).reshape(local.configs.shape)
-    survivors, copies = np.unique(picked, return_counts=True)
+    copies = np.bincount(picked, minlength=len(picked))
     new_w = np.full(len(out), total / len(picked))
     local._rank_layout = share
-    info = {"max branches": np.max(copies), "Number of walkers killed": len(picked) - len(survivors)}
+    info = {"max branches": np.max(copies), "Number of walkers killed": int(np.count_nonzero(copies == 0))}
     if combined is not None:
         info["block_avg"] = combined
     return local, new_w, info

@@ -141,3 +141,20 @@ def test_two_rank_dmc_statistics_and_global_branching(tmp_path, nwalk):
     serial2, w2s, _ = dmc.branch(serial, w2.copy(), base_draw=0.37)
     assert np.array_equal(np.concatenate([res[r]["configs2"] for r in range(world)], axis=0), serial2.configs)
     assert np.allclose(np.concatenate([res[r]["weights2"] for r in range(world)]), w2s)
+
+
+def test_native_comb_equals_the_numpy_definition():
+    """qmcb_comb_indices (one linear pass, native) == cumsum / linspace / mod / searchsorted as the reference's branch
+    writes them (dmc.py:358-366): every offset class (no wrap, wrap, offset 0), equal weights (ties in the ladder),
+    zero weights, one walker."""
+    from pyqmc_b200 import dmc
+
+    rng = np.random.RandomState(3)
+    cases = [(rng.rand(n) * (1 + 3 * (i % 3)), rng.rand()) for i, n in enumerate([1, 2, 7, 64, 1000, 4096, 16384])]
+    cases += [(np.ones(100), 0.0), (np.ones(100), 0.5), (np.ones(64), 0.999999), (np.r_[0.0, 1.0, 0.0, 2.0, 0.0], 0.3),
+              (rng.rand(513), 0.0)]
+    for w, off in cases:
+        got, tot = dmc.comb_indices(w, off)
+        ref, rtot = dmc.comb_indices_numpy(w, off)
+        assert tot == rtot
+        assert np.array_equal(got, ref), (len(w), off)
