@@ -1,7 +1,7 @@
 """Opcode histogram per kernel of the shipped library: python profiles/sass_summary.py > profiles/r2_sass_summary.txt
 (cuobjdump -sass pyqmc_b200/libqmcb200.so).  Shows what the kernels are made of: FP64 (DFMA/DADD/DMUL/MUFU.RCP64H),
-bulk-async table staging (UBLKCP + SYNCS = cp.async.bulk + mbarrier), no tensor-core opcodes (UTCMMA / HMMA / DMMA:
-FP64 has no tcgen05 path and nothing in this path is a dense GEMM worth one)."""
+bulk-async table staging (UBLKCP + SYNCS = cp.async.bulk + mbarrier), and one tensor-core kernel: DMMA in
+k_gemm_tn_dmma, the SR overlap matrix (FP64 has no tcgen05 path, so no UTCMMA)."""
 import collections
 import os
 import re
