@@ -11,6 +11,7 @@ from .wf import JastrowSpin, MultiplyWF, Slater, ThreeBodyJastrow  # noqa: F401
 from .wftools import generate_jastrow, generate_jastrow3, generate_slater, generate_wf  # noqa: F401
 from .accumulators import EnergyAccumulator  # noqa: F401
 from .obdm import OBDMAccumulator, normalize_obdm  # noqa: F401
+from .tbdm import TBDMAccumulator, normalize_tbdm  # noqa: F401
 from .mc import initial_guess, vmc  # noqa: F401
 from .dmc import branch, dmc_propagate, rundmc  # noqa: F401
 from .sr import LinearTransform, ParameterMap, PGradTransform, StochasticReconfiguration, gradient_generator  # noqa: F401
@@ -19,5 +20,5 @@ __all__ = [
     "Walkers", "ElectronView", "OpenConfigs", "OpenElectron", "PeriodicConfigs", "PeriodicElectron", "CutoffCuspFunction",
     "PolyPadeFunction", "JastrowSpin", "MultiplyWF", "Slater", "ThreeBodyJastrow", "generate_jastrow", "generate_jastrow3",
     "generate_slater", "generate_wf", "EnergyAccumulator", "initial_guess", "vmc", "rundmc", "dmc_propagate", "branch",
-    "OBDMAccumulator", "normalize_obdm", "ParameterMap", "LinearTransform", "PGradTransform", "StochasticReconfiguration", "gradient_generator",
+    "OBDMAccumulator", "normalize_obdm", "TBDMAccumulator", "normalize_tbdm", "ParameterMap", "LinearTransform", "PGradTransform", "StochasticReconfiguration", "gradient_generator",
 ]

@@ -12,6 +12,7 @@ path: use the reference's own drivers on these objects for
 """
 from .accumulators import EnergyAccumulator  # noqa: F401
 from .obdm import OBDMAccumulator  # noqa: F401
+from .tbdm import TBDMAccumulator  # noqa: F401
 from .coord import OpenConfigs, PeriodicConfigs  # noqa: F401
 from .dmc import rundmc  # noqa: F401
 from .mc import initial_guess, vmc  # noqa: F401

@@ -240,9 +240,42 @@ def generate_obdm(name="h2o"):
     return out
 
 
+def generate_tbdm(name="h2o"):
+    """TBDMAccumulator of the reference (tbdm.py:26-282; in-tree numba orbital evaluator) on the walkers `configs1`
+    of the main golden file, sectors up-down (full index list) and up-up (a chosen list) -> tests/golden/tbdm_<name>.npz."""
+    import pyqmc.configurations.coord as coord
+    import pyqmc.wf.orbitals
+    from pyqmc.observables.tbdm import TBDMAccumulator
+
+    mol, wf = build_reference(name)
+    mol.cart = False
+    _, mf, _ = helpers.make_system(name)
+    data = dict(np.load(os.path.join(HERE, f"{name}.npz")))
+    configs = coord.OpenConfigs(data["configs1"].copy())
+    wf.recompute(configs)
+    cu = np.ascontiguousarray(np.asarray(mf.mo_coeff[0])[:, :3])
+    cd = np.ascontiguousarray(np.asarray(mf.mo_coeff[1])[:, 1:5])
+    out = {"ijkl_uu": np.array([[0, 0, 0, 0], [0, 1, 1, 0], [2, 1, 0, 2], [1, 1, 2, 2], [2, 0, 1, 1]])}
+    for tag, spin, ijkl in (("ud", (0, 1), None), ("uu", (0, 0), out["ijkl_uu"])):
+        orb = [cu, cd] if tag == "ud" else [cu, cu]
+        acc = TBDMAccumulator(mol, orb, spin, nsweeps=2, tstep=0.5, warmup=7, ijkl=ijkl)
+        acc.orbitals = pyqmc.wf.orbitals.MoleculeOrbitalEvaluator(mol, orb, evaluate_orbitals_with="numba")
+        np.random.seed(71)
+        first = acc(configs, wf)
+        second = acc.avg(configs, wf)  # continues both auxiliary walks
+        for k in ("value", "norm_a", "norm_b"):
+            out[f"{tag}_{k}"], out[f"{tag}_avg_{k}"] = first[k], second[k]
+    return out
+
+
 def main():
     warnings.filterwarnings("ignore")
     refload.load()
+    if len(sys.argv) > 1 and sys.argv[1] == "tbdm":
+        path = os.path.join(HERE, "tbdm_h2o.npz")
+        np.savez_compressed(path, **generate_tbdm("h2o"))
+        print("wrote", path)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "obdm":
         path = os.path.join(HERE, "obdm_h2o.npz")
         np.savez_compressed(path, **generate_obdm("h2o"))
