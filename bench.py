@@ -80,7 +80,8 @@ def workload_config(workload, walkers_per_gpu, world):
         cfg["l2"] = "walker state (2 KB/walker) is L2-resident by design; no flush between blocks"
         cfg["parallelism"] = f"walker-sharded x{world}, one NCCL allreduce of the weighted sums + global branching per block"
     else:
-        cfg["l2"] = f"256 MiB buffer written between timed blocks of {SPB} steps (L2 flush); one library call per block"
+        cfg["l2"] = (f"256 MiB buffer written between timed blocks of {SPB} steps (L2 flush); one library call per block, "
+                     "preceded by the per-block wf.recompute of the resident walkers (inside the timed region)")
         cfg["parallelism"] = f"walker-sharded x{world}, one NCCL allreduce of the energy sums per block of {SPB} steps"
     return cfg
 
@@ -446,7 +447,10 @@ def gpu_arm(args):
         return [(s, min(SPB, hi - s)) for s in range(lo, hi, SPB)]
 
     def run_block(s, n):
-        """n consecutive VMC steps in ONE library call, as the public driver issues them (a block)."""
+        """n consecutive VMC steps in ONE library call, as the public driver issues them (a block); a full block
+        starts, as every block of the reference's driver does (mc.py:110), with wf.recompute of the resident walkers."""
+        if n == SPB and lib.qmcb_recompute_resident_on(ctx.h, wf._which, vp(stream)) != 0:
+            raise RuntimeError(lib.qmcb_last_error().decode())
         rc = lib.qmcb_vmc_block_device(ctx.h, n, TSTEP, 1, vp(d_gauss[s].data_ptr()), vp(d_unif[s].data_ptr()),
                                        vp(d_u[s].data_ptr()), vp(d_rot[s].data_ptr()), None, vp(d_energy.data_ptr()),
                                        vp(d_esum[s].data_ptr()), vp(d_nacc[s].data_ptr()), vp(stream))

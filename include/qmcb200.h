@@ -153,6 +153,8 @@ int qmcb_recompute_pbc(qmcb_ctx *ctx, int which, int nconf, const double *config
  * same kernels as qmcb_recompute without the upload and the value read-back; asynchronous on the
  * context's stream.  Valid only while nothing else changed the walker state. */
 int qmcb_recompute_resident(qmcb_ctx *ctx, int which);
+/* the same, enqueued on a caller-supplied cudaStream_t (NULL = the context's stream) */
+int qmcb_recompute_resident_on(qmcb_ctx *ctx, int which, void *stream);
 
 /* ---- wave-function protocol ---------------------------------------------------------- */
 

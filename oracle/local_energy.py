@@ -219,7 +219,7 @@ class EnergyOracle:
             return {"ratio": np.ones((N, 0)), "weight": np.zeros((N, 0))}
         ratios, weights, positions = [], [], []
         for i, ch in self.ecp_atoms:
-            d = ecp_electron_atom(ch, self.atoms[i], configs, wf, e, self.threshold, self.naip)
+            d = ecp_electron_atom(ch, self.atoms[i], configs, wf, e, self.threshold, None)  # accumulators.py:80-81: no naip
             npts = d["ratio"].shape[1]
             w = np.zeros((N, npts))
             r = np.ones((N, npts), dtype=d["ratio"].dtype)

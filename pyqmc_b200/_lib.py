@@ -51,6 +51,7 @@ SIGNATURES = {
     "qmcb_recompute_pbc": (c_int, [c_void_p, c_int, c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     "qmcb_recompute": (c_int, [c_void_p, c_int, c_int, c_double_p, c_double_p, c_double_p]),
     "qmcb_recompute_resident": (c_int, [c_void_p, c_int]),
+    "qmcb_recompute_resident_on": (c_int, [c_void_p, c_int, c_void_p]),
     "qmcb_value": (c_int, [c_void_p, c_int, c_double_p, c_double_p]),
     "qmcb_gradient": (c_int, [c_void_p, c_int, c_int, c_double_p, c_double_p]),
     "qmcb_gradient_value": (c_int, [c_void_p, c_int, c_int, c_double_p, c_double_p, c_double_p, c_i64_p]),
@@ -157,25 +158,35 @@ def i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
-class PinnedArray:
-    """numpy view of a page-locked host buffer (cudaMallocHost) owned by this object."""
+class _PinnedBlock:
+    """Owner of one cudaMallocHost allocation: freed when the last numpy view of it is gone."""
 
-    def __init__(self, shape, dtype=np.float64):
-        lib = load()
-        self.shape = tuple(int(x) for x in shape)
-        self.dtype = np.dtype(dtype)
-        nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+    def __init__(self, nbytes):
         p = c_void_p()
-        check(lib.qmcb_pinned_alloc(max(nbytes, 1), ctypes.byref(p)))
-        self._ptr = p
-        buf = (ctypes.c_uint8 * max(nbytes, 1)).from_address(p.value)
-        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape, dtype=np.int64))).reshape(self.shape)
+        check(load().qmcb_pinned_alloc(max(nbytes, 1), ctypes.byref(p)))
+        self.ptr = p
 
     def __del__(self):
         try:
-            if self._ptr:
-                self.array = None
-                load().qmcb_pinned_free(self._ptr)
-                self._ptr = None
+            if self.ptr:
+                load().qmcb_pinned_free(self.ptr)
+                self.ptr = None
         except Exception:
             pass
+
+
+class PinnedArray:
+    """numpy view of a page-locked host buffer (cudaMallocHost).  The allocation belongs to the VIEW chain, not to
+    this object: ``array.base`` is a ctypes buffer that references the owning block, so any array (or slice of it)
+    handed out -- to a prefetch thread, a caller-held variates dictionary -- keeps the memory alive after the
+    buffer set that created it was replaced."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.shape = tuple(int(x) for x in shape)
+        self.dtype = np.dtype(dtype)
+        count = int(np.prod(self.shape, dtype=np.int64))
+        nbytes = count * self.dtype.itemsize
+        block = _PinnedBlock(nbytes)
+        buf = (ctypes.c_uint8 * max(nbytes, 1)).from_address(block.ptr.value)
+        buf._pinned_block = block  # ndarray.base -> buf -> block
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=count).reshape(self.shape)

@@ -76,6 +76,9 @@ class EnergyAccumulator:
         self.mol, self.threshold, self.naip = mol, threshold, naip
         self._serial = next(_SERIAL)
         self._ecp = flatten_ecp(mol, naip)
+        # compute_tmoves is called without naip by the reference's nonlocal_tmoves (accumulators.py:80-81): T-move tables
+        # always use the default quadrature sizes (6 / 12 points), whatever the energy evaluation uses
+        self._ecp_tmoves = self._ecp if naip is None else flatten_ecp(mol, None)
         self.necp = len(self._ecp["ecp_atom"])
         self._ewald = None
         if hasattr(mol, "a"):  # accumulators.py:52-55: Ewald replaces the open-boundary Coulomb sums
@@ -83,13 +86,14 @@ class EnergyAccumulator:
 
             self._ewald = pbc.ewald_tables(mol, **kwargs)
 
-    def _attach(self, wf):
+    def _attach(self, wf, tmoves=False):
         ctx = _device_context(wf)
         if ctx is None or ctx.nconf == 0:
             raise RuntimeError("wf.recompute(configs) must be called before the energy accumulator")
-        key = (self._serial, self.threshold, self.naip)
+        tables = self._ecp_tmoves if tmoves else self._ecp
+        key = (self._serial, self.threshold, self.naip, tables is self._ecp)
         if ctx.ecp_key != key:
-            t = self._ecp
+            t = tables
             _lib.check(ctx.lib.qmcb_set_ecp(ctx.h, self.necp, _lib.iptr(t["ecp_atom"]), _lib.iptr(t["chan_off"]),
                                             _lib.iptr(t["term_off"]), _lib.iptr(t["power"]), _lib.dptr(t["alpha"]),
                                             _lib.dptr(t["coef"]), _lib.iptr(t["naip"]), _lib.dptr(t["quad"]),
@@ -136,7 +140,7 @@ class EnergyAccumulator:
         """T-move candidates of electron e (``compute_tmoves``, eval_ecp.py:43-80): ratio (N, M),
         weight (N, M) and the candidate positions (N, M, 3), M = sum of the quadrature sizes of the
         ECP atoms.  Random variates as in the reference: per ECP atom ``random(N)`` then a rotation."""
-        ctx = self._attach(wf)
+        ctx = self._attach(wf, tmoves=True)
         nconf = configs.configs.shape[0]
         if self.necp == 0:
             return {"ratio": np.ones((nconf, 0)), "weight": np.zeros((nconf, 0))}
@@ -145,7 +149,7 @@ class EnergyAccumulator:
         for a in range(self.necp):
             u[a] = np.random.random(size=nconf)
             rot[a] = scipy.spatial.transform.Rotation.random().as_matrix()
-        M = int(np.sum(self._ecp["naip"]))
+        M = int(np.sum(self._ecp_tmoves["naip"]))
         ratio = np.empty((nconf, M), dtype=complex if ctx.cplx else float)
         weight, epos = np.empty((nconf, M)), np.empty((nconf, M, 3))
         _lib.check(ctx.lib.qmcb_tmoves(ctx.h, int(e), float(tau), _lib.dptr(u), _lib.dptr(rot), _lib.dptr(ratio),

@@ -1708,6 +1708,16 @@ int qmcb_recompute_resident(qmcb_ctx* c, int which) {
   return recompute_from_resident(c, which, (int)c->N);
 }
 
+// the same on a caller-supplied stream (bench.py times whole blocks -- recompute + steps -- with events on its own stream)
+int qmcb_recompute_resident_on(qmcb_ctx* c, int which, void* stream_) {
+  if (!stream_) return qmcb_recompute_resident(c, which);
+  cudaStream_t keep = c->stream;
+  c->stream = (cudaStream_t)stream_;
+  const int rc = qmcb_recompute_resident(c, which);
+  c->stream = keep;
+  return rc;
+}
+
 int qmcb_value(qmcb_ctx* c, int which, double* sign, double* logval) {
   Guard g(c);
   if (which_ok(c, which)) return -1;

@@ -32,6 +32,10 @@ def _device_dmc_path(wf, accumulators, ekey):
         return False
     if len(accumulators) != 1 or not isinstance(accumulators.get(ekey[0]), EnergyAccumulator) or ekey[1] != "total":
         return False
+    if accumulators[ekey[0]].naip is not None:
+        # the fused block uses ONE quadrature table for the energy and the T-moves; the reference's T-moves keep the
+        # default sizes when naip is passed (accumulators.py:80-81): that combination runs through the protocol calls
+        return False
     which = getattr(wf, "_which", 0)
     if which & ~(SLATER | JASTROW) or not (which & SLATER) or wf.dtype == complex:
         return False

@@ -221,3 +221,34 @@ def test_resident_recompute_is_dropped_after_protocol_calls(lib, monkeypatch):
         if "time" not in k:
             assert np.array_equal(a[0][k], b[0][k]), k
     assert np.array_equal(a[1], b[1])
+
+
+def test_tmove_tables_keep_the_default_quadrature_when_naip_is_passed(lib):
+    """EnergyAccumulator(naip=12): the energy uses 12 points per ECP atom, the T-move tables the default 6 / 12
+    (the reference's nonlocal_tmoves calls compute_tmoves without naip, accumulators.py:80-81)."""
+    import pyqmc_b200 as pq
+    from oracle.local_energy import EnergyOracle
+
+    mol, mf, wf, orc = helpers.make_pair("h2o", seed=1)
+    np.random.seed(5)
+    configs = pq.initial_guess(mol, 9)
+    oc = helpers.to_oracle_walkers(configs)
+    wf.recompute(configs)
+    orc.recompute(oc)
+    acc, oacc = pq.EnergyAccumulator(mol, naip=12), EnergyOracle(mol, naip=12)
+    np.random.seed(6)
+    en = acc(configs, wf)
+    np.random.seed(6)
+    oen = oacc(oc, orc)
+    assert helpers.relerr(en["ecp"], oen["ecp"]) < 1e-10
+    np.random.seed(7)
+    tm = acc.nonlocal_tmoves(configs, wf, 2, 0.02)
+    np.random.seed(7)
+    otm = oacc.nonlocal_tmoves(oc, orc, 2, 0.02)
+    assert tm["ratio"].shape == otm["ratio"].shape and tm["ratio"].shape[1] < 3 * 12
+    assert helpers.relerr(tm["ratio"], otm["ratio"]) < 1e-10
+    assert helpers.relerr(tm["weight"], otm["weight"]) < 1e-10
+    np.random.seed(8)
+    en2 = acc(configs, wf)  # back to the energy tables
+    np.random.seed(8)
+    assert helpers.relerr(en2["ecp"], oacc(oc, orc)["ecp"]) < 1e-10
