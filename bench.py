@@ -58,9 +58,9 @@ WORKLOADS["c5"] = dict(
     metric="walker-steps/sec (DMC with T-moves, H2O cc-pVTZ SJ, tstep 0.02); Sherman-Morrison HBM GB/s vs roofline",
     text="H2O ccECP-cc-pVTZ-shaped Slater-Jastrow DMC (synthetic basis/MOs), tstep 0.02, 5 steps per block, T-moves, "
          "branching every block, 2048 walkers/GPU")
-# DRAM bytes per launch of k_sm_warp<32> on 131072 matrices from the committed ncu --set full capture
-# (profiles/r1_ncu_k_sm_warp32.txt: dram__bytes_read.sum + dram__bytes_write.sum)
-SM32_TRAFFIC_BYTES = 2.12e9
+# DRAM bytes per launch of k_sm_tma32 on 131072 matrices from the committed ncu --set full capture
+# (profiles/r2_ncu_k_sm_tma32.txt: dram__bytes_read.sum 1.1075 GB + dram__bytes_write.sum 1.0209 GB)
+SM32_TRAFFIC_BYTES = 2.128e9
 # FP64 flop of one C2 step at 4096 walkers from the committed ncu capture (profiles/r2_ncu_c2_step_raw.csv):
 # (2 DFMA + DADD + DMUL) thread instructions per cycle x elapsed cycles, summed over the four step kernels
 SWEEP_STEP_FLOP = 6.49e8
@@ -581,9 +581,9 @@ def gpu_arm(args):
                 "e2e_fill_included": e2e, "e2e_steady": e2e_steady,
                 "steady_definition": f"({nb_long} - {nb_short}) blocks / (t[{nb_long} blocks] - t[{nb_short} blocks])"},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "k_sm_warp<32>: Sherman-Morrison row update, n=32 (C4 shape), 131072 matrices",
+        "roofline": {"kernel": "k_sm_tma32: Sherman-Morrison row update, n=32 (C4 shape), 131072 matrices, staged by cp.async.bulk",
                      "bound": "hbm", "achieved": g32, "peak": peak, "unit": "GB/s", "frac": g32 / peak,
-                     "traffic": SM32_TRAFFIC_BYTES, "traffic_source": "profiles/r1_ncu_k_sm_warp32.txt (ncu --set full, same launch shape)",
+                     "traffic": SM32_TRAFFIC_BYTES, "traffic_source": "profiles/r2_ncu_k_sm_tma32.txt (ncu --set full, same launch shape)",
                      "peak_source": peak_src, "launch_ms": 1e3 * t32, "algorithmic_bytes": b32},
         # the whole VMC step against the same HBM roof (~27.5 KB of algorithmic traffic per
         # walker-step -- 15 KB sweep + ~10 KB energy accumulator); the step is FP64-latency bound, not HBM bound

@@ -998,6 +998,99 @@ __global__ void __launch_bounds__(256) k_sm_warp(const SmArgs a) {
   }
 }
 
+// n = 32 with the matrices staged by the bulk-copy (TMA) engine: every warp owns two 8 KB shared-memory slots; one
+// elected lane issues cp.async.bulk global -> shared for the NEXT matrix (mbarrier complete_tx) while the warp updates
+// the current one in place in shared memory (lane j = column j, conflict-free rows), then hands the slot back to the
+// engine with one cp.async.bulk shared -> global.  No matrix element passes through a register file on its way in or
+// out, so 12 warps per SM keep 24 matrices (192 KB) in flight instead of the register-limited 7 warps of k_sm_warp<32>.
+// Same arithmetic and operation order as sm_warp_apply.  Persistent grid: warps stride over the matrices.
+#define QMCB_SM_TMA_WARPS 4
+__global__ void __launch_bounds__(QMCB_SM_TMA_WARPS * 32) k_sm_tma32(const SmArgs a) {
+  constexpr int N = 32, BYTES = N * N * 8;
+  extern __shared__ __align__(128) unsigned char qmcb_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* slot0 = reinterpret_cast<double*>(qmcb_smem) + (size_t)wib * 2 * N * N;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(qmcb_smem + (size_t)QMCB_SM_TMA_WARPS * 2 * BYTES) + wib * 2;
+  const long long nwarps = (long long)gridDim.x * QMCB_SM_TMA_WARPS;
+  const long long first = (long long)blockIdx.x * QMCB_SM_TMA_WARPS + wib;
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bars)), "r"(1));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bars + 1)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  auto active = [&](long long m) { return m < a.nmat && !(a.mask && !a.mask[m / a.nds]); };
+  auto issue_load = [&](long long m, int s) {  // lane 0 only
+    const uint32_t mb = smem_u32(bars + s);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(slot0 + (size_t)s * N * N)),
+                 "l"(a.inv + m * (long long)(N * N)), "r"(BYTES), "r"(mb)
+                 : "memory");
+  };
+  // next matrix this warp really updates, at or after m
+  auto next_active = [&](long long m) {
+    while (m < a.nmat && !active(m)) m += nwarps;
+    return m;
+  };
+  long long cur = next_active(first);
+  unsigned phase[2] = {0u, 0u};
+  int s = 0;
+  if (lane == 0 && cur < a.nmat) issue_load(cur, 0);
+  while (cur < a.nmat) {
+    const long long nxt = next_active(cur + nwarps);
+    if (lane == 0 && nxt < a.nmat) {
+      // the other slot was handed to the engine one iteration ago: wait until it has been READ before refilling it
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      issue_load(nxt, s ^ 1);
+    }
+    const long long w = cur / a.nds;
+    const int d = (int)(cur - w * a.nds);
+    const double* __restrict__ vb = a.vec + w * a.vec_stride;
+    const double vk = a.occ ? vb[a.occ[d * N + lane]] : vb[(long long)d * N + lane];
+    {  // wait for this slot's bytes
+      const uint32_t mb = smem_u32(bars + s);
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(mb), "r"(phase[s])
+            : "memory");
+      }
+      phase[s] ^= 1u;
+    }
+    double* __restrict__ A = slot0 + (size_t)s * N * N;
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) t = fma(__shfl_sync(0xffffffffu, vk, k), A[k * N + lane], t);
+    const double ratio = __shfl_sync(0xffffffffu, t, a.e);
+    const double col = A[lane * N + a.e] / ratio;  // lane k: inv[k][e] / ratio
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const double ck = __shfl_sync(0xffffffffu, col, k);
+      A[k * N + lane] = (lane == a.e) ? ck : fma(-ck, t, A[k * N + lane]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the copy engine
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.inv + cur * (long long)(N * N)),
+                   "r"(smem_u32(A)), "r"(BYTES)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      if (a.ratio) a.ratio[cur] = ratio;
+      if (a.dsign) a.dsign[cur] *= sgn(ratio);
+      if (a.dlog) a.dlog[cur] += log(fabs(ratio));
+    }
+    cur = nxt;
+    s ^= 1;
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // shared memory must outlive the last stores
+}
+
 // =========================================================================================
 // Device-resident VMC move of electron e (mc.py:115-137): drift at the old position, proposal,
 // drift + ratio at the new position, Metropolis test.  Saves MO row / new position for the

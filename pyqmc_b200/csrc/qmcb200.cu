@@ -669,6 +669,13 @@ int launch_sm(qmcb_ctx* c, const SmArgs& a, cudaStream_t stream, int64_t* nlaunc
     switch (a.n) {
       SM_T(1) SM_T(2) SM_T(3) SM_T(4) SM_T(5) SM_T(6) SM_T(7) SM_T(8)
     }
+  } else if (a.n == 32 && a.nmat >= 148LL * 12 && (reinterpret_cast<uintptr_t>(a.inv) & 15) == 0 &&
+             std::getenv("QMCB_SM_NO_TMA") == nullptr) {
+    // large batches of 32 x 32 matrices: bulk-copy (TMA) staged kernel, three CTAs of four warps per SM
+    const size_t smem = (size_t)QMCB_SM_TMA_WARPS * 2 * 32 * 32 * 8 + QMCB_SM_TMA_WARPS * 2 * 8;
+    if (prep_kernel(k_sm_tma32, smem)) return -1;
+    const long long want = (a.nmat + QMCB_SM_TMA_WARPS - 1) / QMCB_SM_TMA_WARPS;
+    k_sm_tma32<<<(unsigned)std::min<long long>(want, 148LL * 3), QMCB_SM_TMA_WARPS * 32, smem, stream>>>(a);
   } else if (a.n <= 32) {
     const int block = 256;
     const long long grid = (a.nmat * 32 + block - 1) / block;

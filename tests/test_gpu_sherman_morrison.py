@@ -57,3 +57,31 @@ def test_rejects_bad_arguments(lib):
     r = np.zeros(1)
     assert lib.qmcb_sm_update(40, 0, 1, _lib.dptr(a), _lib.dptr(v), None, _lib.dptr(r)) != 0
     assert b"n <= 32" in lib.qmcb_last_error()
+
+
+@pytest.mark.parametrize("use_mask", [False, True])
+def test_bulk_copy_staged_kernel_for_large_batches_of_32x32(lib, use_mask, monkeypatch):
+    """Batches of >= 1776 matrices with n = 32 run k_sm_tma32 (matrices staged in shared memory by cp.async.bulk, updated
+    in place, written back by cp.async.bulk): same answers as numpy and -- bit for bit -- as the register kernel
+    k_sm_warp<32> (QMCB_SM_NO_TMA=1), with masked-out matrices untouched."""
+    n, nmat, e = 32, 4099, 13
+    rng = np.random.RandomState(5)
+    matrix = construct_mat(rng, nmat, n)
+    inv = np.linalg.inv(matrix)
+    vec = np.ascontiguousarray(construct_vec(rng, matrix, e))
+    mask = (rng.rand(nmat) > 0.4).astype(np.uint8) if use_mask else None
+    out = {}
+    for variant in ("tma", "registers"):
+        if variant == "registers":
+            monkeypatch.setenv("QMCB_SM_NO_TMA", "1")
+        work, ratio = np.ascontiguousarray(inv.copy()), np.zeros(nmat)
+        _lib.check(lib.qmcb_sm_update(n, e, nmat, _lib.dptr(work), _lib.dptr(vec), _lib.u8ptr(mask), _lib.dptr(ratio)))
+        out[variant] = (work, ratio)
+    sel = mask.astype(bool) if use_mask else np.ones(nmat, dtype=bool)
+    assert np.array_equal(out["tma"][0], out["registers"][0]) and np.array_equal(out["tma"][1][sel], out["registers"][1][sel])
+    new = matrix.copy()
+    new[:, e, :] = vec
+    assert np.abs(out["tma"][0][sel] - np.linalg.inv(new)[sel]).max() < 1e-12
+    assert np.abs(out["tma"][1][sel] - (np.linalg.det(new) / np.linalg.det(matrix))[sel]).max() < 1e-12
+    if use_mask:
+        assert np.array_equal(out["tma"][0][~sel], inv[~sel])
