@@ -32,9 +32,7 @@ class ElectronView:
     __slots__ = ("configs", "wrap", "lvec", "dist")
 
     def __init__(self, positions, lattice=None, wrap=None, dist=None):
-        self.configs = positions
-        self.lvec = lattice
-        self.dist = dist
+        self.configs, self.lvec, self.dist = positions, lattice, dist
         if lattice is None:
             self.wrap = None
         else:

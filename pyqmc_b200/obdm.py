@@ -82,7 +82,7 @@ class OBDMAccumulator:
         self._ctx = _device_context(wf)
         if self._ctx is None or self._ctx.nconf == 0:
             raise RuntimeError("wf.recompute(configs) must be called before the OBDM accumulator")
-        nconf = configs.configs.shape[0]
+        nconf = len(configs.configs)
         if self._aux is None:
             self._warm_up(nconf if self._naux is None else self._naux)
         naux = len(self._aux)
@@ -104,7 +104,8 @@ class OBDMAccumulator:
         return {"value": value / self._nsweeps, "norm": norm / self._nsweeps}
 
     def avg(self, configs, wf):
-        return {k: np.mean(v, axis=0) for k, v in self(configs, wf).items()}
+        per_walker = self(configs, wf)
+        return {name: per_walker[name].mean(axis=0) for name in per_walker}
 
     def keys(self):
         return {"value", "norm"}

@@ -96,37 +96,36 @@ def estimate_rcut(cell, precision):
     """Stand-in for ``pyscf.pbc.gto.cell.estimate_rcut`` (most diffuse primitive of each shell,
     two fixed-point iterations of  c^2 (2l+1) alpha r^(2l+2) exp(-alpha r^2 / 2) < precision)."""
     rmax = 0.01
-    for ib in range(cell.nbas):
-        l = cell.bas_angular(ib)
-        es = cell.bas_exp(ib)
-        i = int(np.argmin(es))
-        alpha = float(es[i])
-        c = float(abs(cell._libcint_ctr_coeff(ib)[i]).max())
-        C = c * c * (2 * l + 1) * alpha / precision
+    for shell in range(cell.nbas):
+        ang = cell.bas_angular(shell)
+        exps = cell.bas_exp(shell)
+        i = int(np.argmin(exps))
+        alpha = float(exps[i])
+        c = float(abs(cell._libcint_ctr_coeff(shell)[i]).max())
+        C = c * c * (2 * ang + 1) * alpha / precision
         r0 = 20.0
-        for _ in range(2):
-            r0 = np.sqrt(2.0 * np.log(C * (r0 * r0 * alpha) ** (l + 1) + 1.0) / alpha)
+        for _pass in (0, 1):
+            r0 = np.sqrt(2.0 * np.log(C * (r0 * r0 * alpha) ** (ang + 1) + 1.0) / alpha)
         rmax = max(rmax, float(r0))
     return rmax
 
 
 def shell_rcut(cell, eval_gto_precision):
-    """``_estimate_rcut`` of the reference (orbitals.py:258-278 == pbcgto.py:672-695)."""
-    vol = cell.vol
-    init_rcut = estimate_rcut(cell, eval_gto_precision)
-    precision = eval_gto_precision / max(vol, 1)
-    rcut = []
-    for ib in range(cell.nbas):
-        l = cell.bas_angular(ib)
-        es = cell.bas_exp(ib)
-        cs = abs(cell._libcint_ctr_coeff(ib)).max(axis=1)
-        norm_ang = ((2 * l + 1) / (4 * np.pi)) ** 0.5
-        fac = 2 * np.pi / vol * cs * norm_ang / es / precision
-        r = init_rcut
-        for _ in range(2):
-            r = (np.log(fac * r ** (l + 1) + 1.0) / es) ** 0.5
-        rcut.append(r.max())
-    return np.array(rcut)
+    """``_estimate_rcut`` of the reference (orbitals.py:258-278 == pbcgto.py:672-695): per shell, two fixed-point
+    passes of the radius at which the shell has decayed to the requested precision (same arithmetic, term by term:
+    these numbers select the lattice images of every periodic orbital evaluation)."""
+    start = estimate_rcut(cell, eval_gto_precision)
+    precision = eval_gto_precision / max(cell.vol, 1)
+    radii = np.empty(cell.nbas)
+    for shell in range(cell.nbas):
+        ang, exps = cell.bas_angular(shell), cell.bas_exp(shell)
+        largest = abs(cell._libcint_ctr_coeff(shell)).max(axis=1)
+        fac = 2 * np.pi / cell.vol * largest * ((2 * ang + 1) / (4 * np.pi)) ** 0.5 / exps / precision
+        r = start
+        for _pass in (0, 1):
+            r = (np.log(fac * r ** (ang + 1) + 1.0) / exps) ** 0.5
+        radii[shell] = r.max()
+    return radii
 
 
 def _integer_points_in_cell(S):

@@ -52,7 +52,7 @@ class ParameterMap:
     def serialize_parameters(self, parameters):
         parts = [np.ravel(np.asarray(parameters[k]))[i] for k, i in self._picked.items()]
         if not parts:
-            return np.zeros(0)
+            return np.empty(0)
         flat = np.concatenate(parts)
         return np.concatenate((flat.real, flat[self._imag].imag)) if len(self._imag) else np.real(flat)
 
@@ -61,7 +61,7 @@ class ParameterMap:
         with respect to an imaginary part is i times the one with respect to the real part."""
         parts = [np.asarray(pgrad[k]).reshape(len(pgrad[k]), -1)[:, i] for k, i in self._picked.items()]
         if not parts:
-            return np.zeros(0)
+            return np.empty(0)
         dp = np.concatenate(parts, axis=1)
         return np.concatenate((dp, dp[:, self._imag] * 1j), axis=1) if len(self._imag) else dp
 
@@ -128,7 +128,7 @@ class StochasticReconfiguration:
         return out
 
     def avg(self, configs, wf, weights=None):
-        n = configs.configs.shape[0]
+        n = len(configs.configs)
         w = np.ones(n) if weights is None else np.asarray(weights, dtype=float)
         w = w / np.sum(w)
         ctx = self._device(wf)

@@ -74,7 +74,8 @@ def _cusp_atoms(mol, ion_cusp):
         z = mol.atom_charges()
         symbols = [mol.atom_symbol(i) for i in range(len(mol._atom))]
         return [s for s, zi in zip(symbols, z) if s not in mol._ecp and zi > 0]
-    assert isinstance(ion_cusp, list)
+    if not isinstance(ion_cusp, list):
+        raise TypeError("ion_cusp must be True, False, None or a list of atom symbols")
     return ion_cusp
 
 
@@ -90,7 +91,7 @@ def generate_jastrow(mol, ion_cusp=None, na=4, nb=3, rcut=None, cusp_gamma=None,
         z = np.array(mol.atom_charges(), dtype=float)
         z[[atom[0] not in cusped for atom in mol._atom]] = 0.0
         acoeff[:, 0, :] = z[:, None]
-        to_opt["acoeff"][:, 0, :] = False
+        to_opt["acoeff"][:, 0] = False
     bcoeff[0, :] = [PARALLEL_CUSP, ANTIPARALLEL_CUSP, PARALLEL_CUSP]
     to_opt["bcoeff"][0, :] = False
     return wf, to_opt  # cusp rows stay fixed
@@ -98,8 +99,8 @@ def generate_jastrow(mol, ion_cusp=None, na=4, nb=3, rcut=None, cusp_gamma=None,
 
 def generate_jastrow3(mol, na=4, nb=3, rcut=None, jax=False):
     """Electron-electron-ion factor: default basis without the cusp function, all coefficients free."""
-    if jax is True:
-        raise NotImplementedError("JAX 3-body Jastrow not yet implemented")
+    if jax:
+        raise NotImplementedError("there is no JAX three-body Jastrow factor (nor in the reference)")
     j3 = ThreeBodyJastrow(mol, *default_jastrow_basis(mol, False, na, nb, rcut))
     return j3, {"ccoeff": _mask(j3.parameters["ccoeff"].shape)}
 

@@ -25,5 +25,5 @@ def test_product_python_sources_are_not_copies():
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         rows = overlap.report(os.path.join(ROOT, "pyqmc_b200"), REF)
-    worst = [(round(100 * frac, 1), name) for frac, shared, n, name in rows if n >= 20 and frac >= 0.20]
-    assert not worst, f"files sharing >= 20 % of their code lines with the reference: {worst}"
+    worst = [(round(100 * frac, 1), name) for frac, shared, n, name in rows if n >= 20 and frac >= 0.15]
+    assert not worst, f"files sharing >= 15 % of their code lines with the reference: {worst}"
