@@ -49,7 +49,7 @@ WORKLOADS = {
                     "16 atoms, Ewald + ECP, 1024 walkers/GPU"),
 }
 WORKLOADS["c3"] = dict(
-    system="h2o_cas_3b", walkers=4096, cpu_walkers=32, cpu_steps=1, cpu_spb=2, cpu_blocks=1,
+    system="h2o_cas_3b", walkers=4096, cpu_walkers=32, cpu_steps=1, cpu_spb=2, cpu_blocks=2,
     metric="walker-steps/sec (VMC, H2O CAS(8e,8o) 4900 determinants + 3-body Jastrow); Sherman-Morrison HBM GB/s vs roofline",
     text="H2O ccECP-cc-pVTZ-shaped multi-determinant (full CAS(8e,8o): 70 x 70 = 4900 determinants) x 2-body x 3-body "
          "Jastrow VMC (synthetic basis/MOs/CI coefficients), 4096 walkers/GPU")

@@ -610,28 +610,38 @@ __global__ void __launch_bounds__(128) k_cx_ecp_points(const Sys S, const State 
 }
 
 // imaginary part of the ECP energy per walker, summed in the order k_energy_finalize uses for the real part:
-// out [2][N] = Im ecp, Im total (the other terms of the local energy are real)
+// out [2][N] = Im ecp, Im total (the other terms of the local energy are real).  One warp per walker: lanes over the
+// (electron, ECP atom) items, lane 0 adds them in the reference's order; dynamic shared memory: ne * necp doubles per warp.
 __global__ void __launch_bounds__(128) k_cx_ecp_imag(const Sys S, const State st, const EnergyScratch es,
                                                      const double* __restrict__ contrib_im, double* __restrict__ out) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ __align__(128) unsigned char qmcb_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int N = st.N;
   if (w >= N) return;
-  double ecp = 0.0;
-  for (int e = 0; e < S.ne; ++e) {
-    double ecp_e = 0.0;
-    for (int a = 0; a < S.necp; ++a) {
-      const int item = es.item_of[((size_t)e * S.necp + a) * N + w];
-      double nl = 0.0;
-      if (item >= 0) {
-        const int naip = S.iblob[S.o_naip + a];
-        for (int q = 0; q < naip; ++q) nl += contrib_im[(size_t)item * S.max_naip + q];
-      }
-      ecp_e += nl;
+  const int nitem = S.ne * S.necp;
+  double* buf = reinterpret_cast<double*>(qmcb_smem) + (size_t)wib * nitem;
+  for (int t = lane; t < nitem; t += 32) {
+    const int a = t % S.necp;
+    const int item = es.item_of[(size_t)t * N + w];
+    double nl = 0.0;
+    if (item >= 0) {
+      const int naip = S.iblob[S.o_naip + a];
+      for (int q = 0; q < naip; ++q) nl += contrib_im[(size_t)item * S.max_naip + q];
     }
-    ecp += ecp_e;
+    buf[t] = nl;
   }
-  out[w] = ecp;
-  out[(size_t)N + w] = ecp;
+  __syncwarp();
+  if (lane == 0) {
+    double ecp = 0.0;
+    for (int e = 0; e < S.ne; ++e) {
+      double ecp_e = 0.0;
+      for (int a = 0; a < S.necp; ++a) ecp_e += buf[e * S.necp + a];
+      ecp += ecp_e;
+    }
+    out[w] = ecp;
+    out[(size_t)N + w] = ecp;
+  }
 }
 
 // d ln Psi / d det_coeff [N][ndet] (complex, interleaved) and G_s[d] = sum_{D: map_s(D)=d} c_D dPsi_D (complex)

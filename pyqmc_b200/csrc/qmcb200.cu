@@ -1183,7 +1183,8 @@ int launch_energy_t(qmcb_ctx* c, const State& st, const EnergyScratch& es, const
   }
   if (S.cplx) {  // rows 6, 7 of the output: Im ecp, Im total
     if (S.necp > 0) {
-      k_cx_ecp_imag<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(S, st, es, c->e_contrib_im.p, d_out + (size_t)6 * N);
+      k_cx_ecp_imag<<<(unsigned)(((long long)N * 32 + 127) / 128), 128, (size_t)4 * S.ne * S.necp * 8, stream>>>(
+          S, st, es, c->e_contrib_im.p, d_out + (size_t)6 * N);
       c->nlaunch++;
       CK(cudaGetLastError());
     } else
