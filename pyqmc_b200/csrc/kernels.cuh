@@ -825,6 +825,44 @@ __global__ void __launch_bounds__(128) k_jastrow3_recompute(const Sys S, const S
   st.val3[w] = 0.5 * tot;
 }
 
+// the same with G lanes per walker, lanes over electrons: a-values of every electron first, then -- after the group's
+// writes are visible -- the pair sums P_e; lane 0 adds the P_e in electron order (the one-thread order)
+template <int G>
+__global__ void __launch_bounds__(128) k_jastrow3_recompute_group(const Sys S, const State st) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  const int lane32 = threadIdx.x & 31;
+  const int lane = lane32 & (G - 1);
+  const unsigned gm = group_mask<G>(lane32);
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  if (w >= st.N) return;
+  const int na_tot = S.natom * S.na3;
+  double av[QMCB_J3_MAXA], ag[1], al[1];
+  for (int e = lane; e < S.ne; e += G) {
+    j3_a_values<0>(S, sd, si, CONF(st, S, w, e, 0), CONF(st, S, w, e, 1), CONF(st, S, w, e, 2), av, ag, al);
+    for (int i = 0; i < na_tot; ++i) st.a3v[((size_t)w * S.ne + e) * na_tot + i] = av[i];
+  }
+  __syncwarp(gm);
+  for (int e = lane; e < S.ne; e += G) {
+    const double px = CONF(st, S, w, e, 0), py = CONF(st, S, w, e, 1), pz = CONF(st, S, w, e, 2);
+    for (int i = 0; i < na_tot; ++i) av[i] = st.a3v[((size_t)w * S.ne + e) * na_tot + i];
+    double P = 0.0, g[3] = {0.0, 0.0, 0.0}, lap = 0.0;
+    for (int j = 0; j < S.ne; ++j) {
+      if (j == e) continue;
+      j3_pair<0>(S, sd, si, st, w, e, j, px, py, pz, av, ag, al, CONF(st, S, w, j, 0), CONF(st, S, w, j, 1),
+                 CONF(st, S, w, j, 2), P, g, lap);
+    }
+    st.P3[(size_t)w * S.ne + e] = P;
+  }
+  __syncwarp(gm);
+  if (lane == 0) {
+    double tot = 0.0;
+    for (int e = 0; e < S.ne; ++e) tot += st.P3[(size_t)w * S.ne + e];
+    st.val3[w] = 0.5 * tot;
+  }
+}
+
 // d U / d ccoeff [N][I][na][na][nb][3]: thread per (walker, I, k, l)
 __global__ void __launch_bounds__(128) k_jastrow3_pgrad(const Sys S, const State st, double* __restrict__ out) {
   const double* sd;
@@ -1196,15 +1234,28 @@ __global__ void __launch_bounds__(128) k_vmc_move(const Sys S, const State st, c
 // =========================================================================================
 // three-body terms of electron e at (px,py,pz): a-values by lanes over (atom, function) into shared
 // memory, pair terms by lanes over partners (three_body_jastrow.py:454-655); adds to du / g / lap.
+// per-walker scratch of coop_jastrow3 (doubles): a-values / gradient / Laplacian factors of the moved electron
+// [3][natom * na3], then per partner its displacement, in-range flag and the b radial values / derivatives
+__host__ __device__ inline int j3_scratch_doubles(const Sys& S) {
+  return 3 * S.natom * S.na3 + (S.ne > 1 ? S.ne - 1 : 0) * (4 + 3 * S.nb3);
+}
+
+// Three-body terms of electron e at (px, py, pz) with G lanes per walker, in three phases through shared memory:
+//   1  lanes over (atom, k): a_k(r_eI) and its derivative factors                   (three_body_jastrow.py:454-520)
+//   2  lanes over partners j: minimal-image displacement r_ej, b_m(r_ej) and derivative factors
+//   3  lanes over (partner, atom, m) tasks: sum_{kl} C[I,k,l,m,sp] a_k(r_eI) a_l(r_jI) b_m(r_ej) and its gradient /
+//      Laplacian terms (521-655) -- 84 tasks for H2O, so all lanes work, where one lane per partner left 9 of 16 idle
 template <int WANT, int G>
 __device__ __forceinline__ void coop_jastrow3(const Sys& S, const double* __restrict__ sd, const int* __restrict__ si,
                                               const State& st, int w, int e, double px, double py, double pz, int lane,
                                               unsigned gm, double* __restrict__ abuf, double& du, double (&g)[3],
                                               double& lap) {
   const int na_tot = S.natom * S.na3;
+  const int na = S.na3, nb = S.nb3, pstride = 4 + 3 * S.nb3;
   double* __restrict__ av = abuf;
   double* __restrict__ ag = abuf + na_tot;
   double* __restrict__ al = abuf + 2 * na_tot;
+  double* __restrict__ pb = abuf + 3 * na_tot;
   for (int t = lane; t < na_tot; t += G) {
     const int I = t / S.na3, k = t - I * S.na3;
     double dx = px - sd[S.o_xyz + 3 * I], dy = py - sd[S.o_xyz + 3 * I + 1], dz = pz - sd[S.o_xyz + 3 * I + 2];
@@ -1216,12 +1267,57 @@ __device__ __forceinline__ void coop_jastrow3(const Sys& S, const double* __rest
     ag[t] = gg;
     al[t] = ll;
   }
-  __syncwarp(gm);
-  double P = 0.0, gl[3] = {0.0, 0.0, 0.0}, lp = 0.0;
   for (int jj = lane; jj < S.ne - 1; jj += G) {
     const int j = jj < e ? jj : jj + 1;
-    j3_pair<WANT>(S, sd, si, st, w, e, j, px, py, pz, av, ag, al, CONF(st, S, w, j, 0), CONF(st, S, w, j, 1),
-                  CONF(st, S, w, j, 2), P, gl, lp);
+    double dx = px - CONF(st, S, w, j, 0), dy = py - CONF(st, S, w, j, 1), dz = pz - CONF(st, S, w, j, 2);
+    if (S.pbc) min_image(S, sd, dx, dy, dz);
+    const double r = sqrt(dx * dx + dy * dy + dz * dz);
+    double* __restrict__ q = pb + jj * pstride;
+    q[0] = dx;
+    q[1] = dy;
+    q[2] = dz;
+    q[3] = (r < S.rcut_b3) ? 1.0 : 0.0;
+    if (r < S.rcut_b3)
+      for (int m = 0; m < nb; ++m) {
+        double v, gg = 0.0, ll = 0.0;
+        radial_ool<WANT>(si[S.o_b3kind + m], sd[S.o_b3par + m], S.rcut_b3, r, v, gg, ll);
+        q[4 + m] = v;
+        q[4 + nb + m] = gg;
+        q[4 + 2 * nb + m] = ll;
+      }
+  }
+  __syncwarp(gm);
+  double P = 0.0, gl[3] = {0.0, 0.0, 0.0}, lp = 0.0;
+  const int per_partner = S.natom * nb;
+#pragma unroll 1
+  for (int t = lane; t < (S.ne - 1) * per_partner; t += G) {
+    const int jj = t / per_partner, rem = t - jj * per_partner;
+    const int I = rem / nb, m = rem - I * nb;
+    const double* __restrict__ q = pb + jj * pstride;
+    if (q[3] == 0.0) continue;
+    const int j = jj < e ? jj : jj + 1;
+    const int sp = (e >= S.nup ? 1 : 0) + (j >= S.nup ? 1 : 0);
+    const double* __restrict__ C = sd + S.o_c3 + (size_t)I * na * na * nb * 3 + sp;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int k = 0; k < na; ++k) {
+      double tt = 0.0;  // sum_l C[I,k,l,m,sp] a_l(r_jI)
+      for (int l = 0; l < na; ++l) tt = fma(C[((k * na + l) * nb + m) * 3], A3V(st, S, w, j, I, l), tt);
+      s0 = fma(av[I * na + k], tt, s0);
+      if (WANT >= 1) s1 = fma(ag[I * na + k], tt, s1);
+      if (WANT >= 2) s2 = fma(al[I * na + k], tt, s2);
+    }
+    const double bv = q[4 + m];
+    P = fma(s0, bv, P);
+    if (WANT >= 1) {
+      double ax = px - sd[S.o_xyz + 3 * I], ay = py - sd[S.o_xyz + 3 * I + 1], az = pz - sd[S.o_xyz + 3 * I + 2];
+      if (S.pbc) min_image(S, sd, ax, ay, az);
+      const double bg = q[4 + nb + m];
+      const double ca = s1 * bv, cb = s0 * bg;
+      gl[0] += ca * ax + cb * q[0];
+      gl[1] += ca * ay + cb * q[1];
+      gl[2] += ca * az + cb * q[2];
+      if (WANT >= 2) lp += s2 * bv + 2.0 * s1 * bg * (ax * q[0] + ay * q[1] + az * q[2]) + s0 * q[4 + 2 * nb + m];
+    }
   }
   P = group_sum<G>(P, gm);
 #pragma unroll
@@ -1279,7 +1375,7 @@ __global__ void __launch_bounds__(128) k_vmc_move_coop(const Sys S, const State 
   const int N = st.N;
   if (w >= N) return;
   const size_t tab = (16 + (size_t)S.dwords * 8 + (size_t)S.iwords * 4 + 15) & ~(size_t)15;
-  const int j3n = 3 * S.natom * S.na3;
+  const int j3n = j3_scratch_doubles(S);
   double* ws = reinterpret_cast<double*>(qmcb_smem + tab) + (size_t)slot * (L.total + j3n);
   double* abuf = ws + L.total;
   const bool has_s = S.nmo[0] + S.nmo[1] > 0, has_j = (S.na + S.nb) > 0, has_j3 = (S.na3 + S.nb3) > 0;
@@ -1840,7 +1936,7 @@ __global__ void __launch_bounds__(128) k_kinetic(const Sys S, const State st, co
   if (which & QMCB_JASTROW3) {
     extern __shared__ __align__(128) unsigned char qmcb_smem[];
     const size_t tab3 = (16 + (size_t)S.dwords * 8 + (size_t)S.iwords * 4 + 15) & ~(size_t)15;
-    double* abuf = reinterpret_cast<double*>(qmcb_smem + tab3) + (size_t)(threadIdx.x / G) * (3 * S.natom * S.na3);
+    double* abuf = reinterpret_cast<double*>(qmcb_smem + tab3) + (size_t)(threadIdx.x / G) * j3_scratch_doubles(S);
     double du3 = 0.0;
     coop_jastrow3<2, G>(S, sd, si, st, w, e, px, py, pz, lane, gm, abuf, du3, gj, lapj);
   }
@@ -2046,7 +2142,7 @@ __global__ void __launch_bounds__(64) k_ecp_points_coop(const Sys S, const State
   const unsigned gm = group_mask<G>(lane32);
   const int slot = threadIdx.x / G, gper = blockDim.x / G;
   const size_t tab = (16 + (size_t)S.dwords * 8 + (size_t)S.iwords * 4 + 15) & ~(size_t)15;
-  const int j3n = 3 * S.natom * S.na3;
+  const int j3n = j3_scratch_doubles(S);
   double* ws = reinterpret_cast<double*>(qmcb_smem + tab) + (size_t)slot * (L.total + j3n);
   double* abuf = ws + L.total;
   const int N = st.N;

@@ -1108,7 +1108,7 @@ int launch_kinetic(qmcb_ctx* c, const State& st, const EnergyScratch& es, cudaSt
     if (launch_mo_all(c, 0, stream)) return -1;
   }
   // three-body factor: per-group a-value scratch behind the tables
-  const size_t ksm = c->have_j3 ? ((sm + 15) & ~(size_t)15) + (size_t)(128 / 8) * 3 * S.natom * S.na3 * 8 : sm;
+  const size_t ksm = c->have_j3 ? ((sm + 15) & ~(size_t)15) + (size_t)(128 / 8) * j3_scratch_doubles(S) * 8 : sm;
   if (S.cplx) {
     if (prep_kernel(k_cx_kinetic, sm)) return -1;
     k_cx_kinetic<<<(unsigned)((np + 63) / 64), 64, sm, stream>>>(S, st, es);
@@ -1663,7 +1663,13 @@ static int recompute_from_resident(qmcb_ctx* c, int which, int nconf) {
     c->nlaunch++;
     CK(cudaGetLastError());
   }
-  if (which & 4) {
+  if ((which & 4) && S.ne >= 2 && std::getenv("QMCB_NO_COOP_JRECOMPUTE") == nullptr) {
+    constexpr int G3R = 8;  // lanes over electrons
+    if (prep_kernel(k_jastrow3_recompute_group<G3R>, c->smem_bytes)) return -1;
+    k_jastrow3_recompute_group<G3R><<<(unsigned)(((long long)nconf * G3R + 127) / 128), 128, c->smem_bytes, c->stream>>>(S, c->st);
+    c->nlaunch++;
+    CK(cudaGetLastError());
+  } else if (which & 4) {
     const int block = pick_block(nconf);
     if (prep_kernel(k_jastrow3_recompute, c->smem_bytes)) return -1;
     k_jastrow3_recompute<<<(nconf + block - 1) / block, block, c->smem_bytes, c->stream>>>(S, c->st);
@@ -2442,7 +2448,7 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
       ma.scr_stride = N;
       // general wave functions (multi-determinant and / or three-body): G lanes per walker, cached MO rows
       constexpr int GM = 16;
-      const size_t msm = tab + (size_t)(128 / GM) * (CL.total + 3 * S.natom * S.na3) * 8;
+      const size_t msm = tab + (size_t)(128 / GM) * (CL.total + j3_scratch_doubles(S)) * 8;
       if (msm <= 200 * 1024 && std::getenv("QMCB_NO_COOP_MOVE") == nullptr) {
         if (c->have_slater && !c->mocache_valid)
           if (launch_mo_all(c, 0, stream)) return -1;
@@ -2711,7 +2717,7 @@ static int dmc_tmove_electron(qmcb_ctx* c, int e, double tau, const double* d_u,
   const size_t sm = c->smem_bytes;
   constexpr int GE = 8, BE = 64;
   const CoopLayout CLe = coop_layout(S);
-  const size_t esm = ((sm + 15) & ~(size_t)15) + (size_t)(BE / GE) * (CLe.total + 3 * S.natom * S.na3) * 8;
+  const size_t esm = ((sm + 15) & ~(size_t)15) + (size_t)(BE / GE) * (CLe.total + j3_scratch_doubles(S)) * 8;
   if (esm <= 100 * 1024 && std::getenv("QMCB_NO_COOP_ECP") == nullptr) {
     // few points per launch (one electron, masked walkers): lanes cooperate on a point
     const long long cgrid = std::max<long long>(1, std::min<long long>(((long long)npts + (BE / GE) - 1) / (BE / GE), 148LL * 8));
