@@ -472,9 +472,16 @@ __device__ __forceinline__ void det_cache_warp(const Sys& S, const State& st, in
     if (S.dense[s] != nullptr) {  // dense matrix-vector product, coalesced over d
       const double* __restrict__ Cm = S.dense[s];
       for (int d = lane; d < nds; d += 32) {
-        double acc = 0.0;
-        for (int j = 0; j < ndo; ++j) acc = fma(Cm[(size_t)j * nds + d], dvo[j], acc);
-        st.W[s][(size_t)w * nds + d] = acc;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // four independent chains: the sum is latency-bound
+        int j = 0;
+        for (; j + 3 < ndo; j += 4) {
+          a0 = fma(Cm[(size_t)j * nds + d], dvo[j], a0);
+          a1 = fma(Cm[(size_t)(j + 1) * nds + d], dvo[j + 1], a1);
+          a2 = fma(Cm[(size_t)(j + 2) * nds + d], dvo[j + 2], a2);
+          a3 = fma(Cm[(size_t)(j + 3) * nds + d], dvo[j + 3], a3);
+        }
+        for (; j < ndo; ++j) a0 = fma(Cm[(size_t)j * nds + d], dvo[j], a0);
+        st.W[s][(size_t)w * nds + d] = (a0 + a1) + (a2 + a3);
       }
       continue;
     }
@@ -1460,7 +1467,18 @@ __global__ void __launch_bounds__(128) k_vmc_move_coop(const Sys S, const State 
   }
 }
 
-// three-body cache update with G lanes per walker, lanes over partners (three_body_jastrow.py:149-189)
+// per-walker scratch of k_jastrow3_update_coop (doubles): old and new a-values of the moved electron, per partner the
+// b values at the old and at the new distance, per (partner, atom, function) task the old and new contraction
+__host__ __device__ inline int j3_update_scratch_doubles(const Sys& S) {
+  const int np = S.ne > 1 ? S.ne - 1 : 0;
+  return 2 * S.natom * S.na3 + 2 * np * S.nb3 + 2 * np * S.natom * S.nb3;
+}
+
+// three-body cache update with G lanes per walker (three_body_jastrow.py:149-189): the pair terms of the moved
+// electron with its cached a-values at the old position leave the partners' sums, the ones at the accepted position
+// enter.  Phases through shared memory: (1) lanes over (atom, k): new a-values; (2) lanes over partners: b_m at the
+// old and new distance; (3) lanes over (partner, atom, m) tasks: sum_l C a_l(r_jI) once, contracted with the old and
+// the new a_k(r_eI); (4) lanes over partners: the sums over (atom, m) in the order of j3_pair.
 template <int G>
 __global__ void __launch_bounds__(128) k_jastrow3_update_coop(const Sys S, const State st, int e, int move_conf,
                                                               const uint8_t* mask) {
@@ -1476,49 +1494,82 @@ __global__ void __launch_bounds__(128) k_jastrow3_update_coop(const Sys S, const
   if (w >= st.N) return;
   if (mask && !mask[w]) return;
   const size_t tab = (16 + (size_t)S.dwords * 8 + (size_t)S.iwords * 4 + 15) & ~(size_t)15;
-  const int na_tot = S.natom * S.na3;
-  double* av = reinterpret_cast<double*>(qmcb_smem + tab) + (size_t)slot * na_tot;
-  double ag[1], al[1];
+  const int na_tot = S.natom * S.na3, np = S.ne - 1, na = S.na3, nb = S.nb3, ntask = S.natom * nb;
+  double* avo = reinterpret_cast<double*>(qmcb_smem + tab) + (size_t)slot * j3_update_scratch_doubles(S);
+  double* avn = avo + na_tot;
+  double* bo = avn + na_tot;        // [np][nb]
+  double* bn = bo + np * nb;        // [np][nb]
+  double* so = bn + np * nb;        // [np][natom * nb]
+  double* sn = so + np * ntask;     // [np][natom * nb]
   const double nx = st.saved_pos[(size_t)w * 3], ny = st.saved_pos[(size_t)w * 3 + 1], nz = st.saved_pos[(size_t)w * 3 + 2];
   const double ox = CONF(st, S, w, e, 0), oy = CONF(st, S, w, e, 1), oz = CONF(st, S, w, e, 2);
   const size_t abase = ((size_t)w * S.ne + e) * na_tot;
-  for (int i = lane; i < na_tot; i += G) av[i] = st.a3v[abase + i];
-  __syncwarp(gm);
-  // old pair terms (cached a-values, current position) leave the partners' sums ...
-  for (int jj = lane; jj < S.ne - 1; jj += G) {
-    const int j = jj < e ? jj : jj + 1;
-    double Po = 0.0, g[3] = {0.0, 0.0, 0.0}, lap = 0.0;
-    j3_pair<0>(S, sd, si, st, w, e, j, ox, oy, oz, av, ag, al, CONF(st, S, w, j, 0), CONF(st, S, w, j, 1),
-               CONF(st, S, w, j, 2), Po, g, lap);
-    st.P3[(size_t)w * S.ne + j] -= Po;
-  }
-  __syncwarp(gm);
-  // ... and the new ones (a-values at the accepted position) enter
   for (int t = lane; t < na_tot; t += G) {
-    const int I = t / S.na3, k = t - I * S.na3;
+    const int I = t / na, k = t - I * na;
+    avo[t] = st.a3v[abase + t];
     double dx = nx - sd[S.o_xyz + 3 * I], dy = ny - sd[S.o_xyz + 3 * I + 1], dz = nz - sd[S.o_xyz + 3 * I + 2];
     if (S.pbc) min_image(S, sd, dx, dy, dz);
     const double r = sqrt(dx * dx + dy * dy + dz * dz);
     double v = 0.0, gg, ll;
     if (r < S.rcut_a3) radial_ool<0>(si[S.o_a3kind + k], sd[S.o_a3par + k], S.rcut_a3, r, v, gg, ll);
-    av[t] = v;
+    avn[t] = v;
+  }
+  for (int jj = lane; jj < np; jj += G) {
+    const int j = jj < e ? jj : jj + 1;
+    const double jx = CONF(st, S, w, j, 0), jy = CONF(st, S, w, j, 1), jz = CONF(st, S, w, j, 2);
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      double dx = (side ? nx : ox) - jx, dy = (side ? ny : oy) - jy, dz = (side ? nz : oz) - jz;
+      if (S.pbc) min_image(S, sd, dx, dy, dz);
+      const double r = sqrt(dx * dx + dy * dy + dz * dz);
+      double* __restrict__ b = (side ? bn : bo) + jj * nb;
+      for (int m = 0; m < nb; ++m) {
+        double v = 0.0, gg, ll;
+        if (r < S.rcut_b3) radial_ool<0>(si[S.o_b3kind + m], sd[S.o_b3par + m], S.rcut_b3, r, v, gg, ll);
+        b[m] = v;  // 0 beyond the cutoff: the pair term vanishes, as the early return of j3_pair
+      }
+    }
+  }
+  __syncwarp(gm);
+#pragma unroll 1
+  for (int t = lane; t < np * ntask; t += G) {
+    const int jj = t / ntask, rem = t - jj * ntask;
+    const int I = rem / nb, m = rem - I * nb;
+    const int j = jj < e ? jj : jj + 1;
+    const int sp = (e >= S.nup ? 1 : 0) + (j >= S.nup ? 1 : 0);
+    const double* __restrict__ C = sd + S.o_c3 + (size_t)I * na * na * nb * 3 + sp;
+    double s_old = 0.0, s_new = 0.0;
+    for (int k = 0; k < na; ++k) {
+      double tt = 0.0;  // sum_l C[I,k,l,m,sp] a_l(r_jI)
+      for (int l = 0; l < na; ++l) tt = fma(C[((k * na + l) * nb + m) * 3], A3V(st, S, w, j, I, l), tt);
+      s_old = fma(avo[I * na + k], tt, s_old);
+      s_new = fma(avn[I * na + k], tt, s_new);
+    }
+    so[t] = s_old;
+    sn[t] = s_new;
   }
   __syncwarp(gm);
   double newval = 0.0;
-  for (int jj = lane; jj < S.ne - 1; jj += G) {
+  for (int jj = lane; jj < np; jj += G) {
     const int j = jj < e ? jj : jj + 1;
-    double Pn = 0.0, g[3] = {0.0, 0.0, 0.0}, lap = 0.0;
-    j3_pair<0>(S, sd, si, st, w, e, j, nx, ny, nz, av, ag, al, CONF(st, S, w, j, 0), CONF(st, S, w, j, 1),
-               CONF(st, S, w, j, 2), Pn, g, lap);
+    double Po = 0.0, Pn = 0.0;
+    for (int u = 0; u < ntask; ++u) {  // (atom, m) in the order of j3_pair
+      const int m = u % nb;
+      Po = fma(so[jj * ntask + u], bo[jj * nb + m], Po);
+      Pn = fma(sn[jj * ntask + u], bn[jj * nb + m], Pn);
+    }
+    double pj = st.P3[(size_t)w * S.ne + j];
+    pj -= Po;
+    pj += Pn;
+    st.P3[(size_t)w * S.ne + j] = pj;
     newval += Pn;
-    st.P3[(size_t)w * S.ne + j] += Pn;
   }
   newval = group_sum<G>(newval, gm);
   if (lane == 0) {
     st.val3[w] += newval - st.P3[(size_t)w * S.ne + e];
     st.P3[(size_t)w * S.ne + e] = newval;
   }
-  for (int i = lane; i < na_tot; i += G) st.a3v[abase + i] = av[i];
+  for (int i = lane; i < na_tot; i += G) st.a3v[abase + i] = avn[i];
   __syncwarp(gm);
   if (move_conf && lane == 0) {
     CONF(st, S, w, e, 0) = nx;

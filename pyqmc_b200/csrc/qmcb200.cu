@@ -1020,8 +1020,8 @@ int launch_update(qmcb_ctx* c, int which, int e, const uint8_t* d_mask, cudaStre
     CK(cudaGetLastError());
   }
   if (do_j3) {
-    constexpr int G3 = 8;
-    const size_t sm3 = ((c->smem_bytes + 15) & ~(size_t)15) + (size_t)(128 / G3) * S.natom * S.na3 * 8;
+    constexpr int G3 = 16;
+    const size_t sm3 = ((c->smem_bytes + 15) & ~(size_t)15) + (size_t)(128 / G3) * j3_update_scratch_doubles(S) * 8;
     if (prep_kernel(k_jastrow3_update_coop<G3>, sm3)) return -1;
     k_jastrow3_update_coop<G3><<<(unsigned)(((long long)c->N * G3 + 127) / 128), 128, sm3, stream>>>(S, c->st, e, 1, d_mask);
     c->nlaunch++;
