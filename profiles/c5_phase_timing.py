@@ -47,7 +47,7 @@ def main():
                 t[name] += time.perf_counter() - t0
                 return r
             return wrapper
-        dist.all_gather = timed("all_gather(+wait for the slowest rank)", dist.all_gather)
+        dist.all_gather_into_tensor = timed("all_gather(+wait for the slowest rank)", dist.all_gather_into_tensor)
         dist.all_to_all_single = timed("all_to_all", dist.all_to_all_single)
     for b in range(K + 4):
         if b == 4:
