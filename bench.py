@@ -584,7 +584,10 @@ def gpu_arm(args):
         "roofline": {"kernel": "k_sm_tma32: Sherman-Morrison row update, n=32 (C4 shape), 131072 matrices, staged by cp.async.bulk",
                      "bound": "hbm", "achieved": g32, "peak": peak, "unit": "GB/s", "frac": g32 / peak,
                      "traffic": SM32_TRAFFIC_BYTES, "traffic_source": "profiles/r2_ncu_k_sm_tma32.txt (ncu --set full, same launch shape)",
-                     "peak_source": peak_src, "launch_ms": 1e3 * t32, "algorithmic_bytes": b32},
+                     "peak_source": peak_src, "launch_ms": 1e3 * t32, "algorithmic_bytes": b32,
+                     "scope": "the kernel BASELINE.json's metric names, timed alone at the C4 matrix shape (1 GiB of inverses, "
+                              "larger than L2): kernel capability.  Inside the C2 step the update is fused into the sweep and "
+                              "works on L2-resident 4x4 matrices; the step's own roofline is roofline_step"},
         # the whole VMC step against the same HBM roof (~27.5 KB of algorithmic traffic per
         # walker-step -- 15 KB sweep + ~10 KB energy accumulator); the step is FP64-latency bound, not HBM bound
         # the whole VMC step: against the HBM roof (~27.5 KB of algorithmic traffic per walker-step) it sits at
