@@ -1467,6 +1467,101 @@ __global__ void __launch_bounds__(128) k_vmc_move_coop(const Sys S, const State 
   }
 }
 
+// Device-resident move of electron e for GENERAL periodic wave functions (multi-determinant and / or three-body
+// factors on a supercell; mc.py:115-137 with make_irreducible, coord.py:168-194), G lanes per walker, in two launches
+// around the lattice-summed orbital evaluation (k_pbc_mo* -> st.monew):
+//   phase 0  drift at the current position (cached MO rows, lanes over the unique determinants; minimal-image
+//            Jastrow; three-body factor), proposal wrapped into the simulation cell -> saved_pos / saved_wrap / gold
+//   phase 1  ratio and drift at the proposed position from st.monew, Metropolis test, accept mask; the value row goes
+//            to saved_mo for the update kernels, accepted walkers refresh their cached MO rows
+// The internal updates (Sherman-Morrison of every determinant + dv / W, Jastrow and three-body caches, coordinates
+// and wrap vectors) follow through launch_update, as for the open-boundary general path.
+template <int G>
+__global__ void __launch_bounds__(128) k_pbc_move_general(const Sys S, const State st, const MoveArgs ma, int phase) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  extern __shared__ __align__(128) unsigned char qmcb_smem[];
+  const int lane32 = threadIdx.x & 31;
+  const int lane = lane32 & (G - 1);
+  const unsigned gm = group_mask<G>(lane32);
+  const int slot = threadIdx.x / G;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  if (w >= st.N) return;
+  const size_t tab = (16 + (size_t)S.dwords * 8 + (size_t)S.iwords * 4 + 15) & ~(size_t)15;
+  double* abuf = reinterpret_cast<double*>(qmcb_smem + tab) + (size_t)slot * j3_scratch_doubles(S);
+  const bool has_s = S.nmo[0] + S.nmo[1] > 0, has_j = (S.na + S.nb) > 0, has_j3 = (S.na3 + S.nb3) > 0;
+  const int ldmax = S.ldc[0] > S.ldc[1] ? S.ldc[0] : S.ldc[1];
+  const int e = ma.e;
+  const int s = e >= S.nup ? 1 : 0;
+  const int eeff = e - s * S.nup;
+  const double px = phase == 0 ? CONF(st, S, w, e, 0) : st.saved_pos[(size_t)w * 3];
+  const double py = phase == 0 ? CONF(st, S, w, e, 1) : st.saved_pos[(size_t)w * 3 + 1];
+  const double pz = phase == 0 ? CONF(st, S, w, e, 2) : st.saved_pos[(size_t)w * 3 + 2];
+  const double* __restrict__ rows = phase == 0 ? st.mocache + ((size_t)w * S.ne + e) * 5 * ldmax : st.monew + (size_t)w * 5 * ldmax;
+  double grad[3] = {0.0, 0.0, 0.0}, val = 1.0;
+  if (has_s) {
+    double r[4];
+    coop_det_ratio4<G>(S, si, st, w, s, eeff, rows, ldmax, lane, gm, r);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double gs = r[1 + i] / r[0];
+      if (!isfinite(gs)) gs = 0.0;
+      grad[i] = gs;
+    }
+    val = isfinite(r[0]) ? r[0] : 1.0;
+  }
+  {
+    double du = 0.0, gj[3] = {0.0, 0.0, 0.0}, lj = 0.0;
+    if (has_j) coop_jastrow_pbc<1, G>(S, sd, si, st, w, e, px, py, pz, lane, gm, du, gj, lj);
+    if (has_j3) coop_jastrow3<1, G>(S, sd, si, st, w, e, px, py, pz, lane, gm, abuf, du, gj, lj);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) grad[i] = grad[i] + gj[i];
+    val = val * exp(du);
+  }
+  limdrift3(grad);
+  const double* __restrict__ gauss = ma.gauss + (size_t)w * 3;
+  if (phase == 0) {
+    if (lane == 0) {
+      const double nx = __dadd_rn(__dadd_rn(px, gauss[0]), __dmul_rn(grad[0], ma.tstep));
+      const double ny = __dadd_rn(__dadd_rn(py, gauss[1]), __dmul_rn(grad[1], ma.tstep));
+      const double nz = __dadd_rn(__dadd_rn(pz, gauss[2]), __dmul_rn(grad[2], ma.tstep));
+      double o[3], ww[3];
+      wrap_cell(sd + S.o_lat, sd + S.o_latinv, nx, ny, nz, o, ww);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        st.saved_pos[(size_t)w * 3 + i] = o[i];
+        st.saved_wrap[(size_t)w * 3 + i] = st.wrap[((size_t)w * S.ne + e) * 3 + i] + ww[i];
+        st.gold[(size_t)w * 3 + i] = grad[i];
+      }
+    }
+    return;
+  }
+  double fwd = 0.0, bwd = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    fwd = __dadd_rn(fwd, __dmul_rn(gauss[i], gauss[i]));
+    const double b = __dadd_rn(gauss[i], __dmul_rn(ma.tstep, __dadd_rn(st.gold[(size_t)w * 3 + i], grad[i])));
+    bwd = __dadd_rn(bwd, __dmul_rn(b, b));
+  }
+  const double tprob = exp(__dmul_rn(1.0 / (2.0 * ma.tstep), __dadd_rn(fwd, -bwd)));
+  const double aval = fabs(val);
+  const double ratio = __dmul_rn(__dmul_rn(aval, aval), tprob);
+  const bool acc = __shfl_sync(gm, (ratio > ma.unif[w]) ? 1 : 0, 0, G) != 0;
+  if (lane == 0) {
+    ma.accept[w] = acc ? 1 : 0;
+    if (acc) atomicAdd(ma.nacc, 1ULL);
+  }
+  if (has_s) {
+    double* __restrict__ sv = st.saved_mo + (size_t)w * S.ldc[s];
+    for (int j = lane; j < S.ldc[s]; j += G) sv[j] = rows[j];
+    if (acc) {
+      double* __restrict__ mc = st.mocache + ((size_t)w * S.ne + e) * 5 * ldmax;
+      for (int i = lane; i < 5 * ldmax; i += G) mc[i] = rows[i];
+    }
+  }
+}
+
 // per-walker scratch of k_jastrow3_update_coop (doubles): old and new a-values of the moved electron, per partner the
 // b values at the old and at the new distance, per (partner, atom, function) task the old and new contraction
 __host__ __device__ inline int j3_update_scratch_doubles(const Sys& S) {

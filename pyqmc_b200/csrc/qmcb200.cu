@@ -2284,9 +2284,8 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
   const bool use_sweep = (!c->have_slater || S.ndet == 1) && !c->have_j3 && sweep_smem <= 200 * 1024 && !S.pbc &&
                          std::getenv("QMCB_NO_SWEEP") == nullptr;
   const bool use_pbc = S.pbc != 0;
-  if (use_pbc && ((c->have_slater && S.ndet != 1) || c->have_j3))
-    return fail("device-resident periodic VMC supports single-determinant Slater-Jastrow wave functions; "
-                "drive other periodic wave functions through the per-call protocol");
+  // periodic multi-determinant and / or three-body wave functions: k_pbc_move_general around the orbital kernel + launch_update
+  const bool pbc_general = use_pbc && ((c->have_slater && S.ndet != 1) || c->have_j3);
   if (use_pbc && c->have_slater && !c->mocache_valid)
     if (launch_mo_all(c, 0, stream)) return -1;
   if (use_sweep && c->have_slater && !c->mocache_valid) {
@@ -2316,7 +2315,7 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
   // MO rows, 80 KB per walker at C4 -- not worth copying); the ECP, Ewald and finalize kernels (3 of the 8 ms of a C4
   // step) then run from the copy of inverse / coordinates / wrap / Jastrow partial sums while the next step's moves,
   // which leave most of the machine idle at 1024 walkers, proceed.
-  const bool overlap_pbc = use_pbc && with_energy && c->have_slater && c->have_jastrow && nsteps > 1 &&
+  const bool overlap_pbc = use_pbc && !pbc_general && with_energy && c->have_slater && c->have_jastrow && nsteps > 1 &&
                            std::getenv("QMCB_NO_ENERGY_OVERLAP") == nullptr;
   State snap = c->st;
   EnergyScratch es_alt[2] = {c->es, c->es};
@@ -2370,11 +2369,49 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
     // Periodic move chain.  Fused flavour (n <= 32 per spin): [propose(0)] then per electron the orbitals at the
     // proposed points and ONE warp-per-walker kernel doing Metropolis test, cache updates, the Sherman-Morrison
     // update and the proposal of electron e + 1.  QMCB_PBC_UNFUSED=1 keeps the four-launch chain (A/B checks).
-    const bool fuse_pbc = use_pbc && (!c->have_slater || (S.nup <= 32 && S.ndn <= 32)) &&
+    const bool fuse_pbc = use_pbc && !pbc_general && (!c->have_slater || (S.nup <= 32 && S.ndn <= 32)) &&
                           std::getenv("QMCB_PBC_UNFUSED") == nullptr;
     State stf = c->st;  // fused chain: the proposal keeps the pair values at the old position for the cache update
     if (fuse_pbc && c->have_jastrow && S.nb > 0) stf.jold = c->b_jold.p;
-    for (int e = 0; e < S.ne && use_pbc; ++e) {
+    for (int e = 0; e < S.ne && pbc_general; ++e) {
+      const size_t se = (size_t)step * S.ne + e;
+      const int s = e >= S.nup ? 1 : 0;
+      const int ldmax = std::max(S.ldc[0], S.ldc[1]);
+      MoveArgs ma{};
+      ma.e = e;
+      ma.tstep = tstep;
+      ma.gauss = d_gauss + se * N * 3;
+      ma.unif = d_unif + se * N;
+      ma.accept = d_accept ? d_accept + se * N : c->d_accept.p;
+      ma.nacc = nacc + se;
+      constexpr int GM = 16;
+      const size_t msm = tab + (size_t)(128 / GM) * j3_scratch_doubles(S) * 8;
+      const unsigned mgrid = (unsigned)(((long long)N * GM + 127) / 128);
+      if (prep_kernel(k_pbc_move_general<GM>, msm)) return -1;
+      k_pbc_move_general<GM><<<mgrid, 128, msm, stream>>>(S, c->st, ma, 0);
+      c->nlaunch++;
+      CK(cudaGetLastError());
+      if (c->have_slater) {
+        PbcMoArgs a{};
+        a.npoints = (long long)N;
+        a.pos = c->st.saved_pos;
+        a.wrap = c->st.saved_wrap;
+        a.naip = 1;
+        a.spin_mode = 0;
+        a.spin = s;
+        a.out = c->st.monew;
+        a.stride_p = 5 * ldmax;
+        a.stride_c = ldmax;
+        a.stride_j = 1;
+        if (launch_pbc_mo(c, 2, a, (long long)N, stream)) return -1;
+      }
+      k_pbc_move_general<GM><<<mgrid, 128, msm, stream>>>(S, c->st, ma, 1);
+      c->nlaunch++;
+      CK(cudaGetLastError());
+      if (launch_update(c, which, e, ma.accept, stream)) return -1;
+      c->paircache_valid = false;  // the cached MO rows stay valid: accepted walkers refreshed theirs
+    }
+    for (int e = 0; e < S.ne && use_pbc && !pbc_general; ++e) {
       const size_t se = (size_t)step * S.ne + e;
       const int s = e >= S.nup ? 1 : 0;
       const int ldmax = std::max(S.ldc[0], S.ldc[1]);

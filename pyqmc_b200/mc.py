@@ -55,15 +55,8 @@ def _device_path(wf, accumulators):
     factors = getattr(wf, "wf_factors", [wf])
     if wf.dtype == complex:  # complex wave functions run through the protocol calls (csrc/cplx.cuh), not the block kernels
         return False
-    if hasattr(factors[0]._mol, "a"):
-        # the device-resident periodic block covers single-determinant Slater x JastrowSpin; periodic multi-determinant
-        # and three-body wave functions run through the protocol calls (the reference's driver)
-        from .wf import ThreeBodyJastrow
-
-        if any(isinstance(f, ThreeBodyJastrow) for f in factors):
-            return False
-        if any(len(f.parameters.get("det_coeff", [0])) > 1 for f in factors if hasattr(f, "_det_map")):
-            return False
+    # periodic wave functions: single-determinant Slater x JastrowSpin takes the fused two-launch chain, multi-determinant
+    # and three-body ones k_pbc_move_general + the update kernels (qmcb_vmc_block_device decides)
     return all(isinstance(a, EnergyAccumulator) for a in accumulators.values()) and len(accumulators) <= 1
 
 

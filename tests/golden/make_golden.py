@@ -28,7 +28,8 @@ NCONF = 12
 SYSTEMS = ["he", "h2o", "open", "c2", "h2o_md", "h2o_3b", "h2o_md_3b", "h2o_cas", "h2o_cas_3b", "high_l",
            "h2o_cx", "h2o_md_cx"]  # *_cx: complex orbital (and determinant) coefficients
 PBC_SYSTEMS = ["diamond211", "ortho", "rotcubic", "diamond211_3b", "ortho_3b",
-               "ortho_twist", "diamond211_twist"]  # *_twist: general twist = complex Bloch phases
+               "ortho_twist", "diamond211_twist",  # *_twist: general twist = complex Bloch phases
+               "ortho_md", "diamond211_md"]  # periodic multi-determinant expansions (occupations per k-point)
 EWALD_GMAX = 10  # the reference enumerates (2 gmax + 1)^3 / 2 reciprocal points: keep the fixture run small
 
 

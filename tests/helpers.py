@@ -28,6 +28,16 @@ def make_system(name):
     if name == "h2o_cas":
         mol, mf = systems.h2o_ccecp_pvtz()
         return mol, mf, systems.cas_determinants(4, 8, seed=3)
+    if name in ("ortho_md", "diamond211_md"):  # periodic multi-determinant: occupations per spin and per k-point
+        mol, mf = pbc_systems.PBC_SYSTEMS[name[:-3]]()
+        if name == "ortho_md":  # 2 + 2 electrons, one k-point
+            dets = [(0.8, [[[0, 1]], [[0, 1]]]), (0.3, [[[0, 2]], [[0, 1]]]), (-0.25, [[[0, 1]], [[1, 3]]]),
+                    (0.2, [[[1, 2]], [[0, 2]]]), (0.1, [[[2, 3]], [[2, 3]]])]
+        else:  # 8 + 8 electrons, two k-points with 4 occupied orbitals each
+            g = [0, 1, 2, 3]
+            dets = [(0.85, [[g, g], [g, g]]), (0.3, [[[0, 1, 2, 4], g], [g, g]]), (-0.2, [[g, g], [g, [0, 1, 3, 5]]]),
+                    (0.15, [[[0, 1, 2, 4], g], [[0, 2, 3, 4], g]])]
+        return mol, mf, dets
     if name in pbc_systems.PBC_SYSTEMS:
         mol, mf = pbc_systems.PBC_SYSTEMS[name]()
         return mol, mf, None

@@ -52,7 +52,7 @@ def check_internal(wf, data):
         assert helpers.relerr(pg[k], data["pgrad_" + k]) < 1e-9, k
 
 
-@pytest.mark.parametrize("name", PBC_SYSTEMS + ["ortho_3b", "diamond211_3b"])
+@pytest.mark.parametrize("name", PBC_SYSTEMS + ["ortho_3b", "diamond211_3b", "ortho_md", "diamond211_md"])
 def test_cuda_reproduces_reference_golden_periodic(lib, name):
     import pyqmc_b200 as pq
 
@@ -64,10 +64,11 @@ def test_cuda_reproduces_reference_golden_periodic(lib, name):
                          check_internal)
 
 
-@pytest.mark.parametrize("name", PBC_SYSTEMS)
+@pytest.mark.parametrize("name", PBC_SYSTEMS + ["ortho_3b", "diamond211_3b", "ortho_md", "diamond211_md"])
 def test_periodic_per_call_vmc_equals_device_resident_block(lib, name):
     """The reference driver loop over the protocol calls and the device-resident periodic block
-    consume the same variates and must accept the same moves."""
+    consume the same variates and must accept the same moves (single-determinant Slater-Jastrow: the fused
+    two-launch chain; multi-determinant / three-body: k_pbc_move_general + the update kernels)."""
     import pyqmc_b200 as pq
     from pyqmc_b200 import mc
 

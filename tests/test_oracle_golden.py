@@ -67,7 +67,8 @@ def periodic_walkers(cls, data, mol, key="configs0", wkey="wrap0"):
     return w
 
 
-@pytest.mark.parametrize("name", PBC_SYSTEMS + ["ortho_3b", "diamond211_3b", "ortho_twist", "diamond211_twist"])
+@pytest.mark.parametrize("name", PBC_SYSTEMS + ["ortho_3b", "diamond211_3b", "ortho_twist", "diamond211_twist", "ortho_md",
+                                  "diamond211_md"])
 def test_oracle_reproduces_reference_golden_periodic(name):
     """Periodic systems (minimal-image modes diagonal / orthogonal / general, two k-points with the
     wrap phase, Ewald): the oracle replays the reference's recorded calls."""
