@@ -1150,7 +1150,11 @@ struct MoveArgs {
   unsigned long long* nacc;
   double* scr;
   size_t scr_stride;
+  double* r2prop;  // DMC: [N] sum over electrons of |gauss + drift|^2 (dmc.py:68, 190-191)
+  double* r2acc;   // DMC: [N] the same for accepted moves
 };
+
+__device__ __forceinline__ void limdrift_dmc(double (&g)[3], double tau);
 
 __device__ __forceinline__ void limdrift3(double (&g)[3]) {
   // mc.py:76-89 with cutoff = 1; np.linalg.norm = sqrt(sum of squares)
@@ -1367,7 +1371,9 @@ __device__ __forceinline__ void coop_det_ratio4(const Sys& S, const int* __restr
 // determinants, optional two- and three-body Jastrow factors).  The drift at the current position comes
 // from the cached MO rows; accepted walkers refresh their cached rows (value, gradient, Laplacian) from
 // the evaluation at the proposed position.  Saves the value row / position for the update kernels.
-template <int G>
+// DMC = true: the drift-diffusion move of dmc.py:49-70 (Umrigar drift limit, fixed-node rejection, r^2 bookkeeping),
+// the same arithmetic as k_vmc_sweep<G, true>
+template <int G, bool DMC = false>
 __global__ void __launch_bounds__(128) k_vmc_move_coop(const Sys S, const State st, const MoveArgs ma) {
   const double* sd;
   const int* si;
@@ -1409,13 +1415,20 @@ __global__ void __launch_bounds__(128) k_vmc_move_coop(const Sys S, const State 
 #pragma unroll
     for (int i = 0; i < 3; ++i) grad[i] = grad[i] + gj[i];
   }
-  limdrift3(grad);
   double gauss[3], np_[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) gauss[i] = ma.gauss[(size_t)w * 3 + i];
-  np_[0] = __dadd_rn(__dadd_rn(ox, gauss[0]), __dmul_rn(grad[0], ma.tstep));
-  np_[1] = __dadd_rn(__dadd_rn(oy, gauss[1]), __dmul_rn(grad[1], ma.tstep));
-  np_[2] = __dadd_rn(__dadd_rn(oz, gauss[2]), __dmul_rn(grad[2], ma.tstep));
+  if (DMC) {
+    limdrift_dmc(grad, ma.tstep);
+    np_[0] = __dadd_rn(__dadd_rn(ox, gauss[0]), grad[0]);
+    np_[1] = __dadd_rn(__dadd_rn(oy, gauss[1]), grad[1]);
+    np_[2] = __dadd_rn(__dadd_rn(oz, gauss[2]), grad[2]);
+  } else {
+    limdrift3(grad);
+    np_[0] = __dadd_rn(__dadd_rn(ox, gauss[0]), __dmul_rn(grad[0], ma.tstep));
+    np_[1] = __dadd_rn(__dadd_rn(oy, gauss[1]), __dmul_rn(grad[1], ma.tstep));
+    np_[2] = __dadd_rn(__dadd_rn(oz, gauss[2]), __dmul_rn(grad[2], ma.tstep));
+  }
   double ngrad[3] = {0.0, 0.0, 0.0}, val = 1.0;
   if (has_s) {
     coop_eval_mo<2, G>(S, L, sd, si, s, np_[0], np_[1], np_[2], ws, lane, gm);
@@ -1437,21 +1450,36 @@ __global__ void __launch_bounds__(128) k_vmc_move_coop(const Sys S, const State 
     for (int i = 0; i < 3; ++i) ngrad[i] = ngrad[i] + gj[i];
     val = val * exp(du);
   }
-  limdrift3(ngrad);
-  double fwd = 0.0, bwd = 0.0;
+  if (DMC)
+    limdrift_dmc(ngrad, ma.tstep);
+  else
+    limdrift3(ngrad);
+  double fwd = 0.0, bwd = 0.0, r2 = 0.0;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     fwd = __dadd_rn(fwd, __dmul_rn(gauss[i], gauss[i]));
-    const double b = __dadd_rn(gauss[i], __dmul_rn(ma.tstep, __dadd_rn(grad[i], ngrad[i])));
+    double b;
+    if (DMC) {
+      const double gd = __dadd_rn(gauss[i], grad[i]);
+      r2 = __dadd_rn(r2, __dmul_rn(gd, gd));
+      b = __dadd_rn(gd, ngrad[i]);
+    } else {
+      b = __dadd_rn(gauss[i], __dmul_rn(ma.tstep, __dadd_rn(grad[i], ngrad[i])));
+    }
     bwd = __dadd_rn(bwd, __dmul_rn(b, b));
   }
   const double tprob = exp(__dmul_rn(1.0 / (2.0 * ma.tstep), __dadd_rn(fwd, -bwd)));
   const double aval = fabs(val);
-  const double ratio = __dmul_rn(__dmul_rn(aval, aval), tprob);
+  double ratio = __dmul_rn(__dmul_rn(aval, aval), tprob);
+  if (DMC) ratio = __dmul_rn(ratio, val > 0.0 ? 1.0 : (val < 0.0 ? -1.0 : 0.0));  // fixed node (dmc.py:65-66)
   const bool acc = __shfl_sync(gm, (ratio > ma.unif[w]) ? 1 : 0, 0, G) != 0;
   if (lane == 0) {
     ma.accept[w] = acc ? 1 : 0;
     if (acc) atomicAdd(ma.nacc, 1ULL);
+    if (DMC) {
+      ma.r2prop[w] = __dadd_rn(ma.r2prop[w], r2);
+      if (acc) ma.r2acc[w] = __dadd_rn(ma.r2acc[w], r2);
+    }
     st.saved_pos[(size_t)w * 3] = np_[0];
     st.saved_pos[(size_t)w * 3 + 1] = np_[1];
     st.saved_pos[(size_t)w * 3 + 2] = np_[2];
@@ -1476,7 +1504,13 @@ __global__ void __launch_bounds__(128) k_vmc_move_coop(const Sys S, const State 
 //            to saved_mo for the update kernels, accepted walkers refresh their cached MO rows
 // The internal updates (Sherman-Morrison of every determinant + dv / W, Jastrow and three-body caches, coordinates
 // and wrap vectors) follow through launch_update, as for the open-boundary general path.
-template <int G>
+// DMC = true: the drift-diffusion move of dmc.py:49-70 (arithmetic of k_vmc_sweep<G, true>), and two more phases for
+// the T-move of electron e (propose_tmoves + dmc.py:170-177) after k_tmove_select left the chosen position in saved_pos:
+//   phase 3  the position wrapped into the cell TWICE, as the reference does (compute_tmoves wraps the candidates,
+//            eval_ecp.py:117 / coord.py:168-184, and propose_tmoves wraps the selected one again, dmc.py:110) -- the
+//            electron keeps its wrap vector plus whatever the second pass still finds (normally nothing)
+//   phase 2  after the orbital kernel: value row -> saved_mo, accepted walkers refresh their cached MO rows
+template <int G, bool DMC = false>
 __global__ void __launch_bounds__(128) k_pbc_move_general(const Sys S, const State st, const MoveArgs ma, int phase) {
   const double* sd;
   const int* si;
@@ -1495,6 +1529,32 @@ __global__ void __launch_bounds__(128) k_pbc_move_general(const Sys S, const Sta
   const int e = ma.e;
   const int s = e >= S.nup ? 1 : 0;
   const int eeff = e - s * S.nup;
+  if (DMC && phase == 3) {
+    if (lane == 0) {
+      double o1[3], w1[3], o2[3], w2[3];
+      wrap_cell(sd + S.o_lat, sd + S.o_latinv, st.saved_pos[(size_t)w * 3], st.saved_pos[(size_t)w * 3 + 1],
+                st.saved_pos[(size_t)w * 3 + 2], o1, w1);
+      wrap_cell(sd + S.o_lat, sd + S.o_latinv, o1[0], o1[1], o1[2], o2, w2);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        st.saved_pos[(size_t)w * 3 + i] = o2[i];
+        st.saved_wrap[(size_t)w * 3 + i] = st.wrap[((size_t)w * S.ne + e) * 3 + i] + w2[i];
+      }
+    }
+    return;
+  }
+  if (DMC && phase == 2) {
+    if (has_s) {
+      const double* __restrict__ rows2 = st.monew + (size_t)w * 5 * ldmax;
+      double* __restrict__ sv = st.saved_mo + (size_t)w * S.ldc[s];
+      for (int j = lane; j < S.ldc[s]; j += G) sv[j] = rows2[j];
+      if (ma.accept[w]) {
+        double* __restrict__ mc = st.mocache + ((size_t)w * S.ne + e) * 5 * ldmax;
+        for (int i = lane; i < 5 * ldmax; i += G) mc[i] = rows2[i];
+      }
+    }
+    return;
+  }
   const double px = phase == 0 ? CONF(st, S, w, e, 0) : st.saved_pos[(size_t)w * 3];
   const double py = phase == 0 ? CONF(st, S, w, e, 1) : st.saved_pos[(size_t)w * 3 + 1];
   const double pz = phase == 0 ? CONF(st, S, w, e, 2) : st.saved_pos[(size_t)w * 3 + 2];
@@ -1519,13 +1579,16 @@ __global__ void __launch_bounds__(128) k_pbc_move_general(const Sys S, const Sta
     for (int i = 0; i < 3; ++i) grad[i] = grad[i] + gj[i];
     val = val * exp(du);
   }
-  limdrift3(grad);
+  if (DMC)
+    limdrift_dmc(grad, ma.tstep);  // the limited drift already carries the (effective) time step
+  else
+    limdrift3(grad);
   const double* __restrict__ gauss = ma.gauss + (size_t)w * 3;
   if (phase == 0) {
     if (lane == 0) {
-      const double nx = __dadd_rn(__dadd_rn(px, gauss[0]), __dmul_rn(grad[0], ma.tstep));
-      const double ny = __dadd_rn(__dadd_rn(py, gauss[1]), __dmul_rn(grad[1], ma.tstep));
-      const double nz = __dadd_rn(__dadd_rn(pz, gauss[2]), __dmul_rn(grad[2], ma.tstep));
+      const double nx = __dadd_rn(__dadd_rn(px, gauss[0]), DMC ? grad[0] : __dmul_rn(grad[0], ma.tstep));
+      const double ny = __dadd_rn(__dadd_rn(py, gauss[1]), DMC ? grad[1] : __dmul_rn(grad[1], ma.tstep));
+      const double nz = __dadd_rn(__dadd_rn(pz, gauss[2]), DMC ? grad[2] : __dmul_rn(grad[2], ma.tstep));
       double o[3], ww[3];
       wrap_cell(sd + S.o_lat, sd + S.o_latinv, nx, ny, nz, o, ww);
 #pragma unroll
@@ -1537,20 +1600,32 @@ __global__ void __launch_bounds__(128) k_pbc_move_general(const Sys S, const Sta
     }
     return;
   }
-  double fwd = 0.0, bwd = 0.0;
+  double fwd = 0.0, bwd = 0.0, r2 = 0.0;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     fwd = __dadd_rn(fwd, __dmul_rn(gauss[i], gauss[i]));
-    const double b = __dadd_rn(gauss[i], __dmul_rn(ma.tstep, __dadd_rn(st.gold[(size_t)w * 3 + i], grad[i])));
+    double b;
+    if (DMC) {
+      const double gd = __dadd_rn(gauss[i], st.gold[(size_t)w * 3 + i]);
+      r2 = __dadd_rn(r2, __dmul_rn(gd, gd));
+      b = __dadd_rn(gd, grad[i]);
+    } else {
+      b = __dadd_rn(gauss[i], __dmul_rn(ma.tstep, __dadd_rn(st.gold[(size_t)w * 3 + i], grad[i])));
+    }
     bwd = __dadd_rn(bwd, __dmul_rn(b, b));
   }
   const double tprob = exp(__dmul_rn(1.0 / (2.0 * ma.tstep), __dadd_rn(fwd, -bwd)));
   const double aval = fabs(val);
-  const double ratio = __dmul_rn(__dmul_rn(aval, aval), tprob);
+  double ratio = __dmul_rn(__dmul_rn(aval, aval), tprob);
+  if (DMC) ratio = __dmul_rn(ratio, val > 0.0 ? 1.0 : (val < 0.0 ? -1.0 : 0.0));  // fixed node (dmc.py:65-66)
   const bool acc = __shfl_sync(gm, (ratio > ma.unif[w]) ? 1 : 0, 0, G) != 0;
   if (lane == 0) {
     ma.accept[w] = acc ? 1 : 0;
     if (acc) atomicAdd(ma.nacc, 1ULL);
+    if (DMC) {
+      ma.r2prop[w] = __dadd_rn(ma.r2prop[w], r2);
+      if (acc) ma.r2acc[w] = __dadd_rn(ma.r2acc[w], r2);
+    }
   }
   if (has_s) {
     double* __restrict__ sv = st.saved_mo + (size_t)w * S.ldc[s];

@@ -2755,7 +2755,11 @@ static int dmc_tmove_electron(qmcb_ctx* c, int e, double tau, const double* d_u,
   constexpr int GE = 8, BE = 64;
   const CoopLayout CLe = coop_layout(S);
   const size_t esm = ((sm + 15) & ~(size_t)15) + (size_t)(BE / GE) * (CLe.total + j3_scratch_doubles(S)) * 8;
-  if (esm <= 100 * 1024 && std::getenv("QMCB_NO_COOP_ECP") == nullptr) {
+  if (S.pbc) {  // wrapped quadrature points, lattice-summed orbitals there, then the ratios (as qmcb_tmoves)
+    if (prep_kernel(k_ecp_points<0>, sm)) return -1;
+    if (ecp_points_pbc_prepass<0>(c, ea, (long long)npts, grid, stream)) return -1;
+    k_ecp_points<0><<<(unsigned)grid, 128, sm, stream>>>(S, c->st, c->es, ea);
+  } else if (esm <= 100 * 1024 && std::getenv("QMCB_NO_COOP_ECP") == nullptr) {
     // few points per launch (one electron, masked walkers): lanes cooperate on a point
     const long long cgrid = std::max<long long>(1, std::min<long long>(((long long)npts + (BE / GE) - 1) / (BE / GE), 148LL * 8));
     if (prep_kernel(k_ecp_points_coop<GE>, esm)) return -1;
@@ -2794,6 +2798,43 @@ static int dmc_tmove_electron(qmcb_ctx* c, int e, double tau, const double* d_u,
     k_tmove_select<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(S, c->st, ts);
     c->nlaunch++;
     CK(cudaGetLastError());
+    if (S.pbc) {
+      // the selected position wrapped as the reference wraps it, the lattice-summed MO rows there, the rows of the
+      // accepted walkers into saved_mo / the MO cache (k_pbc_move_general phases 3 and 2), then the update kernels
+      constexpr int GM = 16;
+      const size_t msm = ((c->smem_bytes + 15) & ~(size_t)15) + (size_t)(128 / GM) * j3_scratch_doubles(S) * 8;
+      const unsigned mgrid = (unsigned)(((long long)N * GM + 127) / 128);
+      MoveArgs ma{};
+      ma.e = e;
+      ma.tstep = tau;
+      ma.accept = c->d_accept.p;
+      if (prep_kernel(k_pbc_move_general<GM, true>, msm)) return -1;
+      k_pbc_move_general<GM, true><<<mgrid, 128, msm, stream>>>(S, c->st, ma, 3);
+      c->nlaunch++;
+      CK(cudaGetLastError());
+      if (c->have_slater) {
+        const int s = e >= S.nup ? 1 : 0;
+        const int ldmax = std::max(S.ldc[0], S.ldc[1]);
+        PbcMoArgs a{};
+        a.npoints = (long long)N;
+        a.pos = c->st.saved_pos;
+        a.wrap = c->st.saved_wrap;
+        a.naip = 1;
+        a.spin_mode = 0;
+        a.spin = s;
+        a.out = c->st.monew;
+        a.stride_p = 5 * ldmax;
+        a.stride_c = ldmax;
+        a.stride_j = 1;
+        if (launch_pbc_mo(c, 2, a, (long long)N, stream)) return -1;
+        k_pbc_move_general<GM, true><<<mgrid, 128, msm, stream>>>(S, c->st, ma, 2);
+        c->nlaunch++;
+        CK(cudaGetLastError());
+      }
+      if (launch_update(c, which, e, c->d_accept.p, stream)) return -1;
+      c->paircache_valid = false;  // the cached MO rows stay valid: accepted walkers refreshed theirs
+      return 0;
+    }
     if (c->have_slater) {  // MO row at the selected position of the accepted walkers (no saved values, dmc.py:176)
       PointArgs pa{};
       pa.which = 1;
@@ -2825,16 +2866,18 @@ int qmcb_dmc_block(qmcb_ctx* c, int nsteps, double tstep, double branchcut, doub
   const Sys& S = c->S;
   const size_t N = c->N;
   cudaStream_t stream = c->stream;
-  const int which = (c->have_slater ? 1 : 0) | (c->have_jastrow ? 2 : 0);
+  const int which = (c->have_slater ? 1 : 0) | (c->have_jastrow ? 2 : 0) | (c->have_j3 ? 4 : 0);
   if (S.cplx) return fail("complex wave functions are served by the protocol calls and the energy accumulator; the device-resident block / SR drivers are real-only");
-  if (S.pbc || c->have_j3 || (c->have_slater && S.ndet != 1))
-    return fail("device-resident DMC supports open-boundary single-determinant Slater-Jastrow wave functions; "
-                "other wave functions run through the per-call protocol");
   const CoopLayout CL = coop_layout(S);
   const size_t tab = (c->smem_bytes + 15) & ~(size_t)15;
   const int G = 16, sweep_warps = 4, sweep_walkers = sweep_warps * (32 / G);
   const size_t sweep_smem = tab + (size_t)sweep_walkers * CL.total * 8;
-  if (sweep_smem > 200 * 1024) return fail("device-resident DMC: sweep scratch exceeds shared memory");
+  // single-determinant Slater-Jastrow: one sweep launch per step; multi-determinant and / or three-body wave functions:
+  // per electron k_vmc_move_coop<GM, true> + the update kernels, as in the VMC block
+  const bool use_sweep = (!c->have_slater || S.ndet == 1) && !c->have_j3 && !S.pbc && sweep_smem <= 200 * 1024;
+  constexpr int GM = 16;
+  const size_t move_smem = tab + (size_t)(128 / GM) * (CL.total + j3_scratch_doubles(S)) * 8;
+  if (!use_sweep && move_smem > 200 * 1024) return fail("device-resident DMC: move scratch exceeds shared memory");
   const bool tmoves = S.necp > 0;
   if (ensure_energy_scratch(c) || energy_scratch_points(c)) return -1;
   const size_t M = (size_t)S.tot_naip;
@@ -2929,7 +2972,7 @@ int qmcb_dmc_block(qmcb_ctx* c, int nsteps, double tstep, double branchcut, doub
       if (c->have_slater && !c->mocache_valid) {
         if ((rc = launch_mo_all(c, 0, stream))) break;
       }
-      if (c->have_jastrow && !c->paircache_valid) {
+      if (use_sweep && c->have_jastrow && !c->paircache_valid) {
         const long long nt = (long long)N * (S.npair + S.ne);
         if ((rc = prep_kernel(k_pair_cache_build, c->smem_bytes))) break;
         k_pair_cache_build<<<(unsigned)((nt + 127) / 128), 128, c->smem_bytes, stream>>>(S, c->st);
@@ -2938,6 +2981,62 @@ int qmcb_dmc_block(qmcb_ctx* c, int nsteps, double tstep, double branchcut, doub
       }
       cudaMemsetAsync(d_r2p.p, 0, N * 8, stream);
       cudaMemsetAsync(d_r2a.p, 0, N * 8, stream);
+      if (!use_sweep) {
+        for (int e = 0; e < S.ne && rc == 0; ++e) {
+          const size_t se = (size_t)step * S.ne + e;
+          MoveArgs ma{};
+          ma.e = e;
+          ma.tstep = tstep;
+          ma.gauss = pg + se * N * 3;
+          ma.unif = pu + se * N;
+          ma.accept = c->d_accept.p;
+          ma.nacc = c->d_nacc.p + se;
+          ma.r2prop = d_r2p.p;
+          ma.r2acc = d_r2a.p;
+          const unsigned mgrid = (unsigned)(((long long)N * GM + 127) / 128);
+          if (S.pbc) {  // drift + wrapped proposal, lattice-summed orbitals, Metropolis test (as the periodic VMC block)
+            const size_t msm = tab + (size_t)(128 / GM) * j3_scratch_doubles(S) * 8;
+            if ((rc = prep_kernel(k_pbc_move_general<GM, true>, msm))) break;
+            k_pbc_move_general<GM, true><<<mgrid, 128, msm, stream>>>(S, c->st, ma, 0);
+            c->nlaunch++;
+            if (c->have_slater) {
+              const int s = e >= S.nup ? 1 : 0;
+              const int ldmax = std::max(S.ldc[0], S.ldc[1]);
+              PbcMoArgs a{};
+              a.npoints = (long long)N;
+              a.pos = c->st.saved_pos;
+              a.wrap = c->st.saved_wrap;
+              a.naip = 1;
+              a.spin_mode = 0;
+              a.spin = s;
+              a.out = c->st.monew;
+              a.stride_p = 5 * ldmax;
+              a.stride_c = ldmax;
+              a.stride_j = 1;
+              if ((rc = launch_pbc_mo(c, 2, a, (long long)N, stream))) break;
+            }
+            k_pbc_move_general<GM, true><<<mgrid, 128, msm, stream>>>(S, c->st, ma, 1);
+          } else {
+            if ((rc = prep_kernel(k_vmc_move_coop<GM, true>, move_smem))) break;
+            k_vmc_move_coop<GM, true><<<mgrid, 128, move_smem, stream>>>(S, c->st, ma);
+          }
+          c->nlaunch++;
+          if (cudaGetLastError() != cudaSuccess) {
+            rc = fail("DMC move kernel launch failed");
+            break;
+          }
+          rc = launch_update(c, which, e, ma.accept, stream);
+          c->paircache_valid = false;  // the cached MO rows stay valid: accepted walkers refreshed theirs
+        }
+        if (rc) break;
+        c->kinetic_valid = false;
+        if ((rc = launch_energy(c, peu + (size_t)(step + 1) * nu1, per + (size_t)(step + 1) * nr1, c->d_energy.p, stream))) break;
+        k_dmc_weights<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(S, c->st, wa);
+        c->nlaunch++;
+        k_colsum<<<7, 256, 0, stream>>>(d_prod.p, (int)N, d_ws.p + (size_t)step * 8);
+        c->nlaunch++;
+        continue;
+      }
       SweepArgs sa{};
       sa.tstep = tstep;
       sa.gauss = pg + (size_t)step * S.ne * N * 3;

@@ -2,8 +2,8 @@
 ``branch`` (342-376) and ``rundmc`` (412-586) keep the reference's arguments, RNG consumption order,
 output dictionaries and restart-file layout.
 
-When the wave function is a fused single-determinant Slater-Jastrow on an open-boundary system and
-the only accumulator is a ``pyqmc_b200.EnergyAccumulator``, ``dmc_propagate`` runs DEVICE-RESIDENT:
+When the wave function is a fused Slater-Jastrow (single- or multi-determinant, with or without a
+three-body factor; open boundaries or a periodic cell) and the only accumulator is a ``pyqmc_b200.EnergyAccumulator``, ``dmc_propagate`` runs DEVICE-RESIDENT:
 every random variate of the block is drawn up front from the global legacy ``np.random`` stream in
 exactly the order the reference loop consumes it, shipped once, and ``qmcb_dmc_block`` executes the
 T-moves, drift-diffusion sweeps, local energies and weight updates without host round trips.
@@ -20,12 +20,12 @@ import scipy.spatial.transform
 
 from . import _lib, mc
 from .accumulators import KEYS, EnergyAccumulator, _device_context
-from .wf import JASTROW, SLATER
+from .wf import JASTROW, JASTROW3, SLATER
 
 
 def _device_dmc_path(wf, accumulators, ekey):
-    """Device-resident propagation: fused single-determinant Slater x JastrowSpin, open boundary
-    conditions, one EnergyAccumulator under ``ekey[0]``."""
+    """Device-resident propagation: fused real Slater x JastrowSpin [x ThreeBodyJastrow] (any determinant expansion,
+    open or periodic boundary conditions), one EnergyAccumulator under ``ekey[0]``."""
     try:
         ctx = _device_context(wf)
     except TypeError:
@@ -37,14 +37,10 @@ def _device_dmc_path(wf, accumulators, ekey):
         # default sizes when naip is passed (accumulators.py:80-81): that combination runs through the protocol calls
         return False
     which = getattr(wf, "_which", 0)
-    if which & ~(SLATER | JASTROW) or not (which & SLATER) or wf.dtype == complex:
+    if which & ~(SLATER | JASTROW | JASTROW3) or not (which & SLATER) or wf.dtype == complex:
         return False
-    factors = getattr(wf, "wf_factors", [wf])
-    if len(factors[0].parameters["det_coeff"]) != 1:
-        return False
-    mol = factors[0]._mol
     del ctx
-    return not hasattr(mol, "a")
+    return True  # open boundaries: sweep kernel or k_vmc_move_coop<16, true>; periodic: k_pbc_move_general<16, true>
 
 
 def _dmc_buffers(shapes, pinned_owner, slot=0):
@@ -293,6 +289,8 @@ def dmc_propagate_device(wf, configs, weights, tstep, branchcut_start, e_trial, 
             d(wsums), nacc.ctypes.data_as(_lib.c_i64_p), ntacc.ctypes.data_as(_lib.c_i64_p)))
     ctx.epoch += 1  # the block moved the walkers on the device
     configs.configs[...] = newconf
+    if ctx.periodic:
+        configs.wrap[...] = ctx.get_state("wrap", configs.wrap.shape)
     if w is not weights:
         weights[...] = w
     rows = []
@@ -332,8 +330,8 @@ def dmc_propagate(wf, configs, weights, tstep, branchcut_start, e_trial, e_est, 
                                     ekey, variates=variates)
     refdmc = _reference_dmc()
     if refdmc is None:
-        raise TypeError("pyqmc_b200.dmc_propagate runs device-resident blocks (fused single-determinant "
-                        "Slater-Jastrow, open boundaries, one pyqmc_b200.EnergyAccumulator); drive other "
+        raise TypeError("pyqmc_b200.dmc_propagate runs device-resident blocks (fused "
+                        "real Slater-Jastrow, one pyqmc_b200.EnergyAccumulator); drive other "
                         "combinations with pyqmc.method.dmc, which accepts these objects unchanged")
     return refdmc.dmc_propagate(wf, configs, weights, tstep, branchcut_start, e_trial, e_est, nsteps=nsteps,
                                 accumulators=accumulators, ekey=ekey)

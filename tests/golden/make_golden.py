@@ -137,16 +137,20 @@ def generate(name):
         out["vmc_wrap"] = configs.wrap.copy()
     for k in ("energytotal", "energyke", "energyecp", "energyee", "energyei", "energygrad2", "acceptance"):
         out["vmc_" + k] = df[k]
-    if name in ("h2o", "c2", "open"):
+    if name in ("h2o", "c2", "open", "h2o_md", "ortho", "diamond211", "ortho_md"):
         # DMC propagation with T-moves through the reference's own dmc_propagate (dmc.py:123-221)
         import pyqmc.method.dmc as dmc
 
         out["dmc_configs0"] = configs.configs.copy()
+        if periodic:
+            out["dmc_wrap0"] = configs.wrap.copy()
         weights = np.ones(NCONF)
         np.random.seed(41)
         dret, configs, weights = dmc.dmc_propagate(wf, configs, weights, 0.02, 10.0, 1.5, 1.7, nsteps=3,
                                                   accumulators={"energy": EnergyAccumulator(mol, **ekw)})
         out["dmc_configs"] = configs.configs.copy()
+        if periodic:
+            out["dmc_wrap"] = configs.wrap.copy()
         out["dmc_weights"] = weights.copy()
         for k, v in dret.items():
             out["dmc_" + k] = np.asarray(v)

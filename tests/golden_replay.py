@@ -82,6 +82,8 @@ def replay(data, wf, configs, make_energy, vmc_fn, check_internal=None):
 
 def check_dmc(data, out, configs, weights):
     assert np.abs(configs.configs - data["dmc_configs"]).max() < 1e-9
+    if "dmc_wrap" in data:
+        assert np.array_equal(configs.wrap, data["dmc_wrap"])
     assert relerr(weights, data["dmc_weights"]) < 1e-9
     for k in ("energytotal", "energyke", "energyecp", "energygrad2", "weight", "acceptance", "tmove_acceptance"):
         assert abs(out[k] - data["dmc_" + k]) <= 1e-9 * max(1.0, abs(data["dmc_" + k])), k

@@ -9,7 +9,7 @@ import helpers
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["h2o", "c2", "open"])
+@pytest.mark.parametrize("name", ["h2o", "c2", "open", "h2o_md"])
 def test_device_resident_dmc_matches_reference_golden(lib, name):
     """dmc.py:123-221 with T-moves: walkers, weights and weighted block averages of the reference run."""
     import pyqmc_b200 as pq
@@ -29,10 +29,12 @@ def test_device_resident_dmc_matches_reference_golden(lib, name):
     del launches0
 
 
-@pytest.mark.parametrize("name", ["h2o", "he", "hatom"])
+@pytest.mark.parametrize("name", ["h2o", "he", "hatom", "h2o_md", "h2o_3b", "h2o_md_3b"])
 def test_device_resident_dmc_matches_oracle_loop(lib, name):
     """Same seed, more walkers and steps: device block vs the oracle loop over the oracle wave function;
-    the RNG stream must end at the same position (the block draws exactly what the loop consumes)."""
+    the RNG stream must end at the same position (the block draws exactly what the loop consumes).
+    h2o_md / h2o_3b / h2o_md_3b take the general path (k_vmc_move_coop<16, true> + the update kernels, unfused
+    T-moves)."""
     import pyqmc_b200 as pq
     from oracle import dmc_driver
     from oracle.local_energy import EnergyOracle

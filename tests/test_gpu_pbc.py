@@ -198,3 +198,53 @@ def test_periodic_dmc_through_the_protocol(lib, name):
     assert helpers.relerr(w1, w2) < 1e-8
     for k in ("energytotal", "acceptance", "tmove_acceptance", "weight"):
         assert abs(out1[k] - out2[k]) <= 1e-8 * max(1.0, abs(out2[k])), k
+
+
+@pytest.mark.parametrize("name", ["ortho", "diamond211", "ortho_md"])
+def test_device_resident_periodic_dmc_matches_reference_golden(lib, name):
+    """qmcb_dmc_block on periodic wave functions (k_pbc_move_general<16, true>: fixed-node drift-diffusion with the
+    wrapped proposal, T-moves wrapped as propose_tmoves wraps them, Ewald energy) against the reference's own
+    dmc_propagate: walkers, wrap vectors, weights and weighted block averages."""
+    import pyqmc_b200 as pq
+    from pyqmc_b200 import dmc
+
+    data = golden_replay.load(name)
+    mol, mf, wf, _ = helpers.make_pair(name, seed=1)
+    configs = periodic_configs(data, mol, "dmc_configs0", "dmc_wrap0")
+    weights = np.ones(len(configs.configs))
+    acc = {"energy": pq.EnergyAccumulator(mol, ewald_gmax=EWALD_GMAX)}
+    assert dmc._device_dmc_path(wf, acc, ("energy", "total"))
+    np.random.seed(41)
+    out, configs, weights = dmc.dmc_propagate(wf, configs, weights, 0.02, 10.0, 1.5, 1.7, nsteps=3, accumulators=acc)
+    golden_replay.check_dmc(data, out, configs, weights)
+
+
+@pytest.mark.parametrize("name", PBC_SYSTEMS + ["ortho_3b", "diamond211_3b", "ortho_md", "diamond211_md"])
+def test_device_resident_periodic_dmc_matches_oracle_loop(lib, name):
+    """Device block vs the oracle loop over the oracle objects, more walkers: same walkers, wrap vectors, weights,
+    averages, and the same position of the random stream afterwards.  tstep = 0.1 so that T-moves are accepted too
+    (their weight grows with the time step)."""
+    import pyqmc_b200 as pq
+    from oracle import dmc_driver
+    from oracle.local_energy import EnergyOracle
+    from pyqmc_b200 import dmc
+
+    mol, mf, wf, orc = helpers.make_pair(name, seed=1)
+    np.random.seed(3)
+    configs = pq.initial_guess(mol, 24)
+    oc = helpers.to_oracle_walkers(configs)
+    w1, w2 = np.ones(24), np.ones(24)
+    np.random.seed(4)
+    out1, configs, w1 = dmc.dmc_propagate(wf, configs, w1, 0.1, 10.0, -5.0, -5.1, nsteps=2,
+                                          accumulators={"energy": pq.EnergyAccumulator(mol, ewald_gmax=EWALD_GMAX)})
+    tail1 = np.random.rand()
+    np.random.seed(4)
+    out2, oc, w2 = dmc_driver.dmc_propagate(orc, oc, w2, 0.1, 10.0, -5.0, -5.1, nsteps=2,
+                                            accumulators={"energy": EnergyOracle(mol, ewald_gmax=EWALD_GMAX)})
+    tail2 = np.random.rand()
+    assert tail1 == tail2
+    assert np.abs(configs.configs - oc.configs).max() < 1e-9
+    assert np.array_equal(configs.wrap, oc.wrap)
+    assert helpers.relerr(w1, w2) < 1e-9
+    for k in out2:
+        assert abs(out1[k] - out2[k]) <= 1e-9 * max(1.0, abs(out2[k])), k

@@ -184,7 +184,7 @@ def test_device_sph_tables_equal_oracle_tables():
             assert a == b
 
 
-@pytest.mark.parametrize("name", ["h2o", "c2", "open"])
+@pytest.mark.parametrize("name", ["h2o", "c2", "open", "h2o_md"])
 def test_oracle_dmc_propagate_matches_reference_golden(name):
     """oracle/dmc_driver.py (restating dmc.py:22-235) driving the oracle wave function vs the
     reference's own dmc_propagate with T-moves: weights, walkers and weighted averages."""
@@ -199,6 +199,24 @@ def test_oracle_dmc_propagate_matches_reference_golden(name):
     np.random.seed(41)
     out, configs, weights = dmc_driver.dmc_propagate(orc, configs, weights, 0.02, 10.0, 1.5, 1.7, nsteps=3,
                                                      accumulators={"energy": EnergyOracle(mol)})
+    golden_replay.check_dmc(data, out, configs, weights)
+
+
+@pytest.mark.parametrize("name", ["ortho", "diamond211", "ortho_md"])
+def test_oracle_dmc_propagate_matches_reference_golden_periodic(name):
+    """The same for periodic systems (Ewald energy, T-moves wrapped twice as propose_tmoves does, dmc.py:110):
+    walkers, wrap vectors, weights and weighted averages of the reference's dmc_propagate."""
+    from oracle import dmc_driver
+    from oracle.local_energy import EnergyOracle
+    from oracle.pbc import PeriodicWalkers
+
+    data = golden_replay.load(name)
+    mol, mf, _, orc = _oracle_only(name)
+    configs = periodic_walkers(PeriodicWalkers, data, mol, "dmc_configs0", "dmc_wrap0")
+    weights = np.ones(len(configs.configs))
+    np.random.seed(41)
+    out, configs, weights = dmc_driver.dmc_propagate(orc, configs, weights, 0.02, 10.0, 1.5, 1.7, nsteps=3,
+                                                     accumulators={"energy": EnergyOracle(mol, ewald_gmax=EWALD_GMAX)})
     golden_replay.check_dmc(data, out, configs, weights)
 
 
