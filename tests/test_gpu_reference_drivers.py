@@ -213,6 +213,36 @@ def test_periodic_three_body_under_the_reference_driver(lib, name):
         assert helpers.relerr(df[k], odf[k]) < TOL, k
 
 
+@pytest.mark.gpu
+@needs_reference
+@pytest.mark.parametrize("name", ["ortho", "ortho_md", "h2o_md_3b"])
+def test_device_resident_rundmc_equals_the_reference_driver_over_the_protocol(lib, name):
+    """pyqmc_b200.rundmc (device-resident warm-up, propagation and variates, host branching) vs the reference's rundmc
+    driving a second copy of the same device objects call by call: periodic cells and multi-determinant / three-body
+    wave functions take the general DMC kernels (k_pbc_move_general<16, true>, k_vmc_move_coop<16, true>)."""
+    import pyqmc_b200 as pq
+
+    refload.load()
+    import pyqmc.method.dmc as refdmc
+
+    kw = dict(tstep=0.05, nblocks=3, nsteps_per_block=2, vmc_warmup=2)
+    out = []
+    for driver in (pq.rundmc, refdmc.rundmc):
+        mol, mf, wf, _ = helpers.make_pair(name, seed=1)
+        ekw = EWALD if hasattr(mol, "a") else {}
+        np.random.seed(17)
+        configs = pq.initial_guess(mol, 14)
+        np.random.seed(18)
+        out.append(driver(wf, configs, accumulators={"energy": pq.EnergyAccumulator(mol, **ekw)}, **kw))
+    (df1, c1, w1), (df2, c2, w2) = out
+    assert np.abs(c1.configs - c2.configs).max() < 1e-9
+    if hasattr(c1, "wrap"):
+        assert np.array_equal(c1.wrap, c2.wrap)
+    assert helpers.relerr(w1, w2) < 1e-9
+    for k in ("energytotal", "energyke", "energyecp", "weight", "acceptance", "tmove_acceptance", "e_trial", "e_est"):
+        assert helpers.relerr(df1[k], df2[k]) < 1e-9, k
+
+
 # ---- CPU self-check of the harness above: the same functions over the REFERENCE's own wave functions must
 # reproduce the golden files (run in the build container; proves the test plumbing, not the product) ----------
 @needs_reference
