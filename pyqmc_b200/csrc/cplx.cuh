@@ -726,3 +726,77 @@ __global__ void __launch_bounds__(128) k_cx_pgrad_mo(const Sys S, const State st
   }
   out[t] = acc;
 }
+
+// -----------------------------------------------------------------------------------------
+// Device-resident VMC block of a COMPLEX wave function (mc.py:112-137): the per-electron loop chains the query kernels
+// above without host round trips.  Per electron: k_cx_chain<0> gathers the electron's positions, k_cx_point<GRADVAL>
+// gives the drift there, k_cx_chain<1> limits it and writes the (wrapped) proposal, [k_pbc_mo rows +]
+// k_cx_point<GRADVAL> with save gives the drift, the ratio and the MO row there, k_cx_chain<2> runs the Metropolis test
+// on |ratio|^2 (np.abs of a complex number: hypot), and the update kernels (launch_update: k_cx_sm, k_cx_det_cache,
+// Jastrow / three-body caches, coordinates and wrap vectors) commit the accepted walkers.
+// -----------------------------------------------------------------------------------------
+struct CxChainArgs {
+  int e;
+  double tstep;
+  const double* gauss;  // [N][3]
+  const double* unif;   // [N]
+  uint8_t* accept;      // [N]
+  unsigned long long* nacc;
+  double* pos;          // [N][3] staging of the query positions
+  double* pwrap;        // [N][3] periodic: wrap vectors of the proposal (= saved_wrap)
+  const cd* grad;       // [3][N] output of k_cx_point
+  const cd* val;        // [N]
+};
+
+template <int PHASE>
+__global__ void __launch_bounds__(128) k_cx_chain(const Sys S, const State st, const CxChainArgs a) {
+  const double* sd;
+  const int* si;
+  stage_tables(S, sd, si);
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = st.N;
+  if (w >= N) return;
+  if (PHASE == 0) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) a.pos[(size_t)w * 3 + i] = CONF(st, S, w, a.e, i);
+    if (S.pbc) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) a.pwrap[(size_t)w * 3 + i] = st.wrap[((size_t)w * S.ne + a.e) * 3 + i];
+    }
+    return;
+  }
+  double grad[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) grad[i] = a.grad[(size_t)i * N + w].x;  // np.real(g.T)
+  limdrift3(grad);
+  const double* __restrict__ gauss = a.gauss + (size_t)w * 3;
+  if (PHASE == 1) {
+    const double nx = __dadd_rn(__dadd_rn(a.pos[(size_t)w * 3], gauss[0]), __dmul_rn(grad[0], a.tstep));
+    const double ny = __dadd_rn(__dadd_rn(a.pos[(size_t)w * 3 + 1], gauss[1]), __dmul_rn(grad[1], a.tstep));
+    const double nz = __dadd_rn(__dadd_rn(a.pos[(size_t)w * 3 + 2], gauss[2]), __dmul_rn(grad[2], a.tstep));
+    double o[3] = {nx, ny, nz}, ww[3] = {0.0, 0.0, 0.0};
+    if (S.pbc) wrap_cell(sd + S.o_lat, sd + S.o_latinv, nx, ny, nz, o, ww);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      a.pos[(size_t)w * 3 + i] = o[i];
+      if (S.pbc) a.pwrap[(size_t)w * 3 + i] = st.wrap[((size_t)w * S.ne + a.e) * 3 + i] + ww[i];
+      st.gold[(size_t)w * 3 + i] = grad[i];
+    }
+    return;
+  }
+  double fwd = 0.0, bwd = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    fwd = __dadd_rn(fwd, __dmul_rn(gauss[i], gauss[i]));
+    const double b = __dadd_rn(gauss[i], __dmul_rn(a.tstep, __dadd_rn(st.gold[(size_t)w * 3 + i], grad[i])));
+    bwd = __dadd_rn(bwd, __dmul_rn(b, b));
+  }
+  const double tprob = exp(__dmul_rn(1.0 / (2.0 * a.tstep), __dadd_rn(fwd, -bwd)));
+  const cd v = a.val[w];
+  const double aval = hypot(v.x, v.y);
+  const double ratio = __dmul_rn(__dmul_rn(aval, aval), tprob);
+  const bool acc = ratio > a.unif[w];
+  a.accept[w] = acc ? 1 : 0;
+  const unsigned b = __ballot_sync(__activemask(), acc);
+  if (acc && (threadIdx.x & 31) == (__ffs(b) - 1)) atomicAdd(a.nacc, (unsigned long long)__popc(b));
+}

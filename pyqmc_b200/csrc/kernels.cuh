@@ -1544,14 +1544,12 @@ __global__ void __launch_bounds__(128) k_pbc_move_general(const Sys S, const Sta
     return;
   }
   if (DMC && phase == 2) {
-    if (has_s) {
+    if (has_s && ma.accept[w]) {  // the orbital kernel ran for the accepted walkers only
       const double* __restrict__ rows2 = st.monew + (size_t)w * 5 * ldmax;
       double* __restrict__ sv = st.saved_mo + (size_t)w * S.ldc[s];
       for (int j = lane; j < S.ldc[s]; j += G) sv[j] = rows2[j];
-      if (ma.accept[w]) {
-        double* __restrict__ mc = st.mocache + ((size_t)w * S.ne + e) * 5 * ldmax;
-        for (int i = lane; i < 5 * ldmax; i += G) mc[i] = rows2[i];
-      }
+      double* __restrict__ mc = st.mocache + ((size_t)w * S.ne + e) * 5 * ldmax;
+      for (int i = lane; i < 5 * ldmax; i += G) mc[i] = rows2[i];
     }
     return;
   }

@@ -2261,13 +2261,15 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
   const Sys& S = c->S;
   const size_t N = c->N;
   cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : c->stream;
-  if (S.cplx) return fail("complex wave functions are served by the protocol calls and the energy accumulator; the device-resident block / SR drivers are real-only");
+  // complex wave functions: the query kernels of cplx.cuh chained on the device (k_cx_chain), 8 energy rows per step
+  const bool chain = S.cplx != 0;
+  const size_t rows = S.cplx ? 8 : 6;
   const int which = (c->have_slater ? 1 : 0) | (c->have_jastrow ? 2 : 0) | (c->have_j3 ? 4 : 0);
   if (with_energy && (ensure_energy_scratch(c) || energy_scratch_points(c))) return -1;
   if (ensure_scratch(c, N, 5)) return -1;
   if (c->d_accept.ensure(N) || c->d_nacc.ensure((size_t)nsteps * S.ne)) return -1;
   if (!d_energy && with_energy) {
-    if (c->d_energy.ensure(6 * N)) return -1;
+    if (c->d_energy.ensure(rows * N)) return -1;
   }
   unsigned long long* nacc = d_nacc ? (unsigned long long*)d_nacc : c->d_nacc.p;
   CK(cudaMemsetAsync(nacc, 0, (size_t)nsteps * S.ne * 8, stream));
@@ -2281,9 +2283,13 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
   if (const char* env = std::getenv("QMCB_SWEEP_WARPS")) sweep_warps = std::max(1, std::min(4, std::atoi(env)));
   const int sweep_walkers = sweep_warps * (32 / G);
   const size_t sweep_smem = tab + (size_t)sweep_walkers * CL.total * 8;
-  const bool use_sweep = (!c->have_slater || S.ndet == 1) && !c->have_j3 && sweep_smem <= 200 * 1024 && !S.pbc &&
+  const bool use_sweep = (!c->have_slater || S.ndet == 1) && !c->have_j3 && sweep_smem <= 200 * 1024 && !S.pbc && !chain &&
                          std::getenv("QMCB_NO_SWEEP") == nullptr;
-  const bool use_pbc = S.pbc != 0;
+  const bool use_pbc = S.pbc != 0 && !chain;
+  if (chain) {
+    if (c->b_gold.ensure(N * 3) || c->d_in.ensure(N * 3) || c->d_pwrap.ensure(N * 3) || c->d_out.ensure(16 * N)) return -1;
+    c->st.gold = c->b_gold.p;
+  }
   // periodic multi-determinant and / or three-body wave functions: k_pbc_move_general around the orbital kernel + launch_update
   const bool pbc_general = use_pbc && ((c->have_slater && S.ndet != 1) || c->have_j3);
   if (use_pbc && c->have_slater && !c->mocache_valid)
@@ -2472,7 +2478,52 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
       }
       c->paircache_valid = false;
     }
-    for (int e = 0; e < S.ne && !use_sweep && !use_pbc; ++e) {
+    for (int e = 0; e < S.ne && chain; ++e) {
+      const size_t se = (size_t)step * S.ne + e;
+      const unsigned cgrid = (unsigned)((N + 127) / 128);
+      CxChainArgs ca{};
+      ca.e = e;
+      ca.tstep = tstep;
+      ca.gauss = d_gauss + se * N * 3;
+      ca.unif = d_unif + se * N;
+      ca.accept = d_accept ? d_accept + se * N : c->d_accept.p;
+      ca.nacc = nacc + se;
+      ca.pos = c->d_in.p;
+      ca.pwrap = c->d_pwrap.p;
+      ca.grad = reinterpret_cast<const cd*>(c->d_out.p);
+      ca.val = reinterpret_cast<const cd*>(c->d_out.p + 6 * N);
+      PointArgs pa{};
+      pa.which = which;
+      pa.e = e;
+      pa.naip = 1;
+      pa.pos = c->d_in.p;
+      pa.npoints = (int)N;
+      pa.o_grad = c->d_out.p;
+      pa.o_val = c->d_out.p + 6 * N;
+      pa.o_lap = c->d_out.p + 6 * N;
+      pa.scr = c->d_scr.p;
+      pa.scr_stride = N;
+      k_cx_chain<0><<<cgrid, 128, c->smem_bytes, stream>>>(S, c->st, ca);  // positions (and wrap vectors) of electron e
+      c->nlaunch++;
+      CK(cudaGetLastError());
+      if (S.pbc && pbc_point_rows(c, 1, e, c->d_in.p, c->d_pwrap.p, nullptr, 1, (long long)N, N, stream)) return -1;
+      pa.save = 0;
+      if (launch_point<PV_GRADVAL>(c, pa, stream)) return -1;
+      ca.pwrap = c->st.saved_wrap;
+      k_cx_chain<1><<<cgrid, 128, c->smem_bytes, stream>>>(S, c->st, ca);  // limited drift, (wrapped) proposal
+      c->nlaunch++;
+      CK(cudaGetLastError());
+      if (S.pbc && pbc_point_rows(c, 1, e, c->d_in.p, c->st.saved_wrap, nullptr, 1, (long long)N, N, stream)) return -1;
+      pa.save = 1;
+      if (launch_point<PV_GRADVAL>(c, pa, stream)) return -1;
+      k_cx_chain<2><<<cgrid, 128, c->smem_bytes, stream>>>(S, c->st, ca);  // Metropolis test
+      c->nlaunch++;
+      CK(cudaGetLastError());
+      if (launch_update(c, which, e, ca.accept, stream)) return -1;
+      c->mocache_valid = false;
+      c->paircache_valid = false;
+    }
+    for (int e = 0; e < S.ne && !use_sweep && !use_pbc && !chain; ++e) {
       const size_t se = (size_t)step * S.ne + e;
       MoveArgs ma{};
       ma.e = e;
@@ -2504,7 +2555,7 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
       c->paircache_valid = false;
     }
     if (with_energy) {
-      double* eo = d_energy ? d_energy + (size_t)step * 6 * N : c->d_energy.p;
+      double* eo = d_energy ? d_energy + (size_t)step * rows * N : c->d_energy.p;
       const size_t ue = (size_t)step * S.ne * S.necp;
       const double* su = d_ecp_u ? d_ecp_u + ue * N : nullptr;
       const double* sr = d_ecp_rot ? d_ecp_rot + ue * 9 : nullptr;
@@ -2531,7 +2582,7 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
         c->pbc_mo_grid_cap = 0;
         if (erc) return -1;
         if (d_esum) {
-          k_colsum<<<6, 256, 0, es_>>>(eo, (int)N, d_esum + (size_t)step * 6);
+          k_colsum<<<(unsigned)rows, 256, 0, es_>>>(eo, (int)N, d_esum + (size_t)step * rows);
           c->nlaunch++;
           CK(cudaGetLastError());
         }
@@ -2540,7 +2591,7 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
       } else {
         if (launch_energy(c, su, sr, eo, stream)) return -1;
         if (d_esum) {
-          k_colsum<<<6, 256, 0, stream>>>(eo, (int)N, d_esum + (size_t)step * 6);
+          k_colsum<<<(unsigned)rows, 256, 0, stream>>>(eo, (int)N, d_esum + (size_t)step * rows);
           c->nlaunch++;
           CK(cudaGetLastError());
         }
@@ -2574,7 +2625,8 @@ int qmcb_vmc_block(qmcb_ctx* c, int nsteps, double tstep, int with_energy, const
   }
   DBuf<uint8_t> acc_all;
   if (accept && acc_all.ensure(nse * N)) return -1;
-  if (with_energy && (c->d_energy.ensure((size_t)nsteps * 6 * N) || c->d_esum.ensure((size_t)nsteps * 6))) return -1;
+  const size_t rows = S.cplx ? 8 : 6;  // complex wave functions: + Im ecp, Im total per step
+  if (with_energy && (c->d_energy.ensure((size_t)nsteps * rows * N) || c->d_esum.ensure((size_t)nsteps * rows))) return -1;
   int rc = qmcb_vmc_block_device(c, nsteps, tstep, with_energy, c->d_gauss.p, c->d_unif.p, c->d_u.p, c->d_rot.p,
                                  accept ? acc_all.p : nullptr, with_energy ? c->d_energy.p : nullptr,
                                  with_energy ? c->d_esum.p : nullptr, nullptr, c->stream);
@@ -2584,8 +2636,8 @@ int qmcb_vmc_block(qmcb_ctx* c, int nsteps, double tstep, int with_energy, const
   }
   if (accept) CK(cudaMemcpyAsync(accept, acc_all.p, nse * N, cudaMemcpyDeviceToHost, c->stream));
   if (energy && with_energy)
-    CK(cudaMemcpyAsync(energy, c->d_energy.p, (size_t)nsteps * 6 * N * 8, cudaMemcpyDeviceToHost, c->stream));
-  if (esum && with_energy) CK(cudaMemcpyAsync(esum, c->d_esum.p, (size_t)nsteps * 6 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(energy, c->d_energy.p, (size_t)nsteps * rows * N * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (esum && with_energy) CK(cudaMemcpyAsync(esum, c->d_esum.p, (size_t)nsteps * rows * 8, cudaMemcpyDeviceToHost, c->stream));
   if (nacc) CK(cudaMemcpyAsync(nacc, c->d_nacc.p, nse * 8, cudaMemcpyDeviceToHost, c->stream));
   if (configs) {
     const size_t nel = N * S.ne * 3;
@@ -2632,6 +2684,7 @@ int qmcb_vmc_block_slot(qmcb_ctx* c, int slot, int nsteps, double tstep, int wit
   const size_t N = c->N;
   const size_t nse = (size_t)nsteps * S.ne;
   if (c->s_gauss[slot].n < nse * N * 3) return fail("slot was not uploaded for this block shape");
+  if (S.cplx) return fail("complex wave functions run their device-resident blocks through qmcb_vmc_block (no pipelined slots)");
   CK(cudaStreamWaitEvent(c->stream, c->slot_ready[slot], 0));
   DBuf<uint8_t> acc_all;
   if (accept && acc_all.ensure(nse * N)) return -1;
@@ -2676,6 +2729,7 @@ int qmcb_vmc_block_slot_begin(qmcb_ctx* c, int slot, int nsteps, double tstep, i
   const size_t N = c->N;
   const size_t nse = (size_t)nsteps * S.ne;
   if (c->s_gauss[slot].n < nse * N * 3) return fail("slot was not uploaded for this block shape");
+  if (S.cplx) return fail("complex wave functions run their device-resident blocks through qmcb_vmc_block (no pipelined slots)");
   if (recompute_which) {
     if (which_ok(c, recompute_which)) return -1;
     if (recompute_from_resident(c, recompute_which, (int)N)) return -1;
@@ -2826,6 +2880,7 @@ static int dmc_tmove_electron(qmcb_ctx* c, int e, double tau, const double* d_u,
         a.stride_p = 5 * ldmax;
         a.stride_c = ldmax;
         a.stride_j = 1;
+        a.mask = c->d_accept.p;  // T-moves are rarely accepted: only those walkers' rows are evaluated
         if (launch_pbc_mo(c, 2, a, (long long)N, stream)) return -1;
         k_pbc_move_general<GM, true><<<mgrid, 128, msm, stream>>>(S, c->st, ma, 2);
         c->nlaunch++;

@@ -53,8 +53,7 @@ def _device_path(wf, accumulators):
     except TypeError:
         return False
     factors = getattr(wf, "wf_factors", [wf])
-    if wf.dtype == complex:  # complex wave functions run through the protocol calls (csrc/cplx.cuh), not the block kernels
-        return False
+    # complex wave functions: the query kernels of csrc/cplx.cuh chained on the device (k_cx_chain), host-drawn variates
     # periodic wave functions: single-determinant Slater x JastrowSpin takes the fused two-launch chain, multi-determinant
     # and three-body ones k_pbc_move_general + the update kernels (qmcb_vmc_block_device decides)
     return all(isinstance(a, EnergyAccumulator) for a in accumulators.values()) and len(accumulators) <= 1
@@ -63,14 +62,14 @@ def _device_path(wf, accumulators):
 class BlockBuffers:
     """Page-locked host buffers for the variates and results of one device-resident block."""
 
-    def __init__(self, nconf, nelec, nsteps, necp, with_energy):
+    def __init__(self, nconf, nelec, nsteps, necp, with_energy, rows=6):
         P = _lib.PinnedArray
-        self.key = (nconf, nelec, nsteps, necp, with_energy)
+        self.key = (nconf, nelec, nsteps, necp, with_energy, rows)
         self._own = [P((nsteps, nelec, nconf, 3)), P((nsteps, nelec, nconf))]
         self.gauss, self.unif = self._own[0].array, self._own[1].array
         self.ecp_u = self.ecp_rot = self.energy = None
         if with_energy:
-            self._own += [P((nsteps, nelec, necp, nconf)), P((nsteps, nelec, necp, 3, 3)), P((nsteps, 6, nconf))]
+            self._own += [P((nsteps, nelec, necp, nconf)), P((nsteps, nelec, necp, 3, 3)), P((nsteps, rows, nconf))]
             self.ecp_u, self.ecp_rot, self.energy = (x.array for x in self._own[2:5])
         self._own += [P((nconf, nelec, 3)), P((nsteps, nelec), np.int64)]
         self.newconf, self.nacc = self._own[-2].array, self._own[-1].array
@@ -142,7 +141,9 @@ def _draw_block_variates_native(nconf, nelec, tstep, nsteps, necp, out):
 
 def _block_buffers(ctx, nconf, nelec, nsteps, accumulator, slot=0):
     """Two cached sets of pinned buffers per context (double buffering for the RNG prefetch)."""
-    key = (nconf, nelec, nsteps, accumulator.necp if accumulator is not None else 0, accumulator is not None)
+    # per step and walker: ke, ee, ei, ecp, grad2, total; complex wave functions add Im ecp, Im total (eval_ecp.py:26)
+    key = (nconf, nelec, nsteps, accumulator.necp if accumulator is not None else 0, accumulator is not None,
+           8 if ctx.cplx else 6)
     cache = ctx.__dict__.setdefault("_block_buffers", {})
     if cache.get(slot) is None or cache[slot].key != key:
         cache[slot] = BlockBuffers(*key)
@@ -164,7 +165,7 @@ def _recompute_resident(wf, configs):
     except TypeError:
         return False
     res = getattr(ctx, "_resident", None) if ctx is not None else None
-    if res is None or ctx.periodic or res[1] != ctx.epoch or res[0].newconf.shape != configs.configs.shape:
+    if res is None or ctx.periodic or ctx.cplx or res[1] != ctx.epoch or res[0].newconf.shape != configs.configs.shape:
         return False
     if not np.array_equal(res[0].newconf, configs.configs):
         return False
@@ -187,11 +188,15 @@ def _block_averages(buffers, nsteps, nconf, nelec, acc_name, accumulator):
         # per-step walker means (one pairwise-summed reduction per (step, key) row, as np.mean of the row),
         # accumulated over the steps in order as the reference loop does (mc.py:139-147)
         means = np.mean(buffers.energy[:nsteps], axis=2)
+        if means.shape[1] == 8:  # complex wave function: the ECP term and the total carry wf.dtype
+            means = means[:, :6].astype(complex)
+            means[:, 3] += 1j * np.mean(buffers.energy[:nsteps, 6], axis=1)
+            means[:, 5] += 1j * np.mean(buffers.energy[:nsteps, 7], axis=1)
         for i, m in enumerate(KEYS):
             tot = means[0, i] / nsteps
             for step in range(1, nsteps):
                 tot += means[step, i] / nsteps
-            block_avg[acc_name + m] = tot
+            block_avg[acc_name + m] = tot if (means.dtype != complex or m in ("ecp", "total")) else tot.real
     acc = 0.0
     for e in range(nelec):
         acc += (buffers.nacc[nsteps - 1, e] / nconf) / nelec
@@ -543,7 +548,8 @@ def vmc(wf, configs, tstep=0.5, nblocks=10, nsteps_per_block=10, nsteps=None, bl
         logging.warning(f"blockoffset {blockoffset} >= nblocks {nblocks}; no steps will be run.")
     rows = []
     todo = max(0, nblocks - blockoffset)
-    prefetch = _variate_source(wf, configs, tstep, nsteps_per_block, accumulators, todo) if todo else None
+    cplx = wf.dtype == complex  # complex blocks draw their variates on the host and take the plain library call
+    prefetch = _variate_source(wf, configs, tstep, nsteps_per_block, accumulators, todo) if todo and not cplx else None
 
     def finish_block(block, row, walkers):
         row["block"] = block
@@ -554,7 +560,7 @@ def vmc(wf, configs, tstep=0.5, nblocks=10, nsteps_per_block=10, nsteps=None, bl
         rows.append(row)
 
     try:
-        if todo and _can_pipeline(wf, prefetch):
+        if todo and not cplx and _can_pipeline(wf, prefetch):
             configs = _pipelined_blocks(wf, configs, tstep, nsteps_per_block, accumulators, prefetch,
                                         list(range(blockoffset, nblocks)), finish_block)
         else:
@@ -562,7 +568,7 @@ def vmc(wf, configs, tstep=0.5, nblocks=10, nsteps_per_block=10, nsteps=None, bl
                 if verbose:
                     print("-", end="", flush=True)
                 row, configs = vmc_block_device(wf, configs, tstep, nsteps_per_block, accumulators,
-                                                buffers=prefetch.next())
+                                                buffers=None if cplx else prefetch.next())
                 finish_block(block, row, configs)
     finally:
         if prefetch is not None:

@@ -37,7 +37,7 @@ def _energy(mol):
 
 
 def reference_vmc(wf, configs, accumulators):
-    """The reference's own driver over the device objects (complex wave functions have no device-resident block)."""
+    """The reference's own driver over the device objects (the per-call protocol)."""
     if not refload.available():
         pytest.skip("staged reference (oracle/_ref) absent")
     refload.load()
@@ -75,6 +75,59 @@ def test_cuda_reproduces_reference_golden_complex(lib, name):
     assert wf.dtype == complex and wf.wf_factors[0].dtype == complex
     assert np.array_equal(wf.parameters["wf2acoeff"], data["acoeff"])
     golden_replay.replay(data, wf, _configs(data, mol), lambda: _energy(mol), reference_vmc, check_internal)
+
+
+def device_vmc(wf, configs, accumulators):
+    """Device-resident blocks of a complex wave function (k_cx_chain around the query kernels, qmcb_vmc_block)."""
+    from pyqmc_b200 import mc
+
+    rows, accepts = [], []
+    for block in range(2):
+        avg, configs, data = mc.vmc_block_device(wf, configs, 0.5, 3, accumulators, return_walker_data=True)
+        rows.append(avg)
+        accepts.append(data["accept"])
+    df = {k: np.asarray([r[k] for r in rows]) for k in rows[0]}
+    return df, configs, np.array(accepts)
+
+
+@pytest.mark.parametrize("name", OPEN + PERIODIC)
+def test_complex_device_resident_block_reproduces_reference_golden(lib, name):
+    """The same golden replay with the VMC segment run as device-resident blocks: accept masks of the reference's own
+    run bit for bit, walkers, wrap vectors, complex block energies."""
+    data = golden_replay.load(name)
+    mol, mf, wf, _ = helpers.make_pair(name, seed=1)
+    golden_replay.replay(data, wf, _configs(data, mol), lambda: _energy(mol), device_vmc, check_internal)
+
+
+@pytest.mark.parametrize("name", ["h2o_cx", "diamond211_twist"])
+def test_complex_vmc_driver_runs_device_resident(lib, name):
+    """pyqmc_b200.vmc on a complex wave function no longer delegates: block rows equal the reference driver's over the
+    protocol calls (same seed), and kernels were launched without protocol calls in between."""
+    import pyqmc_b200 as pq
+
+    if not refload.available():
+        pytest.skip("staged reference (oracle/_ref) absent")
+    refload.load()
+    import pyqmc.method.mc as refmc
+
+    out = []
+    for driver in (pq.vmc, refmc.vmc):
+        mol, mf, wf, _ = helpers.make_pair(name, seed=1)
+        np.random.seed(9)
+        configs = pq.initial_guess(mol, 20)
+        calls = _spy_accepts(wf)
+        np.random.seed(10)
+        df, configs = driver(wf, configs, nblocks=2, nsteps_per_block=2, accumulators={"energy": _energy(mol)})
+        out.append((df, configs, len(calls)))
+    (df1, c1, n1), (df2, c2, n2) = out
+    assert n1 == 0 and n2 > 0, "pyqmc_b200.vmc must not go through updateinternals calls"
+    assert np.abs(c1.configs - c2.configs).max() < 1e-10
+    if hasattr(c1, "wrap"):
+        assert np.array_equal(c1.wrap, c2.wrap)
+    assert np.array_equal(df1["acceptance"], df2["acceptance"])
+    for k in ("energytotal", "energyke", "energyecp", "energyee", "energyei", "energygrad2"):
+        assert np.iscomplexobj(df1[k]) == np.iscomplexobj(df2[k]), k
+        assert helpers.relerr(df1[k], df2[k]) < 1e-10, k
 
 
 @pytest.mark.parametrize("name", OPEN + PERIODIC)
