@@ -798,6 +798,7 @@ struct PbcMoveArgs {
   uint8_t* accept;      // [N]
   unsigned long long* nacc;
   const double* gauss_next;  // fused kernel: variates of electron e + 1 (nullptr after the last electron)
+  int w0, wn;                // walker range [w0, w0 + wn) of this launch (wn = 0: all walkers)
 };
 
 template <int G>
@@ -871,8 +872,8 @@ __global__ void __launch_bounds__(128) k_pbc_propose(const Sys S, const State st
   const int* si;
   stage_tables(S, sd, si);
   const int lane = threadIdx.x & 31;
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= st.N) return;
+  const int w = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) + a.w0;
+  if (w >= (a.wn > 0 ? a.w0 + a.wn : st.N)) return;
   pbc_propose_warp(S, sd, si, st, w, a.e, a.tstep, a.gauss, lane);
 }
 
@@ -888,9 +889,9 @@ __global__ void __launch_bounds__(128) k_pbc_accept(const Sys S, const State st,
   extern __shared__ __align__(128) unsigned char qmcb_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const unsigned gm = 0xffffffffu;
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int w = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) + a.w0;
   const int N = st.N;
-  if (w >= N) return;
+  if (w >= (a.wn > 0 ? a.w0 + a.wn : N)) return;
   const size_t tab = (16 + (size_t)S.dwords * 8 + (size_t)S.iwords * 4 + 15) & ~(size_t)15;
   const int npb = (S.ne > 1 ? S.ne - 1 : 0) * S.nb;
   const int jper = (npb + S.natom * S.na + 1) & ~1;

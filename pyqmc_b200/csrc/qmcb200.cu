@@ -170,6 +170,9 @@ struct qmcb_ctx {
   // snapshot of the arrays it reads while the sweep of step s+1 already moves the walkers
   cudaStream_t energy_stream = nullptr;
   cudaEvent_t ev_snap = nullptr, ev_edone = nullptr;
+  // periodic fused move chain: walker ranges 1..3 run on their own streams next to range 0 on the block's stream
+  cudaStream_t split_stream[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   DBuf<double> sn_inv[2], sn_conf, sn_ap, sn_bp, sn_wrap, e_ke2, e_g22;
   // grid cap of the persistent periodic orbital kernel while it runs as overlapped background work: its CTAs stride
   // over the points and hold their SM's shared memory until the launch ends, so a full-machine grid would stall the
@@ -1305,6 +1308,14 @@ void qmcb_destroy(qmcb_ctx* c) {
   for (auto* b : {&c->sn_inv[0], &c->sn_inv[1], &c->sn_conf, &c->sn_ap, &c->sn_bp, &c->sn_wrap, &c->e_ke2, &c->e_g22}) b->release();
   if (c->ev_snap) cudaEventDestroy(c->ev_snap);
   if (c->ev_edone) cudaEventDestroy(c->ev_edone);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  for (int i = 0; i < 3; ++i) {
+    if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+    if (c->split_stream[i]) {
+      cudaStreamSynchronize(c->split_stream[i]);
+      cudaStreamDestroy(c->split_stream[i]);
+    }
+  }
   if (c->energy_stream) cudaStreamDestroy(c->energy_stream);
   if (c->d2h_stream) {
     cudaStreamSynchronize(c->d2h_stream);
@@ -2379,6 +2390,81 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
                           std::getenv("QMCB_PBC_UNFUSED") == nullptr;
     State stf = c->st;  // fused chain: the proposal keeps the pair values at the old position for the cache update
     if (fuse_pbc && c->have_jastrow && S.nb > 0) stf.jold = c->b_jold.p;
+    // Both kernels of the fused chain leave most of the machine idle at ~1000 walkers per GPU (one warp per walker:
+    // 7 warps per SM; orbital kernel: one CTA per point, under two waves), and an electron move is their dependent
+    // sequence.  The walkers are independent of each other, so the ensemble is cut into ranges whose chains run
+    // concurrently on separate streams: the orbital kernel of one range overlaps the accept kernel of another.
+    int nsplit = 1;
+    if (fuse_pbc && c->have_slater) {
+      nsplit = N >= 512 ? 2 : 1;
+      if (const char* env = std::getenv("QMCB_PBC_SPLIT")) nsplit = std::atoi(env);
+      nsplit = std::max(1, std::min(4, nsplit));
+      if ((size_t)nsplit > N) nsplit = 1;
+    }
+    if (nsplit > 1) {
+      if (!c->ev_fork) CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+      for (int k = 0; k < nsplit - 1; ++k) {
+        if (!c->split_stream[k]) {
+          int lo = 0, hi = 0;
+          CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+          CK(cudaStreamCreateWithPriority(&c->split_stream[k], cudaStreamNonBlocking, lo > hi ? lo - 1 : lo));
+          CK(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
+        }
+      }
+      CK(cudaEventRecord(c->ev_fork, stream));
+      for (int k = 0; k < nsplit - 1; ++k) CK(cudaStreamWaitEvent(c->split_stream[k], c->ev_fork, 0));
+    }
+    if (nsplit > 1) {
+      const int ldmax = std::max(S.ldc[0], S.ldc[1]);
+      const int jper = ((S.ne > 1 ? S.ne - 1 : 0) * S.nb + S.natom * S.na + 1) & ~1;
+      const size_t asm_ = ((c->smem_bytes + 15) & ~(size_t)15) + (size_t)4 * jper * 8;
+      if (prep_kernel(k_pbc_propose, c->smem_bytes) || prep_kernel(k_pbc_accept<true>, asm_)) return -1;
+      // issue order: electron outer, range inner, so that every stream has work queued from the start
+      for (int e = 0; e < S.ne; ++e) {
+        const size_t se = (size_t)step * S.ne + e;
+        const int s = e >= S.nup ? 1 : 0;
+        for (int part = 0; part < nsplit; ++part) {
+          const size_t w0 = N * part / nsplit, wn = N * (part + 1) / nsplit - w0;
+          cudaStream_t ps = part == 0 ? stream : c->split_stream[part - 1];
+          const unsigned wgrid = (unsigned)((wn * 32 + 127) / 128);
+          PbcMoveArgs ma{};
+          ma.e = e;
+          ma.tstep = tstep;
+          ma.gauss = d_gauss + se * N * 3;
+          ma.unif = d_unif + se * N;
+          ma.accept = d_accept ? d_accept + se * N : c->d_accept.p;
+          ma.nacc = nacc + se;
+          ma.gauss_next = e + 1 < S.ne ? d_gauss + (se + 1) * N * 3 : nullptr;
+          ma.w0 = (int)w0;
+          ma.wn = (int)wn;
+          if (e == 0) {
+            k_pbc_propose<<<wgrid, 128, c->smem_bytes, ps>>>(S, stf, ma);
+            c->nlaunch++;
+            CK(cudaGetLastError());
+          }
+          PbcMoArgs a{};
+          a.npoints = (long long)wn;
+          a.pos = c->st.saved_pos + w0 * 3;
+          a.wrap = c->st.saved_wrap + w0 * 3;
+          a.naip = 1;
+          a.spin_mode = 0;
+          a.spin = s;
+          a.out = c->st.monew + w0 * 5 * ldmax;
+          a.stride_p = 5 * ldmax;
+          a.stride_c = ldmax;
+          a.stride_j = 1;
+          if (launch_pbc_mo(c, 2, a, (long long)wn, ps)) return -1;
+          k_pbc_accept<true><<<wgrid, 128, asm_, ps>>>(S, stf, ma);
+          c->nlaunch++;
+          CK(cudaGetLastError());
+        }
+      }
+      for (int part = 1; part < nsplit; ++part) {
+        CK(cudaEventRecord(c->ev_join[part - 1], c->split_stream[part - 1]));
+        CK(cudaStreamWaitEvent(stream, c->ev_join[part - 1], 0));
+      }
+      c->paircache_valid = false;
+    }
     for (int e = 0; e < S.ne && pbc_general; ++e) {
       const size_t se = (size_t)step * S.ne + e;
       const int s = e >= S.nup ? 1 : 0;
@@ -2417,7 +2503,7 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
       if (launch_update(c, which, e, ma.accept, stream)) return -1;
       c->paircache_valid = false;  // the cached MO rows stay valid: accepted walkers refreshed theirs
     }
-    for (int e = 0; e < S.ne && use_pbc && !pbc_general; ++e) {
+    for (int e = 0; e < S.ne && use_pbc && !pbc_general && nsplit == 1; ++e) {
       const size_t se = (size_t)step * S.ne + e;
       const int s = e >= S.nup ? 1 : 0;
       const int ldmax = std::max(S.ldc[0], S.ldc[1]);

@@ -248,3 +248,30 @@ def test_device_resident_periodic_dmc_matches_oracle_loop(lib, name):
     assert helpers.relerr(w1, w2) < 1e-9
     for k in out2:
         assert abs(out1[k] - out2[k]) <= 1e-9 * max(1.0, abs(out2[k])), k
+
+
+@pytest.mark.parametrize("name,nconf", [("diamond211", 37), ("ortho", 10)])
+def test_periodic_block_walker_ranges_on_separate_streams(lib, monkeypatch, name, nconf):
+    """The fused periodic chain cuts the ensemble into walker ranges whose move chains run concurrently on separate
+    streams (QMCB_PBC_SPLIT, default 2 from 512 walkers): 1, 2, 3 and 4 ranges (ragged sizes) give bit-identical
+    accept masks, walkers, wrap vectors and per-walker energies."""
+    import pyqmc_b200 as pq
+    from pyqmc_b200 import mc
+
+    results = []
+    for nsplit in ("1", "2", "3", "4"):
+        monkeypatch.setenv("QMCB_PBC_SPLIT", nsplit)
+        mol, mf, wf, _ = helpers.make_pair(name, seed=1)
+        np.random.seed(11)
+        configs = pq.initial_guess(mol, nconf)
+        np.random.seed(12)
+        avg, configs, data = mc.vmc_block_device(wf, configs, 0.4, 3, {"energy": pq.EnergyAccumulator(mol, ewald_gmax=EWALD_GMAX)},
+                                                 return_walker_data=True)
+        results.append((avg, configs.configs.copy(), configs.wrap.copy(), data["accept"].copy(), data["energy"].copy()))
+    ref = results[0]
+    assert ref[3].any() and not ref[3].all()
+    for r in results[1:]:
+        assert np.array_equal(r[3], ref[3])
+        assert np.array_equal(r[1], ref[1]) and np.array_equal(r[2], ref[2])
+        assert np.array_equal(r[4], ref[4])
+        assert r[0]["energytotal"] == ref[0]["energytotal"] and r[0]["acceptance"] == ref[0]["acceptance"]
