@@ -762,6 +762,12 @@ int launch_pbc_mo(qmcb_ctx* c, int deriv, const PbcMoArgs& a, long long max_poin
     int T = std::max(std::max(ncol, nc * std::max(c->S.ldc[0], c->S.ldc[1])), 64);
     T = std::min((T + 31) / 32 * 32, 256);
     if (ncol > T) T = std::min(((ncol + 1) / 2 + 31) / 32 * 32, 256);
+    if (deriv == 0) {
+      // value rows (ECP quadrature points): the accumulator columns need few threads (nao), the (pair, shell) tasks of
+      // phase A do not -- more threads per point shorten the CTA's dependent chain (results do not depend on T)
+      static const int t0 = std::getenv("QMCB_PBC_T0") ? std::atoi(std::getenv("QMCB_PBC_T0")) : 0;
+      if (t0 >= 32 && t0 <= 256) T = std::max(T, t0 / 32 * 32);
+    }
     unsigned grid = (unsigned)std::min<long long>(max_points, 148LL * 64);
     if (c->pbc_mo_grid_cap) grid = std::min(grid, c->pbc_mo_grid_cap);
     int maxl = 0;
