@@ -143,6 +143,53 @@ def test_two_rank_dmc_statistics_and_global_branching(tmp_path, nwalk):
     assert np.allclose(np.concatenate([res[r]["weights2"] for r in range(world)]), w2s)
 
 
+def _dmc_periodic_worker(rank, world, port, nwalk, out_dir):
+    import torch.distributed as dist
+
+    from pyqmc_b200 import parallel
+    from pyqmc_b200.coord import PeriodicConfigs
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    allc, allwrap, allw, lat = _periodic_population(nwalk)
+    idx = np.array_split(np.arange(nwalk), world)[rank]
+    local = PeriodicConfigs(allc[idx].copy(), lat, wrap=allwrap[idx].copy())
+    np.random.seed(7)
+    local, w, info = parallel.branch_global(local, allw[idx].copy())
+    np.savez(os.path.join(out_dir, f"pdmc{rank}.npz"), configs=local.configs, wrap=local.wrap, weights=w)
+    dist.destroy_process_group()
+
+
+def _periodic_population(nwalk):
+    rng = np.random.RandomState(3)
+    lat = np.array([[4.0, 0.0, 0.0], [0.5, 5.0, 0.0], [0.0, 0.3, 6.0]])
+    frac = rng.rand(nwalk, 3, 3)
+    return frac @ lat, rng.randint(-2, 3, size=(nwalk, 3, 3)).astype(float), 0.5 + rng.rand(nwalk), lat
+
+
+@pytest.mark.parametrize("nwalk", [11, 16])
+def test_two_rank_global_branching_moves_wrap_vectors_with_the_walkers(tmp_path, nwalk):
+    """Periodic walkers (device-resident DMC on solids shards them like any other): the all-to-all of branch_global
+    carries the wrap vectors with the coordinates; result == serial branch (dmc.py:342-376) on the joined population."""
+    import torch.multiprocessing as mp
+
+    from pyqmc_b200 import dmc
+    from pyqmc_b200.coord import PeriodicConfigs
+
+    world = 2
+    mp.spawn(_dmc_periodic_worker, args=(world, _free_port(), nwalk, str(tmp_path)), nprocs=world, join=True)
+    res = [dict(np.load(tmp_path / f"pdmc{r}.npz")) for r in range(world)]
+    allc, allwrap, allw, lat = _periodic_population(nwalk)
+    serial = PeriodicConfigs(allc.copy(), lat, wrap=allwrap.copy())
+    np.random.seed(7)
+    serial, w, _ = dmc.branch(serial, allw.copy())
+    assert np.array_equal(np.concatenate([res[r]["configs"] for r in range(world)], axis=0), serial.configs)
+    assert np.array_equal(np.concatenate([res[r]["wrap"] for r in range(world)], axis=0), serial.wrap)
+    assert np.abs(serial.wrap).max() > 0
+    assert np.allclose(np.concatenate([res[r]["weights"] for r in range(world)]), w)
+
+
 def test_native_comb_equals_the_numpy_definition():
     """qmcb_comb_indices (one linear pass, native) == cumsum / linspace / mod / searchsorted as the reference's branch
     writes them (dmc.py:358-366): every offset class (no wrap, wrap, offset 0), equal weights (ties in the ladder),
