@@ -19,17 +19,30 @@ def shard(configs, rank, world):
 
 
 def pack_block(block_avg, nconf):
-    keys = sorted(k for k in block_avg if k not in SKIP_KEYS)
-    vec = np.empty(1 + len(keys))
-    vec[0] = nconf
-    for i, k in enumerate(keys):
-        vec[1 + i] = nconf * float(block_avg[k])
-    return keys, vec
+    """[nconf, nconf * value ...] in sorted key order; a complex value (ECP term and total energy of a complex wave
+    function) takes two slots, its key listed as ``(name, "imag")`` for the second."""
+    keys, vals = [], []
+    for k in sorted(k for k in block_avg if k not in SKIP_KEYS):
+        v = block_avg[k]
+        keys.append(k)
+        if np.iscomplexobj(v):
+            vals.append(nconf * float(np.real(v)))
+            keys.append((k, "imag"))
+            vals.append(nconf * float(np.imag(v)))
+        else:
+            vals.append(nconf * float(v))
+    return keys, np.array([float(nconf)] + vals)
 
 
 def unpack_block(keys, vec):
     total = vec[0]
-    return {k: vec[1 + i] / total for i, k in enumerate(keys)}, int(round(total))
+    out = {}
+    for i, k in enumerate(keys):
+        if isinstance(k, tuple):
+            out[k[0]] = out[k[0]] + 1j * (vec[1 + i] / total)
+        else:
+            out[k] = vec[1 + i] / total
+    return out, int(round(total))
 
 
 def allreduce_block(block_avg, nconf, group=None, device=None):

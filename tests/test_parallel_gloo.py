@@ -205,3 +205,17 @@ def test_native_comb_equals_the_numpy_definition():
         ref, rtot = dmc.comb_indices_numpy(w, off)
         assert tot == rtot
         assert np.array_equal(got, ref), (len(w), off)
+
+
+def test_block_allreduce_packs_complex_averages():
+    """Complex wave functions (device-resident blocks since round 2) return complex ECP / total block averages: the
+    one-collective-per-block vector carries real and imaginary parts in separate slots."""
+    from pyqmc_b200 import parallel
+
+    block = {"energytotal": 2.0 + 0.5j, "energyecp": -1.0 - 0.25j, "energyke": 1.5, "acceptance": 0.5, "block": 3}
+    keys, vec = parallel.pack_block(block, 7)
+    assert vec.dtype == np.float64 and len(vec) == 1 + 4 + 2
+    out, total = parallel.unpack_block(keys, 2 * vec)  # two ranks with equal shards
+    assert total == 14
+    assert out["energytotal"] == 2.0 + 0.5j and out["energyecp"] == -1.0 - 0.25j
+    assert out["energyke"] == 1.5 and not np.iscomplexobj(out["energyke"])
