@@ -72,8 +72,10 @@ int qmcb_set_slater(qmcb_ctx *ctx, int nup, int ndn, int nmo_up, const double *m
  * slater.py:32-33), gradient, value / ratio, laplacian, testvalue(_many) ratios, T-move ratios,
  * pgradient of det_coeff / mo_coeff_*, the "inverse_*" / "dets_*" state arrays -- are complex128
  * (interleaved re, im) of the same shape; log values stay real.  qmcb_energy returns 8 rows (see
- * there).  The device-resident block drivers (qmcb_vmc_block*, qmcb_dmc_block*, qmcb_sr_avg) are
- * real-only and fail on a complex context: the reference's drivers run it through the protocol. */
+ * there).  qmcb_vmc_block / qmcb_vmc_block_device run complex contexts too (query kernels chained on
+ * the device, 8 energy rows per step); the pipelined slots (qmcb_vmc_block_slot*), qmcb_dmc_block*
+ * and qmcb_sr_avg are real-only and fail on a complex context: the reference's drivers run those
+ * through the protocol. */
 int qmcb_set_slater_cx(qmcb_ctx *ctx, int nup, int ndn, int nmo_up, const double *mo_up_re,
                        const double *mo_up_im, int nmo_dn, const double *mo_dn_re,
                        const double *mo_dn_im, int ndet_up, const int32_t *occ_up, int ndet_dn,
@@ -215,7 +217,11 @@ int qmcb_tmoves(qmcb_ctx *ctx, int e, double tau, const double *ecp_u /*[necp][N
  * order: gauss [nsteps][ne][N][3] ~ N(0, tstep), unif [nsteps][ne][N], ecp_u
  * [nsteps][ne][necp][N], ecp_rot [nsteps][ne][necp][9].
  * Outputs (any may be NULL): configs [N][ne][3] final positions; accept [nsteps][ne][N]
- * (uint8); energy [nsteps][6][N]; esum [nsteps][6] walker sums; nacc [nsteps][ne]. */
+ * (uint8); energy [nsteps][6][N]; esum [nsteps][6] walker sums; nacc [nsteps][ne].
+ * Complex contexts: energy [nsteps][8][N], esum [nsteps][8] (rows as qmcb_energy).
+ * Every wave function of the path is served: open or periodic boundaries (periodic: the wrap
+ * vectors move with the walkers, read them back with qmcb_get_state "wrap"), single- or
+ * multi-determinant, with or without the three-body factor, real or complex. */
 int qmcb_vmc_block(qmcb_ctx *ctx, int nsteps, double tstep, int with_energy,
                    const double *gauss, const double *unif, const double *ecp_u,
                    const double *ecp_rot, double *configs, uint8_t *accept, double *energy,
@@ -252,8 +258,10 @@ int qmcb_sr_avg(qmcb_ctx *ctx, int nparam, const int32_t *src, const int64_t *of
  * nsteps steps without branching on the walkers held by the context (after qmcb_recompute):
  * initial local energy, then per step T-moves of every electron (propose_tmoves 73-120), the
  * drift-diffusion sweep with Umrigar drift limit and fixed-node rejection (49-70), the local
- * energy and the weight update (compute_S 224-235).  Open-boundary single-determinant
- * Slater-Jastrow only.  Random variates in the reference's consumption order:
+ * energy and the weight update (compute_S 224-235).  Any REAL wave function of the path: open or
+ * periodic boundaries, single- or multi-determinant, with or without the three-body factor
+ * (periodic T-moves are wrapped into the cell twice, as propose_tmoves does, dmc.py:110).
+ * Random variates in the reference's consumption order:
  *   ecp_u [nsteps+1][ne][necp][N], ecp_rot [nsteps+1][ne][necp][9]  energy evaluations (first = before step 0)
  *   tm_u [nsteps][ne][necp][N], tm_rot [nsteps][ne][necp][9]         nonlocal_tmoves masks / rotations
  *   tm_sel [nsteps][ne][N]  select_walker's rand();  tm_acc [nsteps][ne][N]  T-move acceptance
