@@ -188,15 +188,18 @@ def _block_averages(buffers, nsteps, nconf, nelec, acc_name, accumulator):
         # per-step walker means (one pairwise-summed reduction per (step, key) row, as np.mean of the row),
         # accumulated over the steps in order as the reference loop does (mc.py:139-147)
         means = np.mean(buffers.energy[:nsteps], axis=2)
-        if means.shape[1] == 8:  # complex wave function: the ECP term and the total carry wf.dtype
-            means = means[:, :6].astype(complex)
-            means[:, 3] += 1j * np.mean(buffers.energy[:nsteps, 6], axis=1)
-            means[:, 5] += 1j * np.mean(buffers.energy[:nsteps, 7], axis=1)
+        cplx = {}
+        if means.shape[1] == 8:  # complex wave function: the ECP term and the total carry wf.dtype (rows 6, 7 = Im);
+            # the mean is taken over the complex per-walker row, as accumulator.avg does (its pairwise order differs
+            # from that of two real rows)
+            en = buffers.energy[:nsteps]
+            cplx = {"ecp": np.mean(en[:, 3] + 1j * en[:, 6], axis=1), "total": np.mean(en[:, 5] + 1j * en[:, 7], axis=1)}
         for i, m in enumerate(KEYS):
-            tot = means[0, i] / nsteps
+            col = cplx[m] if m in cplx else means[:, i]
+            tot = col[0] / nsteps
             for step in range(1, nsteps):
-                tot += means[step, i] / nsteps
-            block_avg[acc_name + m] = tot if (means.dtype != complex or m in ("ecp", "total")) else tot.real
+                tot += col[step] / nsteps
+            block_avg[acc_name + m] = tot
     acc = 0.0
     for e in range(nelec):
         acc += (buffers.nacc[nsteps - 1, e] / nconf) / nelec

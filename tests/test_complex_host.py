@@ -73,3 +73,34 @@ def test_parameter_map_equals_linear_transform_for_complex_parameters():
     assert set(d_mine) == set(d_ref)
     for k in d_ref:
         assert np.array_equal(d_mine[k], d_ref[k]) and d_mine[k].dtype == d_ref[k].dtype, k
+
+
+def test_block_averages_of_a_complex_block_follow_the_reference_rolling_mean():
+    """Device-resident blocks of a complex wave function return 8 energy rows per step (6 real + Im ecp, Im total);
+    the block dictionary must equal what vmc_worker accumulates from accumulator.avg (mc.py:139-147): complex ecp /
+    total, real ke / ee / ei / grad2."""
+    from types import SimpleNamespace
+
+    from pyqmc_b200 import mc
+    from pyqmc_b200.accumulators import KEYS
+
+    rng = np.random.RandomState(2)
+    nsteps, nconf, nelec = 3, 17, 4
+    energy = rng.randn(nsteps, 8, nconf)
+    nacc = rng.randint(0, nconf, size=(nsteps, nelec))
+    got = mc._block_averages(SimpleNamespace(energy=energy, nacc=nacc), nsteps, nconf, nelec, "energy", object())
+    for i, k in enumerate(KEYS):
+        per_walker = energy[:, i].astype(complex) if k in ("ecp", "total") else energy[:, i]
+        if k == "ecp":
+            per_walker = per_walker + 1j * energy[:, 6]
+        if k == "total":
+            per_walker = per_walker + 1j * energy[:, 7]
+        want = None
+        for step in range(nsteps):  # the reference: block_avg[k] = res / nsteps, then += res / nsteps
+            res = np.mean(per_walker[step], axis=0)
+            want = res / nsteps if want is None else want + res / nsteps
+        assert np.iscomplexobj(got["energy" + k]) == (k in ("ecp", "total")), k
+        assert got["energy" + k] == want, k
+    real = mc._block_averages(SimpleNamespace(energy=energy[:, :6], nacc=nacc), nsteps, nconf, nelec, "energy", object())
+    assert all(not np.iscomplexobj(v) for v in real.values())
+    assert real["energyke"] == got["energyke"] and real["acceptance"] == got["acceptance"]
