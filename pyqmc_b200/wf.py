@@ -634,8 +634,8 @@ class ThreeBodyJastrow(_DeviceFactor):
     _which = JASTROW3
 
     def __init__(self, mol, a_basis, b_basis, device=None):
-        # periodic systems: every displacement goes through the minimal image (distance.py:83-159), evaluated through
-        # the per-call protocol kernels (the device-resident periodic block covers Slater x JastrowSpin)
+        # periodic systems: every displacement goes through the minimal image (distance.py:83-159), in the per-call
+        # protocol kernels and in the device-resident blocks (k_pbc_move_general + k_jastrow3_update_coop)
         self._mol = mol
         self._nelec = tuple(int(x) for x in mol.nelec)
         self._device = device
