@@ -1773,8 +1773,9 @@ __global__ void __launch_bounds__(128) k_pair_cache_build(const Sys S, const Sta
       ++i;
     }
     const int j = i + 1 + rem;
-    const double dx = CONF(st, S, w, i, 0) - CONF(st, S, w, j, 0), dy = CONF(st, S, w, i, 1) - CONF(st, S, w, j, 1),
-                 dz = CONF(st, S, w, i, 2) - CONF(st, S, w, j, 2);
+    double dx = CONF(st, S, w, i, 0) - CONF(st, S, w, j, 0), dy = CONF(st, S, w, i, 1) - CONF(st, S, w, j, 1),
+           dz = CONF(st, S, w, i, 2) - CONF(st, S, w, j, 2);
+    if (S.pbc) min_image(S, sd, dx, dy, dz);  // periodic fused chain (k_pbc_accept<true>): same caches, minimal image
     const double r = sqrt(dx * dx + dy * dy + dz * dz);
     const int sp = (i >= S.nup ? 1 : 0) + (j >= S.nup ? 1 : 0);
     double gs = 0.0, ls = 0.0;
@@ -1794,8 +1795,9 @@ __global__ void __launch_bounds__(128) k_pair_cache_build(const Sys S, const Sta
     const int s = e >= S.nup ? 1 : 0;
     double g0 = 0.0, g1 = 0.0, g2 = 0.0, la = 0.0;
     for (int I = 0; I < S.natom; ++I) {
-      const double dx = CONF(st, S, w, e, 0) - sd[S.o_xyz + 3 * I], dy = CONF(st, S, w, e, 1) - sd[S.o_xyz + 3 * I + 1],
-                   dz = CONF(st, S, w, e, 2) - sd[S.o_xyz + 3 * I + 2];
+      double dx = CONF(st, S, w, e, 0) - sd[S.o_xyz + 3 * I], dy = CONF(st, S, w, e, 1) - sd[S.o_xyz + 3 * I + 1],
+             dz = CONF(st, S, w, e, 2) - sd[S.o_xyz + 3 * I + 2];
+      if (S.pbc) min_image(S, sd, dx, dy, dz);
       const double r = sqrt(dx * dx + dy * dy + dz * dz);
       if (!(r < S.rcut_a)) continue;
       for (int k2 = 0; k2 < S.na; ++k2) {

@@ -555,11 +555,14 @@ __device__ __forceinline__ void coop_jastrow_pbc(const Sys& S, const double* __r
                                                  const int* __restrict__ si, const State& st, int w, int e, double px,
                                                  double py, double pz, int lane, unsigned gm, double& du,
                                                  double (&g)[3], double& lap, double* vb_store = nullptr,
-                                                 double* va_store = nullptr) {
+                                                 double* va_store = nullptr, double* gp_store = nullptr,
+                                                 double* ga_out = nullptr) {
   // vb_store [(ne-1)][nb] / va_store [natom][na]: the radial values at this point (0 beyond the cutoff), kept
-  // by the fused periodic move kernel for the cache update of an accepted move
+  // by the fused periodic move kernel for the cache update of an accepted move; gp_store [(ne-1)][3]: each partner's
+  // term of grad U (the pair-gradient cache entry, coop.cuh GPAIR), ga_out [3]: the electron-ion part of grad U (AGRAD)
   const int s = e >= S.nup ? 1 : 0;
   double unew = 0.0, uold = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0, lp = 0.0;
+  double ga0 = 0.0, ga1 = 0.0, ga2 = 0.0;
   const int npart = (S.nb > 0 ? S.ne - 1 : 0), nat = (S.na > 0 ? S.natom : 0);
 #pragma unroll 1
   for (int t = lane; t < npart + nat; t += G) {
@@ -587,6 +590,7 @@ __device__ __forceinline__ void coop_jastrow_pbc(const Sys& S, const double* __r
     double* vst = isb ? (vb_store ? vb_store + t * S.nb : nullptr) : (va_store ? va_store + I * S.na : nullptr);
     if (vst != nullptr && !(r < rcut))
       for (int l = 0; l < nfun; ++l) vst[l] = 0.0;
+    double gsp = 0.0;  // sum_l c_l b_l'(r) / r of this partner
     if (r < rcut) {
       const int sj = j >= S.nup ? 1 : 0;
       for (int l = 0; l < nfun; ++l) {
@@ -606,8 +610,25 @@ __device__ __forceinline__ void coop_jastrow_pbc(const Sys& S, const double* __r
         g1 = fma(cg, dy, g1);
         g2 = fma(cg, dz, g2);
         if (WANT == 2) lp = fma(c, ll, lp);
+        if (isb) {
+          gsp += cg;
+        } else if (ga_out != nullptr) {
+          ga0 = fma(cg, dx, ga0);
+          ga1 = fma(cg, dy, ga1);
+          ga2 = fma(cg, dz, ga2);
+        }
       }
     }
+    if (isb && gp_store != nullptr) {
+      gp_store[t * 3] = gsp * dx;
+      gp_store[t * 3 + 1] = gsp * dy;
+      gp_store[t * 3 + 2] = gsp * dz;
+    }
+  }
+  if (ga_out != nullptr) {
+    ga_out[0] = group_sum<G>(ga0, gm);
+    ga_out[1] = group_sum<G>(ga1, gm);
+    ga_out[2] = group_sum<G>(ga2, gm);
   }
   if (WANT != 2) {
     const int na_items = S.natom * S.na, nb_items = S.nb * 2;
@@ -729,10 +750,13 @@ __global__ void __launch_bounds__(128) k_jastrow_update_coop(const Sys S, const 
 // Cache update of an accepted move from stored radial values: jnew_b / jnew_a hold b_l / a_k at the new
 // position (coop_jastrow_pbc's vb_store / va_store), jold_b the b_l at the old one (stored by the proposal).
 // Same bookkeeping as coop_jastrow_update_pbc (jastrowspin.py:221-249) without any distance or radial work.
+// gp_new [(ne-1)][3] / ga_new [3]: pair-gradient and electron-ion gradient terms at the new position -> GPAIR / AGRAD;
+// the b_l at the old position come from BPAIR, which takes the new ones (the pair caches of coop.cuh, kept for the
+// proposal of the following electrons: their drift is a sum of cached pair terms, no minimal-image or radial work)
 template <int G>
 __device__ __forceinline__ void coop_jastrow_commit_pbc(const Sys& S, const State& st, int w, int e, int lane,
                                                         unsigned gm, const double* jnew_b, const double* jnew_a,
-                                                        const double* jold_b) {
+                                                        const double* gp_new, const double* ga_new) {
   const int s = e >= S.nup ? 1 : 0;
   if (S.na > 0) {
     for (int t = lane; t < S.natom * S.na; t += G) {
@@ -746,7 +770,9 @@ __device__ __forceinline__ void coop_jastrow_commit_pbc(const Sys& S, const Stat
     for (int t = lane; t < (S.ne - 1) * S.nb; t += G) {
       const int jj = t / S.nb, l = t - jj * S.nb;
       const int j = jj < e ? jj : jj + 1;
-      BPART(st, S, w, j, l, s) += jnew_b[t] - jold_b[t];
+      const int p = e < j ? pair_index(S.ne, e, j) : pair_index(S.ne, j, e);
+      BPART(st, S, w, j, l, s) += jnew_b[t] - BPAIR(st, S, w, p, l);
+      BPAIR(st, S, w, p, l) = jnew_b[t];
     }
 #pragma unroll 1
     for (int t = lane; t < S.nb * 2; t += G) {
@@ -759,8 +785,22 @@ __device__ __forceinline__ void coop_jastrow_commit_pbc(const Sys& S, const Stat
       BVAL(st, S, w, l, s + tt) += bn - BPART(st, S, w, e, l, tt);
       BPART(st, S, w, e, l, tt) = bn;
     }
+    for (int t = lane; t < (S.ne - 1) * 3; t += G) {
+      const int jj = t / 3, x = t - jj * 3;
+      const int j = jj < e ? jj : jj + 1;
+      if (e < j)
+        GPAIR(st, S, w, pair_index(S.ne, e, j), x) = gp_new[t];
+      else
+        GPAIR(st, S, w, pair_index(S.ne, j, e), x) = -gp_new[t];
+    }
   }
+  if (lane < 3) AGRAD(st, S, w, e, lane) = ga_new[lane];
   __syncwarp(gm);
+}
+
+// doubles of shared-memory scratch per warp of k_pbc_accept: b_l / a_k at the proposed point, pair-gradient terms
+__host__ __device__ inline int pbc_accept_jper(const Sys& S) {
+  return ((S.ne > 1 ? S.ne - 1 : 0) * (S.nb + 3) + S.natom * S.na + 3 + 1) & ~1;
 }
 
 // Sherman-Morrison row replacement by one warp, lane j owns column j (n <= NPAD <= 32): the arithmetic of
@@ -845,8 +885,10 @@ __device__ __forceinline__ void pbc_propose_warp(const Sys& S, const double* sd,
   }
   if (S.na + S.nb > 0) {
     double du, gj[3], lj;
-    double* jold = (st.jold != nullptr && S.nb > 0) ? st.jold + (size_t)w * (S.ne - 1) * S.nb : nullptr;
-    coop_jastrow_pbc<1, G>(S, sd, si, st, w, e, ox, oy, oz, lane, gm, du, gj, lj, jold);
+    if (st.jold != nullptr)  // fused chain: the pair caches are kept current (k_pair_cache_build, coop_jastrow_commit_pbc)
+      coop_jastrow_cached_grad<G>(S, st, w, e, lane, gm, gj);
+    else
+      coop_jastrow_pbc<1, G>(S, sd, si, st, w, e, ox, oy, oz, lane, gm, du, gj, lj);
 #pragma unroll
     for (int i = 0; i < 3; ++i) grad[i] = grad[i] + gj[i];
   }
@@ -894,9 +936,11 @@ __global__ void __launch_bounds__(128) k_pbc_accept(const Sys S, const State st,
   if (w >= (a.wn > 0 ? a.w0 + a.wn : N)) return;
   const size_t tab = (16 + (size_t)S.dwords * 8 + (size_t)S.iwords * 4 + 15) & ~(size_t)15;
   const int npb = (S.ne > 1 ? S.ne - 1 : 0) * S.nb;
-  const int jper = (npb + S.natom * S.na + 1) & ~1;
+  const int jper = pbc_accept_jper(S);
   double* jtmp = reinterpret_cast<double*>(qmcb_smem + tab) + (size_t)wib * jper;
-  const bool cached = FUSED && st.jold != nullptr;  // radial values kept from the two point evaluations
+  double* gps = jtmp + npb + S.natom * S.na;  // [(ne-1)][3] pair-gradient terms, then [3] electron-ion gradient
+  double* gas = gps + (S.ne > 1 ? S.ne - 1 : 0) * 3;
+  const bool cached = FUSED && st.jold != nullptr;  // radial values and pair terms kept for the cache update
   const int e = a.e;
   const int s = e >= S.nup ? 1 : 0;
   const int eeff = e - s * S.nup;
@@ -918,8 +962,10 @@ __global__ void __launch_bounds__(128) k_pbc_accept(const Sys S, const State st,
   }
   if (has_j) {
     double du, gj[3], lj;
+    double ga[3] = {0.0, 0.0, 0.0};
     coop_jastrow_pbc<1, G>(S, sd, si, st, w, e, nx, ny, nz, lane, gm, du, gj, lj, cached ? jtmp : nullptr,
-                           cached ? jtmp + npb : nullptr);
+                           cached ? jtmp + npb : nullptr, cached ? gps : nullptr, cached ? ga : nullptr);
+    if (cached && lane < 3) gas[lane] = ga[lane];
 #pragma unroll
     for (int i = 0; i < 3; ++i) ngrad[i] = ngrad[i] + gj[i];
     val = val * exp(du);
@@ -945,7 +991,7 @@ __global__ void __launch_bounds__(128) k_pbc_accept(const Sys S, const State st,
   if (acc) {
     if (has_j && cached) {
       __syncwarp(gm);
-      coop_jastrow_commit_pbc<G>(S, st, w, e, lane, gm, jtmp, jtmp + npb, st.jold + (size_t)w * npb);
+      coop_jastrow_commit_pbc<G>(S, st, w, e, lane, gm, jtmp, jtmp + npb, gps, gas);
     } else if (has_j) {
       coop_jastrow_update_pbc<G>(S, sd, si, st, w, e, nx, ny, nz, lane, gm, jtmp);
     }

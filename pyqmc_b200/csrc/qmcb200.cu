@@ -2395,7 +2395,9 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
     const bool fuse_pbc = use_pbc && !pbc_general && (!c->have_slater || (S.nup <= 32 && S.ndn <= 32)) &&
                           std::getenv("QMCB_PBC_UNFUSED") == nullptr;
     State stf = c->st;  // fused chain: the proposal keeps the pair values at the old position for the cache update
-    if (fuse_pbc && c->have_jastrow && S.nb > 0) stf.jold = c->b_jold.p;
+    // non-null = the fused chain keeps the pair caches (BPAIR / GPAIR / AGRAD) current and takes the drift at an
+    // electron's current position from them; QMCB_PBC_NO_PAIRCACHE=1 recomputes it (A/B checks)
+    if (fuse_pbc && c->have_jastrow && S.nb > 0 && std::getenv("QMCB_PBC_NO_PAIRCACHE") == nullptr) stf.jold = c->b_jold.p;
     // Both kernels of the fused chain leave most of the machine idle at ~1000 walkers per GPU (one warp per walker:
     // 7 warps per SM; orbital kernel: one CTA per point, under two waves), and an electron move is their dependent
     // sequence.  The walkers are independent of each other, so the ensemble is cut into ranges whose chains run
@@ -2406,6 +2408,15 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
       if (const char* env = std::getenv("QMCB_PBC_SPLIT")) nsplit = std::atoi(env);
       nsplit = std::max(1, std::min(4, nsplit));
       if ((size_t)nsplit > N) nsplit = 1;
+    }
+    if (stf.jold != nullptr && step == 0) {
+      // pair caches of the fused chain (b_l per pair, pair-gradient terms, electron-ion gradients) from the current
+      // walkers; the accept kernel keeps them current from here on
+      const long long nt = (long long)N * (S.npair + S.ne);
+      if (prep_kernel(k_pair_cache_build, c->smem_bytes)) return -1;
+      k_pair_cache_build<<<(unsigned)((nt + 127) / 128), 128, c->smem_bytes, stream>>>(S, c->st);
+      c->nlaunch++;
+      CK(cudaGetLastError());
     }
     if (nsplit > 1) {
       if (!c->ev_fork) CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -2422,7 +2433,7 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
     }
     if (nsplit > 1) {
       const int ldmax = std::max(S.ldc[0], S.ldc[1]);
-      const int jper = ((S.ne > 1 ? S.ne - 1 : 0) * S.nb + S.natom * S.na + 1) & ~1;
+      const int jper = pbc_accept_jper(S);
       const size_t asm_ = ((c->smem_bytes + 15) & ~(size_t)15) + (size_t)4 * jper * 8;
       if (prep_kernel(k_pbc_propose, c->smem_bytes) || prep_kernel(k_pbc_accept<true>, asm_)) return -1;
       // issue order: electron outer, range inner, so that every stream has work queued from the start
@@ -2542,7 +2553,7 @@ int qmcb_vmc_block_device(qmcb_ctx* c, int nsteps, double tstep, int with_energy
         a.stride_j = 1;
         if (launch_pbc_mo(c, 2, a, (long long)N, stream)) return -1;
       }
-      const int jper = ((S.ne > 1 ? S.ne - 1 : 0) * S.nb + S.natom * S.na + 1) & ~1;
+      const int jper = pbc_accept_jper(S);
       const size_t asm_ = ((c->smem_bytes + 15) & ~(size_t)15) + (size_t)4 * jper * 8;
       if (fuse_pbc) {
         if (prep_kernel(k_pbc_accept<true>, asm_)) return -1;

@@ -275,3 +275,30 @@ def test_periodic_block_walker_ranges_on_separate_streams(lib, monkeypatch, name
         assert np.array_equal(r[1], ref[1]) and np.array_equal(r[2], ref[2])
         assert np.array_equal(r[4], ref[4])
         assert r[0]["energytotal"] == ref[0]["energytotal"] and r[0]["acceptance"] == ref[0]["acceptance"]
+
+
+def test_periodic_pair_caches_equal_recomputation_at_full_walker_count(lib, monkeypatch):
+    """C4 shape, 1024 walkers: the fused chain with pair caches (drift at the current position from cached pair
+    gradients) against the same chain recomputing the minimal-image Jastrow (QMCB_PBC_NO_PAIRCACHE=1).  The two
+    differ by rounding in the drift only, so the accept masks of the first step are identical and the walkers agree
+    to rounding after it (over long runs rounding differences grow along each walker's trajectory, as they do
+    between any two summation orders)."""
+    import pyqmc_b200 as pq
+    from pyqmc_b200 import mc
+
+    out = []
+    for env in (None, "1"):
+        if env is None:
+            monkeypatch.delenv("QMCB_PBC_NO_PAIRCACHE", raising=False)
+        else:
+            monkeypatch.setenv("QMCB_PBC_NO_PAIRCACHE", env)
+        mol, mf, wf, _ = helpers.make_pair("diamond222", seed=1)
+        np.random.seed(3)
+        configs = pq.initial_guess(mol, 1024)
+        np.random.seed(4)
+        avg, configs, data = mc.vmc_block_device(wf, configs, 0.5, 1, {}, return_walker_data=True)
+        out.append((data["accept"].copy(), configs.configs.copy(), configs.wrap.copy()))
+    (a1, c1, w1), (a2, c2, w2) = out
+    assert 0.2 < a1.mean() < 0.8
+    assert np.array_equal(a1, a2)
+    assert np.array_equal(w1, w2) and np.abs(c1 - c2).max() < 1e-11
