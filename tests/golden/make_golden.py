@@ -137,7 +137,7 @@ def generate(name):
         out["vmc_wrap"] = configs.wrap.copy()
     for k in ("energytotal", "energyke", "energyecp", "energyee", "energyei", "energygrad2", "acceptance"):
         out["vmc_" + k] = df[k]
-    if name in ("h2o", "c2", "open", "h2o_md", "ortho", "diamond211", "ortho_md"):
+    if name in ("h2o", "c2", "open", "h2o_md", "ortho", "diamond211", "ortho_md", "rotcubic", "diamond211_md"):
         # DMC propagation with T-moves through the reference's own dmc_propagate (dmc.py:123-221)
         import pyqmc.method.dmc as dmc
 

@@ -200,7 +200,7 @@ def test_periodic_dmc_through_the_protocol(lib, name):
         assert abs(out1[k] - out2[k]) <= 1e-8 * max(1.0, abs(out2[k])), k
 
 
-@pytest.mark.parametrize("name", ["ortho", "diamond211", "ortho_md"])
+@pytest.mark.parametrize("name", ["ortho", "diamond211", "ortho_md", "rotcubic", "diamond211_md"])
 def test_device_resident_periodic_dmc_matches_reference_golden(lib, name):
     """qmcb_dmc_block on periodic wave functions (k_pbc_move_general<16, true>: fixed-node drift-diffusion with the
     wrapped proposal, T-moves wrapped as propose_tmoves wraps them, Ewald energy) against the reference's own

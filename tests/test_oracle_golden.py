@@ -202,7 +202,7 @@ def test_oracle_dmc_propagate_matches_reference_golden(name):
     golden_replay.check_dmc(data, out, configs, weights)
 
 
-@pytest.mark.parametrize("name", ["ortho", "diamond211", "ortho_md"])
+@pytest.mark.parametrize("name", ["ortho", "diamond211", "ortho_md", "rotcubic", "diamond211_md"])
 def test_oracle_dmc_propagate_matches_reference_golden_periodic(name):
     """The same for periodic systems (Ewald energy, T-moves wrapped twice as propose_tmoves does, dmc.py:110):
     walkers, wrap vectors, weights and weighted averages of the reference's dmc_propagate."""
